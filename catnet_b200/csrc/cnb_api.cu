@@ -1,0 +1,686 @@
+/* cnb_api.cu -- the C ABI (include/catnet_b200.h): device context, orchestration of K1..K5, result export.
+ *
+ * Call structure mirrors the reference: cnb_search_order = RCatnetSearch::estimateCatnets
+ * (src/rcatnet_search.cpp:57-312) around CATNET_SEARCH2::estimate (src/catnet_search2.h:152-897), with the scoring,
+ * selection and DP on the device.  No CPU fallback exists: without a CUDA device every scoring call returns
+ * CNB_ERR_CUDA.
+ */
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include "cnb_device.cuh"
+#include "cnb_kernels.h"
+#include "cnb_result.h"
+#include "cnb_ctx.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
+#define RC(call) do { int rc_ = (call); if (rc_ != CNB_OK) return rc_; } while (0)
+
+extern "C" const char *cnb_version(void) { return "catnet_b200 0.1 (sm_100a)"; }
+
+/* ------------------------------------------------------------------ context ---- */
+int DevBuf::ensure(size_t bytes) {
+	if (bytes <= cap) return CNB_OK;
+	if (ptr) cudaFree(ptr);
+	ptr = nullptr;
+	cap = 0;
+	size_t want = bytes + bytes / 8 + 256;
+	cudaError_t e = cudaMalloc(&ptr, want);
+	if (e != cudaSuccess) {
+		cnb_set_error("Insufficient device memory (%zu bytes): %s", want, cudaGetErrorString(e));
+		return CNB_ERR_MEM;
+	}
+	cap = want;
+	return CNB_OK;
+}
+void DevBuf::release() {
+	if (ptr) cudaFree(ptr);
+	ptr = nullptr;
+	cap = 0;
+}
+
+extern "C" int cnb_ctx_create(int32_t device, cnb_ctx **out) {
+	if (!out) return CNB_ERR_PARAM;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev < 1) {
+		cnb_set_error("no CUDA device: the scoring path has no CPU fallback (%s)", cudaGetErrorString(e));
+		return CNB_ERR_CUDA;
+	}
+	if (device < 0 || device >= ndev) {
+		cnb_set_error("invalid device %d (have %d)", device, ndev);
+		return CNB_ERR_PARAM;
+	}
+	CK(cudaSetDevice(device));
+	cnb_ctx *c = new cnb_ctx();
+	c->device = device;
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < CNB_NEV; i++) CK(cudaEventCreate(&c->ev[i]));
+	*out = c;
+	return CNB_OK;
+}
+
+extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (DevBuf *b : c->all_bufs()) b->release();
+	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+static float ev_ms(cnb_ctx *c, int a, int b) {
+	float ms = 0;
+	cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
+	return ms;
+}
+
+extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples_dev,
+		const int32_t *pert_dev, const int32_t *num_cats) {
+	if (!c || N < 1 || M < 1 || !samples_dev) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	c->N = N;
+	c->M = M;
+	c->W = (M + 31) / 32;
+	c->Mpad = c->W * 32;
+	c->has_pert = pert_dev != nullptr;
+	c->planned = false;
+	cudaStream_t st = c->stream;
+	CK(cudaEventRecord(c->ev[EV_PACK0], st));
+	RC(c->b_vmin.ensure(N * sizeof(int)));
+	RC(c->b_vmax.ensure(N * sizeof(int)));
+	RC(c->b_cats_lbl.ensure(N * sizeof(int)));
+	RC(c->b_flag.ensure(4 * sizeof(int)));
+	std::vector<int> vmin(N, 1), cats(N);
+	if (num_cats) {
+		for (int i = 0; i < N; i++) {
+			cats[i] = num_cats[i];
+			if (cats[i] < 1 || cats[i] > 254) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }
+		}
+	} else {
+		/* categories inferred as max - min + 1 over the non-NA values (catnet_search2.h:208-235) */
+		std::vector<int> hi(N, -INT32_MAX), lo(N, INT32_MAX);
+		CK(cudaMemcpyAsync(c->b_vmin.ptr, lo.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(c->b_vmax.ptr, hi.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+		RC(cnbk_minmax(st, samples_dev, N, M, (int *)c->b_vmin.ptr, (int *)c->b_vmax.ptr));
+		CK(cudaMemcpyAsync(lo.data(), c->b_vmin.ptr, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(hi.data(), c->b_vmax.ptr, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for (int i = 0; i < N; i++) {
+			if (lo[i] > hi[i]) { cnb_set_error("node %d has no observed value", i + 1); return CNB_ERR_PARAM; }
+			vmin[i] = lo[i];
+			cats[i] = hi[i] - lo[i] + 1;
+			if (cats[i] > 254) { cnb_set_error("more than 254 categories"); return CNB_ERR_PARAM; }
+		}
+	}
+	c->cats_lbl = cats;
+	c->max_cats = *std::max_element(cats.begin(), cats.end());
+	CK(cudaMemcpyAsync(c->b_vmin.ptr, vmin.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(c->b_cats_lbl.ptr, cats.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+	CK(cudaMemsetAsync(c->b_flag.ptr, 0, 4 * sizeof(int), st));
+	size_t words = (size_t)c->W * N;
+	RC(c->b_codes.ensure((size_t)N * c->Mpad));
+	RC(c->b_planes_lbl.ensure(words * sizeof(uint4)));
+	RC(c->b_planes.ensure(words * sizeof(uint4)));
+	if (c->has_pert) {
+		RC(c->b_keep_lbl.ensure(words * sizeof(uint32_t)));
+		RC(c->b_keep.ensure(words * sizeof(uint32_t)));
+	}
+	RC(cnbk_pack(st, samples_dev, pert_dev, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr,
+			(uint8_t *)c->b_codes.ptr, (uint4 *)c->b_planes_lbl.ptr,
+			c->has_pert ? (uint32_t *)c->b_keep_lbl.ptr : nullptr, (int *)c->b_flag.ptr));
+	int bad = 0;
+	CK(cudaMemcpyAsync(&bad, c->b_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaEventRecord(c->ev[EV_PACK1], st));
+	CK(cudaStreamSynchronize(st));
+	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
+	if (bad) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
+	c->have_samples = true;
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples,
+		const int32_t *pert, const int32_t *num_cats) {
+	if (!c || N < 1 || M < 1 || !samples) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	size_t bytes = (size_t)N * M * sizeof(int32_t);
+	DevBuf tmp_s, tmp_p;
+	int rc = tmp_s.ensure(bytes);
+	if (rc == CNB_OK && pert) rc = tmp_p.ensure(bytes);
+	if (rc == CNB_OK) {
+		cudaError_t e = cudaMemcpyAsync(tmp_s.ptr, samples, bytes, cudaMemcpyHostToDevice, c->stream);
+		if (e == cudaSuccess && pert) e = cudaMemcpyAsync(tmp_p.ptr, pert, bytes, cudaMemcpyHostToDevice, c->stream);
+		if (e != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; }
+	}
+	if (rc == CNB_OK)
+		rc = cnb_ctx_set_samples_dev(c, N, M, (const int32_t *)tmp_s.ptr, pert ? (const int32_t *)tmp_p.ptr : nullptr, num_cats);
+	cudaStreamSynchronize(c->stream);
+	tmp_s.release();
+	tmp_p.release();
+	return rc;
+}
+
+extern "C" int cnb_ctx_num_cats(const cnb_ctx *c, int32_t *out) {
+	if (!c || !c->have_samples || !out) return CNB_ERR_PARAM;
+	for (int i = 0; i < c->N; i++) out[i] = c->cats_lbl[i];
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
+	if (!c) return CNB_ERR_PARAM;
+	c->force_generic = on != 0;
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_timing(const cnb_ctx *c, cnb_timing *out) {
+	if (!c || !out) return CNB_ERR_PARAM;
+	*out = c->timing;
+	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ plan upload ---- */
+static DevData make_devdata(cnb_ctx *c) {
+	DevData D;
+	D.N = c->N; D.M = c->M; D.W = c->W; D.Mpad = c->Mpad;
+	D.planes = (const uint4 *)c->b_planes.ptr;
+	D.keep = c->has_pert ? (const uint32_t *)c->b_keep.ptr : nullptr;
+	D.codes = (const uint8_t *)c->b_codes.ptr;
+	D.keep_lbl = c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr;
+	D.order = (const int32_t *)c->b_order.ptr;
+	D.cats = (const int32_t *)c->b_cats.ptr;
+	D.lists = (const int32_t *)c->b_lists.ptr;
+	D.blocks = (const CnbBlock *)c->b_blocks.ptr;
+	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
+	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
+	return D;
+}
+
+template <class T>
+static int upload(cnb_ctx *c, DevBuf &b, const std::vector<T> &v) {
+	RC(b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+	if (!v.empty()) CK(cudaMemcpyAsync(b.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32_t world, int64_t *seg_len,
+		int64_t *num_families) {
+	if (!c || !c->have_samples || !p) { cnb_set_error("context has no samples"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	cnb_params q = *p;
+	q.num_nodes = c->N;
+	q.num_samples = c->M;
+	CK(cudaEventRecord(c->ev[EV_PLAN0], c->stream));
+	/* the previous plan's host vectors may still be the source of an async copy */
+	CK(cudaStreamSynchronize(c->stream));
+	std::string err;
+	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err));
+	CnbPlan &pl = c->plan;
+	RC(upload(c, c->b_order, pl.order));
+	RC(upload(c, c->b_cats, pl.cats));
+	RC(upload(c, c->b_lists, pl.lists));
+	RC(upload(c, c->b_blocks, pl.blocks));
+	RC(upload(c, c->b_group_blocks, pl.group_blocks));
+	RC(upload(c, c->b_groups, pl.groups));
+	if (pl.has_prior) RC(upload(c, c->b_edge, pl.edge));
+	c->blk_equal.assign(pl.blocks.size(), 0);
+	for (size_t b = 0; b < pl.blocks.size(); b++) c->blk_equal[b] = pl.nodes[pl.blocks[b].child].equal_branch;
+	RC(upload(c, c->b_blk_equal, c->blk_equal));
+	/* samples into order space (the reference re-copies the int matrix per order, rcatnet_search.cpp:151-160) */
+	RC(cnbk_permute(c->stream, (const uint4 *)c->b_planes_lbl.ptr,
+			c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, (const int *)c->b_order.ptr, c->N, c->W,
+			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr));
+	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
+	c->planned = true;
+	c->dp_done = false;
+	if (seg_len) *seg_len = pl.seg_len;
+	if (num_families) *num_families = pl.num_families;
+	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ scoring ---- */
+static int table_stride(int max_cats, int d) {
+	long long s = max_cats;
+	for (int i = 0; i < d; i++) {
+		s *= max_cats;
+		if (s > (1 << 24)) return 1 << 24;
+	}
+	return (int)s;
+}
+
+/* score families [b, e) of one launch class, choosing the kernel */
+static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d_max, long long b, long long e,
+		ScoreOut O, bool force_generic, bool allow_slicing) {
+	if (e <= b) return CNB_OK;
+	cudaStream_t st = c->stream;
+	bool fast = !force_generic && !F.ex_nd && cnbk_planes_supported(F.d, c->max_cats);
+	c->timing.fast_path = fast ? 1 : 0;
+	if (fast) {
+		int slices = 1;
+		if (allow_slicing) {
+			/* few families x many samples: slice the sample words so that the machine is filled */
+			long long n = e - b, target = 148ll * 1024;
+			if (n < target) slices = (int)std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8));
+		}
+		if (slices > 1 && !O.counts) {
+			int stride = table_stride(c->max_cats, F.d);
+			size_t bytes = (size_t)(e - b) * stride * sizeof(int);
+			RC(c->b_counts.ensure(bytes));
+			CK(cudaMemsetAsync(c->b_counts.ptr, 0, bytes, st));
+			O.counts = (int *)c->b_counts.ptr - (size_t)b * stride;
+			O.counts_stride = stride;
+		}
+		RC(cnbk_score_planes(st, D, F, c->max_cats, b, e, slices, O));
+		c->timing.kernel_launches++;
+		if (slices > 1) {
+			RC(cnbk_epilogue_counts(st, D, F, b, e, O));
+			c->timing.kernel_launches++;
+		}
+		return CNB_OK;
+	}
+	int cells = table_stride(c->max_cats, d_max);
+	if (cells > CNB_HIST_MAX_CELLS) cells = CNB_HIST_MAX_CELLS;
+	RC(cnbk_score_hist(st, D, F, b, e, cells, O, (int *)c->b_flag.ptr + 1));
+	c->timing.kernel_launches++;
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
+	if (!c || !c->planned || !scores_dev) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	CnbPlan &pl = c->plan;
+	DevData D = make_devdata(c);
+	cudaStream_t st = c->stream;
+	c->timing.kernel_launches = 0;
+	c->timing.num_families = 0;
+	c->timing.algorithmic_bytes = 0;
+	memset(c->timing.score_ms_by_parents, 0, sizeof(c->timing.score_ms_by_parents));
+	memset(c->timing.families_by_parents, 0, sizeof(c->timing.families_by_parents));
+	CK(cudaMemsetAsync((int *)c->b_flag.ptr + 1, 0, sizeof(int), st));
+	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
+	int gi = 0;
+	for (const CnbGroup &g : pl.groups) {
+		DevFamilies F;
+		memset(&F, 0, sizeof(F));
+		F.d = g.d; F.nblk = g.nblk; F.blk_off = g.blk_off; F.nfam = g.nfam;
+		long long b = (long long)pl.rank * g.chunk, e = std::min<long long>(g.nfam, b + g.chunk);
+		ScoreOut O;
+		memset(&O, 0, sizeof(O));
+		O.scores = scores_dev; O.chunk = g.chunk; O.seg_off = g.seg_off; O.seg_len = pl.seg_len;
+		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi], st));
+		RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
+		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi + 1], st));
+		if (e > b) {
+			c->timing.num_families += e - b;
+			c->timing.algorithmic_bytes += (e - b) * ((long long)(g.d + 1) * c->M + 8);
+			if (g.d < 8) c->timing.families_by_parents[g.d] += e - b;
+		}
+		gi++;
+	}
+	CK(cudaEventRecord(c->ev[EV_SCORE1], st));
+	int ovf = 0;
+	CK(cudaMemcpyAsync(&ovf, (int *)c->b_flag.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	c->timing.plan_ms = ev_ms(c, EV_PLAN0, EV_PLAN1);
+	c->timing.score_ms = ev_ms(c, EV_SCORE0, EV_SCORE1);
+	gi = 0;
+	for (const CnbGroup &g : pl.groups) {
+		if (gi < CNB_NEV_GROUPS && g.d < 8)
+			c->timing.score_ms_by_parents[g.d] += ev_ms(c, EV_GROUP0 + 2 * gi, EV_GROUP0 + 2 * gi + 1);
+		gi++;
+	}
+	return CNB_OK;
+}
+
+/* explicit family list (positions) -> per-family outputs in device buffers of the context */
+static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const std::vector<int32_t> &pars,
+		const std::vector<int32_t> &nd, int fixed_d, int stride, bool want_counts, bool force_generic) {
+	size_t n = child.size();
+	RC(upload(c, c->b_ex_child, child));
+	RC(upload(c, c->b_ex_pars, pars));
+	bool var_d = fixed_d < 0;
+	if (var_d) RC(upload(c, c->b_ex_nd, nd));
+	RC(c->b_ex_ll.ensure(n * sizeof(double)));
+	RC(c->b_ex_prior.ensure(n * sizeof(double)));
+	RC(c->b_ex_score.ensure(n * sizeof(double)));
+	RC(c->b_ex_ncount.ensure(n * sizeof(int)));
+	ScoreOut O;
+	memset(&O, 0, sizeof(O));
+	O.scores = (double *)c->b_ex_score.ptr; O.chunk = std::max<long long>(n, 1); O.seg_off = 0; O.seg_len = n;
+	O.loglik = (double *)c->b_ex_ll.ptr;
+	O.prior = (double *)c->b_ex_prior.ptr;
+	O.ncount = (int *)c->b_ex_ncount.ptr;
+	if (want_counts) {
+		RC(c->b_ex_counts.ensure(n * stride * sizeof(int)));
+		CK(cudaMemsetAsync(c->b_ex_counts.ptr, 0, n * stride * sizeof(int), c->stream));
+		O.counts = (int *)c->b_ex_counts.ptr;
+		O.counts_stride = stride;
+	}
+	DevFamilies F;
+	memset(&F, 0, sizeof(F));
+	F.explicit_list = 1;
+	F.d = var_d ? 0 : fixed_d;
+	F.nfam = n;
+	F.ex_child = (const int32_t *)c->b_ex_child.ptr;
+	F.ex_pars = (const int32_t *)c->b_ex_pars.ptr;
+	F.ex_nd = var_d ? (const int32_t *)c->b_ex_nd.ptr : nullptr;
+	int dmax = fixed_d;
+	if (var_d) { dmax = 0; for (int v : nd) dmax = std::max(dmax, v); }
+	DevData D = make_devdata(c);
+	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || fixed_d == 0, false));
+	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ selection + DP ---- */
+int cnb_ctx_run_dp(cnb_ctx *c, const double *scores_dev) {
+	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	CnbPlan &pl = c->plan;
+	cudaStream_t st = c->stream;
+	const int N = pl.N, K = pl.K;
+	CK(cudaEventRecord(c->ev[EV_SEL0], st));
+	/* base network: every node with its fixed parents only (catnet_search2.h:359-441) */
+	{
+		std::vector<int32_t> child(N), pars((size_t)N * CNB_MAXP, 0), nd(N);
+		for (int i = 0; i < N; i++) {
+			child[i] = i;
+			nd[i] = pl.nodes[i].nfix;
+			for (int k = 0; k < nd[i]; k++) pars[(size_t)i * CNB_MAXP + k] = pl.lists[pl.nodes[i].fix_off + k];
+		}
+		RC(score_explicit(c, child, pars, nd, -1, 0, false, true));
+		RC(c->b_base_v.ensure(N * sizeof(double)));
+		CK(cudaMemcpyAsync(c->b_base_v.ptr, c->b_ex_score.ptr, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	}
+	DevData D = make_devdata(c);
+	size_t nopt = (size_t)std::max<int64_t>(pl.num_options, 1);
+	RC(c->b_opt_score.ensure(nopt * sizeof(double)));
+	RC(c->b_opt_cx.ensure(nopt * sizeof(int)));
+	RC(c->b_opt_fid.ensure(nopt * sizeof(long long)));
+	RC(cnbk_select(st, D, (int)pl.blocks.size(), (const CnbGroup *)c->b_groups.ptr, (const int *)c->b_blk_equal.ptr,
+			scores_dev, pl.seg_len, (double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr));
+	c->timing.kernel_launches++;
+	CK(cudaEventRecord(c->ev[EV_SEL1], st));
+	/* DP state, double buffered */
+	size_t slots = (size_t)K + 1;
+	RC(c->b_dp_exists.ensure(2 * slots));
+	RC(c->b_dp_L.ensure(2 * slots * sizeof(double)));
+	RC(c->b_dp_pfx.ensure(2 * slots * sizeof(double)));
+	RC(c->b_bp_opt.ensure((size_t)N * slots * sizeof(long long)));
+	RC(c->b_bp_src.ensure((size_t)N * slots * sizeof(int)));
+	DpState S[2];
+	for (int i = 0; i < 2; i++) {
+		S[i].K = K;
+		S[i].exists = (unsigned char *)c->b_dp_exists.ptr + i * slots;
+		S[i].L = (double *)c->b_dp_L.ptr + i * slots;
+		S[i].pfx = (double *)c->b_dp_pfx.ptr + i * slots;
+	}
+	const double *base_v = (const double *)c->b_base_v.ptr;
+	RC(cnbk_dp_init(st, S[0], pl.base_complexity, base_v, N));
+	int cur = 0;
+	for (int n = 1; n < N; n++) {
+		const CnbNodePlan &nd = pl.nodes[n];
+		RC(cnbk_dp_node(st, S[cur], S[cur ^ 1], n, N, nd.base_cx, base_v, nd.opt_begin, nd.opt_end,
+				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr));
+		cur ^= 1;
+	}
+	c->timing.kernel_launches += N;
+	c->dp_final = cur;
+	CK(cudaEventRecord(c->ev[EV_DP1], st));
+	/* summary to the host: which slots exist and their log-lik */
+	c->h_exists.resize(slots);
+	c->h_L.resize(slots);
+	CK(cudaMemcpyAsync(c->h_exists.data(), S[cur].exists, slots, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(c->h_L.data(), S[cur].L, slots * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	c->timing.select_ms = ev_ms(c, EV_SEL0, EV_SEL1);
+	c->timing.dp_ms = ev_ms(c, EV_SEL1, EV_DP1);
+	c->dp_done = true;
+	return CNB_OK;
+}
+
+/* host view of the DP outcome: (complexity, log-lik) of every surviving network */
+int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik) {
+	if (!c || !c->dp_done) return CNB_ERR_PROC;
+	complexity->clear();
+	loglik->clear();
+	for (size_t j = 0; j < c->h_exists.size(); j++)
+		if (c->h_exists[j]) {
+			complexity->push_back((int32_t)j);
+			loglik->push_back(c->h_L[j]);
+		}
+	return CNB_OK;
+}
+
+/* materialise the networks: back-pointer walk on the device, then tables of the distinct selected families */
+int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
+	if (!c || !c->dp_done || !out) return CNB_ERR_PROC;
+	CK(cudaSetDevice(c->device));
+	CnbPlan &pl = c->plan;
+	cudaStream_t st = c->stream;
+	const int N = pl.N, K = pl.K;
+	size_t slots = (size_t)K + 1;
+	CK(cudaEventRecord(c->ev[EV_COL0], st));
+	DpState fin;
+	fin.K = K;
+	fin.exists = (unsigned char *)c->b_dp_exists.ptr + c->dp_final * slots;
+	fin.L = (double *)c->b_dp_L.ptr + c->dp_final * slots;
+	fin.pfx = (double *)c->b_dp_pfx.ptr + c->dp_final * slots;
+	RC(c->b_sel.ensure(slots * N * sizeof(long long)));
+	RC(cnbk_dp_collect(st, fin, N, (const long long *)c->b_bp_opt.ptr, (const int *)c->b_bp_src.ptr,
+			(long long *)c->b_sel.ptr));
+	c->timing.kernel_launches++;
+	std::vector<long long> sel(slots * N);
+	std::vector<long long> opt_fid((size_t)pl.num_options);
+	CK(cudaMemcpyAsync(sel.data(), c->b_sel.ptr, sel.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+	if (pl.num_options)
+		CK(cudaMemcpyAsync(opt_fid.data(), c->b_opt_fid.ptr, opt_fid.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+
+	std::unique_ptr<cnb_result> res(new cnb_result());
+	res->N = N;
+	std::vector<int32_t> ord1(N);
+	for (int i = 0; i < N; i++) ord1[i] = pl.order[i] + 1;
+	res->orders.push_back(ord1);
+	/* distinct families: key = option index (>= 0) or -(node+1) for a base family */
+	std::map<long long, int> fam_of;
+	std::vector<int32_t> ex_child, ex_pars, ex_nd;
+	auto add_family = [&](long long key, int node) -> int {
+		auto it = fam_of.find(key);
+		if (it != fam_of.end()) return it->second;
+		int id = (int)ex_child.size();
+		fam_of[key] = id;
+		ex_child.push_back(node);
+		size_t base = ex_pars.size();
+		ex_pars.resize(base + CNB_MAXP, 0);
+		const CnbNodePlan &nd = pl.nodes[node];
+		if (key < 0) {
+			ex_nd.push_back(nd.nfix);
+			for (int k = 0; k < nd.nfix; k++) ex_pars[base + k] = pl.lists[nd.fix_off + k];
+		} else {
+			/* option -> block (options of a node are laid out block after block) */
+			int bi = nd.first_blk;
+			while (bi + 1 < nd.first_blk + nd.nblk && pl.blocks[bi + 1].opt_off <= key) bi++;
+			const CnbBlock &b = pl.blocks[bi];
+			long long r = opt_fid[key] - b.start;
+			int idx[CNB_MAXP];
+			cnb_unrank_lex(b.nfree, b.d - b.nfix, r, idx);
+			for (int k = 0; k < b.nfix; k++) ex_pars[base + k] = pl.lists[b.fix_off + k];
+			for (int k = 0; k < b.d - b.nfix; k++) ex_pars[base + b.nfix + k] = pl.lists[b.free_off + idx[k]];
+			ex_nd.push_back(b.d);
+		}
+		return id;
+	};
+	for (size_t j = 0; j < slots; j++) {
+		if (!c->h_exists[j]) continue;
+		CnbNet net;
+		net.complexity = (int32_t)j;
+		net.loglik = c->h_L[j];
+		net.fam.resize(N);
+		for (int n = 0; n < N; n++) {
+			long long o = sel[j * N + n];
+			net.fam[n] = add_family(o >= 0 ? o : -(long long)(n + 1), n);
+		}
+		res->nets.push_back(std::move(net));
+	}
+	size_t nf = ex_child.size();
+	int dmax = 0;
+	for (int v : ex_nd) dmax = std::max(dmax, v);
+	int stride = table_stride(c->max_cats, dmax);
+	if (nf) {
+		RC(score_explicit(c, ex_child, ex_pars, ex_nd, -1, stride, true, true));
+		std::vector<int32_t> counts(nf * stride), ncount(nf);
+		std::vector<double> ll(nf), prior(nf);
+		CK(cudaMemcpyAsync(counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(ncount.data(), c->b_ex_ncount.ptr, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(ll.data(), c->b_ex_ll.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(prior.data(), c->b_ex_prior.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+		CK(cudaEventRecord(c->ev[EV_COL1], st));
+		CK(cudaStreamSynchronize(st));
+		res->fams.resize(nf);
+		for (size_t f = 0; f < nf; f++) {
+			CnbFamily &fm = res->fams[f];
+			fm.child = ex_child[f];
+			fm.d = ex_nd[f];
+			fm.cc = pl.cats[fm.child];
+			int ts = fm.cc;
+			for (int k = 0; k < fm.d; k++) {
+				fm.pars[k] = ex_pars[f * CNB_MAXP + k];
+				fm.pc[k] = pl.cats[fm.pars[k]];
+				ts *= fm.pc[k];
+			}
+			fm.counts.assign(counts.begin() + f * stride, counts.begin() + f * stride + ts);
+			fm.loglik = ll[f];
+			fm.prior = prior[f];
+			fm.ncount = ncount[f];
+		}
+		c->timing.collect_ms = ev_ms(c, EV_COL0, EV_COL1);
+	}
+	*out = res.release();
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_finish(cnb_ctx *c, const double *scores_dev, cnb_result **out) {
+	RC(cnb_ctx_run_dp(c, scores_dev));
+	RC(cnb_ctx_collect(c, out));
+	c->timing.total_ms = c->timing.plan_ms + c->timing.score_ms + c->timing.select_ms + c->timing.dp_ms + c->timing.collect_ms;
+	return CNB_OK;
+}
+
+int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p) {
+	int64_t seg = 0, nf = 0;
+	RC(cnb_ctx_plan(c, p, 0, 1, &seg, &nf));
+	RC(c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double)));
+	RC(cnb_ctx_score_shard(c, (double *)c->b_scores.ptr));
+	RC(cnb_ctx_run_dp(c, (const double *)c->b_scores.ptr));
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_search_order(cnb_ctx *c, const cnb_params *p, cnb_result **out) {
+	if (!out) return CNB_ERR_PARAM;
+	*out = nullptr;
+	RC(cnb_ctx_search_light(c, p));
+	RC(cnb_ctx_collect(c, out));
+	c->timing.total_ms = c->timing.plan_ms + c->timing.score_ms + c->timing.select_ms + c->timing.dp_ms + c->timing.collect_ms;
+	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ one-shot entry (the .Call body) ---- */
+static int search_order_multi(const cnb_params *p, cnb_result **out);
+
+extern "C" int cnb_search_order(const cnb_params *p, cnb_result **out) {
+	if (!p || !out) return CNB_ERR_PARAM;
+	*out = nullptr;
+	if (p->num_devices > 1) return search_order_multi(p, out);
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(p->device, &c));
+	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
+	if (rc == CNB_OK) rc = cnb_ctx_search_order(c, p, out);
+	cnb_ctx_destroy(c);
+	return rc;
+}
+
+/* One process, several GPUs (the shape an R session has): every device holds the packed matrix, scores its shard
+ * of the candidate families, the score segments are exchanged with peer copies, device 0 runs selection + DP. */
+static int search_order_multi(const cnb_params *p, cnb_result **out) {
+	const int G = p->num_devices;
+	std::vector<cnb_ctx *> cs(G, nullptr);
+	int rc = CNB_OK;
+	int64_t seg = 0, nf = 0;
+	for (int g = 0; g < G && rc == CNB_OK; g++) {
+		rc = cnb_ctx_create(p->device + g, &cs[g]);
+		if (rc == CNB_OK) rc = cnb_ctx_set_samples(cs[g], p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
+		if (rc == CNB_OK) rc = cnb_ctx_plan(cs[g], p, g, G, &seg, &nf);
+		if (rc == CNB_OK) rc = cs[g]->b_scores.ensure(std::max<int64_t>(seg * G, 1) * sizeof(double));
+	}
+	/* launch all shards, then wait: the devices run concurrently */
+	for (int g = 0; g < G && rc == CNB_OK; g++) rc = cnb_ctx_score_shard(cs[g], (double *)cs[g]->b_scores.ptr);
+	for (int g = 1; g < G && rc == CNB_OK; g++) {
+		cudaError_t e = cudaMemcpyPeerAsync((double *)cs[0]->b_scores.ptr + (size_t)g * seg, cs[0]->device,
+				(double *)cs[g]->b_scores.ptr + (size_t)g * seg, cs[g]->device, seg * sizeof(double), cs[g]->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(cs[g]->stream);
+		if (e != cudaSuccess) { cnb_set_error("CUDA peer copy: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; }
+	}
+	if (rc == CNB_OK) rc = cnb_ctx_finish(cs[0], (const double *)cs[0]->b_scores.ptr, out);
+	for (int g = 0; g < G; g++) if (cs[g]) cnb_ctx_destroy(cs[g]);
+	return rc;
+}
+
+/* ------------------------------------------------------------------ test hooks ---- */
+extern "C" int cnb_family_scores(cnb_ctx *c, int32_t nfam, int32_t d, const int32_t *children, const int32_t *parents,
+		int32_t stride, int32_t *counts_out, double *loglik_out, int32_t *ncount_out, int32_t force_generic) {
+	if (!c || !c->have_samples || nfam < 0 || d < 0 || d > CNB_MAXP) return CNB_ERR_PARAM;
+	CK(cudaSetDevice(c->device));
+	/* identity order, no pools, no prior: families are addressed by label */
+	cnb_params q;
+	memset(&q, 0, sizeof(q));
+	q.num_nodes = c->N;
+	q.num_samples = c->M;
+	q.max_parent_set = 0;
+	q.max_complexity = INT32_MAX / 2;
+	RC(cnb_ctx_plan(c, &q, 0, 1, nullptr, nullptr));
+	std::vector<int32_t> ch(children, children + nfam), pa((size_t)nfam * CNB_MAXP, 0), nd;
+	for (int f = 0; f < nfam; f++)
+		for (int k = 0; k < d; k++) pa[(size_t)f * CNB_MAXP + k] = parents[(size_t)f * d + k];
+	int need = 1;
+	if (counts_out) {
+		need = table_stride(c->max_cats, d);
+		if (stride < need) { cnb_set_error("table_stride %d < %d", stride, need); return CNB_ERR_PARAM; }
+	}
+	RC(score_explicit(c, ch, pa, nd, d, stride, counts_out != nullptr, force_generic != 0));
+	cudaStream_t st = c->stream;
+	if (counts_out) CK(cudaMemcpyAsync(counts_out, c->b_ex_counts.ptr, (size_t)nfam * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
+	if (loglik_out) CK(cudaMemcpyAsync(loglik_out, c->b_ex_ll.ptr, nfam * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (ncount_out) CK(cudaMemcpyAsync(ncount_out, c->b_ex_ncount.ptr, nfam * sizeof(int), cudaMemcpyDeviceToHost, st));
+	int ovf = 0;
+	CK(cudaMemcpyAsync(&ovf, (int *)c->b_flag.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	return CNB_OK;
+}
+
+extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double *out) {
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(device, &c));
+	DevBuf a, b;
+	int rc = a.ensure(n * sizeof(double));
+	if (rc == CNB_OK) rc = b.ensure(n * sizeof(double));
+	if (rc == CNB_OK) {
+		cudaMemcpyAsync(a.ptr, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+		rc = cnbk_device_log(c->stream, (const double *)a.ptr, n, (double *)b.ptr);
+		cudaMemcpyAsync(out, b.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+		if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cnb_set_error("CUDA: device log failed"); rc = CNB_ERR_CUDA; }
+	}
+	a.release();
+	b.release();
+	cnb_ctx_destroy(c);
+	return rc;
+}
+
+extern "C" void cnb_host_log(const double *x, int64_t n, double *out) {
+	for (int64_t i = 0; i < n; i++) out[i] = cnb_log(x[i]);
+}

@@ -1,0 +1,58 @@
+/* cnb_ctx.h -- the device context behind the opaque cnb_ctx of the C ABI. */
+#ifndef CNB_CTX_H
+#define CNB_CTX_H
+#include <cuda_runtime.h>
+#include <vector>
+#include "cnb_internal.h"
+#include "cnb_result.h"
+
+#define CNB_HIST_MAX_CELLS 16384   /* largest conditional table of the generic scorer (shared memory) */
+#define CNB_NEV_GROUPS 8
+
+enum { EV_PACK0, EV_PACK1, EV_PLAN0, EV_PLAN1, EV_SCORE0, EV_SCORE1, EV_SEL0, EV_SEL1, EV_DP1, EV_COL0, EV_COL1,
+	EV_GROUP0, CNB_NEV = EV_GROUP0 + 2 * CNB_NEV_GROUPS };
+
+struct DevBuf {
+	void *ptr = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes);   /* grow-only; contents are not preserved */
+	void release();
+};
+
+struct cnb_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[CNB_NEV];
+	int N = 0, M = 0, W = 0, Mpad = 0, max_cats = 0;
+	bool has_pert = false, have_samples = false, planned = false, dp_done = false, force_generic = false;
+	int dp_final = 0;
+	std::vector<int32_t> cats_lbl;
+	std::vector<int32_t> blk_equal;
+	std::vector<unsigned char> h_exists;
+	std::vector<double> h_L;
+	CnbPlan plan;
+	cnb_timing timing = {};
+	/* packed samples */
+	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep;
+	/* plan */
+	DevBuf b_order, b_cats, b_lists, b_blocks, b_group_blocks, b_groups, b_edge, b_blk_equal;
+	/* scoring */
+	DevBuf b_scores, b_counts, b_ex_child, b_ex_pars, b_ex_nd, b_ex_ll, b_ex_prior, b_ex_score, b_ex_ncount, b_ex_counts;
+	/* selection + DP */
+	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel;
+	std::vector<DevBuf *> all_bufs() {
+		return {&b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
+			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
+			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
+			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
+			&b_bp_src, &b_sel};
+	}
+};
+
+/* internal phases shared with the SA driver (cnb_sa.cpp) */
+int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
+int cnb_ctx_run_dp(cnb_ctx *c, const double *scores_dev);
+int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);
+int cnb_ctx_collect(cnb_ctx *c, cnb_result **out);
+
+#endif

@@ -1,0 +1,121 @@
+/* cnb_device.cuh -- device-side views of the plan and the family enumerator (K3). */
+#ifndef CNB_DEVICE_CUH
+#define CNB_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include "cnb_internal.h"
+#include "cnb_log.h"
+
+/* packed samples + plan tables, all device pointers */
+struct DevData {
+	int32_t N, M, W;            /* W = ceil(M/32) words per node */
+	int32_t Mpad;               /* W*32 */
+	const uint4 *planes;        /* [W][N] order space: .x/.y/.z/.w = one-hot bit planes of categories 0..3 */
+	const uint32_t *keep;       /* [W][N] order space: bit = sample kept for that child (perturbations), or NULL */
+	const uint8_t *codes;       /* [N_label][Mpad] zero-based codes, 255 = NA (label space) */
+	const uint32_t *keep_lbl;   /* [W][N_label] or NULL */
+	const int32_t *order;       /* [N] position -> label */
+	const int32_t *cats;        /* [N] order space */
+	const int32_t *lists;
+	const CnbBlock *blocks;
+	const int32_t *group_blocks;
+	const double *edge;         /* [N*N] order space [parent*N+child] or NULL */
+};
+
+/* one launch class: either a plan group (implicit enumeration) or an explicit family list */
+struct DevFamilies {
+	int32_t d;                  /* parents per family (explicit lists may override per family) */
+	int32_t nblk;
+	int32_t blk_off;
+	int32_t explicit_list;
+	const int32_t *ex_child;    /* [nfam] positions */
+	const int32_t *ex_pars;     /* [nfam][CNB_MAXP] positions */
+	const int32_t *ex_nd;       /* [nfam] or NULL */
+	int64_t nfam;
+};
+
+__device__ __forceinline__ long long dev_binom(int n, int k) {
+	if (k < 0 || k > n) return 0;
+	long long r = 1;
+	for (int j = 1; j <= k; j++) r = r * (n - k + j) / j;
+	return r;
+}
+
+/* lexicographic unrank: the candidate order of combinationSets() (catnet_search2.h:102-147) */
+__device__ __forceinline__ void dev_unrank(int n, int k, long long r, int *out) {
+	int base = 0;
+	for (int t = 0; t < k; t++) {
+		int kk = k - t;
+		int i;
+		if (kk == 1) {
+			i = (int)r;
+			r = 0;
+		} else {
+			long long total = dev_binom(n, kk);
+			int lo = 0, hi = n - kk;
+			while (lo < hi) {
+				int mid = (lo + hi + 1) >> 1;
+				if (total - dev_binom(n - mid, kk) <= r) lo = mid;
+				else hi = mid - 1;
+			}
+			r -= total - dev_binom(n - lo, kk);
+			i = lo;
+		}
+		out[t] = base + i;
+		base += i + 1;
+		n -= i + 1;
+	}
+}
+
+/* family id -> child position and parent positions in table order (fixed parents first, then free ascending;
+ * catnet_search2.h:532-553).  Returns the number of parents. */
+__device__ __forceinline__ int dev_family(const DevData &D, const DevFamilies &F, long long fid, int &child, int *pars) {
+	if (F.explicit_list) {
+		child = F.ex_child[fid];
+		int d = F.ex_nd ? F.ex_nd[fid] : F.d;
+		for (int i = 0; i < d; i++) pars[i] = F.ex_pars[fid * CNB_MAXP + i];
+		return d;
+	}
+	const int32_t *gb = D.group_blocks + F.blk_off;
+	int lo = 0, hi = F.nblk - 1;
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+		if (D.blocks[gb[mid]].start <= fid) lo = mid;
+		else hi = mid - 1;
+	}
+	const CnbBlock &b = D.blocks[gb[lo]];
+	child = b.child;
+	for (int i = 0; i < b.nfix; i++) pars[i] = D.lists[b.fix_off + i];
+	int idx[CNB_MAXP];
+	int k = b.d - b.nfix;
+	dev_unrank(b.nfree, k, fid - b.start, idx);
+	for (int i = 0; i < k; i++) pars[b.nfix + i] = D.lists[b.free_off + idx[i]];
+	return b.d;
+}
+
+/* Bernoulli edge prior of one candidate (catnet_search2.h:584-611): log prod e[p->n] + log prod (1 - e[i->n]) over
+ * the non-parents, products taken in exactly the reference's order; -FLT_MAX if either product is 0. */
+__device__ __forceinline__ double dev_prior(const DevData &D, int child, const int *pars, int d) {
+	const int N = D.N;
+	double t = 1.0;
+	for (int i = 0; i < d; i++) t = __dmul_rn(t, D.edge[(size_t)pars[i] * N + child]);
+	double prior = (t > 0) ? cnb_log(t) : CNB_NEG_INF;
+	double t2 = 1.0;
+	for (int i = 0; i < N; i++) {
+		if (i == child) continue;
+		bool isp = false;
+		for (int j = 0; j < d; j++) isp |= (pars[j] == i);
+		if (!isp) t2 = __dmul_rn(t2, __dsub_rn(1.0, D.edge[(size_t)i * N + child]));
+	}
+	t2 = (t2 > 0) ? cnb_log(t2) : CNB_NEG_INF;
+	if (prior == CNB_NEG_INF || t2 == CNB_NEG_INF) return CNB_NEG_INF;
+	return __dadd_rn(prior, t2);
+}
+
+/* position of family fid of group (chunk, seg_off) in the rank-major score buffer */
+__device__ __forceinline__ long long dev_score_index(long long fid, long long chunk, long long seg_off, long long seg_len) {
+	long long r = fid / chunk;
+	return r * seg_len + seg_off + (fid - r * chunk);
+}
+
+#endif

@@ -1,0 +1,78 @@
+/* cnb_internal.h -- structures shared by the host planner, the CUDA kernels and the C ABI. */
+#ifndef CNB_INTERNAL_H
+#define CNB_INTERNAL_H
+
+#include <stdint.h>
+#include <float.h>
+#include <string>
+#include <vector>
+#include "../../include/catnet_b200.h"
+
+#define CNB_MAXP 8            /* max parents of one family handled by the kernels */
+#define CNB_NEG_INF (-(double)FLT_MAX)   /* the reference's "-infinity" (catnet_search2.h:559) */
+#define CNB_PLANE_CATS 4      /* bit-plane layout holds up to 4 categories per node (one uint4 per 32 samples) */
+
+/* One candidate block = all parent sets of one size for one child (HOT LOOP 2/3, catnet_search2.h:509-553):
+ * the nfix fixed parents first, then every increasing (d - nfix)-subset of the free pool, lexicographic. */
+struct CnbBlock {
+	int32_t child;      /* order position */
+	int32_t d;          /* total parents */
+	int32_t nfix;
+	int32_t nfree;
+	int32_t fix_off;    /* into lists[]: fixed parents (positions, ascending) */
+	int32_t free_off;   /* into lists[]: free pool (positions, ascending) */
+	int32_t group;      /* index of the group (same d) this block belongs to */
+	int32_t pad;
+	int64_t ncomb;      /* C(nfree, d - nfix) */
+	int64_t start;      /* first family id of the block inside its group */
+	int64_t opt_off;    /* first option slot of this block (DP option table) */
+};
+
+/* All blocks with the same number of parents: one kernel launch class. */
+struct CnbGroup {
+	int32_t d;
+	int32_t nblk;
+	int32_t blk_off;    /* into group_blocks[] (block ids sorted by start) */
+	int32_t pad;
+	int64_t nfam;       /* families in the group */
+	int64_t chunk;      /* families per rank: ceil(nfam / world) */
+	int64_t seg_off;    /* offset of the group inside one rank segment of the score buffer */
+};
+
+struct CnbNodePlan {
+	int32_t equal_branch;   /* catnet_search2.h:491-496 */
+	int32_t nfix, fix_off;
+	int32_t base_cx;        /* (C-1) * prod C_fixed */
+	int32_t first_blk, nblk;/* blocks of this node, d ascending */
+	int64_t opt_begin, opt_end;  /* DP options of the node */
+};
+
+struct CnbPlan {
+	int32_t N = 0, M = 0, P = 0, K = 0;        /* K = max complexity (slots 0..K) */
+	int32_t rank = 0, world = 1;
+	bool has_prior = false;
+	std::vector<int32_t> order;                /* position -> 0-based label */
+	std::vector<int32_t> cats;                 /* order space */
+	std::vector<int32_t> lists;
+	std::vector<CnbBlock> blocks;
+	std::vector<CnbGroup> groups;
+	std::vector<int32_t> group_blocks;
+	std::vector<CnbNodePlan> nodes;
+	std::vector<double> edge;                  /* order space [parent*N + child], empty if no prior */
+	int64_t seg_len = 0;                       /* doubles per rank segment */
+	int64_t num_families = 0;
+	int64_t num_options = 0;
+	int32_t base_complexity = 0;
+	int32_t max_cats = 0;
+	int32_t max_d = 0;
+};
+
+/* host planner (no CUDA): cnb_plan.cpp */
+int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
+		std::string *err);
+int64_t cnb_binom(int64_t n, int64_t k);
+int cnb_unrank_lex(int32_t n, int32_t k, int64_t r, int32_t *out);
+
+void cnb_set_error(const char *fmt, ...);
+
+#endif

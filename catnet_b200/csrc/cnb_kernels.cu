@@ -1,0 +1,631 @@
+/* cnb_kernels.cu -- hand-written sm_100a kernels of the structure-search scoring path.
+ *
+ *  K1  k_minmax / k_pack / k_permute   int32 [sample][node] -> uint8 codes + one-hot bit planes (+ keep masks)
+ *                                      replaces the per-call re-marshalling of rcatnet_search.cpp:151-174 and the
+ *                                      recode of catnet_search2.h:201-257
+ *  K2a k_score_planes<D,CM>            family contingency table by AND + POPC over bit planes, one thread per
+ *                                      candidate parent set, fused fp64 log-lik epilogue
+ *                                      replaces CATNET::setNodeSampleProb + PROB_LIST::loglikelihood
+ *                                      (catnet_class.h:818-879, problist.h:224-263)
+ *  K2b k_score_hist                    generic path (any category count / table size): one CTA per family,
+ *                                      shared-memory histogram
+ *  K3  dev_family (cnb_device.cuh)     combinadic unrank of the family id, replaces combinationSets (:102-147)
+ *  K4  k_select                        per (node, d) first-maximum / option table, replaces :613-621
+ *  K5  k_dp_init / k_dp_node / k_dp_collect   knapsack over complexity with the reference's exact fp64
+ *                                      comparison semantics, replaces :653-677, :800-827, :847-865
+ */
+#include <stdio.h>
+#include "cnb_device.cuh"
+#include "cnb_kernels.h"
+
+#define SCORE_BS 128
+
+/* ------------------------------------------------------------------ K1: pack ---- */
+__global__ void k_minmax(const int32_t *__restrict__ samples, int N, int M, int *__restrict__ vmin, int *__restrict__ vmax) {
+	int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= N) return;
+	int lo = INT32_MAX, hi = -INT32_MAX;
+	for (int j = blockIdx.y; j < M; j += gridDim.y) {
+		int x = samples[(size_t)j * N + v];
+		if (x == INT32_MIN || x < 1) continue;            /* NA (rcatnet_search.cpp:156) */
+		lo = min(lo, x);
+		hi = max(hi, x);
+	}
+	if (lo <= hi) {
+		atomicMin(&vmin[v], lo);
+		atomicMax(&vmax[v], hi);
+	}
+}
+
+/* one thread per (32-sample word, node): reads are coalesced across nodes, one uint4 of planes per thread */
+__global__ void k_pack(const int32_t *__restrict__ samples, const int32_t *__restrict__ pert, int N, int M, int W,
+		const int *__restrict__ vmin, const int *__restrict__ cats, uint8_t *__restrict__ codes,
+		uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int *__restrict__ bad) {
+	int v = blockIdx.x * blockDim.x + threadIdx.x;
+	int w = blockIdx.y;
+	if (v >= N) return;
+	const int base = vmin[v], C = cats[v];
+	uint32_t pl[4] = {0, 0, 0, 0}, kp = 0;
+	uint32_t bytes[8];
+#pragma unroll
+	for (int q = 0; q < 8; q++) bytes[q] = 0;
+#pragma unroll 8
+	for (int s = 0; s < 32; s++) {
+		int j = w * 32 + s;
+		int code = 255;
+		if (j < M) {
+			int x = samples[(size_t)j * N + v];
+			if (!(x == INT32_MIN || x < 1)) {
+				code = x - base;
+				if (code < 0 || code >= C) {              /* "Incorrect categories" (catnet_search2.h:247-250) */
+					*bad = 1;
+					code = 255;
+				}
+			}
+			if (!pert || pert[(size_t)j * N + v] == 0) kp |= 1u << s;
+		}
+		if (code < 4) pl[code] |= 1u << s;
+		bytes[s >> 2] |= (uint32_t)code << ((s & 3) * 8);
+	}
+	planes[(size_t)w * N + v] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+	if (keep) keep[(size_t)w * N + v] = kp;
+	uint4 *dst = reinterpret_cast<uint4 *>(codes + (size_t)v * W * 32 + (size_t)w * 32);
+	dst[0] = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+	dst[1] = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
+}
+
+/* label space -> order space for one search (what the reference does by re-copying the whole int matrix) */
+__global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *__restrict__ keep_lbl,
+		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep) {
+	int p = blockIdx.x * blockDim.x + threadIdx.x;
+	int w = blockIdx.y;
+	if (p >= N) return;
+	int l = order[p];
+	planes[(size_t)w * N + p] = planes_lbl[(size_t)w * N + l];
+	if (keep) keep[(size_t)w * N + p] = keep_lbl[(size_t)w * N + l];
+}
+
+/* ------------------------------------------------------------------ epilogue ---- */
+/* log-lik of one count table in the reference's exact operation order (problist.h:224-250 then
+ * catnet_class.h:867-871): for each parent configuration ascending, pp = 1/N_k, loglik += n*log(n*pp) for n > 0
+ * ascending; finally divide by ncount if ncount > 1.  cnt(cfg, k) fetches a cell. */
+template <class Fetch>
+__device__ __forceinline__ double dev_loglik(int ncfg, int cc, Fetch cnt, int *ncount_out) {
+	double ll = 0.0;
+	long long ncount = 0;
+	for (int cfg = 0; cfg < ncfg; cfg++) {
+		long long nk = 0;
+		for (int k = 0; k < cc; k++) nk += cnt(cfg, k);
+		if (nk <= 0) continue;
+		ncount += nk;
+		double pp = __ddiv_rn(1.0, (double)nk);
+		for (int k = 0; k < cc; k++) {
+			int n = cnt(cfg, k);
+			if (n > 0) {
+				double dn = (double)n;
+				ll = __dadd_rn(ll, __dmul_rn(dn, cnb_log(__dmul_rn(dn, pp))));
+			}
+		}
+	}
+	if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
+	*ncount_out = (int)ncount;
+	return ll;
+}
+
+__device__ __forceinline__ void dev_store_outputs(const DevData &D, const ScoreOut &O, long long fid, int child,
+		const int *pars, int d, double ll, int ncount) {
+	double prior = 0.0;
+	double score = ll;
+	if (D.edge) {
+		prior = dev_prior(D, child, pars, d);
+		score = __dadd_rn(ll, prior);                     /* fLogLik += priorLogLik (catnet_search2.h:610) */
+	}
+	if (O.scores) O.scores[dev_score_index(fid, O.chunk, O.seg_off, O.seg_len)] = score;
+	if (O.loglik) O.loglik[fid] = ll;
+	if (O.prior) O.prior[fid] = prior;
+	if (O.ncount) O.ncount[fid] = ncount;
+}
+
+/* ------------------------------------------------------------------ K2a: bit-plane scorer ---- */
+template <int D, int CM> struct CellCount { static constexpr int value = CM * CellCount<D - 1, CM>::value; };
+template <int CM> struct CellCount<0, CM> { static constexpr int value = CM; };
+
+template <int D>
+__device__ __forceinline__ void load_word(const DevData &Dt, int w, int child, const int *pars, uint4 (&v)[D + 1]) {
+	const uint4 *row = Dt.planes + (size_t)w * Dt.N;
+#pragma unroll
+	for (int i = 0; i < D; i++) v[i] = __ldg(row + pars[i]);
+	uint4 c = __ldg(row + child);
+	if (Dt.keep) {
+		uint32_t m = __ldg(Dt.keep + (size_t)w * Dt.N + child);
+		c.x &= m; c.y &= m; c.z &= m; c.w &= m;
+	}
+	v[D] = c;
+}
+
+__device__ __forceinline__ unsigned plane_of(const uint4 &v, int i) {
+	return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+/* counts[((i0*CM+i1)*CM+..)*CM + k] += popc(P0[i0] & P1[i1] & .. & C[k]) : every index is a compile-time constant */
+template <int D, int CM>
+__device__ __forceinline__ void accumulate(unsigned (&cnt)[CellCount<D, CM>::value], const uint4 (&v)[D + 1]) {
+	if constexpr (D == 1) {
+#pragma unroll
+		for (int i = 0; i < CM; i++)
+#pragma unroll
+			for (int k = 0; k < CM; k++)
+				cnt[i * CM + k] += __popc(plane_of(v[0], i) & plane_of(v[1], k));
+	} else if constexpr (D == 2) {
+#pragma unroll
+		for (int i = 0; i < CM; i++)
+#pragma unroll
+			for (int j = 0; j < CM; j++) {
+				unsigned ab = plane_of(v[0], i) & plane_of(v[1], j);
+#pragma unroll
+				for (int k = 0; k < CM; k++)
+					cnt[(i * CM + j) * CM + k] += __popc(ab & plane_of(v[2], k));
+			}
+	} else {
+		static_assert(D == 3, "bit-plane scorer is instantiated for 1..3 parents");
+#pragma unroll
+		for (int i = 0; i < CM; i++)
+#pragma unroll
+			for (int j = 0; j < CM; j++) {
+				unsigned ab = plane_of(v[0], i) & plane_of(v[1], j);
+#pragma unroll
+				for (int l = 0; l < CM; l++) {
+					unsigned abc = ab & plane_of(v[2], l);
+#pragma unroll
+					for (int k = 0; k < CM; k++)
+						cnt[((i * CM + j) * CM + l) * CM + k] += __popc(abc & plane_of(v[3], k));
+				}
+			}
+	}
+}
+
+/* One thread per candidate family; the word loop is software-pipelined one word ahead.
+ * gridDim.y > 1 splits the sample words (few families, many samples): partial tables are then added into
+ * O.counts with atomics and k_epilogue_counts finishes.  Otherwise the epilogue runs here, through a
+ * conflict-free shared-memory transpose of the per-thread counters. */
+template <int D, int CM>
+__global__ void __launch_bounds__(SCORE_BS) k_score_planes(DevData Dt, DevFamilies F, long long fid_begin,
+		long long fid_end, int words_per_slice, ScoreOut O) {
+	constexpr int CELLS = CellCount<D, CM>::value;
+	extern __shared__ __align__(16) int s_cnt[];                           /* [CELLS][SCORE_BS] */
+	const long long fid = fid_begin + (long long)blockIdx.x * SCORE_BS + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	dev_family(Dt, F, fid, child, pars);
+
+	unsigned cnt[CELLS];
+#pragma unroll
+	for (int i = 0; i < CELLS; i++) cnt[i] = 0;
+
+	const int w0 = blockIdx.y * words_per_slice;
+	const int w1 = min(Dt.W, w0 + words_per_slice);
+	uint4 nxt[D + 1], cur[D + 1];
+	if (w0 < w1) load_word<D>(Dt, w0, child, pars, nxt);
+	for (int w = w0; w < w1; w++) {
+#pragma unroll
+		for (int i = 0; i <= D; i++) cur[i] = nxt[i];
+		if (w + 1 < w1) load_word<D>(Dt, w + 1, child, pars, nxt);
+		accumulate<D, CM>(cnt, cur);
+	}
+
+	/* actual category counts: parents (table order) then child */
+	int pc[D], cc = Dt.cats[child];
+	int ncfg = 1;
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		pc[i] = Dt.cats[pars[i]];
+		ncfg *= pc[i];
+	}
+
+	if (O.counts) {
+		/* reference layout: ((p0*C1 + p1)*C2 + ..)*Cc + k  (problist.h:143-155, 252-263) */
+		int *dst = O.counts + (size_t)fid * O.counts_stride;
+#pragma unroll
+		for (int s = 0; s < CELLS; s++) {
+			int k = s % CM, rest = s / CM, ref = 0, mul = 1;
+			bool ok = k < cc;
+#pragma unroll
+			for (int i = D - 1; i >= 0; i--) {
+				int ci = rest % CM;
+				rest /= CM;
+				ok = ok && ci < pc[i];
+				ref += ci * mul;
+				mul *= pc[i];
+			}
+			if (ok && cnt[s]) atomicAdd(dst + ref * cc + k, (int)cnt[s]);
+		}
+		if (gridDim.y > 1) return;                          /* k_epilogue_counts finishes */
+	}
+#pragma unroll
+	for (int s = 0; s < CELLS; s++) s_cnt[s * SCORE_BS + threadIdx.x] = (int)cnt[s];
+	const int *mine = s_cnt + threadIdx.x;
+	int ncount;
+	double ll = dev_loglik(ncfg, cc, [&](int cfg, int k) {
+		/* cfg is the reference's mixed-radix configuration index; map it to the CM-radix register index */
+		int rest = cfg, sidx = 0, mul = 1;
+#pragma unroll
+		for (int i = D - 1; i >= 0; i--) {
+			sidx += (rest % pc[i]) * mul;
+			rest /= pc[i];
+			mul *= CM;
+		}
+		return mine[(sidx * CM + k) * SCORE_BS];
+	}, &ncount);
+	dev_store_outputs(Dt, O, fid, child, pars, D, ll, ncount);
+}
+
+/* epilogue over tables already in global memory (split-sample mode): one thread per family */
+__global__ void k_epilogue_counts(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end, ScoreOut O) {
+	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	int d = dev_family(Dt, F, fid, child, pars);
+	int cc = Dt.cats[child], ncfg = 1;
+	for (int i = 0; i < d; i++) ncfg *= Dt.cats[pars[i]];
+	const int *tab = O.counts + (size_t)fid * O.counts_stride;
+	int ncount;
+	double ll = dev_loglik(ncfg, cc, [&](int cfg, int k) { return tab[cfg * cc + k]; }, &ncount);
+	dev_store_outputs(Dt, O, fid, child, pars, d, ll, ncount);
+}
+
+/* ------------------------------------------------------------------ K2b: generic histogram scorer ---- */
+/* One CTA per family, table in shared memory (ints) followed by the per-cell fp64 terms.  Handles any number of
+ * categories (<= 254) and parents (<= CNB_MAXP) as long as the table fits (tsize <= hist_max_cells). */
+__global__ void __launch_bounds__(256) k_score_hist(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		int max_cells, ScoreOut O, int *__restrict__ overflow) {
+	extern __shared__ __align__(16) int s_tab[];
+	__shared__ int sh_child, sh_d, sh_pars[CNB_MAXP], sh_pc[CNB_MAXP], sh_cc, sh_tsize;
+	double *terms = reinterpret_cast<double *>(s_tab + ((max_cells + 1) & ~1));
+	for (long long fid = fid_begin + blockIdx.x; fid < fid_end; fid += gridDim.x) {
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			int child, pars[CNB_MAXP];
+			int d = dev_family(Dt, F, fid, child, pars);
+			long long ts = Dt.cats[child];
+			for (int i = 0; i < d; i++) {
+				sh_pars[i] = pars[i];
+				sh_pc[i] = Dt.cats[pars[i]];
+				ts *= sh_pc[i];
+				if (ts > max_cells) ts = (long long)max_cells + 1;
+			}
+			sh_child = child;
+			sh_d = d;
+			sh_cc = Dt.cats[child];
+			sh_tsize = (int)ts;
+		}
+		__syncthreads();
+		const int d = sh_d, cc = sh_cc, tsize = sh_tsize, child = sh_child;
+		if (tsize > max_cells) {
+			if (threadIdx.x == 0) *overflow = 1;
+			continue;
+		}
+		for (int i = threadIdx.x; i < tsize; i += blockDim.x) s_tab[i] = 0;
+		__syncthreads();
+		const uint8_t *ccol = Dt.codes + (size_t)Dt.order[child] * Dt.Mpad;
+		const uint8_t *pcol[CNB_MAXP];
+		for (int i = 0; i < d; i++) pcol[i] = Dt.codes + (size_t)Dt.order[sh_pars[i]] * Dt.Mpad;
+		const uint32_t *kcol = Dt.keep_lbl ? Dt.keep_lbl + Dt.order[child] : nullptr;
+		/* four samples per thread per step: 32-bit loads of the uint8 columns */
+		for (int s4 = threadIdx.x; s4 < Dt.Mpad / 4; s4 += blockDim.x) {
+			uint32_t cv = reinterpret_cast<const uint32_t *>(ccol)[s4];
+			uint32_t pv[CNB_MAXP];
+			for (int i = 0; i < d; i++) pv[i] = reinterpret_cast<const uint32_t *>(pcol[i])[s4];
+			uint32_t km = 0xF;
+			if (kcol) km = (kcol[(size_t)(s4 >> 3) * Dt.N] >> ((s4 & 7) * 4)) & 0xF;
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				int x = (cv >> (8 * q)) & 255;
+				bool ok = x < cc && ((km >> q) & 1);
+				int idx = 0;
+				for (int i = 0; i < d; i++) {
+					int pvq = (pv[i] >> (8 * q)) & 255;
+					ok = ok && pvq < sh_pc[i];
+					idx = idx * sh_pc[i] + pvq;
+				}
+				if (ok) atomicAdd(&s_tab[idx * cc + x], 1);
+			}
+		}
+		__syncthreads();
+		/* per-cell terms in parallel, then one thread adds them in the reference's order */
+		const int ncfg = tsize / cc;
+		for (int cell = threadIdx.x; cell < tsize; cell += blockDim.x) {
+			int cfg = cell / cc;
+			long long nk = 0;
+			for (int k = 0; k < cc; k++) nk += s_tab[cfg * cc + k];
+			int n = s_tab[cell];
+			double t = 0.0;
+			if (n > 0) {
+				double pp = __ddiv_rn(1.0, (double)nk);
+				t = __dmul_rn((double)n, cnb_log(__dmul_rn((double)n, pp)));
+			}
+			terms[cell] = t;
+		}
+		if (O.counts)
+			for (int cell = threadIdx.x; cell < tsize; cell += blockDim.x)
+				O.counts[(size_t)fid * O.counts_stride + cell] = s_tab[cell];
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double ll = 0.0;
+			long long ncount = 0;
+			for (int cfg = 0; cfg < ncfg; cfg++)
+				for (int k = 0; k < cc; k++) {
+					int n = s_tab[cfg * cc + k];
+					ncount += n;
+					if (n > 0) ll = __dadd_rn(ll, terms[cfg * cc + k]);
+				}
+			if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
+			int pars[CNB_MAXP];
+			for (int i = 0; i < d; i++) pars[i] = sh_pars[i];
+			dev_store_outputs(Dt, O, fid, child, pars, d, ll, (int)ncount);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ K4: selection / option table ---- */
+/* One CTA per candidate block.  Equal-categories path: first maximum in enumeration order (strict '<' running
+ * max from -FLT_MAX, catnet_search2.h:559,613) -> one DP option.  Otherwise every candidate becomes an option. */
+__global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__restrict__ groups,
+		const int *__restrict__ blk_equal, const double *__restrict__ scores, long long seg_len,
+		double *__restrict__ opt_score, int *__restrict__ opt_cx, long long *__restrict__ opt_fid) {
+	const CnbBlock &b = Dt.blocks[blockIdx.x];
+	const CnbGroup &g = groups[b.group];
+	DevFamilies F;
+	F.d = b.d; F.nblk = g.nblk; F.blk_off = g.blk_off; F.explicit_list = 0; F.nfam = g.nfam;
+	F.ex_child = nullptr; F.ex_pars = nullptr; F.ex_nd = nullptr;
+	auto complexity_of = [&](long long fid) {
+		int child, pars[CNB_MAXP];
+		int d = dev_family(Dt, F, fid, child, pars);
+		int cx = Dt.cats[child] - 1;
+		for (int i = 0; i < d; i++) cx *= Dt.cats[pars[i]];
+		return cx;
+	};
+	if (!blk_equal[blockIdx.x]) {
+		for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
+			long long fid = b.start + r;
+			opt_score[b.opt_off + r] = scores[dev_score_index(fid, g.chunk, g.seg_off, seg_len)];
+			opt_cx[b.opt_off + r] = complexity_of(fid);
+			opt_fid[b.opt_off + r] = fid;
+		}
+		return;
+	}
+	double best = CNB_NEG_INF;
+	long long best_fid = -1;
+	for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
+		long long fid = b.start + r;
+		double s = scores[dev_score_index(fid, g.chunk, g.seg_off, seg_len)];
+		if (s > best) { best = s; best_fid = fid; }       /* ascending r per thread: first max kept */
+	}
+	__shared__ double sh_s[256];
+	__shared__ long long sh_f[256];
+	sh_s[threadIdx.x] = best;
+	sh_f[threadIdx.x] = best_fid;
+	__syncthreads();
+	for (int off = 128; off > 0; off >>= 1) {
+		if (threadIdx.x < off) {
+			double s2 = sh_s[threadIdx.x + off];
+			long long f2 = sh_f[threadIdx.x + off];
+			double s1 = sh_s[threadIdx.x];
+			long long f1 = sh_f[threadIdx.x];
+			if (f2 >= 0 && (f1 < 0 || s2 > s1 || (s2 == s1 && f2 < f1))) {
+				sh_s[threadIdx.x] = s2;
+				sh_f[threadIdx.x] = f2;
+			}
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		long long f = sh_f[0];
+		opt_score[b.opt_off] = sh_s[0];
+		opt_fid[b.opt_off] = f;
+		opt_cx[b.opt_off] = f >= 0 ? complexity_of(f) : 0;
+	}
+}
+
+/* ------------------------------------------------------------------ K5: DP over complexity ---- */
+/* loglik() of a network = sum over nodes in index order of (node loglik + prior), re-summed from zero
+ * (catnet_class.h:469-485).  pfx = that sum over nodes < c, f = the candidate's term for node c. */
+__device__ __forceinline__ double dev_resum(double pfx, double f, int c, int N, const double *__restrict__ base_v) {
+	double acc = __dadd_rn(pfx, f);
+	for (int i = c + 1; i < N; i++) acc = __dadd_rn(acc, base_v[i]);
+	return acc;
+}
+
+__global__ void k_dp_init(DpState S, int base_complexity, const double *__restrict__ base_v, int N) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > S.K) return;
+	bool ex = (j == base_complexity);
+	double l = 0.0;
+	if (ex) for (int i = 0; i < N; i++) l = __dadd_rn(l, base_v[i]);
+	S.exists[j] = ex;
+	S.L[j] = l;
+	S.pfx[j] = ex ? __dadd_rn(0.0, base_v[0]) : 0.0;
+}
+
+/* one launch per node c, one thread per target complexity slot j (the reference loops options outermost and
+ * source slots innermost; per target slot that is a scan over options in order, each with ONE source slot). */
+__global__ void __launch_bounds__(128) k_dp_node(DpState cur, DpState nxt, int c, int N, int base_cx_c,
+		const double *__restrict__ base_v, long long opt_begin, long long opt_end,
+		const double *__restrict__ opt_score, const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid,
+		long long *__restrict__ bp_opt, int *__restrict__ bp_src) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	const int K = cur.K;
+	if (j > K) return;
+	const double bv = base_v[c];
+	bool has = false;
+	double R = CNB_NEG_INF;
+	long long bo = -1;
+	int bs = -1;
+	for (long long o = opt_begin; o < opt_end; o++) {
+		if (opt_fid[o] < 0) continue;                       /* no winner for that d (:637-640) */
+		int k = j + base_cx_c - opt_cx[o];
+		if (k < 0 || k > K || !cur.exists[k]) continue;
+		double f = opt_score[o];
+		double t = __dadd_rn(__dsub_rn(cur.L[k], bv), f);  /* :665-666 */
+		if (!has && t > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+		if (has && R < t) {                                  /* :670-671 strict */
+			bo = o;
+			bs = k;
+			R = dev_resum(cur.pfx[k], f, c, N, base_v);
+		}
+	}
+	bool take = false;
+	if (cur.exists[j]) take = has && bo >= 0 && cur.L[j] < R;   /* :847-859 */
+	else take = has && bo >= 0;
+	size_t bpi = (size_t)c * (K + 1) + j;
+	if (take) {
+		nxt.exists[j] = 1;
+		nxt.L[j] = R;
+		nxt.pfx[j] = __dadd_rn(cur.pfx[bs], opt_score[bo]);
+		bp_opt[bpi] = bo;
+		bp_src[bpi] = bs;
+	} else {
+		nxt.exists[j] = cur.exists[j];
+		nxt.L[j] = cur.L[j];
+		nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
+		bp_opt[bpi] = -1;
+		bp_src[bpi] = j;
+	}
+}
+
+/* walk the back-pointers of every surviving slot: sel[j][c] = option chosen for node c (-1 = base family) */
+__global__ void k_dp_collect(DpState fin, int N, const long long *__restrict__ bp_opt, const int *__restrict__ bp_src,
+		long long *__restrict__ sel) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j > fin.K || !fin.exists[j]) return;
+	int jj = j;
+	sel[(size_t)j * N] = -1;
+	for (int c = N - 1; c >= 1; c--) {
+		size_t bpi = (size_t)c * (fin.K + 1) + jj;
+		sel[(size_t)j * N + c] = bp_opt[bpi];
+		jj = bp_src[bpi];
+	}
+}
+
+__global__ void k_device_log(const double *__restrict__ x, long long n, double *__restrict__ out) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = cnb_log(x[i]);
+}
+
+/* ------------------------------------------------------------------ launchers ---- */
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
+
+int cnbk_minmax(cudaStream_t st, const int32_t *samples, int N, int M, int *vmin, int *vmax) {
+	dim3 grid((N + 127) / 128, min(M, 1024));
+	k_minmax<<<grid, 128, 0, st>>>(samples, N, M, vmin, vmax);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int N, int M, int W, const int *vmin,
+		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad) {
+	dim3 grid((N + 127) / 128, W);
+	k_pack<<<grid, 128, 0, st>>>(samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
+		uint4 *planes, uint32_t *keep) {
+	dim3 grid((N + 127) / 128, W);
+	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+bool cnbk_planes_supported(int d, int max_cats) {
+	if (max_cats > CNB_PLANE_CATS || d < 1 || d > 3) return false;
+	if (d == 3 && max_cats > 3) return false;            /* 256 counters per thread: use the histogram kernel */
+	return true;
+}
+
+template <int D, int CM>
+static int launch_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int slices,
+		const ScoreOut &O) {
+	constexpr int CELLS = CellCount<D, CM>::value;
+	size_t smem = (size_t)CELLS * SCORE_BS * sizeof(int);
+	if (smem > 48 * 1024)     /* per device, so set on every launch (cheap) */
+		CK(cudaFuncSetAttribute(k_score_planes<D, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	long long n = e - b;
+	int wps = (Dt.W + slices - 1) / slices;
+	dim3 grid((unsigned)((n + SCORE_BS - 1) / SCORE_BS), slices);
+	k_score_planes<D, CM><<<grid, SCORE_BS, smem, st>>>(Dt, F, b, e, wps, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
+		long long fid_end, int slices, const ScoreOut &O) {
+	if (fid_end <= fid_begin) return CNB_OK;
+	if (slices > 1 && !O.counts) { cnb_set_error("sample slicing needs a counts buffer"); return CNB_ERR_PROC; }
+	const int cm = max_cats <= 2 ? 2 : (max_cats == 3 ? 3 : 4);
+#define CASE(D_, C_) if (F.d == D_ && cm == C_) return launch_planes<D_, C_>(st, Dt, F, fid_begin, fid_end, slices, O)
+	CASE(1, 2); CASE(1, 3); CASE(1, 4);
+	CASE(2, 2); CASE(2, 3); CASE(2, 4);
+	CASE(3, 2); CASE(3, 3);
+#undef CASE
+	cnb_set_error("bit-plane scorer: unsupported (d=%d, cats=%d)", F.d, max_cats);
+	return CNB_ERR_PROC;
+}
+
+int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
+		const ScoreOut &O) {
+	if (e <= b) return CNB_OK;
+	k_epilogue_counts<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
+		const ScoreOut &O, int *overflow) {
+	if (e <= b) return CNB_OK;
+	size_t smem = (size_t)((max_cells + 1) & ~1) * sizeof(int) + (size_t)max_cells * sizeof(double);
+	if (smem > 48 * 1024)
+		CK(cudaFuncSetAttribute(k_score_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	long long n = e - b;
+	unsigned grid = (unsigned)(n < (1ll << 30) ? n : (1ll << 30));
+	k_score_hist<<<grid, 256, smem, st>>>(Dt, F, b, e, max_cells, O, overflow);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
+		const double *scores, long long seg_len, double *opt_score, int *opt_cx, long long *opt_fid) {
+	if (nblocks <= 0) return CNB_OK;
+	k_select<<<nblocks, 256, 0, st>>>(Dt, groups, blk_equal, scores, seg_len, opt_score, opt_cx, opt_fid);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_dp_init(cudaStream_t st, const DpState &S, int base_complexity, const double *base_v, int N) {
+	k_dp_init<<<(S.K + 1 + 127) / 128, 128, 0, st>>>(S, base_complexity, base_v, N);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c, int N, int base_cx_c,
+		const double *base_v, long long opt_begin, long long opt_end, const double *opt_score, const int *opt_cx,
+		const long long *opt_fid, long long *bp_opt, int *bp_src) {
+	k_dp_node<<<(cur.K + 1 + 127) / 128, 128, 0, st>>>(cur, nxt, c, N, base_cx_c, base_v, opt_begin, opt_end,
+			opt_score, opt_cx, opt_fid, bp_opt, bp_src);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_dp_collect(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
+		long long *sel) {
+	k_dp_collect<<<(fin.K + 1 + 127) / 128, 128, 0, st>>>(fin, N, bp_opt, bp_src, sel);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_device_log(cudaStream_t st, const double *x, long long n, double *out) {
+	if (n <= 0) return CNB_OK;
+	k_device_log<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, out);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}

@@ -1,0 +1,49 @@
+/* cnb_kernels.h -- host-callable launchers of the kernels in cnb_kernels.cu */
+#ifndef CNB_KERNELS_H
+#define CNB_KERNELS_H
+#include <cuda_runtime.h>
+#include "cnb_internal.h"
+
+struct DevData;
+struct DevFamilies;
+
+/* where a scoring launch puts its results (any pointer may be NULL) */
+struct ScoreOut {
+	double *scores;            /* rank-major score buffer, see dev_score_index */
+	long long chunk, seg_off, seg_len;
+	double *loglik;            /* [nfam] sample-averaged log-lik without prior */
+	double *prior;             /* [nfam] */
+	int *ncount;               /* [nfam] */
+	int *counts;               /* [nfam][counts_stride] reference table layout; must be zeroed by the caller */
+	int counts_stride;
+};
+
+struct DpState {
+	int K;
+	unsigned char *exists;     /* [K+1] */
+	double *L;                 /* [K+1] network log-lik (re-summed, catnet_class.h:475-485) */
+	double *pfx;               /* [K+1] in-order partial sum over the nodes already decided */
+};
+
+int cnbk_minmax(cudaStream_t st, const int32_t *samples, int N, int M, int *vmin, int *vmax);
+int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int N, int M, int W, const int *vmin,
+		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad);
+int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
+		uint4 *planes, uint32_t *keep);
+bool cnbk_planes_supported(int d, int max_cats);
+int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
+		long long fid_end, int slices, const ScoreOut &O);
+int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
+		const ScoreOut &O);
+int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
+		const ScoreOut &O, int *overflow);
+int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
+		const double *scores, long long seg_len, double *opt_score, int *opt_cx, long long *opt_fid);
+int cnbk_dp_init(cudaStream_t st, const DpState &S, int base_complexity, const double *base_v, int N);
+int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c, int N, int base_cx_c,
+		const double *base_v, long long opt_begin, long long opt_end, const double *opt_score, const int *opt_cx,
+		const long long *opt_fid, long long *bp_opt, int *bp_src);
+int cnbk_dp_collect(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
+		long long *sel);
+int cnbk_device_log(cudaStream_t st, const double *x, long long n, double *out);
+#endif

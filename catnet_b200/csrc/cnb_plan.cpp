@@ -1,0 +1,226 @@
+/* cnb_plan.cpp -- host-side planner: turns the .Call arguments into the candidate-block table the kernels walk.
+ *
+ * Restates, for one node order, what CATNET_SEARCH2::estimate derives before it scores anything
+ * (/root/reference/src/catnet_search2.h):
+ *   :182-183  maxComplexity clamped up to numnodes
+ *   :456-489  per child: predecessors allowed by parentsPool, split into fixed / free parents
+ *   :491-496  "equal categories" test over the child's pool, which picks one of the two DP code paths
+ *   :498-503  maxpars = min(maxParentSet, parentSizes[child], pool size)
+ *   :509,:530 one candidate block per parent count d: fixed parents + every increasing subset of the free pool
+ * and the order-space marshalling of RCatnetSearch::estimateCatnets (src/rcatnet_search.cpp:141-268).
+ * Pure host C++ (no CUDA) so that it is covered by the CPU test-suite.
+ */
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include "cnb_internal.h"
+
+static thread_local char g_err[512] = "";
+
+void cnb_set_error(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *cnb_last_error(void) { return g_err; }
+
+int64_t cnb_binom(int64_t n, int64_t k) {
+	if (k < 0 || k > n) return 0;
+	if (k > n - k) k = n - k;
+	int64_t r = 1;
+	for (int64_t j = 1; j <= k; j++) {
+		/* r*(n-k+j)/j stays integral; guard overflow */
+		if (r > INT64_MAX / (n - k + j)) return INT64_MAX;
+		r = r * (n - k + j) / j;
+	}
+	return r;
+}
+
+/* rank -> k-subset of {0..n-1} in lexicographic order: the order combinationSets() emits (catnet_search2.h:102-147) */
+int cnb_unrank_lex(int32_t n, int32_t k, int64_t r, int32_t *out) {
+	if (k < 0 || k > n || r < 0 || r >= cnb_binom(n, k)) return CNB_ERR_PARAM;
+	int32_t base = 0;
+	for (int32_t t = 0; t < k; t++) {
+		int32_t kk = k - t;
+		int64_t total = cnb_binom(n, kk);
+		/* largest i with  total - C(n-i, kk) <= r  */
+		int32_t lo = 0, hi = n - kk;
+		while (lo < hi) {
+			int32_t mid = (lo + hi + 1) >> 1;
+			if (total - cnb_binom(n - mid, kk) <= r) lo = mid;
+			else hi = mid - 1;
+		}
+		r -= total - cnb_binom(n - lo, kk);
+		out[t] = base + lo;
+		base += lo + 1;
+		n -= lo + 1;
+	}
+	return CNB_OK;
+}
+
+extern "C" int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_t *out) {
+	return cnb_unrank_lex(n, k, rank, out);
+}
+
+int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
+		std::string *err) {
+	char buf[256];
+#define FAIL(code, ...) do { snprintf(buf, sizeof(buf), __VA_ARGS__); if (err) *err = buf; cnb_set_error("%s", buf); return code; } while (0)
+	if (!p || !plan) FAIL(CNB_ERR_PARAM, "null parameters");
+	const int N = p->num_nodes, M = p->num_samples;
+	if (N < 1 || M < 1) FAIL(CNB_ERR_PARAM, "Invalid sample");   /* catnet_search2.h:180 */
+	if (world < 1 || rank < 0 || rank >= world) FAIL(CNB_ERR_PARAM, "invalid shard %d/%d", rank, world);
+	CnbPlan &pl = *plan;
+	pl = CnbPlan();
+	pl.N = N;
+	pl.M = M;
+	pl.P = p->max_parent_set;
+	pl.K = std::max(p->max_complexity, N);
+	pl.rank = rank;
+	pl.world = world;
+
+	/* order: rcatnet_search.cpp:111-128 */
+	pl.order.resize(N);
+	std::vector<int32_t> pos_of(N, -1);
+	for (int i = 0; i < N; i++) {
+		int lbl = p->order ? p->order[i] : i + 1;
+		if (lbl <= 0 || lbl > N) FAIL(CNB_ERR_PARAM, "Invalid nodeOrder parameter");
+		if (pos_of[lbl - 1] >= 0) FAIL(CNB_ERR_PARAM, "Invalid nodeOrder parameter");
+		pos_of[lbl - 1] = i;
+		pl.order[i] = lbl - 1;
+	}
+	pl.cats.resize(N);
+	for (int i = 0; i < N; i++) {
+		pl.cats[i] = cats_lbl[pl.order[i]];
+		if (pl.cats[i] < 1) FAIL(CNB_ERR_PARAM, "Incorrect categories");
+		pl.max_cats = std::max(pl.max_cats, pl.cats[i]);
+	}
+
+	/* pools -> membership in order space (rcatnet_search.cpp:191-256) */
+	auto load_pool = [&](const int32_t *pool, std::vector<uint8_t> &memb, std::vector<uint8_t> &has_row) {
+		memb.assign((size_t)N * N, 0);
+		has_row.assign(N, 0);
+		for (int i = 0; i < N; i++) {
+			const int32_t *row = pool + (size_t)pl.order[i] * N;
+			for (int j = 0; j < N && row[j] > 0; j++) {
+				has_row[i] = 1;
+				if (row[j] <= N) memb[(size_t)i * N + pos_of[row[j] - 1]] = 1;
+			}
+		}
+	};
+	std::vector<uint8_t> pool_m, pool_has, fix_m, fix_has;
+	if (p->parents_pool) load_pool(p->parents_pool, pool_m, pool_has);
+	if (p->fixed_parents) load_pool(p->fixed_parents, fix_m, fix_has);
+
+	if (p->edge_prob) {
+		pl.has_prior = true;
+		pl.edge.resize((size_t)N * N);
+		for (int j = 0; j < N; j++)
+			for (int i = 0; i < N; i++)
+				pl.edge[(size_t)j * N + i] = p->edge_prob[(size_t)pl.order[j] * N + pl.order[i]];
+	}
+
+	pl.nodes.resize(N);
+	std::vector<int32_t> fix, fre;
+	for (int c = 0; c < N; c++) {
+		CnbNodePlan &nd = pl.nodes[c];
+		fix.clear();
+		fre.clear();
+		for (int j = 0; j < c; j++) {
+			/* an empty parentsPool row is encoded by the reference as a self reference: nothing allowed */
+			bool allow = !p->parents_pool || pool_m[(size_t)c * N + j];
+			if (!allow) continue;
+			bool fixd = p->fixed_parents && fix_m[(size_t)c * N + j];
+			(fixd ? fix : fre).push_back(j);
+		}
+		nd.nfix = (int32_t)fix.size();
+		nd.fix_off = (int32_t)pl.lists.size();
+		pl.lists.insert(pl.lists.end(), fix.begin(), fix.end());
+		int32_t free_off = (int32_t)pl.lists.size();
+		pl.lists.insert(pl.lists.end(), fre.begin(), fre.end());
+		int64_t cx = pl.cats[c] - 1;
+		for (int v : fix) cx *= pl.cats[v];
+		if (cx > INT32_MAX) FAIL(CNB_ERR_PARAM, "fixed parent set of node %d too complex", c + 1);
+		nd.base_cx = (int32_t)cx;
+		pl.base_complexity += nd.base_cx;
+		/* equal categories over parset = free ++ fixed (catnet_search2.h:488-496) */
+		nd.equal_branch = 1;
+		int first_cat = !fre.empty() ? pl.cats[fre[0]] : (!fix.empty() ? pl.cats[fix[0]] : 0);
+		for (int v : fre) if (pl.cats[v] != first_cat) nd.equal_branch = 0;
+		for (int v : fix) if (pl.cats[v] != first_cat) nd.equal_branch = 0;
+		int maxpars = p->max_parent_set;
+		if (p->parent_sizes && p->parent_sizes[pl.order[c]] < maxpars) maxpars = p->parent_sizes[pl.order[c]];
+		if (maxpars > (int)(fre.size() + fix.size())) maxpars = (int)(fre.size() + fix.size());
+		nd.first_blk = (int32_t)pl.blocks.size();
+		nd.nblk = 0;
+		if (nd.nfix > CNB_MAXP) FAIL(CNB_ERR_PARAM, "more than %d fixed parents", CNB_MAXP);
+		if (c == 0) continue;                                   /* main loop starts at node 1 (:444) */
+		for (int d = nd.nfix + 1; d <= maxpars; d++) {
+			if (d > CNB_MAXP) FAIL(CNB_ERR_PARAM, "maxParentSet > %d is not supported", CNB_MAXP);
+			CnbBlock b;
+			memset(&b, 0, sizeof(b));
+			b.child = c;
+			b.d = d;
+			b.nfix = nd.nfix;
+			b.nfree = (int32_t)fre.size();
+			b.fix_off = nd.fix_off;
+			b.free_off = free_off;
+			b.ncomb = cnb_binom(b.nfree, d - nd.nfix);
+			if (b.ncomb <= 0) continue;
+			if (b.ncomb == INT64_MAX) FAIL(CNB_ERR_PARAM, "too many candidate parent sets");
+			pl.blocks.push_back(b);
+			nd.nblk++;
+			pl.max_d = std::max(pl.max_d, d);
+		}
+	}
+	if (pl.base_complexity > pl.K)
+		FAIL(CNB_ERR_PARAM, "maxComplexity %d below the complexity %d of the base network", pl.K, pl.base_complexity);
+
+	/* groups by parent count; family ids inside a group follow block order (child ascending) */
+	for (int d = 1; d <= pl.max_d; d++) {
+		CnbGroup g;
+		memset(&g, 0, sizeof(g));
+		g.d = d;
+		g.blk_off = (int32_t)pl.group_blocks.size();
+		for (size_t b = 0; b < pl.blocks.size(); b++) {
+			if (pl.blocks[b].d != d) continue;
+			pl.blocks[b].group = (int32_t)pl.groups.size();
+			pl.blocks[b].start = g.nfam;
+			g.nfam += pl.blocks[b].ncomb;
+			pl.group_blocks.push_back((int32_t)b);
+			g.nblk++;
+		}
+		if (!g.nblk) continue;
+		g.chunk = (g.nfam + world - 1) / world;
+		g.seg_off = pl.seg_len;
+		pl.seg_len += g.chunk;
+		pl.num_families += g.nfam;
+		pl.groups.push_back(g);
+	}
+	/* DP option table: one slot per block on the equal-categories path, one per candidate otherwise */
+	for (int c = 0; c < N; c++) {
+		CnbNodePlan &nd = pl.nodes[c];
+		nd.opt_begin = pl.num_options;
+		for (int b = nd.first_blk; b < nd.first_blk + nd.nblk; b++) {
+			pl.blocks[b].opt_off = pl.num_options;
+			pl.num_options += nd.equal_branch ? 1 : pl.blocks[b].ncomb;
+		}
+		nd.opt_end = pl.num_options;
+	}
+	return CNB_OK;
+#undef FAIL
+}
+
+extern "C" int64_t cnb_num_families(const cnb_params *p) {
+	if (!p || p->num_nodes < 1) return -1;
+	std::vector<int32_t> cats(p->num_nodes, 2);
+	if (p->num_cats) cats.assign(p->num_cats, p->num_cats + p->num_nodes);
+	CnbPlan pl;
+	cnb_params q = *p;
+	if (q.num_samples < 1) q.num_samples = 1;
+	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr) != CNB_OK) return -1;
+	return pl.num_families;
+}

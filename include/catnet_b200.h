@@ -1,0 +1,176 @@
+/*
+ * catnet_b200.h -- C ABI of the B200-native structure-search scoring path of catnet.
+ *
+ * This is the drop-in boundary: exactly what the reference's .Call glue for cnSearchOrder / cnSearchSA binds.
+ * Plain pointers and sizes only (no torch, no SEXP); all arrays are HOST memory unless a name ends in _dev.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   cnb_search_order      catnetOptimalNetsForOrder (src/catnet_rexport.h:36-40, registered src/ccnInit.c:30)
+ *                         -> RCatnetSearch::estimateCatnets (src/rcatnet_search.cpp:57-312)
+ *                         -> CATNET_SEARCH2::estimate       (src/catnet_search2.h:152-897)
+ *   cnb_search_sa         catnetOptimalNetsSA (src/catnet_rexport.h:42-48, src/ccnInit.c:31)
+ *                         -> RCatnetSearchSA::search        (src/rcatnet_sa.cpp:253-935)
+ *   cnb_release_cache     catnetReleaseCache (src/catnet_rexport.h:62, src/cache.cpp:62-76)
+ *   cnb_set_seed          catnetSetSeed      (src/catnet_rexport.h:64, src/ccnInit.c:26)
+ *   cnb_params            SEARCH_PARAMETERS  (src/search_params.h:39-58) as filled from the .Call arguments
+ *   cnb_result_*          RCatnet::genRcatnet / genProbList (src/rcatnet.cpp:174-345): the S4 catNetwork slots
+ *   cnb_family_scores     CATNET::setParents + setNodeSampleProb (src/catnet_class.h:393-433, 818-879) -- test hook
+ *
+ * Conventions kept from the reference:
+ *   - samples arrive as R hands them to .Call: INTSXP matrix numnodes x numsamples, column-major, i.e. element
+ *     [sample j][node i] at j*numnodes + i; values are 1-based category indices; NA_INTEGER (INT_MIN) or any
+ *     value < 1 is missing (rcatnet_search.cpp:151-160).
+ *   - node order, pools and fixed parents are 1-based node labels, as in R.
+ *   - return codes are the reference's CATNET_ERR_* (src/utils.h:57-60) plus CNB_ERR_CUDA; nothing longjmps
+ *     across this boundary (the R shim turns codes into Rf_error on the calling thread).
+ *   - "-infinity" log-likelihood is -FLT_MAX, as in the reference.
+ *
+ * There is no CPU fallback: every scoring call needs the sm_100a kernels and fails with CNB_ERR_CUDA without a GPU.
+ */
+#ifndef CATNET_B200_H
+#define CATNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNB_OK          0
+#define CNB_ERR_MEM   (-10)   /* CATNET_ERR_MEM   */
+#define CNB_ERR_PARAM (-20)   /* CATNET_ERR_PARAM */
+#define CNB_ERR_PROC  (-30)   /* CATNET_ERR_PROC  */
+#define CNB_ERR_CUDA  (-40)   /* CUDA runtime / no device / kernels missing */
+
+#define CNB_NA_INTEGER INT32_MIN
+
+typedef struct cnb_ctx cnb_ctx;        /* device context: packed sample matrix resident in HBM */
+typedef struct cnb_result cnb_result;  /* list of networks indexed by complexity */
+
+/* ---- arguments of ccnOptimalNetsForOrder (label space, exactly as R passes them) ---- */
+typedef struct cnb_params {
+	int32_t num_nodes;             /* N */
+	int32_t num_samples;           /* M */
+	const int32_t *samples;        /* [M][N], 1-based categories, NA = CNB_NA_INTEGER or < 1 */
+	const int32_t *perturbations;  /* [M][N] or NULL; non-zero = sample excluded for that node as a child */
+	int32_t max_parent_set;        /* rMaxParents */
+	const int32_t *parent_sizes;   /* [N] or NULL (rParentSizes) */
+	int32_t max_complexity;        /* rMaxComplexity (clamped up to N, catnet_search2.h:182) */
+	const int32_t *order;          /* [N] 1-based labels, position -> label; NULL = 1..N (rOrder) */
+	const int32_t *num_cats;       /* [N] categories per node (rNodeCats given as 1..C), or NULL = infer
+	                                  max-min+1 from the data (catnet_search2.h:208-235) */
+	const int32_t *parents_pool;   /* [N][N] rows of 1-based labels, 0-terminated/padded; an empty row means
+	                                  "no parents allowed" (rcatnet_search.cpp:216-222); NULL = unrestricted */
+	const int32_t *fixed_parents;  /* [N][N] same encoding; NULL = none (rFixedParentsPool) */
+	const double  *edge_prob;      /* [N*N] the R matrix edgeProb[child,parent] in R's column-major layout, i.e.
+	                                  element at parent*N + child; NULL = no prior (rMatEdgeLiks) */
+	int32_t echo;                  /* rEcho: progress lines on stderr */
+	/* --- extensions (zero = reference behaviour on one GPU) --- */
+	int32_t device;                /* CUDA device ordinal for the one-shot calls */
+	int32_t num_devices;           /* >1: shard candidate parent sets over devices [device, device+num_devices)
+	                                  of this process; scores exchanged by peer copies */
+} cnb_params;
+
+/* ---- extra arguments of ccnOptimalNetsSA ---- */
+typedef struct cnb_sa_params {
+	int32_t select_mode;           /* rModel: 0 = highest complexity, 1 = "AIC", 2 = "BIC" (rcatnet_sa.cpp:323-327) */
+	const int32_t *start_order;    /* [N] 1-based labels (rStartOrder) */
+	double temp_start, temp_cool_fact;
+	int32_t temp_check_orders, max_iter;
+	double order_shuffles;         /* <0: "jump" moves; fractional part = Bernoulli extra shuffle (:371-377) */
+	double stop_diff;
+	int32_t num_threads;           /* rThreads: proposals evaluated per SA step (first accepted wins, :646-657) */
+	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
+	const double *dir_prob;        /* [N*N] R layout or NULL (rDirProbs) */
+	uint64_t seed;                 /* uniform stream (splitmix64); R's RNG is not reachable through a C ABI */
+} cnb_sa_params;
+
+/* ---- one-shot entry points (what the R shim calls) ---- */
+int cnb_search_order(const cnb_params *p, cnb_result **out);
+int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+void cnb_release_cache(void);
+void cnb_set_seed(int32_t seed);
+const char *cnb_last_error(void);
+const char *cnb_version(void);
+
+/* ---- resident-context API (SA, bench, multi-process sharding) ---- */
+int cnb_ctx_create(int32_t device, cnb_ctx **out);
+void cnb_ctx_destroy(cnb_ctx *ctx);
+/* copy the sample matrix to the device and pack it (K1): uint8 column-major codes + one-hot bit planes */
+int cnb_ctx_set_samples(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, const int32_t *samples,
+		const int32_t *perturbations, const int32_t *num_cats);
+/* same, but the [M][N] int32 matrix (and optional perturbations) already live in device memory */
+int cnb_ctx_set_samples_dev(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, const int32_t *samples_dev,
+		const int32_t *perturbations_dev, const int32_t *num_cats);
+/* categories per node as used on the device (given or inferred), label space */
+int cnb_ctx_num_cats(const cnb_ctx *ctx, int32_t *num_cats_out);
+/* search for one order on the resident data; samples/perturbations/num_cats/device fields of p are ignored */
+int cnb_ctx_search_order(cnb_ctx *ctx, const cnb_params *p, cnb_result **out);
+/* simulated annealing over orders on the resident data (per-order evaluation on the device) */
+int cnb_ctx_search_sa(cnb_ctx *ctx, const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+
+/* sharded search, one process per GPU: plan -> score own shard -> (caller all-gathers) -> finish.
+ * The score buffer is one fp64 per candidate family, laid out rank-major: segment r (seg_len doubles) holds rank r's
+ * families.  cnb_ctx_score_shard writes this rank's segment at scores_dev + rank*seg_len; after an all-gather of
+ * the segments every rank passes the full buffer to cnb_ctx_finish, which runs arg-max + DP on the device. */
+int cnb_ctx_plan(cnb_ctx *ctx, const cnb_params *p, int32_t rank, int32_t world, int64_t *seg_len, int64_t *num_families);
+int cnb_ctx_score_shard(cnb_ctx *ctx, double *scores_dev);
+int cnb_ctx_finish(cnb_ctx *ctx, const double *scores_dev, cnb_result **out);
+
+/* per-phase device times of the last search on this context, CUDA events on the library's stream (ms) */
+typedef struct cnb_timing {
+	float pack_ms, plan_ms, score_ms, select_ms, dp_ms, collect_ms, total_ms;
+	float score_ms_by_parents[8];   /* [d] scoring kernel time for candidate sets with d parents */
+	int64_t families_by_parents[8];
+	int64_t num_families;           /* candidate families scored by this rank */
+	int64_t algorithmic_bytes;      /* sum over scored families of (d+1)*M + 8 */
+	int32_t kernel_launches;
+	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
+} cnb_timing;
+int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
+
+/* ---- test hooks ---- */
+/* counts + log-lik of explicit families; children/parents are 0-based node LABELS; counts_out is
+ * [nfam][table_stride] int32 in the reference's table layout (first listed parent most significant, child
+ * fastest; problist.h:143-155, 252-263); loglik_out is the sample-averaged log-lik (catnet_class.h:867-871). */
+int cnb_family_scores(cnb_ctx *ctx, int32_t nfam, int32_t num_parents, const int32_t *children,
+		const int32_t *parents, int32_t table_stride, int32_t *counts_out, double *loglik_out,
+		int32_t *ncount_out, int32_t force_generic);
+/* route every search of this context through the generic histogram kernel (1) or let the library choose (0) */
+int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
+/* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */
+int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);
+/* the same log evaluated on the host by this library (no GPU needed) */
+void cnb_host_log(const double *x, int64_t n, double *out);
+/* lexicographic unrank used by the device enumerator (host mirror; catnet_search2.h:102-147 order) */
+int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_t *out);
+int64_t cnb_num_families(const cnb_params *p);
+
+/* ---- result accessors (the catNetwork slots) ---- */
+int32_t cnb_result_num_networks(const cnb_result *r);
+int32_t cnb_result_num_nodes(const cnb_result *r);
+/* network i (ascending complexity): complexity, log-likelihood */
+int cnb_result_network(const cnb_result *r, int32_t i, int32_t *complexity, double *loglik);
+/* parents of every node of network i, order space (node k = k-th of the order; 0-based positions):
+ * num_parents[N]; parents [N][max_parents_cap] */
+int cnb_result_parents(const cnb_result *r, int32_t i, int32_t *num_parents, int32_t *parents, int32_t max_parents_cap);
+/* the order network i is expressed in: position -> 1-based node label (differs per network after a merge) */
+int cnb_result_order(const cnb_result *r, int32_t i, int32_t *order_out);
+/* raw sample counts of a node's table (before normalisation); returns the table size */
+int cnb_result_counts(const cnb_result *r, int32_t i, int32_t node, int32_t *counts, int32_t cap);
+/* node-level view: log-lik, prior, sample size, CPT (normalised like problist.h:193-222); returns table size */
+int cnb_result_node(const cnb_result *r, int32_t i, int32_t node, double *loglik, double *prior, int32_t *sample_size,
+		double *probs, int32_t probs_cap);
+/* SA only: accepted order (1-based labels), iterations, accepted steps */
+int cnb_result_sa_info(const cnb_result *r, int32_t *order_out, int32_t *niter, int32_t *naccept);
+/* SA only: log-lik of every evaluated proposal and whether it was accepted; returns the trace length */
+int cnb_result_sa_trace(const cnb_result *r, double *loglik, int32_t *accepted, int32_t cap);
+/* merge b into a per complexity keeping the higher likelihood (R/catnet.search.R:317-332) */
+int cnb_result_merge(cnb_result *a, const cnb_result *b);
+void cnb_result_free(cnb_result *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATNET_B200_H */

@@ -78,7 +78,9 @@ int ref_family_score(const int *samples0, int N, int M, const int *numCats, int 
 		if (numCats[i] > maxcats) maxcats = numCats[i];
 	RefNet net(N, d, maxcats, 0, 0, 0, numCats);
 	std::vector<int> pars(parents, parents + d);
-	net.setParents(child, d > 0 ? &pars[0] : 0, d);
+	/* d == 0: the constructor already made the parent-less table; setParents(.., 0) would free it and bail out
+	 * on CATNET_MALLOC(0) (catnet_class.h:414-419), and estimate() never calls it that way (:387-389) */
+	if (d > 0) net.setParents(child, &pars[0], d);
 	double ll = net.setNodeSampleProb(child, const_cast<int*>(samples0), M);
 	PROB_LIST<double> *pl = net.getNodeProb(child);
 	if (!pl) return -1;
@@ -519,7 +521,7 @@ double ref_score_family_list(const int *samples0, int N, int M, const int *numCa
 	std::vector<int> pars(d > 0 ? d : 1);
 	for (int f = 0; f < nfam; f++) {
 		for (i = 0; i < d; i++) pars[i] = parents[(size_t)f * d + i];
-		net.setParents(children[f], &pars[0], d);
+		if (d > 0) net.setParents(children[f], &pars[0], d);
 		double ll = net.setNodeSampleProb(children[f], const_cast<int*>(samples0), M);
 		if (scores_out) scores_out[f] = ll;
 		acc += ll;

@@ -1,0 +1,56 @@
+"""Shared helpers for the parity tests: random problems and network comparison."""
+import numpy as np
+
+NA = -2147483648
+
+
+def random_problem(seed, n, m, cats=None, na_frac=0.0, structured=True):
+    """[M][N] int32 1-based samples with some dependence between nodes, optional NAs. cats: int, list, or None=mixed 2..4"""
+    rng = np.random.default_rng(seed)
+    if cats is None:
+        c = rng.integers(2, 5, size=n)
+    elif np.isscalar(cats):
+        c = np.full(n, cats)
+    else:
+        c = np.asarray(cats)
+    s = np.zeros((m, n), dtype=np.int32)
+    for i in range(n):
+        base = rng.integers(0, c[i], size=m)
+        if structured and i > 0:
+            p = rng.integers(0, i)
+            copy = rng.random(m) < 0.5
+            base = np.where(copy, (s[:, p] - 1) % c[i], base)
+        s[:, i] = base + 1
+    # make sure every category occurs (so that inferred and given category counts agree)
+    for i in range(n):
+        s[:c[i], i] = np.arange(1, c[i] + 1)
+    if na_frac > 0:
+        mask = rng.random(s.shape) < na_frac
+        mask[:int(c.max()), :] = False
+        s[mask] = NA
+    return s, c.astype(np.int32)
+
+
+def nets_by_complexity(nets):
+    return {n["complexity"]: n for n in nets}
+
+
+def compare_search(ours, theirs, rel=1e-9, check_probs=True):
+    """ours: list from catnet_b200._abi.read_result; theirs: list from oracle.ref.search_order.
+    Returns the number of networks whose log-lik is bit-identical."""
+    a, b = nets_by_complexity(ours), nets_by_complexity(theirs)
+    assert sorted(a) == sorted(b), "different sets of complexity slots: only ours %s, only ref %s" % (
+        sorted(set(a) - set(b))[:10], sorted(set(b) - set(a))[:10])
+    exact = 0
+    for cx in sorted(a):
+        x, y = a[cx], b[cx]
+        assert x["parents"] == y["parents"], "complexity %d: parents differ\n ours %s\n ref  %s" % (
+            cx, x["parents"], y["parents"])
+        assert abs(x["loglik"] - y["loglik"]) <= rel * abs(y["loglik"]) + 1e-300, (cx, x["loglik"], y["loglik"])
+        exact += x["loglik"] == y["loglik"]
+        assert x["sample_sizes"] == y["sample_sizes"], cx
+        for k in range(len(x["parents"])):
+            assert abs(x["node_loglik"][k] - y["node_loglik"][k]) <= rel * abs(y["node_loglik"][k]) + 1e-300
+            if check_probs and len(x["probs"]):
+                np.testing.assert_allclose(x["probs"][k], y["probs"][k], rtol=1e-12, atol=0)
+    return exact
