@@ -42,7 +42,7 @@ class Timing(C.Structure):
                 ("dp_ms", C.c_float), ("collect_ms", C.c_float), ("total_ms", C.c_float),
                 ("score_ms_by_parents", C.c_float * 8), ("families_by_parents", C.c_int64 * 8),
                 ("num_families", C.c_int64), ("algorithmic_bytes", C.c_int64), ("kernel_launches", C.c_int32),
-                ("fast_path", C.c_int32)]
+                ("fast_path", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("score_ms_by_parents", "families_by_parents")}
@@ -56,7 +56,7 @@ SYMBOLS = [
     "cnb_search_order", "cnb_search_sa", "cnb_release_cache", "cnb_set_seed", "cnb_last_error", "cnb_version",
     "cnb_ctx_create", "cnb_ctx_destroy", "cnb_ctx_set_samples", "cnb_ctx_set_samples_dev", "cnb_ctx_num_cats",
     "cnb_ctx_search_order", "cnb_ctx_search_sa", "cnb_ctx_plan", "cnb_ctx_score_shard", "cnb_ctx_finish",
-    "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_device_log", "cnb_host_log",
+    "cnb_ctx_select_dp", "cnb_ctx_collect", "cnb_ctx_set_stream", "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_device_log", "cnb_host_log",
     "cnb_unrank_combination", "cnb_num_families", "cnb_result_num_networks", "cnb_result_num_nodes",
     "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_counts", "cnb_result_node",
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
@@ -92,6 +92,9 @@ def lib():
         "cnb_ctx_plan": (i32, [vp, P(Params), i32, i32, P(i64), P(i64)]),
         "cnb_ctx_score_shard": (i32, [vp, vp]),
         "cnb_ctx_finish": (i32, [vp, vp, P(vp)]),
+        "cnb_ctx_select_dp": (i32, [vp, vp]),
+        "cnb_ctx_collect": (i32, [vp, P(vp)]),
+        "cnb_ctx_set_stream": (i32, [vp, vp]),
         "cnb_ctx_timing": (i32, [vp, P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_family_scores": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32]),
@@ -290,6 +293,17 @@ class Context:
 
     def score_shard(self, scores_dev_ptr):
         check(lib().cnb_ctx_score_shard(self.h, scores_dev_ptr))
+
+    def select_dp(self, scores_dev_ptr):
+        check(lib().cnb_ctx_select_dp(self.h, scores_dev_ptr))
+
+    def collect_raw(self):
+        h = C.c_void_p()
+        check(lib().cnb_ctx_collect(self.h, C.byref(h)))
+        return h
+
+    def set_stream(self, cuda_stream):
+        check(lib().cnb_ctx_set_stream(self.h, cuda_stream))
 
     def finish_raw(self, scores_dev_ptr):
         h = C.c_void_p()

@@ -17,6 +17,8 @@
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 #define RC(call) do { int rc_ = (call); if (rc_ != CNB_OK) return rc_; } while (0)
+#define H2D(c, dst, src, n) do { CK(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyHostToDevice, (c)->stream)); (c)->timing.h2d_bytes += (int64_t)(n); } while (0)
+#define D2H(c, dst, src, n) do { CK(cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, (c)->stream)); (c)->timing.d2h_bytes += (int64_t)(n); } while (0)
 
 extern "C" const char *cnb_version(void) { return "catnet_b200 0.1 (sm_100a)"; }
 
@@ -57,7 +59,8 @@ extern "C" int cnb_ctx_create(int32_t device, cnb_ctx **out) {
 	CK(cudaSetDevice(device));
 	cnb_ctx *c = new cnb_ctx();
 	c->device = device;
-	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
 	for (int i = 0; i < CNB_NEV; i++) CK(cudaEventCreate(&c->ev[i]));
 	*out = c;
 	return CNB_OK;
@@ -69,7 +72,7 @@ extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	for (DevBuf *b : c->all_bufs()) b->release();
 	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
-	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
 
@@ -104,11 +107,11 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	} else {
 		/* categories inferred as max - min + 1 over the non-NA values (catnet_search2.h:208-235) */
 		std::vector<int> hi(N, -INT32_MAX), lo(N, INT32_MAX);
-		CK(cudaMemcpyAsync(c->b_vmin.ptr, lo.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(c->b_vmax.ptr, hi.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+		H2D(c, c->b_vmin.ptr, lo.data(), N * sizeof(int));
+		H2D(c, c->b_vmax.ptr, hi.data(), N * sizeof(int));
 		RC(cnbk_minmax(st, samples_dev, N, M, (int *)c->b_vmin.ptr, (int *)c->b_vmax.ptr));
-		CK(cudaMemcpyAsync(lo.data(), c->b_vmin.ptr, N * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(hi.data(), c->b_vmax.ptr, N * sizeof(int), cudaMemcpyDeviceToHost, st));
+		D2H(c, lo.data(), c->b_vmin.ptr, N * sizeof(int));
+		D2H(c, hi.data(), c->b_vmax.ptr, N * sizeof(int));
 		CK(cudaStreamSynchronize(st));
 		for (int i = 0; i < N; i++) {
 			if (lo[i] > hi[i]) { cnb_set_error("node %d has no observed value", i + 1); return CNB_ERR_PARAM; }
@@ -119,8 +122,8 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	}
 	c->cats_lbl = cats;
 	c->max_cats = *std::max_element(cats.begin(), cats.end());
-	CK(cudaMemcpyAsync(c->b_vmin.ptr, vmin.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
-	CK(cudaMemcpyAsync(c->b_cats_lbl.ptr, cats.data(), N * sizeof(int), cudaMemcpyHostToDevice, st));
+	H2D(c, c->b_vmin.ptr, vmin.data(), N * sizeof(int));
+	H2D(c, c->b_cats_lbl.ptr, cats.data(), N * sizeof(int));
 	CK(cudaMemsetAsync(c->b_flag.ptr, 0, 4 * sizeof(int), st));
 	size_t words = (size_t)c->W * N;
 	RC(c->b_codes.ensure((size_t)N * c->Mpad));
@@ -134,7 +137,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 			(uint8_t *)c->b_codes.ptr, (uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (uint32_t *)c->b_keep_lbl.ptr : nullptr, (int *)c->b_flag.ptr));
 	int bad = 0;
-	CK(cudaMemcpyAsync(&bad, c->b_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+	D2H(c, &bad, c->b_flag.ptr, sizeof(int));
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	CK(cudaStreamSynchronize(st));
 	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
@@ -148,6 +151,7 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 	if (!c || N < 1 || M < 1 || !samples) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
 	size_t bytes = (size_t)N * M * sizeof(int32_t);
+	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
 	DevBuf tmp_s, tmp_p;
 	int rc = tmp_s.ensure(bytes);
 	if (rc == CNB_OK && pert) rc = tmp_p.ensure(bytes);
@@ -155,6 +159,7 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 		cudaError_t e = cudaMemcpyAsync(tmp_s.ptr, samples, bytes, cudaMemcpyHostToDevice, c->stream);
 		if (e == cudaSuccess && pert) e = cudaMemcpyAsync(tmp_p.ptr, pert, bytes, cudaMemcpyHostToDevice, c->stream);
 		if (e != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; }
+		c->timing.h2d_bytes += (int64_t)bytes * (pert ? 2 : 1);
 	}
 	if (rc == CNB_OK)
 		rc = cnb_ctx_set_samples_dev(c, N, M, (const int32_t *)tmp_s.ptr, pert ? (const int32_t *)tmp_p.ptr : nullptr, num_cats);
@@ -167,6 +172,13 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 extern "C" int cnb_ctx_num_cats(const cnb_ctx *c, int32_t *out) {
 	if (!c || !c->have_samples || !out) return CNB_ERR_PARAM;
 	for (int i = 0; i < c->N; i++) out[i] = c->cats_lbl[i];
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_set_stream(cnb_ctx *c, void *cuda_stream) {
+	if (!c) return CNB_ERR_PARAM;
+	cudaStreamSynchronize(c->stream);
+	c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
 	return CNB_OK;
 }
 
@@ -202,7 +214,7 @@ static DevData make_devdata(cnb_ctx *c) {
 template <class T>
 static int upload(cnb_ctx *c, DevBuf &b, const std::vector<T> &v) {
 	RC(b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
-	if (!v.empty()) CK(cudaMemcpyAsync(b.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+	if (!v.empty()) H2D(c, b.ptr, v.data(), v.size() * sizeof(T));
 	return CNB_OK;
 }
 
@@ -234,6 +246,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 			c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, (const int *)c->b_order.ptr, c->N, c->W,
 			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr));
 	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
+	c->timing.kernel_launches = 1;                    /* k_permute; the later phases add theirs */
 	c->planned = true;
 	c->dp_done = false;
 	if (seg_len) *seg_len = pl.seg_len;
@@ -294,7 +307,6 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	CnbPlan &pl = c->plan;
 	DevData D = make_devdata(c);
 	cudaStream_t st = c->stream;
-	c->timing.kernel_launches = 0;
 	c->timing.num_families = 0;
 	c->timing.algorithmic_bytes = 0;
 	memset(c->timing.score_ms_by_parents, 0, sizeof(c->timing.score_ms_by_parents));
@@ -322,7 +334,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	}
 	CK(cudaEventRecord(c->ev[EV_SCORE1], st));
 	int ovf = 0;
-	CK(cudaMemcpyAsync(&ovf, (int *)c->b_flag.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
 	CK(cudaStreamSynchronize(st));
 	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
 	c->timing.plan_ms = ev_ms(c, EV_PLAN0, EV_PLAN1);
@@ -376,7 +388,7 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 }
 
 /* ------------------------------------------------------------------ selection + DP ---- */
-int cnb_ctx_run_dp(cnb_ctx *c, const double *scores_dev) {
+extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
 	CnbPlan &pl = c->plan;
@@ -434,8 +446,8 @@ int cnb_ctx_run_dp(cnb_ctx *c, const double *scores_dev) {
 	/* summary to the host: which slots exist and their log-lik */
 	c->h_exists.resize(slots);
 	c->h_L.resize(slots);
-	CK(cudaMemcpyAsync(c->h_exists.data(), S[cur].exists, slots, cudaMemcpyDeviceToHost, st));
-	CK(cudaMemcpyAsync(c->h_L.data(), S[cur].L, slots * sizeof(double), cudaMemcpyDeviceToHost, st));
+	D2H(c, c->h_exists.data(), S[cur].exists, slots);
+	D2H(c, c->h_L.data(), S[cur].L, slots * sizeof(double));
 	CK(cudaStreamSynchronize(st));
 	c->timing.select_ms = ev_ms(c, EV_SEL0, EV_SEL1);
 	c->timing.dp_ms = ev_ms(c, EV_SEL1, EV_DP1);
@@ -457,7 +469,7 @@ int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::
 }
 
 /* materialise the networks: back-pointer walk on the device, then tables of the distinct selected families */
-int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
+extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	if (!c || !c->dp_done || !out) return CNB_ERR_PROC;
 	CK(cudaSetDevice(c->device));
 	CnbPlan &pl = c->plan;
@@ -476,9 +488,9 @@ int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	c->timing.kernel_launches++;
 	std::vector<long long> sel(slots * N);
 	std::vector<long long> opt_fid((size_t)pl.num_options);
-	CK(cudaMemcpyAsync(sel.data(), c->b_sel.ptr, sel.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+	D2H(c, sel.data(), c->b_sel.ptr, sel.size() * sizeof(long long));
 	if (pl.num_options)
-		CK(cudaMemcpyAsync(opt_fid.data(), c->b_opt_fid.ptr, opt_fid.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+		D2H(c, opt_fid.data(), c->b_opt_fid.ptr, opt_fid.size() * sizeof(long long));
 	CK(cudaStreamSynchronize(st));
 
 	std::unique_ptr<cnb_result> res(new cnb_result());
@@ -535,10 +547,10 @@ int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		RC(score_explicit(c, ex_child, ex_pars, ex_nd, -1, stride, true, true));
 		std::vector<int32_t> counts(nf * stride), ncount(nf);
 		std::vector<double> ll(nf), prior(nf);
-		CK(cudaMemcpyAsync(counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(ncount.data(), c->b_ex_ncount.ptr, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(ll.data(), c->b_ex_ll.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(prior.data(), c->b_ex_prior.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+		D2H(c, counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int));
+		D2H(c, ncount.data(), c->b_ex_ncount.ptr, nf * sizeof(int));
+		D2H(c, ll.data(), c->b_ex_ll.ptr, nf * sizeof(double));
+		D2H(c, prior.data(), c->b_ex_prior.ptr, nf * sizeof(double));
 		CK(cudaEventRecord(c->ev[EV_COL1], st));
 		CK(cudaStreamSynchronize(st));
 		res->fams.resize(nf);
@@ -565,7 +577,7 @@ int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 }
 
 extern "C" int cnb_ctx_finish(cnb_ctx *c, const double *scores_dev, cnb_result **out) {
-	RC(cnb_ctx_run_dp(c, scores_dev));
+	RC(cnb_ctx_select_dp(c, scores_dev));
 	RC(cnb_ctx_collect(c, out));
 	c->timing.total_ms = c->timing.plan_ms + c->timing.score_ms + c->timing.select_ms + c->timing.dp_ms + c->timing.collect_ms;
 	return CNB_OK;
@@ -576,7 +588,7 @@ int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p) {
 	RC(cnb_ctx_plan(c, p, 0, 1, &seg, &nf));
 	RC(c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double)));
 	RC(cnb_ctx_score_shard(c, (double *)c->b_scores.ptr));
-	RC(cnb_ctx_run_dp(c, (const double *)c->b_scores.ptr));
+	RC(cnb_ctx_select_dp(c, (const double *)c->b_scores.ptr));
 	return CNB_OK;
 }
 
@@ -653,11 +665,11 @@ extern "C" int cnb_family_scores(cnb_ctx *c, int32_t nfam, int32_t d, const int3
 	}
 	RC(score_explicit(c, ch, pa, nd, d, stride, counts_out != nullptr, force_generic != 0));
 	cudaStream_t st = c->stream;
-	if (counts_out) CK(cudaMemcpyAsync(counts_out, c->b_ex_counts.ptr, (size_t)nfam * stride * sizeof(int), cudaMemcpyDeviceToHost, st));
-	if (loglik_out) CK(cudaMemcpyAsync(loglik_out, c->b_ex_ll.ptr, nfam * sizeof(double), cudaMemcpyDeviceToHost, st));
-	if (ncount_out) CK(cudaMemcpyAsync(ncount_out, c->b_ex_ncount.ptr, nfam * sizeof(int), cudaMemcpyDeviceToHost, st));
+	if (counts_out) D2H(c, counts_out, c->b_ex_counts.ptr, (size_t)nfam * stride * sizeof(int));
+	if (loglik_out) D2H(c, loglik_out, c->b_ex_ll.ptr, nfam * sizeof(double));
+	if (ncount_out) D2H(c, ncount_out, c->b_ex_ncount.ptr, nfam * sizeof(int));
 	int ovf = 0;
-	CK(cudaMemcpyAsync(&ovf, (int *)c->b_flag.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
 	CK(cudaStreamSynchronize(st));
 	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
 	return CNB_OK;

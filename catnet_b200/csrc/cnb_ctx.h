@@ -21,7 +21,7 @@ struct DevBuf {
 
 struct cnb_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, own_stream = nullptr;
 	cudaEvent_t ev[CNB_NEV];
 	int N = 0, M = 0, W = 0, Mpad = 0, max_cats = 0;
 	bool has_pert = false, have_samples = false, planned = false, dp_done = false, force_generic = false;
@@ -51,8 +51,6 @@ struct cnb_ctx {
 
 /* internal phases shared with the SA driver (cnb_sa.cpp) */
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
-int cnb_ctx_run_dp(cnb_ctx *c, const double *scores_dev);
 int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);
-int cnb_ctx_collect(cnb_ctx *c, cnb_result **out);
 
 #endif

@@ -1,0 +1,70 @@
+"""One process per GPU: shard the candidate parent sets over the ranks, all-gather the per-family scores
+(NCCL over NVLink on the GPU box, gloo in the CPU tests), run selection + DP redundantly on every rank.
+
+Score buffer layout (cnb_ctx_plan / dev_score_index in csrc/cnb_device.cuh): rank-major.  Each group g (= all
+candidate sets with the same parent count) of nfam_g families is cut into `world` contiguous chunks of
+chunk_g = ceil(nfam_g / world); rank r's segment holds its chunk of every group back to back (seg_len = sum chunk_g),
+so one all_gather_into_tensor of equal-sized segments completes the buffer.  cnSearchSA runs one independent chain
+per rank and merges them per complexity like R's .searchSA (R/catnet.search.R:317-332).
+"""
+import numpy as np
+
+
+def segment_layout(group_sizes, world):
+    """python mirror of the planner's layout: -> (chunks, seg_offsets, seg_len)"""
+    chunks = [(int(n) + world - 1) // world for n in group_sizes]
+    offs = np.concatenate([[0], np.cumsum(chunks)])[:-1].astype(np.int64)
+    return chunks, [int(o) for o in offs], int(sum(chunks))
+
+
+def score_index(group, fid, chunks, offs, seg_len):
+    r = fid // chunks[group]
+    return r * seg_len + offs[group] + (fid - r * chunks[group])
+
+
+def owned_range(group_size, chunk, rank):
+    b = rank * chunk
+    return b, max(b, min(group_size, b + chunk))
+
+
+def gather_scores(scores, rank, world, seg_len, group=None):
+    """complete the rank-major buffer in place: every rank contributes scores[rank*seg_len:(rank+1)*seg_len]"""
+    import torch.distributed as dist
+    if world == 1:
+        return scores
+    dist.all_gather_into_tensor(scores, scores[rank * seg_len:(rank + 1) * seg_len].clone(), group=group)
+    return scores
+
+
+def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, **kw):
+    """cnSearchOrder on `world` GPUs; returns the same networks on every rank"""
+    import torch
+    seg, _ = ctx.plan(rank, world, **kw)
+    scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
+    ctx.score_shard(scores.data_ptr())
+    gather_scores(scores, rank, world, seg, group)
+    torch.cuda.synchronize(device)
+    return ctx.finish(scores.data_ptr(), want_probs)
+
+
+def merge_evaluations(evals):
+    """per complexity keep the network with the highest likelihood over the chains (first wins ties)"""
+    best = {}
+    for nets in evals:
+        for net in nets or []:
+            cur = best.get(net["complexity"])
+            if cur is None or net["loglik"] > cur["loglik"]:
+                best[net["complexity"]] = net
+    return [best[k] for k in sorted(best)]
+
+
+def search_sa_chains(ctx, rank, world, sa, group=None, **kw):
+    """one independent SA chain per rank (seed + rank), merged on every rank"""
+    import torch.distributed as dist
+    mine = ctx.search_sa(dict(sa, seed=int(sa.get("seed", 1)) + rank), **kw)
+    if world == 1:
+        return mine, [mine]
+    allr = [None] * world
+    dist.all_gather_object(allr, {"nets": mine["nets"], "order": mine["order"], "niter": mine["niter"],
+                                  "naccept": mine["naccept"]}, group=group)
+    return {"nets": merge_evaluations([r["nets"] for r in allr]), "chains": allr}, allr

@@ -117,6 +117,11 @@ int cnb_ctx_search_sa(cnb_ctx *ctx, const cnb_params *p, const cnb_sa_params *sa
 int cnb_ctx_plan(cnb_ctx *ctx, const cnb_params *p, int32_t rank, int32_t world, int64_t *seg_len, int64_t *num_families);
 int cnb_ctx_score_shard(cnb_ctx *ctx, double *scores_dev);
 int cnb_ctx_finish(cnb_ctx *ctx, const double *scores_dev, cnb_result **out);
+/* the two halves of cnb_ctx_finish: selection + DP on the device (result stays there), then network export */
+int cnb_ctx_select_dp(cnb_ctx *ctx, const double *scores_dev);
+int cnb_ctx_collect(cnb_ctx *ctx, cnb_result **out);
+/* launch on the caller's CUDA stream (e.g. the stream its NCCL collectives use) instead of the context's own */
+int cnb_ctx_set_stream(cnb_ctx *ctx, void *cuda_stream);
 
 /* per-phase device times of the last search on this context, CUDA events on the library's stream (ms) */
 typedef struct cnb_timing {
@@ -127,6 +132,7 @@ typedef struct cnb_timing {
 	int64_t algorithmic_bytes;      /* sum over scored families of (d+1)*M + 8 */
 	int32_t kernel_launches;
 	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
+	int64_t h2d_bytes, d2h_bytes;   /* host<->device traffic since the last cnb_ctx_set_samples* call */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 

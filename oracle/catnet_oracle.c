@@ -1,0 +1,549 @@
+/*
+ * oracle/catnet_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C restatement of the reference's structure-search scoring path (catnet 1.16.0, /root/reference/src).
+ * It exists to check the CUDA path; nothing under catnet_b200/ links, imports or calls it.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ *
+ * Parity status: PINNED against the reference itself -- tests/test_oracle.py compares every function here with
+ * oracle/_ref/libcatnet_ref.so (the reference's own C++ compiled unmodified) and with the committed fixtures in
+ * tests/golden/ that were generated from it (tools/make_golden.py).  The reference ships no golden vectors of its
+ * own.
+ *
+ * Each function cites the reference lines it follows.  The arithmetic that decides ties is kept operation for
+ * operation: counts held exactly, pp = 1/N_k, loglik += n*log(n*pp) in ascending table order, division by the
+ * sample count last, network log-lik re-summed over nodes in index order, strict '<' comparisons.
+ */
+#include "catnet_oracle.h"
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NEG_INF (-(double)FLT_MAX)
+
+/* ------------------------------------------------------------------ family score ---- */
+/* CATNET::setNodeSampleProb (catnet_class.h:818-879) + PROB_LIST::find_slot (problist.h:252-263) +
+ * PROB_LIST::loglikelihood (problist.h:224-250).  samples0: [M][N] zero-based codes; a sample is skipped when the
+ * child or any parent code is outside [0, cats).  keep (optional, [M]): 0 = sample excluded (perturbation). */
+int orc_family_score(const int *samples0, int N, int M, const int *cats, int child, const int *pars, int d,
+		const unsigned char *keep, double *counts, double *loglik_out, int *ncount_out) {
+	int tsize = cats[child], j, i, k;
+	for (i = 0; i < d; i++) tsize *= cats[pars[i]];
+	memset(counts, 0, (size_t)tsize * sizeof(double));
+	int ncount = 0;
+	for (j = 0; j < M; j++) {
+		if (keep && !keep[j]) continue;
+		const int *row = samples0 + (size_t)j * N;
+		int idx = 0, ok = 1;
+		for (i = 0; i < d; i++) {                       /* first listed parent most significant */
+			int v = row[pars[i]];
+			if (v < 0 || v >= cats[pars[i]]) { ok = 0; break; }
+			idx = idx * cats[pars[i]] + v;
+		}
+		int x = row[child];
+		if (ok && x >= 0 && x < cats[child]) {
+			counts[idx * cats[child] + x] += 1;
+			ncount++;
+		}
+	}
+	double ll = 0;
+	int cc = cats[child];
+	for (k = 0; k < tsize; k += cc) {
+		double pp = 0;
+		for (i = 0; i < cc; i++) pp += counts[k + i];
+		if (pp <= 0) continue;
+		pp = 1 / pp;
+		for (i = 0; i < cc; i++)
+			if (counts[k + i] > 0) ll += counts[k + i] * log(counts[k + i] * pp);
+	}
+	if (ncount > 1) ll /= (double)ncount;              /* catnet_class.h:867-870 */
+	*loglik_out = ll;
+	*ncount_out = ncount;
+	return tsize;
+}
+
+/* ------------------------------------------------------------------ result containers ---- */
+typedef struct {
+	int child, d, pars[ORC_MAXP], tsize, ncount, cc;
+	double *counts;
+	double loglik, prior;
+} fam_t;
+
+typedef struct {
+	int exists;
+	int *fam;          /* [N] index into the family table */
+	double m_loglik;   /* cached; 0 means "recompute" exactly like CATNET::loglik (catnet_class.h:469-473) */
+} net_t;
+
+struct orc_result {
+	int N, nslots;
+	net_t *nets;
+	fam_t *fams;
+	int nfams, cap;
+	int *order;        /* SA: accepted order */
+	int niter, naccept, ntrace, trace_cap;
+	double *trace;
+	int *trace_accept;
+};
+
+static int add_family(orc_result *r, const fam_t *f) {
+	if (r->nfams == r->cap) {
+		r->cap = r->cap ? 2 * r->cap : 256;
+		r->fams = (fam_t *)realloc(r->fams, (size_t)r->cap * sizeof(fam_t));
+	}
+	fam_t *g = &r->fams[r->nfams];
+	*g = *f;
+	g->counts = (double *)malloc((size_t)f->tsize * sizeof(double));
+	memcpy(g->counts, f->counts, (size_t)f->tsize * sizeof(double));
+	return r->nfams++;
+}
+
+/* CATNET::findLoglik (catnet_class.h:475-485): sum over nodes in index order of (loglik + priorlik) */
+static double net_loglik(const orc_result *r, net_t *n) {
+	if (n->m_loglik == 0) {
+		double s = 0;
+		for (int i = 0; i < r->N; i++) s += (r->fams[n->fam[i]].loglik + r->fams[n->fam[i]].prior);
+		n->m_loglik = s;
+	}
+	return n->m_loglik;
+}
+
+static int fam_complexity(const fam_t *f, const int *cats) {          /* catnet_class.h:457-467 */
+	int c = cats[f->child] - 1;
+	for (int j = 0; j < f->d; j++) c *= cats[f->pars[j]];
+	return c;
+}
+
+/* Bernoulli edge prior of a candidate (catnet_search2.h:584-611; base network :408-435) */
+static double edge_prior(const double *edge, int N, int node, const int *pars, int d) {
+	double t = 1, t2 = 1, prior;
+	int i, j;
+	for (i = 0; i < d; i++) t *= edge[(size_t)pars[i] * N + node];
+	prior = t > 0 ? log(t) : NEG_INF;
+	for (i = 0; i < N; i++) {
+		int isp = 0;
+		if (i == node) continue;
+		for (j = 0; j < d; j++) isp |= (pars[j] == i);
+		if (!isp) t2 *= (1 - edge[(size_t)i * N + node]);
+	}
+	t2 = t2 > 0 ? log(t2) : NEG_INF;
+	if (prior == NEG_INF || t2 == NEG_INF) return NEG_INF;
+	return prior + t2;
+}
+
+static void score_family(fam_t *f, const int *S, int N, int M, const int *cats, const unsigned char *keep,
+		const double *edge, double *buf) {
+	f->counts = buf;
+	f->cc = cats[f->child];
+	f->tsize = orc_family_score(S, N, M, cats, f->child, f->pars, f->d, keep, buf, &f->loglik, &f->ncount);
+	f->prior = edge ? edge_prior(edge, N, f->child, f->pars, f->d) : 0;
+}
+
+/* next combination in lexicographic order (what combinationSets enumerates, catnet_search2.h:102-147) */
+static int next_comb(int *idx, int k, int n) {
+	int i = k - 1;
+	while (i >= 0 && idx[i] == n - k + i) i--;
+	if (i < 0) return 0;
+	idx[i]++;
+	for (int j = i + 1; j < k; j++) idx[j] = idx[j - 1] + 1;
+	return 1;
+}
+
+/* ------------------------------------------------------------------ search for one order ---- */
+/* RCatnetSearch::estimateCatnets marshalling (rcatnet_search.cpp:111-268) + CATNET_SEARCH2::estimate
+ * (catnet_search2.h:152-897).  All label-space inputs as R passes them; see catnet_oracle.h. */
+orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *order, const int *numCats_lbl,
+		const int *parentsPool_lbl, const int *fixedPool_lbl, const double *edge_lbl) {
+	int i, j, k, d, n;
+	if (N < 1 || M < 1) return NULL;
+	if (maxComplexity < N) maxComplexity = N;                           /* :182-183 */
+	int *ord = (int *)malloc(N * sizeof(int)), *pos_of = (int *)malloc(N * sizeof(int));
+	for (i = 0; i < N; i++) { ord[i] = order ? order[i] - 1 : i; pos_of[ord[i]] = i; }
+
+	/* samples into order space, NA -> INT_MAX (rcatnet_search.cpp:151-160); categories given as 1..C or inferred
+	 * as min..max (catnet_search2.h:201-235); recode to 0-based, NA -> C (:237-257) */
+	int *S = (int *)malloc((size_t)N * M * sizeof(int)), *cats = (int *)malloc(N * sizeof(int));
+	for (i = 0; i < N; i++) {
+		int lo = INT_MAX, hi = -INT_MAX;
+		for (j = 0; j < M; j++) {
+			int v = samples_lbl[(size_t)j * N + ord[i]];
+			if (v == INT_MIN || v < 1) v = INT_MAX;
+			S[(size_t)j * N + i] = v;
+			if (v != INT_MAX) { if (v < lo) lo = v; if (v > hi) hi = v; }
+		}
+		if (numCats_lbl) { cats[i] = numCats_lbl[ord[i]]; lo = 1; }
+		else cats[i] = hi - lo + 1;
+		for (j = 0; j < M; j++) {
+			int v = S[(size_t)j * N + i];
+			S[(size_t)j * N + i] = (v == INT_MAX) ? cats[i] : v - lo;
+		}
+	}
+	double *edge = NULL;
+	if (edge_lbl) {                                                       /* rcatnet_search.cpp:258-268 */
+		edge = (double *)malloc((size_t)N * N * sizeof(double));
+		for (j = 0; j < N; j++)
+			for (i = 0; i < N; i++) edge[(size_t)j * N + i] = edge_lbl[(size_t)ord[j] * N + ord[i]];
+	}
+	unsigned char *allow = NULL, *fixd = NULL;                             /* [child][candidate] in order space */
+	if (parentsPool_lbl) {
+		allow = (unsigned char *)calloc((size_t)N * N, 1);
+		for (i = 0; i < N; i++)
+			for (j = 0; j < N && parentsPool_lbl[(size_t)ord[i] * N + j] > 0; j++) {
+				int l = parentsPool_lbl[(size_t)ord[i] * N + j];
+				if (l <= N) allow[(size_t)i * N + pos_of[l - 1]] = 1;
+			}
+	}
+	if (fixedPool_lbl) {
+		fixd = (unsigned char *)calloc((size_t)N * N, 1);
+		for (i = 0; i < N; i++)
+			for (j = 0; j < N && fixedPool_lbl[(size_t)ord[i] * N + j] > 0; j++) {
+				int l = fixedPool_lbl[(size_t)ord[i] * N + j];
+				if (l <= N) fixd[(size_t)i * N + pos_of[l - 1]] = 1;
+			}
+	}
+
+	orc_result *R = (orc_result *)calloc(1, sizeof(orc_result));
+	R->N = N;
+	R->nslots = maxComplexity + 1;
+	R->nets = (net_t *)calloc(R->nslots, sizeof(net_t));
+	net_t *cur = (net_t *)calloc(R->nslots, sizeof(net_t));
+	int maxcat = 0;
+	for (i = 0; i < N; i++) if (cats[i] > maxcat) maxcat = cats[i];
+	size_t maxtab = maxcat;                      /* largest table: child x up to max(maxParentSet, N-1) parents */
+	for (i = 0; i < N - 1 && maxtab < ((size_t)1 << 26); i++) maxtab *= maxcat;
+	double *cbuf = (double *)malloc(maxtab * sizeof(double)), *bestc = (double *)malloc(maxtab * sizeof(double));
+	unsigned char *keep = pert_lbl ? (unsigned char *)malloc(M) : NULL;
+	int *fix = (int *)malloc(N * sizeof(int)), *fre = (int *)malloc(N * sizeof(int)), *idx = (int *)malloc(N * sizeof(int));
+	int *basefam = (int *)malloc(N * sizeof(int));
+
+#define SET_KEEP(node) do { if (keep) for (int q_ = 0; q_ < M; q_++) keep[q_] = pert_lbl[(size_t)q_ * N + ord[node]] == 0; } while (0)
+	/* base network: every node with its fixed parents (catnet_search2.h:359-441) */
+	int basecx = 0;
+	for (n = 0; n < N; n++) {
+		int nf = 0;
+		for (j = 0; j < n; j++) {
+			int a = !allow || allow[(size_t)n * N + j];
+			if (a && fixd && fixd[(size_t)n * N + j]) fix[nf++] = j;
+		}
+		fam_t f;
+		memset(&f, 0, sizeof(f));
+		f.child = n; f.d = nf;
+		for (j = 0; j < nf; j++) f.pars[j] = fix[j];
+		SET_KEEP(n);
+		score_family(&f, S, N, M, cats, keep, edge, cbuf);
+		basefam[n] = add_family(R, &f);
+		basecx += fam_complexity(&f, cats);
+	}
+	if (basecx > maxComplexity) { /* the reference would write out of bounds here; refuse */
+		free(cur); orc_result_free(R); R = NULL; goto done;
+	}
+	R->nets[basecx].exists = 1;
+	R->nets[basecx].fam = (int *)malloc(N * sizeof(int));
+	memcpy(R->nets[basecx].fam, basefam, N * sizeof(int));
+
+	for (n = 1; n < N; n++) {                                           /* :444 */
+		int nf = 0, nr = 0;
+		for (j = 0; j < n; j++) {                                       /* :456-486 */
+			int a = !allow || allow[(size_t)n * N + j];
+			if (!a) continue;
+			if (fixd && fixd[(size_t)n * N + j]) fix[nf++] = j; else fre[nr++] = j;
+		}
+		int equal = 1, c0 = nr ? cats[fre[0]] : (nf ? cats[fix[0]] : 0);   /* :491-496 over free ++ fixed */
+		for (j = 0; j < nr; j++) if (cats[fre[j]] != c0) equal = 0;
+		for (j = 0; j < nf; j++) if (cats[fix[j]] != c0) equal = 0;
+		int maxpars = maxParentSet;                                    /* :498-503 */
+		if (parentSizes_lbl && parentSizes_lbl[ord[n]] < maxpars) maxpars = parentSizes_lbl[ord[n]];
+		if (maxpars > nr + nf) maxpars = nr + nf;
+		for (k = 0; k < R->nslots; k++) { cur[k].exists = 0; }
+		SET_KEEP(n);
+		const fam_t *bf = &R->fams[basefam[n]];
+		int base_node_cx = fam_complexity(bf, cats);
+		double base_term = bf->loglik + bf->prior;
+
+		for (d = nf + 1; d <= maxpars; d++) {
+			int kk = d - nf;
+			double fMax = NEG_INF;
+			fam_t best, cand;
+			int have_best = 0;
+			memset(&best, 0, sizeof(best));
+			for (j = 0; j < kk; j++) idx[j] = j;
+			do {
+				memset(&cand, 0, sizeof(cand));
+				cand.child = n; cand.d = d;
+				for (j = 0; j < nf; j++) cand.pars[j] = fix[j];       /* fixed first (:532-553) */
+				for (j = 0; j < kk; j++) cand.pars[nf + j] = fre[idx[j]];
+				score_family(&cand, S, N, M, cats, keep, edge, cbuf);
+				double f = cand.loglik;
+				if (edge) f += cand.prior;                              /* :610 */
+				if (equal) {
+					if (fMax < f) {                                     /* :613 strict, first maximum wins */
+						fMax = f;
+						best = cand;
+						best.counts = bestc;
+						memcpy(bestc, cbuf, (size_t)cand.tsize * sizeof(double));
+						have_best = 1;
+					}
+					continue;
+				}
+				/* unequal categories: every candidate runs the DP update (:800-827) */
+				int ncx = fam_complexity(&cand, cats), famid = -1;
+				for (k = 0; k < R->nslots; k++) {
+					if (!R->nets[k].exists) continue;
+					int cx = k - base_node_cx + ncx;
+					if (cx > maxComplexity) continue;
+					double t = net_loglik(R, &R->nets[k]) - base_term + f;
+					if (!cur[cx].exists && t > NEG_INF) {
+						cur[cx].exists = 1;
+						if (!cur[cx].fam) cur[cx].fam = (int *)malloc(N * sizeof(int));
+						cur[cx].fam[0] = -1;                            /* empty CATNET: loglik() = -FLT_MAX */
+					}
+					if (cur[cx].exists && (cur[cx].fam[0] < 0 ? NEG_INF : net_loglik(R, &cur[cx])) < t) {
+						if (famid < 0) famid = add_family(R, &cand);
+						memcpy(cur[cx].fam, R->nets[k].fam, N * sizeof(int));
+						cur[cx].fam[n] = famid;
+						cur[cx].m_loglik = 0;                            /* setParents invalidates (:429-430) */
+					}
+				}
+			} while (next_comb(idx, kk, nr));
+			if (!equal || !have_best) continue;                         /* :637-640 */
+			int ncx = fam_complexity(&best, cats), famid = -1;
+			for (k = 0; k < R->nslots; k++) {                           /* :657-676 */
+				if (!R->nets[k].exists) continue;
+				int cx = k - base_node_cx + ncx;
+				if (cx > maxComplexity) continue;
+				double t = net_loglik(R, &R->nets[k]) - base_term + fMax;
+				if (!cur[cx].exists && t > NEG_INF) {
+					cur[cx].exists = 1;
+					if (!cur[cx].fam) cur[cx].fam = (int *)malloc(N * sizeof(int));
+					cur[cx].fam[0] = -1;
+				}
+				if (cur[cx].exists && (cur[cx].fam[0] < 0 ? NEG_INF : net_loglik(R, &cur[cx])) < t) {
+					if (famid < 0) famid = add_family(R, &best);
+					memcpy(cur[cx].fam, R->nets[k].fam, N * sizeof(int));
+					cur[cx].fam[n] = famid;
+					cur[cx].m_loglik = 0;
+				}
+			}
+		}
+		for (j = 0; j < R->nslots; j++) {                              /* :847-865 */
+			if (!cur[j].exists || cur[j].fam[0] < 0) { cur[j].exists = 0; continue; }
+			int take = !R->nets[j].exists || net_loglik(R, &R->nets[j]) < net_loglik(R, &cur[j]);
+			if (take) {
+				int *t = R->nets[j].fam;
+				R->nets[j].fam = cur[j].fam;
+				R->nets[j].m_loglik = cur[j].m_loglik;
+				R->nets[j].exists = 1;
+				cur[j].fam = t;
+			}
+			cur[j].exists = 0;
+		}
+	}
+	for (k = 0; k < R->nslots; k++) free(cur[k].fam);
+	free(cur);
+done:
+	free(ord); free(pos_of); free(S); free(cats); free(edge); free(allow); free(fixd); free(cbuf); free(bestc);
+	free(keep); free(fix); free(fre); free(idx); free(basefam);
+	return R;
+}
+
+/* ------------------------------------------------------------------ accessors ---- */
+int orc_result_nslots(const orc_result *r) { return r ? r->nslots : 0; }
+int orc_result_exists(const orc_result *r, int k) { return r && k >= 0 && k < r->nslots && r->nets[k].exists; }
+int orc_result_net(orc_result *r, int k, int *complexity, double *loglik) {
+	if (!orc_result_exists(r, k)) return -1;
+	*complexity = k;
+	*loglik = net_loglik(r, &r->nets[k]);
+	return 0;
+}
+/* node view; probs = counts normalised as PROB_LIST::normalize does (problist.h:193-222) */
+int orc_result_node(const orc_result *r, int k, int node, int *npars, int *pars, double *loglik, double *prior,
+		int *sampleSize, int *probsize, double *probs, int cap) {
+	if (!orc_result_exists(r, k)) return -1;
+	const fam_t *f = &r->fams[r->nets[k].fam[node]];
+	*npars = f->d;
+	for (int i = 0; i < f->d; i++) pars[i] = f->pars[i];
+	*loglik = f->loglik;
+	*prior = f->prior;
+	*sampleSize = f->ncount;
+	*probsize = f->tsize;
+	for (int b = 0; probs && b < f->tsize && b + f->cc <= cap; b += f->cc) {
+		double pp = 0;
+		for (int i = 0; i < f->cc; i++) pp += f->counts[b + i];
+		if (pp > 0) {
+			pp = 1 / pp;
+			for (int i = 0; i < f->cc; i++) probs[b + i] = f->counts[b + i] * pp;
+		} else {
+			double favg = (double)1 / (double)f->cc, acc = 0;
+			for (int i = 0; i < f->cc - 1; i++) { probs[b + i] = favg; acc += favg; }
+			probs[b + f->cc - 1] = 1 - acc;
+		}
+	}
+	return 0;
+}
+int orc_result_counts(const orc_result *r, int k, int node, double *counts, int cap) {
+	if (!orc_result_exists(r, k)) return -1;
+	const fam_t *f = &r->fams[r->nets[k].fam[node]];
+	for (int i = 0; i < f->tsize && i < cap; i++) counts[i] = f->counts[i];
+	return f->tsize;
+}
+void orc_result_free(orc_result *r) {
+	if (!r) return;
+	for (int k = 0; k < r->nslots; k++) free(r->nets[k].fam);
+	for (int i = 0; i < r->nfams; i++) free(r->fams[i].counts);
+	free(r->nets); free(r->fams); free(r->order); free(r->trace); free(r->trace_accept);
+	free(r);
+}
+
+/* ------------------------------------------------------------------ SA ---- */
+static unsigned long long g_state = 0x9E3779B97F4A7C15ull;
+void orc_set_seed(unsigned long long seed) { g_state = seed; }
+/* splitmix64 -> (0,1): the injected stand-in for R's unif_rand, identical to oracle/ref_driver.cpp */
+static double unif(void) {
+	unsigned long long z = (g_state += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z = z ^ (z >> 31);
+	return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+static void gen_permutation(int *out, int n) {                          /* utils.h:144-180 */
+	int *aux = (int *)malloc(n * sizeof(int)), cc = 0, brep = 0, i, j;
+	while (++cc < 1e5) {
+		brep = 0;
+		for (i = 0; i < n; i++) aux[i] = (int)(n * n * unif());
+		for (j = 0; j < n; j++) {
+			out[j] = 0;
+			for (i = 0; i < n; i++) {
+				if (i != j && aux[j] == aux[i]) { brep = 1; break; }
+				if (aux[j] >= aux[i]) out[j]++;
+			}
+			if (brep) break;
+		}
+		if (!brep) break;
+	}
+	if (cc >= 1e5 - 1) for (j = 0; j < n; j++) out[j] = j + 1;
+	free(aux);
+}
+
+static void gen_order(const int *curo, int *out, int n, int shuffles, int bjump) {   /* rcatnet_sa.cpp:123-184 */
+	int sh, i, n1, n2;
+	if (shuffles <= 0) { gen_permutation(out, n); return; }
+	int *t = (int *)malloc(n * sizeof(int));
+	memcpy(out, curo, n * sizeof(int));
+	for (sh = 0; sh < shuffles; sh++) {
+		memcpy(t, out, n * sizeof(int));
+		n1 = (int)(unif() * n);
+		if (bjump) { n2 = n1; while (n2 == n1) n2 = (int)(unif() * n); }
+		else { n2 = n1 + 1; if (n1 >= n - 1) n2 = 0; }
+		if (n1 < n2) for (i = n1; i < n2; i++) out[i] = t[i + 1];
+		else for (i = n2; i < n1; i++) out[i + 1] = t[i];
+		out[n2] = t[n1];
+	}
+	free(t);
+}
+
+/* the SA loop of RCatnetSearchSA::search (rcatnet_sa.cpp:471-820), one evaluation after the other, no score cache
+ * (the cache only memoises scores, cache.cpp:142-317); dirProbs proposals are not restated here */
+orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
+		const int *fixedPool_lbl, const double *edge_lbl, int selectMode, const int *startOrder, double tempStart,
+		double tempCoolFact, int tempCheckOrders, int maxIter, double orderShuffles, double stopDiff, int numThreads) {
+	int nDrives = numThreads < 1 ? 1 : numThreads, n, nn, i, bjump = 0;
+	if (orderShuffles < 0) { bjump = 1; orderShuffles = -orderShuffles; }
+	int minShuffles = (int)orderShuffles;
+	orderShuffles -= minShuffles;
+	int *opt = (int *)malloc(N * sizeof(int));
+	memcpy(opt, startOrder, N * sizeof(int));
+	int **test = (int **)malloc(nDrives * sizeof(int *)), *skip = (int *)malloc(nDrives * sizeof(int));
+	for (n = 0; n < nDrives; n++) test[n] = (int *)malloc(N * sizeof(int));
+	orc_result *best = NULL;
+	double fOpt = NEG_INF, tempCur = tempStart, *trace = NULL;
+	int *tacc = NULL, ntrace = 0, tcap = 0;
+	int nstop = 0, nstopCounter = 0, naccept = 0, nLast = 0, niter = 0;
+	while (niter < maxIter) {
+		for (n = 0; n < nDrives; n++) {
+			int extra = 0;
+			if (orderShuffles > 0 && unif() <= orderShuffles) extra = 1;   /* _gen_binomial(1, frac) */
+			gen_order(opt, test[n], N, minShuffles + extra, bjump);
+			skip[n] = 0;
+			for (nn = 0; nn < n && !skip[n]; nn++) skip[n] = !memcmp(test[nn], test[n], N * sizeof(int));
+		}
+		nstop = 1;
+		int stepiters = nDrives, stepaccept = 0;
+		for (n = 0; n < nDrives; n++) {
+			if (skip[n] || stepaccept > 0) continue;
+			nstop = 0;
+			orc_result *r = orc_search_order(N, M, samples_lbl, pert_lbl, maxParentSet, parentSizes_lbl, maxComplexity,
+					test[n], numCats_lbl, parentsPool_lbl, fixedPool_lbl, edge_lbl);
+			if (!r) continue;
+			int pick = -1, k;
+			double fl = NEG_INF;
+			if (selectMode == 1 || selectMode == 2) {
+				double ft = selectMode == 1 ? 1.0 : 0.5 * log((double)M);
+				for (k = 0; k < r->nslots; k++) {
+					if (!r->nets[k].exists) continue;
+					double v = selectMode == 1 ? M * net_loglik(r, &r->nets[k]) - k : M * net_loglik(r, &r->nets[k]) - ft * k;
+					if (v > fl) { fl = v; pick = k; }
+				}
+			}
+			if (pick < 0) for (k = r->nslots - 1; k >= 0; k--) if (r->nets[k].exists) { pick = k; break; }
+			if (pick < 0) { orc_result_free(r); continue; }
+			fl = net_loglik(r, &r->nets[pick]);
+			int accepted = 0;
+			if (!best) { accepted = 1; stepaccept++; }
+			else {
+				double delta = fl - fOpt, ap = 0;
+				if (tempCur > 0 && delta <= 0) ap = exp(delta / tempCur);
+				double u = unif();
+				if (delta > 0 || u < ap) { accepted = 1; stepaccept++; stepiters = n + 1; nstopCounter = 0; }
+				else delta = 0;
+				if (delta < 0) delta = -delta;
+				if (delta < stopDiff) nstopCounter++;
+				if (nstopCounter >= tempCheckOrders) nstop = 1;
+			}
+			if (ntrace == tcap) {
+				tcap = tcap ? 2 * tcap : 256;
+				trace = (double *)realloc(trace, tcap * sizeof(double));
+				tacc = (int *)realloc(tacc, tcap * sizeof(int));
+			}
+			trace[ntrace] = fl;
+			tacc[ntrace++] = accepted;
+			if (accepted) {
+				fOpt = fl;
+				orc_result_free(best);
+				best = r;
+				memcpy(opt, test[n], N * sizeof(int));
+			} else orc_result_free(r);
+		}
+		if (stepaccept > 0) naccept++;
+		niter += stepiters;
+		if (niter - nLast >= tempCheckOrders) { tempCur *= tempCoolFact; nLast = niter; }
+		if (nstop) break;
+	}
+	if (best) {
+		best->order = opt;
+		best->niter = niter;
+		best->naccept = naccept;
+		best->trace = trace;
+		best->trace_accept = tacc;
+		best->ntrace = ntrace;
+	} else { free(opt); free(trace); free(tacc); }
+	for (n = 0; n < nDrives; n++) free(test[n]);
+	free(test); free(skip);
+	return best;
+}
+
+int orc_result_sa_info(const orc_result *r, int *order_out, int *niter, int *naccept) {
+	if (!r || !r->order) return -1;
+	memcpy(order_out, r->order, r->N * sizeof(int));
+	*niter = r->niter;
+	*naccept = r->naccept;
+	return r->ntrace;
+}
+int orc_result_sa_trace(const orc_result *r, double *trace, int *accept, int cap) {
+	for (int i = 0; i < r->ntrace && i < cap; i++) { trace[i] = r->trace[i]; accept[i] = r->trace_accept[i]; }
+	return r->ntrace;
+}

@@ -1,0 +1,29 @@
+/* oracle/catnet_oracle.h -- TEST INFRASTRUCTURE: plain-C restatement of catnet's structure-search scoring path.
+ * See catnet_oracle.c.  Label-space conventions are those of the .Call arguments (and of include/catnet_b200.h):
+ * samples [M][N] 1-based categories (NA = INT_MIN or < 1), order = 1-based labels per position, pools = [N][N]
+ * rows of 1-based labels 0-padded (empty row = no parents allowed), edge = R's column-major edgeProb[child,parent]. */
+#ifndef CATNET_ORACLE_H
+#define CATNET_ORACLE_H
+#define ORC_MAXP 16
+typedef struct orc_result orc_result;
+
+int orc_family_score(const int *samples0, int N, int M, const int *cats, int child, const int *pars, int d,
+		const unsigned char *keep, double *counts, double *loglik_out, int *ncount_out);
+orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *order, const int *numCats_lbl,
+		const int *parentsPool_lbl, const int *fixedPool_lbl, const double *edge_lbl);
+orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
+		const int *fixedPool_lbl, const double *edge_lbl, int selectMode, const int *startOrder, double tempStart,
+		double tempCoolFact, int tempCheckOrders, int maxIter, double orderShuffles, double stopDiff, int numThreads);
+void orc_set_seed(unsigned long long seed);
+int orc_result_nslots(const orc_result *r);
+int orc_result_exists(const orc_result *r, int k);
+int orc_result_net(orc_result *r, int k, int *complexity, double *loglik);
+int orc_result_node(const orc_result *r, int k, int node, int *npars, int *pars, double *loglik, double *prior,
+		int *sampleSize, int *probsize, double *probs, int cap);
+int orc_result_counts(const orc_result *r, int k, int node, double *counts, int cap);
+int orc_result_sa_info(const orc_result *r, int *order_out, int *niter, int *naccept);
+int orc_result_sa_trace(const orc_result *r, double *trace, int *accept, int cap);
+void orc_result_free(orc_result *r);
+#endif

@@ -1,0 +1,81 @@
+"""Seeded search problems shared by the GPU parity tests, the oracle tests and tools/make_golden.py.
+They cover what the reference's estimate() branches on (catnet_search2.h): equal vs mixed categories, NA,
+perturbations, parent pools, fixed parents, edge priors, parentSizes, tiny/ragged sample counts, one node,
+category inference, > 4 categories, maxComplexity cut-off, non-identity order."""
+import numpy as np
+
+from helpers import random_problem
+
+CASES = [
+    dict(seed=1, n=8, m=200, cats=None, P=2),
+    dict(seed=2, n=9, m=120, cats=3, P=3),
+    dict(seed=3, n=10, m=64, cats=2, P=3),
+    dict(seed=4, n=8, m=300, cats=None, P=2, na=0.07),
+    dict(seed=5, n=7, m=90, cats=4, P=2, na=0.05, pert=True),
+    dict(seed=6, n=12, m=40, cats=2, P=2, K=30),
+    dict(seed=7, n=9, m=500, cats=None, P=3, order="random"),
+    dict(seed=8, n=9, m=150, cats=3, P=2, pools=True),
+    dict(seed=9, n=9, m=150, cats=None, P=3, fixed=True),
+    dict(seed=10, n=8, m=150, cats=3, P=2, prior=True),
+    dict(seed=11, n=8, m=150, cats=None, P=2, prior=True, fixed=True, pools=True, psizes=True),
+    dict(seed=12, n=6, m=10, cats=2, P=2),
+    dict(seed=13, n=5, m=2, cats=2, P=2),
+    dict(seed=14, n=1, m=20, cats=3, P=2),
+    dict(seed=15, n=9, m=100, cats=None, P=2, infer=True, na=0.05),
+    dict(seed=16, n=8, m=100, cats=5, P=2),            # > 4 categories: generic histogram kernel
+    dict(seed=17, n=7, m=100, cats=[2, 6, 3, 2, 7, 3, 2], P=2),
+    dict(seed=18, n=8, m=100, cats=4, P=3),            # d=3 with 4 categories: generic kernel for that group
+    dict(seed=19, n=9, m=33, cats=3, P=4),             # 4 parents
+    dict(seed=20, n=8, m=200, cats=2, P=2, pert=True, prior=True, order="random"),
+    dict(seed=21, n=8, m=150, cats=None, P=2, prior="soft"),
+    dict(seed=22, n=9, m=120, cats=3, P=3, prior="soft", fixed=True, order="random"),
+]
+
+SA_CASES = [
+    dict(seed=31, n=7, m=80, cats=None, P=2, K=200,
+         sa=dict(select_mode=0, temp_start=0.01, temp_cool_fact=0.9, temp_check_orders=5, max_iter=40,
+                 order_shuffles=-1.5, stop_diff=1e-10, num_threads=2, seed=99)),
+    dict(seed=32, n=8, m=120, cats=3, P=2, K=150,
+         sa=dict(select_mode=2, temp_start=0.0, temp_cool_fact=1.0, temp_check_orders=1000, max_iter=30,
+                 order_shuffles=0, stop_diff=1e-10, num_threads=4, seed=7)),
+    dict(seed=33, n=6, m=60, cats=2, P=2, K=60,
+         sa=dict(select_mode=1, temp_start=1.0, temp_cool_fact=0.5, temp_check_orders=4, max_iter=50,
+                 order_shuffles=2.3, stop_diff=1e-3, num_threads=1, seed=12345)),
+]
+
+
+def build_case(c):
+    s, cats = random_problem(c["seed"], c["n"], c["m"], c.get("cats"), c.get("na", 0.0))
+    n = c["n"]
+    rng = np.random.default_rng(1000 + c["seed"])
+    kw = dict(max_parent_set=c["P"])
+    kw["max_complexity"] = c.get("K", int(n * (int(cats.max()) ** c["P"]) * (int(cats.max()) - 1)))
+    kw["order"] = (rng.permutation(n) + 1).astype(np.int32) if c.get("order") == "random" else None
+    if not c.get("infer"):
+        kw["num_cats"] = cats
+    if c.get("pert"):
+        kw["perturbations"] = (rng.random(s.shape) < 0.15).astype(np.int32)
+    if c.get("pools"):
+        kw["parents_pool"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, n), replace=False)]
+                              for _ in range(n)]
+    if c.get("fixed"):
+        kw["fixed_parents"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, 3), replace=False)]
+                               for _ in range(n)]
+    if c.get("prior"):
+        e = rng.random((n, n))
+        if c["prior"] == "soft":
+            e = 0.05 + 0.9 * e
+        else:
+            e[rng.random((n, n)) < 0.1] = 0.0
+            e[rng.random((n, n)) < 0.05] = 1.0
+        kw["edge_prob"] = e
+    if c.get("psizes"):
+        kw["parent_sizes"] = rng.integers(0, c["P"] + 1, size=n).astype(np.int32)
+    return s, kw
+
+
+def ref_args(kw):
+    """keyword arguments of oracle.ref.search_order / oracle.port.search_order for a case built by build_case"""
+    return dict(order=kw["order"], perturbations=kw.get("perturbations"), parent_sizes=kw.get("parent_sizes"),
+                num_cats=kw.get("num_cats"), parents_pool=kw.get("parents_pool"),
+                fixed_parents=kw.get("fixed_parents"), edge_prob=kw.get("edge_prob"))

@@ -54,3 +54,28 @@ def compare_search(ours, theirs, rel=1e-9, check_probs=True):
             if check_probs and len(x["probs"]):
                 np.testing.assert_allclose(x["probs"][k], y["probs"][k], rtol=1e-12, atol=0)
     return exact
+
+
+def load_golden(name):
+    import gzip
+    import json
+    import os
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".json.gz"), "rt") as f:
+        return json.load(f)
+
+
+def compare_golden(ours, golden):
+    """ours: list of network dicts; golden: list packed by tools/make_golden.py (hex floats). Bit-exact."""
+    a = nets_by_complexity(ours)
+    b = {g["complexity"]: g for g in golden}
+    assert sorted(a) == sorted(b), "different complexity slots: only ours %s, only reference %s" % (
+        sorted(set(a) - set(b))[:10], sorted(set(b) - set(a))[:10])
+    for cx in sorted(a):
+        x, y = a[cx], b[cx]
+        assert x["parents"] == y["parents"], "complexity %d: parents differ\n ours %s\n ref  %s" % (
+            cx, x["parents"], y["parents"])
+        assert x["loglik"] == float.fromhex(y["loglik"]), (cx, x["loglik"], float.fromhex(y["loglik"]))
+        if "node_loglik" in y:
+            assert [float(v) for v in x["node_loglik"]] == [float.fromhex(v) for v in y["node_loglik"]], cx
+            assert x["sample_sizes"] == y["sample_sizes"], cx
+    return len(a)

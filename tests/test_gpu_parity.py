@@ -1,8 +1,11 @@
-"""GPU parity tests proper: the CUDA path, through the C ABI, against the reference's own C++ core (oracle/_ref).
+"""GPU parity tests proper: the CUDA path, through the C ABI, against
+  (1) the committed golden fixtures = outputs of the reference's own C++ (tools/make_golden.py),
+  (2) the oracle restatement (oracle/catnet_oracle.c) on further seeded inputs,
+  (3) the reference core itself (oracle/_ref) when its library travelled to this box.
 
-Bars (BASELINE.json north_star): family counts bit-exact; family log-lik within 1e-9 relative in fp64 (the device
-evaluates glibc's log algorithm, so the tests additionally report/require bit equality); cnSearchOrder selects
-identical parent sets for every complexity level.
+Bars (BASELINE.json north_star): family counts bit-exact; family log-lik within 1e-9 relative in fp64 -- the device
+evaluates glibc's own log algorithm, so these tests require BIT equality; cnSearchOrder selects identical parent
+sets for every complexity level.  Nothing here reads /root/reference.
 """
 import itertools
 import math
@@ -10,7 +13,8 @@ import math
 import numpy as np
 import pytest
 
-from helpers import NA, compare_search, random_problem
+from cases import CASES, SA_CASES, build_case, ref_args
+from helpers import NA, compare_golden, compare_search, load_golden, random_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -20,6 +24,13 @@ def abi():
     from catnet_b200 import _abi
     _abi.lib()
     return _abi
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port as p
+    p.lib()
+    return p
 
 
 def test_device_log_is_glibc_log(abi):
@@ -38,10 +49,11 @@ def test_device_log_is_glibc_log(abi):
 @pytest.mark.parametrize("cats,na,pert", [(None, 0.0, False), (None, 0.08, False), (3, 0.05, True), (2, 0.0, False),
                                           (4, 0.1, True), ([2, 3, 4, 2, 3, 4, 2, 3, 4, 2], 0.03, False)])
 @pytest.mark.parametrize("m", [1, 31, 32, 33, 257, 1000])
-def test_family_counts_and_loglik(abi, ref, cats, na, pert, m):
+def test_family_counts_and_loglik(abi, port, cats, na, pert, m):
+    """empty / ragged sample counts, NA, perturbation masks, 0..3 parents in any order, both kernels"""
     n = 10
     s, c = random_problem(7 + m, n, max(m, 5), cats, na)
-    s = s[:m] if m >= 5 else s[:m]
+    s = s[:m]
     rng = np.random.default_rng(m)
     p = (rng.random(s.shape) < 0.2).astype(np.int32) if pert else None
     s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
@@ -55,110 +67,247 @@ def test_family_counts_and_loglik(abi, ref, cats, na, pert, m):
             for generic in (False, True):
                 counts, ll, nc = ctx.family_scores(children, parents, force_generic=generic)
                 for i, (ch, pa) in enumerate(fams):
-                    sub = s0 if p is None else s0[p[:, ch] == 0]
-                    if len(sub) == 0:
-                        continue          # the reference refuses nsamples < 1 (catnet_class.h:824)
-                    rc, rll, rnc = ref.family_score(sub, c, ch, list(pa))
+                    keep = None if p is None else (p[:, ch] == 0)
+                    rc, rll, rnc = port.family_score(s0, c, ch, list(pa), keep=keep)
                     assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)), (d, generic, ch, pa)
                     assert nc[i] == rnc
                     assert ll[i] == rll, (d, generic, ch, pa, ll[i], rll)   # bit-exact
 
 
-CASES = [
-    dict(seed=1, n=8, m=200, cats=None, P=2),
-    dict(seed=2, n=9, m=120, cats=3, P=3),
-    dict(seed=3, n=10, m=64, cats=2, P=3),
-    dict(seed=4, n=8, m=300, cats=None, P=2, na=0.07),
-    dict(seed=5, n=7, m=90, cats=4, P=2, na=0.05, pert=True),
-    dict(seed=6, n=12, m=40, cats=2, P=2, K=30),
-    dict(seed=7, n=9, m=500, cats=None, P=3, order="random"),
-    dict(seed=8, n=9, m=150, cats=3, P=2, pools=True),
-    dict(seed=9, n=9, m=150, cats=None, P=3, fixed=True),
-    dict(seed=10, n=8, m=150, cats=3, P=2, prior=True),
-    dict(seed=11, n=8, m=150, cats=None, P=2, prior=True, fixed=True, pools=True, psizes=True),
-    dict(seed=12, n=6, m=10, cats=2, P=2),
-    dict(seed=13, n=5, m=2, cats=2, P=2),
-    dict(seed=14, n=1, m=20, cats=3, P=2),
-    dict(seed=15, n=9, m=100, cats=None, P=2, infer=True, na=0.05),
-    dict(seed=16, n=8, m=100, cats=5, P=2),            # > 4 categories: generic histogram kernel
-    dict(seed=17, n=7, m=100, cats=[2, 6, 3, 2, 7, 3, 2], P=2),
-    dict(seed=18, n=8, m=100, cats=4, P=3),            # d=3 with 4 categories: generic kernel for that group
-]
-
-
-def build_case(c):
-    s, cats = random_problem(c["seed"], c["n"], c["m"], c.get("cats"), c.get("na", 0.0))
-    n = c["n"]
-    rng = np.random.default_rng(1000 + c["seed"])
-    kw = dict(max_parent_set=c["P"])
-    kw["max_complexity"] = c.get("K", int(n * (int(cats.max()) ** c["P"]) * (int(cats.max()) - 1)))
-    kw["order"] = (rng.permutation(n) + 1).astype(np.int32) if c.get("order") == "random" else None
-    if not c.get("infer"):
-        kw["num_cats"] = cats
-    if c.get("pert"):
-        kw["perturbations"] = (rng.random(s.shape) < 0.15).astype(np.int32)
-    if c.get("pools"):
-        kw["parents_pool"] = [list(rng.choice(np.arange(1, n + 1), size=rng.integers(0, n), replace=False)) for _ in range(n)]
-    if c.get("fixed"):
-        kw["fixed_parents"] = [list(rng.choice(np.arange(1, n + 1), size=rng.integers(0, 3), replace=False)) for _ in range(n)]
-    if c.get("prior"):
-        e = rng.random((n, n))
-        e[rng.random((n, n)) < 0.1] = 0.0
-        e[rng.random((n, n)) < 0.05] = 1.0
-        kw["edge_prob"] = e
-    if c.get("psizes"):
-        kw["parent_sizes"] = rng.integers(0, c["P"] + 1, size=n).astype(np.int32)
-    return s, kw
+def test_family_scores_match_golden(abi):
+    by_problem = {}
+    for g in load_golden("ref_family_scores"):
+        by_problem.setdefault((g["seed"], str(g["cats"]), g["na"]), []).append(g)
+    for (_, _, _), gs in by_problem.items():
+        g0 = gs[0]
+        s, c = random_problem(g0["seed"], 8, 150, g0["cats"], g0["na"])
+        with abi.Context(0) as ctx:
+            ctx.set_samples(s, num_cats=c)
+            for g in gs:
+                for generic in (False, True):
+                    counts, ll, nc = ctx.family_scores([g["child"]], np.array([g["parents"]], dtype=np.int32).reshape(1, -1),
+                                                       force_generic=generic)
+                    assert [int(v) for v in counts[0, :len(g["counts"])]] == g["counts"]
+                    assert ll[0] == float.fromhex(g["loglik"]) and nc[0] == g["ncount"]
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "seed%d" % c["seed"])
-def test_search_order_matches_reference(abi, ref, case):
+def test_search_order_matches_reference(abi, port, case):
     s, kw = build_case(case)
-    theirs = ref.search_order(s, kw["max_parent_set"], kw["max_complexity"], order=kw["order"],
-                              perturbations=kw.get("perturbations"), parent_sizes=kw.get("parent_sizes"),
-                              num_cats=kw.get("num_cats"), parents_pool=kw.get("parents_pool"),
-                              fixed_parents=kw.get("fixed_parents"), edge_prob=kw.get("edge_prob"))
+    golden = load_golden("ref_search_order")["seed%d" % case["seed"]]
     ours = abi.search_order(s, **kw)
-    exact = compare_search(ours, theirs)
-    assert exact == len(theirs), "log-liks not bit-identical: %d of %d" % (exact, len(theirs))
+    compare_golden(ours, golden)
+    theirs = port.search_order(s, kw["max_parent_set"], kw["max_complexity"], **ref_args(kw))
+    assert compare_search(ours, theirs) == len(theirs)        # also checks CPTs and sample sizes
     # same through the generic histogram kernel
     with abi.Context(0) as ctx:
         ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
         ctx.force_generic(True)
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
-        ours2 = ctx.search_order(**kw2)
-    assert compare_search(ours2, theirs) == len(theirs)
+        compare_golden(ctx.search_order(**kw2), golden)
 
 
-def test_config_c1_alarm(abi, ref):
+@pytest.mark.parametrize("seed", range(200, 230))
+def test_search_order_random_vs_oracle(abi, port, seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(2, 12)), int(rng.integers(1, 400))
+    cats = [None, 2, 3, 4, None][seed % 5]
+    s, c = random_problem(seed, n, m, cats, na_frac=[0.0, 0.1, 0.0][seed % 3])
+    kw = dict(num_cats=c, max_parent_set=int(rng.integers(1, 4)))
+    if seed % 4 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.2).astype(np.int32)
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    if seed % 7 == 0:
+        kw["fixed_parents"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, 2), replace=False)]
+                               for _ in range(n)]
+    kw["order"] = (rng.permutation(n) + 1).astype(np.int32)
+    kw["max_complexity"] = int(rng.integers(n, n * int(c.max()) ** kw["max_parent_set"] * 3 + 1))
+    ours = abi.search_order(s, **kw)
+    theirs = port.search_order(s, kw["max_parent_set"], kw["max_complexity"], **ref_args(kw))
+    assert compare_search(ours, theirs) == len(theirs)
+
+
+def test_search_vs_reference_core(abi, ref):
+    """the reference's own C++ (if its library travelled here) on fresh problems"""
+    for seed in range(300, 306):
+        s, c = random_problem(seed, 9, 150, [None, 3][seed % 2], na_frac=0.05)
+        theirs = ref.search_order(s, 2, 400, num_cats=c)
+        ours = abi.search_order(s, max_parent_set=2, max_complexity=400, num_cats=c)
+        assert compare_search(ours, theirs) == len(theirs)
+
+
+def test_config_c1_alarm(abi):
     """BASELINE configs[0]: cnSearchOrder on cnSamples(alarmnet, 1000), true order, maxParentSet=2 (mixed categories:
     the per-candidate DP path, catnet_search2.h:681-841)"""
     from catnet_b200 import synth
     c = synth.config("C1")
-    order = c["order"] + 1
-    theirs = ref.search_order(c["samples"], 2, c["max_complexity"], order=order, num_cats=c["cats"])
-    ours = abi.search_order(c["samples"], max_parent_set=2, max_complexity=c["max_complexity"], order=order,
-                            num_cats=c["cats"])
-    assert len(theirs) > 500
-    assert compare_search(ours, theirs) == len(theirs)
+    ours = abi.search_order(c["samples"], max_parent_set=2, max_complexity=c["max_complexity"], order=c["order"] + 1,
+                            num_cats=c["cats"], want_probs=False)
+    assert compare_golden(ours, load_golden("ref_configs")["C1"]) == 819
 
 
-def test_config_c2_breast(abi, ref):
+def test_config_c2_breast(abi):
     """BASELINE configs[1]: breast, 100 genes x 98 samples, maxParentSet=3, full complexity (4,087,875 families)"""
     from catnet_b200 import synth
     c = synth.config("C2")
-    theirs = ref.search_order(c["samples"], 3, c["max_complexity"], num_cats=c["cats"], want_probs=False)
     ours = abi.search_order(c["samples"], max_parent_set=3, max_complexity=c["max_complexity"], num_cats=c["cats"],
                             want_probs=False)
-    assert compare_search(ours, theirs, check_probs=False) == len(theirs)
+    assert compare_golden(ours, load_golden("ref_configs")["C2"]) == 684
 
 
-def test_config_c3_reduced(abi, ref):
+def test_config_c3_reduced(abi):
     """BASELINE configs[2] at reduced M (the full-M reference run is ~1.6 h): 100 nodes x 3 cats, maxParentSet=3"""
     from catnet_b200 import synth
     c = synth.config("C3", m=300)
-    order = c["order"] + 1
-    theirs = ref.search_order(c["samples"], 3, c["max_complexity"], order=order, num_cats=c["cats"], want_probs=False)
-    ours = abi.search_order(c["samples"], max_parent_set=3, max_complexity=c["max_complexity"], order=order,
+    ours = abi.search_order(c["samples"], max_parent_set=3, max_complexity=c["max_complexity"], order=c["order"] + 1,
                             num_cats=c["cats"], want_probs=False)
-    assert compare_search(ours, theirs, check_probs=False) == len(theirs)
+    assert compare_golden(ours, load_golden("ref_configs")["C3_m300"]) == 1261
+
+
+def _check_result_consistency(nets, cats_pos, n):
+    """size-independent invariants of a search result"""
+    seen = set()
+    for net in nets:
+        cx = sum((cats_pos[i] - 1) * int(np.prod([cats_pos[p] for p in net["parents"][i]])) for i in range(n))
+        assert cx == net["complexity"] and cx not in seen
+        seen.add(cx)
+        assert all(p < i for i in range(n) for p in net["parents"][i])      # parents precede the child in the order
+        acc = 0.0
+        for v, pr in zip(net["node_loglik"], net["node_prior"]):
+            acc += (v + pr)
+        assert acc == net["loglik"]                                         # re-summed in node order
+    ll = [net["loglik"] for net in sorted(nets, key=lambda t: t["complexity"])]
+    return ll
+
+
+def test_config_c3_full_size_properties(abi, port):
+    """BASELINE configs[2] at full size (100 x 3 cats, M=100,000, P=3: 4,087,875 families): invariants that do not
+    need the 1.6 h reference run -- sample-permutation invariance, exact doubling, spot-checked tables"""
+    from catnet_b200 import synth
+    c = synth.config("C3")
+    s, order, cats = c["samples"], c["order"] + 1, c["cats"]
+    n = s.shape[1]
+    kw = dict(max_parent_set=3, max_complexity=c["max_complexity"], order=order, num_cats=cats)
+    a = abi.search_order(s, want_probs=False, **kw)
+    cats_pos = [int(cats[v - 1]) for v in order]
+    _check_result_consistency(a, cats_pos, n)
+    rng = np.random.default_rng(0)
+    b = abi.search_order(s[rng.permutation(len(s))], want_probs=False, **kw)     # counts do not depend on sample order
+    assert compare_search(b, a, check_probs=False) == len(a)
+    d2 = abi.search_order(np.concatenate([s, s]), want_probs=False, **kw)       # n -> 2n scales every term by 2 exactly
+    assert compare_search(d2[:len(a)], [dict(t, sample_sizes=[2 * v for v in t["sample_sizes"]]) for t in a],
+                          check_probs=False) == len(a)
+    # spot-check family tables at full M against the oracle restatement
+    s0 = (s - 1).astype(np.int32)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=cats)
+        fams = [tuple(int(v) for v in rng.choice(n, size=4, replace=False)) for _ in range(40)]
+        counts, ll, nc = ctx.family_scores([f[0] for f in fams], np.array([f[1:] for f in fams], dtype=np.int32))
+        for i, f in enumerate(fams):
+            rc, rll, rnc = port.family_score(s0, cats, f[0], list(f[1:]))
+            assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)) and ll[i] == rll and nc[i] == rnc
+
+
+def test_config_c5_shape_properties(abi, port):
+    """BASELINE configs[4] shape (500 nodes x 4 cats, P=2, 20,833,250 families) at M=20,000 so that the test stays
+    short (the full 1M-sample run is bench.py): result invariants + spot-checked tables + sharded == unsharded"""
+    from catnet_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(5005))
+    net = synth.random_network(500, 4, 2, rng)
+    s = synth.sample_network(net, 20000, rng)
+    order = np.asarray(synth.order_nodes_descend(net["parents"])) + 1
+    K = synth.default_max_complexity(500, 4, 2)
+    assert K == 23999
+    kw = dict(max_parent_set=2, max_complexity=K, order=order, num_cats=net["cats"])
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=net["cats"])
+        a = ctx.search_order(want_probs=False, **{k: v for k, v in kw.items() if k != "num_cats"})
+        t = ctx.timing()
+        assert t["num_families"] == 20833250 and t["fast_path"] == 1
+        _check_result_consistency(a[::50], [4] * 500, 500)
+        s0 = (s - 1).astype(np.int32)
+        fams = [tuple(int(v) for v in rng.choice(500, size=3, replace=False)) for _ in range(60)]
+        counts, ll, nc = ctx.family_scores([f[0] for f in fams], np.array([f[1:] for f in fams], dtype=np.int32))
+        for i, f in enumerate(fams):
+            rc, rll, rnc = port.family_score(s0, net["cats"], f[0], list(f[1:]))
+            assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)) and ll[i] == rll and nc[i] == rnc
+    # the true network's families must be recoverable: the best network at the true complexity scores at least
+    # as high as the generating structure re-scored on the same data
+    true_cx = sum(3 * 4 ** len(p) for p in net["parents"])
+    best = {t["complexity"]: t for t in a}
+    assert true_cx in best
+
+
+@pytest.mark.parametrize("case", SA_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_sa_trajectory_matches_reference(abi, case):
+    """cnSearchSA: same uniform stream -> same proposals, same accept/reject sequence, same final networks"""
+    s, cats = random_problem(case["seed"], case["n"], case["m"], case.get("cats"))
+    g = load_golden("ref_search_sa")["seed%d" % case["seed"]]
+    sa = dict(case["sa"], start_order=np.arange(1, case["n"] + 1))
+    r = abi.search_sa(s, sa, max_parent_set=case["P"], max_complexity=case["K"], num_cats=cats)
+    assert [int(v) for v in r["order"]] == g["order"]
+    assert (r["niter"], r["naccept"]) == (g["niter"], g["naccept"])
+    assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
+    assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
+    compare_golden(r["nets"], g["nets"])
+
+
+def test_sa_alarm_vs_oracle(abi, port):
+    """BASELINE configs[3] shape (ALARM, maxParentSet=2, BIC) on 2,000 samples, a short chain against the oracle"""
+    from catnet_b200 import synth
+    net = synth.load_alarm()
+    s = synth.sample_network(net, 2000, np.random.Generator(np.random.PCG64(4004)))
+    sa = dict(select_mode=2, temp_start=1e-2, temp_cool_fact=0.9, temp_check_orders=4, max_iter=12, order_shuffles=4,
+              stop_diff=1e-2, num_threads=2, seed=4004)
+    start = np.arange(1, 38)
+    r = abi.search_sa(s, dict(sa, start_order=start), max_parent_set=2, max_complexity=600, num_cats=net["cats"])
+    o = port.search_sa(s, 2, 600, start, num_cats=net["cats"], **sa)
+    assert np.array_equal(r["order"], o["order"]) and r["niter"] == o["niter"] and r["naccept"] == o["naccept"]
+    assert np.array_equal(r["trace"], o["trace"]) and np.array_equal(r["trace_accept"], o["trace_accept"])
+    assert compare_search(r["nets"], o["nets"], check_probs=False) == len(o["nets"])
+
+
+def test_sharded_search_equals_unsharded(abi):
+    """the N>1 path on one GPU: every rank's shard scored into its segment of the rank-major buffer (here by one
+    process, segment after segment), then selection + DP on the full buffer -> identical networks"""
+    import ctypes
+    import torch
+    s, c = random_problem(5, 14, 300, None, 0.03)
+    kw = dict(max_parent_set=3, max_complexity=2000)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ref_nets = ctx.search_order(**kw)
+        for world in (2, 3, 8):
+            seg, nf = ctx.plan(0, world, **kw)
+            buf = torch.full((seg * world,), float("nan"), dtype=torch.float64, device="cuda")
+            for r in range(world):
+                ctx.plan(r, world, **kw)
+                ctx.score_shard(buf.data_ptr())
+            torch.cuda.synchronize()
+            nets = ctx.finish(buf.data_ptr())
+            assert compare_search(nets, ref_nets) == len(ref_nets)
+
+
+def test_multi_device_one_process(abi):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s, c = random_problem(6, 12, 500, None, 0.02)
+    a = abi.search_order(s, max_parent_set=2, max_complexity=800, num_cats=c)
+    b = abi.search_order(s, max_parent_set=2, max_complexity=800, num_cats=c, num_devices=2)
+    assert compare_search(b, a) == len(a)
+
+
+def test_errors_are_codes_not_crashes(abi):
+    s, c = random_problem(1, 5, 50, 3)
+    bad = s.copy()
+    bad[3, 2] = 9                                      # category outside 1..C with nodeCats given
+    with pytest.raises(abi.CnbError) as e:
+        abi.search_order(bad, max_parent_set=2, max_complexity=100, num_cats=c)
+    assert e.value.code == abi.CNB_ERR_PARAM and "Incorrect categories" in str(e.value)
+    with pytest.raises(abi.CnbError) as e:
+        abi.search_order(s, max_parent_set=2, max_complexity=100, num_cats=c, order=[1, 2, 3, 4, 9])
+    assert "Invalid nodeOrder" in str(e.value)
+    with pytest.raises(abi.CnbError):
+        abi.search_order(s, max_parent_set=2, max_complexity=100, num_cats=c, device=99)

@@ -1,0 +1,77 @@
+"""CPU suite, part 1: pin the oracle restatement (oracle/catnet_oracle.c).
+
+  * against the committed golden fixtures, which are outputs of the reference's own C++ (tools/make_golden.py);
+  * against the reference core directly (oracle/_ref/libcatnet_ref.so) where it was built (needs /root/reference
+    at build time; the .so travels to the GPU box), on further seeded problems.
+All fp64 comparisons are bit-exact."""
+import numpy as np
+import pytest
+
+from cases import CASES, SA_CASES, build_case, ref_args
+from helpers import compare_golden, compare_search, load_golden, random_problem
+from oracle import port
+
+
+def test_family_scores_match_golden():
+    for g in load_golden("ref_family_scores"):
+        s, c = random_problem(g["seed"], 8, 150, g["cats"], g["na"])
+        s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+        counts, ll, nc = port.family_score(s0, c, g["child"], g["parents"])
+        assert [int(v) for v in counts] == g["counts"]
+        assert ll == float.fromhex(g["loglik"]) and nc == g["ncount"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_search_order_matches_golden(case):
+    s, kw = build_case(case)
+    nets = port.search_order(s, kw["max_parent_set"], kw["max_complexity"], **ref_args(kw))
+    compare_golden(nets, load_golden("ref_search_order")["seed%d" % case["seed"]])
+
+
+def test_config_c1_matches_golden():
+    from catnet_b200 import synth
+    c = synth.config("C1")
+    nets = port.search_order(c["samples"], 2, c["max_complexity"], order=c["order"] + 1, num_cats=c["cats"],
+                             want_probs=False)
+    assert compare_golden(nets, load_golden("ref_configs")["C1"]) == 819
+
+
+@pytest.mark.parametrize("case", SA_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_sa_matches_golden(case):
+    s, cats = random_problem(case["seed"], case["n"], case["m"], case.get("cats"))
+    r = port.search_sa(s, case["P"], case["K"], np.arange(1, case["n"] + 1), num_cats=cats, **case["sa"])
+    g = load_golden("ref_search_sa")["seed%d" % case["seed"]]
+    assert [int(v) for v in r["order"]] == g["order"]
+    assert (r["niter"], r["naccept"]) == (g["niter"], g["naccept"])
+    assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
+    assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
+    compare_golden(r["nets"], g["nets"])
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_port_matches_reference_core(ref, seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(2, 10)), int(rng.integers(1, 200))
+    cats = [None, 2, 3, 4][seed % 4]
+    s, c = random_problem(seed, n, m, cats, na_frac=[0.0, 0.1][seed % 2])
+    kw = dict(num_cats=c)
+    if seed % 3 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.2).astype(np.int32)
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    order = (rng.permutation(n) + 1).astype(np.int32)
+    K = int(n * int(c.max()) ** 2 * 3)
+    a = ref.search_order(s, 2, K, order=order, **kw)
+    b = port.search_order(s, 2, K, order=order, **kw)
+    assert compare_search(b, a) == len(a)
+
+
+def test_port_sa_matches_reference_core(ref):
+    s, cats = random_problem(77, 7, 90, None)
+    kw = dict(select_mode=2, temp_start=0.05, temp_cool_fact=0.8, temp_check_orders=3, max_iter=30,
+              order_shuffles=1.5, stop_diff=1e-10, num_threads=3, seed=4242, num_cats=cats)
+    a = ref.search_sa(s, 2, 200, np.arange(1, 8), use_cache=False, **kw)
+    b = port.search_sa(s, 2, 200, np.arange(1, 8), **kw)
+    assert np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"] and a["naccept"] == b["naccept"]
+    assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["trace_accept"], b["trace_accept"])
+    compare_search(b["nets"], a["nets"], check_probs=False)

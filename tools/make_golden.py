@@ -1,0 +1,99 @@
+"""Generate tests/golden/ref_*.json from the reference itself (oracle/_ref/libcatnet_ref.so, i.e. the unmodified C++
+under /root/reference/src).  Run in the build container:  python tools/make_golden.py
+
+The reference ships no golden vectors for this path; these fixtures are its outputs on seeded
+inputs, so that the CPU suite (and the GPU box, where /root/reference does not exist) can pin the oracle restatement
+and the CUDA path without re-running it.  fp64 values are stored as C99 hex floats: comparisons are bit-exact.
+"""
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import random_problem  # noqa: E402
+from cases import CASES, SA_CASES, build_case  # noqa: E402
+
+from catnet_b200 import synth  # noqa: E402
+from oracle import ref  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def dump(obj, name):
+    with gzip.open(os.path.join(OUT, name + ".gz"), "wt") as f:
+        json.dump(obj, f)
+
+
+def pack_nets(nets, with_nodes=True):
+    out = []
+    for n in nets:
+        d = {"complexity": n["complexity"], "loglik": float(n["loglik"]).hex(), "parents": n["parents"]}
+        if with_nodes:
+            d["node_loglik"] = [float(v).hex() for v in n["node_loglik"]]
+            d["sample_sizes"] = n["sample_sizes"]
+        out.append(d)
+    return out
+
+
+def main():
+    fam = []
+    for seed, cats, na in [(1, None, 0.0), (2, 3, 0.1), (3, 2, 0.0), (4, 4, 0.05)]:
+        s, c = random_problem(seed, 8, 150, cats, na)
+        s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+        rng = np.random.default_rng(seed)
+        for d in (0, 1, 2, 3):
+            for _ in range(6):
+                nodes = rng.choice(8, size=d + 1, replace=False)
+                counts, ll, nc = ref.family_score(s0, c, int(nodes[0]), [int(v) for v in nodes[1:]])
+                fam.append({"seed": seed, "cats": cats, "na": na, "child": int(nodes[0]),
+                            "parents": [int(v) for v in nodes[1:]], "counts": [int(v) for v in counts],
+                            "loglik": float(ll).hex(), "ncount": nc})
+    dump(fam, "ref_family_scores.json")
+    print("ref_family_scores.json", len(fam))
+
+    searches = {}
+    for case in CASES:
+        s, kw = build_case(case)
+        nets = ref.search_order(s, kw["max_parent_set"], kw["max_complexity"], order=kw["order"],
+                                perturbations=kw.get("perturbations"), parent_sizes=kw.get("parent_sizes"),
+                                num_cats=kw.get("num_cats"), parents_pool=kw.get("parents_pool"),
+                                fixed_parents=kw.get("fixed_parents"), edge_prob=kw.get("edge_prob"), want_probs=False)
+        searches["seed%d" % case["seed"]] = pack_nets(nets)
+    dump(searches, "ref_search_order.json")
+    print("ref_search_order.json", {k: len(v) for k, v in searches.items()})
+
+    sa = {}
+    for case in SA_CASES:
+        s, cats = random_problem(case["seed"], case["n"], case["m"], case.get("cats"))
+        r = ref.search_sa(s, case["P"], case["K"], np.arange(1, case["n"] + 1), num_cats=cats, use_cache=False,
+                          **case["sa"])
+        sa["seed%d" % case["seed"]] = {"order": [int(v) for v in r["order"]], "niter": r["niter"],
+                                       "naccept": r["naccept"], "trace": [float(v).hex() for v in r["trace"]],
+                                       "trace_accept": [int(v) for v in r["trace_accept"]],
+                                       "nets": pack_nets(r["nets"], with_nodes=False)}
+    dump(sa, "ref_search_sa.json")
+    print("ref_search_sa.json", {k: (v["niter"], v["naccept"]) for k, v in sa.items()})
+    if "--skip-configs" in sys.argv:
+        return
+    big = {}
+    c = synth.config("C1")
+    big["C1"] = pack_nets(ref.search_order(c["samples"], 2, c["max_complexity"], order=c["order"] + 1,
+                                           num_cats=c["cats"], want_probs=False), with_nodes=False)
+    c = synth.config("C2")
+    big["C2"] = pack_nets(ref.search_order(c["samples"], 3, c["max_complexity"], num_cats=c["cats"],
+                                           want_probs=False), with_nodes=False)
+    c = synth.config("C3", m=300)
+    big["C3_m300"] = pack_nets(ref.search_order(c["samples"], 3, c["max_complexity"], order=c["order"] + 1,
+                                                num_cats=c["cats"], want_probs=False), with_nodes=False)
+    dump(big, "ref_configs.json")
+    print("ref_configs.json", {k: len(v) for k, v in big.items()})
+
+
+
+if __name__ == "__main__":
+    main()
