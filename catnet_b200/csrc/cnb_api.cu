@@ -136,12 +136,20 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	RC(cnbk_pack(st, samples_dev, pert_dev, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr,
 			(uint8_t *)c->b_codes.ptr, (uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (uint32_t *)c->b_keep_lbl.ptr : nullptr, (int *)c->b_flag.ptr));
-	int bad = 0;
-	D2H(c, &bad, c->b_flag.ptr, sizeof(int));
+	int flags[4] = {0, 0, 0, 0};
+	D2H(c, flags, c->b_flag.ptr, sizeof(flags));
+	CK(cudaStreamSynchronize(st));
+	if (flags[0]) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
+	/* two-way margins for the inclusion-exclusion scorer: only meaningful without missing values / masks */
+	c->pairs_valid = false;
+	if (!flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS && N >= 3 && !c->no_ie) {
+		RC(c->b_pairs.ensure((size_t)N * (N - 1) / 2 * 16 * sizeof(int)));
+		RC(cnbk_pair_tables(st, (const uint4 *)c->b_planes_lbl.ptr, N, c->W, (int *)c->b_pairs.ptr));
+		c->pairs_valid = true;
+	}
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	CK(cudaStreamSynchronize(st));
 	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
-	if (bad) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
 	c->have_samples = true;
 	return CNB_OK;
 }
@@ -184,7 +192,9 @@ extern "C" int cnb_ctx_set_stream(cnb_ctx *c, void *cuda_stream) {
 
 extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	if (!c) return CNB_ERR_PARAM;
-	c->force_generic = on != 0;
+	c->force_generic = (on & 1) != 0;     /* bit 0: generic histogram kernel everywhere */
+	c->no_ie = (on & 2) != 0;             /* bit 1: keep the direct bit-plane scorer (no inclusion-exclusion) */
+	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
 
@@ -270,13 +280,18 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 	if (e <= b) return CNB_OK;
 	cudaStream_t st = c->stream;
 	bool fast = !force_generic && !F.ex_nd && cnbk_planes_supported(F.d, c->max_cats);
-	c->timing.fast_path = fast ? 1 : 0;
+	c->last_fast = fast;
 	if (fast) {
 		int slices = 1;
 		if (allow_slicing) {
 			/* few families x many samples: slice the sample words so that the machine is filled */
 			long long n = e - b, target = 148ll * 1024;
 			if (n < target) slices = (int)std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8));
+		}
+		if (slices == 1 && !O.counts && F.d == 2 && c->pairs_valid && !F.explicit_list) {
+			RC(cnbk_score_planes_ie2(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
+			c->timing.kernel_launches++;
+			return CNB_OK;
 		}
 		if (slices > 1 && !O.counts) {
 			int stride = table_stride(c->max_cats, F.d);
@@ -313,6 +328,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	memset(c->timing.families_by_parents, 0, sizeof(c->timing.families_by_parents));
 	CK(cudaMemsetAsync((int *)c->b_flag.ptr + 1, 0, sizeof(int), st));
 	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
+	c->timing.fast_path = 1;
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		DevFamilies F;
@@ -324,6 +340,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		O.scores = scores_dev; O.chunk = g.chunk; O.seg_off = g.seg_off; O.seg_len = pl.seg_len;
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi], st));
 		RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
+		if (e > b && !c->last_fast) c->timing.fast_path = 0;
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi + 1], st));
 		if (e > b) {
 			c->timing.num_families += e - b;

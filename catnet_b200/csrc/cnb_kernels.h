@@ -33,6 +33,9 @@ int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_
 bool cnbk_planes_supported(int d, int max_cats);
 int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
 		long long fid_end, int slices, const ScoreOut &O);
+int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int *out);
+int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
+		long long e, const ScoreOut &O, const int *pair_tab);
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,

@@ -105,6 +105,9 @@ def test_search_order_matches_reference(abi, port, case):
         ctx.force_generic(True)
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
         compare_golden(ctx.search_order(**kw2), golden)
+        # and through the direct bit-plane scorer (no inclusion-exclusion over the pair tables)
+        ctx.force_generic(2)
+        compare_golden(ctx.search_order(**kw2), golden)
 
 
 @pytest.mark.parametrize("seed", range(200, 230))
