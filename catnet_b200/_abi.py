@@ -58,7 +58,7 @@ SYMBOLS = [
     "cnb_ctx_search_order", "cnb_ctx_search_sa", "cnb_ctx_plan", "cnb_ctx_score_shard", "cnb_ctx_finish",
     "cnb_ctx_select_dp", "cnb_ctx_collect", "cnb_ctx_set_stream", "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_device_log", "cnb_host_log",
     "cnb_unrank_combination", "cnb_num_families", "cnb_result_num_networks", "cnb_result_num_nodes",
-    "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_counts", "cnb_result_node",
+    "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_cats", "cnb_result_counts", "cnb_result_node",
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
 ]
 
@@ -107,6 +107,7 @@ def lib():
         "cnb_result_network": (i32, [vp, i32, P(i32), P(dbl)]),
         "cnb_result_parents": (i32, [vp, i32, vp, vp, i32]),
         "cnb_result_order": (i32, [vp, i32, vp]),
+        "cnb_result_cats": (i32, [vp, i32, vp]),
         "cnb_result_counts": (i32, [vp, i32, i32, vp, i32]),
         "cnb_result_node": (i32, [vp, i32, i32, P(dbl), P(dbl), P(i32), vp, i32]),
         "cnb_result_sa_info": (i32, [vp, vp, P(i32), P(i32)]),

@@ -515,6 +515,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	std::vector<int32_t> ord1(N);
 	for (int i = 0; i < N; i++) ord1[i] = pl.order[i] + 1;
 	res->orders.push_back(ord1);
+	res->order_cats.push_back(pl.cats);
 	/* distinct families: key = option index (>= 0) or -(node+1) for a base family */
 	std::map<long long, int> fam_of;
 	std::vector<int32_t> ex_child, ex_pars, ex_nd;

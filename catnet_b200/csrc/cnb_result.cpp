@@ -23,6 +23,13 @@ int cnb_result_order(const cnb_result *r, int32_t i, int32_t *order_out) {
 	return CNB_OK;
 }
 
+int cnb_result_cats(const cnb_result *r, int32_t i, int32_t *cats_out) {
+	if (!r || i < 0 || i >= (int32_t)r->nets.size() || !cats_out) return CNB_ERR_PARAM;
+	const std::vector<int32_t> &c = r->order_cats[r->nets[i].order_id];
+	memcpy(cats_out, c.data(), c.size() * sizeof(int32_t));
+	return CNB_OK;
+}
+
 int cnb_result_parents(const cnb_result *r, int32_t i, int32_t *num_parents, int32_t *parents, int32_t cap) {
 	if (!r || i < 0 || i >= (int32_t)r->nets.size() || !num_parents) return CNB_ERR_PARAM;
 	const CnbNet &net = r->nets[i];
@@ -102,6 +109,7 @@ int cnb_result_merge(cnb_result *a, const cnb_result *b) {
 			if (na.complexity != nb.complexity || !(nb.loglik > na.loglik)) continue;
 			if (!copied) {
 				a->orders.insert(a->orders.end(), b->orders.begin(), b->orders.end());
+				a->order_cats.insert(a->order_cats.end(), b->order_cats.begin(), b->order_cats.end());
 				a->fams.insert(a->fams.end(), b->fams.begin(), b->fams.end());
 				copied = true;
 			}

@@ -26,6 +26,7 @@ struct CnbNet {
 struct cnb_result {
 	int32_t N = 0;
 	std::vector<std::vector<int32_t>> orders;   /* 1-based labels per position */
+	std::vector<std::vector<int32_t>> order_cats; /* categories per position, one entry per order */
 	std::vector<CnbFamily> fams;
 	std::vector<CnbNet> nets;                   /* ascending complexity */
 	/* SA bookkeeping (rcatnet_sa.cpp) */

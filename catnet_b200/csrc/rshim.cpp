@@ -1,0 +1,312 @@
+/* rshim.cpp -- the R-facing side of the drop-in: a catnet.so replacement's .Call entry points for the search path.
+ *
+ * Exports what R's useDynLib(catnet) resolves for this path (reference src/ccnInit.c:29-52, prototypes
+ * src/catnet_rexport.h:31-64):
+ *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnReleaseCache/0   ccnSetSeed/1
+ * and registers them in R_init_catnet.  Every other routine of the reference's table keeps its reference
+ * implementation (this shim is linked INTO the package next to the reference sources).
+ *
+ * SEXP <-> C ABI only: all computation happens behind include/catnet_b200.h.  R API calls (coercion, allocation,
+ * Rf_error) stay on the calling thread; nothing longjmps while library resources are held.
+ *
+ * This file needs R's headers.  It is NOT part of libcatnet_b200.so; the image used to develop it has no R, so it
+ * is only syntax-checked there against tests/rstub (tests/test_rshim.py).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <Rdefines.h>
+#include <R_ext/Rdynload.h>
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../include/catnet_b200.h"
+
+namespace {
+
+/* list (length N) of integer vectors, or R_NilValue -> [N][N] rows of 1-based labels, 0 padded */
+bool pool_matrix(SEXP rPool, int N, std::vector<int32_t> &out) {
+	if (isNull(rPool) || length(rPool) != N) return false;
+	out.assign((size_t)N * N, 0);
+	for (int i = 0; i < N; i++) {
+		SEXP el = PROTECT(coerceVector(VECTOR_ELT(rPool, i), INTSXP));
+		int len = length(el);
+		if (len > 0 && len <= N)
+			for (int j = 0; j < len; j++) out[(size_t)i * N + j] = INTEGER(el)[j];
+		UNPROTECT(1);
+	}
+	return true;
+}
+
+struct Marshalled {
+	cnb_params p;
+	std::vector<int32_t> parent_sizes, order, num_cats, pool, fixed;
+	int nprotect;
+};
+
+/* the 12 arguments of ccnOptimalNetsForOrder (catnet_rexport.h:36-40) -> cnb_params */
+void marshal(Marshalled &m, SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes,
+		SEXP rMaxComplexity, SEXP rOrder, SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool,
+		SEXP rMatEdgeLiks, SEXP rEcho) {
+	memset(&m.p, 0, sizeof(m.p));
+	m.nprotect = 0;
+	if (!isMatrix(rSamples)) error("Data is not a matrix");                 /* rcatnet_search.cpp:69-70 */
+	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
+	m.nprotect++;
+	SEXP dim = getAttrib(rSamples, R_DimSymbol);
+	const int N = INTEGER(dim)[0], M = INTEGER(dim)[1];
+	m.p.num_nodes = N;
+	m.p.num_samples = M;
+	m.p.samples = INTEGER(rSamples);                /* N x M column-major == [sample][node], NA_INTEGER == INT_MIN */
+	if (!isNull(rPerturbations)) {
+		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
+		m.nprotect++;
+		m.p.perturbations = INTEGER(rPerturbations);
+	}
+	m.p.max_parent_set = asInteger(rMaxParents);
+	m.p.max_complexity = asInteger(rMaxComplexity);
+	m.p.echo = asLogical(rEcho);
+	if (!isNull(rParentSizes) && length(rParentSizes) == N) {
+		SEXP v = PROTECT(coerceVector(rParentSizes, INTSXP));
+		m.parent_sizes.assign(INTEGER(v), INTEGER(v) + N);
+		UNPROTECT(1);
+		m.p.parent_sizes = m.parent_sizes.data();
+	}
+	if (!isNull(rOrder) && length(rOrder) >= N) {
+		SEXP v = PROTECT(coerceVector(rOrder, INTSXP));
+		m.order.assign(INTEGER(v), INTEGER(v) + N);
+		UNPROTECT(1);
+		m.p.order = m.order.data();
+	} else if (!isNull(rOrder)) {
+		warning("Invalid nodeOrder parameter - reset to default node order.");   /* rcatnet_search.cpp:112-116 */
+	}
+	if (!isNull(rNodeCats) && length(rNodeCats) == N) {                     /* catIndices = 1..C per node */
+		m.num_cats.resize(N);
+		for (int i = 0; i < N; i++) m.num_cats[i] = length(VECTOR_ELT(rNodeCats, i));
+		m.p.num_cats = m.num_cats.data();
+	}
+	if (pool_matrix(rParentsPool, N, m.pool)) m.p.parents_pool = m.pool.data();
+	if (pool_matrix(rFixedParentsPool, N, m.fixed)) m.p.fixed_parents = m.fixed.data();
+	if (!isNull(rMatEdgeLiks) && length(rMatEdgeLiks) == N * N) {
+		rMatEdgeLiks = PROTECT(coerceVector(rMatEdgeLiks, REALSXP));
+		m.nprotect++;
+		m.p.edge_prob = REAL(rMatEdgeLiks);           /* R's own column-major buffer, exactly what the ABI expects */
+	}
+}
+
+/* nested probability lists, first listed parent outermost (rcatnet.cpp:318-345) */
+SEXP prob_list(const double *probs, const int *pc, int d, int cc, int level, int offset) {
+	if (level >= d) {
+		SEXP v = PROTECT(allocVector(REALSXP, cc));
+		memcpy(REAL(v), probs + (size_t)offset * cc, cc * sizeof(double));
+		UNPROTECT(1);
+		return v;
+	}
+	SEXP l = PROTECT(allocVector(VECSXP, pc[level]));
+	for (int j = 0; j < pc[level]; j++)
+		SET_VECTOR_ELT(l, j, prob_list(probs, pc, d, cc, level + 1, offset * pc[level] + j));
+	UNPROTECT(1);
+	return l;
+}
+
+/* one S4 catNetwork with the slots RCatnet::genRcatnet fills (rcatnet.cpp:174-316) */
+SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP rNodeNames) {
+	const int N = cnb_result_num_nodes(r);
+	std::vector<int32_t> order(N), npar(N), pars((size_t)N * 8);
+	cnb_result_order(r, i, order.data());
+	cnb_result_parents(r, i, npar.data(), pars.data(), 8);
+	int maxpar = 0, maxcat = 0, complexity = 0;
+	double loglik = 0;
+	cnb_result_network(r, i, &complexity, &loglik);
+	for (int n = 0; n < N; n++) {
+		if (npar[n] > maxpar) maxpar = npar[n];
+		if (cats_pos[n] > maxcat) maxcat = cats_pos[n];
+	}
+	SEXP cnet = PROTECT(NEW_OBJECT(MAKE_CLASS("catNetwork")));
+	SET_SLOT(cnet, install("objectName"), mkString("catNetwork"));
+	SET_SLOT(cnet, install("numnodes"), ScalarInteger(N));
+	SEXP names = PROTECT(allocVector(STRSXP, N));
+	char buf[64];
+	for (int n = 0; n < N; n++) {
+		if (!isNull(rNodeNames) && length(rNodeNames) == N) {
+			SET_STRING_ELT(names, n, STRING_ELT(rNodeNames, order[n] - 1));        /* rcatnet_sa.cpp:902 */
+		} else {
+			snprintf(buf, sizeof(buf), "N%d", (int)order[n]);                      /* setNodesOrder, catnet_class.h:290 */
+			SET_STRING_ELT(names, n, mkChar(buf));
+		}
+	}
+	SET_SLOT(cnet, install("nodes"), names);
+	SET_SLOT(cnet, install("maxParents"), ScalarInteger(maxpar));
+	SEXP plist = PROTECT(allocVector(VECSXP, N));
+	for (int n = 0; n < N; n++) {
+		if (npar[n] <= 0) continue;                                                /* NULL entry */
+		SEXP pv = PROTECT(allocVector(INTSXP, npar[n]));
+		for (int k = 0; k < npar[n]; k++) INTEGER(pv)[k] = pars[(size_t)n * 8 + k] + 1;   /* 1-based positions */
+		SET_VECTOR_ELT(plist, n, pv);
+		UNPROTECT(1);
+	}
+	SET_SLOT(cnet, install("parents"), plist);
+	SET_SLOT(cnet, install("maxCategories"), ScalarInteger(maxcat));
+	SEXP clist = PROTECT(allocVector(VECSXP, N));
+	for (int n = 0; n < N; n++) {
+		SEXP cv = PROTECT(allocVector(STRSXP, cats_pos[n]));
+		for (int k = 0; k < cats_pos[n]; k++) {
+			snprintf(buf, sizeof(buf), "%d", k + 1);                               /* catIndices 1..C */
+			SET_STRING_ELT(cv, k, mkChar(buf));
+		}
+		SET_VECTOR_ELT(clist, n, cv);
+		UNPROTECT(1);
+	}
+	SET_SLOT(cnet, install("categories"), clist);
+	SEXP problists = PROTECT(allocVector(VECSXP, N));
+	SEXP sizes = PROTECT(allocVector(INTSXP, N));
+	std::vector<double> probs;
+	for (int n = 0; n < N; n++) {
+		double ll, pr;
+		int32_t ss = 0;
+		int ts = cnb_result_node(r, i, n, &ll, &pr, &ss, NULL, 0);
+		probs.assign(ts > 0 ? ts : 1, 0.0);
+		cnb_result_node(r, i, n, &ll, &pr, &ss, probs.data(), ts);
+		int pc[8];
+		for (int k = 0; k < npar[n]; k++) pc[k] = cats_pos[pars[(size_t)n * 8 + k]];
+		SET_VECTOR_ELT(problists, n, prob_list(probs.data(), pc, npar[n], cats_pos[n], 0, 0));
+		INTEGER(sizes)[n] = ss;
+	}
+	SET_SLOT(cnet, install("probabilities"), problists);
+	SET_SLOT(cnet, install("meta"), mkString("catNetwork object"));
+	SET_SLOT(cnet, install("complexity"), ScalarInteger(complexity));
+	SET_SLOT(cnet, install("likelihood"), ScalarReal(loglik > -(double)FLT_MAX ? loglik : R_NegInf));   /* :295-300 */
+	SET_SLOT(cnet, install("nodeSampleSizes"), sizes);
+	UNPROTECT(6);
+	return cnet;
+}
+
+SEXP export_result(cnb_result *r, const cnb_params &p, SEXP rNodeNames) {
+	const int N = p.num_nodes, K = cnb_result_num_networks(r);
+	if (K < 1) {
+		cnb_result_free(r);
+		warning("No networks are found");                                          /* rcatnet_search.cpp:279-282 */
+		return R_NilValue;
+	}
+	std::vector<int32_t> cats_pos(N);
+	SEXP out = PROTECT(allocVector(VECSXP, K));
+	for (int i = 0; i < K; i++) {
+		cnb_result_cats(r, i, cats_pos.data());
+		SET_VECTOR_ELT(out, i, make_catnetwork(r, i, cats_pos.data(), rNodeNames));
+	}
+	cnb_result_free(r);
+	UNPROTECT(1);
+	return out;
+}
+
+void fail(int rc) {
+	/* copy the message first: Rf_error longjmps */
+	char msg[512];
+	strncpy(msg, cnb_last_error(), sizeof(msg) - 1);
+	msg[sizeof(msg) - 1] = 0;
+	error("catnet (B200): %s [code %d]", msg, rc);
+}
+
+} /* namespace */
+
+extern "C" {
+
+/* catnetOptimalNetsForOrder (catnet_rexport.h:36-40); rUseCache is accepted and ignored: the device re-scores */
+SEXP ccnOptimalNetsForOrder(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes,
+		SEXP rMaxComplexity, SEXP rOrder, SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool,
+		SEXP rMatEdgeLiks, SEXP rUseCache, SEXP rEcho) {
+	(void)rUseCache;
+	Marshalled m;
+	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, rOrder, rNodeCats, rParentsPool,
+			rFixedParentsPool, rMatEdgeLiks, rEcho);
+	cnb_result *res = NULL;
+	int rc = cnb_search_order(&m.p, &res);
+	UNPROTECT(m.nprotect);
+	if (rc != CNB_OK) fail(rc);
+	return export_result(res, m.p, R_NilValue);
+}
+
+/* catnetOptimalNetsSA (catnet_rexport.h:42-48) */
+SEXP ccnOptimalNetsSA(SEXP rNodeNames, SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes,
+		SEXP rMaxComplexity, SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool, SEXP rMaxParentsPool,
+		SEXP rMatEdgeLiks, SEXP rDirProbs, SEXP rModel, SEXP rStartOrder, SEXP rTempStart, SEXP rTempCoolFact,
+		SEXP rTempCheckOrders, SEXP rMaxIter, SEXP rOrderShuffles, SEXP rStopDiff, SEXP rThreads, SEXP rUseCache,
+		SEXP rEcho) {
+	(void)rMaxParentsPool;            /* R hard-codes maxParentsPool <- 0 (R/catnet.search.R:523) */
+	Marshalled m;
+	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
+			rFixedParentsPool, rMatEdgeLiks, rEcho);
+	const int N = m.p.num_nodes;
+	cnb_sa_params sa;
+	memset(&sa, 0, sizeof(sa));
+	const char *model = CHAR(STRING_ELT(PROTECT(coerceVector(rModel, STRSXP)), 0));
+	sa.select_mode = !strncmp(model, "AIC", 3) ? 1 : (!strncmp(model, "BIC", 3) ? 2 : 0);   /* rcatnet_sa.cpp:323-327 */
+	UNPROTECT(1);
+	std::vector<int32_t> start(N);
+	if (length(rStartOrder) < N) {
+		warning("Invalid nodeStartOrder parameter - reset to default node order.");
+		for (int i = 0; i < N; i++) start[i] = i + 1;
+	} else {
+		SEXP v = PROTECT(coerceVector(rStartOrder, INTSXP));
+		start.assign(INTEGER(v), INTEGER(v) + N);
+		UNPROTECT(1);
+	}
+	sa.start_order = start.data();
+	sa.temp_start = asReal(rTempStart);
+	sa.temp_cool_fact = asReal(rTempCoolFact);
+	sa.temp_check_orders = asInteger(rTempCheckOrders);
+	sa.max_iter = asInteger(rMaxIter);
+	sa.order_shuffles = asReal(rOrderShuffles);
+	sa.stop_diff = asReal(rStopDiff);
+	sa.num_threads = asInteger(rThreads);
+	sa.use_cache = asLogical(rUseCache);
+	int nprot = 0;
+	if (!isNull(rDirProbs) && length(rDirProbs) == N * N) {
+		rDirProbs = PROTECT(coerceVector(rDirProbs, REALSXP));
+		nprot++;
+		sa.dir_prob = REAL(rDirProbs);
+	}
+	/* seed the library's uniform stream from R's RNG on the calling thread, so set.seed() governs the chain */
+	GetRNGstate();
+	sa.seed = (uint64_t)(unif_rand() * 9007199254740992.0);
+	PutRNGstate();
+	cnb_result *res = NULL;
+	int rc = cnb_search_sa(&m.p, &sa, &res);
+	UNPROTECT(m.nprotect + nprot);
+	if (rc != CNB_OK) fail(rc);
+	return export_result(res, m.p, rNodeNames);
+}
+
+SEXP ccnReleaseCache(void) {
+	cnb_release_cache();
+	return R_NilValue;
+}
+
+SEXP ccnSetSeed(SEXP rSeed) {
+	cnb_set_seed(asInteger(rSeed));
+	return R_NilValue;
+}
+
+/* registration of the routines this shim owns; the package's ccnInit.c keeps registering the rest and calls this */
+static const R_CallMethodDef cnb_call_methods[] = {
+	{"ccnOptimalNetsForOrder", (DL_FUNC)&ccnOptimalNetsForOrder, 12},
+	{"ccnOptimalNetsSA", (DL_FUNC)&ccnOptimalNetsSA, 23},
+	{"ccnReleaseCache", (DL_FUNC)&ccnReleaseCache, 0},
+	{"ccnSetSeed", (DL_FUNC)&ccnSetSeed, 1},
+	{NULL, NULL, 0}};
+
+const R_CallMethodDef *cnb_r_call_methods(void) { return cnb_call_methods; }
+
+#ifdef CNB_STANDALONE_RSHIM
+/* build as a complete catnet.so for the search path only (the other 10 routines are then unavailable) */
+void R_init_catnet(DllInfo *info) {
+	R_registerRoutines(info, NULL, cnb_call_methods, NULL, NULL);
+	R_useDynamicSymbols(info, (Rboolean)1);
+}
+void R_unload_catnet(DllInfo *info) {
+	(void)info;
+	cnb_release_cache();
+}
+#endif
+
+} /* extern "C" */

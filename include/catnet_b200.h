@@ -163,6 +163,8 @@ int cnb_result_network(const cnb_result *r, int32_t i, int32_t *complexity, doub
 int cnb_result_parents(const cnb_result *r, int32_t i, int32_t *num_parents, int32_t *parents, int32_t max_parents_cap);
 /* the order network i is expressed in: position -> 1-based node label (differs per network after a merge) */
 int cnb_result_order(const cnb_result *r, int32_t i, int32_t *order_out);
+/* categories per node of network i, in its order space */
+int cnb_result_cats(const cnb_result *r, int32_t i, int32_t *cats_out);
 /* raw sample counts of a node's table (before normalisation); returns the table size */
 int cnb_result_counts(const cnb_result *r, int32_t i, int32_t node, int32_t *counts, int32_t cap);
 /* node-level view: log-lik, prior, sample size, CPT (normalised like problist.h:193-222); returns table size */

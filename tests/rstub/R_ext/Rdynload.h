@@ -1,0 +1,14 @@
+#ifndef CNB_RSTUB_RDYNLOAD_H
+#define CNB_RSTUB_RDYNLOAD_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef void *(*DL_FUNC)(void);
+typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
+typedef struct _DllInfo DllInfo;
+int R_registerRoutines(DllInfo *, const void *, const R_CallMethodDef *, const void *, const void *);
+int R_useDynamicSymbols(DllInfo *, int);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,69 @@
+/* tests/rstub -- declarations-only stand-in for R's C API, just enough to SYNTAX-CHECK catnet_b200/csrc/rshim.cpp in
+ * an image without R (tests/test_rshim.py runs g++ -fsyntax-only).  Nothing here is ever linked or executed. */
+#ifndef CNB_RSTUB_RINTERNALS_H
+#define CNB_RSTUB_RINTERNALS_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct SEXPREC *SEXP;
+typedef int Rboolean;
+#define INTSXP 13
+#define REALSXP 14
+#define STRSXP 16
+#define VECSXP 19
+extern SEXP R_NilValue, R_DimSymbol;
+extern double R_NegInf;
+SEXP Rf_protect(SEXP);
+void Rf_unprotect(int);
+SEXP Rf_coerceVector(SEXP, unsigned int);
+SEXP Rf_allocVector(unsigned int, long);
+SEXP Rf_getAttrib(SEXP, SEXP);
+SEXP Rf_install(const char *);
+SEXP Rf_mkChar(const char *);
+SEXP Rf_mkString(const char *);
+SEXP Rf_ScalarInteger(int);
+SEXP Rf_ScalarReal(double);
+int Rf_isNull(SEXP);
+int Rf_isMatrix(SEXP);
+int Rf_length(SEXP);
+int Rf_asInteger(SEXP);
+int Rf_asLogical(SEXP);
+double Rf_asReal(SEXP);
+int *INTEGER(SEXP);
+double *REAL(SEXP);
+const char *CHAR(SEXP);
+SEXP VECTOR_ELT(SEXP, long);
+SEXP SET_VECTOR_ELT(SEXP, long, SEXP);
+SEXP STRING_ELT(SEXP, long);
+void SET_STRING_ELT(SEXP, long, SEXP);
+SEXP R_do_slot_assign(SEXP, SEXP, SEXP);
+SEXP R_do_MAKE_CLASS(const char *);
+SEXP R_do_new_object(SEXP);
+void Rf_error(const char *, ...);
+void Rf_warning(const char *, ...);
+void GetRNGstate(void);
+void PutRNGstate(void);
+double unif_rand(void);
+#define PROTECT(s) Rf_protect(s)
+#define UNPROTECT(n) Rf_unprotect(n)
+#define coerceVector Rf_coerceVector
+#define allocVector Rf_allocVector
+#define getAttrib Rf_getAttrib
+#define install Rf_install
+#define mkChar Rf_mkChar
+#define mkString Rf_mkString
+#define ScalarInteger Rf_ScalarInteger
+#define ScalarReal Rf_ScalarReal
+#define isNull Rf_isNull
+#define isMatrix Rf_isMatrix
+#define length Rf_length
+#define asInteger Rf_asInteger
+#define asLogical Rf_asLogical
+#define asReal Rf_asReal
+#define error Rf_error
+#define warning Rf_warning
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,101 @@
+"""CPU suite, part 5: host-side logic above the C ABI -- the Python mirror of the R front-ends and the fixtures."""
+import math
+
+import numpy as np
+import pytest
+
+from catnet_b200 import _abi, search, synth
+
+
+def test_default_max_complexity_truncates_like_r():
+    # R: as.integer(numnodes * exp(log(maxCategories)*maxParentSet) * (maxCategories-1)); SURVEY.md section 3.1
+    assert synth.default_max_complexity(37, 4, 2) == 1775
+    assert synth.default_max_complexity(100, 2, 3) == 799
+    assert synth.default_max_complexity(100, 3, 3) == 5400
+    assert synth.default_max_complexity(500, 4, 2) == 23999
+
+
+def test_alarm_fixture_and_true_order():
+    net = synth.load_alarm()
+    assert len(net["cats"]) == 37 and sum((net["cats"][i] - 1) * int(np.prod([net["cats"][p] for p in net["parents"][i]]))
+                                         for i in range(37)) == 509
+    order = [v + 1 for v in synth.order_nodes_descend(net["parents"])]
+    assert order == [4, 6, 7, 8, 11, 13, 14, 15, 17, 19, 23, 25, 27, 28, 29, 30, 31, 32, 33, 1, 5, 16, 18, 20, 22, 24,
+                     26, 2, 3, 21, 34, 35, 36, 37, 9, 10, 12]
+    for c in net["cpts"]:
+        assert np.allclose(c.sum(axis=1), 1.0)
+    s = synth.sample_network(net, 500, np.random.Generator(np.random.PCG64(1)))
+    assert s.shape == (500, 37) and s.min() >= 1 and (s.max(axis=0) <= net["cats"]).all()
+
+
+def test_breast_fixture():
+    s = synth.load_breast()
+    assert s.shape == (98, 100) and set(np.unique(s)) == {1, 2}
+
+
+def test_random_network_is_a_dag_with_valid_cpts():
+    rng = np.random.Generator(np.random.PCG64(3))
+    net = synth.random_network(40, 3, 3, rng)
+    order = synth.order_nodes_descend(net["parents"])
+    assert sorted(order) == list(range(40))
+    pos = {v: i for i, v in enumerate(order)}
+    assert all(pos[p] < pos[i] for i in range(40) for p in net["parents"][i])
+    assert all(len(p) <= 3 for p in net["parents"])
+    for c in net["cpts"]:
+        assert np.allclose(c.sum(axis=1), 1.0) and (c >= 0).all()
+
+
+def test_discretize_uniform():
+    x = np.array([[0.0, 1.0, 2.0, 3.0, 4.0], [5.0, 5.0, 5.0, 5.0, 6.0]])
+    d = synth.discretize_uniform(x, 2)
+    assert d.tolist() == [[1, 1, 2, 2, 2], [1, 1, 1, 1, 2]]
+
+
+def test_categorize_sample():
+    data = [[3.0, 1.0, float("nan"), 2.0], [10.0, 20.0, 10.0, 20.0]]
+    out, pert, cats, mc = search.categorize_sample(data)
+    assert out.tolist() == [[3, 1, _abi.NA_INTEGER, 2], [1, 2, 1, 2]]
+    assert cats == [[1.0, 2.0, 3.0], [10.0, 20.0]] and mc == 3
+    with pytest.raises(ValueError):
+        search.categorize_sample([[1.0, 5.0]], node_cats=[[1.0, 2.0]])
+
+
+def test_cnsearchorder_marshalling(monkeypatch):
+    seen = {}
+
+    def fake(samples, **kw):
+        seen.update(kw, samples=samples)
+        return []
+    monkeypatch.setattr(_abi, "search_order", fake)
+    data = np.array([[1, 2, 1, 2, 3], [1, 1, 2, 2, 1], [2, 1, 2, 1, 1]], dtype=float)
+    e = np.array([[0, 1.0, 0.3], [0.2, 0, 1.7], [np.nan, -1, 0]])
+    ev = search.cnSearchOrder(data, maxParentSet=0, parentSizes=[1, 5, -2], nodeOrder=["c", "a", "b"], edgeProb=e,
+                              nodeNames=["a", "b", "c"], fixedParents=[["b", "c"], [], []])
+    assert ev.nets == []
+    assert seen["samples"].shape == (5, 3)                       # [sample][node], as R's column-major N x M matrix
+    assert seen["max_parent_set"] == 5 and seen["order"] == [3, 1, 2]
+    assert list(seen["parent_sizes"]) == [1, 5, 0]
+    assert seen["num_cats"] is None                               # nodeCats not given -> the library infers them
+    assert seen["max_complexity"] == int(3 * math.exp(math.log(3) * 5) * 2)
+    ep = seen["edge_prob"]
+    assert ep[1, 2] == 1.0 and ep[2, 0] == 0.5 and ep[2, 1] == 0.0
+    # edgeProb == 1 entries are appended to the fixed parents, duplicates included, exactly as R's c() does (:127-133)
+    assert seen["fixed_parents"][0] == [2, 3, 2] and seen["fixed_parents"][1] == [3]
+
+
+def test_cnsearchsa_argument_clamps(monkeypatch):
+    seen = {}
+
+    def fake(samples, sa, **kw):
+        seen.update(kw, sa=sa)
+        return {"nets": [], "order": np.arange(1, 4)}
+    monkeypatch.setattr(_abi, "search_sa", fake)
+    data = np.array([[1, 2, 1, 2], [1, 1, 2, 2], [2, 1, 2, 1]], dtype=float)
+    with pytest.warns(UserWarning):
+        search.cnSearchSA(data, maxParentSet=2, tempStart=-1, tempCoolFact=3, tempCheckOrders=0, maxIter=0,
+                          selectMode="AIC", seed=5, dirProb=np.array([[0, 2.0, 1], [1, 0, 1], [1, 1, 0.0]]))
+    sa = seen["sa"]
+    assert sa["temp_start"] == 0 and sa["temp_cool_fact"] == 1 and sa["temp_check_orders"] == 1 and sa["max_iter"] == 1
+    assert sa["select_mode"] == 1 and sorted(sa["start_order"].tolist()) == [1, 2, 3]
+    d = sa["dir_prob"]
+    assert abs(d[0, 1] - 2.0 / 3.0) < 1e-15 and d[0, 0] == 0.5
