@@ -142,6 +142,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	if (flags[0]) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
 	/* two-way margins for the inclusion-exclusion scorer: only meaningful without missing values / masks */
 	c->pairs_valid = false;
+	c->clean = !flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS;   /* no NA, no masks, bit planes valid */
 	if (!flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS && N >= 3 && !c->no_ie) {
 		RC(c->b_pairs.ensure((size_t)N * (N - 1) / 2 * 16 * sizeof(int)));
 		RC(cnbk_pair_tables(st, (const uint4 *)c->b_planes_lbl.ptr, N, c->W, (int *)c->b_pairs.ptr));
@@ -194,6 +195,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	if (!c) return CNB_ERR_PARAM;
 	c->force_generic = (on & 1) != 0;     /* bit 0: generic histogram kernel everywhere */
 	c->no_ie = (on & 2) != 0;             /* bit 1: keep the direct bit-plane scorer (no inclusion-exclusion) */
+	c->tensor_mode = (on & 4) ? 1 : ((on & 8) ? -1 : 0);   /* bit 2: tensor-core path whenever applicable; bit 3: never */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -218,6 +220,8 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.blocks = (const CnbBlock *)c->b_blocks.ptr;
 	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
 	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
+	D.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
+	D.nct = c->plan.tile_base.empty() ? 0 : (int)c->plan.tile_base.size() - 1;
 	return D;
 }
 
@@ -239,8 +243,12 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* the previous plan's host vectors may still be the source of an async copy */
 	CK(cudaStreamSynchronize(c->stream));
 	std::string err;
-	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err));
+	/* tensor-core tiling of the two-parent group: clean data (no NA, no masks, <= 4 categories) and enough samples
+	 * per family to amortise a 128 x 256 tile (or forced on by the test hook) */
+	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192);
+	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tiled));
 	CnbPlan &pl = c->plan;
+	if (!pl.tile_base.empty()) RC(upload(c, c->b_tile_base, pl.tile_base));
 	RC(upload(c, c->b_order, pl.order));
 	RC(upload(c, c->b_cats, pl.cats));
 	RC(upload(c, c->b_lists, pl.lists));
@@ -329,6 +337,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	CK(cudaMemsetAsync((int *)c->b_flag.ptr + 1, 0, sizeof(int), st));
 	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
 	c->timing.fast_path = 1;
+	c->timing.tensor_tiles = 0;
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		DevFamilies F;
@@ -339,8 +348,25 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		memset(&O, 0, sizeof(O));
 		O.scores = scores_dev; O.chunk = g.chunk; O.seg_off = g.seg_off; O.seg_len = pl.seg_len;
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi], st));
-		RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
-		if (e > b && !c->last_fast) c->timing.fast_path = 0;
+		if (g.tiled) {
+			/* tcgen05 path: integer tables by one-hot GEMM, tile batches bounded by the table buffer */
+			long long t0 = (long long)pl.rank * g.tiles_per_rank, t1 = std::min<long long>(g.ntiles, t0 + g.tiles_per_rank);
+			const long long batch = 16384, slot_bytes = CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
+			for (long long tb = t0; tb < t1; tb += batch) {
+				long long te = std::min(t1, tb + batch);
+				RC(cnbk_umma_tables(st, D.planes, c->N, c->W, D.tile_base, D.nct, tb, te, (int *)c->b_counts.ptr));
+				RC(cnbk_umma_epilogue(st, D, D.tile_base, D.nct, tb, te, (const int *)c->b_counts.ptr,
+						(const int *)c->b_pairs.ptr, O));
+				c->timing.kernel_launches += 2;
+			}
+			c->timing.tensor_tiles += t1 - t0;
+			b = 0;
+			e = t1 > t0 ? (long long)((double)g.nfam * (double)(t1 - t0) / (double)g.ntiles) : 0;
+		} else {
+			RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
+			if (e > b && !c->last_fast) c->timing.fast_path = 0;
+		}
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi + 1], st));
 		if (e > b) {
 			c->timing.num_families += e - b;

@@ -20,7 +20,13 @@ struct DevData {
 	const CnbBlock *blocks;
 	const int32_t *group_blocks;
 	const double *edge;         /* [N*N] order space [parent*N+child] or NULL */
+	const long long *tile_base; /* tensor-core tiling of the two-parent group (NULL if not tiled) */
+	int32_t nct;
 };
+
+__device__ __forceinline__ unsigned plane_of(const uint4 &v, int i) {
+	return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
 
 /* one launch class: either a plan group (implicit enumeration) or an explicit family list */
 struct DevFamilies {
@@ -110,6 +116,32 @@ __device__ __forceinline__ double dev_prior(const DevData &D, int child, const i
 	t2 = (t2 > 0) ? cnb_log(t2) : CNB_NEG_INF;
 	if (prior == CNB_NEG_INF || t2 == CNB_NEG_INF) return CNB_NEG_INF;
 	return __dadd_rn(prior, t2);
+}
+
+/* log-lik of one count table in the reference's exact operation order (problist.h:224-250 then
+ * catnet_class.h:867-871): for each parent configuration ascending, pp = 1/N_k, loglik += n*log(n*pp) for n > 0
+ * ascending; finally divide by ncount if ncount > 1.  cnt(cfg, k) fetches a cell. */
+template <class Fetch>
+__device__ __forceinline__ double dev_loglik(int ncfg, int cc, Fetch cnt, int *ncount_out) {
+	double ll = 0.0;
+	long long ncount = 0;
+	for (int cfg = 0; cfg < ncfg; cfg++) {
+		long long nk = 0;
+		for (int k = 0; k < cc; k++) nk += cnt(cfg, k);
+		if (nk <= 0) continue;
+		ncount += nk;
+		double pp = __ddiv_rn(1.0, (double)nk);
+		for (int k = 0; k < cc; k++) {
+			int n = cnt(cfg, k);
+			if (n > 0) {
+				double dn = (double)n;
+				ll = __dadd_rn(ll, __dmul_rn(dn, cnb_log(__dmul_rn(dn, pp))));
+			}
+		}
+	}
+	if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
+	*ncount_out = (int)ncount;
+	return ll;
 }
 
 /* position of family fid of group (chunk, seg_off) in the rank-major score buffer */

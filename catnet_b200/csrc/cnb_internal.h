@@ -33,11 +33,16 @@ struct CnbGroup {
 	int32_t d;
 	int32_t nblk;
 	int32_t blk_off;    /* into group_blocks[] (block ids sorted by start) */
-	int32_t pad;
+	int32_t tiled;      /* 1: scored by the tensor-core kernel; scores are addressed by tile slot, not family id */
 	int64_t nfam;       /* families in the group */
-	int64_t chunk;      /* families per rank: ceil(nfam / world) */
+	int64_t chunk;      /* score slots per rank: ceil(nfam / world), or tiles_per_rank * 512 when tiled */
 	int64_t seg_off;    /* offset of the group inside one rank segment of the score buffer */
+	int64_t ntiles;     /* tiled only */
+	int64_t tiles_per_rank;
 };
+
+#define CNB_TILE_PAIRS 14     /* tensor-core tile: 14 parent pairs x 9 rows (126 of 128) ... */
+#define CNB_TILE_CHILD 85     /* ... x 85 children x 3 columns (255 of 256): 1190 families per tile */
 
 struct CnbNodePlan {
 	int32_t equal_branch;   /* catnet_search2.h:491-496 */
@@ -59,6 +64,7 @@ struct CnbPlan {
 	std::vector<int32_t> group_blocks;
 	std::vector<CnbNodePlan> nodes;
 	std::vector<double> edge;                  /* order space [parent*N + child], empty if no prior */
+	std::vector<int64_t> tile_base;            /* tiled group: first tile of every child tile (+ total at the end) */
 	int64_t seg_len = 0;                       /* doubles per rank segment */
 	int64_t num_families = 0;
 	int64_t num_options = 0;
@@ -69,7 +75,7 @@ struct CnbPlan {
 
 /* host planner (no CUDA): cnb_plan.cpp */
 int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
-		std::string *err);
+		std::string *err, bool allow_tiled = false);
 int64_t cnb_binom(int64_t n, int64_t k);
 int cnb_unrank_lex(int32_t n, int32_t k, int64_t r, int32_t *out);
 

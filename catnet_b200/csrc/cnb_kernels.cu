@@ -90,32 +90,6 @@ __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *
 }
 
 /* ------------------------------------------------------------------ epilogue ---- */
-/* log-lik of one count table in the reference's exact operation order (problist.h:224-250 then
- * catnet_class.h:867-871): for each parent configuration ascending, pp = 1/N_k, loglik += n*log(n*pp) for n > 0
- * ascending; finally divide by ncount if ncount > 1.  cnt(cfg, k) fetches a cell. */
-template <class Fetch>
-__device__ __forceinline__ double dev_loglik(int ncfg, int cc, Fetch cnt, int *ncount_out) {
-	double ll = 0.0;
-	long long ncount = 0;
-	for (int cfg = 0; cfg < ncfg; cfg++) {
-		long long nk = 0;
-		for (int k = 0; k < cc; k++) nk += cnt(cfg, k);
-		if (nk <= 0) continue;
-		ncount += nk;
-		double pp = __ddiv_rn(1.0, (double)nk);
-		for (int k = 0; k < cc; k++) {
-			int n = cnt(cfg, k);
-			if (n > 0) {
-				double dn = (double)n;
-				ll = __dadd_rn(ll, __dmul_rn(dn, cnb_log(__dmul_rn(dn, pp))));
-			}
-		}
-	}
-	if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
-	*ncount_out = (int)ncount;
-	return ll;
-}
-
 __device__ __forceinline__ void dev_store_outputs(const DevData &D, const ScoreOut &O, long long fid, int child,
 		const int *pars, int d, double ll, int ncount) {
 	double prior = 0.0;
@@ -145,10 +119,6 @@ __device__ __forceinline__ void load_word(const DevData &Dt, int w, int child, c
 		c.x &= m; c.y &= m; c.z &= m; c.w &= m;
 	}
 	v[D] = c;
-}
-
-__device__ __forceinline__ unsigned plane_of(const uint4 &v, int i) {
-	return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
 /* counts[((i0*CM+i1)*CM+..)*CM + k] += popc(P0[i0] & P1[i1] & .. & C[k]) : every index is a compile-time constant */
@@ -491,10 +461,22 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 		for (int i = 0; i < d; i++) cx *= Dt.cats[pars[i]];
 		return cx;
 	};
+	/* where the score of candidate `fid` lives: by family id, or by tile slot for the tensor-core group */
+	auto score_of = [&](long long fid) {
+		long long slot = fid;
+		if (g.tiled) {
+			int ab[2];
+			dev_unrank(b.nfree, 2, fid - b.start, ab);      /* unrestricted block: positions themselves */
+			long long q = (long long)ab[1] * (ab[1] - 1) / 2 + ab[0];
+			long long tile = Dt.tile_base[b.child / CNB_TILE_CHILD] + q / CNB_TILE_PAIRS;
+			slot = tile * (CNB_TILE_PAIRS * CNB_TILE_CHILD) + (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + b.child % CNB_TILE_CHILD;
+		}
+		return scores[dev_score_index(slot, g.chunk, g.seg_off, seg_len)];
+	};
 	if (!blk_equal[blockIdx.x]) {
 		for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
 			long long fid = b.start + r;
-			opt_score[b.opt_off + r] = scores[dev_score_index(fid, g.chunk, g.seg_off, seg_len)];
+			opt_score[b.opt_off + r] = score_of(fid);
 			opt_cx[b.opt_off + r] = complexity_of(fid);
 			opt_fid[b.opt_off + r] = fid;
 		}
@@ -504,7 +486,7 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 	long long best_fid = -1;
 	for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
 		long long fid = b.start + r;
-		double s = scores[dev_score_index(fid, g.chunk, g.seg_off, seg_len)];
+		double s = score_of(fid);
 		if (s > best) { best = s; best_fid = fid; }       /* ascending r per thread: first max kept */
 	}
 	__shared__ double sh_s[256];

@@ -36,6 +36,11 @@ int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, 
 int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int *out);
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
+int cnbk_umma_tables(cudaStream_t st, const uint4 *planes, int N, int W, const long long *tile_base, int nct,
+		long long tile_begin, long long tile_end, int *counts);
+int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, const long long *tile_base, int nct, long long tile_begin,
+		long long tile_end, const int *counts, const int *pair_tab, const ScoreOut &O);
+#define CNBK_UMMA_SLOT_INTS 36
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,

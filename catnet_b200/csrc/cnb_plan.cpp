@@ -66,7 +66,7 @@ extern "C" int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_
 }
 
 int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
-		std::string *err) {
+		std::string *err, bool allow_tiled) {
 	char buf[256];
 #define FAIL(code, ...) do { snprintf(buf, sizeof(buf), __VA_ARGS__); if (err) *err = buf; cnb_set_error("%s", buf); return code; } while (0)
 	if (!p || !plan) FAIL(CNB_ERR_PARAM, "null parameters");
@@ -195,6 +195,29 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 		}
 		if (!g.nblk) continue;
 		g.chunk = (g.nfam + world - 1) / world;
+		/* Tensor-core tiling of the two-parent group: only when every node c >= 2 offers all pairs of its
+		 * predecessors (no pools, no fixed parents, no size limit), so that tile (child tile, pair tile) slots map
+		 * one-to-one onto candidate families.  Tiles cost the same, so ranks get equal contiguous tile ranges. */
+		if (allow_tiled && d == 2 && N >= 3 && g.nblk == N - 2) {
+			bool full = true;
+			for (int k = 0; k < g.nblk; k++) {
+				const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
+				full = full && b.nfix == 0 && b.nfree == b.child;
+			}
+			if (full) {
+				int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+				pl.tile_base.assign(nct + 1, 0);
+				for (int ct = 0; ct < nct; ct++) {
+					int64_t cmax = std::min<int64_t>(N - 1, (int64_t)ct * CNB_TILE_CHILD + CNB_TILE_CHILD - 1);
+					int64_t npairs = cmax * (cmax - 1) / 2;          /* pairs (a < b) with b < cmax */
+					pl.tile_base[ct + 1] = pl.tile_base[ct] + (npairs + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS;
+				}
+				g.tiled = 1;
+				g.ntiles = pl.tile_base[nct];
+				g.tiles_per_rank = (g.ntiles + world - 1) / world;
+				g.chunk = g.tiles_per_rank * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+			}
+		}
 		g.seg_off = pl.seg_len;
 		pl.seg_len += g.chunk;
 		pl.num_families += g.nfam;

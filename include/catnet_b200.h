@@ -133,6 +133,7 @@ typedef struct cnb_timing {
 	int32_t kernel_launches;
 	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
 	int64_t h2d_bytes, d2h_bytes;   /* host<->device traffic since the last cnb_ctx_set_samples* call */
+	int64_t tensor_tiles;           /* 128x256 tcgen05 tiles run by this rank (0 = tensor-core path not used) */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 

@@ -110,6 +110,51 @@ def test_search_order_matches_reference(abi, port, case):
         compare_golden(ctx.search_order(**kw2), golden)
 
 
+def _tensor_eligible(case, cats):
+    return (not any(case.get(k) for k in ("na", "pert", "pools", "fixed", "psizes")) and int(np.max(cats)) <= 4
+            and case["n"] >= 3 and case["P"] >= 2)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_search_order_tensor_core_path(abi, case):
+    """the tcgen05 one-hot GEMM scorer of the two-parent group, forced on for these small problems"""
+    s, kw = build_case(case)
+    golden = load_golden("ref_search_order")["seed%d" % case["seed"]]
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
+        ctx.force_generic(4)
+        kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
+        nets = ctx.search_order(**kw2)
+        used = ctx.timing()["tensor_tiles"] > 0
+        assert used == _tensor_eligible(case, ctx.num_cats())
+        compare_golden(nets, golden)
+
+
+@pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4)])
+def test_tensor_core_path_multi_tile(abi, n, m, cats):
+    """several child tiles / pair tiles / K stages, ragged M: tensor-core scores == bit-plane scores"""
+    s, c = random_problem(n + m, n, m, cats)
+    kw = dict(max_parent_set=2, max_complexity=n * 8, order=(np.random.default_rng(n).permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.force_generic(8)                      # never the tensor path
+        a = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(4)                      # always
+        b = ctx.search_order(want_probs=False, **kw)
+        assert ctx.timing()["tensor_tiles"] > 0
+        for world in (1, 3):                      # sharded over tile ranges
+            import torch
+            seg, nf = ctx.plan(0, world, **kw)
+            buf = torch.full((seg * world,), float("nan"), dtype=torch.float64, device="cuda")
+            for r in range(world):
+                ctx.plan(r, world, **kw)
+                ctx.score_shard(buf.data_ptr())
+            torch.cuda.synchronize()
+            c2 = ctx.finish(buf.data_ptr(), want_probs=False)
+            assert compare_search(c2, a, check_probs=False) == len(a)
+    assert compare_search(b, a, check_probs=False) == len(a)
+
+
 @pytest.mark.parametrize("seed", range(200, 230))
 def test_search_order_random_vs_oracle(abi, port, seed):
     rng = np.random.default_rng(seed)
