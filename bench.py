@@ -292,28 +292,49 @@ def main():
     ms = float(t_ms.item())
     value = n_fam_total * args.steps / (ms / 1000.0)
 
-    # ---- roofline of the dominant kernel (the scorer of the largest parent count), measured live (CUDA events)
+    # ---- roofline of the dominant kernel, measured live (the library's CUDA events on the launching stream)
     d_dom = wl["P"]
-    dom_ms = float(np.mean([p["score_ms_by_parents"][d_dom] for p in phases]))
-    dom_fam = phases[-1]["families_by_parents"][d_dom]
-    alg_bytes = dom_fam * ((d_dom + 1) * m + 8)
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ph_last = phases[-1]
+    peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            peaks = json.load(f)
     except Exception:
         pass
-    achieved = alg_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom_ms = float(np.mean([p["score_ms_by_parents"][d_dom] for p in phases]))
+    dom_fam = ph_last["families_by_parents"][d_dom]
+    alg_bytes = dom_fam * ((d_dom + 1) * m + 8)
+    hbm_model = {"achieved_gbs": alg_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
+                 "frac": (alg_bytes / (dom_ms / 1000.0) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
+                 "algorithmic_bytes_per_launch": alg_bytes, "group_ms": dom_ms,
+                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f).get("%s_gpus%d" % (wl["name"], world))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_score_planes<%d,%d>" % (d_dom, min(4, max(2, int(max(wl["cats"]))))),
-                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "cell_updates_per_s": dom_fam * m / (dom_ms / 1000.0) if dom_ms > 0 else 0.0}
+    if ph_last["tensor_tiles"] > 0:
+        # tcgen05 scorer: bound by the tensor pipe.  u8 x u8 -> s32 runs at twice the bf16 rate on B200 (nominal 4.5 vs
+        # 2.25 PFLOP/s dense); the denominator is the MEASURED sustained bf16 cuBLAS figure scaled by that factor.
+        t_ms = float(np.mean([p["tensor_ms"] for p in phases]))
+        ops = 2.0 * ph_last["tensor_macs"]
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = ops / (t_ms / 1000.0) / 1e12 if t_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": ach, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": ach / (2.0 * bf16),
+                    "traffic": traffic, "kernel": "k_umma_tables (tcgen05.mma kind::i8)", "kernel_ms": t_ms,
+                    "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
+                    "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 = 2x bf16 rate on B200)"
+                    if peaks else "2 x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)",
+                    "useful_mac_fraction": dom_fam * 27.0 * m / max(ph_last["tensor_macs"], 1),
+                    "hbm_model": hbm_model}
+    else:
+        roofline = {"bound": "hbm", "achieved": hbm_model["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_model["frac"], "traffic": traffic,
+                    "kernel": "k_score_planes%s<%d,%d>" % ("_ie2" if d_dom == 2 else "", d_dom, min(4, max(2, int(max(wl["cats"]))))),
+                    "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_model["peak_source"]}
+    roofline["family_samples_per_s"] = dom_fam * m / (dom_ms / 1000.0) if dom_ms > 0 else 0.0
 
     # ---- e2e through the C ABI with host buffers
     e2e = None

@@ -245,10 +245,14 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	std::string err;
 	/* tensor-core tiling of the two-parent group: clean data (no NA, no masks, <= 4 categories) and enough samples
 	 * per family to amortise a 128 x 256 tile (or forced on by the test hook) */
-	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192);
+	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192)
+			&& c->M < (1 << 24);          /* accumulators hold 128 x count in s32 */
 	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tiled));
 	CnbPlan &pl = c->plan;
-	if (!pl.tile_base.empty()) RC(upload(c, c->b_tile_base, pl.tile_base));
+	if (!pl.tile_base.empty()) {
+		RC(upload(c, c->b_tile_base, pl.tile_base));
+		RC(c->b_planes_rev.ensure((size_t)c->W * c->N * sizeof(uint4)));
+	}
 	RC(upload(c, c->b_order, pl.order));
 	RC(upload(c, c->b_cats, pl.cats));
 	RC(upload(c, c->b_lists, pl.lists));
@@ -262,7 +266,8 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* samples into order space (the reference re-copies the int matrix per order, rcatnet_search.cpp:151-160) */
 	RC(cnbk_permute(c->stream, (const uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, (const int *)c->b_order.ptr, c->N, c->W,
-			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr));
+			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr,
+			pl.tile_base.empty() ? nullptr : (uint4 *)c->b_planes_rev.ptr));
 	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
 	c->timing.kernel_launches = 1;                    /* k_permute; the later phases add theirs */
 	c->planned = true;
@@ -338,6 +343,9 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
 	c->timing.fast_path = 1;
 	c->timing.tensor_tiles = 0;
+	c->timing.tensor_ms = 0;
+	c->timing.tensor_macs = 0;
+	c->tensor_batches = 0;
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		DevFamilies F;
@@ -353,14 +361,20 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			long long t0 = (long long)pl.rank * g.tiles_per_rank, t1 = std::min<long long>(g.ntiles, t0 + g.tiles_per_rank);
 			const long long batch = 16384, slot_bytes = CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
 			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
-			for (long long tb = t0; tb < t1; tb += batch) {
+			int nb = 0;
+			for (long long tb = t0; tb < t1; tb += batch, nb++) {
 				long long te = std::min(t1, tb + batch);
-				RC(cnbk_umma_tables(st, D.planes, c->N, c->W, D.tile_base, D.nct, tb, te, (int *)c->b_counts.ptr));
+				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb], st));
+				RC(cnbk_umma_tables(st, D.planes, (const uint4 *)c->b_planes_rev.ptr, c->N, c->W, D.tile_base, D.nct, tb, te,
+						(int *)c->b_counts.ptr));
+				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb + 1], st));
 				RC(cnbk_umma_epilogue(st, D, D.tile_base, D.nct, tb, te, (const int *)c->b_counts.ptr,
 						(const int *)c->b_pairs.ptr, O));
 				c->timing.kernel_launches += 2;
 			}
 			c->timing.tensor_tiles += t1 - t0;
+			c->tensor_batches = nb;
+			c->timing.tensor_macs = (t1 - t0) * 128ll * 256ll * (((long long)c->W + 3) / 4 * 128);
 			b = 0;
 			e = t1 > t0 ? (long long)((double)g.nfam * (double)(t1 - t0) / (double)g.ntiles) : 0;
 		} else {
@@ -382,6 +396,8 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
 	c->timing.plan_ms = ev_ms(c, EV_PLAN0, EV_PLAN1);
 	c->timing.score_ms = ev_ms(c, EV_SCORE0, EV_SCORE1);
+	for (int i = 0; i < c->tensor_batches && i < CNB_NEV_TEN; i++) c->timing.tensor_ms += ev_ms(c, EV_TEN0 + 2 * i, EV_TEN0 + 2 * i + 1);
+	if (c->tensor_batches > CNB_NEV_TEN) c->timing.tensor_ms *= (float)c->tensor_batches / CNB_NEV_TEN;
 	gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		if (gi < CNB_NEV_GROUPS && g.d < 8)

@@ -8,9 +8,10 @@
 
 #define CNB_HIST_MAX_CELLS 16384   /* largest conditional table of the generic scorer (shared memory) */
 #define CNB_NEV_GROUPS 8
+#define CNB_NEV_TEN 8        /* timed batches of the tensor-core kernel */
 
 enum { EV_PACK0, EV_PACK1, EV_PLAN0, EV_PLAN1, EV_SCORE0, EV_SCORE1, EV_SEL0, EV_SEL1, EV_DP1, EV_COL0, EV_COL1,
-	EV_GROUP0, CNB_NEV = EV_GROUP0 + 2 * CNB_NEV_GROUPS };
+	EV_GROUP0, EV_TEN0 = EV_GROUP0 + 2 * CNB_NEV_GROUPS, CNB_NEV = EV_TEN0 + 2 * CNB_NEV_TEN };
 
 struct DevBuf {
 	void *ptr = nullptr;
@@ -26,7 +27,7 @@ struct cnb_ctx {
 	int N = 0, M = 0, W = 0, Mpad = 0, max_cats = 0;
 	bool has_pert = false, have_samples = false, planned = false, dp_done = false, force_generic = false, last_fast = false, pairs_valid = false, no_ie = false, clean = false;
 	int tensor_mode = 0;               /* 0 auto (large M), 1 always when applicable, -1 never */
-	int dp_final = 0;
+	int dp_final = 0, tensor_batches = 0;
 	std::vector<int32_t> cats_lbl;
 	std::vector<int32_t> blk_equal;
 	std::vector<unsigned char> h_exists;
@@ -34,7 +35,7 @@ struct cnb_ctx {
 	CnbPlan plan;
 	cnb_timing timing = {};
 	/* packed samples */
-	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs;
+	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_planes_rev;
 	/* plan */
 	DevBuf b_order, b_cats, b_lists, b_blocks, b_group_blocks, b_groups, b_edge, b_blk_equal, b_tile_base;
 	/* scoring */
@@ -46,7 +47,7 @@ struct cnb_ctx {
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_planes_rev};
 	}
 };
 

@@ -80,12 +80,18 @@ __global__ void k_pack(const int32_t *__restrict__ samples, const int32_t *__res
 
 /* label space -> order space for one search (what the reference does by re-copying the whole int matrix) */
 __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *__restrict__ keep_lbl,
-		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep) {
+		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep,
+		uint4 *__restrict__ planes_rev) {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	int w = blockIdx.y;
 	if (p >= N) return;
 	int l = order[p];
-	planes[(size_t)w * N + p] = planes_lbl[(size_t)w * N + l];
+	uint4 v = planes_lbl[(size_t)w * N + l];
+	planes[(size_t)w * N + p] = v;
+	if (planes_rev) {      /* bits reversed inside every byte: the B operand of the tensor-core scorer */
+		planes_rev[(size_t)w * N + p] = make_uint4(__byte_perm(__brev(v.x), 0, 0x0123), __byte_perm(__brev(v.y), 0, 0x0123),
+				__byte_perm(__brev(v.z), 0, 0x0123), __byte_perm(__brev(v.w), 0, 0x0123));
+	}
 	if (keep) keep[(size_t)w * N + p] = keep_lbl[(size_t)w * N + l];
 }
 
@@ -619,9 +625,9 @@ int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int 
 }
 
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
-		uint4 *planes, uint32_t *keep) {
+		uint4 *planes, uint32_t *keep, uint4 *planes_rev) {
 	dim3 grid((N + 127) / 128, W);
-	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep);
+	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep, planes_rev);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -62,11 +62,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 	return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-/* 4 bits -> 4 bytes of 0/1 (bit t -> byte t): the products of the four bits land in disjoint bit ranges */
-__device__ __forceinline__ uint32_t expand4(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
-__device__ __forceinline__ uint4 expand16(uint32_t x) {
-	return make_uint4(expand4(x), expand4(x >> 4), expand4(x >> 8), expand4(x >> 12));
-}
 /* byte offset of (row r, 16-byte chunk ch) in the K-major SWIZZLE_128B layout: 8-row groups of 1024 B, the chunk
  * index XOR-ed with the row inside the group (Swizzle<3,4,3>) */
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t ch) {
@@ -92,8 +87,9 @@ __device__ __forceinline__ void tile_of(const long long *__restrict__ tile_base,
 	pt = tile - tile_base[lo];
 }
 
-__global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__restrict__ planes, int N, int W,
-		const long long *__restrict__ tile_base, int nct, long long tile_begin, int *__restrict__ counts) {
+__global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__restrict__ planes,
+		const uint4 *__restrict__ planes_rev, int N, int W, const long long *__restrict__ tile_base, int nct,
+		long long tile_begin, int *__restrict__ counts) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ __align__(8) uint64_t bar_empty[2], bar_done;
 	__shared__ uint32_t tmem_base_sh;
@@ -123,7 +119,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__re
 	/* ---- per-thread generation roles (fixed for the whole K loop) ----
 	 * task = (row, 16-byte chunk); 256 threads -> chunk = tid & 7 (word tid>>1 & 3, half tid & 1), rows tid>>3 + 32k.
 	 * A row r = pair*9 + i*3 + j (i, j < 3); B row r = child*3 + k (k < 3).  Unused rows are zeroed once. */
-	const int ch = tid & 7, wi = ch >> 1, hs = (ch & 1) * 16, r0 = tid >> 3;
+	const int ch = tid & 7, wi = ch >> 1, u0 = (ch & 1) * 4, r0 = tid >> 3;
 	int a_na[4], a_nb[4], a_ci[4], a_cj[4];          /* node positions and categories of the 4 A rows; -1 = no row */
 	uint32_t a_off[4];
 #pragma unroll
@@ -166,6 +162,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__re
 		const int w = st * 4 + wi;
 		const bool in = w < W;
 		const uint32_t *row = reinterpret_cast<const uint32_t *>(planes + (size_t)(in ? w : 0) * N);
+		const uint32_t *rrow = reinterpret_cast<const uint32_t *>(planes_rev + (size_t)(in ? w : 0) * N);
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			fa[k] = fb[k] = 0;
@@ -175,26 +172,34 @@ __global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__re
 			}
 		}
 #pragma unroll
-		for (int k = 0; k < 8; k++) fc[k] = (in && b_n[k] >= 0) ? __ldg(row + 4 * b_n[k] + b_ck[k]) : 0;
+		for (int k = 0; k < 8; k++) fc[k] = (in && b_n[k] >= 0) ? __ldg(rrow + 4 * b_n[k] + b_ck[k]) : 0;
 	};
 	fetch(0);
 
 	for (int it = 0; it < nst; it++) {
 		const int s = it & 1;
 		uint8_t *buf = smem + s * UM_STAGE;
+		/* Operand bytes without shifts or multiplies.  Inside a 32-sample word the K position 4u+v holds sample
+		 * u + 8v: the A byte is  x & (0x01 << u)  = bit * 2^u, the B byte comes from the plane word with the bits of
+		 * every byte reversed,  y' & (0x01 << (7-u))  = bit * 2^(7-u); every product is bit*bit*128, so the
+		 * accumulators hold 128 x count (exact in s32 for M < 2^24; the epilogue shifts right by 7). */
 		uint32_t ga[4], gc[8];
 #pragma unroll
-		for (int k = 0; k < 4; k++) ga[k] = (fa[k] & fb[k]) >> hs;
+		for (int k = 0; k < 4; k++) ga[k] = fa[k] & fb[k];
 #pragma unroll
-		for (int k = 0; k < 8; k++) gc[k] = fc[k] >> hs;
+		for (int k = 0; k < 8; k++) gc[k] = fc[k];
 		if (it + 1 < nst) fetch(it + 1);                  /* loads for the next stage fly during this one */
 		if (it >= 2) mbar_wait(&bar_empty[s], ((it >> 1) - 1) & 1);   /* MMAs of stage it-2 have read this buffer */
 #pragma unroll
 		for (int k = 0; k < 4; k++)
-			if (a_na[k] >= 0) *reinterpret_cast<uint4 *>(buf + a_off[k]) = expand16(ga[k]);
+			if (a_na[k] >= 0)
+				*reinterpret_cast<uint4 *>(buf + a_off[k]) = make_uint4(ga[k] & (0x01010101u << u0), ga[k] & (0x02020202u << u0),
+						ga[k] & (0x04040404u << u0), ga[k] & (0x08080808u << u0));
 #pragma unroll
 		for (int k = 0; k < 8; k++)
-			if (b_n[k] >= 0) *reinterpret_cast<uint4 *>(buf + b_off[k]) = expand16(gc[k]);
+			if (b_n[k] >= 0)
+				*reinterpret_cast<uint4 *>(buf + b_off[k]) = make_uint4(gc[k] & (0x80808080u >> u0), gc[k] & (0x40404040u >> u0),
+						gc[k] & (0x20202020u >> u0), gc[k] & (0x10101010u >> u0));
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy stores -> async proxy (MMA) */
 		__syncthreads();
 		if (warp == 0) {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(UM_THREADS, 2) k_umma_tables(const uint4 *__re
 			for (int j16 = 0; j16 < 16; j16++)
 				if (j16 < nchild)
 					*reinterpret_cast<int4 *>(out + (size_t)(q * 16 + j16) * UM_SLOT_INTS) =
-							make_int4((int)v[j16 * 3], (int)v[j16 * 3 + 1], (int)v[j16 * 3 + 2], 0);
+							make_int4((int)(v[j16 * 3] >> 7), (int)(v[j16 * 3 + 1] >> 7), (int)(v[j16 * 3 + 2] >> 7), 0);
 		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
@@ -304,11 +309,11 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, const long lo
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
-int cnbk_umma_tables(cudaStream_t st, const uint4 *planes, int N, int W, const long long *tile_base, int nct,
-		long long tile_begin, long long tile_end, int *counts) {
+int cnbk_umma_tables(cudaStream_t st, const uint4 *planes, const uint4 *planes_rev, int N, int W,
+		const long long *tile_base, int nct, long long tile_begin, long long tile_end, int *counts) {
 	if (tile_end <= tile_begin) return CNB_OK;
 	CK(cudaFuncSetAttribute(k_umma_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-	k_umma_tables<<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>(planes, N, W, tile_base, nct, tile_begin, counts);
+	k_umma_tables<<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>(planes, planes_rev, N, W, tile_base, nct, tile_begin, counts);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

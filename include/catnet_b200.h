@@ -134,6 +134,9 @@ typedef struct cnb_timing {
 	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
 	int64_t h2d_bytes, d2h_bytes;   /* host<->device traffic since the last cnb_ctx_set_samples* call */
 	int64_t tensor_tiles;           /* 128x256 tcgen05 tiles run by this rank (0 = tensor-core path not used) */
+	float tensor_ms;                /* device time of the tcgen05 table kernel alone (CUDA events) */
+	float pad_;
+	int64_t tensor_macs;            /* u8 multiply-accumulates it executed: tiles * 128 * 256 * padded samples */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 
