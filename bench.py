@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--samples", type=int, default=None, help="override M (debug only; the line is then not a bench line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-bits", type=int, default=0,
+                    help="debug: cnb_ctx_force_generic bits (8 = no tensor cores, 16 = u8 operands); not a bench line")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
 
@@ -253,6 +255,8 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_samples_dev(samples_dev.data_ptr(), n, m, num_cats=wl["cats"])
+    if args.kernel_bits:
+        ctx.force_generic(args.kernel_bits)
     seg, nfam = ctx.plan(rank, world, **kw)
     assert nfam == n_fam_total, (nfam, n_fam_total)
     scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=dev)
@@ -316,17 +320,22 @@ def main():
     except Exception:
         pass
     if ph_last["tensor_tiles"] > 0:
-        # tcgen05 scorer: bound by the tensor pipe.  u8 x u8 -> s32 runs at twice the bf16 rate on B200 (nominal 4.5 vs
-        # 2.25 PFLOP/s dense); the denominator is the MEASURED sustained bf16 cuBLAS figure scaled by that factor.
+        # tcgen05 scorer: bound by the tensor pipe.  Nominal dense rates on B200: bf16 2.25, fp8/int8 4.5, fp4 9 PFLOP/s;
+        # the denominator is the MEASURED sustained bf16 cuBLAS figure scaled by that factor (4 for E2M1 operands with
+        # kind::mxf4, 2 for u8 operands with kind::i8).
+        fp4 = ph_last.get("tensor_kind", 8) == 4
+        mult = 4.0 if fp4 else 2.0
         t_ms = float(np.mean([p["tensor_ms"] for p in phases]))
         ops = 2.0 * ph_last["tensor_macs"]
         bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = ops / (t_ms / 1000.0) / 1e12 if t_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "achieved": ach, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": ach / (2.0 * bf16),
-                    "traffic": traffic, "kernel": "k_umma_tables (tcgen05.mma kind::i8)", "kernel_ms": t_ms,
-                    "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
-                    "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 = 2x bf16 rate on B200)"
-                    if peaks else "2 x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)",
+        roofline = {"bound": "tensor", "achieved": ach, "peak": mult * bf16, "unit": "TFLOP/s", "frac": ach / (mult * bf16),
+                    "traffic": traffic,
+                    "kernel": "k_umma_tables (tcgen05.mma %s)" % ("kind::mxf4.block_scale" if fp4 else "kind::i8"),
+                    "kernel_ms": t_ms, "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
+                    "peak_source": ("%g x bf16_tflops_sustained of MEASURED_PEAKS.json (%s = %gx the bf16 rate on B200)"
+                                    % (mult, "fp4" if fp4 else "int8", mult)) if peaks
+                    else "%g x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)" % mult,
                     "useful_mac_fraction": dom_fam * 27.0 * m / max(ph_last["tensor_macs"], 1),
                     "hbm_model": hbm_model}
     else:

@@ -42,7 +42,7 @@ class Timing(C.Structure):
                 ("dp_ms", C.c_float), ("collect_ms", C.c_float), ("total_ms", C.c_float),
                 ("score_ms_by_parents", C.c_float * 8), ("families_by_parents", C.c_int64 * 8),
                 ("num_families", C.c_int64), ("algorithmic_bytes", C.c_int64), ("kernel_launches", C.c_int32),
-                ("fast_path", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("tensor_tiles", C.c_int64), ("tensor_ms", C.c_float), ("pad_", C.c_float),
+                ("fast_path", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("tensor_tiles", C.c_int64), ("tensor_ms", C.c_float), ("tensor_kind", C.c_int32),
                 ("tensor_macs", C.c_int64)]
 
     def as_dict(self):

@@ -196,6 +196,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->force_generic = (on & 1) != 0;     /* bit 0: generic histogram kernel everywhere */
 	c->no_ie = (on & 2) != 0;             /* bit 1: keep the direct bit-plane scorer (no inclusion-exclusion) */
 	c->tensor_mode = (on & 4) ? 1 : ((on & 8) ? -1 : 0);   /* bit 2: tensor-core path whenever applicable; bit 3: never */
+	c->tensor_i8 = (on & 16) ? 1 : 0;                      /* bit 4: u8 operands (kind::i8) instead of E2M1 (kind::mxf4) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -220,8 +221,11 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.blocks = (const CnbBlock *)c->b_blocks.ptr;
 	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
 	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
-	D.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
-	D.nct = c->plan.tile_base.empty() ? 0 : (int)c->plan.tile_base.size() - 1;
+	D.tiles.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
+	D.tiles.nct = c->plan.tile_base.empty() ? 0 : (int)c->plan.tile_base.size() - 1;
+	D.tiles.child = c->plan.tile_child;
+	D.tiles.rank = c->plan.rank;
+	D.tiles.world = c->plan.world;
 	return D;
 }
 
@@ -246,12 +250,14 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* tensor-core tiling of the two-parent group: clean data (no NA, no masks, <= 4 categories) and enough samples
 	 * per family to amortise a 128 x 256 tile (or forced on by the test hook) */
 	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192)
-			&& c->M < (1 << 24);          /* accumulators hold 128 x count in s32 */
+			&& c->M < (1 << 24);          /* accumulators hold counts in f32 (mxf4) or 128 x count in s32 (i8) */
 	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tiled));
 	CnbPlan &pl = c->plan;
 	if (!pl.tile_base.empty()) {
 		RC(upload(c, c->b_tile_base, pl.tile_base));
-		RC(c->b_planes_rev.ensure((size_t)c->W * c->N * sizeof(uint4)));
+		size_t row_bytes = (size_t)cnbk_umma_row_words(c->W, !c->tensor_i8, nullptr) * sizeof(uint32_t) * 3 * c->N;
+		RC(c->b_rows_a.ensure(row_bytes));
+		RC(c->b_rows_b.ensure(row_bytes));
 	}
 	RC(upload(c, c->b_order, pl.order));
 	RC(upload(c, c->b_cats, pl.cats));
@@ -266,10 +272,15 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* samples into order space (the reference re-copies the int matrix per order, rcatnet_search.cpp:151-160) */
 	RC(cnbk_permute(c->stream, (const uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, (const int *)c->b_order.ptr, c->N, c->W,
-			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr,
-			pl.tile_base.empty() ? nullptr : (uint4 *)c->b_planes_rev.ptr));
-	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
+			(uint4 *)c->b_planes.ptr, c->has_pert ? (uint32_t *)c->b_keep.ptr : nullptr));
 	c->timing.kernel_launches = 1;                    /* k_permute; the later phases add theirs */
+	if (!pl.tile_base.empty()) {
+		/* operand bit rows of the tensor-core scorer, order space */
+		RC(cnbk_umma_rows(c->stream, (const uint4 *)c->b_planes.ptr, c->N, c->W, !c->tensor_i8, (uint32_t *)c->b_rows_a.ptr,
+				(uint32_t *)c->b_rows_b.ptr));
+		c->timing.kernel_launches++;
+	}
+	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
 	c->planned = true;
 	c->dp_done = false;
 	if (seg_len) *seg_len = pl.seg_len;
@@ -345,6 +356,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	c->timing.tensor_tiles = 0;
 	c->timing.tensor_ms = 0;
 	c->timing.tensor_macs = 0;
+	c->timing.tensor_kind = 0;
 	c->tensor_batches = 0;
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
@@ -358,23 +370,28 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi], st));
 		if (g.tiled) {
 			/* tcgen05 path: integer tables by one-hot GEMM, tile batches bounded by the table buffer */
-			long long t0 = (long long)pl.rank * g.tiles_per_rank, t1 = std::min<long long>(g.ntiles, t0 + g.tiles_per_rank);
+			/* tiles are dealt round-robin (tile t -> rank t % world): every rank gets the same mix of full and
+			 * diagonal tiles; t0..t1 are LOCAL tile indices */
+			long long t0 = 0, t1 = (g.ntiles - pl.rank + pl.world - 1) / pl.world;
 			const long long batch = 16384, slot_bytes = CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
 			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
 			int nb = 0;
 			for (long long tb = t0; tb < t1; tb += batch, nb++) {
 				long long te = std::min(t1, tb + batch);
 				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb], st));
-				RC(cnbk_umma_tables(st, D.planes, (const uint4 *)c->b_planes_rev.ptr, c->N, c->W, D.tile_base, D.nct, tb, te,
-						(int *)c->b_counts.ptr));
+				RC(cnbk_umma_tables(st, (const uint32_t *)c->b_rows_a.ptr, (const uint32_t *)c->b_rows_b.ptr, c->N, c->W,
+						!c->tensor_i8, D.tiles, tb, te, (int *)c->b_counts.ptr));
 				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb + 1], st));
-				RC(cnbk_umma_epilogue(st, D, D.tile_base, D.nct, tb, te, (const int *)c->b_counts.ptr,
+				RC(cnbk_umma_epilogue(st, D, tb, te, (const int *)c->b_counts.ptr,
 						(const int *)c->b_pairs.ptr, O));
 				c->timing.kernel_launches += 2;
 			}
 			c->timing.tensor_tiles += t1 - t0;
 			c->tensor_batches = nb;
-			c->timing.tensor_macs = (t1 - t0) * 128ll * 256ll * (((long long)c->W + 3) / 4 * 128);
+			long long cols = 0;
+			for (long long t = t0; t < t1; t++) cols += cnb_tile_columns(pl, pl.rank + t * pl.world);
+			c->timing.tensor_macs = cols * cnbk_umma_column_macs(c->W, !c->tensor_i8);
+			c->timing.tensor_kind = c->tensor_i8 ? 8 : 4;
 			b = 0;
 			e = t1 > t0 ? (long long)((double)g.nfam * (double)(t1 - t0) / (double)g.ntiles) : 0;
 		} else {

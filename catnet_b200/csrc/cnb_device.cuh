@@ -20,8 +20,7 @@ struct DevData {
 	const CnbBlock *blocks;
 	const int32_t *group_blocks;
 	const double *edge;         /* [N*N] order space [parent*N+child] or NULL */
-	const long long *tile_base; /* tensor-core tiling of the two-parent group (NULL if not tiled) */
-	int32_t nct;
+	CnbTiles tiles;             /* tensor-core tiling of the two-parent group (tile_base NULL if not tiled) */
 };
 
 __device__ __forceinline__ unsigned plane_of(const uint4 &v, int i) {

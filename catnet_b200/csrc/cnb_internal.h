@@ -35,14 +35,23 @@ struct CnbGroup {
 	int32_t blk_off;    /* into group_blocks[] (block ids sorted by start) */
 	int32_t tiled;      /* 1: scored by the tensor-core kernel; scores are addressed by tile slot, not family id */
 	int64_t nfam;       /* families in the group */
-	int64_t chunk;      /* score slots per rank: ceil(nfam / world), or tiles_per_rank * 512 when tiled */
+	int64_t chunk;      /* score slots per rank: ceil(nfam / world), or tiles_per_rank * slots per tile when tiled */
 	int64_t seg_off;    /* offset of the group inside one rank segment of the score buffer */
-	int64_t ntiles;     /* tiled only */
-	int64_t tiles_per_rank;
+	int64_t ntiles;     /* tiled only: tiles of the group; tile t belongs to rank t % world (local index t / world) */
+	int64_t tiles_per_rank;   /* ceil(ntiles / world): local tile slots of every rank segment */
+	int32_t tile_world;
+	int32_t tile_child; /* children per child tile (<= CNB_TILE_CHILD, the slot stride) */
 };
 
-#define CNB_TILE_PAIRS 14     /* tensor-core tile: 14 parent pairs x 9 rows (126 of 128) ... */
-#define CNB_TILE_CHILD 85     /* ... x 85 children x 3 columns (255 of 256): 1190 families per tile */
+/* tensor-core tiling handed to the kernels of cnb_umma.cu and to k_select */
+struct CnbTiles {
+	const long long *tile_base;   /* [nct + 1] first tile of every child tile */
+	int32_t nct, child;           /* child tiles, children per child tile */
+	int32_t rank, world;
+};
+
+#define CNB_TILE_PAIRS 28     /* tensor-core tile: 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128) ... */
+#define CNB_TILE_CHILD 80     /* ... x 80 children x 3 columns (240): 2240 families per tile */
 
 struct CnbNodePlan {
 	int32_t equal_branch;   /* catnet_search2.h:491-496 */
@@ -65,6 +74,7 @@ struct CnbPlan {
 	std::vector<CnbNodePlan> nodes;
 	std::vector<double> edge;                  /* order space [parent*N + child], empty if no prior */
 	std::vector<int64_t> tile_base;            /* tiled group: first tile of every child tile (+ total at the end) */
+	int32_t tile_child = 0;                    /* children per child tile */
 	int64_t seg_len = 0;                       /* doubles per rank segment */
 	int64_t num_families = 0;
 	int64_t num_options = 0;
@@ -77,6 +87,8 @@ struct CnbPlan {
 int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
 		std::string *err, bool allow_tiled = false);
 int64_t cnb_binom(int64_t n, int64_t k);
+/* MMA columns (children x 3, rounded up to 16) tile `tile` of the tiled group really contracts */
+int cnb_tile_columns(const CnbPlan &pl, int64_t tile);
 int cnb_unrank_lex(int32_t n, int32_t k, int64_t r, int32_t *out);
 
 void cnb_set_error(const char *fmt, ...);

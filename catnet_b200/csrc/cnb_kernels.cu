@@ -80,18 +80,13 @@ __global__ void k_pack(const int32_t *__restrict__ samples, const int32_t *__res
 
 /* label space -> order space for one search (what the reference does by re-copying the whole int matrix) */
 __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *__restrict__ keep_lbl,
-		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep,
-		uint4 *__restrict__ planes_rev) {
+		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep) {
 	int p = blockIdx.x * blockDim.x + threadIdx.x;
 	int w = blockIdx.y;
 	if (p >= N) return;
 	int l = order[p];
 	uint4 v = planes_lbl[(size_t)w * N + l];
 	planes[(size_t)w * N + p] = v;
-	if (planes_rev) {      /* bits reversed inside every byte: the B operand of the tensor-core scorer */
-		planes_rev[(size_t)w * N + p] = make_uint4(__byte_perm(__brev(v.x), 0, 0x0123), __byte_perm(__brev(v.y), 0, 0x0123),
-				__byte_perm(__brev(v.z), 0, 0x0123), __byte_perm(__brev(v.w), 0, 0x0123));
-	}
 	if (keep) keep[(size_t)w * N + p] = keep_lbl[(size_t)w * N + l];
 }
 
@@ -474,8 +469,10 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 			int ab[2];
 			dev_unrank(b.nfree, 2, fid - b.start, ab);      /* unrestricted block: positions themselves */
 			long long q = (long long)ab[1] * (ab[1] - 1) / 2 + ab[0];
-			long long tile = Dt.tile_base[b.child / CNB_TILE_CHILD] + q / CNB_TILE_PAIRS;
-			slot = tile * (CNB_TILE_PAIRS * CNB_TILE_CHILD) + (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + b.child % CNB_TILE_CHILD;
+			long long tile = Dt.tiles.tile_base[b.child / g.tile_child] + q / CNB_TILE_PAIRS;
+			/* tile t is scored by rank t % world as its local tile t / world */
+			return scores[(tile % g.tile_world) * seg_len + g.seg_off + (tile / g.tile_world) * (CNB_TILE_PAIRS * CNB_TILE_CHILD)
+					+ (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + b.child % g.tile_child];
 		}
 		return scores[dev_score_index(slot, g.chunk, g.seg_off, seg_len)];
 	};
@@ -625,9 +622,9 @@ int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int 
 }
 
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
-		uint4 *planes, uint32_t *keep, uint4 *planes_rev) {
+		uint4 *planes, uint32_t *keep) {
 	dim3 grid((N + 127) / 128, W);
-	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep, planes_rev);
+	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

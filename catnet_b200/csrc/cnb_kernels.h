@@ -29,17 +29,22 @@ int cnbk_minmax(cudaStream_t st, const int32_t *samples, int N, int M, int *vmin
 int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int N, int M, int W, const int *vmin,
 		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad);
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
-		uint4 *planes, uint32_t *keep, uint4 *planes_rev);
+		uint4 *planes, uint32_t *keep);
 bool cnbk_planes_supported(int d, int max_cats);
 int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
 		long long fid_end, int slices, const ScoreOut &O);
 int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int *out);
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
-int cnbk_umma_tables(cudaStream_t st, const uint4 *planes, const uint4 *planes_rev, int N, int W,
-		const long long *tile_base, int nct, long long tile_begin, long long tile_end, int *counts);
-int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, const long long *tile_base, int nct, long long tile_begin,
-		long long tile_end, const int *counts, const int *pair_tab, const ScoreOut &O);
+/* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
+int cnbk_umma_row_words(int W, int fp4, int *ngroups);
+int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint32_t *rows_a, uint32_t *rows_b);
+/* local tiles [local_begin, local_end) of rank T.rank (global tile = rank + local * world) */
+int cnbk_umma_tables(cudaStream_t st, const uint32_t *rows_a, const uint32_t *rows_b, int N, int W, int fp4,
+		const CnbTiles &T, long long local_begin, long long local_end, int *counts);
+long long cnbk_umma_column_macs(int W, int fp4);   /* multiply-accumulates per MMA column of one tile, padding included */
+int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
+		const int *pair_tab, const ScoreOut &O);
 #define CNBK_UMMA_SLOT_INTS 36
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);

@@ -206,15 +206,19 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 			}
 			if (full) {
 				int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+				int cpt = (N + nct - 1) / nct;                      /* equal child tiles (500 nodes: 7 x 72, not 6 x 80 + 20) */
+				pl.tile_child = cpt;
 				pl.tile_base.assign(nct + 1, 0);
 				for (int ct = 0; ct < nct; ct++) {
-					int64_t cmax = std::min<int64_t>(N - 1, (int64_t)ct * CNB_TILE_CHILD + CNB_TILE_CHILD - 1);
+					int64_t cmax = std::min<int64_t>(N - 1, (int64_t)ct * cpt + cpt - 1);
 					int64_t npairs = cmax * (cmax - 1) / 2;          /* pairs (a < b) with b < cmax */
 					pl.tile_base[ct + 1] = pl.tile_base[ct] + (npairs + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS;
 				}
 				g.tiled = 1;
 				g.ntiles = pl.tile_base[nct];
 				g.tiles_per_rank = (g.ntiles + world - 1) / world;
+				g.tile_world = world;
+				g.tile_child = cpt;
 				g.chunk = g.tiles_per_rank * CNB_TILE_PAIRS * CNB_TILE_CHILD;
 			}
 		}
@@ -235,6 +239,18 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 	}
 	return CNB_OK;
 #undef FAIL
+}
+
+int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
+	const int nct = (int)pl.tile_base.size() - 1;
+	int ct = 0;
+	while (ct + 1 < nct && pl.tile_base[ct + 1] <= tile) ct++;
+	const int64_t q = (tile - pl.tile_base[ct]) * CNB_TILE_PAIRS;     /* first pair of the tile: q = b(b-1)/2 + a */
+	int64_t b = 1;
+	while ((b + 1) * b / 2 <= q) b++;
+	const int c0 = ct * pl.tile_child, ce = std::min(c0 + pl.tile_child, pl.N);
+	const int cb = std::max<int64_t>(c0, b + 1);
+	return (3 * (ce - cb) + 15) / 16 * 16;
 }
 
 extern "C" int64_t cnb_num_families(const cnb_params *p) {

@@ -133,10 +133,11 @@ typedef struct cnb_timing {
 	int32_t kernel_launches;
 	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
 	int64_t h2d_bytes, d2h_bytes;   /* host<->device traffic since the last cnb_ctx_set_samples* call */
-	int64_t tensor_tiles;           /* 128x256 tcgen05 tiles run by this rank (0 = tensor-core path not used) */
+	int64_t tensor_tiles;           /* tcgen05 tiles (2 x 128 rows x 240 columns) run by this rank (0 = tensor-core
+	                                   path not used) */
 	float tensor_ms;                /* device time of the tcgen05 table kernel alone (CUDA events) */
-	float pad_;
-	int64_t tensor_macs;            /* u8 multiply-accumulates it executed: tiles * 128 * 256 * padded samples */
+	int32_t tensor_kind;            /* operand type of that kernel: 4 = E2M1 (kind::mxf4), 8 = u8 (kind::i8), 0 = none */
+	int64_t tensor_macs;            /* multiply-accumulates it executed: tiles * 256 * 240 * padded samples */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 

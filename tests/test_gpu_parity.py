@@ -115,23 +115,29 @@ def _tensor_eligible(case, cats):
             and case["n"] >= 3 and case["P"] >= 2)
 
 
+TENSOR_KINDS = [(4, 4), (4 | 16, 8)]          # force_generic bits -> cnb_timing.tensor_kind (E2M1 / u8 operands)
+
+
+@pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "seed%d" % c["seed"])
-def test_search_order_tensor_core_path(abi, case):
+def test_search_order_tensor_core_path(abi, case, bits, kind):
     """the tcgen05 one-hot GEMM scorer of the two-parent group, forced on for these small problems"""
     s, kw = build_case(case)
     golden = load_golden("ref_search_order")["seed%d" % case["seed"]]
     with abi.Context(0) as ctx:
         ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
-        ctx.force_generic(4)
+        ctx.force_generic(bits)
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
         nets = ctx.search_order(**kw2)
         used = ctx.timing()["tensor_tiles"] > 0
         assert used == _tensor_eligible(case, ctx.num_cats())
+        assert ctx.timing()["tensor_kind"] == (kind if used else 0)
         compare_golden(nets, golden)
 
 
-@pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4)])
-def test_tensor_core_path_multi_tile(abi, n, m, cats):
+@pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
+@pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4), (90, 20001, 4)])
+def test_tensor_core_path_multi_tile(abi, n, m, cats, bits, kind):
     """several child tiles / pair tiles / K stages, ragged M: tensor-core scores == bit-plane scores"""
     s, c = random_problem(n + m, n, m, cats)
     kw = dict(max_parent_set=2, max_complexity=n * 8, order=(np.random.default_rng(n).permutation(n) + 1))
@@ -139,9 +145,9 @@ def test_tensor_core_path_multi_tile(abi, n, m, cats):
         ctx.set_samples(s, num_cats=c)
         ctx.force_generic(8)                      # never the tensor path
         a = ctx.search_order(want_probs=False, **kw)
-        ctx.force_generic(4)                      # always
+        ctx.force_generic(bits)                   # always
         b = ctx.search_order(want_probs=False, **kw)
-        assert ctx.timing()["tensor_tiles"] > 0
+        assert ctx.timing()["tensor_tiles"] > 0 and ctx.timing()["tensor_kind"] == kind
         for world in (1, 3):                      # sharded over tile ranges
             import torch
             seg, nf = ctx.plan(0, world, **kw)
