@@ -255,7 +255,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	CnbPlan &pl = c->plan;
 	if (!pl.tile_base.empty()) {
 		RC(upload(c, c->b_tile_base, pl.tile_base));
-		size_t row_bytes = (size_t)cnbk_umma_row_words(c->W, !c->tensor_i8, nullptr) * sizeof(uint32_t) * 3 * c->N;
+		size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, !c->tensor_i8, nullptr) * sizeof(uint4) * 3 * c->N;
 		RC(c->b_rows_a.ensure(row_bytes));
 		RC(c->b_rows_b.ensure(row_bytes));
 	}
@@ -276,8 +276,8 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	c->timing.kernel_launches = 1;                    /* k_permute; the later phases add theirs */
 	if (!pl.tile_base.empty()) {
 		/* operand bit rows of the tensor-core scorer, order space */
-		RC(cnbk_umma_rows(c->stream, (const uint4 *)c->b_planes.ptr, c->N, c->W, !c->tensor_i8, (uint32_t *)c->b_rows_a.ptr,
-				(uint32_t *)c->b_rows_b.ptr));
+		RC(cnbk_umma_rows(c->stream, (const uint4 *)c->b_planes.ptr, c->N, c->W, !c->tensor_i8, (uint4 *)c->b_rows_a.ptr,
+				(uint4 *)c->b_rows_b.ptr));
 		c->timing.kernel_launches++;
 	}
 	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
@@ -379,7 +379,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			for (long long tb = t0; tb < t1; tb += batch, nb++) {
 				long long te = std::min(t1, tb + batch);
 				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb], st));
-				RC(cnbk_umma_tables(st, (const uint32_t *)c->b_rows_a.ptr, (const uint32_t *)c->b_rows_b.ptr, c->N, c->W,
+				RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, c->N, c->W,
 						!c->tensor_i8, D.tiles, tb, te, (int *)c->b_counts.ptr));
 				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb + 1], st));
 				RC(cnbk_umma_epilogue(st, D, tb, te, (const int *)c->b_counts.ptr,

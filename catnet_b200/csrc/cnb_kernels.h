@@ -37,10 +37,10 @@ int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
 /* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
-int cnbk_umma_row_words(int W, int fp4, int *ngroups);
-int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint32_t *rows_a, uint32_t *rows_b);
+int cnbk_umma_row_quads(int W, int fp4, int *ngroups);
+int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b);
 /* local tiles [local_begin, local_end) of rank T.rank (global tile = rank + local * world) */
-int cnbk_umma_tables(cudaStream_t st, const uint32_t *rows_a, const uint32_t *rows_b, int N, int W, int fp4,
+int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
 		const CnbTiles &T, long long local_begin, long long local_end, int *counts);
 long long cnbk_umma_column_macs(int W, int fp4);   /* multiply-accumulates per MMA column of one tile, padding included */
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,

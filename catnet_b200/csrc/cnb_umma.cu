@@ -115,8 +115,10 @@ __device__ __forceinline__ void tile_children(const CnbTiles &T, int N, int ct, 
 }
 
 /* ---- operand rows --------------------------------------------------------------------------------------------
- * k_umma_rows turns the order-space bit planes [word][node] into one contiguous bit row per (node, category < 3):
- * rows_a[(node*3 + cat) * roww + w] holds samples 32w..32w+31 (bit s = sample 32w+s), rows_b the same samples with
+ * k_umma_rows turns the order-space bit planes [word][node] (uint4 = the 4 categories of one 32-sample word) into
+ * operand bit rows [quad][node*3 + cat] (uint4 = 4 consecutive 32-sample words = 128 samples of one (node, cat < 3)
+ * row): the generator threads of a warp own consecutive rows, so their 16-byte loads of a stage coalesce into a
+ * few 128-byte lines.  rows_a holds the plain bits (bit s of word w = sample 32w+s), rows_b the same samples with
  * the bits permuted so that both operands are produced by one AND per output word:
  *   mxf4: K position (word j < 4, nibble i < 8) of a 32-sample source word holds sample 4i+j.
  *         A nibble = x & (1<<j) for j < 3 (E2M1 0.5, 1, 2) and (x>>1) & 4 for j = 3 (2);
@@ -124,34 +126,29 @@ __device__ __forceinline__ void tile_children(const CnbTiles &T, int N, int ct, 
  *         every product is bit * bit * 1.
  *   i8:   K position (word j < 8, byte i < 4) holds sample 8i+j; A byte = x & (1<<j) = bit * 2^j, B byte from y'
  *         (bits reversed inside every byte) = y' & (0x80>>j) = bit * 2^(7-j): every product is bit * bit * 128.
- * Rows are zero-padded to roww words (whole stages + one stage of prefetch slack). */
+ * Quads past the last sample word are zero (whole stages + one stage of prefetch slack). */
 __device__ __forceinline__ uint32_t rows_b_word(uint32_t y, int fp4) {
 	if (fp4) return ((y & 0x11111111u) << 2) | (y & 0x22222222u) | ((y & 0x44444444u) >> 2) | (y & 0x88888888u);
 	return __byte_perm(__brev(y), 0, 0x0123);
 }
 
-__global__ void __launch_bounds__(256) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int roww,
-		uint32_t *__restrict__ rows_a, uint32_t *__restrict__ rows_b, int fp4) {
-	__shared__ uint32_t ta[96][33], tb[96][33];
-	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-	const int n0 = blockIdx.x * 32, w0 = blockIdx.y * 32;
-	for (int j = ty; j < 32; j += 8) {
-		const int w = w0 + j, n = n0 + tx;
-		uint4 v = make_uint4(0, 0, 0, 0);
-		if (w < W && n < N) v = __ldg(planes + (size_t)w * N + n);
-		ta[tx * 3 + 0][j] = v.x; ta[tx * 3 + 1][j] = v.y; ta[tx * 3 + 2][j] = v.z;
-		tb[tx * 3 + 0][j] = rows_b_word(v.x, fp4); tb[tx * 3 + 1][j] = rows_b_word(v.y, fp4); tb[tx * 3 + 2][j] = rows_b_word(v.z, fp4);
+__global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int nquads,
+		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int fp4) {
+	const int n = blockIdx.x * blockDim.x + threadIdx.x, qd = blockIdx.y;
+	if (n >= N) return;
+	uint4 v[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int w = qd * 4 + k;
+		v[k] = w < W ? __ldg(planes + (size_t)w * N + n) : make_uint4(0, 0, 0, 0);
 	}
-	__syncthreads();
-	const int w = w0 + tx;
-	if (w >= roww) return;
-	for (int rr = ty; rr < 96; rr += 8) {
-		const int n = n0 + rr / 3;
-		if (n >= N) break;
-		const size_t o = ((size_t)n * 3 + rr % 3) * roww + w;
-		rows_a[o] = ta[rr][tx];
-		rows_b[o] = tb[rr][tx];
-	}
+	const size_t o = (size_t)qd * (3 * N) + 3 * n;
+	rows_a[o + 0] = make_uint4(v[0].x, v[1].x, v[2].x, v[3].x);
+	rows_a[o + 1] = make_uint4(v[0].y, v[1].y, v[2].y, v[3].y);
+	rows_a[o + 2] = make_uint4(v[0].z, v[1].z, v[2].z, v[3].z);
+	rows_b[o + 0] = make_uint4(rows_b_word(v[0].x, fp4), rows_b_word(v[1].x, fp4), rows_b_word(v[2].x, fp4), rows_b_word(v[3].x, fp4));
+	rows_b[o + 1] = make_uint4(rows_b_word(v[0].y, fp4), rows_b_word(v[1].y, fp4), rows_b_word(v[2].y, fp4), rows_b_word(v[3].y, fp4));
+	rows_b[o + 2] = make_uint4(rows_b_word(v[0].z, fp4), rows_b_word(v[1].z, fp4), rows_b_word(v[2].z, fp4), rows_b_word(v[3].z, fp4));
 }
 
 /* ---- operand generation: one 32-sample source word -> output words ------------------------------------------- */
@@ -190,8 +187,9 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x 
 
 template <bool FP4>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
-		int N, int rowq, int ngroups, CnbTiles T, long long local_begin, int *__restrict__ counts) {
-	constexpr int SRCQ = FP4 ? 2 : 1;       /* uint4 of source bits per row and stage */
+		int N, int ngroups, CnbTiles T, long long local_begin, int *__restrict__ counts) {
+	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
+	const int NR = 3 * N;                   /* operand rows per quad */
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ __align__(8) uint64_t bar_full[UM_STAGES], bar_empty[UM_STAGES], bar_done;
 	__shared__ uint32_t tmem_base_sh;
@@ -248,15 +246,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			int pa, pb;
 			pair_of(pt * UM_PAIRS + h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb);
 			if (pb >= N) { pa = 0; pb = 1; }
-			s0 = rows_a + (size_t)(pa * 3 + (r % 9) / 3) * rowq;
-			s1 = rows_a + (size_t)(pb * 3 + r % 3) * rowq;
+			s0 = rows_a + (pa * 3 + (r % 9) / 3);
+			s1 = rows_a + (pb * 3 + r % 3);
 			dst = h * UM_A_BYTES + (r >> 3) * 1024u + (r & 7u) * 128u;
 		} else {
 			/* row r = child*3 + k of the tile's children [cb, ce); rows past the MMA's columns are not generated */
 			const int r = min(tid - 256, UM_N - 1);
 			active = tid - 256 < ncols;
 			const int c = min(cb + r / 3, ce - 1);
-			s0 = s1 = rows_b + (size_t)(c * 3 + r % 3) * rowq;
+			s0 = s1 = rows_b + (c * 3 + r % 3);
 			dst = UM_B_OFF + (r >> 3) * 1024u + (r & 7u) * 128u;
 		}
 		uint32_t off[8];
@@ -267,9 +265,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		}
 		uint4 n0, n1, m0, m1;          /* next stage's source bits (row 0 / row 1 of an A thread) */
 		n0 = __ldg(s0);
-		n1 = FP4 ? __ldg(s0 + 1) : n0;
+		n1 = FP4 ? __ldg(s0 + NR) : n0;
 		m0 = a_side ? __ldg(s1) : n0;
-		m1 = (a_side && FP4) ? __ldg(s1 + 1) : n0;
+		m1 = (a_side && FP4) ? __ldg(s1 + NR) : n0;
 		if (!active) {
 			/* idle child-row threads only keep their warp's arrivals going */
 			for (int g = 0; g < ngroups; g++) {
@@ -286,10 +284,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 #define UM_STAGE_BODY(u) { \
 			uint4 v0 = n0, v1 = n1; \
 			if (a_side) { v0 = and4(n0, m0); v1 = and4(n1, m1); } \
-			s0 += SRCQ; s1 += SRCQ; \
+			s0 += SRCQ * NR; s1 += SRCQ * NR; \
 			n0 = __ldg(s0); \
-			if (FP4) n1 = __ldg(s0 + 1); \
-			if (a_side) { m0 = __ldg(s1); if (FP4) m1 = __ldg(s1 + 1); } \
+			if (FP4) n1 = __ldg(s0 + NR); \
+			if (a_side) { m0 = __ldg(s1); if (FP4) m1 = __ldg(s1 + NR); } \
 			if (g > 0) mbar_wait(&bar_empty[u], (g - 1) & 1); \
 			if (a_side) gen_row<FP4, false, (u) * UM_STAGE>(off, v0, v1); \
 			else gen_row<FP4, true, (u) * UM_STAGE>(off, v0, v1); \
@@ -430,35 +428,34 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
-/* words per operand row for W sample words: whole groups of UM_STAGES stages plus one stage of prefetch slack */
-int cnbk_umma_row_words(int W, int fp4, int *ngroups) {
-	const int wps = fp4 ? 8 : 4;                          /* source words per stage */
-	const int nst = (W + wps - 1) / wps, ng = (nst + UM_STAGES - 1) / UM_STAGES;
+/* quads (4 sample words) per operand row for W sample words: whole groups of UM_STAGES stages plus one stage of
+ * prefetch slack */
+int cnbk_umma_row_quads(int W, int fp4, int *ngroups) {
+	const int qps = fp4 ? 2 : 1;                          /* quads per stage */
+	const int nst = (W + 4 * qps - 1) / (4 * qps), ng = (nst + UM_STAGES - 1) / UM_STAGES;
 	if (ngroups) *ngroups = ng;
-	return (ng * UM_STAGES + 1) * wps;
+	return (ng * UM_STAGES + 1) * qps;
 }
 
-int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint32_t *rows_a, uint32_t *rows_b) {
-	const int roww = cnbk_umma_row_words(W, fp4, nullptr);
-	dim3 grid((N + 31) / 32, (roww + 31) / 32);
-	k_umma_rows<<<grid, 256, 0, st>>>(planes, N, W, roww, rows_a, rows_b, fp4);
+int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
+	const int nq = cnbk_umma_row_quads(W, fp4, nullptr);
+	dim3 grid((N + 127) / 128, nq);
+	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a, rows_b, fp4);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
 
-int cnbk_umma_tables(cudaStream_t st, const uint32_t *rows_a, const uint32_t *rows_b, int N, int W, int fp4,
+int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
 		const CnbTiles &T, long long tile_begin, long long tile_end, int *counts) {
 	if (tile_end <= tile_begin) return CNB_OK;
 	int ng;
-	const int roww = cnbk_umma_row_words(W, fp4, &ng);
+	cnbk_umma_row_quads(W, fp4, &ng);
 	if (fp4) {
 		CK(cudaFuncSetAttribute(k_umma_tables<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true><<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>((const uint4 *)rows_a, (const uint4 *)rows_b,
-				N, roww / 4, ng, T, tile_begin, counts);
+		k_umma_tables<true><<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, T, tile_begin, counts);
 	} else {
 		CK(cudaFuncSetAttribute(k_umma_tables<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<false><<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>((const uint4 *)rows_a, (const uint4 *)rows_b,
-				N, roww / 4, ng, T, tile_begin, counts);
+		k_umma_tables<false><<<(unsigned)(tile_end - tile_begin), UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, T, tile_begin, counts);
 	}
 	CK(cudaGetLastError());
 	return CNB_OK;
@@ -466,7 +463,7 @@ int cnbk_umma_tables(cudaStream_t st, const uint32_t *rows_a, const uint32_t *ro
 
 long long cnbk_umma_column_macs(int W, int fp4) {
 	int ng;
-	cnbk_umma_row_words(W, fp4, &ng);
+	cnbk_umma_row_quads(W, fp4, &ng);
 	return (long long)UM_NA * 128 * ((long long)ng * UM_STAGES * (fp4 ? 256 : 128));
 }
 
