@@ -10,10 +10,15 @@
  *     tcgen05.mma.kind::i8                 (u8 x u8 -> s32; 128 samples per 128-byte row; test/fallback kind).
  * Every product is exactly 1 (mxf4) or 128 (i8), so the TMEM accumulators hold exact counts (M < 2^24).
  *
- * One CTA per SM (all 512 TMEM columns): 16 operand-generator warps (one thread per operand row), one MMA-issuing
- * warp, a 3-stage shared-memory ring handed over with mbarriers (generators -> full[s] -> MMA -> tcgen05.commit ->
- * empty[s]).  A tile is 2 blocks of 14 parent pairs (2 x 126 of 128 rows, two accumulators) x 80 children
- * (240 columns): the child rows of a stage are generated once and consumed by both pair blocks.
+ * One CTA per SM (all 512 TMEM columns), warp-specialised:
+ *   warps 0-7   pair rows: thread = one A row (2 blocks x 128); A goes to TENSOR MEMORY with tcgen05.st (2-slot ring)
+ *   warps 8-13  child rows: thread = one B row (176); B goes to shared memory, SWIZZLE_128B K-major (4-stage ring)
+ *   warps 14-15 one elected lane each issues the tcgen05.mma of one pair block: A from TMEM, B from shared memory
+ * handed over with mbarriers (generators -> full -> MMA -> tcgen05.commit -> empty).  A tile is 2 blocks of 14
+ * parent pairs (2 x 126 of 128 rows, two accumulators) x up to 58 children (176 columns): the child rows of a stage
+ * are generated once and consumed by both pair blocks, and the pair rows never touch shared memory -- the shared
+ * memory pipe (generator stores + tensor-core operand reads) was the measured limiter of the all-shared-memory
+ * version (profiles/r01_umma_v3_ss_summary.txt).
  *
  * Replaces, for unrestricted two-parent candidate sets without missing values, the counting loop of
  * CATNET::setNodeSampleProb (/root/reference/src/catnet_class.h:842-857); the log-lik epilogue
@@ -31,19 +36,22 @@
 #define UM_CHILD CNB_TILE_CHILD
 #define UM_SLOTS (UM_PAIRS * UM_CHILD)
 #define UM_SLOT_INTS 36                   /* 9 configurations x (3 counts + 1 pad): int4 stores */
-#define UM_N (UM_CHILD * 3)               /* 240 = MMA N */
-#define UM_A_BYTES (128 * 128)            /* one pair block of a stage: 128 rows x 128 B */
-#define UM_B_OFF (UM_NA * UM_A_BYTES)
-#define UM_STAGE (UM_B_OFF + UM_N * 128)  /* 63,488 B */
-#define UM_STAGES 3
-#define UM_SMEM (UM_STAGES * UM_STAGE + 1024)
-#define UM_GEN_WARPS 16                   /* warps 0-7: pair rows (2 x 128), warps 8-15: child rows (240 of 256) */
-#define UM_THREADS ((UM_GEN_WARPS + 1) * 32)
+#define UM_N ((UM_CHILD * 3 + 15) / 16 * 16)   /* 176 = largest MMA N */
+#define UM_STAGE (UM_N * 128)             /* child rows of one stage: 22,528 B */
+#define UM_BSTAGES 4                      /* shared-memory ring of the child rows */
+#define UM_ASTAGES 2                      /* tensor-memory ring of the pair rows */
+#define UM_SMEM (UM_BSTAGES * UM_STAGE + 1024)
+#define UM_A_WARPS 8
+#define UM_B_WARPS 6
+#define UM_MMA_WARP (UM_A_WARPS + UM_B_WARPS)   /* first of the UM_NA MMA-issuing warps (one per pair block) */
+#define UM_THREADS ((UM_MMA_WARP + UM_NA) * 32)
 #define UM_TMEM_COLS 512
+#define UM_TMEM_A (UM_NA * UM_N)          /* 352: pair rows, UM_ASTAGES x UM_NA x 4 k-steps x 8 columns = 128 columns */
 #define UM_TMEM_SF 480                    /* mxf4: unit scale factors in columns 480..511 */
 static_assert(UM_PAIRS == UM_NA * UM_BLK_PAIRS, "tile geometry");
-static_assert(UM_N % 16 == 0 && UM_N <= 256 && UM_NA * UM_N <= UM_TMEM_SF, "tile geometry");
+static_assert(UM_N <= 256 && UM_TMEM_A + UM_ASTAGES * UM_NA * 32 <= UM_TMEM_SF, "tensor memory budget");
 static_assert(UM_STAGE % 1024 == 0, "stages keep the 1024-byte swizzle alignment");
+static_assert(UM_B_WARPS * 32 >= UM_N && UM_BSTAGES == 2 * UM_ASTAGES, "warp roles / ring geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -59,22 +67,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 	asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+/* The MMA-side instructions are issued by ONE lane, but from warp-convergent code: the whole warp executes the asm
+ * and the instruction itself is predicated on `issue` (non-zero in the elected lane only).  Inside a divergent
+ * `if (lane == 0)` the compiler has to move every operand to uniform registers with an ELECT / R2UR.BROADCAST /
+ * BRA.U.ANY loop per instruction, which made the issuing warp the bottleneck of the whole kernel. */
+__device__ __forceinline__ void umma_commit(uint32_t bar_addr, uint32_t issue) {
+	asm volatile("{\n.reg .pred e;\nsetp.ne.b32 e, %1, 0;\n"
+			"@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar_addr), "r"(issue) : "memory");
 }
-/* D[tmem] (+)= A[smem desc] * B[smem desc]^T, u8 x u8 -> s32, M = 128, K = 32 */
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+/* D[tmem] (+)= A[tmem] * B[smem desc]^T, u8 x u8 -> s32, M = 128, K = 32 */
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+		uint32_t issue) {
 	uint32_t z = 0;
-	asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-			"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n"
-			::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+	asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 e, %6, 0;\n"
+			"@e tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}\n"
+			::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z), "r"(issue) : "memory");
 }
-/* D[tmem] (+)= (A * sfa) * (B * sfb)^T, E2M1 x E2M1 -> f32, one E8M0 scale per 32 elements, M = 128, K = 64 */
-__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
-		uint32_t tmem_sfa, uint32_t tmem_sfb) {
-	asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-			"tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n}\n"
-			::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb) : "memory");
+/* D[tmem] (+)= (A[tmem] * sfa) * (B[smem desc] * sfb)^T, E2M1 x E2M1 -> f32, one E8M0 scale per 32 elements,
+ * M = 128, K = 64 */
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+		uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t issue) {
+	asm volatile("{\n.reg .pred p, e;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 e, %7, 0;\n"
+			"@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n}\n"
+			::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb), "r"(issue) : "memory");
 }
 /* K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 in [0,14),
  * LBO = 1 in [16,30), SBO = 1024 B >> 4 in [32,46) (stride between 8-row groups), version 1 in [46,48),
@@ -154,33 +169,45 @@ __global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ pla
 /* ---- operand generation: one 32-sample source word -> output words ------------------------------------------- */
 #define STS128(addr, imm, a, b, c, d) asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};" \
 		::"r"(addr), "n"(imm), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
+#define STTM8(addr, a, b, c, d, e, f, g, h) asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" \
+		::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory")
 
-/* mxf4: source word -> one 16-byte chunk */
-template <bool B_SIDE, int IMM>
-__device__ __forceinline__ void gen4(uint32_t addr, uint32_t x) {
-	if (!B_SIDE) STS128(addr, IMM, x & 0x11111111u, x & 0x22222222u, x & 0x44444444u, (x >> 1) & 0x44444444u);
-	else STS128(addr, IMM, x & 0x44444444u, x & 0x22222222u, x & 0x11111111u, (x >> 3) & 0x11111111u);
-}
-/* i8: source word -> two 16-byte chunks */
-template <bool B_SIDE, int IMM>
-__device__ __forceinline__ void gen8(uint32_t addr_lo, uint32_t addr_hi, uint32_t x) {
-	if (!B_SIDE) {
-		STS128(addr_lo, IMM, x & 0x01010101u, x & 0x02020202u, x & 0x04040404u, x & 0x08080808u);
-		STS128(addr_hi, IMM, x & 0x10101010u, x & 0x20202020u, x & 0x40404040u, x & 0x80808080u);
+/* child row (B operand), one stage -> 8 chunks of 16 bytes in shared memory.  mxf4: chunk c = source word c;
+ * i8: chunks 2c, 2c+1 = source word c */
+template <bool FP4, int IMM>
+__device__ __forceinline__ void gen_row_b(const uint32_t (&off)[8], uint4 v0, uint4 v1) {
+	if (FP4) {
+		const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+		for (int c = 0; c < 8; c++)
+			STS128(off[c], IMM, x[c] & 0x44444444u, x[c] & 0x22222222u, x[c] & 0x11111111u, (x[c] >> 3) & 0x11111111u);
 	} else {
-		STS128(addr_lo, IMM, x & 0x80808080u, x & 0x40404040u, x & 0x20202020u, x & 0x10101010u);
-		STS128(addr_hi, IMM, x & 0x08080808u, x & 0x04040404u, x & 0x02020202u, x & 0x01010101u);
+		const uint32_t x[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			STS128(off[2 * c], IMM, x[c] & 0x80808080u, x[c] & 0x40404040u, x[c] & 0x20202020u, x[c] & 0x10101010u);
+			STS128(off[2 * c + 1], IMM, x[c] & 0x08080808u, x[c] & 0x04040404u, x[c] & 0x02020202u, x[c] & 0x01010101u);
+		}
 	}
 }
-/* one stage of one operand row: FP4 consumes two uint4 (256 samples), I8 one (128 samples) */
-template <bool FP4, bool B_SIDE, int IMM>
-__device__ __forceinline__ void gen_row(const uint32_t (&off)[8], uint4 v0, uint4 v1) {
+/* pair row (A operand), one stage -> 4 k-steps of 8 tensor-memory columns (32 bytes of K each) in this thread's lane;
+ * column j of a k-step = bytes 4j..4j+3 of the 32-byte K slice, the same order as the shared-memory chunks above */
+template <bool FP4>
+__device__ __forceinline__ void gen_row_a(uint32_t taddr, uint4 v0, uint4 v1) {
 	if (FP4) {
-		gen4<B_SIDE, IMM>(off[0], v0.x); gen4<B_SIDE, IMM>(off[1], v0.y); gen4<B_SIDE, IMM>(off[2], v0.z); gen4<B_SIDE, IMM>(off[3], v0.w);
-		gen4<B_SIDE, IMM>(off[4], v1.x); gen4<B_SIDE, IMM>(off[5], v1.y); gen4<B_SIDE, IMM>(off[6], v1.z); gen4<B_SIDE, IMM>(off[7], v1.w);
+		const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t p = x[2 * k], q = x[2 * k + 1];
+			STTM8(taddr + k * 8, p & 0x11111111u, p & 0x22222222u, p & 0x44444444u, (p >> 1) & 0x44444444u,
+					q & 0x11111111u, q & 0x22222222u, q & 0x44444444u, (q >> 1) & 0x44444444u);
+		}
 	} else {
-		gen8<B_SIDE, IMM>(off[0], off[1], v0.x); gen8<B_SIDE, IMM>(off[2], off[3], v0.y);
-		gen8<B_SIDE, IMM>(off[4], off[5], v0.z); gen8<B_SIDE, IMM>(off[6], off[7], v0.w);
+		const uint32_t x[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			STTM8(taddr + k * 8, x[k] & 0x01010101u, x[k] & 0x02020202u, x[k] & 0x04040404u, x[k] & 0x08080808u,
+					x[k] & 0x10101010u, x[k] & 0x20202020u, x[k] & 0x40404040u, x[k] & 0x80808080u);
 	}
 }
 __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
@@ -191,7 +218,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
 	const int NR = 3 * N;                   /* operand rows per quad */
 	extern __shared__ uint8_t smem_raw[];
-	__shared__ __align__(8) uint64_t bar_full[UM_STAGES], bar_empty[UM_STAGES], bar_done;
+	__shared__ __align__(8) uint64_t bar_full_b[UM_BSTAGES], bar_empty_b[UM_BSTAGES], bar_full_a[UM_ASTAGES], bar_empty_a[UM_ASTAGES], bar_done;
 	__shared__ uint32_t tmem_base_sh;
 	const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -202,22 +229,27 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	tile_children(T, N, ct, pt, c0, cb, ce);
 	const int nchild = ce - cb, ncols = (3 * nchild + 15) & ~15;        /* MMA N of this tile */
 
-	if (warp == UM_GEN_WARPS) {
+	if (warp == UM_MMA_WARP) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(UM_TMEM_COLS));
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
 	}
 	if (tid == 0) {
-		for (int s = 0; s < UM_STAGES; s++) {
-			mbar_init(&bar_full[s], UM_GEN_WARPS);
-			mbar_init(&bar_empty[s], 1);
+		for (int s = 0; s < UM_BSTAGES; s++) {
+			mbar_init(&bar_full_b[s], UM_B_WARPS);
+			mbar_init(&bar_empty_b[s], UM_NA);           /* one tcgen05.commit per MMA warp */
 		}
-		mbar_init(&bar_done, 1);
+		for (int s = 0; s < UM_ASTAGES; s++) {
+			mbar_init(&bar_full_a[s], UM_A_WARPS);
+			mbar_init(&bar_empty_a[s], UM_NA);
+		}
+		mbar_init(&bar_done, UM_NA);
 		asm volatile("fence.mbarrier_init.release.cluster;");
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
 	asm volatile("tcgen05.fence::after_thread_sync;");
 	const uint32_t tmem = tmem_base_sh;
+	if (tmem != 0) __trap();                 /* all 512 columns are ours: the MMA issuer uses literal column addresses */
 	if (FP4) {
 		/* unit scale factors (E8M0 127 = 2^0) in every byte of columns 480..511 of all 128 lanes */
 		if (warp < 4) {
@@ -233,99 +265,64 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		asm volatile("tcgen05.fence::after_thread_sync;");
 	}
 
-	if (warp < UM_GEN_WARPS) {
-		/* ---- operand generators: thread = one operand row for the whole K loop ---- */
-		const bool a_side = warp < 8;
-		bool active = true;
-		const uint4 *s0, *s1;
-		uint32_t dst;
-		if (a_side) {
-			/* row r = pair*9 + i*3 + j of pair block h; rows 126/127 and pairs past the end repeat valid data whose
-			 * accumulators nobody reads */
-			const int h = warp >> 2, r = tid & 127;
-			int pa, pb;
-			pair_of(pt * UM_PAIRS + h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb);
-			if (pb >= N) { pa = 0; pb = 1; }
-			s0 = rows_a + (pa * 3 + (r % 9) / 3);
-			s1 = rows_a + (pb * 3 + r % 3);
-			dst = h * UM_A_BYTES + (r >> 3) * 1024u + (r & 7u) * 128u;
-		} else {
-			/* row r = child*3 + k of the tile's children [cb, ce); rows past the MMA's columns are not generated */
-			const int r = min(tid - 256, UM_N - 1);
-			active = tid - 256 < ncols;
-			const int c = min(cb + r / 3, ce - 1);
-			s0 = s1 = rows_b + (c * 3 + r % 3);
-			dst = UM_B_OFF + (r >> 3) * 1024u + (r & 7u) * 128u;
-		}
-		uint32_t off[8];
-		{
-			const uint32_t r7 = (dst >> 7) & 7u;
-#pragma unroll
-			for (int k = 0; k < 8; k++) off[k] = smem + dst + ((k ^ r7) << 4);
-		}
-		uint4 n0, n1, m0, m1;          /* next stage's source bits (row 0 / row 1 of an A thread) */
+	if (warp < UM_A_WARPS) {
+		/* ---- pair rows -> tensor memory.  Thread = row r = pair*9 + i*3 + j of pair block h, TMEM lane r; rows
+		 * 126/127 and pairs past the end repeat valid data whose accumulators nobody reads ---- */
+		const int h = warp >> 2, r = tid & 127;
+		int pa, pb;
+		pair_of(pt * UM_PAIRS + h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb);
+		if (pb >= N) { pa = 0; pb = 1; }
+		const uint4 *s0 = rows_a + (pa * 3 + (r % 9) / 3), *s1 = rows_a + (pb * 3 + r % 3);
+		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * 32;
+		uint4 n0, n1, m0, m1;          /* next stage's source bits of the two nodes */
 		n0 = __ldg(s0);
+		m0 = __ldg(s1);
 		n1 = FP4 ? __ldg(s0 + NR) : n0;
-		m0 = a_side ? __ldg(s1) : n0;
-		m1 = (a_side && FP4) ? __ldg(s1 + NR) : n0;
-		if (!active) {
-			/* idle child-row threads only keep their warp's arrivals going */
-			for (int g = 0; g < ngroups; g++) {
-#pragma unroll
-				for (int u = 0; u < UM_STAGES; u++) {
-					if (g > 0) mbar_wait(&bar_empty[u], (g - 1) & 1);
-					asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-					__syncwarp();
-					if (lane == 0) mbar_arrive(&bar_full[u]);
-				}
-			}
-		} else
+		m1 = FP4 ? __ldg(s1 + NR) : m0;
 		for (int g = 0; g < ngroups; g++) {
-#define UM_STAGE_BODY(u) { \
-			uint4 v0 = n0, v1 = n1; \
-			if (a_side) { v0 = and4(n0, m0); v1 = and4(n1, m1); } \
-			s0 += SRCQ * NR; s1 += SRCQ * NR; \
-			n0 = __ldg(s0); \
-			if (FP4) n1 = __ldg(s0 + NR); \
-			if (a_side) { m0 = __ldg(s1); if (FP4) m1 = __ldg(s1 + NR); } \
-			if (g > 0) mbar_wait(&bar_empty[u], (g - 1) & 1); \
-			if (a_side) gen_row<FP4, false, (u) * UM_STAGE>(off, v0, v1); \
-			else gen_row<FP4, true, (u) * UM_STAGE>(off, v0, v1); \
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
-			__syncwarp(); \
-			if (lane == 0) mbar_arrive(&bar_full[u]); }
-			UM_STAGE_BODY(0)
-			UM_STAGE_BODY(1)
-			UM_STAGE_BODY(2)
-#undef UM_STAGE_BODY
+#pragma unroll
+			for (int u = 0; u < UM_BSTAGES; u++) {
+				const uint4 v0 = and4(n0, m0), v1 = and4(n1, m1);
+				s0 += SRCQ * NR; s1 += SRCQ * NR;
+				n0 = __ldg(s0);
+				m0 = __ldg(s1);
+				if (FP4) { n1 = __ldg(s0 + NR); m1 = __ldg(s1 + NR); }
+				/* slot u & 1 is used twice per group: use number 2g + (u >> 1) */
+				if (g > 0 || u >= UM_ASTAGES) mbar_wait(&bar_empty_a[u & 1], ((u >> 1) + 1) & 1);
+				asm volatile("tcgen05.fence::after_thread_sync;");
+				gen_row_a<FP4>(ta + (u & 1) * (UM_NA * 32), v0, v1);
+				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+				asm volatile("tcgen05.fence::before_thread_sync;");
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&bar_full_a[u & 1]);
+			}
 		}
 
-		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair*9 + (i*3+j); column = child*3 + k.
-		 * A warp may only touch its own lane quarter (warp & 3); the four warps of a quarter split the two
-		 * accumulators in halves of 120 columns (40 children), read in chunks of 24 columns (8 children). */
+		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair*9 + (i*3+j); accumulator column 3j+k =
+		 * child cb + j (slot (cb - c0) + j of the tile).  A warp may only touch its own lane quarter (warp & 3);
+		 * each of the 8 warps reads its rows of one accumulator in chunks of 24 columns (8 children). */
 		mbar_wait(&bar_done, 0);
 		asm volatile("tcgen05.fence::after_thread_sync;");
-		const int lq = warp & 3, h = warp >> 3, half = (warp >> 2) & 1;
+		const int lq = warp & 3;
 		const int row = lq * 32 + lane, cfg = row % 9;
 		const bool row_ok = row < UM_BLK_PAIRS * 9;
-		/* accumulator column 3j+k = child cb + j, whose slot inside the tile is (cb - c0) + j */
-		int *out = counts + ((size_t)blockIdx.x * UM_SLOTS + (size_t)(h * UM_BLK_PAIRS + row / 9) * UM_CHILD + (cb - c0) + half * 40) * UM_SLOT_INTS + cfg * 4;
+		int *out = counts + ((size_t)blockIdx.x * UM_SLOTS + (size_t)(h * UM_BLK_PAIRS + row / 9) * UM_CHILD + (cb - c0)) * UM_SLOT_INTS + cfg * 4;
 #pragma unroll 1
-		for (int q = 0; q < 5 && half * 40 + q * 8 < nchild; q++) {
+		for (int q = 0; q * 8 < nchild; q++) {
 			uint32_t v[24];
-			const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(h * UM_N + half * 120 + q * 24);
+			const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(h * UM_N + q * 24);
 #define LD8(o, a) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
 			: "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]) \
 			: "r"(a))
 			LD8(0, taddr);
 			LD8(8, taddr + 8);
-			LD8(16, taddr + 16);
+			if (q * 24 + 16 < UM_N) LD8(16, taddr + 16);       /* the last chunk of 176 columns has 8 + 8 */
 #undef LD8
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			if (row_ok) {
 #pragma unroll
 				for (int j = 0; j < 8; j++) {
-					if (half * 40 + q * 8 + j >= nchild) break;
+					if (q * 8 + j >= nchild) break;
 					int x0, x1, x2;
 					if (FP4) {
 						x0 = __float2int_rn(__uint_as_float(v[j * 3])); x1 = __float2int_rn(__uint_as_float(v[j * 3 + 1]));
@@ -337,38 +334,72 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 				}
 			}
 		}
+	} else if (warp < UM_MMA_WARP) {
+		/* ---- child rows -> shared memory.  Thread = row r = child*3 + k of the tile's children [cb, ce); rows past
+		 * the MMA's columns are not generated, their threads only keep the warp's arrivals going ---- */
+		const int rr = tid - UM_A_WARPS * 32, r = min(rr, UM_N - 1);
+		const bool active = rr < ncols;
+		const uint4 *s0 = rows_b + (min(cb + r / 3, ce - 1) * 3 + r % 3);
+		uint32_t off[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) off[k] = smem + (r >> 3) * 1024u + (r & 7u) * 128u + ((k ^ (r & 7u)) << 4);
+		uint4 n0, n1;
+		n0 = __ldg(s0);
+		n1 = FP4 ? __ldg(s0 + NR) : n0;
+		for (int g = 0; g < ngroups; g++) {
+#define UM_STAGE_BODY(u) { \
+			const uint4 v0 = n0, v1 = n1; \
+			s0 += SRCQ * NR; \
+			if (active) { n0 = __ldg(s0); if (FP4) n1 = __ldg(s0 + NR); } \
+			if (g > 0) mbar_wait(&bar_empty_b[u], (g - 1) & 1); \
+			if (active) gen_row_b<FP4, (u) * UM_STAGE>(off, v0, v1); \
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
+			__syncwarp(); \
+			if (lane == 0) mbar_arrive(&bar_full_b[u]); }
+			UM_STAGE_BODY(0)
+			UM_STAGE_BODY(1)
+			UM_STAGE_BODY(2)
+			UM_STAGE_BODY(3)
+#undef UM_STAGE_BODY
+		}
 	} else {
-		/* ---- MMA issuer: one elected lane, four K = 32-byte instructions per pair block and stage ---- */
+		/* ---- MMA issuers: warp UM_MMA_WARP + h owns pair block h (its own accumulator, so the two instruction
+		 * streams never touch the same tensor-memory columns); one elected lane issues four K = 32-byte MMAs per
+		 * stage.  A single issuing warp was the bottleneck (profiles/r01_umma_v4_ts_summary.txt: 92 % of its
+		 * samples inside the issue sequence, 7 cycles per instruction).  Operands are compile-time constants or
+		 * warp-uniform values: the CTA owns all 512 tensor-memory columns, so its allocation starts at column 0
+		 * (checked above). ---- */
+		const int h = warp - UM_MMA_WARP;
 		const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | (1u << 23) | (8u << 24))   /* E2M1 x E2M1, E8M0 scales */
 		                           : ((2u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24));                           /* s32 acc, u8 x u8 */
+		/* warp reductions return their result in a uniform register: the compiler then knows these are the same in all lanes */
+		const uint32_t idesc_u = __reduce_max_sync(0xffffffffu, idesc);
+		const uint64_t db0 = umma_desc(__reduce_max_sync(0xffffffffu, smem));
+		const uint32_t issue = lane == 0;
+		const uint32_t b_ea = smem_u32(&bar_empty_a[0]), b_eb = smem_u32(&bar_empty_b[0]);
+		const uint32_t td = h * UM_N, ta0 = UM_TMEM_A + h * 32;
 		for (int g = 0; g < ngroups; g++) {
 #pragma unroll
-			for (int u = 0; u < UM_STAGES; u++) {
-				mbar_wait(&bar_full[u], g & 1);
+			for (int u = 0; u < UM_BSTAGES; u++) {
+				mbar_wait(&bar_full_a[u & 1], (u >> 1) & 1);
+				mbar_wait(&bar_full_b[u], g & 1);
 				asm volatile("tcgen05.fence::after_thread_sync;");
-				if (lane == 0) {
-					const uint32_t buf = smem + u * UM_STAGE;
-					const uint64_t db = umma_desc(buf + UM_B_OFF);
 #pragma unroll
-					for (int k = 0; k < 4; k++) {                  /* +2: 32 bytes in 16-byte units */
-#pragma unroll
-						for (int h = 0; h < UM_NA; h++) {
-							const uint64_t da = umma_desc(buf + h * UM_A_BYTES);
-							if (FP4) umma_mxf4(tmem + h * UM_N, da + 2 * k, db + 2 * k, idesc, (g | u | k) != 0, tmem + UM_TMEM_SF, tmem + UM_TMEM_SF + 16);
-							else umma_i8(tmem + h * UM_N, da + 2 * k, db + 2 * k, idesc, (g | u | k) != 0);
-						}
-					}
-					umma_commit(&bar_empty[u]);
+				for (int k = 0; k < 4; k++) {                  /* +2: 32 bytes of K in 16-byte units */
+					const uint32_t ta = ta0 + (u & 1) * (UM_NA * 32) + k * 8;
+					const uint64_t db = db0 + (uint64_t)(u * (UM_STAGE >> 4) + 2 * k);
+					if (FP4) umma_mxf4(td, ta, db, idesc_u, (g | u | k) != 0, UM_TMEM_SF, UM_TMEM_SF + 16, issue);
+					else umma_i8(td, ta, db, idesc_u, (g | u | k) != 0, issue);
 				}
-				__syncwarp();
+				umma_commit(b_ea + (u & 1) * 8, issue);
+				umma_commit(b_eb + u * 8, issue);
 			}
 		}
-		if (lane == 0) umma_commit(&bar_done);
-		__syncwarp();
+		umma_commit(smem_u32(&bar_done), issue);
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
-	if (warp == UM_GEN_WARPS)
+	if (warp == UM_MMA_WARP)
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(UM_TMEM_COLS));
 }
 
@@ -428,13 +459,13 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
-/* quads (4 sample words) per operand row for W sample words: whole groups of UM_STAGES stages plus one stage of
+/* quads (4 sample words) per operand row for W sample words: whole groups of UM_BSTAGES stages plus one stage of
  * prefetch slack */
 int cnbk_umma_row_quads(int W, int fp4, int *ngroups) {
 	const int qps = fp4 ? 2 : 1;                          /* quads per stage */
-	const int nst = (W + 4 * qps - 1) / (4 * qps), ng = (nst + UM_STAGES - 1) / UM_STAGES;
+	const int nst = (W + 4 * qps - 1) / (4 * qps), ng = (nst + UM_BSTAGES - 1) / UM_BSTAGES;
 	if (ngroups) *ngroups = ng;
-	return (ng * UM_STAGES + 1) * qps;
+	return (ng * UM_BSTAGES + 1) * qps;
 }
 
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
@@ -464,7 +495,7 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 long long cnbk_umma_column_macs(int W, int fp4) {
 	int ng;
 	cnbk_umma_row_quads(W, fp4, &ng);
-	return (long long)UM_NA * 128 * ((long long)ng * UM_STAGES * (fp4 ? 256 : 128));
+	return (long long)UM_NA * 128 * ((long long)ng * UM_BSTAGES * (fp4 ? 256 : 128));
 }
 
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long tile_begin, long long tile_end, const int *counts,
