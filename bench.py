@@ -356,13 +356,22 @@ def main():
         ctx2.set_stream(stream.cuda_stream)
         L = _abi.lib()
 
+        wall = {"set_samples_ms": 0.0, "plan_score_ms": 0.0, "finish_ms": 0.0}
+
         def e2e_step():
-            ctx2.set_samples(hnp, num_cats=wl["cats"])
+            t_a = time.perf_counter()
+            ctx2.set_samples(hnp, num_cats=wl["cats"])           # H2D + pack + pair tables; returns synchronised
+            t_b = time.perf_counter()
             ctx2.plan(rank, world, **kw)
             ctx2.score_shard(scores.data_ptr())
             if world > 1:
                 dist.all_gather_into_tensor(scores, scores[rank * seg:(rank + 1) * seg].clone())
-            h = ctx2.finish_raw(scores.data_ptr())
+            t_c = time.perf_counter()
+            h = ctx2.finish_raw(scores.data_ptr())                # selection + DP + network export (D2H)
+            t_d = time.perf_counter()
+            wall["set_samples_ms"] += (t_b - t_a) * 1e3
+            wall["plan_score_ms"] += (t_c - t_b) * 1e3
+            wall["finish_ms"] += (t_d - t_c) * 1e3
             nn = L.cnb_result_num_networks(h)
             import ctypes
             cx, ll = ctypes.c_int32(), ctypes.c_double()
@@ -372,6 +381,8 @@ def main():
 
         e2e_step()
         barrier()
+        for k_ in wall:
+            wall[k_] = 0.0
         e_steps = max(1, min(args.steps, 3))
         ev0.record(stream)
         for _ in range(e_steps):
@@ -387,6 +398,8 @@ def main():
         e2e = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s",
                "h2d_bytes_per_step": int(tm["h2d_bytes"]) * world, "d2h_bytes_per_step": int(tm["d2h_bytes"]) * world,
                "ms_per_step": ems / e_steps, "steps": e_steps,
+               "host_wall_ms_per_step": {k_: v_ / e_steps for k_, v_ in wall.items()},
+               "device_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
                "result": {"networks": res[0], "max_complexity": res[1], "loglik": res[2]}}
         ctx2.close()
 

@@ -197,6 +197,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->no_ie = (on & 2) != 0;             /* bit 1: keep the direct bit-plane scorer (no inclusion-exclusion) */
 	c->tensor_mode = (on & 4) ? 1 : ((on & 8) ? -1 : 0);   /* bit 2: tensor-core path whenever applicable; bit 3: never */
 	c->tensor_i8 = (on & 16) ? 1 : 0;                      /* bit 4: u8 operands (kind::i8) instead of E2M1 (kind::mxf4) */
+	c->dp_per_node = (on & 32) != 0;                       /* bit 5: one DP launch per node (no cooperative kernel) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -266,6 +267,14 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	RC(upload(c, c->b_group_blocks, pl.group_blocks));
 	RC(upload(c, c->b_groups, pl.groups));
 	if (pl.has_prior) RC(upload(c, c->b_edge, pl.edge));
+	c->dp_nodes.resize(pl.nodes.size());
+	for (size_t i = 0; i < pl.nodes.size(); i++) {
+		c->dp_nodes[i].opt_begin = pl.nodes[i].opt_begin;
+		c->dp_nodes[i].opt_end = pl.nodes[i].opt_end;
+		c->dp_nodes[i].base_cx = pl.nodes[i].base_cx;
+		c->dp_nodes[i].pad = 0;
+	}
+	RC(upload(c, c->b_dp_nodes, c->dp_nodes));
 	c->blk_equal.assign(pl.blocks.size(), 0);
 	for (size_t b = 0; b < pl.blocks.size(); b++) c->blk_equal[b] = pl.nodes[pl.blocks[b].child].equal_branch;
 	RC(upload(c, c->b_blk_equal, c->blk_equal));
@@ -311,6 +320,12 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 			/* few families x many samples: slice the sample words so that the machine is filled */
 			long long n = e - b, target = 148ll * 1024;
 			if (n < target) slices = (int)std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8));
+		}
+		if (F.d == 1 && c->pairs_valid && !F.ex_nd) {
+			/* one parent, clean data: the table was counted with the pair tables */
+			RC(cnbk_score_pairs1(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
+			c->timing.kernel_launches++;
+			return CNB_OK;
 		}
 		if (slices == 1 && !O.counts && F.d == 2 && c->pairs_valid && !F.explicit_list) {
 			RC(cnbk_score_planes_ie2(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
@@ -507,16 +522,27 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 		S[i].pfx = (double *)c->b_dp_pfx.ptr + i * slots;
 	}
 	const double *base_v = (const double *)c->b_base_v.ptr;
-	RC(cnbk_dp_init(st, S[0], pl.base_complexity, base_v, N));
 	int cur = 0;
-	for (int n = 1; n < N; n++) {
-		const CnbNodePlan &nd = pl.nodes[n];
-		RC(cnbk_dp_node(st, S[cur], S[cur ^ 1], n, N, nd.base_cx, base_v, nd.opt_begin, nd.opt_end,
+	/* all nodes in one cooperative launch (grid barrier per node); one launch per node if that is refused */
+	int fused = c->dp_per_node ? CNB_ERR_PROC
+			: cnbk_dp_all(st, S[0], S[1], N, pl.base_complexity, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
 				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
-				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr));
-		cur ^= 1;
-	}
-	c->timing.kernel_launches += N;
+				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr);
+	if (fused == CNB_OK) {
+		cur = (N - 1) & 1;                /* node c reads S[(c & 1) ^ 1] and writes S[c & 1] */
+		c->timing.kernel_launches += 1;
+	} else if (fused == CNB_ERR_PROC) {
+		RC(cnbk_dp_init(st, S[0], pl.base_complexity, base_v, N));
+		for (int n = 1; n < N; n++) {
+			const CnbNodePlan &nd = pl.nodes[n];
+			RC(cnbk_dp_node(st, S[cur], S[cur ^ 1], n, N, nd.base_cx, base_v, nd.opt_begin, nd.opt_end,
+					(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+					(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr));
+			cur ^= 1;
+		}
+		c->timing.kernel_launches += N;
+	} else
+		return fused;
 	c->dp_final = cur;
 	CK(cudaEventRecord(c->ev[EV_DP1], st));
 	/* summary to the host: which slots exist and their log-lik */

@@ -28,9 +28,11 @@ struct cnb_ctx {
 	bool has_pert = false, have_samples = false, planned = false, dp_done = false, force_generic = false, last_fast = false, pairs_valid = false, no_ie = false, clean = false;
 	int tensor_mode = 0;               /* 0 auto (large M), 1 always when applicable, -1 never */
 	int tensor_i8 = 0;                 /* 1: kind::i8 operands instead of kind::mxf4 (test hook) */
+	bool dp_per_node = false;          /* one DP launch per node instead of the fused cooperative kernel (test hook) */
 	int dp_final = 0, tensor_batches = 0;
 	std::vector<int32_t> cats_lbl;
 	std::vector<int32_t> blk_equal;
+	std::vector<CnbDpNode> dp_nodes;
 	std::vector<unsigned char> h_exists;
 	std::vector<double> h_L;
 	CnbPlan plan;
@@ -42,13 +44,13 @@ struct cnb_ctx {
 	/* scoring */
 	DevBuf b_scores, b_counts, b_ex_child, b_ex_pars, b_ex_nd, b_ex_ll, b_ex_prior, b_ex_score, b_ex_ncount, b_ex_counts;
 	/* selection + DP */
-	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel;
+	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes;
 	std::vector<DevBuf *> all_bufs() {
 		return {&b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_rows_a, &b_rows_b};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_rows_a, &b_rows_b, &b_dp_nodes};
 	}
 };
 

@@ -43,6 +43,12 @@ struct CnbGroup {
 	int32_t tile_child; /* children per child tile (<= CNB_TILE_CHILD, the slot stride) */
 };
 
+/* per-node arguments of the DP recurrence (k_dp_all) */
+struct CnbDpNode {
+	int64_t opt_begin, opt_end;
+	int32_t base_cx, pad;
+};
+
 /* tensor-core tiling handed to the kernels of cnb_umma.cu and to k_select */
 struct CnbTiles {
 	const long long *tile_base;   /* [nct + 1] first tile of every child tile */

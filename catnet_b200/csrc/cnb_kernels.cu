@@ -15,6 +15,7 @@
  *                                      comparison semantics, replaces :653-677, :800-827, :847-865
  */
 #include <stdio.h>
+#include <cooperative_groups.h>
 #include "cnb_device.cuh"
 #include "cnb_kernels.h"
 
@@ -337,6 +338,27 @@ __global__ void __launch_bounds__(SCORE_BS) k_score_planes_ie2(DevData Dt, DevFa
 	dev_store_outputs(Dt, O, fid, child, pars, 2, ll, ncount);
 }
 
+/* Single-parent families when no value is missing: the family table IS the two-way table of (parent, child) that
+ * k_pair_tables counted once per data set -- no pass over the samples at all, only the log-lik epilogue
+ * (problist.h:224-250) and, when asked for, the table in the reference's layout. */
+__global__ void __launch_bounds__(128) k_score_pairs1(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		ScoreOut O, const int *__restrict__ pair_tab) {
+	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	dev_family(Dt, F, fid, child, pars);
+	const int lp = Dt.order[pars[0]], lc = Dt.order[child];
+	const int pc = Dt.cats[pars[0]], cc = Dt.cats[child];
+	int ncount;
+	double ll = dev_loglik(pc, cc, [&](int i, int k) { return pair_count(pair_tab, lp, lc, i, k); }, &ncount);
+	if (O.counts) {
+		int *tab = O.counts + (size_t)fid * O.counts_stride;
+		for (int i = 0; i < pc; i++)
+			for (int k = 0; k < cc; k++) tab[i * cc + k] = pair_count(pair_tab, lp, lc, i, k);
+	}
+	dev_store_outputs(Dt, O, fid, child, pars, 1, ll, ncount);
+}
+
 /* epilogue over tables already in global memory (split-sample mode): one thread per family */
 __global__ void k_epilogue_counts(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end, ScoreOut O) {
 	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -584,6 +606,103 @@ __global__ void __launch_bounds__(128) k_dp_node(DpState cur, DpState nxt, int c
 	}
 }
 
+/* The same recurrence for every node in ONE cooperative launch (grid barrier between nodes) instead of N - 1
+ * launches: at C5 the 499 launches cost 7 ms, which is a quarter of an 8-GPU step. */
+__global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, int base_complexity,
+		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
+		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
+		int *__restrict__ bp_src) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	extern __shared__ double sbase[];                    /* base_v: every re-summation walks it */
+	const int K = s0.K, nthr = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) sbase[i] = base_v[i];
+	__syncthreads();
+	for (int j = t0; j <= K; j += nthr) {
+		bool ex = (j == base_complexity);
+		double l = 0.0;
+		if (ex) for (int i = 0; i < N; i++) l = __dadd_rn(l, base_v[i]);
+		s0.exists[j] = ex;
+		s0.L[j] = l;
+		s0.pfx[j] = ex ? __dadd_rn(0.0, base_v[0]) : 0.0;
+	}
+	grid.sync();
+	for (int c = 1; c < N; c++) {
+		const DpState &cur = (c & 1) ? s0 : s1, &nxt = (c & 1) ? s1 : s0;
+		const CnbDpNode nd = nodes[c];
+		const double bv = sbase[c];
+		const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
+		for (int j = t0; j <= K; j += nthr) {
+			bool has = false;
+			double R = CNB_NEG_INF;
+			long long bo = -1;
+			int bs = -1;
+			if (nopt <= 4) {
+				/* few options (one per parent count on the equal-categories path): the re-summations, chains of
+				 * N - c dependent fp64 adds, run side by side for all of them before the sequential decision */
+				double acc[4] = {0.0, 0.0, 0.0, 0.0}, t[4];
+				int ks[4];
+				bool ok[4] = {false, false, false, false}, any = false;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (q >= nopt) continue;
+					const long long o = nd.opt_begin + q;
+					if (opt_fid[o] < 0) continue;
+					const int k = j + nd.base_cx - opt_cx[o];
+					if (k < 0 || k > K || !cur.exists[k]) continue;
+					const double f = opt_score[o];
+					ok[q] = any = true;
+					ks[q] = k;
+					t[q] = __dadd_rn(__dsub_rn(cur.L[k], bv), f);
+					acc[q] = __dadd_rn(cur.pfx[k], f);
+				}
+				if (any)
+					for (int i = c + 1; i < N; i++) {
+						const double b = sbase[i];
+#pragma unroll
+						for (int q = 0; q < 4; q++) acc[q] = __dadd_rn(acc[q], b);
+					}
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (!ok[q]) continue;
+					if (!has && t[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }
+					if (has && R < t[q]) { bo = nd.opt_begin + q; bs = ks[q]; R = acc[q]; }
+				}
+			} else
+			for (long long o = nd.opt_begin; o < nd.opt_end; o++) {
+				if (opt_fid[o] < 0) continue;                       /* no winner for that d (:637-640) */
+				int k = j + nd.base_cx - opt_cx[o];
+				if (k < 0 || k > K || !cur.exists[k]) continue;
+				double f = opt_score[o];
+				double t = __dadd_rn(__dsub_rn(cur.L[k], bv), f);  /* :665-666 */
+				if (!has && t > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+				if (has && R < t) {                                  /* :670-671 strict */
+					bo = o;
+					bs = k;
+					R = dev_resum(cur.pfx[k], f, c, N, sbase);
+				}
+			}
+			bool take = false;
+			if (cur.exists[j]) take = has && bo >= 0 && cur.L[j] < R;   /* :847-859 */
+			else take = has && bo >= 0;
+			size_t bpi = (size_t)c * (K + 1) + j;
+			if (take) {
+				nxt.exists[j] = 1;
+				nxt.L[j] = R;
+				nxt.pfx[j] = __dadd_rn(cur.pfx[bs], opt_score[bo]);
+				bp_opt[bpi] = bo;
+				bp_src[bpi] = bs;
+			} else {
+				nxt.exists[j] = cur.exists[j];
+				nxt.L[j] = cur.L[j];
+				nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
+				bp_opt[bpi] = -1;
+				bp_src[bpi] = j;
+			}
+		}
+		grid.sync();
+	}
+}
+
 /* walk the back-pointers of every surviving slot: sel[j][c] = option chosen for node c (-1 = base family) */
 __global__ void k_dp_collect(DpState fin, int N, const long long *__restrict__ bp_opt, const int *__restrict__ bp_src,
 		long long *__restrict__ sel) {
@@ -693,6 +812,15 @@ int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies 
 	return launch_ie2<4>(st, Dt, F, b, e, O, pair_tab);
 }
 
+int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
+		const ScoreOut &O, const int *pair_tab) {
+	if (e <= b) return CNB_OK;
+	if (F.d != 1 || max_cats > 4 || !pair_tab) { cnb_set_error("pair-table scorer: unsupported launch"); return CNB_ERR_PROC; }
+	k_score_pairs1<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O) {
 	if (e <= b) return CNB_OK;
@@ -734,6 +862,26 @@ int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c,
 	k_dp_node<<<(cur.K + 1 + 127) / 128, 128, 0, st>>>(cur, nxt, c, N, base_cx_c, base_v, opt_begin, opt_end,
 			opt_score, opt_cx, opt_fid, bp_opt, bp_src);
 	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* all nodes in one cooperative launch; returns CNB_ERR_PROC (and launches nothing) when the device cannot co-schedule
+ * the grid, so that the caller falls back to one launch per node */
+int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, int base_complexity, const CnbDpNode *nodes,
+		const double *base_v, const double *opt_score, const int *opt_cx, const long long *opt_fid, long long *bp_opt,
+		int *bp_src) {
+	int dev = 0, coop = 0, sms = 0, per_sm = 0;
+	CK(cudaGetDevice(&dev));
+	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	const size_t smem = (size_t)N * sizeof(double);
+	if (smem > 48 * 1024) return CNB_ERR_PROC;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_all, 256, smem));
+	if (!coop || per_sm < 1) return CNB_ERR_PROC;
+	const int blocks = std::min(sms * per_sm, std::max(1, (s0.K + 1 + 255) / 256));   /* one slot per thread if it fits */
+	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
+		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src};
+	CK(cudaLaunchCooperativeKernel((const void *)k_dp_all, dim3(blocks), dim3(256), args, smem, st));
 	return CNB_OK;
 }
 

@@ -34,6 +34,8 @@ bool cnbk_planes_supported(int d, int max_cats);
 int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
 		long long fid_end, int slices, const ScoreOut &O);
 int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int *out);
+int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
+		const ScoreOut &O, const int *pair_tab);
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
 /* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
@@ -56,6 +58,9 @@ int cnbk_dp_init(cudaStream_t st, const DpState &S, int base_complexity, const d
 int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c, int N, int base_cx_c,
 		const double *base_v, long long opt_begin, long long opt_end, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src);
+int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, int base_complexity, const CnbDpNode *nodes,
+		const double *base_v, const double *opt_score, const int *opt_cx, const long long *opt_fid, long long *bp_opt,
+		int *bp_src);
 int cnbk_dp_collect(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
 		long long *sel);
 int cnbk_device_log(cudaStream_t st, const double *x, long long n, double *out);
