@@ -57,7 +57,7 @@ struct CnbTiles {
 };
 
 #define CNB_TILE_PAIRS 28     /* tensor-core tile: 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128) ... */
-#define CNB_TILE_CHILD 58     /* ... x up to 58 children x 3 columns (174 of 176): 1624 family slots per tile */
+#define CNB_TILE_CHILD 64     /* ... x up to 64 children x 3 columns (192): 1792 family slots per tile */
 
 struct CnbNodePlan {
 	int32_t equal_branch;   /* catnet_search2.h:491-496 */

@@ -36,22 +36,27 @@
 #define UM_CHILD CNB_TILE_CHILD
 #define UM_SLOTS (UM_PAIRS * UM_CHILD)
 #define UM_SLOT_INTS 36                   /* 9 configurations x (3 counts + 1 pad): int4 stores */
-#define UM_N ((UM_CHILD * 3 + 15) / 16 * 16)   /* 176 = largest MMA N */
-#define UM_STAGE (UM_N * 128)             /* child rows of one stage: 22,528 B */
-#define UM_BSTAGES 4                      /* shared-memory ring of the child rows */
-#define UM_ASTAGES 2                      /* tensor-memory ring of the pair rows */
+#define UM_N ((UM_CHILD * 3 + 15) / 16 * 16)   /* 192 = largest MMA N */
+#define UM_STAGE (UM_N * 128)             /* child rows of one stage: 24,576 B */
+#define UM_BSTAGES 3                      /* shared-memory ring of the child rows (stages) */
+#define UM_ASTAGES 3                      /* tensor-memory ring of the pair rows, per pair block: 3 slots of HALF a stage
+                                             (2 k-steps = 16 columns), i.e. 1.5 stages deep */
 #define UM_SMEM (UM_BSTAGES * UM_STAGE + 1024)
 #define UM_A_WARPS 8
 #define UM_B_WARPS 6
 #define UM_MMA_WARP (UM_A_WARPS + UM_B_WARPS)   /* first of the UM_NA MMA-issuing warps (one per pair block) */
 #define UM_THREADS ((UM_MMA_WARP + UM_NA) * 32)
 #define UM_TMEM_COLS 512
-#define UM_TMEM_A (UM_NA * UM_N)          /* 352: pair rows, UM_ASTAGES x UM_NA x 4 k-steps x 8 columns = 128 columns */
+#define UM_TMEM_A (UM_NA * UM_N)          /* 384: pair rows, UM_NA blocks x UM_ASTAGES slots x 2 k-steps x 8 columns = 96 columns */
 #define UM_TMEM_SF 480                    /* mxf4: unit scale factors in columns 480..511 */
 static_assert(UM_PAIRS == UM_NA * UM_BLK_PAIRS, "tile geometry");
-static_assert(UM_N <= 256 && UM_TMEM_A + UM_ASTAGES * UM_NA * 32 <= UM_TMEM_SF, "tensor memory budget");
+static_assert(UM_N <= 256 && UM_TMEM_A + UM_NA * UM_ASTAGES * 16 <= UM_TMEM_SF, "tensor memory budget");
 static_assert(UM_STAGE % 1024 == 0, "stages keep the 1024-byte swizzle alignment");
-static_assert(UM_B_WARPS * 32 >= UM_N && UM_BSTAGES == 2 * UM_ASTAGES, "warp roles / ring geometry");
+static_assert(UM_B_WARPS * 32 >= UM_N && UM_NA == 2 && UM_BSTAGES == 3 && UM_ASTAGES == 3, "warp roles / ring geometry");
+/* half-stage 2u + p (stage u of a group, half p) of a pair block lives in slot (2u + p) % 3 of that block's ring; every
+ * slot is used twice per group of 3 stages */
+#define UM_ASLOT(u, p) ((2 * (u) + (p)) % 3)
+#define UM_AUSE(u, p) ((2 * (u) + (p)) / 3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -192,25 +197,61 @@ __device__ __forceinline__ void gen_row_b(const uint32_t (&off)[8], uint4 v0, ui
 }
 /* pair row (A operand), one stage -> 4 k-steps of 8 tensor-memory columns (32 bytes of K each) in this thread's lane;
  * column j of a k-step = bytes 4j..4j+3 of the 32-byte K slice, the same order as the shared-memory chunks above */
-template <bool FP4>
-__device__ __forceinline__ void gen_row_a(uint32_t taddr, uint4 v0, uint4 v1) {
+/* HALF selects k-steps 2*HALF, 2*HALF+1 of the stage (mxf4: the uint4 v holds their 4 source words; i8: v holds the
+ * stage's 4 source words, one per k-step) and writes them to the 16 columns at taddr */
+template <bool FP4, int HALF>
+__device__ __forceinline__ void gen_half_a(uint32_t taddr, uint4 v) {
 	if (FP4) {
-		const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+		const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-		for (int k = 0; k < 4; k++) {
+		for (int k = 0; k < 2; k++) {
 			const uint32_t p = x[2 * k], q = x[2 * k + 1];
 			STTM8(taddr + k * 8, p & 0x11111111u, p & 0x22222222u, p & 0x44444444u, (p >> 1) & 0x44444444u,
 					q & 0x11111111u, q & 0x22222222u, q & 0x44444444u, (q >> 1) & 0x44444444u);
 		}
 	} else {
-		const uint32_t x[4] = {v0.x, v0.y, v0.z, v0.w};
+		const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-		for (int k = 0; k < 4; k++)
-			STTM8(taddr + k * 8, x[k] & 0x01010101u, x[k] & 0x02020202u, x[k] & 0x04040404u, x[k] & 0x08080808u,
-					x[k] & 0x10101010u, x[k] & 0x20202020u, x[k] & 0x40404040u, x[k] & 0x80808080u);
+		for (int k = 0; k < 2; k++) {
+			const uint32_t p = x[2 * HALF + k];
+			STTM8(taddr + k * 8, p & 0x01010101u, p & 0x02020202u, p & 0x04040404u, p & 0x08080808u,
+					p & 0x10101010u, p & 0x20202020u, p & 0x40404040u, p & 0x80808080u);
+		}
 	}
 }
 __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+
+/* issue loop of pair block H (one thread): everything but the barrier phase and the instruction descriptor is a
+ * compile-time constant */
+template <bool FP4, int H>
+__device__ __forceinline__ void mma_issue_loop(uint32_t smem, uint32_t idesc, int ngroups, uint64_t *bar_full_a,
+		uint64_t *bar_empty_a, uint64_t *bar_full_b, uint64_t *bar_empty_b, uint64_t *bar_done) {
+	const uint64_t db0 = umma_desc(smem);
+	const uint32_t b_ea = smem_u32(&bar_empty_a[H * UM_ASTAGES]), b_eb = smem_u32(&bar_empty_b[0]);
+	constexpr uint32_t td = H * UM_N, ta0 = UM_TMEM_A + H * (UM_ASTAGES * 16);
+	for (int g = 0; g < ngroups; g++) {
+#pragma unroll
+		for (int u = 0; u < UM_BSTAGES; u++) {
+			mbar_wait(&bar_full_b[u], g & 1);
+#pragma unroll
+			for (int p = 0; p < 2; p++) {
+				mbar_wait(&bar_full_a[H * UM_ASTAGES + UM_ASLOT(u, p)], UM_AUSE(u, p) & 1);
+				asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+				for (int kk = 0; kk < 2; kk++) {               /* +2: 32 bytes of K in 16-byte units */
+					const int k = 2 * p + kk;
+					const uint32_t ta = ta0 + UM_ASLOT(u, p) * 16 + kk * 8;
+					const uint64_t db = db0 + (uint64_t)(u * (UM_STAGE >> 4) + 2 * k);
+					if (FP4) umma_mxf4(td, ta, db, idesc, (g | u | k) != 0, UM_TMEM_SF, UM_TMEM_SF + 16, 1);
+					else umma_i8(td, ta, db, idesc, (g | u | k) != 0, 1);
+				}
+				umma_commit(b_ea + UM_ASLOT(u, p) * 8, 1);
+			}
+			umma_commit(b_eb + u * 8, 1);
+		}
+	}
+	umma_commit(smem_u32(bar_done), 1);
+}
 
 template <bool FP4>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
@@ -218,7 +259,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
 	const int NR = 3 * N;                   /* operand rows per quad */
 	extern __shared__ uint8_t smem_raw[];
-	__shared__ __align__(8) uint64_t bar_full_b[UM_BSTAGES], bar_empty_b[UM_BSTAGES], bar_full_a[UM_ASTAGES], bar_empty_a[UM_ASTAGES], bar_done;
+	__shared__ __align__(8) uint64_t bar_full_b[UM_BSTAGES], bar_empty_b[UM_BSTAGES], bar_full_a[UM_NA * UM_ASTAGES], bar_empty_a[UM_NA * UM_ASTAGES], bar_done;
 	__shared__ uint32_t tmem_base_sh;
 	const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -238,9 +279,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			mbar_init(&bar_full_b[s], UM_B_WARPS);
 			mbar_init(&bar_empty_b[s], UM_NA);           /* one tcgen05.commit per MMA warp */
 		}
-		for (int s = 0; s < UM_ASTAGES; s++) {
-			mbar_init(&bar_full_a[s], UM_A_WARPS);
-			mbar_init(&bar_empty_a[s], UM_NA);
+		for (int s = 0; s < UM_NA * UM_ASTAGES; s++) {
+			mbar_init(&bar_full_a[s], UM_A_WARPS / UM_NA);   /* the 4 warps of one pair block */
+			mbar_init(&bar_empty_a[s], 1);                   /* the commit of that block's MMA warp */
 		}
 		mbar_init(&bar_done, UM_NA);
 		asm volatile("fence.mbarrier_init.release.cluster;");
@@ -273,7 +314,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		pair_of(pt * UM_PAIRS + h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb);
 		if (pb >= N) { pa = 0; pb = 1; }
 		const uint4 *s0 = rows_a + (pa * 3 + (r % 9) / 3), *s1 = rows_a + (pb * 3 + r % 3);
-		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * 32;
+		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * (UM_ASTAGES * 16);
+		uint64_t *const full_a = &bar_full_a[h * UM_ASTAGES], *const empty_a = &bar_empty_a[h * UM_ASTAGES];
 		uint4 n0, n1, m0, m1;          /* next stage's source bits of the two nodes */
 		n0 = __ldg(s0);
 		m0 = __ldg(s1);
@@ -287,14 +329,18 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 				n0 = __ldg(s0);
 				m0 = __ldg(s1);
 				if (FP4) { n1 = __ldg(s0 + NR); m1 = __ldg(s1 + NR); }
-				/* slot u & 1 is used twice per group: use number 2g + (u >> 1) */
-				if (g > 0 || u >= UM_ASTAGES) mbar_wait(&bar_empty_a[u & 1], ((u >> 1) + 1) & 1);
-				asm volatile("tcgen05.fence::after_thread_sync;");
-				gen_row_a<FP4>(ta + (u & 1) * (UM_NA * 32), v0, v1);
-				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-				asm volatile("tcgen05.fence::before_thread_sync;");
-				__syncwarp();
-				if (lane == 0) mbar_arrive(&bar_full_a[u & 1]);
+				/* each half of the stage goes to its own ring slot (use number 2g + UM_AUSE of that slot) */
+#define UM_HALF_BODY(p, v) { \
+				if (g > 0 || UM_AUSE(u, p) > 0) mbar_wait(&empty_a[UM_ASLOT(u, p)], (UM_AUSE(u, p) + 1) & 1); \
+				asm volatile("tcgen05.fence::after_thread_sync;"); \
+				gen_half_a<FP4, p>(ta + UM_ASLOT(u, p) * 16, v); \
+				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); \
+				asm volatile("tcgen05.fence::before_thread_sync;"); \
+				__syncwarp(); \
+				if (lane == 0) mbar_arrive(&full_a[UM_ASLOT(u, p)]); }
+				UM_HALF_BODY(0, v0)
+				UM_HALF_BODY(1, (FP4 ? v1 : v0))
+#undef UM_HALF_BODY
 			}
 		}
 
@@ -316,7 +362,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			: "r"(a))
 			LD8(0, taddr);
 			LD8(8, taddr + 8);
-			if (q * 24 + 16 < UM_N) LD8(16, taddr + 16);       /* the last chunk of 176 columns has 8 + 8 */
+			LD8(16, taddr + 16);
 #undef LD8
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			if (row_ok) {
@@ -359,43 +405,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			UM_STAGE_BODY(0)
 			UM_STAGE_BODY(1)
 			UM_STAGE_BODY(2)
-			UM_STAGE_BODY(3)
 #undef UM_STAGE_BODY
 		}
 	} else {
 		/* ---- MMA issuers: warp UM_MMA_WARP + h owns pair block h (its own accumulator, so the two instruction
-		 * streams never touch the same tensor-memory columns); one elected lane issues four K = 32-byte MMAs per
-		 * stage.  A single issuing warp was the bottleneck (profiles/r01_umma_v4_ts_summary.txt: 92 % of its
-		 * samples inside the issue sequence, 7 cycles per instruction).  Operands are compile-time constants or
-		 * warp-uniform values: the CTA owns all 512 tensor-memory columns, so its allocation starts at column 0
-		 * (checked above). ---- */
-		const int h = warp - UM_MMA_WARP;
+		 * streams never touch the same tensor-memory columns); ONE lane per warp runs the issue loop, four
+		 * K = 32-byte MMAs per stage.  A single issuing warp was the bottleneck (profiles/r01_umma_v4_ts_summary.txt:
+		 * 92 % of its samples inside the issue sequence, 7 cycles per instruction).  Operands are compile-time
+		 * constants or warp-uniform values: the CTA owns all 512 tensor-memory columns, so its allocation starts at
+		 * column 0 (checked above). ---- */
 		const uint32_t idesc = FP4 ? ((1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | (1u << 23) | (8u << 24))   /* E2M1 x E2M1, E8M0 scales */
 		                           : ((2u << 4) | ((uint32_t)(ncols >> 3) << 17) | (8u << 24));                           /* s32 acc, u8 x u8 */
-		/* warp reductions return their result in a uniform register: the compiler then knows these are the same in all lanes */
-		const uint32_t idesc_u = __reduce_max_sync(0xffffffffu, idesc);
-		const uint64_t db0 = umma_desc(__reduce_max_sync(0xffffffffu, smem));
-		const uint32_t issue = lane == 0;
-		const uint32_t b_ea = smem_u32(&bar_empty_a[0]), b_eb = smem_u32(&bar_empty_b[0]);
-		const uint32_t td = h * UM_N, ta0 = UM_TMEM_A + h * 32;
-		for (int g = 0; g < ngroups; g++) {
-#pragma unroll
-			for (int u = 0; u < UM_BSTAGES; u++) {
-				mbar_wait(&bar_full_a[u & 1], (u >> 1) & 1);
-				mbar_wait(&bar_full_b[u], g & 1);
-				asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-				for (int k = 0; k < 4; k++) {                  /* +2: 32 bytes of K in 16-byte units */
-					const uint32_t ta = ta0 + (u & 1) * (UM_NA * 32) + k * 8;
-					const uint64_t db = db0 + (uint64_t)(u * (UM_STAGE >> 4) + 2 * k);
-					if (FP4) umma_mxf4(td, ta, db, idesc_u, (g | u | k) != 0, UM_TMEM_SF, UM_TMEM_SF + 16, issue);
-					else umma_i8(td, ta, db, idesc_u, (g | u | k) != 0, issue);
-				}
-				umma_commit(b_ea + (u & 1) * 8, issue);
-				umma_commit(b_eb + u * 8, issue);
-			}
+		if (lane == 0) {
+			if (warp == UM_MMA_WARP) mma_issue_loop<FP4, 0>(smem, idesc, ngroups, bar_full_a, bar_empty_a, bar_full_b, bar_empty_b, &bar_done);
+			else mma_issue_loop<FP4, 1>(smem, idesc, ngroups, bar_full_a, bar_empty_a, bar_full_b, bar_empty_b, &bar_done);
 		}
-		umma_commit(smem_u32(&bar_done), issue);
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;");
 	__syncthreads();
