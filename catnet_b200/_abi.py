@@ -57,7 +57,7 @@ SYMBOLS = [
     "cnb_search_order", "cnb_search_sa", "cnb_release_cache", "cnb_set_seed", "cnb_last_error", "cnb_version",
     "cnb_ctx_create", "cnb_ctx_destroy", "cnb_ctx_set_samples", "cnb_ctx_set_samples_dev", "cnb_ctx_num_cats",
     "cnb_ctx_search_order", "cnb_ctx_search_sa", "cnb_ctx_plan", "cnb_ctx_score_shard", "cnb_ctx_finish",
-    "cnb_ctx_select_dp", "cnb_ctx_collect", "cnb_ctx_set_stream", "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_device_log", "cnb_host_log",
+    "cnb_ctx_select_dp", "cnb_ctx_collect", "cnb_ctx_set_stream", "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_tile_selftest", "cnb_device_log", "cnb_host_log",
     "cnb_unrank_combination", "cnb_num_families", "cnb_result_num_networks", "cnb_result_num_nodes",
     "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_cats", "cnb_result_counts", "cnb_result_node",
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
@@ -98,6 +98,7 @@ def lib():
         "cnb_ctx_set_stream": (i32, [vp, vp]),
         "cnb_ctx_timing": (i32, [vp, P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
+        "cnb_tile_selftest": (C.c_int64, [i32]),
         "cnb_family_scores": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32]),
         "cnb_device_log": (i32, [i32, vp, i64, vp]),
         "cnb_host_log": (None, [vp, i64, vp]),

@@ -223,6 +223,7 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
 	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
 	D.tiles.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
+	D.tiles.dtile_off = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_dtile_off.ptr;
 	D.tiles.nct = c->plan.tile_base.empty() ? 0 : (int)c->plan.tile_base.size() - 1;
 	D.tiles.child = c->plan.tile_child;
 	D.tiles.rank = c->plan.rank;
@@ -256,6 +257,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	CnbPlan &pl = c->plan;
 	if (!pl.tile_base.empty()) {
 		RC(upload(c, c->b_tile_base, pl.tile_base));
+		RC(upload(c, c->b_dtile_off, pl.dtile_off));
 		size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, !c->tensor_i8, nullptr) * sizeof(uint4) * 3 * c->N;
 		RC(c->b_rows_a.ensure(row_bytes));
 		RC(c->b_rows_b.ensure(row_bytes));

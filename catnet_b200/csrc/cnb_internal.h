@@ -52,6 +52,7 @@ struct CnbDpNode {
 /* tensor-core tiling handed to the kernels of cnb_umma.cu and to k_select */
 struct CnbTiles {
 	const long long *tile_base;   /* [nct + 1] first tile of every child tile */
+	const long long *dtile_off;   /* [nct][CNB_DT_STRIDE] D tiles of the child tile before each of its D pair tiles */
 	int32_t nct, child;           /* child tiles, children per child tile */
 	int32_t rank, world;
 };
@@ -80,6 +81,7 @@ struct CnbPlan {
 	std::vector<CnbNodePlan> nodes;
 	std::vector<double> edge;                  /* order space [parent*N + child], empty if no prior */
 	std::vector<int64_t> tile_base;            /* tiled group: first tile of every child tile (+ total at the end) */
+	std::vector<int64_t> dtile_off;            /* see cnb_tiles.h */
 	int32_t tile_child = 0;                    /* children per child tile */
 	int64_t seg_len = 0;                       /* doubles per rank segment */
 	int64_t num_families = 0;

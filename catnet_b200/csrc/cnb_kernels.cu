@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include "cnb_device.cuh"
 #include "cnb_kernels.h"
+#include "cnb_tiles.h"
 
 #define SCORE_BS 128
 
@@ -490,11 +491,12 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 		if (g.tiled) {
 			int ab[2];
 			dev_unrank(b.nfree, 2, fid - b.start, ab);      /* unrestricted block: positions themselves */
-			long long q = (long long)ab[1] * (ab[1] - 1) / 2 + ab[0];
-			long long tile = Dt.tiles.tile_base[b.child / g.tile_child] + q / CNB_TILE_PAIRS;
+			long long tile;
+			int within;
+			cnb_family_slot(Dt.tiles, Dt.N, ab[0], ab[1], b.child, tile, within);
 			/* tile t is scored by rank t % world as its local tile t / world */
 			return scores[(tile % g.tile_world) * seg_len + g.seg_off + (tile / g.tile_world) * (CNB_TILE_PAIRS * CNB_TILE_CHILD)
-					+ (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + b.child % g.tile_child];
+					+ within];
 		}
 		return scores[dev_score_index(slot, g.chunk, g.seg_off, seg_len)];
 	};

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <algorithm>
 #include "cnb_internal.h"
+#include "cnb_tiles.h"
 
 static thread_local char g_err[512] = "";
 
@@ -206,13 +207,17 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 			}
 			if (full) {
 				int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
-				int cpt = (N + nct - 1) / nct;                      /* equal child tiles (500 nodes: 7 x 72, not 6 x 80 + 20) */
+				int cpt = (N + nct - 1) / nct;                      /* equal child tiles (500 nodes: 8 x 63, not 7 x 64 + 52) */
 				pl.tile_child = cpt;
 				pl.tile_base.assign(nct + 1, 0);
+				pl.dtile_off.assign((size_t)nct * CNB_DT_STRIDE, 0);
 				for (int ct = 0; ct < nct; ct++) {
-					int64_t cmax = std::min<int64_t>(N - 1, (int64_t)ct * cpt + cpt - 1);
-					int64_t npairs = cmax * (cmax - 1) / 2;          /* pairs (a < b) with b < cmax */
-					pl.tile_base[ct + 1] = pl.tile_base[ct] + (npairs + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS;
+					const int c0 = ct * cpt, ce = std::min(c0 + cpt, N);
+					int64_t *off = &pl.dtile_off[(size_t)ct * CNB_DT_STRIDE];
+					const int ndp = cnb_d_pairs(c0, ce), ndt = (ndp + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS;
+					for (int p = 0; p < ndt; p++) off[p + 1] = off[p] + cnb_d_chunks(c0, ce, p);
+					for (int p = ndt + 1; p < CNB_DT_STRIDE; p++) off[p] = off[ndt];
+					pl.tile_base[ct + 1] = pl.tile_base[ct] + cnb_f_tiles(c0) + off[ndt];
 				}
 				g.tiled = 1;
 				g.ntiles = pl.tile_base[nct];
@@ -242,15 +247,69 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 }
 
 int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
-	const int nct = (int)pl.tile_base.size() - 1;
-	int ct = 0;
-	while (ct + 1 < nct && pl.tile_base[ct + 1] <= tile) ct++;
-	const int64_t q = (tile - pl.tile_base[ct]) * CNB_TILE_PAIRS;     /* first pair of the tile: q = b(b-1)/2 + a */
-	int64_t b = 1;
-	while ((b + 1) * b / 2 <= q) b++;
-	const int c0 = ct * pl.tile_child, ce = std::min(c0 + pl.tile_child, pl.N);
-	const int cb = std::max<int64_t>(c0, b + 1);
-	return (3 * (ce - cb) + 15) / 16 * 16;
+	CnbTiles T;
+	T.tile_base = (const long long *)pl.tile_base.data();
+	T.dtile_off = (const long long *)pl.dtile_off.data();
+	T.nct = (int)pl.tile_base.size() - 1;
+	T.child = pl.tile_child;
+	T.rank = 0;
+	T.world = 1;
+	CnbTileInfo ti;
+	cnb_tile_decode(T, pl.N, tile, ti);
+	return (3 * (ti.ze - ti.zb) + 15) / 16 * 16;
+}
+
+/* test hook: the tiling of the unrestricted two-parent group of N nodes is a bijection between families and tile
+ * slots (family -> slot -> family), every tile has at least one column, and no two families share a slot.
+ * Returns the number of tiles, or a negative value at the first inconsistency. */
+extern "C" int64_t cnb_tile_selftest(int32_t N) {
+	if (N < 3) return 0;
+	cnb_params q;
+	memset(&q, 0, sizeof(q));
+	q.num_nodes = N;
+	q.num_samples = 1;
+	q.max_parent_set = 2;
+	q.max_complexity = 1 << 30;
+	std::vector<int32_t> cats(N, 2);
+	CnbPlan pl;
+	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr, true) != CNB_OK || pl.tile_base.empty()) return -1;
+	CnbTiles T;
+	T.tile_base = (const long long *)pl.tile_base.data();
+	T.dtile_off = (const long long *)pl.dtile_off.data();
+	T.nct = (int)pl.tile_base.size() - 1;
+	T.child = pl.tile_child;
+	T.rank = 0;
+	T.world = 1;
+	const int64_t ntiles = pl.tile_base[T.nct];
+	std::vector<unsigned char> used((size_t)ntiles * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
+	int64_t nfam = 0;
+	for (int c = 2; c < N; c++)
+		for (int b = 1; b < c; b++)
+			for (int a = 0; a < b; a++) {
+				long long tile;
+				int within;
+				cnb_family_slot(T, N, a, b, c, tile, within);
+				if (tile < 0 || tile >= ntiles || within < 0 || within >= CNB_TILE_PAIRS * CNB_TILE_CHILD) return -2;
+				unsigned char &u = used[(size_t)tile * CNB_TILE_PAIRS * CNB_TILE_CHILD + within];
+				if (u) return -3;
+				u = 1;
+				CnbTileInfo ti;
+				cnb_tile_decode(T, N, tile, ti);
+				int x, y;
+				const int p = within / CNB_TILE_CHILD, j = within % CNB_TILE_CHILD;
+				if (j >= ti.ze - ti.zb || !cnb_tile_pair(ti, p, x, y)) return -4;
+				const bool dk = ti.kind != 0;
+				const int a2 = dk ? ti.zb + j : x, b2 = dk ? x : y, c2 = dk ? y : ti.zb + j;
+				if (a2 != a || b2 != b || c2 != c) return -5;
+				nfam++;
+			}
+	if (nfam != (int64_t)N * (N - 1) * (N - 2) / 6) return -6;
+	for (int64_t t = 0; t < ntiles; t++) {
+		CnbTileInfo ti;
+		cnb_tile_decode(T, N, t, ti);
+		if (ti.ze <= ti.zb || ti.ze - ti.zb > CNB_TILE_CHILD || cnb_tile_columns(pl, t) < 16) return -7;
+	}
+	return ntiles;
 }
 
 extern "C" int64_t cnb_num_families(const cnb_params *p) {

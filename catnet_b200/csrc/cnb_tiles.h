@@ -1,0 +1,125 @@
+/* cnb_tiles.h -- geometry of the tensor-core tiling of the two-parent group, shared by the host planner
+ * (cnb_plan.cpp), the table kernel and its epilogue (cnb_umma.cu) and the selection kernel (cnb_kernels.cu).
+ *
+ * Families (a < b | c) with a, b < c in order space; the children are cut into child tiles of T.child <= 64
+ * consecutive positions [c0, ce).  Inside child tile ct there are two kinds of MMA tiles, both 28 "pair" slots
+ * (2 blocks x 14 pairs x 9 configurations = the A rows) by up to 64 "column" nodes (x 3 categories = the B rows):
+ *
+ *   F tiles  pairs (a, b) with b < c0, ranked q = b(b-1)/2 + a; columns = the children c0..ce-1.  Every slot is a
+ *            family.
+ *   D tiles  the "diagonal" families whose second parent lies inside the child tile: pairs (b, c) with
+ *            c0 <= b < c < ce, ranked by b then c; columns = the FIRST parent a, in chunks of 64 positions,
+ *            as far as the largest b of the tile's pairs.  (With (a, b) as the pair and c > b as the columns, as in
+ *            the F tiles, a diagonal tile would use half its columns on average and every MMA has a fixed cost.)
+ *
+ * Tile ids: tile_base[ct] + [0, nF) are the F tiles of ct, then the D tiles pair tile after pair tile, chunk after
+ * chunk; dtile_off[ct * CNB_DT_STRIDE + p] = D tiles of ct before pair tile p.
+ */
+#ifndef CNB_TILES_H
+#define CNB_TILES_H
+#include "cnb_internal.h"
+#include <math.h>
+
+#ifdef __CUDACC__
+#define CNB_HD __host__ __device__ __forceinline__
+#else
+#define CNB_HD inline
+#endif
+
+#define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 pair tiles of D pairs per child tile, plus the total */
+
+struct CnbTileInfo {
+	int kind;                 /* 0 = F, 1 = D */
+	int ct, c0, ce;           /* child tile and its children [c0, ce) */
+	long long pair0;          /* rank of the tile's first pair inside its region (F: q, D: rank among the D pairs) */
+	long long npairs;         /* pairs of the region */
+	int zb, ze;               /* column nodes [zb, ze): children (F) or first parents (D); slot column = node - zb */
+};
+
+CNB_HD void cnb_pair_of(long long q, int &a, int &b) {      /* q = b(b-1)/2 + a, a < b */
+	b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+	while ((long long)b * (b - 1) / 2 > q) b--;
+	while ((long long)(b + 1) * b / 2 <= q) b++;
+	a = (int)(q - (long long)b * (b - 1) / 2);
+}
+CNB_HD long long cnb_f_pairs(int c0) { return (long long)c0 * (c0 - 1) / 2; }
+CNB_HD long long cnb_f_tiles(int c0) { return (cnb_f_pairs(c0) + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }
+CNB_HD int cnb_d_pairs(int c0, int ce) { return (ce - c0) * (ce - c0 - 1) / 2; }
+/* rank of D pair (b, c) of child tile [c0, ce), and back */
+CNB_HD int cnb_d_rank(int c0, int ce, int b, int c) {
+	const int k = b - c0;                                  /* pairs with a smaller b: sum_{t<k} (w - 1 - t) */
+	return k * (ce - c0 - 1) - k * (k - 1) / 2 + (c - b - 1);
+}
+CNB_HD void cnb_d_pair(int c0, int ce, int q, int &b, int &c) {
+	b = c0;
+	while (q >= ce - 1 - b) { q -= ce - 1 - b; b++; }
+	c = b + 1 + q;
+}
+/* chunks of 64 first parents a D pair tile needs: up to the b of its last pair */
+CNB_HD int cnb_d_chunks(int c0, int ce, int ptile) {
+	const int np = cnb_d_pairs(c0, ce);
+	int last = ptile * CNB_TILE_PAIRS + CNB_TILE_PAIRS - 1;
+	if (last > np - 1) last = np - 1;
+	int b, c;
+	cnb_d_pair(c0, ce, last, b, c);
+	return (b + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+}
+
+CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInfo &ti) {
+	int lo = 0, hi = T.nct - 1;
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+		if (T.tile_base[mid] <= tile) lo = mid;
+		else hi = mid - 1;
+	}
+	ti.ct = lo;
+	ti.c0 = lo * T.child;
+	ti.ce = ti.c0 + T.child < N ? ti.c0 + T.child : N;
+	const long long pt = tile - T.tile_base[lo], nf = cnb_f_tiles(ti.c0);
+	if (pt < nf) {
+		ti.kind = 0;
+		ti.pair0 = pt * CNB_TILE_PAIRS;
+		ti.npairs = cnb_f_pairs(ti.c0);
+		ti.zb = ti.c0;
+		ti.ze = ti.ce;
+		return;
+	}
+	const long long *off = T.dtile_off + (size_t)lo * CNB_DT_STRIDE;
+	const int d = (int)(pt - nf);
+	int p = 0;
+	while (off[p + 1] <= d) p++;
+	ti.kind = 1;
+	ti.pair0 = (long long)p * CNB_TILE_PAIRS;
+	ti.npairs = cnb_d_pairs(ti.c0, ti.ce);
+	int last = p * CNB_TILE_PAIRS + CNB_TILE_PAIRS - 1;
+	if (last > ti.npairs - 1) last = (int)ti.npairs - 1;
+	int b, c;
+	cnb_d_pair(ti.c0, ti.ce, last, b, c);
+	ti.zb = (d - (int)off[p]) * CNB_TILE_CHILD;
+	ti.ze = ti.zb + CNB_TILE_CHILD < b ? ti.zb + CNB_TILE_CHILD : b;
+}
+
+/* the two "pair" nodes (x, y) of pair slot ps of a tile; false if the slot is past the end of the region */
+CNB_HD bool cnb_tile_pair(const CnbTileInfo &ti, int ps, int &x, int &y) {
+	const long long q = ti.pair0 + ps;
+	if (q >= ti.npairs) return false;
+	if (ti.kind == 0) cnb_pair_of(q, x, y);
+	else cnb_d_pair(ti.c0, ti.ce, (int)q, x, y);
+	return true;
+}
+
+/* family (a < b | c) -> tile and slot inside the tile (pair slot * CNB_TILE_CHILD + column slot) */
+CNB_HD void cnb_family_slot(const CnbTiles &T, int N, int a, int b, int c, long long &tile, int &within) {
+	const int ct = c / T.child, c0 = ct * T.child, ce = c0 + T.child < N ? c0 + T.child : N;
+	if (b < c0) {
+		const long long q = (long long)b * (b - 1) / 2 + a;
+		tile = T.tile_base[ct] + q / CNB_TILE_PAIRS;
+		within = (int)(q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + (c - c0);
+	} else {
+		const int q = cnb_d_rank(c0, ce, b, c), p = q / CNB_TILE_PAIRS;
+		tile = T.tile_base[ct] + cnb_f_tiles(c0) + T.dtile_off[(size_t)ct * CNB_DT_STRIDE + p] + a / CNB_TILE_CHILD;
+		within = (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + a % CNB_TILE_CHILD;
+	}
+}
+
+#endif

@@ -27,6 +27,7 @@
 #include <stdio.h>
 #include "cnb_device.cuh"
 #include "cnb_kernels.h"
+#include "cnb_tiles.h"
 
 /* Inclusion-exclusion (see k_score_planes_ie2): only the 3 x 3 x 3 "free" cells of every table are contracted;
  * cells with a last category follow from the pair tables.  So a pair needs 9 rows and a child 3 columns. */
@@ -101,37 +102,6 @@ __device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint32_t tmem_a, uint
  * layout SWIZZLE_128B = 2 in [61,64) */
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 	return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void pair_of(long long q, int &a, int &b) {      /* q = b(b-1)/2 + a, a < b */
-	b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
-	while ((long long)b * (b - 1) / 2 > q) b--;
-	while ((long long)(b + 1) * b / 2 <= q) b++;
-	a = (int)(q - (long long)b * (b - 1) / 2);
-}
-
-/* tile id -> (child tile, pair tile); tile_base[ct] = first tile of child tile ct */
-__device__ __forceinline__ void tile_of(const long long *__restrict__ tile_base, int nct, long long tile, int &ct, long long &pt) {
-	int lo = 0, hi = nct - 1;
-	while (lo < hi) {
-		int mid = (lo + hi + 1) >> 1;
-		if (tile_base[mid] <= tile) lo = mid;
-		else hi = mid - 1;
-	}
-	ct = lo;
-	pt = tile - tile_base[lo];
-}
-
-/* Children a tile really contracts.  Pairs are ranked by their larger member b first, so the 28 pairs of a tile
- * share (almost) one b; only children behind the tile's smallest b can form a family, which trims the "diagonal"
- * tiles (b inside the child tile) to the columns that count.  [cb, ce) = child positions, c0 = first of the
- * child tile (slot origin).  Host mirror: cnb_tile_columns (cnb_plan.cpp). */
-__device__ __forceinline__ void tile_children(const CnbTiles &T, int N, int ct, long long pt, int &c0, int &cb, int &ce) {
-	int a, b;
-	pair_of(pt * UM_PAIRS, a, b);
-	c0 = ct * T.child;
-	ce = min(c0 + T.child, N);
-	cb = max(c0, b + 1);
 }
 
 /* ---- operand rows --------------------------------------------------------------------------------------------
@@ -264,11 +234,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const long long tile = T.rank + (local_begin + blockIdx.x) * T.world;
-	int ct, c0, cb, ce;
-	long long pt;
-	tile_of(T.tile_base, T.nct, tile, ct, pt);
-	tile_children(T, N, ct, pt, c0, cb, ce);
-	const int nchild = ce - cb, ncols = (3 * nchild + 15) & ~15;        /* MMA N of this tile */
+	CnbTileInfo ti;                          /* cnb_tiles.h: pair slots (A rows) and column nodes (B rows) of this tile */
+	cnb_tile_decode(T, N, tile, ti);
+	const int nchild = ti.ze - ti.zb, ncols = (3 * nchild + 15) & ~15;   /* column nodes and MMA N of this tile */
 
 	if (warp == UM_MMA_WARP) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(UM_TMEM_COLS));
@@ -308,11 +276,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 
 	if (warp < UM_A_WARPS) {
 		/* ---- pair rows -> tensor memory.  Thread = row r = pair*9 + i*3 + j of pair block h, TMEM lane r; rows
-		 * 126/127 and pairs past the end repeat valid data whose accumulators nobody reads ---- */
+		 * 126/127 and pair slots past the end repeat valid data whose accumulators nobody reads ---- */
 		const int h = warp >> 2, r = tid & 127;
 		int pa, pb;
-		pair_of(pt * UM_PAIRS + h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb);
-		if (pb >= N) { pa = 0; pb = 1; }
+		if (!cnb_tile_pair(ti, h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb)) { pa = 0; pb = 1; }
 		const uint4 *s0 = rows_a + (pa * 3 + (r % 9) / 3), *s1 = rows_a + (pb * 3 + r % 3);
 		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * (UM_ASTAGES * 16);
 		uint64_t *const full_a = &bar_full_a[h * UM_ASTAGES], *const empty_a = &bar_empty_a[h * UM_ASTAGES];
@@ -344,15 +311,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			}
 		}
 
-		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair*9 + (i*3+j); accumulator column 3j+k =
-		 * child cb + j (slot (cb - c0) + j of the tile).  A warp may only touch its own lane quarter (warp & 3);
-		 * each of the 8 warps reads its rows of one accumulator in chunks of 24 columns (8 children). */
+		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair slot*9 + (i*3+j); accumulator column
+		 * 3j+k = column node zb + j (column slot j of the tile).  A warp may only touch its own lane quarter
+		 * (warp & 3); each of the 8 warps reads its rows of one accumulator in chunks of 24 columns (8 nodes). */
 		mbar_wait(&bar_done, 0);
 		asm volatile("tcgen05.fence::after_thread_sync;");
 		const int lq = warp & 3;
 		const int row = lq * 32 + lane, cfg = row % 9;
 		const bool row_ok = row < UM_BLK_PAIRS * 9;
-		int *out = counts + ((size_t)blockIdx.x * UM_SLOTS + (size_t)(h * UM_BLK_PAIRS + row / 9) * UM_CHILD + (cb - c0)) * UM_SLOT_INTS + cfg * 4;
+		int *out = counts + ((size_t)blockIdx.x * UM_SLOTS + (size_t)(h * UM_BLK_PAIRS + row / 9) * UM_CHILD) * UM_SLOT_INTS + cfg * 4;
 #pragma unroll 1
 		for (int q = 0; q * 8 < nchild; q++) {
 			uint32_t v[24];
@@ -381,11 +348,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			}
 		}
 	} else if (warp < UM_MMA_WARP) {
-		/* ---- child rows -> shared memory.  Thread = row r = child*3 + k of the tile's children [cb, ce); rows past
-		 * the MMA's columns are not generated, their threads only keep the warp's arrivals going ---- */
+		/* ---- column rows -> shared memory.  Thread = row r = node*3 + k of the tile's column nodes [zb, ze); rows
+		 * past the MMA's columns are not generated, their threads only keep the warp's arrivals going ---- */
 		const int rr = tid - UM_A_WARPS * 32, r = min(rr, UM_N - 1);
 		const bool active = rr < ncols;
-		const uint4 *s0 = rows_b + (min(cb + r / 3, ce - 1) * 3 + r % 3);
+		const uint4 *s0 = rows_b + (min(ti.zb + r / 3, ti.ze - 1) * 3 + r % 3);
 		uint32_t off[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) off[k] = smem + (r >> 3) * 1024u + (r & 7u) * 128u + ((k ^ (r & 7u)) << 4);
@@ -443,19 +410,21 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	if (local >= local_end) return;
 	const long long tile = T.rank + local * T.world;
 	const int within = (int)(slot % UM_SLOTS), p = within / UM_CHILD, j = within % UM_CHILD;
-	int ct;
-	long long pt;
-	tile_of(T.tile_base, T.nct, tile, ct, pt);
-	int a, b;
-	pair_of(pt * UM_PAIRS + p, a, b);
-	const int c = ct * T.child + j;
-	if (j >= T.child || c >= Dt.N || b >= c) return;      /* not a family: parents must precede the child */
+	CnbTileInfo ti;
+	cnb_tile_decode(T, Dt.N, tile, ti);
+	int x, y;
+	if (j >= ti.ze - ti.zb || !cnb_tile_pair(ti, p, x, y)) return;
+	/* F tile: pair (a, b), column = child c.  D tile: pair (b, c), column = first parent a, which must precede b. */
+	const bool dk = ti.kind != 0;
+	const int a = dk ? ti.zb + j : x, b = dk ? x : y, c = dk ? y : ti.zb + j;
+	if (a >= b) return;
 	const int *tab = counts + (size_t)slot * UM_SLOT_INTS;
 	int full[64];
 #define CELL(i, jj, k) full[((i) * 4 + (jj)) * 4 + (k)]
+	/* slot layout: 9 pair configurations x (3 column categories + pad) */
 	for (int i = 0; i < 3; i++)
 		for (int jj = 0; jj < 3; jj++)
-			for (int k = 0; k < 3; k++) CELL(i, jj, k) = tab[(i * 3 + jj) * 4 + k];
+			for (int k = 0; k < 3; k++) CELL(i, jj, k) = dk ? tab[(jj * 3 + k) * 4 + i] : tab[(i * 3 + jj) * 4 + k];
 	const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
 	for (int i = 0; i < 3; i++)
 		for (int jj = 0; jj < 3; jj++)

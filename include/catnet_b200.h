@@ -157,6 +157,9 @@ void cnb_host_log(const double *x, int64_t n, double *out);
 /* lexicographic unrank used by the device enumerator (host mirror; catnet_search2.h:102-147 order) */
 int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_t *out);
 int64_t cnb_num_families(const cnb_params *p);
+/* consistency of the tensor-core tiling of the unrestricted two-parent group of N nodes (host only): number of
+ * tiles, or < 0 if family <-> tile slot is not a bijection */
+int64_t cnb_tile_selftest(int32_t num_nodes);
 
 /* ---- result accessors (the catNetwork slots) ---- */
 int32_t cnb_result_num_networks(const cnb_result *r);

@@ -99,3 +99,16 @@ def test_cnsearchsa_argument_clamps(monkeypatch):
     assert sa["select_mode"] == 1 and sorted(sa["start_order"].tolist()) == [1, 2, 3]
     d = sa["dir_prob"]
     assert abs(d[0, 1] - 2.0 / 3.0) < 1e-15 and d[0, 0] == 0.5
+
+
+@pytest.mark.parametrize("n", [3, 4, 9, 29, 63, 64, 65, 66, 127, 128, 129, 200, 500])
+def test_tensor_tiling_is_a_bijection(n):
+    """cnb_tiles.h: every two-parent family of the unrestricted group owns exactly one slot of one tile (F tiles:
+    pairs (a,b) x children; D tiles: pairs (b,c) x first parents), and the slot decodes back to the family"""
+    from catnet_b200 import _abi
+    ntiles = _abi.lib().cnb_tile_selftest(n)
+    assert ntiles > 0, ntiles
+    fam = n * (n - 1) * (n - 2) // 6
+    assert ntiles * 28 * 64 >= fam
+    if n == 500:
+        assert ntiles < 12500          # 15,762 before the diagonal tiles were transposed
