@@ -320,24 +320,49 @@ def main():
     except Exception:
         pass
     if ph_last["tensor_tiles"] > 0:
-        # tcgen05 scorer: bound by the tensor pipe.  Nominal dense rates on B200: bf16 2.25, fp8/int8 4.5, fp4 9 PFLOP/s;
-        # the denominator is the MEASURED sustained bf16 cuBLAS figure scaled by that factor (4 for E2M1 operands with
-        # kind::mxf4, 2 for u8 operands with kind::i8).
+        # tcgen05 scorer: bound by the tensor pipe.  MEASURED_PEAKS.json only has a bf16 cuBLAS figure (nominal dense rates
+        # on B200: bf16 2.25, fp8/int8 4.5, fp4 9 PFLOP/s), and 4 x that figure is EXCEEDED by this kernel, so the
+        # denominator for E2M1 operands is measured here, live, by tools/umma_peak --quick: back-to-back
+        # tcgen05.mma.kind::mxf4 M128 N256 on every SM (the best rate the instruction reaches; the table kernel issues
+        # the A-from-tensor-memory form at N <= 192, whose own ceiling is reported as ts_ceiling).  u8 operands
+        # (kind::i8, test path): 2 x the measured sustained bf16 figure.
         fp4 = ph_last.get("tensor_kind", 8) == 4
-        mult = 4.0 if fp4 else 2.0
         t_ms = float(np.mean([p["tensor_ms"] for p in phases]))
         ops = 2.0 * ph_last["tensor_macs"]
         bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
         ach = ops / (t_ms / 1000.0) / 1e12 if t_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "achieved": ach, "peak": mult * bf16, "unit": "TFLOP/s", "frac": ach / (mult * bf16),
+        extra = {}
+        if fp4:
+            live = None
+            try:
+                if rank == 0:
+                    out = subprocess.run([os.path.join(ROOT, "tools", "umma_peak"), "--quick"], capture_output=True, text=True,
+                                         timeout=60).stdout.strip().splitlines()[-1]
+                    live = json.loads(out)
+            except Exception:
+                live = None
+            if live and "mxf4_ss_n256_tflops" in live:
+                peak = float(live["mxf4_ss_n256_tflops"])
+                extra = {"ts_ceiling": float(live["mxf4_ts_n192_tflops"]), "ts_clk_per_mma": live["mxf4_ts_n192_clk_per_mma"]}
+                src = ("measured live by tools/umma_peak --quick (back-to-back tcgen05.mma kind::mxf4 M128 N256, all SMs); "
+                       "MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
+            else:
+                peak = 8835.9
+                extra = {"ts_ceiling": 8369.2}
+                src = ("tools/umma_peak on this pool, recorded in profiles/r01_umma_peak_b200.txt (the binary did not run "
+                       "here); MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
+        else:
+            peak = 2.0 * bf16
+            src = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 nominal = 2 x bf16)" if peaks
+                   else "2 x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)")
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic,
                     "kernel": "k_umma_tables (tcgen05.mma %s)" % ("kind::mxf4.block_scale" if fp4 else "kind::i8"),
                     "kernel_ms": t_ms, "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
-                    "peak_source": ("%g x bf16_tflops_sustained of MEASURED_PEAKS.json (%s = %gx the bf16 rate on B200)"
-                                    % (mult, "fp4" if fp4 else "int8", mult)) if peaks
-                    else "%g x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)" % mult,
+                    "peak_source": src,
                     "useful_mac_fraction": dom_fam * 27.0 * m / max(ph_last["tensor_macs"], 1),
                     "hbm_model": hbm_model}
+        roofline.update(extra)
     else:
         roofline = {"bound": "hbm", "achieved": hbm_model["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_model["frac"], "traffic": traffic,

@@ -66,10 +66,30 @@ extern "C" int cnb_ctx_create(int32_t device, cnb_ctx **out) {
 	return CNB_OK;
 }
 
+int PinBuf::ensure(size_t bytes) {
+	if (bytes <= cap) return CNB_OK;
+	if (ptr) cudaFreeHost(ptr);
+	ptr = nullptr;
+	cap = 0;
+	if (cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		ptr = nullptr;
+		cnb_set_error("Insufficient memory (pinned host, %zu bytes)", bytes);
+		return CNB_ERR_MEM;
+	}
+	cap = bytes;
+	return CNB_OK;
+}
+void PinBuf::release() {
+	if (ptr) cudaFreeHost(ptr);
+	ptr = nullptr;
+	cap = 0;
+}
+
 extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	c->pin_sel.release();
 	for (DevBuf *b : c->all_bufs()) b->release();
 	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
 	cudaStreamDestroy(c->own_stream);
@@ -481,6 +501,44 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 }
 
 /* ------------------------------------------------------------------ selection + DP ---- */
+/* explicit families sorted by parent count: one launch class per count (fixed d, so the bit-plane / pair-table
+ * kernels apply), tables + log-lik + prior + sample size into the b_ex_* buffers */
+static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, const std::vector<int32_t> &pars,
+		const std::vector<int32_t> &nd, int stride) {
+	size_t n = child.size();
+	RC(upload(c, c->b_ex_child, child));
+	RC(upload(c, c->b_ex_pars, pars));
+	RC(c->b_ex_ll.ensure(n * sizeof(double)));
+	RC(c->b_ex_prior.ensure(n * sizeof(double)));
+	RC(c->b_ex_score.ensure(n * sizeof(double)));
+	RC(c->b_ex_ncount.ensure(n * sizeof(int)));
+	RC(c->b_ex_counts.ensure(n * stride * sizeof(int)));
+	CK(cudaMemsetAsync(c->b_ex_counts.ptr, 0, n * stride * sizeof(int), c->stream));
+	ScoreOut O;
+	memset(&O, 0, sizeof(O));
+	O.scores = (double *)c->b_ex_score.ptr; O.chunk = std::max<long long>(n, 1); O.seg_off = 0; O.seg_len = n;
+	O.loglik = (double *)c->b_ex_ll.ptr;
+	O.prior = (double *)c->b_ex_prior.ptr;
+	O.ncount = (int *)c->b_ex_ncount.ptr;
+	O.counts = (int *)c->b_ex_counts.ptr;
+	O.counts_stride = stride;
+	DevData D = make_devdata(c);
+	for (size_t b = 0; b < n;) {
+		size_t e = b;
+		while (e < n && nd[e] == nd[b]) e++;
+		DevFamilies F;
+		memset(&F, 0, sizeof(F));
+		F.explicit_list = 1;
+		F.d = nd[b];
+		F.nfam = n;
+		F.ex_child = (const int32_t *)c->b_ex_child.ptr;
+		F.ex_pars = (const int32_t *)c->b_ex_pars.ptr;
+		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || nd[b] == 0, true));
+		b = e;
+	}
+	return CNB_OK;
+}
+
 extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
@@ -586,15 +644,21 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	fin.exists = (unsigned char *)c->b_dp_exists.ptr + c->dp_final * slots;
 	fin.L = (double *)c->b_dp_L.ptr + c->dp_final * slots;
 	fin.pfx = (double *)c->b_dp_pfx.ptr + c->dp_final * slots;
-	RC(c->b_sel.ensure(slots * N * sizeof(long long)));
-	RC(cnbk_dp_collect(st, fin, N, (const long long *)c->b_bp_opt.ptr, (const int *)c->b_bp_src.ptr,
-			(long long *)c->b_sel.ptr));
+	/* back-pointer walk for the surviving slots only; the selection table comes back through pinned memory */
+	std::vector<int32_t> live;
+	for (size_t j = 0; j < slots; j++)
+		if (c->h_exists[j]) live.push_back((int32_t)j);
+	const size_t nlive = live.size();
+	RC(c->b_sel.ensure(std::max<size_t>(nlive, 1) * N * sizeof(long long)));
+	RC(upload(c, c->b_sel_slots, live));
+	RC(cnbk_dp_collect_list(st, fin, N, (const long long *)c->b_bp_opt.ptr, (const int *)c->b_bp_src.ptr,
+			(const int *)c->b_sel_slots.ptr, (int)nlive, (long long *)c->b_sel.ptr));
 	c->timing.kernel_launches++;
-	std::vector<long long> sel(slots * N);
-	std::vector<long long> opt_fid((size_t)pl.num_options);
-	D2H(c, sel.data(), c->b_sel.ptr, sel.size() * sizeof(long long));
-	if (pl.num_options)
-		D2H(c, opt_fid.data(), c->b_opt_fid.ptr, opt_fid.size() * sizeof(long long));
+	const size_t nopt = (size_t)pl.num_options;
+	RC(c->pin_sel.ensure(std::max<size_t>((nlive * N + nopt) * sizeof(long long), 16)));
+	const long long *sel = (const long long *)c->pin_sel.ptr, *opt_fid = sel + nlive * N;
+	if (nlive) D2H(c, c->pin_sel.ptr, c->b_sel.ptr, nlive * N * sizeof(long long));
+	if (nopt) D2H(c, (void *)opt_fid, c->b_opt_fid.ptr, nopt * sizeof(long long));
 	CK(cudaStreamSynchronize(st));
 
 	std::unique_ptr<cnb_result> res(new cnb_result());
@@ -603,27 +667,27 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	for (int i = 0; i < N; i++) ord1[i] = pl.order[i] + 1;
 	res->orders.push_back(ord1);
 	res->order_cats.push_back(pl.cats);
-	/* distinct families: key = option index (>= 0) or -(node+1) for a base family */
-	std::map<long long, int> fam_of;
+	/* distinct families: one per option index, one per base family of a node */
+	std::vector<int32_t> fam_of_opt(nopt, -1), fam_of_base(N, -1);
 	std::vector<int32_t> ex_child, ex_pars, ex_nd;
-	auto add_family = [&](long long key, int node) -> int {
-		auto it = fam_of.find(key);
-		if (it != fam_of.end()) return it->second;
+	auto add_family = [&](long long o, int node) -> int {
+		int32_t &slot = o >= 0 ? fam_of_opt[(size_t)o] : fam_of_base[node];
+		if (slot >= 0) return slot;
 		int id = (int)ex_child.size();
-		fam_of[key] = id;
+		slot = id;
 		ex_child.push_back(node);
 		size_t base = ex_pars.size();
 		ex_pars.resize(base + CNB_MAXP, 0);
 		const CnbNodePlan &nd = pl.nodes[node];
-		if (key < 0) {
+		if (o < 0) {
 			ex_nd.push_back(nd.nfix);
 			for (int k = 0; k < nd.nfix; k++) ex_pars[base + k] = pl.lists[nd.fix_off + k];
 		} else {
 			/* option -> block (options of a node are laid out block after block) */
 			int bi = nd.first_blk;
-			while (bi + 1 < nd.first_blk + nd.nblk && pl.blocks[bi + 1].opt_off <= key) bi++;
+			while (bi + 1 < nd.first_blk + nd.nblk && pl.blocks[bi + 1].opt_off <= o) bi++;
 			const CnbBlock &b = pl.blocks[bi];
-			long long r = opt_fid[key] - b.start;
+			long long r = opt_fid[o] - b.start;
 			int idx[CNB_MAXP];
 			cnb_unrank_lex(b.nfree, b.d - b.nfix, r, idx);
 			for (int k = 0; k < b.nfix; k++) ex_pars[base + k] = pl.lists[b.fix_off + k];
@@ -632,16 +696,14 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		}
 		return id;
 	};
-	for (size_t j = 0; j < slots; j++) {
-		if (!c->h_exists[j]) continue;
+	res->nets.reserve(nlive);
+	for (size_t e = 0; e < nlive; e++) {
+		const size_t j = (size_t)live[e];
 		CnbNet net;
 		net.complexity = (int32_t)j;
 		net.loglik = c->h_L[j];
 		net.fam.resize(N);
-		for (int n = 0; n < N; n++) {
-			long long o = sel[j * N + n];
-			net.fam[n] = add_family(o >= 0 ? o : -(long long)(n + 1), n);
-		}
+		for (int n = 0; n < N; n++) net.fam[n] = add_family(sel[e * N + n], n);
 		res->nets.push_back(std::move(net));
 	}
 	size_t nf = ex_child.size();
@@ -649,7 +711,19 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	for (int v : ex_nd) dmax = std::max(dmax, v);
 	int stride = table_stride(c->max_cats, dmax);
 	if (nf) {
-		RC(score_explicit(c, ex_child, ex_pars, ex_nd, -1, stride, true, true));
+		/* tables of the distinct families, grouped by parent count so that each group runs on its fast kernel */
+		std::vector<int32_t> perm(nf), pos(nf);
+		for (size_t f = 0; f < nf; f++) perm[f] = (int32_t)f;
+		std::stable_sort(perm.begin(), perm.end(), [&](int32_t u, int32_t v) { return ex_nd[u] < ex_nd[v]; });
+		std::vector<int32_t> s_child(nf), s_pars(nf * CNB_MAXP), s_nd(nf);
+		for (size_t k = 0; k < nf; k++) {
+			const int32_t f = perm[k];
+			pos[f] = (int32_t)k;
+			s_child[k] = ex_child[f];
+			s_nd[k] = ex_nd[f];
+			for (int q = 0; q < CNB_MAXP; q++) s_pars[k * CNB_MAXP + q] = ex_pars[(size_t)f * CNB_MAXP + q];
+		}
+		RC(score_explicit_groups(c, s_child, s_pars, s_nd, stride));
 		std::vector<int32_t> counts(nf * stride), ncount(nf);
 		std::vector<double> ll(nf), prior(nf);
 		D2H(c, counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int));
@@ -670,10 +744,11 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 				fm.pc[k] = pl.cats[fm.pars[k]];
 				ts *= fm.pc[k];
 			}
-			fm.counts.assign(counts.begin() + f * stride, counts.begin() + f * stride + ts);
-			fm.loglik = ll[f];
-			fm.prior = prior[f];
-			fm.ncount = ncount[f];
+			const size_t k = (size_t)pos[f];              /* where the grouped launch put this family */
+			fm.counts.assign(counts.begin() + k * stride, counts.begin() + k * stride + ts);
+			fm.loglik = ll[k];
+			fm.prior = prior[k];
+			fm.ncount = ncount[k];
 		}
 		c->timing.collect_ms = ev_ms(c, EV_COL0, EV_COL1);
 	}

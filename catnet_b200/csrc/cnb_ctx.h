@@ -20,6 +20,14 @@ struct DevBuf {
 	void release();
 };
 
+/* grow-only page-locked host staging buffer (device -> host results) */
+struct PinBuf {
+	void *ptr = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes);
+	void release();
+};
+
 struct cnb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -37,6 +45,8 @@ struct cnb_ctx {
 	std::vector<double> h_L;
 	CnbPlan plan;
 	cnb_timing timing = {};
+	PinBuf pin_sel;
+	DevBuf b_sel_slots;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
 	/* plan */
@@ -50,7 +60,7 @@ struct cnb_ctx {
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots};
 	}
 };
 

@@ -719,6 +719,20 @@ __global__ void k_dp_collect(DpState fin, int N, const long long *__restrict__ b
 	}
 }
 
+/* same walk for a list of slots only (the surviving ones): sel[e][c] for e-th listed slot */
+__global__ void k_dp_collect_list(DpState fin, int N, const long long *__restrict__ bp_opt, const int *__restrict__ bp_src,
+		const int *__restrict__ slots, int nslots, long long *__restrict__ sel) {
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nslots) return;
+	int jj = slots[e];
+	sel[(size_t)e * N] = -1;
+	for (int c = N - 1; c >= 1; c--) {
+		size_t bpi = (size_t)c * (fin.K + 1) + jj;
+		sel[(size_t)e * N + c] = bp_opt[bpi];
+		jj = bp_src[bpi];
+	}
+}
+
 __global__ void k_device_log(const double *__restrict__ x, long long n, double *__restrict__ out) {
 	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = cnb_log(x[i]);
@@ -890,6 +904,14 @@ int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, in
 int cnbk_dp_collect(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
 		long long *sel) {
 	k_dp_collect<<<(fin.K + 1 + 127) / 128, 128, 0, st>>>(fin, N, bp_opt, bp_src, sel);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_dp_collect_list(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
+		const int *slots, int nslots, long long *sel) {
+	if (nslots <= 0) return CNB_OK;
+	k_dp_collect_list<<<(nslots + 63) / 64, 64, 0, st>>>(fin, N, bp_opt, bp_src, slots, nslots, sel);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -63,5 +63,7 @@ int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, in
 		int *bp_src);
 int cnbk_dp_collect(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
 		long long *sel);
+int cnbk_dp_collect_list(cudaStream_t st, const DpState &fin, int N, const long long *bp_opt, const int *bp_src,
+		const int *slots, int nslots, long long *sel);
 int cnbk_device_log(cudaStream_t st, const double *x, long long n, double *out);
 #endif

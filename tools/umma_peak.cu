@@ -89,7 +89,42 @@ __global__ void __launch_bounds__(128, 1) k_peak(int variant, int N, int iters, 
 	if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-int main() {
+/* --quick: only the two shapes bench.py quotes, as one JSON line */
+static double run_one(int sms, int smem, long long *cyc, int v, int N, int nacc, int iters, double *clk_per_mma) {
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	k_peak<<<sms, 128, smem>>>(v, N, 64, nacc, cyc);
+	cudaEventRecord(e0);
+	k_peak<<<sms, 128, smem>>>(v, N, iters, nacc, cyc);
+	cudaEventRecord(e1);
+	if (cudaDeviceSynchronize() != cudaSuccess) return -1.0;
+	float ms;
+	cudaEventElapsedTime(&ms, e0, e1);
+	long long h[1024];
+	cudaMemcpy(h, cyc, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+	double avg = 0;
+	for (int i = 0; i < sms; i++) avg += (double)h[i];
+	*clk_per_mma = avg / sms / iters;
+	const double kel = v < 2 ? 64.0 : 32.0;
+	return 2.0 * 128.0 * N * kel * iters * sms / (ms * 1e-3) / 1e12;
+}
+
+int main(int argc, char **argv) {
+	if (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 'q') {
+		int sms = 0;
+		cudaSetDevice(0);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+		long long *cyc;
+		cudaMalloc(&cyc, sms * sizeof(long long));
+		const int smem = (128 + 256) * 128 + 1024;
+		cudaFuncSetAttribute(k_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		double c_ss, c_ts;
+		const double ss = run_one(sms, smem, cyc, 0, 256, 1, 16384, &c_ss), ts = run_one(sms, smem, cyc, 1, 192, 2, 16384, &c_ts);
+		if (ss < 0 || ts < 0) { printf("{\"error\": \"cuda\"}\n"); return 1; }
+		printf("{\"mxf4_ss_n256_tflops\": %.1f, \"mxf4_ss_n256_clk_per_mma\": %.2f, \"mxf4_ts_n192_tflops\": %.1f, "
+				"\"mxf4_ts_n192_clk_per_mma\": %.2f, \"sms\": %d}\n", ss, c_ss, ts, c_ts, sms);
+		return 0;
+	}
 	int dev = 0, sms = 0, khz = 0;
 	cudaSetDevice(dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
