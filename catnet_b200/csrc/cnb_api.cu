@@ -334,6 +334,13 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 		ScoreOut O, bool force_generic, bool allow_slicing) {
 	if (e <= b) return CNB_OK;
 	cudaStream_t st = c->stream;
+	if (!force_generic && !F.ex_nd && F.d == 0 && c->pairs_valid) {
+		/* no parents, clean data: marginal counts from the pair tables */
+		c->last_fast = true;
+		RC(cnbk_score_pairs1(c->stream, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
+		c->timing.kernel_launches++;
+		return CNB_OK;
+	}
 	bool fast = !force_generic && !F.ex_nd && cnbk_planes_supported(F.d, c->max_cats);
 	c->last_fast = fast;
 	if (fast) {
@@ -496,7 +503,7 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 	int dmax = fixed_d;
 	if (var_d) { dmax = 0; for (int v : nd) dmax = std::max(dmax, v); }
 	DevData D = make_devdata(c);
-	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || fixed_d == 0, false));
+	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || (fixed_d == 0 && !c->pairs_valid), false));
 	return CNB_OK;
 }
 
@@ -533,7 +540,7 @@ static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, 
 		F.nfam = n;
 		F.ex_child = (const int32_t *)c->b_ex_child.ptr;
 		F.ex_pars = (const int32_t *)c->b_ex_pars.ptr;
-		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || nd[b] == 0, true));
+		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || (nd[b] == 0 && !c->pairs_valid), true));
 		b = e;
 	}
 	return CNB_OK;
@@ -554,7 +561,10 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 			nd[i] = pl.nodes[i].nfix;
 			for (int k = 0; k < nd[i]; k++) pars[(size_t)i * CNB_MAXP + k] = pl.lists[pl.nodes[i].fix_off + k];
 		}
-		RC(score_explicit(c, child, pars, nd, -1, 0, false, true));
+		bool no_fixed = true;
+		for (int i = 0; i < N; i++) no_fixed = no_fixed && nd[i] == 0;
+		if (no_fixed && c->pairs_valid && !c->force_generic) RC(score_explicit(c, child, pars, nd, 0, 0, false, false));
+		else RC(score_explicit(c, child, pars, nd, -1, 0, false, true));
 		RC(c->b_base_v.ensure(N * sizeof(double)));
 		CK(cudaMemcpyAsync(c->b_base_v.ptr, c->b_ex_score.ptr, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	}

@@ -360,6 +360,29 @@ __global__ void __launch_bounds__(128) k_score_pairs1(DevData Dt, DevFamilies F,
 	dev_store_outputs(Dt, O, fid, child, pars, 1, ll, ncount);
 }
 
+/* Families without parents on clean data: the marginal counts are row sums of any two-way table of the node. */
+__global__ void __launch_bounds__(128) k_score_pairs0(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		ScoreOut O, const int *__restrict__ pair_tab) {
+	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	dev_family(Dt, F, fid, child, pars);
+	const int lc = Dt.order[child], lo = lc == 0 ? 1 : 0, cc = Dt.cats[child];
+	int marg[CNB_PLANE_CATS];
+	for (int k = 0; k < CNB_PLANE_CATS; k++) {
+		int s = 0;
+		for (int i = 0; i < CNB_PLANE_CATS; i++) s += pair_count(pair_tab, lo, lc, i, k);
+		marg[k] = s;
+	}
+	int ncount;
+	double ll = dev_loglik(1, cc, [&](int, int k) { return marg[k]; }, &ncount);
+	if (O.counts) {
+		int *tab = O.counts + (size_t)fid * O.counts_stride;
+		for (int k = 0; k < cc; k++) tab[k] = marg[k];
+	}
+	dev_store_outputs(Dt, O, fid, child, pars, 0, ll, ncount);
+}
+
 /* epilogue over tables already in global memory (split-sample mode): one thread per family */
 __global__ void k_epilogue_counts(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end, ScoreOut O) {
 	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -627,10 +650,33 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 		s0.L[j] = l;
 		s0.pfx[j] = ex ? __dadd_rn(0.0, base_v[0]) : 0.0;
 	}
+	/* the node's arguments and its first four options do not depend on the DP state: they are fetched one node ahead,
+	 * behind the grid barrier */
+	CnbDpNode nd_n = nodes[N > 1 ? 1 : 0];
+	long long pf_fid[4];
+	int pf_cx[4];
+	double pf_sc[4];
+#define DP_PREFETCH(node) { \
+		_Pragma("unroll") for (int q = 0; q < 4; q++) { \
+			const long long o = (node).opt_begin + q; \
+			const bool in = o < (node).opt_end; \
+			pf_fid[q] = in ? opt_fid[o] : -1; \
+			pf_cx[q] = in ? opt_cx[o] : 0; \
+			pf_sc[q] = in ? opt_score[o] : 0.0; } }
+	DP_PREFETCH(nd_n)
 	grid.sync();
 	for (int c = 1; c < N; c++) {
 		const DpState &cur = (c & 1) ? s0 : s1, &nxt = (c & 1) ? s1 : s0;
-		const CnbDpNode nd = nodes[c];
+		const CnbDpNode nd = nd_n;
+		long long o_fid[4];
+		int o_cx[4];
+		double o_sc[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) { o_fid[q] = pf_fid[q]; o_cx[q] = pf_cx[q]; o_sc[q] = pf_sc[q]; }
+		if (c + 1 < N) {
+			nd_n = nodes[c + 1];
+			DP_PREFETCH(nd_n)
+		}
 		const double bv = sbase[c];
 		const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
 		for (int j = t0; j <= K; j += nthr) {
@@ -638,26 +684,36 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 			double R = CNB_NEG_INF;
 			long long bo = -1;
 			int bs = -1;
+			double bf = 0.0;
 			if (nopt <= 4) {
 				/* few options (one per parent count on the equal-categories path): the re-summations, chains of
-				 * N - c dependent fp64 adds, run side by side for all of them before the sequential decision */
-				double acc[4] = {0.0, 0.0, 0.0, 0.0}, t[4];
-				int ks[4];
-				bool ok[4] = {false, false, false, false}, any = false;
+				 * N - c dependent fp64 adds, run side by side for the viable ones (compacted to the front, as many
+				 * chains as the busiest lane of the warp needs) before the sequential decision */
+				double acc[4] = {0.0, 0.0, 0.0, 0.0}, t[4] = {0.0, 0.0, 0.0, 0.0}, fs[4] = {0.0, 0.0, 0.0, 0.0};
+				int ks[4] = {0, 0, 0, 0}, qs[4] = {0, 0, 0, 0}, nq = 0;
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
-					if (q >= nopt) continue;
-					const long long o = nd.opt_begin + q;
-					if (opt_fid[o] < 0) continue;
-					const int k = j + nd.base_cx - opt_cx[o];
+					if (q >= nopt || o_fid[q] < 0) continue;            /* no winner for that d (:637-640) */
+					const int k = j + nd.base_cx - o_cx[q];
 					if (k < 0 || k > K || !cur.exists[k]) continue;
-					const double f = opt_score[o];
-					ok[q] = any = true;
-					ks[q] = k;
-					t[q] = __dadd_rn(__dsub_rn(cur.L[k], bv), f);
-					acc[q] = __dadd_rn(cur.pfx[k], f);
+					const double f = o_sc[q];
+					ks[nq] = k;
+					qs[nq] = q;
+					fs[nq] = f;
+					t[nq] = __dadd_rn(__dsub_rn(cur.L[k], bv), f);      /* :665-666 */
+					acc[nq] = __dadd_rn(cur.pfx[k], f);
+					nq++;
 				}
-				if (any)
+				const int nqmax = __reduce_max_sync(__activemask(), nq);
+				if (nqmax == 1)
+					for (int i = c + 1; i < N; i++) acc[0] = __dadd_rn(acc[0], sbase[i]);
+				else if (nqmax == 2)
+					for (int i = c + 1; i < N; i++) {
+						const double b = sbase[i];
+						acc[0] = __dadd_rn(acc[0], b);
+						acc[1] = __dadd_rn(acc[1], b);
+					}
+				else if (nqmax > 2)
 					for (int i = c + 1; i < N; i++) {
 						const double b = sbase[i];
 #pragma unroll
@@ -665,9 +721,9 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 					}
 #pragma unroll
 				for (int q = 0; q < 4; q++) {
-					if (!ok[q]) continue;
-					if (!has && t[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }
-					if (has && R < t[q]) { bo = nd.opt_begin + q; bs = ks[q]; R = acc[q]; }
+					if (q >= nq) continue;
+					if (!has && t[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+					if (has && R < t[q]) { bo = nd.opt_begin + qs[q]; bs = ks[q]; R = acc[q]; bf = fs[q]; }   /* :670-671 strict */
 				}
 			} else
 			for (long long o = nd.opt_begin; o < nd.opt_end; o++) {
@@ -681,6 +737,7 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 					bo = o;
 					bs = k;
 					R = dev_resum(cur.pfx[k], f, c, N, sbase);
+					bf = f;
 				}
 			}
 			bool take = false;
@@ -690,7 +747,7 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 			if (take) {
 				nxt.exists[j] = 1;
 				nxt.L[j] = R;
-				nxt.pfx[j] = __dadd_rn(cur.pfx[bs], opt_score[bo]);
+				nxt.pfx[j] = __dadd_rn(cur.pfx[bs], bf);
 				bp_opt[bpi] = bo;
 				bp_src[bpi] = bs;
 			} else {
@@ -703,6 +760,7 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 		}
 		grid.sync();
 	}
+#undef DP_PREFETCH
 }
 
 /* walk the back-pointers of every surviving slot: sel[j][c] = option chosen for node c (-1 = base family) */
@@ -831,8 +889,9 @@ int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies 
 int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
 		const ScoreOut &O, const int *pair_tab) {
 	if (e <= b) return CNB_OK;
-	if (F.d != 1 || max_cats > 4 || !pair_tab) { cnb_set_error("pair-table scorer: unsupported launch"); return CNB_ERR_PROC; }
-	k_score_pairs1<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	if (F.d > 1 || max_cats > 4 || !pair_tab) { cnb_set_error("pair-table scorer: unsupported launch"); return CNB_ERR_PROC; }
+	if (F.d == 0) k_score_pairs0<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	else k_score_pairs1<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
