@@ -381,11 +381,17 @@ def main():
         ctx2.set_stream(stream.cuda_stream)
         L = _abi.lib()
 
-        wall = {"set_samples_ms": 0.0, "plan_score_ms": 0.0, "finish_ms": 0.0}
+        wall = {"set_samples_ms": 0.0, "plan_score_ms": 0.0, "finish_ms": 0.0, "h2d_bytes": 0}
 
         def e2e_step():
             t_a = time.perf_counter()
-            ctx2.set_samples(hnp, num_cats=wl["cats"])           # H2D + pack + pair tables; returns synchronised
+            if world == 1:
+                ctx2.set_samples(hnp, num_cats=wl["cats"])       # H2D + pack + pair tables; returns synchronised
+            else:
+                # every rank copies 1/world of the host matrix, NVLink all-gather, pack (catnet_b200/dist.py)
+                from catnet_b200 import dist as cdist
+                _, nb = cdist.set_samples_sharded(ctx2, host, rank, world, dev, num_cats=wl["cats"])
+                wall["h2d_bytes"] = nb
             t_b = time.perf_counter()
             ctx2.plan(rank, world, **kw)
             ctx2.score_shard(scores.data_ptr())
@@ -406,7 +412,7 @@ def main():
 
         e2e_step()
         barrier()
-        for k_ in wall:
+        for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms"):
             wall[k_] = 0.0
         e_steps = max(1, min(args.steps, 3))
         ev0.record(stream)
@@ -421,9 +427,10 @@ def main():
         ems = float(t_ms.item())
         tm = ctx2.timing()
         e2e = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s",
-               "h2d_bytes_per_step": int(tm["h2d_bytes"]) * world, "d2h_bytes_per_step": int(tm["d2h_bytes"]) * world,
+               "h2d_bytes_per_step": (int(tm["h2d_bytes"]) + int(wall["h2d_bytes"])) * world,
+               "d2h_bytes_per_step": int(tm["d2h_bytes"]) * world,
                "ms_per_step": ems / e_steps, "steps": e_steps,
-               "host_wall_ms_per_step": {k_: v_ / e_steps for k_, v_ in wall.items()},
+               "host_wall_ms_per_step": {k_: wall[k_] / e_steps for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms")},
                "device_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
                "result": {"networks": res[0], "max_complexity": res[1], "loglik": res[2]}}
         ctx2.close()

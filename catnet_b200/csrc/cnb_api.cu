@@ -112,6 +112,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	c->Mpad = c->W * 32;
 	c->has_pert = pert_dev != nullptr;
 	c->planned = false;
+	if (!c->in_host_set) c->timing.h2d_bytes = c->timing.d2h_bytes = 0;   /* traffic is counted per data set */
 	cudaStream_t st = c->stream;
 	CK(cudaEventRecord(c->ev[EV_PACK0], st));
 	RC(c->b_vmin.ensure(N * sizeof(int)));
@@ -190,8 +191,11 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 		if (e != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; }
 		c->timing.h2d_bytes += (int64_t)bytes * (pert ? 2 : 1);
 	}
-	if (rc == CNB_OK)
+	if (rc == CNB_OK) {
+		c->in_host_set = true;
 		rc = cnb_ctx_set_samples_dev(c, N, M, (const int32_t *)tmp_s.ptr, pert ? (const int32_t *)tmp_p.ptr : nullptr, num_cats);
+		c->in_host_set = false;
+	}
 	cudaStreamSynchronize(c->stream);
 	tmp_s.release();
 	tmp_p.release();
@@ -218,6 +222,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->tensor_mode = (on & 4) ? 1 : ((on & 8) ? -1 : 0);   /* bit 2: tensor-core path whenever applicable; bit 3: never */
 	c->tensor_i8 = (on & 16) ? 1 : 0;                      /* bit 4: u8 operands (kind::i8) instead of E2M1 (kind::mxf4) */
 	c->dp_per_node = (on & 32) != 0;                       /* bit 5: one DP launch per node (no cooperative kernel) */
+	c->dp_no_wave = (on & 64) != 0;                        /* bit 6: grid-barrier DP kernel instead of the wavefront one */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -579,13 +584,13 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	CK(cudaEventRecord(c->ev[EV_SEL1], st));
 	/* DP state, double buffered */
 	size_t slots = (size_t)K + 1;
-	RC(c->b_dp_exists.ensure(2 * slots));
-	RC(c->b_dp_L.ensure(2 * slots * sizeof(double)));
-	RC(c->b_dp_pfx.ensure(2 * slots * sizeof(double)));
+	RC(c->b_dp_exists.ensure(3 * slots));
+	RC(c->b_dp_L.ensure(3 * slots * sizeof(double)));
+	RC(c->b_dp_pfx.ensure(3 * slots * sizeof(double)));
 	RC(c->b_bp_opt.ensure((size_t)N * slots * sizeof(long long)));
 	RC(c->b_bp_src.ensure((size_t)N * slots * sizeof(int)));
-	DpState S[2];
-	for (int i = 0; i < 2; i++) {
+	DpState S[3];
+	for (int i = 0; i < 3; i++) {
 		S[i].K = K;
 		S[i].exists = (unsigned char *)c->b_dp_exists.ptr + i * slots;
 		S[i].L = (double *)c->b_dp_L.ptr + i * slots;
@@ -593,14 +598,37 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	}
 	const double *base_v = (const double *)c->b_base_v.ptr;
 	int cur = 0;
-	/* all nodes in one cooperative launch (grid barrier per node); one launch per node if that is refused */
-	int fused = c->dp_per_node ? CNB_ERR_PROC
-			: cnbk_dp_all(st, S[0], S[1], N, pl.base_complexity, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
+	/* All nodes in one cooperative launch: as a wavefront over CTAs of 256 slots when no option reaches further left
+	 * than that (an option moves a network by its extra complexity, at most (C - 1) * maxC^d slots), else with a grid
+	 * barrier per node; one launch per node if cooperative launches are refused. */
+	int halo = 0;
+	for (const CnbBlock &bk : pl.blocks) {
+		long long reach = pl.cats[bk.child] - 1;
+		for (int k = 0; k < bk.d && reach <= 4096; k++) reach *= c->max_cats;
+		halo = (int)std::max<long long>(halo, std::min<long long>(reach, 1 << 20));
+	}
+	const int flag_cap = 4096;
+	RC(c->b_dp_flags.ensure(flag_cap * sizeof(unsigned)));
+	int fused = CNB_ERR_PROC;
+	if (!c->dp_per_node && !c->dp_no_wave) {
+		fused = cnbk_dp_wave(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
+				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap);
+		if (fused == CNB_OK) {
+			cur = (N - 1) % 3;                /* step c reads S[(c - 1) % 3] and writes S[c % 3] */
+			c->timing.kernel_launches += 1;
+		}
+	}
+	if (fused == CNB_ERR_PROC && !c->dp_per_node) {
+		fused = cnbk_dp_all(st, S[0], S[1], N, pl.base_complexity, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
 				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
 				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr);
+		if (fused == CNB_OK) {
+			cur = (N - 1) & 1;                /* node c reads S[(c & 1) ^ 1] and writes S[c & 1] */
+			c->timing.kernel_launches += 1;
+		}
+	}
 	if (fused == CNB_OK) {
-		cur = (N - 1) & 1;                /* node c reads S[(c & 1) ^ 1] and writes S[c & 1] */
-		c->timing.kernel_launches += 1;
 	} else if (fused == CNB_ERR_PROC) {
 		RC(cnbk_dp_init(st, S[0], pl.base_complexity, base_v, N));
 		for (int n = 1; n < N; n++) {

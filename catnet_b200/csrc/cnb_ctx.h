@@ -37,6 +37,8 @@ struct cnb_ctx {
 	int tensor_mode = 0;               /* 0 auto (large M), 1 always when applicable, -1 never */
 	int tensor_i8 = 0;                 /* 1: kind::i8 operands instead of kind::mxf4 (test hook) */
 	bool dp_per_node = false;          /* one DP launch per node instead of the fused cooperative kernel (test hook) */
+	bool in_host_set = false;          /* cnb_ctx_set_samples is calling cnb_ctx_set_samples_dev (keeps its H2D count) */
+	bool dp_no_wave = false;           /* grid-barrier DP kernel instead of the wavefront one (test hook) */
 	int dp_final = 0, tensor_batches = 0;
 	std::vector<int32_t> cats_lbl;
 	std::vector<int32_t> blk_equal;
@@ -54,13 +56,13 @@ struct cnb_ctx {
 	/* scoring */
 	DevBuf b_scores, b_counts, b_ex_child, b_ex_pars, b_ex_nd, b_ex_ll, b_ex_prior, b_ex_score, b_ex_ncount, b_ex_counts;
 	/* selection + DP */
-	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes;
+	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes, b_dp_flags;
 	std::vector<DevBuf *> all_bufs() {
 		return {&b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags};
 	}
 };
 

@@ -631,6 +631,109 @@ __global__ void __launch_bounds__(128) k_dp_node(DpState cur, DpState nxt, int c
 	}
 }
 
+/* One target slot j of node c (shared by the two fused DP kernels).  CG = loads of the previous state bypass L1
+ * (another CTA wrote them during this launch). */
+template <bool CG> __device__ __forceinline__ double dp_ld(const double *p) { return CG ? __ldcg(p) : *p; }
+template <bool CG> __device__ __forceinline__ unsigned char dp_ld(const unsigned char *p) { return CG ? __ldcg(p) : *p; }
+
+template <bool CG>
+__device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, int j, int c, int N, int K,
+		const CnbDpNode &nd, int nopt, const long long (&o_fid)[4], const int (&o_cx)[4], const double (&o_sc)[4],
+		const double *sbase, double bv, const double *__restrict__ opt_score, const int *__restrict__ opt_cx,
+		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src) {
+	bool has = false;
+	double R = CNB_NEG_INF;
+	long long bo = -1;
+	int bs = -1;
+	double bf = 0.0;
+	if (nopt <= 4) {
+		/* few options (one per parent count on the equal-categories path): the re-summations, chains of
+		 * N - c dependent fp64 adds, run side by side for the viable ones (compacted to the front, as many
+		 * chains as the busiest lane of the warp needs) before the sequential decision */
+		double acc[4] = {0.0, 0.0, 0.0, 0.0}, t[4] = {0.0, 0.0, 0.0, 0.0}, fs[4] = {0.0, 0.0, 0.0, 0.0};
+		int ks[4] = {0, 0, 0, 0}, qs[4] = {0, 0, 0, 0}, nq = 0;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if (q >= nopt || o_fid[q] < 0) continue;            /* no winner for that d (:637-640) */
+			const int k = j + nd.base_cx - o_cx[q];
+			if (k < 0 || k > K || !dp_ld<CG>(cur.exists + k)) continue;
+			const double f = o_sc[q];
+			ks[nq] = k;
+			qs[nq] = q;
+			fs[nq] = f;
+			t[nq] = __dadd_rn(__dsub_rn(dp_ld<CG>(cur.L + k), bv), f);      /* :665-666 */
+			acc[nq] = __dadd_rn(dp_ld<CG>(cur.pfx + k), f);
+			nq++;
+		}
+		const int nqmax = __reduce_max_sync(__activemask(), nq);
+		/* the terms are fetched 8 ahead of the dependent adds (shared-memory latency off the chain) */
+#define DP_CHAIN(NQ) { \
+			int i = c + 1; \
+			for (; i + 8 <= N; i += 8) { \
+				double b[8]; \
+				_Pragma("unroll") for (int u = 0; u < 8; u++) b[u] = sbase[i + u]; \
+				_Pragma("unroll") for (int u = 0; u < 8; u++) \
+					_Pragma("unroll") for (int q = 0; q < NQ; q++) acc[q] = __dadd_rn(acc[q], b[u]); \
+			} \
+			for (; i < N; i++) { \
+				const double b = sbase[i]; \
+				_Pragma("unroll") for (int q = 0; q < NQ; q++) acc[q] = __dadd_rn(acc[q], b); \
+			} }
+		if (nqmax == 1) DP_CHAIN(1)
+		else if (nqmax == 2) DP_CHAIN(2)
+		else if (nqmax > 2) DP_CHAIN(4)
+#undef DP_CHAIN
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			if (q >= nq) continue;
+			if (!has && t[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+			if (has && R < t[q]) { bo = nd.opt_begin + qs[q]; bs = ks[q]; R = acc[q]; bf = fs[q]; }   /* :670-671 strict */
+		}
+	} else
+		for (long long o = nd.opt_begin; o < nd.opt_end; o++) {
+			if (opt_fid[o] < 0) continue;                       /* no winner for that d (:637-640) */
+			int k = j + nd.base_cx - opt_cx[o];
+			if (k < 0 || k > K || !dp_ld<CG>(cur.exists + k)) continue;
+			double f = opt_score[o];
+			double t = __dadd_rn(__dsub_rn(dp_ld<CG>(cur.L + k), bv), f);  /* :665-666 */
+			if (!has && t > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+			if (has && R < t) {                                  /* :670-671 strict */
+				bo = o;
+				bs = k;
+				R = dev_resum(dp_ld<CG>(cur.pfx + k), f, c, N, sbase);
+				bf = f;
+			}
+		}
+	const bool cur_ex = dp_ld<CG>(cur.exists + j) != 0;
+	bool take = false;
+	if (cur_ex) take = has && bo >= 0 && dp_ld<CG>(cur.L + j) < R;   /* :847-859 */
+	else take = has && bo >= 0;
+	size_t bpi = (size_t)c * (K + 1) + j;
+	if (take) {
+		nxt.exists[j] = 1;
+		nxt.L[j] = R;
+		nxt.pfx[j] = __dadd_rn(dp_ld<CG>(cur.pfx + bs), bf);
+		bp_opt[bpi] = bo;
+		bp_src[bpi] = bs;
+	} else {
+		nxt.exists[j] = cur_ex;
+		nxt.L[j] = dp_ld<CG>(cur.L + j);
+		nxt.pfx[j] = __dadd_rn(dp_ld<CG>(cur.pfx + j), bv);
+		bp_opt[bpi] = -1;
+		bp_src[bpi] = j;
+	}
+}
+
+/* the node's arguments and its first four options do not depend on the DP state: both fused kernels fetch them one
+ * node ahead, behind the barrier */
+#define DP_PREFETCH(node) { \
+		_Pragma("unroll") for (int q = 0; q < 4; q++) { \
+			const long long o = (node).opt_begin + q; \
+			const bool in = o < (node).opt_end; \
+			pf_fid[q] = in ? opt_fid[o] : -1; \
+			pf_cx[q] = in ? opt_cx[o] : 0; \
+			pf_sc[q] = in ? opt_score[o] : 0.0; } }
+
 /* The same recurrence for every node in ONE cooperative launch (grid barrier between nodes) instead of N - 1
  * launches: at C5 the 499 launches cost 7 ms, which is a quarter of an 8-GPU step. */
 __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, int base_complexity,
@@ -650,19 +753,10 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 		s0.L[j] = l;
 		s0.pfx[j] = ex ? __dadd_rn(0.0, base_v[0]) : 0.0;
 	}
-	/* the node's arguments and its first four options do not depend on the DP state: they are fetched one node ahead,
-	 * behind the grid barrier */
 	CnbDpNode nd_n = nodes[N > 1 ? 1 : 0];
 	long long pf_fid[4];
 	int pf_cx[4];
 	double pf_sc[4];
-#define DP_PREFETCH(node) { \
-		_Pragma("unroll") for (int q = 0; q < 4; q++) { \
-			const long long o = (node).opt_begin + q; \
-			const bool in = o < (node).opt_end; \
-			pf_fid[q] = in ? opt_fid[o] : -1; \
-			pf_cx[q] = in ? opt_cx[o] : 0; \
-			pf_sc[q] = in ? opt_score[o] : 0.0; } }
 	DP_PREFETCH(nd_n)
 	grid.sync();
 	for (int c = 1; c < N; c++) {
@@ -677,91 +771,79 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 			nd_n = nodes[c + 1];
 			DP_PREFETCH(nd_n)
 		}
-		const double bv = sbase[c];
 		const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
-		for (int j = t0; j <= K; j += nthr) {
-			bool has = false;
-			double R = CNB_NEG_INF;
-			long long bo = -1;
-			int bs = -1;
-			double bf = 0.0;
-			if (nopt <= 4) {
-				/* few options (one per parent count on the equal-categories path): the re-summations, chains of
-				 * N - c dependent fp64 adds, run side by side for the viable ones (compacted to the front, as many
-				 * chains as the busiest lane of the warp needs) before the sequential decision */
-				double acc[4] = {0.0, 0.0, 0.0, 0.0}, t[4] = {0.0, 0.0, 0.0, 0.0}, fs[4] = {0.0, 0.0, 0.0, 0.0};
-				int ks[4] = {0, 0, 0, 0}, qs[4] = {0, 0, 0, 0}, nq = 0;
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					if (q >= nopt || o_fid[q] < 0) continue;            /* no winner for that d (:637-640) */
-					const int k = j + nd.base_cx - o_cx[q];
-					if (k < 0 || k > K || !cur.exists[k]) continue;
-					const double f = o_sc[q];
-					ks[nq] = k;
-					qs[nq] = q;
-					fs[nq] = f;
-					t[nq] = __dadd_rn(__dsub_rn(cur.L[k], bv), f);      /* :665-666 */
-					acc[nq] = __dadd_rn(cur.pfx[k], f);
-					nq++;
-				}
-				const int nqmax = __reduce_max_sync(__activemask(), nq);
-				if (nqmax == 1)
-					for (int i = c + 1; i < N; i++) acc[0] = __dadd_rn(acc[0], sbase[i]);
-				else if (nqmax == 2)
-					for (int i = c + 1; i < N; i++) {
-						const double b = sbase[i];
-						acc[0] = __dadd_rn(acc[0], b);
-						acc[1] = __dadd_rn(acc[1], b);
-					}
-				else if (nqmax > 2)
-					for (int i = c + 1; i < N; i++) {
-						const double b = sbase[i];
-#pragma unroll
-						for (int q = 0; q < 4; q++) acc[q] = __dadd_rn(acc[q], b);
-					}
-#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					if (q >= nq) continue;
-					if (!has && t[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
-					if (has && R < t[q]) { bo = nd.opt_begin + qs[q]; bs = ks[q]; R = acc[q]; bf = fs[q]; }   /* :670-671 strict */
-				}
-			} else
-			for (long long o = nd.opt_begin; o < nd.opt_end; o++) {
-				if (opt_fid[o] < 0) continue;                       /* no winner for that d (:637-640) */
-				int k = j + nd.base_cx - opt_cx[o];
-				if (k < 0 || k > K || !cur.exists[k]) continue;
-				double f = opt_score[o];
-				double t = __dadd_rn(__dsub_rn(cur.L[k], bv), f);  /* :665-666 */
-				if (!has && t > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
-				if (has && R < t) {                                  /* :670-671 strict */
-					bo = o;
-					bs = k;
-					R = dev_resum(cur.pfx[k], f, c, N, sbase);
-					bf = f;
-				}
-			}
-			bool take = false;
-			if (cur.exists[j]) take = has && bo >= 0 && cur.L[j] < R;   /* :847-859 */
-			else take = has && bo >= 0;
-			size_t bpi = (size_t)c * (K + 1) + j;
-			if (take) {
-				nxt.exists[j] = 1;
-				nxt.L[j] = R;
-				nxt.pfx[j] = __dadd_rn(cur.pfx[bs], bf);
-				bp_opt[bpi] = bo;
-				bp_src[bpi] = bs;
-			} else {
-				nxt.exists[j] = cur.exists[j];
-				nxt.L[j] = cur.L[j];
-				nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
-				bp_opt[bpi] = -1;
-				bp_src[bpi] = j;
-			}
-		}
+		for (int j = t0; j <= K; j += nthr)
+			dp_slot<false>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid, bp_opt, bp_src);
 		grid.sync();
 	}
-#undef DP_PREFETCH
 }
+
+/* Wavefront version.  An option only ever looks LEFT, at slot j - (option complexity - base complexity), and by at
+ * most `halo` <= 256 slots: a CTA that owns 256 consecutive slots needs, for node c, its own slots and its left
+ * neighbour's of node c - 1.  So instead of a grid barrier per node every CTA waits for its left neighbour's progress
+ * counter (flags[b] = steps finished; step 0 = initialisation, step c = node c) and the CTAs run as a diagonal
+ * wavefront.  Three state buffers: step c writes S[c % 3], which the RIGHT neighbour last read during its step
+ * c - 2, hence the second, rarely blocking wait.  All CTAs are co-resident (cooperative launch). */
+__device__ __forceinline__ unsigned dp_flag_load(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__global__ void __launch_bounds__(256) k_dp_wave(DpState s0, DpState s1, DpState s2, int N, int base_complexity,
+		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
+		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
+		int *__restrict__ bp_src, unsigned *flags) {
+	extern __shared__ double sbase[];
+	const int K = s0.K, b = blockIdx.x, nb = gridDim.x, j = b * blockDim.x + threadIdx.x;
+	const bool mine = j <= K;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) sbase[i] = base_v[i];
+	__syncthreads();
+	if (mine) {
+		bool ex = (j == base_complexity);
+		double l = 0.0;
+		if (ex) for (int i = 0; i < N; i++) l = __dadd_rn(l, sbase[i]);
+		s0.exists[j] = ex;
+		s0.L[j] = l;
+		s0.pfx[j] = ex ? __dadd_rn(0.0, sbase[0]) : 0.0;
+	}
+	CnbDpNode nd_n = nodes[N > 1 ? 1 : 0];
+	long long pf_fid[4];
+	int pf_cx[4];
+	double pf_sc[4];
+	DP_PREFETCH(nd_n)
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicExch(&flags[b], 1u);
+	}
+	for (int c = 1; c < N; c++) {
+		const DpState &cur = c % 3 == 1 ? s0 : (c % 3 == 2 ? s1 : s2), &nxt = c % 3 == 1 ? s1 : (c % 3 == 2 ? s2 : s0);
+		const CnbDpNode nd = nd_n;
+		long long o_fid[4];
+		int o_cx[4];
+		double o_sc[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) { o_fid[q] = pf_fid[q]; o_cx[q] = pf_cx[q]; o_sc[q] = pf_sc[q]; }
+		if (c + 1 < N) {
+			nd_n = nodes[c + 1];
+			DP_PREFETCH(nd_n)
+		}
+		if (threadIdx.x == 0) {
+			if (b > 0) while (dp_flag_load(&flags[b - 1]) < (unsigned)c) { }
+			if (b + 1 < nb) while (dp_flag_load(&flags[b + 1]) + 1 < (unsigned)c) { }
+		}
+		__syncthreads();
+		const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
+		if (mine)
+			dp_slot<true>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid, bp_opt, bp_src);
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			atomicExch(&flags[b], (unsigned)c + 1u);
+		}
+	}
+}
+#undef DP_PREFETCH
 
 /* walk the back-pointers of every surviving slot: sel[j][c] = option chosen for node c (-1 = base family) */
 __global__ void k_dp_collect(DpState fin, int N, const long long *__restrict__ bp_opt, const int *__restrict__ bp_src,
@@ -957,6 +1039,27 @@ int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, in
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
 		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_all, dim3(blocks), dim3(256), args, smem, st));
+	return CNB_OK;
+}
+
+/* wavefront DP: needs one slot per thread in co-resident CTAs and options that look at most 256 slots left;
+ * CNB_ERR_PROC (nothing launched) otherwise.  flags: gridDim.x counters, zeroed here. */
+int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
+		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
+		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap) {
+	int dev = 0, coop = 0, sms = 0, per_sm = 0;
+	CK(cudaGetDevice(&dev));
+	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	const size_t smem = (size_t)N * sizeof(double);
+	if (smem > 48 * 1024 || halo > 256 || halo < 0) return CNB_ERR_PROC;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_wave, 256, smem));
+	const int blocks = (s0.K + 1 + 255) / 256;
+	if (!coop || per_sm < 1 || blocks > sms * per_sm || blocks > flags_cap) return CNB_ERR_PROC;
+	CK(cudaMemsetAsync(flags, 0, (size_t)blocks * sizeof(unsigned), st));
+	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
+		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags};
+	CK(cudaLaunchCooperativeKernel((const void *)k_dp_wave, dim3(blocks), dim3(256), args, smem, st));
 	return CNB_OK;
 }
 

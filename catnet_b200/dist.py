@@ -4,8 +4,14 @@
 Score buffer layout (cnb_ctx_plan / dev_score_index in csrc/cnb_device.cuh): rank-major.  Each group g (= all
 candidate sets with the same parent count) of nfam_g families is cut into `world` contiguous chunks of
 chunk_g = ceil(nfam_g / world); rank r's segment holds its chunk of every group back to back (seg_len = sum chunk_g),
-so one all_gather_into_tensor of equal-sized segments completes the buffer.  cnSearchSA runs one independent chain
-per rank and merges them per complexity like R's .searchSA (R/catnet.search.R:317-332).
+so one all_gather_into_tensor of equal-sized segments completes the buffer.  The two-parent group, when it runs on
+the tensor cores, is dealt tile by tile instead (tile t -> rank t % world, csrc/cnb_tiles.h): its chunk is
+ceil(ntiles / world) tiles of 28 x 64 score slots.  cnSearchSA runs one independent chain per rank and merges them
+per complexity like R's .searchSA (R/catnet.search.R:317-332).
+
+The sample matrix is replicated on every GPU.  When it starts in HOST memory (the R-facing call), every rank copies
+only its 1/world of the samples over PCIe and the ranks complete each other's copy with one all-gather over NVLink
+(set_samples_sharded): the host-to-device time divides by the number of GPUs instead of multiplying the PCIe load.
 """
 import numpy as np
 
@@ -34,6 +40,25 @@ def gather_scores(scores, rank, world, seg_len, group=None):
         return scores
     dist.all_gather_into_tensor(scores, scores[rank * seg_len:(rank + 1) * seg_len].clone(), group=group)
     return scores
+
+
+def set_samples_sharded(ctx, host_samples, rank, world, device, num_cats=None, group=None):
+    """host_samples: torch int32 [M][N] CPU tensor (pinned for speed), identical on every rank.  Rank r copies rows
+    [r*ceil(M/world), (r+1)*ceil(M/world)) to its GPU, one all_gather_into_tensor over NVLink completes the matrix on
+    every GPU, then the matrix is packed (cnb_ctx_set_samples_dev).  Returns (device tensor, bytes copied H2D)."""
+    import torch
+    import torch.distributed as dist
+    m, n = host_samples.shape
+    rows = (m + world - 1) // world
+    full = torch.empty((rows * world, n), dtype=torch.int32, device=device)
+    r0, r1 = min(m, rank * rows), min(m, (rank + 1) * rows)
+    mine = full[rank * rows:(rank + 1) * rows]
+    if r1 > r0:
+        mine[:r1 - r0].copy_(host_samples[r0:r1], non_blocking=True)
+    if world > 1:
+        dist.all_gather_into_tensor(full, mine.clone(), group=group)
+    ctx.set_samples_dev(full.data_ptr(), n, m, num_cats=num_cats)
+    return full, (r1 - r0) * n * 4
 
 
 def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, **kw):

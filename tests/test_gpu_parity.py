@@ -110,14 +110,16 @@ def test_search_order_matches_reference(abi, port, case):
         compare_golden(ctx.search_order(**kw2), golden)
 
 
+@pytest.mark.parametrize("bits", [32, 64], ids=["per_node", "grid_barrier"])
 @pytest.mark.parametrize("case", CASES[::3], ids=lambda c: "seed%d" % c["seed"])
-def test_search_order_dp_one_launch_per_node(abi, case):
-    """the DP normally runs as one cooperative kernel (grid barrier per node); the per-node launches must agree"""
+def test_search_order_dp_variants(abi, case, bits):
+    """the DP normally runs as one cooperative wavefront kernel; the grid-barrier kernel and the per-node launches
+    must give the same networks"""
     s, kw = build_case(case)
     golden = load_golden("ref_search_order")["seed%d" % case["seed"]]
     with abi.Context(0) as ctx:
         ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
-        ctx.force_generic(32)
+        ctx.force_generic(bits)
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
         compare_golden(ctx.search_order(**kw2), golden)
 
