@@ -167,6 +167,56 @@ def cpu_reference_rate(samples0, cats, order0, p_max, budget_s, threads):
     return threads * k / wall, threads * k, wall
 
 
+# ------------------------------------------------------------------------------------------------- cnSearchSA (C4)
+def sa_workload():
+    """BASELINE config C4: ALARM, 20,000 samples, maxParentSet=2, maxComplexity=600, demo/alarm.r:23-26 schedule"""
+    from catnet_b200 import synth
+    cfg = synth.config("C4")
+    s = np.ascontiguousarray(cfg["samples"], dtype=np.int32)
+    order1 = (np.asarray(cfg["order"]) + 1).astype(np.int32)
+    start = order1[np.random.default_rng(7).permutation(len(order1))]
+    sa = dict(select_mode=2, start_order=start, temp_start=0.0, temp_cool_fact=1.0, temp_check_orders=1000,
+              order_shuffles=0.0, stop_diff=1e-10, num_threads=4, use_cache=True)
+    return s, cfg["cats"], sa
+
+
+def sa_leg_ours(rank, world, max_iter, dist_mod=None, dev=None):
+    """wall time of one cnb_search_sa call per GPU (independent chains, seed + rank), host buffers in, networks out"""
+    import torch
+    from catnet_b200 import _abi
+    s, cats, sa = sa_workload()
+    kw = dict(max_parent_set=2, max_complexity=600, num_cats=cats)
+    _abi.search_sa(s, dict(sa, max_iter=3, seed=1), **kw)
+    t0 = time.perf_counter()
+    r = _abi.search_sa(s, dict(sa, max_iter=max_iter, seed=4004 + rank), **kw)
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        wall = float(t.item())
+    return {"workload": "C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
+                        "numThreads=4 (proposals per step), one chain per GPU" % max_iter,
+            "wall_s": wall, "chains": world, "iterations": int(r["niter"]), "orders_evaluated": int(len(r["trace"])),
+            "ms_per_order": 1000.0 * wall / max(len(r["trace"]), 1),
+            "best_loglik": float(max(x["loglik"] for x in r["nets"])) if r["nets"] else None}
+
+
+def sa_leg_reference(budget_iter):
+    """the reference's SA loop around its own estimate(), threads and cache (oracle/_ref), bounded to budget_iter
+    iterations; the first iterations are the expensive ones (empty cache)"""
+    from oracle import ref
+    s, cats, sa = sa_workload()
+    t0 = time.perf_counter()
+    r = ref.search_sa(s, 2, 600, sa["start_order"], select_mode=2, temp_start=0.0, temp_cool_fact=1.0,
+                      temp_check_orders=1000, max_iter=budget_iter, order_shuffles=0.0, stop_diff=1e-10, num_threads=4,
+                      use_cache=True, seed=4004, num_cats=cats)
+    wall = time.perf_counter() - t0
+    return {"workload": "C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
+                        "numThreads=4, cache on (reference core, bounded)" % budget_iter,
+            "wall_s": wall, "chains": 1, "iterations": int(r["niter"]), "orders_evaluated": int(len(r["trace"])),
+            "ms_per_order": 1000.0 * wall / max(len(r["trace"]), 1)}
+
+
 # ------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -181,6 +231,8 @@ def main():
     ap.add_argument("--kernel-bits", type=int, default=0,
                     help="debug: cnb_ctx_force_generic bits (8 = no tensor cores, 16 = u8 operands); not a bench line")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-sa", action="store_true", help="skip the cnSearchSA wall-time leg (BASELINE config C4)")
+    ap.add_argument("--sa-iter", type=int, default=1000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -216,13 +268,20 @@ def main():
         v = float(np.mean(rates))
         sample = "%d random candidate families with %d parents at full M=%d per step, %d concurrent reference scorers" % (
             nfam, wl["P"], wl["m"], threads)
+        sa_ref = None
+        if not args.no_sa:
+            try:
+                sa_ref = sa_leg_reference(30)
+            except Exception as e:
+                sa_ref = {"unavailable": str(e)}
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": v, "unit": "families/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "families": n_fam_total},
             "cpu_baseline": {"value": v, "unit": "families/s", "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": v, "unit": "families/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "families/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "sa": sa_ref}))
         return 0
 
     import torch
@@ -447,18 +506,29 @@ def main():
         except Exception as e:  # the checker library is optional for the product path
             cpu = {"value": None, "unit": "families/s", "cores": threads, "kind": "reference", "sample": "unavailable: %s" % e}
 
+    # ---- cnSearchSA wall time (second half of the BASELINE metric): one chain per GPU
+    sa_res = None
+    if not args.no_sa and args.config == "C5" and args.samples is None:
+        try:
+            sa_res = sa_leg_ours(rank, world, args.sa_iter, dist if world > 1 else None, dev)
+        except Exception as e:
+            sa_res = {"unavailable": str(e)}
+
     if rank == 0:
         ph = phases[-1]
         line = {
             "metric": metric, "value": value, "unit": "families/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 counts + f64 log-lik", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": ("e2m1 one-hot operands, f32 accumulators holding exact counts, f64 log-lik"
+                      if ph.get("tensor_kind", 0) == 4 else "u32 counts + f64 log-lik"), "data": "synthetic",
             "config": {"workload": wl["desc"], "families": n_fam_total, "families_per_rank": int(ph["num_families"]),
                        "l2": "inputs larger than L2 (bit planes %.0f MB)" % (n * ((m + 31) // 32) * 16 / 1e6),
                        "data_rng": "network numpy PCG64(%d); samples torch CUDA Philox(%d)" % (wl["seed"], wl["seed"])},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(ph["kernel_launches"]) * args.steps,
             "phases_ms": {k: ph[k] for k in ("plan_ms", "score_ms", "select_ms", "dp_ms")},
+            "sa": sa_res,
         }
         print(json.dumps(line))
     ctx.close()
