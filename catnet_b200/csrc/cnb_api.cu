@@ -610,7 +610,18 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	const int flag_cap = 4096;
 	RC(c->b_dp_flags.ensure(flag_cap * sizeof(unsigned)));
 	int fused = CNB_ERR_PROC;
-	if (!c->dp_per_node && !c->dp_no_wave) {
+	long long max_opts = 0;
+	for (const CnbNodePlan &nd : pl.nodes) max_opts = std::max<long long>(max_opts, nd.opt_end - nd.opt_begin);
+	if (!c->dp_per_node && !c->dp_no_wave && max_opts > 4) {
+		/* some node hands every candidate to the DP (unequal categories): a warp per slot */
+		fused = cnbk_dp_mixed(st, S[0], S[1], N, pl.base_complexity, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
+				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr);
+		if (fused == CNB_OK) {
+			cur = (N - 1) & 1;
+			c->timing.kernel_launches += 1;
+		}
+	} else if (!c->dp_per_node && !c->dp_no_wave) {
 		fused = cnbk_dp_wave(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
 				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
 				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap);

@@ -778,6 +778,96 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
 	}
 }
 
+/* Nodes whose pool has unequal category counts hand EVERY candidate to the DP (catnet_search2.h:491-496, :800-827):
+ * hundreds of options per node on ALARM.  The per-slot scan "R < t ? take" is sequential in the option order, but
+ * its state only changes at record-breaking options, so a WARP takes a slot: the lanes evaluate 32 options at a time
+ * (t = delta-updated log-lik), a ballot finds the first option that beats the running R, only that one is re-summed
+ * (the reference's loglik() re-summation, a chain of N - c fp64 adds), and the ballot is repeated for the lanes behind
+ * it.  One cooperative launch, grid barrier per node.  Identical decisions to the sequential scan. */
+__global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N, int base_complexity,
+		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
+		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
+		int *__restrict__ bp_src) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	extern __shared__ double sbase[];
+	const int K = s0.K, nthr = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, gw = t0 >> 5, nwarps = nthr >> 5;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) sbase[i] = base_v[i];
+	__syncthreads();
+	for (int j = t0; j <= K; j += nthr) {
+		bool ex = (j == base_complexity);
+		double l = 0.0;
+		if (ex) for (int i = 0; i < N; i++) l = __dadd_rn(l, sbase[i]);
+		s0.exists[j] = ex;
+		s0.L[j] = l;
+		s0.pfx[j] = ex ? __dadd_rn(0.0, sbase[0]) : 0.0;
+	}
+	grid.sync();
+	for (int c = 1; c < N; c++) {
+		const DpState &cur = (c & 1) ? s0 : s1, &nxt = (c & 1) ? s1 : s0;
+		const CnbDpNode nd = nodes[c];
+		const double bv = sbase[c];
+		const long long nopt = nd.opt_end - nd.opt_begin;
+		for (int j = gw; j <= K; j += nwarps) {
+			bool has = false;
+			double R = CNB_NEG_INF, bf = 0.0;
+			long long bo = -1;
+			int bs = -1;
+			for (long long o0 = 0; o0 < nopt; o0 += 32) {
+				const long long o = nd.opt_begin + o0 + lane;
+				bool viable = false;
+				double t = 0.0, f = 0.0;
+				int k = 0;
+				if (o0 + lane < nopt && opt_fid[o] >= 0) {           /* no winner for that d (:637-640) */
+					k = j + nd.base_cx - opt_cx[o];
+					if (k >= 0 && k <= K && cur.exists[k]) {
+						viable = true;
+						f = opt_score[o];
+						t = __dadd_rn(__dsub_rn(cur.L[k], bv), f);      /* :665-666 */
+					}
+				}
+				unsigned behind = 0xffffffffu;                         /* lanes not yet passed by the scan */
+				for (;;) {
+					/* empty net: loglik() = -FLT_MAX, the first finite t replaces it; then strict '<' (:670-671) */
+					const bool cand = viable && ((behind >> lane) & 1u) && (has ? R < t : t > CNB_NEG_INF);
+					const unsigned m = __ballot_sync(0xffffffffu, cand);
+					if (!m) break;
+					const int l = __ffs(m) - 1;
+					double r = 0.0;
+					if (lane == l) r = dev_resum(cur.pfx[k], f, c, N, sbase);
+					R = __shfl_sync(0xffffffffu, r, l);
+					bf = __shfl_sync(0xffffffffu, f, l);
+					bs = __shfl_sync(0xffffffffu, k, l);
+					bo = nd.opt_begin + o0 + l;
+					has = true;
+					behind = l == 31 ? 0u : (0xffffffffu << (l + 1));
+				}
+			}
+			if (lane == 0) {
+				const bool cur_ex = cur.exists[j] != 0;
+				bool take = false;
+				if (cur_ex) take = has && bo >= 0 && cur.L[j] < R;   /* :847-859 */
+				else take = has && bo >= 0;
+				size_t bpi = (size_t)c * (K + 1) + j;
+				if (take) {
+					nxt.exists[j] = 1;
+					nxt.L[j] = R;
+					nxt.pfx[j] = __dadd_rn(cur.pfx[bs], bf);
+					bp_opt[bpi] = bo;
+					bp_src[bpi] = bs;
+				} else {
+					nxt.exists[j] = cur_ex;
+					nxt.L[j] = cur.L[j];
+					nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
+					bp_opt[bpi] = -1;
+					bp_src[bpi] = j;
+				}
+			}
+		}
+		grid.sync();
+	}
+}
+
 /* Wavefront version.  An option only ever looks LEFT, at slot j - (option complexity - base complexity), and by at
  * most `halo` <= 256 slots: a CTA that owns 256 consecutive slots needs, for node c, its own slots and its left
  * neighbour's of node c - 1.  So instead of a grid barrier per node every CTA waits for its left neighbour's progress
@@ -1039,6 +1129,25 @@ int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, in
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
 		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_all, dim3(blocks), dim3(256), args, smem, st));
+	return CNB_OK;
+}
+
+/* warp-per-slot DP for searches with many options per node; CNB_ERR_PROC (nothing launched) when refused */
+int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, int base_complexity, const CnbDpNode *nodes,
+		const double *base_v, const double *opt_score, const int *opt_cx, const long long *opt_fid, long long *bp_opt,
+		int *bp_src) {
+	int dev = 0, coop = 0, sms = 0, per_sm = 0;
+	CK(cudaGetDevice(&dev));
+	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	const size_t smem = (size_t)N * sizeof(double);
+	if (smem > 48 * 1024) return CNB_ERR_PROC;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_mixed, 256, smem));
+	if (!coop || per_sm < 1) return CNB_ERR_PROC;
+	const int blocks = std::min(sms * per_sm, std::max(1, (s0.K + 1 + 7) / 8));      /* one warp per slot if it fits */
+	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
+		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src};
+	CK(cudaLaunchCooperativeKernel((const void *)k_dp_mixed, dim3(blocks), dim3(256), args, smem, st));
 	return CNB_OK;
 }
 

@@ -61,6 +61,9 @@ int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c,
 int cnbk_dp_all(cudaStream_t st, const DpState &s0, const DpState &s1, int N, int base_complexity, const CnbDpNode *nodes,
 		const double *base_v, const double *opt_score, const int *opt_cx, const long long *opt_fid, long long *bp_opt,
 		int *bp_src);
+int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, int base_complexity, const CnbDpNode *nodes,
+		const double *base_v, const double *opt_score, const int *opt_cx, const long long *opt_fid, long long *bp_opt,
+		int *bp_src);
 int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap);

@@ -150,7 +150,8 @@ def test_search_order_tensor_core_path(abi, case, bits, kind):
 
 
 @pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
-@pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4), (90, 20001, 4)])
+@pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4), (90, 20001, 4),
+                                      (3, 40, 3), (4, 33, 2), (64, 64, 4), (65, 300, 2), (129, 100, 4), (193, 40, 3)])
 def test_tensor_core_path_multi_tile(abi, n, m, cats, bits, kind):
     """several child tiles / pair tiles / K stages, ragged M: tensor-core scores == bit-plane scores"""
     s, c = random_problem(n + m, n, m, cats)
