@@ -37,6 +37,11 @@ class SaParams(C.Structure):
                 ("use_cache", C.c_int32), ("dir_prob", C.c_void_p), ("seed", C.c_uint64)]
 
 
+class HistParams(C.Structure):
+    _fields_ = [("score", C.c_int32), ("weight", C.c_int32), ("max_iter", C.c_int32), ("num_threads", C.c_int32),
+                ("use_cache", C.c_int32), ("seed", C.c_uint64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("pack_ms", C.c_float), ("plan_ms", C.c_float), ("score_ms", C.c_float), ("select_ms", C.c_float),
                 ("dp_ms", C.c_float), ("collect_ms", C.c_float), ("total_ms", C.c_float),
@@ -54,7 +59,7 @@ class Timing(C.Structure):
 
 # every symbol include/catnet_b200.h declares (tests/test_abi.py checks the library exports them all)
 SYMBOLS = [
-    "cnb_search_order", "cnb_search_sa", "cnb_release_cache", "cnb_set_seed", "cnb_last_error", "cnb_version",
+    "cnb_search_order", "cnb_search_sa", "cnb_search_hist", "cnb_ctx_search_hist", "cnb_release_cache", "cnb_set_seed", "cnb_last_error", "cnb_version",
     "cnb_ctx_create", "cnb_ctx_destroy", "cnb_ctx_set_samples", "cnb_ctx_set_samples_dev", "cnb_ctx_num_cats",
     "cnb_ctx_search_order", "cnb_ctx_search_sa", "cnb_ctx_plan", "cnb_ctx_score_shard", "cnb_ctx_finish",
     "cnb_ctx_select_dp", "cnb_ctx_collect", "cnb_ctx_set_stream", "cnb_ctx_timing", "cnb_ctx_force_generic", "cnb_family_scores", "cnb_tile_selftest", "cnb_device_log", "cnb_host_log",
@@ -90,6 +95,8 @@ def lib():
         "cnb_ctx_num_cats": (i32, [vp, vp]),
         "cnb_ctx_search_order": (i32, [vp, P(Params), P(vp)]),
         "cnb_ctx_search_sa": (i32, [vp, P(Params), P(SaParams), P(vp)]),
+        "cnb_ctx_search_hist": (i32, [vp, P(Params), P(HistParams), vp, P(i32)]),
+        "cnb_search_hist": (i32, [P(Params), P(HistParams), vp, P(i32)]),
         "cnb_ctx_plan": (i32, [vp, P(Params), i32, i32, P(i64), P(i64)]),
         "cnb_ctx_score_shard": (i32, [vp, vp]),
         "cnb_ctx_finish": (i32, [vp, vp, P(vp)]),
@@ -334,6 +341,15 @@ class Context:
                                       int(force_generic)))
         return counts, ll, nc
 
+    def search_hist(self, hist, **kw):
+        keep = Keep()
+        p = make_params(keep, self.n, self.m, **kw)
+        hp = make_hist_params(**hist)
+        out = np.zeros((self.n, self.n), dtype=np.float64)
+        it = C.c_int32()
+        check(lib().cnb_ctx_search_hist(self.h, C.byref(p), C.byref(hp), ptr(out), C.byref(it)))
+        return out, it.value
+
     def search_sa(self, sa, want_probs=False, **kw):
         keep = Keep()
         p = make_params(keep, self.n, self.m, **kw)
@@ -344,6 +360,13 @@ class Context:
             return read_sa_result(h, self.n, want_probs)
         finally:
             lib().cnb_result_free(h)
+
+
+def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=True, seed=1):
+    h = HistParams()
+    h.score, h.weight, h.max_iter, h.num_threads = int(score), int(weight), int(max_iter), int(num_threads)
+    h.use_cache, h.seed = int(bool(use_cache)), int(seed)
+    return h
 
 
 def make_sa_params(keep, select_mode=0, start_order=None, temp_start=1.0, temp_cool_fact=0.9, temp_check_orders=10,
@@ -401,6 +424,20 @@ def search_sa(samples, sa, want_probs=False, **kw):
         return read_sa_result(h, n, want_probs)
     finally:
         lib().cnb_result_free(h)
+
+
+def search_hist(samples, hist, **kw):
+    """one-shot cnb_search_hist (host buffers in, histogram out): the call the R shim makes for cnSearchHist.
+    hist: dict of cnb_hist_params fields.  Returns (matrix [N][N] with [parent][child], iterations)."""
+    s = i32(samples)
+    m, n = s.shape
+    keep = Keep()
+    p = make_params(keep, n, m, samples=s, **kw)
+    hp = make_hist_params(**hist)
+    out = np.zeros((n, n), dtype=np.float64)
+    it = C.c_int32()
+    check(lib().cnb_search_hist(C.byref(p), C.byref(hp), ptr(out), C.byref(it)))
+    return out, it.value
 
 
 def device_log(x, device=0):

@@ -679,6 +679,56 @@ int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::
 	return CNB_OK;
 }
 
+/* parents of ONE surviving network (cnSearchHist needs nothing else): back-pointer walk for its slot, option ->
+ * candidate parent set on the host */
+int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t> *num_parents, std::vector<int32_t> *parents) {
+	if (!c || !c->dp_done || !num_parents || !parents) return CNB_ERR_PROC;
+	CK(cudaSetDevice(c->device));
+	CnbPlan &pl = c->plan;
+	cudaStream_t st = c->stream;
+	const int N = pl.N, K = pl.K;
+	if (complexity < 0 || complexity > K || !c->h_exists[complexity]) return CNB_ERR_PARAM;
+	size_t slots = (size_t)K + 1;
+	DpState fin;
+	fin.K = K;
+	fin.exists = (unsigned char *)c->b_dp_exists.ptr + c->dp_final * slots;
+	fin.L = (double *)c->b_dp_L.ptr + c->dp_final * slots;
+	fin.pfx = (double *)c->b_dp_pfx.ptr + c->dp_final * slots;
+	std::vector<int32_t> one(1, complexity);
+	RC(c->b_sel.ensure((size_t)N * sizeof(long long)));
+	RC(upload(c, c->b_sel_slots, one));
+	RC(cnbk_dp_collect_list(st, fin, N, (const long long *)c->b_bp_opt.ptr, (const int *)c->b_bp_src.ptr,
+			(const int *)c->b_sel_slots.ptr, 1, (long long *)c->b_sel.ptr));
+	c->timing.kernel_launches++;
+	RC(c->pin_sel.ensure(std::max<size_t>(2 * (size_t)N * sizeof(long long), 16)));
+	long long *sel = (long long *)c->pin_sel.ptr, *fid = sel + N;
+	D2H(c, sel, c->b_sel.ptr, (size_t)N * sizeof(long long));
+	CK(cudaStreamSynchronize(st));
+	for (int n = 0; n < N; n++)
+		if (sel[n] >= 0) D2H(c, &fid[n], (const long long *)c->b_opt_fid.ptr + sel[n], sizeof(long long));
+	CK(cudaStreamSynchronize(st));
+	num_parents->assign(N, 0);
+	parents->assign((size_t)N * CNB_MAXP, 0);
+	for (int n = 0; n < N; n++) {
+		const CnbNodePlan &nd = pl.nodes[n];
+		int32_t *out = parents->data() + (size_t)n * CNB_MAXP;
+		if (sel[n] < 0) {                         /* base family: fixed parents only */
+			(*num_parents)[n] = nd.nfix;
+			for (int k = 0; k < nd.nfix; k++) out[k] = pl.lists[nd.fix_off + k];
+			continue;
+		}
+		int bi = nd.first_blk;
+		while (bi + 1 < nd.first_blk + nd.nblk && pl.blocks[bi + 1].opt_off <= sel[n]) bi++;
+		const CnbBlock &b = pl.blocks[bi];
+		int idx[CNB_MAXP];
+		cnb_unrank_lex(b.nfree, b.d - b.nfix, fid[n] - b.start, idx);
+		for (int k = 0; k < b.nfix; k++) out[k] = pl.lists[b.fix_off + k];
+		for (int k = 0; k < b.d - b.nfix; k++) out[b.nfix + k] = pl.lists[b.free_off + idx[k]];
+		(*num_parents)[n] = b.d;
+	}
+	return CNB_OK;
+}
+
 /* materialise the networks: back-pointer walk on the device, then tables of the distinct selected families */
 extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	if (!c || !c->dp_done || !out) return CNB_ERR_PROC;

@@ -69,5 +69,7 @@ struct cnb_ctx {
 /* internal phases shared with the SA driver (cnb_sa.cpp) */
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
 int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);
+/* parents (order positions, [N][CNB_MAXP]) of the surviving network with the given complexity, after select_dp */
+int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t> *num_parents, std::vector<int32_t> *parents);
 
 #endif

@@ -1,0 +1,95 @@
+/* cnb_hist.cpp -- cnSearchHist: parent histogram over random node orders, host driver around the device per-order
+ * evaluation (the caller right next to cnSearchSA on the same path).
+ *
+ * Restates the loop of RCatnetSearchHist::search (/root/reference/src/rcatnet_hist.cpp:282-548):
+ *   orders      batches of numThreads fresh random permutations (_gen_permutation, utils.h:144-180), duplicates
+ *               inside a batch skipped (:300-316)
+ *   evaluation  one CATNET_SEARCH2::estimate per order -- here plan + K2..K5 on the device (cnb_ctx_search_light)
+ *   selection   AIC / BIC / highest complexity (:463-503)
+ *   weight      1, exp(loglik / (M N)) or exp(score / (M N)) (:510-515)
+ *   histogram   hist[parent label][child label] += weight for every edge of the selected network (:517-528)
+ * The reference evaluates the orders of a batch on pthreads and memoises family scores in a process-wide cache;
+ * the device evaluates them one after the other and re-scores.  The uniform stream is drawn in the reference's order.
+ */
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "cnb_ctx.h"
+#include "cnb_rng.h"
+
+#define RC(call) do { int rc_ = (call); if (rc_ != CNB_OK) return rc_; } while (0)
+
+void cnb_gen_permutation(std::vector<int> &out, int n, CnbRng &rng);      /* cnb_sa.cpp */
+
+extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hist_params *hp, double *hist,
+		int32_t *iterations) {
+	if (!c || !p || !hp || !hist) return CNB_ERR_PARAM;
+	if (!c->have_samples) { cnb_set_error("context has no samples"); return CNB_ERR_PARAM; }
+	const int N = c->N, M = c->M;
+	const int nDrives = hp->num_threads < 1 ? 1 : hp->num_threads;
+	memset(hist, 0, sizeof(double) * (size_t)N * N);
+	CnbRng rng(hp->seed);
+	std::vector<std::vector<int>> test(nDrives, std::vector<int>(N));
+	std::vector<char> skip(nDrives);
+	std::vector<int32_t> cx, npar, pars;
+	std::vector<double> ll;
+	cnb_params q = *p;
+	q.edge_prob = nullptr;                       /* rcatnet_hist.cpp:268-277: no edge priors on this entry point */
+	int niter = 0, nstop = 0;
+	while (niter < hp->max_iter) {
+		for (int n = 0; n < nDrives; n++) {
+			cnb_gen_permutation(test[n], N, rng);
+			skip[n] = 0;
+			for (int nn = 0; nn < n && !skip[n]; nn++) skip[n] = (test[nn] == test[n]);
+		}
+		nstop = 1;
+		for (int n = 0; n < nDrives; n++) {
+			if (skip[n]) continue;
+			nstop = 0;
+			q.order = test[n].data();
+			RC(cnb_ctx_search_light(c, &q));
+			RC(cnb_ctx_dp_summary(c, &cx, &ll));
+			if (cx.empty()) continue;                /* slots but no network: `continue` before niter++ (:506) */
+			int pick = -1;
+			double fLogLik = 0;
+			if (hp->score == 1) {                    /* AIC :464-476 */
+				fLogLik = -(double)FLT_MAX;
+				for (size_t i = 0; i < cx.size(); i++) {
+					double v = M * ll[i] - cx[i];
+					if (v > fLogLik) { fLogLik = v; pick = (int)i; }
+				}
+			} else if (hp->score == 2) {             /* BIC :477-489 */
+				fLogLik = -(double)FLT_MAX;
+				double ft = 0.5 * log((double)M);
+				for (size_t i = 0; i < cx.size(); i++) {
+					double v = M * ll[i] - ft * cx[i];
+					if (v > fLogLik) { fLogLik = v; pick = (int)i; }
+				}
+			}
+			if (pick < 0) pick = (int)cx.size() - 1; /* highest complexity :492-500 */
+			double w;
+			if (hp->weight <= 0) w = 1;
+			else if (hp->weight == 1) w = exp(ll[pick] / (double)(M * N));
+			else w = exp(fLogLik / (double)(M * N));
+			RC(cnb_ctx_network_parents(c, cx[pick], &npar, &pars));
+			for (int j = 0; j < N; j++)
+				for (int i = 0; i < npar[j]; i++)
+					hist[(size_t)(test[n][pars[(size_t)j * CNB_MAXP + i]] - 1) * N + test[n][j] - 1] += w;
+			niter++;
+			if (p->echo) fprintf(stderr, "Iteration %d\\%d\n", niter, hp->max_iter);
+		}
+		if (nstop) break;
+	}
+	if (iterations) *iterations = niter;
+	return CNB_OK;
+}
+
+extern "C" int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations) {
+	if (!p || !hp || !hist) return CNB_ERR_PARAM;
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(p->device, &c));
+	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
+	if (rc == CNB_OK) rc = cnb_ctx_search_hist(c, p, hp, hist, iterations);
+	cnb_ctx_destroy(c);
+	return rc;
+}

@@ -10,6 +10,7 @@
  * The reference evaluates the numThreads proposals of a batch on pthreads; the device evaluates them one after the
  * other and skips the ones that can no longer matter.  The uniform stream is drawn in the reference's order.
  */
+#include <stdio.h>
 #include <math.h>
 #include <string.h>
 #include <memory>
@@ -20,7 +21,10 @@
 #define RC(call) do { int rc_ = (call); if (rc_ != CNB_OK) return rc_; } while (0)
 
 /* utils.h:144-180 */
-static void gen_permutation(std::vector<int> &out, int n, CnbRng &rng) {
+void cnb_gen_permutation(std::vector<int> &out, int n, CnbRng &rng);
+static void gen_permutation(std::vector<int> &out, int n, CnbRng &rng) { cnb_gen_permutation(out, n, rng); }
+void cnb_gen_permutation(std::vector<int> &out, int n, CnbRng &rng) {
+	out.resize(n);
 	std::vector<int> aux(n);
 	int cc = 0, brep = 0;
 	while (++cc < 1e5) {

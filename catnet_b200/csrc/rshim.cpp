@@ -2,7 +2,7 @@
  *
  * Exports what R's useDynLib(catnet) resolves for this path (reference src/ccnInit.c:29-52, prototypes
  * src/catnet_rexport.h:31-64):
- *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnReleaseCache/0   ccnSetSeed/1
+ *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnParHistogram/14   ccnReleaseCache/0   ccnSetSeed/1
  * and registers them in R_init_catnet.  Every other routine of the reference's table keeps its reference
  * implementation (this shim is linked INTO the package next to the reference sources).
  *
@@ -277,6 +277,33 @@ SEXP ccnOptimalNetsSA(SEXP rNodeNames, SEXP rSamples, SEXP rPerturbations, SEXP 
 	return export_result(res, m.p, rNodeNames);
 }
 
+/* catnetParHistogram (catnet_rexport.h:49-54): cnSearchHist, R/catnet.histo.R:116-129 */
+SEXP ccnParHistogram(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes, SEXP rMaxComplexity,
+		SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool, SEXP rScore, SEXP rWeight, SEXP rMaxIter,
+		SEXP rThreads, SEXP rUseCache, SEXP rEcho) {
+	Marshalled m;
+	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
+			rFixedParentsPool, R_NilValue, rEcho);
+	const int N = m.p.num_nodes;
+	cnb_hist_params hp;
+	memset(&hp, 0, sizeof(hp));
+	const char *score = CHAR(STRING_ELT(PROTECT(coerceVector(rScore, STRSXP)), 0));
+	hp.score = !strncmp(score, "AIC", 3) ? 1 : (!strncmp(score, "BIC", 3) ? 2 : 0);        /* rcatnet_hist.cpp:212-216 */
+	UNPROTECT(1);
+	hp.weight = asInteger(rWeight);
+	hp.max_iter = asInteger(rMaxIter);
+	hp.num_threads = asInteger(rThreads);
+	hp.use_cache = asLogical(rUseCache);
+	GetRNGstate();
+	hp.seed = (uint64_t)(unif_rand() * 9007199254740992.0);
+	PutRNGstate();
+	SEXP rmat = PROTECT(allocVector(REALSXP, N * N));                              /* :229-233 */
+	int rc = cnb_search_hist(&m.p, &hp, REAL(rmat), NULL);
+	UNPROTECT(m.nprotect + 1);
+	if (rc != CNB_OK) fail(rc);
+	return rmat;
+}
+
 SEXP ccnReleaseCache(void) {
 	cnb_release_cache();
 	return R_NilValue;
@@ -291,6 +318,7 @@ SEXP ccnSetSeed(SEXP rSeed) {
 static const R_CallMethodDef cnb_call_methods[] = {
 	{"ccnOptimalNetsForOrder", (DL_FUNC)&ccnOptimalNetsForOrder, 12},
 	{"ccnOptimalNetsSA", (DL_FUNC)&ccnOptimalNetsSA, 23},
+	{"ccnParHistogram", (DL_FUNC)&ccnParHistogram, 14},
 	{"ccnReleaseCache", (DL_FUNC)&ccnReleaseCache, 0},
 	{"ccnSetSeed", (DL_FUNC)&ccnSetSeed, 1},
 	{NULL, NULL, 0}};

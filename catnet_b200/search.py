@@ -243,3 +243,28 @@ def cnSearchSA(data, perturbations=None, maxParentSet=0, parentSizes=None, maxCo
     ev.time = (prior.time if prior else 0.0) + time.time() - t1
     ev.order = res["order"]
     return ev
+
+
+def cnSearchHist(data, perturbations=None, maxParentSet=1, parentSizes=None, maxComplexity=0, nodeCats=None,
+                 parentsPool=None, fixedParents=None, score="BIC", weight="likelihood", maxIter=32, numThreads=2,
+                 echo=False, nodeNames=None, seed=None, device=0):
+    """R/catnet.histo.R:45-138.  Returns the numnodes x numnodes matrix R builds with
+    matrix(vhisto, nrow=numnodes): element [child, parent] = summed weight of the edge parent -> child over the
+    networks selected for `maxIter` random node orders.  `seed` feeds the library's uniform stream."""
+    (data, perturbations, categories, max_categories, n, m, nodenames, maxParentSet, parentSizes, parentsPool,
+     fixedParents, maxComplexity) = _common(data, perturbations, maxParentSet, parentSizes, maxComplexity, nodeCats,
+                                            parentsPool, fixedParents, nodeNames)
+    numThreads = max(int(numThreads), 1)
+    maxIter = max(int(maxIter), numThreads)
+    nweight = {"likelihood": 1, "score": 2}.get(weight, 0)
+    rng = np.random.default_rng(seed)
+    hist = dict(score={"AIC": 1, "BIC": 2}.get(score, 0), weight=nweight, max_iter=maxIter, num_threads=numThreads,
+                use_cache=True, seed=int(rng.integers(1, 2 ** 62)))
+    num_cats = None if nodeCats is None else [len(c) for c in categories]
+    v, _ = _abi.search_hist(np.ascontiguousarray(data.T), hist,
+                            perturbations=None if perturbations is None else np.ascontiguousarray(perturbations.T),
+                            max_parent_set=maxParentSet, parent_sizes=parentSizes, max_complexity=maxComplexity,
+                            num_cats=num_cats, parents_pool=parentsPool, fixed_parents=fixedParents, echo=echo,
+                            device=device)
+    # the C vector is [parent*N + child]; R's matrix(v, nrow = N) is column-major, i.e. element [child, parent]
+    return np.ascontiguousarray(v.T)

@@ -10,6 +10,8 @@
  *                         -> CATNET_SEARCH2::estimate       (src/catnet_search2.h:152-897)
  *   cnb_search_sa         catnetOptimalNetsSA (src/catnet_rexport.h:42-48, src/ccnInit.c:31)
  *                         -> RCatnetSearchSA::search        (src/rcatnet_sa.cpp:253-935)
+ *   cnb_search_hist       catnetParHistogram (src/catnet_rexport.h:50-54, src/ccnInit.c:32)
+ *                         -> RCatnetSearchHist::search      (src/rcatnet_hist.cpp:164-573)
  *   cnb_release_cache     catnetReleaseCache (src/catnet_rexport.h:62, src/cache.cpp:62-76)
  *   cnb_set_seed          catnetSetSeed      (src/catnet_rexport.h:64, src/ccnInit.c:26)
  *   cnb_params            SEARCH_PARAMETERS  (src/search_params.h:39-58) as filled from the .Call arguments
@@ -86,9 +88,22 @@ typedef struct cnb_sa_params {
 	uint64_t seed;                 /* uniform stream (splitmix64); R's RNG is not reachable through a C ABI */
 } cnb_sa_params;
 
+/* ---- extra arguments of ccnParHistogram (cnSearchHist, R/catnet.histo.R:45-138) ---- */
+typedef struct cnb_hist_params {
+	int32_t score;                 /* rScore: 0 = highest complexity, 1 = "AIC", 2 = "BIC" (rcatnet_hist.cpp:212-216) */
+	int32_t weight;                /* rWeight: 0 = 1, 1 = exp(loglik/(M N)) ("likelihood"), 2 = exp(score/(M N)) */
+	int32_t max_iter;              /* rMaxIter: orders to evaluate (rounded up to whole batches of num_threads) */
+	int32_t num_threads;           /* rThreads: orders per batch (duplicates inside a batch are skipped) */
+	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
+	uint64_t seed;                 /* uniform stream (splitmix64), as for cnb_sa_params */
+} cnb_hist_params;
+
 /* ---- one-shot entry points (what the R shim calls) ---- */
 int cnb_search_order(const cnb_params *p, cnb_result **out);
 int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+/* hist_out: double[N*N], element [parent*N + child] in label space -- the vector the R code reshapes with
+ * matrix(vhisto, nrow = numnodes) (R/catnet.histo.R:131); iterations_out may be NULL */
+int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist_out, int32_t *iterations_out);
 void cnb_release_cache(void);
 void cnb_set_seed(int32_t seed);
 const char *cnb_last_error(void);
@@ -109,6 +124,9 @@ int cnb_ctx_num_cats(const cnb_ctx *ctx, int32_t *num_cats_out);
 int cnb_ctx_search_order(cnb_ctx *ctx, const cnb_params *p, cnb_result **out);
 /* simulated annealing over orders on the resident data (per-order evaluation on the device) */
 int cnb_ctx_search_sa(cnb_ctx *ctx, const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+/* cnSearchHist on the resident data */
+int cnb_ctx_search_hist(cnb_ctx *ctx, const cnb_params *p, const cnb_hist_params *hp, double *hist_out,
+		int32_t *iterations_out);
 
 /* sharded search, one process per GPU: plan -> score own shard -> (caller all-gathers) -> finish.
  * The score buffer is one fp64 per candidate family, laid out rank-major: segment r (seg_len doubles) holds rank r's

@@ -536,6 +536,62 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 	return best;
 }
 
+/* cnSearchHist: the loop of RCatnetSearchHist::search (rcatnet_hist.cpp:282-548).  Batches of numThreads fresh random
+ * orders (duplicates inside a batch skipped, :300-316), one search per order, network picked by AIC / BIC / highest
+ * complexity (:463-503), weight 1 / exp(loglik/(M N)) / exp(score/(M N)) (:510-515) added to
+ * hist[parent * N + child] in label space (:517-528).  Returns the iteration count (:530). */
+int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
+		const int *fixedPool_lbl, int scoreSel, int weight, int maxIter, int numThreads, double *hist) {
+	int nDrives = numThreads < 1 ? 1 : numThreads, n, nn, k, i, j;
+	int **test = (int **)malloc(nDrives * sizeof(int *)), *skip = (int *)malloc(nDrives * sizeof(int));
+	for (n = 0; n < nDrives; n++) test[n] = (int *)malloc(N * sizeof(int));
+	memset(hist, 0, sizeof(double) * N * N);
+	int niter = 0, nstop = 0;
+	while (niter < maxIter) {
+		for (n = 0; n < nDrives; n++) {
+			gen_permutation(test[n], N);
+			skip[n] = 0;
+			for (nn = 0; nn < n && !skip[n]; nn++) skip[n] = !memcmp(test[nn], test[n], N * sizeof(int));
+		}
+		nstop = 1;
+		for (n = 0; n < nDrives; n++) {
+			if (skip[n]) continue;
+			nstop = 0;
+			orc_result *r = orc_search_order(N, M, samples_lbl, pert_lbl, maxParentSet, parentSizes_lbl, maxComplexity,
+					test[n], numCats_lbl, parentsPool_lbl, fixedPool_lbl, NULL);
+			int pick = -1;
+			double fl = 0;
+			if (r && (scoreSel == 1 || scoreSel == 2)) {
+				double ft = 0.5 * log((double)M);
+				fl = NEG_INF;
+				for (k = 0; k < r->nslots; k++) {
+					if (!r->nets[k].exists) continue;
+					double v = scoreSel == 1 ? M * net_loglik(r, &r->nets[k]) - k : M * net_loglik(r, &r->nets[k]) - ft * k;
+					if (v > fl) { fl = v; pick = k; }
+				}
+			}
+			if (r && pick < 0) for (k = r->nslots - 1; k >= 0; k--) if (r->nets[k].exists) { pick = k; break; }
+			if (!r) { niter++; continue; }                       /* no slots at all: the iteration still counts (:530) */
+			if (pick < 0) { orc_result_free(r); continue; }      /* slots but no network: `continue` before niter++ (:506) */
+			double w;
+			if (weight <= 0) w = 1;
+			else if (weight == 1) w = exp(net_loglik(r, &r->nets[pick]) / (double)(M * N));
+			else w = exp(fl / (double)(M * N));
+			for (j = 0; j < N; j++) {
+				const fam_t *f = &r->fams[r->nets[pick].fam[j]];
+				for (i = 0; i < f->d; i++) hist[(test[n][f->pars[i]] - 1) * N + test[n][j] - 1] += w;
+			}
+			orc_result_free(r);
+			niter++;
+		}
+		if (nstop) break;
+	}
+	for (n = 0; n < nDrives; n++) free(test[n]);
+	free(test); free(skip);
+	return niter;
+}
+
 int orc_result_sa_info(const orc_result *r, int *order_out, int *niter, int *naccept) {
 	if (!r || !r->order) return -1;
 	memcpy(order_out, r->order, r->N * sizeof(int));

@@ -16,6 +16,9 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
 		const int *fixedPool_lbl, const double *edge_lbl, int selectMode, const int *startOrder, double tempStart,
 		double tempCoolFact, int tempCheckOrders, int maxIter, double orderShuffles, double stopDiff, int numThreads);
+int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
+		const int *fixedPool_lbl, int scoreSel, int weight, int maxIter, int numThreads, double *hist);
 void orc_set_seed(unsigned long long seed);
 int orc_result_nslots(const orc_result *r);
 int orc_result_exists(const orc_result *r, int k);

@@ -24,6 +24,9 @@ def lib():
         L.orc_search_sa.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_int, vp,
                                     C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         L.orc_search_sa.restype = vp
+        L.orc_search_hist.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, vp]
+        L.orc_search_hist.restype = C.c_int
         L.orc_set_seed.argtypes = [C.c_ulonglong]
         L.orc_result_nslots.argtypes = [vp]
         L.orc_result_exists.argtypes = [vp, C.c_int]
@@ -140,3 +143,18 @@ def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=
                 "trace_accept": acc[:nt]}
     finally:
         L.orc_result_free(h)
+
+
+def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_iter=32, num_threads=2, seed=1,
+                perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None):
+    """cnSearchHist: returns (hist [N][N] with hist[parent][child], iterations).  score: 0 highest complexity, 1 AIC,
+    2 BIC; weight: 0 one, 1 exp(loglik/(M N)), 2 exp(score/(M N))."""
+    L = lib()
+    s = _i32(samples)
+    M, N = s.shape
+    L.orc_set_seed(int(seed))
+    hist = np.zeros((N, N), dtype=np.float64)
+    it = L.orc_search_hist(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
+                           int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),
+                           _p(_pool(fixed_parents, N)), int(score), int(weight), int(max_iter), int(num_threads), _p(hist))
+    return hist, it

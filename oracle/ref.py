@@ -34,6 +34,9 @@ def lib():
                                     C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, C.c_int]
         L.ref_search_sa.restype = vp
+        L.ref_search_hist.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, vp]
+        L.ref_search_hist.restype = C.c_int
         L.ref_result_nslots.argtypes = [vp]
         L.ref_result_exists.argtypes = [vp, C.c_int]
         L.ref_result_net.argtypes = [vp, C.c_int, ip, dp]
@@ -180,3 +183,21 @@ def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=
     finally:
         L.ref_result_free(h)
         L.ref_release_cache()
+
+
+def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_iter=32, num_threads=2, use_cache=True,
+                seed=1, perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None):
+    """cnSearchHist through the reference's own estimate()/threads/cache (ref_driver.cpp:ref_search_hist).
+    Returns (hist [N][N] with hist[parent][child], iterations)."""
+    L = lib()
+    s = _i32(samples)
+    M, N = s.shape
+    L.ref_release_cache()
+    L.ref_set_seed(int(seed))
+    hist = np.zeros((N, N), dtype=np.float64)
+    it = L.ref_search_hist(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
+                           int(max_complexity), _p(_i32(num_cats)), _p(_pool_matrix(parents_pool, N)),
+                           _p(_pool_matrix(fixed_parents, N)), int(score), int(weight), int(max_iter),
+                           int(num_threads), int(bool(use_cache)), _p(hist))
+    L.ref_release_cache()
+    return hist, it

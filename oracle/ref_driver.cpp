@@ -509,6 +509,111 @@ void *ref_search_sa(int N, int M, const int *samples_lbl, const int *pert_lbl,
 	return res;
 }
 
+/* ---------------- cnSearchHist (rcatnet_hist.cpp:164-573) ----------------
+ * The reference's loop is welded to SEXP; restated here around its own estimate(), threads and cache: batches of
+ * numThreads fresh random orders (_gen_permutation, duplicates inside a batch skipped :300-316), one estimate() per
+ * order, network picked by AIC / BIC / highest complexity (:463-503), weight 1 / exp(loglik/(M N)) / exp(score/(M N))
+ * (:510-515) added to hist[parent][child] in label space (:517-528).  Returns the iteration count. */
+int ref_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
+		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
+		const int *fixedPool_lbl, int scoreSel, int weight, int maxIter, int numThreads, int useCache,
+		double *hist /* [N*N], [parent*N + child] */) {
+	int n, nn, i, j, nDrives = numThreads < 1 ? 1 : numThreads;
+	int bUseCache = useCache, m_maxParentSet = maxParentSet;
+	if (bUseCache && nDrives > 8) bUseCache = 0;                  /* :205-209 */
+	MUTEX cache_mutex;
+	memset(hist, 0, sizeof(double) * N * N);
+	std::vector<int*> testOrder(nDrives, (int*)0);
+	std::vector<std::vector<int> > testInv(nDrives, std::vector<int>(N));
+	std::vector<RefSearch*> drives(nDrives);
+	std::vector<SEARCH_PARAMETERS*> sps(nDrives);
+	for (n = 0; n < nDrives; n++) drives[n] = new RefSearch();
+	if (bUseCache) MUTEX_INIT(cache_mutex);
+	for (n = 0; n < nDrives; n++)                                  /* :268-277 */
+		sps[n] = new SEARCH_PARAMETERS(N, M, m_maxParentSet, maxComplexity, 0,
+				numCats_lbl != 0, parentSizes_lbl != 0, pert_lbl != 0, parentsPool_lbl != 0,
+				fixedPool_lbl != 0, 0, 0, bUseCache ? &cache_mutex : NULL, drives[n]);
+	int nstop = 0, niter = 0, nCatnets, nCurNet;
+	double fLogLik, complx, ftemp;
+	RefNet *pCurNet, **pCatnets;
+	while (niter < maxIter) {                                      /* :282 */
+		for (n = 0; n < nDrives; n++) {
+			if (testOrder[n]) free(testOrder[n]);
+			testOrder[n] = sa_gen_order(0, N, 0, 0);                   /* _gen_permutation */
+			nstop = 0;
+			for (nn = 0; nn < n; nn++) {
+				nstop = 1;
+				for (i = 0; i < N; i++)
+					if (testOrder[nn][i] != testOrder[n][i]) { nstop = 0; break; }
+				if (nstop) break;
+			}
+			if (nstop) continue;
+			for (i = 0; i < N; i++) testInv[n][testOrder[n][i] - 1] = i + 1;
+			if (bUseCache)
+				drives[n]->setCacheParams(N, m_maxParentSet, testOrder[n], &testInv[n][0]);
+			fill_params(sps[n], N, M, samples_lbl, pert_lbl, testOrder[n], parentSizes_lbl, numCats_lbl,
+					parentsPool_lbl, fixedPool_lbl, 0, &m_maxParentSet);
+			drives[n]->_start_thread(RefSaThreadProc, sps[n]);        /* :443 */
+		}
+		nstop = 1;
+		for (n = 0; n < nDrives; n++) {                              /* :449 */
+			if (!drives[n]->_is_running()) continue;
+			nstop = 0;
+			int threadres = drives[n]->_join_thread();
+			threadres = drives[n]->_stop_thread();
+			nCatnets = 0;
+			pCatnets = 0;
+			if (threadres == 0) { nCatnets = drives[n]->numCatnets(); pCatnets = drives[n]->catnets(); }
+			if (nCatnets > 0 && pCatnets) {
+				fLogLik = 0;
+				pCurNet = NULL;
+				switch (scoreSel) {
+				case 1:
+					fLogLik = -FLT_MAX;
+					for (nCurNet = 0; nCurNet < nCatnets; nCurNet++) {
+						if (!pCatnets[nCurNet]) continue;
+						complx = M * pCatnets[nCurNet]->loglik() - pCatnets[nCurNet]->complexity();
+						if (complx > fLogLik) { fLogLik = complx; pCurNet = pCatnets[nCurNet]; }
+					}
+					break;
+				case 2:
+					fLogLik = -FLT_MAX;
+					ftemp = 0.5 * log((double)M);
+					for (nCurNet = 0; nCurNet < nCatnets; nCurNet++) {
+						if (!pCatnets[nCurNet]) continue;
+						complx = M * pCatnets[nCurNet]->loglik() - ftemp * pCatnets[nCurNet]->complexity();
+						if (complx > fLogLik) { fLogLik = complx; pCurNet = pCatnets[nCurNet]; }
+					}
+					break;
+				}
+				if (!pCurNet)
+					for (nCurNet = nCatnets - 1; nCurNet >= 0; nCurNet--)
+						if (pCatnets[nCurNet]) { pCurNet = pCatnets[nCurNet]; break; }
+				if (!pCurNet) continue;
+				if (weight <= 0) ftemp = 1;
+				else if (weight == 1) ftemp = (double)exp(pCurNet->loglik() / (double)(M * N));
+				else ftemp = (double)exp((double)fLogLik / (double)(M * N));
+				const int *pNumParents = pCurNet->numParents();
+				const int **pParents = pCurNet->parents();
+				for (j = 0; j < N; j++) {
+					if (pNumParents[j] <= 0) continue;
+					for (i = 0; i < pNumParents[j]; i++)
+						hist[(testOrder[n][pParents[j][i]] - 1) * N + testOrder[n][j] - 1] += ftemp;
+				}
+			}
+			niter++;
+		}
+		if (nstop) break;
+	}
+	for (n = 0; n < nDrives; n++) {
+		if (testOrder[n]) free(testOrder[n]);
+		delete sps[n];
+		delete drives[n];
+	}
+	if (bUseCache) MUTEX_DESTROY(cache_mutex);
+	return niter;
+}
+
 /* CPU baseline helper: score `nfam` explicit families back to back with the reference primitive
  * (setParents + setNodeSampleProb), returns the sum of log-liks (to defeat dead-code elimination). */
 double ref_score_family_list(const int *samples0, int N, int M, const int *numCats,

@@ -44,6 +44,26 @@ SA_CASES = [
 ]
 
 
+# cnSearchHist (rcatnet_hist.cpp): score 0 highest complexity / 1 AIC / 2 BIC; weight 0 one / 1 likelihood / 2 score
+HIST_CASES = [
+    dict(seed=41, n=7, m=90, cats=3, P=2, K=200, na=0.0, hist=dict(score=2, weight=1, max_iter=12, num_threads=2, seed=5)),
+    dict(seed=42, n=6, m=70, cats=None, P=2, K=150, na=0.0, hist=dict(score=1, weight=2, max_iter=7, num_threads=3, seed=17)),
+    dict(seed=43, n=8, m=120, cats=2, P=3, K=120, na=0.08, hist=dict(score=0, weight=0, max_iter=6, num_threads=1, seed=3)),
+    dict(seed=44, n=9, m=200, cats=4, P=2, K=400, na=0.0, pert=True, hist=dict(score=2, weight=1, max_iter=8, num_threads=4, seed=11)),
+    dict(seed=45, n=3, m=40, cats=2, P=2, K=30, na=0.0, hist=dict(score=2, weight=1, max_iter=9, num_threads=4, seed=2)),
+]
+
+
+def build_hist_case(c):
+    """-> (samples [M][N], kwargs of the checkers' search_hist)"""
+    from helpers import random_problem
+    s, cats = random_problem(c["seed"], c["n"], c["m"], c.get("cats"), c.get("na", 0.0))
+    kw = dict(num_cats=cats)
+    if c.get("pert"):
+        kw["perturbations"] = (np.random.default_rng(c["seed"]).random(s.shape) < 0.15).astype(np.int32)
+    return s, kw
+
+
 def build_case(c):
     s, cats = random_problem(c["seed"], c["n"], c["m"], c.get("cats"), c.get("na", 0.0))
     n = c["n"]

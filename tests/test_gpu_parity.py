@@ -13,7 +13,7 @@ import math
 import numpy as np
 import pytest
 
-from cases import CASES, SA_CASES, build_case, ref_args
+from cases import CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case
 from helpers import NA, compare_golden, compare_search, load_golden, random_problem
 
 pytestmark = pytest.mark.gpu
@@ -320,6 +320,32 @@ def test_sa_trajectory_matches_reference(abi, case):
     assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
     assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
     compare_golden(r["nets"], g["nets"])
+
+
+@pytest.mark.parametrize("case", HIST_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_search_hist_matches_reference(abi, case):
+    """cnSearchHist: same uniform stream -> same random orders, same selected networks, the
+    parent histogram of the reference core bit for bit; one-shot call and resident context agree"""
+    s, kw = build_hist_case(case)
+    g = load_golden("ref_search_hist")["seed%d" % case["seed"]]
+    args = dict(max_parent_set=case["P"], max_complexity=case["K"], num_cats=kw["num_cats"],
+                perturbations=kw.get("perturbations"))
+    h, it = abi.search_hist(s, case["hist"], **args)
+    assert it == g["iterations"]
+    assert h.tolist() == [[float.fromhex(v) for v in row] for row in g["hist"]]
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw["num_cats"])
+        h2, it2 = ctx.search_hist(case["hist"], max_parent_set=case["P"], max_complexity=case["K"])
+        assert it2 == it and np.array_equal(h2, h)
+
+
+def test_search_hist_python_front_end(abi):
+    """catnet_b200.search.cnSearchHist: R's matrix(vhisto, nrow=numnodes) is [child, parent]"""
+    from catnet_b200 import search
+    s, cats = random_problem(46, 6, 150, 3)
+    m = search.cnSearchHist(s.T.astype(float), maxParentSet=2, score="BIC", weight="likelihood", maxIter=6, numThreads=2,
+                            seed=3)
+    assert m.shape == (6, 6) and np.all(np.diag(m) == 0) and m.sum() > 0
 
 
 def test_sa_alarm_vs_oracle(abi, port):

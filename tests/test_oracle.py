@@ -7,7 +7,7 @@ All fp64 comparisons are bit-exact."""
 import numpy as np
 import pytest
 
-from cases import CASES, SA_CASES, build_case, ref_args
+from cases import CASES, HIST_CASES, SA_CASES, build_case, build_hist_case, ref_args
 from helpers import compare_golden, compare_search, load_golden, random_problem
 from oracle import port
 
@@ -46,6 +46,24 @@ def test_sa_matches_golden(case):
     assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
     assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
     compare_golden(r["nets"], g["nets"])
+
+
+@pytest.mark.parametrize("case", HIST_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_hist_matches_golden(case):
+    """cnSearchHist: the restatement reproduces the reference core's histogram bit for bit"""
+    s, kw = build_hist_case(case)
+    h, it = port.search_hist(s, case["P"], case["K"], **kw, **case["hist"])
+    g = load_golden("ref_search_hist")["seed%d" % case["seed"]]
+    assert it == g["iterations"]
+    assert h.tolist() == [[float.fromhex(v) for v in row] for row in g["hist"]]
+
+
+def test_port_hist_matches_reference_core(ref):
+    s, cats = random_problem(78, 7, 110, 3)
+    kw = dict(score=2, weight=1, max_iter=10, num_threads=3, seed=99, num_cats=cats)
+    a, ia = ref.search_hist(s, 2, 150, use_cache=True, **kw)
+    b, ib = port.search_hist(s, 2, 150, **kw)
+    assert ia == ib and np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("seed", range(100, 112))

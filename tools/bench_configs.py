@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C1,C2,C3,C4")
+    ap.add_argument("--configs", default="C1,C2,C3,C4,H4")
     ap.add_argument("--ref-budget", type=float, default=120.0, help="skip the reference when its estimate exceeds this")
     ap.add_argument("--sa-iter", type=int, default=1000)
     ap.add_argument("--repeat", type=int, default=3)
@@ -29,6 +29,29 @@ def main():
     from oracle import ref
     have_ref = ref.available()
     for name in args.configs.split(","):
+        if name == "H4":
+            # cnSearchHist on the C4 data: 32 random orders, 2 per batch, BIC, likelihood weights
+            cfg = synth.config("C4")
+            s = np.ascontiguousarray(cfg["samples"], dtype=np.int32)
+            hp = dict(score=2, weight=1, max_iter=32, num_threads=2, seed=4004)
+            kw = dict(max_parent_set=2, max_complexity=600, num_cats=cfg["cats"])
+            _abi.search_hist(s, dict(hp, max_iter=2), **kw)
+            ts = []
+            for _ in range(args.repeat):
+                t0 = time.perf_counter()
+                h, it = _abi.search_hist(s, hp, **kw)
+                ts.append(time.perf_counter() - t0)
+            out = {"config": "H4: cnSearchHist on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, "
+                             "likelihood weights, maxIter=32, numThreads=2", "ours_s": min(ts), "iterations": it,
+                   "hist_sum": float(h.sum())}
+            if have_ref:
+                t0 = time.perf_counter()
+                hr, itr = ref.search_hist(s, 2, 600, score=2, weight=1, max_iter=8, num_threads=2, use_cache=True,
+                                          seed=4004, num_cats=cfg["cats"])
+                out.update({"ref_s_first_8_iterations": time.perf_counter() - t0, "ref_iterations": itr,
+                            "ref_threads": 2, "ref_cache": True})
+            print(json.dumps(out), flush=True)
+            continue
         cfg = synth.config(name)
         s = np.ascontiguousarray(cfg["samples"], dtype=np.int32)
         m, n = s.shape

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import random_problem  # noqa: E402
-from cases import CASES, SA_CASES, build_case  # noqa: E402
+from cases import CASES, HIST_CASES, SA_CASES, build_case, build_hist_case  # noqa: E402
 
 from catnet_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
@@ -78,6 +78,15 @@ def main():
                                        "nets": pack_nets(r["nets"], with_nodes=False)}
     dump(sa, "ref_search_sa.json")
     print("ref_search_sa.json", {k: (v["niter"], v["naccept"]) for k, v in sa.items()})
+    hist = {}
+    for case in HIST_CASES:
+        s, kw = build_hist_case(case)
+        h, it = ref.search_hist(s, case["P"], case["K"], use_cache=False, **kw, **case["hist"])
+        hc, itc = ref.search_hist(s, case["P"], case["K"], use_cache=True, **kw, **case["hist"])
+        assert it == itc and (np.abs(h - hc) <= 1e-12 * np.abs(h).max()).all()     # the cache only memoises scores
+        hist["seed%d" % case["seed"]] = {"iterations": it, "hist": [[float(v).hex() for v in row] for row in h]}
+    dump(hist, "ref_search_hist.json")
+    print("ref_search_hist.json", {k: v["iterations"] for k, v in hist.items()})
     if "--skip-configs" in sys.argv:
         return
     big = {}
