@@ -313,7 +313,11 @@ class Context:
         return h
 
     def set_stream(self, cuda_stream):
-        check(lib().cnb_ctx_set_stream(self.h, cuda_stream))
+        """launch on the caller's stream.  torch reports its default stream as handle 0, which the C ABI reads as
+        "the context's own (non-blocking) stream": pass CUDA's explicit legacy-default-stream handle instead, so
+        that the library's kernels and the caller's copies / NCCL collectives stay ordered."""
+        CUDA_STREAM_LEGACY = 1
+        check(lib().cnb_ctx_set_stream(self.h, int(cuda_stream) if cuda_stream else CUDA_STREAM_LEGACY))
 
     def finish_raw(self, scores_dev_ptr):
         h = C.c_void_p()

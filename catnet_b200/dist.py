@@ -48,6 +48,7 @@ def set_samples_sharded(ctx, host_samples, rank, world, device, num_cats=None, g
     every GPU, then the matrix is packed (cnb_ctx_set_samples_dev).  Returns (device tensor, bytes copied H2D)."""
     import torch
     import torch.distributed as dist
+    ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)   # the copy, the all-gather and the pack stay ordered
     m, n = host_samples.shape
     rows = (m + world - 1) // world
     full = torch.empty((rows * world, n), dtype=torch.int32, device=device)
@@ -64,6 +65,7 @@ def set_samples_sharded(ctx, host_samples, rank, world, device, num_cats=None, g
 def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, **kw):
     """cnSearchOrder on `world` GPUs; returns the same networks on every rank"""
     import torch
+    ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)   # kernels and the all-gather on one stream
     seg, _ = ctx.plan(rank, world, **kw)
     scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
     ctx.score_shard(scores.data_ptr())

@@ -138,7 +138,10 @@ int cnb_ctx_finish(cnb_ctx *ctx, const double *scores_dev, cnb_result **out);
 /* the two halves of cnb_ctx_finish: selection + DP on the device (result stays there), then network export */
 int cnb_ctx_select_dp(cnb_ctx *ctx, const double *scores_dev);
 int cnb_ctx_collect(cnb_ctx *ctx, cnb_result **out);
-/* launch on the caller's CUDA stream (e.g. the stream its NCCL collectives use) instead of the context's own */
+/* launch on the caller's CUDA stream (e.g. the stream its NCCL collectives use) instead of the context's own
+ * non-blocking stream; NULL selects the context's own stream again -- to name the legacy default stream pass
+ * cudaStreamLegacy ((cudaStream_t)0x1).  Work the caller orders against this library (copies into the sample
+ * matrix, the all-gather of the score segments) must be on that stream. */
 int cnb_ctx_set_stream(cnb_ctx *ctx, void *cuda_stream);
 
 /* per-phase device times of the last search on this context, CUDA events on the library's stream (ms) */
