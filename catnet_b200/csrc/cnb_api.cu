@@ -182,7 +182,8 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 	CK(cudaSetDevice(c->device));
 	size_t bytes = (size_t)N * M * sizeof(int32_t);
 	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
-	DevBuf tmp_s, tmp_p;
+	/* staging buffers stay with the context (grow-only): allocating and freeing 2 GB per call costs more than the copy */
+	DevBuf &tmp_s = c->b_stage_s, &tmp_p = c->b_stage_p;
 	int rc = tmp_s.ensure(bytes);
 	if (rc == CNB_OK && pert) rc = tmp_p.ensure(bytes);
 	if (rc == CNB_OK) {
@@ -197,8 +198,6 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 		c->in_host_set = false;
 	}
 	cudaStreamSynchronize(c->stream);
-	tmp_s.release();
-	tmp_p.release();
 	return rc;
 }
 
