@@ -166,7 +166,16 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	c->clean = !flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS;   /* no NA, no masks, bit planes valid */
 	if (!flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS && N >= 3 && !c->no_ie) {
 		RC(c->b_pairs.ensure((size_t)N * (N - 1) / 2 * 16 * sizeof(int)));
-		RC(cnbk_pair_tables(st, (const uint4 *)c->b_planes_lbl.ptr, N, c->W, (int *)c->b_pairs.ptr));
+		if (M >= 8192 && M < (1 << 24) && !c->pairs_popc && c->tensor_mode >= 0) {
+			/* enough samples to fill the MMA pipeline: one-hot GEMM of all nodes against all nodes (18 -> 2 ms at C5) */
+			const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * 3 * N;
+			RC(c->b_rows_a.ensure(row_bytes));
+			RC(c->b_rows_b.ensure(row_bytes));
+			RC(c->b_counts.ensure((size_t)cnbk_pair_tiles(N) * CNB_TILE_PAIRS * CNB_TILE_CHILD * CNBK_UMMA_SLOT_INTS * sizeof(int)));
+			RC(cnbk_pair_tables_umma(st, (const uint4 *)c->b_planes_lbl.ptr, N, M, c->W, (uint4 *)c->b_rows_a.ptr,
+					(uint4 *)c->b_rows_b.ptr, (int *)c->b_counts.ptr, (int *)c->b_pairs.ptr));
+		} else
+			RC(cnbk_pair_tables(st, (const uint4 *)c->b_planes_lbl.ptr, N, c->W, (int *)c->b_pairs.ptr));
 		c->pairs_valid = true;
 	}
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
@@ -222,6 +231,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->tensor_i8 = (on & 16) ? 1 : 0;                      /* bit 4: u8 operands (kind::i8) instead of E2M1 (kind::mxf4) */
 	c->dp_per_node = (on & 32) != 0;                       /* bit 5: one DP launch per node (no cooperative kernel) */
 	c->dp_no_wave = (on & 64) != 0;                        /* bit 6: grid-barrier DP kernel instead of the wavefront one */
+	c->pairs_popc = (on & 128) != 0;                       /* bit 7: pair tables by the POPC kernel (set BEFORE set_samples) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -252,6 +262,8 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.tiles.child = c->plan.tile_child;
 	D.tiles.rank = c->plan.rank;
 	D.tiles.world = c->plan.world;
+	D.tiles.self_pairs = 0;
+	D.tiles.pad = 0;
 	return D;
 }
 

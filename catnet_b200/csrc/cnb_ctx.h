@@ -38,6 +38,7 @@ struct cnb_ctx {
 	int tensor_i8 = 0;                 /* 1: kind::i8 operands instead of kind::mxf4 (test hook) */
 	bool dp_per_node = false;          /* one DP launch per node instead of the fused cooperative kernel (test hook) */
 	bool in_host_set = false;          /* cnb_ctx_set_samples is calling cnb_ctx_set_samples_dev (keeps its H2D count) */
+	bool pairs_popc = false;           /* pair tables by the POPC kernel even for large M (test hook) */
 	bool dp_no_wave = false;           /* grid-barrier DP kernel instead of the wavefront one (test hook) */
 	int dp_final = 0, tensor_batches = 0;
 	std::vector<int32_t> cats_lbl;

@@ -55,6 +55,8 @@ struct CnbTiles {
 	const long long *dtile_off;   /* [nct][CNB_DT_STRIDE] D tiles of the child tile before each of its D pair tiles */
 	int32_t nct, child;           /* child tiles, children per child tile */
 	int32_t rank, world;
+	int32_t self_pairs;           /* 1: the pair-table tiling instead (cnb_tiles.h, kind 2); tile_base/dtile_off unused */
+	int32_t pad;
 };
 
 #define CNB_TILE_PAIRS 28     /* tensor-core tile: 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128) ... */

@@ -44,7 +44,11 @@ int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, 
 /* local tiles [local_begin, local_end) of rank T.rank (global tile = rank + local * world) */
 int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
 		const CnbTiles &T, long long local_begin, long long local_end, int *counts);
-long long cnbk_umma_column_macs(int W, int fp4);   /* multiply-accumulates per MMA column of one tile, padding included */
+long long cnbk_umma_column_macs(int W, int fp4);
+/* all two-way tables on the tensor cores (no missing values, M < 2^24); scratch sized by the caller */
+long long cnbk_pair_tiles(int N);
+int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M, int W, uint4 *rows_a, uint4 *rows_b,
+		int *counts, int *pair_tab);   /* multiply-accumulates per MMA column of one tile, padding included */
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O);
 #define CNBK_UMMA_SLOT_INTS 36

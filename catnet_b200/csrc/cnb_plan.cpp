@@ -254,6 +254,8 @@ int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
 	T.child = pl.tile_child;
 	T.rank = 0;
 	T.world = 1;
+	T.self_pairs = 0;
+	T.pad = 0;
 	CnbTileInfo ti;
 	cnb_tile_decode(T, pl.N, tile, ti);
 	return (3 * (ti.ze - ti.zb) + 15) / 16 * 16;
@@ -280,6 +282,8 @@ extern "C" int64_t cnb_tile_selftest(int32_t N) {
 	T.child = pl.tile_child;
 	T.rank = 0;
 	T.world = 1;
+	T.self_pairs = 0;
+	T.pad = 0;
 	const int64_t ntiles = pl.tile_base[T.nct];
 	std::vector<unsigned char> used((size_t)ntiles * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
 	int64_t nfam = 0;

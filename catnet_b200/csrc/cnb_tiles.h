@@ -12,6 +12,11 @@
  *            as far as the largest b of the tile's pairs.  (With (a, b) as the pair and c > b as the columns, as in
  *            the F tiles, a diagonal tile would use half its columns on average and every MMA has a fixed cost.)
  *
+ *   P tiles  (T.self_pairs, used once per data set for the two-way tables of ALL node pairs, label space): "pair"
+ *            slot q is the single node q (both members of the pair are q, so only the 3 configurations (i, i) of
+ *            its 9 rows are non-zero and row (i, i) is the plain one-hot row of category i); columns = all nodes in
+ *            chunks of 64.  Tile t = (pair tile t / nchunks, chunk t % nchunks).
+ *
  * Tile ids: tile_base[ct] + [0, nF) are the F tiles of ct, then the D tiles pair tile after pair tile, chunk after
  * chunk; dtile_off[ct * CNB_DT_STRIDE + p] = D tiles of ct before pair tile p.
  */
@@ -29,7 +34,7 @@
 #define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 pair tiles of D pairs per child tile, plus the total */
 
 struct CnbTileInfo {
-	int kind;                 /* 0 = F, 1 = D */
+	int kind;                 /* 0 = F, 1 = D, 2 = P */
 	int ct, c0, ce;           /* child tile and its children [c0, ce) */
 	long long pair0;          /* rank of the tile's first pair inside its region (F: q, D: rank among the D pairs) */
 	long long npairs;         /* pairs of the region */
@@ -66,6 +71,18 @@ CNB_HD int cnb_d_chunks(int c0, int ce, int ptile) {
 }
 
 CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInfo &ti) {
+	if (T.self_pairs) {
+		const int nch = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+		ti.kind = 2;
+		ti.ct = 0;
+		ti.c0 = 0;
+		ti.ce = N;
+		ti.pair0 = (tile / nch) * CNB_TILE_PAIRS;
+		ti.npairs = N;
+		ti.zb = (int)(tile % nch) * CNB_TILE_CHILD;
+		ti.ze = ti.zb + CNB_TILE_CHILD < N ? ti.zb + CNB_TILE_CHILD : N;
+		return;
+	}
 	int lo = 0, hi = T.nct - 1;
 	while (lo < hi) {
 		int mid = (lo + hi + 1) >> 1;
@@ -104,7 +121,8 @@ CNB_HD bool cnb_tile_pair(const CnbTileInfo &ti, int ps, int &x, int &y) {
 	const long long q = ti.pair0 + ps;
 	if (q >= ti.npairs) return false;
 	if (ti.kind == 0) cnb_pair_of(q, x, y);
-	else cnb_d_pair(ti.c0, ti.ce, (int)q, x, y);
+	else if (ti.kind == 1) cnb_d_pair(ti.c0, ti.ce, (int)q, x, y);
+	else x = y = (int)q;
 	return true;
 }
 

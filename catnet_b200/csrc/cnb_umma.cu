@@ -450,6 +450,40 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	O.scores[T.rank * O.seg_len + O.seg_off + local * UM_SLOTS + within] = score;
 }
 
+/* pair tables from the P tiles: one thread per unordered node pair (u < v).  The 3 x 3 free cells come from the tile
+ * slot (pair slot u, column v), rows (i, i); the margins of u and v from the diagonal slots (u, u) and (v, v); cells
+ * with a last category by inclusion-exclusion (no value is missing, so every margin sums to M). */
+__global__ void __launch_bounds__(128) k_pairs_from_tiles(const int *__restrict__ counts, int N, int M, int *__restrict__ pair_tab) {
+	const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= (long long)N * (N - 1) / 2) return;
+	int u, v;
+	cnb_pair_of(q, u, v);
+	const int nch = (N + UM_CHILD - 1) / UM_CHILD;
+	auto slot = [&](int x, int z) {
+		const long long tile = (long long)(x / UM_PAIRS) * nch + z / UM_CHILD;
+		return counts + ((size_t)tile * UM_SLOTS + (size_t)(x % UM_PAIRS) * UM_CHILD + z % UM_CHILD) * UM_SLOT_INTS;
+	};
+	const int *uv = slot(u, v), *uu = slot(u, u), *vv = slot(v, v);
+	int n[4][4], mu[4], mv[4], su = 0, sv = 0;
+	for (int i = 0; i < 3; i++) {
+		mu[i] = uu[(i * 3 + i) * 4 + i];
+		mv[i] = vv[(i * 3 + i) * 4 + i];
+		su += mu[i];
+		sv += mv[i];
+	}
+	mu[3] = M - su;
+	mv[3] = M - sv;
+	for (int i = 0; i < 3; i++) {
+		int s = 0;
+		for (int k = 0; k < 3; k++) { n[i][k] = uv[(i * 3 + i) * 4 + k]; s += n[i][k]; }
+		n[i][3] = mu[i] - s;
+	}
+	for (int k = 0; k < 4; k++) n[3][k] = mv[k] - (n[0][k] + n[1][k] + n[2][k]);
+	int *out = pair_tab + q * 16;
+	for (int i = 0; i < 4; i++)
+		for (int k = 0; k < 4; k++) out[i * 4 + k] = n[i][k];
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
 /* quads (4 sample words) per operand row for W sample words: whole groups of UM_BSTAGES stages plus one stage of
@@ -496,6 +530,29 @@ int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long tile_begin,
 	long long slots = (tile_end - tile_begin) * UM_SLOTS;
 	if (slots <= 0) return CNB_OK;
 	k_umma_epilogue<<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* two-way tables of all node pairs on the tensor cores (label space, once per data set): operand rows of the label-space
+ * planes, P tiles, conversion.  rows_a/rows_b/counts are scratch of the caller's size (cnbk_umma_row_quads,
+ * cnbk_pair_tiles * slots). */
+long long cnbk_pair_tiles(int N) {
+	return (long long)((N + UM_PAIRS - 1) / UM_PAIRS) * ((N + UM_CHILD - 1) / UM_CHILD);
+}
+
+int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M, int W, uint4 *rows_a, uint4 *rows_b,
+		int *counts, int *pair_tab) {
+	int rc = cnbk_umma_rows(st, planes_lbl, N, W, 1, rows_a, rows_b);
+	if (rc != CNB_OK) return rc;
+	CnbTiles T;
+	memset(&T, 0, sizeof(T));
+	T.self_pairs = 1;
+	T.world = 1;
+	rc = cnbk_umma_tables(st, rows_a, rows_b, N, W, 1, T, 0, cnbk_pair_tiles(N), counts);
+	if (rc != CNB_OK) return rc;
+	const long long np = (long long)N * (N - 1) / 2;
+	k_pairs_from_tiles<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, N, M, pair_tab);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

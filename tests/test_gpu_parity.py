@@ -339,6 +339,23 @@ def test_search_hist_matches_reference(abi, case):
         assert it2 == it and np.array_equal(h2, h)
 
 
+def test_pair_tables_on_tensor_cores(abi):
+    """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
+    kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
+    s, c = random_problem(91, 70, 9000, 4)
+    kw = dict(max_parent_set=2, max_complexity=70 * 16 * 3)
+    with abi.Context(0) as ctx:
+        ctx.force_generic(128)                    # POPC pair tables
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(want_probs=True, **kw)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)            # tensor-core pair tables
+        b = ctx.search_order(want_probs=True, **kw)
+        ctx.force_generic(8)                      # ... consumed by the bit-plane inclusion-exclusion scorer
+        d = ctx.search_order(want_probs=True, **kw)
+    assert compare_search(b, a) == len(a) and compare_search(d, a) == len(a)
+
+
 def test_search_hist_python_front_end(abi):
     """catnet_b200.search.cnSearchHist: R's matrix(vhisto, nrow=numnodes) is [child, parent]"""
     from catnet_b200 import search
