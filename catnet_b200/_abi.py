@@ -66,6 +66,7 @@ SYMBOLS = [
     "cnb_unrank_combination", "cnb_num_families", "cnb_result_num_networks", "cnb_result_num_nodes",
     "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_cats", "cnb_result_counts", "cnb_result_node",
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
+    "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
 ]
 
 _lib = None
@@ -123,6 +124,10 @@ def lib():
         "cnb_result_sa_trace": (i32, [vp, vp, vp, i32]),
         "cnb_result_merge": (i32, [vp, vp]),
         "cnb_result_free": (None, [vp]),
+        "cnb_pairwise": (i32, [i32, i32, i32, vp, vp, i32, vp]),
+        "cnb_entropy_order": (i32, [i32, i32, vp, vp, i32, vp]),
+        "cnb_ctx_pairwise": (i32, [vp, i32, vp]),
+        "cnb_ctx_entropy_order": (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -345,6 +350,17 @@ class Context:
                                       int(force_generic)))
         return counts, ll, nc
 
+    def pairwise(self, kind):
+        """kind "entropy" | "kl" | "pearson" -> numpy [N][N] laid out like R's matrix(mat, N, N): out[n1][n2]"""
+        out = np.zeros((self.n, self.n), dtype=np.float64)
+        check(lib().cnb_ctx_pairwise(self.h, PAIRWISE_KINDS[kind], ptr(out)))
+        return out.T.copy()
+
+    def entropy_order(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        check(lib().cnb_ctx_entropy_order(self.h, ptr(out)))
+        return out
+
     def search_hist(self, hist, **kw):
         keep = Keep()
         p = make_params(keep, self.n, self.m, **kw)
@@ -364,6 +380,27 @@ class Context:
             return read_sa_result(h, self.n, want_probs)
         finally:
             lib().cnb_result_free(h)
+
+
+PAIRWISE_KINDS = {"entropy": 0, "kl": 1, "pearson": 2}
+
+
+def pairwise(kind, samples, perturbations=None, device=0):
+    """one-shot cnb_pairwise (what ccnEntropyPairwise / ccnKLPairwise / ccnPearsonPairwise call in the R shim):
+    samples [M][N] int32 1-based -> [N][N] with out[n1][n2] (R's matrix(mat, N, N))"""
+    s = i32(samples)
+    m, n = s.shape
+    out = np.zeros((n, n), dtype=np.float64)
+    check(lib().cnb_pairwise(PAIRWISE_KINDS[kind], n, m, ptr(s), ptr(i32(perturbations)), int(device), ptr(out)))
+    return out.T.copy()
+
+
+def entropy_order(samples, perturbations=None, device=0):
+    s = i32(samples)
+    m, n = s.shape
+    out = np.zeros(n, dtype=np.int32)
+    check(lib().cnb_entropy_order(n, m, ptr(s), ptr(i32(perturbations)), int(device), ptr(out)))
+    return out
 
 
 def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=True, seed=1):

@@ -163,8 +163,12 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	if (flags[0]) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
 	/* two-way margins for the inclusion-exclusion scorer: only meaningful without missing values / masks */
 	c->pairs_valid = false;
+	c->pairs_full = false;
+	c->has_na = flags[2] != 0;
 	c->clean = !flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS;   /* no NA, no masks, bit planes valid */
-	if (!flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS && N >= 3 && !c->no_ie) {
+	/* the tables count ALL samples: with perturbation masks they serve only the "whole sample" side of the pairwise
+	 * metrics (pairs_full), never the search */
+	if (!flags[2] && c->max_cats <= CNB_PLANE_CATS && N >= 3 && !c->no_ie) {
 		RC(c->b_pairs.ensure((size_t)N * (N - 1) / 2 * 16 * sizeof(int)));
 		if (M >= 8192 && M < (1 << 24) && !c->pairs_popc && c->tensor_mode >= 0) {
 			/* enough samples to fill the MMA pipeline: one-hot GEMM of all nodes against all nodes (18 -> 2 ms at C5) */
@@ -176,7 +180,8 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 					(uint4 *)c->b_rows_b.ptr, (int *)c->b_counts.ptr, (int *)c->b_pairs.ptr));
 		} else
 			RC(cnbk_pair_tables(st, (const uint4 *)c->b_planes_lbl.ptr, N, c->W, (int *)c->b_pairs.ptr));
-		c->pairs_valid = true;
+		c->pairs_valid = !c->has_pert;
+		c->pairs_full = true;
 	}
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	CK(cudaStreamSynchronize(st));
@@ -247,9 +252,10 @@ static DevData make_devdata(cnb_ctx *c) {
 	DevData D;
 	D.N = c->N; D.M = c->M; D.W = c->W; D.Mpad = c->Mpad;
 	D.planes = (const uint4 *)c->b_planes.ptr;
-	D.keep = c->has_pert ? (const uint32_t *)c->b_keep.ptr : nullptr;
+	const bool masks = c->has_pert && !c->ignore_pert;
+	D.keep = masks ? (const uint32_t *)c->b_keep.ptr : nullptr;
 	D.codes = (const uint8_t *)c->b_codes.ptr;
-	D.keep_lbl = c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr;
+	D.keep_lbl = masks ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr;
 	D.order = (const int32_t *)c->b_order.ptr;
 	D.cats = (const int32_t *)c->b_cats.ptr;
 	D.lists = (const int32_t *)c->b_lists.ptr;
@@ -350,7 +356,8 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 		ScoreOut O, bool force_generic, bool allow_slicing) {
 	if (e <= b) return CNB_OK;
 	cudaStream_t st = c->stream;
-	if (!force_generic && !F.ex_nd && F.d == 0 && c->pairs_valid) {
+	const bool pairs_ok = c->ignore_pert ? c->pairs_full : c->pairs_valid;
+	if (!force_generic && !F.ex_nd && F.d == 0 && pairs_ok) {
 		/* no parents, clean data: marginal counts from the pair tables */
 		c->last_fast = true;
 		RC(cnbk_score_pairs1(c->stream, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
@@ -366,13 +373,13 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 			long long n = e - b, target = 148ll * 1024;
 			if (n < target) slices = (int)std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8));
 		}
-		if (F.d == 1 && c->pairs_valid && !F.ex_nd) {
+		if (F.d == 1 && pairs_ok && !F.ex_nd) {
 			/* one parent, clean data: the table was counted with the pair tables */
 			RC(cnbk_score_pairs1(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
 			c->timing.kernel_launches++;
 			return CNB_OK;
 		}
-		if (slices == 1 && !O.counts && F.d == 2 && c->pairs_valid && !F.explicit_list) {
+		if (slices == 1 && !O.counts && F.d == 2 && pairs_ok && !F.explicit_list) {
 			RC(cnbk_score_planes_ie2(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
 			c->timing.kernel_launches++;
 			return CNB_OK;
@@ -519,7 +526,7 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 	int dmax = fixed_d;
 	if (var_d) { dmax = 0; for (int v : nd) dmax = std::max(dmax, v); }
 	DevData D = make_devdata(c);
-	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || (fixed_d == 0 && !c->pairs_valid), false));
+	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || (fixed_d == 0 && !(c->ignore_pert ? c->pairs_full : c->pairs_valid)), false));
 	return CNB_OK;
 }
 
@@ -963,6 +970,102 @@ extern "C" int cnb_family_scores(cnb_ctx *c, int32_t nfam, int32_t d, const int3
 	CK(cudaStreamSynchronize(st));
 	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
 	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ pairwise metrics ---- */
+/* catnet_entropy.cpp:38-911 on the resident data.  The tables of all ordered pairs are those of the explicit
+ * one-parent families (child n1, parent n2) -- counted by the search path's scorers: pair tables from the tensor
+ * cores / POPC on complete data, bit planes under the child's perturbation mask, shared-memory histograms beyond 4
+ * categories -- then reduced by cnbk_pairwise_metric.  out: double[N*N], out[n2*N + n1]. */
+extern "C" int cnb_ctx_pairwise(cnb_ctx *c, int32_t kind, double *out) {
+	if (!c || !c->have_samples || !out || kind < CNB_PAIRWISE_ENTROPY || kind > CNB_PAIRWISE_PEARSON) {
+		cnb_set_error("cnb_ctx_pairwise: bad arguments");
+		return CNB_ERR_PARAM;
+	}
+	/* the reference decrements every value and takes the range (catnet_entropy.cpp:61-95): a missing value is
+	 * undefined behaviour there; here it is an error */
+	if (c->has_na) { cnb_set_error("pairwise metrics need complete data (no NA)"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	const int N = c->N;
+	if (kind != CNB_PAIRWISE_ENTROPY && !c->has_pert) {
+		/* the "perturbed sub-sample" of KL / Pearson is empty without perturbations (numsamplesPert = 0, :594-602):
+		 * every distance is +0 */
+		memset(out, 0, (size_t)N * N * sizeof(double));
+		return CNB_OK;
+	}
+	cnb_params q;
+	memset(&q, 0, sizeof(q));
+	q.num_nodes = N;
+	q.num_samples = c->M;
+	q.max_parent_set = 0;
+	q.max_complexity = INT32_MAX / 2;
+	RC(cnb_ctx_plan(c, &q, 0, 1, nullptr, nullptr));           /* identity order */
+	cudaStream_t st = c->stream;
+	const int stride = table_stride(c->max_cats, 1);
+	const size_t nfam = (size_t)N * (N - 1);
+	std::vector<int32_t> ch(nfam), pa(nfam * CNB_MAXP, 0), nd;
+	for (int n1 = 0, f = 0; n1 < N; n1++)
+		for (int n2 = 0; n2 < N; n2++)
+			if (n2 != n1) { ch[f] = n1; pa[(size_t)f * CNB_MAXP] = n2; f++; }
+	const int *kept = nullptr, *full = nullptr, *diag = nullptr;
+	if (N == 1) {
+		std::vector<int32_t> c0(1, 0), p0(CNB_MAXP, 0);
+		RC(score_explicit(c, c0, p0, nd, 0, stride, true, c->force_generic));
+		diag = (const int *)c->b_ex_counts.ptr;
+	} else if (kind == CNB_PAIRWISE_ENTROPY) {
+		RC(score_explicit(c, ch, pa, nd, 1, stride, true, c->force_generic));
+		kept = (const int *)c->b_ex_counts.ptr;
+	} else {
+		RC(score_explicit(c, ch, pa, nd, 1, stride, true, c->force_generic));
+		RC(c->b_pw_kept.ensure(nfam * stride * sizeof(int)));
+		CK(cudaMemcpyAsync(c->b_pw_kept.ptr, c->b_ex_counts.ptr, nfam * stride * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		kept = (const int *)c->b_pw_kept.ptr;
+		c->ignore_pert = true;                                 /* whole-sample tables (:609-611, :832-834) */
+		int rc = score_explicit(c, ch, pa, nd, 1, stride, true, c->force_generic);
+		c->ignore_pert = false;
+		RC(rc);
+		full = (const int *)c->b_ex_counts.ptr;
+	}
+	RC(c->b_pw_out.ensure((size_t)N * N * sizeof(double)));
+	RC(cnbk_pairwise_metric(st, kind, N, (const int *)c->b_cats_lbl.ptr, kept, full, diag, stride, (double *)c->b_pw_out.ptr));
+	c->timing.kernel_launches++;
+	D2H(c, out, c->b_pw_out.ptr, (size_t)N * N * sizeof(double));
+	int ovf = 0;
+	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
+	CK(cudaStreamSynchronize(st));
+	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_entropy_order(cnb_ctx *c, int32_t *order_out) {
+	if (!c || !c->have_samples || !order_out) { cnb_set_error("cnb_ctx_entropy_order: bad arguments"); return CNB_ERR_PARAM; }
+	std::vector<double> mat((size_t)c->N * c->N);
+	RC(cnb_ctx_pairwise(c, CNB_PAIRWISE_ENTROPY, mat.data()));
+	cnb_entropy_order_from_matrix(mat.data(), c->N, order_out);
+	return CNB_OK;
+}
+
+static int pairwise_one_shot(int32_t kind, int32_t N, int32_t M, const int32_t *samples, const int32_t *pert,
+		int32_t device, double *out, int32_t *order_out) {
+	if (N < 1 || M < 1 || !samples) { cnb_set_error("Data should be a matrix"); return CNB_ERR_PARAM; }
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(device, &c));
+	int rc = cnb_ctx_set_samples(c, N, M, samples, pert, nullptr);   /* categories = value range, as the reference */
+	if (rc == CNB_OK) rc = order_out ? cnb_ctx_entropy_order(c, order_out) : cnb_ctx_pairwise(c, kind, out);
+	cnb_ctx_destroy(c);
+	return rc;
+}
+
+extern "C" int cnb_pairwise(int32_t kind, int32_t N, int32_t M, const int32_t *samples, const int32_t *pert,
+		int32_t device, double *out) {
+	if (!out) { cnb_set_error("cnb_pairwise: no output"); return CNB_ERR_PARAM; }
+	return pairwise_one_shot(kind, N, M, samples, pert, device, out, nullptr);
+}
+
+extern "C" int cnb_entropy_order(int32_t N, int32_t M, const int32_t *samples, const int32_t *pert, int32_t device,
+		int32_t *order_out) {
+	if (!order_out) { cnb_set_error("cnb_entropy_order: no output"); return CNB_ERR_PARAM; }
+	return pairwise_one_shot(CNB_PAIRWISE_ENTROPY, N, M, samples, pert, device, nullptr, order_out);
 }
 
 extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double *out) {

@@ -52,6 +52,11 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O);
 #define CNBK_UMMA_SLOT_INTS 36
+/* pairwise metrics (cnb_pairwise.cu): kind 0 entropy, 1 KL, 2 Pearson from the tables of the families (child n1,
+ * parent n2), family index n1 * (N - 1) + rank of n2 among the others; out[n2 * N + n1] */
+int cnbk_pairwise_metric(cudaStream_t st, int kind, int N, const int *cats, const int *kept, const int *full,
+		const int *diag_tab, int stride, double *out);
+void cnb_entropy_order_from_matrix(const double *mat, int N, int32_t *order_out);
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,

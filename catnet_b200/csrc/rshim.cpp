@@ -3,6 +3,7 @@
  * Exports what R's useDynLib(catnet) resolves for this path (reference src/ccnInit.c:29-52, prototypes
  * src/catnet_rexport.h:31-64):
  *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnParHistogram/14   ccnReleaseCache/0   ccnSetSeed/1
+ *     ccnEntropyPairwise/2   ccnEntropyOrder/2   ccnKLPairwise/2   ccnPearsonPairwise/2
  * and registers them in R_init_catnet.  Every other routine of the reference's table keeps its reference
  * implementation (this shim is linked INTO the package next to the reference sources).
  *
@@ -304,6 +305,56 @@ SEXP ccnParHistogram(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP 
 	return rmat;
 }
 
+/* catnetEntropyPairwise / catnetKLpairwise / catnetPearsonPairwise / catnetEntropyOrder (catnet_rexport.h;
+ * catnet_entropy.cpp:38-911), called from R/catnet.entropy.R:60-62, :94-96, :125-127 and R/catnet.chisq.R:27-29 */
+static void pairwise_args(SEXP &rSamples, SEXP &rPerturbations, int &N, int &M, int &nprot) {
+	if (!isMatrix(rSamples)) error("Data should be a matrix");                          /* catnet_entropy.cpp:47-48 */
+	if (!isNull(rPerturbations) && !isMatrix(rPerturbations)) error("Perturbations should be a matrix");
+	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
+	nprot = 1;
+	SEXP dim = getAttrib(rSamples, R_DimSymbol);
+	N = INTEGER(dim)[0];
+	M = INTEGER(dim)[1];
+	if (!isNull(rPerturbations)) {
+		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
+		nprot++;
+	}
+}
+
+static SEXP pairwise_call(int kind, SEXP rSamples, SEXP rPerturbations) {
+	int N, M, nprot;
+	pairwise_args(rSamples, rPerturbations, N, M, nprot);
+	SEXP rvec = PROTECT(allocVector(REALSXP, N * N));
+	int rc = cnb_pairwise(kind, N, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
+			REAL(rvec));
+	UNPROTECT(nprot + 1);
+	if (rc != CNB_OK) fail(rc);
+	return rvec;
+}
+
+SEXP ccnEntropyPairwise(SEXP rSamples, SEXP rPerturbations) {
+	return pairwise_call(CNB_PAIRWISE_ENTROPY, rSamples, rPerturbations);
+}
+
+SEXP ccnKLPairwise(SEXP rSamples, SEXP rPerturbations) {
+	return pairwise_call(CNB_PAIRWISE_KL, rSamples, rPerturbations);
+}
+
+SEXP ccnPearsonPairwise(SEXP rSamples, SEXP rPerturbations) {
+	return pairwise_call(CNB_PAIRWISE_PEARSON, rSamples, rPerturbations);
+}
+
+SEXP ccnEntropyOrder(SEXP rSamples, SEXP rPerturbations) {
+	int N, M, nprot;
+	pairwise_args(rSamples, rPerturbations, N, M, nprot);
+	SEXP rvec = PROTECT(allocVector(INTSXP, N));
+	int rc = cnb_entropy_order(N, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
+			INTEGER(rvec));
+	UNPROTECT(nprot + 1);
+	if (rc != CNB_OK) fail(rc);
+	return rvec;
+}
+
 SEXP ccnReleaseCache(void) {
 	cnb_release_cache();
 	return R_NilValue;
@@ -321,12 +372,16 @@ static const R_CallMethodDef cnb_call_methods[] = {
 	{"ccnParHistogram", (DL_FUNC)&ccnParHistogram, 14},
 	{"ccnReleaseCache", (DL_FUNC)&ccnReleaseCache, 0},
 	{"ccnSetSeed", (DL_FUNC)&ccnSetSeed, 1},
+	{"ccnEntropyPairwise", (DL_FUNC)&ccnEntropyPairwise, 2},
+	{"ccnEntropyOrder", (DL_FUNC)&ccnEntropyOrder, 2},
+	{"ccnKLPairwise", (DL_FUNC)&ccnKLPairwise, 2},
+	{"ccnPearsonPairwise", (DL_FUNC)&ccnPearsonPairwise, 2},
 	{NULL, NULL, 0}};
 
 const R_CallMethodDef *cnb_r_call_methods(void) { return cnb_call_methods; }
 
 #ifdef CNB_STANDALONE_RSHIM
-/* build as a complete catnet.so for the search path only (the other 10 routines are then unavailable) */
+/* build as a complete catnet.so for the search path only (the other 5 routines are then unavailable) */
 void R_init_catnet(DllInfo *info) {
 	R_registerRoutines(info, NULL, cnb_call_methods, NULL, NULL);
 	R_useDynamicSymbols(info, (Rboolean)1);

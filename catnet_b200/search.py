@@ -268,3 +268,44 @@ def cnSearchHist(data, perturbations=None, maxParentSet=1, parentSizes=None, max
                             device=device)
     # the C vector is [parent*N + child]; R's matrix(v, nrow = N) is column-major, i.e. element [child, parent]
     return np.ascontiguousarray(v.T)
+
+
+# ------------------------------------------------------------------ pairwise metrics ----
+def _pairwise_front(data, perturbations):
+    """argument handling shared by cnEntropy / cnEdgeDistanceKL / cnEdgeDistancePearson / cnEntropyOrder
+    (R/catnet.entropy.R:39-58): matrix of categories (nodes x samples) -> categorised int32 [M][N] for the C ABI"""
+    x = np.asarray(data)
+    if x.ndim != 2:
+        raise ValueError("'data' should be a matrix or data frame of categories")
+    cat, pert, _, _ = categorize_sample(x, perturbations)
+    if (cat == NA).any():
+        raise ValueError("pairwise metrics need complete data")
+    return np.ascontiguousarray(cat.T), None if pert is None else np.ascontiguousarray(pert.T)
+
+
+def cnEntropy(data, perturbations=None, device=0):
+    """R/catnet.entropy.R:39-67: matrix of conditional entropies, [n1, n2] = H(n1 | n2), diagonal H(n1)"""
+    s, p = _pairwise_front(data, perturbations)
+    return _abi.pairwise("entropy", s, p, device)
+
+
+def cnEdgeDistanceKL(data, perturbations, device=0):
+    """R/catnet.entropy.R:69-101"""
+    if perturbations is None:
+        warnings.warn("Perturbations are essential for estimating the pairwise causality")
+    s, p = _pairwise_front(data, perturbations)
+    return _abi.pairwise("kl", s, p, device)
+
+
+def cnEdgeDistancePearson(data, perturbations, device=0):
+    """R/catnet.chisq.R:2-34"""
+    if perturbations is None:
+        warnings.warn("Perturbations are essential for estimating the pairwise causality")
+    s, p = _pairwise_front(data, perturbations)
+    return _abi.pairwise("pearson", s, p, device)
+
+
+def cnEntropyOrder(data, perturbations=None, device=0):
+    """R/catnet.entropy.R:103-132: node order (1-based) by decreasing total mutual information"""
+    s, p = _pairwise_front(data, perturbations)
+    return _abi.entropy_order(s, p, device)

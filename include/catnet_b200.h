@@ -109,6 +109,26 @@ void cnb_set_seed(int32_t seed);
 const char *cnb_last_error(void);
 const char *cnb_version(void);
 
+/* ---- pairwise metrics: catnetEntropyPairwise / catnetKLpairwise / catnetPearsonPairwise /
+ * catnetEntropyOrder, src/catnet_entropy.cpp:38-911, prototypes src/catnet_rexport.h, .Call table src/ccnInit.c:29-45
+ * (ccnEntropyPairwise/2, ccnKLPairwise/2, ccnPearsonPairwise/2, ccnEntropyOrder/2) ----
+ * samples / perturbations: int32 [M][N] as in cnb_params (R's N x M column-major matrices), categories >= 1, no
+ * missing value (CNB_ERR_PARAM otherwise; the reference is undefined there); categories of a node = its value range.
+ * out: double[N*N], out[n2*N + n1] = the reference's klmat -- R reshapes it with matrix(mat, N, N) to [n1, n2]:
+ *   ENTROPY  H(n1 | n2) over the samples where n1 is not perturbed, diagonal H(n1);
+ *   KL       sum_i2,i1 p(i1|i2) log(p(i1|i2) / q(i1|i2)), p from the samples where n1 is not perturbed, q from all;
+ *   PEARSON  sum_i2,i1 (n(i2,i1) - n(i2) q(i1|i2))^2 / (n(i2) q(i1|i2)), n from the unperturbed samples of n1.
+ * Without perturbations KL and PEARSON are identically 0, as in the reference (its unperturbed sub-sample is empty). */
+#define CNB_PAIRWISE_ENTROPY 0
+#define CNB_PAIRWISE_KL 1
+#define CNB_PAIRWISE_PEARSON 2
+int cnb_pairwise(int32_t kind, int32_t num_nodes, int32_t num_samples, const int32_t *samples,
+		const int32_t *perturbations, int32_t device, double *out);
+/* order_out: int32[N], 1-based nodes by decreasing sum of mutual informations, ties handled like the reference's
+ * _order (src/utils.h:97-133): a run of equal ranks yields one node and zeros */
+int cnb_entropy_order(int32_t num_nodes, int32_t num_samples, const int32_t *samples, const int32_t *perturbations,
+		int32_t device, int32_t *order_out);
+
 /* ---- resident-context API (SA, bench, multi-process sharding) ---- */
 int cnb_ctx_create(int32_t device, cnb_ctx **out);
 void cnb_ctx_destroy(cnb_ctx *ctx);
@@ -127,6 +147,10 @@ int cnb_ctx_search_sa(cnb_ctx *ctx, const cnb_params *p, const cnb_sa_params *sa
 /* cnSearchHist on the resident data */
 int cnb_ctx_search_hist(cnb_ctx *ctx, const cnb_params *p, const cnb_hist_params *hp, double *hist_out,
 		int32_t *iterations_out);
+
+/* pairwise metrics on the resident data (whatever categories the context was given: empty categories change nothing) */
+int cnb_ctx_pairwise(cnb_ctx *ctx, int32_t kind, double *out);
+int cnb_ctx_entropy_order(cnb_ctx *ctx, int32_t *order_out);
 
 /* sharded search, one process per GPU: plan -> score own shard -> (caller all-gathers) -> finish.
  * The score buffer is one fp64 per candidate family, laid out rank-major: segment r (seg_len doubles) holds rank r's

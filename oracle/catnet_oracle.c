@@ -603,3 +603,166 @@ int orc_result_sa_trace(const orc_result *r, double *trace, int *accept, int cap
 	for (int i = 0; i < r->ntrace && i < cap; i++) { trace[i] = r->trace[i]; accept[i] = r->trace_accept[i]; }
 	return r->ntrace;
 }
+
+/* ------------------------------------------------------------------ pairwise metrics ---- */
+/* catnet_entropy.cpp:38-911 (catnetEntropyPairwise, catnetEntropyOrder, catnetKLpairwise, catnetPearsonPairwise).
+ * All four are functions of two kinds of two-way tables per ordered node pair (n1, n2):
+ *   kept[i2][i1] = samples with x_n2 = i2, x_n1 = i1 among those where n1 is NOT perturbed (every sample without
+ *                  perturbations; :144-157), and
+ *   full[i2][i1] = the same over all samples (:609-611, :832-834).
+ * Categories are the value range of the node, code = value - min (:63-107).  No missing values (the reference
+ * decrements NA_INTEGER, :61-63, which is undefined); this restatement returns -1 for any value < 1.
+ * out[n2*N + n1] as the reference fills klmat.  kind 0 entropy, 1 KL, 2 Pearson, 3 entropy order (order_out, 1-based). */
+static void orc_pair_table(const int *code, const int *pert, int N, int M, int n1, int n2, int C, int masked, int *tab) {
+	int j;
+	memset(tab, 0, (size_t)C * C * sizeof(int));
+	for (j = 0; j < M; j++) {
+		if (masked && pert && pert[(size_t)j * N + n1]) continue;
+		if (n1 == n2) tab[code[(size_t)j * N + n1]]++;                                  /* :165-167 marginal */
+		else tab[C * code[(size_t)j * N + n2] + code[(size_t)j * N + n1]]++;             /* :184-185 */
+	}
+}
+
+/* :163-203 -- conditional entropy H(n1 | n2) (n1 == n2: marginal entropy) from integer counts */
+static double orc_entropy_cell(const int *tab, int C, int c1, int c2, int same) {
+	double floglik = 0, fsum = 0, faux;
+	int i, j;
+	if (same) {
+		for (j = 0; j < c1; j++) {
+			fsum += tab[j];
+			if (tab[j] > 0) floglik += tab[j] * (double)log((double)tab[j]);
+		}
+		if (fsum > 0) {
+			floglik -= fsum * (double)log((double)fsum);
+			floglik /= fsum;
+		}
+		return -floglik;
+	}
+	for (i = 0; i < c2; i++) {
+		faux = 0;
+		for (j = 0; j < c1; j++) {
+			faux += tab[C * i + j];
+			if (tab[C * i + j] > 0) floglik += tab[C * i + j] * (double)log((double)tab[C * i + j]);
+		}
+		fsum += faux;
+		if (faux > 0) floglik -= faux * (double)log((double)faux);
+	}
+	if (fsum > 0) floglik /= fsum;
+	return -floglik;
+}
+
+/* row-normalise a table of doubles (:613-634, :836-846) */
+static void orc_row_normalise(double *p, int C, int c1, int c2) {
+	int i, j;
+	for (i = 0; i < c2; i++) {
+		double fsum = 0, faux;
+		for (j = 0; j < c1; j++) fsum += p[C * i + j];
+		if (fsum <= 0) continue;
+		faux = 1 / fsum;
+		for (j = 0; j < c1; j++) p[C * i + j] *= faux;
+	}
+}
+
+/* the reference's _order (utils.h:97-133) for decreasing = 1, holes and all: equal values mark each other used, so
+ * a run of t equal ranks fills one position (with the LAST of the tied indices) and leaves t-1 positions at -1 */
+static int orc_cmp_double(const void *a, const void *b) {
+	double x = *(const double *)a, y = *(const double *)b;
+	return x < y ? -1 : x > y;
+}
+static void orc_order_decreasing(const double *v, int n, int *porder) {
+	double *sorted = (double *)malloc((size_t)n * sizeof(double)), *aux = (double *)malloc((size_t)n * sizeof(double));
+	int i, j;
+	memcpy(sorted, v, (size_t)n * sizeof(double));
+	memcpy(aux, v, (size_t)n * sizeof(double));
+	qsort(sorted, (size_t)n, sizeof(double), orc_cmp_double);      /* _quick_sort: ascending */
+	if (n < 2) { free(sorted); free(aux); return; }                /* utils.h:98-99: porder untouched */
+	for (j = 1; j < n; j++) porder[j] = -1;
+	for (j = n - 1; j >= 0; j--)
+		for (i = 0; i < n; i++)
+			if (aux[i] == sorted[j]) {
+				porder[n - 1 - j] = i;
+				aux[i] = (double)FLT_MAX;
+			}
+	free(sorted);
+	free(aux);
+}
+
+int orc_pairwise(int kind, int N, int M, const int *samples, const int *pert, double *out, int *order_out) {
+	int *code = (int *)malloc((size_t)N * M * sizeof(int)), *cats = (int *)malloc((size_t)N * sizeof(int));
+	int i, j, n1, n2, C = 1;
+	for (i = 0; i < N; i++) {                                      /* :81-107 */
+		int lo = INT_MAX, hi = -INT_MAX;
+		for (j = 0; j < M; j++) {
+			int v = samples[(size_t)j * N + i];
+			if (v < 1) { free(code); free(cats); return -1; }
+			if (v < lo) lo = v;
+			if (v > hi) hi = v;
+		}
+		cats[i] = hi - lo + 1;
+		for (j = 0; j < M; j++) code[(size_t)j * N + i] = samples[(size_t)j * N + i] - lo;
+		if (cats[i] > C) C = cats[i];
+	}
+	int *tab = (int *)malloc((size_t)C * C * sizeof(int));
+	double *p1 = (double *)malloc((size_t)C * C * sizeof(double)), *p2 = (double *)malloc((size_t)C * C * sizeof(double));
+	double *mat = (double *)calloc((size_t)N * N, sizeof(double));
+	for (n1 = 0; n1 < N; n1++)
+		for (n2 = 0; n2 < N; n2++) {
+			if (kind == 0 || kind == 3) {
+				orc_pair_table(code, pert, N, M, n1, n2, C, 1, tab);
+				mat[(size_t)n2 * N + n1] = orc_entropy_cell(tab, C, cats[n1], cats[n2], n1 == n2);
+				continue;
+			}
+			if (n1 == n2) continue;                                /* :604-605, :827-828 */
+			/* without perturbations the "perturbed sub-sample" is EMPTY here (numsamplesPert = 0, :594-602), not
+			 * the whole sample as in the entropy functions */
+			if (pert) orc_pair_table(code, pert, N, M, n1, n2, C, 1, tab);
+			else memset(tab, 0, (size_t)C * C * sizeof(int));
+			for (i = 0; i < C * C; i++) p1[i] = tab[i];
+			orc_pair_table(code, pert, N, M, n1, n2, C, 0, tab);
+			for (i = 0; i < C * C; i++) p2[i] = tab[i];
+			double floglik = 0;
+			if (kind == 1) {                                       /* :613-647 */
+				orc_row_normalise(p1, C, cats[n1], cats[n2]);
+				orc_row_normalise(p2, C, cats[n1], cats[n2]);
+				for (i = 0; i < cats[n2]; i++)
+					for (j = 0; j < cats[n1]; j++) {
+						double a = p1[C * i + j], b = p2[C * i + j];
+						if (a > 0 && b > 0) floglik += a * (double)log((double)a / (double)b);
+						else if (a != 0 && b == 0) floglik = FLT_MAX;
+					}
+			} else {                                               /* :836-864 */
+				orc_row_normalise(p2, C, cats[n1], cats[n2]);
+				for (i = 0; i < cats[n2]; i++) {
+					double fsum = 0, faux;
+					for (j = 0; j < cats[n1]; j++) fsum += p1[C * i + j];
+					if (fsum <= 0) continue;
+					for (j = 0; j < cats[n1]; j++) {
+						double b = p2[C * i + j];
+						faux = p1[C * i + j] - fsum * b;
+						if (b > 0) floglik += (double)(faux * faux) / (double)(fsum * b);
+						else if (faux != 0 && b == 0) floglik = FLT_MAX;
+					}
+				}
+			}
+			mat[(size_t)n2 * N + n1] += floglik;
+		}
+	if (kind == 3) {                                               /* :428-440 */
+		double *ranks = (double *)malloc((size_t)N * sizeof(double));
+		for (n1 = 0; n1 < N; n1++) {
+			double faux = mat[(size_t)n1 * N + n1], s = 0;
+			for (n2 = 0; n2 < N; n2++) {
+				mat[(size_t)n2 * N + n1] = faux - mat[(size_t)n2 * N + n1];
+				s += mat[(size_t)n2 * N + n1];
+			}
+			ranks[n1] = s;
+		}
+		/* porder comes from CATNET_MALLOC without initialisation; position 0 is always written for N >= 2 */
+		for (i = 0; i < N; i++) order_out[i] = 0;
+		orc_order_decreasing(ranks, N, order_out);
+		for (i = 0; i < N; i++) order_out[i]++;
+		free(ranks);
+	} else
+		memcpy(out, mat, (size_t)N * N * sizeof(double));
+	free(code); free(cats); free(tab); free(p1); free(p2); free(mat);
+	return 0;
+}

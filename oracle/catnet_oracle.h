@@ -19,6 +19,8 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
 		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
 		const int *fixedPool_lbl, int scoreSel, int weight, int maxIter, int numThreads, double *hist);
+/* catnet_entropy.cpp pairwise metrics: kind 0 entropy, 1 KL, 2 Pearson -> out[n2*N + n1]; 3 entropy order -> order_out */
+int orc_pairwise(int kind, int N, int M, const int *samples_lbl, const int *pert_lbl, double *out, int *order_out);
 void orc_set_seed(unsigned long long seed);
 int orc_result_nslots(const orc_result *r);
 int orc_result_exists(const orc_result *r, int k);

@@ -158,3 +158,21 @@ def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_
                            int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),
                            _p(_pool(fixed_parents, N)), int(score), int(weight), int(max_iter), int(num_threads), _p(hist))
     return hist, it
+
+
+PAIRWISE_KINDS = {"entropy": 0, "kl": 1, "pearson": 2, "order": 3}
+
+
+def pairwise(kind, samples, perturbations=None):
+    """catnet_entropy.cpp restated (orc_pairwise).  samples [M][N] 1-based, no NA.  Returns out[n1][n2] like
+    oracle.ref.pairwise (R's matrix(mat, N, N)); for "order" the 1-based order vector."""
+    L = lib()
+    L.orc_pairwise.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    s = _i32(samples)
+    M, N = s.shape
+    out = np.zeros((N, N), dtype=np.float64)
+    order = np.zeros(N, dtype=np.int32)
+    rc = L.orc_pairwise(PAIRWISE_KINDS[kind], N, M, _p(s), _p(_i32(perturbations)), _p(out), _p(order))
+    if rc != 0:
+        raise ValueError("orc_pairwise: missing or non-positive category")
+    return order if kind == "order" else out.T.copy()

@@ -201,3 +201,37 @@ def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_
                            int(num_threads), int(bool(use_cache)), _p(hist))
     L.ref_release_cache()
     return hist, it
+
+
+# ---------------------------------------------------------------- pairwise metrics ----
+_PW_PATH = os.path.join(_HERE, "_ref", "libcatnet_ref_pairwise.so")
+_pw = None
+PAIRWISE_KINDS = {"entropy": 0, "kl": 1, "pearson": 2, "order": 3}
+
+
+def pairwise_available():
+    return os.path.exists(_PW_PATH)
+
+
+def pairwise(kind, samples, perturbations=None):
+    """The reference's own catnetEntropyPairwise / catnetKLpairwise / catnetPearsonPairwise / catnetEntropyOrder
+    (catnet_entropy.cpp, compiled unmodified; ref_pairwise.cpp).  samples: [M][N] int32 1-based categories, no NA.
+    Returns the R matrix `matrix(mat, N, N)` as numpy [N][N] with out[n1][n2] (= mat[n2*N + n1]); for "order" the
+    1-based node order (0 where the reference's tie handling leaves a hole, utils.h:97-133)."""
+    global _pw
+    if _pw is None:
+        if not pairwise_available():
+            raise RuntimeError("oracle/_ref/libcatnet_ref_pairwise.so missing: run `make -C oracle ref` where /root/reference exists")
+        _pw = C.CDLL(_PW_PATH)
+        _pw.ref_pairwise.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _pw.ref_pairwise.restype = C.c_int
+        _pw.ref_pairwise_last_error.restype = C.c_char_p
+    s = _i32(samples)
+    M, N = s.shape
+    p = _i32(perturbations)
+    out = np.zeros((N, N), dtype=np.float64)
+    order = np.zeros(N, dtype=np.int32)
+    rc = _pw.ref_pairwise(PAIRWISE_KINDS[kind], N, M, _p(s), _p(p), _p(out), _p(order))
+    if rc != 0:
+        raise RuntimeError("reference pairwise: " + _pw.ref_pairwise_last_error().decode())
+    return order if kind == "order" else out.T.copy()

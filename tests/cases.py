@@ -54,6 +54,41 @@ HIST_CASES = [
 ]
 
 
+# pairwise metrics (catnet_entropy.cpp): pert = fraction of perturbed (node, sample) entries; dup = a duplicated column
+# (ties in the entropy order); shift = categories not starting at 1; allpert = one node perturbed in every sample
+PAIRWISE_CASES = [
+    dict(seed=51, n=7, m=200, cats=None),
+    dict(seed=52, n=6, m=150, cats=3, pert=0.3),
+    dict(seed=53, n=8, m=100, cats=2, pert=0.5, dup=True),
+    dict(seed=54, n=5, m=90, cats=6, pert=0.2),                    # > 4 categories: histogram kernel
+    dict(seed=55, n=1, m=30, cats=3),
+    dict(seed=56, n=2, m=5, cats=2, pert=0.4),
+    dict(seed=57, n=9, m=257, cats=4, pert=0.25, allpert=True, dup=True),
+    dict(seed=58, n=40, m=9000, cats=None, shift=True),            # M >= 8192: pair tables from the tensor cores
+    dict(seed=59, n=12, m=9000, cats=4, pert=0.35),
+    dict(seed=60, n=6, m=33, cats=[2, 7, 3, 2, 5, 3], pert=0.3, shift=True),
+]
+
+
+def build_pairwise_case(c):
+    """-> (samples [M][N] 1-based without NA, perturbations [M][N] or None)"""
+    from helpers import random_problem
+    s, _ = random_problem(c["seed"], c["n"], c["m"], c.get("cats"))
+    rng = np.random.default_rng(2000 + c["seed"])
+    if c.get("dup") and c["n"] > 2:
+        s[:, 2] = s[:, 1]
+    if c.get("shift"):
+        s[:, ::2] += 2
+    p = None
+    if c.get("pert"):
+        p = (rng.random(s.shape) < c["pert"]).astype(np.int32)
+        if c.get("allpert"):
+            p[:, 0] = 1
+        if c.get("dup") and c["n"] > 2:
+            p[:, 2] = p[:, 1]
+    return s, p
+
+
 def build_hist_case(c):
     """-> (samples [M][N], kwargs of the checkers' search_hist)"""
     from helpers import random_problem

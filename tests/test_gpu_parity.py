@@ -13,7 +13,7 @@ import math
 import numpy as np
 import pytest
 
-from cases import CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case
+from cases import CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case, PAIRWISE_CASES, build_pairwise_case
 from helpers import NA, compare_golden, compare_search, load_golden, random_problem
 
 pytestmark = pytest.mark.gpu
@@ -354,6 +354,91 @@ def test_pair_tables_on_tensor_cores(abi):
         ctx.force_generic(8)                      # ... consumed by the bit-plane inclusion-exclusion scorer
         d = ctx.search_order(want_probs=True, **kw)
     assert compare_search(b, a) == len(a) and compare_search(d, a) == len(a)
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["auto", "histogram"])
+@pytest.mark.parametrize("case", PAIRWISE_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_pairwise_matches_reference(abi, case, generic):
+    """cnEntropy / cnEdgeDistanceKL / cnEdgeDistancePearson / cnEntropyOrder (catnet_entropy.cpp) against the outputs
+    of the reference's own functions, bit for bit; `generic` forces the shared-memory histogram scorer"""
+    s, p = build_pairwise_case(case)
+    g = load_golden("ref_pairwise")["seed%d" % case["seed"]]
+    with abi.Context(0) as ctx:
+        if generic:
+            ctx.force_generic(1)
+        ctx.set_samples(s, perturbations=p)
+        for kind in ("entropy", "kl", "pearson"):
+            assert ctx.pairwise(kind).tolist() == [[float.fromhex(v) for v in row] for row in g[kind]], kind
+        if g["order"] is not None:
+            assert ctx.entropy_order().tolist() == g["order"]
+    if not generic:
+        # the one-shot entry points the R shim calls
+        assert abi.pairwise("kl", s, p).tolist() == [[float.fromhex(v) for v in row] for row in g["kl"]]
+        if g["order"] is not None:
+            assert abi.entropy_order(s, p).tolist() == g["order"]
+
+
+@pytest.mark.parametrize("seed", range(400, 420))
+def test_pairwise_random_vs_oracle(abi, port, seed):
+    rng = np.random.default_rng(seed)
+    m, n, c = int(rng.integers(1, 700)), int(rng.integers(1, 30)), int(rng.integers(1, 9))
+    s = rng.integers(1, c + 1, size=(m, n)).astype(np.int32) + int(rng.integers(0, 3))
+    if n > 2:
+        s[:, 2] = np.where(rng.random(m) < 0.7, s[:, 1], s[:, 2])
+    p = (rng.random((m, n)) < rng.random()).astype(np.int32) if seed % 2 else None
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=p)
+        for kind in ("entropy", "kl", "pearson"):
+            assert np.array_equal(ctx.pairwise(kind), port.pairwise(kind, s, p)), kind
+        if n > 1:
+            assert np.array_equal(ctx.entropy_order(), port.pairwise("order", s, p))
+
+
+def test_pairwise_large_properties(abi, port):
+    """C5-shaped data (reduced M): the matrices agree with the oracle on a sample of entries, H(n1|n2) <= H(n1),
+    mutual information is symmetric, and permuting the samples changes nothing"""
+    rng = np.random.default_rng(7)
+    m, n = 40000, 120
+    s = rng.integers(1, 5, size=(m, n)).astype(np.int32)
+    s[:, 1::2] = np.where(rng.random((m, n // 2)) < 0.6, s[:, 0::2], s[:, 1::2])
+    p = (rng.random((m, n)) < 0.3).astype(np.int32)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s)
+        h = ctx.pairwise("entropy")
+        assert np.array_equal(ctx.pairwise("kl"), np.zeros((n, n)))
+    d = np.diag(h)
+    assert (h <= d[:, None] + 1e-12).all()
+    mi = d[:, None] - h
+    assert np.allclose(mi, mi.T, rtol=0, atol=1e-12)
+    sub = [0, 1, 2, 57, 119]
+    ho = port.pairwise("entropy", s[:, sub])
+    assert np.array_equal(h[np.ix_(sub, sub)], ho)
+    perm = rng.permutation(m)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=p)
+        e1, k1, x1 = ctx.pairwise("entropy"), ctx.pairwise("kl"), ctx.pairwise("pearson")
+        o1 = ctx.entropy_order()
+        ctx.set_samples(s[perm], perturbations=p[perm])
+        assert np.array_equal(e1, ctx.pairwise("entropy")) and np.array_equal(k1, ctx.pairwise("kl"))
+        assert np.array_equal(x1, ctx.pairwise("pearson")) and np.array_equal(o1, ctx.entropy_order())
+    for kind, mat in (("entropy", e1), ("kl", k1), ("pearson", x1)):
+        assert np.array_equal(mat[np.ix_(sub, sub)], port.pairwise(kind, s[:, sub], p[:, sub])), kind
+
+
+def test_pairwise_python_front_end(abi, port):
+    from catnet_b200 import search
+    s, _ = random_problem(77, 6, 120, 3)
+    p = (np.random.default_rng(5).random(s.shape) < 0.3).astype(np.int32)
+    data = (s.T * 10).astype(np.float64)           # nodes x samples, arbitrary category values
+    assert np.array_equal(search.cnEntropy(data), port.pairwise("entropy", s))
+    assert np.array_equal(search.cnEdgeDistanceKL(data, p.T), port.pairwise("kl", s, p))
+    assert np.array_equal(search.cnEdgeDistancePearson(data, p.T), port.pairwise("pearson", s, p))
+    assert np.array_equal(search.cnEntropyOrder(data, p.T), port.pairwise("order", s, p))
+    bad = s.copy()
+    bad[4, 2] = NA
+    with pytest.raises(abi.CnbError) as e:
+        abi.pairwise("entropy", bad)
+    assert e.value.code == abi.CNB_ERR_PARAM
 
 
 def test_search_hist_python_front_end(abi):

@@ -7,7 +7,7 @@ All fp64 comparisons are bit-exact."""
 import numpy as np
 import pytest
 
-from cases import CASES, HIST_CASES, SA_CASES, build_case, build_hist_case, ref_args
+from cases import CASES, HIST_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case, build_pairwise_case, ref_args
 from helpers import compare_golden, compare_search, load_golden, random_problem
 from oracle import port
 
@@ -93,3 +93,38 @@ def test_port_sa_matches_reference_core(ref):
     assert np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"] and a["naccept"] == b["naccept"]
     assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["trace_accept"], b["trace_accept"])
     compare_search(b["nets"], a["nets"], check_probs=False)
+
+
+@pytest.mark.parametrize("case", PAIRWISE_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_pairwise_matches_golden(case):
+    """catnet_entropy.cpp: entropy / KL / Pearson matrices and the entropy order, bit for bit"""
+    s, p = build_pairwise_case(case)
+    g = load_golden("ref_pairwise")["seed%d" % case["seed"]]
+    for kind in ("entropy", "kl", "pearson"):
+        assert port.pairwise(kind, s, p).tolist() == [[float.fromhex(v) for v in row] for row in g[kind]], kind
+    if g["order"] is not None:
+        assert port.pairwise("order", s, p).tolist() == g["order"]
+
+
+@pytest.mark.parametrize("seed", range(300, 330))
+def test_port_pairwise_matches_reference(ref, seed):
+    from oracle import ref as r
+    if not r.pairwise_available():
+        pytest.skip("oracle/_ref/libcatnet_ref_pairwise.so not built")
+    rng = np.random.default_rng(seed)
+    m, n, c = int(rng.integers(1, 300)), int(rng.integers(2, 9)), int(rng.integers(1, 7))
+    s = rng.integers(1, c + 1, size=(m, n)).astype(np.int32)
+    if n > 2:
+        s[:, 2] = np.where(rng.random(m) < 0.7, s[:, 1], s[:, 2])
+    if seed % 5 == 0:
+        s[:, 0] = s[:, 1]
+    p = (rng.random((m, n)) < rng.random()).astype(np.int32) if seed % 2 else None
+    for kind in ("entropy", "kl", "pearson", "order"):
+        assert np.array_equal(r.pairwise(kind, s, p), port.pairwise(kind, s, p)), kind
+
+
+def test_port_pairwise_rejects_missing_values():
+    s, _ = random_problem(1, 4, 20, 3)
+    s[3, 1] = -2147483648
+    with pytest.raises(ValueError):
+        port.pairwise("entropy", s)

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import random_problem  # noqa: E402
-from cases import CASES, HIST_CASES, SA_CASES, build_case, build_hist_case  # noqa: E402
+from cases import CASES, HIST_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case, build_pairwise_case  # noqa: E402
 
 from catnet_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
@@ -40,7 +40,24 @@ def pack_nets(nets, with_nodes=True):
     return out
 
 
+def make_pairwise():
+    """catnetEntropyPairwise / KLpairwise / PearsonPairwise / EntropyOrder of the reference's own catnet_entropy.cpp
+    (oracle/_ref/libcatnet_ref_pairwise.so)"""
+    pw = {}
+    for case in PAIRWISE_CASES:
+        s, p = build_pairwise_case(case)
+        g = {}
+        for kind in ("entropy", "kl", "pearson"):
+            g[kind] = [[float(v).hex() for v in row] for row in ref.pairwise(kind, s, p)]
+        g["order"] = [int(v) for v in ref.pairwise("order", s, p)] if case["n"] > 1 else None   # N = 1: uninitialised there
+        pw["seed%d" % case["seed"]] = g
+    dump(pw, "ref_pairwise.json")
+    print("ref_pairwise.json", len(pw))
+
+
 def main():
+    if "--only-pairwise" in sys.argv:
+        return make_pairwise()
     fam = []
     for seed, cats, na in [(1, None, 0.0), (2, 3, 0.1), (3, 2, 0.0), (4, 4, 0.05)]:
         s, c = random_problem(seed, 8, 150, cats, na)
@@ -87,6 +104,7 @@ def main():
         hist["seed%d" % case["seed"]] = {"iterations": it, "hist": [[float(v).hex() for v in row] for row in h]}
     dump(hist, "ref_search_hist.json")
     print("ref_search_hist.json", {k: v["iterations"] for k, v in hist.items()})
+    make_pairwise()
     if "--skip-configs" in sys.argv:
         return
     big = {}
