@@ -42,6 +42,12 @@ class HistParams(C.Structure):
                 ("use_cache", C.c_int32), ("seed", C.c_uint64)]
 
 
+class Network(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("max_parents", C.c_int32), ("num_cats", C.c_void_p),
+                ("num_parents", C.c_void_p), ("parents", C.c_void_p), ("probs", C.c_void_p),
+                ("prob_offsets", C.c_void_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [("pack_ms", C.c_float), ("plan_ms", C.c_float), ("score_ms", C.c_float), ("select_ms", C.c_float),
                 ("dp_ms", C.c_float), ("collect_ms", C.c_float), ("total_ms", C.c_float),
@@ -67,6 +73,7 @@ SYMBOLS = [
     "cnb_result_network", "cnb_result_parents", "cnb_result_order", "cnb_result_cats", "cnb_result_counts", "cnb_result_node",
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
     "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
+    "cnb_loglik", "cnb_node_loglik", "cnb_set_prob", "cnb_ctx_loglik", "cnb_ctx_set_prob",
 ]
 
 _lib = None
@@ -128,6 +135,11 @@ def lib():
         "cnb_entropy_order": (i32, [i32, i32, vp, vp, i32, vp]),
         "cnb_ctx_pairwise": (i32, [vp, i32, vp]),
         "cnb_ctx_entropy_order": (i32, [vp, vp]),
+        "cnb_loglik": (i32, [P(Network), i32, vp, vp, i32, i32, vp]),
+        "cnb_node_loglik": (i32, [P(Network), i32, vp, i32, vp, vp, i32, vp]),
+        "cnb_set_prob": (i32, [P(Network), i32, vp, vp, i32, vp, vp, vp]),
+        "cnb_ctx_loglik": (i32, [vp, P(Network), i32, i32, vp, vp]),
+        "cnb_ctx_set_prob": (i32, [vp, P(Network), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -361,6 +373,27 @@ class Context:
         check(lib().cnb_ctx_entropy_order(self.h, ptr(out)))
         return out
 
+    def loglik(self, cats, parents, probs, mode="nodes", nodes=None):
+        """likelihood of the resident data under a given network (parents: lists of 0-based nodes in listed order;
+        probs: list of flat tables).  mode "nodes" -> [N] (or the listed 1-based `nodes`), "bysample" -> [M]"""
+        keep = Keep()
+        net, off = make_network(keep, cats, parents, probs)
+        sel = i32(nodes)
+        nsel = 0 if sel is None else len(sel)
+        out = np.zeros(self.m if mode == "bysample" else (nsel or self.n), dtype=np.float64)
+        check(lib().cnb_ctx_loglik(self.h, C.byref(net), LOGLIK_MODES[mode], nsel, ptr(sel), ptr(out)))
+        return out
+
+    def set_prob(self, cats, parents):
+        """cnSetProb on the resident data -> (list of tables, loglik [N], sample sizes [N])"""
+        keep = Keep()
+        net, off = make_network(keep, cats, parents, None)
+        probs = np.zeros(off[-1], dtype=np.float64)
+        ll = np.zeros(self.n, dtype=np.float64)
+        sizes = np.zeros(self.n, dtype=np.int32)
+        check(lib().cnb_ctx_set_prob(self.h, C.byref(net), ptr(probs), ptr(ll), ptr(sizes)))
+        return [probs[off[k]:off[k + 1]].copy() for k in range(self.n)], ll, sizes
+
     def search_hist(self, hist, **kw):
         keep = Keep()
         p = make_params(keep, self.n, self.m, **kw)
@@ -380,6 +413,70 @@ class Context:
             return read_sa_result(h, self.n, want_probs)
         finally:
             lib().cnb_result_free(h)
+
+
+LOGLIK_MODES = {"nodes": 0, "bysample": 1}
+
+
+def make_network(keep, cats, parents, probs=None):
+    """(cats [N], parents: list of lists of 0-BASED nodes in listed order, probs: list of flat tables or None)
+    -> (Network struct, offsets).  The ABI takes 1-based parents, as the S4 object holds them."""
+    cats = i32(cats)
+    n = len(cats)
+    maxp = max([len(p) for p in parents] + [1])
+    npar = np.array([len(p) for p in parents], dtype=np.int32)
+    pars = np.zeros((n, maxp), dtype=np.int32)
+    off = np.zeros(n + 1, dtype=np.int64)
+    for k, p in enumerate(parents):
+        pars[k, :len(p)] = np.asarray(p, dtype=np.int32) + 1
+        size = int(cats[k])
+        for q in p:
+            size *= int(cats[q]) if 0 <= q < n else 1       # the library reports the invalid parent
+        off[k + 1] = off[k] + size
+    flat = None
+    if probs is not None:
+        flat = f64(np.concatenate([np.asarray(t, dtype=np.float64).ravel() for t in probs]))
+        if len(flat) != off[-1]:
+            raise ValueError("probability tables do not match the network")
+    net = Network()
+    net.num_nodes, net.max_parents = n, maxp
+    net.num_cats, net.num_parents, net.parents = keep(cats), keep(npar), keep(pars)
+    net.probs, net.prob_offsets = keep(flat), keep(off)
+    return net, off
+
+
+def loglik(samples, cats, parents, probs, perturbations=None, mode="nodes", device=0):
+    """one-shot cnb_loglik (ccnLoglik in the R shim)"""
+    s = i32(samples)
+    m, n = s.shape
+    keep = Keep()
+    net, _ = make_network(keep, cats, parents, probs)
+    out = np.zeros(m if mode == "bysample" else n, dtype=np.float64)
+    check(lib().cnb_loglik(C.byref(net), m, ptr(s), ptr(i32(perturbations)), LOGLIK_MODES[mode], int(device), ptr(out)))
+    return out
+
+
+def node_loglik(samples, cats, parents, probs, nodes, perturbations=None, device=0):
+    s = i32(samples)
+    m, n = s.shape
+    keep = Keep()
+    net, _ = make_network(keep, cats, parents, probs)
+    sel = i32(nodes)
+    out = np.zeros(len(sel), dtype=np.float64)
+    check(lib().cnb_node_loglik(C.byref(net), len(sel), ptr(sel), m, ptr(s), ptr(i32(perturbations)), int(device), ptr(out)))
+    return out
+
+
+def set_prob(samples, cats, parents, perturbations=None, device=0):
+    s = i32(samples)
+    m, n = s.shape
+    keep = Keep()
+    net, off = make_network(keep, cats, parents, None)
+    probs = np.zeros(off[-1], dtype=np.float64)
+    ll = np.zeros(n, dtype=np.float64)
+    sizes = np.zeros(n, dtype=np.int32)
+    check(lib().cnb_set_prob(C.byref(net), m, ptr(s), ptr(i32(perturbations)), int(device), ptr(probs), ptr(ll), ptr(sizes)))
+    return [probs[off[k]:off[k + 1]].copy() for k in range(n)], ll, sizes
 
 
 PAIRWISE_KINDS = {"entropy": 0, "kl": 1, "pearson": 2}

@@ -1068,6 +1068,201 @@ extern "C" int cnb_entropy_order(int32_t N, int32_t M, const int32_t *samples, c
 	return pairwise_one_shot(CNB_PAIRWISE_ENTROPY, N, M, samples, pert, device, nullptr, order_out);
 }
 
+/* ------------------------------------------------------------------ a given network ---- */
+/* validate a cnb_network against the resident data and flatten it: 0-based parents, table sizes */
+static int check_network(cnb_ctx *c, const cnb_network *net, bool need_probs, std::vector<int32_t> *ints,
+		std::vector<long long> *off) {
+	if (!c || !c->have_samples || !net || !net->num_cats || !net->num_parents || !net->prob_offsets
+			|| (need_probs && !net->probs) || net->max_parents < 0 || (net->max_parents > 0 && !net->parents)) {
+		cnb_set_error("network: bad arguments");
+		return CNB_ERR_PARAM;
+	}
+	const int N = c->N, maxp = std::max(net->max_parents, 1);
+	if (net->num_nodes != N) { cnb_set_error("The number of nodes in the object and data should be equal"); return CNB_ERR_PARAM; }
+	ints->assign((size_t)2 * N + (size_t)N * maxp, 0);
+	off->assign(N + 1, 0);
+	for (int i = 0; i < N; i++) {
+		if (net->num_cats[i] != c->cats_lbl[i]) {
+			cnb_set_error("node %d: the object has %d categories, the resident data %d", i + 1, net->num_cats[i], c->cats_lbl[i]);
+			return CNB_ERR_PARAM;
+		}
+		const int d = net->num_parents[i];
+		if (d < 0 || d > net->max_parents || d > CNB_MAXP) { cnb_set_error("node %d: %d parents (at most %d)", i + 1, d, CNB_MAXP); return CNB_ERR_PARAM; }
+		(*ints)[i] = net->num_cats[i];
+		(*ints)[N + i] = d;
+		long long size = net->num_cats[i];
+		for (int k = 0; k < d; k++) {
+			const int q = net->parents[(size_t)i * net->max_parents + k] - 1;
+			if (q < 0 || q >= N || q == i) { cnb_set_error("node %d: invalid parent", i + 1); return CNB_ERR_PARAM; }
+			(*ints)[(size_t)2 * N + (size_t)i * maxp + k] = q;
+			size *= net->num_cats[q];
+		}
+		if (net->prob_offsets[i + 1] - net->prob_offsets[i] != size || net->prob_offsets[i] < 0) {
+			cnb_set_error("node %d: table of %lld cells expected", i + 1, size);
+			return CNB_ERR_PARAM;
+		}
+		(*off)[i] = net->prob_offsets[i];
+		(*off)[i + 1] = net->prob_offsets[i + 1];
+	}
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_loglik(cnb_ctx *c, const cnb_network *net, int32_t mode, int32_t num_sel, const int32_t *nodes,
+		double *out) {
+	std::vector<int32_t> ints;
+	std::vector<long long> off;
+	RC(check_network(c, net, true, &ints, &off));
+	if (!out || (mode != CNB_LOGLIK_NODES && mode != CNB_LOGLIK_BYSAMPLE) || num_sel < 0 || (num_sel > 0 && !nodes)) {
+		cnb_set_error("cnb_ctx_loglik: bad arguments");
+		return CNB_ERR_PARAM;
+	}
+	CK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int N = c->N, maxp = std::max(net->max_parents, 1);
+	const long long base = off[0], total = off[N] - base;
+	bool any_zero = false;
+	for (long long k = 0; k < total && !any_zero; k++) any_zero = !(net->probs[base + k] > 0);
+	for (auto &o : off) o -= base;
+	RC(upload(c, c->b_net_int, ints));
+	RC(upload(c, c->b_net_off, off));
+	RC(c->b_net_probs.ensure(std::max<long long>(total, 1) * sizeof(double)));
+	RC(c->b_net_logp.ensure(std::max<long long>(total, 1) * sizeof(double)));
+	H2D(c, c->b_net_probs.ptr, net->probs + base, total * sizeof(double));
+	RC(cnbk_net_logp(st, (const double *)c->b_net_probs.ptr, total, (double *)c->b_net_logp.ptr));
+	CnbDevNet dn;
+	dn.N = N;
+	dn.maxp = maxp;
+	dn.cats = (const int *)c->b_net_int.ptr;
+	dn.npar = dn.cats + N;
+	dn.pars = dn.cats + 2 * N;
+	dn.off = (const long long *)c->b_net_off.ptr;
+	dn.logp = (const double *)c->b_net_logp.ptr;
+	const uint32_t *keep = c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr;
+	size_t nout;
+	if (mode == CNB_LOGLIK_NODES) {
+		std::vector<int32_t> sel(num_sel);
+		for (int k = 0; k < num_sel; k++) {
+			if (nodes[k] < 1 || nodes[k] > N) { cnb_set_error("Wrong node"); return CNB_ERR_PARAM; }   /* R/catnet.loglik.R:341 */
+			sel[k] = nodes[k] - 1;
+		}
+		nout = num_sel ? num_sel : N;
+		if (num_sel) RC(upload(c, c->b_net_sel, sel));
+		RC(c->b_pw_out.ensure(nout * sizeof(double)));
+		RC(cnbk_net_nodes(st, dn, (const uint8_t *)c->b_codes.ptr, keep, c->Mpad, num_sel ? (const int *)c->b_net_sel.ptr : nullptr,
+				(int)nout, (double *)c->b_pw_out.ptr));
+		c->timing.kernel_launches = 2;
+	} else {
+		nout = c->M;
+		RC(c->b_pw_out.ensure(nout * sizeof(double)));
+		RC(c->b_net_fz.ensure((size_t)N * sizeof(int)));
+		RC(cnbk_net_bysample(st, dn, (const uint8_t *)c->b_codes.ptr, keep, c->M, c->Mpad, (int *)c->b_net_fz.ptr, any_zero,
+				(double *)c->b_pw_out.ptr));
+		c->timing.kernel_launches = any_zero ? 3 : 2;
+	}
+	D2H(c, out, c->b_pw_out.ptr, nout * sizeof(double));
+	CK(cudaStreamSynchronize(st));
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_set_prob(cnb_ctx *c, const cnb_network *net, double *probs_out, double *loglik_out,
+		int32_t *sizes_out) {
+	std::vector<int32_t> ints;
+	std::vector<long long> off;
+	RC(check_network(c, net, false, &ints, &off));
+	if (!probs_out) { cnb_set_error("cnb_ctx_set_prob: no output"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	const int N = c->N, maxp = std::max(net->max_parents, 1);
+	cnb_params q;
+	memset(&q, 0, sizeof(q));
+	q.num_nodes = N;
+	q.num_samples = c->M;
+	q.max_complexity = INT32_MAX / 2;
+	RC(cnb_ctx_plan(c, &q, 0, 1, nullptr, nullptr));           /* identity order: families by label */
+	/* the families of the network, grouped by parent count (one launch class each) */
+	std::vector<int32_t> perm(N), ch(N), pa((size_t)N * CNB_MAXP, 0), nd(N);
+	for (int i = 0; i < N; i++) perm[i] = i;
+	std::stable_sort(perm.begin(), perm.end(), [&](int u, int v) { return ints[N + u] < ints[N + v]; });
+	int dmax = 0;
+	for (int k = 0; k < N; k++) {
+		const int i = perm[k];
+		ch[k] = i;
+		nd[k] = ints[N + i];
+		dmax = std::max(dmax, nd[k]);
+		for (int p = 0; p < nd[k]; p++) pa[(size_t)k * CNB_MAXP + p] = ints[(size_t)2 * N + (size_t)i * maxp + p];
+	}
+	const int stride = table_stride(c->max_cats, dmax);
+	if (stride >= (1 << 24)) { cnb_set_error("conditional table too large"); return CNB_ERR_MEM; }
+	RC(score_explicit_groups(c, ch, pa, nd, stride));
+	cudaStream_t st = c->stream;
+	std::vector<int32_t> counts((size_t)N * stride), ncount(N), kept(N, c->M);
+	std::vector<double> ll(N);
+	D2H(c, counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int));
+	D2H(c, ncount.data(), c->b_ex_ncount.ptr, N * sizeof(int));
+	D2H(c, ll.data(), c->b_ex_ll.ptr, N * sizeof(double));
+	if (c->has_pert) {
+		RC(c->b_net_fz.ensure((size_t)N * sizeof(int)));
+		RC(cnbk_keep_count(st, (const uint32_t *)c->b_keep_lbl.ptr, N, c->W, (int *)c->b_net_fz.ptr));
+		D2H(c, kept.data(), c->b_net_fz.ptr, N * sizeof(int));
+	}
+	int ovf = 0;
+	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
+	CK(cudaStreamSynchronize(st));
+	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	for (int k = 0; k < N; k++) {
+		const int i = perm[k], cc = c->cats_lbl[i];
+		const long long size = off[i + 1] - off[i];
+		const int32_t *tab = counts.data() + (size_t)k * stride;
+		double *dst = probs_out + off[i];
+		for (long long b = 0; b < size; b += cc) {                /* problist.h:193-222 */
+			double pp = 0;
+			for (int x = 0; x < cc; x++) pp += (double)tab[b + x];
+			if (pp > 0) {
+				pp = 1 / pp;
+				for (int x = 0; x < cc; x++) dst[b + x] = (double)tab[b + x] * pp;
+			} else {
+				const double favg = (double)1 / (double)cc;
+				double acc = 0;
+				for (int x = 0; x < cc - 1; x++) { dst[b + x] = favg; acc += favg; }
+				dst[b + cc - 1] = 1 - acc;
+			}
+		}
+		/* setNodeSampleProb on an empty sample returns -FLT_MAX before touching the table (catnet_class.h:824-826) */
+		if (loglik_out) loglik_out[i] = kept[i] < 1 ? CNB_NEG_INF : ll[k];
+		if (sizes_out) sizes_out[i] = ncount[k];
+	}
+	return CNB_OK;
+}
+
+/* one-shot forms: what ccnLoglik / ccnNodeLoglik / ccnSetProb call */
+template <class Fn>
+static int with_network_ctx(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert, int32_t device, Fn fn) {
+	if (!net || !net->num_cats || net->num_nodes < 1 || M < 1 || !samples) { cnb_set_error("'data' should be a matrix of categories"); return CNB_ERR_PARAM; }
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(device, &c));
+	int rc = cnb_ctx_set_samples(c, net->num_nodes, M, samples, pert, net->num_cats);
+	if (rc == CNB_OK) rc = fn(c);
+	cnb_ctx_destroy(c);
+	return rc;
+}
+
+extern "C" int cnb_loglik(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert, int32_t mode,
+		int32_t device, double *out) {
+	return with_network_ctx(net, M, samples, pert, device, [&](cnb_ctx *c) { return cnb_ctx_loglik(c, net, mode, 0, nullptr, out); });
+}
+
+extern "C" int cnb_node_loglik(const cnb_network *net, int32_t num_sel, const int32_t *nodes, int32_t M,
+		const int32_t *samples, const int32_t *pert, int32_t device, double *out) {
+	if (num_sel < 1 || !nodes) { cnb_set_error("Wrong node"); return CNB_ERR_PARAM; }
+	return with_network_ctx(net, M, samples, pert, device,
+			[&](cnb_ctx *c) { return cnb_ctx_loglik(c, net, CNB_LOGLIK_NODES, num_sel, nodes, out); });
+}
+
+extern "C" int cnb_set_prob(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert,
+		int32_t device, double *probs_out, double *loglik_out, int32_t *sizes_out) {
+	return with_network_ctx(net, M, samples, pert, device,
+			[&](cnb_ctx *c) { return cnb_ctx_set_prob(c, net, probs_out, loglik_out, sizes_out); });
+}
+
 extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double *out) {
 	cnb_ctx *c = nullptr;
 	RC(cnb_ctx_create(device, &c));

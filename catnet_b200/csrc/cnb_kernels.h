@@ -57,6 +57,19 @@ int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin
 int cnbk_pairwise_metric(cudaStream_t st, int kind, int N, const int *cats, const int *kept, const int *full,
 		const int *diag_tab, int stride, double *out);
 void cnb_entropy_order_from_matrix(const double *mat, int N, int32_t *order_out);
+/* a fixed network on the device (cnb_network.cu): parents 0-based labels in listed order, tables concatenated by off */
+struct CnbDevNet {
+	int N, maxp;
+	const int *cats, *npar, *pars;   /* [N], [N], [N][maxp] */
+	const long long *off;            /* [N + 1] */
+	const double *logp;              /* log of every table cell, +inf where the probability is not > 0 */
+};
+int cnbk_net_logp(cudaStream_t st, const double *probs, long long n, double *logp);
+int cnbk_net_nodes(cudaStream_t st, const CnbDevNet &net, const uint8_t *codes, const uint32_t *keep_lbl, int Mpad,
+		const int *sel, int nsel, double *out);
+int cnbk_net_bysample(cudaStream_t st, const CnbDevNet &net, const uint8_t *codes, const uint32_t *keep_lbl, int M,
+		int Mpad, int *first_zero, bool any_zero, double *out);
+int cnbk_keep_count(cudaStream_t st, const uint32_t *keep_lbl, int N, int W, int *out);
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,

@@ -129,6 +129,39 @@ int cnb_pairwise(int32_t kind, int32_t num_nodes, int32_t num_samples, const int
 int cnb_entropy_order(int32_t num_nodes, int32_t num_samples, const int32_t *samples, const int32_t *perturbations,
 		int32_t device, int32_t *order_out);
 
+/* ---- a given network against data: cnLoglik, cnNodeLoglik, cnSetProb ----
+ * R: .Call("ccnLoglik", object, data, perturbations, bysample) R/catnet.loglik.R:98-100, .Call("ccnNodeLoglik", object,
+ * node, data, perturbations) :354-356, .Call("ccnSetProb", object, data, perturbations) R/catnet.samples.R:423-425;
+ * registered in src/ccnInit.c:32-34, prototypes src/catnet_rexport.h.  The bodies of that glue are absent from the
+ * reference snapshot; the semantics are those of the class methods it forwards to: CATNET::sampleLoglikVector,
+ * bySampleLoglikVector, sampleNodeLoglik (src/catnet_class.h:616-815) and setNodeSampleProb (:818-879).
+ * cnb_network is what RCatnet::RCatnet(SEXP) reads off the S4 catNetwork (src/rcatnet.cpp:38-172). */
+typedef struct cnb_network {
+	int32_t num_nodes;
+	int32_t max_parents;          /* row stride of parents[] (>= every num_parents[i], <= 8) */
+	const int32_t *num_cats;      /* [N] categories per node */
+	const int32_t *num_parents;   /* [N] */
+	const int32_t *parents;       /* [N][max_parents] 1-based nodes in the object's listed order: the first listed parent is
+	                                 the most significant index of the node's table (src/problist.h:252-263) */
+	const double *probs;          /* conditional tables, node after node, child category fastest; NULL for cnb_set_prob */
+	const int64_t *prob_offsets;  /* [N + 1] start of every node's table in probs[] */
+} cnb_network;
+#define CNB_LOGLIK_NODES 0        /* out[N]: per node, mean over its complete unperturbed samples of log P(x | parents) */
+#define CNB_LOGLIK_BYSAMPLE 1     /* out[M]: per sample, sum over the nodes */
+/* samples / perturbations as in cnb_params; values outside 1..num_cats[i] (NA_INTEGER, < 1) are missing and skip the
+ * sample for the families they touch; a value above num_cats[i] is CNB_ERR_PARAM ("Data has more categories than the
+ * object", R/catnet.loglik.R:91-92).  A zero probability met by a counted sample gives -FLT_MAX. */
+int cnb_loglik(const cnb_network *net, int32_t num_samples, const int32_t *samples, const int32_t *perturbations,
+		int32_t mode, int32_t device, double *out);
+/* the per-node values of CNB_LOGLIK_NODES for the listed nodes only (1-based) */
+int cnb_node_loglik(const cnb_network *net, int32_t num_sel, const int32_t *nodes, int32_t num_samples,
+		const int32_t *samples, const int32_t *perturbations, int32_t device, double *out);
+/* cnSetProb: tables of the network's families estimated from the data (counts normalised per parent configuration,
+ * unobserved configurations uniform, src/problist.h:193-222) into probs_out (laid out by net->prob_offsets), the
+ * families' sample-averaged log-likelihoods into loglik_out[N], their sample sizes into sizes_out[N] */
+int cnb_set_prob(const cnb_network *net, int32_t num_samples, const int32_t *samples, const int32_t *perturbations,
+		int32_t device, double *probs_out, double *loglik_out, int32_t *sizes_out);
+
 /* ---- resident-context API (SA, bench, multi-process sharding) ---- */
 int cnb_ctx_create(int32_t device, cnb_ctx **out);
 void cnb_ctx_destroy(cnb_ctx *ctx);
@@ -151,6 +184,10 @@ int cnb_ctx_search_hist(cnb_ctx *ctx, const cnb_params *p, const cnb_hist_params
 /* pairwise metrics on the resident data (whatever categories the context was given: empty categories change nothing) */
 int cnb_ctx_pairwise(cnb_ctx *ctx, int32_t kind, double *out);
 int cnb_ctx_entropy_order(cnb_ctx *ctx, int32_t *order_out);
+
+/* a given network on the resident data (the context must have been given net->num_cats as its categories) */
+int cnb_ctx_loglik(cnb_ctx *ctx, const cnb_network *net, int32_t mode, int32_t num_sel, const int32_t *nodes, double *out);
+int cnb_ctx_set_prob(cnb_ctx *ctx, const cnb_network *net, double *probs_out, double *loglik_out, int32_t *sizes_out);
 
 /* sharded search, one process per GPU: plan -> score own shard -> (caller all-gathers) -> finish.
  * The score buffer is one fp64 per candidate family, laid out rank-major: segment r (seg_len doubles) holds rank r's

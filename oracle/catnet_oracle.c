@@ -766,3 +766,114 @@ int orc_pairwise(int kind, int N, int M, const int *samples, const int *pert, do
 	free(code); free(cats); free(tab); free(p1); free(p2); free(mat);
 	return 0;
 }
+
+/* ------------------------------------------------------------------ fixed network ---- */
+/* cnLoglik / cnNodeLoglik / cnSetProb on a given network.  The reference's .Call glue for these is
+ * missing from the snapshot; what is restated here are the CATNET methods it forwards to.
+ * Network: cats[N], numParents[N], parents0[N][maxParents] (0-based, listed order: first parent = most significant
+ * table index, problist.h:252-263), tables concatenated by offsets[N+1] (child category fastest).
+ * samples0 [M][N] zero-based codes, outside [0, cats) = missing. */
+static int orc_net_cell(const int *row, const int *cats, int node, const int *pars, int d) {
+	int idx = 0, i;
+	for (i = 0; i < d; i++) {
+		int v = row[pars[i]];
+		if (v < 0 || v >= cats[pars[i]]) return -1;              /* find_slot returns 0 -> sample skipped */
+		idx = idx * cats[pars[i]] + v;
+	}
+	int x = row[node];
+	if (x < 0 || x >= cats[node]) return -1;
+	return idx * cats[node] + x;
+}
+
+/* mode 0: CATNET::sampleLoglikVector (catnet_class.h:616-687) -> out[N]: per node, the log-probabilities of its
+ *         unperturbed, complete samples summed IN SAMPLE ORDER, -FLT_MAX at the first zero probability, divided by
+ *         the count if > 1.
+ * mode 1: CATNET::bySampleLoglikVector (:689-765) -> out[M]: nodes outer, samples inner; a zero probability sets
+ *         that sample's value to -FLT_MAX and ENDS the node's pass over the samples (the `break` leaves the sample
+ *         loop), later nodes keep adding to every sample.
+ * mode 2: CATNET::sampleNodeLoglik (:767-815) for every node -> out[N] (= mode 0 without perturbations).
+ * mode 3: CATNET::sampleLoglik (:551-614) -> out[0]: sum over nodes in index order, -FLT_MAX as soon as one node is. */
+int orc_net_loglik(int N, int M, const int *samples0, const int *pert, const int *cats, int maxParents,
+		const int *numParents, const int *parents0, const double *probs, const long long *offsets, int mode,
+		double *out) {
+	int i, j;
+	if (mode == 1) memset(out, 0, (size_t)M * sizeof(double));
+	double total = 0;
+	for (i = 0; i < N; i++) {
+		const int *pars = parents0 + (size_t)i * maxParents;
+		const double *tab = probs + offsets[i];
+		double acc = 0;
+		int ncount = 0;
+		for (j = 0; j < M; j++) {
+			if (pert && mode < 2 && pert[(size_t)j * N + i]) continue;
+			int cell = orc_net_cell(samples0 + (size_t)j * N, cats, i, pars, numParents[i]);
+			if (cell < 0) continue;
+			if (mode == 1) {
+				if (tab[cell] > 0) out[j] += log(tab[cell]);
+				else { out[j] = NEG_INF; break; }
+				continue;
+			}
+			if (tab[cell] > 0) acc += log(tab[cell]);
+			else { acc = NEG_INF; break; }
+			ncount++;
+		}
+		if (mode == 1) continue;
+		if (ncount > 1 && acc > NEG_INF) acc /= (double)ncount;
+		if (mode == 3) {
+			if (acc == NEG_INF) { total = NEG_INF; break; }
+			total += acc;
+		} else
+			out[i] = acc;
+	}
+	if (mode == 3) out[0] = total;
+	return 0;
+}
+
+/* cnSetProb: CATNET::setNodeSampleProb(node, samples, M, bNormalize = 1) (catnet_class.h:818-879) for every node, on
+ * the sub-sample where the node is not perturbed; PROB_LIST::normalize (problist.h:193-222): rows without a sample
+ * become uniform with the last cell 1 - sum.  An empty sub-sample gives -FLT_MAX, size 0 and uniform rows. */
+int orc_net_set_prob(int N, int M, const int *samples0, const int *pert, const int *cats, int maxParents,
+		const int *numParents, const int *parents0, const long long *offsets, double *probs_out, double *loglik_out,
+		int *sizes_out) {
+	int i, j, k;
+	for (i = 0; i < N; i++) {
+		const int *pars = parents0 + (size_t)i * maxParents;
+		double *tab = probs_out + offsets[i];
+		int size = (int)(offsets[i + 1] - offsets[i]), cc = cats[i], ncount = 0, m = 0;
+		memset(tab, 0, (size_t)size * sizeof(double));
+		for (j = 0; j < M; j++) {
+			if (pert && pert[(size_t)j * N + i]) continue;
+			m++;
+			int cell = orc_net_cell(samples0 + (size_t)j * N, cats, i, pars, numParents[i]);
+			if (cell < 0) continue;
+			tab[cell] += 1;
+			ncount++;
+		}
+		double ll = 0;
+		for (k = 0; k < size; k += cc) {                          /* problist.h:224-250 */
+			double pp = 0;
+			for (j = 0; j < cc; j++) pp += tab[k + j];
+			if (pp <= 0) continue;
+			pp = 1 / pp;
+			for (j = 0; j < cc; j++)
+				if (tab[k + j] > 0) ll += tab[k + j] * log(tab[k + j] * pp);
+		}
+		if (ncount > 1) ll /= (double)ncount;
+		loglik_out[i] = m < 1 ? NEG_INF : ll;
+		sizes_out[i] = m < 1 ? 0 : ncount;
+		for (k = 0; k < size; k += cc) {                          /* problist.h:193-222 */
+			double pp = 0;
+			for (j = 0; j < cc; j++) pp += tab[k + j];
+			if (pp > 0) {
+				pp = 1 / pp;
+				for (j = 0; j < cc; j++) tab[k + j] *= pp;
+			} else {
+				double favg = (double)1 / (double)cc;
+				pp = 0;
+				for (j = 0; j < cc - 1; j++) { tab[k + j] = favg; pp += favg; }
+				tab[k + cc - 1] = 1 - pp;
+			}
+		}
+	}
+	return 0;
+}

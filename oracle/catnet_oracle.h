@@ -21,6 +21,14 @@ int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, i
 		const int *fixedPool_lbl, int scoreSel, int weight, int maxIter, int numThreads, double *hist);
 /* catnet_entropy.cpp pairwise metrics: kind 0 entropy, 1 KL, 2 Pearson -> out[n2*N + n1]; 3 entropy order -> order_out */
 int orc_pairwise(int kind, int N, int M, const int *samples_lbl, const int *pert_lbl, double *out, int *order_out);
+/* fixed network (catnet_class.h:551-879): mode 0 sampleLoglikVector, 1 bySampleLoglikVector, 2 sampleNodeLoglik of
+ * every node, 3 sampleLoglik; samples0 zero-based, parents0 [N][maxParents] 0-based in listed order */
+int orc_net_loglik(int N, int M, const int *samples0, const int *pert, const int *cats, int maxParents,
+		const int *numParents, const int *parents0, const double *probs, const long long *offsets, int mode,
+		double *out);
+int orc_net_set_prob(int N, int M, const int *samples0, const int *pert, const int *cats, int maxParents,
+		const int *numParents, const int *parents0, const long long *offsets, double *probs_out, double *loglik_out,
+		int *sizes_out);
 void orc_set_seed(unsigned long long seed);
 int orc_result_nslots(const orc_result *r);
 int orc_result_exists(const orc_result *r, int k);

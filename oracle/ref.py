@@ -235,3 +235,60 @@ def pairwise(kind, samples, perturbations=None):
     if rc != 0:
         raise RuntimeError("reference pairwise: " + _pw.ref_pairwise_last_error().decode())
     return order if kind == "order" else out.T.copy()
+
+
+# ---------------------------------------------------------------- fixed network ----
+def flatten_network(cats, parents, probs=None):
+    """cats [N]; parents: list of lists of 0-based nodes in listed order (first = most significant table index);
+    probs: list of flat tables (child fastest) or None -> the arrays the C entry points take"""
+    cats = _i32(cats)
+    N = len(cats)
+    maxp = max([len(p) for p in parents] + [1])
+    npar = np.array([len(p) for p in parents], dtype=np.int32)
+    pars = np.zeros((N, maxp), dtype=np.int32)
+    off = np.zeros(N + 1, dtype=np.int64)
+    for i, p in enumerate(parents):
+        pars[i, :len(p)] = p
+        size = int(cats[i])
+        for q in p:
+            size *= int(cats[q])
+        off[i + 1] = off[i] + size
+    flat = None
+    if probs is not None:
+        flat = np.concatenate([np.asarray(t, dtype=np.float64).ravel() for t in probs])
+        assert len(flat) == off[-1]
+    return cats, maxp, npar, pars, flat, off
+
+
+NET_MODES = {"nodes": 0, "bysample": 1, "node": 2, "total": 3}
+
+
+def net_loglik(mode, samples0, cats, parents, probs, perturbations=None):
+    """CATNET::sampleLoglikVector ("nodes") / bySampleLoglikVector ("bysample") / sampleNodeLoglik per node ("node") /
+    sampleLoglik ("total") of the reference, on a network given by (cats, parents, probs)"""
+    L = lib()
+    L.ref_net_loglik.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    s = _i32(samples0)
+    M, N = s.shape
+    cats, maxp, npar, pars, flat, off = flatten_network(cats, parents, probs)
+    out = np.zeros(M if mode == "bysample" else N, dtype=np.float64)
+    rc = L.ref_net_loglik(N, M, _p(s), _p(_i32(perturbations)), _p(cats), maxp, _p(npar), _p(pars), _p(flat), _p(off),
+                          NET_MODES[mode], _p(out))
+    assert rc == 0
+    return out[0] if mode == "total" else out
+
+
+def net_set_prob(samples0, cats, parents, perturbations=None):
+    """cnSetProb through CATNET::setNodeSampleProb(.., bNormalize=1): (list of tables, loglik [N], sample sizes [N])"""
+    L = lib()
+    L.ref_net_set_prob.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6
+    s = _i32(samples0)
+    M, N = s.shape
+    cats, maxp, npar, pars, _, off = flatten_network(cats, parents)
+    probs = np.zeros(off[-1], dtype=np.float64)
+    ll = np.zeros(N, dtype=np.float64)
+    sizes = np.zeros(N, dtype=np.int32)
+    rc = L.ref_net_set_prob(N, M, _p(s), _p(_i32(perturbations)), _p(cats), maxp, _p(npar), _p(pars), _p(off), _p(probs),
+                            _p(ll), _p(sizes))
+    assert rc == 0
+    return [probs[off[i]:off[i + 1]].copy() for i in range(N)], ll, sizes

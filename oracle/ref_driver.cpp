@@ -634,4 +634,83 @@ double ref_score_family_list(const int *samples0, int N, int M, const int *numCa
 	return acc;
 }
 
+/* ---------------- fixed network: cnLoglik / cnNodeLoglik / cnSetProb ----------------
+ * The .Call glue of these (catnetLoglik, catnetNodeLoglik, catnetSetProb; catnet_rexport.h) is absent from the
+ * snapshot, the class methods they forward to are not: CATNET::sampleLoglikVector / bySampleLoglikVector /
+ * sampleNodeLoglik (catnet_class.h:616-815) and setNodeSampleProb (:818-879).  These entry points build the CATNET the
+ * glue would build from the S4 object (setParents + setCondProb, as RCatnet::RCatnet(SEXP) does, rcatnet.cpp:38-172)
+ * and call those methods.  samples0: [M][N] zero-based codes, anything outside [0, numCats) is missing. */
+static RefNet *make_net(int N, const int *numCats, int maxParents, const int *numParents, const int *parents0,
+		const double *probs, const long long *offsets) {
+	int maxcats = 0, i;
+	for (i = 0; i < N; i++)
+		if (numCats[i] > maxcats) maxcats = numCats[i];
+	RefNet *net = new RefNet(N, maxParents, maxcats, 0, 0, 0, numCats);
+	for (i = 0; i < N; i++) {
+		if (numParents[i] > 0) net->setParents(i, const_cast<int *>(parents0 + (size_t)i * maxParents), numParents[i]);
+		if (probs) net->setCondProb(i, const_cast<double *>(probs + offsets[i]), (int)(offsets[i + 1] - offsets[i]));
+	}
+	return net;
+}
+
+/* mode 0: sampleLoglikVector -> out[N]; 1: bySampleLoglikVector -> out[M]; 2: sampleNodeLoglik of every node -> out[N]
+ * (no perturbations there); 3: sampleLoglik -> out[0] */
+int ref_net_loglik(int N, int M, const int *samples0, const int *pert, const int *numCats, int maxParents,
+		const int *numParents, const int *parents0, const double *probs, const long long *offsets, int mode,
+		double *out) {
+	RefNet *net = make_net(N, numCats, maxParents, numParents, parents0, probs, offsets);
+	int *s = const_cast<int *>(samples0), *p = const_cast<int *>(pert);
+	double *v = 0;
+	int i;
+	switch (mode) {
+	case 0:
+		v = net->sampleLoglikVector(s, M, p);
+		if (v) memcpy(out, v, (size_t)N * sizeof(double));
+		break;
+	case 1:
+		v = net->bySampleLoglikVector(s, M, p);
+		if (v) memcpy(out, v, (size_t)M * sizeof(double));
+		break;
+	case 2:
+		for (i = 0; i < N; i++) out[i] = net->sampleNodeLoglik(i, s, M);
+		break;
+	default:
+		out[0] = net->sampleLoglik(s, M);
+		break;
+	}
+	if (v) CATNET_FREE(v);
+	delete net;
+	return (mode < 2 && !v) ? -1 : 0;
+}
+
+/* cnSetProb: setNodeSampleProb(node, samples, M, bNormalize = 1) for every node; with perturbations the node sees the
+ * sub-sample where it is not perturbed (the way estimate() feeds it, catnet_search2.h:458-472).  probs_out is laid out
+ * by `offsets`; loglik_out[N] the returned family log-liks, sizes_out[N] the sample sizes. */
+int ref_net_set_prob(int N, int M, const int *samples0, const int *pert, const int *numCats, int maxParents,
+		const int *numParents, const int *parents0, const long long *offsets, double *probs_out, double *loglik_out,
+		int *sizes_out) {
+	RefNet *net = make_net(N, numCats, maxParents, numParents, parents0, 0, offsets);
+	std::vector<int> sub;
+	for (int i = 0; i < N; i++) {
+		const int *s = samples0;
+		int m = M;
+		if (pert) {
+			sub.clear();
+			for (int j = 0; j < M; j++)
+				if (!pert[(size_t)j * N + i]) sub.insert(sub.end(), samples0 + (size_t)j * N, samples0 + (size_t)(j + 1) * N);
+			s = sub.empty() ? 0 : &sub[0];
+			m = (int)(sub.size() / N);
+		}
+		double ll = net->setNodeSampleProb(i, const_cast<int *>(s), m, 1);
+		PROB_LIST<double> *pl = net->getNodeProb(i);
+		if (!pl || pl->nProbSize != offsets[i + 1] - offsets[i]) { delete net; return -1; }
+		if (m < 1) pl->normalize();      /* setNodeSampleProb bails out before normalising an empty sample */
+		memcpy(probs_out + offsets[i], pl->pProbs, (size_t)pl->nProbSize * sizeof(double));
+		loglik_out[i] = ll;
+		sizes_out[i] = m < 1 ? 0 : pl->sampleSize;
+	}
+	delete net;
+	return 0;
+}
+
 } /* extern "C" */

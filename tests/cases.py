@@ -89,6 +89,41 @@ def build_pairwise_case(c):
     return s, p
 
 
+# a given network against data (cnSetProb / cnLoglik / cnNodeLoglik): maxpar = parents per node at most, rev = parents
+# listed in descending order (the listed order is the table's index order), zero = probabilities below 0.15 replaced
+# by 0 before the likelihood is taken (zero-probability cells hit by samples)
+NETWORK_CASES = [
+    dict(seed=61, n=6, m=200, cats=None, maxpar=2),
+    dict(seed=62, n=8, m=150, cats=3, maxpar=2, na=0.08),
+    dict(seed=63, n=7, m=120, cats=2, maxpar=3, pert=0.3),
+    dict(seed=64, n=5, m=90, cats=6, maxpar=2, na=0.05, pert=0.2),
+    dict(seed=65, n=1, m=30, cats=3, maxpar=0),
+    dict(seed=66, n=8, m=300, cats=4, maxpar=2, pert=0.25, zero=True),
+    dict(seed=67, n=9, m=3000, cats=None, maxpar=3, na=0.04, zero=True, rev=True),
+    dict(seed=68, n=6, m=40, cats=3, maxpar=3, rev=True),
+    dict(seed=69, n=4, m=64, cats=2, maxpar=1, pert=0.5, allpert=True),
+]
+
+
+def build_network_case(c):
+    """-> (samples [M][N] 1-based with NA, cats [N], parents (lists of 0-based nodes, listed order), perturbations);
+    the tables are estimated on the first half of the samples"""
+    from helpers import random_problem
+    s, cats = random_problem(c["seed"], c["n"], c["m"], c.get("cats"), c.get("na", 0.0))
+    rng = np.random.default_rng(3000 + c["seed"])
+    parents = []
+    for i in range(c["n"]):
+        k = min(i, int(rng.integers(0, c["maxpar"] + 1)))
+        p = sorted(int(v) for v in rng.choice(i, size=k, replace=False)) if k else []
+        parents.append(p[::-1] if c.get("rev") else p)
+    pert = None
+    if c.get("pert"):
+        pert = (rng.random(s.shape) < c["pert"]).astype(np.int32)
+        if c.get("allpert"):
+            pert[:, 1] = 1
+    return s, cats, parents, pert
+
+
 def build_hist_case(c):
     """-> (samples [M][N], kwargs of the checkers' search_hist)"""
     from helpers import random_problem

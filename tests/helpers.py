@@ -79,3 +79,23 @@ def compare_golden(ours, golden):
             assert [float(v) for v in x["node_loglik"]] == [float.fromhex(v) for v in y["node_loglik"]], cx
             assert x["sample_sizes"] == y["sample_sizes"], cx
     return len(a)
+
+
+def unhex(v):
+    return np.array([float.fromhex(x) for x in v], dtype=np.float64)
+
+
+def check_network_case(impl, case, build, g, zero_based=True):
+    """impl: object with net_set_prob(samples0, cats, parents, pert) and net_loglik(mode, samples0, cats, parents, probs,
+    pert) (oracle.port / oracle.ref signatures); compares with the fixture g bit for bit"""
+    s, cats, parents, pert = build(case)
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    h = max(1, len(s) // 2)
+    probs, ll, sizes = impl.net_set_prob(s0[:h], cats, parents, None if pert is None else pert[:h])
+    assert all(np.array_equal(a, unhex(b)) for a, b in zip(probs, g["set_prob"]))
+    assert np.array_equal(ll, unhex(g["set_loglik"])) and [int(v) for v in sizes] == g["set_sizes"]
+    used = [unhex(t) for t in g["probs_used"]]
+    assert np.array_equal(impl.net_loglik("nodes", s0, cats, parents, used, pert), unhex(g["nodes"]))
+    assert np.array_equal(impl.net_loglik("node", s0, cats, parents, used), unhex(g["node"]))
+    if "bysample" in g:
+        assert np.array_equal(impl.net_loglik("bysample", s0, cats, parents, used, pert), unhex(g["bysample"]))

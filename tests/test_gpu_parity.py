@@ -13,8 +13,9 @@ import math
 import numpy as np
 import pytest
 
-from cases import CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case, PAIRWISE_CASES, build_pairwise_case
-from helpers import NA, compare_golden, compare_search, load_golden, random_problem
+from cases import (CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case, PAIRWISE_CASES, build_pairwise_case,
+                   NETWORK_CASES, build_network_case)
+from helpers import NA, check_network_case, compare_golden, compare_search, load_golden, random_problem, unhex
 
 pytestmark = pytest.mark.gpu
 
@@ -439,6 +440,99 @@ def test_pairwise_python_front_end(abi, port):
     with pytest.raises(abi.CnbError) as e:
         abi.pairwise("entropy", bad)
     assert e.value.code == abi.CNB_ERR_PARAM
+
+
+class _DeviceNetwork:
+    """the product behind the signatures of oracle.port.net_* (zero-based codes in, NA = anything out of range)"""
+
+    def __init__(self, abi, generic=False, one_shot=False):
+        self.abi, self.generic, self.one_shot = abi, generic, one_shot
+
+    @staticmethod
+    def _lbl(s0, cats):
+        s0 = np.asarray(s0)
+        return np.where((s0 < 0) | (s0 >= np.asarray(cats)[None, :]), NA, s0 + 1).astype(np.int32)
+
+    def net_set_prob(self, s0, cats, parents, pert=None):
+        s = self._lbl(s0, cats)
+        if self.one_shot:
+            return self.abi.set_prob(s, cats, parents, pert)
+        with self.abi.Context(0) as ctx:
+            if self.generic:
+                ctx.force_generic(1)
+            ctx.set_samples(s, perturbations=pert, num_cats=cats)
+            return ctx.set_prob(cats, parents)
+
+    def net_loglik(self, mode, s0, cats, parents, probs, pert=None):
+        s = self._lbl(s0, cats)
+        if mode == "node":        # sampleNodeLoglik of every node: no perturbations, listed one by one
+            return self.abi.node_loglik(s, cats, parents, probs, np.arange(1, len(cats) + 1))
+        if self.one_shot:
+            return self.abi.loglik(s, cats, parents, probs, pert, mode)
+        with self.abi.Context(0) as ctx:
+            ctx.set_samples(s, perturbations=pert, num_cats=cats)
+            return ctx.loglik(cats, parents, probs, mode)
+
+
+@pytest.mark.parametrize("variant", ["ctx", "histogram", "one_shot"])
+@pytest.mark.parametrize("case", NETWORK_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_network_matches_reference(abi, case, variant):
+    """cnSetProb / cnLoglik / cnNodeLoglik on the device against the reference's CATNET methods, bit for bit"""
+    impl = _DeviceNetwork(abi, generic=variant == "histogram", one_shot=variant == "one_shot")
+    check_network_case(impl, case, build_network_case, load_golden("ref_network")["seed%d" % case["seed"]])
+
+
+@pytest.mark.parametrize("seed", range(600, 616))
+def test_network_random_vs_oracle(abi, port, seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(1, 40)), int(rng.integers(6, 5000))
+    s, c = random_problem(seed, n, m, [None, 2, 4, 7][seed % 4], na_frac=[0, 0.05][seed % 2])
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    parents = [sorted(rng.choice(i, size=min(i, int(rng.integers(0, 4))), replace=False).tolist(), reverse=seed % 3 == 0)
+               for i in range(n)]
+    pert = (rng.random(s.shape) < 0.3).astype(np.int32) if seed % 3 == 1 else None
+    impl = _DeviceNetwork(abi)
+    pa, la, sa = impl.net_set_prob(s0, c, parents, pert)
+    pb, lb, sb = port.net_set_prob(s0, c, parents, pert)
+    assert all(np.array_equal(x, y) for x, y in zip(pa, pb)) and np.array_equal(la, lb) and np.array_equal(sa, sb)
+    if seed % 4 == 0:
+        pa = [np.where(t < 0.1, 0.0, t) for t in pa]
+    for mode in ("nodes", "bysample"):
+        assert np.array_equal(impl.net_loglik(mode, s0, c, parents, pa, pert), port.net_loglik(mode, s0, c, parents, pa, pert)), mode
+    sel = rng.choice(n, size=min(n, 3), replace=False) + 1
+    a = abi.node_loglik(impl._lbl(s0, c), c, parents, pa, sel, pert)
+    assert np.array_equal(a, port.net_loglik("nodes", s0, c, parents, pa, pert)[sel - 1])
+
+
+def test_network_errors(abi):
+    s, c = random_problem(5, 4, 50, 3)
+    parents = [[], [0], [0, 1], [2]]
+    probs, _, _ = abi.set_prob(s, c, parents)
+    for bad_par in ([[], [1], [0, 1], [2]], [[], [7], [0, 1], [2]]):          # self-parent, out of range
+        with pytest.raises(abi.CnbError) as e:
+            abi.loglik(s, c, bad_par, probs)
+        assert e.value.code == abi.CNB_ERR_PARAM
+    s2 = s.copy()
+    s2[3, 2] = 4                                                              # more categories than the object
+    with pytest.raises(abi.CnbError) as e:
+        abi.loglik(s2, c, parents, probs)
+    assert e.value.code == abi.CNB_ERR_PARAM
+    with pytest.raises(abi.CnbError):
+        abi.node_loglik(s, c, parents, probs, [9])
+
+
+def test_search_then_loglik_round_trip(abi):
+    """the networks cnSearchOrder returns carry likelihoods that cnLoglik reproduces from their own tables:
+    mean over samples of the by-sample values = sum of the node values = the network's log-lik (to rounding)"""
+    s, c = random_problem(21, 9, 400, 3)
+    nets = abi.search_order(s, max_parent_set=2, max_complexity=9 * 27 * 2, num_cats=c)
+    net = nets[len(nets) // 2]
+    parents = [[q for q in p] for p in net["parents"]]           # identity order: positions = labels
+    nodes = abi.loglik(s, c, parents, net["probs"], mode="nodes")
+    assert np.allclose(nodes, net["node_loglik"], rtol=1e-12, atol=0)
+    assert abs(nodes.sum() - net["loglik"]) <= 1e-12 * abs(net["loglik"])
+    by = abi.loglik(s, c, parents, net["probs"], mode="bysample")
+    assert abs(by.mean() - net["loglik"]) <= 1e-10 * abs(net["loglik"])
 
 
 def test_search_hist_python_front_end(abi):

@@ -7,8 +7,9 @@ All fp64 comparisons are bit-exact."""
 import numpy as np
 import pytest
 
-from cases import CASES, HIST_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case, build_pairwise_case, ref_args
-from helpers import compare_golden, compare_search, load_golden, random_problem
+from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case,
+                   build_network_case, build_pairwise_case, ref_args)
+from helpers import check_network_case, compare_golden, compare_search, load_golden, random_problem
 from oracle import port
 
 
@@ -128,3 +129,30 @@ def test_port_pairwise_rejects_missing_values():
     s[3, 1] = -2147483648
     with pytest.raises(ValueError):
         port.pairwise("entropy", s)
+
+
+@pytest.mark.parametrize("case", NETWORK_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_network_matches_golden(case):
+    """cnSetProb / cnLoglik / cnNodeLoglik: the restatement against the reference's own CATNET methods, bit for bit"""
+    check_network_case(port, case, build_network_case, load_golden("ref_network")["seed%d" % case["seed"]])
+
+
+@pytest.mark.parametrize("seed", range(500, 520))
+def test_port_network_matches_reference(ref, seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(1, 9)), int(rng.integers(6, 300))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 5][seed % 4], na_frac=[0, 0.08][seed % 2])
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    parents = [sorted(rng.choice(i, size=min(i, int(rng.integers(0, 4))), replace=False).tolist(), reverse=seed % 3 == 0)
+               for i in range(n)]
+    pert = (rng.random(s.shape) < 0.3).astype(np.int32) if seed % 3 == 1 else None
+    h = max(1, m // 2)
+    pa, la, sa = ref.net_set_prob(s0[:h], c, parents, None if pert is None else pert[:h])
+    pb, lb, sb = port.net_set_prob(s0[:h], c, parents, None if pert is None else pert[:h])
+    assert all(np.array_equal(x, y) for x, y in zip(pa, pb)) and np.array_equal(la, lb) and np.array_equal(sa, sb)
+    if seed % 5 == 0:
+        pa = [np.where(t < 0.2, 0.0, t) for t in pa]
+    for mode in ("nodes", "bysample", "node", "total"):
+        if mode == "bysample" and max(len(p) for p in parents) == 0 and pert is None:
+            continue
+        assert np.array_equal(ref.net_loglik(mode, s0, c, parents, pa, pert), port.net_loglik(mode, s0, c, parents, pa, pert))

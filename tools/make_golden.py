@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import random_problem  # noqa: E402
-from cases import CASES, HIST_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case, build_pairwise_case  # noqa: E402
+from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case,  # noqa: E402
+                   build_network_case, build_pairwise_case)
 
 from catnet_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
@@ -55,9 +56,36 @@ def make_pairwise():
     print("ref_pairwise.json", len(pw))
 
 
+def hexes(v):
+    return [float(x).hex() for x in np.asarray(v, dtype=np.float64).ravel()]
+
+
+def make_network():
+    """cnSetProb / cnLoglik / cnNodeLoglik through the reference's own CATNET methods (ref_driver.cpp: ref_net_set_prob,
+    ref_net_loglik): tables estimated on the first half of the samples, likelihoods taken on all of them"""
+    out = {}
+    for case in NETWORK_CASES:
+        s, cats, parents, pert = build_network_case(case)
+        s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+        h = max(1, len(s) // 2)
+        probs, ll, sizes = ref.net_set_prob(s0[:h], cats, parents, None if pert is None else pert[:h])
+        used = [np.where(t < 0.15, 0.0, t) for t in probs] if case.get("zero") else probs
+        g = {"set_prob": [hexes(t) for t in probs], "set_loglik": hexes(ll), "set_sizes": [int(v) for v in sizes],
+             "probs_used": [hexes(t) for t in used],
+             "nodes": hexes(ref.net_loglik("nodes", s0, cats, parents, used, pert)),
+             "node": hexes(ref.net_loglik("node", s0, cats, parents, used))}
+        if max(len(p) for p in parents) > 0 or pert is not None:      # the reference dereferences NULL otherwise
+            g["bysample"] = hexes(ref.net_loglik("bysample", s0, cats, parents, used, pert))
+        out["seed%d" % case["seed"]] = g
+    dump(out, "ref_network.json")
+    print("ref_network.json", len(out))
+
+
 def main():
     if "--only-pairwise" in sys.argv:
         return make_pairwise()
+    if "--only-network" in sys.argv:
+        return make_network()
     fam = []
     for seed, cats, na in [(1, None, 0.0), (2, 3, 0.1), (3, 2, 0.0), (4, 4, 0.05)]:
         s, c = random_problem(seed, 8, 150, cats, na)
@@ -105,6 +133,7 @@ def main():
     dump(hist, "ref_search_hist.json")
     print("ref_search_hist.json", {k: v["iterations"] for k, v in hist.items()})
     make_pairwise()
+    make_network()
     if "--skip-configs" in sys.argv:
         return
     big = {}
