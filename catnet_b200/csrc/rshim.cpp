@@ -4,6 +4,7 @@
  * src/catnet_rexport.h:31-64):
  *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnParHistogram/14   ccnReleaseCache/0   ccnSetSeed/1
  *     ccnEntropyPairwise/2   ccnEntropyOrder/2   ccnKLPairwise/2   ccnPearsonPairwise/2
+ *     ccnLoglik/4   ccnNodeLoglik/4   ccnSetProb/3
  * and registers them in R_init_catnet.  Every other routine of the reference's table keeps its reference
  * implementation (this shim is linked INTO the package next to the reference sources).
  *
@@ -355,6 +356,156 @@ SEXP ccnEntropyOrder(SEXP rSamples, SEXP rPerturbations) {
 	return rvec;
 }
 
+/* ---- a given catNetwork against data: ccnLoglik, ccnNodeLoglik, ccnSetProb (src/ccnInit.c:32-34) ----
+ * The reference's glue for these is absent from the snapshot; the object is read the way RCatnet::RCatnet(SEXP) reads
+ * it (rcatnet.cpp:38-172): parents 1-based in listed order, categories by length, nested probability lists flattened
+ * first-parent-outermost (gen_prob_vector). */
+struct RNetwork {
+	cnb_network net;
+	std::vector<int32_t> cats, npar, pars;
+	std::vector<double> probs;
+	std::vector<int64_t> off;
+};
+
+static void flatten_probs(SEXP node, const int *pc, int d, int level, int cc, std::vector<double> &out) {
+	if (level >= d) {
+		SEXP v = PROTECT(coerceVector(node, REALSXP));
+		for (int k = 0; k < cc; k++) out.push_back(k < length(v) ? REAL(v)[k] : 0.0);
+		UNPROTECT(1);
+		return;
+	}
+	for (int j = 0; j < pc[level]; j++) {
+		if (!isNewList(node) || j >= length(node)) error("probabilities do not match the parents' categories");
+		flatten_probs(VECTOR_ELT(node, j), pc, d, level + 1, cc, out);
+	}
+}
+
+static void read_network(SEXP cnet, RNetwork &r, bool want_probs) {
+	if (!isS4(cnet)) error("cnet should be a catNetwork");
+	const int N = INTEGER(GET_SLOT(cnet, install("numnodes")))[0];
+	SEXP rparents = GET_SLOT(cnet, install("parents")), rcats = GET_SLOT(cnet, install("categories"));
+	SEXP rprobs = GET_SLOT(cnet, install("probabilities"));
+	if (length(rparents) != N || length(rcats) != N || (want_probs && length(rprobs) != N)) error("invalid catNetwork");
+	int maxp = 1;
+	for (int i = 0; i < N; i++) maxp = std::max(maxp, (int)length(VECTOR_ELT(rparents, i)));
+	r.cats.resize(N);
+	r.npar.resize(N);
+	r.pars.assign((size_t)N * maxp, 0);
+	r.off.assign(N + 1, 0);
+	r.probs.clear();
+	for (int i = 0; i < N; i++) r.cats[i] = length(VECTOR_ELT(rcats, i));
+	for (int i = 0; i < N; i++) {
+		SEXP pv = PROTECT(coerceVector(VECTOR_ELT(rparents, i), INTSXP));
+		const int d = length(pv);
+		r.npar[i] = d;
+		int pc[64];
+		int64_t size = r.cats[i];
+		if (d > 8) error("more than 8 parents");
+		for (int k = 0; k < d; k++) {
+			const int q = INTEGER(pv)[k];
+			if (q < 1 || q > N) error("invalid parent");
+			r.pars[(size_t)i * maxp + k] = q;
+			pc[k] = r.cats[q - 1];
+			size *= pc[k];
+		}
+		UNPROTECT(1);
+		r.off[i + 1] = r.off[i] + size;
+		if (want_probs) flatten_probs(VECTOR_ELT(rprobs, i), pc, d, 0, r.cats[i], r.probs);
+	}
+	memset(&r.net, 0, sizeof(r.net));
+	r.net.num_nodes = N;
+	r.net.max_parents = maxp;
+	r.net.num_cats = r.cats.data();
+	r.net.num_parents = r.npar.data();
+	r.net.parents = r.pars.data();
+	r.net.probs = want_probs ? r.probs.data() : NULL;
+	r.net.prob_offsets = r.off.data();
+}
+
+static void network_data(SEXP &rSamples, SEXP &rPerturbations, int N, int &M, int &nprot) {
+	if (!isMatrix(rSamples)) error("'data' should be a matrix or data frame of categories");   /* R/catnet.loglik.R:57-58 */
+	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
+	nprot = 1;
+	SEXP dim = getAttrib(rSamples, R_DimSymbol);
+	if (INTEGER(dim)[0] != N) error("The number of nodes in  the object and data should be equal");   /* :69-70 */
+	M = INTEGER(dim)[1];
+	if (!isNull(rPerturbations)) {
+		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
+		nprot++;
+	}
+}
+
+/* -FLT_MAX is the library's "minus infinity" (rcatnet.cpp:295-300 exports it as -Inf) */
+static void export_neg_inf(double *v, int n) {
+	for (int k = 0; k < n; k++)
+		if (!(v[k] > -(double)FLT_MAX)) v[k] = R_NegInf;
+}
+
+SEXP ccnLoglik(SEXP cnet, SEXP rSamples, SEXP rPerturbations, SEXP rBySample) {
+	RNetwork r;
+	read_network(cnet, r, true);
+	int M, nprot;
+	network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
+	const int bysample = asLogical(rBySample) == 1;
+	const int nout = bysample ? M : r.net.num_nodes;
+	SEXP rvec = PROTECT(allocVector(REALSXP, nout));
+	int rc = cnb_loglik(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations),
+			bysample ? CNB_LOGLIK_BYSAMPLE : CNB_LOGLIK_NODES, 0, REAL(rvec));
+	if (rc == CNB_OK) export_neg_inf(REAL(rvec), nout);
+	UNPROTECT(nprot + 1);
+	if (rc != CNB_OK) fail(rc);
+	return rvec;                                   /* R sums the per-node values (R/catnet.loglik.R:103-105) */
+}
+
+SEXP ccnNodeLoglik(SEXP cnet, SEXP rNodes, SEXP rSamples, SEXP rPerturbations) {
+	RNetwork r;
+	read_network(cnet, r, true);
+	int M, nprot;
+	network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
+	SEXP nodes = PROTECT(coerceVector(rNodes, INTSXP));
+	const int nsel = length(nodes);
+	SEXP rvec = PROTECT(allocVector(REALSXP, nsel));
+	int rc = cnb_node_loglik(&r.net, nsel, INTEGER(nodes), M, INTEGER(rSamples),
+			isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0, REAL(rvec));
+	if (rc == CNB_OK) export_neg_inf(REAL(rvec), nsel);
+	UNPROTECT(nprot + 2);
+	if (rc != CNB_OK) fail(rc);
+	return rvec;
+}
+
+SEXP ccnSetProb(SEXP cnet, SEXP rSamples, SEXP rPerturbations) {
+	RNetwork r;
+	read_network(cnet, r, false);
+	const int N = r.net.num_nodes;
+	int M, nprot;
+	network_data(rSamples, rPerturbations, N, M, nprot);
+	std::vector<double> probs((size_t)r.off[N]), ll(N);
+	std::vector<int32_t> sizes(N);
+	int rc = cnb_set_prob(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
+			probs.data(), ll.data(), sizes.data());
+	UNPROTECT(nprot);
+	if (rc != CNB_OK) fail(rc);
+	/* the object with its tables, likelihood and sample sizes replaced (R keeps nodes / categories, catnet.samples.R:427-436) */
+	SEXP out = PROTECT(duplicate(cnet));
+	SEXP problists = PROTECT(allocVector(VECSXP, N));
+	SEXP rsizes = PROTECT(allocVector(INTSXP, N));
+	double total = 0;
+	bool neg_inf = false;
+	for (int i = 0; i < N; i++) {
+		int pc[8];
+		for (int k = 0; k < r.npar[i]; k++) pc[k] = r.cats[r.pars[(size_t)i * r.net.max_parents + k] - 1];
+		SET_VECTOR_ELT(problists, i, prob_list(probs.data() + r.off[i], pc, r.npar[i], r.cats[i], 0, 0));
+		INTEGER(rsizes)[i] = sizes[i];
+		if (!(ll[i] > -(double)FLT_MAX)) neg_inf = true;
+		total += ll[i];                                /* CATNET::loglik: nodes in index order (catnet_class.h:469-485) */
+	}
+	SET_SLOT(out, install("probabilities"), problists);
+	SET_SLOT(out, install("likelihood"), ScalarReal(neg_inf ? R_NegInf : total));
+	SET_SLOT(out, install("nodeSampleSizes"), rsizes);
+	UNPROTECT(3);
+	return out;
+}
+
 SEXP ccnReleaseCache(void) {
 	cnb_release_cache();
 	return R_NilValue;
@@ -376,12 +527,15 @@ static const R_CallMethodDef cnb_call_methods[] = {
 	{"ccnEntropyOrder", (DL_FUNC)&ccnEntropyOrder, 2},
 	{"ccnKLPairwise", (DL_FUNC)&ccnKLPairwise, 2},
 	{"ccnPearsonPairwise", (DL_FUNC)&ccnPearsonPairwise, 2},
+	{"ccnLoglik", (DL_FUNC)&ccnLoglik, 4},
+	{"ccnNodeLoglik", (DL_FUNC)&ccnNodeLoglik, 4},
+	{"ccnSetProb", (DL_FUNC)&ccnSetProb, 3},
 	{NULL, NULL, 0}};
 
 const R_CallMethodDef *cnb_r_call_methods(void) { return cnb_call_methods; }
 
 #ifdef CNB_STANDALONE_RSHIM
-/* build as a complete catnet.so for the search path only (the other 5 routines are then unavailable) */
+/* build as a complete catnet.so for the search path only (ccnMarginalProb and ccnSamples are then unavailable) */
 void R_init_catnet(DllInfo *info) {
 	R_registerRoutines(info, NULL, cnb_call_methods, NULL, NULL);
 	R_useDynamicSymbols(info, (Rboolean)1);

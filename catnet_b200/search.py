@@ -309,3 +309,61 @@ def cnEntropyOrder(data, perturbations=None, device=0):
     """R/catnet.entropy.R:103-132: node order (1-based) by decreasing total mutual information"""
     s, p = _pairwise_front(data, perturbations)
     return _abi.entropy_order(s, p, device)
+
+
+# ------------------------------------------------------------------ a given network against data ----
+def _network_front(obj, data, perturbations):
+    """argument handling of cnLoglik / cnNodeLoglik (R/catnet.loglik.R:54-96, 300-350): data is nodes x samples with the
+    object's category values; returns (samples [M][N] int32, perturbations [M][N] or None, cats, parents 0-based)"""
+    x = np.asarray(data)
+    if x.ndim != 2:
+        raise ValueError("'data' should be a matrix or data frame of categories")
+    if x.shape[0] != obj["numnodes"]:
+        raise ValueError("The number of nodes in  the object and data should be equal")
+    cat, pert, _, _ = categorize_sample(x, perturbations, obj["categories"])
+    cats = np.array([len(c) for c in obj["categories"]], dtype=np.int32)
+    parents = [[int(q) - 1 for q in (p or [])] for p in obj["parents"]]
+    return (np.ascontiguousarray(cat.T), None if pert is None else np.ascontiguousarray(pert.T), cats, parents)
+
+
+def _neg_inf(v):
+    v = np.asarray(v, dtype=np.float64).copy()
+    v[v <= -3.4028234663852886e38] = -np.inf          # -FLT_MAX is the library's minus infinity (rcatnet.cpp:295-300)
+    return v
+
+
+def cnLoglik(obj, data, perturbations=None, bysample=False, device=0):
+    """R/catnet.loglik.R:54-106: log-likelihood of the data under the network; by sample, or summed over the nodes"""
+    s, p, cats, parents = _network_front(obj, data, perturbations)
+    v = _neg_inf(_abi.loglik(s, cats, parents, obj["probabilities"], p, "bysample" if bysample else "nodes", device))
+    return v if bysample else float(v.sum())
+
+
+def cnNodeLoglik(obj, node, data, perturbations=None, device=0):
+    """R/catnet.loglik.R:300-364: per-node log-likelihood of the listed nodes (1-based indices or names)"""
+    s, p, cats, parents = _network_front(obj, data, perturbations)
+    nodes = [obj["nodes"].index(v) + 1 if isinstance(v, str) else int(v) for v in np.atleast_1d(node)]
+    if any(v < 1 or v > obj["numnodes"] for v in nodes):
+        raise ValueError("Wrong node")
+    return _neg_inf(_abi.node_loglik(s, cats, parents, obj["probabilities"], nodes, p, device))
+
+
+def cnSetProb(obj, data, perturbations=None, nodeCats=None, device=0):
+    """R/catnet.samples.R:368-441: the network with its tables re-estimated from the data (categories from the data or
+    from nodeCats)"""
+    x = np.asarray(data)
+    if x.ndim != 2:
+        raise ValueError("'data' should be a matrix or data frame of categories")
+    if x.shape[0] != obj["numnodes"]:
+        raise ValueError("The number of nodes in the object and data should be equal.")
+    cat, pert, categories, max_categories = categorize_sample(x, perturbations, nodeCats)
+    cats = np.array([len(c) for c in categories], dtype=np.int32)
+    parents = [[int(q) - 1 for q in (p or [])] for p in obj["parents"]]
+    probs, ll, sizes = _abi.set_prob(np.ascontiguousarray(cat.T), cats, parents,
+                                     None if pert is None else np.ascontiguousarray(pert.T), device)
+    ll = _neg_inf(ll)
+    complexity = int(sum((cats[i] - 1) * np.prod([cats[q] for q in parents[i]], dtype=np.int64) for i in range(len(cats))))
+    new = CatNetwork(obj)
+    new.update(categories=categories, maxCategories=max_categories, probabilities=probs, likelihood=float(ll.sum()),
+               nodeSampleSizes=[int(v) for v in sizes], complexity=complexity)
+    return new

@@ -38,6 +38,10 @@ SEXP SET_VECTOR_ELT(SEXP, long, SEXP);
 SEXP STRING_ELT(SEXP, long);
 void SET_STRING_ELT(SEXP, long, SEXP);
 SEXP R_do_slot_assign(SEXP, SEXP, SEXP);
+SEXP R_do_slot(SEXP, SEXP);
+SEXP Rf_duplicate(SEXP);
+int Rf_isNewList(SEXP);
+int IS_S4_OBJECT(SEXP);
 SEXP R_do_MAKE_CLASS(const char *);
 SEXP R_do_new_object(SEXP);
 void Rf_error(const char *, ...);
@@ -61,6 +65,9 @@ double unif_rand(void);
 #define asInteger Rf_asInteger
 #define asLogical Rf_asLogical
 #define asReal Rf_asReal
+#define duplicate Rf_duplicate
+#define isNewList Rf_isNewList
+#define isS4(x) IS_S4_OBJECT(x)
 #define error Rf_error
 #define warning Rf_warning
 #ifdef __cplusplus

@@ -535,6 +535,23 @@ def test_search_then_loglik_round_trip(abi):
     assert abs(by.mean() - net["loglik"]) <= 1e-10 * abs(net["loglik"])
 
 
+def test_network_python_front_end(abi, port):
+    """cnSearchOrder -> cnSetProb on other data -> cnLoglik / cnNodeLoglik, through the mirrors of the R front-ends"""
+    from catnet_b200 import search
+    s, c = random_problem(33, 7, 300, 3)
+    data = s.T.astype(np.float64) * 5
+    ev = search.cnSearchOrder(data[:, :150], maxParentSet=2)
+    net = ev.nets[len(ev.nets) // 2]
+    fit = search.cnSetProb(net, data[:, 150:])
+    parents = [[q - 1 for q in p] for p in net["parents"]]
+    s0 = (s - 1).astype(np.int32)
+    probs, ll, sizes = port.net_set_prob(s0[150:], c, parents)
+    assert all(np.array_equal(a, b) for a, b in zip(fit["probabilities"], probs)) and fit["likelihood"] == float(ll.sum())
+    assert search.cnLoglik(fit, data) == float(port.net_loglik("nodes", s0, c, parents, probs).sum())
+    assert np.array_equal(search.cnLoglik(fit, data, bysample=True), port.net_loglik("bysample", s0, c, parents, probs))
+    assert np.array_equal(search.cnNodeLoglik(fit, [2, 5], data), port.net_loglik("nodes", s0, c, parents, probs)[[1, 4]])
+
+
 def test_search_hist_python_front_end(abi):
     """catnet_b200.search.cnSearchHist: R's matrix(vhisto, nrow=numnodes) is [child, parent]"""
     from catnet_b200 import search
