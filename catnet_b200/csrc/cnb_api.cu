@@ -322,6 +322,16 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	c->blk_equal.assign(pl.blocks.size(), 0);
 	for (size_t b = 0; b < pl.blocks.size(); b++) c->blk_equal[b] = pl.nodes[pl.blocks[b].child].equal_branch;
 	RC(upload(c, c->b_blk_equal, c->blk_equal));
+	/* selection: large candidate blocks are cut into chunks, one CTA each */
+	c->sel_chunks.clear();
+	c->sel_chunk0.assign(pl.blocks.size() + 1, 0);
+	for (size_t b = 0; b < pl.blocks.size(); b++) {
+		const int64_t nch = std::max<int64_t>(1, (pl.blocks[b].ncomb + cnbk_select_chunk() - 1) / cnbk_select_chunk());
+		for (int64_t k = 0; k < nch; k++) { c->sel_chunks.push_back((int32_t)b); c->sel_chunks.push_back((int32_t)k); }
+		c->sel_chunk0[b + 1] = c->sel_chunk0[b] + (int32_t)nch;
+	}
+	RC(upload(c, c->b_sel_chunks, c->sel_chunks));
+	RC(upload(c, c->b_sel_chunk0, c->sel_chunk0));
 	/* samples into order space (the reference re-copies the int matrix per order, rcatnet_search.cpp:151-160) */
 	RC(cnbk_permute(c->stream, (const uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, (const int *)c->b_order.ptr, c->N, c->W,
@@ -596,9 +606,14 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	RC(c->b_opt_score.ensure(nopt * sizeof(double)));
 	RC(c->b_opt_cx.ensure(nopt * sizeof(int)));
 	RC(c->b_opt_fid.ensure(nopt * sizeof(long long)));
+	const int nchunks = (int)(c->sel_chunks.size() / 2);
+	RC(c->b_sel_part_s.ensure(std::max(nchunks, 1) * sizeof(double)));
+	RC(c->b_sel_part_f.ensure(std::max(nchunks, 1) * sizeof(long long)));
 	RC(cnbk_select(st, D, (int)pl.blocks.size(), (const CnbGroup *)c->b_groups.ptr, (const int *)c->b_blk_equal.ptr,
-			scores_dev, pl.seg_len, (double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr));
-	c->timing.kernel_launches++;
+			(const int2 *)c->b_sel_chunks.ptr, nchunks, (const int *)c->b_sel_chunk0.ptr, scores_dev, pl.seg_len,
+			(double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr,
+			(double *)c->b_sel_part_s.ptr, (long long *)c->b_sel_part_f.ptr));
+	c->timing.kernel_launches += 2;
 	CK(cudaEventRecord(c->ev[EV_SEL1], st));
 	/* DP state, double buffered */
 	size_t slots = (size_t)K + 1;

@@ -493,11 +493,16 @@ __global__ void __launch_bounds__(256) k_score_hist(DevData Dt, DevFamilies F, l
 /* ------------------------------------------------------------------ K4: selection / option table ---- */
 /* One CTA per candidate block.  Equal-categories path: first maximum in enumeration order (strict '<' running
  * max from -FLT_MAX, catnet_search2.h:559,613) -> one DP option.  Otherwise every candidate becomes an option. */
+#define SEL_CHUNK 4096        /* candidates per CTA of k_select: large blocks are cut so that the machine is filled evenly */
 __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__restrict__ groups,
-		const int *__restrict__ blk_equal, const double *__restrict__ scores, long long seg_len,
-		double *__restrict__ opt_score, int *__restrict__ opt_cx, long long *__restrict__ opt_fid) {
-	const CnbBlock &b = Dt.blocks[blockIdx.x];
+		const int *__restrict__ blk_equal, const int2 *__restrict__ chunks, const double *__restrict__ scores,
+		long long seg_len, double *__restrict__ opt_score, int *__restrict__ opt_cx, long long *__restrict__ opt_fid,
+		double *__restrict__ part_score, long long *__restrict__ part_fid) {
+	const int blk = chunks[blockIdx.x].x;
+	const CnbBlock &b = Dt.blocks[blk];
 	const CnbGroup &g = groups[b.group];
+	const long long r_begin = (long long)chunks[blockIdx.x].y * SEL_CHUNK;
+	const long long r_end = r_begin + SEL_CHUNK < b.ncomb ? r_begin + SEL_CHUNK : b.ncomb;
 	DevFamilies F;
 	F.d = b.d; F.nblk = g.nblk; F.blk_off = g.blk_off; F.explicit_list = 0; F.nfam = g.nfam;
 	F.ex_child = nullptr; F.ex_pars = nullptr; F.ex_nd = nullptr;
@@ -523,8 +528,8 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 		}
 		return scores[dev_score_index(slot, g.chunk, g.seg_off, seg_len)];
 	};
-	if (!blk_equal[blockIdx.x]) {
-		for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
+	if (!blk_equal[blk]) {
+		for (long long r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
 			long long fid = b.start + r;
 			opt_score[b.opt_off + r] = score_of(fid);
 			opt_cx[b.opt_off + r] = complexity_of(fid);
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 	}
 	double best = CNB_NEG_INF;
 	long long best_fid = -1;
-	for (long long r = threadIdx.x; r < b.ncomb; r += blockDim.x) {
+	for (long long r = r_begin + threadIdx.x; r < r_end; r += blockDim.x) {
 		long long fid = b.start + r;
 		double s = score_of(fid);
 		if (s > best) { best = s; best_fid = fid; }       /* ascending r per thread: first max kept */
@@ -558,11 +563,37 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) {
-		long long f = sh_f[0];
-		opt_score[b.opt_off] = sh_s[0];
-		opt_fid[b.opt_off] = f;
-		opt_cx[b.opt_off] = f >= 0 ? complexity_of(f) : 0;
+		part_score[blockIdx.x] = sh_s[0];
+		part_fid[blockIdx.x] = sh_f[0];
 	}
+}
+
+/* one thread per equal-category block: its chunks in enumeration order, strict '>' keeps the first maximum */
+__global__ void k_select_combine(DevData Dt, const CnbGroup *__restrict__ groups, const int *__restrict__ blk_equal,
+		const int *__restrict__ blk_chunk0, int nblocks, const double *__restrict__ part_score,
+		const long long *__restrict__ part_fid, double *__restrict__ opt_score, int *__restrict__ opt_cx,
+		long long *__restrict__ opt_fid) {
+	const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+	if (blk >= nblocks || !blk_equal[blk]) return;
+	const CnbBlock &b = Dt.blocks[blk];
+	const CnbGroup &g = groups[b.group];
+	double best = CNB_NEG_INF;
+	long long f = -1;
+	for (int ch = blk_chunk0[blk]; ch < blk_chunk0[blk + 1]; ch++)
+		if (part_fid[ch] >= 0 && (f < 0 || part_score[ch] > best)) { best = part_score[ch]; f = part_fid[ch]; }
+	int cx = 0;
+	if (f >= 0) {
+		DevFamilies F;
+		F.d = b.d; F.nblk = g.nblk; F.blk_off = g.blk_off; F.explicit_list = 0; F.nfam = g.nfam;
+		F.ex_child = nullptr; F.ex_pars = nullptr; F.ex_nd = nullptr;
+		int child, pars[CNB_MAXP];
+		int d = dev_family(Dt, F, f, child, pars);
+		cx = Dt.cats[child] - 1;
+		for (int i = 0; i < d; i++) cx *= Dt.cats[pars[i]];
+	}
+	opt_score[b.opt_off] = best;
+	opt_fid[b.opt_off] = f;
+	opt_cx[b.opt_off] = cx;
 }
 
 /* ------------------------------------------------------------------ K5: DP over complexity ---- */
@@ -1089,10 +1120,16 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 	return CNB_OK;
 }
 
+int cnbk_select_chunk(void) { return SEL_CHUNK; }
+
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
-		const double *scores, long long seg_len, double *opt_score, int *opt_cx, long long *opt_fid) {
-	if (nblocks <= 0) return CNB_OK;
-	k_select<<<nblocks, 256, 0, st>>>(Dt, groups, blk_equal, scores, seg_len, opt_score, opt_cx, opt_fid);
+		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
+		int *opt_cx, long long *opt_fid, double *part_score, long long *part_fid) {
+	if (nblocks <= 0 || nchunks <= 0) return CNB_OK;
+	k_select<<<nchunks, 256, 0, st>>>(Dt, groups, blk_equal, chunks, scores, seg_len, opt_score, opt_cx, opt_fid, part_score, part_fid);
+	CK(cudaGetLastError());
+	k_select_combine<<<(nblocks + 127) / 128, 128, 0, st>>>(Dt, groups, blk_equal, blk_chunk0, nblocks, part_score, part_fid,
+			opt_score, opt_cx, opt_fid);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -74,8 +74,12 @@ int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
 		const ScoreOut &O, int *overflow);
+/* arg-max per (child, parent count) block: `chunks` = (block, chunk) per CTA, cnbk_select_chunk() candidates each;
+ * blk_chunk0[nblocks + 1] = first chunk of every block; part_* = nchunks partial results */
+int cnbk_select_chunk(void);
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
-		const double *scores, long long seg_len, double *opt_score, int *opt_cx, long long *opt_fid);
+		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
+		int *opt_cx, long long *opt_fid, double *part_score, long long *part_fid);
 int cnbk_dp_init(cudaStream_t st, const DpState &S, int base_complexity, const double *base_v, int N);
 int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c, int N, int base_cx_c,
 		const double *base_v, long long opt_begin, long long opt_end, const double *opt_score, const int *opt_cx,
