@@ -152,7 +152,8 @@ def test_search_order_tensor_core_path(abi, case, bits, kind):
 
 @pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
 @pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4), (90, 20001, 4),
-                                      (3, 40, 3), (4, 33, 2), (64, 64, 4), (65, 300, 2), (129, 100, 4), (193, 40, 3)])
+                                      (3, 40, 3), (4, 33, 2), (64, 64, 4), (65, 300, 2), (129, 100, 4), (193, 40, 3),
+                                      (130, 7000, 4), (200, 6200, 3)])    # the last two: sample-sliced tail wave
 def test_tensor_core_path_multi_tile(abi, n, m, cats, bits, kind):
     """several child tiles / pair tiles / K stages, ragged M: tensor-core scores == bit-plane scores"""
     s, c = random_problem(n + m, n, m, cats)
@@ -547,9 +548,12 @@ def test_network_python_front_end(abi, port):
     s0 = (s - 1).astype(np.int32)
     probs, ll, sizes = port.net_set_prob(s0[150:], c, parents)
     assert all(np.array_equal(a, b) for a, b in zip(fit["probabilities"], probs)) and fit["likelihood"] == float(ll.sum())
-    assert search.cnLoglik(fit, data) == float(port.net_loglik("nodes", s0, c, parents, probs).sum())
-    assert np.array_equal(search.cnLoglik(fit, data, bysample=True), port.net_loglik("bysample", s0, c, parents, probs))
-    assert np.array_equal(search.cnNodeLoglik(fit, [2, 5], data), port.net_loglik("nodes", s0, c, parents, probs)[[1, 4]])
+    def inf(v):                                   # the front-ends export -FLT_MAX as -Inf, like rcatnet.cpp:295-300
+        return np.where(v <= -3.4028234663852886e38, -np.inf, v)
+    assert search.cnLoglik(fit, data) == float(inf(port.net_loglik("nodes", s0, c, parents, probs)).sum())
+    assert np.array_equal(search.cnLoglik(fit, data, bysample=True), inf(port.net_loglik("bysample", s0, c, parents, probs)))
+    assert np.array_equal(search.cnNodeLoglik(fit, [2, 5], data), inf(port.net_loglik("nodes", s0, c, parents, probs))[[1, 4]])
+    assert np.isfinite(search.cnLoglik(fit, data[:, 150:]))        # its own training data: no zero-probability hit
 
 
 def test_search_hist_python_front_end(abi):
