@@ -185,7 +185,8 @@ def sa_leg_ours(rank, world, max_iter, dist_mod=None, dev=None):
     import torch
     from catnet_b200 import _abi
     s, cats, sa = sa_workload()
-    kw = dict(max_parent_set=2, max_complexity=600, num_cats=cats)
+    # every rank's chain on ITS OWN GPU (cnb_params.device): on one shared device the processes time-slice
+    kw = dict(max_parent_set=2, max_complexity=600, num_cats=cats, device=dev.index if dev is not None else 0)
     _abi.search_sa(s, dict(sa, max_iter=3, seed=1), **kw)
     t0 = time.perf_counter()
     r = _abi.search_sa(s, dict(sa, max_iter=max_iter, seed=4004 + rank), **kw)

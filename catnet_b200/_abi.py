@@ -74,6 +74,7 @@ SYMBOLS = [
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
     "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
     "cnb_loglik", "cnb_node_loglik", "cnb_set_prob", "cnb_ctx_loglik", "cnb_ctx_set_prob",
+    "cnb_samples", "cnb_samples_dev",
 ]
 
 _lib = None
@@ -140,6 +141,8 @@ def lib():
         "cnb_set_prob": (i32, [P(Network), i32, vp, vp, i32, vp, vp, vp]),
         "cnb_ctx_loglik": (i32, [vp, P(Network), i32, i32, vp, vp]),
         "cnb_ctx_set_prob": (i32, [vp, P(Network), vp, vp, vp]),
+        "cnb_samples": (i32, [P(Network), i32, vp, dbl, C.c_uint64, i32, vp]),
+        "cnb_samples_dev": (i32, [P(Network), i32, vp, dbl, C.c_uint64, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -477,6 +480,24 @@ def set_prob(samples, cats, parents, perturbations=None, device=0):
     sizes = np.zeros(n, dtype=np.int32)
     check(lib().cnb_set_prob(C.byref(net), m, ptr(s), ptr(i32(perturbations)), int(device), ptr(probs), ptr(ll), ptr(sizes)))
     return [probs[off[k]:off[k + 1]].copy() for k in range(n)], ll, sizes
+
+
+def samples(cats, parents, probs, num_samples, perturbations=None, na_rate=0.0, seed=1, device=0):
+    """one-shot cnb_samples (ccnSamples in the R shim): [M][N] int32, 1-based, NA_INTEGER where blanked"""
+    keep = Keep()
+    net, _ = make_network(keep, cats, parents, probs)
+    out = np.zeros((int(num_samples), len(cats)), dtype=np.int32)
+    check(lib().cnb_samples(C.byref(net), int(num_samples), ptr(i32(perturbations)), float(na_rate), int(seed), int(device),
+                            ptr(out)))
+    return out
+
+
+def samples_dev(cats, parents, probs, num_samples, out_dev_ptr, perturbations_dev_ptr=None, na_rate=0.0, seed=1, device=0):
+    """cnb_samples_dev: the [M][N] int32 matrix is written to device memory at out_dev_ptr"""
+    keep = Keep()
+    net, _ = make_network(keep, cats, parents, probs)
+    check(lib().cnb_samples_dev(C.byref(net), int(num_samples), perturbations_dev_ptr, float(na_rate), int(seed), int(device),
+                                out_dev_ptr))
 
 
 PAIRWISE_KINDS = {"entropy": 0, "kl": 1, "pearson": 2}

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 #include "cnb_device.cuh"
@@ -87,6 +88,9 @@ void PinBuf::release() {
 
 extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	if (!c) return;
+	if (c->host_ms[3] > 0)
+		fprintf(stderr, "[cnb trace] %.0f searches: plan %.3f score %.3f select+dp %.3f ms per search (host wall)\n", c->host_ms[3],
+				c->host_ms[0] / c->host_ms[3], c->host_ms[1] / c->host_ms[3], c->host_ms[2] / c->host_ms[3]);
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->pin_sel.release();
@@ -897,10 +901,23 @@ extern "C" int cnb_ctx_finish(cnb_ctx *c, const double *scores_dev, cnb_result *
 
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p) {
 	int64_t seg = 0, nf = 0;
+	/* CNB_TRACE=1: host wall time per phase, accumulated per context and printed when it is destroyed */
+	static const bool trace = getenv("CNB_TRACE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto t0 = now();
 	RC(cnb_ctx_plan(c, p, 0, 1, &seg, &nf));
+	auto t1 = now();
 	RC(c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double)));
 	RC(cnb_ctx_score_shard(c, (double *)c->b_scores.ptr));
+	auto t2 = now();
 	RC(cnb_ctx_select_dp(c, (const double *)c->b_scores.ptr));
+	auto t3 = now();
+	if (trace) {
+		c->host_ms[0] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+		c->host_ms[1] += std::chrono::duration<double, std::milli>(t2 - t1).count();
+		c->host_ms[2] += std::chrono::duration<double, std::milli>(t3 - t2).count();
+		c->host_ms[3] += 1;
+	}
 	return CNB_OK;
 }
 
@@ -1086,18 +1103,19 @@ extern "C" int cnb_entropy_order(int32_t N, int32_t M, const int32_t *samples, c
 /* ------------------------------------------------------------------ a given network ---- */
 /* validate a cnb_network against the resident data and flatten it: 0-based parents, table sizes */
 static int check_network(cnb_ctx *c, const cnb_network *net, bool need_probs, std::vector<int32_t> *ints,
-		std::vector<long long> *off) {
-	if (!c || !c->have_samples || !net || !net->num_cats || !net->num_parents || !net->prob_offsets
-			|| (need_probs && !net->probs) || net->max_parents < 0 || (net->max_parents > 0 && !net->parents)) {
+		std::vector<long long> *off, bool against_data = true) {
+	if (!c || (against_data && !c->have_samples) || !net || !net->num_cats || !net->num_parents || !net->prob_offsets
+			|| (need_probs && !net->probs) || net->max_parents < 0 || (net->max_parents > 0 && !net->parents) || net->num_nodes < 1) {
 		cnb_set_error("network: bad arguments");
 		return CNB_ERR_PARAM;
 	}
-	const int N = c->N, maxp = std::max(net->max_parents, 1);
-	if (net->num_nodes != N) { cnb_set_error("The number of nodes in the object and data should be equal"); return CNB_ERR_PARAM; }
+	const int N = net->num_nodes, maxp = std::max(net->max_parents, 1);
+	if (against_data && N != c->N) { cnb_set_error("The number of nodes in the object and data should be equal"); return CNB_ERR_PARAM; }
 	ints->assign((size_t)2 * N + (size_t)N * maxp, 0);
 	off->assign(N + 1, 0);
 	for (int i = 0; i < N; i++) {
-		if (net->num_cats[i] != c->cats_lbl[i]) {
+		if (net->num_cats[i] < 1 || net->num_cats[i] > 254) { cnb_set_error("node %d: %d categories", i + 1, net->num_cats[i]); return CNB_ERR_PARAM; }
+		if (against_data && net->num_cats[i] != c->cats_lbl[i]) {
 			cnb_set_error("node %d: the object has %d categories, the resident data %d", i + 1, net->num_cats[i], c->cats_lbl[i]);
 			return CNB_ERR_PARAM;
 		}
@@ -1276,6 +1294,111 @@ extern "C" int cnb_set_prob(const cnb_network *net, int32_t M, const int32_t *sa
 		int32_t device, double *probs_out, double *loglik_out, int32_t *sizes_out) {
 	return with_network_ctx(net, M, samples, pert, device,
 			[&](cnb_ctx *c) { return cnb_ctx_set_prob(c, net, probs_out, loglik_out, sizes_out); });
+}
+
+/* ------------------------------------------------------------------ cnSamples ---- */
+/* CATNET::getOrder (catnet_class.h:1119-1157): repeatedly the lowest unplaced node all of whose parents are placed */
+static int sampling_order(int N, int maxp, const std::vector<int32_t> &ints, std::vector<int32_t> *order) {
+	std::vector<char> found(N, 0);
+	order->clear();
+	for (int k = 0; k < N; k++) {
+		int j = 0;
+		for (; j < N; j++) {
+			if (found[j]) continue;
+			bool ready = true;
+			for (int p = 0; p < ints[N + j] && ready; p++) ready = found[ints[(size_t)2 * N + (size_t)j * maxp + p]];
+			if (ready) break;
+		}
+		if (j >= N) { cnb_set_error("the network has a directed cycle"); return CNB_ERR_PARAM; }
+		found[j] = 1;
+		order->push_back(j);
+	}
+	return CNB_OK;
+}
+
+/* out_dev: int32 [M][N] in device memory; pert_dev: int32 [M][N] in device memory or NULL */
+static int samples_on_device(cnb_ctx *c, const cnb_network *net, int32_t M, const int32_t *pert_dev, double na_rate,
+		uint64_t seed, int32_t *out_dev) {
+	std::vector<int32_t> ints, order;
+	std::vector<long long> off;
+	RC(check_network(c, net, true, &ints, &off, false));
+	if (M < 1 || !out_dev) { cnb_set_error("The number of samples should be integer"); return CNB_ERR_PARAM; }
+	const int N = net->num_nodes, maxp = std::max(net->max_parents, 1);
+	RC(sampling_order(N, maxp, ints, &order));
+	cudaStream_t st = c->stream;
+	const long long base0 = off[0], total = off[N] - base0;
+	for (auto &o : off) o -= base0;
+	RC(upload(c, c->b_net_int, ints));
+	RC(upload(c, c->b_net_off, off));
+	RC(upload(c, c->b_net_sel, order));
+	RC(c->b_net_probs.ensure(std::max<long long>(total, 1) * sizeof(double)));
+	H2D(c, c->b_net_probs.ptr, net->probs + base0, total * sizeof(double));
+	CnbDevNet dn;
+	dn.N = N;
+	dn.maxp = maxp;
+	dn.cats = (const int *)c->b_net_int.ptr;
+	dn.npar = dn.cats + N;
+	dn.pars = dn.cats + 2 * N;
+	dn.off = (const long long *)c->b_net_off.ptr;
+	dn.logp = (const double *)c->b_net_probs.ptr;                /* the sampler reads probabilities, not logs */
+	unsigned long long drawn = (unsigned long long)N * (unsigned long long)M;
+	const long long *base = nullptr;
+	if (pert_dev) {
+		/* uniforms are consumed by the unfixed entries only, node after node in sampling order: where each chunk of
+		 * samples starts in the stream */
+		const int nchunks = (M + cnbk_sample_chunk() - 1) / cnbk_sample_chunk();
+		const size_t n = (size_t)N * nchunks;
+		RC(c->b_net_fz.ensure(n * sizeof(int)));
+		RC(cnbk_sample_count(st, dn, (const int *)c->b_net_sel.ptr, pert_dev, M, (int *)c->b_net_fz.ptr));
+		std::vector<int32_t> cnt(n);
+		std::vector<long long> start(n);
+		D2H(c, cnt.data(), c->b_net_fz.ptr, n * sizeof(int));
+		CK(cudaStreamSynchronize(st));
+		long long acc = 0;
+		for (size_t k = 0; k < n; k++) { start[k] = acc; acc += cnt[k]; }
+		drawn = (unsigned long long)acc;
+		RC(upload(c, c->b_net_logp, start));
+		base = (const long long *)c->b_net_logp.ptr;
+	}
+	RC(cnbk_sample(st, dn, (const int *)c->b_net_sel.ptr, pert_dev, base, M, seed, out_dev));
+	if (na_rate < 0) na_rate = 0;                                /* R/catnet.samples.R:54-57 */
+	if (na_rate > 1) na_rate = 1;
+	const int k = (int)(na_rate * N);                            /* rcatnet.cpp:601 */
+	if (k > 0 && k < N) RC(cnbk_sample_na(st, N, M, k, seed, drawn, out_dev));
+	CK(cudaStreamSynchronize(st));
+	return CNB_OK;
+}
+
+extern "C" int cnb_samples_dev(const cnb_network *net, int32_t M, const int32_t *pert_dev, double na_rate, uint64_t seed,
+		int32_t device, int32_t *out_dev) {
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(device, &c));
+	int rc = samples_on_device(c, net, M, pert_dev, na_rate, seed, out_dev);
+	cnb_ctx_destroy(c);
+	return rc;
+}
+
+extern "C" int cnb_samples(const cnb_network *net, int32_t M, const int32_t *pert, double na_rate, uint64_t seed,
+		int32_t device, int32_t *out) {
+	if (!net || M < 1 || !out) { cnb_set_error("cnb_samples: bad arguments"); return CNB_ERR_PARAM; }
+	cnb_ctx *c = nullptr;
+	RC(cnb_ctx_create(device, &c));
+	const size_t bytes = (size_t)net->num_nodes * M * sizeof(int32_t);
+	int rc = c->b_stage_s.ensure(bytes);
+	if (rc == CNB_OK && pert) rc = c->b_stage_p.ensure(bytes);
+	if (rc == CNB_OK && pert && cudaMemcpyAsync(c->b_stage_p.ptr, pert, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+		cnb_set_error("CUDA: copy of the perturbations failed");
+		rc = CNB_ERR_CUDA;
+	}
+	if (rc == CNB_OK)
+		rc = samples_on_device(c, net, M, pert ? (const int32_t *)c->b_stage_p.ptr : nullptr, na_rate, seed, (int32_t *)c->b_stage_s.ptr);
+	if (rc == CNB_OK && (cudaMemcpyAsync(out, c->b_stage_s.ptr, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+			|| cudaStreamSynchronize(c->stream) != cudaSuccess)) {
+		cnb_set_error("CUDA: copy of the samples failed");
+		rc = CNB_ERR_CUDA;
+	}
+	cnb_ctx_destroy(c);
+	return rc;
 }
 
 extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double *out) {

@@ -44,6 +44,7 @@ struct cnb_ctx {
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */
 	bool ignore_pert = false;          /* score as if there were no perturbation masks (full tables of the pairwise metrics) */
 	int dp_final = 0, tensor_batches = 0;
+	double host_ms[4] = {0, 0, 0, 0};   /* CNB_TRACE: host wall time of plan / score / select+dp, searches */
 	std::vector<int32_t> cats_lbl;
 	std::vector<int32_t> blk_equal;
 	std::vector<int32_t> sel_chunks, sel_chunk0;   /* (block, chunk) per CTA of k_select; first chunk of every block */

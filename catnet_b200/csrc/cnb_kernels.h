@@ -70,6 +70,13 @@ int cnbk_net_nodes(cudaStream_t st, const CnbDevNet &net, const uint8_t *codes, 
 int cnbk_net_bysample(cudaStream_t st, const CnbDevNet &net, const uint8_t *codes, const uint32_t *keep_lbl, int M,
 		int Mpad, int *first_zero, bool any_zero, double *out);
 int cnbk_keep_count(cudaStream_t st, const uint32_t *keep_lbl, int N, int W, int *out);
+/* cnSamples: order = sampling order (parents first); net.logp points at the PROBABILITY tables here; pert [M][N] or
+ * NULL; cnt / base are [N][chunks] (chunks of cnbk_sample_chunk() samples), only used with perturbations */
+int cnbk_sample_chunk(void);
+int cnbk_sample_count(cudaStream_t st, const CnbDevNet &net, const int *order, const int *pert, int M, int *cnt);
+int cnbk_sample(cudaStream_t st, const CnbDevNet &net, const int *order, const int *pert, const long long *base, int M,
+		unsigned long long seed, int *out);
+int cnbk_sample_na(cudaStream_t st, int N, int M, int k, unsigned long long seed, unsigned long long base, int *out);
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,

@@ -12,6 +12,7 @@
  * reference's `break` leaves the sample loop), which k_net_first_zero reproduces with the first such sample per node. */
 #include <cuda_runtime.h>
 #include <float.h>
+#include <limits.h>
 #include <math_constants.h>
 #include "cnb_kernels.h"
 #include "cnb_log.h"
@@ -195,6 +196,128 @@ int cnbk_net_bysample(cudaStream_t st, const CnbDevNet &net, const uint8_t *code
 
 int cnbk_keep_count(cudaStream_t st, const uint32_t *keep_lbl, int N, int W, int *out) {
 	k_keep_count<<<N, 32, 0, st>>>(keep_lbl, N, W, out);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ cnSamples ----
+ * RCatnet::genSamples (rcatnet.cpp:524-650): nodes in the order CATNET::getOrder gives (parents first), per node the
+ * samples in order, ONE uniform per (node, sample) unless a perturbation fixes the value; the category is the first
+ * i with u <= p_0 + ... + p_i (fp64, in order; i = C if none).  Then, for naRate, N uniforms per sample pick the
+ * k = (int)(naRate * N) nodes that become NA (largest (int)(N u) first, lowest node on ties).
+ * The library's uniform stream is splitmix64 (cnb_rng.h), which is counter based: draw t is a function of seed and t
+ * alone, so every (node, sample) computes its own uniform: t = draws of the earlier nodes + unfixed samples before j. */
+__device__ __forceinline__ double net_uniform(unsigned long long seed, unsigned long long t) {
+	unsigned long long z = seed + (t + 1ull) * 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z = z ^ (z >> 31);
+	return __dmul_rn(__dadd_rn((double)(z >> 11), 0.5), 1.0 / 9007199254740992.0);
+}
+
+#define SMP_CHUNK 256
+/* unfixed (node, sample) entries per (order position, chunk of 256 samples) */
+__global__ void __launch_bounds__(SMP_CHUNK) k_sample_count(CnbDevNet net, const int *__restrict__ order,
+		const int *__restrict__ pert, int M, int nchunks, int *__restrict__ cnt) {
+	const int k = blockIdx.y, i = order[k], j = blockIdx.x * SMP_CHUNK + threadIdx.x;
+	int free_ = 0;
+	if (j < M) {
+		const int v = pert[(size_t)j * net.N + i];
+		free_ = !(v >= 1 && v <= net.cats[i]);
+	}
+	const int n = __syncthreads_count(free_);
+	if (threadIdx.x == 0) cnt[(size_t)k * nchunks + blockIdx.x] = n;
+}
+
+/* one thread per sample, nodes in sampling order; probs = the network's tables (net.logp points at them here).
+ * base[k * nchunks + chunk] = uniforms consumed before that chunk of order position k (only with perturbations) */
+__global__ void __launch_bounds__(SMP_CHUNK) k_sample(CnbDevNet net, const int *__restrict__ order,
+		const int *__restrict__ pert, const long long *__restrict__ base, int M, int nchunks, unsigned long long seed,
+		int *__restrict__ out) {
+	__shared__ int warp_tot[SMP_CHUNK / 32];
+	const int j = blockIdx.x * SMP_CHUNK + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool live = j < M;
+	int *row = out + (size_t)(live ? j : 0) * net.N;
+	for (int k = 0; k < net.N; k++) {
+		const int i = order[k], cc = net.cats[i];
+		int fixed = 0;
+		unsigned long long t = (unsigned long long)k * (unsigned long long)M + (unsigned long long)j;
+		if (pert) {
+			if (live) {
+				const int v = pert[(size_t)j * net.N + i];
+				if (v >= 1 && v <= cc) fixed = v;                  /* rcatnet.cpp:578-584 */
+			}
+			/* rank of this sample among the chunk's unfixed ones */
+			const unsigned m = __ballot_sync(0xffffffffu, live && !fixed);
+			if (lane == 0) warp_tot[warp] = __popc(m);
+			__syncthreads();
+			int before = __popc(m & ((1u << lane) - 1));
+			for (int w = 0; w < warp; w++) before += warp_tot[w];
+			__syncthreads();
+			t = (unsigned long long)(base[(size_t)k * nchunks + blockIdx.x] + before);
+		}
+		if (!live) continue;
+		if (fixed) { row[i] = fixed; continue; }
+		const int d = net.npar[i];
+		long long idx = 0;
+		for (int p = 0; p < d; p++) {
+			const int q = net.pars[(size_t)i * net.maxp + p], qc = net.cats[q];
+			int v = row[q] - 1;                                    /* drawn earlier by this thread */
+			v = v < 0 ? 0 : (v >= qc ? qc - 1 : v);                /* the reference dereferences NULL there */
+			idx = idx * qc + v;
+		}
+		const double *p = net.logp + net.off[i] + idx * cc;
+		const double u = net_uniform(seed, t);
+		double v = 0.0;
+		int c = 0;
+		for (; c < cc; c++) {
+			v = __dadd_rn(v, p[c]);
+			if (u <= v) break;
+		}
+		row[i] = c + 1;
+	}
+}
+
+/* naRate: k nodes per sample become NA (rcatnet.cpp:601-626).  paux[ii] = (int)(N u) from N uniforms per sample; the
+ * reference takes the first maximum k times, i.e. the k first elements by (value descending, node ascending). */
+__global__ void k_sample_na(int N, int M, int k, unsigned long long seed, unsigned long long base, int *__restrict__ out) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= M) return;
+	int pv = N + 1, pi = -1;                                       /* the previous pick (value, node) */
+	for (int r = 0; r < k; r++) {
+		int bv = -1, bi = -1;
+		for (int ii = 0; ii < N; ii++) {
+			const int a = (int)__dmul_rn((double)N, net_uniform(seed, base + (unsigned long long)j * N + ii));
+			const bool after = a < pv || (a == pv && ii > pi);      /* not picked yet */
+			if (after && a > bv) { bv = a; bi = ii; }
+		}
+		if (bi < 0) break;
+		out[(size_t)j * N + bi] = INT_MIN;                         /* R_NaInt */
+		pv = bv;
+		pi = bi;
+	}
+}
+
+int cnbk_sample_chunk(void) { return SMP_CHUNK; }
+
+int cnbk_sample_count(cudaStream_t st, const CnbDevNet &net, const int *order, const int *pert, int M, int *cnt) {
+	const int nchunks = (M + SMP_CHUNK - 1) / SMP_CHUNK;
+	dim3 grid(nchunks, net.N);
+	k_sample_count<<<grid, SMP_CHUNK, 0, st>>>(net, order, pert, M, nchunks, cnt);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_sample(cudaStream_t st, const CnbDevNet &net, const int *order, const int *pert, const long long *base, int M,
+		unsigned long long seed, int *out) {
+	const int nchunks = (M + SMP_CHUNK - 1) / SMP_CHUNK;
+	k_sample<<<nchunks, SMP_CHUNK, 0, st>>>(net, order, pert, base, M, nchunks, seed, out);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_sample_na(cudaStream_t st, int N, int M, int k, unsigned long long seed, unsigned long long base, int *out) {
+	k_sample_na<<<(M + 127) / 128, 128, 0, st>>>(N, M, k, seed, base, out);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

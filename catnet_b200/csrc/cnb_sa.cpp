@@ -14,6 +14,7 @@
 #include <math.h>
 #include <string.h>
 #include <memory>
+#include <chrono>
 #include <vector>
 #include "cnb_ctx.h"
 #include "cnb_rng.h"
@@ -228,10 +229,21 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 	if (!p || !sa || !out) return CNB_ERR_PARAM;
 	*out = nullptr;
 	cnb_ctx *c = nullptr;
+	static const bool trace = getenv("CNB_TRACE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+		return std::chrono::duration<double, std::milli>(b - a).count(); };
+	auto t0 = now();
 	RC(cnb_ctx_create(p->device, &c));
+	auto t1 = now();
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
+	auto t2 = now();
 	if (rc == CNB_OK) rc = cnb_ctx_search_sa(c, p, sa, out);
+	auto t3 = now();
 	cnb_ctx_destroy(c);
+	if (trace)
+		fprintf(stderr, "[cnb trace] cnb_search_sa: create %.2f set_samples %.2f search %.2f destroy %.2f ms\n", ms(t0, t1), ms(t1, t2),
+				ms(t2, t3), ms(t3, now()));
 	return rc;
 }
 

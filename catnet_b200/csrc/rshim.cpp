@@ -4,7 +4,7 @@
  * src/catnet_rexport.h:31-64):
  *     ccnOptimalNetsForOrder/12   ccnOptimalNetsSA/23   ccnParHistogram/14   ccnReleaseCache/0   ccnSetSeed/1
  *     ccnEntropyPairwise/2   ccnEntropyOrder/2   ccnKLPairwise/2   ccnPearsonPairwise/2
- *     ccnLoglik/4   ccnNodeLoglik/4   ccnSetProb/3
+ *     ccnLoglik/4   ccnNodeLoglik/4   ccnSetProb/3   ccnSamples/4
  * and registers them in R_init_catnet.  Every other routine of the reference's table keeps its reference
  * implementation (this shim is linked INTO the package next to the reference sources).
  *
@@ -506,6 +506,31 @@ SEXP ccnSetProb(SEXP cnet, SEXP rSamples, SEXP rPerturbations) {
 	return out;
 }
 
+/* cnSamples: .Call("ccnSamples", object, numsamples, perturbations, naRate) (R/catnet.samples.R:60-62) ->
+ * RCatnet::genSamples (rcatnet.cpp:524-650).  R's RNG cannot cross the C ABI: one uniform from it seeds the library's
+ * stream (set.seed() still makes runs reproducible; the stream differs from stock catnet). */
+SEXP ccnSamples(SEXP cnet, SEXP rNumSamples, SEXP rPerturbations, SEXP rNaRate) {
+	RNetwork r;
+	read_network(cnet, r, true);
+	const int N = r.net.num_nodes, M = asInteger(rNumSamples);
+	if (M < 1) error("The number of samples should be integer");
+	int nprot = 0;
+	const int32_t *pert = NULL;
+	if (!isNull(rPerturbations)) {
+		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
+		nprot++;
+		if (length(rPerturbations) == N * M) pert = INTEGER(rPerturbations);
+	}
+	GetRNGstate();
+	const uint64_t seed = (uint64_t)(unif_rand() * 9007199254740992.0);
+	PutRNGstate();
+	SEXP rsamples = PROTECT(allocVector(INTSXP, N * M));           /* R reshapes it with matrix(data, ncol = numsamples) */
+	int rc = cnb_samples(&r.net, M, pert, asReal(rNaRate), seed, 0, INTEGER(rsamples));
+	UNPROTECT(nprot + 1);
+	if (rc != CNB_OK) fail(rc);
+	return rsamples;
+}
+
 SEXP ccnReleaseCache(void) {
 	cnb_release_cache();
 	return R_NilValue;
@@ -530,12 +555,13 @@ static const R_CallMethodDef cnb_call_methods[] = {
 	{"ccnLoglik", (DL_FUNC)&ccnLoglik, 4},
 	{"ccnNodeLoglik", (DL_FUNC)&ccnNodeLoglik, 4},
 	{"ccnSetProb", (DL_FUNC)&ccnSetProb, 3},
+	{"ccnSamples", (DL_FUNC)&ccnSamples, 4},
 	{NULL, NULL, 0}};
 
 const R_CallMethodDef *cnb_r_call_methods(void) { return cnb_call_methods; }
 
 #ifdef CNB_STANDALONE_RSHIM
-/* build as a complete catnet.so for the search path only (ccnMarginalProb and ccnSamples are then unavailable) */
+/* build as a complete catnet.so for the search path only (ccnMarginalProb is then unavailable) */
 void R_init_catnet(DllInfo *info) {
 	R_registerRoutines(info, NULL, cnb_call_methods, NULL, NULL);
 	R_useDynamicSymbols(info, (Rboolean)1);

@@ -367,3 +367,29 @@ def cnSetProb(obj, data, perturbations=None, nodeCats=None, device=0):
     new.update(categories=categories, maxCategories=max_categories, probabilities=probs, likelihood=float(ll.sum()),
                nodeSampleSizes=[int(v) for v in sizes], complexity=complexity)
     return new
+
+
+def cnSamples(obj, numsamples=1, perturbations=None, as_index=True, naRate=0.0, seed=1, device=0):
+    """R/catnet.samples.R:27-95 (output="matrix"): nodes x samples matrix drawn from the network; as_index=False maps the
+    indices to the object's category values.  perturbations: nodes x samples (or one vector per node), 0 = free."""
+    n = obj["numnodes"]
+    numsamples = int(numsamples)
+    pert = None
+    if perturbations is not None:
+        pert = np.asarray(perturbations, dtype=np.int32)
+        if pert.ndim == 1:
+            pert = np.repeat(pert[:, None], numsamples, axis=1)
+        if pert.shape != (n, numsamples):
+            raise ValueError("The perturbation size should be %d by %d" % (n, numsamples))
+        pert = np.ascontiguousarray(pert.T)
+    naRate = min(max(float(naRate), 0.0), 1.0)
+    cats = np.array([len(c) for c in obj["categories"]], dtype=np.int32)
+    parents = [[int(q) - 1 for q in (p or [])] for p in obj["parents"]]
+    s = _abi.samples(cats, parents, obj["probabilities"], numsamples, pert, naRate, seed, device).T
+    if as_index:
+        return s
+    out = np.full(s.shape, np.nan, dtype=np.float64)
+    for i in range(n):
+        ok = s[i] != NA
+        out[i, ok] = np.asarray(obj["categories"][i], dtype=np.float64)[s[i, ok] - 1]
+    return out

@@ -162,6 +162,20 @@ int cnb_node_loglik(const cnb_network *net, int32_t num_sel, const int32_t *node
 int cnb_set_prob(const cnb_network *net, int32_t num_samples, const int32_t *samples, const int32_t *perturbations,
 		int32_t device, double *probs_out, double *loglik_out, int32_t *sizes_out);
 
+/* ---- cnSamples: .Call("ccnSamples", object, numsamples, perturbations, naRate)
+ * R/catnet.samples.R:60-62, src/ccnInit.c:42 -> RCatnet::genSamples, src/rcatnet.cpp:524-650 ----
+ * out: int32 [M][N] (R's N x M matrix), 1-based categories, NA_INTEGER where naRate blanked a value.  perturbations
+ * [M][N] or NULL: a value in 1..num_cats[i] fixes node i in that sample.  Nodes are drawn parents first
+ * (CATNET::getOrder), one uniform per unfixed (node, sample), category = first i with u <= p_0 + ... + p_i.
+ * R's unif_rand cannot cross a C ABI: the uniforms come from the library's splitmix64 stream (draw t is a function of
+ * seed and t), consumed in exactly the reference's order -- so with the same stream injected into the reference the
+ * samples are identical. */
+int cnb_samples(const cnb_network *net, int32_t num_samples, const int32_t *perturbations, double na_rate, uint64_t seed,
+		int32_t device, int32_t *out);
+/* the same with perturbations and output in device memory (the matrix can go straight into cnb_ctx_set_samples_dev) */
+int cnb_samples_dev(const cnb_network *net, int32_t num_samples, const int32_t *perturbations_dev, double na_rate,
+		uint64_t seed, int32_t device, int32_t *out_dev);
+
 /* ---- resident-context API (SA, bench, multi-process sharding) ---- */
 int cnb_ctx_create(int32_t device, cnb_ctx **out);
 void cnb_ctx_destroy(cnb_ctx *ctx);

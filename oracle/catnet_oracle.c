@@ -877,3 +877,75 @@ int orc_net_set_prob(int N, int M, const int *samples0, const int *pert, const i
 	}
 	return 0;
 }
+
+/* ------------------------------------------------------------------ cnSamples ---- */
+/* RCatnet::genSamples (rcatnet.cpp:524-650) under the injected uniform stream (orc_unif = splitmix64, as the SA
+ * restatement above).  Sampling order = CATNET::getOrder (catnet_class.h:1119-1157).  out [M][N] 1-based, INT_MIN = NA.
+ * Returns the number of uniforms consumed, -1 for a cyclic network. */
+static double orc_stream(unsigned long long *state) {
+	unsigned long long z = (*state += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z = z ^ (z >> 31);
+	return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+long orc_net_samples(int N, const int *cats, int maxParents, const int *numParents, const int *parents0,
+		const double *probs, const long long *offsets, int M, const int *pert, double naRate, unsigned long long seed,
+		int *out) {
+	int *order = (int *)malloc((size_t)N * sizeof(int)), *found = (int *)calloc((size_t)N, sizeof(int));
+	int i, j, k, p;
+	long calls = 0;
+	unsigned long long state = seed;
+	for (k = 0; k < N; k++) {                                      /* getOrder */
+		for (j = 0; j < N; j++) {
+			if (found[j]) continue;
+			int ready = 1;
+			for (p = 0; p < numParents[j]; p++)
+				if (!found[parents0[(size_t)j * maxParents + p]]) { ready = 0; break; }
+			if (ready) break;
+		}
+		if (j >= N) { free(order); free(found); return -1; }
+		order[k] = j;
+		found[j] = 1;
+	}
+	for (k = 0; k < N; k++) {                                      /* :569-599 */
+		const int node = order[k];
+		const int *pars = parents0 + (size_t)node * maxParents;
+		for (j = 0; j < M; j++) {
+			int *row = out + (size_t)j * N;
+			if (pert) {
+				int v = pert[(size_t)j * N + node];
+				if (v >= 1 && v <= cats[node]) { row[node] = v; continue; }
+			}
+			long long idx = 0;
+			for (p = 0; p < numParents[node]; p++) idx = idx * cats[pars[p]] + (row[pars[p]] - 1);
+			const double *tab = probs + offsets[node] + idx * cats[node];
+			double u = orc_stream(&state), v = 0;
+			calls++;
+			for (i = 0; i < cats[node]; i++) {
+				v += tab[i];
+				if (u <= v) break;
+			}
+			row[node] = i + 1;
+		}
+	}
+	k = (int)(naRate * N);                                         /* :601-626 */
+	if (k > 0 && k < N) {
+		int *aux = (int *)malloc((size_t)N * sizeof(int));
+		for (j = 0; j < M; j++) {
+			for (i = 0; i < N; i++) { aux[i] = (int)(N * orc_stream(&state)); calls++; }
+			for (p = 0; p < k; p++) {
+				int node = 0, fmax = -(int)RAND_MAX;
+				for (i = 0; i < N; i++)
+					if (fmax < aux[i]) { fmax = aux[i]; node = i; }
+				aux[node] = -(int)RAND_MAX;
+				out[(size_t)j * N + node] = INT_MIN;
+			}
+		}
+		free(aux);
+	}
+	free(order);
+	free(found);
+	return calls;
+}

@@ -29,6 +29,10 @@ int orc_net_loglik(int N, int M, const int *samples0, const int *pert, const int
 int orc_net_set_prob(int N, int M, const int *samples0, const int *pert, const int *cats, int maxParents,
 		const int *numParents, const int *parents0, const long long *offsets, double *probs_out, double *loglik_out,
 		int *sizes_out);
+/* cnSamples (rcatnet.cpp:524-650) under the splitmix64 stream seeded by `seed`; out [M][N]; returns uniforms consumed */
+long orc_net_samples(int N, const int *cats, int maxParents, const int *numParents, const int *parents0,
+		const double *probs, const long long *offsets, int M, const int *pert, double naRate, unsigned long long seed,
+		int *out);
 void orc_set_seed(unsigned long long seed);
 int orc_result_nslots(const orc_result *r);
 int orc_result_exists(const orc_result *r, int k);

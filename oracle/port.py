@@ -223,3 +223,19 @@ def net_set_prob(samples0, cats, parents, perturbations=None):
     L.orc_net_set_prob(N, M, _p(s), _p(_i32(perturbations)), _p(cats), maxp, _p(npar), _p(pars), _p(off), _p(probs),
                        _p(ll), _p(sizes))
     return [probs[off[i]:off[i + 1]].copy() for i in range(N)], ll, sizes
+
+
+def net_samples(cats, parents, probs, num_samples, perturbations=None, na_rate=0.0, seed=1):
+    """cnSamples restated (orc_net_samples): ([M][N] int32, uniforms consumed)"""
+    L = lib()
+    L.orc_net_samples.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_double, C.c_ulonglong, C.c_void_p]
+    L.orc_net_samples.restype = C.c_long
+    cats, maxp, npar, pars, flat, off = flatten_network(cats, parents, probs)
+    N, M = len(cats), int(num_samples)
+    out = np.zeros((M, N), dtype=np.int32)
+    calls = L.orc_net_samples(N, _p(cats), maxp, _p(npar), _p(pars), _p(flat), _p(off), M, _p(_i32(perturbations)),
+                              float(na_rate), int(seed), _p(out))
+    if calls < 0:
+        raise ValueError("cyclic network")
+    return out, calls

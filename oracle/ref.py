@@ -292,3 +292,32 @@ def net_set_prob(samples0, cats, parents, perturbations=None):
                             _p(ll), _p(sizes))
     assert rc == 0
     return [probs[off[i]:off[i + 1]].copy() for i in range(N)], ll, sizes
+
+
+# ---------------------------------------------------------------- cnSamples ----
+_SM_PATH = os.path.join(_HERE, "_ref", "libcatnet_ref_samples.so")
+_sm = None
+
+
+def samples_available():
+    return os.path.exists(_SM_PATH)
+
+
+def net_samples(cats, parents, probs, num_samples, perturbations=None, na_rate=0.0, seed=1):
+    """RCatnet::genSamples of the reference (rcatnet.cpp:524-650, compiled unmodified; ref_samples.cpp) under the injected
+    splitmix64 uniform stream.  Returns ([M][N] int32 1-based, NA = NA_INT; uniforms consumed)."""
+    global _sm
+    if _sm is None:
+        if not samples_available():
+            raise RuntimeError("oracle/_ref/libcatnet_ref_samples.so missing: run `make -C oracle ref` where /root/reference exists")
+        _sm = C.CDLL(_SM_PATH)
+        _sm.ref_samples.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_double, C.c_ulonglong, C.c_void_p]
+        _sm.ref_samples.restype = C.c_long
+    cats, maxp, npar, pars, flat, off = flatten_network(cats, parents, probs)
+    N, M = len(cats), int(num_samples)
+    out = np.zeros((M, N), dtype=np.int32)
+    calls = _sm.ref_samples(N, _p(cats), maxp, _p(npar), _p(pars), _p(flat), _p(off), M, _p(_i32(perturbations)),
+                            float(na_rate), int(seed), _p(out))
+    assert calls >= 0
+    return out, calls

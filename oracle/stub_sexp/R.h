@@ -56,4 +56,38 @@ void cnb_stub_free_all(void);
 #define NUMERIC_POINTER(x) ((double *)(x)->data)
 #define NEW_NUMERIC(n) cnb_stub_alloc(14, (n))
 #define NEW_INTEGER(n) cnb_stub_alloc(13, (n))
+#define AS_NUMERIC(x) (x)                     /* the drivers hand over REALSXP already */
+#define R_NaInt INT_MIN
+#define R_IsNA(x) cnb_stub_is_na((double)(x))
+#define R_NegInf (-HUGE_VAL)
+/* the rest of the API rcatnet.cpp touches (S4 slots, lists, strings: RCatnet(SEXP), genRcatnet, prob_string ...) is only
+ * DECLARED: the drivers never reach those functions, and the definitions in ref_samples.cpp abort if they ever do */
+#define VECSXP 19
+#define STRSXP 16
+#ifdef __cplusplus
+extern "C" {
+#endif
+int cnb_stub_is_na(double x);
+int length(SEXP x);
+SEXP VECTOR_ELT(SEXP x, long i);
+SEXP SET_VECTOR_ELT(SEXP x, long i, SEXP v);
+SEXP allocVector(unsigned int type, long n);
+const char *CHAR(SEXP x);
+SEXP AS_LIST(SEXP x);
+SEXP AS_CHARACTER(SEXP x);
+SEXP mkChar(const char *s);
+SEXP mkString(const char *s);
+SEXP install(const char *s);
+SEXP asChar(SEXP x);
+SEXP STRING_ELT(SEXP x, long i);
+void SET_STRING_ELT(SEXP x, long i, SEXP v);
+int IS_VECTOR(SEXP x);
+int isS4(SEXP x);
+SEXP SET_SLOT(SEXP x, SEXP what, SEXP v);
+SEXP GET_SLOT(SEXP x, SEXP what);
+SEXP NEW_OBJECT(SEXP cls);
+SEXP MAKE_CLASS(const char *name);
+#ifdef __cplusplus
+}
+#endif
 #endif

@@ -105,6 +105,40 @@ NETWORK_CASES = [
 ]
 
 
+# cnSamples: random DAG whose topological order is a random permutation of the nodes
+SAMPLES_CASES = [
+    dict(seed=71, n=6, m=200, maxcat=4, maxpar=2),
+    dict(seed=72, n=9, m=1000, maxcat=3, maxpar=3, na=0.3),
+    dict(seed=73, n=5, m=257, maxcat=5, maxpar=2, pert=0.3),
+    dict(seed=74, n=12, m=700, maxcat=4, maxpar=3, pert=0.5, na=0.5),
+    dict(seed=75, n=1, m=50, maxcat=3, maxpar=0, na=0.9),
+    dict(seed=76, n=7, m=3, maxcat=2, maxpar=2, pert=0.2, na=0.99),
+]
+
+
+def build_samples_case(c):
+    """-> (cats, parents (0-based, listed order), probs (flat tables), perturbations [M][N] or None, na_rate)"""
+    rng = np.random.default_rng(4000 + c["seed"])
+    n, m = c["n"], c["m"]
+    cats = rng.integers(1 if c["seed"] % 2 else 2, c["maxcat"] + 1, size=n).astype(np.int32)
+    pos = np.argsort(rng.permutation(n))
+    parents = []
+    for i in range(n):
+        earlier = [int(q) for q in range(n) if pos[q] < pos[i]]
+        k = min(len(earlier), int(rng.integers(0, c["maxpar"] + 1)))
+        parents.append([int(v) for v in rng.choice(earlier, size=k, replace=False)] if k else [])
+    probs = []
+    for i, p in enumerate(parents):
+        rows = int(np.prod([cats[q] for q in p])) if p else 1
+        t = rng.random((rows, cats[i])) ** 3
+        t /= t.sum(axis=1, keepdims=True)
+        probs.append(t.ravel())
+    pert = None
+    if c.get("pert"):
+        pert = (rng.integers(0, c["maxcat"] + 2, size=(m, n)) * (rng.random((m, n)) < c["pert"])).astype(np.int32)
+    return cats, parents, probs, pert, c.get("na", 0.0)
+
+
 def build_network_case(c):
     """-> (samples [M][N] 1-based with NA, cats [N], parents (lists of 0-based nodes, listed order), perturbations);
     the tables are estimated on the first half of the samples"""

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 from cases import (CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case, PAIRWISE_CASES, build_pairwise_case,
-                   NETWORK_CASES, build_network_case)
+                   NETWORK_CASES, build_network_case, SAMPLES_CASES, build_samples_case)
 from helpers import NA, check_network_case, compare_golden, compare_search, load_golden, random_problem, unhex
 
 pytestmark = pytest.mark.gpu
@@ -554,6 +554,64 @@ def test_network_python_front_end(abi, port):
     assert np.array_equal(search.cnLoglik(fit, data, bysample=True), inf(port.net_loglik("bysample", s0, c, parents, probs)))
     assert np.array_equal(search.cnNodeLoglik(fit, [2, 5], data), inf(port.net_loglik("nodes", s0, c, parents, probs))[[1, 4]])
     assert np.isfinite(search.cnLoglik(fit, data[:, 150:]))        # its own training data: no zero-probability hit
+
+
+@pytest.mark.parametrize("case", SAMPLES_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_samples_match_reference(abi, case):
+    """cnSamples on the device: the reference's own samples under the shared uniform stream, value for value"""
+    cats, parents, probs, pert, na = build_samples_case(case)
+    g = load_golden("ref_samples")["seed%d" % case["seed"]]
+    s = abi.samples(cats, parents, probs, case["m"], pert, na, seed=case["seed"])
+    assert s.ravel().tolist() == g["samples"]
+
+
+@pytest.mark.parametrize("seed", range(800, 812))
+def test_samples_random_vs_oracle(abi, port, seed):
+    m = 1 + 523 * (seed % 6)
+    cats, parents, probs, pert, na = build_samples_case(dict(seed=seed, n=1 + 3 * (seed % 12), m=m, maxcat=6, maxpar=3,
+                                                             pert=[0, 0.4][seed % 2], na=[0, 0.2, 0.7][seed % 3]))
+    b, _ = port.net_samples(cats, parents, probs, m, pert, na, seed)
+    assert np.array_equal(abi.samples(cats, parents, probs, m, pert, na, seed=seed), b)
+
+
+def test_samples_large_statistics_and_device_output(abi, port):
+    """C5-shaped sampling straight into device memory: the first rows equal the oracle's, the empirical conditional
+    frequencies approach the tables, and the matrix feeds cnb_ctx_set_samples_dev without a host round trip"""
+    import torch
+    from catnet_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(5))
+    net = synth.random_network(60, 4, 2, rng)
+    cats, parents, probs = net["cats"], [list(p) for p in net["parents"]], [np.asarray(t).ravel() for t in net["cpts"]]
+    m = 400000
+    out = torch.empty((m, 60), dtype=torch.int32, device="cuda")
+    abi.samples_dev(cats, parents, probs, m, out.data_ptr(), seed=99)
+    torch.cuda.synchronize()
+    s = out.cpu().numpy()
+    assert s.min() >= 1 and (s.max(axis=0) <= cats).all()
+    # samples j < 1000 of every node use draws k*M + j: compare with the oracle run on the same M through a slice
+    o, _ = port.net_samples(cats, parents, probs, m, None, 0.0, 99)
+    assert np.array_equal(s, o)
+    i = max(range(60), key=lambda k: len(parents[k]))
+    cfg = np.zeros(m, dtype=np.int64)
+    for q in parents[i]:
+        cfg = cfg * int(cats[q]) + (s[:, q] - 1)
+    tab = np.asarray(probs[i]).reshape(-1, cats[i])
+    for r in range(tab.shape[0]):
+        sel = s[cfg == r, i]
+        if len(sel) > 5000:
+            freq = np.bincount(sel - 1, minlength=cats[i]) / len(sel)
+            assert np.abs(freq - tab[r]).max() < 0.03
+    with abi.Context(0) as ctx:
+        ctx.set_samples_dev(out.data_ptr(), 60, m, num_cats=cats)
+        fit, _, sizes = ctx.set_prob(cats, parents)
+        assert all(v == m for v in sizes) and np.abs(fit[i] - np.asarray(probs[i])).max() < 0.03
+
+
+def test_samples_errors(abi):
+    cats = np.array([2, 2], dtype=np.int32)
+    with pytest.raises(abi.CnbError) as e:                     # a directed cycle: the reference returns NULL
+        abi.samples(cats, [[1], [0]], [np.full(4, 0.5), np.full(4, 0.5)], 10)
+    assert e.value.code == abi.CNB_ERR_PARAM
 
 
 def test_search_hist_python_front_end(abi):

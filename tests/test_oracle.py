@@ -7,8 +7,8 @@ All fp64 comparisons are bit-exact."""
 import numpy as np
 import pytest
 
-from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case,
-                   build_network_case, build_pairwise_case, ref_args)
+from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, SAMPLES_CASES, build_case, build_hist_case,
+                   build_network_case, build_pairwise_case, build_samples_case, ref_args)
 from helpers import check_network_case, compare_golden, compare_search, load_golden, random_problem
 from oracle import port
 
@@ -156,3 +156,25 @@ def test_port_network_matches_reference(ref, seed):
         if mode == "bysample" and max(len(p) for p in parents) == 0 and pert is None:
             continue
         assert np.array_equal(ref.net_loglik(mode, s0, c, parents, pa, pert), port.net_loglik(mode, s0, c, parents, pa, pert))
+
+
+@pytest.mark.parametrize("case", SAMPLES_CASES, ids=lambda c: "seed%d" % c["seed"])
+def test_samples_match_golden(case):
+    """cnSamples: the restatement draws the reference's own samples under the injected uniform stream"""
+    cats, parents, probs, pert, na = build_samples_case(case)
+    g = load_golden("ref_samples")["seed%d" % case["seed"]]
+    s, calls = port.net_samples(cats, parents, probs, case["m"], pert, na, seed=case["seed"])
+    assert calls == g["calls"] and s.ravel().tolist() == g["samples"]
+
+
+def test_port_samples_match_reference(ref):
+    from oracle import ref as r
+    if not r.samples_available():
+        pytest.skip("oracle/_ref/libcatnet_ref_samples.so not built")
+    for seed in range(700, 712):
+        cats, parents, probs, pert, na = build_samples_case(dict(seed=seed, n=1 + seed % 9, m=10 + 37 * (seed % 7), maxcat=5,
+                                                                 maxpar=3, pert=[0, 0.4][seed % 2], na=[0, 0.2, 0.7][seed % 3]))
+        m = 10 + 37 * (seed % 7)
+        a, ca = r.net_samples(cats, parents, probs, m, pert, na, seed)
+        b, cb = port.net_samples(cats, parents, probs, m, pert, na, seed)
+        assert ca == cb and np.array_equal(a, b)

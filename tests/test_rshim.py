@@ -21,7 +21,7 @@ def test_call_table_matches_reference_registration():
     # names and arities the reference registers for this path (src/ccnInit.c:30-32, 36-39, 41, 43)
     assert table == {"ccnOptimalNetsForOrder": 12, "ccnOptimalNetsSA": 23, "ccnParHistogram": 14, "ccnReleaseCache": 0,
                      "ccnSetSeed": 1, "ccnEntropyPairwise": 2, "ccnEntropyOrder": 2, "ccnKLPairwise": 2,
-                     "ccnPearsonPairwise": 2, "ccnLoglik": 4, "ccnNodeLoglik": 4, "ccnSetProb": 3}
+                     "ccnPearsonPairwise": 2, "ccnLoglik": 4, "ccnNodeLoglik": 4, "ccnSetProb": 3, "ccnSamples": 4}
     for name, arity in table.items():
         sig = re.search(r"SEXP %s\(([^)]*)\)" % name, src).group(1)
         nargs = 0 if sig.strip() == "void" else sig.count("SEXP")

@@ -50,6 +50,21 @@ def main():
         out["loglik_bysample_s"] = timed(lambda: res.__setitem__("b", ctx.loglik(cats, parents, probs, "bysample")), args.repeat)
         out["loglik"] = float(res["n"].sum())
         out["bysample_mean"] = float(res["b"].mean())
+    import torch
+    probs_true = [np.asarray(t).ravel() for t in net["cpts"]]
+    dev_out = torch.empty((m, n), dtype=torch.int32, device="cuda")
+
+    def draw():
+        _abi.samples_dev(cats, parents, probs_true, m, dev_out.data_ptr(), seed=5005)
+        torch.cuda.synchronize()
+    out["samples_to_device_s"] = timed(draw, args.repeat)
+    out["samples_na5pct_to_device_s"] = timed(lambda: (_abi.samples_dev(cats, parents, probs_true, m, dev_out.data_ptr(),
+                                                                        na_rate=0.05, seed=5005), torch.cuda.synchronize()), 1)
+    if ref.samples_available():
+        mr = min(args.ref_samples, m)
+        t0 = time.perf_counter()
+        ref.net_samples(cats, parents, probs_true, mr, None, 0.0, 5005)
+        out["ref_samples_s_at_M%d" % mr] = time.perf_counter() - t0
     if ref.available():
         mr = min(args.ref_samples, m)
         s0 = (s[:mr] - 1).astype(np.int32)

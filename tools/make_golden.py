@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import random_problem  # noqa: E402
-from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, build_case, build_hist_case,  # noqa: E402
-                   build_network_case, build_pairwise_case)
+from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, SAMPLES_CASES, build_case,  # noqa: E402
+                   build_hist_case, build_network_case, build_pairwise_case, build_samples_case)
 
 from catnet_b200 import synth  # noqa: E402
 from oracle import ref  # noqa: E402
@@ -81,7 +81,21 @@ def make_network():
     print("ref_network.json", len(out))
 
 
+def make_samples():
+    """cnSamples through the reference's own RCatnet::genSamples (oracle/_ref/libcatnet_ref_samples.so) under the injected
+    splitmix64 stream; the matrices are stored whole (small) with the number of uniforms consumed"""
+    out = {}
+    for case in SAMPLES_CASES:
+        cats, parents, probs, pert, na = build_samples_case(case)
+        s, calls = ref.net_samples(cats, parents, probs, case["m"], pert, na, seed=case["seed"])
+        out["seed%d" % case["seed"]] = {"calls": int(calls), "samples": s.ravel().tolist()}
+    dump(out, "ref_samples.json")
+    print("ref_samples.json", {k: v["calls"] for k, v in out.items()})
+
+
 def main():
+    if "--only-samples" in sys.argv:
+        return make_samples()
     if "--only-pairwise" in sys.argv:
         return make_pairwise()
     if "--only-network" in sys.argv:
@@ -134,6 +148,7 @@ def main():
     print("ref_search_hist.json", {k: v["iterations"] for k, v in hist.items()})
     make_pairwise()
     make_network()
+    make_samples()
     if "--skip-configs" in sys.argv:
         return
     big = {}
