@@ -168,6 +168,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	/* two-way margins for the inclusion-exclusion scorer: only meaningful without missing values / masks */
 	c->pairs_valid = false;
 	c->pairs_full = false;
+	c->triples_valid = false;
 	c->has_na = flags[2] != 0;
 	c->clean = !flags[2] && !c->has_pert && c->max_cats <= CNB_PLANE_CATS;   /* no NA, no masks, bit planes valid */
 	/* the tables count ALL samples: with perturbation masks they serve only the "whole sample" side of the pairwise
@@ -241,6 +242,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->dp_per_node = (on & 32) != 0;                       /* bit 5: one DP launch per node (no cooperative kernel) */
 	c->dp_no_wave = (on & 64) != 0;                        /* bit 6: grid-barrier DP kernel instead of the wavefront one */
 	c->pairs_popc = (on & 128) != 0;                       /* bit 7: pair tables by the POPC kernel (set BEFORE set_samples) */
+	c->no_ie3 = (on & 512) != 0;                           /* bit 9: no inclusion-exclusion for three-parent families */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -377,6 +379,25 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 		RC(cnbk_score_pairs1(c->stream, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
 		c->timing.kernel_launches++;
 		return CNB_OK;
+	}
+	if (!force_generic && !F.ex_nd && F.d == 3 && c->pairs_valid && !c->ignore_pert && !O.counts && !c->no_ie && !c->no_ie3
+			&& c->max_cats <= CNB_PLANE_CATS) {
+		/* three parents, clean data: only the free cells are counted; the rest from the three-way tables of the data set,
+		 * built on first use (C(N,3) x 256 B; not for node counts where that would not fit comfortably) */
+		const long long nt = (long long)c->N * (c->N - 1) * (c->N - 2) / 6;
+		if (nt * 256 <= (8ll << 30)) {
+			if (!c->triples_valid) {
+				RC(c->b_triples.ensure((size_t)nt * 64 * sizeof(int)));
+				RC(cnbk_triple_tables(st, (const uint4 *)c->b_planes_lbl.ptr, c->N, c->W, c->max_cats, (const int *)c->b_pairs.ptr,
+						(int *)c->b_triples.ptr));
+				c->timing.kernel_launches++;
+				c->triples_valid = true;
+			}
+			c->last_fast = true;
+			RC(cnbk_score_planes_ie3(st, D, F, c->max_cats, b, e, O, (const int *)c->b_triples.ptr));
+			c->timing.kernel_launches++;
+			return CNB_OK;
+		}
 	}
 	bool fast = !force_generic && !F.ex_nd && cnbk_planes_supported(F.d, c->max_cats);
 	c->last_fast = fast;

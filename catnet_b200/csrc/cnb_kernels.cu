@@ -339,6 +339,183 @@ __global__ void __launch_bounds__(SCORE_BS) k_score_planes_ie2(DevData Dt, DevFa
 	dev_store_outputs(Dt, O, fid, child, pars, 2, ll, ncount);
 }
 
+/* ---- three-way tables of all node triples (label space, once per data set) and the three-parent scorer built on them ----
+ * triple (u < v < w) lives at rank C(w,3) + C(v,2) + u, 64 ints: cell [i_u][i_v][i_w] at (i_u * 4 + i_v) * 4 + i_w. */
+__device__ __forceinline__ long long triple_index(int u, int v, int w) {
+	return (long long)w * (w - 1) * (w - 2) / 6 + (long long)v * (v - 1) / 2 + u;
+}
+
+/* one thread per triple: (CM-1)^3 free cells by POPC, the rest from the pair tables (as k_score_planes_ie2) */
+template <int CM>
+__global__ void __launch_bounds__(128) k_triple_tables(const uint4 *__restrict__ planes_lbl, int N, int W, long long ntriples,
+		const int *__restrict__ pair_tab, int *__restrict__ out) {
+	constexpr int F1 = CM - 1;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= ntriples) return;
+	/* unrank: largest w with C(w,3) <= t, then v with C(v,2) <= rest */
+	int w = (int)cbrt(6.0 * (double)t) + 2;
+	while ((long long)w * (w - 1) * (w - 2) / 6 > t) w--;
+	while ((long long)(w + 1) * w * (w - 1) / 6 <= t) w++;
+	long long r = t - (long long)w * (w - 1) * (w - 2) / 6;
+	int v = (int)((1.0 + sqrt(1.0 + 8.0 * (double)r)) / 2.0);
+	while ((long long)v * (v - 1) / 2 > r) v--;
+	while ((long long)(v + 1) * v / 2 <= r) v++;
+	const int u = (int)(r - (long long)v * (v - 1) / 2);
+	unsigned cnt[F1 * F1 * F1 > 0 ? F1 * F1 * F1 : 1];
+#pragma unroll
+	for (int i = 0; i < F1 * F1 * F1; i++) cnt[i] = 0;
+	for (int q = 0; q < W; q++) {
+		const uint4 a = __ldg(planes_lbl + (size_t)q * N + u), b = __ldg(planes_lbl + (size_t)q * N + v),
+				c = __ldg(planes_lbl + (size_t)q * N + w);
+#pragma unroll
+		for (int i = 0; i < F1; i++)
+#pragma unroll
+			for (int j = 0; j < F1; j++) {
+				const unsigned ab = plane_of(a, i) & plane_of(b, j);
+#pragma unroll
+				for (int k = 0; k < F1; k++) cnt[(i * F1 + j) * F1 + k] += __popc(ab & plane_of(c, k));
+			}
+	}
+	int tab[64];
+#pragma unroll
+	for (int i = 0; i < 64; i++) tab[i] = 0;
+#define CELL(i, j, k) tab[((i) * 4 + (j)) * 4 + (k)]
+#pragma unroll
+	for (int i = 0; i < F1; i++)
+#pragma unroll
+		for (int j = 0; j < F1; j++)
+#pragma unroll
+			for (int k = 0; k < F1; k++) CELL(i, j, k) = (int)cnt[(i * F1 + j) * F1 + k];
+#pragma unroll
+	for (int i = 0; i < F1; i++)
+#pragma unroll
+		for (int j = 0; j < F1; j++) {
+			int s = 0;
+#pragma unroll
+			for (int k = 0; k < F1; k++) s += CELL(i, j, k);
+			CELL(i, j, F1) = pair_count(pair_tab, u, v, i, j) - s;
+		}
+#pragma unroll
+	for (int i = 0; i < F1; i++)
+#pragma unroll
+		for (int k = 0; k < CM; k++) {
+			int s = 0;
+#pragma unroll
+			for (int j = 0; j < F1; j++) s += CELL(i, j, k);
+			CELL(i, F1, k) = pair_count(pair_tab, u, w, i, k) - s;
+		}
+#pragma unroll
+	for (int j = 0; j < CM; j++)
+#pragma unroll
+		for (int k = 0; k < CM; k++) {
+			int s = 0;
+#pragma unroll
+			for (int i = 0; i < F1; i++) s += CELL(i, j, k);
+			CELL(F1, j, k) = pair_count(pair_tab, v, w, j, k) - s;
+		}
+#undef CELL
+	int4 *dst = reinterpret_cast<int4 *>(out + t * 64);
+#pragma unroll
+	for (int i = 0; i < 16; i++) dst[i] = make_int4(tab[4 * i], tab[4 * i + 1], tab[4 * i + 2], tab[4 * i + 3]);
+}
+
+/* n(a = i, b = j, c = k) for node labels a, b, c in any order */
+__device__ __forceinline__ int triple_count(const int *__restrict__ tt, int a, int i, int b, int j, int c, int k) {
+	int t;
+	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
+	if (b > c) { t = b; b = c; c = t; t = j; j = k; k = t; }
+	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
+	return tt[triple_index(a, b, c) * 64 + (i * 4 + j) * 4 + k];
+}
+
+/* K2a'': three-parent scorer with inclusion-exclusion.  Only the (CM-1)^4 free cells are counted over the samples
+ * (16 AND+POPC per word instead of 81 at CM = 3, 81 instead of 256 at CM = 4); the slices with a last category follow,
+ * axis after axis, from the complete three-way tables of the four triples inside {p0, p1, p2, child}. */
+template <int CM, int BS>
+__global__ void __launch_bounds__(BS) k_score_planes_ie3(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		ScoreOut O, const int *__restrict__ tt) {
+	constexpr int F1 = CM - 1, FREE = F1 * F1 * F1 * F1;
+	extern __shared__ __align__(16) int s_cnt[];          /* [CM^4][BS] */
+	const long long fid = fid_begin + (long long)blockIdx.x * BS + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	dev_family(Dt, F, fid, child, pars);
+	unsigned cnt[FREE > 0 ? FREE : 1];
+#pragma unroll
+	for (int i = 0; i < FREE; i++) cnt[i] = 0;
+	uint4 nxt[4], cur[4];
+	const int W = Dt.W;
+	load_word<3>(Dt, 0, child, pars, nxt);
+	for (int w = 0; w < W; w++) {
+#pragma unroll
+		for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+		if (w + 1 < W) load_word<3>(Dt, w + 1, child, pars, nxt);
+#pragma unroll
+		for (int i = 0; i < F1; i++)
+#pragma unroll
+			for (int j = 0; j < F1; j++) {
+				const unsigned ab = plane_of(cur[0], i) & plane_of(cur[1], j);
+#pragma unroll
+				for (int k = 0; k < F1; k++) {
+					const unsigned abc = ab & plane_of(cur[2], k);
+#pragma unroll
+					for (int l = 0; l < F1; l++) cnt[((i * F1 + j) * F1 + k) * F1 + l] += __popc(abc & plane_of(cur[3], l));
+				}
+			}
+	}
+	int *mine = s_cnt + threadIdx.x;
+#define CELL(i, j, k, l) mine[((((i) * CM + (j)) * CM + (k)) * CM + (l)) * BS]
+#pragma unroll
+	for (int i = 0; i < F1; i++)
+#pragma unroll
+		for (int j = 0; j < F1; j++)
+#pragma unroll
+			for (int k = 0; k < F1; k++)
+#pragma unroll
+				for (int l = 0; l < F1; l++) CELL(i, j, k, l) = (int)cnt[((i * F1 + j) * F1 + k) * F1 + l];
+	const int l0 = Dt.order[pars[0]], l1 = Dt.order[pars[1]], l2 = Dt.order[pars[2]], lc = Dt.order[child];
+	/* axis of p0: known afterwards for every i, and j, k, l free */
+	for (int j = 0; j < F1; j++)
+		for (int k = 0; k < F1; k++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int i = 0; i < F1; i++) s += CELL(i, j, k, l);
+				CELL(F1, j, k, l) = triple_count(tt, l1, j, l2, k, lc, l) - s;
+			}
+	/* axis of p1 */
+	for (int i = 0; i < CM; i++)
+		for (int k = 0; k < F1; k++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int j = 0; j < F1; j++) s += CELL(i, j, k, l);
+				CELL(i, F1, k, l) = triple_count(tt, l0, i, l2, k, lc, l) - s;
+			}
+	/* axis of p2 */
+	for (int i = 0; i < CM; i++)
+		for (int j = 0; j < CM; j++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int k = 0; k < F1; k++) s += CELL(i, j, k, l);
+				CELL(i, j, F1, l) = triple_count(tt, l0, i, l1, j, lc, l) - s;
+			}
+	/* axis of the child */
+	for (int i = 0; i < CM; i++)
+		for (int j = 0; j < CM; j++)
+			for (int k = 0; k < CM; k++) {
+				int s = 0;
+				for (int l = 0; l < F1; l++) s += CELL(i, j, k, l);
+				CELL(i, j, k, F1) = triple_count(tt, l0, i, l1, j, l2, k) - s;
+			}
+#undef CELL
+	const int pc0 = Dt.cats[pars[0]], pc1 = Dt.cats[pars[1]], pc2 = Dt.cats[pars[2]], cc = Dt.cats[child];
+	int ncount;
+	double ll = dev_loglik(pc0 * pc1 * pc2, cc, [&](int cfg, int l) {
+		const int k = cfg % pc2, ij = cfg / pc2, j = ij % pc1, i = ij / pc1;
+		return mine[(((i * CM + j) * CM + k) * CM + l) * BS];
+	}, &ncount);
+	dev_store_outputs(Dt, O, fid, child, pars, 3, ll, ncount);
+}
+
 /* Single-parent families when no value is missing: the family table IS the two-way table of (parent, child) that
  * k_pair_tables counted once per data set -- no pass over the samples at all, only the log-lik epilogue
  * (problist.h:224-250) and, when asked for, the table in the reference's layout. */
@@ -1087,6 +1264,40 @@ int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies 
 	if (max_cats <= 2) return launch_ie2<2>(st, Dt, F, b, e, O, pair_tab);
 	if (max_cats == 3) return launch_ie2<3>(st, Dt, F, b, e, O, pair_tab);
 	return launch_ie2<4>(st, Dt, F, b, e, O, pair_tab);
+}
+
+/* three-way tables of all node triples, label space: out [C(N,3)][64] */
+int cnbk_triple_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int max_cats, const int *pair_tab, int *out) {
+	const long long nt = (long long)N * (N - 1) * (N - 2) / 6;
+	if (nt <= 0) return CNB_OK;
+	if (max_cats > 4 || !pair_tab) { cnb_set_error("triple tables: unsupported data"); return CNB_ERR_PROC; }
+	const unsigned grid = (unsigned)((nt + 127) / 128);
+	if (max_cats <= 2) k_triple_tables<2><<<grid, 128, 0, st>>>(planes_lbl, N, W, nt, pair_tab, out);
+	else if (max_cats == 3) k_triple_tables<3><<<grid, 128, 0, st>>>(planes_lbl, N, W, nt, pair_tab, out);
+	else k_triple_tables<4><<<grid, 128, 0, st>>>(planes_lbl, N, W, nt, pair_tab, out);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+template <int CM, int BS>
+static int launch_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
+		const ScoreOut &O, const int *triple_tab) {
+	size_t smem = (size_t)CM * CM * CM * CM * BS * sizeof(int);
+	if (smem > 48 * 1024)
+		CK(cudaFuncSetAttribute(k_score_planes_ie3<CM, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_score_planes_ie3<CM, BS><<<(unsigned)((e - b + BS - 1) / BS), BS, smem, st>>>(Dt, F, b, e, O, triple_tab);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* three-parent families, no missing values, no perturbation mask: inclusion-exclusion over the triple tables */
+int cnbk_score_planes_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
+		long long e, const ScoreOut &O, const int *triple_tab) {
+	if (e <= b) return CNB_OK;
+	if (F.d != 3 || max_cats > 4 || !triple_tab) { cnb_set_error("ie3 scorer: unsupported launch"); return CNB_ERR_PROC; }
+	if (max_cats <= 2) return launch_ie3<2, 128>(st, Dt, F, b, e, O, triple_tab);
+	if (max_cats == 3) return launch_ie3<3, 128>(st, Dt, F, b, e, O, triple_tab);
+	return launch_ie3<4, 64>(st, Dt, F, b, e, O, triple_tab);
 }
 
 int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,

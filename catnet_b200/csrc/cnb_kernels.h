@@ -38,6 +38,10 @@ int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, 
 		const ScoreOut &O, const int *pair_tab);
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
+/* three-way tables of all node triples (label space, [C(N,3)][64]) and the three-parent inclusion-exclusion scorer */
+int cnbk_triple_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int max_cats, const int *pair_tab, int *out);
+int cnbk_score_planes_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
+		long long e, const ScoreOut &O, const int *triple_tab);
 /* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
 int cnbk_umma_row_quads(int W, int fp4, int *ngroups);
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b);

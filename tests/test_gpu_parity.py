@@ -341,6 +341,24 @@ def test_search_hist_matches_reference(abi, case):
         assert it2 == it and np.array_equal(h2, h)
 
 
+@pytest.mark.parametrize("n,m,cats", [(12, 300, 3), (10, 257, 4), (14, 64, 2), (11, 1000, None), (9, 33, [2, 4, 3, 2, 4, 3, 2, 4, 3])])
+def test_three_parent_inclusion_exclusion(abi, port, n, m, cats):
+    """three-parent families on complete data: free cells + three-way tables (k_score_planes_ie3) against the direct
+    bit-plane / histogram scorers and the oracle"""
+    s, c = random_problem(7 * n + m, n, m, cats)
+    kw = dict(max_parent_set=3, max_complexity=n * 40, order=(np.random.default_rng(m).permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(want_probs=True, **kw)
+        assert ctx.timing()["fast_path"] == 1
+        ctx.force_generic(512)                    # no inclusion-exclusion for three parents
+        b = ctx.search_order(want_probs=True, **kw)
+    assert compare_search(a, b) == len(b)
+    if m <= 300:
+        o = port.search_order(s, 3, kw["max_complexity"], order=kw["order"], num_cats=c)
+        assert compare_search(a, o) == len(o)
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
