@@ -190,6 +190,9 @@ __device__ __forceinline__ void gen_half_a(uint32_t taddr, uint4 v) {
 	}
 }
 __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+/* the generators load their source bits one stage ahead; this pulls the stage after that into L1, so that the load
+ * proper finds it there (ncu: 6.9 % of the kernel's stall samples sat on the first use of the loaded rows) */
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 /* issue loop of pair block H (one thread): everything but the barrier phase and the instruction descriptor is a
  * compile-time constant */
@@ -236,6 +239,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	const int g_first = sliced ? (int)((long long)slice * ngroups_all / split) : 0;
 	const int ngroups = (sliced ? (int)((long long)(slice + 1) * ngroups_all / split) : ngroups_all) - g_first;
 	const size_t src_skip = (size_t)g_first * UM_BSTAGES * SRCQ * NR;   /* quads before this CTA's first stage */
+	const int pf = T.pad;                   /* L1 prefetch distance in stages beyond the one being loaded */
+	const size_t pf_off = (size_t)pf * SRCQ * NR;
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ __align__(8) uint64_t bar_full_b[UM_BSTAGES], bar_empty_b[UM_BSTAGES], bar_full_a[UM_NA * UM_ASTAGES], bar_empty_a[UM_NA * UM_ASTAGES], bar_done;
 	__shared__ uint32_t tmem_base_sh;
@@ -304,6 +309,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 				n0 = __ldg(s0);
 				m0 = __ldg(s1);
 				if (FP4) { n1 = __ldg(s0 + NR); m1 = __ldg(s1 + NR); }
+				if (g * UM_BSTAGES + u + 1 + pf <= ngroups * UM_BSTAGES) {   /* inside the rows (one stage of slack) */
+					prefetch_l1(s0 + pf_off);
+					prefetch_l1(s1 + pf_off);
+					if (FP4) { prefetch_l1(s0 + pf_off + NR); prefetch_l1(s1 + pf_off + NR); }
+				}
+
 				/* each half of the stage goes to its own ring slot (use number 2g + UM_AUSE of that slot) */
 #define UM_HALF_BODY(p, v) { \
 				if (g > 0 || UM_AUSE(u, p) > 0) mbar_wait(&empty_a[UM_ASLOT(u, p)], (UM_AUSE(u, p) + 1) & 1); \
@@ -374,6 +385,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			const uint4 v0 = n0, v1 = n1; \
 			s0 += SRCQ * NR; \
 			if (active) { n0 = __ldg(s0); if (FP4) n1 = __ldg(s0 + NR); } \
+			if (active && g * UM_BSTAGES + (u) + 1 + pf <= ngroups * UM_BSTAGES) { prefetch_l1(s0 + pf_off); if (FP4) prefetch_l1(s0 + pf_off + NR); } \
 			if (g > 0) mbar_wait(&bar_empty_b[u], (g - 1) & 1); \
 			if (active) gen_row_b<FP4, (u) * UM_STAGE>(off, v0, v1); \
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
@@ -540,6 +552,10 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 	/* one CTA per SM (all of tensor memory): with T tiles the last wave holds T mod SMs of them; those are cut into
 	 * sample slices so that the wave is full and shorter (1535 tiles per rank at C5 on 8 GPUs: 10.5 instead of 11 waves) */
 	const long long tiles = tile_end - tile_begin;
+	static int pf_dist = -1;
+	if (pf_dist < 0) { const char *e = getenv("CNB_PF_DIST"); pf_dist = e ? atoi(e) : 1; }
+	CnbTiles Tp = T;
+	Tp.pad = pf_dist;
 	const int split = T.self_pairs ? 1 : tail_split(tiles, sms, ng);
 	const long long whole = split > 1 ? tiles - tiles % sms : tiles;
 	const long long grid = whole + (tiles - whole) * split;
@@ -547,10 +563,10 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 		CK(cudaMemsetAsync(counts + (size_t)whole * UM_SLOTS * UM_SLOT_INTS, 0, (size_t)(tiles - whole) * UM_SLOTS * UM_SLOT_INTS * sizeof(int), st));
 	if (fp4) {
 		CK(cudaFuncSetAttribute(k_umma_tables<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, T, tile_begin, counts, (int)whole, split);
+		k_umma_tables<true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
 	} else {
 		CK(cudaFuncSetAttribute(k_umma_tables<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, T, tile_begin, counts, (int)whole, split);
+		k_umma_tables<false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
 	}
 	CK(cudaGetLastError());
 	return CNB_OK;
