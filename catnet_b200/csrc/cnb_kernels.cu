@@ -992,14 +992,22 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
  * (t = delta-updated log-lik), a ballot finds the first option that beats the running R, only that one is re-summed
  * (the reference's loglik() re-summation, a chain of N - c fp64 adds), and the ballot is repeated for the lanes behind
  * it.  One cooperative launch, grid barrier per node.  Identical decisions to the sequential scan. */
+#define DPM_OPTS 2048          /* options of a node staged in shared memory (score + complexity) */
+#define DPM_SLOTS 4096         /* DP slots staged in shared memory (log-lik + exists) */
 __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
-		int *__restrict__ bp_src) {
+		int *__restrict__ bp_src, int stage_state) {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	/* sbase[N] | s_sc[DPM_OPTS] | s_L[slots] | s_cx[DPM_OPTS] | s_ex[slots]: the scan of a slot reads a node's options and
+	 * the previous state 32 at a time; out of global memory every such read is an L2 round trip (21 per node on ALARM) */
 	extern __shared__ double sbase[];
 	const int K = s0.K, nthr = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31, gw = t0 >> 5, nwarps = nthr >> 5;
+	const int nslots = stage_state ? K + 1 : 0;
+	double *s_sc = sbase + N, *s_L = s_sc + DPM_OPTS;
+	int *s_cx = reinterpret_cast<int *>(s_L + nslots);
+	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_cx + DPM_OPTS);
 	for (int i = threadIdx.x; i < N; i += blockDim.x) sbase[i] = base_v[i];
 	__syncthreads();
 	for (int j = t0; j <= K; j += nthr) {
@@ -1016,6 +1024,20 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 		const CnbDpNode nd = nodes[c];
 		const double bv = sbase[c];
 		const long long nopt = nd.opt_end - nd.opt_begin;
+		/* stage the node's options (complexity INT_MIN = no winner for that d) and the previous state */
+		const bool opts_staged = nopt <= DPM_OPTS;
+		if (opts_staged)
+			for (int o = threadIdx.x; o < (int)nopt; o += blockDim.x) {
+				s_sc[o] = opt_score[nd.opt_begin + o];
+				s_cx[o] = opt_fid[nd.opt_begin + o] >= 0 ? opt_cx[nd.opt_begin + o] : INT_MIN;
+			}
+		for (int k = threadIdx.x; k < nslots; k += blockDim.x) {
+			s_L[k] = cur.L[k];
+			s_ex[k] = cur.exists[k];
+		}
+		__syncthreads();
+		const double *Lp = stage_state ? s_L : cur.L;
+		const unsigned char *Ep = stage_state ? s_ex : cur.exists;
 		for (int j = gw; j <= K; j += nwarps) {
 			bool has = false;
 			double R = CNB_NEG_INF, bf = 0.0;
@@ -1026,12 +1048,15 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 				bool viable = false;
 				double t = 0.0, f = 0.0;
 				int k = 0;
-				if (o0 + lane < nopt && opt_fid[o] >= 0) {           /* no winner for that d (:637-640) */
-					k = j + nd.base_cx - opt_cx[o];
-					if (k >= 0 && k <= K && cur.exists[k]) {
-						viable = true;
-						f = opt_score[o];
-						t = __dadd_rn(__dsub_rn(cur.L[k], bv), f);      /* :665-666 */
+				if (o0 + lane < nopt) {
+					const int cx = opts_staged ? s_cx[o0 + lane] : (opt_fid[o] >= 0 ? opt_cx[o] : INT_MIN);   /* :637-640 */
+					if (cx != INT_MIN) {
+						k = j + nd.base_cx - cx;
+						if (k >= 0 && k <= K && Ep[k]) {
+							viable = true;
+							f = opts_staged ? s_sc[o0 + lane] : opt_score[o];
+							t = __dadd_rn(__dsub_rn(Lp[k], bv), f);      /* :665-666 */
+						}
 					}
 				}
 				unsigned behind = 0xffffffffu;                         /* lanes not yet passed by the scan */
@@ -1052,9 +1077,9 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 				}
 			}
 			if (lane == 0) {
-				const bool cur_ex = cur.exists[j] != 0;
+				const bool cur_ex = Ep[j] != 0;
 				bool take = false;
-				if (cur_ex) take = has && bo >= 0 && cur.L[j] < R;   /* :847-859 */
+				if (cur_ex) take = has && bo >= 0 && Lp[j] < R;   /* :847-859 */
 				else take = has && bo >= 0;
 				size_t bpi = (size_t)c * (K + 1) + j;
 				if (take) {
@@ -1065,7 +1090,7 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 					bp_src[bpi] = bs;
 				} else {
 					nxt.exists[j] = cur_ex;
-					nxt.L[j] = cur.L[j];
+					nxt.L[j] = Lp[j];
 					nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
 					bp_opt[bpi] = -1;
 					bp_src[bpi] = j;
@@ -1388,13 +1413,19 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 	CK(cudaGetDevice(&dev));
 	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-	const size_t smem = (size_t)N * sizeof(double);
-	if (smem > 48 * 1024) return CNB_ERR_PROC;
+	if ((size_t)N * sizeof(double) > 16 * 1024) return CNB_ERR_PROC;
+	/* the previous state is staged in shared memory when it fits (K + 1 <= DPM_SLOTS), a node's options when there are
+	 * at most DPM_OPTS of them */
+	int stage_state = s0.K + 1 <= DPM_SLOTS;
+	const size_t smem = (size_t)N * sizeof(double) + (size_t)DPM_OPTS * (sizeof(double) + sizeof(int))
+			+ (stage_state ? (size_t)(s0.K + 1) * sizeof(double) + (size_t)((s0.K + 1 + 15) & ~15) : 0);
+	if (smem > 48 * 1024)
+		CK(cudaFuncSetAttribute(k_dp_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_mixed, 256, smem));
 	if (!coop || per_sm < 1) return CNB_ERR_PROC;
 	const int blocks = std::min(sms * per_sm, std::max(1, (s0.K + 1 + 7) / 8));      /* one warp per slot if it fits */
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
-		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src};
+		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&stage_state};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_mixed, dim3(blocks), dim3(256), args, smem, st));
 	return CNB_OK;
 }
