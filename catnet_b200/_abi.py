@@ -54,7 +54,7 @@ class Timing(C.Structure):
                 ("score_ms_by_parents", C.c_float * 8), ("families_by_parents", C.c_int64 * 8),
                 ("num_families", C.c_int64), ("algorithmic_bytes", C.c_int64), ("kernel_launches", C.c_int32),
                 ("fast_path", C.c_int32), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("tensor_tiles", C.c_int64), ("tensor_ms", C.c_float), ("tensor_kind", C.c_int32),
-                ("tensor_macs", C.c_int64)]
+                ("tensor_macs", C.c_int64), ("tensor3_tiles", C.c_int64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("score_ms_by_parents", "families_by_parents")}

@@ -15,6 +15,7 @@
 #include "cnb_kernels.h"
 #include "cnb_result.h"
 #include "cnb_ctx.h"
+#include "cnb_tiles.h"
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 #define RC(call) do { int rc_ = (call); if (rc_ != CNB_OK) return rc_; } while (0)
@@ -243,6 +244,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->dp_no_wave = (on & 64) != 0;                        /* bit 6: grid-barrier DP kernel instead of the wavefront one */
 	c->pairs_popc = (on & 128) != 0;                       /* bit 7: pair tables by the POPC kernel (set BEFORE set_samples) */
 	c->no_ie3 = (on & 512) != 0;                           /* bit 9: no inclusion-exclusion for three-parent families */
+	c->no_tensor3 = (on & 1024) != 0;                      /* bit 10: three-parent families never on the tensor cores */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -276,6 +278,8 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.tiles.world = c->plan.world;
 	D.tiles.self_pairs = 0;
 	D.tiles.pad = 0;
+	D.tiles.f1 = 0;
+	D.tiles.nvirt = 0;
 	return D;
 }
 
@@ -367,6 +371,83 @@ static int table_stride(int max_cats, int d) {
 	return (int)s;
 }
 
+/* three-way tables of the data set, built on first use (C(N,3) x 256 B); false when they would not fit comfortably */
+static int ensure_triples(cnb_ctx *c, bool *ok) {
+	const long long nt = (long long)c->N * (c->N - 1) * (c->N - 2) / 6;
+	*ok = nt * 256 <= (8ll << 30) && c->pairs_valid;
+	if (!*ok || c->triples_valid) return CNB_OK;
+	RC(c->b_triples.ensure((size_t)std::max<long long>(nt, 1) * 64 * sizeof(int)));
+	RC(cnbk_triple_tables(c->stream, (const uint4 *)c->b_planes_lbl.ptr, c->N, c->W, c->max_cats, (const int *)c->b_pairs.ptr,
+			(int *)c->b_triples.ptr));
+	c->timing.kernel_launches++;
+	c->triples_valid = true;
+	return CNB_OK;
+}
+
+/* the whole unrestricted three-parent group on the tensor cores (T tiles, cnb_tiles.h): per column tile of 64 children the
+ * table kernel contracts (virtual pair node (a, b, i), c) x children, the epilogue completes the four-way tables from the
+ * three-way tables of the data set.  *done = false (nothing launched) when the group does not qualify. */
+static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, const CnbGroup &g, const ScoreOut &O, bool *done) {
+	*done = false;
+	const CnbPlan &pl = c->plan;
+	const int N = c->N;
+	if (g.d != 3 || !g.full || pl.world != 1 || pl.tile_base.empty() || !c->clean || !c->pairs_valid || c->force_generic
+			|| c->no_ie || c->no_ie3 || c->no_tensor3 || c->tensor_i8 || c->tensor_mode < 0 || (c->tensor_mode == 0 && c->M < 8192)
+			|| c->M >= (1 << 24) || N < 4 || N > 64 * 32) return CNB_OK;
+	bool ok = false;
+	RC(ensure_triples(c, &ok));
+	if (!ok) return CNB_OK;
+	const int cm = c->max_cats <= 2 ? 2 : (c->max_cats == 3 ? 3 : 4), f1 = cm - 1;
+	const long long nvirt = (long long)N * (N - 1) / 2 * f1;
+	const int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+	std::vector<long long> base3(nct + 1, 0);
+	long long largest = 0;
+	for (int ct = 0; ct < nct; ct++) {
+		const int ce = std::min((ct + 1) * CNB_TILE_CHILD, N);
+		const long long n = cnb_t_tiles(ce, f1);
+		base3[ct + 1] = base3[ct] + n;
+		largest = std::max(largest, n);
+	}
+	const long long slot_bytes = (long long)CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+	const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * 3 * (size_t)(N + nvirt);
+	if (largest * slot_bytes > (8ll << 30) || row_bytes > (16ull << 30) || nvirt > (1ll << 28)) return CNB_OK;
+	cudaStream_t st = c->stream;
+	RC(upload(c, c->b_tile_base3, base3));
+	RC(c->b_rows_a3.ensure(row_bytes));
+	RC(cnbk_umma_rows3(st, (const uint4 *)c->b_planes.ptr, N, c->W, (int)nvirt, f1, (uint4 *)c->b_rows_a3.ptr));
+	c->timing.kernel_launches += 2;
+	RC(c->b_counts.ensure((size_t)std::max<long long>(largest, 1) * slot_bytes));
+	CnbTiles T3;
+	memset(&T3, 0, sizeof(T3));
+	T3.tile_base = (const long long *)c->b_tile_base3.ptr;
+	T3.nct = nct;
+	T3.child = CNB_TILE_CHILD;
+	T3.world = 1;
+	T3.self_pairs = 2;
+	T3.f1 = f1;
+	T3.nvirt = (int)nvirt;
+	/* families of the group by child: block k of the group belongs to child 3 + k and starts at blocks[..].start */
+	for (int ct = 0; ct < nct; ct++) {
+		const int c0 = ct * CNB_TILE_CHILD, ce = std::min(c0 + CNB_TILE_CHILD, N);
+		long long fb = -1, fe = -1;
+		for (int k = 0; k < g.nblk; k++) {
+			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
+			if (b.child < c0 || b.child >= ce) continue;
+			if (fb < 0) fb = b.start;
+			fe = b.start + b.ncomb;
+		}
+		if (fb < 0 || fe <= fb || base3[ct + 1] <= base3[ct]) continue;
+		RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a3.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, T3, base3[ct],
+				base3[ct + 1], (int *)c->b_counts.ptr));
+		RC(cnbk_umma_epilogue3(st, D, F, c->max_cats, fb, fe, (const int *)c->b_counts.ptr, (const int *)c->b_triples.ptr, O));
+		c->timing.kernel_launches += 2;
+	}
+	c->tensor3_tiles = (int)base3[nct];
+	c->timing.tensor3_tiles = base3[nct];
+	*done = true;
+	return CNB_OK;
+}
+
 /* score families [b, e) of one launch class, choosing the kernel */
 static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d_max, long long b, long long e,
 		ScoreOut O, bool force_generic, bool allow_slicing) {
@@ -382,17 +463,10 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 	}
 	if (!force_generic && !F.ex_nd && F.d == 3 && c->pairs_valid && !c->ignore_pert && !O.counts && !c->no_ie && !c->no_ie3
 			&& c->max_cats <= CNB_PLANE_CATS) {
-		/* three parents, clean data: only the free cells are counted; the rest from the three-way tables of the data set,
-		 * built on first use (C(N,3) x 256 B; not for node counts where that would not fit comfortably) */
-		const long long nt = (long long)c->N * (c->N - 1) * (c->N - 2) / 6;
-		if (nt * 256 <= (8ll << 30)) {
-			if (!c->triples_valid) {
-				RC(c->b_triples.ensure((size_t)nt * 64 * sizeof(int)));
-				RC(cnbk_triple_tables(st, (const uint4 *)c->b_planes_lbl.ptr, c->N, c->W, c->max_cats, (const int *)c->b_pairs.ptr,
-						(int *)c->b_triples.ptr));
-				c->timing.kernel_launches++;
-				c->triples_valid = true;
-			}
+		/* three parents, clean data: only the free cells are counted; the rest from the three-way tables of the data set */
+		bool ok = false;
+		RC(ensure_triples(c, &ok));
+		if (ok) {
 			c->last_fast = true;
 			RC(cnbk_score_planes_ie3(st, D, F, c->max_cats, b, e, O, (const int *)c->b_triples.ptr));
 			c->timing.kernel_launches++;
@@ -460,6 +534,8 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	c->timing.tensor_macs = 0;
 	c->timing.tensor_kind = 0;
 	c->tensor_batches = 0;
+	c->tensor3_tiles = 0;
+	c->timing.tensor3_tiles = 0;
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		DevFamilies F;
@@ -497,8 +573,12 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			b = 0;
 			e = t1 > t0 ? (long long)((double)g.nfam * (double)(t1 - t0) / (double)g.ntiles) : 0;
 		} else {
-			RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
-			if (e > b && !c->last_fast) c->timing.fast_path = 0;
+			bool done = false;
+			RC(score_tensor3(c, D, F, g, O, &done));
+			if (!done) {
+				RC(score_range(c, D, F, g.d, b, e, O, c->force_generic, true));
+				if (e > b && !c->last_fast) c->timing.fast_path = 0;
+			}
 		}
 		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi + 1], st));
 		if (e > b) {

@@ -41,6 +41,8 @@ struct cnb_ctx {
 	bool pairs_popc = false;           /* pair tables by the POPC kernel even for large M (test hook) */
 	bool dp_no_wave = false;           /* grid-barrier DP kernel instead of the wavefront one (test hook) */
 	bool triples_valid = false;        /* b_triples holds the three-way tables of this data set (built on first use) */
+	bool no_tensor3 = false;           /* three-parent families never on the tensor cores (test hook) */
+	int tensor3_tiles = 0;             /* T tiles of the last search (0 = three-parent group not on the tensor cores) */
 	bool no_ie3 = false;               /* three-parent families by the direct bit-plane / histogram scorers (test hook) */
 	bool has_na = false;               /* the data set has missing values */
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */
@@ -56,7 +58,7 @@ struct cnb_ctx {
 	CnbPlan plan;
 	cnb_timing timing = {};
 	PinBuf pin_sel;
-	DevBuf b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples;
+	DevBuf b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
 	/* plan */
@@ -70,7 +72,7 @@ struct cnb_ctx {
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3};
 	}
 };
 

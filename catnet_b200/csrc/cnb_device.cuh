@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include "cnb_internal.h"
+#include "cnb_kernels.h"      /* ScoreOut */
 #include "cnb_log.h"
 
 /* packed samples + plan tables, all device pointers */
@@ -147,6 +148,88 @@ __device__ __forceinline__ double dev_loglik(int ncfg, int cc, Fetch cnt, int *n
 __device__ __forceinline__ long long dev_score_index(long long fid, long long chunk, long long seg_off, long long seg_len) {
 	long long r = fid / chunk;
 	return r * seg_len + seg_off + (fid - r * chunk);
+}
+
+
+/* score (+ prior), log-lik, prior and sample size of family fid into whatever outputs the launch asked for */
+__device__ __forceinline__ void dev_store_outputs(const DevData &D, const ScoreOut &O, long long fid, int child,
+		const int *pars, int d, double ll, int ncount) {
+	double prior = 0.0;
+	double score = ll;
+	if (D.edge) {
+		prior = dev_prior(D, child, pars, d);
+		score = __dadd_rn(ll, prior);                     /* fLogLik += priorLogLik (catnet_search2.h:610) */
+	}
+	if (O.scores) O.scores[dev_score_index(fid, O.chunk, O.seg_off, O.seg_len)] = score;
+	if (O.loglik) O.loglik[fid] = ll;
+	if (O.prior) O.prior[fid] = prior;
+	if (O.ncount) O.ncount[fid] = ncount;
+}
+
+/* ---- three-way tables of the data set (label space): triple (u < v < w) at rank C(w,3) + C(v,2) + u, 64 ints,
+ * cell [i_u][i_v][i_w] at (i_u * 4 + i_v) * 4 + i_w ---- */
+__device__ __forceinline__ long long triple_index(int u, int v, int w) {
+	return (long long)w * (w - 1) * (w - 2) / 6 + (long long)v * (v - 1) / 2 + u;
+}
+
+/* n(a = i, b = j, c = k) for node labels a, b, c in any order */
+__device__ __forceinline__ int triple_count(const int *__restrict__ tt, int a, int i, int b, int j, int c, int k) {
+	int t;
+	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
+	if (b > c) { t = b; b = c; c = t; t = j; j = k; k = t; }
+	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
+	return tt[triple_index(a, b, c) * 64 + (i * 4 + j) * 4 + k];
+}
+
+
+/* Complete the four-way table of family (p0, p1, p2 | child) whose (CM-1)^4 free cells sit in `mine`
+ * (cell (i,j,k,l) at ((((i*CM+j)*CM+k)*CM+l) * BS), strided over the threads of the CTA in shared memory): the slices with a
+ * last category follow, axis after axis, from the three-way tables of the four triples inside the family (no value is
+ * missing, so every margin is complete).  Returns the reference-order log-likelihood (problist.h:224-250). */
+template <int CM, int BS>
+__device__ __forceinline__ double dev_ie3_finish(int *mine, const DevData &Dt, const int *__restrict__ tt, const int *pars,
+		int child, int *ncount) {
+	constexpr int F1 = CM - 1;
+#define CELL(i, j, k, l) mine[((((i) * CM + (j)) * CM + (k)) * CM + (l)) * BS]
+	const int l0 = Dt.order[pars[0]], l1 = Dt.order[pars[1]], l2 = Dt.order[pars[2]], lc = Dt.order[child];
+	/* axis of p0: known afterwards for every i, and j, k, l free */
+	for (int j = 0; j < F1; j++)
+		for (int k = 0; k < F1; k++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int i = 0; i < F1; i++) s += CELL(i, j, k, l);
+				CELL(F1, j, k, l) = triple_count(tt, l1, j, l2, k, lc, l) - s;
+			}
+	/* axis of p1 */
+	for (int i = 0; i < CM; i++)
+		for (int k = 0; k < F1; k++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int j = 0; j < F1; j++) s += CELL(i, j, k, l);
+				CELL(i, F1, k, l) = triple_count(tt, l0, i, l2, k, lc, l) - s;
+			}
+	/* axis of p2 */
+	for (int i = 0; i < CM; i++)
+		for (int j = 0; j < CM; j++)
+			for (int l = 0; l < F1; l++) {
+				int s = 0;
+				for (int k = 0; k < F1; k++) s += CELL(i, j, k, l);
+				CELL(i, j, F1, l) = triple_count(tt, l0, i, l1, j, lc, l) - s;
+			}
+	/* axis of the child */
+	for (int i = 0; i < CM; i++)
+		for (int j = 0; j < CM; j++)
+			for (int k = 0; k < CM; k++) {
+				int s = 0;
+				for (int l = 0; l < F1; l++) s += CELL(i, j, k, l);
+				CELL(i, j, k, F1) = triple_count(tt, l0, i, l1, j, l2, k) - s;
+			}
+#undef CELL
+	const int pc0 = Dt.cats[pars[0]], pc1 = Dt.cats[pars[1]], pc2 = Dt.cats[pars[2]], cc = Dt.cats[child];
+	return dev_loglik(pc0 * pc1 * pc2, cc, [&](int cfg, int l) {
+		const int k = cfg % pc2, ij = cfg / pc2, j = ij % pc1, i = ij / pc1;
+		return mine[(((i * CM + j) * CM + k) * CM + l) * BS];
+	}, ncount);
 }
 
 #endif

@@ -41,6 +41,8 @@ struct CnbGroup {
 	int64_t tiles_per_rank;   /* ceil(ntiles / world): local tile slots of every rank segment */
 	int32_t tile_world;
 	int32_t tile_child; /* children per child tile (<= CNB_TILE_CHILD, the slot stride) */
+	int32_t full;       /* every block offers all d-subsets of the child's predecessors (no pools, fixed parents, limits) */
+	int32_t pad2;
 };
 
 /* per-node arguments of the DP recurrence (k_dp_all) */
@@ -55,8 +57,11 @@ struct CnbTiles {
 	const long long *dtile_off;   /* [nct][CNB_DT_STRIDE] D tiles of the child tile before each of its D pair tiles */
 	int32_t nct, child;           /* child tiles, children per child tile */
 	int32_t rank, world;
-	int32_t self_pairs;           /* 1: the pair-table tiling instead (cnb_tiles.h, kind 2); tile_base/dtile_off unused */
-	int32_t pad;
+	int32_t self_pairs;           /* 1: the pair-table tiling instead (cnb_tiles.h, kind 2); tile_base/dtile_off unused;
+	                                 2: the three-parent tiling (kind 3): tile_base = first tile of every column tile */
+	int32_t pad;                  /* table kernel: L1 prefetch distance of the generators */
+	int32_t f1;                   /* kind 3: free categories per node (max categories - 1) */
+	int32_t nvirt;                /* kind 3: virtual pair nodes behind the N real ones in the A operand rows */
 };
 
 #define CNB_TILE_PAIRS 28     /* tensor-core tile: 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128) ... */

@@ -93,19 +93,6 @@ __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *
 }
 
 /* ------------------------------------------------------------------ epilogue ---- */
-__device__ __forceinline__ void dev_store_outputs(const DevData &D, const ScoreOut &O, long long fid, int child,
-		const int *pars, int d, double ll, int ncount) {
-	double prior = 0.0;
-	double score = ll;
-	if (D.edge) {
-		prior = dev_prior(D, child, pars, d);
-		score = __dadd_rn(ll, prior);                     /* fLogLik += priorLogLik (catnet_search2.h:610) */
-	}
-	if (O.scores) O.scores[dev_score_index(fid, O.chunk, O.seg_off, O.seg_len)] = score;
-	if (O.loglik) O.loglik[fid] = ll;
-	if (O.prior) O.prior[fid] = prior;
-	if (O.ncount) O.ncount[fid] = ncount;
-}
 
 /* ------------------------------------------------------------------ K2a: bit-plane scorer ---- */
 template <int D, int CM> struct CellCount { static constexpr int value = CM * CellCount<D - 1, CM>::value; };
@@ -341,10 +328,6 @@ __global__ void __launch_bounds__(SCORE_BS) k_score_planes_ie2(DevData Dt, DevFa
 
 /* ---- three-way tables of all node triples (label space, once per data set) and the three-parent scorer built on them ----
  * triple (u < v < w) lives at rank C(w,3) + C(v,2) + u, 64 ints: cell [i_u][i_v][i_w] at (i_u * 4 + i_v) * 4 + i_w. */
-__device__ __forceinline__ long long triple_index(int u, int v, int w) {
-	return (long long)w * (w - 1) * (w - 2) / 6 + (long long)v * (v - 1) / 2 + u;
-}
-
 /* one thread per triple: (CM-1)^3 free cells by POPC, the rest from the pair tables (as k_score_planes_ie2) */
 template <int CM>
 __global__ void __launch_bounds__(128) k_triple_tables(const uint4 *__restrict__ planes_lbl, int N, int W, long long ntriples,
@@ -419,15 +402,6 @@ __global__ void __launch_bounds__(128) k_triple_tables(const uint4 *__restrict__
 	for (int i = 0; i < 16; i++) dst[i] = make_int4(tab[4 * i], tab[4 * i + 1], tab[4 * i + 2], tab[4 * i + 3]);
 }
 
-/* n(a = i, b = j, c = k) for node labels a, b, c in any order */
-__device__ __forceinline__ int triple_count(const int *__restrict__ tt, int a, int i, int b, int j, int c, int k) {
-	int t;
-	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
-	if (b > c) { t = b; b = c; c = t; t = j; j = k; k = t; }
-	if (a > b) { t = a; a = b; b = t; t = i; i = j; j = t; }
-	return tt[triple_index(a, b, c) * 64 + (i * 4 + j) * 4 + k];
-}
-
 /* K2a'': three-parent scorer with inclusion-exclusion.  Only the (CM-1)^4 free cells are counted over the samples
  * (16 AND+POPC per word instead of 81 at CM = 3, 81 instead of 256 at CM = 4); the slices with a last category follow,
  * axis after axis, from the complete three-way tables of the four triples inside {p0, p1, p2, child}. */
@@ -473,46 +447,9 @@ __global__ void __launch_bounds__(BS) k_score_planes_ie3(DevData Dt, DevFamilies
 			for (int k = 0; k < F1; k++)
 #pragma unroll
 				for (int l = 0; l < F1; l++) CELL(i, j, k, l) = (int)cnt[((i * F1 + j) * F1 + k) * F1 + l];
-	const int l0 = Dt.order[pars[0]], l1 = Dt.order[pars[1]], l2 = Dt.order[pars[2]], lc = Dt.order[child];
-	/* axis of p0: known afterwards for every i, and j, k, l free */
-	for (int j = 0; j < F1; j++)
-		for (int k = 0; k < F1; k++)
-			for (int l = 0; l < F1; l++) {
-				int s = 0;
-				for (int i = 0; i < F1; i++) s += CELL(i, j, k, l);
-				CELL(F1, j, k, l) = triple_count(tt, l1, j, l2, k, lc, l) - s;
-			}
-	/* axis of p1 */
-	for (int i = 0; i < CM; i++)
-		for (int k = 0; k < F1; k++)
-			for (int l = 0; l < F1; l++) {
-				int s = 0;
-				for (int j = 0; j < F1; j++) s += CELL(i, j, k, l);
-				CELL(i, F1, k, l) = triple_count(tt, l0, i, l2, k, lc, l) - s;
-			}
-	/* axis of p2 */
-	for (int i = 0; i < CM; i++)
-		for (int j = 0; j < CM; j++)
-			for (int l = 0; l < F1; l++) {
-				int s = 0;
-				for (int k = 0; k < F1; k++) s += CELL(i, j, k, l);
-				CELL(i, j, F1, l) = triple_count(tt, l0, i, l1, j, lc, l) - s;
-			}
-	/* axis of the child */
-	for (int i = 0; i < CM; i++)
-		for (int j = 0; j < CM; j++)
-			for (int k = 0; k < CM; k++) {
-				int s = 0;
-				for (int l = 0; l < F1; l++) s += CELL(i, j, k, l);
-				CELL(i, j, k, F1) = triple_count(tt, l0, i, l1, j, l2, k) - s;
-			}
 #undef CELL
-	const int pc0 = Dt.cats[pars[0]], pc1 = Dt.cats[pars[1]], pc2 = Dt.cats[pars[2]], cc = Dt.cats[child];
 	int ncount;
-	double ll = dev_loglik(pc0 * pc1 * pc2, cc, [&](int cfg, int l) {
-		const int k = cfg % pc2, ij = cfg / pc2, j = ij % pc1, i = ij / pc1;
-		return mine[(((i * CM + j) * CM + k) * CM + l) * BS];
-	}, &ncount);
+	const double ll = dev_ie3_finish<CM, BS>(mine, Dt, tt, pars, child, &ncount);
 	dev_store_outputs(Dt, O, fid, child, pars, 3, ll, ncount);
 }
 

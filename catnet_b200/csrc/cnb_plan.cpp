@@ -196,6 +196,11 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 		}
 		if (!g.nblk) continue;
 		g.chunk = (g.nfam + world - 1) / world;
+		g.full = g.nblk == N - d;
+		for (int k = 0; k < g.nblk && g.full; k++) {
+			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
+			g.full = b.nfix == 0 && b.nfree == b.child;
+		}
 		/* Tensor-core tiling of the two-parent group: only when every node c >= 2 offers all pairs of its
 		 * predecessors (no pools, no fixed parents, no size limit), so that tile (child tile, pair tile) slots map
 		 * one-to-one onto candidate families.  Tiles cost the same, so ranks get equal contiguous tile ranges. */
@@ -256,6 +261,8 @@ int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
 	T.world = 1;
 	T.self_pairs = 0;
 	T.pad = 0;
+	T.f1 = 0;
+	T.nvirt = 0;
 	CnbTileInfo ti;
 	cnb_tile_decode(T, pl.N, tile, ti);
 	return (3 * (ti.ze - ti.zb) + 15) / 16 * 16;
@@ -284,6 +291,8 @@ extern "C" int64_t cnb_tile_selftest(int32_t N) {
 	T.world = 1;
 	T.self_pairs = 0;
 	T.pad = 0;
+	T.f1 = 0;
+	T.nvirt = 0;
 	const int64_t ntiles = pl.tile_base[T.nct];
 	std::vector<unsigned char> used((size_t)ntiles * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
 	int64_t nfam = 0;

@@ -17,6 +17,13 @@
  *            its 9 rows are non-zero and row (i, i) is the plain one-hot row of category i); columns = all nodes in
  *            chunks of 64.  Tile t = (pair tile t / nchunks, chunk t % nchunks).
  *
+ *   T tiles  (T.self_pairs == 2, three-parent families (a < b < c | x)): columns = the children x of column tile ct =
+ *            [64 ct, 64 ct + 64); "pair" slot q of that column tile = (triple t = q / f1, value i = q % f1 of a) with the
+ *            triples (a < b < c), c < ce - 1, ranked t = C(c,3) + C(b,2) + a; its two "pair" nodes are the VIRTUAL node
+ *            N + (b(b-1)/2 + a) f1 + i -- whose three operand rows are [x_a = i][x_b = j], j < 3 -- and the real node c,
+ *            so the slot's 9 x 3 cells are n(a = i, b = j, c = k, x = l).  tile_base[ct] = first tile of column tile ct.
+ *            The slots of children x <= c hold no family (the diagonal is not transposed here).
+ *
  * Tile ids: tile_base[ct] + [0, nF) are the F tiles of ct, then the D tiles pair tile after pair tile, chunk after
  * chunk; dtile_off[ct * CNB_DT_STRIDE + p] = D tiles of ct before pair tile p.
  */
@@ -34,7 +41,8 @@
 #define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 pair tiles of D pairs per child tile, plus the total */
 
 struct CnbTileInfo {
-	int kind;                 /* 0 = F, 1 = D, 2 = P */
+	int kind;                 /* 0 = F, 1 = D, 2 = P, 3 = T */
+	int n, f1;                /* kind 3: real nodes, free categories */
 	int ct, c0, ce;           /* child tile and its children [c0, ce) */
 	long long pair0;          /* rank of the tile's first pair inside its region (F: q, D: rank among the D pairs) */
 	long long npairs;         /* pairs of the region */
@@ -70,7 +78,31 @@ CNB_HD int cnb_d_chunks(int c0, int ce, int ptile) {
 	return (b + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
 }
 
+CNB_HD long long cnb_binom3(long long n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
+/* t = C(c,3) + C(b,2) + a, a < b < c */
+CNB_HD void cnb_triple_of(long long t, int &a, int &b, int &c) {
+	c = (int)cbrt(6.0 * (double)t) + 2;
+	while (cnb_binom3(c) > t) c--;
+	while (cnb_binom3(c + 1) <= t) c++;
+	cnb_pair_of(t - cnb_binom3(c), a, b);
+}
+
 CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInfo &ti) {
+	ti.n = N;
+	ti.f1 = T.f1;
+	if (T.self_pairs == 2) {
+		int ct = 0;
+		while (ct + 1 < T.nct && T.tile_base[ct + 1] <= tile) ct++;
+		ti.kind = 3;
+		ti.ct = ct;
+		ti.c0 = ct * CNB_TILE_CHILD;
+		ti.ce = ti.c0 + CNB_TILE_CHILD < N ? ti.c0 + CNB_TILE_CHILD : N;
+		ti.pair0 = (tile - T.tile_base[ct]) * CNB_TILE_PAIRS;
+		ti.npairs = cnb_binom3(ti.ce - 1) * T.f1;
+		ti.zb = ti.c0;
+		ti.ze = ti.ce;
+		return;
+	}
 	if (T.self_pairs) {
 		const int nch = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
 		ti.kind = 2;
@@ -122,7 +154,13 @@ CNB_HD bool cnb_tile_pair(const CnbTileInfo &ti, int ps, int &x, int &y) {
 	if (q >= ti.npairs) return false;
 	if (ti.kind == 0) cnb_pair_of(q, x, y);
 	else if (ti.kind == 1) cnb_d_pair(ti.c0, ti.ce, (int)q, x, y);
-	else x = y = (int)q;
+	else if (ti.kind == 2) x = y = (int)q;
+	else {
+		int a, b, c;
+		cnb_triple_of(q / ti.f1, a, b, c);
+		x = ti.n + (int)(((long long)b * (b - 1) / 2 + a) * ti.f1 + q % ti.f1);
+		y = c;
+	}
 	return true;
 }
 
@@ -139,5 +177,8 @@ CNB_HD void cnb_family_slot(const CnbTiles &T, int N, int a, int b, int c, long 
 		within = (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + a % CNB_TILE_CHILD;
 	}
 }
+
+/* kind 3: tiles of column tile [c0, ce) and the slot of (triple rank t, value i of a, child x) */
+CNB_HD long long cnb_t_tiles(int ce, int f1) { return (cnb_binom3(ce - 1) * f1 + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }
 
 #endif

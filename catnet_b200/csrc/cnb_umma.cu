@@ -123,7 +123,7 @@ __device__ __forceinline__ uint32_t rows_b_word(uint32_t y, int fp4) {
 }
 
 __global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int nquads,
-		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int fp4) {
+		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int fp4, int stride_a) {
 	const int n = blockIdx.x * blockDim.x + threadIdx.x, qd = blockIdx.y;
 	if (n >= N) return;
 	uint4 v[4];
@@ -132,10 +132,11 @@ __global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ pla
 		const int w = qd * 4 + k;
 		v[k] = w < W ? __ldg(planes + (size_t)w * N + n) : make_uint4(0, 0, 0, 0);
 	}
-	const size_t o = (size_t)qd * (3 * N) + 3 * n;
-	rows_a[o + 0] = make_uint4(v[0].x, v[1].x, v[2].x, v[3].x);
-	rows_a[o + 1] = make_uint4(v[0].y, v[1].y, v[2].y, v[3].y);
-	rows_a[o + 2] = make_uint4(v[0].z, v[1].z, v[2].z, v[3].z);
+	const size_t o = (size_t)qd * (3 * N) + 3 * n, oa = (size_t)qd * stride_a + 3 * n;
+	rows_a[oa + 0] = make_uint4(v[0].x, v[1].x, v[2].x, v[3].x);
+	rows_a[oa + 1] = make_uint4(v[0].y, v[1].y, v[2].y, v[3].y);
+	rows_a[oa + 2] = make_uint4(v[0].z, v[1].z, v[2].z, v[3].z);
+	if (!rows_b) return;
 	rows_b[o + 0] = make_uint4(rows_b_word(v[0].x, fp4), rows_b_word(v[1].x, fp4), rows_b_word(v[2].x, fp4), rows_b_word(v[3].x, fp4));
 	rows_b[o + 1] = make_uint4(rows_b_word(v[0].y, fp4), rows_b_word(v[1].y, fp4), rows_b_word(v[2].y, fp4), rows_b_word(v[3].y, fp4));
 	rows_b[o + 2] = make_uint4(rows_b_word(v[0].z, fp4), rows_b_word(v[1].z, fp4), rows_b_word(v[2].z, fp4), rows_b_word(v[3].z, fp4));
@@ -230,7 +231,7 @@ template <bool FP4>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
 		int N, int ngroups_all, CnbTiles T, long long local_begin, int *__restrict__ counts, int whole, int split) {
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
-	const int NR = 3 * N;                   /* operand rows per quad */
+	const int NRB = 3 * N, NRA = 3 * (N + T.nvirt);   /* operand rows per quad: column side, pair side (real + virtual nodes) */
 	/* CTAs [0, whole) contract all the samples of one tile each; the tiles behind them -- the launch's last, partial
 	 * wave -- are cut into `split` sample slices, one CTA each, whose counts are added up in global memory */
 	const bool sliced = (int)blockIdx.x >= whole;
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	const int slice = sliced ? ((int)blockIdx.x - whole) % split : 0;
 	const int g_first = sliced ? (int)((long long)slice * ngroups_all / split) : 0;
 	const int ngroups = (sliced ? (int)((long long)(slice + 1) * ngroups_all / split) : ngroups_all) - g_first;
-	const size_t src_skip = (size_t)g_first * UM_BSTAGES * SRCQ * NR;   /* quads before this CTA's first stage */
+	const size_t src_quads = (size_t)g_first * UM_BSTAGES * SRCQ;   /* quads before this CTA's first stage */
 	const int pf = T.pad;                   /* L1 prefetch distance in stages beyond the one being loaded */
-	const size_t pf_off = (size_t)pf * SRCQ * NR;
+	const size_t pf_quads = (size_t)pf * SRCQ;
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ __align__(8) uint64_t bar_full_b[UM_BSTAGES], bar_empty_b[UM_BSTAGES], bar_full_a[UM_NA * UM_ASTAGES], bar_empty_a[UM_NA * UM_ASTAGES], bar_done;
 	__shared__ uint32_t tmem_base_sh;
@@ -293,26 +294,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		const int h = warp >> 2, r = tid & 127;
 		int pa, pb;
 		if (!cnb_tile_pair(ti, h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb)) { pa = 0; pb = 1; }
-		const uint4 *s0 = rows_a + src_skip + (pa * 3 + (r % 9) / 3), *s1 = rows_a + src_skip + (pb * 3 + r % 3);
+		const uint4 *s0 = rows_a + src_quads * NRA + (pa * 3 + (r % 9) / 3), *s1 = rows_a + src_quads * NRA + (pb * 3 + r % 3);
 		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * (UM_ASTAGES * 16);
 		uint64_t *const full_a = &bar_full_a[h * UM_ASTAGES], *const empty_a = &bar_empty_a[h * UM_ASTAGES];
 		uint4 n0, n1, m0, m1;          /* next stage's source bits of the two nodes */
 		n0 = __ldg(s0);
 		m0 = __ldg(s1);
-		n1 = FP4 ? __ldg(s0 + NR) : n0;
-		m1 = FP4 ? __ldg(s1 + NR) : m0;
+		n1 = FP4 ? __ldg(s0 + NRA) : n0;
+		m1 = FP4 ? __ldg(s1 + NRA) : m0;
 		for (int g = 0; g < ngroups; g++) {
 #pragma unroll
 			for (int u = 0; u < UM_BSTAGES; u++) {
 				const uint4 v0 = and4(n0, m0), v1 = and4(n1, m1);
-				s0 += SRCQ * NR; s1 += SRCQ * NR;
+				s0 += SRCQ * NRA; s1 += SRCQ * NRA;
 				n0 = __ldg(s0);
 				m0 = __ldg(s1);
-				if (FP4) { n1 = __ldg(s0 + NR); m1 = __ldg(s1 + NR); }
+				if (FP4) { n1 = __ldg(s0 + NRA); m1 = __ldg(s1 + NRA); }
 				if (g * UM_BSTAGES + u + 1 + pf <= ngroups * UM_BSTAGES) {   /* inside the rows (one stage of slack) */
-					prefetch_l1(s0 + pf_off);
-					prefetch_l1(s1 + pf_off);
-					if (FP4) { prefetch_l1(s0 + pf_off + NR); prefetch_l1(s1 + pf_off + NR); }
+					prefetch_l1(s0 + pf_quads * NRA);
+					prefetch_l1(s1 + pf_quads * NRA);
+					if (FP4) { prefetch_l1(s0 + pf_quads * NRA + NRA); prefetch_l1(s1 + pf_quads * NRA + NRA); }
 				}
 
 				/* each half of the stage goes to its own ring slot (use number 2g + UM_AUSE of that slot) */
@@ -373,19 +374,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		 * past the MMA's columns are not generated, their threads only keep the warp's arrivals going ---- */
 		const int rr = tid - UM_A_WARPS * 32, r = min(rr, UM_N - 1);
 		const bool active = rr < ncols;
-		const uint4 *s0 = rows_b + src_skip + (min(ti.zb + r / 3, ti.ze - 1) * 3 + r % 3);
+		const uint4 *s0 = rows_b + src_quads * NRB + (min(ti.zb + r / 3, ti.ze - 1) * 3 + r % 3);
 		uint32_t off[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) off[k] = smem + (r >> 3) * 1024u + (r & 7u) * 128u + ((k ^ (r & 7u)) << 4);
 		uint4 n0, n1;
 		n0 = __ldg(s0);
-		n1 = FP4 ? __ldg(s0 + NR) : n0;
+		n1 = FP4 ? __ldg(s0 + NRB) : n0;
 		for (int g = 0; g < ngroups; g++) {
 #define UM_STAGE_BODY(u) { \
 			const uint4 v0 = n0, v1 = n1; \
-			s0 += SRCQ * NR; \
-			if (active) { n0 = __ldg(s0); if (FP4) n1 = __ldg(s0 + NR); } \
-			if (active && g * UM_BSTAGES + (u) + 1 + pf <= ngroups * UM_BSTAGES) { prefetch_l1(s0 + pf_off); if (FP4) prefetch_l1(s0 + pf_off + NR); } \
+			s0 += SRCQ * NRB; \
+			if (active) { n0 = __ldg(s0); if (FP4) n1 = __ldg(s0 + NRB); } \
+			if (active && g * UM_BSTAGES + (u) + 1 + pf <= ngroups * UM_BSTAGES) { prefetch_l1(s0 + pf_quads * NRB); if (FP4) prefetch_l1(s0 + pf_quads * NRB + NRB); } \
 			if (g > 0) mbar_wait(&bar_empty_b[u], (g - 1) & 1); \
 			if (active) gen_row_b<FP4, (u) * UM_STAGE>(off, v0, v1); \
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); \
@@ -506,6 +507,41 @@ __global__ void __launch_bounds__(128) k_pairs_from_tiles(const int *__restrict_
 		for (int k = 0; k < 4; k++) out[i * 4 + k] = n[i][k];
 }
 
+/* three-parent families of one column tile from its T tiles: one thread per family (a < b < c | x).  The f1 slots
+ * (triple, i) hold the cells n(a = i, b = j, c = k, x = l) at (j * 3 + k) * 4 + l; the free ones (all indices < CM - 1) go
+ * to shared memory, dev_ie3_finish completes the table from the three-way tables and sums the log-likelihood. */
+template <int CM, int BS>
+__global__ void __launch_bounds__(BS) k_umma_epilogue3(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		long long tile0, const int *__restrict__ counts, const int *__restrict__ tt, ScoreOut O) {
+	constexpr int F1 = CM - 1;
+	extern __shared__ __align__(16) int s_cnt[];          /* [CM^4][BS] */
+	const long long fid = fid_begin + (long long)blockIdx.x * BS + threadIdx.x;
+	if (fid >= fid_end) return;
+	int child, pars[CNB_MAXP];
+	dev_family(Dt, F, fid, child, pars);
+	const int a = pars[0], b = pars[1], c = pars[2];
+	const long long t = cnb_binom3(c) + (long long)b * (b - 1) / 2 + a;
+	int *mine = s_cnt + threadIdx.x;
+#pragma unroll
+	for (int i = 0; i < F1; i++) {
+		const long long q = t * F1 + i;
+		const int *tab = counts + ((size_t)(q / UM_PAIRS - tile0) * UM_SLOTS + (size_t)(q % UM_PAIRS) * UM_CHILD
+				+ (child % UM_CHILD)) * UM_SLOT_INTS;
+#pragma unroll
+		for (int j = 0; j < F1; j++)
+#pragma unroll
+			for (int k = 0; k < F1; k++) {
+				const int4 v = *reinterpret_cast<const int4 *>(tab + (j * 3 + k) * 4);
+				const int x[3] = {v.x, v.y, v.z};
+#pragma unroll
+				for (int l = 0; l < F1; l++) mine[((((i * CM + j) * CM + k) * CM + l)) * BS] = x[l];
+			}
+	}
+	int ncount;
+	const double ll = dev_ie3_finish<CM, BS>(mine, Dt, tt, pars, child, &ncount);
+	dev_store_outputs(Dt, O, fid, child, pars, 3, ll, ncount);
+}
+
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
 /* quads (4 sample words) per operand row for W sample words: whole groups of UM_BSTAGES stages plus one stage of
@@ -520,7 +556,44 @@ int cnbk_umma_row_quads(int W, int fp4, int *ngroups) {
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
 	const int nq = cnbk_umma_row_quads(W, fp4, nullptr);
 	dim3 grid((N + 127) / 128, nq);
-	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a, rows_b, fp4);
+	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a, rows_b, fp4, 3 * N);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* ---- three-parent families on the tensor cores (T tiles, cnb_tiles.h) ---------------------------------------------
+ * pair-side rows of the real nodes (stride 3 (N + nvirt)) followed by those of the virtual pair nodes
+ * v = (b(b-1)/2 + a) f1 + i: row j = [x_a = i][x_b = j], j < 3 (mxf4 only) */
+__global__ void __launch_bounds__(128) k_umma_rows_virtual(const uint4 *__restrict__ planes, int N, int W, int nvirt, int f1,
+		uint4 *__restrict__ rows_a) {
+	const int v = blockIdx.x * blockDim.x + threadIdx.x, qd = blockIdx.y;
+	if (v >= nvirt) return;
+	int a, b;
+	cnb_pair_of(v / f1, a, b);
+	const int i = v % f1;
+	uint32_t r[3][4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int w = qd * 4 + k;
+		uint4 pa = make_uint4(0, 0, 0, 0), pb = pa;
+		if (w < W) { pa = __ldg(planes + (size_t)w * N + a); pb = __ldg(planes + (size_t)w * N + b); }
+		const uint32_t m = i == 0 ? pa.x : (i == 1 ? pa.y : pa.z);
+		r[0][k] = m & pb.x;
+		r[1][k] = m & pb.y;
+		r[2][k] = m & pb.z;
+	}
+	const size_t o = (size_t)qd * (3 * (size_t)(N + nvirt)) + 3 * (size_t)(N + v);
+#pragma unroll
+	for (int j = 0; j < 3; j++) rows_a[o + j] = make_uint4(r[j][0], r[j][1], r[j][2], r[j][3]);
+}
+
+int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvirt, int f1, uint4 *rows_a3) {
+	const int nq = cnbk_umma_row_quads(W, 1, nullptr);
+	dim3 grid((N + 127) / 128, nq);
+	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a3, nullptr, 1, 3 * (N + nvirt));
+	CK(cudaGetLastError());
+	dim3 gv((nvirt + 127) / 128, nq);
+	k_umma_rows_virtual<<<gv, 128, 0, st>>>(planes, N, W, nvirt, f1, rows_a3);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
@@ -608,4 +681,26 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 	k_pairs_from_tiles<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, N, M, pair_tab);
 	CK(cudaGetLastError());
 	return CNB_OK;
+}
+
+/* T tiles [tile_begin, tile_end) of one column tile (T.self_pairs == 2, T.tile_base on the device) */
+template <int CM, int BS>
+static int launch_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, long long tile0,
+		const int *counts, const int *tt, const ScoreOut &O) {
+	const size_t smem = (size_t)CM * CM * CM * CM * BS * sizeof(int);
+	if (smem > 48 * 1024)
+		CK(cudaFuncSetAttribute(k_umma_epilogue3<CM, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	k_umma_epilogue3<CM, BS><<<(unsigned)((e - b + BS - 1) / BS), BS, smem, st>>>(Dt, F, b, e, tile0, counts, tt, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* families [b, e) = those whose child lies in the column tile whose first tile (relative to the column tile) is tile0 = 0:
+ * counts holds the tables of that column tile's tiles from its first one on */
+int cnbk_umma_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
+		const int *counts, const int *triple_tab, const ScoreOut &O) {
+	if (e <= b) return CNB_OK;
+	if (max_cats <= 2) return launch_epilogue3<2, 128>(st, Dt, F, b, e, 0, counts, triple_tab, O);
+	if (max_cats == 3) return launch_epilogue3<3, 128>(st, Dt, F, b, e, 0, counts, triple_tab, O);
+	return launch_epilogue3<4, 64>(st, Dt, F, b, e, 0, counts, triple_tab, O);
 }

@@ -234,6 +234,7 @@ typedef struct cnb_timing {
 	float tensor_ms;                /* device time of the tcgen05 table kernel alone (CUDA events) */
 	int32_t tensor_kind;            /* operand type of that kernel: 4 = E2M1 (kind::mxf4), 8 = u8 (kind::i8), 0 = none */
 	int64_t tensor_macs;            /* multiply-accumulates it executed: tiles * 256 * 240 * padded samples */
+	int64_t tensor3_tiles;          /* tcgen05 tiles of the three-parent group (0 = that group ran on the bit-plane kernels) */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 

@@ -359,6 +359,24 @@ def test_three_parent_inclusion_exclusion(abi, port, n, m, cats):
         assert compare_search(a, o) == len(o)
 
 
+@pytest.mark.parametrize("n,m,cats", [(12, 300, 3), (10, 257, 4), (14, 64, 2), (11, 1000, None), (70, 200, 3), (66, 9000, 2),
+                                      (30, 8300, 4)])
+def test_three_parent_tensor_core_path(abi, n, m, cats):
+    """the unrestricted three-parent group as T tiles on the tensor cores (virtual pair nodes x third parent x children)
+    against the bit-plane inclusion-exclusion kernel; two column tiles at n > 64; forced on for small M"""
+    s, c = random_problem(11 * n + m, n, m, cats)
+    kw = dict(max_parent_set=3, max_complexity=n * 30, order=(np.random.default_rng(n + m).permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.force_generic(1024)                   # bit planes
+        a = ctx.search_order(want_probs=False, **kw)
+        assert ctx.timing()["tensor3_tiles"] == 0
+        ctx.force_generic(4 if m < 8192 else 0)   # tensor cores (forced below the sample threshold)
+        b = ctx.search_order(want_probs=False, **kw)
+        assert ctx.timing()["tensor3_tiles"] > 0
+    assert compare_search(b, a, check_probs=False) == len(a)
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
