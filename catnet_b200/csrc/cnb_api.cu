@@ -403,7 +403,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	std::vector<long long> base3(nct + 1, 0);
 	long long largest = 0;
 	for (int ct = 0; ct < nct; ct++) {
-		const int ce = std::min((ct + 1) * CNB_TILE_CHILD, N);
+		const int ce = cnb_t_ce(N, nct, ct);
 		const long long n = cnb_t_tiles(ce, f1);
 		base3[ct + 1] = base3[ct] + n;
 		largest = std::max(largest, n);
@@ -428,7 +428,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	T3.nvirt = (int)nvirt;
 	/* families of the group by child: block k of the group belongs to child 3 + k and starts at blocks[..].start */
 	for (int ct = 0; ct < nct; ct++) {
-		const int c0 = ct * CNB_TILE_CHILD, ce = std::min(c0 + CNB_TILE_CHILD, N);
+		const int c0 = cnb_t_c0(N, nct, ct), ce = cnb_t_ce(N, nct, ct);
 		long long fb = -1, fe = -1;
 		for (int k = 0; k < g.nblk; k++) {
 			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
@@ -439,7 +439,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 		if (fb < 0 || fe <= fb || base3[ct + 1] <= base3[ct]) continue;
 		RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a3.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, T3, base3[ct],
 				base3[ct + 1], (int *)c->b_counts.ptr));
-		RC(cnbk_umma_epilogue3(st, D, F, c->max_cats, fb, fe, (const int *)c->b_counts.ptr, (const int *)c->b_triples.ptr, O));
+		RC(cnbk_umma_epilogue3(st, D, F, c->max_cats, fb, fe, c0, (const int *)c->b_counts.ptr, (const int *)c->b_triples.ptr, O));
 		c->timing.kernel_launches += 2;
 	}
 	c->tensor3_tiles = (int)base3[nct];

@@ -60,7 +60,7 @@ int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin
  * CnbTiles of kind 3 and cnbk_umma_epilogue3 per column tile */
 int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvirt, int f1, uint4 *rows_a3);
 int cnbk_umma_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
-		const int *counts, const int *triple_tab, const ScoreOut &O);
+		int c0, const int *counts, const int *triple_tab, const ScoreOut &O);
 /* pairwise metrics (cnb_pairwise.cu): kind 0 entropy, 1 KL, 2 Pearson from the tables of the families (child n1,
  * parent n2), family index n1 * (N - 1) + rank of n2 among the others; out[n2 * N + n1] */
 int cnbk_pairwise_metric(cudaStream_t st, int kind, int N, const int *cats, const int *kept, const int *full,

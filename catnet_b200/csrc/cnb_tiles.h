@@ -17,9 +17,10 @@
  *            its 9 rows are non-zero and row (i, i) is the plain one-hot row of category i); columns = all nodes in
  *            chunks of 64.  Tile t = (pair tile t / nchunks, chunk t % nchunks).
  *
- *   T tiles  (T.self_pairs == 2, three-parent families (a < b < c | x)): columns = the children x of column tile ct =
- *            [64 ct, 64 ct + 64); "pair" slot q of that column tile = (triple t = q / f1, value i = q % f1 of a) with the
- *            triples (a < b < c), c < ce - 1, ranked t = C(c,3) + C(b,2) + a; its two "pair" nodes are the VIRTUAL node
+ *   T tiles  (T.self_pairs == 2, three-parent families (a < b < c | x)): columns = the children x of column tile ct; the
+ *            column tiles are aligned to the END of the order ([N - 64, N), [N - 128, N - 64), ... the first one takes
+ *            the rest), because a column tile [c0, ce) costs C(ce - 1, 3) f1 / 28 tiles whatever its width; "pair" slot q
+ *            of that column tile = (triple t = q / f1, value i = q % f1 of a) with the triples (a < b < c), c < ce - 1, ranked t = C(c,3) + C(b,2) + a; its two "pair" nodes are the VIRTUAL node
  *            N + (b(b-1)/2 + a) f1 + i -- whose three operand rows are [x_a = i][x_b = j], j < 3 -- and the real node c,
  *            so the slot's 9 x 3 cells are n(a = i, b = j, c = k, x = l).  tile_base[ct] = first tile of column tile ct.
  *            The slots of children x <= c hold no family (the diagonal is not transposed here).
@@ -79,6 +80,9 @@ CNB_HD int cnb_d_chunks(int c0, int ce, int ptile) {
 }
 
 CNB_HD long long cnb_binom3(long long n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
+/* kind 3: children [c0, ce) of column tile ct of nct = ceil(N / 64), aligned to the end of the order */
+CNB_HD int cnb_t_ce(int N, int nct, int ct) { return N - CNB_TILE_CHILD * (nct - 1 - ct); }
+CNB_HD int cnb_t_c0(int N, int nct, int ct) { return ct == 0 ? 0 : N - CNB_TILE_CHILD * (nct - ct); }
 /* t = C(c,3) + C(b,2) + a, a < b < c */
 CNB_HD void cnb_triple_of(long long t, int &a, int &b, int &c) {
 	c = (int)cbrt(6.0 * (double)t) + 2;
@@ -95,8 +99,8 @@ CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInf
 		while (ct + 1 < T.nct && T.tile_base[ct + 1] <= tile) ct++;
 		ti.kind = 3;
 		ti.ct = ct;
-		ti.c0 = ct * CNB_TILE_CHILD;
-		ti.ce = ti.c0 + CNB_TILE_CHILD < N ? ti.c0 + CNB_TILE_CHILD : N;
+		ti.c0 = cnb_t_c0(N, T.nct, ct);
+		ti.ce = cnb_t_ce(N, T.nct, ct);
 		ti.pair0 = (tile - T.tile_base[ct]) * CNB_TILE_PAIRS;
 		ti.npairs = cnb_binom3(ti.ce - 1) * T.f1;
 		ti.zb = ti.c0;

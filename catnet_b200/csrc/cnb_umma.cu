@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(128) k_pairs_from_tiles(const int *__restrict_
  * to shared memory, dev_ie3_finish completes the table from the three-way tables and sums the log-likelihood. */
 template <int CM, int BS>
 __global__ void __launch_bounds__(BS) k_umma_epilogue3(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
-		long long tile0, const int *__restrict__ counts, const int *__restrict__ tt, ScoreOut O) {
+		int c0, const int *__restrict__ counts, const int *__restrict__ tt, ScoreOut O) {
 	constexpr int F1 = CM - 1;
 	extern __shared__ __align__(16) int s_cnt[];          /* [CM^4][BS] */
 	const long long fid = fid_begin + (long long)blockIdx.x * BS + threadIdx.x;
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(BS) k_umma_epilogue3(DevData Dt, DevFamilies F
 #pragma unroll
 	for (int i = 0; i < F1; i++) {
 		const long long q = t * F1 + i;
-		const int *tab = counts + ((size_t)(q / UM_PAIRS - tile0) * UM_SLOTS + (size_t)(q % UM_PAIRS) * UM_CHILD
-				+ (child % UM_CHILD)) * UM_SLOT_INTS;
+		const int *tab = counts + ((size_t)(q / UM_PAIRS) * UM_SLOTS + (size_t)(q % UM_PAIRS) * UM_CHILD
+				+ (child - c0)) * UM_SLOT_INTS;
 #pragma unroll
 		for (int j = 0; j < F1; j++)
 #pragma unroll
@@ -685,22 +685,22 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 
 /* T tiles [tile_begin, tile_end) of one column tile (T.self_pairs == 2, T.tile_base on the device) */
 template <int CM, int BS>
-static int launch_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, long long tile0,
+static int launch_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int c0,
 		const int *counts, const int *tt, const ScoreOut &O) {
 	const size_t smem = (size_t)CM * CM * CM * CM * BS * sizeof(int);
 	if (smem > 48 * 1024)
 		CK(cudaFuncSetAttribute(k_umma_epilogue3<CM, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	k_umma_epilogue3<CM, BS><<<(unsigned)((e - b + BS - 1) / BS), BS, smem, st>>>(Dt, F, b, e, tile0, counts, tt, O);
+	k_umma_epilogue3<CM, BS><<<(unsigned)((e - b + BS - 1) / BS), BS, smem, st>>>(Dt, F, b, e, c0, counts, tt, O);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
 
-/* families [b, e) = those whose child lies in the column tile whose first tile (relative to the column tile) is tile0 = 0:
- * counts holds the tables of that column tile's tiles from its first one on */
+/* families [b, e) = those whose child lies in the column tile that starts at child c0; counts holds the tables of that
+ * column tile's tiles from its first one on */
 int cnbk_umma_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
-		const int *counts, const int *triple_tab, const ScoreOut &O) {
+		int c0, const int *counts, const int *triple_tab, const ScoreOut &O) {
 	if (e <= b) return CNB_OK;
-	if (max_cats <= 2) return launch_epilogue3<2, 128>(st, Dt, F, b, e, 0, counts, triple_tab, O);
-	if (max_cats == 3) return launch_epilogue3<3, 128>(st, Dt, F, b, e, 0, counts, triple_tab, O);
-	return launch_epilogue3<4, 64>(st, Dt, F, b, e, 0, counts, triple_tab, O);
+	if (max_cats <= 2) return launch_epilogue3<2, 128>(st, Dt, F, b, e, c0, counts, triple_tab, O);
+	if (max_cats == 3) return launch_epilogue3<3, 128>(st, Dt, F, b, e, c0, counts, triple_tab, O);
+	return launch_epilogue3<4, 64>(st, Dt, F, b, e, c0, counts, triple_tab, O);
 }
