@@ -101,6 +101,55 @@ extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	delete c;
 }
 
+/* ---- idle context kept for the one-shot entry points ----
+ * Every .Call of the R shim is a one-shot: create a context, copy and pack the samples, search, destroy.  For small
+ * problems creating the streams / events and allocating (then freeing) some forty device buffers costs more than the
+ * search (C1: 5-16 ms against 1.1 ms).  So a released one-shot context is parked, one per device, with its grow-only
+ * buffers, and the next one-shot on that device takes it over.  cnb_release_cache() frees the parked contexts. */
+#include <mutex>
+static std::mutex g_pool_mutex;
+static cnb_ctx *g_pool[64];
+
+int cnb_ctx_acquire(int32_t device, cnb_ctx **out) {
+	{
+		std::lock_guard<std::mutex> lock(g_pool_mutex);
+		if (device >= 0 && device < 64 && g_pool[device]) {
+			*out = g_pool[device];
+			g_pool[device] = nullptr;
+			(*out)->have_samples = (*out)->planned = (*out)->dp_done = false;
+			return CNB_OK;
+		}
+	}
+	return cnb_ctx_create(device, out);
+}
+
+void cnb_ctx_park(cnb_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	c->stream = c->own_stream;
+	{
+		std::lock_guard<std::mutex> lock(g_pool_mutex);
+		if (c->device >= 0 && c->device < 64 && !g_pool[c->device]) {
+			g_pool[c->device] = c;
+			return;
+		}
+	}
+	cnb_ctx_destroy(c);
+}
+
+void cnb_pool_release(void) {
+	for (int d = 0; d < 64; d++) {
+		cnb_ctx *c = nullptr;
+		{
+			std::lock_guard<std::mutex> lock(g_pool_mutex);
+			c = g_pool[d];
+			g_pool[d] = nullptr;
+		}
+		if (c) cnb_ctx_destroy(c);
+	}
+}
+
 static float ev_ms(cnb_ctx *c, int a, int b) {
 	float ms = 0;
 	cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
@@ -1039,10 +1088,10 @@ extern "C" int cnb_search_order(const cnb_params *p, cnb_result **out) {
 	*out = nullptr;
 	if (p->num_devices > 1) return search_order_multi(p, out);
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(p->device, &c));
+	RC(cnb_ctx_acquire(p->device, &c));
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	if (rc == CNB_OK) rc = cnb_ctx_search_order(c, p, out);
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 
@@ -1182,10 +1231,10 @@ static int pairwise_one_shot(int32_t kind, int32_t N, int32_t M, const int32_t *
 		int32_t device, double *out, int32_t *order_out) {
 	if (N < 1 || M < 1 || !samples) { cnb_set_error("Data should be a matrix"); return CNB_ERR_PARAM; }
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(device, &c));
+	RC(cnb_ctx_acquire(device, &c));
 	int rc = cnb_ctx_set_samples(c, N, M, samples, pert, nullptr);   /* categories = value range, as the reference */
 	if (rc == CNB_OK) rc = order_out ? cnb_ctx_entropy_order(c, order_out) : cnb_ctx_pairwise(c, kind, out);
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 
@@ -1372,10 +1421,10 @@ template <class Fn>
 static int with_network_ctx(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert, int32_t device, Fn fn) {
 	if (!net || !net->num_cats || net->num_nodes < 1 || M < 1 || !samples) { cnb_set_error("'data' should be a matrix of categories"); return CNB_ERR_PARAM; }
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(device, &c));
+	RC(cnb_ctx_acquire(device, &c));
 	int rc = cnb_ctx_set_samples(c, net->num_nodes, M, samples, pert, net->num_cats);
 	if (rc == CNB_OK) rc = fn(c);
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 
@@ -1473,9 +1522,9 @@ static int samples_on_device(cnb_ctx *c, const cnb_network *net, int32_t M, cons
 extern "C" int cnb_samples_dev(const cnb_network *net, int32_t M, const int32_t *pert_dev, double na_rate, uint64_t seed,
 		int32_t device, int32_t *out_dev) {
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(device, &c));
+	RC(cnb_ctx_acquire(device, &c));
 	int rc = samples_on_device(c, net, M, pert_dev, na_rate, seed, out_dev);
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 
@@ -1483,7 +1532,7 @@ extern "C" int cnb_samples(const cnb_network *net, int32_t M, const int32_t *per
 		int32_t device, int32_t *out) {
 	if (!net || M < 1 || !out) { cnb_set_error("cnb_samples: bad arguments"); return CNB_ERR_PARAM; }
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(device, &c));
+	RC(cnb_ctx_acquire(device, &c));
 	const size_t bytes = (size_t)net->num_nodes * M * sizeof(int32_t);
 	int rc = c->b_stage_s.ensure(bytes);
 	if (rc == CNB_OK && pert) rc = c->b_stage_p.ensure(bytes);
@@ -1498,13 +1547,13 @@ extern "C" int cnb_samples(const cnb_network *net, int32_t M, const int32_t *per
 		cnb_set_error("CUDA: copy of the samples failed");
 		rc = CNB_ERR_CUDA;
 	}
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 
 extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double *out) {
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(device, &c));
+	RC(cnb_ctx_acquire(device, &c));
 	DevBuf a, b;
 	int rc = a.ensure(n * sizeof(double));
 	if (rc == CNB_OK) rc = b.ensure(n * sizeof(double));
@@ -1516,7 +1565,7 @@ extern "C" int cnb_device_log(int32_t device, const double *x, int64_t n, double
 	}
 	a.release();
 	b.release();
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }
 

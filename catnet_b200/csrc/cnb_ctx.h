@@ -76,6 +76,10 @@ struct cnb_ctx {
 	}
 };
 
+/* one-shot entry points: take over / park the idle context of a device (cnb_api.cu) */
+int cnb_ctx_acquire(int32_t device, cnb_ctx **out);
+void cnb_ctx_park(cnb_ctx *c);
+void cnb_pool_release(void);
 /* internal phases shared with the SA driver (cnb_sa.cpp) */
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
 int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);

@@ -87,9 +87,9 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 extern "C" int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations) {
 	if (!p || !hp || !hist) return CNB_ERR_PARAM;
 	cnb_ctx *c = nullptr;
-	RC(cnb_ctx_create(p->device, &c));
+	RC(cnb_ctx_acquire(p->device, &c));
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	if (rc == CNB_OK) rc = cnb_ctx_search_hist(c, p, hp, hist, iterations);
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	return rc;
 }

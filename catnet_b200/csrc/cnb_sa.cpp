@@ -234,13 +234,13 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
 		return std::chrono::duration<double, std::milli>(b - a).count(); };
 	auto t0 = now();
-	RC(cnb_ctx_create(p->device, &c));
+	RC(cnb_ctx_acquire(p->device, &c));
 	auto t1 = now();
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	auto t2 = now();
 	if (rc == CNB_OK) rc = cnb_ctx_search_sa(c, p, sa, out);
 	auto t3 = now();
-	cnb_ctx_destroy(c);
+	cnb_ctx_park(c);
 	if (trace)
 		fprintf(stderr, "[cnb trace] cnb_search_sa: create %.2f set_samples %.2f search %.2f destroy %.2f ms\n", ms(t0, t1), ms(t1, t2),
 				ms(t2, t3), ms(t3, now()));
@@ -248,7 +248,8 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 }
 
 /* The reference keeps a process-global score cache between .Call's (cache.cpp:58-76); the device re-scores every
- * order from the resident bit planes, so there is nothing to release.  Kept for the .Call table. */
-extern "C" void cnb_release_cache(void) {}
+ * order from the resident bit planes, so there are no scores to release.  What the library does keep between one-shot
+ * calls is an idle context per device with its device buffers (cnb_api.cu: cnb_ctx_park); this frees them. */
+extern "C" void cnb_release_cache(void) { cnb_pool_release(); }
 static int32_t g_seed = 0;
 extern "C" void cnb_set_seed(int32_t seed) { g_seed = seed; }

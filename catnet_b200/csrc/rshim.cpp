@@ -531,8 +531,9 @@ SEXP ccnSamples(SEXP cnet, SEXP rNumSamples, SEXP rPerturbations, SEXP rNaRate) 
 	return rsamples;
 }
 
+/* R calls this right BEFORE every search (R/catnet.search.R:204, 279) to drop the reference's memoised scores.  The
+ * library has none; its idle device buffers are worth keeping across searches and go at unload (R_unload_catnet). */
 SEXP ccnReleaseCache(void) {
-	cnb_release_cache();
 	return R_NilValue;
 }
 

@@ -104,6 +104,7 @@ int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out
 /* hist_out: double[N*N], element [parent*N + child] in label space -- the vector the R code reshapes with
  * matrix(vhisto, nrow = numnodes) (R/catnet.histo.R:131); iterations_out may be NULL */
 int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist_out, int32_t *iterations_out);
+/* frees the idle per-device context (streams, events, grow-only device buffers) that one-shot calls park for the next one */
 void cnb_release_cache(void);
 void cnb_set_seed(int32_t seed);
 const char *cnb_last_error(void);
