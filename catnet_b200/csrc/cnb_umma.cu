@@ -444,10 +444,18 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	const int *tab = counts + (size_t)slot * UM_SLOT_INTS;
 	int full[64];
 #define CELL(i, jj, k) full[((i) * 4 + (jj)) * 4 + (k)]
-	/* slot layout: 9 pair configurations x (3 column categories + pad) */
-	for (int i = 0; i < 3; i++)
-		for (int jj = 0; jj < 3; jj++)
-			for (int k = 0; k < 3; k++) CELL(i, jj, k) = dk ? tab[(jj * 3 + k) * 4 + i] : tab[(i * 3 + jj) * 4 + k];
+	/* slot layout: 9 pair configurations x (3 column categories + pad): nine 16-byte loads */
+#pragma unroll
+	for (int r = 0; r < 9; r++) {
+		const int4 v = __ldg(reinterpret_cast<const int4 *>(tab) + r);
+		const int x3[3] = {v.x, v.y, v.z};
+#pragma unroll
+		for (int q = 0; q < 3; q++) {
+			/* F tile: row r = (i, jj), column category q = k.  D tile: row r = (jj, k) of the pair (b, c), column q = i */
+			if (dk) CELL(q, r / 3, r % 3) = x3[q];
+			else CELL(r / 3, r % 3, q) = x3[q];
+		}
+	}
 	const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
 	for (int i = 0; i < 3; i++)
 		for (int jj = 0; jj < 3; jj++)
