@@ -95,6 +95,7 @@ extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->pin_sel.release();
+	c->pin_stage.release();
 	for (DevBuf *b : c->all_bufs()) b->release();
 	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
 	cudaStreamDestroy(c->own_stream);
@@ -156,7 +157,8 @@ static float ev_ms(cnb_ctx *c, int a, int b) {
 	return ms;
 }
 
-extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples_dev,
+/* samples_dev: [M][N] int32 (elem_bytes 4) or uint8 with 0 = missing (elem_bytes 1) in device memory */
+static int set_samples_dev_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes,
 		const int32_t *pert_dev, const int32_t *num_cats) {
 	if (!c || N < 1 || M < 1 || !samples_dev) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
@@ -184,7 +186,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 		std::vector<int> hi(N, -INT32_MAX), lo(N, INT32_MAX);
 		H2D(c, c->b_vmin.ptr, lo.data(), N * sizeof(int));
 		H2D(c, c->b_vmax.ptr, hi.data(), N * sizeof(int));
-		RC(cnbk_minmax(st, samples_dev, N, M, (int *)c->b_vmin.ptr, (int *)c->b_vmax.ptr));
+		RC(cnbk_minmax(st, samples_dev, elem_bytes, N, M, (int *)c->b_vmin.ptr, (int *)c->b_vmax.ptr));
 		D2H(c, lo.data(), c->b_vmin.ptr, N * sizeof(int));
 		D2H(c, hi.data(), c->b_vmax.ptr, N * sizeof(int));
 		CK(cudaStreamSynchronize(st));
@@ -208,7 +210,7 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 		RC(c->b_keep_lbl.ensure(words * sizeof(uint32_t)));
 		RC(c->b_keep.ensure(words * sizeof(uint32_t)));
 	}
-	RC(cnbk_pack(st, samples_dev, pert_dev, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr,
+	RC(cnbk_pack(st, samples_dev, elem_bytes, pert_dev, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr,
 			(uint8_t *)c->b_codes.ptr, (uint4 *)c->b_planes_lbl.ptr,
 			c->has_pert ? (uint32_t *)c->b_keep_lbl.ptr : nullptr, (int *)c->b_flag.ptr));
 	int flags[4] = {0, 0, 0, 0};
@@ -245,12 +247,86 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	return CNB_OK;
 }
 
+extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples_dev,
+		const int32_t *pert_dev, const int32_t *num_cats) {
+	return set_samples_dev_impl(c, N, M, samples_dev, 4, pert_dev, num_cats);
+}
+
+/* int32 -> uint8 with saturation (x < 1, NA_INTEGER included -> 0 = missing; x > 255 -> 255, which no node has as a
+ * category, so the pack kernel reports it): 16 values per step, SSE2 */
+#include <emmintrin.h>
+#include <atomic>
+#include <thread>
+static void compact_rows(const int32_t *src, uint8_t *dst, size_t n) {
+	size_t i = 0;
+	for (; i + 16 <= n; i += 16) {
+		const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 4));
+		const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 8)), d = _mm_loadu_si128((const __m128i *)(src + i + 12));
+		_mm_storeu_si128((__m128i *)(dst + i), _mm_packus_epi16(_mm_packs_epi32(a, b), _mm_packs_epi32(c, d)));
+	}
+	for (; i < n; i++) dst[i] = (uint8_t)(src[i] < 1 ? 0 : (src[i] > 255 ? 255 : src[i]));
+}
+
+/* Large host matrices cross PCIe as bytes: the categories fit 8 bits, the int32 matrix R holds is 4x that.  Host threads
+ * compact chunk after chunk into a pinned buffer while the copy engine moves the chunks already done (C5: 2 GB in 40 ms
+ * as int32 against 0.5 GB behind the compaction).  Not with perturbations (a second int32 matrix: plain path). */
+static int set_samples_compacted(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples, const int32_t *num_cats) {
+	const size_t total = (size_t)N * M;
+	RC(c->pin_stage.ensure(total));
+	RC(c->b_stage_s.ensure(total));
+	uint8_t *pin = (uint8_t *)c->pin_stage.ptr;
+	const size_t chunk = (size_t)8 << 20;                       /* values per chunk: 32 MB of int32 -> 8 MB */
+	const int nchunks = (int)((total + chunk - 1) / chunk);
+	unsigned hw = std::thread::hardware_concurrency();
+	const int nthreads = (int)std::max(1u, std::min(std::min(hw ? hw : 4u, 16u), (unsigned)nchunks));
+	std::vector<std::atomic<int>> done(nchunks);
+	for (auto &d : done) d.store(0, std::memory_order_relaxed);
+	std::atomic<int> next(0);
+	std::vector<std::thread> pool;
+	for (int t = 0; t < nthreads; t++)
+		pool.emplace_back([&]() {
+			for (;;) {
+				const int k = next.fetch_add(1);
+				if (k >= nchunks) return;
+				const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
+				compact_rows(samples + b, pin + b, e - b);
+				done[k].store(1, std::memory_order_release);
+			}
+		});
+	cudaError_t err = cudaSuccess;
+	for (int k = 0; k < nchunks; k++) {
+		while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
+		const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
+		if (err == cudaSuccess)
+			err = cudaMemcpyAsync((uint8_t *)c->b_stage_s.ptr + b, pin + b, e - b, cudaMemcpyHostToDevice, c->stream);
+	}
+	for (auto &th : pool) th.join();
+	if (err != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(err)); return CNB_ERR_CUDA; }
+	c->timing.h2d_bytes += (int64_t)total;
+	c->in_host_set = true;
+	int rc = set_samples_dev_impl(c, N, M, c->b_stage_s.ptr, 1, nullptr, num_cats);
+	c->in_host_set = false;
+	return rc;
+}
+
 extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples,
 		const int32_t *pert, const int32_t *num_cats) {
 	if (!c || N < 1 || M < 1 || !samples) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
 	size_t bytes = (size_t)N * M * sizeof(int32_t);
 	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
+	/* CNB_HOST_COMPACT_MIN: smallest matrix (bytes) that takes the compacting route; "off" disables it (tests, tuning) */
+	size_t compact_min = (size_t)256 << 20;
+	bool no_compact = false;
+	if (const char *e = getenv("CNB_HOST_COMPACT_MIN")) {
+		if (!strcmp(e, "off")) no_compact = true;
+		else compact_min = (size_t)strtoull(e, nullptr, 10);
+	}
+	if (!pert && bytes >= compact_min && !no_compact) {
+		int rc = set_samples_compacted(c, N, M, samples, num_cats);
+		cudaStreamSynchronize(c->stream);
+		return rc;
+	}
 	/* staging buffers stay with the context (grow-only): allocating and freeing 2 GB per call costs more than the copy */
 	DevBuf &tmp_s = c->b_stage_s, &tmp_p = c->b_stage_p;
 	int rc = tmp_s.ensure(bytes);

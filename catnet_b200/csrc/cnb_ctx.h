@@ -57,7 +57,7 @@ struct cnb_ctx {
 	std::vector<double> h_L;
 	CnbPlan plan;
 	cnb_timing timing = {};
-	PinBuf pin_sel;
+	PinBuf pin_sel, pin_stage;         /* pin_stage: host-compacted copy of a large sample matrix on its way to the device */
 	DevBuf b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;

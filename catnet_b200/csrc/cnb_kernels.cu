@@ -23,7 +23,9 @@
 #define SCORE_BS 128
 
 /* ------------------------------------------------------------------ K1: pack ---- */
-__global__ void k_minmax(const int32_t *__restrict__ samples, int N, int M, int *__restrict__ vmin, int *__restrict__ vmax) {
+/* T = int32_t (what R hands over) or uint8_t (the host-compacted copy: 0 = missing, 255 = not a category) */
+template <class T>
+__global__ void k_minmax(const T *__restrict__ samples, int N, int M, int *__restrict__ vmin, int *__restrict__ vmax) {
 	int v = blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= N) return;
 	int lo = INT32_MAX, hi = -INT32_MAX;
@@ -40,7 +42,8 @@ __global__ void k_minmax(const int32_t *__restrict__ samples, int N, int M, int 
 }
 
 /* one thread per (32-sample word, node): reads are coalesced across nodes, one uint4 of planes per thread */
-__global__ void k_pack(const int32_t *__restrict__ samples, const int32_t *__restrict__ pert, int N, int M, int W,
+template <class T>
+__global__ void k_pack(const T *__restrict__ samples, const int32_t *__restrict__ pert, int N, int M, int W,
 		const int *__restrict__ vmin, const int *__restrict__ cats, uint8_t *__restrict__ codes,
 		uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int *__restrict__ bad) {
 	/* bad[0]: a value outside the node's categories; bad[2]: at least one missing value in the matrix */
@@ -1141,17 +1144,19 @@ __global__ void k_device_log(const double *__restrict__ x, long long n, double *
 /* ------------------------------------------------------------------ launchers ---- */
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
 
-int cnbk_minmax(cudaStream_t st, const int32_t *samples, int N, int M, int *vmin, int *vmax) {
+int cnbk_minmax(cudaStream_t st, const void *samples, int elem_bytes, int N, int M, int *vmin, int *vmax) {
 	dim3 grid((N + 127) / 128, min(M, 1024));
-	k_minmax<<<grid, 128, 0, st>>>(samples, N, M, vmin, vmax);
+	if (elem_bytes == 1) k_minmax<uint8_t><<<grid, 128, 0, st>>>((const uint8_t *)samples, N, M, vmin, vmax);
+	else k_minmax<int32_t><<<grid, 128, 0, st>>>((const int32_t *)samples, N, M, vmin, vmax);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
 
-int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int N, int M, int W, const int *vmin,
+int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_t *pert, int N, int M, int W, const int *vmin,
 		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad) {
 	dim3 grid((N + 127) / 128, W);
-	k_pack<<<grid, 128, 0, st>>>(samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
+	if (elem_bytes == 1) k_pack<uint8_t><<<grid, 128, 0, st>>>((const uint8_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
+	else k_pack<int32_t><<<grid, 128, 0, st>>>((const int32_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -25,8 +25,9 @@ struct DpState {
 	double *pfx;               /* [K+1] in-order partial sum over the nodes already decided */
 };
 
-int cnbk_minmax(cudaStream_t st, const int32_t *samples, int N, int M, int *vmin, int *vmax);
-int cnbk_pack(cudaStream_t st, const int32_t *samples, const int32_t *pert, int N, int M, int W, const int *vmin,
+/* samples: [M][N] of int32 (elem_bytes 4) or of uint8 with 0 = missing (elem_bytes 1, the host-compacted copy) */
+int cnbk_minmax(cudaStream_t st, const void *samples, int elem_bytes, int N, int M, int *vmin, int *vmax);
+int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_t *pert, int N, int M, int W, const int *vmin,
 		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad);
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
 		uint4 *planes, uint32_t *keep);

@@ -377,6 +377,27 @@ def test_three_parent_tensor_core_path(abi, n, m, cats):
     assert compare_search(b, a, check_probs=False) == len(a)
 
 
+def test_host_compacted_upload(abi, monkeypatch):
+    """large host matrices cross PCIe as bytes (int32 -> uint8 by host threads, 0 = missing): same packed data, hence the
+    same search, as the plain int32 upload; NA and category inference included; a value above 255 is still an error"""
+    s, c = random_problem(123, 9, 70000, None, na_frac=0.03)
+    kw = dict(max_parent_set=2, max_complexity=9 * 16 * 3)
+    res = {}
+    for mode in ("off", "1"):
+        monkeypatch.setenv("CNB_HOST_COMPACT_MIN", mode)
+        with abi.Context(0) as ctx:
+            ctx.set_samples(s)                          # categories inferred on the device
+            res[mode] = (ctx.num_cats().tolist(), ctx.search_order(want_probs=True, **kw), ctx.timing()["h2d_bytes"])
+    assert res["off"][0] == res["1"][0] == c.tolist()
+    assert compare_search(res["1"][1], res["off"][1]) == len(res["off"][1])
+    assert res["1"][2] < res["off"][2] / 3                  # a quarter of the bytes
+    bad = s.copy()
+    bad[5, 2] = 300
+    with abi.Context(0) as ctx, pytest.raises(abi.CnbError) as e:
+        ctx.set_samples(bad, num_cats=c)
+    assert e.value.code == abi.CNB_ERR_PARAM
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
