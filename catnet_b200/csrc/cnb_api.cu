@@ -259,12 +259,16 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 #include <thread>
 static void compact_rows(const int32_t *src, uint8_t *dst, size_t n) {
 	size_t i = 0;
+	const bool stream = ((uintptr_t)dst & 15) == 0;              /* non-temporal stores: the bytes are read next by the copy engine */
 	for (; i + 16 <= n; i += 16) {
 		const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 4));
 		const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 8)), d = _mm_loadu_si128((const __m128i *)(src + i + 12));
-		_mm_storeu_si128((__m128i *)(dst + i), _mm_packus_epi16(_mm_packs_epi32(a, b), _mm_packs_epi32(c, d)));
+		const __m128i v = _mm_packus_epi16(_mm_packs_epi32(a, b), _mm_packs_epi32(c, d));
+		if (stream) _mm_stream_si128((__m128i *)(dst + i), v);
+		else _mm_storeu_si128((__m128i *)(dst + i), v);
 	}
 	for (; i < n; i++) dst[i] = (uint8_t)(src[i] < 1 ? 0 : (src[i] > 255 ? 255 : src[i]));
+	_mm_sfence();
 }
 
 /* Large host matrices cross PCIe as bytes: the categories fit 8 bits, the int32 matrix R holds is 4x that.  Host threads
