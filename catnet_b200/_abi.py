@@ -74,7 +74,7 @@ SYMBOLS = [
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
     "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
     "cnb_loglik", "cnb_node_loglik", "cnb_set_prob", "cnb_ctx_loglik", "cnb_ctx_set_prob",
-    "cnb_samples", "cnb_samples_dev",
+    "cnb_samples", "cnb_samples_dev", "cnb_ctx_set_samples_dev8",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def lib():
         "cnb_ctx_destroy": (None, [vp]),
         "cnb_ctx_set_samples": (i32, [vp, i32, i32, vp, vp, vp]),
         "cnb_ctx_set_samples_dev": (i32, [vp, i32, i32, vp, vp, vp]),
+        "cnb_ctx_set_samples_dev8": (i32, [vp, i32, i32, vp, vp, vp]),
         "cnb_ctx_num_cats": (i32, [vp, vp]),
         "cnb_ctx_search_order": (i32, [vp, P(Params), P(vp)]),
         "cnb_ctx_search_sa": (i32, [vp, P(Params), P(SaParams), P(vp)]),
@@ -286,6 +287,11 @@ class Context:
     def set_samples_dev(self, samples_dev_ptr, n, m, perturbations_dev_ptr=None, num_cats=None):
         self.n, self.m = n, m
         check(lib().cnb_ctx_set_samples_dev(self.h, n, m, samples_dev_ptr, perturbations_dev_ptr, ptr(i32(num_cats))))
+
+    def set_samples_dev8(self, samples_dev_ptr, n, m, perturbations_dev_ptr=None, num_cats=None):
+        """device matrix [M][N] of bytes: 0 = missing, 1..254 = category"""
+        self.n, self.m = n, m
+        check(lib().cnb_ctx_set_samples_dev8(self.h, n, m, samples_dev_ptr, perturbations_dev_ptr, ptr(i32(num_cats))))
 
     def num_cats(self):
         out = np.zeros(self.n, dtype=np.int32)

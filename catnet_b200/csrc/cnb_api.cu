@@ -252,6 +252,11 @@ extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const i
 	return set_samples_dev_impl(c, N, M, samples_dev, 4, pert_dev, num_cats);
 }
 
+extern "C" int cnb_ctx_set_samples_dev8(cnb_ctx *c, int32_t N, int32_t M, const uint8_t *samples_dev,
+		const int32_t *pert_dev, const int32_t *num_cats) {
+	return set_samples_dev_impl(c, N, M, samples_dev, 1, pert_dev, num_cats);
+}
+
 /* int32 -> uint8 with saturation (x < 1, NA_INTEGER included -> 0 = missing; x > 255 -> 255, which no node has as a
  * category, so the pack kernel reports it): 16 values per step, SSE2 */
 #include <emmintrin.h>

@@ -44,21 +44,25 @@ def gather_scores(scores, rank, world, seg_len, group=None):
 
 def set_samples_sharded(ctx, host_samples, rank, world, device, num_cats=None, group=None):
     """host_samples: torch int32 [M][N] CPU tensor (pinned for speed), identical on every rank.  Rank r copies rows
-    [r*ceil(M/world), (r+1)*ceil(M/world)) to its GPU, one all_gather_into_tensor over NVLink completes the matrix on
-    every GPU, then the matrix is packed (cnb_ctx_set_samples_dev).  Returns (device tensor, bytes copied H2D)."""
+    [r*ceil(M/world), (r+1)*ceil(M/world)) to its GPU and narrows them to bytes (0 = missing, saturated at 255: the form
+    cnb_ctx_set_samples_dev8 takes), one all_gather_into_tensor over NVLink completes the BYTE matrix on every GPU (a
+    quarter of the int32 traffic), then the matrix is packed.  Returns (device byte tensor, bytes copied H2D)."""
     import torch
     import torch.distributed as dist
     ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)   # the copy, the all-gather and the pack stay ordered
     m, n = host_samples.shape
     rows = (m + world - 1) // world
-    full = torch.empty((rows * world, n), dtype=torch.int32, device=device)
+    full = torch.empty((rows * world, n), dtype=torch.uint8, device=device)
     r0, r1 = min(m, rank * rows), min(m, (rank + 1) * rows)
-    mine = full[rank * rows:(rank + 1) * rows]
+    mine = torch.zeros((rows, n), dtype=torch.uint8, device=device)
     if r1 > r0:
-        mine[:r1 - r0].copy_(host_samples[r0:r1], non_blocking=True)
+        part = host_samples[r0:r1].to(device, non_blocking=True)
+        mine[:r1 - r0] = part.clamp_(0, 255).to(torch.uint8)
     if world > 1:
-        dist.all_gather_into_tensor(full, mine.clone(), group=group)
-    ctx.set_samples_dev(full.data_ptr(), n, m, num_cats=num_cats)
+        dist.all_gather_into_tensor(full, mine, group=group)
+    else:
+        full = mine
+    ctx.set_samples_dev8(full.data_ptr(), n, m, num_cats=num_cats)
     return full, (r1 - r0) * n * 4
 
 

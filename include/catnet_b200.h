@@ -186,6 +186,10 @@ int cnb_ctx_set_samples(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, co
 /* same, but the [M][N] int32 matrix (and optional perturbations) already live in device memory */
 int cnb_ctx_set_samples_dev(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, const int32_t *samples_dev,
 		const int32_t *perturbations_dev, const int32_t *num_cats);
+/* same with one BYTE per value: 0 = missing, 1..254 = category, 255 = not a category (the form in which the library
+ * itself moves large host matrices over PCIe; multi-process callers all-gather this instead of the int32 matrix) */
+int cnb_ctx_set_samples_dev8(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, const uint8_t *samples_dev,
+		const int32_t *perturbations_dev, const int32_t *num_cats);
 /* categories per node as used on the device (given or inferred), label space */
 int cnb_ctx_num_cats(const cnb_ctx *ctx, int32_t *num_cats_out);
 /* search for one order on the resident data; samples/perturbations/num_cats/device fields of p are ignored */

@@ -398,6 +398,25 @@ def test_host_compacted_upload(abi, monkeypatch):
     assert e.value.code == abi.CNB_ERR_PARAM
 
 
+def test_byte_matrix_on_device(abi):
+    """cnb_ctx_set_samples_dev8 (what the multi-process upload all-gathers) and dist.set_samples_sharded at world 1"""
+    import torch
+    from catnet_b200 import dist as cdist
+    s, c = random_problem(321, 8, 3000, None, na_frac=0.04)
+    kw = dict(max_parent_set=2, max_complexity=8 * 16 * 3)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(want_probs=True, **kw)
+        d8 = torch.as_tensor(s, device="cuda").clamp_(0, 255).to(torch.uint8)
+        ctx.set_samples_dev8(d8.data_ptr(), 8, 3000, num_cats=c)
+        b = ctx.search_order(want_probs=True, **kw)
+        host = torch.as_tensor(s).pin_memory()
+        full, nbytes = cdist.set_samples_sharded(ctx, host, 0, 1, torch.device("cuda", 0), num_cats=c)
+        torch.cuda.synchronize()
+        d = ctx.search_order(want_probs=True, **kw)
+    assert compare_search(b, a) == len(a) and compare_search(d, a) == len(a) and nbytes == s.size * 4
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
