@@ -76,6 +76,7 @@ struct cnb_ctx {
 	}
 };
 
+uint64_t cnb_default_seed(void);   /* what cnb_set_seed stored (cnb_sa.cpp) */
 /* one-shot entry points: take over / park the idle context of a device (cnb_api.cu) */
 int cnb_ctx_acquire(int32_t device, cnb_ctx **out);
 void cnb_ctx_park(cnb_ctx *c);

@@ -28,7 +28,7 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 	const int N = c->N, M = c->M;
 	const int nDrives = hp->num_threads < 1 ? 1 : hp->num_threads;
 	memset(hist, 0, sizeof(double) * (size_t)N * N);
-	CnbRng rng(hp->seed);
+	CnbRng rng(hp->seed ? hp->seed : cnb_default_seed());
 	std::vector<std::vector<int>> test(nDrives, std::vector<int>(N));
 	std::vector<char> skip(nDrives);
 	std::vector<int32_t> cx, npar, pars;

@@ -266,8 +266,8 @@ __device__ __forceinline__ int pair_count(const int *__restrict__ pt, int u, int
 template <int CM>
 __global__ void __launch_bounds__(SCORE_BS) k_score_planes_ie2(DevData Dt, DevFamilies F, long long fid_begin,
 		long long fid_end, ScoreOut O, const int *__restrict__ pair_tab) {
-	constexpr int F1 = CM - 1, FREE = F1 * F1 * F1, CELLS = CM * CM * CM;
-	extern __shared__ __align__(16) int s_cnt[];          /* [CELLS][SCORE_BS] */
+	constexpr int F1 = CM - 1, FREE = F1 * F1 * F1;
+	extern __shared__ __align__(16) int s_cnt[];          /* [CM^3][SCORE_BS] */
 	const long long fid = fid_begin + (long long)blockIdx.x * SCORE_BS + threadIdx.x;
 	if (fid >= fid_end) return;
 	int child, pars[CNB_MAXP];

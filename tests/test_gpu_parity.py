@@ -417,6 +417,25 @@ def test_byte_matrix_on_device(abi):
     assert compare_search(b, a) == len(a) and compare_search(d, a) == len(a) and nbytes == s.size * 4
 
 
+def test_one_shot_context_is_parked_and_released(abi):
+    """one-shot calls reuse the context the previous one parked (streams, events, device buffers), also when the data set
+    changes shape; cnb_release_cache frees it and the next call starts from scratch -- same results every time"""
+    L = abi.lib()
+    s1, c1 = random_problem(1, 9, 400, None)
+    s2, c2 = random_problem(2, 14, 90, 3, na_frac=0.05)
+    kw1 = dict(max_parent_set=2, max_complexity=9 * 16 * 3, num_cats=c1)
+    kw2 = dict(max_parent_set=3, max_complexity=14 * 27 * 2, num_cats=c2)
+    a1 = abi.search_order(s1, **kw1)
+    a2 = abi.search_order(s2, **kw2)                 # bigger N, different categories, NA: takes over a1's context
+    b1 = abi.search_order(s1, **kw1)
+    L.cnb_release_cache()
+    d2 = abi.search_order(s2, **kw2)
+    e = abi.pairwise("entropy", np.where(s1 < 1, 1, s1))
+    L.cnb_release_cache()
+    f = abi.pairwise("entropy", np.where(s1 < 1, 1, s1))
+    assert compare_search(b1, a1) == len(a1) and compare_search(d2, a2) == len(a2) and np.array_equal(e, f)
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
