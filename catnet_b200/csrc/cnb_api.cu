@@ -527,7 +527,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	const int N = c->N;
 	if (g.d != 3 || !g.full || pl.world != 1 || pl.tile_base.empty() || !c->clean || !c->pairs_valid || c->force_generic
 			|| c->no_ie || c->no_ie3 || c->no_tensor3 || c->tensor_i8 || c->tensor_mode < 0 || (c->tensor_mode == 0 && c->M < 8192)
-			|| c->M >= (1 << 24) || N < 4 || N > 64 * 32) return CNB_OK;
+			|| c->M >= (1 << 24) || N < 4 || N > 64 * 32 || cnbk_umma_row_quads(c->W, 1, nullptr) > 65535) return CNB_OK;
 	bool ok = false;
 	RC(ensure_triples(c, &ok));
 	if (!ok) return CNB_OK;
@@ -614,7 +614,7 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 		if (allow_slicing) {
 			/* few families x many samples: slice the sample words so that the machine is filled */
 			long long n = e - b, target = 148ll * 1024;
-			if (n < target) slices = (int)std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8));
+			if (n < target) slices = (int)std::min<long long>(std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8)), 65535);
 		}
 		if (F.d == 1 && pairs_ok && !F.ex_nd) {
 			/* one parent, clean data: the table was counted with the pair tables */

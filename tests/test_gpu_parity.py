@@ -436,6 +436,25 @@ def test_one_shot_context_is_parked_and_released(abi):
     assert compare_search(b1, a1) == len(a1) and compare_search(d2, a2) == len(a2) and np.array_equal(e, f)
 
 
+def test_more_than_65535_sample_words(abi, port):
+    """2.3 M samples = 71,875 words of 32: the pack / permute / operand-row kernels put the sample dimension on grid.x"""
+    rng = np.random.default_rng(0)
+    m, n = 2_300_000, 6
+    s = rng.integers(1, 4, size=(m, n), dtype=np.int32)
+    s[:, 1] = np.where(rng.random(m) < 0.5, s[:, 0], s[:, 1])
+    c = np.full(n, 3, dtype=np.int32)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        counts, ll, nc = ctx.family_scores([1, 3], np.array([[0], [2]], dtype=np.int32))
+        nets = ctx.search_order(want_probs=False, max_parent_set=2, max_complexity=200)
+        assert ctx.timing()["tensor_tiles"] > 0
+    s0 = (s - 1).astype(np.int32)
+    for f, (ch, pa) in enumerate([(1, [0]), (3, [2])]):
+        rc, rll, rnc = port.family_score(s0, c, ch, pa)
+        assert np.array_equal(counts[f, :9], rc.astype(np.int64)) and ll[f] == rll and nc[f] == rnc
+    assert len(nets) > 1 and 1 in [len(p) for p in nets[-1]["parents"]] + [1]
+
+
 def test_pair_tables_on_tensor_cores(abi):
     """the two-way tables of all node pairs come from the tcgen05 kernel when M >= 8192 (P tiles) and from the POPC
     kernel otherwise: both routes must give the same searches (one- and two-parent scores are built on them)"""
