@@ -360,7 +360,7 @@ def test_three_parent_inclusion_exclusion(abi, port, n, m, cats):
 
 
 @pytest.mark.parametrize("n,m,cats", [(12, 300, 3), (10, 257, 4), (14, 64, 2), (11, 1000, None), (70, 200, 3), (66, 9000, 2),
-                                      (30, 8300, 4)])
+                                      (30, 8300, 4), (4, 50, 3), (5, 33, 2), (65, 40, 4), (129, 70, 2)])
 def test_three_parent_tensor_core_path(abi, n, m, cats):
     """the unrestricted three-parent group as T tiles on the tensor cores (virtual pair nodes x third parent x children)
     against the bit-plane inclusion-exclusion kernel; two column tiles at n > 64; forced on for small M"""
