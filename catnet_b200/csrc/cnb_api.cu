@@ -379,6 +379,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->pairs_popc = (on & 128) != 0;                       /* bit 7: pair tables by the POPC kernel (set BEFORE set_samples) */
 	c->no_ie3 = (on & 512) != 0;                           /* bit 9: no inclusion-exclusion for three-parent families */
 	c->no_tensor3 = (on & 1024) != 0;                      /* bit 10: three-parent families never on the tensor cores */
+	c->dp_no_trap = (on & 2048) != 0;                      /* bit 11: wavefront DP one node per exchange (k_dp_wave) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -894,12 +895,23 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 			c->timing.kernel_launches += 1;
 		}
 	} else if (!c->dp_per_node && !c->dp_no_wave) {
-		fused = cnbk_dp_wave(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
-				(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
-				(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap);
+		/* few options per node: the trapezoid wavefront (T nodes per neighbour exchange), else one node per exchange */
+		int steps = 0;
+		if (!c->dp_no_trap)
+			fused = cnbk_dp_trap(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
+					(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+					(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap, &steps);
 		if (fused == CNB_OK) {
-			cur = (N - 1) % 3;                /* step c reads S[(c - 1) % 3] and writes S[c % 3] */
+			cur = steps % 3;                  /* macro-step m reads S[(m - 1) % 3] and writes S[m % 3] */
 			c->timing.kernel_launches += 1;
+		} else if (fused == CNB_ERR_PROC) {
+			fused = cnbk_dp_wave(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
+					(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
+					(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap);
+			if (fused == CNB_OK) {
+				cur = (N - 1) % 3;            /* step c reads S[(c - 1) % 3] and writes S[c % 3] */
+				c->timing.kernel_launches += 1;
+			}
 		}
 	}
 	if (fused == CNB_ERR_PROC && !c->dp_per_node) {

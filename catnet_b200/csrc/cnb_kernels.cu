@@ -788,7 +788,7 @@ template <bool CG>
 __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, int j, int c, int N, int K,
 		const CnbDpNode &nd, int nopt, const long long (&o_fid)[4], const int (&o_cx)[4], const double (&o_sc)[4],
 		const double *sbase, double bv, const double *__restrict__ opt_score, const int *__restrict__ opt_cx,
-		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src) {
+		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src, bool write_bp = true) {
 	bool has = false;
 	double R = CNB_NEG_INF;
 	long long bo = -1;
@@ -861,14 +861,12 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 		nxt.exists[j] = 1;
 		nxt.L[j] = R;
 		nxt.pfx[j] = __dadd_rn(dp_ld<CG>(cur.pfx + bs), bf);
-		bp_opt[bpi] = bo;
-		bp_src[bpi] = bs;
+		if (write_bp) { bp_opt[bpi] = bo; bp_src[bpi] = bs; }
 	} else {
 		nxt.exists[j] = cur_ex;
 		nxt.L[j] = dp_ld<CG>(cur.L + j);
 		nxt.pfx[j] = __dadd_rn(dp_ld<CG>(cur.pfx + j), bv);
-		bp_opt[bpi] = -1;
-		bp_src[bpi] = j;
+		if (write_bp) { bp_opt[bpi] = -1; bp_src[bpi] = j; }
 	}
 }
 
@@ -1103,6 +1101,103 @@ __global__ void __launch_bounds__(256) k_dp_wave(DpState s0, DpState s1, DpState
 		if (threadIdx.x == 0) {
 			__threadfence();
 			atomicExch(&flags[b], (unsigned)c + 1u);
+		}
+	}
+}
+/* Trapezoid version of the wavefront: a CTA owns 256 consecutive slots and ALSO recomputes the 256 slots to their left,
+ * in shared memory, so that it can take T nodes per exchange with its neighbours instead of one: after t nodes the
+ * recomputed slots are still right from the (t * halo)-th on, and T * halo <= 256 keeps the owned ones right.  The
+ * flag / state round trips through L2 (what bounds k_dp_wave: 499 + 94 steps of ~6 us at C5) are paid once per T
+ * nodes; the state lives in shared memory in between.  Back-pointers are written by the owner only.  Same three
+ * global state buffers and neighbour protocol as k_dp_wave, per macro-step. */
+#define TRAP_S 256            /* recomputed slots to the left of the owned ones */
+#define TRAP_TMAX 8
+/* blockDim.x = owned slots + TRAP_S (the launcher uses 256 + 256) */
+__global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpState s2, int N, int base_complexity,
+		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
+		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
+		int *__restrict__ bp_src, unsigned *flags, int T, int halo) {
+	extern __shared__ double sbase[];                    /* [N], then the two state buffers */
+	__shared__ CnbDpNode s_nd[TRAP_TMAX];
+	__shared__ long long s_fid[TRAP_TMAX][4];
+	__shared__ int s_cx[TRAP_TMAX][4];
+	__shared__ double s_sc[TRAP_TMAX][4];
+	const int BW = blockDim.x, SO = BW - TRAP_S;            /* buffer width, owned slots */
+	double *s_L = sbase + N, *s_pfx = s_L + 2 * BW;
+	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_pfx + 2 * BW);
+	const int K = s0.K, b = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
+	const int lo = b * SO - TRAP_S, j = lo + tid;            /* threads [0, 256) recompute the left neighbour's slots */
+	const bool owned = tid >= TRAP_S, in_range = j >= 0 && j <= K;
+	for (int i = tid; i < N; i += blockDim.x) sbase[i] = base_v[i];
+	__syncthreads();
+	if (owned && in_range) {
+		bool ex = (j == base_complexity);
+		double l = 0.0;
+		if (ex) for (int i = 0; i < N; i++) l = __dadd_rn(l, sbase[i]);
+		s0.exists[j] = ex;
+		s0.L[j] = l;
+		s0.pfx[j] = ex ? __dadd_rn(0.0, sbase[0]) : 0.0;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		__threadfence();
+		atomicExch(&flags[b], 1u);
+	}
+	const int nsteps = (N - 1 + T - 1) / T;
+	for (int m = 1; m <= nsteps; m++) {
+		const DpState &gin = (m - 1) % 3 == 0 ? s0 : ((m - 1) % 3 == 1 ? s1 : s2), &gout = m % 3 == 0 ? s0 : (m % 3 == 1 ? s1 : s2);
+		const int c_lo = (m - 1) * T + 1, nT = min(T, N - c_lo);
+		if (tid == 0) {
+			if (b > 0) while (dp_flag_load(&flags[b - 1]) < (unsigned)m) { }
+			if (b + 1 < nb) while (dp_flag_load(&flags[b + 1]) + 1 < (unsigned)m) { }
+		}
+		if (tid >= 32 && tid < 32 + nT) {                    /* the nodes of this macro-step and their options */
+			const int t = tid - 32;
+			const CnbDpNode nd = nodes[c_lo + t];
+			s_nd[t] = nd;
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const long long o = nd.opt_begin + q;
+				const bool in = o < nd.opt_end;
+				s_fid[t][q] = in ? opt_fid[o] : -1;
+				s_cx[t][q] = in ? opt_cx[o] : 0;
+				s_sc[t][q] = in ? opt_score[o] : 0.0;
+			}
+		}
+		__syncthreads();
+		s_ex[tid] = in_range ? __ldcg(gin.exists + j) : 0;
+		s_L[tid] = in_range ? __ldcg(gin.L + j) : 0.0;
+		s_pfx[tid] = in_range ? __ldcg(gin.pfx + j) : 0.0;
+		__syncthreads();
+		for (int t = 0; t < nT; t++) {
+			const int c = c_lo + t, rb = (t & 1) * BW, wb = ((t + 1) & 1) * BW;
+			DpState cur, nxt;
+			cur.K = nxt.K = K;
+			cur.exists = s_ex + rb - lo; cur.L = s_L + rb - lo; cur.pfx = s_pfx + rb - lo;
+			nxt.exists = s_ex + wb - lo; nxt.L = s_L + wb - lo; nxt.pfx = s_pfx + wb - lo;
+			if (in_range && j >= lo + (t + 1) * halo) {
+				const CnbDpNode nd = s_nd[t];
+				long long o_fid[4];
+				int o_cx[4];
+				double o_sc[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++) { o_fid[q] = s_fid[t][q]; o_cx[q] = s_cx[t][q]; o_sc[q] = s_sc[t][q]; }
+				const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
+				dp_slot<false>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
+						bp_opt, bp_src, owned);
+			}
+			__syncthreads();
+		}
+		if (owned && in_range) {
+			const int fb = (nT & 1) * BW + tid;
+			gout.exists[j] = s_ex[fb];
+			gout.L[j] = s_L[fb];
+			gout.pfx[j] = s_pfx[fb];
+		}
+		__syncthreads();
+		if (tid == 0) {
+			__threadfence();
+			atomicExch(&flags[b], (unsigned)m + 1u);
 		}
 	}
 }
@@ -1390,6 +1485,35 @@ int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
 		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_wave, dim3(blocks), dim3(256), args, smem, st));
+	return CNB_OK;
+}
+
+/* trapezoid DP: at most 4 options per node, halo * T <= 256; *steps_out = macro-steps (final state in buffer steps % 3);
+ * CNB_ERR_PROC (nothing launched) when it does not apply */
+int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
+		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
+		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out) {
+	int dev = 0, coop = 0, sms = 0, per_sm = 0;
+	CK(cudaGetDevice(&dev));
+	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	if (halo < 1 || N < 3) return CNB_ERR_PROC;
+	int T = std::min(TRAP_TMAX, TRAP_S / halo);
+	if (T < 2) return CNB_ERR_PROC;
+	/* 256 owned slots per CTA: with 768 (fewer CTAs, a shorter pipeline fill) the DP of C5 took 4.8 instead of 2.3 ms --
+	 * the re-summation chains of 1024 slots per SM cost more than the fill saves */
+	const int threads = 512, owned = threads - TRAP_S;
+	const size_t smem = (size_t)N * sizeof(double) + (size_t)2 * threads * (2 * sizeof(double) + 1);
+	if (smem > 48 * 1024) return CNB_ERR_PROC;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_trap, threads, smem));
+	const int blocks = (s0.K + 1 + owned - 1) / owned;
+	if (!coop || per_sm < 1 || blocks > sms * per_sm || blocks > flags_cap) return CNB_ERR_PROC;
+	CK(cudaMemsetAsync(flags, 0, (size_t)blocks * sizeof(unsigned), st));
+	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
+		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags,
+		(void *)&T, (void *)&halo};
+	CK(cudaLaunchCooperativeKernel((const void *)k_dp_trap, dim3(blocks), dim3(threads), args, smem, st));
+	*steps_out = (N - 1 + T - 1) / T;
 	return CNB_OK;
 }
 

@@ -111,11 +111,11 @@ def test_search_order_matches_reference(abi, port, case):
         compare_golden(ctx.search_order(**kw2), golden)
 
 
-@pytest.mark.parametrize("bits", [32, 64], ids=["per_node", "grid_barrier"])
+@pytest.mark.parametrize("bits", [32, 64, 2048], ids=["per_node", "grid_barrier", "wave"])
 @pytest.mark.parametrize("case", CASES[::3], ids=lambda c: "seed%d" % c["seed"])
 def test_search_order_dp_variants(abi, case, bits):
-    """the DP normally runs as one cooperative wavefront kernel; the grid-barrier kernel and the per-node launches
-    must give the same networks"""
+    """the DP normally runs as one cooperative trapezoid-wavefront kernel (several nodes per neighbour exchange); the
+    one-node-per-exchange wavefront, the grid-barrier kernel and the per-node launches must give the same networks"""
     s, kw = build_case(case)
     golden = load_golden("ref_search_order")["seed%d" % case["seed"]]
     with abi.Context(0) as ctx:
@@ -453,6 +453,22 @@ def test_more_than_65535_sample_words(abi, port):
         rc, rll, rnc = port.family_score(s0, c, ch, pa)
         assert np.array_equal(counts[f, :9], rc.astype(np.int64)) and ll[f] == rll and nc[f] == rnc
     assert len(nets) > 1 and 1 in [len(p) for p in nets[-1]["parents"]] + [1]
+
+
+@pytest.mark.parametrize("n,m,cats,P", [(300, 400, 4, 2), (120, 300, 2, 2), (90, 200, 3, 2), (40, 3000, 4, 3), (513, 64, 2, 1)])
+def test_dp_trapezoid_equals_wavefront(abi, n, m, cats, P):
+    """equal-category searches with many complexity slots (several CTAs of 256 slots, halos of different widths, node
+    counts that are not a multiple of the macro-step): k_dp_trap == k_dp_wave == per-node launches, network by network"""
+    s, c = random_problem(5 * n + m, n, m, cats)
+    kw = dict(max_parent_set=P, max_complexity=n * (cats ** P) * (cats - 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(2048)
+        b = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(32)
+        d = ctx.search_order(want_probs=False, **kw)
+    assert compare_search(a, b, check_probs=False) == len(b) and compare_search(a, d, check_probs=False) == len(d)
 
 
 def test_pair_tables_on_tensor_cores(abi):
