@@ -47,8 +47,10 @@ __global__ void k_pack(const T *__restrict__ samples, const int32_t *__restrict_
 		const int *__restrict__ vmin, const int *__restrict__ cats, uint8_t *__restrict__ codes,
 		uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int *__restrict__ bad) {
 	/* bad[0]: a value outside the node's categories; bad[2]: at least one missing value in the matrix */
-	int v = blockIdx.y * blockDim.x + threadIdx.x;
-	int w = blockIdx.x;                                    /* the long dimension (samples) on x: no 65,535 limit */
+	/* one-dimensional grid (no 65,535 limit on the sample words), node chunks of a word adjacent */
+	const int nchunk = (N + blockDim.x - 1) / blockDim.x;
+	int v = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x;
+	int w = blockIdx.x / nchunk;
 	if (v >= N) return;
 	const int base = vmin[v], C = cats[v];
 	bool any_na = false;
@@ -86,8 +88,9 @@ __global__ void k_pack(const T *__restrict__ samples, const int32_t *__restrict_
 /* label space -> order space for one search (what the reference does by re-copying the whole int matrix) */
 __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *__restrict__ keep_lbl,
 		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep) {
-	int p = blockIdx.y * blockDim.x + threadIdx.x;
-	int w = blockIdx.x;
+	const int nchunk = (N + blockDim.x - 1) / blockDim.x;
+	int p = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x;
+	int w = blockIdx.x / nchunk;
 	if (p >= N) return;
 	int l = order[p];
 	uint4 v = planes_lbl[(size_t)w * N + l];
@@ -1249,7 +1252,7 @@ int cnbk_minmax(cudaStream_t st, const void *samples, int elem_bytes, int N, int
 
 int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_t *pert, int N, int M, int W, const int *vmin,
 		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad) {
-	dim3 grid(W, (N + 127) / 128);
+	dim3 grid((unsigned)((long long)W * ((N + 127) / 128)));
 	if (elem_bytes == 1) k_pack<uint8_t><<<grid, 128, 0, st>>>((const uint8_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
 	else k_pack<int32_t><<<grid, 128, 0, st>>>((const int32_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
 	CK(cudaGetLastError());
@@ -1258,7 +1261,7 @@ int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_
 
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
 		uint4 *planes, uint32_t *keep) {
-	dim3 grid(W, (N + 127) / 128);
+	dim3 grid((unsigned)((long long)W * ((N + 127) / 128)));
 	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep);
 	CK(cudaGetLastError());
 	return CNB_OK;

@@ -124,7 +124,8 @@ __device__ __forceinline__ uint32_t rows_b_word(uint32_t y, int fp4) {
 
 __global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int nquads,
 		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int fp4, int stride_a) {
-	const int n = blockIdx.y * blockDim.x + threadIdx.x, qd = blockIdx.x;   /* the long dimension (samples) on x */
+	const int nchunk = (N + blockDim.x - 1) / blockDim.x;   /* one-dimensional grid: no 65,535 limit on the quads */
+	const int n = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x, qd = blockIdx.x / nchunk;
 	if (n >= N) return;
 	uint4 v[4];
 #pragma unroll
@@ -563,7 +564,7 @@ int cnbk_umma_row_quads(int W, int fp4, int *ngroups) {
 
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
 	const int nq = cnbk_umma_row_quads(W, fp4, nullptr);
-	dim3 grid(nq, (N + 127) / 128);
+	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
 	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a, rows_b, fp4, 3 * N);
 	CK(cudaGetLastError());
 	return CNB_OK;
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(128) k_umma_rows_virtual(const uint4 *__restri
 int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvirt, int f1, uint4 *rows_a3) {
 	const int nq = cnbk_umma_row_quads(W, 1, nullptr);
 	if (nq > 65535) { cnb_set_error("three-parent tensor path: too many samples"); return CNB_ERR_PROC; }
-	dim3 grid(nq, (N + 127) / 128);
+	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
 	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a3, nullptr, 1, 3 * (N + nvirt));
 	CK(cudaGetLastError());
 	dim3 gv((nvirt + 127) / 128, nq);
