@@ -74,7 +74,7 @@ SYMBOLS = [
     "cnb_result_sa_info", "cnb_result_sa_trace", "cnb_result_merge", "cnb_result_free",
     "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
     "cnb_loglik", "cnb_node_loglik", "cnb_set_prob", "cnb_ctx_loglik", "cnb_ctx_set_prob",
-    "cnb_samples", "cnb_samples_dev", "cnb_ctx_set_samples_dev8",
+    "cnb_samples", "cnb_samples_dev", "cnb_ctx_set_samples_dev8", "cnb_tile3_selftest", "cnb_host_entropy_order",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib():
         "cnb_ctx_timing": (i32, [vp, P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_tile_selftest": (C.c_int64, [i32]),
+        "cnb_tile3_selftest": (C.c_int64, [i32, i32]),
+        "cnb_host_entropy_order": (None, [vp, i32, vp]),
         "cnb_family_scores": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32]),
         "cnb_device_log": (i32, [i32, vp, i64, vp]),
         "cnb_host_log": (None, [vp, i64, vp]),

@@ -335,3 +335,48 @@ extern "C" int64_t cnb_num_families(const cnb_params *p) {
 	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr) != CNB_OK) return -1;
 	return pl.num_families;
 }
+
+/* test hook: the T tiling of the unrestricted three-parent group (cnb_tiles.h, kind 3) is consistent between the side that
+ * builds the tiles (cnb_tile_decode / cnb_tile_pair, as the table kernel uses them) and the side that reads a family's
+ * slots (the arithmetic of k_umma_epilogue3): every family (a < b < c | x) and value i < f1 of a finds, in the column tile
+ * of x, the slot whose "pair" is (virtual node of (a, b, i), c) and whose column is x, no two share a slot.  Returns the
+ * number of tiles, negative at the first inconsistency. */
+extern "C" int64_t cnb_tile3_selftest(int32_t N, int32_t f1) {
+	if (N < 4 || f1 < 1 || f1 > 3) return 0;
+	const int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+	std::vector<long long> base3(nct + 1, 0);
+	for (int ct = 0; ct < nct; ct++) base3[ct + 1] = base3[ct] + cnb_t_tiles(cnb_t_ce(N, nct, ct), f1);
+	CnbTiles T;
+	memset(&T, 0, sizeof(T));
+	T.tile_base = base3.data();
+	T.nct = nct;
+	T.child = CNB_TILE_CHILD;
+	T.world = 1;
+	T.self_pairs = 2;
+	T.f1 = f1;
+	T.nvirt = N * (N - 1) / 2 * f1;
+	std::vector<unsigned char> used((size_t)base3[nct] * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
+	for (int x = 3; x < N; x++) {
+		int ct = 0;
+		while (cnb_t_ce(N, nct, ct) <= x) ct++;
+		const int c0 = cnb_t_c0(N, nct, ct), ce = cnb_t_ce(N, nct, ct);
+		if (x < c0 || x >= ce) return -1;
+		for (int c = 2; c < x; c++)
+			for (int b = 1; b < c; b++)
+				for (int a = 0; a < b; a++)
+					for (int i = 0; i < f1; i++) {
+						const long long t = cnb_binom3(c) + (long long)b * (b - 1) / 2 + a, q = t * f1 + i;
+						const long long tile = base3[ct] + q / CNB_TILE_PAIRS;
+						if (tile >= base3[ct + 1]) return -2;
+						unsigned char &u = used[((size_t)tile * CNB_TILE_PAIRS + q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + (x - c0)];
+						if (u) return -3;
+						u = 1;
+						CnbTileInfo ti;
+						cnb_tile_decode(T, N, tile, ti);
+						int px, py;
+						if (ti.kind != 3 || ti.zb != c0 || ti.ze != ce || !cnb_tile_pair(ti, (int)(q % CNB_TILE_PAIRS), px, py)) return -4;
+						if (py != c || px != N + (int)(((long long)b * (b - 1) / 2 + a) * f1 + i)) return -5;
+					}
+	}
+	return base3[nct];
+}

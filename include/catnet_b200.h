@@ -256,12 +256,17 @@ int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);
 /* the same log evaluated on the host by this library (no GPU needed) */
 void cnb_host_log(const double *x, int64_t n, double *out);
+/* the host tail of cnb_entropy_order (ranks = sums of mutual informations, the reference's _order with its tie behaviour)
+ * on a given entropy matrix mat[n2 * N + n1]; no GPU needed */
+void cnb_host_entropy_order(const double *mat, int32_t num_nodes, int32_t *order_out);
 /* lexicographic unrank used by the device enumerator (host mirror; catnet_search2.h:102-147 order) */
 int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_t *out);
 int64_t cnb_num_families(const cnb_params *p);
 /* consistency of the tensor-core tiling of the unrestricted two-parent group of N nodes (host only): number of
  * tiles, or < 0 if family <-> tile slot is not a bijection */
 int64_t cnb_tile_selftest(int32_t num_nodes);
+/* the same for the tiling of the unrestricted three-parent group (free_cats = max categories - 1) */
+int64_t cnb_tile3_selftest(int32_t num_nodes, int32_t free_cats);
 
 /* ---- result accessors (the catNetwork slots) ---- */
 int32_t cnb_result_num_networks(const cnb_result *r);

@@ -112,3 +112,32 @@ def test_tensor_tiling_is_a_bijection(n):
     assert ntiles * 28 * 64 >= fam
     if n == 500:
         assert ntiles < 12500          # 15,762 before the diagonal tiles were transposed
+
+
+@pytest.mark.parametrize("n,f1", [(4, 1), (5, 2), (30, 3), (64, 2), (65, 2), (70, 3), (100, 2), (129, 1)])
+def test_three_parent_tiling_is_consistent(n, f1):
+    """cnb_tiles.h, T tiles: every three-parent family (a < b < c | x) and free value i of a owns one slot in the column
+    tile of x, and the table kernel's decode of that tile puts (virtual node of (a, b, i), c) there"""
+    from catnet_b200 import _abi
+    ntiles = _abi.lib().cnb_tile3_selftest(n, f1)
+    assert ntiles > 0, ntiles
+    if (n, f1) == (100, 2):
+        assert ntiles == 11672             # C3: column tiles [0, 36) and [36, 100)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_entropy_order_host_tail(seed):
+    """cnb_entropy_order's host half (ranks from the entropy matrix, the reference's _order with its holes at tied ranks)
+    against the oracle's order for the same data, fed with the oracle's entropy matrix"""
+    from oracle import port
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(5, 200)), int(rng.integers(2, 9))
+    s = rng.integers(1, 4, size=(m, n)).astype(np.int32)
+    if seed % 2 and n > 2:
+        s[:, 2] = s[:, 1]                                   # tied ranks
+    p = (rng.random((m, n)) < 0.3).astype(np.int32) if seed % 3 == 0 else None
+    ent = port.pairwise("entropy", s, p)                    # [n1][n2] = mat[n2 * N + n1]
+    mat = np.ascontiguousarray(ent.T)
+    out = np.zeros(n, dtype=np.int32)
+    _abi.lib().cnb_host_entropy_order(_abi.ptr(mat), n, _abi.ptr(out))
+    assert out.tolist() == port.pairwise("order", s, p).tolist()
