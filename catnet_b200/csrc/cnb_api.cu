@@ -127,7 +127,11 @@ int cnb_ctx_acquire(int32_t device, cnb_ctx **out) {
 void cnb_ctx_park(cnb_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	cudaStreamSynchronize(c->stream);
+	/* a context whose last call left a CUDA error behind is not worth keeping */
+	if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaPeekAtLastError() != cudaSuccess) {
+		cnb_ctx_destroy(c);
+		return;
+	}
 	c->stream = c->own_stream;
 	{
 		std::lock_guard<std::mutex> lock(g_pool_mutex);
