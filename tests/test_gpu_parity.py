@@ -684,6 +684,16 @@ def test_network_python_front_end(abi, port):
     assert np.array_equal(search.cnLoglik(fit, data, bysample=True), inf(port.net_loglik("bysample", s0, c, parents, probs)))
     assert np.array_equal(search.cnNodeLoglik(fit, [2, 5], data), inf(port.net_loglik("nodes", s0, c, parents, probs))[[1, 4]])
     assert np.isfinite(search.cnLoglik(fit, data[:, 150:]))        # its own training data: no zero-probability hit
+    # cnSamples from the fitted network: indices, category values, perturbations, NA rate
+    draw = search.cnSamples(fit, 500, seed=3)
+    o, _ = port.net_samples(c, parents, probs, 500, None, 0.0, 3)
+    assert draw.shape == (7, 500) and np.array_equal(draw, o.T)
+    vals = search.cnSamples(fit, 500, as_index=False, seed=3)
+    assert set(np.unique(vals)) <= {5.0, 10.0, 15.0}
+    fixed = np.zeros(7, dtype=np.int32)
+    fixed[2] = 3
+    pert = search.cnSamples(fit, 50, perturbations=fixed, naRate=0.3, seed=4)
+    assert ((pert[2] == 3) | (pert[2] == NA)).all() and (pert == NA).sum() == 50 * int(0.3 * 7)
 
 
 @pytest.mark.parametrize("case", SAMPLES_CASES, ids=lambda c: "seed%d" % c["seed"])
