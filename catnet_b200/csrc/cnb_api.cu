@@ -384,6 +384,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->no_ie3 = (on & 512) != 0;                           /* bit 9: no inclusion-exclusion for three-parent families */
 	c->no_tensor3 = (on & 1024) != 0;                      /* bit 10: three-parent families never on the tensor cores */
 	c->dp_no_trap = (on & 2048) != 0;                      /* bit 11: wavefront DP one node per exchange (k_dp_wave) */
+	c->generic_epilogue = (on & 4096) != 0;                /* bit 12: generic epilogue of the tensor-core scorer also for 4-category data */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -690,6 +691,8 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			/* tiles are dealt round-robin (tile t -> rank t % world): every rank gets the same mix of full and
 			 * diagonal tiles; t0..t1 are LOCAL tile indices */
 			long long t0 = 0, t1 = (g.ntiles - pl.rank + pl.world - 1) / pl.world;
+			bool uni4 = true;                                   /* every node with exactly 4 categories: specialised epilogue */
+			for (int v : pl.cats) uni4 = uni4 && v == 4;
 			const long long batch = 16384, slot_bytes = CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
 			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
 			int nb = 0;
@@ -700,7 +703,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 						!c->tensor_i8, D.tiles, tb, te, (int *)c->b_counts.ptr));
 				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb + 1], st));
 				RC(cnbk_umma_epilogue(st, D, tb, te, (const int *)c->b_counts.ptr,
-						(const int *)c->b_pairs.ptr, O));
+						(const int *)c->b_pairs.ptr, O, uni4 && !c->generic_epilogue));
 				c->timing.kernel_launches += 2;
 			}
 			c->timing.tensor_tiles += t1 - t0;

@@ -44,6 +44,7 @@ struct cnb_ctx {
 	bool no_tensor3 = false;           /* three-parent families never on the tensor cores (test hook) */
 	int tensor3_tiles = 0;             /* T tiles of the last search (0 = three-parent group not on the tensor cores) */
 	bool no_ie3 = false;               /* three-parent families by the direct bit-plane / histogram scorers (test hook) */
+	bool generic_epilogue = false;     /* k_umma_epilogue<false> also when every node has 4 categories (test hook) */
 	bool dp_no_trap = false;           /* k_dp_wave instead of the trapezoid kernel (test hook) */
 	bool has_na = false;               /* the data set has missing values */
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */

@@ -55,7 +55,7 @@ long long cnbk_pair_tiles(int N);
 int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M, int W, uint4 *rows_a, uint4 *rows_b,
 		int *counts, int *pair_tab);   /* multiply-accumulates per MMA column of one tile, padding included */
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
-		const int *pair_tab, const ScoreOut &O);
+		const int *pair_tab, const ScoreOut &O, bool all_four_cats = false);   /* all_four_cats: every node has 4 categories */
 #define CNBK_UMMA_SLOT_INTS 36
 /* three-parent families on the tensor cores: pair-side rows incl. the virtual pair nodes, then cnbk_umma_tables with a
  * CnbTiles of kind 3 and cnbk_umma_epilogue3 per column tile */
