@@ -250,7 +250,12 @@ int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 int cnb_family_scores(cnb_ctx *ctx, int32_t nfam, int32_t num_parents, const int32_t *children,
 		const int32_t *parents, int32_t table_stride, int32_t *counts_out, double *loglik_out,
 		int32_t *ncount_out, int32_t force_generic);
-/* route every search of this context through the generic histogram kernel (1) or let the library choose (0) */
+/* kernel selection of this context for the parity tests (0 = the library chooses).  Bits of `on`: 1 generic histogram
+ * kernel everywhere; 2 direct bit-plane scorer (no inclusion-exclusion); 4 tensor-core scorer whenever applicable, 8
+ * never; 16 u8 operands (kind::i8) instead of E2M1; 32 one DP launch per node; 64 grid-barrier DP; 128 pair tables by
+ * the POPC kernel (set before the samples); 512 no inclusion-exclusion for three parents; 1024 three parents never on
+ * the tensor cores; 2048 wavefront DP with one node per exchange; 4096 generic tensor-core epilogue also for
+ * 4-category data.  Every combination gives the same networks. */
 int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 /* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */
 int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);

@@ -178,6 +178,28 @@ def test_tensor_core_path_multi_tile(abi, n, m, cats, bits, kind):
     assert compare_search(b, a, check_probs=False) == len(a)
 
 
+@pytest.mark.parametrize("n,m,sparse", [(70, 300, False), (130, 9000, False), (66, 40, True)])
+def test_tensor_core_epilogue_four_categories(abi, n, m, sparse):
+    """the epilogue specialised for data whose nodes all have 4 categories == the generic epilogue, also with empty
+    parent configurations and empty cells (few samples)"""
+    s, c = random_problem(7 * n + m, n, m, 4)
+    if sparse:
+        s[:, : n // 2] = np.minimum(s[:, : n // 2], 2)  # categories 3 and 4 declared but never seen
+    kw = dict(max_parent_set=2, max_complexity=n * 20, want_probs=False)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.force_generic(4 | 4096)
+        a = ctx.search_order(**kw)
+        assert ctx.timing()["tensor_tiles"] > 0
+        ctx.force_generic(4)
+        b = ctx.search_order(**kw)
+        assert ctx.timing()["tensor_tiles"] > 0
+        ctx.force_generic(8)
+        d = ctx.search_order(**kw)
+    assert compare_search(b, a, check_probs=False) == len(a)
+    assert compare_search(b, d, check_probs=False) == len(d)
+
+
 @pytest.mark.parametrize("seed", range(200, 230))
 def test_search_order_random_vs_oracle(abi, port, seed):
     rng = np.random.default_rng(seed)
