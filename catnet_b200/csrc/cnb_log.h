@@ -59,8 +59,36 @@ static inline double cnb_asf64_(uint64_t u) { double x; memcpy(&x, &u, 8); retur
 #define CNB_ASF64(u) cnb_asf64_(u)
 #endif
 
+/* the table path of the algorithm for the bits ix of a NORMAL x outside [1 - 2^-4, 1 + 0x1.09p-4): branch-free, so
+ * several of them can be interleaved (cnb_umma.cu evaluates the four terms of a parent configuration side by side) */
+CNB_HD double cnb_log_far(uint64_t ix) {
+	const double *A = CNB_TA;
+	uint64_t tmp = ix - 0x3fe6000000000000ull;
+	int i = (int)((tmp >> 45) & 127);
+	int k = (int)((int64_t)tmp >> 52);
+	uint64_t iz = ix - (tmp & (0xfffull << 52));
+	double invc = CNB_TT[2 * i], logc = CNB_TT[2 * i + 1];
+	double z = CNB_ASF64(iz);
+	double kd = (double)k;
+	double w = CNB_FMA(kd, CNB_LN2HI, logc);
+	double r = CNB_FMA(z, invc, -1.0);
+	double p1 = CNB_FMA(r, A[2], A[1]);
+	double hi = CNB_ADD(r, w);
+	double r2 = CNB_MUL(r, r);
+	double lo = CNB_FMA(kd, CNB_LN2LO, CNB_ADD(CNB_SUB(w, hi), r));
+	double r3 = CNB_MUL(r, r2);
+	double q = CNB_FMA(r, A[4], A[3]);
+	lo = CNB_FMA(r2, A[0], lo);
+	q = CNB_FMA(q, r2, p1);
+	return CNB_ADD(CNB_FMA(r3, q, lo), hi);
+}
+/* true if cnb_log(x) takes the table path without the subnormal rescaling, i.e. equals cnb_log_far(bits of x) */
+CNB_HD bool cnb_log_is_far(uint64_t ix) {
+	return !(ix - 0x3fee000000000000ull < 0x0003090000000000ull) && !((uint32_t)(ix >> 48) - 0x0010u >= 0x7ff0u - 0x0010u);
+}
+
 CNB_HD double cnb_log(double x) {
-	const double *A = CNB_TA, *B = CNB_TB;
+	const double *B = CNB_TB;
 	uint64_t ix = CNB_ASU64(x);
 	/* |x - 1| small: 1 - 2^-4 <= x < 1 + 0x1.09p-4 */
 	if (ix - 0x3fee000000000000ull < 0x0003090000000000ull) {
@@ -86,23 +114,6 @@ CNB_HD double cnb_log(double x) {
 		ix = CNB_ASU64(CNB_MUL(x, 0x1p52));
 		ix -= 52ull << 52;
 	}
-	uint64_t tmp = ix - 0x3fe6000000000000ull;
-	int i = (int)((tmp >> 45) & 127);
-	int k = (int)((int64_t)tmp >> 52);
-	uint64_t iz = ix - (tmp & (0xfffull << 52));
-	double invc = CNB_TT[2 * i], logc = CNB_TT[2 * i + 1];
-	double z = CNB_ASF64(iz);
-	double kd = (double)k;
-	double w = CNB_FMA(kd, CNB_LN2HI, logc);
-	double r = CNB_FMA(z, invc, -1.0);
-	double p1 = CNB_FMA(r, A[2], A[1]);
-	double hi = CNB_ADD(r, w);
-	double r2 = CNB_MUL(r, r);
-	double lo = CNB_FMA(kd, CNB_LN2LO, CNB_ADD(CNB_SUB(w, hi), r));
-	double r3 = CNB_MUL(r, r2);
-	double q = CNB_FMA(r, A[4], A[3]);
-	lo = CNB_FMA(r2, A[0], lo);
-	q = CNB_FMA(q, r2, p1);
-	return CNB_ADD(CNB_FMA(r3, q, lo), hi);
+	return cnb_log_far(ix);
 }
 #endif

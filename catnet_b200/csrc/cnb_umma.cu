@@ -443,8 +443,36 @@ __device__ __forceinline__ void um_pair_table(const int *__restrict__ pt, int u,
 		for (int j = 0; j < 4; j++) t[i * 4 + j] = sw ? r[j * 4 + i] : r[i * 4 + j];
 }
 
-/* one term n * log(n * pp) of the family log-likelihood; a call, not 64 inlined copies of the log (150 KB of code) */
-__device__ __noinline__ double um_term(double dn, double pp) { return __dmul_rn(dn, cnb_log(__dmul_rn(dn, pp))); }
+/* the terms n * log(n * pp), pp = 1 / N_k, of one parent configuration added to ll in the reference's order (child
+ * categories ascending, empty cells skipped; problist.h:236-247).  A call, not 16 inlined copies (150 KB of code with
+ * the logs).  The four logs are independent -- only the additions are ordered -- so when all of them take the
+ * branch-free table path of glibc's algorithm (cnb_log_far: every ratio outside [0.9375, 1.065)) they are evaluated
+ * side by side, four dependency chains deep instead of one. */
+__device__ __noinline__ double um_config_terms(double ll, int n0, int n1, int n2, int n3, long long nk) {
+	const double pp = __ddiv_rn(1.0, (double)nk);
+	const int nn[4] = {n0, n1, n2, n3};
+	double dn[4], x[4];
+	bool far = true;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		dn[k] = (double)nn[k];
+		x[k] = __dmul_rn(dn[k], pp);
+		far = far && (nn[k] <= 0 || cnb_log_is_far((uint64_t)__double_as_longlong(x[k])));
+	}
+	if (far) {
+		double t[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) t[k] = __dmul_rn(dn[k], cnb_log_far((uint64_t)__double_as_longlong(x[k])));   /* empty cell: unused */
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (nn[k] > 0) ll = __dadd_rn(ll, t[k]);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (nn[k] > 0) ll = __dadd_rn(ll, __dmul_rn(dn[k], cnb_log(x[k])));
+	}
+	return ll;
+}
 
 /* UNI4: every node has exactly 4 categories (C5): all loop bounds and table indices are compile-time constants, the
  * 64-cell table stays in registers (the generic path indexes it dynamically through local memory: 7,185 instructions
@@ -513,14 +541,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 			const long long nk = (long long)n0 + n1 + n2 + n3;
 			if (nk > 0) {
 				ncount += nk;
-				const double pp = __ddiv_rn(1.0, (double)nk);
-				const int nn[4] = {n0, n1, n2, n3};
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					if (nn[k] > 0) {
-						const double dn = (double)nn[k];
-						ll = __dadd_rn(ll, um_term(dn, pp));
-					}
+				ll = um_config_terms(ll, n0, n1, n2, n3, nk);
 			}
 		}
 		if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
