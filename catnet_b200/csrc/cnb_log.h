@@ -7,7 +7,7 @@
  * sysdeps/ieee754/dbl-64/e_log.c (ARM optimized-routines log, N = 128 table, order-5 polynomial, order-11 near 1),
  * in the operation order and with the FMA contractions of the ifunc-selected FMA build, using glibc's own table
  * (cnb_log_data.h, extracted by tools/extract_libm_log.py).  Every operation below is a single IEEE-754 fp64
- * add/mul/fma, so CUDA and x86 agree bit for bit.  tests/test_exact_log.py checks it against libm.
+ * add/mul/fma, so CUDA and x86 agree bit for bit.  tests/test_abi.py::test_host_log_is_libm_log and tests/test_gpu_parity.py::test_device_log_is_glibc_log check it against libm.
  *
  * Domain: finite x > 0 (normal or subnormal).  The hot path only ever passes n/N in (0, 1] and positive priors.
  */
