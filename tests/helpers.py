@@ -99,3 +99,29 @@ def check_network_case(impl, case, build, g, zero_based=True):
     assert np.array_equal(impl.net_loglik("node", s0, cats, parents, used), unhex(g["node"]))
     if "bysample" in g:
         assert np.array_equal(impl.net_loglik("bysample", s0, cats, parents, used, pert), unhex(g["bysample"]))
+
+
+def constrained_problem(seed):
+    """a small seeded search problem with everything the R front-end can pass (parent pools, fixed parents, per-node
+    parent-set sizes, perturbations, edge priors, 1..3 parents, a tight or loose complexity limit):
+    -> samples, max_parent_set, max_complexity, keyword arguments of oracle.ref / oracle.port search_order"""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 9)), int(rng.integers(2, 150))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4, None][seed % 5], na_frac=[0.0, 0.15, 0.0][seed % 3])
+    P = 1 + seed % 3
+    kw = dict(num_cats=c, order=(rng.permutation(n) + 1).astype(np.int32))
+    if seed % 2 == 0:
+        kw["parents_pool"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, n), replace=False)
+                               if v != i + 1] for i in range(n)]
+    if seed % 3 == 1:
+        kw["fixed_parents"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, 2), replace=False)
+                                if v != i + 1] for i in range(n)]
+    if seed % 4 == 1:
+        kw["parent_sizes"] = rng.integers(0, P + 1, size=n).astype(np.int32)
+    if seed % 4 == 2:
+        kw["perturbations"] = (rng.random(s.shape) < 0.25).astype(np.int32)
+    if seed % 5 == 3:
+        kw["edge_prob"] = 0.05 + 0.9 * rng.random((n, n))
+    lo = int(np.sum(c - 1))
+    K = int(rng.integers(lo, lo + n * int(c.max()) ** P * 2 + 1))
+    return s, P, K, kw

@@ -15,7 +15,8 @@ import pytest
 
 from cases import (CASES, SA_CASES, build_case, ref_args, HIST_CASES, build_hist_case, PAIRWISE_CASES, build_pairwise_case,
                    NETWORK_CASES, build_network_case, SAMPLES_CASES, build_samples_case)
-from helpers import NA, check_network_case, compare_golden, compare_search, load_golden, random_problem, unhex
+from helpers import (NA, check_network_case, compare_golden, compare_search, constrained_problem, load_golden,
+                     random_problem, unhex)
 
 pytestmark = pytest.mark.gpu
 
@@ -198,6 +199,16 @@ def test_tensor_core_epilogue_four_categories(abi, n, m, sparse):
         d = ctx.search_order(**kw)
     assert compare_search(b, a, check_probs=False) == len(a)
     assert compare_search(b, d, check_probs=False) == len(d)
+
+
+@pytest.mark.parametrize("seed", range(700, 740))
+def test_search_order_constraints_vs_oracle(abi, port, seed):
+    """parent pools, fixed parents, per-node parent-set sizes, perturbations, priors, 1..3 parents, tight complexity
+    limits -- the problems tests/test_oracle.py pins the restatement on against the compiled reference"""
+    s, P, K, kw = constrained_problem(seed)
+    ours = abi.search_order(s, max_parent_set=P, max_complexity=K, **kw)
+    theirs = port.search_order(s, P, K, **kw)
+    assert len(ours) == len(theirs) and compare_search(ours, theirs) == len(theirs)
 
 
 @pytest.mark.parametrize("seed", range(200, 230))

@@ -9,7 +9,7 @@ import pytest
 
 from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, SAMPLES_CASES, build_case, build_hist_case,
                    build_network_case, build_pairwise_case, build_samples_case, ref_args)
-from helpers import check_network_case, compare_golden, compare_search, load_golden, random_problem
+from helpers import check_network_case, compare_golden, compare_search, constrained_problem, load_golden, random_problem
 from oracle import port
 
 
@@ -83,6 +83,16 @@ def test_port_matches_reference_core(ref, seed):
     a = ref.search_order(s, 2, K, order=order, **kw)
     b = port.search_order(s, 2, K, order=order, **kw)
     assert compare_search(b, a) == len(a)
+
+
+@pytest.mark.parametrize("seed", range(700, 740))
+def test_port_matches_reference_core_constraints(ref, seed):
+    """the restatement against the compiled reference with everything the R front-end can pass: parent pools, fixed
+    parents, per-node parent-set sizes, 1..3 parents, tight and loose complexity limits, the reference's cache on/off"""
+    s, P, K, kw = constrained_problem(seed)
+    a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
+    b = port.search_order(s, P, K, **kw)
+    assert len(a) == len(b) and compare_search(b, a) == len(a)
 
 
 def test_port_sa_matches_reference_core(ref):
