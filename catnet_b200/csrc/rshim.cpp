@@ -11,8 +11,9 @@
  * SEXP <-> C ABI only: all computation happens behind include/catnet_b200.h.  R API calls (coercion, allocation,
  * Rf_error) stay on the calling thread; nothing longjmps while library resources are held.
  *
- * This file needs R's headers.  It is NOT part of libcatnet_b200.so; the image used to develop it has no R, so it
- * is only syntax-checked there against tests/rstub (tests/test_rshim.py).
+ * This file needs R's headers.  It is NOT part of libcatnet_b200.so; the image used to develop it has no R, so there
+ * it is compiled against tests/rstub and run against the miniature R API of tests/rstub/minir.cpp
+ * (tests/test_rshim.py on the CPU with the C ABI answered by the oracle, tests/test_zz_rshim_gpu.py over the library).
  */
 #include <R.h>
 #include <Rinternals.h>

@@ -1,5 +1,7 @@
-/* tests/rstub -- declarations-only stand-in for R's C API, just enough to SYNTAX-CHECK catnet_b200/csrc/rshim.cpp in
- * an image without R (tests/test_rshim.py runs g++ -fsyntax-only).  Nothing here is ever linked or executed. */
+/* tests/rstub -- stand-in for R's C API, just enough for catnet_b200/csrc/rshim.cpp in an image without R:
+ * tests/test_rshim.py syntax-checks the shim against these declarations and RUNS it against their miniature
+ * implementation in minir.cpp (values, coercion, attributes, S4 slots, Rf_error as a C++ exception).  Test
+ * infrastructure only. */
 #ifndef CNB_RSTUB_RINTERNALS_H
 #define CNB_RSTUB_RINTERNALS_H
 #include <stddef.h>

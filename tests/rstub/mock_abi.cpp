@@ -1,0 +1,141 @@
+/* tests/rstub/mock_abi.cpp -- the C ABI of include/catnet_b200.h answered by the ORACLE (oracle/catnet_oracle.c)
+ * instead of the GPU library, for the CPU test of the R shim (tests/test_rshim.py): with it, rshim.cpp + minir.cpp run
+ * end to end in an image with neither R nor a GPU, and the S4 objects the shim builds can be compared with the
+ * oracle's own answer.  Test infrastructure only: nothing in the product links this file.  On a GPU box the same test
+ * links the shim against the real libcatnet_b200.so instead.
+ *
+ * Implemented: cnb_search_order + the result accessors the shim reads, cnb_pairwise, cnb_entropy_order,
+ * cnb_set_seed, cnb_release_cache, cnb_last_error.  The other entry points the shim references return CNB_ERR_PARAM
+ * ("not in the mock"). */
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/catnet_b200.h"
+extern "C" {
+#include "../../oracle/catnet_oracle.h"
+}
+
+struct cnb_result {
+	orc_result *h = NULL;
+	int N = 0;
+	std::vector<int> slots;                /* oracle slots that hold a network, ascending complexity */
+	std::vector<int32_t> order, cats_pos;  /* position -> 1-based label; categories per position */
+};
+
+static std::string g_err;
+static int g_released = 0, g_seed = 0;
+
+extern "C" {
+
+const char *cnb_last_error(void) { return g_err.c_str(); }
+const char *cnb_version(void) { return "mock (oracle-backed)"; }
+void cnb_release_cache(void) { g_released++; }
+void cnb_set_seed(int32_t seed) { g_seed = seed; }
+int mock_released(void) { return g_released; }
+int mock_seed(void) { return g_seed; }
+
+int cnb_search_order(const cnb_params *p, cnb_result **out) {
+	const int N = p->num_nodes, M = p->num_samples;
+	std::vector<int32_t> order(N);
+	for (int i = 0; i < N; i++) order[i] = p->order ? p->order[i] : i + 1;
+	std::vector<int32_t> cats(N);
+	if (p->num_cats) cats.assign(p->num_cats, p->num_cats + N);
+	else {                                 /* inferred like catnet_search2.h:208-235: max - min + 1 over the non-missing values */
+		for (int i = 0; i < N; i++) {
+			int lo = 0x7fffffff, hi = -0x7fffffff;
+			for (int j = 0; j < M; j++) {
+				int v = p->samples[(size_t)j * N + i];
+				if (v < 1) continue;
+				if (v < lo) lo = v;
+				if (v > hi) hi = v;
+			}
+			cats[i] = hi >= lo ? hi - lo + 1 : 1;
+		}
+	}
+	orc_result *h = orc_search_order(N, M, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
+			p->max_complexity, order.data(), p->num_cats, p->parents_pool, p->fixed_parents, p->edge_prob);
+	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
+	cnb_result *r = new cnb_result;
+	r->h = h;
+	r->N = N;
+	r->order = order;
+	r->cats_pos.resize(N);
+	for (int i = 0; i < N; i++) r->cats_pos[i] = cats[order[i] - 1];
+	for (int k = 0; k < orc_result_nslots(h); k++)
+		if (orc_result_exists(h, k)) r->slots.push_back(k);
+	*out = r;
+	return CNB_OK;
+}
+
+int32_t cnb_result_num_networks(const cnb_result *r) { return (int32_t)r->slots.size(); }
+int32_t cnb_result_num_nodes(const cnb_result *r) { return r->N; }
+int cnb_result_network(const cnb_result *r, int32_t i, int32_t *complexity, double *loglik) {
+	int cx;
+	double ll;
+	orc_result_net(r->h, r->slots[i], &cx, &ll);
+	*complexity = cx;
+	*loglik = ll;
+	return CNB_OK;
+}
+int cnb_result_parents(const cnb_result *r, int32_t i, int32_t *num_parents, int32_t *parents, int32_t cap) {
+	for (int n = 0; n < r->N; n++) {
+		int np = 0, pars[64], ss, ps;
+		double ll, pr;
+		orc_result_node(r->h, r->slots[i], n, &np, pars, &ll, &pr, &ss, &ps, NULL, 0);
+		num_parents[n] = np;
+		for (int k = 0; k < np && k < cap; k++) parents[(size_t)n * cap + k] = pars[k];
+	}
+	return CNB_OK;
+}
+int cnb_result_order(const cnb_result *r, int32_t, int32_t *order_out) {
+	memcpy(order_out, r->order.data(), r->N * sizeof(int32_t));
+	return CNB_OK;
+}
+int cnb_result_cats(const cnb_result *r, int32_t, int32_t *cats_out) {
+	memcpy(cats_out, r->cats_pos.data(), r->N * sizeof(int32_t));
+	return CNB_OK;
+}
+int cnb_result_node(const cnb_result *r, int32_t i, int32_t node, double *loglik, double *prior, int32_t *sample_size,
+		double *probs, int32_t cap) {
+	int np = 0, pars[64], ss = 0, ps = 0;
+	std::vector<double> buf(1 << 16);
+	orc_result_node(r->h, r->slots[i], node, &np, pars, loglik, prior, &ss, &ps, buf.data(), (int)buf.size());
+	*sample_size = ss;
+	if (probs)
+		for (int k = 0; k < ps && k < cap; k++) probs[k] = buf[k];
+	return ps;
+}
+void cnb_result_free(cnb_result *r) {
+	if (!r) return;
+	orc_result_free(r->h);
+	delete r;
+}
+
+int cnb_pairwise(int32_t kind, int32_t N, int32_t M, const int32_t *samples, const int32_t *pert, int32_t, double *out) {
+	std::vector<int> order(N);
+	if (orc_pairwise(kind, N, M, samples, pert, out, order.data())) { g_err = "oracle: missing or non-positive category"; return CNB_ERR_PARAM; }
+	return CNB_OK;
+}
+int cnb_entropy_order(int32_t N, int32_t M, const int32_t *samples, const int32_t *pert, int32_t, int32_t *order_out) {
+	std::vector<double> mat((size_t)N * N);
+	if (orc_pairwise(3, N, M, samples, pert, mat.data(), order_out)) { g_err = "oracle: missing or non-positive category"; return CNB_ERR_PARAM; }
+	return CNB_OK;
+}
+
+static int not_in_mock(const char *what) {
+	g_err = std::string(what) + ": not in the mock";
+	return CNB_ERR_PARAM;
+}
+int cnb_search_sa(const cnb_params *, const cnb_sa_params *, cnb_result **) { return not_in_mock("cnb_search_sa"); }
+int cnb_search_hist(const cnb_params *, const cnb_hist_params *, double *, int32_t *) { return not_in_mock("cnb_search_hist"); }
+int cnb_loglik(const cnb_network *, int32_t, const int32_t *, const int32_t *, int32_t, int32_t, double *) { return not_in_mock("cnb_loglik"); }
+int cnb_node_loglik(const cnb_network *, int32_t, const int32_t *, int32_t, const int32_t *, const int32_t *, int32_t, double *) {
+	return not_in_mock("cnb_node_loglik");
+}
+int cnb_set_prob(const cnb_network *, int32_t, const int32_t *, const int32_t *, int32_t, double *, double *, int32_t *) {
+	return not_in_mock("cnb_set_prob");
+}
+int cnb_samples(const cnb_network *, int32_t, const int32_t *, double, uint64_t, int32_t, int32_t *) { return not_in_mock("cnb_samples"); }
+
+} /* extern "C" */

@@ -1,9 +1,17 @@
-"""CPU suite, part 4: the R-facing shim (catnet_b200/csrc/rshim.cpp) cannot be built here (no R in the image), so it
-is syntax-checked against declaration-only stand-ins of R's headers, and its .Call table is compared with the
-reference's registration (names and arity, src/ccnInit.c:29-45)."""
+"""CPU suite, part 4: the R-facing shim (catnet_b200/csrc/rshim.cpp).  The image has no R, so the shim is
+(1) syntax-checked against stand-ins of R's headers (tests/rstub), (2) its .Call table is compared with the reference's
+registration (names and arity, src/ccnInit.c:29-45), and (3) it is RUN against a miniature implementation of the R API
+(tests/rstub/minir.cpp) with the C ABI answered by the oracle (tests/rstub/mock_abi.cpp): the S4 catNetwork objects it
+builds from R-style arguments must be the oracle's networks.  tests/test_zz_rshim_gpu.py runs the same shim over the
+real library on a B200."""
 import os
 import re
 import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import constrained_problem, random_problem
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "catnet_b200", "csrc", "rshim.cpp")
@@ -26,3 +34,76 @@ def test_call_table_matches_reference_registration():
         sig = re.search(r"SEXP %s\(([^)]*)\)" % name, src).group(1)
         nargs = 0 if sig.strip() == "void" else sig.count("SEXP")
         assert nargs == arity, (name, nargs, arity)
+
+
+def check_networks(nets, theirs, order, cats):
+    """nets: catNetwork dicts read back from the shim; theirs: oracle.port.search_order on the same problem"""
+    assert [n["complexity"] for n in nets] == [t["complexity"] for t in theirs]
+    cats_pos = [int(cats[o - 1]) for o in order]
+    for a, b in zip(nets, theirs):
+        assert a["parents"] == b["parents"] and a["loglik"] == b["loglik"] and a["sample_sizes"] == b["sample_sizes"]
+        assert a["nodes"] == ["N%d" % o for o in order]
+        assert [len(c) for c in a["categories"]] == cats_pos and a["maxCategories"] == max(cats_pos)
+        assert a["maxParents"] == max(len(p) for p in a["parents"])
+        for x, y in zip(a["probs"], b["probs"]):
+            assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("seed", range(700, 724))
+def test_shim_runs_against_mini_r(seed):
+    from oracle import port
+    from rshim_harness import R, optimal_nets_for_order
+    s, P, K, kw = constrained_problem(seed)
+    r = R("mock")
+    nets = optimal_nets_for_order(r, s, P, K, real_args=bool(seed % 2), **kw)
+    theirs = port.search_order(s, P, K, **kw)
+    assert len(theirs) > 0
+    check_networks(nets, theirs, kw["order"], kw["num_cats"])
+    assert r.warnings() == ""
+
+
+def test_shim_argument_handling():
+    from oracle import port
+    from rshim_harness import R, RError, optimal_nets_for_order
+    s, c = random_problem(3, 6, 80, 3)
+    r = R("mock")
+    # data that is not a matrix -> R error with the reference's message (rcatnet_search.cpp:69-70)
+    with pytest.raises(RError, match="Data is not a matrix"):
+        r.call("ccnOptimalNetsForOrder", r.integer(s), *([r.NULL] * 11))
+    # a short nodeOrder -> warning + default order (rcatnet_search.cpp:112-116); no catIndices -> inferred categories
+    nets = optimal_nets_for_order(r, s, 2, 60, order=[1, 2, 3])
+    assert "Invalid nodeOrder" in r.warnings()
+    check_networks(nets, port.search_order(s, 2, 60), list(range(1, 7)), c)
+    # wrong arity and unknown routines never reach the shim
+    with pytest.raises(RError, match="wrong number of arguments"):
+        r.call("ccnOptimalNetsForOrder", r.NULL)
+    with pytest.raises(RError, match="no such routine"):
+        r.call("ccnMarginalProb", r.NULL)
+    # an ABI error becomes an R error carrying the library's message
+    with pytest.raises(RError, match="not in the mock"):
+        r.call("ccnParHistogram", r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([60]), r.NULL, r.NULL, r.NULL,
+               r.string("BIC"), r.integer([1]), r.integer([4]), r.integer([2]), r.logical(True), r.logical(False))
+    with pytest.raises(RError, match="cnet should be a catNetwork"):
+        r.call("ccnSamples", r.NULL, r.integer([5]), r.NULL, r.numeric([0.0]))
+    # ccnSetSeed / ccnReleaseCache
+    r.call("ccnSetSeed", r.integer([77]))
+    assert r.L.mock_seed() == 77
+    assert r.is_null(r.call("ccnReleaseCache"))
+
+
+@pytest.mark.parametrize("kind,routine", [("entropy", "ccnEntropyPairwise"), ("kl", "ccnKLPairwise"),
+                                          ("pearson", "ccnPearsonPairwise")])
+def test_shim_pairwise(kind, routine):
+    from oracle import port
+    from rshim_harness import R, RError
+    s, c = random_problem(11, 7, 120, None)
+    pert = (np.random.default_rng(1).random(s.shape) < 0.2).astype(np.int32)
+    r = R("mock")
+    for p in (None, pert):
+        out = r.call(routine, r.data_matrix(s, real=True), r.NULL if p is None else r.data_matrix(p))
+        mat = r.reals(out).reshape(7, 7).T          # R: matrix(mat, numnodes, numnodes), column-major
+        assert np.array_equal(mat, port.pairwise(kind, s, p))
+    order = r.ints(r.call("ccnEntropyOrder", r.data_matrix(s), r.NULL))
+    assert order == [int(v) for v in port.pairwise("order", s)]
+    with pytest.raises(RError, match="Data should be a matrix"):
+        r.call(routine, r.integer(s), r.NULL)
