@@ -28,7 +28,8 @@ def lib(backend):
                                 ("mr_chars", C.c_char_p, [vp]), ("mr_ints", C.POINTER(C.c_int), [vp]),
                                 ("mr_reals", C.POINTER(C.c_double), [vp]), ("mr_slot", vp, [vp, C.c_char_p]),
                                 ("mr_last_error", C.c_char_p, []), ("mr_warnings", C.c_char_p, []), ("mr_clear", None, []),
-                                ("mr_set_rng", None, [C.c_ulonglong]), ("mr_call", vp, [C.c_char_p, C.POINTER(vp), C.c_int])]:
+                                ("mr_set_rng", None, [C.c_ulonglong]), ("mr_new_s4", vp, [C.c_char_p]),
+                                ("mr_set_slot", None, [vp, C.c_char_p, vp]), ("mr_category_names", vp, [C.c_int]), ("mr_call", vp, [C.c_char_p, C.POINTER(vp), C.c_int])]:
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
         _libs[backend] = L
@@ -76,6 +77,35 @@ class R:
 
     def int_lists(self, lists):
         return self.NULL if lists is None else self.list([self.integer(v) for v in lists])
+
+    def nested_probs(self, flat, parent_cats, cc):
+        """flat table (first listed parent most significant, child fastest) -> R's nested lists of numeric vectors"""
+        flat = np.asarray(flat, dtype=np.float64)
+        if not parent_cats:
+            return self.numeric(flat[:cc])
+        step = len(flat) // parent_cats[0]
+        return self.list([self.nested_probs(flat[j * step:(j + 1) * step], parent_cats[1:], cc) for j in range(parent_cats[0])])
+
+    def new_catnetwork(self, cats, parents, probs=None):
+        """S4 catNetwork with the slots RCatnet::RCatnet(SEXP) reads; parents: lists of 0-based nodes in listed order"""
+        n = len(cats)
+        obj = self.L.mr_new_s4(b"catNetwork")
+        self.L.mr_set_slot(obj, b"numnodes", self.integer([n]))
+        self.L.mr_set_slot(obj, b"nodes", self.L.mr_category_names(n))
+        self.L.mr_set_slot(obj, b"parents", self.list([self.integer([q + 1 for q in p]) if len(p) else self.NULL for p in parents]))
+        self.L.mr_set_slot(obj, b"categories", self.list([self.L.mr_category_names(int(c)) for c in cats]))
+        self.L.mr_set_slot(obj, b"maxParents", self.integer([max([len(p) for p in parents] + [0])]))
+        self.L.mr_set_slot(obj, b"maxCategories", self.integer([int(max(cats))]))
+        self.L.mr_set_slot(obj, b"complexity", self.integer([int(sum(
+            (int(cats[i]) - 1) * int(np.prod([cats[q] for q in parents[i]], dtype=np.int64)) for i in range(n)))]))
+        self.L.mr_set_slot(obj, b"likelihood", self.numeric([0.0]))
+        self.L.mr_set_slot(obj, b"nodeSampleSizes", self.integer([0] * n))
+        if probs is None:
+            probs = [np.full(int(cats[i]) * int(np.prod([cats[q] for q in parents[i]], dtype=np.int64)), 1.0 / cats[i])
+                     for i in range(n)]
+        self.L.mr_set_slot(obj, b"probabilities", self.list([
+            self.nested_probs(probs[i], [int(cats[q]) for q in parents[i]], int(cats[i])) for i in range(n)]))
+        return obj
 
     def call(self, name, *args):
         self.L.mr_clear()
@@ -149,3 +179,13 @@ def optimal_nets_for_order(r, samples, max_parent_set, max_complexity, order=Non
     if r.is_null(out):
         return []
     return [r.catnetwork(e) for e in r.elts(out)]
+
+
+def mini_r_uniform(state):
+    """the miniature R's unif_rand (splitmix64, tests/rstub/minir.cpp) after mr_set_rng(state): first draw"""
+    mask = (1 << 64) - 1
+    z = (state + 0x9e3779b97f4a7c15) & mask
+    z = ((z ^ (z >> 30)) * 0xbf58476d1ce4e5b9) & mask
+    z = ((z ^ (z >> 27)) * 0x94d049bb133111eb) & mask
+    z ^= z >> 31
+    return (z >> 11) * (1.0 / 9007199254740992.0)

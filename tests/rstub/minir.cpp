@@ -212,6 +212,14 @@ SEXP mr_set_dim(SEXP s, int nrow, int ncol) {
 	s->attrs["dim"] = d;
 	return s;
 }
+SEXP mr_new_s4(const char *cls) { return R_do_new_object(R_do_MAKE_CLASS(cls)); }
+void mr_set_slot(SEXP obj, const char *name, SEXP v) { obj->attrs[name] = v; }
+/* c("1", ..., "n") */
+SEXP mr_category_names(int n) {
+	SEXP v = Rf_allocVector(STRSXP, n);
+	for (int k = 0; k < n; k++) v->elts[k] = Rf_mkChar(std::to_string(k + 1).c_str());
+	return v;
+}
 int mr_type(SEXP s) { return s->type; }
 int mr_length(SEXP s) { return Rf_length(s); }
 SEXP mr_elt(SEXP s, int i) { return s->elts.at(i); }

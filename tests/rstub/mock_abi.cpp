@@ -4,9 +4,9 @@
  * oracle's own answer.  Test infrastructure only: nothing in the product links this file.  On a GPU box the same test
  * links the shim against the real libcatnet_b200.so instead.
  *
- * Implemented: cnb_search_order + the result accessors the shim reads, cnb_pairwise, cnb_entropy_order,
- * cnb_set_seed, cnb_release_cache, cnb_last_error.  The other entry points the shim references return CNB_ERR_PARAM
- * ("not in the mock"). */
+ * Implemented: cnb_search_order + the result accessors the shim reads, cnb_pairwise, cnb_entropy_order, cnb_loglik,
+ * cnb_node_loglik, cnb_set_prob, cnb_samples, cnb_set_seed, cnb_release_cache, cnb_last_error.  cnb_search_sa and
+ * cnb_search_hist return CNB_ERR_PARAM ("not in the mock"). */
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -129,13 +129,53 @@ static int not_in_mock(const char *what) {
 }
 int cnb_search_sa(const cnb_params *, const cnb_sa_params *, cnb_result **) { return not_in_mock("cnb_search_sa"); }
 int cnb_search_hist(const cnb_params *, const cnb_hist_params *, double *, int32_t *) { return not_in_mock("cnb_search_hist"); }
-int cnb_loglik(const cnb_network *, int32_t, const int32_t *, const int32_t *, int32_t, int32_t, double *) { return not_in_mock("cnb_loglik"); }
-int cnb_node_loglik(const cnb_network *, int32_t, const int32_t *, int32_t, const int32_t *, const int32_t *, int32_t, double *) {
-	return not_in_mock("cnb_node_loglik");
+/* cnb_network + 1-based samples (values < 1 = missing) -> the oracle's zero-based forms */
+struct MockNet {
+	std::vector<int> s0, pars0, cats, npar;
+	std::vector<long long> off;
+	int N, maxp;
+	MockNet(const cnb_network *net, int M, const int32_t *samples) : N(net->num_nodes), maxp(net->max_parents) {
+		cats.assign(net->num_cats, net->num_cats + N);
+		npar.assign(net->num_parents, net->num_parents + N);
+		pars0.assign((size_t)N * maxp, 0);
+		for (int i = 0; i < N; i++)
+			for (int k = 0; k < npar[i]; k++) pars0[(size_t)i * maxp + k] = net->parents[(size_t)i * maxp + k] - 1;
+		off.assign(net->prob_offsets, net->prob_offsets + N + 1);
+		if (samples) {
+			s0.resize((size_t)M * N);
+			for (size_t j = 0; j < s0.size(); j++) s0[j] = samples[j] < 1 ? 99 : samples[j] - 1;
+		}
+	}
+};
+int cnb_loglik(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert, int32_t mode, int32_t, double *out) {
+	MockNet m(net, M, samples);
+	return orc_net_loglik(m.N, M, m.s0.data(), pert, m.cats.data(), m.maxp, m.npar.data(), m.pars0.data(), net->probs,
+			m.off.data(), mode == CNB_LOGLIK_BYSAMPLE ? 1 : 0, out) ? not_in_mock("orc_net_loglik failed") : CNB_OK;
 }
-int cnb_set_prob(const cnb_network *, int32_t, const int32_t *, const int32_t *, int32_t, double *, double *, int32_t *) {
-	return not_in_mock("cnb_set_prob");
+int cnb_node_loglik(const cnb_network *net, int32_t nsel, const int32_t *nodes, int32_t M, const int32_t *samples,
+		const int32_t *pert, int32_t, double *out) {
+	MockNet m(net, M, samples);
+	std::vector<double> all(m.N);
+	if (orc_net_loglik(m.N, M, m.s0.data(), pert, m.cats.data(), m.maxp, m.npar.data(), m.pars0.data(), net->probs,
+			m.off.data(), 0, all.data())) return not_in_mock("orc_net_loglik failed");
+	for (int k = 0; k < nsel; k++) {
+		if (nodes[k] < 1 || nodes[k] > m.N) { g_err = "invalid node"; return CNB_ERR_PARAM; }
+		out[k] = all[nodes[k] - 1];
+	}
+	return CNB_OK;
 }
-int cnb_samples(const cnb_network *, int32_t, const int32_t *, double, uint64_t, int32_t, int32_t *) { return not_in_mock("cnb_samples"); }
+int cnb_set_prob(const cnb_network *net, int32_t M, const int32_t *samples, const int32_t *pert, int32_t, double *probs_out,
+		double *loglik_out, int32_t *sizes_out) {
+	MockNet m(net, M, samples);
+	return orc_net_set_prob(m.N, M, m.s0.data(), pert, m.cats.data(), m.maxp, m.npar.data(), m.pars0.data(), m.off.data(),
+			probs_out, loglik_out, sizes_out) ? not_in_mock("orc_net_set_prob failed") : CNB_OK;
+}
+int cnb_samples(const cnb_network *net, int32_t M, const int32_t *pert, double na_rate, uint64_t seed, int32_t, int32_t *out) {
+	MockNet m(net, 0, NULL);
+	long calls = orc_net_samples(m.N, m.cats.data(), m.maxp, m.npar.data(), m.pars0.data(), net->probs, m.off.data(), M, pert,
+			na_rate, seed, out);
+	if (calls < 0) { g_err = "cyclic network"; return CNB_ERR_PARAM; }
+	return CNB_OK;
+}
 
 } /* extern "C" */

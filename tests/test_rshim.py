@@ -107,3 +107,66 @@ def test_shim_pairwise(kind, routine):
     assert order == [int(v) for v in port.pairwise("order", s)]
     with pytest.raises(RError, match="Data should be a matrix"):
         r.call(routine, r.integer(s), r.NULL)
+
+
+def network_problem(seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(2, 9)), int(rng.integers(5, 200))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4][seed % 4], na_frac=[0.0, 0.1][seed % 2])
+    parents = [sorted(rng.choice(i, size=min(i, int(rng.integers(0, 4))), replace=False).tolist(), reverse=seed % 3 == 0)
+               for i in range(n)]
+    pert = (rng.random(s.shape) < 0.3).astype(np.int32) if seed % 3 == 1 else None
+    return s, c, parents, pert
+
+
+def check_given_network_calls(r, port, seed):
+    """ccnSetProb -> ccnLoglik (per node / by sample) -> ccnNodeLoglik -> ccnSamples on one seeded network"""
+    from rshim_harness import mini_r_uniform
+    s, c, parents, pert = network_problem(seed)
+    n = len(c)
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    data = r.data_matrix(s)
+    rp = r.NULL if pert is None else r.data_matrix(pert)
+    fitted = r.call("ccnSetProb", r.new_catnetwork(c, parents), data, rp)
+    net = r.catnetwork(fitted)
+    probs, ll, sizes = port.net_set_prob(s0, c, parents, pert)
+    assert net["parents"] == [list(p) for p in parents] and net["sample_sizes"] == [int(v) for v in sizes]
+    assert all(np.array_equal(a, b) for a, b in zip(net["probs"], probs))
+    total = 0.0
+    for v in ll:
+        total += float(v)
+    assert net["loglik"] == (total if np.all(ll > -3.4e38) else -np.inf)
+    nodes = port.net_loglik("nodes", s0, c, parents, probs, pert)
+    expect = np.where(nodes > -3.4e38, nodes, -np.inf)
+    assert np.array_equal(r.reals(r.call("ccnLoglik", fitted, data, rp, r.logical(False))), expect)
+    by = port.net_loglik("bysample", s0, c, parents, probs, pert)
+    assert np.array_equal(r.reals(r.call("ccnLoglik", fitted, data, rp, r.logical(True))), np.where(by > -3.4e38, by, -np.inf))
+    sel = [n, 1] if n > 1 else [1]
+    assert np.array_equal(r.reals(r.call("ccnNodeLoglik", fitted, r.numeric(sel), data, rp)), expect[np.array(sel) - 1])
+    r.L.mr_set_rng(1000 + seed)
+    drawn = r.ints(r.call("ccnSamples", fitted, r.numeric([57]), r.NULL, r.numeric([0.1 * (seed % 2)])))
+    lib_seed = int(mini_r_uniform(1000 + seed) * 9007199254740992.0)
+    theirs, _ = port.net_samples(c, parents, probs, 57, None, 0.1 * (seed % 2), lib_seed)
+    assert np.array_equal(np.array(drawn, dtype=np.int64).reshape(57, n), theirs.astype(np.int64))
+
+
+@pytest.mark.parametrize("seed", range(800, 816))
+def test_shim_given_network_calls(seed):
+    from oracle import port
+    from rshim_harness import R
+    check_given_network_calls(R("mock"), port, seed)
+
+
+def test_shim_network_argument_errors():
+    from rshim_harness import R, RError
+    s, c, parents, _ = network_problem(801)
+    r = R("mock")
+    obj = r.new_catnetwork(c, parents)
+    with pytest.raises(RError, match="cnet should be a catNetwork"):
+        r.call("ccnLoglik", r.list([]), r.data_matrix(s), r.NULL, r.logical(False))
+    with pytest.raises(RError, match="should be a matrix"):
+        r.call("ccnLoglik", obj, r.integer(s), r.NULL, r.logical(False))
+    with pytest.raises(RError, match="number of nodes"):
+        r.call("ccnSetProb", obj, r.data_matrix(s[:, :-1]), r.NULL)
+    with pytest.raises(RError, match="number of samples"):
+        r.call("ccnSamples", obj, r.numeric([0]), r.NULL, r.numeric([0.0]))

@@ -1,12 +1,12 @@
 """GPU suite, last file: the R shim (catnet_b200/csrc/rshim.cpp) linked against the REAL libcatnet_b200.so and driven
 through the miniature R API of tests/rstub/minir.cpp -- `.Call("ccnOptimalNetsForOrder", ...)` with R-style arguments
-in, S4 catNetwork objects out, compared with the oracle.  (tests/test_rshim.py runs the same shim on the CPU with the
+in, S4 catNetwork objects out, the pairwise metrics and the given-network routines, compared with the oracle.  (tests/test_rshim.py runs the same shim on the CPU with the
 C ABI answered by the oracle.)"""
 import numpy as np
 import pytest
 
 from helpers import constrained_problem, random_problem
-from test_rshim import check_networks
+from test_rshim import check_given_network_calls, check_networks
 
 pytestmark = pytest.mark.gpu
 
@@ -36,3 +36,10 @@ def test_dot_call_pairwise(r):
             out = r.call(routine, r.data_matrix(s, real=True), r.NULL if p is None else r.data_matrix(p))
             assert np.array_equal(r.reals(out).reshape(7, 7).T, port.pairwise(kind, s, p))
     assert r.ints(r.call("ccnEntropyOrder", r.data_matrix(s), r.NULL)) == [int(v) for v in port.pairwise("order", s)]
+
+
+@pytest.mark.parametrize("seed", range(800, 808))
+def test_dot_call_given_network(r, seed):
+    """ccnSetProb -> ccnLoglik -> ccnNodeLoglik -> ccnSamples over the library, against the oracle"""
+    from oracle import port
+    check_given_network_calls(r, port, seed)
