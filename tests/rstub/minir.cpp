@@ -220,6 +220,7 @@ SEXP mr_category_names(int n) {
 	for (int k = 0; k < n; k++) v->elts[k] = Rf_mkChar(std::to_string(k + 1).c_str());
 	return v;
 }
+void mr_set_string(SEXP v, int i, const char *s) { SET_STRING_ELT(v, i, Rf_mkChar(s)); }
 int mr_type(SEXP s) { return s->type; }
 int mr_length(SEXP s) { return Rf_length(s); }
 SEXP mr_elt(SEXP s, int i) { return s->elts.at(i); }

@@ -5,8 +5,8 @@
  * links the shim against the real libcatnet_b200.so instead.
  *
  * Implemented: cnb_search_order + the result accessors the shim reads, cnb_pairwise, cnb_entropy_order, cnb_loglik,
- * cnb_node_loglik, cnb_set_prob, cnb_samples, cnb_set_seed, cnb_release_cache, cnb_last_error.  cnb_search_sa and
- * cnb_search_hist return CNB_ERR_PARAM ("not in the mock"). */
+ * cnb_node_loglik, cnb_set_prob, cnb_samples, cnb_search_sa (without dirProb), cnb_search_hist, cnb_set_seed,
+ * cnb_release_cache, cnb_last_error. */
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -35,24 +35,34 @@ void cnb_set_seed(int32_t seed) { g_seed = seed; }
 int mock_released(void) { return g_released; }
 int mock_seed(void) { return g_seed; }
 
+static int not_in_mock(const char *what) {
+	g_err = std::string(what) + ": not in the mock";
+	return CNB_ERR_PARAM;
+}
+
+/* categories per node: given, or inferred like catnet_search2.h:208-235 (max - min + 1 over the non-missing values) */
+static std::vector<int32_t> mock_cats(const cnb_params *p) {
+	const int N = p->num_nodes, M = p->num_samples;
+	std::vector<int32_t> cats(N);
+	if (p->num_cats) { cats.assign(p->num_cats, p->num_cats + N); return cats; }
+	for (int i = 0; i < N; i++) {
+		int lo = 0x7fffffff, hi = -0x7fffffff;
+		for (int j = 0; j < M; j++) {
+			int v = p->samples[(size_t)j * N + i];
+			if (v < 1) continue;
+			if (v < lo) lo = v;
+			if (v > hi) hi = v;
+		}
+		cats[i] = hi >= lo ? hi - lo + 1 : 1;
+	}
+	return cats;
+}
+
 int cnb_search_order(const cnb_params *p, cnb_result **out) {
 	const int N = p->num_nodes, M = p->num_samples;
 	std::vector<int32_t> order(N);
 	for (int i = 0; i < N; i++) order[i] = p->order ? p->order[i] : i + 1;
-	std::vector<int32_t> cats(N);
-	if (p->num_cats) cats.assign(p->num_cats, p->num_cats + N);
-	else {                                 /* inferred like catnet_search2.h:208-235: max - min + 1 over the non-missing values */
-		for (int i = 0; i < N; i++) {
-			int lo = 0x7fffffff, hi = -0x7fffffff;
-			for (int j = 0; j < M; j++) {
-				int v = p->samples[(size_t)j * N + i];
-				if (v < 1) continue;
-				if (v < lo) lo = v;
-				if (v > hi) hi = v;
-			}
-			cats[i] = hi >= lo ? hi - lo + 1 : 1;
-		}
-	}
+	std::vector<int32_t> cats = mock_cats(p);
 	orc_result *h = orc_search_order(N, M, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
 			p->max_complexity, order.data(), p->num_cats, p->parents_pool, p->fixed_parents, p->edge_prob);
 	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
@@ -123,12 +133,40 @@ int cnb_entropy_order(int32_t N, int32_t M, const int32_t *samples, const int32_
 	return CNB_OK;
 }
 
-static int not_in_mock(const char *what) {
-	g_err = std::string(what) + ": not in the mock";
-	return CNB_ERR_PARAM;
+/* one chain; the returned networks are those of the accepted order (rcatnet_sa.cpp:873-905) */
+int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out) {
+	const int N = p->num_nodes;
+	if (sa->dir_prob) return not_in_mock("cnb_search_sa with dirProb");
+	orc_set_seed(sa->seed);
+	orc_result *h = orc_search_sa(N, p->num_samples, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
+			p->max_complexity, p->num_cats, p->parents_pool, p->fixed_parents, p->edge_prob, sa->select_mode, sa->start_order,
+			sa->temp_start, sa->temp_cool_fact, sa->temp_check_orders, sa->max_iter, sa->order_shuffles, sa->stop_diff,
+			sa->num_threads);
+	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
+	cnb_result *r = new cnb_result;
+	r->h = h;
+	r->N = N;
+	r->order.resize(N);
+	int niter, naccept;
+	std::vector<int> ord(N);
+	orc_result_sa_info(h, ord.data(), &niter, &naccept);
+	std::vector<int32_t> cats = mock_cats(p);
+	r->cats_pos.resize(N);
+	for (int i = 0; i < N; i++) { r->order[i] = ord[i]; r->cats_pos[i] = cats[ord[i] - 1]; }
+	for (int k = 0; k < orc_result_nslots(h); k++)
+		if (orc_result_exists(h, k)) r->slots.push_back(k);
+	*out = r;
+	return CNB_OK;
 }
-int cnb_search_sa(const cnb_params *, const cnb_sa_params *, cnb_result **) { return not_in_mock("cnb_search_sa"); }
-int cnb_search_hist(const cnb_params *, const cnb_hist_params *, double *, int32_t *) { return not_in_mock("cnb_search_hist"); }
+int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations) {
+	orc_set_seed(hp->seed);
+	int it = orc_search_hist(p->num_nodes, p->num_samples, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
+			p->max_complexity, p->num_cats, p->parents_pool, p->fixed_parents, hp->score, hp->weight, hp->max_iter,
+			hp->num_threads, hist);
+	if (it < 0) { g_err = "oracle: histogram failed"; return CNB_ERR_PARAM; }
+	if (iterations) *iterations = it;
+	return CNB_OK;
+}
 /* cnb_network + 1-based samples (values < 1 = missing) -> the oracle's zero-based forms */
 struct MockNet {
 	std::vector<int> s0, pars0, cats, npar;

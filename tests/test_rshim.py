@@ -36,13 +36,13 @@ def test_call_table_matches_reference_registration():
         assert nargs == arity, (name, nargs, arity)
 
 
-def check_networks(nets, theirs, order, cats):
+def check_networks(nets, theirs, order, cats, names=None):
     """nets: catNetwork dicts read back from the shim; theirs: oracle.port.search_order on the same problem"""
     assert [n["complexity"] for n in nets] == [t["complexity"] for t in theirs]
     cats_pos = [int(cats[o - 1]) for o in order]
     for a, b in zip(nets, theirs):
         assert a["parents"] == b["parents"] and a["loglik"] == b["loglik"] and a["sample_sizes"] == b["sample_sizes"]
-        assert a["nodes"] == ["N%d" % o for o in order]
+        assert a["nodes"] == [names[o - 1] if names else "N%d" % o for o in order]
         assert [len(c) for c in a["categories"]] == cats_pos and a["maxCategories"] == max(cats_pos)
         assert a["maxParents"] == max(len(p) for p in a["parents"])
         for x, y in zip(a["probs"], b["probs"]):
@@ -81,8 +81,10 @@ def test_shim_argument_handling():
         r.call("ccnMarginalProb", r.NULL)
     # an ABI error becomes an R error carrying the library's message
     with pytest.raises(RError, match="not in the mock"):
-        r.call("ccnParHistogram", r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([60]), r.NULL, r.NULL, r.NULL,
-               r.string("BIC"), r.integer([1]), r.integer([4]), r.integer([2]), r.logical(True), r.logical(False))
+        r.call("ccnOptimalNetsSA", r.NULL, r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([60]), r.NULL, r.NULL,
+               r.NULL, r.numeric([0]), r.NULL, r.matrix(r.numeric(np.full(36, 0.5)), 6, 6), r.string("BIC"),
+               r.integer(np.arange(1, 7)), r.numeric([1]), r.numeric([0.9]), r.numeric([2]), r.numeric([4]), r.numeric([1]),
+               r.numeric([1e-10]), r.numeric([1]), r.logical(True), r.logical(False))
     with pytest.raises(RError, match="cnet should be a catNetwork"):
         r.call("ccnSamples", r.NULL, r.integer([5]), r.NULL, r.numeric([0.0]))
     # ccnSetSeed / ccnReleaseCache
@@ -170,3 +172,54 @@ def test_shim_network_argument_errors():
         r.call("ccnSetProb", obj, r.data_matrix(s[:, :-1]), r.NULL)
     with pytest.raises(RError, match="number of samples"):
         r.call("ccnSamples", obj, r.numeric([0]), r.NULL, r.numeric([0.0]))
+
+
+SA_KW = dict(temp_start=0.05, temp_cool_fact=0.8, temp_check_orders=3, max_iter=24, order_shuffles=1.5, stop_diff=1e-10,
+             num_threads=3)
+
+
+def check_sa_and_histogram(r, port, seed):
+    """.Call("ccnOptimalNetsSA", ...23) and .Call("ccnParHistogram", ...14) with the arguments R/catnet.search.R:280-296
+    and R/catnet.histo.R:116-129 pass; the library's seed is the one uniform the shim draws from R's RNG"""
+    from rshim_harness import mini_r_uniform
+    s, c = random_problem(seed, 6 + seed % 3, 90, [None, 3][seed % 2])
+    n = len(c)
+    names = ["G%d" % (i + 1) for i in range(n)]
+    start = (np.random.default_rng(seed).permutation(n) + 1).astype(np.int32)
+    model = ["BIC", "AIC", "none"][seed % 3]
+    cat_indices = r.list([r.integer(np.arange(1, v + 1)) for v in c])
+    r.L.mr_set_rng(50 + seed)
+    out = r.call("ccnOptimalNetsSA", _names(r, names),
+                 r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([n * 20]), cat_indices, r.NULL, r.NULL,
+                 r.numeric([0]), r.NULL, r.NULL, r.string(model), r.numeric(start), r.numeric([SA_KW["temp_start"]]),
+                 r.numeric([SA_KW["temp_cool_fact"]]), r.numeric([SA_KW["temp_check_orders"]]), r.numeric([SA_KW["max_iter"]]),
+                 r.numeric([SA_KW["order_shuffles"]]), r.numeric([SA_KW["stop_diff"]]), r.numeric([SA_KW["num_threads"]]),
+                 r.logical(True), r.logical(False))
+    lib_seed = int(mini_r_uniform(50 + seed) * 9007199254740992.0)
+    theirs = port.search_sa(s, 2, n * 20, start, select_mode={"AIC": 1, "BIC": 2}.get(model, 0), seed=lib_seed, num_cats=c,
+                            want_probs=True, **SA_KW)
+    nets = [r.catnetwork(e) for e in r.elts(out)]
+    check_networks(nets, theirs["nets"], [int(v) for v in theirs["order"]], c, names)
+    # the parent histogram: numeric vector N*N that R reshapes with matrix(vhisto, nrow = numnodes)
+    r.L.mr_set_rng(90 + seed)
+    vh = r.reals(r.call("ccnParHistogram", r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([n * 20]), cat_indices,
+                        r.NULL, r.NULL, r.string(model), r.numeric([seed % 3]), r.numeric([8]), r.numeric([2]),
+                        r.logical(True), r.logical(False)))
+    hist, _ = port.search_hist(s, 2, n * 20, score={"AIC": 1, "BIC": 2}.get(model, 0), weight=seed % 3, max_iter=8,
+                               num_threads=2, seed=int(mini_r_uniform(90 + seed) * 9007199254740992.0), num_cats=c)
+    assert np.array_equal(vh.reshape(n, n), hist)
+
+
+def _names(r, names):
+    """character vector"""
+    v = r.L.mr_category_names(len(names))
+    for i, nm in enumerate(names):
+        r.L.mr_set_string(v, i, nm.encode())
+    return v
+
+
+@pytest.mark.parametrize("seed", range(900, 906))
+def test_shim_sa_and_histogram(seed):
+    from oracle import port
+    from rshim_harness import R
+    check_sa_and_histogram(R("mock"), port, seed)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from helpers import constrained_problem, random_problem
-from test_rshim import check_given_network_calls, check_networks
+from test_rshim import check_given_network_calls, check_networks, check_sa_and_histogram
 
 pytestmark = pytest.mark.gpu
 
@@ -43,3 +43,11 @@ def test_dot_call_given_network(r, seed):
     """ccnSetProb -> ccnLoglik -> ccnNodeLoglik -> ccnSamples over the library, against the oracle"""
     from oracle import port
     check_given_network_calls(r, port, seed)
+
+
+@pytest.mark.parametrize("seed", range(900, 903))
+def test_dot_call_sa_and_histogram(r, seed):
+    """ccnOptimalNetsSA and ccnParHistogram over the library: the chain and the histogram of the oracle under the seed
+    the shim draws from (the miniature) R's RNG"""
+    from oracle import port
+    check_sa_and_histogram(r, port, seed)
