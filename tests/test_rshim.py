@@ -74,6 +74,13 @@ def test_shim_argument_handling():
     nets = optimal_nets_for_order(r, s, 2, 60, order=[1, 2, 3])
     assert "Invalid nodeOrder" in r.warnings()
     check_networks(nets, port.search_order(s, 2, 60), list(range(1, 7)), c)
+    # parent pools as R hands them over: NULL entries and empty vectors are nodes without candidates
+    pool = [None, [1], [], [1, 2], [3], [2, 4]]
+    out = r.call("ccnOptimalNetsForOrder", r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([100]), r.NULL,
+                 r.list([r.integer(np.arange(1, v + 1)) for v in c]),
+                 r.list([r.NULL if p is None else r.integer(p) for p in pool]), r.NULL, r.NULL, r.logical(False), r.logical(False))
+    check_networks([r.catnetwork(e) for e in r.elts(out)],
+                   port.search_order(s, 2, 100, num_cats=c, parents_pool=[p or [] for p in pool]), list(range(1, 7)), c)
     # wrong arity and unknown routines never reach the shim
     with pytest.raises(RError, match="wrong number of arguments"):
         r.call("ccnOptimalNetsForOrder", r.NULL)
