@@ -221,6 +221,20 @@ static int set_samples_dev_impl(cnb_ctx *c, int32_t N, int32_t M, const void *sa
 	D2H(c, flags, c->b_flag.ptr, sizeof(flags));
 	CK(cudaStreamSynchronize(st));
 	if (flags[0]) { cnb_set_error("Incorrect categories"); return CNB_ERR_PARAM; }   /* catnet_search2.h:248 */
+	/* nodes perturbed in EVERY sample: the reference scores their candidates on zero samples, setNodeSampleProb returns
+	 * -FLT_MAX (catnet_class.h:824-826) and no candidate is ever taken (catnet_search2.h:637-640, 813-826): the planner
+	 * gives such a node no candidate parent sets (cnb_ctx_plan) */
+	c->never_kept.assign(N, 0);
+	c->any_never_kept = false;
+	if (c->has_pert) {
+		std::vector<uint32_t> kp(words), any(N, 0);
+		D2H(c, kp.data(), c->b_keep_lbl.ptr, words * sizeof(uint32_t));
+		CK(cudaStreamSynchronize(st));
+		for (size_t w = 0; w < (size_t)c->W; w++)
+			for (int v = 0; v < N; v++) any[v] |= kp[w * N + v];
+		for (int v = 0; v < N; v++)
+			if (!any[v]) { c->never_kept[v] = 1; c->any_never_kept = true; }
+	}
 	/* two-way margins for the inclusion-exclusion scorer: only meaningful without missing values / masks */
 	c->pairs_valid = false;
 	c->pairs_full = false;
@@ -441,6 +455,13 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* the previous plan's host vectors may still be the source of an async copy */
 	CK(cudaStreamSynchronize(c->stream));
 	std::string err;
+	std::vector<int32_t> eff_sizes;
+	if (c->any_never_kept) {                       /* label space, like parent_sizes: no candidates for those nodes */
+		eff_sizes.resize(c->N);
+		for (int i = 0; i < c->N; i++)
+			eff_sizes[i] = c->never_kept[i] ? 0 : (p->parent_sizes ? p->parent_sizes[i] : p->max_parent_set);
+		q.parent_sizes = eff_sizes.data();
+	}
 	/* tensor-core tiling of the two-parent group: clean data (no NA, no masks, <= 4 categories) and enough samples
 	 * per family to amortise a 128 x 256 tile (or forced on by the test hook) */
 	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192)

@@ -44,6 +44,8 @@ struct cnb_ctx {
 	bool no_tensor3 = false;           /* three-parent families never on the tensor cores (test hook) */
 	int tensor3_tiles = 0;             /* T tiles of the last search (0 = three-parent group not on the tensor cores) */
 	bool no_ie3 = false;               /* three-parent families by the direct bit-plane / histogram scorers (test hook) */
+	std::vector<uint8_t> never_kept;   /* [N] label space: node perturbed in every sample (no candidate parent sets) */
+	bool any_never_kept = false;
 	bool generic_epilogue = false;     /* k_umma_epilogue<false> also when every node has 4 categories (test hook) */
 	bool dp_no_trap = false;           /* k_dp_wave instead of the trapezoid kernel (test hook) */
 	bool has_na = false;               /* the data set has missing values */

@@ -259,6 +259,15 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 		if (maxpars > nr + nf) maxpars = nr + nf;
 		for (k = 0; k < R->nslots; k++) { cur[k].exists = 0; }
 		SET_KEEP(n);
+		/* a node that is perturbed in EVERY sample has no sample to score a candidate with: setNodeSampleProb returns
+		 * -FLT_MAX for nsamples < 1 (catnet_class.h:824-826), so no candidate beats the initial fMaxLogLik = -FLT_MAX and
+		 * the node keeps its base family (equal categories: ncombMaxLogLik < 0 -> continue, catnet_search2.h:637-640;
+		 * mixed: tempLogLik == -FLT_MAX never creates or replaces a slot, :813-826) */
+		if (keep) {
+			int nkept = 0;
+			for (j = 0; j < M; j++) nkept += keep[j];
+			if (nkept < 1) maxpars = 0;
+		}
 		const fam_t *bf = &R->fams[basefam[n]];
 		int base_node_cx = fam_complexity(bf, cats);
 		double base_term = bf->loglik + bf->prior;

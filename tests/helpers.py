@@ -125,3 +125,22 @@ def constrained_problem(seed):
     lo = int(np.sum(c - 1))
     K = int(rng.integers(lo, lo + n * int(c.max()) ** P * 2 + 1))
     return s, P, K, kw
+
+
+def fully_perturbed_problem(seed):
+    """a search problem in which one or two nodes are perturbed in EVERY sample (the reference then scores their
+    candidates on zero samples and never gives them parents: catnet_class.h:824-826, catnet_search2.h:637-640)"""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(4, 9)), int(rng.integers(5, 120))
+    s, c = random_problem(seed, n, m, [3, None, 2, None][seed % 4], na_frac=[0.0, 0.1][seed % 2])
+    pert = (rng.random(s.shape) < 0.2).astype(np.int32)
+    for v in rng.choice(n, size=1 + seed % 2, replace=False):
+        pert[:, v] = 1
+    kw = dict(num_cats=c, order=(rng.permutation(n) + 1).astype(np.int32), perturbations=pert)
+    if seed % 3 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    if seed % 5 == 1:
+        kw["fixed_parents"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, 2), replace=False)
+                                if v != i + 1] for i in range(n)]
+    P = 1 + seed % 3
+    return s, P, int(np.sum(c - 1)) + n * int(c.max()) ** P, kw

@@ -9,7 +9,8 @@ import pytest
 
 from cases import (CASES, HIST_CASES, NETWORK_CASES, PAIRWISE_CASES, SA_CASES, SAMPLES_CASES, build_case, build_hist_case,
                    build_network_case, build_pairwise_case, build_samples_case, ref_args)
-from helpers import check_network_case, compare_golden, compare_search, constrained_problem, load_golden, random_problem
+from helpers import (check_network_case, compare_golden, compare_search, constrained_problem, fully_perturbed_problem,
+                     load_golden, random_problem)
 from oracle import port
 
 
@@ -93,6 +94,21 @@ def test_port_matches_reference_core_constraints(ref, seed):
     a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
     b = port.search_order(s, P, K, **kw)
     assert len(a) == len(b) and compare_search(b, a) == len(a)
+
+
+@pytest.mark.parametrize("seed", range(1100, 1130))
+def test_port_node_perturbed_in_every_sample(ref, seed):
+    """found by fuzzing the restatement against the compiled reference (constrained_problem(3042)): a node without a
+    single unperturbed sample never gets parents"""
+    s, P, K, kw = fully_perturbed_problem(seed)
+    a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
+    b = port.search_order(s, P, K, **kw)
+    assert len(a) == len(b) and compare_search(b, a) == len(a)
+    gone = [int(np.where(kw["order"] == v + 1)[0][0]) for v in np.where((kw["perturbations"] != 0).all(axis=0))[0]]
+    fixed = kw.get("fixed_parents")
+    for net in b:
+        for pos in gone:
+            assert len(net["parents"][pos]) == (len(fixed[kw["order"][pos] - 1]) if fixed else 0) or fixed
 
 
 def test_port_sa_matches_reference_core(ref):

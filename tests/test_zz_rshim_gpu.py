@@ -1,11 +1,12 @@
-"""GPU suite, last file: the R shim (catnet_b200/csrc/rshim.cpp) linked against the REAL libcatnet_b200.so and driven
+"""GPU suite, last file (tests written after the round's GPU budget was spent, so their first run is the round-end
+suite; they sort last so that they cannot mask the others under -x): the R shim (catnet_b200/csrc/rshim.cpp) linked against the REAL libcatnet_b200.so and driven
 through the miniature R API of tests/rstub/minir.cpp -- `.Call("ccnOptimalNetsForOrder", ...)` with R-style arguments
 in, S4 catNetwork objects out, the pairwise metrics and the given-network routines, compared with the oracle.  (tests/test_rshim.py runs the same shim on the CPU with the
 C ABI answered by the oracle.)"""
 import numpy as np
 import pytest
 
-from helpers import constrained_problem, random_problem
+from helpers import compare_search, constrained_problem, fully_perturbed_problem, random_problem
 from test_rshim import check_given_network_calls, check_networks, check_sa_and_histogram
 
 pytestmark = pytest.mark.gpu
@@ -51,3 +52,20 @@ def test_dot_call_sa_and_histogram(r, seed):
     the shim draws from (the miniature) R's RNG"""
     from oracle import port
     check_sa_and_histogram(r, port, seed)
+
+
+@pytest.mark.parametrize("seed", range(1100, 1112))
+def test_node_perturbed_in_every_sample(seed):
+    """a node without a single unperturbed sample never gets parents (tests/test_oracle.py pins the restatement on
+    this against the compiled reference); one-shot call and resident context"""
+    from catnet_b200 import _abi
+    from oracle import port
+    s, P, K, kw = fully_perturbed_problem(seed)
+    theirs = port.search_order(s, P, K, **kw)
+    ours = _abi.search_order(s, max_parent_set=P, max_complexity=K, **kw)
+    assert len(ours) == len(theirs) and compare_search(ours, theirs) == len(theirs)
+    with _abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=kw["perturbations"], num_cats=kw["num_cats"])
+        kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
+        again = ctx.search_order(max_parent_set=P, max_complexity=K, **kw2)
+    assert compare_search(again, theirs) == len(theirs)
