@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Fuzz the plain-C restatement (oracle/catnet_oracle.c) against the reference's own C++ compiled where it lies
+(oracle/_ref, needs /root/reference): every problem runs in a forked child, because the reference corrupts its heap
+on some inputs (e.g. fixed parents whose base network exceeds maxComplexity).  CPU only; test infrastructure.
+
+    python tools/fuzz_oracle.py search 1000 6000      # tests/helpers.py::constrained_problem
+    python tools/fuzz_oracle.py wide 0 3000           # inferred categories, NA-heavy, 1-4 parents, priors with 0 and 1
+    python tools/fuzz_oracle.py sa 0 1500             # cnSearchSA trajectories (cache off) + cnSearchHist
+    python tools/fuzz_oracle.py rest 0 3000           # pairwise metrics, cnSetProb / cnLoglik / cnNodeLoglik, cnSamples
+
+Round 1: 4,956 + 2,973 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
+since) and one reference crash (search 3886: the documented out-of-bounds write)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+from helpers import compare_search, constrained_problem, random_problem  # noqa: E402
+from oracle import port, ref  # noqa: E402
+
+
+def check_search(seed):
+    s, P, K, kw = constrained_problem(seed)
+    a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
+    b = port.search_order(s, P, K, **kw)
+    assert len(a) == len(b), (len(a), len(b))
+    assert compare_search(b, a) == len(a)
+
+
+def check_wide(seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(1, 11)), int(rng.integers(4, 60))
+    cats = [None, 2, 3, 4, 5, [2, 3, 4, 5, 6, 7, 2, 3, 4, 5][:n]][seed % 6]
+    s, c = random_problem(seed, n, m, cats, na_frac=[0, 0.3, 0.05][seed % 3])
+    kw = {}
+    if seed % 2 == 0:
+        kw["num_cats"] = c
+    elif seed % 4 == 1:                              # inferred categories with a missing bottom category
+        col = int(rng.integers(0, n))
+        s[s[:, col] == 1, col] = 2
+    P = int(rng.integers(1, 5))
+    kw["order"] = (rng.permutation(n) + 1).astype(np.int32)
+    if seed % 5 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < [0.1, 0.6, 0.95][seed % 3]).astype(np.int32)
+    if seed % 7 == 0:
+        kw["edge_prob"] = np.round(rng.random((n, n)), 1)          # includes exact 0 and 1
+    if seed % 11 == 0:
+        kw["parent_sizes"] = rng.integers(0, P + 1, size=n).astype(np.int32)
+    lo = int(np.sum(c - 1))
+    K = int(rng.integers(lo, lo + n * int(c.max()) ** min(P, 3) + 2))
+    a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
+    b = port.search_order(s, P, K, **kw)
+    assert len(a) == len(b), (len(a), len(b))
+    assert compare_search(b, a) == len(a)
+
+
+def check_sa(seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 9)), int(rng.integers(8, 120))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4][seed % 4], na_frac=[0, 0.1][seed % 2])
+    kw = dict(num_cats=c)
+    if seed % 3 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.2).astype(np.int32)
+    kh = dict(kw)
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0][seed % 3], temp_cool_fact=[0.9, 0.5][seed % 2],
+              temp_check_orders=int(rng.integers(1, 5)), max_iter=int(rng.integers(5, 40)),
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=[1e-10, 0.01][seed % 2],
+              num_threads=int(rng.integers(1, 5)), seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** 2
+    a = ref.search_sa(s, 2, K, start, use_cache=False, **sa, **kw)
+    b = port.search_sa(s, 2, K, start, **sa, **kw)
+    assert np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"] and a["naccept"] == b["naccept"]
+    assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["trace_accept"], b["trace_accept"])
+    compare_search(b["nets"], a["nets"], check_probs=False)
+    hk = dict(score=seed % 3, weight=seed % 3, max_iter=6, num_threads=1 + seed % 3, seed=sa["seed"])
+    h1, i1 = ref.search_hist(s, 2, K, use_cache=False, **hk, **kh)
+    h2, i2 = port.search_hist(s, 2, K, **hk, **kh)
+    assert i1 == i2 and np.array_equal(h1, h2)
+
+
+def check_rest(seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(1, 10)), int(rng.integers(7, 150))
+    cats = [None, 2, 3, 4, 7][seed % 5]
+    s, c = random_problem(seed, n, m, cats)                        # the pairwise metrics take no missing values
+    if seed % 4 == 0:
+        s[:, 0] = s[:, -1]                                         # duplicated column: ties in the entropy order
+    if seed % 6 == 1:
+        s = s + 2                                                  # categories not starting at 1
+    pert = None
+    if seed % 3 != 0:
+        pert = (rng.random(s.shape) < [0.2, 0.7][seed % 2]).astype(np.int32)
+        if seed % 7 == 0:
+            pert[:, int(rng.integers(0, n))] = 1
+    for kind in ("entropy", "kl", "pearson", "order"):
+        if kind == "order" and n == 1:
+            continue                                               # the reference returns uninitialised memory there
+        assert np.array_equal(ref.pairwise(kind, s, pert), port.pairwise(kind, s, pert), equal_nan=True), kind
+    s, c = random_problem(seed + 7, n, m, cats, na_frac=[0, 0.2][seed % 2])
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    parents = [sorted(rng.choice(i, size=min(i, int(rng.integers(0, 4))), replace=False).tolist(), reverse=seed % 3 == 0)
+               for i in range(n)]
+    pa, la, sa = ref.net_set_prob(s0, c, parents, pert)
+    pb, lb, sb = port.net_set_prob(s0, c, parents, pert)
+    assert all(np.array_equal(x, y) for x, y in zip(pa, pb)) and np.array_equal(la, lb) and np.array_equal(sa, sb)
+    valid = pa
+    if seed % 4 == 0:
+        pa = [np.where(t < 0.15, 0.0, t) for t in pa]              # zero probabilities met by counted samples
+    for mode in ("nodes", "bysample", "node", "total"):
+        pe = None if mode == "node" else pert
+        assert np.array_equal(ref.net_loglik(mode, s0, c, parents, pa, pe), port.net_loglik(mode, s0, c, parents, pa, pe)), mode
+    if ref.samples_available():
+        fixed = None
+        if seed % 3 == 1:
+            fixed = (rng.integers(0, int(c.max()) + 2, size=(40, n)) * (rng.random((40, n)) < 0.3)).astype(np.int32)
+        a, ca = ref.net_samples(c, parents, valid, 40, fixed, [0.0, 0.3][seed % 2], seed + 1)
+        b, cb = port.net_samples(c, parents, valid, 40, fixed, [0.0, 0.3][seed % 2], seed + 1)
+        assert ca == cb and np.array_equal(a, b)
+
+
+def main():
+    check = {"search": check_search, "wide": check_wide, "sa": check_sa, "rest": check_rest}[sys.argv[1]]
+    lo, hi = int(sys.argv[2]), int(sys.argv[3])
+    if not ref.available():
+        sys.exit("oracle/_ref is not built (needs /root/reference)")
+    port.lib()
+    ref.lib()
+    ran, mismatch, crash = 0, [], []
+    for seed in range(lo, hi):
+        pid = os.fork()
+        if pid == 0:
+            code = 0
+            try:
+                check(seed)
+            except ValueError as e:                                # degenerate problem (fewer samples than categories)
+                code = 4 if "broadcast" in str(e) else 3
+                if code == 3:
+                    sys.stderr.write("seed %d: %r\n" % (seed, str(e)[:300]))
+            except BaseException as e:
+                sys.stderr.write("seed %d: %r\n" % (seed, str(e)[:300]))
+                code = 3
+            os._exit(code)
+        _, st = os.waitpid(pid, 0)
+        if os.WIFSIGNALED(st):
+            crash.append(seed)
+        elif os.WEXITSTATUS(st) == 3:
+            mismatch.append(seed)
+        if not os.WIFSIGNALED(st) and os.WEXITSTATUS(st) != 4:
+            ran += 1
+    print("problems %d  mismatches %s  reference crashes %s" % (ran, mismatch, crash))
+    sys.exit(1 if mismatch else 0)
+
+
+if __name__ == "__main__":
+    main()
