@@ -29,7 +29,8 @@ def check_search(seed):
     assert compare_search(b, a) == len(a)
 
 
-def check_wide(seed):
+def wide_problem(seed):
+    """inferred categories, heavy NA, 1-4 parents, priors with exact 0 and 1, parent-set sizes"""
     rng = np.random.default_rng(seed)
     n, m = int(rng.integers(1, 11)), int(rng.integers(4, 60))
     cats = [None, 2, 3, 4, 5, [2, 3, 4, 5, 6, 7, 2, 3, 4, 5][:n]][seed % 6]
@@ -50,6 +51,11 @@ def check_wide(seed):
         kw["parent_sizes"] = rng.integers(0, P + 1, size=n).astype(np.int32)
     lo = int(np.sum(c - 1))
     K = int(rng.integers(lo, lo + n * int(c.max()) ** min(P, 3) + 2))
+    return s, P, K, kw
+
+
+def check_wide(seed):
+    s, P, K, kw = wide_problem(seed)
     a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
     b = port.search_order(s, P, K, **kw)
     assert len(a) == len(b), (len(a), len(b))
