@@ -8,8 +8,9 @@ on some inputs (e.g. fixed parents whose base network exceeds maxComplexity, SUR
     python tools/fuzz_oracle.py sa 0 1500             # cnSearchSA trajectories (cache off) + cnSearchHist
     python tools/fuzz_oracle.py rest 0 3000           # pairwise metrics, cnSetProb / cnLoglik / cnNodeLoglik, cnSamples
 
-Round 1: 4,956 + 2,973 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
-since) and one reference crash (search 3886: the documented out-of-bounds write)."""
+Round 1: 10,911 + 5,955 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
+since) and five reference crashes (search 3886, 9556, 10501, 11146, 11995: fixed parents put the base
+network above maxComplexity, the documented out-of-bounds write)."""
 import os
 import sys
 
