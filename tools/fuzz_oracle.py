@@ -5,10 +5,11 @@ on some inputs (e.g. fixed parents whose base network exceeds maxComplexity, SUR
 
     python tools/fuzz_oracle.py search 1000 6000      # tests/helpers.py::constrained_problem
     python tools/fuzz_oracle.py wide 0 3000           # inferred categories, NA-heavy, 1-4 parents, priors with 0 and 1
+    python tools/fuzz_oracle.py unseen 0 2000         # declared but unseen categories, limits from the base network up
     python tools/fuzz_oracle.py sa 0 1500             # cnSearchSA trajectories (cache off) + cnSearchHist
     python tools/fuzz_oracle.py rest 0 3000           # pairwise metrics, cnSetProb / cnLoglik / cnNodeLoglik, cnSamples
 
-Round 1: 10,911 + 5,955 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
+Round 1: 10,911 + 5,955 + 2,000 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
 since) and five reference crashes (search 3886, 9556, 10501, 11146, 11995: fixed parents put the base
 network above maxComplexity, the documented out-of-bounds write)."""
 import os
@@ -57,6 +58,24 @@ def wide_problem(seed):
 
 def check_wide(seed):
     s, P, K, kw = wide_problem(seed)
+    a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
+    b = port.search_order(s, P, K, **kw)
+    assert len(a) == len(b), (len(a), len(b))
+    assert compare_search(b, a) == len(a)
+
+
+def check_unseen(seed):
+    """declared categories that never occur; complexity limits from exactly the base network to unbounded"""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(2, 9)), int(rng.integers(5, 80))
+    s, c = random_problem(seed, n, m, [None, 2, 3][seed % 3], na_frac=[0, 0.1][seed % 2])
+    c2 = (c + rng.integers(0, 3, size=n)).astype(np.int32)
+    P = int(rng.integers(1, 4))
+    kw = dict(num_cats=c2, order=(rng.permutation(n) + 1).astype(np.int32))
+    if seed % 4 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.3).astype(np.int32)
+    lo = int(np.sum(c2 - 1))
+    K = [lo, lo + 1, lo + int(c2.max()), 10 ** 6][seed % 4]
     a = ref.search_order(s, P, K, use_cache=bool(seed % 2), **kw)
     b = port.search_order(s, P, K, **kw)
     assert len(a) == len(b), (len(a), len(b))
@@ -131,7 +150,7 @@ def check_rest(seed):
 
 
 def main():
-    check = {"search": check_search, "wide": check_wide, "sa": check_sa, "rest": check_rest}[sys.argv[1]]
+    check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest}[sys.argv[1]]
     lo, hi = int(sys.argv[2]), int(sys.argv[3])
     if not ref.available():
         sys.exit("oracle/_ref is not built (needs /root/reference)")
