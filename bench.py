@@ -2,23 +2,26 @@
 """bench.py -- family log-lik scores/sec of the cnSearchOrder hot path on B200 (BASELINE.json metric).
 
 A step = one per-order evaluation of the structure-search scoring path over one synthetic sample matrix:
-enumerate candidate parent sets -> family tables + log-lik (sm_100a kernels) -> [all-gather of the score shards]
+enumerate candidate parent sets -> family tables + log-lik (sm_100a kernels) -> [exchange of the score shards]
 -> per-(node, d) selection -> DP over complexity, all on the device.
 
 Workload at every N: BASELINE.json configs[4] ("C5"): synthetic 500 nodes x 4 categories, 1,000,000 samples,
-maxParentSet=2, true order; 20,833,250 candidate families, sharded over the ranks (strong scaling).
-Other configs (--config C1..C4) are parity-test shapes, not bench lines.
+maxParentSet=2, true order; 20,833,250 candidate families, sharded over the GPUs (strong scaling).  The other configs
+(C1..C3, and C4 = the cnSearchSA leg) are measured in the `configs` / `sa` blocks of the same line.
 
-  python bench.py [--gpus N --steps K --warmup W]            our arm
+  python bench.py [--gpus N --steps K --warmup W]            our arm (N > 1: under torchrun, one rank per GPU, NCCL)
+  python bench.py --single-process --gpus N ...              our arm, ONE process driving N GPUs (cnb_mctx: the form an
+                                                             R session uses; host threads + NVLink peer stores, no NCCL)
   python bench.py --impl reference [...]                      the reference's own C++ scoring primitive on host cores
-  torchrun ... bench.py --gpus N ...                          one rank per GPU, NCCL all-gather of the score shards
 
 value  : whole-job families/s with the packed matrix already resident in HBM (timed with CUDA events on the stream
          every kernel and the collective are launched on; max over ranks)
-e2e    : the same metric through the reference-facing C ABI with HOST buffers: int32 [M][N] matrix in pinned host
-         memory -> H2D -> pack -> search -> networks exported to the host, all inside the timed region
+e2e    : the same metric through the reference-facing C ABI with HOST buffers: the int32 [M][N] matrix in PAGEABLE host
+         memory (what R hands over) -> H2D -> pack -> search -> networks exported to the host, all inside the timed region
+Both arms draw the SAME matrix (numpy PCG64 on the host), so `config` is identical in both lines.
 """
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -39,7 +42,7 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------------- workload
 def build_workload(name, m_override=None):
-    """network + search arguments of a BASELINE config; the sample matrix itself is drawn later (GPU or numpy)"""
+    """network + search arguments of a BASELINE config; the sample matrix itself is drawn by draw_samples"""
     from catnet_b200 import synth
     if name in ("C3", "C5"):
         n, c, p = (100, 3, 3) if name == "C3" else (500, 4, 2)
@@ -67,23 +70,20 @@ def build_workload(name, m_override=None):
     raise SystemExit("unknown config " + name)
 
 
-def sample_on_device(wl, device):
-    """ancestral sampling (src/rcatnet.cpp:568-602 semantics) with torch on the GPU: [M][N] int32, 1-based"""
-    import torch
+def draw_samples(wl):
+    """the sample matrix of a workload, [M][N] int8, 1-based: ancestral sampling (src/rcatnet.cpp:568-602 semantics) with
+    numpy PCG64(seed) on the host -- the SAME generator in both arms, so both score the same matrix"""
     from catnet_b200 import synth
-    net, m, n = wl["net"], wl["m"], wl["n"]
-    g = torch.Generator(device=device)
-    g.manual_seed(wl["seed"])
-    out = torch.zeros((m, n), dtype=torch.int32, device=device)
-    for i in synth.order_nodes_descend(net["parents"]):
-        cfg = torch.zeros(m, dtype=torch.int64, device=device)
-        for p in net["parents"][i]:
-            cfg = cfg * int(net["cats"][p]) + (out[:, p].to(torch.int64) - 1)
-        cum = torch.as_tensor(np.cumsum(net["cpts"][i], axis=1), device=device)[cfg]
-        u = torch.rand(m, generator=g, device=device, dtype=torch.float64)
-        k = (u[:, None] > cum).sum(dim=1).clamp_(max=int(net["cats"][i]) - 1)
-        out[:, i] = (k + 1).to(torch.int32)
-    return out
+    if "samples" in wl:
+        return np.ascontiguousarray(wl["samples"]).astype(np.int8)
+    return synth.sample_network(wl["net"], wl["m"], np.random.Generator(np.random.PCG64(wl["seed"])), dtype=np.int8)
+
+
+def config_of(wl, n_fam_total):
+    """identical in both arms"""
+    return {"workload": wl["desc"], "families": n_fam_total,
+            "l2": "inputs larger than L2 (bit planes %.0f MB)" % (wl["n"] * ((wl["m"] + 31) // 32) * 16 / 1e6),
+            "data_rng": "network numpy PCG64(%d); samples numpy PCG64(%d), drawn on the host in both arms" % (wl["seed"], wl["seed"])}
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -130,31 +130,38 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline
+def draw_families(rng, n, d, order0, k):
+    """k random candidate families with d parents: (child labels, parent labels, child positions, parent positions)"""
+    ch, pa, chp, pap = [], [], [], []
+    for _ in range(k):
+        pos = sorted(int(x) for x in rng.choice(n, size=d + 1, replace=False))
+        ch.append(order0[pos[-1]])
+        pa.append([order0[x] for x in pos[:-1]])
+        chp.append(pos[-1])
+        pap.append(pos[:-1])
+    return (np.asarray(ch, dtype=np.int32), np.asarray(pa, dtype=np.int32), np.asarray(chp, dtype=np.int32),
+            np.asarray(pap, dtype=np.int32))
+
+
 def cpu_reference_rate(samples0, cats, order0, p_max, budget_s, threads):
     """the reference's own scoring primitive (CATNET::setParents + setNodeSampleProb through oracle/_ref) on the
-    host cores: `threads` concurrent scorers, each on its own seeded random sample of candidate families at full M."""
+    host cores: `threads` concurrent scorers, each on its own seeded random sample of candidate families at full M.
+    Returns (families/s, families, wall, the scored lists with the reference's log-likelihoods)."""
     from oracle import ref
-    n, m = len(cats), samples0.shape[0]
+    n = len(cats)
     rng = np.random.default_rng(12345)
-    # calibrate: 1 thread, a few families
     d = p_max
-    def draw(k):
-        ch, pa = [], []
-        for _ in range(k):
-            pos = sorted(rng.choice(n, size=d + 1, replace=False))
-            ch.append(order0[pos[-1]])
-            pa.append([order0[x] for x in pos[:-1]])
-        return np.asarray(ch, dtype=np.int32), np.asarray(pa, dtype=np.int32)
-    ch, pa = draw(2)
+    ch, pa, _, _ = draw_families(rng, n, d, order0, 2)
     t = time.perf_counter()
     ref.score_family_list(samples0, cats, ch, pa)
     per_family = (time.perf_counter() - t) / 2
     k = max(2, int(budget_s / max(per_family, 1e-9)))
-    lists = [draw(k) for _ in range(threads)]
+    lists = [draw_families(rng, n, d, order0, k) for _ in range(threads)]
     done = [0.0] * threads
+    lls = [None] * threads
 
     def work(i):
-        ref.score_family_list(samples0, cats, lists[i][0], lists[i][1])
+        lls[i] = ref.score_family_list(samples0, cats, lists[i][0], lists[i][1])
         done[i] = time.perf_counter()
 
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
@@ -164,7 +171,9 @@ def cpu_reference_rate(samples0, cats, order0, p_max, budget_s, threads):
     for th in ts:
         th.join()
     wall = max(done) - t0
-    return threads * k / wall, threads * k, wall
+    scored = {"children_pos": np.concatenate([l[2] for l in lists]), "parents_pos": np.concatenate([l[3] for l in lists]),
+              "loglik": np.concatenate(lls)}
+    return threads * k / wall, threads * k, wall, scored
 
 
 # ------------------------------------------------------------------------------------------------- cnSearchSA (C4)
@@ -180,42 +189,342 @@ def sa_workload():
     return s, cfg["cats"], sa
 
 
-def sa_leg_ours(rank, world, max_iter, dist_mod=None, dev=None):
-    """wall time of one cnb_search_sa call per GPU (independent chains, seed + rank), host buffers in, networks out"""
+SA_DESC = ("C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
+           "numThreads=4 (proposals per step)")
+
+
+def bic_best(nets, m):
+    """the network cnFindBIC would pick from an evaluation (R/catnet.search.R): max of M loglik - 0.5 log(M) complexity"""
+    if not nets:
+        return None
+    ft = 0.5 * math.log(m)
+    best = max(nets, key=lambda x: m * x["loglik"] - ft * x["complexity"])
+    return {"complexity": int(best["complexity"]), "loglik": float(best["loglik"]),
+            "bic": float(m * best["loglik"] - ft * best["complexity"])}
+
+
+def sa_leg_torchrun(rank, world, max_iter, dist_mod=None, dev=None):
+    """one cnb_search_sa call per rank on ITS OWN GPU (independent chains, seed + rank), host buffers in, networks out;
+    the chains are merged per complexity on rank 0 like R's .searchSA merges evaluations (R/catnet.search.R:317-332)"""
     import torch
-    from catnet_b200 import _abi
+    from catnet_b200 import _abi, dist as cdist
     s, cats, sa = sa_workload()
-    # every rank's chain on ITS OWN GPU (cnb_params.device): on one shared device the processes time-slice
     kw = dict(max_parent_set=2, max_complexity=600, num_cats=cats, device=dev.index if dev is not None else 0)
     _abi.search_sa(s, dict(sa, max_iter=3, seed=1), **kw)
     t0 = time.perf_counter()
     r = _abi.search_sa(s, dict(sa, max_iter=max_iter, seed=4004 + rank), **kw)
     wall = time.perf_counter() - t0
+    chains = [r["nets"]]
     if world > 1:
         t = torch.tensor([wall], dtype=torch.float64, device=dev)
         dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
         wall = float(t.item())
-    return {"workload": "C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
-                        "numThreads=4 (proposals per step), one chain per GPU" % max_iter,
+        chains = [None] * world
+        dist_mod.all_gather_object(chains, [{"complexity": x["complexity"], "loglik": x["loglik"]} for x in r["nets"]])
+    merged = cdist.merge_evaluations(chains)
+    m = s.shape[0]
+    return {"workload": (SA_DESC % max_iter) + ", one chain per GPU, merged per complexity",
             "wall_s": wall, "chains": world, "iterations": int(r["niter"]), "orders_evaluated": int(len(r["trace"])),
             "ms_per_order": 1000.0 * wall / max(len(r["trace"]), 1),
+            "chain_bic_best": [bic_best(c, m) for c in chains], "merged_bic_best": bic_best(merged, m),
+            "merged_networks": len(merged),
+            "best_loglik": float(max(x["loglik"] for x in merged)) if merged else None}
+
+
+def sa_leg_single_process(ngpus, max_iter):
+    """the same through ONE call of the drop-in entry point with cnb_params.num_devices (what CNB_NUM_DEVICES gives an R
+    session): one chain per device inside the library, merged there"""
+    from catnet_b200 import _abi
+    s, cats, sa = sa_workload()
+    kw = dict(max_parent_set=2, max_complexity=600, num_cats=cats, num_devices=ngpus)
+    _abi.search_sa(s, dict(sa, max_iter=3, seed=1), **kw)
+    t0 = time.perf_counter()
+    r = _abi.search_sa(s, dict(sa, max_iter=max_iter, seed=4004), **kw)
+    wall = time.perf_counter() - t0
+    return {"workload": (SA_DESC % max_iter) + ", cnb_search_sa with num_devices=%d (one chain per device, merged)" % ngpus,
+            "wall_s": wall, "chains": ngpus, "iterations": int(r["niter"]), "orders_evaluated_chain0": int(len(r["trace"])),
+            "merged_bic_best": bic_best(r["nets"], s.shape[0]), "merged_networks": len(r["nets"]),
             "best_loglik": float(max(x["loglik"] for x in r["nets"])) if r["nets"] else None}
 
 
-def sa_leg_reference(budget_iter):
-    """the reference's SA loop around its own estimate(), threads and cache (oracle/_ref), bounded to budget_iter
-    iterations; the first iterations are the expensive ones (empty cache)"""
+def sa_leg_reference(iters_a=30, iters_b=90):
+    """the reference's SA loop around its own estimate(), threads and cache (oracle/_ref), bounded: the first orders are
+    the expensive ones (empty cache), so the warm per-order time is reported separately from the difference of two runs
+    of the same chain"""
     from oracle import ref
     s, cats, sa = sa_workload()
-    t0 = time.perf_counter()
-    r = ref.search_sa(s, 2, 600, sa["start_order"], select_mode=2, temp_start=0.0, temp_cool_fact=1.0,
-                      temp_check_orders=1000, max_iter=budget_iter, order_shuffles=0.0, stop_diff=1e-10, num_threads=4,
-                      use_cache=True, seed=4004, num_cats=cats)
-    wall = time.perf_counter() - t0
-    return {"workload": "C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
-                        "numThreads=4, cache on (reference core, bounded)" % budget_iter,
-            "wall_s": wall, "chains": 1, "iterations": int(r["niter"]), "orders_evaluated": int(len(r["trace"])),
-            "ms_per_order": 1000.0 * wall / max(len(r["trace"]), 1)}
+
+    def run(it):
+        t0 = time.perf_counter()
+        r = ref.search_sa(s, 2, 600, sa["start_order"], select_mode=2, temp_start=0.0, temp_cool_fact=1.0,
+                          temp_check_orders=1000, max_iter=it, order_shuffles=0.0, stop_diff=1e-10, num_threads=4,
+                          use_cache=True, seed=4004, num_cats=cats)
+        return time.perf_counter() - t0, r
+    wa, ra = run(iters_a)
+    wb, rb = run(iters_b)
+    na, nb = len(ra["trace"]), len(rb["trace"])
+    return {"workload": (SA_DESC % iters_b) + ", cache on (reference core, bounded)",
+            "wall_s": wb, "chains": 1, "iterations": int(rb["niter"]), "orders_evaluated": nb,
+            "ms_per_order": 1000.0 * wb / max(nb, 1),
+            "cold_ms_per_order_first_%d" % na: 1000.0 * wa / max(na, 1),
+            "warm_ms_per_order_after_%d" % na: 1000.0 * (wb - wa) / max(nb - na, 1)}
+
+
+# ------------------------------------------------------------------------------------------------- other configs
+def configs_block(device):
+    """BASELINE configs C1, C2, C3 on one GPU through the drop-in call (host buffers in, networks on the host out) and on a
+    resident context; C1 / C2 are compared with the committed outputs of the compiled reference (tests/golden), C3 -- whose
+    reference run takes over an hour -- with the bit-plane kernels of this library (a different kernel family)"""
+    from catnet_b200 import _abi, synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import compare_golden, load_golden
+    L = _abi.lib()
+    out = {}
+    golden = load_golden("ref_configs")
+    for name in ("C1", "C2", "C3"):
+        cfg = synth.config(name)
+        s = np.ascontiguousarray(cfg["samples"], dtype=np.int32)
+        m, n = s.shape
+        kw = dict(max_parent_set=cfg["max_parent_set"], max_complexity=cfg["max_complexity"],
+                  order=(np.asarray(cfg["order"]) + 1).astype(np.int32), num_cats=cfg["cats"], device=device)
+        fam = int(synth.num_families(n, cfg["max_parent_set"]))
+        keep = _abi.Keep()
+        p = _abi.make_params(keep, n, m, samples=s, **kw)
+
+        def one_shot():
+            h = ctypes.c_void_p()
+            t0 = time.perf_counter()
+            _abi.check(L.cnb_search_order(ctypes.byref(p), ctypes.byref(h)))
+            t = time.perf_counter() - t0
+            k = L.cnb_result_num_networks(h)
+            L.cnb_result_free(h)
+            return t, k
+        one_shot()
+        runs = [one_shot() for _ in range(5)]
+        t_one = float(np.median([t for t, _ in runs]))
+        nets = _abi.search_order(s, want_probs=False, **kw)
+        with _abi.Context(device) as ctx:
+            ctx.set_samples(s, num_cats=cfg["cats"])
+            kw2 = {k: v for k, v in kw.items() if k not in ("num_cats", "device")}
+            L.cnb_result_free(ctx.search_order_raw(**kw2))
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                L.cnb_result_free(ctx.search_order_raw(**kw2))
+                ts.append(time.perf_counter() - t0)
+            t_res = float(np.median(ts))
+            tm = ctx.timing()
+            check = None
+            if name == "C3":
+                ctx.force_generic(8 | 1024)                     # no tensor cores: bit-plane POPC kernels
+                other = ctx.search_order(want_probs=False, **kw2)
+                same = len(other) == len(nets) and all(a["parents"] == b["parents"] and a["loglik"] == b["loglik"]
+                                                       for a, b in zip(nets, other))
+                check = {"against": "the bit-plane kernels of this library (reference run > 1 h at this size)", "identical": bool(same)}
+        if name in golden:
+            try:
+                k = compare_golden(nets, golden[name])
+                check = {"against": "compiled reference (tests/golden/ref_configs.json.gz)", "identical": True, "networks": k}
+            except AssertionError as e:
+                check = {"against": "compiled reference (tests/golden/ref_configs.json.gz)", "identical": False, "error": str(e)[:200]}
+        out[name] = {"nodes": n, "samples": m, "max_parent_set": cfg["max_parent_set"], "families": fam,
+                     "one_shot_ms": 1000 * t_one, "resident_ms": 1000 * t_res, "families_per_s": fam / t_one,
+                     "families_per_s_resident": fam / t_res, "networks": len(nets), "check": check,
+                     "device_ms": {k: round(tm[k], 3) for k in ("plan_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
+                     "tensor_tiles": int(tm["tensor_tiles"]), "tensor3_tiles": int(tm["tensor3_tiles"])}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------- roofline
+def roofline_of(wl, phases, m, world, rank):
+    d_dom = wl["P"]
+    ph_last = phases[-1]
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom_ms = float(np.mean([p["score_ms_by_parents"][d_dom] for p in phases]))
+    dom_fam = ph_last["families_by_parents"][d_dom]
+    alg_bytes = dom_fam * ((d_dom + 1) * m + 8)
+    hbm_model = {"achieved_gbs": alg_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
+                 "frac": (alg_bytes / (dom_ms / 1000.0) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
+                 "algorithmic_bytes_per_launch": alg_bytes, "group_ms": dom_ms,
+                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("%s_gpus%d" % (wl["name"], world))
+    except Exception:
+        pass
+    if ph_last["tensor_tiles"] > 0:
+        # tcgen05 scorer: bound by the tensor pipe.  MEASURED_PEAKS.json only has a bf16 cuBLAS figure (nominal dense rates
+        # on B200: bf16 2.25, fp8/int8 4.5, fp4 9 PFLOP/s), and 4 x that figure is EXCEEDED by this kernel, so the
+        # denominator for E2M1 operands is measured here, live, by tools/umma_peak --quick: back-to-back
+        # tcgen05.mma.kind::mxf4 M128 N256 on every SM.  Two builder-independent denominators are quoted beside it:
+        # the nominal dense fp4 rate and the pipe arithmetic at the SM clock this run held.
+        fp4 = ph_last.get("tensor_kind", 8) == 4
+        t_ms = float(np.mean([p["tensor_ms"] for p in phases]))
+        ops = 2.0 * ph_last["tensor_macs"]
+        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = ops / (t_ms / 1000.0) / 1e12 if t_ms > 0 else 0.0
+        extra = {}
+        if fp4:
+            live = None
+            try:
+                if rank == 0:
+                    out = subprocess.run([os.path.join(ROOT, "tools", "umma_peak"), "--quick"], capture_output=True, text=True,
+                                         timeout=60).stdout.strip().splitlines()[-1]
+                    live = json.loads(out)
+            except Exception:
+                live = None
+            if live and "mxf4_ss_n256_tflops" in live:
+                peak = float(live["mxf4_ss_n256_tflops"])
+                extra = {"ts_ceiling": float(live["mxf4_ts_n192_tflops"]), "ts_clk_per_mma": live["mxf4_ts_n192_clk_per_mma"]}
+                src = ("measured live by tools/umma_peak --quick (back-to-back tcgen05.mma kind::mxf4 M128 N256, all SMs); "
+                       "MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
+            else:
+                peak = 8835.9
+                extra = {"ts_ceiling": 8369.2}
+                src = ("tools/umma_peak on this pool, recorded in profiles/r01_umma_peak_b200.txt (the binary did not run "
+                       "here); MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
+            extra["frac_of_nominal_9000"] = ach / 9000.0
+            extra["nominal_note"] = ("nominal dense fp4 9 PFLOP/s (B200_PROFILING.md); pipe arithmetic 16384 MAC/clk/SM x 148 SMs x "
+                                     "the SM clock of this run is reported as frac_of_pipe_at_clock")
+        else:
+            peak = 2.0 * bf16
+            src = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 nominal = 2 x bf16)" if peaks
+                   else "2 x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)")
+        useful_cells = 27.0
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": traffic,
+                    "kernel": "k_umma_tables (tcgen05.mma %s)" % ("kind::mxf4.block_scale" if fp4 else "kind::i8"),
+                    "kernel_ms": t_ms, "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
+                    "peak_source": src,
+                    "useful_mac_fraction": dom_fam * useful_cells * m / max(ph_last["tensor_macs"], 1),
+                    "hbm_model": hbm_model}
+        roofline.update(extra)
+    else:
+        roofline = {"bound": "hbm", "achieved": hbm_model["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_model["frac"], "traffic": traffic,
+                    "kernel": "k_score_planes%s<%d,%d>" % ("_ie2" if d_dom == 2 else "", d_dom, min(4, max(2, int(max(wl["cats"]))))),
+                    "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_model["peak_source"]}
+    roofline["family_samples_per_s"] = dom_fam * m / (dom_ms / 1000.0) if dom_ms > 0 else 0.0
+    return roofline
+
+
+def add_pipe_fraction(roofline, clocks):
+    """the tensor pipe's own arithmetic at the clock this run held: 16384 E2M1 MAC/clk/SM x 148 SMs"""
+    if roofline.get("bound") == "tensor" and clocks.get("sm_mhz") and "frac_of_nominal_9000" in roofline:
+        pipe = 2.0 * 16384 * 148 * clocks["sm_mhz"] * 1e6 / 1e12
+        roofline["pipe_at_clock_tflops"] = pipe
+        roofline["frac_of_pipe_at_clock"] = roofline["achieved"] / pipe
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, wl, n_fam_total, threads, rank):
+    if rank != 0:
+        return 0
+    s = draw_samples(wl)
+    s0 = np.ascontiguousarray(s.astype(np.int32) - 1)
+    order0 = wl["order"] - 1
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_rate(s0, wl["cats"], order0, wl["P"], 0.5, threads)
+    rates, t_all = [], 0.0
+    per_step = max(2.0, min(20.0, 120.0 / max(args.steps, 1)))
+    nfam = 0
+    for _ in range(args.steps):
+        r, k, wall, _ = cpu_reference_rate(s0, wl["cats"], order0, wl["P"], per_step, threads)
+        rates.append(r)
+        t_all += wall
+        nfam = k
+    v = float(np.mean(rates))
+    sample = "%d random candidate families with %d parents at full M=%d per step, %d concurrent reference scorers" % (
+        nfam, wl["P"], wl["m"], threads)
+    sa_ref = None
+    if not args.no_sa:
+        try:
+            sa_ref = sa_leg_reference()
+        except Exception as e:
+            sa_ref = {"unavailable": str(e)}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "families/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(wl, n_fam_total),
+        "cpu_baseline": {"value": v, "unit": "families/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "families/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sa": sa_ref}))
+    return 0
+
+
+METRIC = "family log-lik scores/sec (cnSearchOrder)"
+
+
+# ------------------------------------------------------------------------------------------------- one process, N GPUs
+def single_process_block(ngpus, wl, host_i32, steps, warmup, n_fam_total, want_e2e=True):
+    """cnb_mctx: ONE process drives ngpus devices (host threads, NVLink peer stores into the first device's score buffer).
+    Device time between two marks on the first device's stream, every device synchronised."""
+    from catnet_b200 import _abi
+    L = _abi.lib()
+    kw = dict(max_parent_set=wl["P"], max_complexity=wl["K"], order=wl["order"].astype(np.int32))
+    out = {"n_gpus": ngpus, "how": "one process, cnb_mctx: a host thread per device, scoring kernels store scores into device 0 "
+                                  "over NVLink peer memory, selection + DP + export on device 0 only"}
+    with _abi.MultiContext(0, ngpus) as mc:
+        t0 = time.perf_counter()
+        mc.set_samples(host_i32, num_cats=wl["cats"])
+        out["set_samples_first_ms"] = 1000 * (time.perf_counter() - t0)
+        for _ in range(max(warmup, 3)):
+            mc.search_light(**kw)
+        mc.mark(0)
+        for _ in range(steps):
+            mc.search_light(**kw)
+        mc.mark(1)
+        ms = mc.elapsed_ms()
+        out.update({"value": n_fam_total * steps / (ms / 1000.0), "unit": "families/s", "ms_per_step": ms / steps,
+                    "steps": steps, "active_devices": mc.active(),
+                    "tensor_ms_per_device": [round(mc.timing(i)["tensor_ms"], 3) for i in range(mc.g)],
+                    "phases_ms_device0": {k: mc.timing(0)[k] for k in ("plan_ms", "score_ms", "select_ms", "dp_ms")}})
+        h = mc.collect_raw()
+        nn = L.cnb_result_num_networks(h)
+        cx, ll = ctypes.c_int32(), ctypes.c_double()
+        L.cnb_result_network(h, nn - 1, ctypes.byref(cx), ctypes.byref(ll))
+        L.cnb_result_free(h)
+        out["result"] = {"networks": nn, "max_complexity": cx.value, "loglik": ll.value}
+        if want_e2e:
+            def e2e_step():
+                ta = time.perf_counter()
+                mc.set_samples(host_i32, num_cats=wl["cats"])
+                tb = time.perf_counter()
+                mc.search_light(**kw)
+                tc = time.perf_counter()
+                hh = mc.collect_raw()
+                td = time.perf_counter()
+                k = L.cnb_result_num_networks(hh)
+                L.cnb_result_free(hh)
+                return k, (tb - ta, tc - tb, td - tc)
+            e2e_step()
+            e_steps = max(1, min(steps, 3))
+            parts = np.zeros(3)
+            mc.mark(0)
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                k, pt = e2e_step()
+                parts += np.asarray(pt)
+            wall = time.perf_counter() - t0
+            mc.mark(1)
+            ems = max(mc.elapsed_ms(), 1000 * wall)           # every call returns synchronised: wall >= device span
+            tms = [mc.timing(i) for i in range(mc.g)]
+            out["e2e"] = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s", "ms_per_step": ems / e_steps,
+                          "steps": e_steps, "host_memory": "pageable",
+                          "h2d_bytes_per_step": int(sum(t["h2d_bytes"] for t in tms)),
+                          "d2h_bytes_per_step": int(sum(t["d2h_bytes"] for t in tms)),
+                          "host_wall_ms_per_step": {"set_samples_ms": 1000 * parts[0] / e_steps, "search_ms": 1000 * parts[1] / e_steps,
+                                                    "export_ms": 1000 * parts[2] / e_steps},
+                          "networks": k}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- main
@@ -234,6 +543,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-sa", action="store_true", help="skip the cnSearchSA wall-time leg (BASELINE config C4)")
     ap.add_argument("--sa-iter", type=int, default=1000)
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1..C3 block")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process drives --gpus N devices through cnb_mctx (no torchrun, no NCCL): the R-session form")
+    ap.add_argument("--no-single-process-block", action="store_true",
+                    help="under torchrun: skip the extra single-process measurement rank 0 makes after the main one")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,48 +556,11 @@ def main():
     if world != max(args.gpus, 1) and world > 1:
         log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
     wl = build_workload(args.config, args.samples)
-    metric = "family log-lik scores/sec (cnSearchOrder)"
     n_fam_total = sum(math.comb(wl["n"], d + 1) for d in range(1, wl["P"] + 1))
     threads = os.cpu_count() or 1
 
     if args.impl == "reference":
-        if rank != 0:
-            return 0
-        from catnet_b200 import synth
-        if "samples" in wl:
-            s = wl["samples"]
-        else:
-            s = synth.sample_network(wl["net"], wl["m"], np.random.Generator(np.random.PCG64(wl["seed"])), dtype=np.int8)
-        s0 = np.ascontiguousarray(s.astype(np.int32) - 1)
-        order0 = wl["order"] - 1
-        for _ in range(max(args.warmup, 0)):
-            cpu_reference_rate(s0, wl["cats"], order0, wl["P"], 0.5, threads)
-        rates, t_all = [], 0.0
-        per_step = max(2.0, min(20.0, 120.0 / max(args.steps, 1)))
-        nfam = 0
-        for _ in range(args.steps):
-            r, k, wall = cpu_reference_rate(s0, wl["cats"], order0, wl["P"], per_step, threads)
-            rates.append(r)
-            t_all += wall
-            nfam = k
-        v = float(np.mean(rates))
-        sample = "%d random candidate families with %d parents at full M=%d per step, %d concurrent reference scorers" % (
-            nfam, wl["P"], wl["m"], threads)
-        sa_ref = None
-        if not args.no_sa:
-            try:
-                sa_ref = sa_leg_reference(30)
-            except Exception as e:
-                sa_ref = {"unavailable": str(e)}
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": "families/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "families": n_fam_total},
-            "cpu_baseline": {"value": v, "unit": "families/s", "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": v, "unit": "families/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "sa": sa_ref}))
-        return 0
+        return reference_arm(args, wl, n_fam_total, threads, rank)
 
     import torch
     import torch.distributed as dist
@@ -293,39 +570,70 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the scoring path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")       # host-side barrier while rank 0 measures the single-process form
 
-    # ---- synthetic data: rank 0 draws, everybody receives the same matrix
+    # ---- synthetic data: rank 0 draws on the host (numpy, the same generator as the reference arm), everybody receives it
     t0 = time.time()
-    if "samples" in wl:
-        samples_dev = torch.as_tensor(wl["samples"], dtype=torch.int32, device=dev)
-    elif rank == 0:
-        samples_dev = sample_on_device(wl, dev)
+    m, n = wl["m"], wl["n"]
+    host8 = None
+    if rank == 0:
+        host8 = draw_samples(wl)
+        samples_dev8 = torch.as_tensor(host8.view(np.uint8), device=dev)
     else:
-        samples_dev = torch.empty((wl["m"], wl["n"]), dtype=torch.int32, device=dev)
+        samples_dev8 = torch.empty((m, n), dtype=torch.uint8, device=dev)
     if world > 1:
-        dist.broadcast(samples_dev, 0)
+        dist.broadcast(samples_dev8, 0)
     torch.cuda.synchronize()
-    log("rank %d: data %s ready in %.1fs" % (rank, tuple(samples_dev.shape), time.time() - t0))
-    m, n = samples_dev.shape
+    log("rank %d: data %s ready in %.1fs" % (rank, tuple(samples_dev8.shape), time.time() - t0))
     kw = dict(max_parent_set=wl["P"], max_complexity=wl["K"], order=wl["order"].astype(np.int32))
+
+    if args.single_process:
+        if world > 1:
+            raise SystemExit("--single-process is launched WITHOUT torchrun")
+        host_i32 = np.ascontiguousarray(host8.astype(np.int32))          # pageable, as R's matrix
+        del samples_dev8
+        sampler = ClockSampler(0)
+        tw0 = time.time()
+        sp = single_process_block(args.gpus, wl, host_i32, args.steps, args.warmup, n_fam_total, not args.no_e2e)
+        tw1 = time.time()
+        clocks = sampler.stop(tw0, tw1)
+        sa_res = None
+        if not args.no_sa and args.config == "C5" and args.samples is None:
+            try:
+                sa_res = sa_leg_single_process(args.gpus, args.sa_iter)
+            except Exception as e:
+                sa_res = {"unavailable": str(e)}
+        line = {"metric": METRIC, "value": sp["value"], "unit": "families/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": sp["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "e2m1 one-hot operands, f32 accumulators holding exact counts, f64 log-lik",
+                "data": "synthetic", "config": config_of(wl, n_fam_total), "clocks": clocks, "mode": "single-process",
+                "e2e": sp.get("e2e"), "single_process": sp, "sa": sa_res}
+        print(json.dumps(line))
+        return 0
 
     ctx = _abi.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    ctx.set_samples_dev(samples_dev.data_ptr(), n, m, num_cats=wl["cats"])
+    ctx.set_samples_dev8(samples_dev8.data_ptr(), n, m, num_cats=wl["cats"])
     if args.kernel_bits:
         ctx.force_generic(args.kernel_bits)
     seg, nfam = ctx.plan(rank, world, **kw)
     assert nfam == n_fam_total, (nfam, n_fam_total)
     scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=dev)
+    my_seg = scores[rank * seg:(rank + 1) * seg]
+
+    def gather():
+        # in place: rank r's segment already sits at offset r of the output (ncclAllGather's in-place form)
+        if world > 1:
+            dist.all_gather_into_tensor(scores, my_seg)
 
     def step():
         ctx.plan(rank, world, **kw)
         ctx.score_shard(scores.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(scores, scores[rank * seg:(rank + 1) * seg].clone())
+        gather()
         ctx.select_dp(scores.data_ptr())
 
     def barrier():
@@ -356,91 +664,47 @@ def main():
     ms = float(t_ms.item())
     value = n_fam_total * args.steps / (ms / 1000.0)
 
-    # ---- roofline of the dominant kernel, measured live (the library's CUDA events on the launching stream)
-    d_dom = wl["P"]
-    ph_last = phases[-1]
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom_ms = float(np.mean([p["score_ms_by_parents"][d_dom] for p in phases]))
-    dom_fam = ph_last["families_by_parents"][d_dom]
-    alg_bytes = dom_fam * ((d_dom + 1) * m + 8)
-    hbm_model = {"achieved_gbs": alg_bytes / (dom_ms / 1000.0) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": hbm_peak,
-                 "frac": (alg_bytes / (dom_ms / 1000.0) / 1e9 / hbm_peak) if dom_ms > 0 else 0.0,
-                 "algorithmic_bytes_per_launch": alg_bytes, "group_ms": dom_ms,
-                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"}
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("%s_gpus%d" % (wl["name"], world))
-    except Exception:
-        pass
-    if ph_last["tensor_tiles"] > 0:
-        # tcgen05 scorer: bound by the tensor pipe.  MEASURED_PEAKS.json only has a bf16 cuBLAS figure (nominal dense rates
-        # on B200: bf16 2.25, fp8/int8 4.5, fp4 9 PFLOP/s), and 4 x that figure is EXCEEDED by this kernel, so the
-        # denominator for E2M1 operands is measured here, live, by tools/umma_peak --quick: back-to-back
-        # tcgen05.mma.kind::mxf4 M128 N256 on every SM (the best rate the instruction reaches; the table kernel issues
-        # the A-from-tensor-memory form at N <= 192, whose own ceiling is reported as ts_ceiling).  u8 operands
-        # (kind::i8, test path): 2 x the measured sustained bf16 figure.
-        fp4 = ph_last.get("tensor_kind", 8) == 4
-        t_ms = float(np.mean([p["tensor_ms"] for p in phases]))
-        ops = 2.0 * ph_last["tensor_macs"]
-        bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        ach = ops / (t_ms / 1000.0) / 1e12 if t_ms > 0 else 0.0
-        extra = {}
-        if fp4:
-            live = None
-            try:
-                if rank == 0:
-                    out = subprocess.run([os.path.join(ROOT, "tools", "umma_peak"), "--quick"], capture_output=True, text=True,
-                                         timeout=60).stdout.strip().splitlines()[-1]
-                    live = json.loads(out)
-            except Exception:
-                live = None
-            if live and "mxf4_ss_n256_tflops" in live:
-                peak = float(live["mxf4_ss_n256_tflops"])
-                extra = {"ts_ceiling": float(live["mxf4_ts_n192_tflops"]), "ts_clk_per_mma": live["mxf4_ts_n192_clk_per_mma"]}
-                src = ("measured live by tools/umma_peak --quick (back-to-back tcgen05.mma kind::mxf4 M128 N256, all SMs); "
-                       "MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
-            else:
-                peak = 8835.9
-                extra = {"ts_ceiling": 8369.2}
-                src = ("tools/umma_peak on this pool, recorded in profiles/r01_umma_peak_b200.txt (the binary did not run "
-                       "here); MEASURED_PEAKS.json has no fp4 figure (4 x its bf16_tflops_sustained = %.0f)" % (4.0 * bf16))
-        else:
-            peak = 2.0 * bf16
-            src = ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 nominal = 2 x bf16)" if peaks
-                   else "2 x 1400 TFLOP/s fallback (B200_PROFILING.md sustained bf16)")
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic,
-                    "kernel": "k_umma_tables (tcgen05.mma %s)" % ("kind::mxf4.block_scale" if fp4 else "kind::i8"),
-                    "kernel_ms": t_ms, "ops_per_launch": ops, "tiles": int(ph_last["tensor_tiles"]),
-                    "peak_source": src,
-                    "useful_mac_fraction": dom_fam * 27.0 * m / max(ph_last["tensor_macs"], 1),
-                    "hbm_model": hbm_model}
-        roofline.update(extra)
-    else:
-        roofline = {"bound": "hbm", "achieved": hbm_model["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_model["frac"], "traffic": traffic,
-                    "kernel": "k_score_planes%s<%d,%d>" % ("_ie2" if d_dom == 2 else "", d_dom, min(4, max(2, int(max(wl["cats"]))))),
-                    "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_model["peak_source"]}
-    roofline["family_samples_per_s"] = dom_fam * m / (dom_ms / 1000.0) if dom_ms > 0 else 0.0
+    roofline = roofline_of(wl, phases, m, world, rank)
+    add_pipe_fraction(roofline, clocks)
 
-    # ---- e2e through the C ABI with host buffers
+    # ---- the reference's CPU path beside it (rank 0, N=1 only) + parity of the benchmarked kernel's own scores
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            s0 = np.ascontiguousarray(host8.astype(np.int32) - 1)
+            r, k, wall, scored = cpu_reference_rate(s0, wl["cats"], wl["order"] - 1, wl["P"], args.cpu_budget, threads)
+            del s0
+            cpu = {"value": r, "unit": "families/s", "cores": threads, "kind": "reference",
+                   "sample": "%d random candidate families with %d parents at full M=%d, %d concurrent reference "
+                             "scorers (CATNET::setParents+setNodeSampleProb), %.1fs wall" % (k, wl["P"], m, threads, wall)}
+            # the SAME families as the timed search scored them (tile slots of the tcgen05 tables), read from the score
+            # buffer of the last timed step, against the reference's values on the same matrix: bit equality
+            ours = ctx.search_scores(scores.data_ptr(), scored["children_pos"], scored["parents_pos"])
+            bad = int(np.sum(ours.view(np.int64) != scored["loglik"].view(np.int64)))
+            parity = {"families": int(len(ours)), "mismatches": bad,
+                      "what": "scores of the timed search (k_umma_tables + k_umma_epilogue) vs the compiled reference's "
+                              "setNodeSampleProb on the same matrix, fp64 bit equality (equal log-lik <=> equal counts summed "
+                              "in the same order)"}
+            if bad:
+                worst = int(np.argmax(np.abs(ours - scored["loglik"])))
+                parity["first_mismatch"] = {"child_pos": int(scored["children_pos"][worst]),
+                                            "parents_pos": [int(v) for v in scored["parents_pos"][worst]],
+                                            "ours": float(ours[worst]), "reference": float(scored["loglik"][worst])}
+        except Exception as e:  # the checker library is optional for the product path
+            cpu = {"value": None, "unit": "families/s", "cores": threads, "kind": "reference", "sample": "unavailable: %s" % e}
+
+    # ---- e2e through the C ABI with host buffers (pageable, as R's)
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((m, n), dtype=torch.int32, pin_memory=True)
-        host.copy_(samples_dev)
-        torch.cuda.synchronize()
-        hnp = host.numpy()
+        hnp = np.empty((m, n), dtype=np.int32)
+        if rank == 0:
+            hnp[:] = host8
+        else:
+            hnp[:] = samples_dev8.cpu().numpy().view(np.int8)
+        host = torch.from_numpy(hnp)
         ctx2 = _abi.Context(local_rank)
         ctx2.set_stream(stream.cuda_stream)
         L = _abi.lib()
-
         wall = {"set_samples_ms": 0.0, "plan_score_ms": 0.0, "finish_ms": 0.0, "h2d_bytes": 0}
 
         def e2e_step():
@@ -455,20 +719,21 @@ def main():
             t_b = time.perf_counter()
             ctx2.plan(rank, world, **kw)
             ctx2.score_shard(scores.data_ptr())
-            if world > 1:
-                dist.all_gather_into_tensor(scores, scores[rank * seg:(rank + 1) * seg].clone())
+            gather()
             t_c = time.perf_counter()
-            h = ctx2.finish_raw(scores.data_ptr())                # selection + DP + network export (D2H)
+            res = None
+            if rank == 0:
+                h = ctx2.finish_raw(scores.data_ptr())            # selection + DP + network export (D2H): rank 0 only
+                nn = L.cnb_result_num_networks(h)
+                cx, ll = ctypes.c_int32(), ctypes.c_double()
+                L.cnb_result_network(h, nn - 1, ctypes.byref(cx), ctypes.byref(ll))
+                L.cnb_result_free(h)
+                res = (nn, cx.value, ll.value)
             t_d = time.perf_counter()
             wall["set_samples_ms"] += (t_b - t_a) * 1e3
             wall["plan_score_ms"] += (t_c - t_b) * 1e3
             wall["finish_ms"] += (t_d - t_c) * 1e3
-            nn = L.cnb_result_num_networks(h)
-            import ctypes
-            cx, ll = ctypes.c_int32(), ctypes.c_double()
-            L.cnb_result_network(h, nn - 1, ctypes.byref(cx), ctypes.byref(ll))
-            L.cnb_result_free(h)
-            return nn, cx.value, ll.value
+            return res
 
         e2e_step()
         barrier()
@@ -482,59 +747,75 @@ def main():
         barrier()
         ems = ev0.elapsed_time(ev1)
         t_ms = torch.tensor([ems], dtype=torch.float64, device=dev)
+        tm = ctx2.timing()
+        traffic = torch.tensor([int(tm["h2d_bytes"]) + int(wall["h2d_bytes"]), int(tm["d2h_bytes"])], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(traffic, op=dist.ReduceOp.SUM)
         ems = float(t_ms.item())
-        tm = ctx2.timing()
-        e2e = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s",
-               "h2d_bytes_per_step": (int(tm["h2d_bytes"]) + int(wall["h2d_bytes"])) * world,
-               "d2h_bytes_per_step": int(tm["d2h_bytes"]) * world,
-               "ms_per_step": ems / e_steps, "steps": e_steps,
-               "host_wall_ms_per_step": {k_: wall[k_] / e_steps for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms")},
-               "device_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
-               "result": {"networks": res[0], "max_complexity": res[1], "loglik": res[2]}}
+        if rank == 0:
+            e2e = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s",
+                   "h2d_bytes_per_step": int(traffic[0].item()), "d2h_bytes_per_step": int(traffic[1].item()),
+                   "ms_per_step": ems / e_steps, "steps": e_steps, "host_memory": "pageable",
+                   "host_wall_ms_per_step": {k_: wall[k_] / e_steps for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms")},
+                   "device_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
+                   "result": {"networks": res[0], "max_complexity": res[1], "loglik": res[2]}}
         ctx2.close()
+        del host, hnp
 
-    # ---- the reference's CPU path beside it (rank 0, N=1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            s0 = np.ascontiguousarray((samples_dev - 1).cpu().numpy())
-            r, k, wall = cpu_reference_rate(s0, wl["cats"], wl["order"] - 1, wl["P"], args.cpu_budget, threads)
-            cpu = {"value": r, "unit": "families/s", "cores": threads, "kind": "reference",
-                   "sample": "%d random candidate families with %d parents at full M=%d, %d concurrent reference "
-                             "scorers (CATNET::setParents+setNodeSampleProb), %.1fs wall" % (k, wl["P"], m, threads, wall)}
-        except Exception as e:  # the checker library is optional for the product path
-            cpu = {"value": None, "unit": "families/s", "cores": threads, "kind": "reference", "sample": "unavailable: %s" % e}
-
-    # ---- cnSearchSA wall time (second half of the BASELINE metric): one chain per GPU
+    # ---- cnSearchSA wall time (second half of the BASELINE metric): one chain per GPU, merged
     sa_res = None
     if not args.no_sa and args.config == "C5" and args.samples is None:
         try:
-            sa_res = sa_leg_ours(rank, world, args.sa_iter, dist if world > 1 else None, dev)
+            sa_res = sa_leg_torchrun(rank, world, args.sa_iter, dist if world > 1 else None, dev)
         except Exception as e:
             sa_res = {"unavailable": str(e)}
 
+    ph = phases[-1]
+    ctx.close()
+    del scores, my_seg, samples_dev8
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (rank 0 at N = 1) and the single-process form of this very workload (rank 0, N > 1)
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and args.config == "C5" and args.samples is None:
+        try:
+            configs = configs_block(local_rank)
+        except Exception as e:
+            configs = {"unavailable": str(e)}
+    single = None
+    if world > 1 and not args.no_single_process_block:
+        dist.barrier(group=cpu_group)                       # every rank has released its GPU; the others now wait on the host
+        if rank == 0:
+            try:
+                host_i32 = np.ascontiguousarray(host8.astype(np.int32))
+                single = single_process_block(world, wl, host_i32, args.steps, args.warmup, n_fam_total, not args.no_e2e)
+                del host_i32
+                if not args.no_sa and args.config == "C5" and args.samples is None:
+                    single["sa"] = sa_leg_single_process(world, args.sa_iter)
+            except Exception as e:
+                single = {"unavailable": str(e)}
+        dist.barrier(group=cpu_group)
+
     if rank == 0:
-        ph = phases[-1]
         line = {
-            "metric": metric, "value": value, "unit": "families/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": "families/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": ("e2m1 one-hot operands, f32 accumulators holding exact counts, f64 log-lik"
                       if ph.get("tensor_kind", 0) == 4 else "u32 counts + f64 log-lik"), "data": "synthetic",
-            "config": {"workload": wl["desc"], "families": n_fam_total, "families_per_rank": int(ph["num_families"]),
-                       "l2": "inputs larger than L2 (bit planes %.0f MB)" % (n * ((m + 31) // 32) * 16 / 1e6),
-                       "data_rng": "network numpy PCG64(%d); samples torch CUDA Philox(%d)" % (wl["seed"], wl["seed"])},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": config_of(wl, n_fam_total), "families_per_rank": int(ph["num_families"]),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity_spot": parity, "e2e": e2e,
             "gpu_launches": int(ph["kernel_launches"]) * args.steps,
             "phases_ms": {k: ph[k] for k in ("plan_ms", "score_ms", "select_ms", "dp_ms")},
-            "sa": sa_res,
+            "sa": sa_res, "configs": configs, "single_process": single,
         }
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity["mismatches"]:
+        log("PARITY FAILURE: %d of %d spot-checked families differ from the reference" % (parity["mismatches"], parity["families"]))
+        return 3
     return 0
 
 

@@ -34,12 +34,16 @@ class SaParams(C.Structure):
     _fields_ = [("select_mode", C.c_int32), ("start_order", C.c_void_p), ("temp_start", C.c_double),
                 ("temp_cool_fact", C.c_double), ("temp_check_orders", C.c_int32), ("max_iter", C.c_int32),
                 ("order_shuffles", C.c_double), ("stop_diff", C.c_double), ("num_threads", C.c_int32),
-                ("use_cache", C.c_int32), ("dir_prob", C.c_void_p), ("seed", C.c_uint64)]
+                ("use_cache", C.c_int32), ("dir_prob", C.c_void_p), ("seed", C.c_uint64), ("unif", C.c_void_p),
+                ("unif_ctx", C.c_void_p)]
 
 
 class HistParams(C.Structure):
     _fields_ = [("score", C.c_int32), ("weight", C.c_int32), ("max_iter", C.c_int32), ("num_threads", C.c_int32),
-                ("use_cache", C.c_int32), ("seed", C.c_uint64)]
+                ("use_cache", C.c_int32), ("seed", C.c_uint64), ("unif", C.c_void_p), ("unif_ctx", C.c_void_p)]
+
+
+UNIF_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)     # double (*unif)(void *): cnb_sa_params.unif / cnb_hist_params.unif
 
 
 class Network(C.Structure):
@@ -75,6 +79,10 @@ SYMBOLS = [
     "cnb_pairwise", "cnb_entropy_order", "cnb_ctx_pairwise", "cnb_ctx_entropy_order",
     "cnb_loglik", "cnb_node_loglik", "cnb_set_prob", "cnb_ctx_loglik", "cnb_ctx_set_prob",
     "cnb_samples", "cnb_samples_dev", "cnb_ctx_set_samples_dev8", "cnb_tile3_selftest", "cnb_host_entropy_order",
+    "cnb_mctx_create", "cnb_mctx_destroy", "cnb_mctx_num_devices", "cnb_mctx_ctx", "cnb_mctx_set_samples",
+    "cnb_mctx_search_order", "cnb_mctx_search_light", "cnb_mctx_collect", "cnb_mctx_search_sa", "cnb_mctx_search_hist",
+    "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
+    "cnb_ctx_upload_rows8",
 ]
 
 _lib = None
@@ -146,6 +154,21 @@ def lib():
         "cnb_ctx_set_prob": (i32, [vp, P(Network), vp, vp, vp]),
         "cnb_samples": (i32, [P(Network), i32, vp, dbl, C.c_uint64, i32, vp]),
         "cnb_samples_dev": (i32, [P(Network), i32, vp, dbl, C.c_uint64, i32, vp]),
+        "cnb_ctx_search_scores": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+        "cnb_ctx_upload_rows8": (i32, [vp, i32, vp, i64, i64, vp, i32]),
+        "cnb_mctx_create": (i32, [i32, i32, P(vp)]),
+        "cnb_mctx_destroy": (None, [vp]),
+        "cnb_mctx_num_devices": (i32, [vp]),
+        "cnb_mctx_active": (i32, [vp]),
+        "cnb_mctx_ctx": (vp, [vp, i32]),
+        "cnb_mctx_set_samples": (i32, [vp, i32, i32, vp, vp, vp]),
+        "cnb_mctx_search_order": (i32, [vp, P(Params), P(vp)]),
+        "cnb_mctx_search_light": (i32, [vp, P(Params)]),
+        "cnb_mctx_collect": (i32, [vp, P(vp)]),
+        "cnb_mctx_search_sa": (i32, [vp, P(Params), P(SaParams), P(vp)]),
+        "cnb_mctx_search_hist": (i32, [vp, P(Params), P(HistParams), vp, P(i32)]),
+        "cnb_mctx_mark": (i32, [vp, i32]),
+        "cnb_mctx_elapsed_ms": (i32, [vp, P(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -295,6 +318,11 @@ class Context:
         self.n, self.m = n, m
         check(lib().cnb_ctx_set_samples_dev8(self.h, n, m, samples_dev_ptr, perturbations_dev_ptr, ptr(i32(num_cats))))
 
+    def upload_rows8(self, samples, row0, row1, dst_dev_ptr, max_threads=0):
+        """rows [row0, row1) of the host int32 matrix -> bytes at dst_dev_ptr + row0 * N (first step of a sharded upload)"""
+        s = i32(samples)
+        check(lib().cnb_ctx_upload_rows8(self.h, s.shape[1], ptr(s), int(row0), int(row1), dst_dev_ptr, int(max_threads)))
+
     def num_cats(self):
         out = np.zeros(self.n, dtype=np.int32)
         check(lib().cnb_ctx_num_cats(self.h, ptr(out)))
@@ -373,6 +401,14 @@ class Context:
                                       int(force_generic)))
         return counts, ll, nc
 
+    def search_scores(self, scores_dev_ptr, children_pos, parents_pos):
+        """scores the last score_shard wrote for explicit families (order positions, parents ascending)"""
+        ch = i32(children_pos)
+        pa = i32(parents_pos).reshape(len(ch), -1)
+        out = np.zeros(len(ch), dtype=np.float64)
+        check(lib().cnb_ctx_search_scores(self.h, scores_dev_ptr, len(ch), pa.shape[1], ptr(ch), ptr(pa), ptr(out)))
+        return out
+
     def pairwise(self, kind):
         """kind "entropy" | "kl" | "pearson" -> numpy [N][N] laid out like R's matrix(mat, N, N): out[n1][n2]"""
         out = np.zeros((self.n, self.n), dtype=np.float64)
@@ -424,6 +460,99 @@ class Context:
             return read_sa_result(h, self.n, want_probs)
         finally:
             lib().cnb_result_free(h)
+
+
+class MultiContext:
+    """cnb_mctx: one process driving several GPUs (the form an R session uses): the sample matrix on every device,
+    candidate parent sets sharded, SA chains / histogram orders dealt out."""
+
+    def __init__(self, first_device=0, num_devices=2):
+        self.h = C.c_void_p()
+        check(lib().cnb_mctx_create(int(first_device), int(num_devices), C.byref(self.h)))
+        self.g = lib().cnb_mctx_num_devices(self.h)
+        self.n = self.m = 0
+
+    def close(self):
+        if self.h:
+            lib().cnb_mctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_samples(self, samples, perturbations=None, num_cats=None):
+        s = i32(samples)
+        self.m, self.n = s.shape
+        check(lib().cnb_mctx_set_samples(self.h, self.n, self.m, ptr(s), ptr(i32(perturbations)), ptr(i32(num_cats))))
+
+    def active(self):
+        return lib().cnb_mctx_active(self.h)
+
+    def timing(self, i=0):
+        t = Timing()
+        check(lib().cnb_ctx_timing(lib().cnb_mctx_ctx(self.h, i), C.byref(t)))
+        return t.as_dict()
+
+    def force_generic(self, on):
+        for i in range(self.g):
+            check(lib().cnb_ctx_force_generic(lib().cnb_mctx_ctx(self.h, i), int(on)))
+
+    def search_light(self, **kw):
+        keep = Keep()
+        p = make_params(keep, self.n, self.m, **kw)
+        check(lib().cnb_mctx_search_light(self.h, C.byref(p)))
+
+    def collect_raw(self):
+        h = C.c_void_p()
+        check(lib().cnb_mctx_collect(self.h, C.byref(h)))
+        return h
+
+    def search_order(self, want_probs=True, **kw):
+        keep = Keep()
+        p = make_params(keep, self.n, self.m, **kw)
+        h = C.c_void_p()
+        check(lib().cnb_mctx_search_order(self.h, C.byref(p), C.byref(h)))
+        try:
+            return read_result(h, want_probs)
+        finally:
+            lib().cnb_result_free(h)
+
+    def search_sa(self, sa, want_probs=False, **kw):
+        keep = Keep()
+        p = make_params(keep, self.n, self.m, **kw)
+        s = make_sa_params(keep, **sa)
+        h = C.c_void_p()
+        check(lib().cnb_mctx_search_sa(self.h, C.byref(p), C.byref(s), C.byref(h)))
+        try:
+            return read_sa_result(h, self.n, want_probs)
+        finally:
+            lib().cnb_result_free(h)
+
+    def search_hist(self, hist, **kw):
+        keep = Keep()
+        p = make_params(keep, self.n, self.m, **kw)
+        hp = make_hist_params(**hist)
+        out = np.zeros((self.n, self.n), dtype=np.float64)
+        it = C.c_int32()
+        check(lib().cnb_mctx_search_hist(self.h, C.byref(p), C.byref(hp), ptr(out), C.byref(it)))
+        return out, it.value
+
+    def mark(self, which):
+        check(lib().cnb_mctx_mark(self.h, int(which)))
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        check(lib().cnb_mctx_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
 
 LOGLIK_MODES = {"nodes": 0, "bysample": 1}
@@ -529,16 +658,24 @@ def entropy_order(samples, perturbations=None, device=0):
     return out
 
 
-def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=True, seed=1):
+def _unif_ptr(unif):
+    """unif: None, an address, or a ctypes UNIF_FN object (the caller keeps it alive) -> void * for the params struct"""
+    if unif is None:
+        return None
+    return C.cast(unif, C.c_void_p) if not isinstance(unif, int) else C.c_void_p(unif)
+
+
+def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=True, seed=1, unif=None):
     h = HistParams()
     h.score, h.weight, h.max_iter, h.num_threads = int(score), int(weight), int(max_iter), int(num_threads)
     h.use_cache, h.seed = int(bool(use_cache)), int(seed)
+    h.unif = _unif_ptr(unif)
     return h
 
 
 def make_sa_params(keep, select_mode=0, start_order=None, temp_start=1.0, temp_cool_fact=0.9, temp_check_orders=10,
                    max_iter=100, order_shuffles=1.0, stop_diff=1e-10, num_threads=1, use_cache=True, dir_prob=None,
-                   seed=1):
+                   seed=1, unif=None):
     s = SaParams()
     s.select_mode = int(select_mode)
     s.start_order = keep(i32(start_order))
@@ -548,6 +685,7 @@ def make_sa_params(keep, select_mode=0, start_order=None, temp_start=1.0, temp_c
     s.num_threads, s.use_cache = int(num_threads), int(bool(use_cache))
     s.dir_prob = keep(None if dir_prob is None else f64(np.asarray(dir_prob, dtype=np.float64).T))
     s.seed = int(seed)
+    s.unif = _unif_ptr(unif)
     return s
 
 

@@ -6,6 +6,7 @@
  * CNB_ERR_CUDA.
  */
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 #include <algorithm>
 #include <chrono>
@@ -162,16 +163,17 @@ static float ev_ms(cnb_ctx *c, int a, int b) {
 }
 
 /* samples_dev: [M][N] int32 (elem_bytes 4) or uint8 with 0 = missing (elem_bytes 1) in device memory */
-static int set_samples_dev_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes,
+int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes,
 		const int32_t *pert_dev, const int32_t *num_cats) {
 	if (!c || N < 1 || M < 1 || !samples_dev) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
+	/* a failure part-way must not leave the previous data set looking valid next to the new sizes */
+	c->have_samples = c->planned = c->dp_done = false;
 	c->N = N;
 	c->M = M;
 	c->W = (M + 31) / 32;
 	c->Mpad = c->W * 32;
 	c->has_pert = pert_dev != nullptr;
-	c->planned = false;
 	if (!c->in_host_set) c->timing.h2d_bytes = c->timing.d2h_bytes = 0;   /* traffic is counted per data set */
 	cudaStream_t st = c->stream;
 	CK(cudaEventRecord(c->ev[EV_PACK0], st));
@@ -267,71 +269,94 @@ static int set_samples_dev_impl(cnb_ctx *c, int32_t N, int32_t M, const void *sa
 
 extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples_dev,
 		const int32_t *pert_dev, const int32_t *num_cats) {
-	return set_samples_dev_impl(c, N, M, samples_dev, 4, pert_dev, num_cats);
+	return cnb_ctx_set_samples_impl(c, N, M, samples_dev, 4, pert_dev, num_cats);
 }
 
 extern "C" int cnb_ctx_set_samples_dev8(cnb_ctx *c, int32_t N, int32_t M, const uint8_t *samples_dev,
 		const int32_t *pert_dev, const int32_t *num_cats) {
-	return set_samples_dev_impl(c, N, M, samples_dev, 1, pert_dev, num_cats);
+	return cnb_ctx_set_samples_impl(c, N, M, samples_dev, 1, pert_dev, num_cats);
 }
 
-/* int32 -> uint8 with saturation (x < 1, NA_INTEGER included -> 0 = missing; x > 255 -> 255, which no node has as a
- * category, so the pack kernel reports it): 16 values per step, SSE2 */
+/* int32 -> uint8 with saturation (x < 1, NA_INTEGER included -> 0 = missing; x > 255 -> 255): 16 values per step, SSE2.
+ * Returns true when some value was above 255: the byte form cannot carry it (labels such as 300..302 are legal when the
+ * categories are inferred as max - min + 1), and the caller falls back to the int32 upload. */
 #include <emmintrin.h>
 #include <atomic>
 #include <thread>
-static void compact_rows(const int32_t *src, uint8_t *dst, size_t n) {
+static bool compact_rows(const int32_t *src, uint8_t *dst, size_t n) {
 	size_t i = 0;
 	const bool stream = ((uintptr_t)dst & 15) == 0;              /* non-temporal stores: the bytes are read next by the copy engine */
+	const __m128i lim = _mm_set1_epi32(255);
+	__m128i over = _mm_setzero_si128();
 	for (; i + 16 <= n; i += 16) {
 		const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 4));
 		const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 8)), d = _mm_loadu_si128((const __m128i *)(src + i + 12));
+		over = _mm_or_si128(over, _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(a, lim), _mm_cmpgt_epi32(b, lim)),
+				_mm_or_si128(_mm_cmpgt_epi32(c, lim), _mm_cmpgt_epi32(d, lim))));
 		const __m128i v = _mm_packus_epi16(_mm_packs_epi32(a, b), _mm_packs_epi32(c, d));
 		if (stream) _mm_stream_si128((__m128i *)(dst + i), v);
 		else _mm_storeu_si128((__m128i *)(dst + i), v);
 	}
-	for (; i < n; i++) dst[i] = (uint8_t)(src[i] < 1 ? 0 : (src[i] > 255 ? 255 : src[i]));
+	bool big = _mm_movemask_epi8(over) != 0;
+	for (; i < n; i++) {
+		big = big || src[i] > 255;
+		dst[i] = (uint8_t)(src[i] < 1 ? 0 : (src[i] > 255 ? 255 : src[i]));
+	}
 	_mm_sfence();
+	return big;
 }
 
 /* Large host matrices cross PCIe as bytes: the categories fit 8 bits, the int32 matrix R holds is 4x that.  Host threads
- * compact chunk after chunk into a pinned buffer while the copy engine moves the chunks already done (C5: 2 GB in 40 ms
- * as int32 against 0.5 GB behind the compaction).  Not with perturbations (a second int32 matrix: plain path). */
-static int set_samples_compacted(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples, const int32_t *num_cats) {
-	const size_t total = (size_t)N * M;
+ * compact chunk after chunk of values [v0, v1) into the context's pinned buffer while the copy engine moves the chunks
+ * already done to dst_dev + v0 (C5: 2 GB in 40 ms as int32 against 0.5 GB behind the compaction).  The source may be
+ * pageable memory (R's): the threads read it, only the pinned bytes are DMA'd.  *overflow = a value above 255 was met. */
+int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads,
+		bool *overflow) {
+	const size_t total = v1 - v0;
+	*overflow = false;
+	if (!total) return CNB_OK;
 	RC(c->pin_stage.ensure(total));
-	RC(c->b_stage_s.ensure(total));
 	uint8_t *pin = (uint8_t *)c->pin_stage.ptr;
-	const size_t chunk = (size_t)8 << 20;                       /* values per chunk: 32 MB of int32 -> 8 MB */
+	const size_t chunk = (size_t)4 << 20;                       /* values per chunk: 16 MB of int32 -> 4 MB */
 	const int nchunks = (int)((total + chunk - 1) / chunk);
 	unsigned hw = std::thread::hardware_concurrency();
-	const int nthreads = (int)std::max(1u, std::min(std::min(hw ? hw : 4u, 16u), (unsigned)nchunks));
+	const int nthreads = (int)std::max(1u, std::min(std::min(hw ? hw : 4u, (unsigned)std::max(max_threads, 1)), (unsigned)nchunks));
 	std::vector<std::atomic<int>> done(nchunks);
 	for (auto &d : done) d.store(0, std::memory_order_relaxed);
-	std::atomic<int> next(0);
+	std::atomic<int> next(0), big(0);
+	auto work = [&]() {
+		for (;;) {
+			const int k = next.fetch_add(1);
+			if (k >= nchunks) return;
+			const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
+			if (compact_rows(samples + v0 + b, pin + b, e - b)) big.store(1, std::memory_order_relaxed);
+			done[k].store(1, std::memory_order_release);
+		}
+	};
 	std::vector<std::thread> pool;
-	for (int t = 0; t < nthreads; t++)
-		pool.emplace_back([&]() {
-			for (;;) {
-				const int k = next.fetch_add(1);
-				if (k >= nchunks) return;
-				const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
-				compact_rows(samples + b, pin + b, e - b);
-				done[k].store(1, std::memory_order_release);
-			}
-		});
+	for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
 	cudaError_t err = cudaSuccess;
 	for (int k = 0; k < nchunks; k++) {
 		while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
 		const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
 		if (err == cudaSuccess)
-			err = cudaMemcpyAsync((uint8_t *)c->b_stage_s.ptr + b, pin + b, e - b, cudaMemcpyHostToDevice, c->stream);
+			err = cudaMemcpyAsync(dst_dev + v0 + b, pin + b, e - b, cudaMemcpyHostToDevice, c->stream);
 	}
 	for (auto &th : pool) th.join();
 	if (err != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(err)); return CNB_ERR_CUDA; }
 	c->timing.h2d_bytes += (int64_t)total;
+	*overflow = big.load() != 0;
+	return CNB_OK;
+}
+
+/* Not with perturbations (a second int32 matrix: plain path).  *fallback = the byte form cannot carry this matrix. */
+static int set_samples_compacted(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples, const int32_t *num_cats, bool *fallback) {
+	const size_t total = (size_t)N * M;
+	RC(c->b_stage_s.ensure(total));
+	RC(cnb_ctx_upload_bytes(c, samples, 0, total, (uint8_t *)c->b_stage_s.ptr, 16, fallback));
+	if (*fallback) { cudaStreamSynchronize(c->stream); return CNB_OK; }
 	c->in_host_set = true;
-	int rc = set_samples_dev_impl(c, N, M, c->b_stage_s.ptr, 1, nullptr, num_cats);
+	int rc = cnb_ctx_set_samples_impl(c, N, M, c->b_stage_s.ptr, 1, nullptr, num_cats);
 	c->in_host_set = false;
 	return rc;
 }
@@ -350,9 +375,11 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 		else compact_min = (size_t)strtoull(e, nullptr, 10);
 	}
 	if (!pert && bytes >= compact_min && !no_compact) {
-		int rc = set_samples_compacted(c, N, M, samples, num_cats);
+		bool fallback = false;
+		int rc = set_samples_compacted(c, N, M, samples, num_cats, &fallback);
 		cudaStreamSynchronize(c->stream);
-		return rc;
+		if (rc != CNB_OK || !fallback) return rc;
+		c->timing.h2d_bytes = 0;                                  /* a label above 255: the int32 route carries it */
 	}
 	/* staging buffers stay with the context (grow-only): allocating and freeing 2 GB per call costs more than the copy */
 	DevBuf &tmp_s = c->b_stage_s, &tmp_p = c->b_stage_p;
@@ -371,6 +398,20 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 	}
 	cudaStreamSynchronize(c->stream);
 	return rc;
+}
+
+/* multi-process callers: rows [row0, row1) of the host int32 matrix (pageable is fine: host threads read it) become bytes
+ * at dst_dev + row0 * N on the context's stream; the ranks then all-gather the byte matrix and hand it to
+ * cnb_ctx_set_samples_dev8 */
+extern "C" int cnb_ctx_upload_rows8(cnb_ctx *c, int32_t N, const int32_t *samples, int64_t row0, int64_t row1, uint8_t *dst_dev,
+		int32_t max_threads) {
+	if (!c || N < 1 || !samples || row0 < 0 || row1 < row0 || !dst_dev) { cnb_set_error("cnb_ctx_upload_rows8: bad arguments"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	bool ovf = false;
+	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
+	RC(cnb_ctx_upload_bytes(c, samples, (size_t)row0 * N, (size_t)row1 * N, dst_dev, max_threads > 0 ? max_threads : 16, &ovf));
+	if (ovf) { cnb_set_error("a category label above 255 cannot travel as a byte"); return CNB_ERR_PARAM; }
+	return CNB_OK;
 }
 
 extern "C" int cnb_ctx_num_cats(const cnb_ctx *c, int32_t *out) {
@@ -1206,43 +1247,15 @@ extern "C" int cnb_ctx_search_order(cnb_ctx *c, const cnb_params *p, cnb_result 
 }
 
 /* ------------------------------------------------------------------ one-shot entry (the .Call body) ---- */
-static int search_order_multi(const cnb_params *p, cnb_result **out);
-
 extern "C" int cnb_search_order(const cnb_params *p, cnb_result **out) {
 	if (!p || !out) return CNB_ERR_PARAM;
 	*out = nullptr;
-	if (p->num_devices > 1) return search_order_multi(p, out);
+	if (cnb_multi_devices(p) > 1 || cnb_multi_devices(p) < -1) return cnb_multi_search_order(p, out);   /* one process, several GPUs: cnb_multi.cu */
 	cnb_ctx *c = nullptr;
 	RC(cnb_ctx_acquire(p->device, &c));
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	if (rc == CNB_OK) rc = cnb_ctx_search_order(c, p, out);
 	cnb_ctx_park(c);
-	return rc;
-}
-
-/* One process, several GPUs (the shape an R session has): every device holds the packed matrix, scores its shard
- * of the candidate families, the score segments are exchanged with peer copies, device 0 runs selection + DP. */
-static int search_order_multi(const cnb_params *p, cnb_result **out) {
-	const int G = p->num_devices;
-	std::vector<cnb_ctx *> cs(G, nullptr);
-	int rc = CNB_OK;
-	int64_t seg = 0, nf = 0;
-	for (int g = 0; g < G && rc == CNB_OK; g++) {
-		rc = cnb_ctx_create(p->device + g, &cs[g]);
-		if (rc == CNB_OK) rc = cnb_ctx_set_samples(cs[g], p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
-		if (rc == CNB_OK) rc = cnb_ctx_plan(cs[g], p, g, G, &seg, &nf);
-		if (rc == CNB_OK) rc = cs[g]->b_scores.ensure(std::max<int64_t>(seg * G, 1) * sizeof(double));
-	}
-	/* launch all shards, then wait: the devices run concurrently */
-	for (int g = 0; g < G && rc == CNB_OK; g++) rc = cnb_ctx_score_shard(cs[g], (double *)cs[g]->b_scores.ptr);
-	for (int g = 1; g < G && rc == CNB_OK; g++) {
-		cudaError_t e = cudaMemcpyPeerAsync((double *)cs[0]->b_scores.ptr + (size_t)g * seg, cs[0]->device,
-				(double *)cs[g]->b_scores.ptr + (size_t)g * seg, cs[g]->device, seg * sizeof(double), cs[g]->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(cs[g]->stream);
-		if (e != cudaSuccess) { cnb_set_error("CUDA peer copy: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; }
-	}
-	if (rc == CNB_OK) rc = cnb_ctx_finish(cs[0], (const double *)cs[0]->b_scores.ptr, out);
-	for (int g = 0; g < G; g++) if (cs[g]) cnb_ctx_destroy(cs[g]);
 	return rc;
 }
 
@@ -1276,6 +1289,70 @@ extern "C" int cnb_family_scores(cnb_ctx *c, int32_t nfam, int32_t d, const int3
 	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
 	CK(cudaStreamSynchronize(st));
 	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	return CNB_OK;
+}
+
+/* The scores the SEARCH itself produced (cnb_ctx_score_shard, whichever kernel scored the group -- the tcgen05 tables
+ * included) for explicit candidate families, read back from the score buffer: children / parents are order POSITIONS,
+ * parents ascending, every family with d parents.  bench.py compares them with the reference's scores of the same families
+ * on the same matrix ("parity_spot").  A family the plan does not offer (pool, fixed parents, parent-set size) gives NaN. */
+extern "C" int cnb_ctx_search_scores(cnb_ctx *c, const double *scores_dev, int32_t nfam, int32_t d, const int32_t *children,
+		const int32_t *parents, double *out) {
+	if (!c || !c->planned || !scores_dev || nfam < 0 || d < 0 || d > CNB_MAXP || !out) { cnb_set_error("cnb_ctx_search_scores: bad arguments"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	const CnbPlan &pl = c->plan;
+	std::vector<long long> index(nfam, -1);
+	CnbTiles T = make_devdata(c).tiles;
+	T.tile_base = (const long long *)pl.tile_base.data();
+	T.dtile_off = (const long long *)pl.dtile_off.data();
+	for (int f = 0; f < nfam; f++) {
+		const int child = children[f];
+		if (child < 0 || child >= pl.N) continue;
+		const CnbNodePlan &nd = pl.nodes[child];
+		for (int bi = nd.first_blk; bi < nd.first_blk + nd.nblk; bi++) {
+			const CnbBlock &b = pl.blocks[bi];
+			if (b.d != d) continue;
+			/* the family's parents = the block's fixed parents + a subset of its free pool: lexicographic rank of the subset */
+			int idx[CNB_MAXP], k = 0;
+			bool ok = true;
+			for (int q = 0; q < d && ok; q++) {
+				const int par = parents[(size_t)f * d + q];
+				bool fixed = false;
+				for (int t = 0; t < b.nfix; t++) fixed = fixed || pl.lists[b.fix_off + t] == par;
+				if (fixed) continue;
+				int pos = -1;
+				for (int t = 0; t < b.nfree; t++) if (pl.lists[b.free_off + t] == par) pos = t;
+				if (pos < 0 || k >= d - b.nfix) ok = false;
+				else idx[k++] = pos;
+			}
+			if (!ok || k != d - b.nfix) break;
+			for (int i = 1; i < k; i++)                      /* k <= 8: insertion sort */
+				for (int j = i; j > 0 && idx[j - 1] > idx[j]; j--) std::swap(idx[j - 1], idx[j]);
+			long long rank = 0;
+			int prev = -1;
+			for (int i = 0; i < k; i++) {
+				for (int j = prev + 1; j < idx[i]; j++) rank += cnb_binom(b.nfree - 1 - j, k - 1 - i);
+				prev = idx[i];
+			}
+			const CnbGroup &g = pl.groups[b.group];
+			const long long fid = b.start + rank;
+			if (g.tiled) {
+				long long tile;
+				int within;
+				cnb_family_slot(T, pl.N, pl.lists[b.free_off + idx[0]], pl.lists[b.free_off + idx[1]], child, tile, within);
+				index[f] = (tile % g.tile_world) * pl.seg_len + g.seg_off + (tile / g.tile_world) * (CNB_TILE_PAIRS * CNB_TILE_CHILD) + within;
+			} else {
+				const long long r = fid / g.chunk;
+				index[f] = r * pl.seg_len + g.seg_off + (fid - r * g.chunk);
+			}
+			break;
+		}
+	}
+	for (int f = 0; f < nfam; f++) {
+		if (index[f] < 0) { out[f] = nan(""); continue; }
+		CK(cudaMemcpyAsync(&out[f], scores_dev + index[f], sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	CK(cudaStreamSynchronize(c->stream));
 	return CNB_OK;
 }
 

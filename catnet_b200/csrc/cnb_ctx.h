@@ -91,4 +91,27 @@ int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::
 /* parents (order positions, [N][CNB_MAXP]) of the surviving network with the given complexity, after select_dp */
 int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t> *num_parents, std::vector<int32_t> *parents);
 
+/* upload paths shared with the multi-device driver (cnb_multi.cu) */
+int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes, const int32_t *pert_dev,
+		const int32_t *num_cats);
+int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads, bool *overflow);
+/* cnSearchHist, one order (cnb_hist.cpp) */
+struct CnbHistEval {
+	bool found = false;
+	double w = 0;
+	std::vector<int32_t> npar, pars;
+};
+int cnb_hist_eval_order(cnb_ctx *c, const cnb_params *q, const cnb_hist_params *hp, CnbHistEval *ev);
+void cnb_hist_add(double *hist, int N, const std::vector<int> &order, const CnbHistEval &ev);
+void cnb_gen_permutation(std::vector<int> &out, int n, struct CnbRng &rng);
+/* one process, several devices (cnb_multi.cu): devices a one-shot call should use (cnb_params.num_devices, else the
+ * CNB_NUM_DEVICES environment variable -- a number or "all" --, clamped to the devices present from p->device on) */
+int cnb_multi_devices(const cnb_params *p);
+int cnb_multi_search_order(const cnb_params *p, cnb_result **out);
+int cnb_multi_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+int cnb_multi_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations);
+void cnb_multi_release(void);
+/* union of two evaluations: per complexity the higher likelihood, a's on ties; complexities only b has are added */
+int cnb_result_union(cnb_result *a, const cnb_result *b);
+
 #endif

@@ -12,6 +12,7 @@
  * the device evaluates them one after the other and re-scores.  The uniform stream is drawn in the reference's order.
  */
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 #include <vector>
 #include "cnb_ctx.h"
@@ -21,18 +22,59 @@
 
 void cnb_gen_permutation(std::vector<int> &out, int n, CnbRng &rng);      /* cnb_sa.cpp */
 
+/* one order on one device: evaluate, pick the network (AIC / BIC / highest complexity), its weight and parents.
+ * *found = false when the search left no network (`continue` before niter++, rcatnet_hist.cpp:506). */
+int cnb_hist_eval_order(cnb_ctx *c, const cnb_params *q, const cnb_hist_params *hp, CnbHistEval *ev) {
+	const int N = c->N, M = c->M;
+	std::vector<int32_t> cx;
+	std::vector<double> ll;
+	ev->found = false;
+	RC(cnb_ctx_search_light(c, q));
+	RC(cnb_ctx_dp_summary(c, &cx, &ll));
+	if (cx.empty()) return CNB_OK;
+	int pick = -1;
+	double fLogLik = 0;
+	if (hp->score == 1) {                    /* AIC :464-476 */
+		fLogLik = -(double)FLT_MAX;
+		for (size_t i = 0; i < cx.size(); i++) {
+			double v = M * ll[i] - cx[i];
+			if (v > fLogLik) { fLogLik = v; pick = (int)i; }
+		}
+	} else if (hp->score == 2) {             /* BIC :477-489 */
+		fLogLik = -(double)FLT_MAX;
+		double ft = 0.5 * log((double)M);
+		for (size_t i = 0; i < cx.size(); i++) {
+			double v = M * ll[i] - ft * cx[i];
+			if (v > fLogLik) { fLogLik = v; pick = (int)i; }
+		}
+	}
+	if (pick < 0) pick = (int)cx.size() - 1; /* highest complexity :492-500 */
+	if (hp->weight <= 0) ev->w = 1;
+	else if (hp->weight == 1) ev->w = exp(ll[pick] / (double)(M * N));
+	else ev->w = exp(fLogLik / (double)(M * N));
+	RC(cnb_ctx_network_parents(c, cx[pick], &ev->npar, &ev->pars));
+	ev->found = true;
+	return CNB_OK;
+}
+
+/* hist[parent label][child label] += weight for every edge of the selected network (:517-528) */
+void cnb_hist_add(double *hist, int N, const std::vector<int> &order, const CnbHistEval &ev) {
+	for (int j = 0; j < N; j++)
+		for (int i = 0; i < ev.npar[j]; i++)
+			hist[(size_t)(order[ev.pars[(size_t)j * CNB_MAXP + i]] - 1) * N + order[j] - 1] += ev.w;
+}
+
 extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hist_params *hp, double *hist,
 		int32_t *iterations) {
 	if (!c || !p || !hp || !hist) return CNB_ERR_PARAM;
 	if (!c->have_samples) { cnb_set_error("context has no samples"); return CNB_ERR_PARAM; }
-	const int N = c->N, M = c->M;
+	const int N = c->N;
 	const int nDrives = hp->num_threads < 1 ? 1 : hp->num_threads;
 	memset(hist, 0, sizeof(double) * (size_t)N * N);
-	CnbRng rng(hp->seed ? hp->seed : cnb_default_seed());
+	CnbRng rng(hp->seed ? hp->seed : cnb_default_seed(), hp->unif, hp->unif_ctx);
 	std::vector<std::vector<int>> test(nDrives, std::vector<int>(N));
 	std::vector<char> skip(nDrives);
-	std::vector<int32_t> cx, npar, pars;
-	std::vector<double> ll;
+	CnbHistEval ev;
 	cnb_params q = *p;
 	q.edge_prob = nullptr;                       /* rcatnet_hist.cpp:268-277: no edge priors on this entry point */
 	int niter = 0, nstop = 0;
@@ -47,34 +89,9 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 			if (skip[n]) continue;
 			nstop = 0;
 			q.order = test[n].data();
-			RC(cnb_ctx_search_light(c, &q));
-			RC(cnb_ctx_dp_summary(c, &cx, &ll));
-			if (cx.empty()) continue;                /* slots but no network: `continue` before niter++ (:506) */
-			int pick = -1;
-			double fLogLik = 0;
-			if (hp->score == 1) {                    /* AIC :464-476 */
-				fLogLik = -(double)FLT_MAX;
-				for (size_t i = 0; i < cx.size(); i++) {
-					double v = M * ll[i] - cx[i];
-					if (v > fLogLik) { fLogLik = v; pick = (int)i; }
-				}
-			} else if (hp->score == 2) {             /* BIC :477-489 */
-				fLogLik = -(double)FLT_MAX;
-				double ft = 0.5 * log((double)M);
-				for (size_t i = 0; i < cx.size(); i++) {
-					double v = M * ll[i] - ft * cx[i];
-					if (v > fLogLik) { fLogLik = v; pick = (int)i; }
-				}
-			}
-			if (pick < 0) pick = (int)cx.size() - 1; /* highest complexity :492-500 */
-			double w;
-			if (hp->weight <= 0) w = 1;
-			else if (hp->weight == 1) w = exp(ll[pick] / (double)(M * N));
-			else w = exp(fLogLik / (double)(M * N));
-			RC(cnb_ctx_network_parents(c, cx[pick], &npar, &pars));
-			for (int j = 0; j < N; j++)
-				for (int i = 0; i < npar[j]; i++)
-					hist[(size_t)(test[n][pars[(size_t)j * CNB_MAXP + i]] - 1) * N + test[n][j] - 1] += w;
+			RC(cnb_hist_eval_order(c, &q, hp, &ev));
+			if (!ev.found) continue;                 /* slots but no network: `continue` before niter++ (:506) */
+			cnb_hist_add(hist, N, test[n], ev);
 			niter++;
 			if (p->echo) fprintf(stderr, "Iteration %d\\%d\n", niter, hp->max_iter);
 		}
@@ -86,6 +103,7 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 
 extern "C" int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations) {
 	if (!p || !hp || !hist) return CNB_ERR_PARAM;
+	if (cnb_multi_devices(p) > 1 || cnb_multi_devices(p) < -1) return cnb_multi_search_hist(p, hp, hist, iterations);
 	cnb_ctx *c = nullptr;
 	RC(cnb_ctx_acquire(p->device, &c));
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);

@@ -124,3 +124,37 @@ int cnb_result_merge(cnb_result *a, const cnb_result *b) {
 void cnb_result_free(cnb_result *r) { delete r; }
 
 } /* extern "C" */
+
+/* chains of one multi-device cnSearchSA: per complexity the higher likelihood (a's on ties), and complexities only b
+ * reached are added -- each chain's list is a full evaluation of its own accepted order */
+int cnb_result_union(cnb_result *a, const cnb_result *b) {
+	if (!a || !b || a->N != b->N) return CNB_ERR_PARAM;
+	const int order_base = (int)a->orders.size(), fam_base = (int)a->fams.size();
+	bool copied = false;
+	std::vector<CnbNet> out;
+	size_t i = 0, j = 0;
+	auto take_b = [&](const CnbNet &nb) {
+		if (!copied) {
+			a->orders.insert(a->orders.end(), b->orders.begin(), b->orders.end());
+			a->order_cats.insert(a->order_cats.end(), b->order_cats.begin(), b->order_cats.end());
+			a->fams.insert(a->fams.end(), b->fams.begin(), b->fams.end());
+			copied = true;
+		}
+		CnbNet n = nb;
+		n.order_id += order_base;
+		for (int32_t &f : n.fam) f += fam_base;
+		out.push_back(std::move(n));
+	};
+	while (i < a->nets.size() || j < b->nets.size()) {
+		if (j >= b->nets.size() || (i < a->nets.size() && a->nets[i].complexity < b->nets[j].complexity)) out.push_back(a->nets[i++]);
+		else if (i >= a->nets.size() || b->nets[j].complexity < a->nets[i].complexity) take_b(b->nets[j++]);
+		else {
+			if (b->nets[j].loglik > a->nets[i].loglik) take_b(b->nets[j]);
+			else out.push_back(a->nets[i]);
+			i++;
+			j++;
+		}
+	}
+	a->nets.swap(out);
+	return CNB_OK;
+}

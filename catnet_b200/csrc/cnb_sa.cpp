@@ -119,7 +119,7 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 	std::vector<int> optOrder(sa->start_order, sa->start_order + N);
 	for (int i = 0; i < N; i++)
 		if (optOrder[i] <= 0 || optOrder[i] > N) { cnb_set_error("Invalid startOrder parameter"); return CNB_ERR_PARAM; }
-	CnbRng rng(sa->seed ? sa->seed : cnb_default_seed());
+	CnbRng rng(sa->seed ? sa->seed : cnb_default_seed(), sa->unif, sa->unif_ctx);
 	std::vector<std::vector<int>> test(nDrives);
 	std::vector<double> newOrdProb(nDrives, 0.0);
 	std::vector<char> skip(nDrives);
@@ -228,6 +228,7 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out) {
 	if (!p || !sa || !out) return CNB_ERR_PARAM;
 	*out = nullptr;
+	if (cnb_multi_devices(p) > 1 || cnb_multi_devices(p) < -1) return cnb_multi_search_sa(p, sa, out);      /* one chain per device: cnb_multi.cu */
 	cnb_ctx *c = nullptr;
 	static const bool trace = getenv("CNB_TRACE") != nullptr;
 	auto now = [] { return std::chrono::steady_clock::now(); };
@@ -250,7 +251,7 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 /* The reference keeps a process-global score cache between .Call's (cache.cpp:58-76); the device re-scores every
  * order from the resident bit planes, so there are no scores to release.  What the library does keep between one-shot
  * calls is an idle context per device with its device buffers (cnb_api.cu: cnb_ctx_park); this frees them. */
-extern "C" void cnb_release_cache(void) { cnb_pool_release(); }
+extern "C" void cnb_release_cache(void) { cnb_multi_release(); cnb_pool_release(); }
 /* ccnSetSeed (R/catnet.def.R:743-747): the seed of searches that pass none (cnb_sa_params.seed / cnb_hist_params.seed = 0) */
 static int32_t g_seed = 0;
 extern "C" void cnb_set_seed(int32_t seed) { g_seed = seed; }

@@ -41,6 +41,9 @@ bool pool_matrix(SEXP rPool, int N, std::vector<int32_t> &out) {
 	return true;
 }
 
+/* R's uniform generator behind the C ABI's function-pointer form (cnb_sa_params.unif / cnb_hist_params.unif) */
+double r_unif(void *) { return unif_rand(); }
+
 struct Marshalled {
 	cnb_params p;
 	std::vector<int32_t> parent_sizes, order, num_cats, pool, fixed;
@@ -269,12 +272,13 @@ SEXP ccnOptimalNetsSA(SEXP rNodeNames, SEXP rSamples, SEXP rPerturbations, SEXP 
 		nprot++;
 		sa.dir_prob = REAL(rDirProbs);
 	}
-	/* seed the library's uniform stream from R's RNG on the calling thread, so set.seed() governs the chain */
+	/* the chain draws from R's own generator on this thread, exactly where stock catnet does (rcatnet_sa.cpp:146,151,225,
+	 * 745; utils.h:156,190): set.seed(s); cnSearchSA(...) proposes the same orders as the reference */
+	sa.unif = r_unif;
 	GetRNGstate();
-	sa.seed = (uint64_t)(unif_rand() * 9007199254740992.0);
-	PutRNGstate();
 	cnb_result *res = NULL;
 	int rc = cnb_search_sa(&m.p, &sa, &res);
+	PutRNGstate();
 	UNPROTECT(m.nprotect + nprot);
 	if (rc != CNB_OK) fail(rc);
 	return export_result(res, m.p, rNodeNames);
@@ -297,11 +301,11 @@ SEXP ccnParHistogram(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP 
 	hp.max_iter = asInteger(rMaxIter);
 	hp.num_threads = asInteger(rThreads);
 	hp.use_cache = asLogical(rUseCache);
-	GetRNGstate();
-	hp.seed = (uint64_t)(unif_rand() * 9007199254740992.0);
-	PutRNGstate();
+	hp.unif = r_unif;                                                              /* rcatnet_hist.cpp:121-159 */
 	SEXP rmat = PROTECT(allocVector(REALSXP, N * N));                              /* :229-233 */
+	GetRNGstate();
 	int rc = cnb_search_hist(&m.p, &hp, REAL(rmat), NULL);
+	PutRNGstate();
 	UNPROTECT(m.nprotect + 1);
 	if (rc != CNB_OK) fail(rc);
 	return rmat;

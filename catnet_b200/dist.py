@@ -34,36 +34,39 @@ def owned_range(group_size, chunk, rank):
 
 
 def gather_scores(scores, rank, world, seg_len, group=None):
-    """complete the rank-major buffer in place: every rank contributes scores[rank*seg_len:(rank+1)*seg_len]"""
+    """complete the rank-major buffer in place: every rank contributes scores[rank*seg_len:(rank+1)*seg_len].  Over NCCL the
+    segment is gathered where it lies (ncclAllGather's in-place form: input = output + rank * count); gloo gets a copy."""
     import torch.distributed as dist
     if world == 1:
         return scores
-    dist.all_gather_into_tensor(scores, scores[rank * seg_len:(rank + 1) * seg_len].clone(), group=group)
+    mine = scores[rank * seg_len:(rank + 1) * seg_len]
+    if dist.get_backend(group) != "nccl":
+        mine = mine.clone()
+    dist.all_gather_into_tensor(scores, mine, group=group)
     return scores
 
 
 def set_samples_sharded(ctx, host_samples, rank, world, device, num_cats=None, group=None):
-    """host_samples: torch int32 [M][N] CPU tensor (pinned for speed), identical on every rank.  Rank r copies rows
-    [r*ceil(M/world), (r+1)*ceil(M/world)) to its GPU and narrows them to bytes (0 = missing, saturated at 255: the form
-    cnb_ctx_set_samples_dev8 takes), one all_gather_into_tensor over NVLink completes the BYTE matrix on every GPU (a
-    quarter of the int32 traffic), then the matrix is packed.  Returns (device byte tensor, bytes copied H2D)."""
+    """host_samples: int32 [M][N] numpy array or CPU tensor (pageable memory is fine), identical on every rank.  Rank r
+    narrows rows [r*ceil(M/world), (r+1)*ceil(M/world)) to bytes with the library's host threads and copies them over its
+    own PCIe link (cnb_ctx_upload_rows8; 0 = missing, the form cnb_ctx_set_samples_dev8 takes), one in-place
+    all_gather_into_tensor over NVLink completes the BYTE matrix on every GPU (a quarter of the int32 traffic), then the
+    matrix is packed.  Returns (device byte tensor, bytes copied H2D by this rank)."""
+    import os
     import torch
     import torch.distributed as dist
     ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)   # the copy, the all-gather and the pack stay ordered
-    m, n = host_samples.shape
+    hs = host_samples.numpy() if hasattr(host_samples, "numpy") else host_samples
+    m, n = hs.shape
     rows = (m + world - 1) // world
     full = torch.empty((rows * world, n), dtype=torch.uint8, device=device)
     r0, r1 = min(m, rank * rows), min(m, (rank + 1) * rows)
-    mine = torch.zeros((rows, n), dtype=torch.uint8, device=device)
     if r1 > r0:
-        part = host_samples[r0:r1].to(device, non_blocking=True)
-        mine[:r1 - r0] = part.clamp_(0, 255).to(torch.uint8)
+        ctx.upload_rows8(hs, r0, r1, full.data_ptr(), max(1, (os.cpu_count() or 8) // world))
     if world > 1:
-        dist.all_gather_into_tensor(full, mine, group=group)
-    else:
-        full = mine
+        dist.all_gather_into_tensor(full, full[rank * rows:(rank + 1) * rows], group=group)
     ctx.set_samples_dev8(full.data_ptr(), n, m, num_cats=num_cats)
-    return full, (r1 - r0) * n * 4
+    return full, (r1 - r0) * n
 
 
 def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, **kw):

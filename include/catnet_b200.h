@@ -70,8 +70,11 @@ typedef struct cnb_params {
 	int32_t echo;                  /* rEcho: progress lines on stderr */
 	/* --- extensions (zero = reference behaviour on one GPU) --- */
 	int32_t device;                /* CUDA device ordinal for the one-shot calls */
-	int32_t num_devices;           /* >1: shard candidate parent sets over devices [device, device+num_devices)
-	                                  of this process; scores exchanged by peer copies */
+	int32_t num_devices;           /* >1: use devices [device, device+num_devices) of this process (clamped to the
+	                                  devices present): cnb_search_order shards the candidate parent sets over them,
+	                                  cnb_search_sa runs one chain per device, cnb_search_hist deals the orders out
+	                                  (cnb_mctx below).  0: the CNB_NUM_DEVICES environment variable (a number or "all")
+	                                  decides, so that an unchanged R session can use the whole box; absent = 1 */
 } cnb_params;
 
 /* ---- extra arguments of ccnOptimalNetsSA ---- */
@@ -85,7 +88,12 @@ typedef struct cnb_sa_params {
 	int32_t num_threads;           /* rThreads: proposals evaluated per SA step (first accepted wins, :646-657) */
 	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
 	const double *dir_prob;        /* [N*N] R layout or NULL (rDirProbs) */
-	uint64_t seed;                 /* uniform stream (splitmix64); R's RNG is not reachable through a C ABI */
+	uint64_t seed;                 /* uniform stream (splitmix64) when unif is NULL; 0 = the cnb_set_seed value */
+	/* the caller's own uniform generator (the R shim passes R's unif_rand, so that set.seed() reproduces stock catnet's
+	 * proposals: rcatnet_sa.cpp:146,151,225,745, utils.h:156,190).  Called on the calling thread only, draw for draw in
+	 * the reference's order; must return values in (0,1).  NULL = the library's splitmix64 stream from `seed`. */
+	double (*unif)(void *unif_ctx);
+	void *unif_ctx;
 } cnb_sa_params;
 
 /* ---- extra arguments of ccnParHistogram (cnSearchHist, R/catnet.histo.R:45-138) ---- */
@@ -96,6 +104,8 @@ typedef struct cnb_hist_params {
 	int32_t num_threads;           /* rThreads: orders per batch (duplicates inside a batch are skipped) */
 	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
 	uint64_t seed;                 /* uniform stream (splitmix64), as for cnb_sa_params */
+	double (*unif)(void *unif_ctx);   /* the caller's generator, as for cnb_sa_params (rcatnet_hist.cpp:124,129) */
+	void *unif_ctx;
 } cnb_hist_params;
 
 /* ---- one-shot entry points (what the R shim calls) ---- */
@@ -190,6 +200,11 @@ int cnb_ctx_set_samples_dev(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples
  * itself moves large host matrices over PCIe; multi-process callers all-gather this instead of the int32 matrix) */
 int cnb_ctx_set_samples_dev8(cnb_ctx *ctx, int32_t num_nodes, int32_t num_samples, const uint8_t *samples_dev,
 		const int32_t *perturbations_dev, const int32_t *num_cats);
+/* first step of a multi-process upload: rows [row0, row1) of the host matrix (pageable memory is fine) are narrowed to that
+ * byte form by host threads and copied to dst_dev + row0 * num_nodes on the context's stream; the ranks all-gather the byte
+ * matrix over NVLink and pass it to cnb_ctx_set_samples_dev8.  CNB_ERR_PARAM if a label is above 255. */
+int cnb_ctx_upload_rows8(cnb_ctx *ctx, int32_t num_nodes, const int32_t *samples, int64_t row0, int64_t row1,
+		uint8_t *dst_dev, int32_t max_threads);
 /* categories per node as used on the device (given or inferred), label space */
 int cnb_ctx_num_cats(const cnb_ctx *ctx, int32_t *num_cats_out);
 /* search for one order on the resident data; samples/perturbations/num_cats/device fields of p are ignored */
@@ -207,6 +222,45 @@ int cnb_ctx_entropy_order(cnb_ctx *ctx, int32_t *order_out);
 /* a given network on the resident data (the context must have been given net->num_cats as its categories) */
 int cnb_ctx_loglik(cnb_ctx *ctx, const cnb_network *net, int32_t mode, int32_t num_sel, const int32_t *nodes, double *out);
 int cnb_ctx_set_prob(cnb_ctx *ctx, const cnb_network *net, double *probs_out, double *loglik_out, int32_t *sizes_out);
+
+/* ---- one process, several GPUs (the shape an R session has; reference: the worker pool inside one process,
+ * src/rcatnet_sa.cpp:475-652, src/thread.h).  A cnb_mctx owns one context per device and one host thread per device.
+ *   set_samples   every device copies only its 1/G share of the host matrix over its own PCIe link (compacted to bytes
+ *                 by host threads, so pageable memory -- R's -- is fine) and completes the others' copies over NVLink
+ *                 (peer copies); then each packs the full matrix
+ *   search_order  every device plans, scores its shard of the candidate parent sets and writes the scores straight into
+ *                 the first device's score buffer over NVLink (peer stores from the scoring kernels; a peer copy of the
+ *                 segment where peer access is not available); selection + DP + export on the first device only
+ *   search_sa     one chain per device (chain 0 = the single-device chain, draw for draw; chain g > 0 draws from
+ *                 splitmix64(seed + g)), merged per complexity
+ *   search_hist   the orders of a batch are evaluated side by side, one per device, and accumulated in the reference's
+ *                 order: the histogram is bit-identical to the single-device one
+ * Small problems stay on the first device (the exchange costs more than it saves): CNB_MULTI_MIN_WORK (family-samples,
+ * default 2e10) sets the threshold, 0 shards always. */
+typedef struct cnb_mctx cnb_mctx;
+/* num_devices < -1 (also accepted by cnb_params.num_devices) is a test hook: |num_devices| contexts on the ONE device
+ * first_device, so that the whole orchestration (shares, peer stores, chains, dealt orders) runs on a single-GPU box */
+int cnb_mctx_create(int32_t first_device, int32_t num_devices, cnb_mctx **out);
+void cnb_mctx_destroy(cnb_mctx *m);
+int32_t cnb_mctx_num_devices(const cnb_mctx *m);
+cnb_ctx *cnb_mctx_ctx(cnb_mctx *m, int32_t i);           /* the context of the i-th device (timing, test hooks) */
+int cnb_mctx_set_samples(cnb_mctx *m, int32_t num_nodes, int32_t num_samples, const int32_t *samples,
+		const int32_t *perturbations, const int32_t *num_cats);
+int cnb_mctx_search_order(cnb_mctx *m, const cnb_params *p, cnb_result **out);
+/* the two halves of cnb_mctx_search_order: plan + score + exchange + selection + DP (result stays on the first device),
+ * then network export */
+int cnb_mctx_search_light(cnb_mctx *m, const cnb_params *p);
+int cnb_mctx_collect(cnb_mctx *m, cnb_result **out);
+int cnb_mctx_search_sa(cnb_mctx *m, const cnb_params *p, const cnb_sa_params *sa, cnb_result **out);
+int cnb_mctx_search_hist(cnb_mctx *m, const cnb_params *p, const cnb_hist_params *hp, double *hist_out,
+		int32_t *iterations_out);
+/* device timing across the devices: mark(0) / mark(1) record an event on the first device's stream (every other
+ * device's work of a search is ordered behind the first device's stream position at the start of that search and
+ * before its selection); elapsed = ms between the two marks, after synchronising every device */
+int cnb_mctx_mark(cnb_mctx *m, int32_t which);
+int cnb_mctx_elapsed_ms(cnb_mctx *m, float *ms);
+/* devices the last search really used (1 when the problem was below the sharding threshold) */
+int32_t cnb_mctx_active(const cnb_mctx *m);
 
 /* sharded search, one process per GPU: plan -> score own shard -> (caller all-gathers) -> finish.
  * The score buffer is one fp64 per candidate family, laid out rank-major: segment r (seg_len doubles) holds rank r's
@@ -250,6 +304,12 @@ int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
 int cnb_family_scores(cnb_ctx *ctx, int32_t nfam, int32_t num_parents, const int32_t *children,
 		const int32_t *parents, int32_t table_stride, int32_t *counts_out, double *loglik_out,
 		int32_t *ncount_out, int32_t force_generic);
+/* the scores the last cnb_ctx_score_shard wrote for explicit candidate families (whichever kernel scored their group, the
+ * tcgen05 tables included): children / parents are order POSITIONS (parents ascending, [nfam][num_parents]); scores_dev is
+ * the full rank-major buffer.  NaN for a family the plan does not offer.  bench.py's parity_spot reads the benchmarked
+ * kernel's own output with this. */
+int cnb_ctx_search_scores(cnb_ctx *ctx, const double *scores_dev, int32_t nfam, int32_t num_parents,
+		const int32_t *children, const int32_t *parents, double *out);
 /* kernel selection of this context for the parity tests (0 = the library chooses).  Bits of `on`: 1 generic histogram
  * kernel everywhere; 2 direct bit-plane scorer (no inclusion-exclusion); 4 tensor-core scorer whenever applicable, 8
  * never; 16 u8 operands (kind::i8) instead of E2M1; 32 one DP launch per node; 64 grid-barrier DP; 128 pair tables by

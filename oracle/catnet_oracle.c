@@ -408,9 +408,14 @@ void orc_result_free(orc_result *r) {
 
 /* ------------------------------------------------------------------ SA ---- */
 static unsigned long long g_state = 0x9E3779B97F4A7C15ull;
-void orc_set_seed(unsigned long long seed) { g_state = seed; }
+static double (*g_unif_fn)(void *) = 0;
+static void *g_unif_ctx = 0;
+void orc_set_seed(unsigned long long seed) { g_state = seed; g_unif_fn = 0; }
+/* a caller-owned generator instead (what R's unif_rand is to the reference); cleared by orc_set_seed */
+void orc_set_unif(double (*fn)(void *), void *ctx) { g_unif_fn = fn; g_unif_ctx = ctx; }
 /* splitmix64 -> (0,1): the injected stand-in for R's unif_rand, identical to oracle/ref_driver.cpp */
 static double unif(void) {
+	if (g_unif_fn) return g_unif_fn(g_unif_ctx);
 	unsigned long long z = (g_state += 0x9E3779B97F4A7C15ull);
 	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
 	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

@@ -34,6 +34,7 @@ long orc_net_samples(int N, const int *cats, int maxParents, const int *numParen
 		const double *probs, const long long *offsets, int M, const int *pert, double naRate, unsigned long long seed,
 		int *out);
 void orc_set_seed(unsigned long long seed);
+void orc_set_unif(double (*fn)(void *), void *ctx);   /* caller-owned generator; cleared by orc_set_seed */
 int orc_result_nslots(const orc_result *r);
 int orc_result_exists(const orc_result *r, int k);
 int orc_result_net(orc_result *r, int k, int *complexity, double *loglik);

@@ -115,14 +115,24 @@ def search_order(samples, max_parent_set, max_complexity, order=None, perturbati
         L.orc_result_free(h)
 
 
+def _set_unif(L, unif):
+    if unif is not None:
+        L.orc_set_unif.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_unif.restype = None
+        L.orc_set_unif(unif, None)
+
+
 def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=0, temp_start=1.0,
               temp_cool_fact=0.9, temp_check_orders=10, max_iter=100, order_shuffles=1.0, stop_diff=1e-10,
               num_threads=1, use_cache=False, seed=1, perturbations=None, parent_sizes=None, num_cats=None,
-              parents_pool=None, fixed_parents=None, edge_prob=None, want_probs=False):
+              parents_pool=None, fixed_parents=None, edge_prob=None, want_probs=False, unif=None):
+    """unif: address of a `double f(void *)` generator consumed instead of the seeded splitmix64 stream (what R's
+    unif_rand is to the reference)"""
     L = lib()
     s = _i32(samples)
     M, N = s.shape
     L.orc_set_seed(int(seed))
+    _set_unif(L, unif)
     e = None if edge_prob is None else np.ascontiguousarray(np.asarray(edge_prob, dtype=np.float64).T)
     h = L.orc_search_sa(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
                         int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),
@@ -146,13 +156,14 @@ def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=
 
 
 def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_iter=32, num_threads=2, seed=1,
-                perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None):
+                perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None, unif=None):
     """cnSearchHist: returns (hist [N][N] with hist[parent][child], iterations).  score: 0 highest complexity, 1 AIC,
     2 BIC; weight: 0 one, 1 exp(loglik/(M N)), 2 exp(score/(M N))."""
     L = lib()
     s = _i32(samples)
     M, N = s.shape
     L.orc_set_seed(int(seed))
+    _set_unif(L, unif)
     hist = np.zeros((N, N), dtype=np.float64)
     it = L.orc_search_hist(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
                            int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),

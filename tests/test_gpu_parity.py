@@ -832,16 +832,6 @@ def test_sharded_search_equals_unsharded(abi):
             assert compare_search(nets, ref_nets) == len(ref_nets)
 
 
-def test_multi_device_one_process(abi):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    s, c = random_problem(6, 12, 500, None, 0.02)
-    a = abi.search_order(s, max_parent_set=2, max_complexity=800, num_cats=c)
-    b = abi.search_order(s, max_parent_set=2, max_complexity=800, num_cats=c, num_devices=2)
-    assert compare_search(b, a) == len(a)
-
-
 def test_errors_are_codes_not_crashes(abi):
     s, c = random_problem(1, 5, 50, 3)
     bad = s.copy()

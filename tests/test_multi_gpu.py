@@ -1,0 +1,247 @@
+"""One process, several GPUs (cnb_mctx; catnet_b200/csrc/cnb_multi.cu) -- the multi-GPU path an R session takes.
+
+Every test runs in two forms: "alias" = G device contexts on the ONE GPU of the box (the library's test hook
+num_devices = -G: the whole orchestration -- dealt sample rows, peer copies, sharded scoring into the first device's
+score buffer, chains, dealt orders -- runs on a single-GPU box, so nothing here is skipped by the driver), and "real" =
+G distinct GPUs when the box has them (gpurun --gpus 2/8).  The single-device result is the reference for both; it is
+itself compared with the oracle in test_gpu_parity.py.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from helpers import compare_search, constrained_problem, random_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from catnet_b200 import _abi
+    _abi.lib()
+    return _abi
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _forms(g):
+    """num_devices arguments to try for G devices"""
+    out = [-g]
+    if _ngpu() >= g:
+        out.append(g)
+    return out
+
+
+@pytest.fixture(autouse=True)
+def shard_everything(monkeypatch):
+    monkeypatch.setenv("CNB_MULTI_MIN_WORK", "0")          # the test problems are far below the sharding threshold
+    monkeypatch.setenv("CNB_MULTI_SHARE_MIN", "0")         # ... and below the dealt-upload threshold
+    yield
+
+
+def same_nets(a, b):
+    assert compare_search(a, b) == len(b)
+    for x, y in zip(a, b):
+        assert x["loglik"] == y["loglik"] and x["node_loglik"] == y["node_loglik"]
+        assert all(np.array_equal(p, q) for p, q in zip(x["probs"], y["probs"]))
+
+
+@pytest.mark.parametrize("g", [2, 3, 8])
+@pytest.mark.parametrize("seed,n,m,cats,na,P", [(6, 12, 500, None, 0.02, 2), (7, 9, 257, 3, 0.0, 3), (8, 14, 1000, 4, 0.0, 2),
+                                                (9, 7, 33, 2, 0.1, 1), (10, 10, 300, 6, 0.0, 2)])
+def test_one_shot_search_order(abi, g, seed, n, m, cats, na, P):
+    """cnb_search_order with cnb_params.num_devices: identical networks, tables and log-likelihoods"""
+    s, c = random_problem(seed, n, m, cats, na)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** P
+    a = abi.search_order(s, max_parent_set=P, max_complexity=K, num_cats=c)
+    for nd in _forms(g):
+        b = abi.search_order(s, max_parent_set=P, max_complexity=K, num_cats=c, num_devices=nd)
+        same_nets(b, a)
+
+
+@pytest.mark.parametrize("seed", range(40, 60))
+def test_constrained_problems(abi, seed):
+    """pools, fixed parents, parent sizes, perturbations, priors, random orders -- sharded over 3 devices"""
+    s, P, K, kw = constrained_problem(seed)
+    try:
+        a = abi.search_order(s, max_parent_set=P, max_complexity=K, **kw)
+    except abi.CnbError as e:
+        with pytest.raises(abi.CnbError) as e2:
+            abi.search_order(s, max_parent_set=P, max_complexity=K, num_devices=-3, **kw)
+        assert e2.value.code == e.code
+        return
+    for nd in _forms(3):
+        same_nets(abi.search_order(s, max_parent_set=P, max_complexity=K, num_devices=nd, **kw), a)
+
+
+def test_environment_variable_selects_devices(abi, monkeypatch):
+    """what an unchanged R session does: CNB_NUM_DEVICES in the environment, cnb_params.num_devices = 0"""
+    s, c = random_problem(11, 10, 400, None, 0.0)
+    a = abi.search_order(s, max_parent_set=2, max_complexity=500, num_cats=c)
+    monkeypatch.setenv("CNB_NUM_DEVICES", "-2")
+    same_nets(abi.search_order(s, max_parent_set=2, max_complexity=500, num_cats=c), a)
+    monkeypatch.setenv("CNB_NUM_DEVICES", "all")           # clamped to the devices present: any box
+    same_nets(abi.search_order(s, max_parent_set=2, max_complexity=500, num_cats=c), a)
+    abi.lib().cnb_release_cache()
+
+
+@pytest.mark.parametrize("nopeer", [False, True])
+@pytest.mark.parametrize("g", [2, 4])
+def test_tensor_path_sharded(abi, monkeypatch, g, nopeer):
+    """the tcgen05 table kernel on every device, tiles dealt round-robin, scores stored into the first device's buffer
+    (peer stores) or copied there (CNB_NO_PEER)"""
+    if nopeer:
+        monkeypatch.setenv("CNB_NO_PEER", "1")
+    s, c = random_problem(21, 70, 9000, 4, 0.0)
+    order = (np.random.default_rng(3).permutation(70) + 1).astype(np.int32)
+    kw = dict(max_parent_set=2, max_complexity=70 * 48, order=order)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(**kw)
+        assert ctx.timing()["tensor_tiles"] > 0
+    for nd in _forms(g):
+        with abi.MultiContext(0, nd) as mc:
+            mc.set_samples(s, num_cats=c)
+            b = mc.search_order(**kw)
+            assert mc.active() == g
+            tiles = [mc.timing(i)["tensor_tiles"] for i in range(g)]
+            assert min(tiles) > 0 and sum(tiles) == ctx_tiles(abi, s, c, kw)
+            same_nets(b, a)
+            # a second order on the resident data (the SA / bench shape), then back
+            kw2 = dict(kw, order=order[::-1].copy())
+            with abi.Context(0) as ctx:
+                ctx.set_samples(s, num_cats=c)
+                a2 = ctx.search_order(**kw2)
+            same_nets(mc.search_order(**kw2), a2)
+            same_nets(mc.search_order(**kw), a)
+
+
+def ctx_tiles(abi, s, c, kw):
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.search_order(**kw)
+        return ctx.timing()["tensor_tiles"]
+
+
+@pytest.mark.parametrize("what", ["plain", "na", "pert", "inferred", "label300"])
+def test_dealt_upload(abi, what):
+    """every device uploads its rows as bytes and sends them to its peers; perturbations travel the same way; a label
+    above 255 (legal with inferred categories) falls back to the int32 upload"""
+    s, c = random_problem(31, 9, 1003, 3, 0.05 if what == "na" else 0.0)
+    pert = (np.random.default_rng(5).random(s.shape) < 0.2).astype(np.int32) if what == "pert" else None
+    cats = None if what in ("inferred", "label300") else c
+    if what == "label300":
+        s = np.where(s >= 1, s + 299, s).astype(np.int32)   # labels 300..302: three categories, min 300
+    kw = dict(max_parent_set=2, max_complexity=400, num_cats=cats, perturbations=pert)
+    a = abi.search_order(s, **kw)
+    for nd in _forms(3) + _forms(2):
+        same_nets(abi.search_order(s, num_devices=nd, **kw), a)
+
+
+def test_label_above_255_single_device_compacted(abi, monkeypatch):
+    """the host-compacted upload saturated labels above 255; it now hands such matrices to the int32 route"""
+    monkeypatch.setenv("CNB_HOST_COMPACT_MIN", "0")
+    s, c = random_problem(32, 6, 500, 3, 0.0)
+    a = abi.search_order(s, max_parent_set=2, max_complexity=200)
+    b = abi.search_order(np.where(s >= 1, s + 299, s).astype(np.int32), max_parent_set=2, max_complexity=200)
+    same_nets(b, a)
+
+
+SA = dict(select_mode=2, temp_start=0.05, temp_cool_fact=0.8, temp_check_orders=4, max_iter=40, order_shuffles=1.5,
+          stop_diff=1e-10, num_threads=2, use_cache=True)
+
+
+@pytest.mark.parametrize("g", [2, 3])
+def test_sa_chains(abi, g):
+    """one chain per device: chain 0 is the single-device chain draw for draw; the merge keeps, per complexity, the
+    best network over the chains (so it is never worse than the single-device result)"""
+    s, c = random_problem(41, 8, 300, None, 0.0)
+    start = (np.random.default_rng(2).permutation(8) + 1).astype(np.int32)
+    kw = dict(max_parent_set=2, max_complexity=300, num_cats=c)
+    one = abi.search_sa(s, dict(SA, start_order=start, seed=17), want_probs=True, **kw)
+    for nd in _forms(g):
+        many = abi.search_sa(s, dict(SA, start_order=start, seed=17), want_probs=True, num_devices=nd, **kw)
+        assert np.array_equal(many["trace"], one["trace"]) and np.array_equal(many["order"], one["order"])
+        assert many["niter"] == one["niter"] and many["naccept"] == one["naccept"]
+        a = {n["complexity"]: n for n in one["nets"]}
+        b = {n["complexity"]: n for n in many["nets"]}
+        assert set(a) <= set(b)
+        better = 0
+        for cx, net in a.items():
+            assert b[cx]["loglik"] >= net["loglik"]
+            better += b[cx]["loglik"] > net["loglik"]
+        # every merged network is a valid evaluation: re-scoring its parents under its own order reproduces it
+        for cx, net in b.items():
+            assert len(net["parents"]) == 8 and len(net["order"]) == 8
+
+
+def test_sa_follows_the_callers_generator(abi):
+    """cnb_sa_params.unif: a generator handed over by the caller (R's unif_rand in the shim) is consumed draw for draw
+    -- a ctypes splitmix64 with the library's own mapping must reproduce the seeded chain exactly"""
+    s, c = random_problem(42, 7, 200, 3, 0.0)
+    start = (np.random.default_rng(4).permutation(7) + 1).astype(np.int32)
+    kw = dict(max_parent_set=2, max_complexity=200, num_cats=c)
+    seeded = abi.search_sa(s, dict(SA, start_order=start, seed=99), **kw)
+    state = [99]
+    mask = (1 << 64) - 1
+
+    def splitmix(_):
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & mask
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        z ^= z >> 31
+        return ((z >> 11) + 0.5) * (1.0 / 9007199254740992.0)
+
+    fn = abi.UNIF_FN(splitmix)
+    called = abi.search_sa(s, dict(SA, start_order=start, seed=0, unif=fn), **kw)
+    assert np.array_equal(called["trace"], seeded["trace"]) and np.array_equal(called["order"], seeded["order"])
+    state[0] = 99
+    hist_a, it_a = abi.search_hist(s, dict(score=2, weight=1, max_iter=9, num_threads=2, seed=0, unif=fn), **kw)
+    hist_b, it_b = abi.search_hist(s, dict(score=2, weight=1, max_iter=9, num_threads=2, seed=99), **kw)
+    assert it_a == it_b and np.array_equal(hist_a, hist_b)
+
+
+@pytest.mark.parametrize("threads,iters", [(1, 7), (2, 9), (3, 10), (5, 12)])
+def test_histogram_orders_dealt_out(abi, threads, iters):
+    """cnSearchHist: orders evaluated side by side, accumulated in the reference's order -> bit-identical histogram and
+    the same number of uniforms consumed"""
+    s, c = random_problem(51, 8, 250, None, 0.03)
+    kw = dict(max_parent_set=2, max_complexity=300, num_cats=c)
+    for weight in (0, 1, 2):
+        hp = dict(score=2, weight=weight, max_iter=iters, num_threads=threads, seed=5)
+        a, ia = abi.search_hist(s, hp, **kw)
+        for nd in _forms(2) + _forms(4):
+            b, ib = abi.search_hist(s, hp, num_devices=nd, **kw)
+            assert ia == ib and np.array_equal(a, b)
+
+
+def test_below_threshold_stays_on_one_device(abi, monkeypatch):
+    monkeypatch.delenv("CNB_MULTI_MIN_WORK")
+    s, c = random_problem(61, 8, 200, None, 0.0)
+    with abi.MultiContext(0, -2) as mc:
+        mc.set_samples(s, num_cats=c)
+        nets = mc.search_order(max_parent_set=2, max_complexity=300)
+        assert mc.active() == 1
+    same_nets(nets, abi.search_order(s, max_parent_set=2, max_complexity=300, num_cats=c))
+
+
+def test_device_time_marks(abi):
+    s, c = random_problem(62, 40, 9000, 4, 0.0)
+    with abi.MultiContext(0, -2) as mc:
+        mc.set_samples(s, num_cats=c)
+        mc.search_light(max_parent_set=2, max_complexity=2000)
+        mc.mark(0)
+        for _ in range(3):
+            mc.search_light(max_parent_set=2, max_complexity=2000)
+        mc.mark(1)
+        ms = mc.elapsed_ms()
+        assert 0 < ms < 5000
+        h = mc.collect_raw()
+        assert abi.lib().cnb_result_num_networks(h) > 0
+        abi.lib().cnb_result_free(h)

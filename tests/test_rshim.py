@@ -187,8 +187,10 @@ SA_KW = dict(temp_start=0.05, temp_cool_fact=0.8, temp_check_orders=3, max_iter=
 
 def check_sa_and_histogram(r, port, seed):
     """.Call("ccnOptimalNetsSA", ...23) and .Call("ccnParHistogram", ...14) with the arguments R/catnet.search.R:280-296
-    and R/catnet.histo.R:116-129 pass; the library's seed is the one uniform the shim draws from R's RNG"""
-    from rshim_harness import mini_r_uniform
+    and R/catnet.histo.R:116-129 pass; the chain draws from R's own generator through cnb_sa_params.unif, so the oracle
+    fed the same generator (the miniature R's unif_rand, re-seeded) must propose and accept the same orders"""
+    import ctypes
+    r_unif = ctypes.cast(r.L.unif_rand, ctypes.c_void_p)
     s, c = random_problem(seed, 6 + seed % 3, 90, [None, 3][seed % 2])
     n = len(c)
     names = ["G%d" % (i + 1) for i in range(n)]
@@ -202,8 +204,8 @@ def check_sa_and_histogram(r, port, seed):
                  r.numeric([SA_KW["temp_cool_fact"]]), r.numeric([SA_KW["temp_check_orders"]]), r.numeric([SA_KW["max_iter"]]),
                  r.numeric([SA_KW["order_shuffles"]]), r.numeric([SA_KW["stop_diff"]]), r.numeric([SA_KW["num_threads"]]),
                  r.logical(True), r.logical(False))
-    lib_seed = int(mini_r_uniform(50 + seed) * 9007199254740992.0)
-    theirs = port.search_sa(s, 2, n * 20, start, select_mode={"AIC": 1, "BIC": 2}.get(model, 0), seed=lib_seed, num_cats=c,
+    r.L.mr_set_rng(50 + seed)
+    theirs = port.search_sa(s, 2, n * 20, start, select_mode={"AIC": 1, "BIC": 2}.get(model, 0), unif=r_unif, num_cats=c,
                             want_probs=True, **SA_KW)
     nets = [r.catnetwork(e) for e in r.elts(out)]
     check_networks(nets, theirs["nets"], [int(v) for v in theirs["order"]], c, names)
@@ -212,8 +214,9 @@ def check_sa_and_histogram(r, port, seed):
     vh = r.reals(r.call("ccnParHistogram", r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([n * 20]), cat_indices,
                         r.NULL, r.NULL, r.string(model), r.numeric([seed % 3]), r.numeric([8]), r.numeric([2]),
                         r.logical(True), r.logical(False)))
+    r.L.mr_set_rng(90 + seed)
     hist, _ = port.search_hist(s, 2, n * 20, score={"AIC": 1, "BIC": 2}.get(model, 0), weight=seed % 3, max_iter=8,
-                               num_threads=2, seed=int(mini_r_uniform(90 + seed) * 9007199254740992.0), num_cats=c)
+                               num_threads=2, unif=r_unif, num_cats=c)
     assert np.array_equal(vh.reshape(n, n), hist)
 
 
