@@ -62,7 +62,15 @@ struct CnbTiles {
 	int32_t pad;                  /* table kernel: L1 prefetch distance of the generators */
 	int32_t f1;                   /* kind 3: free categories per node (max categories - 1) */
 	int32_t nvirt;                /* kind 3: virtual pair nodes behind the N real ones in the A operand rows */
+	int32_t tp, tc;               /* pair slots x column slots of a tile: 28 x 64 (inclusion-exclusion tiles, P and T tiles) or
+	                                 16 x 48 (full-table tiles); slot stride inside a tile = tc */
+	int32_t full;                 /* 1: full-table tiles -- 16 rows per pair (all (i, j)), 4 columns per column node, the child's
+	                                 keep mask ANDed into its rows, a missing value sets no bit: no inclusion-exclusion, so
+	                                 missing values and perturbation masks count correctly */
+	int32_t row_stride;           /* full: operand rows per node, 4 (no masks) or 8 (4 plain, then 4 under the node's own keep mask) */
 };
+#define CNB_FULL_PAIRS 16     /* full-table tile: 2 blocks of 8 parent pairs x 16 rows ... */
+#define CNB_FULL_CHILD 48     /* ... x up to 48 column nodes x 4 columns (192): 768 family slots per tile */
 
 #define CNB_TILE_PAIRS 28     /* tensor-core tile: 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128) ... */
 #define CNB_TILE_CHILD 64     /* ... x up to 64 children x 3 columns (192): 1792 family slots per tile */
@@ -90,6 +98,8 @@ struct CnbPlan {
 	std::vector<int64_t> tile_base;            /* tiled group: first tile of every child tile (+ total at the end) */
 	std::vector<int64_t> dtile_off;            /* see cnb_tiles.h */
 	int32_t tile_child = 0;                    /* children per child tile */
+	int32_t tile_pairs = CNB_TILE_PAIRS, tile_cols = CNB_TILE_CHILD;   /* geometry of the tiled group (CnbTiles.tp / .tc) */
+	int32_t tile_full = 0;                     /* the tiled group runs as full-table tiles */
 	int64_t seg_len = 0;                       /* doubles per rank segment */
 	int64_t num_families = 0;
 	int64_t num_options = 0;
@@ -99,8 +109,9 @@ struct CnbPlan {
 };
 
 /* host planner (no CUDA): cnb_plan.cpp */
+/* tile_mode: 0 = the two-parent group is not tiled, 1 = inclusion-exclusion tiles (complete data), 2 = full-table tiles */
 int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
-		std::string *err, bool allow_tiled = false);
+		std::string *err, int tile_mode = 0);
 int64_t cnb_binom(int64_t n, int64_t k);
 /* MMA columns (children x 3, rounded up to 16) tile `tile` of the tiled group really contracts */
 int cnb_tile_columns(const CnbPlan &pl, int64_t tile);

@@ -67,7 +67,7 @@ extern "C" int cnb_unrank_combination(int32_t n, int32_t k, int64_t rank, int32_
 }
 
 int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, int32_t world, CnbPlan *plan,
-		std::string *err, bool allow_tiled) {
+		std::string *err, int tile_mode) {
 	char buf[256];
 #define FAIL(code, ...) do { snprintf(buf, sizeof(buf), __VA_ARGS__); if (err) *err = buf; cnb_set_error("%s", buf); return code; } while (0)
 	if (!p || !plan) FAIL(CNB_ERR_PARAM, "null parameters");
@@ -204,14 +204,18 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 		/* Tensor-core tiling of the two-parent group: only when every node c >= 2 offers all pairs of its
 		 * predecessors (no pools, no fixed parents, no size limit), so that tile (child tile, pair tile) slots map
 		 * one-to-one onto candidate families.  Tiles cost the same, so ranks get equal contiguous tile ranges. */
-		if (allow_tiled && d == 2 && N >= 3 && g.nblk == N - 2) {
+		if (tile_mode && d == 2 && N >= 3 && g.nblk == N - 2) {
 			bool full = true;
 			for (int k = 0; k < g.nblk; k++) {
 				const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
 				full = full && b.nfix == 0 && b.nfree == b.child;
 			}
 			if (full) {
-				int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+				const int tp = tile_mode == 2 ? CNB_FULL_PAIRS : CNB_TILE_PAIRS, tc = tile_mode == 2 ? CNB_FULL_CHILD : CNB_TILE_CHILD;
+				pl.tile_pairs = tp;
+				pl.tile_cols = tc;
+				pl.tile_full = tile_mode == 2;
+				int nct = (N + tc - 1) / tc;
 				int cpt = (N + nct - 1) / nct;                      /* equal child tiles (500 nodes: 8 x 63, not 7 x 64 + 52) */
 				pl.tile_child = cpt;
 				pl.tile_base.assign(nct + 1, 0);
@@ -219,17 +223,17 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 				for (int ct = 0; ct < nct; ct++) {
 					const int c0 = ct * cpt, ce = std::min(c0 + cpt, N);
 					int64_t *off = &pl.dtile_off[(size_t)ct * CNB_DT_STRIDE];
-					const int ndp = cnb_d_pairs(c0, ce), ndt = (ndp + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS;
-					for (int p = 0; p < ndt; p++) off[p + 1] = off[p] + cnb_d_chunks(c0, ce, p);
+					const int ndp = cnb_d_pairs(c0, ce), ndt = (ndp + tp - 1) / tp;
+					for (int p = 0; p < ndt; p++) off[p + 1] = off[p] + cnb_d_chunks(c0, ce, p, tp, tc);
 					for (int p = ndt + 1; p < CNB_DT_STRIDE; p++) off[p] = off[ndt];
-					pl.tile_base[ct + 1] = pl.tile_base[ct] + cnb_f_tiles(c0) + off[ndt];
+					pl.tile_base[ct + 1] = pl.tile_base[ct] + cnb_f_tiles(c0, tp) + off[ndt];
 				}
 				g.tiled = 1;
 				g.ntiles = pl.tile_base[nct];
 				g.tiles_per_rank = (g.ntiles + world - 1) / world;
 				g.tile_world = world;
 				g.tile_child = cpt;
-				g.chunk = g.tiles_per_rank * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+				g.chunk = g.tiles_per_rank * tp * tc;
 			}
 		}
 		g.seg_off = pl.seg_len;
@@ -251,27 +255,32 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 #undef FAIL
 }
 
+/* host-side view of the plan's tiling (tile_base / dtile_off point into the plan's vectors) */
+void cnb_plan_tiles(const CnbPlan &pl, CnbTiles *T) {
+	memset(T, 0, sizeof(*T));
+	T->tile_base = (const long long *)pl.tile_base.data();
+	T->dtile_off = (const long long *)pl.dtile_off.data();
+	T->nct = pl.tile_base.empty() ? 0 : (int)pl.tile_base.size() - 1;
+	T->child = pl.tile_child;
+	T->world = 1;
+	T->tp = pl.tile_pairs;
+	T->tc = pl.tile_cols;
+	T->full = pl.tile_full;
+	T->row_stride = 4;
+}
+
 int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
 	CnbTiles T;
-	T.tile_base = (const long long *)pl.tile_base.data();
-	T.dtile_off = (const long long *)pl.dtile_off.data();
-	T.nct = (int)pl.tile_base.size() - 1;
-	T.child = pl.tile_child;
-	T.rank = 0;
-	T.world = 1;
-	T.self_pairs = 0;
-	T.pad = 0;
-	T.f1 = 0;
-	T.nvirt = 0;
+	cnb_plan_tiles(pl, &T);
 	CnbTileInfo ti;
 	cnb_tile_decode(T, pl.N, tile, ti);
-	return (3 * (ti.ze - ti.zb) + 15) / 16 * 16;
+	return ((pl.tile_full ? 4 : 3) * (ti.ze - ti.zb) + 15) / 16 * 16;
 }
 
 /* test hook: the tiling of the unrestricted two-parent group of N nodes is a bijection between families and tile
  * slots (family -> slot -> family), every tile has at least one column, and no two families share a slot.
  * Returns the number of tiles, or a negative value at the first inconsistency. */
-extern "C" int64_t cnb_tile_selftest(int32_t N) {
+static int64_t tile_selftest(int32_t N, int tile_mode) {
 	if (N < 3) return 0;
 	cnb_params q;
 	memset(&q, 0, sizeof(q));
@@ -281,20 +290,12 @@ extern "C" int64_t cnb_tile_selftest(int32_t N) {
 	q.max_complexity = 1 << 30;
 	std::vector<int32_t> cats(N, 2);
 	CnbPlan pl;
-	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr, true) != CNB_OK || pl.tile_base.empty()) return -1;
+	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr, tile_mode) != CNB_OK || pl.tile_base.empty()) return -1;
 	CnbTiles T;
-	T.tile_base = (const long long *)pl.tile_base.data();
-	T.dtile_off = (const long long *)pl.dtile_off.data();
-	T.nct = (int)pl.tile_base.size() - 1;
-	T.child = pl.tile_child;
-	T.rank = 0;
-	T.world = 1;
-	T.self_pairs = 0;
-	T.pad = 0;
-	T.f1 = 0;
-	T.nvirt = 0;
+	cnb_plan_tiles(pl, &T);
+	const int tp = T.tp, tc = T.tc;
 	const int64_t ntiles = pl.tile_base[T.nct];
-	std::vector<unsigned char> used((size_t)ntiles * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
+	std::vector<unsigned char> used((size_t)ntiles * tp * tc, 0);
 	int64_t nfam = 0;
 	for (int c = 2; c < N; c++)
 		for (int b = 1; b < c; b++)
@@ -302,14 +303,14 @@ extern "C" int64_t cnb_tile_selftest(int32_t N) {
 				long long tile;
 				int within;
 				cnb_family_slot(T, N, a, b, c, tile, within);
-				if (tile < 0 || tile >= ntiles || within < 0 || within >= CNB_TILE_PAIRS * CNB_TILE_CHILD) return -2;
-				unsigned char &u = used[(size_t)tile * CNB_TILE_PAIRS * CNB_TILE_CHILD + within];
+				if (tile < 0 || tile >= ntiles || within < 0 || within >= tp * tc) return -2;
+				unsigned char &u = used[(size_t)tile * tp * tc + within];
 				if (u) return -3;
 				u = 1;
 				CnbTileInfo ti;
 				cnb_tile_decode(T, N, tile, ti);
 				int x, y;
-				const int p = within / CNB_TILE_CHILD, j = within % CNB_TILE_CHILD;
+				const int p = within / tc, j = within % tc;
 				if (j >= ti.ze - ti.zb || !cnb_tile_pair(ti, p, x, y)) return -4;
 				const bool dk = ti.kind != 0;
 				const int a2 = dk ? ti.zb + j : x, b2 = dk ? x : y, c2 = dk ? y : ti.zb + j;
@@ -320,10 +321,14 @@ extern "C" int64_t cnb_tile_selftest(int32_t N) {
 	for (int64_t t = 0; t < ntiles; t++) {
 		CnbTileInfo ti;
 		cnb_tile_decode(T, N, t, ti);
-		if (ti.ze <= ti.zb || ti.ze - ti.zb > CNB_TILE_CHILD || cnb_tile_columns(pl, t) < 16) return -7;
+		if (ti.ze <= ti.zb || ti.ze - ti.zb > tc || cnb_tile_columns(pl, t) < 16) return -7;
 	}
 	return ntiles;
 }
+
+extern "C" int64_t cnb_tile_selftest(int32_t N) { return tile_selftest(N, 1); }
+/* the same for the full-table geometry (16 pairs x 48 column nodes) */
+extern "C" int64_t cnb_tile_selftest_full(int32_t N) { return tile_selftest(N, 2); }
 
 extern "C" int64_t cnb_num_families(const cnb_params *p) {
 	if (!p || p->num_nodes < 1) return -1;
@@ -348,6 +353,7 @@ extern "C" int64_t cnb_tile3_selftest(int32_t N, int32_t f1) {
 	for (int ct = 0; ct < nct; ct++) base3[ct + 1] = base3[ct] + cnb_t_tiles(cnb_t_ce(N, nct, ct), f1);
 	CnbTiles T;
 	memset(&T, 0, sizeof(T));
+	CNB_TILES_DEFAULT_GEOMETRY(T);
 	T.tile_base = base3.data();
 	T.nct = nct;
 	T.child = CNB_TILE_CHILD;

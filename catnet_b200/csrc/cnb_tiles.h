@@ -39,10 +39,14 @@
 #define CNB_HD inline
 #endif
 
-#define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 pair tiles of D pairs per child tile, plus the total */
+#define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 (default geometry) and >= ceil(48 * 47 / 2 / 16) + 1 = 72 (full-table
+                                 geometry) pair tiles of D pairs per child tile, plus the total */
+/* default geometry of a CnbTiles (the inclusion-exclusion tiles, the P and the T tiles) */
+#define CNB_TILES_DEFAULT_GEOMETRY(T) do { (T).tp = CNB_TILE_PAIRS; (T).tc = CNB_TILE_CHILD; } while (0)
 
 struct CnbTileInfo {
 	int kind;                 /* 0 = F, 1 = D, 2 = P, 3 = T */
+	int tp, tc;               /* pair slots and column slots of a tile (CnbTiles) */
 	int n, f1;                /* kind 3: real nodes, free categories */
 	int ct, c0, ce;           /* child tile and its children [c0, ce) */
 	long long pair0;          /* rank of the tile's first pair inside its region (F: q, D: rank among the D pairs) */
@@ -57,7 +61,7 @@ CNB_HD void cnb_pair_of(long long q, int &a, int &b) {      /* q = b(b-1)/2 + a,
 	a = (int)(q - (long long)b * (b - 1) / 2);
 }
 CNB_HD long long cnb_f_pairs(int c0) { return (long long)c0 * (c0 - 1) / 2; }
-CNB_HD long long cnb_f_tiles(int c0) { return (cnb_f_pairs(c0) + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }
+CNB_HD long long cnb_f_tiles(int c0, int tp) { return (cnb_f_pairs(c0) + tp - 1) / tp; }
 CNB_HD int cnb_d_pairs(int c0, int ce) { return (ce - c0) * (ce - c0 - 1) / 2; }
 /* rank of D pair (b, c) of child tile [c0, ce), and back */
 CNB_HD int cnb_d_rank(int c0, int ce, int b, int c) {
@@ -69,14 +73,14 @@ CNB_HD void cnb_d_pair(int c0, int ce, int q, int &b, int &c) {
 	while (q >= ce - 1 - b) { q -= ce - 1 - b; b++; }
 	c = b + 1 + q;
 }
-/* chunks of 64 first parents a D pair tile needs: up to the b of its last pair */
-CNB_HD int cnb_d_chunks(int c0, int ce, int ptile) {
+/* chunks of tc first parents a D pair tile (tp pairs) needs: up to the b of its last pair */
+CNB_HD int cnb_d_chunks(int c0, int ce, int ptile, int tp, int tc) {
 	const int np = cnb_d_pairs(c0, ce);
-	int last = ptile * CNB_TILE_PAIRS + CNB_TILE_PAIRS - 1;
+	int last = ptile * tp + tp - 1;
 	if (last > np - 1) last = np - 1;
 	int b, c;
 	cnb_d_pair(c0, ce, last, b, c);
-	return (b + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+	return (b + tc - 1) / tc;
 }
 
 CNB_HD long long cnb_binom3(long long n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
@@ -94,6 +98,8 @@ CNB_HD void cnb_triple_of(long long t, int &a, int &b, int &c) {
 CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInfo &ti) {
 	ti.n = N;
 	ti.f1 = T.f1;
+	ti.tp = T.tp;
+	ti.tc = T.tc;
 	if (T.self_pairs == 2) {
 		int ct = 0;
 		while (ct + 1 < T.nct && T.tile_base[ct + 1] <= tile) ct++;
@@ -101,22 +107,22 @@ CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInf
 		ti.ct = ct;
 		ti.c0 = cnb_t_c0(N, T.nct, ct);
 		ti.ce = cnb_t_ce(N, T.nct, ct);
-		ti.pair0 = (tile - T.tile_base[ct]) * CNB_TILE_PAIRS;
+		ti.pair0 = (tile - T.tile_base[ct]) * T.tp;
 		ti.npairs = cnb_binom3(ti.ce - 1) * T.f1;
 		ti.zb = ti.c0;
 		ti.ze = ti.ce;
 		return;
 	}
 	if (T.self_pairs) {
-		const int nch = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+		const int nch = (N + T.tc - 1) / T.tc;
 		ti.kind = 2;
 		ti.ct = 0;
 		ti.c0 = 0;
 		ti.ce = N;
-		ti.pair0 = (tile / nch) * CNB_TILE_PAIRS;
+		ti.pair0 = (tile / nch) * T.tp;
 		ti.npairs = N;
-		ti.zb = (int)(tile % nch) * CNB_TILE_CHILD;
-		ti.ze = ti.zb + CNB_TILE_CHILD < N ? ti.zb + CNB_TILE_CHILD : N;
+		ti.zb = (int)(tile % nch) * T.tc;
+		ti.ze = ti.zb + T.tc < N ? ti.zb + T.tc : N;
 		return;
 	}
 	int lo = 0, hi = T.nct - 1;
@@ -128,10 +134,10 @@ CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInf
 	ti.ct = lo;
 	ti.c0 = lo * T.child;
 	ti.ce = ti.c0 + T.child < N ? ti.c0 + T.child : N;
-	const long long pt = tile - T.tile_base[lo], nf = cnb_f_tiles(ti.c0);
+	const long long pt = tile - T.tile_base[lo], nf = cnb_f_tiles(ti.c0, T.tp);
 	if (pt < nf) {
 		ti.kind = 0;
-		ti.pair0 = pt * CNB_TILE_PAIRS;
+		ti.pair0 = pt * T.tp;
 		ti.npairs = cnb_f_pairs(ti.c0);
 		ti.zb = ti.c0;
 		ti.ze = ti.ce;
@@ -142,14 +148,14 @@ CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInf
 	int p = 0;
 	while (off[p + 1] <= d) p++;
 	ti.kind = 1;
-	ti.pair0 = (long long)p * CNB_TILE_PAIRS;
+	ti.pair0 = (long long)p * T.tp;
 	ti.npairs = cnb_d_pairs(ti.c0, ti.ce);
-	int last = p * CNB_TILE_PAIRS + CNB_TILE_PAIRS - 1;
+	int last = p * T.tp + T.tp - 1;
 	if (last > ti.npairs - 1) last = (int)ti.npairs - 1;
 	int b, c;
 	cnb_d_pair(ti.c0, ti.ce, last, b, c);
-	ti.zb = (d - (int)off[p]) * CNB_TILE_CHILD;
-	ti.ze = ti.zb + CNB_TILE_CHILD < b ? ti.zb + CNB_TILE_CHILD : b;
+	ti.zb = (d - (int)off[p]) * T.tc;
+	ti.ze = ti.zb + T.tc < b ? ti.zb + T.tc : b;
 }
 
 /* the two "pair" nodes (x, y) of pair slot ps of a tile; false if the slot is past the end of the region */
@@ -168,21 +174,21 @@ CNB_HD bool cnb_tile_pair(const CnbTileInfo &ti, int ps, int &x, int &y) {
 	return true;
 }
 
-/* family (a < b | c) -> tile and slot inside the tile (pair slot * CNB_TILE_CHILD + column slot) */
+/* family (a < b | c) -> tile and slot inside the tile (pair slot * T.tc + column slot) */
 CNB_HD void cnb_family_slot(const CnbTiles &T, int N, int a, int b, int c, long long &tile, int &within) {
 	const int ct = c / T.child, c0 = ct * T.child, ce = c0 + T.child < N ? c0 + T.child : N;
 	if (b < c0) {
 		const long long q = (long long)b * (b - 1) / 2 + a;
-		tile = T.tile_base[ct] + q / CNB_TILE_PAIRS;
-		within = (int)(q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + (c - c0);
+		tile = T.tile_base[ct] + q / T.tp;
+		within = (int)(q % T.tp) * T.tc + (c - c0);
 	} else {
-		const int q = cnb_d_rank(c0, ce, b, c), p = q / CNB_TILE_PAIRS;
-		tile = T.tile_base[ct] + cnb_f_tiles(c0) + T.dtile_off[(size_t)ct * CNB_DT_STRIDE + p] + a / CNB_TILE_CHILD;
-		within = (q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + a % CNB_TILE_CHILD;
+		const int q = cnb_d_rank(c0, ce, b, c), p = q / T.tp;
+		tile = T.tile_base[ct] + cnb_f_tiles(c0, T.tp) + T.dtile_off[(size_t)ct * CNB_DT_STRIDE + p] + a / T.tc;
+		within = (q % T.tp) * T.tc + a % T.tc;
 	}
 }
 
 /* kind 3: tiles of column tile [c0, ce) and the slot of (triple rank t, value i of a, child x) */
-CNB_HD long long cnb_t_tiles(int ce, int f1) { return (cnb_binom3(ce - 1) * f1 + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }
+CNB_HD long long cnb_t_tiles(int ce, int f1) { return (cnb_binom3(ce - 1) * f1 + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }   /* T tiles: default geometry */
 
 #endif
