@@ -82,7 +82,7 @@ SYMBOLS = [
     "cnb_mctx_create", "cnb_mctx_destroy", "cnb_mctx_num_devices", "cnb_mctx_ctx", "cnb_mctx_set_samples",
     "cnb_mctx_search_order", "cnb_mctx_search_light", "cnb_mctx_collect", "cnb_mctx_search_sa", "cnb_mctx_search_hist",
     "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
-    "cnb_ctx_upload_rows8",
+    "cnb_ctx_upload_rows8", "cnb_tile_selftest_full",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def lib():
         "cnb_ctx_timing": (i32, [vp, P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_tile_selftest": (C.c_int64, [i32]),
+        "cnb_tile_selftest_full": (C.c_int64, [i32]),
         "cnb_tile3_selftest": (C.c_int64, [i32, i32]),
         "cnb_host_entropy_order": (None, [vp, i32, vp]),
         "cnb_family_scores": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32]),

@@ -440,6 +440,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->no_tensor3 = (on & 1024) != 0;                      /* bit 10: three-parent families never on the tensor cores */
 	c->dp_no_trap = (on & 2048) != 0;                      /* bit 11: wavefront DP one node per exchange (k_dp_wave) */
 	c->generic_epilogue = (on & 4096) != 0;                /* bit 12: generic epilogue of the tensor-core scorer also for 4-category data */
+	c->force_full = (on & 8192) != 0;                      /* bit 13: full-table tiles also on complete data (no inclusion-exclusion) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -465,16 +466,12 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.blocks = (const CnbBlock *)c->b_blocks.ptr;
 	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
 	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
+	cnb_plan_tiles(c->plan, &D.tiles);
 	D.tiles.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
 	D.tiles.dtile_off = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_dtile_off.ptr;
-	D.tiles.nct = c->plan.tile_base.empty() ? 0 : (int)c->plan.tile_base.size() - 1;
-	D.tiles.child = c->plan.tile_child;
 	D.tiles.rank = c->plan.rank;
 	D.tiles.world = c->plan.world;
-	D.tiles.self_pairs = 0;
-	D.tiles.pad = 0;
-	D.tiles.f1 = 0;
-	D.tiles.nvirt = 0;
+	D.tiles.row_stride = masks ? 8 : 4;
 	return D;
 }
 
@@ -505,14 +502,21 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	}
 	/* tensor-core tiling of the two-parent group: clean data (no NA, no masks, <= 4 categories) and enough samples
 	 * per family to amortise a 128 x 256 tile (or forced on by the test hook) */
-	bool tiled = c->clean && c->pairs_valid && !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192)
+	const bool tensor_ok = !c->force_generic && c->tensor_mode >= 0 && (c->tensor_mode > 0 || c->M >= 8192)
 			&& c->M < (1 << 24);          /* accumulators hold counts in f32 (mxf4) or 128 x count in s32 (i8) */
-	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tiled));
+	/* 1: inclusion-exclusion tiles (27 cells contracted, the rest from the pair tables: complete data only);
+	 * 2: full-table tiles (all 64 cells: missing values and perturbation masks count correctly) */
+	int tile_mode = 0;
+	if (tensor_ok && c->clean && c->pairs_valid && !c->force_full) tile_mode = 1;
+	else if (tensor_ok && c->max_cats <= CNB_PLANE_CATS && !c->tensor_i8) tile_mode = 2;
+	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
 	CnbPlan &pl = c->plan;
+	const bool masks = c->has_pert && !c->ignore_pert;
 	if (!pl.tile_base.empty()) {
 		RC(upload(c, c->b_tile_base, pl.tile_base));
 		RC(upload(c, c->b_dtile_off, pl.dtile_off));
-		size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, !c->tensor_i8, nullptr) * sizeof(uint4) * 3 * c->N;
+		const size_t rows_per_node = pl.tile_full ? (masks ? 8 : 4) : 3;
+		size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, !c->tensor_i8, nullptr) * sizeof(uint4) * rows_per_node * c->N;
 		RC(c->b_rows_a.ensure(row_bytes));
 		RC(c->b_rows_b.ensure(row_bytes));
 	}
@@ -551,8 +555,12 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	c->timing.kernel_launches = 1;                    /* k_permute; the later phases add theirs */
 	if (!pl.tile_base.empty()) {
 		/* operand bit rows of the tensor-core scorer, order space */
-		RC(cnbk_umma_rows(c->stream, (const uint4 *)c->b_planes.ptr, c->N, c->W, !c->tensor_i8, (uint4 *)c->b_rows_a.ptr,
-				(uint4 *)c->b_rows_b.ptr));
+		if (pl.tile_full)
+			RC(cnbk_umma_rows_full(c->stream, (const uint4 *)c->b_planes.ptr, masks ? (const uint32_t *)c->b_keep.ptr : nullptr, c->N, c->W,
+					(uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr));
+		else
+			RC(cnbk_umma_rows(c->stream, (const uint4 *)c->b_planes.ptr, c->N, c->W, !c->tensor_i8, (uint4 *)c->b_rows_a.ptr,
+					(uint4 *)c->b_rows_b.ptr));
 		c->timing.kernel_launches++;
 	}
 	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
@@ -593,7 +601,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	*done = false;
 	const CnbPlan &pl = c->plan;
 	const int N = c->N;
-	if (g.d != 3 || !g.full || pl.world != 1 || pl.tile_base.empty() || !c->clean || !c->pairs_valid || c->force_generic
+	if (g.d != 3 || !g.full || pl.world != 1 || pl.tile_base.empty() || pl.tile_full || !c->clean || !c->pairs_valid || c->force_generic
 			|| c->no_ie || c->no_ie3 || c->no_tensor3 || c->tensor_i8 || c->tensor_mode < 0 || (c->tensor_mode == 0 && c->M < 8192)
 			|| c->M >= (1 << 24) || N < 4 || N > 64 * 32 || cnbk_umma_row_quads(c->W, 1, nullptr) > 65535) return CNB_OK;
 	bool ok = false;
@@ -621,6 +629,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	RC(c->b_counts.ensure((size_t)std::max<long long>(largest, 1) * slot_bytes));
 	CnbTiles T3;
 	memset(&T3, 0, sizeof(T3));
+	CNB_TILES_DEFAULT_GEOMETRY(T3);
 	T3.tile_base = (const long long *)c->b_tile_base3.ptr;
 	T3.nct = nct;
 	T3.child = CNB_TILE_CHILD;
@@ -755,7 +764,8 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			long long t0 = 0, t1 = (g.ntiles - pl.rank + pl.world - 1) / pl.world;
 			bool uni4 = true;                                   /* every node with exactly 4 categories: specialised epilogue */
 			for (int v : pl.cats) uni4 = uni4 && v == 4;
-			const long long batch = 16384, slot_bytes = CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+			const long long batch = 16384, slot_bytes = (pl.tile_full ? CNBK_UMMA_FULL_SLOT_INTS : CNBK_UMMA_SLOT_INTS) * sizeof(int)
+					* (long long)pl.tile_pairs * pl.tile_cols;
 			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
 			int nb = 0;
 			for (long long tb = t0; tb < t1; tb += batch, nb++) {
@@ -1302,9 +1312,8 @@ extern "C" int cnb_ctx_search_scores(cnb_ctx *c, const double *scores_dev, int32
 	CK(cudaSetDevice(c->device));
 	const CnbPlan &pl = c->plan;
 	std::vector<long long> index(nfam, -1);
-	CnbTiles T = make_devdata(c).tiles;
-	T.tile_base = (const long long *)pl.tile_base.data();
-	T.dtile_off = (const long long *)pl.dtile_off.data();
+	CnbTiles T;
+	cnb_plan_tiles(pl, &T);
 	for (int f = 0; f < nfam; f++) {
 		const int child = children[f];
 		if (child < 0 || child >= pl.N) continue;
@@ -1340,7 +1349,7 @@ extern "C" int cnb_ctx_search_scores(cnb_ctx *c, const double *scores_dev, int32
 				long long tile;
 				int within;
 				cnb_family_slot(T, pl.N, pl.lists[b.free_off + idx[0]], pl.lists[b.free_off + idx[1]], child, tile, within);
-				index[f] = (tile % g.tile_world) * pl.seg_len + g.seg_off + (tile / g.tile_world) * (CNB_TILE_PAIRS * CNB_TILE_CHILD) + within;
+				index[f] = (tile % g.tile_world) * pl.seg_len + g.seg_off + (tile / g.tile_world) * ((long long)T.tp * T.tc) + within;
 			} else {
 				const long long r = fid / g.chunk;
 				index[f] = r * pl.seg_len + g.seg_off + (fid - r * g.chunk);

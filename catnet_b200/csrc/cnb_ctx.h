@@ -47,6 +47,7 @@ struct cnb_ctx {
 	std::vector<uint8_t> never_kept;   /* [N] label space: node perturbed in every sample (no candidate parent sets) */
 	bool any_never_kept = false;
 	bool generic_epilogue = false;     /* k_umma_epilogue<false> also when every node has 4 categories (test hook) */
+	bool force_full = false;           /* full-table tensor tiles also on complete data (test hook) */
 	bool dp_no_trap = false;           /* k_dp_wave instead of the trapezoid kernel (test hook) */
 	bool has_na = false;               /* the data set has missing values */
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */

@@ -115,6 +115,8 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 int64_t cnb_binom(int64_t n, int64_t k);
 /* MMA columns (children x 3, rounded up to 16) tile `tile` of the tiled group really contracts */
 int cnb_tile_columns(const CnbPlan &pl, int64_t tile);
+/* host-side view of the plan's tiling: geometry, mode, tile_base / dtile_off pointing into the plan's vectors */
+void cnb_plan_tiles(const CnbPlan &pl, CnbTiles *T);
 int cnb_unrank_lex(int32_t n, int32_t k, int64_t r, int32_t *out);
 
 void cnb_set_error(const char *fmt, ...);

@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 			int within;
 			cnb_family_slot(Dt.tiles, Dt.N, ab[0], ab[1], b.child, tile, within);
 			/* tile t is scored by rank t % world as its local tile t / world */
-			return scores[(tile % g.tile_world) * seg_len + g.seg_off + (tile / g.tile_world) * (CNB_TILE_PAIRS * CNB_TILE_CHILD)
+			return scores[(tile % g.tile_world) * seg_len + g.seg_off + (tile / g.tile_world) * (Dt.tiles.tp * Dt.tiles.tc)
 					+ within];
 		}
 		return scores[dev_score_index(slot, g.chunk, g.seg_off, seg_len)];

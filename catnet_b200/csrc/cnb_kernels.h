@@ -46,6 +46,8 @@ int cnbk_score_planes_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies 
 /* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
 int cnbk_umma_row_quads(int W, int fp4, int *ngroups);
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b);
+/* operand rows of the full-table tiles: 4 rows per node, or 8 with keep masks (4 plain + 4 under the node's own mask) */
+int cnbk_umma_rows_full(cudaStream_t st, const uint4 *planes, const uint32_t *keep, int N, int W, uint4 *rows_a, uint4 *rows_b);
 /* local tiles [local_begin, local_end) of rank T.rank (global tile = rank + local * world) */
 int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
 		const CnbTiles &T, long long local_begin, long long local_end, int *counts);
@@ -57,6 +59,7 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O, bool all_four_cats = false);   /* all_four_cats: every node has 4 categories */
 #define CNBK_UMMA_SLOT_INTS 36
+#define CNBK_UMMA_FULL_SLOT_INTS 64
 /* three-parent families on the tensor cores: pair-side rows incl. the virtual pair nodes, then cnbk_umma_tables with a
  * CnbTiles of kind 3 and cnbk_umma_epilogue3 per column tile */
 int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvirt, int f1, uint4 *rows_a3);

@@ -50,6 +50,15 @@
 #define UM_TMEM_COLS 512
 #define UM_TMEM_A (UM_NA * UM_N)          /* 384: pair rows, UM_NA blocks x UM_ASTAGES slots x 2 k-steps x 8 columns = 96 columns */
 #define UM_TMEM_SF 480                    /* mxf4: unit scale factors in columns 480..511 */
+/* Full-table tiles (CnbTiles.full): every cell is contracted -- 16 rows per pair (all (i, j)), 4 columns per column node;
+ * a missing value sets no bit in any of its node's rows and a child's rows carry its perturbation keep mask, so the
+ * 64 counts of a slot ARE the family's table whatever the data (no inclusion-exclusion).  64 / 27 = 2.4 x the MACs. */
+#define UMF_BLK_PAIRS 8                   /* 8 pairs x 16 rows = 128 rows of one MMA */
+#define UMF_PAIRS CNB_FULL_PAIRS
+#define UMF_CHILD CNB_FULL_CHILD
+#define UMF_SLOTS (UMF_PAIRS * UMF_CHILD)
+#define UMF_SLOT_INTS 64                  /* 16 configurations x 4 counts: int4 stores */
+static_assert(UMF_PAIRS == UM_NA * UMF_BLK_PAIRS && UMF_CHILD * 4 <= UM_N, "full-table tile geometry");
 static_assert(UM_PAIRS == UM_NA * UM_BLK_PAIRS, "tile geometry");
 static_assert(UM_N <= 256 && UM_TMEM_A + UM_NA * UM_ASTAGES * 16 <= UM_TMEM_SF, "tensor memory budget");
 static_assert(UM_STAGE % 1024 == 0, "stages keep the 1024-byte swizzle alignment");
@@ -143,6 +152,35 @@ __global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ pla
 	rows_b[o + 2] = make_uint4(rows_b_word(v[0].z, fp4), rows_b_word(v[1].z, fp4), rows_b_word(v[2].z, fp4), rows_b_word(v[3].z, fp4));
 }
 
+/* operand rows of the full-table tiles: [quad][node * RS + v * 4 + cat], cat < 4; v = 0 the node's plain one-hot rows
+ * (the node as a parent), v = 1 (RS = 8, perturbation masks present) the same rows under the node's own keep mask (the
+ * node as the child).  A missing value has no bit in any plane, so it drops out of every product by itself. */
+__global__ void __launch_bounds__(128) k_umma_rows_full(const uint4 *__restrict__ planes, const uint32_t *__restrict__ keep, int N, int W,
+		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int RS) {
+	const int nchunk = (N + blockDim.x - 1) / blockDim.x;
+	const int n = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x, qd = blockIdx.x / nchunk;
+	if (n >= N) return;
+	uint32_t v[4][4], m[4];                  /* [cat][word of the quad] */
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int w = qd * 4 + k;
+		const uint4 x = w < W ? __ldg(planes + (size_t)w * N + n) : make_uint4(0, 0, 0, 0);
+		v[0][k] = x.x; v[1][k] = x.y; v[2][k] = x.z; v[3][k] = x.w;
+		m[k] = (keep && w < W) ? __ldg(keep + (size_t)w * N + n) : 0xFFFFFFFFu;
+	}
+	const size_t o = (size_t)qd * ((size_t)RS * N) + (size_t)RS * n;
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		rows_a[o + c] = make_uint4(v[c][0], v[c][1], v[c][2], v[c][3]);
+		rows_b[o + c] = make_uint4(rows_b_word(v[c][0], 1), rows_b_word(v[c][1], 1), rows_b_word(v[c][2], 1), rows_b_word(v[c][3], 1));
+		if (RS == 8) {
+			rows_a[o + 4 + c] = make_uint4(v[c][0] & m[0], v[c][1] & m[1], v[c][2] & m[2], v[c][3] & m[3]);
+			rows_b[o + 4 + c] = make_uint4(rows_b_word(v[c][0] & m[0], 1), rows_b_word(v[c][1] & m[1], 1), rows_b_word(v[c][2] & m[2], 1),
+					rows_b_word(v[c][3] & m[3], 1));
+		}
+	}
+}
+
 /* ---- operand generation: one 32-sample source word -> output words ------------------------------------------- */
 #define STS128(addr, imm, a, b, c, d) asm volatile("st.shared.v4.b32 [%0+%1], {%2, %3, %4, %5};" \
 		::"r"(addr), "n"(imm), "r"(a), "r"(b), "r"(c), "r"(d) : "memory")
@@ -228,11 +266,16 @@ __device__ __forceinline__ void mma_issue_loop(uint32_t smem, uint32_t idesc, in
 	umma_commit(smem_u32(bar_done), 1);
 }
 
-template <bool FP4>
+template <bool FP4, bool FULL>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
 		int N, int ngroups_all, CnbTiles T, long long local_begin, int *__restrict__ counts, int whole, int split) {
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
-	const int NRB = 3 * N, NRA = 3 * (N + T.nvirt);   /* operand rows per quad: column side, pair side (real + virtual nodes) */
+	constexpr int CPC = FULL ? 4 : 3;       /* columns per column node */
+	constexpr int RPP = FULL ? 16 : 9;      /* rows per pair */
+	constexpr int BLKP = FULL ? UMF_BLK_PAIRS : UM_BLK_PAIRS;
+	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS, TC = FULL ? UMF_CHILD : UM_CHILD;
+	const int RS = FULL ? T.row_stride : 3; /* operand rows per node */
+	const int NRB = RS * N, NRA = RS * (N + T.nvirt);   /* operand rows per quad: column side, pair side (real + virtual nodes) */
 	/* CTAs [0, whole) contract all the samples of one tile each; the tiles behind them -- the launch's last, partial
 	 * wave -- are cut into `split` sample slices, one CTA each, whose counts are added up in global memory */
 	const bool sliced = (int)blockIdx.x >= whole;
@@ -251,7 +294,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	const long long tile = T.rank + (local_begin + tile_local) * T.world;
 	CnbTileInfo ti;                          /* cnb_tiles.h: pair slots (A rows) and column nodes (B rows) of this tile */
 	cnb_tile_decode(T, N, tile, ti);
-	const int nchild = ti.ze - ti.zb, ncols = (3 * nchild + 15) & ~15;   /* column nodes and MMA N of this tile */
+	const int nchild = ti.ze - ti.zb, ncols = (CPC * nchild + 15) & ~15;   /* column nodes and MMA N of this tile */
 
 	if (warp == UM_MMA_WARP) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(UM_TMEM_COLS));
@@ -294,8 +337,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		 * 126/127 and pair slots past the end repeat valid data whose accumulators nobody reads ---- */
 		const int h = warp >> 2, r = tid & 127;
 		int pa, pb;
-		if (!cnb_tile_pair(ti, h * UM_BLK_PAIRS + min(r / 9, UM_BLK_PAIRS - 1), pa, pb)) { pa = 0; pb = 1; }
-		const uint4 *s0 = rows_a + src_quads * NRA + (pa * 3 + (r % 9) / 3), *s1 = rows_a + src_quads * NRA + (pb * 3 + r % 3);
+		if (!cnb_tile_pair(ti, h * BLKP + min(r / RPP, BLKP - 1), pa, pb)) { pa = 0; pb = 1; }
+		/* full tables: in a D tile the pair is (second parent, CHILD): the child's rows are the ones under its keep mask */
+		const int vb = (FULL && ti.kind == 1 && RS == 8) ? 4 : 0;
+		const uint4 *s0 = rows_a + src_quads * NRA + (pa * RS + (r % RPP) / CPC), *s1 = rows_a + src_quads * NRA + (pb * RS + vb + r % CPC);
 		const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + UM_TMEM_A + h * (UM_ASTAGES * 16);
 		uint64_t *const full_a = &bar_full_a[h * UM_ASTAGES], *const empty_a = &bar_empty_a[h * UM_ASTAGES];
 		uint4 n0, n1, m0, m1;          /* next stage's source bits of the two nodes */
@@ -332,41 +377,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			}
 		}
 
-		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair slot*9 + (i*3+j); accumulator column
-		 * 3j+k = column node zb + j (column slot j of the tile).  A warp may only touch its own lane quarter
-		 * (warp & 3); each of the 8 warps reads its rows of one accumulator in chunks of 24 columns (8 nodes). */
+		/* ---- epilogue: TMEM -> registers -> global tables.  Row = pair slot*RPP + configuration; accumulator column
+		 * CPC*j+k = column node zb + j (column slot j of the tile).  A warp may only touch its own lane quarter
+		 * (warp & 3); each of the 8 warps reads its rows of one accumulator in chunks of 8 nodes. */
 		mbar_wait(&bar_done, 0);
 		asm volatile("tcgen05.fence::after_thread_sync;");
 		const int lq = warp & 3;
-		const int row = lq * 32 + lane, cfg = row % 9;
-		const bool row_ok = row < UM_BLK_PAIRS * 9;
-		int *out = counts + ((size_t)tile_local * UM_SLOTS + (size_t)(h * UM_BLK_PAIRS + row / 9) * UM_CHILD) * UM_SLOT_INTS + cfg * 4;
+		const int row = lq * 32 + lane, cfg = row % RPP;
+		const bool row_ok = row < BLKP * RPP;
+		int *out = counts + ((size_t)tile_local * SLOTS + (size_t)(h * BLKP + row / RPP) * TC) * SLOT_INTS + cfg * 4;
 #pragma unroll 1
 		for (int q = 0; q * 8 < nchild; q++) {
-			uint32_t v[24];
-			const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(h * UM_N + q * 24);
+			uint32_t v[8 * CPC];
+			const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(h * UM_N + q * 8 * CPC);
 #define LD8(o, a) asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
 			: "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]) \
 			: "r"(a))
 			LD8(0, taddr);
 			LD8(8, taddr + 8);
 			LD8(16, taddr + 16);
+			if constexpr (FULL) LD8(24, taddr + 24);
 #undef LD8
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			if (row_ok) {
 #pragma unroll
 				for (int j = 0; j < 8; j++) {
 					if (q * 8 + j >= nchild) break;
-					int x0, x1, x2;
-					if (FP4) {
-						x0 = __float2int_rn(__uint_as_float(v[j * 3])); x1 = __float2int_rn(__uint_as_float(v[j * 3 + 1]));
-						x2 = __float2int_rn(__uint_as_float(v[j * 3 + 2]));
-					} else {
-						x0 = (int)(v[j * 3] >> 7); x1 = (int)(v[j * 3 + 1] >> 7); x2 = (int)(v[j * 3 + 2] >> 7);
-					}
-					int *dst = out + (size_t)(q * 8 + j) * UM_SLOT_INTS;
-					if (sliced) { atomicAdd(dst, x0); atomicAdd(dst + 1, x1); atomicAdd(dst + 2, x2); }
-					else *reinterpret_cast<int4 *>(dst) = make_int4(x0, x1, x2, 0);
+					int x[4] = {0, 0, 0, 0};
+#pragma unroll
+					for (int k = 0; k < CPC; k++)
+						x[k] = FP4 ? __float2int_rn(__uint_as_float(v[j * CPC + k])) : (int)(v[j * CPC + k] >> 7);
+					int *dst = out + (size_t)(q * 8 + j) * SLOT_INTS;
+					if (sliced) {
+#pragma unroll
+						for (int k = 0; k < CPC; k++) atomicAdd(dst + k, x[k]);
+					} else *reinterpret_cast<int4 *>(dst) = make_int4(x[0], x[1], x[2], x[3]);
 				}
 			}
 		}
@@ -375,7 +420,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		 * past the MMA's columns are not generated, their threads only keep the warp's arrivals going ---- */
 		const int rr = tid - UM_A_WARPS * 32, r = min(rr, UM_N - 1);
 		const bool active = rr < ncols;
-		const uint4 *s0 = rows_b + src_quads * NRB + (min(ti.zb + r / 3, ti.ze - 1) * 3 + r % 3);
+		/* full tables: in an F tile the columns are the CHILDREN: their rows under the keep mask */
+		const int vc = (FULL && ti.kind == 0 && RS == 8) ? 4 : 0;
+		const uint4 *s0 = rows_b + src_quads * NRB + (min(ti.zb + r / CPC, ti.ze - 1) * RS + vc + r % CPC);
 		uint32_t off[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) off[k] = smem + (r >> 3) * 1024u + (r & 7u) * 128u + ((k ^ (r & 7u)) << 4);
@@ -477,15 +524,16 @@ __device__ __noinline__ double um_config_terms(double ll, int n0, int n1, int n2
 /* UNI4: every node has exactly 4 categories (C5): all loop bounds and table indices are compile-time constants, the
  * 64-cell table stays in registers (the generic path indexes it dynamically through local memory: 7,185 instructions
  * per family, 17 % of them fp64 arithmetic, profiles/r01_umma_epilogue_summary.txt) */
-template <bool UNI4>
+template <bool UNI4, bool FULL>
 __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long local_begin, long long local_end,
 		const int *__restrict__ counts, const int *__restrict__ pair_tab, ScoreOut O) {
+	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS, TC = FULL ? UMF_CHILD : UM_CHILD;
 	const CnbTiles &T = Dt.tiles;
 	const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long local = local_begin + slot / UM_SLOTS;
+	const long long local = local_begin + slot / SLOTS;
 	if (local >= local_end) return;
 	const long long tile = T.rank + local * T.world;
-	const int within = (int)(slot % UM_SLOTS), p = within / UM_CHILD, j = within % UM_CHILD;
+	const int within = (int)(slot % SLOTS), p = within / TC, j = within % TC;
 	CnbTileInfo ti;
 	cnb_tile_decode(T, Dt.N, tile, ti);
 	int x, y;
@@ -494,9 +542,22 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	const bool dk = ti.kind != 0;
 	const int a = dk ? ti.zb + j : x, b = dk ? x : y, c = dk ? y : ti.zb + j;
 	if (a >= b) return;
-	const int *tab = counts + (size_t)slot * UM_SLOT_INTS;
+	const int *tab = counts + (size_t)slot * SLOT_INTS;   /* the tables of a launch start at its first tile */
 	int full[64];
 #define CELL(i, jj, k) full[((i) * 4 + (jj)) * 4 + (k)]
+	if (FULL) {
+		/* slot layout: 16 pair configurations x 4 column categories: the table itself, sixteen 16-byte loads */
+#pragma unroll
+		for (int r = 0; r < 16; r++) {
+			const int4 v = __ldg(reinterpret_cast<const int4 *>(tab) + r);
+			const int x4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				if (dk) CELL(q, r / 4, r % 4) = x4[q];
+				else CELL(r / 4, r % 4, q) = x4[q];
+			}
+		}
+	} else {
 	/* slot layout: 9 pair configurations x (3 column categories + pad): nine 16-byte loads */
 #pragma unroll
 	for (int r = 0; r < 9; r++) {
@@ -509,9 +570,11 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 			else CELL(r / 3, r % 3, q) = x3[q];
 		}
 	}
+	}
 	const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
 	double ll;
 	if (UNI4) {
+		if (!FULL) {
 		int p01[16], p0c[16], p1c[16];
 		um_pair_table(pair_tab, l0, l1, p01);
 		um_pair_table(pair_tab, l0, lc, p0c);
@@ -531,6 +594,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 #pragma unroll
 			for (int k = 0; k < 4; k++)
 				CELL(3, jj, k) = p1c[jj * 4 + k] - (CELL(0, jj, k) + CELL(1, jj, k) + CELL(2, jj, k));
+		}
 		/* dev_loglik with constant bounds, same operation order: configurations ascending, pp = 1 / N_k,
 		 * ll += n * log(n * pp) for n > 0, division by the sample count last */
 		ll = 0.0;
@@ -546,6 +610,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 		}
 		if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
 	} else {
+	if (!FULL) {
 	for (int i = 0; i < 3; i++)
 		for (int jj = 0; jj < 3; jj++)
 			CELL(i, jj, 3) = um_pair_count(pair_tab, l0, l1, i, jj) - (CELL(i, jj, 0) + CELL(i, jj, 1) + CELL(i, jj, 2));
@@ -555,6 +620,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	for (int jj = 0; jj < 4; jj++)
 		for (int k = 0; k < 4; k++)
 			CELL(3, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - (CELL(0, jj, k) + CELL(1, jj, k) + CELL(2, jj, k));
+	}
 	const int pc0 = Dt.cats[a], pc1 = Dt.cats[b], cc = Dt.cats[c];
 	int ncount;
 	ll = dev_loglik(pc0 * pc1, cc, [&](int cfg, int k) {
@@ -568,7 +634,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 		int pars[2] = {a, b};
 		score = __dadd_rn(ll, dev_prior(Dt, c, pars, 2));
 	}
-	O.scores[T.rank * O.seg_len + O.seg_off + local * UM_SLOTS + within] = score;
+	O.scores[T.rank * O.seg_len + O.seg_off + local * SLOTS + within] = score;
 }
 
 /* pair tables from the P tiles: one thread per unordered node pair (u < v).  The 3 x 3 free cells come from the tile
@@ -651,6 +717,14 @@ int cnbk_umma_row_quads(int W, int fp4, int *ngroups) {
 	return (ng * UM_BSTAGES + 1) * qps;
 }
 
+int cnbk_umma_rows_full(cudaStream_t st, const uint4 *planes, const uint32_t *keep, int N, int W, uint4 *rows_a, uint4 *rows_b) {
+	const int nq = cnbk_umma_row_quads(W, 1, nullptr);
+	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
+	k_umma_rows_full<<<grid, 128, 0, st>>>(planes, keep, N, W, rows_a, rows_b, keep ? 8 : 4);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
 int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
 	const int nq = cnbk_umma_row_quads(W, fp4, nullptr);
 	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
@@ -731,14 +805,19 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 	const int split = T.self_pairs ? 1 : tail_split(tiles, sms, ng);
 	const long long whole = split > 1 ? tiles - tiles % sms : tiles;
 	const long long grid = whole + (tiles - whole) * split;
+	const size_t tile_ints = T.full ? (size_t)UMF_SLOTS * UMF_SLOT_INTS : (size_t)UM_SLOTS * UM_SLOT_INTS;
 	if (split > 1)
-		CK(cudaMemsetAsync(counts + (size_t)whole * UM_SLOTS * UM_SLOT_INTS, 0, (size_t)(tiles - whole) * UM_SLOTS * UM_SLOT_INTS * sizeof(int), st));
-	if (fp4) {
-		CK(cudaFuncSetAttribute(k_umma_tables<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+		CK(cudaMemsetAsync(counts + (size_t)whole * tile_ints, 0, (size_t)(tiles - whole) * tile_ints * sizeof(int), st));
+	if (T.full) {
+		if (!fp4) { cnb_set_error("full-table tiles need E2M1 operands"); return CNB_ERR_PROC; }
+		CK(cudaFuncSetAttribute(k_umma_tables<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+		k_umma_tables<true, true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+	} else if (fp4) {
+		CK(cudaFuncSetAttribute(k_umma_tables<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+		k_umma_tables<true, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
 	} else {
-		CK(cudaFuncSetAttribute(k_umma_tables<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+		CK(cudaFuncSetAttribute(k_umma_tables<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
+		k_umma_tables<false, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
 	}
 	CK(cudaGetLastError());
 	return CNB_OK;
@@ -752,10 +831,14 @@ long long cnbk_umma_column_macs(int W, int fp4) {
 
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long tile_begin, long long tile_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O, bool all_four_cats) {
-	long long slots = (tile_end - tile_begin) * UM_SLOTS;
+	const bool full = Dt.tiles.full != 0;
+	long long slots = (tile_end - tile_begin) * (full ? UMF_SLOTS : UM_SLOTS);
 	if (slots <= 0) return CNB_OK;
-	if (all_four_cats) k_umma_epilogue<true><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
-	else k_umma_epilogue<false><<<(unsigned)((slots + 127) / 128), 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	const unsigned grid = (unsigned)((slots + 127) / 128);
+	if (full && all_four_cats) k_umma_epilogue<true, true><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	else if (full) k_umma_epilogue<false, true><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	else if (all_four_cats) k_umma_epilogue<true, false><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	else k_umma_epilogue<false, false><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
@@ -773,6 +856,7 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 	if (rc != CNB_OK) return rc;
 	CnbTiles T;
 	memset(&T, 0, sizeof(T));
+	CNB_TILES_DEFAULT_GEOMETRY(T);
 	T.self_pairs = 1;
 	T.world = 1;
 	rc = cnbk_umma_tables(st, rows_a, rows_b, N, W, 1, T, 0, cnbk_pair_tiles(N), counts);

@@ -315,7 +315,8 @@ int cnb_ctx_search_scores(cnb_ctx *ctx, const double *scores_dev, int32_t nfam, 
  * never; 16 u8 operands (kind::i8) instead of E2M1; 32 one DP launch per node; 64 grid-barrier DP; 128 pair tables by
  * the POPC kernel (set before the samples); 512 no inclusion-exclusion for three parents; 1024 three parents never on
  * the tensor cores; 2048 wavefront DP with one node per exchange; 4096 generic tensor-core epilogue also for
- * 4-category data.  Every combination gives the same networks. */
+ * 4-category data; 8192 full-table tensor tiles (the form that takes missing values and perturbation masks) also on
+ * complete data.  Every combination gives the same networks. */
 int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 /* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */
 int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);
@@ -330,6 +331,7 @@ int64_t cnb_num_families(const cnb_params *p);
 /* consistency of the tensor-core tiling of the unrestricted two-parent group of N nodes (host only): number of
  * tiles, or < 0 if family <-> tile slot is not a bijection */
 int64_t cnb_tile_selftest(int32_t num_nodes);
+int64_t cnb_tile_selftest_full(int32_t num_nodes);   /* the full-table geometry (16 pairs x 48 column nodes per tile) */
 /* the same for the tiling of the unrestricted three-parent group (free_cats = max categories - 1) */
 int64_t cnb_tile3_selftest(int32_t num_nodes, int32_t free_cats);
 

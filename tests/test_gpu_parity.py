@@ -126,12 +126,16 @@ def test_search_order_dp_variants(abi, case, bits):
         compare_golden(ctx.search_order(**kw2), golden)
 
 
-def _tensor_eligible(case, cats):
-    return (not any(case.get(k) for k in ("na", "pert", "pools", "fixed", "psizes")) and int(np.max(cats)) <= 4
-            and case["n"] >= 3 and case["P"] >= 2)
+def _tensor_eligible(case, cats, bits):
+    """missing values and perturbation masks run as full-table tiles (E2M1 operands only); pools, fixed parents and
+    parent-set sizes leave the tiled layout"""
+    masked_ok = not (bits & 16)
+    return (not any(case.get(k) for k in ("pools", "fixed", "psizes")) and int(np.max(cats)) <= 4
+            and (masked_ok or not any(case.get(k) for k in ("na", "pert"))) and case["n"] >= 3 and case["P"] >= 2)
 
 
 TENSOR_KINDS = [(4, 4), (4 | 16, 8)]          # force_generic bits -> cnb_timing.tensor_kind (E2M1 / u8 operands)
+TENSOR_KINDS_FULL = TENSOR_KINDS + [(4 | 8192, 4)]   # + full-table tiles forced on complete data
 
 
 @pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
@@ -146,12 +150,12 @@ def test_search_order_tensor_core_path(abi, case, bits, kind):
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
         nets = ctx.search_order(**kw2)
         used = ctx.timing()["tensor_tiles"] > 0
-        assert used == _tensor_eligible(case, ctx.num_cats())
+        assert used == _tensor_eligible(case, ctx.num_cats(), bits)
         assert ctx.timing()["tensor_kind"] == (kind if used else 0)
         compare_golden(nets, golden)
 
 
-@pytest.mark.parametrize("bits,kind", TENSOR_KINDS, ids=["mxf4", "i8"])
+@pytest.mark.parametrize("bits,kind", TENSOR_KINDS_FULL, ids=["mxf4", "i8", "mxf4_full"])
 @pytest.mark.parametrize("n,m,cats", [(70, 300, 4), (130, 257, 3), (66, 4100, None), (9, 3, 2), (200, 129, 4), (90, 20001, 4),
                                       (3, 40, 3), (4, 33, 2), (64, 64, 4), (65, 300, 2), (129, 100, 4), (193, 40, 3),
                                       (130, 7000, 4), (200, 6200, 3)])    # the last two: sample-sliced tail wave
@@ -177,6 +181,52 @@ def test_tensor_core_path_multi_tile(abi, n, m, cats, bits, kind):
             c2 = ctx.finish(buf.data_ptr(), want_probs=False)
             assert compare_search(c2, a, check_probs=False) == len(a)
     assert compare_search(b, a, check_probs=False) == len(a)
+
+
+@pytest.mark.parametrize("n,m,cats,na,pert", [(70, 300, 4, 0.05, False), (130, 257, 3, 0.0, True), (66, 4100, None, 0.1, True),
+                                              (9, 3, 2, 0.2, False), (100, 129, 4, 0.02, True), (60, 9001, 4, 0.05, False),
+                                              (3, 40, 3, 0.0, True), (49, 64, 4, 0.3, True), (97, 300, 2, 0.01, False),
+                                              (150, 7000, 4, 0.05, True)])
+def test_tensor_core_full_tables_masked_data(abi, port, n, m, cats, na, pert):
+    """missing values and perturbation masks on the tensor cores: full-table tiles (16 rows per pair, 4 columns per child,
+    the child's keep mask in its rows) == the bit-plane scorer, sharded and not; spot-checked tables against the oracle"""
+    s, c = random_problem(3 * n + m, n, m, cats, na)
+    rng = np.random.default_rng(n + m)
+    p = (rng.random(s.shape) < 0.3).astype(np.int32) if pert else None
+    kw = dict(max_parent_set=2, max_complexity=n * 8, order=(rng.permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=p, num_cats=c)
+        ctx.force_generic(8)                      # never the tensor path
+        a = ctx.search_order(want_probs=True, **kw)
+        assert ctx.timing()["tensor_tiles"] == 0
+        ctx.force_generic(4)                      # always
+        b = ctx.search_order(want_probs=True, **kw)
+        assert ctx.timing()["tensor_tiles"] > 0 and ctx.timing()["tensor_kind"] == 4
+        import torch
+        for world in (1, 3):
+            seg, nf = ctx.plan(0, world, **kw)
+            buf = torch.full((seg * world,), float("nan"), dtype=torch.float64, device="cuda")
+            for r in range(world):
+                ctx.plan(r, world, **kw)
+                ctx.score_shard(buf.data_ptr())
+            torch.cuda.synchronize()
+            c2 = ctx.finish(buf.data_ptr(), want_probs=False)
+            assert compare_search(c2, a, check_probs=False) == len(a)
+        # the search's own scores of random families against the oracle's family score
+        ctx.plan(0, 1, **kw)
+        buf = torch.full((ctx.plan(0, 1, **kw)[0],), float("nan"), dtype=torch.float64, device="cuda")
+        ctx.score_shard(buf.data_ptr())
+        torch.cuda.synchronize()
+        if n >= 3:
+            order0 = np.asarray(kw["order"]) - 1
+            pos = np.array([sorted(rng.choice(n, size=3, replace=False)) for _ in range(40)])
+            got = ctx.search_scores(buf.data_ptr(), pos[:, 2], pos[:, :2])
+            s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+            for f in range(len(pos)):
+                ch, pa = int(order0[pos[f, 2]]), [int(order0[pos[f, 0]]), int(order0[pos[f, 1]])]
+                keep = None if p is None else (p[:, ch] == 0)
+                assert got[f] == port.family_score(s0, c, ch, pa, keep=keep)[1], (f, ch, pa)
+    assert compare_search(b, a) == len(a)
 
 
 @pytest.mark.parametrize("n,m,sparse", [(70, 300, False), (130, 9000, False), (66, 40, True)])

@@ -114,6 +114,17 @@ def test_tensor_tiling_is_a_bijection(n):
         assert ntiles < 12500          # 15,762 before the diagonal tiles were transposed
 
 
+@pytest.mark.parametrize("n", [3, 4, 9, 29, 47, 48, 49, 50, 95, 96, 97, 145, 200, 500])
+def test_full_table_tiling_is_a_bijection(n):
+    """the same for the full-table geometry (16 pairs x 48 column nodes per tile: missing values / perturbation masks)"""
+    from catnet_b200 import _abi
+    ntiles = _abi.lib().cnb_tile_selftest_full(n)
+    assert ntiles > 0, ntiles
+    assert ntiles * 16 * 48 >= n * (n - 1) * (n - 2) // 6
+    if n == 500:
+        assert ntiles < 29500          # 27,127 slots-worth + diagonal overhead; 2.33 x the 12,279 inclusion-exclusion tiles
+
+
 @pytest.mark.parametrize("n,f1", [(4, 1), (5, 2), (30, 3), (64, 2), (65, 2), (70, 3), (100, 2), (129, 1)])
 def test_three_parent_tiling_is_consistent(n, f1):
     """cnb_tiles.h, T tiles: every three-parent family (a < b < c | x) and free value i of a owns one slot in the column
