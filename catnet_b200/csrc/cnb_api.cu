@@ -260,6 +260,21 @@ int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *sampl
 		c->pairs_valid = !c->has_pert;
 		c->pairs_full = true;
 	}
+	/* missing values or perturbation masks: the tables of all ORDERED pairs (parent, child) -- under the child's keep mask,
+	 * samples with a missing value skipped -- on the tensor cores (full-table P tiles), so that the 0- and 1-parent families
+	 * need no pass over the samples either (124,750 one-parent families at C5: 17 ms of POPC per order otherwise) */
+	c->pairs_ord = false;
+	if ((c->has_na || c->has_pert) && c->max_cats <= CNB_PLANE_CATS && M < (1 << 24) && c->tensor_mode >= 0 && !c->pairs_popc
+			&& !c->no_ie && !c->tensor_i8) {
+		const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * (c->has_pert ? 8 : 4) * N;
+		RC(c->b_rows_a.ensure(row_bytes));
+		RC(c->b_rows_b.ensure(row_bytes));
+		RC(c->b_counts.ensure((size_t)cnbk_pair_tiles_full(N) * CNB_FULL_PAIRS * CNB_FULL_CHILD * CNBK_UMMA_FULL_SLOT_INTS * sizeof(int)));
+		RC(c->b_pairs_ord.ensure((size_t)N * N * 16 * sizeof(int)));
+		RC(cnbk_pair_tables_umma_full(st, (const uint4 *)c->b_planes_lbl.ptr, c->has_pert ? (const uint32_t *)c->b_keep_lbl.ptr : nullptr, N,
+				c->W, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr, (int *)c->b_counts.ptr, (int *)c->b_pairs_ord.ptr));
+		c->pairs_ord = true;
+	}
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	CK(cudaStreamSynchronize(st));
 	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
@@ -659,16 +674,28 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	return CNB_OK;
 }
 
+/* the 0- and 1-parent families can be read off two-way tables of the data set (unordered ones of complete data, ordered
+ * ones under the child's keep mask otherwise) */
+static bool have_pair_tables(const cnb_ctx *c) {
+	if (c->ignore_pert) return c->pairs_full;
+	return c->pairs_valid || (c->pairs_ord && !c->no_ie);
+}
+
 /* score families [b, e) of one launch class, choosing the kernel */
 static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d_max, long long b, long long e,
 		ScoreOut O, bool force_generic, bool allow_slicing) {
 	if (e <= b) return CNB_OK;
 	cudaStream_t st = c->stream;
-	const bool pairs_ok = c->ignore_pert ? c->pairs_full : c->pairs_valid;
+	/* two-way tables that hold the 0- and 1-parent families outright: the unordered ones of complete data, or the ordered
+	 * ones counted under the child's keep mask / without missing values */
+	const bool pairs_unord = c->ignore_pert ? c->pairs_full : c->pairs_valid;
+	const bool ordered = !pairs_unord && c->pairs_ord && !c->ignore_pert && !c->no_ie;
+	const bool pairs_ok = pairs_unord || ordered;
+	const int *pair_tab = ordered ? (const int *)c->b_pairs_ord.ptr : (const int *)c->b_pairs.ptr;
 	if (!force_generic && !F.ex_nd && F.d == 0 && pairs_ok) {
-		/* no parents, clean data: marginal counts from the pair tables */
+		/* no parents: marginal counts from the pair tables */
 		c->last_fast = true;
-		RC(cnbk_score_pairs1(c->stream, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
+		RC(cnbk_score_pairs1(c->stream, D, F, c->max_cats, b, e, O, pair_tab, ordered));
 		c->timing.kernel_launches++;
 		return CNB_OK;
 	}
@@ -694,12 +721,12 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 			if (n < target) slices = (int)std::min<long long>(std::min<long long>((target + n - 1) / n, std::max(1, c->W / 8)), 65535);
 		}
 		if (F.d == 1 && pairs_ok && !F.ex_nd) {
-			/* one parent, clean data: the table was counted with the pair tables */
-			RC(cnbk_score_pairs1(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
+			/* one parent: the table was counted with the pair tables */
+			RC(cnbk_score_pairs1(st, D, F, c->max_cats, b, e, O, pair_tab, ordered));
 			c->timing.kernel_launches++;
 			return CNB_OK;
 		}
-		if (slices == 1 && !O.counts && F.d == 2 && pairs_ok && !F.explicit_list) {
+		if (slices == 1 && !O.counts && F.d == 2 && pairs_unord && !F.explicit_list) {
 			RC(cnbk_score_planes_ie2(st, D, F, c->max_cats, b, e, O, (const int *)c->b_pairs.ptr));
 			c->timing.kernel_launches++;
 			return CNB_OK;
@@ -855,7 +882,7 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 	int dmax = fixed_d;
 	if (var_d) { dmax = 0; for (int v : nd) dmax = std::max(dmax, v); }
 	DevData D = make_devdata(c);
-	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || (fixed_d == 0 && !(c->ignore_pert ? c->pairs_full : c->pairs_valid)), false));
+	RC(score_range(c, D, F, dmax, 0, (long long)n, O, force_generic || var_d || (fixed_d == 0 && !have_pair_tables(c)), false));
 	return CNB_OK;
 }
 
@@ -892,7 +919,7 @@ static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, 
 		F.nfam = n;
 		F.ex_child = (const int32_t *)c->b_ex_child.ptr;
 		F.ex_pars = (const int32_t *)c->b_ex_pars.ptr;
-		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || (nd[b] == 0 && !c->pairs_valid), true));
+		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || (nd[b] == 0 && !have_pair_tables(c)), true));
 		b = e;
 	}
 	return CNB_OK;
@@ -915,7 +942,7 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 		}
 		bool no_fixed = true;
 		for (int i = 0; i < N; i++) no_fixed = no_fixed && nd[i] == 0;
-		if (no_fixed && c->pairs_valid && !c->force_generic) RC(score_explicit(c, child, pars, nd, 0, 0, false, false));
+		if (no_fixed && have_pair_tables(c) && !c->force_generic) RC(score_explicit(c, child, pars, nd, 0, 0, false, false));
 		else RC(score_explicit(c, child, pars, nd, -1, 0, false, true));
 		RC(c->b_base_v.ensure(N * sizeof(double)));
 		CK(cudaMemcpyAsync(c->b_base_v.ptr, c->b_ex_score.ptr, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1348,7 +1375,8 @@ extern "C" int cnb_ctx_search_scores(cnb_ctx *c, const double *scores_dev, int32
 			if (g.tiled) {
 				long long tile;
 				int within;
-				cnb_family_slot(T, pl.N, pl.lists[b.free_off + idx[0]], pl.lists[b.free_off + idx[1]], child, tile, within);
+				const int p0 = parents[(size_t)f * d], p1 = parents[(size_t)f * d + 1];
+				cnb_family_slot(T, pl.N, std::min(p0, p1), std::max(p0, p1), child, tile, within);
 				index[f] = (tile % g.tile_world) * pl.seg_len + g.seg_off + (tile / g.tile_world) * ((long long)T.tp * T.tc) + within;
 			} else {
 				const long long r = fid / g.chunk;

@@ -33,7 +33,8 @@ struct CnbGroup {
 	int32_t d;
 	int32_t nblk;
 	int32_t blk_off;    /* into group_blocks[] (block ids sorted by start) */
-	int32_t tiled;      /* 1: scored by the tensor-core kernel; scores are addressed by tile slot, not family id */
+	int32_t tiled;      /* 1, 2: scored by the tensor-core kernel; scores are addressed by tile slot, not family id (1: the group
+	                       is the unrestricted one, slot from the candidate's rank; 2: a subset of it, slot from its parents) */
 	int64_t nfam;       /* families in the group */
 	int64_t chunk;      /* score slots per rank: ceil(nfam / world), or tiles_per_rank * slots per tile when tiled */
 	int64_t seg_off;    /* offset of the group inside one rank segment of the score buffer */

@@ -462,6 +462,10 @@ __global__ void __launch_bounds__(BS) k_score_planes_ie3(DevData Dt, DevFamilies
 /* Single-parent families when no value is missing: the family table IS the two-way table of (parent, child) that
  * k_pair_tables counted once per data set -- no pass over the samples at all, only the log-lik epilogue
  * (problist.h:224-250) and, when asked for, the table in the reference's layout. */
+/* ORDERED: pair_tab holds one table per ORDERED pair (parent u, child v) at (u N + v) 16 + i 4 + k -- the counts over the
+ * samples where both values are present and v is not perturbed (data with missing values / perturbation masks; tables
+ * from the full-table P tiles, cnbk_pair_tables_umma_full) */
+template <bool ORDERED>
 __global__ void __launch_bounds__(128) k_score_pairs1(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
 		ScoreOut O, const int *__restrict__ pair_tab) {
 	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,17 +474,20 @@ __global__ void __launch_bounds__(128) k_score_pairs1(DevData Dt, DevFamilies F,
 	dev_family(Dt, F, fid, child, pars);
 	const int lp = Dt.order[pars[0]], lc = Dt.order[child];
 	const int pc = Dt.cats[pars[0]], cc = Dt.cats[child];
+	const int *ot = pair_tab + ((long long)lp * Dt.N + lc) * 16;
+	auto count = [&](int i, int k) { return ORDERED ? ot[i * 4 + k] : pair_count(pair_tab, lp, lc, i, k); };
 	int ncount;
-	double ll = dev_loglik(pc, cc, [&](int i, int k) { return pair_count(pair_tab, lp, lc, i, k); }, &ncount);
+	double ll = dev_loglik(pc, cc, count, &ncount);
 	if (O.counts) {
 		int *tab = O.counts + (size_t)fid * O.counts_stride;
 		for (int i = 0; i < pc; i++)
-			for (int k = 0; k < cc; k++) tab[i * cc + k] = pair_count(pair_tab, lp, lc, i, k);
+			for (int k = 0; k < cc; k++) tab[i * cc + k] = count(i, k);
 	}
 	dev_store_outputs(Dt, O, fid, child, pars, 1, ll, ncount);
 }
 
 /* Families without parents on clean data: the marginal counts are row sums of any two-way table of the node. */
+template <bool ORDERED>
 __global__ void __launch_bounds__(128) k_score_pairs0(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
 		ScoreOut O, const int *__restrict__ pair_tab) {
 	const long long fid = fid_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,7 +498,8 @@ __global__ void __launch_bounds__(128) k_score_pairs0(DevData Dt, DevFamilies F,
 	int marg[CNB_PLANE_CATS];
 	for (int k = 0; k < CNB_PLANE_CATS; k++) {
 		int s = 0;
-		for (int i = 0; i < CNB_PLANE_CATS; i++) s += pair_count(pair_tab, lo, lc, i, k);
+		if (ORDERED) s = pair_tab[((long long)lc * Dt.N + lc) * 16 + k * 4 + k];   /* the node against itself, under its own mask */
+		else for (int i = 0; i < CNB_PLANE_CATS; i++) s += pair_count(pair_tab, lo, lc, i, k);
 		marg[k] = s;
 	}
 	int ncount;
@@ -638,7 +646,14 @@ __global__ void __launch_bounds__(256) k_select(DevData Dt, const CnbGroup *__re
 		long long slot = fid;
 		if (g.tiled) {
 			int ab[2];
-			dev_unrank(b.nfree, 2, fid - b.start, ab);      /* unrestricted block: positions themselves */
+			if (g.tiled == 1) dev_unrank(b.nfree, 2, fid - b.start, ab);      /* unrestricted block: positions themselves */
+			else {
+				/* a subset of the unrestricted group (pools, fixed parents): the candidate's two parents, ascending */
+				int ch, pars[CNB_MAXP];
+				dev_family(Dt, F, fid, ch, pars);
+				ab[0] = min(pars[0], pars[1]);
+				ab[1] = max(pars[0], pars[1]);
+			}
 			long long tile;
 			int within;
 			cnb_family_slot(Dt.tiles, Dt.N, ab[0], ab[1], b.child, tile, within);
@@ -1366,11 +1381,14 @@ int cnbk_score_planes_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies 
 }
 
 int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
-		const ScoreOut &O, const int *pair_tab) {
+		const ScoreOut &O, const int *pair_tab, bool ordered) {
 	if (e <= b) return CNB_OK;
 	if (F.d > 1 || max_cats > 4 || !pair_tab) { cnb_set_error("pair-table scorer: unsupported launch"); return CNB_ERR_PROC; }
-	if (F.d == 0) k_score_pairs0<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
-	else k_score_pairs1<<<(unsigned)((e - b + 127) / 128), 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	const unsigned grid = (unsigned)((e - b + 127) / 128);
+	if (F.d == 0 && ordered) k_score_pairs0<true><<<grid, 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	else if (F.d == 0) k_score_pairs0<false><<<grid, 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	else if (ordered) k_score_pairs1<true><<<grid, 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
+	else k_score_pairs1<false><<<grid, 128, 0, st>>>(Dt, F, b, e, O, pair_tab);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -35,8 +35,10 @@ bool cnbk_planes_supported(int d, int max_cats);
 int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
 		long long fid_end, int slices, const ScoreOut &O);
 int cnbk_pair_tables(cudaStream_t st, const uint4 *planes_lbl, int N, int W, int *out);
+/* ordered: pair_tab = one table per ORDERED (parent, child) pair, counted under the child's keep mask and without the
+ * samples where either value is missing (cnbk_pair_tables_umma_full) */
 int cnbk_score_pairs1(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
-		const ScoreOut &O, const int *pair_tab);
+		const ScoreOut &O, const int *pair_tab, bool ordered = false);
 int cnbk_score_planes_ie2(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b,
 		long long e, const ScoreOut &O, const int *pair_tab);
 /* three-way tables of all node triples (label space, [C(N,3)][64]) and the three-parent inclusion-exclusion scorer */
@@ -56,6 +58,11 @@ long long cnbk_umma_column_macs(int W, int fp4);
 long long cnbk_pair_tiles(int N);
 int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M, int W, uint4 *rows_a, uint4 *rows_b,
 		int *counts, int *pair_tab);   /* multiply-accumulates per MMA column of one tile, padding included */
+/* the same for data with missing values / perturbation masks: tables of all ORDERED pairs (parent u, child v), label space,
+ * [u N + v][16]: samples where both values are present and v is not perturbed (keep_lbl may be NULL); full-table P tiles */
+long long cnbk_pair_tiles_full(int N);
+int cnbk_pair_tables_umma_full(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, int N, int W, uint4 *rows_a,
+		uint4 *rows_b, int *counts, int *pair_ord);
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O, bool all_four_cats = false);   /* all_four_cats: every node has 4 categories */
 #define CNBK_UMMA_SLOT_INTS 36

@@ -201,15 +201,22 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
 			g.full = b.nfix == 0 && b.nfree == b.child;
 		}
-		/* Tensor-core tiling of the two-parent group: only when every node c >= 2 offers all pairs of its
-		 * predecessors (no pools, no fixed parents, no size limit), so that tile (child tile, pair tile) slots map
-		 * one-to-one onto candidate families.  Tiles cost the same, so ranks get equal contiguous tile ranges. */
-		if (tile_mode && d == 2 && N >= 3 && g.nblk == N - 2) {
-			bool full = true;
-			for (int k = 0; k < g.nblk; k++) {
+		/* Tensor-core tiling of the two-parent group.  The tiles always cover ALL families (a < b | c) of the order: tile (child
+		 * tile, pair tile) slots map one-to-one onto the unrestricted candidate families.  tiled = 1: every node c >= 2 offers all
+		 * pairs of its predecessors (no pools, no fixed parents, no size limit), a candidate's rank gives its slot directly.
+		 * tiled = 2: the candidates are a subset (parent pools, fixed parents, per-node parent-set sizes; every candidate is still
+		 * two predecessors of its child): the selection looks each candidate's slot up from its parents -- worth it while the
+		 * subset is at least 1/16 of the full group (a tensor-core slot costs 1/27 .. 1/60 of a bit-plane family).  Tiles cost
+		 * the same, so ranks get equal shares, dealt round-robin. */
+		if (tile_mode && d == 2 && N >= 3) {
+			bool full = g.nblk == N - 2;
+			for (int k = 0; k < g.nblk && full; k++) {
 				const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
 				full = full && b.nfix == 0 && b.nfree == b.child;
 			}
+			const bool subset = !full && g.nfam * 16 >= cnb_binom(N, 3);
+			if (subset) full = true;
+			const int tiled_kind = subset ? 2 : 1;
 			if (full) {
 				const int tp = tile_mode == 2 ? CNB_FULL_PAIRS : CNB_TILE_PAIRS, tc = tile_mode == 2 ? CNB_FULL_CHILD : CNB_TILE_CHILD;
 				pl.tile_pairs = tp;
@@ -228,7 +235,7 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 					for (int p = ndt + 1; p < CNB_DT_STRIDE; p++) off[p] = off[ndt];
 					pl.tile_base[ct + 1] = pl.tile_base[ct] + cnb_f_tiles(c0, tp) + off[ndt];
 				}
-				g.tiled = 1;
+				g.tiled = tiled_kind;
 				g.ntiles = pl.tile_base[nct];
 				g.tiles_per_rank = (g.ntiles + world - 1) / world;
 				g.tile_world = world;

@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		const int rr = tid - UM_A_WARPS * 32, r = min(rr, UM_N - 1);
 		const bool active = rr < ncols;
 		/* full tables: in an F tile the columns are the CHILDREN: their rows under the keep mask */
-		const int vc = (FULL && ti.kind == 0 && RS == 8) ? 4 : 0;
+		const int vc = (FULL && (ti.kind == 0 || ti.kind == 2) && RS == 8) ? 4 : 0;   /* P tiles: the columns are the children too */
 		const uint4 *s0 = rows_b + src_quads * NRB + (min(ti.zb + r / CPC, ti.ze - 1) * RS + vc + r % CPC);
 		uint32_t off[8];
 #pragma unroll
@@ -863,6 +863,44 @@ int cnbk_pair_tables_umma(cudaStream_t st, const uint4 *planes_lbl, int N, int M
 	if (rc != CNB_OK) return rc;
 	const long long np = (long long)N * (N - 1) / 2;
 	k_pairs_from_tiles<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, N, M, pair_tab);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* ordered pair tables from the full-table P tiles: "pair" slot u is the single node u, whose rows (i, i) are its plain
+ * one-hot rows; column node v carries its keep mask: cell ((i, i), k) = n(x_u = i, x_v = k | v kept, both present) */
+__global__ void __launch_bounds__(128) k_ordered_pairs_from_tiles(const int *__restrict__ counts, int N, int *__restrict__ pair_ord) {
+	const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= (long long)N * N) return;
+	const int u = (int)(q / N), v = (int)(q % N);
+	const int nch = (N + UMF_CHILD - 1) / UMF_CHILD;
+	const long long tile = (long long)(u / UMF_PAIRS) * nch + v / UMF_CHILD;
+	const int *src = counts + ((size_t)tile * UMF_SLOTS + (size_t)(u % UMF_PAIRS) * UMF_CHILD + v % UMF_CHILD) * UMF_SLOT_INTS;
+	int4 *out = reinterpret_cast<int4 *>(pair_ord + q * 16);
+#pragma unroll
+	for (int i = 0; i < 4; i++) out[i] = *reinterpret_cast<const int4 *>(src + (i * 4 + i) * 4);
+}
+
+long long cnbk_pair_tiles_full(int N) {
+	return (long long)((N + UMF_PAIRS - 1) / UMF_PAIRS) * ((N + UMF_CHILD - 1) / UMF_CHILD);
+}
+
+int cnbk_pair_tables_umma_full(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, int N, int W, uint4 *rows_a,
+		uint4 *rows_b, int *counts, int *pair_ord) {
+	int rc = cnbk_umma_rows_full(st, planes_lbl, keep_lbl, N, W, rows_a, rows_b);
+	if (rc != CNB_OK) return rc;
+	CnbTiles T;
+	memset(&T, 0, sizeof(T));
+	T.tp = UMF_PAIRS;
+	T.tc = UMF_CHILD;
+	T.full = 1;
+	T.row_stride = keep_lbl ? 8 : 4;
+	T.self_pairs = 1;
+	T.world = 1;
+	rc = cnbk_umma_tables(st, rows_a, rows_b, N, W, 1, T, 0, cnbk_pair_tiles_full(N), counts);
+	if (rc != CNB_OK) return rc;
+	const long long np = (long long)N * N;
+	k_ordered_pairs_from_tiles<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, N, pair_ord);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

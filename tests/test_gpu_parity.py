@@ -127,11 +127,14 @@ def test_search_order_dp_variants(abi, case, bits):
 
 
 def _tensor_eligible(case, cats, bits):
-    """missing values and perturbation masks run as full-table tiles (E2M1 operands only); pools, fixed parents and
-    parent-set sizes leave the tiled layout"""
+    """missing values and perturbation masks run as full-table tiles (E2M1 operands only); under pools, fixed parents and
+    parent-set sizes the tiles are used while the candidates are at least 1/16 of the unrestricted group (None = depends)"""
     masked_ok = not (bits & 16)
-    return (not any(case.get(k) for k in ("pools", "fixed", "psizes")) and int(np.max(cats)) <= 4
-            and (masked_ok or not any(case.get(k) for k in ("na", "pert"))) and case["n"] >= 3 and case["P"] >= 2)
+    ok = (int(np.max(cats)) <= 4 and (masked_ok or not any(case.get(k) for k in ("na", "pert"))) and case["n"] >= 3
+          and case["P"] >= 2)
+    if ok and any(case.get(k) for k in ("pools", "fixed", "psizes")):
+        return None
+    return ok
 
 
 TENSOR_KINDS = [(4, 4), (4 | 16, 8)]          # force_generic bits -> cnb_timing.tensor_kind (E2M1 / u8 operands)
@@ -150,7 +153,8 @@ def test_search_order_tensor_core_path(abi, case, bits, kind):
         kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
         nets = ctx.search_order(**kw2)
         used = ctx.timing()["tensor_tiles"] > 0
-        assert used == _tensor_eligible(case, ctx.num_cats(), bits)
+        want = _tensor_eligible(case, ctx.num_cats(), bits)
+        assert want is None or used == want
         assert ctx.timing()["tensor_kind"] == (kind if used else 0)
         compare_golden(nets, golden)
 
@@ -249,6 +253,38 @@ def test_tensor_core_epilogue_four_categories(abi, n, m, sparse):
         d = ctx.search_order(**kw)
     assert compare_search(b, a, check_probs=False) == len(a)
     assert compare_search(b, d, check_probs=False) == len(d)
+
+
+def _constrained_on_tiles(abi, port, seed):
+    """-> True when the problem is restricted (pools / fixed parents / sizes) AND its two-parent group ran on the tiles"""
+    s, P, K, kw = constrained_problem(seed)
+    theirs = port.search_order(s, P, K, **kw)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
+        ctx.force_generic(4)
+        kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
+        if theirs is None:
+            with pytest.raises(abi.CnbError):
+                ctx.search_order(max_parent_set=P, max_complexity=K, **kw2)
+            return False
+        ours = ctx.search_order(max_parent_set=P, max_complexity=K, **kw2)
+        restricted = any(k in kw for k in ("parents_pool", "fixed_parents", "parent_sizes"))
+        used = ctx.timing()["tensor_tiles"] > 0 and restricted
+    assert compare_search(ours, theirs) == len(theirs)
+    return used
+
+
+@pytest.mark.parametrize("seed", range(700, 760))
+def test_constrained_search_on_tensor_tiles(abi, port, seed):
+    """pools, fixed parents, parent-set sizes, perturbations, priors, missing values with the tensor-core path forced on: the
+    candidates are a SUBSET of the unrestricted two-parent group, the tiles cover all of it and the selection looks every
+    candidate's slot up from its parents; result == the oracle's"""
+    _constrained_on_tiles(abi, port, seed)
+
+
+def test_constrained_search_reaches_the_tiles(abi, port):
+    """the previous test would be vacuous if no restricted problem reached the tiles"""
+    assert sum(_constrained_on_tiles(abi, port, seed) for seed in range(760, 800)) >= 5
 
 
 @pytest.mark.parametrize("seed", range(700, 740))
