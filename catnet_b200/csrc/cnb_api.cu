@@ -16,6 +16,7 @@
 #include "cnb_kernels.h"
 #include "cnb_result.h"
 #include "cnb_ctx.h"
+#include "cnb_crew.h"
 #include "cnb_tiles.h"
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cnb_set_error("CUDA: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); return CNB_ERR_CUDA; } } while (0)
@@ -90,6 +91,13 @@ void PinBuf::release() {
 
 extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	if (!c) return;
+	if (c->crew) {
+		c->crew->stop();
+		delete c->crew;
+		c->crew = nullptr;
+	}
+	for (cnb_ctx *s : c->siblings) cnb_ctx_destroy(s);
+	c->siblings.clear();
 	if (c->host_ms[3] > 0)
 		fprintf(stderr, "[cnb trace] %.0f searches: plan %.3f score %.3f select+dp %.3f ms per search (host wall)\n", c->host_ms[3],
 				c->host_ms[0] / c->host_ms[3], c->host_ms[1] / c->host_ms[3], c->host_ms[2] / c->host_ms[3]);
@@ -279,7 +287,87 @@ int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *sampl
 	CK(cudaStreamSynchronize(st));
 	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
 	c->have_samples = true;
+	c->data_epoch++;
 	return CNB_OK;
+}
+
+/* ------------------------------------------------------------------ sibling contexts ---- */
+/* the packed data set of src (label space: codes, bit planes, keep masks, pair tables) copied device to device into dst */
+static int clone_data(cnb_ctx *src, cnb_ctx *dst) {
+	CK(cudaSetDevice(src->device));
+	const int N = src->N;
+	dst->N = N; dst->M = src->M; dst->W = src->W; dst->Mpad = src->Mpad; dst->max_cats = src->max_cats;
+	dst->has_pert = src->has_pert; dst->clean = src->clean; dst->has_na = src->has_na;
+	dst->pairs_valid = src->pairs_valid; dst->pairs_full = src->pairs_full; dst->pairs_ord = src->pairs_ord;
+	dst->triples_valid = false;
+	dst->cats_lbl = src->cats_lbl; dst->never_kept = src->never_kept; dst->any_never_kept = src->any_never_kept;
+	dst->force_generic = src->force_generic; dst->no_ie = src->no_ie; dst->tensor_mode = src->tensor_mode; dst->tensor_i8 = src->tensor_i8;
+	dst->dp_per_node = src->dp_per_node; dst->dp_no_wave = src->dp_no_wave; dst->pairs_popc = src->pairs_popc; dst->no_ie3 = src->no_ie3;
+	dst->no_tensor3 = src->no_tensor3; dst->dp_no_trap = src->dp_no_trap; dst->generic_epilogue = src->generic_epilogue;
+	dst->force_full = src->force_full;
+	dst->planned = dst->dp_done = false;
+	const size_t words = (size_t)src->W * N;
+	struct { DevBuf *d; DevBuf *s; size_t n; bool on; } cp[] = {
+		{&dst->b_vmin, &src->b_vmin, N * sizeof(int), true},
+		{&dst->b_cats_lbl, &src->b_cats_lbl, N * sizeof(int), true},
+		{&dst->b_codes, &src->b_codes, (size_t)N * src->Mpad, true},
+		{&dst->b_planes_lbl, &src->b_planes_lbl, words * sizeof(uint4), true},
+		{&dst->b_keep_lbl, &src->b_keep_lbl, words * sizeof(uint32_t), src->has_pert},
+		{&dst->b_pairs, &src->b_pairs, (size_t)N * (N - 1) / 2 * 16 * sizeof(int), src->pairs_full || src->pairs_valid},
+		{&dst->b_pairs_ord, &src->b_pairs_ord, (size_t)N * N * 16 * sizeof(int), src->pairs_ord},
+	};
+	for (auto &e : cp) {
+		if (!e.on || !e.n) continue;
+		RC(e.d->ensure(e.n));
+		CK(cudaMemcpyAsync(e.d->ptr, e.s->ptr, e.n, cudaMemcpyDeviceToDevice, src->stream));
+	}
+	RC(dst->b_flag.ensure(4 * sizeof(int)));
+	CK(cudaMemsetAsync(dst->b_flag.ptr, 0, 4 * sizeof(int), src->stream));
+	RC(dst->b_planes.ensure(words * sizeof(uint4)));
+	if (src->has_pert) RC(dst->b_keep.ensure(words * sizeof(uint32_t)));
+	CK(cudaStreamSynchronize(src->stream));
+	dst->have_samples = true;
+	dst->cloned_epoch = src->data_epoch;
+	return CNB_OK;
+}
+
+int cnb_ctx_batch(cnb_ctx *c, int want, std::vector<cnb_ctx *> *ctxs) {
+	ctxs->assign(1, c);
+	if (!c || !c->have_samples || want <= 1) return CNB_OK;
+	/* a copy of the data per concurrent order: worth it for the small matrices SA runs on (ALARM: 3 MB), not for C5 */
+	static const char *env = getenv("CNB_BATCH_MAX_BYTES");
+	const size_t cap = env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)64 << 20);
+	const size_t bytes = (size_t)c->N * c->Mpad + (size_t)c->W * c->N * 20;
+	if (bytes > cap) return CNB_OK;
+	want = std::min(want, 16);
+	while ((int)c->siblings.size() < want - 1) {
+		cnb_ctx *s = nullptr;
+		RC(cnb_ctx_create(c->device, &s));
+		c->siblings.push_back(s);
+	}
+	for (int k = 0; k < want - 1; k++) {
+		cnb_ctx *s = c->siblings[k];
+		if (s->cloned_epoch != c->data_epoch || !s->have_samples) RC(clone_data(c, s));
+		ctxs->push_back(s);
+	}
+	if (!c->crew || c->crew->G < want) {
+		if (c->crew) { c->crew->stop(); delete c->crew; }
+		c->crew = new Crew();
+		c->crew->start(want);
+	}
+	return CNB_OK;
+}
+
+int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders) {
+	if (n < 1) return CNB_OK;
+	if (n > (int)ctxs.size() || (n > 1 && (!c->crew || c->crew->G < n))) { cnb_set_error("cnb_ctx_batch_run: %d orders, %d contexts", n, (int)ctxs.size()); return CNB_ERR_PROC; }
+	auto job = [&](int t) -> int {
+		cnb_params q = *p;
+		q.order = orders[t];
+		return cnb_ctx_search_light(ctxs[t], &q);
+	};
+	if (n == 1) return job(0);
+	return c->crew->run(n, job);
 }
 
 extern "C" int cnb_ctx_set_samples_dev(cnb_ctx *c, int32_t N, int32_t M, const int32_t *samples_dev,

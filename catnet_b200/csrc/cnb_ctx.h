@@ -54,6 +54,11 @@ struct cnb_ctx {
 	bool has_na = false;               /* the data set has missing values */
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */
 	bool ignore_pert = false;          /* score as if there were no perturbation masks (full tables of the pairwise metrics) */
+	/* concurrent evaluation of several orders on this device (the numThreads proposals of a cnSearchSA step, the orders of a
+	 * cnSearchHist batch): sibling contexts holding a copy of the packed data, one host thread each (cnb_ctx_batch) */
+	std::vector<cnb_ctx *> siblings;
+	struct Crew *crew = nullptr;
+	unsigned long long data_epoch = 0, cloned_epoch = 0;   /* set_samples count of this context / of the data a sibling holds */
 	int dp_final = 0, tensor_batches = 0;
 	double host_ms[4] = {0, 0, 0, 0};   /* CNB_TRACE: host wall time of plan / score / select+dp, searches */
 	std::vector<int32_t> cats_lbl;
@@ -88,6 +93,11 @@ uint64_t cnb_default_seed(void);   /* what cnb_set_seed stored (cnb_sa.cpp) */
 int cnb_ctx_acquire(int32_t device, cnb_ctx **out);
 void cnb_ctx_park(cnb_ctx *c);
 void cnb_pool_release(void);
+/* contexts able to evaluate `want` orders at once on c's device: c itself and up to want - 1 siblings holding a copy of its
+ * packed data (small data sets only; 1 = evaluate one after the other).  cnb_ctx_batch_run evaluates orders[t] on ctxs[t]
+ * (plan + score + selection + DP, no export) concurrently, one host thread each. */
+int cnb_ctx_batch(cnb_ctx *c, int want, std::vector<cnb_ctx *> *ctxs);
+int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders);
 /* internal phases shared with the SA driver (cnb_sa.cpp) */
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
 int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);
@@ -105,6 +115,7 @@ struct CnbHistEval {
 	std::vector<int32_t> npar, pars;
 };
 int cnb_hist_eval_order(cnb_ctx *c, const cnb_params *q, const cnb_hist_params *hp, CnbHistEval *ev);
+int cnb_hist_pick(cnb_ctx *c, const cnb_hist_params *hp, CnbHistEval *ev);   /* after cnb_ctx_search_light on c */
 void cnb_hist_add(double *hist, int N, const std::vector<int> &order, const CnbHistEval &ev);
 void cnb_gen_permutation(std::vector<int> &out, int n, struct CnbRng &rng);
 /* one process, several devices (cnb_multi.cu): devices a one-shot call should use (cnb_params.num_devices, else the

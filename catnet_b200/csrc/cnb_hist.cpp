@@ -25,11 +25,16 @@ void cnb_gen_permutation(std::vector<int> &out, int n, CnbRng &rng);      /* cnb
 /* one order on one device: evaluate, pick the network (AIC / BIC / highest complexity), its weight and parents.
  * *found = false when the search left no network (`continue` before niter++, rcatnet_hist.cpp:506). */
 int cnb_hist_eval_order(cnb_ctx *c, const cnb_params *q, const cnb_hist_params *hp, CnbHistEval *ev) {
+	RC(cnb_ctx_search_light(c, q));
+	return cnb_hist_pick(c, hp, ev);
+}
+
+/* the second half: the context holds an evaluated order */
+int cnb_hist_pick(cnb_ctx *c, const cnb_hist_params *hp, CnbHistEval *ev) {
 	const int N = c->N, M = c->M;
 	std::vector<int32_t> cx;
 	std::vector<double> ll;
 	ev->found = false;
-	RC(cnb_ctx_search_light(c, q));
 	RC(cnb_ctx_dp_summary(c, &cx, &ll));
 	if (cx.empty()) return CNB_OK;
 	int pick = -1;
@@ -78,6 +83,11 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 	cnb_params q = *p;
 	q.edge_prob = nullptr;                       /* rcatnet_hist.cpp:268-277: no edge priors on this entry point */
 	int niter = 0, nstop = 0;
+	/* the orders of a batch are independent: evaluated concurrently on sibling contexts when the data set is small */
+	std::vector<cnb_ctx *> lanes, where(nDrives, c);
+	RC(cnb_ctx_batch(c, nDrives, &lanes));
+	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1;
+	std::vector<const int32_t *> todo_orders;
 	while (niter < hp->max_iter) {
 		for (int n = 0; n < nDrives; n++) {
 			cnb_gen_permutation(test[n], N, rng);
@@ -85,11 +95,21 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 			for (int nn = 0; nn < n && !skip[n]; nn++) skip[n] = (test[nn] == test[n]);
 		}
 		nstop = 1;
+		if (batched) {
+			todo_orders.clear();
+			int t = 0;
+			for (int n = 0; n < nDrives; n++)
+				if (!skip[n]) { where[n] = lanes[t++]; todo_orders.push_back(test[n].data()); }
+			RC(cnb_ctx_batch_run(c, lanes, &q, t, todo_orders.data()));
+		}
 		for (int n = 0; n < nDrives; n++) {
 			if (skip[n]) continue;
 			nstop = 0;
-			q.order = test[n].data();
-			RC(cnb_hist_eval_order(c, &q, hp, &ev));
+			if (batched) RC(cnb_hist_pick(where[n], hp, &ev));
+			else {
+				q.order = test[n].data();
+				RC(cnb_hist_eval_order(c, &q, hp, &ev));
+			}
 			if (!ev.found) continue;                 /* slots but no network: `continue` before niter++ (:506) */
 			cnb_hist_add(hist, N, test[n], ev);
 			niter++;

@@ -1162,7 +1162,20 @@ __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpStat
 		atomicExch(&flags[b], 1u);
 	}
 	const int nsteps = (N - 1 + T - 1) / T;
-	for (int m = 1; m <= nsteps; m++) {
+	/* A node raises a network's complexity by at most `halo`, so after macro-step m no slot above base_complexity + m T halo
+	 * exists: a CTA whose owned slots all lie above that has nothing to do in steps 1..m_skip -- it announces them as done and
+	 * starts at m_skip + 1 (its slots read "no network" from the zeroed state buffers).  Without this the CTAs run in lockstep
+	 * down a diagonal, nsteps + CTAs macro-steps long; with it the DP ends after about nsteps of them (C5: 194 -> ~100). */
+	int m_skip = 0;
+	if (b * SO > base_complexity) m_skip = min(nsteps, (b * SO - base_complexity - 1) / (T * halo));
+	if (m_skip > 0) {
+		__syncthreads();
+		if (tid == 0) {
+			__threadfence();
+			atomicExch(&flags[b], (unsigned)m_skip + 1u);
+		}
+	}
+	for (int m = m_skip + 1; m <= nsteps; m++) {
 		const DpState &gin = (m - 1) % 3 == 0 ? s0 : ((m - 1) % 3 == 1 ? s1 : s2), &gout = m % 3 == 0 ? s0 : (m % 3 == 1 ? s1 : s2);
 		const int c_lo = (m - 1) * T + 1, nT = min(T, N - c_lo);
 		if (tid == 0) {
@@ -1530,6 +1543,10 @@ int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 	const int blocks = (s0.K + 1 + owned - 1) / owned;
 	if (!coop || per_sm < 1 || blocks > sms * per_sm || blocks > flags_cap) return CNB_ERR_PROC;
 	CK(cudaMemsetAsync(flags, 0, (size_t)blocks * sizeof(unsigned), st));
+	/* CTAs skip the macro-steps in which none of their slots can exist yet: every state buffer starts as "no network" */
+	CK(cudaMemsetAsync(s0.exists, 0, (size_t)s0.K + 1, st));
+	CK(cudaMemsetAsync(s1.exists, 0, (size_t)s0.K + 1, st));
+	CK(cudaMemsetAsync(s2.exists, 0, (size_t)s0.K + 1, st));
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
 		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags,
 		(void *)&T, (void *)&halo};

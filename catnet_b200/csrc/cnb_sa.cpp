@@ -132,6 +132,14 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 	std::vector<int32_t> cx;
 	std::vector<double> ll;
 	cnb_params q = *p;
+	/* the numThreads proposals of a step are independent evaluations (the reference hands one to each worker thread,
+	 * rcatnet_sa.cpp:475-652): here they run concurrently on this device, one sibling context and host thread each, when the
+	 * data set is small enough to copy; the decisions below then look at them in proposal order, exactly as before */
+	std::vector<cnb_ctx *> lanes;
+	RC(cnb_ctx_batch(c, nDrives, &lanes));
+	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1;
+	std::vector<cnb_ctx *> where(nDrives, c);
+	std::vector<const int32_t *> todo_orders;
 
 	while (niter < sa->max_iter) {
 		for (int n = 0; n < nDrives; n++) {
@@ -147,13 +155,23 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 		}
 		nstop = 1;
 		int stepiters = nDrives, stepaccept = 0;
+		if (batched) {
+			todo_orders.clear();
+			int t = 0;
+			for (int n = 0; n < nDrives; n++)
+				if (!skip[n]) { where[n] = lanes[t++]; todo_orders.push_back(test[n].data()); }
+			RC(cnb_ctx_batch_run(c, lanes, &q, t, todo_orders.data()));
+		}
 		for (int n = 0; n < nDrives; n++) {
 			if (skip[n]) continue;
 			if (stepaccept > 0) continue;                /* a previous drive was accepted: discard the rest */
 			nstop = 0;
-			q.order = test[n].data();
-			RC(cnb_ctx_search_light(c, &q));
-			RC(cnb_ctx_dp_summary(c, &cx, &ll));
+			cnb_ctx *ce = batched ? where[n] : c;        /* the context that holds this proposal's evaluation */
+			if (!batched) {
+				q.order = test[n].data();
+				RC(cnb_ctx_search_light(c, &q));
+			}
+			RC(cnb_ctx_dp_summary(ce, &cx, &ll));
 			if (cx.empty()) continue;
 			int pick = -1;
 			double fLogLik = -(double)FLT_MAX;
@@ -201,7 +219,7 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 				haveOpt = true;
 				fOptLogLik = fLogLik;
 				cnb_result *r = nullptr;
-				RC(cnb_ctx_collect(c, &r));
+				RC(cnb_ctx_collect(ce, &r));
 				best.reset(r);
 				optOrder = test[n];
 			}

@@ -109,6 +109,39 @@ def check_sa(seed):
     assert i1 == i2 and np.array_equal(h1, h2)
 
 
+def check_sacache(seed):
+    """R always runs cnSearchSA with the score cache ON (R/catnet.search.R:293-294), the library never caches: the
+    reference with its cache against the reference without it, same uniform stream -- a `mismatch` here is a DIVERGENCE of
+    cache-on from cache-off (the cached table was computed under an earlier order, with its parents in another order, so
+    its fp64 sum can differ in the last bit and flip a comparison)"""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 11)), int(rng.integers(8, 400))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4][seed % 4], na_frac=[0, 0.1][seed % 2])
+    kw = dict(num_cats=c)
+    if seed % 3 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.2).astype(np.int32)
+    kh = dict(kw)
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0, 0.0][seed % 4], temp_cool_fact=[0.9, 0.5][seed % 2],
+              temp_check_orders=int(rng.integers(1, 8)), max_iter=int(rng.integers(20, 120)),
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=[1e-10, 0.01][seed % 2],
+              num_threads=int(rng.integers(1, 5)), seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    P = 2 + (seed % 7 == 0)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** P
+    a = ref.search_sa(s, P, K, start, use_cache=False, **sa, **kw)
+    b = ref.search_sa(s, P, K, start, use_cache=True, **sa, **kw)
+    assert np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"] and a["naccept"] == b["naccept"], "trajectory"
+    assert np.array_equal(a["trace_accept"], b["trace_accept"]), "acceptances"
+    assert np.array_equal(a["trace"], b["trace"]), "trace values (last bit)"
+    assert compare_search(b["nets"], a["nets"], check_probs=False) == len(a["nets"]), "network log-likelihoods (last bit)"
+    hk = dict(score=seed % 3, weight=seed % 3, max_iter=12, num_threads=1 + seed % 3, seed=sa["seed"])
+    h1, i1 = ref.search_hist(s, 2, K, use_cache=False, **hk, **kh)
+    h2, i2 = ref.search_hist(s, 2, K, use_cache=True, **hk, **kh)
+    assert i1 == i2 and np.array_equal(h1, h2), "histogram"
+
+
 def check_rest(seed):
     rng = np.random.default_rng(seed)
     n, m = int(rng.integers(1, 10)), int(rng.integers(7, 150))
@@ -150,7 +183,7 @@ def check_rest(seed):
 
 
 def main():
-    check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest}[sys.argv[1]]
+    check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest, "sacache": check_sacache}[sys.argv[1]]
     lo, hi = int(sys.argv[2]), int(sys.argv[3])
     if not ref.available():
         sys.exit("oracle/_ref is not built (needs /root/reference)")
