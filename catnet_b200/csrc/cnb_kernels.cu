@@ -740,6 +740,58 @@ __device__ __forceinline__ double dev_resum(double pfx, double f, int c, int N, 
 	return acc;
 }
 
+/* The re-summation in ONE addition.  Every term behind node c is a node's base log-likelihood (<= 0) and x = pfx + f < 0, so
+ * the running sum only grows in magnitude: if x and the final sum lie in the same binade [2^e, 2^(e+1)), every intermediate
+ * does, all of them are multiples of u = 2^(e-52), and each IEEE addition acc + b rounds the exact sum to the nearest
+ * multiple of u, which is acc + rn_u(b) unless b sits exactly half-way between two multiples (a tie, decided by the parity of
+ * acc).  Hence  x + b_{c+1} + ... + b_{N-1}  (left to right, rounded each time)  =  x + D[e][c]  EXACTLY, with
+ * D[e][c] = sum_{i>c} rn_u(b_i) a sum of multiples of u (exact).  k_dp_prepare builds D for 20 binades and flags the
+ * suffixes that contain a tie or a positive term; dp_resum falls back to the explicit chain for those, for an x outside the
+ * table's binades and when the result leaves x's binade.  C5: 250 dependent fp64 additions per candidate on average -> 1;
+ * the DP was bound by the fp64 pipe (512 threads x 4 candidates x (N - c) additions per node and CTA). */
+#define DPF_E 20                         /* binades 2^-4 .. 2^15 */
+#define DPF_ELO (1023 - 4)
+struct DpFast {
+	const double *D;                     /* [DPF_E][N] */
+	const unsigned char *bad;            /* [DPF_E][N]: no shortcut for this suffix in this binade */
+};
+
+__global__ void k_dp_prepare(const double *__restrict__ base_v, int N, double *__restrict__ D, unsigned char *__restrict__ bad) {
+	const int e = threadIdx.x;
+	if (e >= DPF_E) return;
+	const double u = __longlong_as_double((long long)(DPF_ELO + e - 52) << 52), inv_u = __longlong_as_double((long long)(2046 - (DPF_ELO + e - 52)) << 52);
+	double units = 0.0;                  /* sum of rn_u(b_i) / u: an integer, exact below 2^53 */
+	unsigned char b = 0;
+	D[(size_t)e * N + N - 1] = 0.0;
+	bad[(size_t)e * N + N - 1] = 0;
+	for (int c = N - 2; c >= 0; c--) {
+		const double v = base_v[c + 1];
+		if (!(v <= 0.0) || !(v > -1.0e300)) b = 1;               /* positive, NaN or a "-infinity" sentinel */
+		else {
+			const double t = __dmul_rn(v, inv_u);                /* exact: a power of two */
+			const double r = rint(t);
+			if (fabs(__dsub_rn(t, trunc(t))) == 0.5) b = 1;      /* half-way: the rounding would depend on the running sum */
+			units = __dadd_rn(units, r);
+			if (fabs(units) >= 4503599627370496.0) b = 1;        /* 2^52: keep the integer sum exact */
+		}
+		D[(size_t)e * N + c] = __dmul_rn(units, u);
+		bad[(size_t)e * N + c] = b;
+	}
+}
+
+/* x + base_v[c+1] + ... + base_v[N-1], added left to right (the chain dev_resum walks), by the shortcut when it applies */
+__device__ __forceinline__ double dp_resum(double x, int c, int N, const double *__restrict__ sbase, const DpFast &F) {
+	const long long xb = __double_as_longlong(x);
+	const int eb = (int)((xb >> 52) & 0x7ff), idx = eb - DPF_ELO;
+	if (xb < 0 && idx >= 0 && idx < DPF_E && !__ldg(F.bad + (size_t)idx * N + c)) {
+		const double r = __dadd_rn(x, __ldg(F.D + (size_t)idx * N + c));
+		if ((int)((__double_as_longlong(r) >> 52) & 0x7ff) == eb) return r;
+	}
+	double acc = x;
+	for (int i = c + 1; i < N; i++) acc = __dadd_rn(acc, sbase[i]);
+	return acc;
+}
+
 __global__ void k_dp_init(DpState S, int base_complexity, const double *__restrict__ base_v, int N) {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j > S.K) return;
@@ -802,11 +854,12 @@ __global__ void __launch_bounds__(128) k_dp_node(DpState cur, DpState nxt, int c
 template <bool CG> __device__ __forceinline__ double dp_ld(const double *p) { return CG ? __ldcg(p) : *p; }
 template <bool CG> __device__ __forceinline__ unsigned char dp_ld(const unsigned char *p) { return CG ? __ldcg(p) : *p; }
 
-template <bool CG>
+template <bool CG, bool FAST = false>
 __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, int j, int c, int N, int K,
 		const CnbDpNode &nd, int nopt, const long long (&o_fid)[4], const int (&o_cx)[4], const double (&o_sc)[4],
 		const double *sbase, double bv, const double *__restrict__ opt_score, const int *__restrict__ opt_cx,
-		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src, bool write_bp = true) {
+		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src, bool write_bp = true,
+		DpFast FT = DpFast()) {
 	bool has = false;
 	double R = CNB_NEG_INF;
 	long long bo = -1;
@@ -831,6 +884,12 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 			acc[nq] = __dadd_rn(dp_ld<CG>(cur.pfx + k), f);
 			nq++;
 		}
+		if (FAST) {
+			/* one addition per candidate instead of the chain (dp_resum) */
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+				if (q < nq) acc[q] = dp_resum(acc[q], c, N, sbase, FT);
+		} else {
 		const int nqmax = __reduce_max_sync(__activemask(), nq);
 		/* the terms are fetched 8 ahead of the dependent adds (shared-memory latency off the chain) */
 #define DP_CHAIN(NQ) { \
@@ -849,6 +908,7 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 		else if (nqmax == 2) DP_CHAIN(2)
 		else if (nqmax > 2) DP_CHAIN(4)
 #undef DP_CHAIN
+		}
 #pragma unroll
 		for (int q = 0; q < 4; q++) {
 			if (q >= nq) continue;
@@ -866,7 +926,7 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 			if (has && R < t) {                                  /* :670-671 strict */
 				bo = o;
 				bs = k;
-				R = dev_resum(dp_ld<CG>(cur.pfx + k), f, c, N, sbase);
+				R = FAST ? dp_resum(__dadd_rn(dp_ld<CG>(cur.pfx + k), f), c, N, sbase, FT) : dev_resum(dp_ld<CG>(cur.pfx + k), f, c, N, sbase);
 				bf = f;
 			}
 		}
@@ -1134,7 +1194,7 @@ __global__ void __launch_bounds__(256) k_dp_wave(DpState s0, DpState s1, DpState
 __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpState s2, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
-		int *__restrict__ bp_src, unsigned *flags, int T, int halo) {
+		int *__restrict__ bp_src, unsigned *flags, int T, int halo, DpFast FT) {
 	extern __shared__ double sbase[];                    /* [N], then the two state buffers */
 	__shared__ CnbDpNode s_nd[TRAP_TMAX];
 	__shared__ long long s_fid[TRAP_TMAX][4];
@@ -1214,8 +1274,12 @@ __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpStat
 #pragma unroll
 				for (int q = 0; q < 4; q++) { o_fid[q] = s_fid[t][q]; o_cx[q] = s_cx[t][q]; o_sc[q] = s_sc[t][q]; }
 				const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
-				dp_slot<false>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
-						bp_opt, bp_src, owned);
+				if (FT.D)
+					dp_slot<false, true>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
+							bp_opt, bp_src, owned, FT);
+				else
+					dp_slot<false>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
+							bp_opt, bp_src, owned);
 			}
 			__syncthreads();
 		}
@@ -1428,6 +1492,7 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 }
 
 int cnbk_select_chunk(void) { return SEL_CHUNK; }
+int cnbk_dp_fast_binades(void) { return DPF_E; }
 
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
 		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
@@ -1526,7 +1591,8 @@ int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
  * CNB_ERR_PROC (nothing launched) when it does not apply */
 int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
-		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out) {
+		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out,
+		double *fast_D, unsigned char *fast_bad) {
 	int dev = 0, coop = 0, sms = 0, per_sm = 0;
 	CK(cudaGetDevice(&dev));
 	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1547,9 +1613,18 @@ int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 	CK(cudaMemsetAsync(s0.exists, 0, (size_t)s0.K + 1, st));
 	CK(cudaMemsetAsync(s1.exists, 0, (size_t)s0.K + 1, st));
 	CK(cudaMemsetAsync(s2.exists, 0, (size_t)s0.K + 1, st));
+	DpFast FT;
+	FT.D = fast_D;
+	FT.bad = fast_bad;
+	if (fast_D && fast_bad) {
+		/* the shortcut tables of this search's base network (one addition instead of N - c per re-summation) */
+		k_dp_prepare<<<1, 32, 0, st>>>(base_v, N, fast_D, fast_bad);
+		CK(cudaGetLastError());
+	} else
+		FT.D = nullptr;
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
 		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags,
-		(void *)&T, (void *)&halo};
+		(void *)&T, (void *)&halo, (void *)&FT};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_trap, dim3(blocks), dim3(threads), args, smem, st));
 	*steps_out = (N - 1 + T - 1) / T;
 	return CNB_OK;

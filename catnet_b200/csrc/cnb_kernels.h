@@ -120,7 +120,10 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 /* trapezoid wavefront (T nodes per neighbour exchange); final state in buffer (*steps_out) % 3 */
 int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
-		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out);
+		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out,
+		double *fast_D = nullptr, unsigned char *fast_bad = nullptr);   /* scratch [cnbk_dp_fast_binades()][N] each: the one-addition
+		                                                                   re-summation (NULL = the explicit chains) */
+int cnbk_dp_fast_binades(void);
 int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap);

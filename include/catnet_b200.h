@@ -316,7 +316,8 @@ int cnb_ctx_search_scores(cnb_ctx *ctx, const double *scores_dev, int32_t nfam, 
  * the POPC kernel (set before the samples); 512 no inclusion-exclusion for three parents; 1024 three parents never on
  * the tensor cores; 2048 wavefront DP with one node per exchange; 4096 generic tensor-core epilogue also for
  * 4-category data; 8192 full-table tensor tiles (the form that takes missing values and perturbation masks) also on
- * complete data.  Every combination gives the same networks. */
+ * complete data; 16384 trapezoid DP with the explicit re-summation chains (no one-addition shortcut).  Every combination
+ * gives the same networks. */
 int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 /* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */
 int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);

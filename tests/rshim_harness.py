@@ -18,7 +18,12 @@ _libs = {}
 def lib(backend):
     if backend not in _libs:
         path = os.path.join(HERE, "_build", "librshim_%s.so" % backend)
-        rc = subprocess.call(["make", "-s", "-C", HERE, "_build/librshim_%s.so" % backend])
+        # pytest-xdist workers share the tree: one of them (re)builds at a time, the others wait and find it up to date
+        import fcntl
+        os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+        with open(os.path.join(HERE, "_build", ".lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            rc = subprocess.call(["make", "-s", "-C", HERE, "_build/librshim_%s.so" % backend])
         if rc != 0 and not os.path.exists(path):     # a prebuilt library (from __graft_entry__.build()) is good enough
             raise RuntimeError("cannot build %s" % path)
         L = C.CDLL(path)

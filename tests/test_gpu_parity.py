@@ -587,7 +587,29 @@ def test_dp_trapezoid_equals_wavefront(abi, n, m, cats, P):
         b = ctx.search_order(want_probs=False, **kw)
         ctx.force_generic(32)
         d = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(16384)                  # trapezoid with the explicit re-summation chains (no one-addition shortcut)
+        e = ctx.search_order(want_probs=False, **kw)
     assert compare_search(a, b, check_probs=False) == len(b) and compare_search(a, d, check_probs=False) == len(d)
+    assert compare_search(a, e, check_probs=False) == len(e)
+
+
+@pytest.mark.parametrize("n,m,cats,P,grid", [(150, 64, 2, 2, True), (120, 4096, 3, 2, True), (200, 333, 4, 2, False), (90, 1024, 2, 3, True),
+                                             (257, 50, 3, 2, False)])
+def test_dp_resummation_shortcut(abi, n, m, cats, P, grid):
+    """the DP re-sums a network's log-likelihood in one addition (x + D[binade][node], exact) instead of N - c: same
+    networks and bit-identical log-likelihoods as the explicit chains, also on data whose node terms sit on coarse grids
+    (sample counts that are powers of two: ties in the rounding, where the shortcut must step aside)"""
+    s, c = random_problem(11 * n + m, n, m, cats, structured=not grid)
+    kw = dict(max_parent_set=P, max_complexity=n * (cats ** P) * (cats - 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        a = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(16384)
+        b = ctx.search_order(want_probs=False, **kw)
+        ctx.force_generic(64)                     # grid-barrier kernel
+        d = ctx.search_order(want_probs=False, **kw)
+    assert compare_search(a, b, check_probs=False) == len(b) and compare_search(a, d, check_probs=False) == len(d)
+    assert [x["loglik"] for x in a] == [x["loglik"] for x in b] == [x["loglik"] for x in d]
 
 
 def test_pair_tables_on_tensor_cores(abi):
