@@ -544,7 +544,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->dp_no_trap = (on & 2048) != 0;                      /* bit 11: wavefront DP one node per exchange (k_dp_wave) */
 	c->generic_epilogue = (on & 4096) != 0;                /* bit 12: generic epilogue of the tensor-core scorer also for 4-category data */
 	c->force_full = (on & 8192) != 0;
-	c->dp_chains = (on & 16384) != 0;                      /* bit 14: trapezoid DP with the explicit re-summation chains */                      /* bit 13: full-table tiles also on complete data (no inclusion-exclusion) */
+	c->dp_chains = (on & 16384) != 0;                      /* bit 14: trapezoid DP, every slot re-sums its own candidates (no work list) */                      /* bit 13: full-table tiles also on complete data (no inclusion-exclusion) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
 }
@@ -1093,13 +1093,12 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 		/* few options per node: the trapezoid wavefront (T nodes per neighbour exchange), else one node per exchange */
 		int steps = 0;
 		if (!c->dp_no_trap) {
-			const size_t fe = (size_t)cnbk_dp_fast_binades() * N;
-			RC(c->b_dp_fast.ensure(fe * (sizeof(double) + 1)));
-			double *fast_D = c->dp_chains ? nullptr : (double *)c->b_dp_fast.ptr;
+			RC(c->b_dp_fast.ensure(cnbk_dp_table_bytes(N)));
+			double *fast_P = (double *)c->b_dp_fast.ptr;
 			fused = cnbk_dp_trap(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
 					(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
 					(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap, &steps,
-					fast_D, fast_D ? (unsigned char *)(fast_D + fe) : nullptr);
+					c->dp_chains ? 0 : 1, fast_P, (unsigned char *)(fast_P + (size_t)20 * N));
 		}
 		if (fused == CNB_OK) {
 			cur = steps % 3;                  /* macro-step m reads S[(m - 1) % 3] and writes S[m % 3] */

@@ -49,7 +49,7 @@ struct cnb_ctx {
 	bool generic_epilogue = false;     /* k_umma_epilogue<false> also when every node has 4 categories (test hook) */
 	bool pairs_ord = false;            /* b_pairs_ord holds the tables of all ORDERED pairs under the child's keep mask, missing values
 	                                      skipped: the 0- and 1-parent families of masked data need no pass over the samples */
-	bool dp_chains = false;            /* trapezoid DP re-sums with the explicit chains instead of the one-addition shortcut (test hook) */
+	bool dp_chains = false;            /* trapezoid DP: every slot re-sums its own candidates instead of the CTA-wide work list (test hook) */
 	bool force_full = false;           /* full-table tensor tiles also on complete data (test hook) */
 	bool dp_no_trap = false;           /* k_dp_wave instead of the trapezoid kernel (test hook) */
 	bool has_na = false;               /* the data set has missing values */

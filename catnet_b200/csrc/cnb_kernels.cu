@@ -10,9 +10,18 @@
  *  K2b k_score_hist                    generic path (any category count / table size): one CTA per family,
  *                                      shared-memory histogram
  *  K3  dev_family (cnb_device.cuh)     combinadic unrank of the family id, replaces combinationSets (:102-147)
- *  K4  k_select                        per (node, d) first-maximum / option table, replaces :613-621
- *  K5  k_dp_init / k_dp_node / k_dp_collect   knapsack over complexity with the reference's exact fp64
- *                                      comparison semantics, replaces :653-677, :800-827, :847-865
+ *      k_score_planes_ie2 / _ie3       the same on complete data: only the free cells are counted, the rest follows from the
+ *                                      two- / three-way tables of the data set (k_pair_tables, k_triple_tables)
+ *      k_score_pairs0 / k_score_pairs1 zero- and one-parent families read straight off those tables (ordered variants for
+ *                                      data with missing values / perturbation masks)
+ *  K4  k_select / k_select_combine     per (node, d) first-maximum / option table, replaces :613-621
+ *  K5  k_dp_trap (default)             knapsack over complexity with the reference's exact fp64 comparison semantics,
+ *      k_dp_wave / k_dp_all / k_dp_mixed / k_dp_init + k_dp_node, k_dp_collect_list
+ *                                      replaces :653-677, :800-827, :847-865: one cooperative launch for all nodes --
+ *                                      trapezoid wavefront (several nodes per neighbour exchange, candidates of a CTA
+ *                                      re-summed from a dense work list in blocks of 16 terms), one-node wavefront,
+ *                                      grid barrier per node, a warp per slot for mixed-category nodes -- or a launch per node
+ *  The two-parent tables on the tensor cores (tcgen05) are in cnb_umma.cu.
  */
 #include <stdio.h>
 #include <cooperative_groups.h>
@@ -740,55 +749,70 @@ __device__ __forceinline__ double dev_resum(double pfx, double f, int c, int N, 
 	return acc;
 }
 
-/* The re-summation in ONE addition.  Every term behind node c is a node's base log-likelihood (<= 0) and x = pfx + f < 0, so
- * the running sum only grows in magnitude: if x and the final sum lie in the same binade [2^e, 2^(e+1)), every intermediate
- * does, all of them are multiples of u = 2^(e-52), and each IEEE addition acc + b rounds the exact sum to the nearest
- * multiple of u, which is acc + rn_u(b) unless b sits exactly half-way between two multiples (a tie, decided by the parity of
- * acc).  Hence  x + b_{c+1} + ... + b_{N-1}  (left to right, rounded each time)  =  x + D[e][c]  EXACTLY, with
- * D[e][c] = sum_{i>c} rn_u(b_i) a sum of multiples of u (exact).  k_dp_prepare builds D for 20 binades and flags the
- * suffixes that contain a tie or a positive term; dp_resum falls back to the explicit chain for those, for an x outside the
- * table's binades and when the result leaves x's binade.  C5: 250 dependent fp64 additions per candidate on average -> 1;
- * the DP was bound by the fp64 pipe (512 threads x 4 candidates x (N - c) additions per node and CTA). */
+/* Re-summation in blocks of 16 terms.  Every term behind node c is a node's base log-likelihood (<= 0) and x = pfx + f < 0,
+ * so the running sum only grows in magnitude.  While it stays inside one binade [2^e, 2^(e+1)) it is a multiple of
+ * u = 2^(e-52), and each IEEE addition acc + b rounds the exact sum to the nearest multiple of u, which is acc + rn_u(b)
+ * unless b sits exactly half-way between two multiples (a tie: the rounding then depends on the parity of acc).  So a block
+ * of terms without a tie is added EXACTLY by one addition of P = sum rn_u(b_i) (a sum of multiples of u, exact) whenever
+ * acc and acc + P lie in the same binade (then, the sum being monotone, every intermediate did).  k_dp_prepare tabulates,
+ * for 20 binades, the running sum of rn_u(b_i) inside every aligned block of 16 terms and the blocks that hold a tie, a
+ * positive term or a sentinel; dp_resum_blocks walks the chain block by block and adds a block term by term when the
+ * shortcut does not apply (a tie, a binade crossing, an x outside the table).  The chain of N - c dependent fp64 additions
+ * is the critical path of the DP (C5: 250 on average per node, ~20 clock cycles each): about 16 block additions plus the
+ * few blocks that cross a binade instead. */
 #define DPF_E 20                         /* binades 2^-4 .. 2^15 */
 #define DPF_ELO (1023 - 4)
+#define DPF_B 16
 struct DpFast {
-	const double *D;                     /* [DPF_E][N] */
-	const unsigned char *bad;            /* [DPF_E][N]: no shortcut for this suffix in this binade */
+	const double *P;                     /* [DPF_E][N]: sum of rn_u(b_t) over t from the start of i's block to i */
+	const unsigned char *bad;            /* [DPF_E][ceil(N / 16)]: block without shortcut in this binade */
+	int nblk;
 };
 
-__global__ void k_dp_prepare(const double *__restrict__ base_v, int N, double *__restrict__ D, unsigned char *__restrict__ bad) {
+__global__ void k_dp_prepare(const double *__restrict__ base_v, int N, double *__restrict__ P, unsigned char *__restrict__ bad) {
 	const int e = threadIdx.x;
 	if (e >= DPF_E) return;
 	const double u = __longlong_as_double((long long)(DPF_ELO + e - 52) << 52), inv_u = __longlong_as_double((long long)(2046 - (DPF_ELO + e - 52)) << 52);
-	double units = 0.0;                  /* sum of rn_u(b_i) / u: an integer, exact below 2^53 */
-	unsigned char b = 0;
-	D[(size_t)e * N + N - 1] = 0.0;
-	bad[(size_t)e * N + N - 1] = 0;
-	for (int c = N - 2; c >= 0; c--) {
-		const double v = base_v[c + 1];
-		if (!(v <= 0.0) || !(v > -1.0e300)) b = 1;               /* positive, NaN or a "-infinity" sentinel */
-		else {
-			const double t = __dmul_rn(v, inv_u);                /* exact: a power of two */
-			const double r = rint(t);
-			if (fabs(__dsub_rn(t, trunc(t))) == 0.5) b = 1;      /* half-way: the rounding would depend on the running sum */
-			units = __dadd_rn(units, r);
-			if (fabs(units) >= 4503599627370496.0) b = 1;        /* 2^52: keep the integer sum exact */
+	const int nblk = (N + DPF_B - 1) / DPF_B;
+	for (int k = 0; k < nblk; k++) {
+		double units = 0.0;              /* an integer: exact below 2^52 */
+		bool b = false;
+		for (int i = k * DPF_B; i < min(N, (k + 1) * DPF_B); i++) {
+			const double v = base_v[i];
+			if (!(v <= 0.0) || !(v > -1.0e300)) b = true;            /* positive, NaN or a "-infinity" sentinel */
+			else {
+				const double t = __dmul_rn(v, inv_u);                /* exact: a power of two */
+				if (fabs(__dsub_rn(t, trunc(t))) == 0.5) b = true;   /* half-way: the rounding depends on the running sum */
+				units = __dadd_rn(units, rint(t));
+				if (fabs(units) >= 4503599627370496.0) b = true;
+			}
+			P[(size_t)e * N + i] = __dmul_rn(units, u);
 		}
-		D[(size_t)e * N + c] = __dmul_rn(units, u);
-		bad[(size_t)e * N + c] = b;
+		bad[(size_t)e * nblk + k] = b;
 	}
 }
 
-/* x + base_v[c+1] + ... + base_v[N-1], added left to right (the chain dev_resum walks), by the shortcut when it applies */
-__device__ __forceinline__ double dp_resum(double x, int c, int N, const double *__restrict__ sbase, const DpFast &F) {
-	const long long xb = __double_as_longlong(x);
-	const int eb = (int)((xb >> 52) & 0x7ff), idx = eb - DPF_ELO;
-	if (xb < 0 && idx >= 0 && idx < DPF_E && !__ldg(F.bad + (size_t)idx * N + c)) {
-		const double r = __dadd_rn(x, __ldg(F.D + (size_t)idx * N + c));
-		if ((int)((__double_as_longlong(r) >> 52) & 0x7ff) == eb) return r;
-	}
+/* x + base_v[c+1] + ... + base_v[N-1], added left to right (the chain dev_resum walks) */
+__device__ __forceinline__ double dp_resum_blocks(double x, int c, int N, const double *__restrict__ sbase, const DpFast &F) {
 	double acc = x;
-	for (int i = c + 1; i < N; i++) acc = __dadd_rn(acc, sbase[i]);
+	int i = c + 1;
+	while (i < N) {
+		const int k = i / DPF_B, end = min(N, (k + 1) * DPF_B);
+		const long long ab = __double_as_longlong(acc);
+		const int eb = (int)((ab >> 52) & 0x7ff), idx = eb - DPF_ELO;
+		if (ab < 0 && idx >= 0 && idx < DPF_E && !__ldg(F.bad + (size_t)idx * F.nblk + k)) {
+			const double *Pp = F.P + (size_t)idx * N;
+			double d = __ldg(Pp + end - 1);
+			if (i > k * DPF_B) d = __dsub_rn(d, __ldg(Pp + i - 1));      /* multiples of u below 2^52 u: exact */
+			const double r = __dadd_rn(acc, d);
+			if ((int)((__double_as_longlong(r) >> 52) & 0x7ff) == eb) {
+				acc = r;
+				i = end;
+				continue;
+			}
+		}
+		for (; i < end; i++) acc = __dadd_rn(acc, sbase[i]);
+	}
 	return acc;
 }
 
@@ -854,12 +878,11 @@ __global__ void __launch_bounds__(128) k_dp_node(DpState cur, DpState nxt, int c
 template <bool CG> __device__ __forceinline__ double dp_ld(const double *p) { return CG ? __ldcg(p) : *p; }
 template <bool CG> __device__ __forceinline__ unsigned char dp_ld(const unsigned char *p) { return CG ? __ldcg(p) : *p; }
 
-template <bool CG, bool FAST = false>
+template <bool CG>
 __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, int j, int c, int N, int K,
 		const CnbDpNode &nd, int nopt, const long long (&o_fid)[4], const int (&o_cx)[4], const double (&o_sc)[4],
 		const double *sbase, double bv, const double *__restrict__ opt_score, const int *__restrict__ opt_cx,
-		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src, bool write_bp = true,
-		DpFast FT = DpFast()) {
+		const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt, int *__restrict__ bp_src, bool write_bp = true) {
 	bool has = false;
 	double R = CNB_NEG_INF;
 	long long bo = -1;
@@ -884,12 +907,6 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 			acc[nq] = __dadd_rn(dp_ld<CG>(cur.pfx + k), f);
 			nq++;
 		}
-		if (FAST) {
-			/* one addition per candidate instead of the chain (dp_resum) */
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-				if (q < nq) acc[q] = dp_resum(acc[q], c, N, sbase, FT);
-		} else {
 		const int nqmax = __reduce_max_sync(__activemask(), nq);
 		/* the terms are fetched 8 ahead of the dependent adds (shared-memory latency off the chain) */
 #define DP_CHAIN(NQ) { \
@@ -908,7 +925,6 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 		else if (nqmax == 2) DP_CHAIN(2)
 		else if (nqmax > 2) DP_CHAIN(4)
 #undef DP_CHAIN
-		}
 #pragma unroll
 		for (int q = 0; q < 4; q++) {
 			if (q >= nq) continue;
@@ -926,7 +942,7 @@ __device__ __forceinline__ void dp_slot(const DpState &cur, const DpState &nxt, 
 			if (has && R < t) {                                  /* :670-671 strict */
 				bo = o;
 				bs = k;
-				R = FAST ? dp_resum(__dadd_rn(dp_ld<CG>(cur.pfx + k), f), c, N, sbase, FT) : dev_resum(dp_ld<CG>(cur.pfx + k), f, c, N, sbase);
+				R = dev_resum(dp_ld<CG>(cur.pfx + k), f, c, N, sbase);
 				bf = f;
 			}
 		}
@@ -1188,21 +1204,23 @@ __global__ void __launch_bounds__(256) k_dp_wave(DpState s0, DpState s1, DpState
  * flag / state round trips through L2 (what bounds k_dp_wave: 499 + 94 steps of ~6 us at C5) are paid once per T
  * nodes; the state lives in shared memory in between.  Back-pointers are written by the owner only.  Same three
  * global state buffers and neighbour protocol as k_dp_wave, per macro-step. */
-#define TRAP_S 256            /* recomputed slots to the left of the owned ones */
-#define TRAP_TMAX 8
-/* blockDim.x = owned slots + TRAP_S (the launcher uses 256 + 256) */
+#define TRAP_TMAX 16          /* nodes per neighbour exchange at most */
+/* blockDim.x = owned slots + TRAP_S recomputed slots to their left (the launcher uses 256 + 512: with the work list the
+ * recomputed slots cost a gather and a decision each, not a re-summation chain, so a wide left margin -- more nodes per
+ * exchange -- is cheap) */
 __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpState s2, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
-		int *__restrict__ bp_src, unsigned *flags, int T, int halo, DpFast FT) {
-	extern __shared__ double sbase[];                    /* [N], then the two state buffers */
+		int *__restrict__ bp_src, unsigned *flags, int T, int halo, int compact, int TRAP_S, DpFast FT) {
+	extern __shared__ double sbase[];                    /* [N], then the two state buffers, then the work list */
+	__shared__ int s_nwork;
 	__shared__ CnbDpNode s_nd[TRAP_TMAX];
 	__shared__ long long s_fid[TRAP_TMAX][4];
 	__shared__ int s_cx[TRAP_TMAX][4];
 	__shared__ double s_sc[TRAP_TMAX][4];
 	const int BW = blockDim.x, SO = BW - TRAP_S;            /* buffer width, owned slots */
-	double *s_L = sbase + N, *s_pfx = s_L + 2 * BW;
-	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_pfx + 2 * BW);
+	double *s_L = sbase + N, *s_pfx = s_L + 2 * BW, *s_work = s_pfx + 2 * BW;   /* work list: 4 candidates per thread at most */
+	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_work + 4 * BW);
 	const int K = s0.K, b = blockIdx.x, nb = gridDim.x, tid = threadIdx.x;
 	const int lo = b * SO - TRAP_S, j = lo + tid;            /* threads [0, 256) recompute the left neighbour's slots */
 	const bool owned = tid >= TRAP_S, in_range = j >= 0 && j <= K;
@@ -1266,20 +1284,100 @@ __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpStat
 			cur.K = nxt.K = K;
 			cur.exists = s_ex + rb - lo; cur.L = s_L + rb - lo; cur.pfx = s_pfx + rb - lo;
 			nxt.exists = s_ex + wb - lo; nxt.L = s_L + wb - lo; nxt.pfx = s_pfx + wb - lo;
-			if (in_range && j >= lo + (t + 1) * halo) {
-				const CnbDpNode nd = s_nd[t];
-				long long o_fid[4];
-				int o_cx[4];
-				double o_sc[4];
+			const bool act = in_range && j >= lo + (t + 1) * halo;
+			if (!compact) {
+				if (act) {
+					const CnbDpNode nd = s_nd[t];
+					long long o_fid[4];
+					int o_cx[4];
+					double o_sc[4];
 #pragma unroll
-				for (int q = 0; q < 4; q++) { o_fid[q] = s_fid[t][q]; o_cx[q] = s_cx[t][q]; o_sc[q] = s_sc[t][q]; }
-				const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
-				if (FT.D)
-					dp_slot<false, true>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
-							bp_opt, bp_src, owned, FT);
-				else
+					for (int q = 0; q < 4; q++) { o_fid[q] = s_fid[t][q]; o_cx[q] = s_cx[t][q]; o_sc[q] = s_sc[t][q]; }
+					const int nopt = (int)min((long long)5, (long long)(nd.opt_end - nd.opt_begin));
 					dp_slot<false>(cur, nxt, j, c, N, K, nd, nopt, o_fid, o_cx, o_sc, sbase, sbase[c], opt_score, opt_cx, opt_fid,
 							bp_opt, bp_src, owned);
+				}
+				__syncthreads();
+				continue;
+			}
+			/* Only one slot in ten holds a network (C5: 2,489 of 24,001), so a warp's 32 slots have a handful of viable
+			 * candidates -- and every one of them needs the reference's re-summation, a chain of N - c dependent fp64
+			 * additions, which a warp pays for in full however few of its lanes take part (the DP was bound by the fp64 pipe:
+			 * 512 threads x up to 4 chains per node and CTA).  So the candidates of the whole CTA are first compacted into a work
+			 * list, the chains run on as few full warps as that takes, and each slot then decides on the re-summed values. */
+			if (tid == 0) s_nwork = 0;
+			__syncthreads();
+			const CnbDpNode nd = s_nd[t];
+			const double bv = sbase[c];
+			int nq = 0, ks[4], qs[4], w0 = 0;
+			double tq[4], fs[4];
+			if (act) {
+				const int nopt = (int)min((long long)4, (long long)(nd.opt_end - nd.opt_begin));
+				double xs[4];
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (q >= nopt || s_fid[t][q] < 0) continue;           /* no winner for that d (:637-640) */
+					const int k = j + nd.base_cx - s_cx[t][q];
+					if (k < 0 || k > K || !cur.exists[k]) continue;
+					const double f = s_sc[t][q];
+					ks[nq] = k;
+					qs[nq] = q;
+					fs[nq] = f;
+					tq[nq] = __dadd_rn(__dsub_rn(cur.L[k], bv), f);          /* :665-666 */
+					xs[nq] = __dadd_rn(cur.pfx[k], f);
+					nq++;
+				}
+				if (nq) {
+					w0 = atomicAdd(&s_nwork, nq);
+#pragma unroll
+					for (int q = 0; q < 4; q++)
+						if (q < nq) s_work[w0 + q] = xs[q];
+				}
+			}
+			__syncthreads();
+			for (int w = tid; w < s_nwork; w += BW) {
+				double acc = s_work[w];
+				if (FT.P) {
+					s_work[w] = dp_resum_blocks(acc, c, N, sbase, FT);
+					continue;
+				}
+				int i = c + 1;
+				for (; i + 8 <= N; i += 8) {                           /* terms fetched 8 ahead of the dependent additions */
+					double bb[8];
+#pragma unroll
+					for (int u = 0; u < 8; u++) bb[u] = sbase[i + u];
+#pragma unroll
+					for (int u = 0; u < 8; u++) acc = __dadd_rn(acc, bb[u]);
+				}
+				for (; i < N; i++) acc = __dadd_rn(acc, sbase[i]);
+				s_work[w] = acc;
+			}
+			__syncthreads();
+			if (act) {
+				bool has = false;
+				double R = CNB_NEG_INF, bf = 0.0;
+				long long bo = -1;
+				int bs = -1;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					if (q >= nq) continue;
+					if (!has && tq[q] > CNB_NEG_INF) { has = true; R = CNB_NEG_INF; }   /* empty net: loglik() = -FLT_MAX */
+					if (has && R < tq[q]) { bo = nd.opt_begin + qs[q]; bs = ks[q]; R = s_work[w0 + q]; bf = fs[q]; }   /* :670-671 strict */
+				}
+				const bool cur_ex = cur.exists[j] != 0;
+				const bool take = cur_ex ? (has && bo >= 0 && cur.L[j] < R) : (has && bo >= 0);   /* :847-859 */
+				const size_t bpi = (size_t)c * (K + 1) + j;
+				if (take) {
+					nxt.exists[j] = 1;
+					nxt.L[j] = R;
+					nxt.pfx[j] = __dadd_rn(cur.pfx[bs], bf);
+					if (owned) { bp_opt[bpi] = bo; bp_src[bpi] = bs; }
+				} else {
+					nxt.exists[j] = cur_ex;
+					nxt.L[j] = cur.L[j];
+					nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
+					if (owned) { bp_opt[bpi] = -1; bp_src[bpi] = j; }
+				}
 			}
 			__syncthreads();
 		}
@@ -1492,7 +1590,7 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 }
 
 int cnbk_select_chunk(void) { return SEL_CHUNK; }
-int cnbk_dp_fast_binades(void) { return DPF_E; }
+size_t cnbk_dp_table_bytes(int N) { return (size_t)DPF_E * N * sizeof(double) + (size_t)DPF_E * ((N + DPF_B - 1) / DPF_B) + 64; }
 
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
 		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
@@ -1592,19 +1690,23 @@ int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out,
-		double *fast_D, unsigned char *fast_bad) {
+		int compact, double *fast_P, unsigned char *fast_bad) {
 	int dev = 0, coop = 0, sms = 0, per_sm = 0;
 	CK(cudaGetDevice(&dev));
 	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
 	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 	if (halo < 1 || N < 3) return CNB_ERR_PROC;
+	/* the recomputed margin must not reach past the left neighbour's own slots: the neighbour protocol waits for one CTA on
+	 * either side (wider margins measured no faster anyway: the per-node latency dominates, not the exchanges) */
+	int TRAP_S = 256;
 	int T = std::min(TRAP_TMAX, TRAP_S / halo);
 	if (T < 2) return CNB_ERR_PROC;
 	/* 256 owned slots per CTA: with 768 (fewer CTAs, a shorter pipeline fill) the DP of C5 took 4.8 instead of 2.3 ms --
 	 * the re-summation chains of 1024 slots per SM cost more than the fill saves */
-	const int threads = 512, owned = threads - TRAP_S;
-	const size_t smem = (size_t)N * sizeof(double) + (size_t)2 * threads * (2 * sizeof(double) + 1);
-	if (smem > 48 * 1024) return CNB_ERR_PROC;
+	const int owned = 256, threads = owned + TRAP_S;
+	const size_t smem = (size_t)N * sizeof(double) + (size_t)2 * threads * (2 * sizeof(double) + 1) + (size_t)4 * threads * sizeof(double);
+	if (smem > 160 * 1024) return CNB_ERR_PROC;
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_dp_trap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_trap, threads, smem));
 	const int blocks = (s0.K + 1 + owned - 1) / owned;
 	if (!coop || per_sm < 1 || blocks > sms * per_sm || blocks > flags_cap) return CNB_ERR_PROC;
@@ -1614,17 +1716,20 @@ int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 	CK(cudaMemsetAsync(s1.exists, 0, (size_t)s0.K + 1, st));
 	CK(cudaMemsetAsync(s2.exists, 0, (size_t)s0.K + 1, st));
 	DpFast FT;
-	FT.D = fast_D;
-	FT.bad = fast_bad;
-	if (fast_D && fast_bad) {
-		/* the shortcut tables of this search's base network (one addition instead of N - c per re-summation) */
-		k_dp_prepare<<<1, 32, 0, st>>>(base_v, N, fast_D, fast_bad);
+	FT.P = nullptr;
+	FT.bad = nullptr;
+	FT.nblk = (N + DPF_B - 1) / DPF_B;
+	static int use_tables = -1;
+	if (use_tables < 0) { const char *e = getenv("CNB_DP_TABLES"); use_tables = e ? atoi(e) : 1; }
+	if (compact && use_tables && fast_P && fast_bad) {
+		k_dp_prepare<<<1, 32, 0, st>>>(base_v, N, fast_P, fast_bad);
 		CK(cudaGetLastError());
-	} else
-		FT.D = nullptr;
+		FT.P = fast_P;
+		FT.bad = fast_bad;
+	}
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
 		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags,
-		(void *)&T, (void *)&halo, (void *)&FT};
+		(void *)&T, (void *)&halo, (void *)&compact, (void *)&TRAP_S, (void *)&FT};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_trap, dim3(blocks), dim3(threads), args, smem, st));
 	*steps_out = (N - 1 + T - 1) / T;
 	return CNB_OK;

@@ -9,6 +9,13 @@
  * (cnb_log_data.h, extracted by tools/extract_libm_log.py).  Every operation below is a single IEEE-754 fp64
  * add/mul/fma, so CUDA and x86 agree bit for bit.  tests/test_abi.py::test_host_log_is_libm_log and tests/test_gpu_parity.py::test_device_log_is_glibc_log check it against libm.
  *
+ * Origin and licence: the ALGORITHM is that of glibc's sysdeps/ieee754/dbl-64/e_log.c, which is ARM's optimized-routines
+ * log (Szabolcs Nagy; optimized-routines is MIT / Apache-2.0 WITH LLVM-exception, glibc ships it under the LGPL-2.1+); this
+ * file is an independent restatement of that published algorithm, not a copy of either source file, and the 128-entry table
+ * and the polynomial coefficients in cnb_log_data.h are numeric constants read out of this image's libm.so.6 by
+ * tools/extract_libm_log.py.  A redistributor who treats the table as LGPL-covered data can regenerate cnb_log_data.h from
+ * the libm of the target system with that script (it is the target's libm the results must match anyway).
+ *
  * Domain: finite x > 0 (normal or subnormal).  The hot path only ever passes n/N in (0, 1] and positive priors.
  */
 #ifndef CNB_LOG_H

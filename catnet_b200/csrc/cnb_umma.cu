@@ -11,17 +11,23 @@
  * Every product is exactly 1 (mxf4) or 128 (i8), so the TMEM accumulators hold exact counts (M < 2^24).
  *
  * One CTA per SM (all 512 TMEM columns), warp-specialised:
- *   warps 0-7   pair rows: thread = one A row (2 blocks x 128); A goes to TENSOR MEMORY with tcgen05.st (2-slot ring)
- *   warps 8-13  child rows: thread = one B row (176); B goes to shared memory, SWIZZLE_128B K-major (4-stage ring)
+ *   warps 0-7   pair rows: thread = one A row (2 blocks x 128); A goes to TENSOR MEMORY with tcgen05.st (per block a ring
+ *               of 3 half-stage slots, UM_ASTAGES)
+ *   warps 8-13  column rows: thread = one B row (192); B goes to shared memory, SWIZZLE_128B K-major (3-stage ring,
+ *               UM_BSTAGES)
  *   warps 14-15 one elected lane each issues the tcgen05.mma of one pair block: A from TMEM, B from shared memory
- * handed over with mbarriers (generators -> full -> MMA -> tcgen05.commit -> empty).  A tile is 2 blocks of 14
- * parent pairs (2 x 126 of 128 rows, two accumulators) x up to 58 children (176 columns): the child rows of a stage
- * are generated once and consumed by both pair blocks, and the pair rows never touch shared memory -- the shared
- * memory pipe (generator stores + tensor-core operand reads) was the measured limiter of the all-shared-memory
- * version (profiles/r01_umma_v3_ss_summary.txt).
+ * handed over with mbarriers (generators -> full -> MMA -> tcgen05.commit -> empty).  Two tile geometries:
+ *   inclusion-exclusion tiles (complete data): 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128 rows, two
+ *               accumulators) x up to 64 column nodes x 3 columns (192): only the 27 free cells of a table are
+ *               contracted, the rest follows from the pair tables
+ *   full-table tiles (missing values, perturbation masks): 2 blocks of 8 pairs x 16 rows x up to 48 column nodes x 4
+ *               columns (192): all 64 cells, the child's keep mask in its rows, a missing value sets no bit
+ * The column rows of a stage are generated once and consumed by both pair blocks, and the pair rows never touch shared
+ * memory -- the shared memory pipe (generator stores + tensor-core operand reads) was the measured limiter of the
+ * all-shared-memory version (profiles/r01_umma_v3_ss_summary.txt).
  *
- * Replaces, for unrestricted two-parent candidate sets without missing values, the counting loop of
- * CATNET::setNodeSampleProb (/root/reference/src/catnet_class.h:842-857); the log-lik epilogue
+ * Replaces, for two-parent candidate sets (all of them, or a pooled / fixed-parent subset looked up by slot), the
+ * counting loop of CATNET::setNodeSampleProb (/root/reference/src/catnet_class.h:842-857); the log-lik epilogue
  * (problist.h:224-250) runs in k_umma_epilogue over the integer tables, in the reference's operation order.
  */
 #include <stdio.h>

@@ -288,11 +288,11 @@ typedef struct cnb_timing {
 	int32_t kernel_launches;
 	int32_t fast_path;              /* 1 = bit-plane kernels, 0 = generic histogram kernel */
 	int64_t h2d_bytes, d2h_bytes;   /* host<->device traffic since the last cnb_ctx_set_samples* call */
-	int64_t tensor_tiles;           /* tcgen05 tiles (2 x 128 rows x 240 columns) run by this rank (0 = tensor-core
+	int64_t tensor_tiles;           /* tcgen05 tiles (2 x 128 rows x up to 192 columns) run by this rank (0 = tensor-core
 	                                   path not used) */
 	float tensor_ms;                /* device time of the tcgen05 table kernel alone (CUDA events) */
 	int32_t tensor_kind;            /* operand type of that kernel: 4 = E2M1 (kind::mxf4), 8 = u8 (kind::i8), 0 = none */
-	int64_t tensor_macs;            /* multiply-accumulates it executed: tiles * 256 * 240 * padded samples */
+	int64_t tensor_macs;            /* multiply-accumulates it executed: sum over tiles of 256 rows * its columns * padded samples */
 	int64_t tensor3_tiles;          /* tcgen05 tiles of the three-parent group (0 = that group ran on the bit-plane kernels) */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
@@ -316,7 +316,7 @@ int cnb_ctx_search_scores(cnb_ctx *ctx, const double *scores_dev, int32_t nfam, 
  * the POPC kernel (set before the samples); 512 no inclusion-exclusion for three parents; 1024 three parents never on
  * the tensor cores; 2048 wavefront DP with one node per exchange; 4096 generic tensor-core epilogue also for
  * 4-category data; 8192 full-table tensor tiles (the form that takes missing values and perturbation masks) also on
- * complete data; 16384 trapezoid DP with the explicit re-summation chains (no one-addition shortcut).  Every combination
+ * complete data; 16384 trapezoid DP in which every slot re-sums its own candidates (no CTA-wide work list).  Every combination
  * gives the same networks. */
 int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 /* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */

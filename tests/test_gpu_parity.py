@@ -587,7 +587,7 @@ def test_dp_trapezoid_equals_wavefront(abi, n, m, cats, P):
         b = ctx.search_order(want_probs=False, **kw)
         ctx.force_generic(32)
         d = ctx.search_order(want_probs=False, **kw)
-        ctx.force_generic(16384)                  # trapezoid with the explicit re-summation chains (no one-addition shortcut)
+        ctx.force_generic(16384)                  # trapezoid without the CTA-wide work list of re-summation chains
         e = ctx.search_order(want_probs=False, **kw)
     assert compare_search(a, b, check_probs=False) == len(b) and compare_search(a, d, check_probs=False) == len(d)
     assert compare_search(a, e, check_probs=False) == len(e)
@@ -595,10 +595,9 @@ def test_dp_trapezoid_equals_wavefront(abi, n, m, cats, P):
 
 @pytest.mark.parametrize("n,m,cats,P,grid", [(150, 64, 2, 2, True), (120, 4096, 3, 2, True), (200, 333, 4, 2, False), (90, 1024, 2, 3, True),
                                              (257, 50, 3, 2, False)])
-def test_dp_resummation_shortcut(abi, n, m, cats, P, grid):
-    """the DP re-sums a network's log-likelihood in one addition (x + D[binade][node], exact) instead of N - c: same
-    networks and bit-identical log-likelihoods as the explicit chains, also on data whose node terms sit on coarse grids
-    (sample counts that are powers of two: ties in the rounding, where the shortcut must step aside)"""
+def test_dp_work_list(abi, n, m, cats, P, grid):
+    """the trapezoid DP compacts the viable candidates of a CTA into a work list before re-summing them: same networks and
+    bit-identical log-likelihoods as the per-slot chains and as the grid-barrier kernel"""
     s, c = random_problem(11 * n + m, n, m, cats, structured=not grid)
     kw = dict(max_parent_set=P, max_complexity=n * (cats ** P) * (cats - 1))
     with abi.Context(0) as ctx:
