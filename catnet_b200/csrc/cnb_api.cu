@@ -1092,14 +1092,11 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	} else if (!c->dp_per_node && !c->dp_no_wave) {
 		/* few options per node: the trapezoid wavefront (T nodes per neighbour exchange), else one node per exchange */
 		int steps = 0;
-		if (!c->dp_no_trap) {
-			RC(c->b_dp_fast.ensure(cnbk_dp_table_bytes(N)));
-			double *fast_P = (double *)c->b_dp_fast.ptr;
+		if (!c->dp_no_trap)
 			fused = cnbk_dp_trap(st, S[0], S[1], S[2], N, pl.base_complexity, halo, (const CnbDpNode *)c->b_dp_nodes.ptr, base_v,
 					(const double *)c->b_opt_score.ptr, (const int *)c->b_opt_cx.ptr, (const long long *)c->b_opt_fid.ptr,
 					(long long *)c->b_bp_opt.ptr, (int *)c->b_bp_src.ptr, (unsigned *)c->b_dp_flags.ptr, flag_cap, &steps,
-					c->dp_chains ? 0 : 1, fast_P, (unsigned char *)(fast_P + (size_t)20 * N));
-		}
+					c->dp_chains ? 0 : 1);
 		if (fused == CNB_OK) {
 			cur = steps % 3;                  /* macro-step m reads S[(m - 1) % 3] and writes S[m % 3] */
 			c->timing.kernel_launches += 1;

@@ -71,7 +71,7 @@ struct cnb_ctx {
 	CnbPlan plan;
 	cnb_timing timing = {};
 	PinBuf pin_sel, pin_stage;         /* pin_stage: host-compacted copy of a large sample matrix on its way to the device */
-	DevBuf b_dp_fast, b_pairs_ord, b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
+	DevBuf b_pairs_ord, b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
 	/* plan */
@@ -81,7 +81,7 @@ struct cnb_ctx {
 	/* selection + DP */
 	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes, b_dp_flags;
 	std::vector<DevBuf *> all_bufs() {
-		return {&b_dp_fast, &b_pairs_ord, &b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
+		return {&b_pairs_ord, &b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,

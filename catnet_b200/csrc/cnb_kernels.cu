@@ -19,7 +19,7 @@
  *      k_dp_wave / k_dp_all / k_dp_mixed / k_dp_init + k_dp_node, k_dp_collect_list
  *                                      replaces :653-677, :800-827, :847-865: one cooperative launch for all nodes --
  *                                      trapezoid wavefront (several nodes per neighbour exchange, candidates of a CTA
- *                                      re-summed from a dense work list in blocks of 16 terms), one-node wavefront,
+ *                                      re-summed from a dense work list), one-node wavefront,
  *                                      grid barrier per node, a warp per slot for mixed-category nodes -- or a launch per node
  *  The two-parent tables on the tensor cores (tcgen05) are in cnb_umma.cu.
  */
@@ -749,73 +749,6 @@ __device__ __forceinline__ double dev_resum(double pfx, double f, int c, int N, 
 	return acc;
 }
 
-/* Re-summation in blocks of 16 terms.  Every term behind node c is a node's base log-likelihood (<= 0) and x = pfx + f < 0,
- * so the running sum only grows in magnitude.  While it stays inside one binade [2^e, 2^(e+1)) it is a multiple of
- * u = 2^(e-52), and each IEEE addition acc + b rounds the exact sum to the nearest multiple of u, which is acc + rn_u(b)
- * unless b sits exactly half-way between two multiples (a tie: the rounding then depends on the parity of acc).  So a block
- * of terms without a tie is added EXACTLY by one addition of P = sum rn_u(b_i) (a sum of multiples of u, exact) whenever
- * acc and acc + P lie in the same binade (then, the sum being monotone, every intermediate did).  k_dp_prepare tabulates,
- * for 20 binades, the running sum of rn_u(b_i) inside every aligned block of 16 terms and the blocks that hold a tie, a
- * positive term or a sentinel; dp_resum_blocks walks the chain block by block and adds a block term by term when the
- * shortcut does not apply (a tie, a binade crossing, an x outside the table).  The chain of N - c dependent fp64 additions
- * is the critical path of the DP (C5: 250 on average per node, ~20 clock cycles each): about 16 block additions plus the
- * few blocks that cross a binade instead. */
-#define DPF_E 20                         /* binades 2^-4 .. 2^15 */
-#define DPF_ELO (1023 - 4)
-#define DPF_B 16
-struct DpFast {
-	const double *P;                     /* [DPF_E][N]: sum of rn_u(b_t) over t from the start of i's block to i */
-	const unsigned char *bad;            /* [DPF_E][ceil(N / 16)]: block without shortcut in this binade */
-	int nblk;
-};
-
-__global__ void k_dp_prepare(const double *__restrict__ base_v, int N, double *__restrict__ P, unsigned char *__restrict__ bad) {
-	const int e = threadIdx.x;
-	if (e >= DPF_E) return;
-	const double u = __longlong_as_double((long long)(DPF_ELO + e - 52) << 52), inv_u = __longlong_as_double((long long)(2046 - (DPF_ELO + e - 52)) << 52);
-	const int nblk = (N + DPF_B - 1) / DPF_B;
-	for (int k = 0; k < nblk; k++) {
-		double units = 0.0;              /* an integer: exact below 2^52 */
-		bool b = false;
-		for (int i = k * DPF_B; i < min(N, (k + 1) * DPF_B); i++) {
-			const double v = base_v[i];
-			if (!(v <= 0.0) || !(v > -1.0e300)) b = true;            /* positive, NaN or a "-infinity" sentinel */
-			else {
-				const double t = __dmul_rn(v, inv_u);                /* exact: a power of two */
-				if (fabs(__dsub_rn(t, trunc(t))) == 0.5) b = true;   /* half-way: the rounding depends on the running sum */
-				units = __dadd_rn(units, rint(t));
-				if (fabs(units) >= 4503599627370496.0) b = true;
-			}
-			P[(size_t)e * N + i] = __dmul_rn(units, u);
-		}
-		bad[(size_t)e * nblk + k] = b;
-	}
-}
-
-/* x + base_v[c+1] + ... + base_v[N-1], added left to right (the chain dev_resum walks) */
-__device__ __forceinline__ double dp_resum_blocks(double x, int c, int N, const double *__restrict__ sbase, const DpFast &F) {
-	double acc = x;
-	int i = c + 1;
-	while (i < N) {
-		const int k = i / DPF_B, end = min(N, (k + 1) * DPF_B);
-		const long long ab = __double_as_longlong(acc);
-		const int eb = (int)((ab >> 52) & 0x7ff), idx = eb - DPF_ELO;
-		if (ab < 0 && idx >= 0 && idx < DPF_E && !__ldg(F.bad + (size_t)idx * F.nblk + k)) {
-			const double *Pp = F.P + (size_t)idx * N;
-			double d = __ldg(Pp + end - 1);
-			if (i > k * DPF_B) d = __dsub_rn(d, __ldg(Pp + i - 1));      /* multiples of u below 2^52 u: exact */
-			const double r = __dadd_rn(acc, d);
-			if ((int)((__double_as_longlong(r) >> 52) & 0x7ff) == eb) {
-				acc = r;
-				i = end;
-				continue;
-			}
-		}
-		for (; i < end; i++) acc = __dadd_rn(acc, sbase[i]);
-	}
-	return acc;
-}
-
 __global__ void k_dp_init(DpState S, int base_complexity, const double *__restrict__ base_v, int N) {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j > S.K) return;
@@ -1211,7 +1144,7 @@ __global__ void __launch_bounds__(256) k_dp_wave(DpState s0, DpState s1, DpState
 __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpState s2, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
-		int *__restrict__ bp_src, unsigned *flags, int T, int halo, int compact, int TRAP_S, DpFast FT) {
+		int *__restrict__ bp_src, unsigned *flags, int T, int halo, int compact, int TRAP_S) {
 	extern __shared__ double sbase[];                    /* [N], then the two state buffers, then the work list */
 	__shared__ int s_nwork;
 	__shared__ CnbDpNode s_nd[TRAP_TMAX];
@@ -1337,10 +1270,6 @@ __global__ void __launch_bounds__(1024) k_dp_trap(DpState s0, DpState s1, DpStat
 			__syncthreads();
 			for (int w = tid; w < s_nwork; w += BW) {
 				double acc = s_work[w];
-				if (FT.P) {
-					s_work[w] = dp_resum_blocks(acc, c, N, sbase, FT);
-					continue;
-				}
 				int i = c + 1;
 				for (; i + 8 <= N; i += 8) {                           /* terms fetched 8 ahead of the dependent additions */
 					double bb[8];
@@ -1590,7 +1519,6 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 }
 
 int cnbk_select_chunk(void) { return SEL_CHUNK; }
-size_t cnbk_dp_table_bytes(int N) { return (size_t)DPF_E * N * sizeof(double) + (size_t)DPF_E * ((N + DPF_B - 1) / DPF_B) + 64; }
 
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
 		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
@@ -1690,7 +1618,7 @@ int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out,
-		int compact, double *fast_P, unsigned char *fast_bad) {
+		int compact) {
 	int dev = 0, coop = 0, sms = 0, per_sm = 0;
 	CK(cudaGetDevice(&dev));
 	CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -1715,21 +1643,9 @@ int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const Dp
 	CK(cudaMemsetAsync(s0.exists, 0, (size_t)s0.K + 1, st));
 	CK(cudaMemsetAsync(s1.exists, 0, (size_t)s0.K + 1, st));
 	CK(cudaMemsetAsync(s2.exists, 0, (size_t)s0.K + 1, st));
-	DpFast FT;
-	FT.P = nullptr;
-	FT.bad = nullptr;
-	FT.nblk = (N + DPF_B - 1) / DPF_B;
-	static int use_tables = -1;
-	if (use_tables < 0) { const char *e = getenv("CNB_DP_TABLES"); use_tables = e ? atoi(e) : 1; }
-	if (compact && use_tables && fast_P && fast_bad) {
-		k_dp_prepare<<<1, 32, 0, st>>>(base_v, N, fast_P, fast_bad);
-		CK(cudaGetLastError());
-		FT.P = fast_P;
-		FT.bad = fast_bad;
-	}
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&s2, (void *)&N, (void *)&base_complexity, (void *)&nodes,
 		(void *)&base_v, (void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&flags,
-		(void *)&T, (void *)&halo, (void *)&compact, (void *)&TRAP_S, (void *)&FT};
+		(void *)&T, (void *)&halo, (void *)&compact, (void *)&TRAP_S};
 	CK(cudaLaunchCooperativeKernel((const void *)k_dp_trap, dim3(blocks), dim3(threads), args, smem, st));
 	*steps_out = (N - 1 + T - 1) / T;
 	return CNB_OK;

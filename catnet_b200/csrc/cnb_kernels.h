@@ -121,10 +121,7 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 int cnbk_dp_trap(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap, int *steps_out,
-		int compact = 1, double *fast_P = nullptr, unsigned char *fast_bad = nullptr);
-/* compact: the re-summation chains of a CTA's viable candidates run from a dense work list; fast_P / fast_bad: scratch of
- * cnbk_dp_table_bytes(N) in all (P first) for the block tables that shorten those chains (NULL = term by term) */
-size_t cnbk_dp_table_bytes(int N);
+		int compact = 1);   /* compact: the re-summation chains of a CTA's viable candidates run from a dense work list */
 int cnbk_dp_wave(cudaStream_t st, const DpState &s0, const DpState &s1, const DpState &s2, int N, int base_complexity,
 		int halo, const CnbDpNode *nodes, const double *base_v, const double *opt_score, const int *opt_cx,
 		const long long *opt_fid, long long *bp_opt, int *bp_src, unsigned *flags, int flags_cap);
