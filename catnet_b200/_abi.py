@@ -82,7 +82,7 @@ SYMBOLS = [
     "cnb_mctx_create", "cnb_mctx_destroy", "cnb_mctx_num_devices", "cnb_mctx_ctx", "cnb_mctx_set_samples",
     "cnb_mctx_search_order", "cnb_mctx_search_light", "cnb_mctx_collect", "cnb_mctx_search_sa", "cnb_mctx_search_hist",
     "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
-    "cnb_ctx_upload_rows8", "cnb_tile_selftest_full",
+    "cnb_ctx_upload_rows8", "cnb_tile_selftest_full", "cnb_last_call_timing",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def lib():
         "cnb_ctx_collect": (i32, [vp, P(vp)]),
         "cnb_ctx_set_stream": (i32, [vp, vp]),
         "cnb_ctx_timing": (i32, [vp, P(Timing)]),
+        "cnb_last_call_timing": (i32, [P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_tile_selftest": (C.c_int64, [i32]),
         "cnb_tile_selftest_full": (C.c_int64, [i32]),
@@ -702,6 +703,12 @@ def read_sa_result(h, n, want_probs=False):
     L.cnb_result_sa_trace(h, ptr(trace), ptr(acc), nt)
     return {"nets": nets, "order": order, "niter": niter.value, "naccept": nacc.value, "trace": trace[:nt],
             "trace_accept": acc[:nt]}
+
+
+def last_call_timing():
+    t = Timing()
+    check(lib().cnb_last_call_timing(C.byref(t)))
+    return t.as_dict()
 
 
 def search_order(samples, want_probs=True, **kw):

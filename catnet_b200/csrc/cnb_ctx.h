@@ -31,6 +31,10 @@ struct PinBuf {
 struct cnb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
+	cudaStream_t copy_stream = nullptr;   /* host -> device copies of the streamed one-shot search (created on first use) */
+	std::vector<cudaEvent_t> ev_slices;   /* "slice k is on the device" */
+	bool streaming = false;               /* the streamed one-shot search is driving this context: cnb_ctx_plan leaves the data
+	                                         kernels to it, cnb_ctx_score_shard finds the two-parent tables contracted already */
 	cudaEvent_t ev[CNB_NEV];
 	int N = 0, M = 0, W = 0, Mpad = 0, max_cats = 0;
 	bool has_pert = false, have_samples = false, planned = false, dp_done = false, force_generic = false, last_fast = false, pairs_valid = false, no_ie = false, clean = false;
@@ -71,7 +75,7 @@ struct cnb_ctx {
 	CnbPlan plan;
 	cnb_timing timing = {};
 	PinBuf pin_sel, pin_stage;         /* pin_stage: host-compacted copy of a large sample matrix on its way to the device */
-	DevBuf b_pairs_ord, b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
+	DevBuf b_counts_p, b_pairs_ord, b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
 	/* plan */
@@ -81,7 +85,7 @@ struct cnb_ctx {
 	/* selection + DP */
 	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes, b_dp_flags;
 	std::vector<DevBuf *> all_bufs() {
-		return {&b_pairs_ord, &b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
+		return {&b_counts_p, &b_pairs_ord, &b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
@@ -108,7 +112,8 @@ int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t>
 /* upload paths shared with the multi-device driver (cnb_multi.cu) */
 int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes, const int32_t *pert_dev,
 		const int32_t *num_cats);
-int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads, bool *overflow);
+int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads, bool *overflow,
+		cudaStream_t copy_stream = nullptr, size_t pin_origin = 0, size_t pin_values = 0);
 /* cnSearchHist, one order (cnb_hist.cpp) */
 struct CnbHistEval {
 	bool found = false;

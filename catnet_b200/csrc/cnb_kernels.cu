@@ -54,12 +54,12 @@ __global__ void k_minmax(const T *__restrict__ samples, int N, int M, int *__res
 template <class T>
 __global__ void k_pack(const T *__restrict__ samples, const int32_t *__restrict__ pert, int N, int M, int W,
 		const int *__restrict__ vmin, const int *__restrict__ cats, uint8_t *__restrict__ codes,
-		uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int *__restrict__ bad) {
+		uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int *__restrict__ bad, int w_begin) {
 	/* bad[0]: a value outside the node's categories; bad[2]: at least one missing value in the matrix */
 	/* one-dimensional grid (no 65,535 limit on the sample words), node chunks of a word adjacent */
 	const int nchunk = (N + blockDim.x - 1) / blockDim.x;
 	int v = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x;
-	int w = blockIdx.x / nchunk;
+	int w = w_begin + blockIdx.x / nchunk;                 /* the launch covers the sample words from w_begin on */
 	if (v >= N) return;
 	const int base = vmin[v], C = cats[v];
 	bool any_na = false;
@@ -96,10 +96,10 @@ __global__ void k_pack(const T *__restrict__ samples, const int32_t *__restrict_
 
 /* label space -> order space for one search (what the reference does by re-copying the whole int matrix) */
 __global__ void k_permute(const uint4 *__restrict__ planes_lbl, const uint32_t *__restrict__ keep_lbl,
-		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep) {
+		const int *__restrict__ order, int N, int W, uint4 *__restrict__ planes, uint32_t *__restrict__ keep, int w_begin) {
 	const int nchunk = (N + blockDim.x - 1) / blockDim.x;
 	int p = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x;
-	int w = blockIdx.x / nchunk;
+	int w = w_begin + blockIdx.x / nchunk;
 	if (p >= N) return;
 	int l = order[p];
 	uint4 v = planes_lbl[(size_t)w * N + l];
@@ -1370,18 +1370,22 @@ int cnbk_minmax(cudaStream_t st, const void *samples, int elem_bytes, int N, int
 }
 
 int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_t *pert, int N, int M, int W, const int *vmin,
-		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad) {
-	dim3 grid((unsigned)((long long)W * ((N + 127) / 128)));
-	if (elem_bytes == 1) k_pack<uint8_t><<<grid, 128, 0, st>>>((const uint8_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
-	else k_pack<int32_t><<<grid, 128, 0, st>>>((const int32_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad);
+		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad, int w_begin, int w_end) {
+	if (w_end < 0) w_end = W;
+	if (w_end <= w_begin) return CNB_OK;
+	dim3 grid((unsigned)((long long)(w_end - w_begin) * ((N + 127) / 128)));
+	if (elem_bytes == 1) k_pack<uint8_t><<<grid, 128, 0, st>>>((const uint8_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad, w_begin);
+	else k_pack<int32_t><<<grid, 128, 0, st>>>((const int32_t *)samples, pert, N, M, W, vmin, cats, codes, planes, keep, bad, w_begin);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
 
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
-		uint4 *planes, uint32_t *keep) {
-	dim3 grid((unsigned)((long long)W * ((N + 127) / 128)));
-	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep);
+		uint4 *planes, uint32_t *keep, int w_begin, int w_end) {
+	if (w_end < 0) w_end = W;
+	if (w_end <= w_begin) return CNB_OK;
+	dim3 grid((unsigned)((long long)(w_end - w_begin) * ((N + 127) / 128)));
+	k_permute<<<grid, 128, 0, st>>>(planes_lbl, keep_lbl, order, N, W, planes, keep, w_begin);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

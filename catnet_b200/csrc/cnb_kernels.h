@@ -27,10 +27,11 @@ struct DpState {
 
 /* samples: [M][N] of int32 (elem_bytes 4) or of uint8 with 0 = missing (elem_bytes 1, the host-compacted copy) */
 int cnbk_minmax(cudaStream_t st, const void *samples, int elem_bytes, int N, int M, int *vmin, int *vmax);
+/* [w_begin, w_end): the 32-sample words this launch covers (w_end < 0 = all W) -- a slice of the samples on its way in */
 int cnbk_pack(cudaStream_t st, const void *samples, int elem_bytes, const int32_t *pert, int N, int M, int W, const int *vmin,
-		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad);
+		const int *cats, uint8_t *codes, uint4 *planes, uint32_t *keep, int *bad, int w_begin = 0, int w_end = -1);
 int cnbk_permute(cudaStream_t st, const uint4 *planes_lbl, const uint32_t *keep_lbl, const int *order, int N, int W,
-		uint4 *planes, uint32_t *keep);
+		uint4 *planes, uint32_t *keep, int w_begin = 0, int w_end = -1);
 bool cnbk_planes_supported(int d, int max_cats);
 int cnbk_score_planes(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long fid_begin,
 		long long fid_end, int slices, const ScoreOut &O);
@@ -47,12 +48,23 @@ int cnbk_score_planes_ie3(cudaStream_t st, const DevData &Dt, const DevFamilies 
 		long long e, const ScoreOut &O, const int *triple_tab);
 /* tensor-core scorer (cnb_umma.cu): operand bit rows, the tcgen05 table kernel (fp4 = 1: kind::mxf4, 0: kind::i8) */
 int cnbk_umma_row_quads(int W, int fp4, int *ngroups);
-int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b);
+/* [q_begin, q_end): the quads (4 sample words) this launch writes (q_end < 0 = all of cnbk_umma_row_quads) */
+int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b, int q_begin = 0,
+		int q_end = -1);
 /* operand rows of the full-table tiles: 4 rows per node, or 8 with keep masks (4 plain + 4 under the node's own mask) */
 int cnbk_umma_rows_full(cudaStream_t st, const uint4 *planes, const uint32_t *keep, int N, int W, uint4 *rows_a, uint4 *rows_b);
 /* local tiles [local_begin, local_end) of rank T.rank (global tile = rank + local * world) */
+/* [g_begin, g_end): the sample groups (3 stages x 256 samples with E2M1 operands) this launch contracts (g_end < 0 = all);
+ * accumulate: add to the counts already there (a later slice of the samples) instead of storing */
 int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
-		const CnbTiles &T, long long local_begin, long long local_end, int *counts);
+		const CnbTiles &T, long long local_begin, long long local_end, int *counts, int g_begin = 0, int g_end = -1,
+		int accumulate = 0);
+/* samples per group of the table kernel */
+int cnbk_umma_group_samples(int fp4);
+/* pair tables (label space) from P tiles that ran on ORDER-space operand rows: order[pos] = label */
+int cnbk_pairs_from_tiles_order(cudaStream_t st, const int *counts, const int *order, int N, int M, int *pair_tab);
+long long cnbk_pair_tile_run(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int *counts, int g_begin,
+		int g_end, int accumulate);
 long long cnbk_umma_column_macs(int W, int fp4);
 /* all two-way tables on the tensor cores (no missing values, M < 2^24); scratch sized by the caller */
 long long cnbk_pair_tiles(int N);

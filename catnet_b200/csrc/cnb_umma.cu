@@ -137,10 +137,10 @@ __device__ __forceinline__ uint32_t rows_b_word(uint32_t y, int fp4) {
 	return __byte_perm(__brev(y), 0, 0x0123);
 }
 
-__global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int nquads,
+__global__ void __launch_bounds__(128) k_umma_rows(const uint4 *__restrict__ planes, int N, int W, int q_begin,
 		uint4 *__restrict__ rows_a, uint4 *__restrict__ rows_b, int fp4, int stride_a) {
 	const int nchunk = (N + blockDim.x - 1) / blockDim.x;   /* one-dimensional grid: no 65,535 limit on the quads */
-	const int n = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x, qd = blockIdx.x / nchunk;
+	const int n = (blockIdx.x % nchunk) * blockDim.x + threadIdx.x, qd = q_begin + blockIdx.x / nchunk;
 	if (n >= N) return;
 	uint4 v[4];
 #pragma unroll
@@ -274,8 +274,9 @@ __device__ __forceinline__ void mma_issue_loop(uint32_t smem, uint32_t idesc, in
 
 template <bool FP4, bool FULL>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
-		int N, int ngroups_all, CnbTiles T, long long local_begin, int *__restrict__ counts, int whole, int split) {
+		int N, int g_begin, int g_end, CnbTiles T, long long local_begin, int *__restrict__ counts, int whole, int split, int accumulate) {
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
+	const int ngroups_all = g_end - g_begin;   /* the sample groups of this launch (all of them, or a slice of the samples) */
 	constexpr int CPC = FULL ? 4 : 3;       /* columns per column node */
 	constexpr int RPP = FULL ? 16 : 9;      /* rows per pair */
 	constexpr int BLKP = FULL ? UMF_BLK_PAIRS : UM_BLK_PAIRS;
@@ -287,8 +288,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 	const bool sliced = (int)blockIdx.x >= whole;
 	const int tile_local = sliced ? whole + ((int)blockIdx.x - whole) / split : (int)blockIdx.x;
 	const int slice = sliced ? ((int)blockIdx.x - whole) % split : 0;
-	const int g_first = sliced ? (int)((long long)slice * ngroups_all / split) : 0;
-	const int ngroups = (sliced ? (int)((long long)(slice + 1) * ngroups_all / split) : ngroups_all) - g_first;
+	const int g_first = g_begin + (sliced ? (int)((long long)slice * ngroups_all / split) : 0);
+	const int ngroups = g_begin + (sliced ? (int)((long long)(slice + 1) * ngroups_all / split) : ngroups_all) - g_first;
 	const size_t src_quads = (size_t)g_first * UM_BSTAGES * SRCQ;   /* quads before this CTA's first stage */
 	const int pf = T.pad;                   /* L1 prefetch distance in stages beyond the one being loaded */
 	const size_t pf_quads = (size_t)pf * SRCQ;
@@ -417,6 +418,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 					if (sliced) {
 #pragma unroll
 						for (int k = 0; k < CPC; k++) atomicAdd(dst + k, x[k]);
+					} else if (accumulate) {
+						/* a later slice of the samples: this CTA alone owns the tile in this launch */
+						const int4 o = *reinterpret_cast<const int4 *>(dst);
+						*reinterpret_cast<int4 *>(dst) = make_int4(o.x + x[0], o.y + x[1], o.z + x[2], o.w + x[3]);
 					} else *reinterpret_cast<int4 *>(dst) = make_int4(x[0], x[1], x[2], x[3]);
 				}
 			}
@@ -677,6 +682,43 @@ __global__ void __launch_bounds__(128) k_pairs_from_tiles(const int *__restrict_
 		for (int k = 0; k < 4; k++) out[i * 4 + k] = n[i][k];
 }
 
+/* the same from P tiles that ran on ORDER-space operand rows (the streamed one-shot search builds only those): pair slot /
+ * column = positions, the table goes to its label pair, oriented [lower label][higher label] */
+__global__ void __launch_bounds__(128) k_pairs_from_tiles_order(const int *__restrict__ counts, const int *__restrict__ order, int N, int M,
+		int *__restrict__ pair_tab) {
+	const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= (long long)N * (N - 1) / 2) return;
+	int u, v;
+	cnb_pair_of(q, u, v);                                   /* positions u < v */
+	const int nch = (N + UM_CHILD - 1) / UM_CHILD;
+	auto slot = [&](int x, int z) {
+		const long long tile = (long long)(x / UM_PAIRS) * nch + z / UM_CHILD;
+		return counts + ((size_t)tile * UM_SLOTS + (size_t)(x % UM_PAIRS) * UM_CHILD + z % UM_CHILD) * UM_SLOT_INTS;
+	};
+	const int *uv = slot(u, v), *uu = slot(u, u), *vv = slot(v, v);
+	int n[4][4], mu[4], mv[4], su = 0, sv = 0;
+	for (int i = 0; i < 3; i++) {
+		mu[i] = uu[(i * 3 + i) * 4 + i];
+		mv[i] = vv[(i * 3 + i) * 4 + i];
+		su += mu[i];
+		sv += mv[i];
+	}
+	mu[3] = M - su;
+	mv[3] = M - sv;
+	for (int i = 0; i < 3; i++) {
+		int s = 0;
+		for (int k = 0; k < 3; k++) { n[i][k] = uv[(i * 3 + i) * 4 + k]; s += n[i][k]; }
+		n[i][3] = mu[i] - s;
+	}
+	for (int k = 0; k < 4; k++) n[3][k] = mv[k] - (n[0][k] + n[1][k] + n[2][k]);
+	const int lu = order[u], lv = order[v];
+	const bool sw = lu > lv;
+	const int lo = sw ? lv : lu, hi = sw ? lu : lv;
+	int *out = pair_tab + ((long long)hi * (hi - 1) / 2 + lo) * 16;
+	for (int i = 0; i < 4; i++)
+		for (int k = 0; k < 4; k++) out[sw ? k * 4 + i : i * 4 + k] = n[i][k];
+}
+
 /* three-parent families of one column tile from its T tiles: one thread per family (a < b < c | x).  The f1 slots
  * (triple, i) hold the cells n(a = i, b = j, c = k, x = l) at (j * 3 + k) * 4 + l; the free ones (all indices < CM - 1) go
  * to shared memory, dev_ie3_finish completes the table from the three-way tables and sums the log-likelihood. */
@@ -731,10 +773,12 @@ int cnbk_umma_rows_full(cudaStream_t st, const uint4 *planes, const uint32_t *ke
 	return CNB_OK;
 }
 
-int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b) {
+int cnbk_umma_rows(cudaStream_t st, const uint4 *planes, int N, int W, int fp4, uint4 *rows_a, uint4 *rows_b, int q_begin, int q_end) {
 	const int nq = cnbk_umma_row_quads(W, fp4, nullptr);
-	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
-	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a, rows_b, fp4, 3 * N);
+	if (q_end < 0 || q_end > nq) q_end = nq;
+	if (q_end <= q_begin) return CNB_OK;
+	dim3 grid((unsigned)((long long)(q_end - q_begin) * ((N + 127) / 128)));
+	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, q_begin, rows_a, rows_b, fp4, 3 * N);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
@@ -769,7 +813,7 @@ int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvir
 	const int nq = cnbk_umma_row_quads(W, 1, nullptr);
 	if (nq > 65535) { cnb_set_error("three-parent tensor path: too many samples"); return CNB_ERR_PROC; }
 	dim3 grid((unsigned)((long long)nq * ((N + 127) / 128)));
-	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, nq, rows_a3, nullptr, 1, 3 * (N + nvirt));
+	k_umma_rows<<<grid, 128, 0, st>>>(planes, N, W, 0, rows_a3, nullptr, 1, 3 * (N + nvirt));
 	CK(cudaGetLastError());
 	dim3 gv((nvirt + 127) / 128, nq);
 	k_umma_rows_virtual<<<gv, 128, 0, st>>>(planes, N, W, nvirt, f1, rows_a3);
@@ -790,11 +834,16 @@ static int tail_split(long long tiles, int sms, int ngroups) {
 	return best;
 }
 
+int cnbk_umma_group_samples(int fp4) { return UM_BSTAGES * (fp4 ? 256 : 128); }
+
 int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int fp4,
-		const CnbTiles &T, long long tile_begin, long long tile_end, int *counts) {
+		const CnbTiles &T, long long tile_begin, long long tile_end, int *counts, int g_begin, int g_end, int accumulate) {
 	if (tile_end <= tile_begin) return CNB_OK;
-	int ng;
-	cnbk_umma_row_quads(W, fp4, &ng);
+	int ng_all;
+	cnbk_umma_row_quads(W, fp4, &ng_all);
+	if (g_end < 0 || g_end > ng_all) g_end = ng_all;
+	if (g_end <= g_begin) return CNB_OK;
+	const int ng = g_end - g_begin;
 	static int sms = 0;
 	if (!sms) {
 		int dev = 0;
@@ -812,18 +861,18 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 	const long long whole = split > 1 ? tiles - tiles % sms : tiles;
 	const long long grid = whole + (tiles - whole) * split;
 	const size_t tile_ints = T.full ? (size_t)UMF_SLOTS * UMF_SLOT_INTS : (size_t)UM_SLOTS * UM_SLOT_INTS;
-	if (split > 1)
+	if (split > 1 && !accumulate)
 		CK(cudaMemsetAsync(counts + (size_t)whole * tile_ints, 0, (size_t)(tiles - whole) * tile_ints * sizeof(int), st));
 	if (T.full) {
 		if (!fp4) { cnb_set_error("full-table tiles need E2M1 operands"); return CNB_ERR_PROC; }
 		CK(cudaFuncSetAttribute(k_umma_tables<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true, true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+		k_umma_tables<true, true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
 	} else if (fp4) {
 		CK(cudaFuncSetAttribute(k_umma_tables<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+		k_umma_tables<true, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
 	} else {
 		CK(cudaFuncSetAttribute(k_umma_tables<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<false, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, ng, Tp, tile_begin, counts, (int)whole, split);
+		k_umma_tables<false, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
 	}
 	CK(cudaGetLastError());
 	return CNB_OK;
@@ -907,6 +956,25 @@ int cnbk_pair_tables_umma_full(cudaStream_t st, const uint4 *planes_lbl, const u
 	if (rc != CNB_OK) return rc;
 	const long long np = (long long)N * N;
 	k_ordered_pairs_from_tiles<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, N, pair_ord);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* P tiles over one slice of the samples, on operand rows that already exist (order or label space) */
+long long cnbk_pair_tile_run(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, int N, int W, int *counts, int g_begin,
+		int g_end, int accumulate) {
+	CnbTiles T;
+	memset(&T, 0, sizeof(T));
+	CNB_TILES_DEFAULT_GEOMETRY(T);
+	T.self_pairs = 1;
+	T.world = 1;
+	return cnbk_umma_tables(st, rows_a, rows_b, N, W, 1, T, 0, cnbk_pair_tiles(N), counts, g_begin, g_end, accumulate);
+}
+
+int cnbk_pairs_from_tiles_order(cudaStream_t st, const int *counts, const int *order, int N, int M, int *pair_tab) {
+	const long long np = (long long)N * (N - 1) / 2;
+	if (np < 1) return CNB_OK;
+	k_pairs_from_tiles_order<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(counts, order, N, M, pair_tab);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -296,6 +296,9 @@ typedef struct cnb_timing {
 	int64_t tensor3_tiles;          /* tcgen05 tiles of the three-parent group (0 = that group ran on the bit-plane kernels) */
 } cnb_timing;
 int cnb_ctx_timing(const cnb_ctx *ctx, cnb_timing *out);
+/* the same for the last one-shot cnb_search_order of the calling thread (its context is parked, not reachable);
+ * fast_path = 2 there means the streamed form ran (upload overlapped with the table kernel) */
+int cnb_last_call_timing(cnb_timing *out);
 
 /* ---- test hooks ---- */
 /* counts + log-lik of explicit families; children/parents are 0-based node LABELS; counts_out is

@@ -939,6 +939,62 @@ def test_sharded_search_equals_unsharded(abi):
             assert compare_search(nets, ref_nets) == len(ref_nets)
 
 
+@pytest.mark.parametrize("n,m,cats,slices", [(70, 9000, 4, "1,3,4,4,4"), (40, 8192, 3, "1"), (130, 20001, 4, "1,1"), (65, 12345, 2, "1,2,3,4,5,6"),
+                                             (30, 100000, 4, "1,3,4,4,4"), (200, 8500, 4, "2,1")])
+def test_streamed_one_shot_search(abi, monkeypatch, n, m, cats, slices):
+    """cnb_search_order on a large complete matrix uploads the samples in slices and contracts every slice while the next
+    one is on its way (pair tables and two-parent tables accumulate over the slices): same networks, tables and
+    log-likelihoods as the resident path, whatever the slicing"""
+    s, c = random_problem(13 * n + m, n, m, cats)
+    kw = dict(max_parent_set=2, max_complexity=n * 16 * 3, num_cats=c, order=(np.random.default_rng(m).permutation(n) + 1))
+    monkeypatch.setenv("CNB_STREAM_MIN", "off")
+    a = abi.search_order(s, **kw)
+    assert abi.last_call_timing()["fast_path"] != 2
+    monkeypatch.setenv("CNB_STREAM_MIN", "0")
+    monkeypatch.setenv("CNB_STREAM_SLICES", slices)
+    b = abi.search_order(s, **kw)
+    assert abi.last_call_timing()["fast_path"] == 2 and abi.last_call_timing()["tensor_tiles"] > 0
+    assert compare_search(b, a) == len(a)
+    for x, y in zip(a, b):
+        assert x["loglik"] == y["loglik"] and all(np.array_equal(p, q) for p, q in zip(x["probs"], y["probs"]))
+    # three parents: the groups behind the streamed one run on the resident planes
+    kw3 = dict(kw, max_parent_set=3, max_complexity=n * 64 * 3)
+    if n <= 70:
+        monkeypatch.setenv("CNB_STREAM_MIN", "off")
+        a3 = abi.search_order(s, want_probs=False, **kw3)
+        monkeypatch.setenv("CNB_STREAM_MIN", "0")
+        b3 = abi.search_order(s, want_probs=False, **kw3)
+        assert abi.last_call_timing()["fast_path"] == 2 and compare_search(b3, a3, check_probs=False) == len(a3)
+
+
+def test_streamed_search_steps_aside(abi, monkeypatch):
+    """a missing value, a value outside its node's categories, perturbations, pools: the streamed form hands over to the
+    resident path (which scores the data with the kernels that take them, or reports the error)"""
+    monkeypatch.setenv("CNB_STREAM_MIN", "0")
+    s, c = random_problem(77, 40, 9000, 4)
+    kw = dict(max_parent_set=2, max_complexity=40 * 48, num_cats=c)
+    ok = abi.search_order(s, **kw)
+    assert abi.last_call_timing()["fast_path"] == 2
+    s_na = s.copy()
+    s_na[8000, 7] = NA                                      # found while packing the LAST slice
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s_na, num_cats=c)
+        want = ctx.search_order(max_parent_set=2, max_complexity=40 * 48)
+    got = abi.search_order(s_na, **kw)
+    assert abi.last_call_timing()["fast_path"] != 2 and compare_search(got, want) == len(want)
+    bad = s.copy()
+    bad[8100, 3] = 9
+    with pytest.raises(abi.CnbError) as e:
+        abi.search_order(bad, **kw)
+    assert "Incorrect categories" in str(e.value)
+    pert = np.zeros_like(s)
+    pert[::3, 5] = 1
+    abi.search_order(s, perturbations=pert, **kw)
+    assert abi.last_call_timing()["fast_path"] != 2
+    again = abi.search_order(s, **kw)                       # and the parked context streams again afterwards
+    assert abi.last_call_timing()["fast_path"] == 2 and compare_search(again, ok) == len(ok)
+
+
 def test_errors_are_codes_not_crashes(abi):
     s, c = random_problem(1, 5, 50, 3)
     bad = s.copy()
