@@ -109,6 +109,7 @@ extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
 	for (cudaEvent_t ev : c->ev_slices) cudaEventDestroy(ev);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
 	cudaStreamDestroy(c->own_stream);
 	delete c;
 }
@@ -178,7 +179,7 @@ int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *sampl
 	if (!c || N < 1 || M < 1 || !samples_dev) { cnb_set_error("Invalid sample"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
 	/* a failure part-way must not leave the previous data set looking valid next to the new sizes */
-	c->have_samples = c->planned = c->dp_done = false;
+	c->have_samples = c->planned = c->dp_done = c->tables_resident = false;
 	c->N = N;
 	c->M = M;
 	c->W = (M + 31) / 32;
@@ -628,6 +629,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	int tile_mode = 0;
 	if (tensor_ok && c->clean && c->pairs_valid && !c->force_full) tile_mode = 1;
 	else if (tensor_ok && c->max_cats <= CNB_PLANE_CATS && !c->tensor_i8) tile_mode = 2;
+	c->tables_resident = false;
 	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
 	CnbPlan &pl = c->plan;
 	const bool masks = c->has_pert && !c->ignore_pert;
@@ -754,6 +756,7 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	RC(c->b_rows_a3.ensure(row_bytes));
 	RC(cnbk_umma_rows3(st, (const uint4 *)c->b_planes.ptr, N, c->W, (int)nvirt, f1, (uint4 *)c->b_rows_a3.ptr));
 	c->timing.kernel_launches += 2;
+	c->tables_resident = false;                        /* the T tiles take the table buffer */
 	RC(c->b_counts.ensure((size_t)std::max<long long>(largest, 1) * slot_bytes));
 	CnbTiles T3;
 	memset(&T3, 0, sizeof(T3));
@@ -847,6 +850,7 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 		if (slices > 1 && !O.counts) {
 			int stride = table_stride(c->max_cats, F.d);
 			size_t bytes = (size_t)(e - b) * stride * sizeof(int);
+			c->tables_resident = false;
 			RC(c->b_counts.ensure(bytes));
 			CK(cudaMemsetAsync(c->b_counts.ptr, 0, bytes, st));
 			O.counts = (int *)c->b_counts.ptr - (size_t)b * stride;
@@ -921,6 +925,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			}
 			c->timing.tensor_tiles += t1 - t0;
 			c->tensor_batches = nb;
+			c->tables_resident = nb == 1 && pl.world == 1;
 			long long cols = 0;
 			for (long long t = t0; t < t1; t++) cols += cnb_tile_columns(pl, pl.rank + t * pl.world);
 			c->timing.tensor_macs = cols * cnbk_umma_column_macs(c->W, !c->tensor_i8);
@@ -1004,7 +1009,7 @@ static int score_explicit(cnb_ctx *c, const std::vector<int32_t> &child, const s
 /* explicit families sorted by parent count: one launch class per count (fixed d, so the bit-plane / pair-table
  * kernels apply), tables + log-lik + prior + sample size into the b_ex_* buffers */
 static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, const std::vector<int32_t> &pars,
-		const std::vector<int32_t> &nd, int stride) {
+		const std::vector<int32_t> &nd, int stride, bool from_search = false) {
 	size_t n = child.size();
 	RC(upload(c, c->b_ex_child, child));
 	RC(upload(c, c->b_ex_pars, pars));
@@ -1033,7 +1038,13 @@ static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, 
 		F.nfam = n;
 		F.ex_child = (const int32_t *)c->b_ex_child.ptr;
 		F.ex_pars = (const int32_t *)c->b_ex_pars.ptr;
-		RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || (nd[b] == 0 && !have_pair_tables(c)), true));
+		if (nd[b] == 2 && c->tables_resident && from_search && !c->force_generic) {
+			/* the two-parent tables of the search are still on the device: read the families' tables from their tile slots */
+			RC(cnbk_umma_export(c->stream, D, (long long)b, (long long)e, F.ex_child, F.ex_pars, (const int *)c->b_counts.ptr,
+					(const int *)c->b_pairs.ptr, O));
+			c->timing.kernel_launches++;
+		} else
+			RC(score_range(c, D, F, nd[b], (long long)b, (long long)e, O, c->force_generic || (nd[b] == 0 && !have_pair_tables(c)), true));
 		b = e;
 	}
 	return CNB_OK;
@@ -1327,7 +1338,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 			s_nd[k] = ex_nd[f];
 			for (int q = 0; q < CNB_MAXP; q++) s_pars[k * CNB_MAXP + q] = ex_pars[(size_t)f * CNB_MAXP + q];
 		}
-		RC(score_explicit_groups(c, s_child, s_pars, s_nd, stride));
+		RC(score_explicit_groups(c, s_child, s_pars, s_nd, stride, true));     /* families in the order space of the plan */
 		std::vector<int32_t> counts(nf * stride), ncount(nf);
 		std::vector<double> ll(nf), prior(nf);
 		D2H(c, counts.data(), c->b_ex_counts.ptr, counts.size() * sizeof(int));
@@ -1412,7 +1423,7 @@ extern "C" int cnb_ctx_search_order(cnb_ctx *c, const cnb_params *p, cnb_result 
 static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **out, bool *done) {
 	*done = false;
 	const int N = p->num_nodes, M = p->num_samples;
-	static const char *e_min = getenv("CNB_STREAM_MIN");
+	const char *e_min = getenv("CNB_STREAM_MIN");     /* read per call: tests switch it */
 	const size_t stream_min = e_min ? (!strcmp(e_min, "off") ? (size_t)-1 : (size_t)strtoull(e_min, nullptr, 10)) : ((size_t)256 << 20);
 	if (!p->samples || !p->num_cats || p->perturbations || p->parents_pool || p->fixed_parents || p->parent_sizes || N < 3
 			|| M < 8192 || M >= (1 << 24) || p->max_parent_set < 2 || (size_t)N * M * sizeof(int32_t) < stream_min
@@ -1425,6 +1436,7 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 	CK(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
 	if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	if (!c->prep_stream) CK(cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
 	const size_t total = (size_t)N * M;
 	/* ---- what cnb_ctx_set_samples would set up, minus the data ---- */
 	c->have_samples = c->planned = c->dp_done = false;
@@ -1474,9 +1486,9 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 	/* ---- slices: whole sample groups, a small first one ---- */
 	int ng_all = 0;
 	const int nq_all = cnbk_umma_row_quads(c->W, 1, &ng_all), gs = cnbk_umma_group_samples(1);
-	static const char *e_sl = getenv("CNB_STREAM_SLICES");
+	const char *e_sl = getenv("CNB_STREAM_SLICES");
 	std::vector<int> parts;
-	for (const char *q = e_sl ? e_sl : "1,3,4,4,4"; *q;) {
+	for (const char *q = e_sl ? e_sl : "1,5,10"; *q;) {             /* measured at C5: 174 / 170 / 178 ms for 5 / 3 / 2 slices */
 		parts.push_back(std::max(1, atoi(q)));
 		while (*q && *q != ',') q++;
 		if (*q == ',') q++;
@@ -1490,11 +1502,15 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 		if (k + 1 == parts.size()) ge = ng_all;
 		if (ge > (gend.empty() ? 0 : gend.back())) gend.push_back(ge);
 	}
-	while (c->ev_slices.size() < gend.size()) {
+	while (c->ev_slices.size() < 2 * gend.size()) {                /* per slice: "copied", "packed" */
 		cudaEvent_t ev;
 		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 		c->ev_slices.push_back(ev);
 	}
+	/* three streams: copies; packing of a slice (k_pack / k_permute / k_umma_rows: memory-bound, they share the SMs with the
+	 * table kernel's one CTA per SM); the table passes.  The packing of slice k + 1 runs under the pass over slice k. */
+	CK(cudaEventRecord(c->ev[EV_PLAN1], st));
+	CK(cudaStreamWaitEvent(c->prep_stream, c->ev[EV_PLAN1], 0));   /* the plan's uploads (order, categories) precede the packing */
 	bool overflow = false;
 	int g0 = 0;
 	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
@@ -1506,15 +1522,19 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 		rc = cnb_ctx_upload_bytes(c, p->samples, r0 * N, r1 * N, (uint8_t *)c->b_stage_s.ptr, 16, &ovf, c->copy_stream, 0, total);
 		overflow = overflow || ovf;
 		if (rc != CNB_OK) break;
-		CK(cudaEventRecord(c->ev_slices[k], c->copy_stream));
-		CK(cudaStreamWaitEvent(st, c->ev_slices[k], 0));
+		cudaStream_t ps = c->prep_stream;
+		CK(cudaEventRecord(c->ev_slices[2 * k], c->copy_stream));
+		CK(cudaStreamWaitEvent(ps, c->ev_slices[2 * k], 0));
 		const int w0 = (int)(r0 / 32), w1 = last ? c->W : (int)(r1 / 32);
-		rc = cnbk_pack(st, c->b_stage_s.ptr, 1, nullptr, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr, (uint8_t *)c->b_codes.ptr,
+		rc = cnbk_pack(ps, c->b_stage_s.ptr, 1, nullptr, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr, (uint8_t *)c->b_codes.ptr,
 				(uint4 *)c->b_planes_lbl.ptr, nullptr, (int *)c->b_flag.ptr, w0, w1);
-		if (rc == CNB_OK) rc = cnbk_permute(st, (const uint4 *)c->b_planes_lbl.ptr, nullptr, (const int *)c->b_order.ptr, N, c->W,
+		if (rc == CNB_OK) rc = cnbk_permute(ps, (const uint4 *)c->b_planes_lbl.ptr, nullptr, (const int *)c->b_order.ptr, N, c->W,
 				(uint4 *)c->b_planes.ptr, nullptr, w0, w1);
-		if (rc == CNB_OK) rc = cnbk_umma_rows(st, (const uint4 *)c->b_planes.ptr, N, c->W, 1, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr,
+		if (rc == CNB_OK) rc = cnbk_umma_rows(ps, (const uint4 *)c->b_planes.ptr, N, c->W, 1, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr,
 				w0 / 4, last ? nq_all : w1 / 4);
+		if (rc != CNB_OK) break;
+		CK(cudaEventRecord(c->ev_slices[2 * k + 1], ps));
+		CK(cudaStreamWaitEvent(st, c->ev_slices[2 * k + 1], 0));
 		if (rc == CNB_OK) rc = (int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W,
 				(int *)c->b_counts_p.ptr, g0, g1, k > 0);
 		if (rc == CNB_OK) rc = cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, D.tiles, 0, ntiles,
@@ -1527,9 +1547,11 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 		D2H(c, flags, c->b_flag.ptr, sizeof(flags));
 		CK(cudaStreamSynchronize(st));
 		CK(cudaStreamSynchronize(c->copy_stream));
+		CK(cudaStreamSynchronize(c->prep_stream));
 	} else {
 		cudaStreamSynchronize(st);
 		cudaStreamSynchronize(c->copy_stream);
+		cudaStreamSynchronize(c->prep_stream);
 	}
 	if (rc != CNB_OK || overflow || flags[0] || flags[2]) {
 		/* an error, a label above 255, a value outside its node's categories or a missing value: the resident path decides

@@ -32,7 +32,10 @@ struct cnb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr;   /* host -> device copies of the streamed one-shot search (created on first use) */
+	cudaStream_t prep_stream = nullptr;   /* ... and the packing of a slice, under the table pass over the previous one */
 	std::vector<cudaEvent_t> ev_slices;   /* "slice k is on the device" */
+	bool tables_resident = false;         /* b_counts still holds the tile tables of the whole two-parent group of the current plan
+	                                         (one batch, one rank): the export reads the returned networks' tables from there */
 	bool streaming = false;               /* the streamed one-shot search is driving this context: cnb_ctx_plan leaves the data
 	                                         kernels to it, cnb_ctx_score_shard finds the two-parent tables contracted already */
 	cudaEvent_t ev[CNB_NEV];

@@ -77,6 +77,10 @@ int cnbk_pair_tables_umma_full(cudaStream_t st, const uint4 *planes_lbl, const u
 		uint4 *rows_b, int *counts, int *pair_ord);
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long local_begin, long long local_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O, bool all_four_cats = false);   /* all_four_cats: every node has 4 categories */
+/* tables, log-likelihoods and sample sizes of the explicit two-parent families [f_begin, f_end) (positions; ex_pars
+ * [..][CNB_MAXP]) read off the resident tile tables of the whole tiled group (world 1, one batch) */
+int cnbk_umma_export(cudaStream_t st, const DevData &Dt, long long f_begin, long long f_end, const int *ex_child, const int *ex_pars,
+		const int *counts, const int *pair_tab, const ScoreOut &O);
 #define CNBK_UMMA_SLOT_INTS 36
 #define CNBK_UMMA_FULL_SLOT_INTS 64
 /* three-parent families on the tensor cores: pair-side rows incl. the virtual pair nodes, then cnbk_umma_tables with a

@@ -648,6 +648,70 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	O.scores[T.rank * O.seg_len + O.seg_off + local * SLOTS + within] = score;
 }
 
+/* The tables of explicit two-parent families (the networks a search returns) read back from the tile tables that are still
+ * resident after the search, instead of counting them again over the samples: slot -> 64 cells (completed from the pair
+ * tables for inclusion-exclusion tiles) -> the reference's table layout (first listed parent most significant, child
+ * fastest), log-likelihood, sample size. */
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_umma_export(DevData Dt, long long f_begin, long long f_end, const int *__restrict__ ex_child,
+		const int *__restrict__ ex_pars, const int *__restrict__ counts, const int *__restrict__ pair_tab, ScoreOut O) {
+	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS;
+	const long long f = f_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= f_end) return;
+	const CnbTiles &T = Dt.tiles;
+	const int c = ex_child[f], p0 = ex_pars[f * CNB_MAXP], p1 = ex_pars[f * CNB_MAXP + 1];
+	const int a = min(p0, p1), b = max(p0, p1);
+	long long tile;
+	int within;
+	cnb_family_slot(T, Dt.N, a, b, c, tile, within);
+	const bool dk = b >= (c / T.child) * T.child;           /* D tile: pair (b, c), column a */
+	const int *tab = counts + ((size_t)tile * SLOTS + within) * SLOT_INTS;
+	int full[64];
+#define CELL(i, jj, k) full[((i) * 4 + (jj)) * 4 + (k)]
+	if (FULL) {
+		for (int r = 0; r < 16; r++)
+			for (int q = 0; q < 4; q++) {
+				const int v = tab[r * 4 + q];
+				if (dk) CELL(q, r / 4, r % 4) = v;
+				else CELL(r / 4, r % 4, q) = v;
+			}
+	} else {
+		for (int r = 0; r < 9; r++)
+			for (int q = 0; q < 3; q++) {
+				const int v = tab[r * 4 + q];
+				if (dk) CELL(q, r / 3, r % 3) = v;
+				else CELL(r / 3, r % 3, q) = v;
+			}
+		const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
+		for (int i = 0; i < 3; i++)
+			for (int jj = 0; jj < 3; jj++)
+				CELL(i, jj, 3) = um_pair_count(pair_tab, l0, l1, i, jj) - (CELL(i, jj, 0) + CELL(i, jj, 1) + CELL(i, jj, 2));
+		for (int i = 0; i < 3; i++)
+			for (int k = 0; k < 4; k++)
+				CELL(i, 3, k) = um_pair_count(pair_tab, l0, lc, i, k) - (CELL(i, 0, k) + CELL(i, 1, k) + CELL(i, 2, k));
+		for (int jj = 0; jj < 4; jj++)
+			for (int k = 0; k < 4; k++)
+				CELL(3, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - (CELL(0, jj, k) + CELL(1, jj, k) + CELL(2, jj, k));
+	}
+	/* table order = the family's LISTED parents (p0 most significant) */
+	const bool sw = p0 > p1;
+	const int pc0 = Dt.cats[p0], pc1 = Dt.cats[p1], cc = Dt.cats[c];
+	auto cell = [&](int i0, int i1, int k) { return sw ? CELL(i1, i0, k) : CELL(i0, i1, k); };
+	int ncount;
+	const double ll = dev_loglik(pc0 * pc1, cc, [&](int cfg, int k) { return cell(cfg / pc1, cfg % pc1, k); }, &ncount);
+	if (O.counts) {
+		int *dst = O.counts + (size_t)f * O.counts_stride;
+		for (int i0 = 0; i0 < pc0; i0++)
+			for (int i1 = 0; i1 < pc1; i1++)
+				for (int k = 0; k < cc; k++) dst[(i0 * pc1 + i1) * cc + k] = cell(i0, i1, k);
+	}
+#undef CELL
+	int pars[CNB_MAXP];
+	pars[0] = p0;
+	pars[1] = p1;
+	dev_store_outputs(Dt, O, f, c, pars, 2, ll, ncount);
+}
+
 /* pair tables from the P tiles: one thread per unordered node pair (u < v).  The 3 x 3 free cells come from the tile
  * slot (pair slot u, column v), rows (i, i); the margins of u and v from the diagonal slots (u, u) and (v, v); cells
  * with a last category by inclusion-exclusion (no value is missing, so every margin sums to M). */
@@ -894,6 +958,16 @@ int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long tile_begin,
 	else if (full) k_umma_epilogue<false, true><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
 	else if (all_four_cats) k_umma_epilogue<true, false><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
 	else k_umma_epilogue<false, false><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_umma_export(cudaStream_t st, const DevData &Dt, long long f_begin, long long f_end, const int *ex_child, const int *ex_pars,
+		const int *counts, const int *pair_tab, const ScoreOut &O) {
+	if (f_end <= f_begin) return CNB_OK;
+	const unsigned grid = (unsigned)((f_end - f_begin + 127) / 128);
+	if (Dt.tiles.full) k_umma_export<true><<<grid, 128, 0, st>>>(Dt, f_begin, f_end, ex_child, ex_pars, counts, pair_tab, O);
+	else k_umma_export<false><<<grid, 128, 0, st>>>(Dt, f_begin, f_end, ex_child, ex_pars, counts, pair_tab, O);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
