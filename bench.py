@@ -493,37 +493,33 @@ def single_process_block(ngpus, wl, host_i32, steps, warmup, n_fam_total, want_e
         L.cnb_result_network(h, nn - 1, ctypes.byref(cx), ctypes.byref(ll))
         L.cnb_result_free(h)
         out["result"] = {"networks": nn, "max_complexity": cx.value, "loglik": ll.value}
-        if want_e2e:
-            def e2e_step():
-                ta = time.perf_counter()
-                mc.set_samples(host_i32, num_cats=wl["cats"])
-                tb = time.perf_counter()
-                mc.search_light(**kw)
-                tc = time.perf_counter()
-                hh = mc.collect_raw()
-                td = time.perf_counter()
-                k = L.cnb_result_num_networks(hh)
-                L.cnb_result_free(hh)
-                return k, (tb - ta, tc - tb, td - tc)
-            e2e_step()
-            e_steps = max(1, min(steps, 3))
-            parts = np.zeros(3)
-            mc.mark(0)
-            t0 = time.perf_counter()
-            for _ in range(e_steps):
-                k, pt = e2e_step()
-                parts += np.asarray(pt)
-            wall = time.perf_counter() - t0
-            mc.mark(1)
-            ems = max(mc.elapsed_ms(), 1000 * wall)           # every call returns synchronised: wall >= device span
-            tms = [mc.timing(i) for i in range(mc.g)]
-            out["e2e"] = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s", "ms_per_step": ems / e_steps,
-                          "steps": e_steps, "host_memory": "pageable",
-                          "h2d_bytes_per_step": int(sum(t["h2d_bytes"] for t in tms)),
-                          "d2h_bytes_per_step": int(sum(t["d2h_bytes"] for t in tms)),
-                          "host_wall_ms_per_step": {"set_samples_ms": 1000 * parts[0] / e_steps, "search_ms": 1000 * parts[1] / e_steps,
-                                                    "export_ms": 1000 * parts[2] / e_steps},
-                          "networks": k}
+    if want_e2e:
+        # THE drop-in call an R session makes: cnb_search_order with the pageable host matrix in, networks on the host out,
+        # cnb_params.num_devices = ngpus (or CNB_NUM_DEVICES in the environment).  Inside: slices of the samples dealt over
+        # the devices, peer copies, one table-kernel pass per slice on every device (cnb_multi.cu::mctx_search_streamed).
+        keep = _abi.Keep()
+        p1 = _abi.make_params(keep, host_i32.shape[1], host_i32.shape[0], samples=host_i32, num_cats=wl["cats"], device=0,
+                              num_devices=ngpus, **kw)
+
+        def e2e_step():
+            h = ctypes.c_void_p()
+            _abi.check(L.cnb_search_order(ctypes.byref(p1), ctypes.byref(h)))
+            k = L.cnb_result_num_networks(h)
+            L.cnb_result_free(h)
+            return k
+        e2e_step()
+        e_steps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            k = e2e_step()
+        ems = 1000 * (time.perf_counter() - t0)                # the call returns synchronised: host wall time is the span
+        tm = _abi.last_call_timing()
+        out["e2e"] = {"value": n_fam_total * e_steps / (ems / 1000.0), "unit": "families/s", "ms_per_step": ems / e_steps,
+                      "steps": e_steps, "host_memory": "pageable", "timed": "host wall clock around the synchronous calls",
+                      "call": "cnb_search_order(num_devices=%d), %s" % (ngpus, "streamed" if tm["fast_path"] == 2 else "resident path"),
+                      "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
+                      "device0_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
+                      "networks": k}
     return out
 
 
@@ -723,27 +719,21 @@ def main():
                 L.cnb_result_free(h)
                 wall["plan_score_ms"] += (time.perf_counter() - t_a) * 1e3
                 return (nn, cx.value, ll.value)
-            # every rank copies 1/world of the host matrix, NVLink all-gather, pack (catnet_b200/dist.py)
+            # every rank narrows and copies 1/world of every slice of the host matrix, an NVLink all-gather completes the slice,
+            # the table kernel contracts it while the next slice is on its way (catnet_b200/dist.py::search_order_streamed);
+            # selection + DP + network export (D2H) on rank 0 only
             from catnet_b200 import dist as cdist
-            _, nb = cdist.set_samples_sharded(ctx2, host, rank, world, dev, num_cats=wl["cats"])
-            wall["h2d_bytes"] = nb
-            t_b = time.perf_counter()
-            ctx2.plan(rank, world, **kw)
-            ctx2.score_shard(scores.data_ptr())
-            gather()
-            t_c = time.perf_counter()
+            h, info = cdist.search_order_streamed(ctx2, host, rank, world, dev, wl["cats"], finish_rank=0, raw=True, **kw)
+            wall["h2d_bytes"] = info["h2d_bytes"]
+            wall["streamed"] = info["streamed"]
             res = None
             if rank == 0:
-                h = ctx2.finish_raw(scores.data_ptr())            # selection + DP + network export (D2H): rank 0 only
                 nn = L.cnb_result_num_networks(h)
                 cx, ll = ctypes.c_int32(), ctypes.c_double()
                 L.cnb_result_network(h, nn - 1, ctypes.byref(cx), ctypes.byref(ll))
                 L.cnb_result_free(h)
                 res = (nn, cx.value, ll.value)
-            t_d = time.perf_counter()
-            wall["set_samples_ms"] += (t_b - t_a) * 1e3
-            wall["plan_score_ms"] += (t_c - t_b) * 1e3
-            wall["finish_ms"] += (t_d - t_c) * 1e3
+            wall["plan_score_ms"] += (time.perf_counter() - t_a) * 1e3
             return res
 
         e2e_step()
@@ -761,7 +751,9 @@ def main():
             ems = max(ems, sum(wall[k_] for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms")))   # the call returns synchronised
         t_ms = torch.tensor([ems], dtype=torch.float64, device=dev)
         tm = ctx2.timing() if world > 1 else _abi.last_call_timing()
-        traffic = torch.tensor([int(tm["h2d_bytes"]) + int(wall["h2d_bytes"]), int(tm["d2h_bytes"])], dtype=torch.int64, device=dev)
+        # streamed: the library counted the uploaded slices itself; resident fall-back: set_samples_dev8 restarts the count
+        traffic = torch.tensor([int(tm["h2d_bytes"]) + (0 if wall.get("streamed") or world == 1 else int(wall["h2d_bytes"])),
+                                int(tm["d2h_bytes"])], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(traffic, op=dist.ReduceOp.SUM)
@@ -772,7 +764,9 @@ def main():
                    "ms_per_step": ems / e_steps, "steps": e_steps, "host_memory": "pageable",
                    "call": ("cnb_search_order (one-shot C ABI call, %s)" % ("streamed: upload overlapped with the table kernel"
                                                                           if tm.get("fast_path") == 2 else "resident path")
-                            if world == 1 else "upload_rows8 + all-gather + set_samples_dev8 + plan + score_shard + all-gather + finish on rank 0"),
+                            if world == 1 else ("dist.search_order_streamed: per slice upload_rows8_on + all-gather + stream_slice (pack, table "
+                                                "kernel pass); stream_end, score all-gather, finish on rank 0" if wall.get("streamed") else
+                                                "upload_rows8 + all-gather + set_samples_dev8 + plan + score_shard + all-gather + finish on rank 0")),
                    "host_wall_ms_per_step": {k_: wall[k_] / e_steps for k_ in ("set_samples_ms", "plan_score_ms", "finish_ms")},
                    "device_ms": {k_: float(tm[k_]) for k_ in ("pack_ms", "score_ms", "select_ms", "dp_ms", "collect_ms")},
                    "result": {"networks": res[0], "max_complexity": res[1], "loglik": res[2]}}

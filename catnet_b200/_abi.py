@@ -83,6 +83,7 @@ SYMBOLS = [
     "cnb_mctx_search_order", "cnb_mctx_search_light", "cnb_mctx_collect", "cnb_mctx_search_sa", "cnb_mctx_search_hist",
     "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
     "cnb_ctx_upload_rows8", "cnb_tile_selftest_full", "cnb_last_call_timing",
+    "cnb_ctx_upload_rows8_on", "cnb_ctx_stream_begin", "cnb_ctx_stream_slice", "cnb_ctx_stream_end",
 ]
 
 _lib = None
@@ -158,6 +159,10 @@ def lib():
         "cnb_samples_dev": (i32, [P(Network), i32, vp, dbl, C.c_uint64, i32, vp]),
         "cnb_ctx_search_scores": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "cnb_ctx_upload_rows8": (i32, [vp, i32, vp, i64, i64, vp, i32]),
+        "cnb_ctx_upload_rows8_on": (i32, [vp, i32, vp, i64, i64, vp, i32, vp, i64, i64]),
+        "cnb_ctx_stream_begin": (i32, [vp, P(Params), i32, i32, P(i64), P(i64), P(i32), vp, i32]),
+        "cnb_ctx_stream_slice": (i32, [vp, i32, vp, vp]),
+        "cnb_ctx_stream_end": (i32, [vp, vp, P(i32)]),
         "cnb_mctx_create": (i32, [i32, i32, P(vp)]),
         "cnb_mctx_destroy": (None, [vp]),
         "cnb_mctx_num_devices": (i32, [vp]),
@@ -324,6 +329,31 @@ class Context:
         """rows [row0, row1) of the host int32 matrix -> bytes at dst_dev_ptr + row0 * N (first step of a sharded upload)"""
         s = i32(samples)
         check(lib().cnb_ctx_upload_rows8(self.h, s.shape[1], ptr(s), int(row0), int(row1), dst_dev_ptr, int(max_threads)))
+
+    def upload_rows8_on(self, samples, row0, row1, dst_dev_ptr, max_threads, cuda_stream, stage_offset, stage_capacity):
+        """the same on the caller's stream, staged at stage_offset (values) of a pinned buffer of stage_capacity values"""
+        s = i32(samples)
+        check(lib().cnb_ctx_upload_rows8_on(self.h, s.shape[1], ptr(s), int(row0), int(row1), dst_dev_ptr, int(max_threads),
+                                            int(cuda_stream) if cuda_stream else None, int(stage_offset), int(stage_capacity)))
+
+    def stream_begin(self, rank, world, n, m, **kw):
+        """plan a streamed search (samples still on the host) -> (seg_len, num_families, slice row bounds); no bounds = the
+        problem does not qualify, use the resident calls.  kw as for plan() plus num_cats (required)."""
+        self.n, self.m = n, m
+        keep = Keep()
+        p = make_params(keep, n, m, **kw)
+        seg, nf, ns = C.c_int64(), C.c_int64(), C.c_int32()
+        rows = np.zeros(65, dtype=np.int64)
+        check(lib().cnb_ctx_stream_begin(self.h, C.byref(p), int(rank), int(world), C.byref(seg), C.byref(nf), C.byref(ns), ptr(rows), 65))
+        return seg.value, nf.value, [int(r) for r in rows[:ns.value + 1]] if ns.value else []
+
+    def stream_slice(self, k, bytes_dev_ptr, ready_event=None):
+        check(lib().cnb_ctx_stream_slice(self.h, int(k), bytes_dev_ptr, int(ready_event) if ready_event else None))
+
+    def stream_end(self, scores_dev_ptr):
+        ok = C.c_int32()
+        check(lib().cnb_ctx_stream_end(self.h, scores_dev_ptr, C.byref(ok)))
+        return bool(ok.value)
 
     def num_cats(self):
         out = np.zeros(self.n, dtype=np.int32)

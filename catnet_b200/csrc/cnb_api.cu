@@ -417,17 +417,18 @@ static bool compact_rows(const int32_t *src, uint8_t *dst, size_t n) {
  * already done to dst_dev + v0 (C5: 2 GB in 40 ms as int32 against 0.5 GB behind the compaction).  The source may be
  * pageable memory (R's): the threads read it, only the pinned bytes are DMA'd.  *overflow = a value above 255 was met. */
 int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads,
-		bool *overflow, cudaStream_t copy_stream, size_t pin_origin, size_t pin_values) {
-	/* copy_stream: the stream the chunks are copied on (NULL = the context's); the pinned buffer holds values
-	 * [pin_origin, pin_origin + pin_values) (default: just this call's): a caller that uploads slice after slice gives every
-	 * slice its own part of the buffer, so that a slice is compacted while the previous one is still being copied */
+		bool *overflow, cudaStream_t copy_stream, size_t pin_offset, size_t pin_capacity) {
+	/* copy_stream: the stream the chunks are copied on (NULL = the context's); the values are staged at pin_offset of a
+	 * pinned buffer of pin_capacity values (default: a buffer for just this call): a caller that uploads slice after slice
+	 * gives every slice its own part of the buffer, so that a slice is compacted while the previous one is still being copied */
 	const size_t total = v1 - v0;
 	*overflow = false;
 	if (!total) return CNB_OK;
 	if (!copy_stream) copy_stream = c->stream;
-	if (!pin_values) { pin_origin = v0; pin_values = total; }
-	RC(c->pin_stage.ensure(pin_values));
-	uint8_t *pin = (uint8_t *)c->pin_stage.ptr + (v0 - pin_origin);
+	if (!pin_capacity) { pin_offset = 0; pin_capacity = total; }
+	if (pin_offset + total > pin_capacity) { cnb_set_error("upload: staging range %zu + %zu exceeds %zu", pin_offset, total, pin_capacity); return CNB_ERR_PARAM; }
+	RC(c->pin_stage.ensure(pin_capacity));
+	uint8_t *pin = (uint8_t *)c->pin_stage.ptr + pin_offset;
 	const size_t chunk = (size_t)4 << 20;                       /* values per chunk: 16 MB of int32 -> 4 MB */
 	const int nchunks = (int)((total + chunk - 1) / chunk);
 	unsigned hw = std::thread::hardware_concurrency();
@@ -514,15 +515,24 @@ extern "C" int cnb_ctx_set_samples(cnb_ctx *c, int32_t N, int32_t M, const int32
 /* multi-process callers: rows [row0, row1) of the host int32 matrix (pageable is fine: host threads read it) become bytes
  * at dst_dev + row0 * N on the context's stream; the ranks then all-gather the byte matrix and hand it to
  * cnb_ctx_set_samples_dev8 */
-extern "C" int cnb_ctx_upload_rows8(cnb_ctx *c, int32_t N, const int32_t *samples, int64_t row0, int64_t row1, uint8_t *dst_dev,
-		int32_t max_threads) {
-	if (!c || N < 1 || !samples || row0 < 0 || row1 < row0 || !dst_dev) { cnb_set_error("cnb_ctx_upload_rows8: bad arguments"); return CNB_ERR_PARAM; }
+extern "C" int cnb_ctx_upload_rows8_on(cnb_ctx *c, int32_t N, const int32_t *samples, int64_t row0, int64_t row1, uint8_t *dst_dev,
+		int32_t max_threads, void *copy_stream, int64_t stage_offset, int64_t stage_capacity) {
+	if (!c || N < 1 || !samples || row0 < 0 || row1 < row0 || !dst_dev || stage_offset < 0 || stage_capacity < 0) {
+		cnb_set_error("cnb_ctx_upload_rows8: bad arguments");
+		return CNB_ERR_PARAM;
+	}
 	CK(cudaSetDevice(c->device));
 	bool ovf = false;
-	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
-	RC(cnb_ctx_upload_bytes(c, samples, (size_t)row0 * N, (size_t)row1 * N, dst_dev, max_threads > 0 ? max_threads : 16, &ovf));
+	RC(cnb_ctx_upload_bytes(c, samples, (size_t)row0 * N, (size_t)row1 * N, dst_dev, max_threads > 0 ? max_threads : 16, &ovf,
+			(cudaStream_t)copy_stream, (size_t)stage_offset, (size_t)stage_capacity));
 	if (ovf) { cnb_set_error("a category label above 255 cannot travel as a byte"); return CNB_ERR_PARAM; }
 	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_upload_rows8(cnb_ctx *c, int32_t N, const int32_t *samples, int64_t row0, int64_t row1, uint8_t *dst_dev,
+		int32_t max_threads) {
+	if (c) c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
+	return cnb_ctx_upload_rows8_on(c, N, samples, row0, row1, dst_dev, max_threads, nullptr, 0, 0);
 }
 
 extern "C" int cnb_ctx_num_cats(const cnb_ctx *c, int32_t *out) {
@@ -565,6 +575,7 @@ extern "C" int cnb_ctx_timing(const cnb_ctx *c, cnb_timing *out) {
 
 static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **out, bool *done);
 static thread_local cnb_timing g_last_timing = {};
+void cnb_set_last_call_timing(const cnb_timing &t) { g_last_timing = t; }
 extern "C" int cnb_last_call_timing(cnb_timing *out) {
 	if (!out) return CNB_ERR_PARAM;
 	*out = g_last_timing;
@@ -1409,24 +1420,43 @@ extern "C" int cnb_ctx_search_order(cnb_ctx *c, const cnb_params *p, cnb_result 
 	return CNB_OK;
 }
 
-/* ------------------------------------------------------------------ streamed one-shot search ---- */
-/* The one-shot call on a large complete matrix: host -> device copy, packing and the tensor-core contraction overlap.
- * The planner needs no samples (the categories are given), so the search is planned first; the samples then come in
- * SLICES of whole sample groups: host threads narrow a slice to bytes while the copy engine moves the previous one (copy
- * stream), the compute stream packs it (k_pack / k_permute / k_umma_rows on the slice's words) and runs one pass of the
- * table kernel over ALL tiles for the slice's sample groups -- the first pass stores, the later ones add (each tile is
- * owned by one CTA per pass: plain 16-byte read-modify-writes).  The pair tables are contracted the same way (P tiles on the
- * same order-space operand rows).  After the last slice: pair tables, 0/1-parent groups, epilogue, selection, DP, export as
- * in the resident path.  The first slice is small, so that the tensor pipe starts after ~2 ms instead of after the whole
- * upload (C5: 2 GB of int32, 28 ms).  Falls back (*done = false, nothing scored) when the problem does not qualify, and
- * when a missing value turns up in the data (found while packing) -- the bytes are then on the device already. */
-static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **out, bool *done) {
-	*done = false;
+/* ------------------------------------------------------------------ streamed search ---- */
+/* A search on a large complete matrix that is still on its way to the device: host -> device copy, packing and the
+ * tensor-core contraction overlap.  The planner needs no samples (the categories are given), so the search is planned
+ * first (cnb_ctx_stream_begin); the samples then come in SLICES of whole sample groups (cnb_ctx_stream_slice): while the
+ * caller moves slice k + 1 (host threads narrow it to bytes, the copy engine / NVLink carries it), the packing stream
+ * turns slice k into bit planes and operand rows (k_pack / k_permute / k_umma_rows on the slice's words -- memory-bound
+ * kernels that share the SMs with the table kernel's one CTA per SM) and the context's stream runs one pass of the table
+ * kernel over ALL of this rank's tiles for the slice's sample groups -- the first pass stores, the later ones add (each tile
+ * is owned by one CTA per pass: plain 16-byte read-modify-writes).  The pair tables are contracted the same way (P tiles on
+ * the same order-space operand rows).  cnb_ctx_stream_end completes the pair tables and scores this rank's shard as the
+ * resident path does (the tiled group finds its tables in place).  A problem that does not qualify gets no slices; a
+ * missing value or a bad category found while packing makes stream_end report ok = 0: the caller then takes the resident
+ * path (the byte matrix is on the device by then). */
+static void stream_abort(cnb_ctx *c) {
+	c->streaming = false;
+	c->stream_active = false;
+	c->have_samples = c->planned = false;
+	c->clean = c->pairs_valid = c->pairs_full = false;
+}
+
+void cnb_ctx_stream_cancel(cnb_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+	if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
+	cudaStreamSynchronize(c->stream);
+	stream_abort(c);
+}
+
+extern "C" int cnb_ctx_stream_begin(cnb_ctx *c, const cnb_params *p, int32_t rank, int32_t world, int64_t *seg_len,
+		int64_t *num_families, int32_t *num_slices, int64_t *slice_rows, int32_t slice_cap) {
+	if (!c || !p || !num_slices) return CNB_ERR_PARAM;
+	*num_slices = 0;
+	c->stream_active = false;
 	const int N = p->num_nodes, M = p->num_samples;
-	const char *e_min = getenv("CNB_STREAM_MIN");     /* read per call: tests switch it */
-	const size_t stream_min = e_min ? (!strcmp(e_min, "off") ? (size_t)-1 : (size_t)strtoull(e_min, nullptr, 10)) : ((size_t)256 << 20);
-	if (!p->samples || !p->num_cats || p->perturbations || p->parents_pool || p->fixed_parents || p->parent_sizes || N < 3
-			|| M < 8192 || M >= (1 << 24) || p->max_parent_set < 2 || (size_t)N * M * sizeof(int32_t) < stream_min
+	if (!p->num_cats || p->perturbations || p->parents_pool || p->fixed_parents || p->parent_sizes || N < 3
+			|| M < 8192 || M >= (1 << 24) || p->max_parent_set < 2
 			|| c->force_generic || c->tensor_mode < 0 || c->tensor_i8 || c->no_ie || c->force_full || c->pairs_popc) return CNB_OK;
 	int max_cats = 0;
 	for (int i = 0; i < N; i++) {
@@ -1435,11 +1465,9 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 	}
 	CK(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
-	if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	if (!c->prep_stream) CK(cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
-	const size_t total = (size_t)N * M;
 	/* ---- what cnb_ctx_set_samples would set up, minus the data ---- */
-	c->have_samples = c->planned = c->dp_done = false;
+	c->have_samples = c->planned = c->dp_done = c->tables_resident = false;
 	c->N = N; c->M = M; c->W = (M + 31) / 32; c->Mpad = c->W * 32;
 	c->has_pert = false;
 	c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
@@ -1458,119 +1486,174 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 	RC(c->b_codes.ensure((size_t)N * c->Mpad));
 	RC(c->b_planes_lbl.ensure(words * sizeof(uint4)));
 	RC(c->b_planes.ensure(words * sizeof(uint4)));
-	RC(c->b_stage_s.ensure(total));
 	RC(c->b_pairs.ensure((size_t)N * (N - 1) / 2 * 16 * sizeof(int)));
 	H2D(c, c->b_vmin.ptr, vmin.data(), N * sizeof(int));
 	H2D(c, c->b_cats_lbl.ptr, c->cats_lbl.data(), N * sizeof(int));
 	CK(cudaMemsetAsync(c->b_flag.ptr, 0, 4 * sizeof(int), st));
 	/* ---- plan (as for complete data: inclusion-exclusion tiles) ---- */
-	c->clean = c->pairs_valid = c->pairs_full = true;          /* provisional: checked against the pack flags below */
+	c->clean = c->pairs_valid = c->pairs_full = true;          /* provisional: checked against the pack flags in stream_end */
 	c->have_samples = true;
 	c->streaming = true;
 	int64_t seg = 0, nf = 0;
-	int rc = cnb_ctx_plan(c, p, 0, 1, &seg, &nf);
+	int rc = cnb_ctx_plan(c, p, rank, world, &seg, &nf);
 	const CnbPlan &pl = c->plan;
 	const CnbGroup *g2 = nullptr;
 	for (const CnbGroup &g : pl.groups) if (g.tiled) g2 = &g;
-	if (rc != CNB_OK || !g2 || g2->tiled != 1 || pl.tile_full || g2->ntiles > 16384) {
-		c->streaming = false;
-		c->have_samples = c->planned = false;
+	if (rc != CNB_OK || !g2 || g2->tiled != 1 || pl.tile_full || g2->tiles_per_rank > 16384) {
+		stream_abort(c);
 		return rc;                                                 /* not a tiled search after all: the resident path */
 	}
-	DevData D = make_devdata(c);
-	const long long ntiles = g2->ntiles;
+	c->stream_tiles = (g2->ntiles - pl.rank + pl.world - 1) / pl.world;   /* this rank's tiles (dealt round-robin) */
 	const size_t slot_bytes = (size_t)CNBK_UMMA_SLOT_INTS * sizeof(int) * pl.tile_pairs * pl.tile_cols;
-	rc = c->b_counts.ensure((size_t)ntiles * slot_bytes);
-	if (rc == CNB_OK) rc = c->b_counts_p.ensure((size_t)cnbk_pair_tiles(N) * CNB_TILE_PAIRS * CNB_TILE_CHILD * CNBK_UMMA_SLOT_INTS * sizeof(int));
-	if (rc == CNB_OK) rc = c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double));
+	RC(c->b_counts.ensure((size_t)std::max<long long>(c->stream_tiles, 1) * slot_bytes));
+	RC(c->b_counts_p.ensure((size_t)cnbk_pair_tiles(N) * CNB_TILE_PAIRS * CNB_TILE_CHILD * CNBK_UMMA_SLOT_INTS * sizeof(int)));
 	/* ---- slices: whole sample groups, a small first one ---- */
 	int ng_all = 0;
-	const int nq_all = cnbk_umma_row_quads(c->W, 1, &ng_all), gs = cnbk_umma_group_samples(1);
+	c->stream_nq = cnbk_umma_row_quads(c->W, 1, &ng_all);
+	const int gs = cnbk_umma_group_samples(1);
 	const char *e_sl = getenv("CNB_STREAM_SLICES");
 	std::vector<int> parts;
-	for (const char *q = e_sl ? e_sl : "1,5,10"; *q;) {             /* measured at C5: 174 / 170 / 178 ms for 5 / 3 / 2 slices */
+	/* one device: the table kernel outlasts the upload, so a small first slice starts it early (measured at C5: 174 / 170 /
+	 * 178 ms for 5 / 3 / 2 slices); four ranks and more: the upload outlasts each rank's share of the contraction, so the
+	 * last slice is small too -- its pass is all that is left when the upload ends */
+	for (const char *q = e_sl ? e_sl : (world >= 4 ? "1,3,4,4,3,1" : "1,5,10"); *q;) {
 		parts.push_back(std::max(1, atoi(q)));
 		while (*q && *q != ',') q++;
 		if (*q == ',') q++;
 	}
 	int psum = 0;
 	for (int v : parts) psum += v;
-	std::vector<int> gend;                                         /* last group (exclusive) of every slice */
+	c->stream_gend.clear();                                        /* last group (exclusive) of every slice */
 	for (size_t k = 0, acc = 0; k < parts.size(); k++) {
 		acc += parts[k];
 		int ge = (int)((long long)ng_all * acc / psum);
 		if (k + 1 == parts.size()) ge = ng_all;
-		if (ge > (gend.empty() ? 0 : gend.back())) gend.push_back(ge);
+		if (ge > (c->stream_gend.empty() ? 0 : c->stream_gend.back())) c->stream_gend.push_back(ge);
 	}
-	while (c->ev_slices.size() < 2 * gend.size()) {                /* per slice: "copied", "packed" */
+	const int ns = (int)c->stream_gend.size();
+	if (slice_rows && slice_cap < ns + 1) { stream_abort(c); cnb_set_error("cnb_ctx_stream_begin: %d slices", ns); return CNB_ERR_PARAM; }
+	while ((int)c->ev_slices.size() < 2 * ns) {                    /* per slice: "copied" (the one-shot form), "packed" */
 		cudaEvent_t ev;
 		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 		c->ev_slices.push_back(ev);
 	}
-	/* three streams: copies; packing of a slice (k_pack / k_permute / k_umma_rows: memory-bound, they share the SMs with the
-	 * table kernel's one CTA per SM); the table passes.  The packing of slice k + 1 runs under the pass over slice k. */
+	if (slice_rows) {
+		slice_rows[0] = 0;
+		for (int k = 0; k < ns; k++) slice_rows[k + 1] = k + 1 == ns ? M : std::min<int64_t>(M, (int64_t)c->stream_gend[k] * gs);
+	}
+	/* the plan's uploads (order, categories) precede the packing */
 	CK(cudaEventRecord(c->ev[EV_PLAN1], st));
-	CK(cudaStreamWaitEvent(c->prep_stream, c->ev[EV_PLAN1], 0));   /* the plan's uploads (order, categories) precede the packing */
-	bool overflow = false;
-	int g0 = 0;
+	CK(cudaStreamWaitEvent(c->prep_stream, c->ev[EV_PLAN1], 0));
 	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
-	for (size_t k = 0; k < gend.size() && rc == CNB_OK; k++) {
-		const int g1 = gend[k];
-		const bool last = k + 1 == gend.size();
-		const size_t r0 = std::min<size_t>(M, (size_t)g0 * gs), r1 = last ? (size_t)M : std::min<size_t>(M, (size_t)g1 * gs);
-		bool ovf = false;
-		rc = cnb_ctx_upload_bytes(c, p->samples, r0 * N, r1 * N, (uint8_t *)c->b_stage_s.ptr, 16, &ovf, c->copy_stream, 0, total);
-		overflow = overflow || ovf;
-		if (rc != CNB_OK) break;
-		cudaStream_t ps = c->prep_stream;
-		CK(cudaEventRecord(c->ev_slices[2 * k], c->copy_stream));
+	c->stream_active = true;
+	c->stream_next = 0;
+	*num_slices = ns;
+	if (seg_len) *seg_len = seg;
+	if (num_families) *num_families = nf;
+	return CNB_OK;
+}
+
+/* rows [slice_rows[k], slice_rows[k + 1]) of the byte matrix [M][N] (base bytes_dev) are complete once ready_event (a
+ * cudaEvent_t) has happened -- NULL: once the work already queued on the context's stream has */
+extern "C" int cnb_ctx_stream_slice(cnb_ctx *c, int32_t k, const uint8_t *bytes_dev, void *ready_event) {
+	if (!c || !c->stream_active || k != c->stream_next || k >= (int)c->stream_gend.size() || !bytes_dev) {
+		cnb_set_error("cnb_ctx_stream_slice: slices come in order after cnb_ctx_stream_begin");
+		return CNB_ERR_PARAM;
+	}
+	CK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream, ps = c->prep_stream;
+	const int N = c->N, M = c->M, gs = cnbk_umma_group_samples(1), ns = (int)c->stream_gend.size();
+	const int g0 = k ? c->stream_gend[k - 1] : 0, g1 = c->stream_gend[k];
+	const bool last = k + 1 == ns;
+	const size_t r0 = std::min<size_t>(M, (size_t)g0 * gs), r1 = last ? (size_t)M : std::min<size_t>(M, (size_t)g1 * gs);
+	if (ready_event) CK(cudaStreamWaitEvent(ps, (cudaEvent_t)ready_event, 0));
+	else {
+		CK(cudaEventRecord(c->ev_slices[2 * k], st));
 		CK(cudaStreamWaitEvent(ps, c->ev_slices[2 * k], 0));
-		const int w0 = (int)(r0 / 32), w1 = last ? c->W : (int)(r1 / 32);
-		rc = cnbk_pack(ps, c->b_stage_s.ptr, 1, nullptr, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr, (uint8_t *)c->b_codes.ptr,
-				(uint4 *)c->b_planes_lbl.ptr, nullptr, (int *)c->b_flag.ptr, w0, w1);
-		if (rc == CNB_OK) rc = cnbk_permute(ps, (const uint4 *)c->b_planes_lbl.ptr, nullptr, (const int *)c->b_order.ptr, N, c->W,
-				(uint4 *)c->b_planes.ptr, nullptr, w0, w1);
-		if (rc == CNB_OK) rc = cnbk_umma_rows(ps, (const uint4 *)c->b_planes.ptr, N, c->W, 1, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr,
-				w0 / 4, last ? nq_all : w1 / 4);
-		if (rc != CNB_OK) break;
-		CK(cudaEventRecord(c->ev_slices[2 * k + 1], ps));
-		CK(cudaStreamWaitEvent(st, c->ev_slices[2 * k + 1], 0));
-		if (rc == CNB_OK) rc = (int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W,
-				(int *)c->b_counts_p.ptr, g0, g1, k > 0);
-		if (rc == CNB_OK) rc = cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, D.tiles, 0, ntiles,
-				(int *)c->b_counts.ptr, g0, g1, k > 0);
-		c->timing.kernel_launches += 5;
-		g0 = g1;
 	}
+	const int w0 = (int)(r0 / 32), w1 = last ? c->W : (int)(r1 / 32);
+	RC(cnbk_pack(ps, bytes_dev, 1, nullptr, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr, (uint8_t *)c->b_codes.ptr,
+			(uint4 *)c->b_planes_lbl.ptr, nullptr, (int *)c->b_flag.ptr, w0, w1));
+	RC(cnbk_permute(ps, (const uint4 *)c->b_planes_lbl.ptr, nullptr, (const int *)c->b_order.ptr, N, c->W, (uint4 *)c->b_planes.ptr, nullptr, w0, w1));
+	RC(cnbk_umma_rows(ps, (const uint4 *)c->b_planes.ptr, N, c->W, 1, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr, w0 / 4,
+			last ? c->stream_nq : w1 / 4));
+	CK(cudaEventRecord(c->ev_slices[2 * k + 1], ps));
+	CK(cudaStreamWaitEvent(st, c->ev_slices[2 * k + 1], 0));
+	DevData D = make_devdata(c);
+	RC((int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, (int *)c->b_counts_p.ptr, g0, g1, k > 0));
+	RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, D.tiles, 0, c->stream_tiles,
+			(int *)c->b_counts.ptr, g0, g1, k > 0));
+	c->timing.kernel_launches += 5;
+	c->stream_next = k + 1;
+	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_stream_end(cnb_ctx *c, double *scores_dev, int32_t *ok) {
+	if (!c || !ok || !c->stream_active || !scores_dev) { cnb_set_error("cnb_ctx_stream_end: no streamed search"); return CNB_ERR_PARAM; }
+	*ok = 0;
+	CK(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const bool complete = c->stream_next == (int)c->stream_gend.size();
 	int flags[4] = {0, 0, 0, 0};
-	if (rc == CNB_OK) {
-		D2H(c, flags, c->b_flag.ptr, sizeof(flags));
-		CK(cudaStreamSynchronize(st));
-		CK(cudaStreamSynchronize(c->copy_stream));
-		CK(cudaStreamSynchronize(c->prep_stream));
-	} else {
-		cudaStreamSynchronize(st);
-		cudaStreamSynchronize(c->copy_stream);
-		cudaStreamSynchronize(c->prep_stream);
+	D2H(c, flags, c->b_flag.ptr, sizeof(flags));
+	cudaError_t e1 = cudaStreamSynchronize(c->prep_stream), e2 = cudaStreamSynchronize(st);
+	if (e1 != cudaSuccess || e2 != cudaSuccess) {
+		stream_abort(c);
+		cnb_set_error("CUDA: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+		return CNB_ERR_CUDA;
 	}
-	if (rc != CNB_OK || overflow || flags[0] || flags[2]) {
-		/* an error, a label above 255, a value outside its node's categories or a missing value: the resident path decides
-		 * (it reports the error, or scores the data with the kernels that take missing values) */
-		c->streaming = false;
-		c->have_samples = c->planned = false;
-		c->clean = c->pairs_valid = c->pairs_full = false;
-		return rc;
+	if (!complete || flags[0] || flags[2]) {
+		/* a value outside its node's categories or a missing value: the resident path decides (it reports the error, or
+		 * scores the data with the kernels that take missing values) */
+		stream_abort(c);
+		return CNB_OK;
 	}
-	rc = cnbk_pairs_from_tiles_order(st, (const int *)c->b_counts_p.ptr, (const int *)c->b_order.ptr, N, M, (int *)c->b_pairs.ptr);
+	c->stream_active = false;
+	int rc = cnbk_pairs_from_tiles_order(st, (const int *)c->b_counts_p.ptr, (const int *)c->b_order.ptr, c->N, c->M, (int *)c->b_pairs.ptr);
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	c->data_epoch++;
-	/* ---- the rest of the search on the resident data: the tiled group finds its tables in place ---- */
-	if (rc == CNB_OK) rc = cnb_ctx_score_shard(c, (double *)c->b_scores.ptr);
+	if (rc == CNB_OK) rc = cnb_ctx_score_shard(c, scores_dev);   /* the tiled group finds its tables in place */
 	c->streaming = false;
-	if (rc == CNB_OK) rc = cnb_ctx_select_dp(c, (const double *)c->b_scores.ptr);
-	if (rc == CNB_OK) rc = cnb_ctx_collect(c, out);
 	if (rc != CNB_OK) return rc;
 	c->timing.pack_ms = ev_ms(c, EV_PACK0, EV_PACK1);
+	*ok = 1;
+	return CNB_OK;
+}
+
+/* the one-shot form: this process owns the host matrix and one device */
+static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **out, bool *done) {
+	*done = false;
+	const int N = p->num_nodes, M = p->num_samples;
+	const char *e_min = getenv("CNB_STREAM_MIN");     /* read per call: tests switch it */
+	const size_t stream_min = e_min ? (!strcmp(e_min, "off") ? (size_t)-1 : (size_t)strtoull(e_min, nullptr, 10)) : ((size_t)256 << 20);
+	if (!p->samples || N < 1 || M < 1 || (size_t)N * M * sizeof(int32_t) < stream_min) return CNB_OK;
+	int64_t seg = 0, nf = 0, rows[65];
+	int32_t ns = 0;
+	RC(cnb_ctx_stream_begin(c, p, 0, 1, &seg, &nf, &ns, rows, 65));
+	if (ns < 1) return CNB_OK;
+	CK(cudaSetDevice(c->device));
+	if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	const size_t total = (size_t)N * M;
+	int rc = c->b_stage_s.ensure(total);
+	if (rc == CNB_OK) rc = c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double));
+	bool overflow = false;
+	for (int k = 0; k < ns && rc == CNB_OK && !overflow; k++) {
+		/* host threads narrow slice k to bytes while the copy engine moves the chunks already done and the device works on
+		 * the slices before it */
+		rc = cnb_ctx_upload_bytes(c, p->samples, (size_t)rows[k] * N, (size_t)rows[k + 1] * N, (uint8_t *)c->b_stage_s.ptr, 16, &overflow,
+				c->copy_stream, (size_t)rows[k] * N, total);
+		if (rc != CNB_OK || overflow) break;
+		cudaError_t e = cudaEventRecord(c->ev_slices[2 * k], c->copy_stream);
+		if (e != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; break; }
+		rc = cnb_ctx_stream_slice(c, k, (const uint8_t *)c->b_stage_s.ptr, c->ev_slices[2 * k]);
+	}
+	cudaStreamSynchronize(c->copy_stream);
+	int32_t ok = 0;
+	if (rc == CNB_OK) rc = cnb_ctx_stream_end(c, (double *)c->b_scores.ptr, &ok);   /* a label above 255 left slices out: ok = 0 */
+	else { cudaStreamSynchronize(c->prep_stream); cudaStreamSynchronize(c->stream); stream_abort(c); }
+	if (rc != CNB_OK || !ok) return rc;
+	RC(cnb_ctx_select_dp(c, (const double *)c->b_scores.ptr));
+	RC(cnb_ctx_collect(c, out));
 	c->timing.total_ms = c->timing.pack_ms + c->timing.score_ms + c->timing.select_ms + c->timing.dp_ms + c->timing.collect_ms;
 	*done = true;
 	return CNB_OK;

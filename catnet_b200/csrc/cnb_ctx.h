@@ -36,6 +36,10 @@ struct cnb_ctx {
 	std::vector<cudaEvent_t> ev_slices;   /* "slice k is on the device" */
 	bool tables_resident = false;         /* b_counts still holds the tile tables of the whole two-parent group of the current plan
 	                                         (one batch, one rank): the export reads the returned networks' tables from there */
+	bool stream_active = false;           /* between cnb_ctx_stream_begin and cnb_ctx_stream_end */
+	std::vector<int> stream_gend;         /* last sample group (exclusive) of every slice */
+	int stream_next = 0, stream_nq = 0;
+	long long stream_tiles = 0;           /* this rank's tiles of the two-parent group */
 	bool streaming = false;               /* the streamed one-shot search is driving this context: cnb_ctx_plan leaves the data
 	                                         kernels to it, cnb_ctx_score_shard finds the two-parent tables contracted already */
 	cudaEvent_t ev[CNB_NEV];
@@ -116,7 +120,9 @@ int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t>
 int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes, const int32_t *pert_dev,
 		const int32_t *num_cats);
 int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v1, uint8_t *dst_dev, int max_threads, bool *overflow,
-		cudaStream_t copy_stream = nullptr, size_t pin_origin = 0, size_t pin_values = 0);
+		cudaStream_t copy_stream = nullptr, size_t pin_offset = 0, size_t pin_capacity = 0);
+void cnb_set_last_call_timing(const cnb_timing &t);   /* what cnb_last_call_timing reports for the calling thread */
+void cnb_ctx_stream_cancel(cnb_ctx *c);   /* drop a streamed search begun with cnb_ctx_stream_begin (drains the context's streams) */
 /* cnSearchHist, one order (cnb_hist.cpp) */
 struct CnbHistEval {
 	bool found = false;

@@ -36,6 +36,7 @@ struct cnb_mctx {
 	bool alias = false;                    /* test hook: all G contexts on the ONE device `first` */
 	std::vector<cnb_ctx *> cs;
 	std::vector<cudaEvent_t> ev_done, ev_share;
+	std::vector<std::vector<cudaEvent_t>> ev_slice;   /* streamed search: [device][slice] "this device's share of the slice has reached every peer" */
 	cudaEvent_t ev_start = nullptr, ev_mark[2] = {nullptr, nullptr};
 	bool peer = false;
 	int N = 0, M = 0;
@@ -128,6 +129,7 @@ extern "C" void cnb_mctx_destroy(cnb_mctx *m) {
 		if (m->cs[g]) cudaStreamSynchronize(m->cs[g]->stream);
 		if (m->ev_done[g]) cudaEventDestroy(m->ev_done[g]);
 		if (m->ev_share[g]) cudaEventDestroy(m->ev_share[g]);
+		if (g < (int)m->ev_slice.size()) for (cudaEvent_t ev : m->ev_slice[g]) cudaEventDestroy(ev);
 	}
 	cudaSetDevice(m->first);
 	if (m->ev_start) cudaEventDestroy(m->ev_start);
@@ -447,14 +449,161 @@ void cnb_multi_release(void) {
 	if (m) cnb_mctx_destroy(m);
 }
 
+/* The one-shot search on a large complete host matrix, streamed over A devices (the multi-device form of
+ * search_order_streamed in cnb_api.cu): every device plans its shard of the candidate parent sets first, then the samples
+ * come in slices -- device g narrows its 1/A share of a slice's rows to bytes and copies it over its own PCIe link, sends
+ * it to its peers over NVLink (copy engines, on the copy stream), and every device packs the completed slice and runs one
+ * pass of the table kernel over its own tiles while the host threads are already narrowing the next slice.  *done = false:
+ * the problem does not qualify or the data has missing values -- the caller takes the resident path (from the byte
+ * matrices on the devices when they are complete: m->loaded says so). */
+static int mctx_search_streamed(cnb_mctx *m, int A, const cnb_params *p, cnb_result **out, bool *done) {
+	*done = false;
+	const int N = p->num_nodes, M = p->num_samples;
+	const char *e_min = getenv("CNB_STREAM_MIN");
+	const size_t stream_min = e_min ? (!strcmp(e_min, "off") ? (size_t)-1 : (size_t)strtoull(e_min, nullptr, 10)) : ((size_t)256 << 20);
+	if (A < 2 || !p->samples || p->perturbations || N < 1 || M < 1 || (size_t)N * M * sizeof(int32_t) < stream_min) return CNB_OK;
+	const size_t total = (size_t)N * M;
+	m->loaded = 0;
+	m->N = N;
+	m->M = M;
+	m->active = A;
+	std::vector<int64_t> seg(A, 0);
+	std::vector<int32_t> ns(A, 0);
+	std::vector<std::vector<int64_t>> rows(A, std::vector<int64_t>(65, 0));
+	cnb_ctx *c0 = m->cs[0];
+	CK(cudaSetDevice(c0->device));
+	CK(cudaEventRecord(m->ev_start, c0->stream));
+	int rc = m->crew.run(A, [&](int g) -> int {
+		cnb_ctx *c = m->cs[g];
+		CK(cudaSetDevice(c->device));
+		if (g) CK(cudaStreamWaitEvent(c->stream, m->ev_start, 0));
+		int64_t nf = 0;
+		RC(cnb_ctx_stream_begin(c, p, g, A, &seg[g], &nf, &ns[g], rows[g].data(), 65));
+		if (ns[g] < 1) return CNB_OK;
+		if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		RC(c->b_stage_s.ensure(total));
+		return CNB_OK;
+	});
+	bool all = rc == CNB_OK;
+	for (int g = 0; g < A; g++) all = all && ns[g] == ns[0] && ns[g] > 0 && seg[g] == seg[0];
+	auto cancel = [&]() { for (int g = 0; g < A; g++) cnb_ctx_stream_cancel(m->cs[g]); };
+	if (!all) { cancel(); return rc; }
+	const int S = ns[0];
+	if ((int)m->ev_slice.size() < m->G) m->ev_slice.resize(m->G);
+	for (int g = 0; g < A; g++) {
+		CK(cudaSetDevice(m->cs[g]->device));
+		while ((int)m->ev_slice[g].size() < S) {
+			cudaEvent_t ev;
+			CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			m->ev_slice[g].push_back(ev);
+		}
+	}
+	const size_t score_bytes = (size_t)std::max<int64_t>(seg[0] * A, 1) * sizeof(double);
+	CK(cudaSetDevice(c0->device));
+	rc = c0->b_scores.ensure(score_bytes);
+	if (rc != CNB_OK) { cancel(); return rc; }
+	unsigned hw = std::thread::hardware_concurrency();
+	const int per_dev_threads = (int)std::max(1u, std::min(16u, (hw ? hw : 8u) / (unsigned)A));
+	std::vector<char> big(A, 0);
+	size_t stage_cap = 0;                                          /* values a device stages in all: its share of every slice */
+	for (int k = 0; k < S; k++) stage_cap += (size_t)((rows[0][k + 1] - rows[0][k] + A - 1) / A) * N;
+	std::vector<size_t> stage_off(A, 0);
+	for (int k = 0; k < S && rc == CNB_OK; k++) {
+		const int64_t r0 = rows[0][k], r1 = rows[0][k + 1], sh = (r1 - r0 + A - 1) / A;
+		/* own share of the slice: host -> device, device -> every peer (both on the copy stream) */
+		rc = m->crew.run(A, [&](int g) -> int {
+			cnb_ctx *c = m->cs[g];
+			CK(cudaSetDevice(c->device));
+			const size_t v0 = (size_t)std::min(r1, r0 + g * sh) * N, v1 = (size_t)std::min(r1, r0 + (g + 1) * sh) * N;
+			bool ovf = false;
+			RC(cnb_ctx_upload_bytes(c, p->samples, v0, v1, (uint8_t *)c->b_stage_s.ptr, per_dev_threads, &ovf, c->copy_stream, stage_off[g], stage_cap));
+			stage_off[g] += v1 - v0;
+			big[g] = big[g] || ovf;
+			for (int j = 1; j < A && v1 > v0; j++) {
+				cnb_ctx *d = m->cs[(g + j) % A];
+				CK(cudaMemcpyPeerAsync((uint8_t *)d->b_stage_s.ptr + v0, d->device, (uint8_t *)c->b_stage_s.ptr + v0, c->device, v1 - v0, c->copy_stream));
+			}
+			CK(cudaEventRecord(m->ev_slice[g][k], c->copy_stream));
+			return CNB_OK;
+		});
+		bool any_big = false;
+		for (int g = 0; g < A; g++) any_big = any_big || big[g];
+		if (rc != CNB_OK || any_big) break;
+		/* every share's event is recorded: each device waits for all of them, packs the slice, contracts it */
+		rc = m->crew.run(A, [&](int g) -> int {
+			cnb_ctx *c = m->cs[g];
+			CK(cudaSetDevice(c->device));
+			for (int h = 0; h < A; h++)                            /* the packing stream waits, the copy stream goes on with slice k + 1 */
+				if (h != g) CK(cudaStreamWaitEvent(c->prep_stream, m->ev_slice[h][k], 0));
+			return cnb_ctx_stream_slice(c, k, (const uint8_t *)c->b_stage_s.ptr, m->ev_slice[g][k]);
+		});
+	}
+	bool any_big = false;
+	for (int g = 0; g < A; g++) any_big = any_big || big[g];
+	if (rc != CNB_OK || any_big) { cancel(); return rc; }       /* a label above 255: the int32 route carries it */
+	std::vector<int32_t> ok(A, 0);
+	rc = m->crew.run(A, [&](int g) -> int {
+		cnb_ctx *c = m->cs[g];
+		CK(cudaSetDevice(c->device));
+		CK(cudaStreamSynchronize(c->copy_stream));
+		double *target = (double *)c0->b_scores.ptr;
+		if (g && !m->peer) {
+			RC(c->b_scores.ensure(score_bytes));
+			target = (double *)c->b_scores.ptr;
+		}
+		RC(cnb_ctx_stream_end(c, target, &ok[g]));
+		if (!ok[g]) return CNB_OK;
+		if (g && !m->peer)
+			CK(cudaMemcpyPeerAsync((double *)c0->b_scores.ptr + (size_t)g * seg[0], c0->device, target + (size_t)g * seg[0], c->device,
+					(size_t)seg[0] * sizeof(double), c->stream));
+		if (g) CK(cudaEventRecord(m->ev_done[g], c->stream));
+		return CNB_OK;
+	});
+	bool all_ok = rc == CNB_OK;
+	for (int g = 0; g < A; g++) all_ok = all_ok && ok[g];
+	if (!all_ok) {
+		cancel();
+		if (rc != CNB_OK) return rc;
+		/* missing values (or a value outside its node's categories: the resident path reports it): the byte matrix is
+		 * complete on every device, pack it there */
+		RC(m->crew.run(A, [&](int g) -> int {
+			cnb_ctx *c = m->cs[g];
+			CK(cudaSetDevice(c->device));
+			c->in_host_set = true;
+			int r = cnb_ctx_set_samples_impl(c, N, M, c->b_stage_s.ptr, 1, nullptr, p->num_cats);
+			c->in_host_set = false;
+			return r;
+		}));
+		m->loaded = A;
+		return CNB_OK;
+	}
+	m->loaded = A;
+	CK(cudaSetDevice(c0->device));
+	for (int g = 1; g < A; g++) CK(cudaStreamWaitEvent(c0->stream, m->ev_done[g], 0));
+	RC(cnb_ctx_select_dp(c0, (const double *)c0->b_scores.ptr));
+	RC(cnb_ctx_collect(c0, out));
+	cnb_timing &t = c0->timing;
+	t.total_ms = t.pack_ms + t.score_ms + t.select_ms + t.dp_ms + t.collect_ms;
+	*done = true;
+	return CNB_OK;
+}
+
 int cnb_multi_search_order(const cnb_params *p, cnb_result **out) {
 	const int G = cnb_multi_devices(p);
 	cnb_mctx *m = nullptr;
 	RC(mctx_acquire(p->device, G, &m));
 	/* only the devices this search will use receive the samples */
 	const int A = devices_for(m, p, p->num_samples, m->G);
-	int rc = mctx_load(m, A, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
-	if (rc == CNB_OK) rc = cnb_mctx_search_order(m, p, out);
+	bool done = false;
+	int rc = mctx_search_streamed(m, A, p, out, &done);
+	if (rc == CNB_OK && !done) {
+		if (m->loaded != A) rc = mctx_load(m, A, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
+		if (rc == CNB_OK) rc = cnb_mctx_search_order(m, p, out);
+	}
+	cnb_timing t = m->cs[0]->timing;                              /* the first device's phases, the copies of all devices */
+	for (int g = 1; g < m->G; g++) { t.h2d_bytes += m->cs[g]->timing.h2d_bytes; t.d2h_bytes += m->cs[g]->timing.d2h_bytes; }
+	if (done) t.fast_path = 2;                                    /* 2 = the streamed form ran */
+	cnb_set_last_call_timing(t);
 	mctx_park(m);
 	return rc;
 }

@@ -81,6 +81,82 @@ def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, 
     return ctx.finish(scores.data_ptr(), want_probs)
 
 
+_side_streams = {}
+
+
+def search_order_streamed(ctx, host_samples, rank, world, device, num_cats, want_probs=True, group=None, finish_rank=None,
+                          raw=False, **kw):
+    """cnSearchOrder on `world` GPUs from a HOST matrix (int32 [M][N], pageable is fine, identical on every rank), the upload
+    overlapped with the scoring (the multi-process form of the streamed search, include/catnet_b200.h): the samples travel in
+    slices; of every slice rank r narrows its 1/world share of the rows to bytes and copies it over its own PCIe link, an
+    in-place all-gather over NVLink completes the slice on every GPU (both on a side stream), and the library packs the slice
+    and runs one pass of the tensor-core table kernel over this rank's tiles while the host threads already narrow the next
+    slice.  Problems the streamed form does not take (missing values, perturbations, pools, more than four categories, small
+    matrices) go through set_samples_sharded + search_order_sharded.  finish_rank: only that rank runs selection, DP and
+    export (the others return None); default every rank.  Returns (networks | result handle if raw | None, info)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    stream = torch.cuda.current_stream(device)
+    ctx.set_stream(stream.cuda_stream)
+    hs = host_samples.numpy() if hasattr(host_samples, "numpy") else host_samples
+    m, n = hs.shape
+    seg, _, rows = ctx.stream_begin(rank, world, n, m, num_cats=num_cats, **kw)
+    info = {"streamed": bool(rows), "slices": max(len(rows) - 1, 0), "h2d_bytes": 0}
+
+    def finish(scores):
+        if finish_rank is not None and rank != finish_rank:
+            return None
+        return ctx.finish_raw(scores.data_ptr()) if raw else ctx.finish(scores.data_ptr(), want_probs)
+
+    if not rows:
+        _, info["h2d_bytes"] = set_samples_sharded(ctx, hs, rank, world, device, num_cats=num_cats, group=group)
+        seg, _ = ctx.plan(rank, world, **kw)
+        scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
+        ctx.score_shard(scores.data_ptr())
+        gather_scores(scores, rank, world, seg, group)
+        torch.cuda.synchronize(device)
+        return finish(scores), info
+    ns = len(rows) - 1
+    shares = [(rows[k + 1] - rows[k] + world - 1) // world for k in range(ns)]
+    full = torch.empty((max(rows[k] + world * shares[k] for k in range(ns)), n), dtype=torch.uint8, device=device)
+    scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
+    side = _side_streams.get(str(device))
+    if side is None:
+        side = _side_streams[str(device)] = torch.cuda.Stream(device)
+    side.wait_stream(stream)                                   # `full` is allocated in the current stream's order
+    cap, off = sum(shares) * n, 0
+    threads = max(1, (os.cpu_count() or 8) // world)
+    events = []
+    for k in range(ns):
+        r0, r1, sh = rows[k], rows[k + 1], shares[k]
+        a, b = min(r1, r0 + rank * sh), min(r1, r0 + (rank + 1) * sh)
+        if b > a:
+            try:
+                ctx.upload_rows8_on(hs, a, b, full.data_ptr(), threads, side.cuda_stream, off, cap)
+            except Exception as e:                             # a label above 255: it travelled as 255 = "no category", which the
+                if "above 255" not in str(e):                  # packing reports on EVERY rank (stream_end: not ok) -- no rank may
+                    raise                                      # leave the collectives early
+            off += (b - a) * n
+            info["h2d_bytes"] += (b - a) * n
+        with torch.cuda.stream(side):
+            if world > 1:
+                dist.all_gather_into_tensor(full[r0:r0 + world * sh], full[r0 + rank * sh:r0 + (rank + 1) * sh], group=group)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        events.append(ev)
+        ctx.stream_slice(k, full.data_ptr(), ev.cuda_event)
+    if not ctx.stream_end(scores.data_ptr()):
+        info["streamed"] = False                               # missing values: the byte matrix is complete on every rank
+        ctx.set_samples_dev8(full.data_ptr(), n, m, num_cats=num_cats)
+        seg, _ = ctx.plan(rank, world, **kw)
+        ctx.score_shard(scores.data_ptr())
+    full.record_stream(side)
+    gather_scores(scores, rank, world, seg, group)
+    torch.cuda.synchronize(device)
+    return finish(scores), info
+
+
 def merge_evaluations(evals):
     """per complexity keep the network with the highest likelihood over the chains (first wins ties)"""
     best = {}

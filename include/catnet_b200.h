@@ -205,6 +205,11 @@ int cnb_ctx_set_samples_dev8(cnb_ctx *ctx, int32_t num_nodes, int32_t num_sample
  * matrix over NVLink and pass it to cnb_ctx_set_samples_dev8.  CNB_ERR_PARAM if a label is above 255. */
 int cnb_ctx_upload_rows8(cnb_ctx *ctx, int32_t num_nodes, const int32_t *samples, int64_t row0, int64_t row1,
 		uint8_t *dst_dev, int32_t max_threads);
+/* the same on a stream of the caller's (NULL = the context's), staging the bytes at stage_offset of a pinned buffer of
+ * stage_capacity values (0 = a buffer for just this call): successive calls with disjoint staging ranges let the host
+ * threads narrow one slice while the copy engine still moves the previous one (the streamed search below) */
+int cnb_ctx_upload_rows8_on(cnb_ctx *ctx, int32_t num_nodes, const int32_t *samples, int64_t row0, int64_t row1,
+		uint8_t *dst_dev, int32_t max_threads, void *copy_stream, int64_t stage_offset, int64_t stage_capacity);
 /* categories per node as used on the device (given or inferred), label space */
 int cnb_ctx_num_cats(const cnb_ctx *ctx, int32_t *num_cats_out);
 /* search for one order on the resident data; samples/perturbations/num_cats/device fields of p are ignored */
@@ -272,6 +277,24 @@ int cnb_ctx_finish(cnb_ctx *ctx, const double *scores_dev, cnb_result **out);
 /* the two halves of cnb_ctx_finish: selection + DP on the device (result stays there), then network export */
 int cnb_ctx_select_dp(cnb_ctx *ctx, const double *scores_dev);
 int cnb_ctx_collect(cnb_ctx *ctx, cnb_result **out);
+/* ---- streamed search: the samples are still on their way to the device ----
+ * For a large complete matrix (categories given, <= 4 of them, no perturbations / pools / fixed parents, >= 8192 samples)
+ * the host -> device copy, the packing and the tensor-core contraction overlap: cnb_ctx_stream_begin plans the search
+ * (rank / world as in cnb_ctx_plan) and cuts the samples into num_slices slices of whole sample groups, rows
+ * [slice_rows[k], slice_rows[k+1]) (num_slices = 0: the problem does not qualify, use the resident calls);
+ * cnb_ctx_stream_slice(k) is told that slice k of the BYTE matrix [M][N] (cnb_ctx_set_samples_dev8's form, base pointer
+ * bytes_dev) is complete once ready_event (a cudaEvent_t; NULL = once the work already queued on the context's stream is
+ * done) has happened: it packs the slice on a side stream and runs one pass of the table kernel over this rank's tiles for
+ * the slice's samples, adding to the passes before it -- the caller meanwhile uploads / all-gathers slice k + 1
+ * (cnb_ctx_upload_rows8_on a stream of its own); cnb_ctx_stream_end scores this rank's shard into scores_dev exactly as
+ * cnb_ctx_score_shard would (then: gather, cnb_ctx_finish).  ok = 0: a missing value or a category outside its node's
+ * range turned up -- nothing was scored, the caller continues with cnb_ctx_set_samples_dev8 + cnb_ctx_plan +
+ * cnb_ctx_score_shard on the byte matrix it has assembled.  cnb_search_order does all this by itself for host matrices
+ * of 256 MB and more (CNB_STREAM_MIN, bytes or "off"; CNB_STREAM_SLICES, relative slice sizes, default "1,5,10"). */
+int cnb_ctx_stream_begin(cnb_ctx *ctx, const cnb_params *p, int32_t rank, int32_t world, int64_t *seg_len,
+		int64_t *num_families, int32_t *num_slices, int64_t *slice_rows, int32_t slice_rows_cap);
+int cnb_ctx_stream_slice(cnb_ctx *ctx, int32_t k, const uint8_t *bytes_dev, void *ready_event);
+int cnb_ctx_stream_end(cnb_ctx *ctx, double *scores_dev, int32_t *ok);
 /* launch on the caller's CUDA stream (e.g. the stream its NCCL collectives use) instead of the context's own
  * non-blocking stream; NULL selects the context's own stream again -- to name the legacy default stream pass
  * cudaStreamLegacy ((cudaStream_t)0x1).  Work the caller orders against this library (copies into the sample

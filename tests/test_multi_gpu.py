@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import compare_search, constrained_problem, random_problem
+from helpers import NA, compare_search, constrained_problem, random_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -245,3 +245,145 @@ def test_device_time_marks(abi):
         h = mc.collect_raw()
         assert abi.lib().cnb_result_num_networks(h) > 0
         abi.lib().cnb_result_free(h)
+
+
+# ------------------------------------------------------------------ streamed search over several devices
+@pytest.mark.parametrize("n,m,cats,slices,g", [(70, 9000, 4, "1,3,4,4,3,1", 2), (40, 8192, 3, "1", 3), (130, 20001, 4, "1,1", 2),
+                                               (65, 12345, 2, "1,2,3", 4), (30, 100000, 4, "1,5,10", 8)])
+def test_streamed_search_over_devices(abi, monkeypatch, n, m, cats, slices, g):
+    """cnb_search_order(num_devices = G) on a large complete matrix: every slice of the samples is dealt over the devices
+    (1/G of its rows over each PCIe link, peer copies complete it everywhere) and contracted on every device -- over that
+    device's tiles -- while the next slice is on its way.  Same networks, tables and log-likelihoods as one device."""
+    s, c = random_problem(17 * n + m, n, m, cats)
+    kw = dict(max_parent_set=2, max_complexity=n * 16 * 3, num_cats=c, order=(np.random.default_rng(m).permutation(n) + 1))
+    monkeypatch.setenv("CNB_STREAM_MIN", "off")
+    a = abi.search_order(s, **kw)
+    assert abi.last_call_timing()["fast_path"] != 2
+    monkeypatch.setenv("CNB_STREAM_SLICES", slices)
+    for nd in _forms(g):
+        monkeypatch.setenv("CNB_STREAM_MIN", "off")
+        same_nets(abi.search_order(s, num_devices=nd, **kw), a)
+        assert abi.last_call_timing()["fast_path"] != 2
+        monkeypatch.setenv("CNB_STREAM_MIN", "0")
+        b = abi.search_order(s, num_devices=nd, **kw)
+        t = abi.last_call_timing()
+        assert t["fast_path"] == 2 and t["tensor_tiles"] > 0 and t["h2d_bytes"] >= s.size
+        same_nets(b, a)
+    abi.lib().cnb_release_cache()
+
+
+def test_streamed_search_over_devices_steps_aside(abi, monkeypatch):
+    """a missing value found while packing the last slice: every device packs the byte matrix it has assembled and the
+    resident kernels score it; a value outside its node's categories is reported; a label above 255 goes the int32 way"""
+    monkeypatch.setenv("CNB_STREAM_MIN", "0")
+    s, c = random_problem(78, 40, 9000, 4)
+    kw = dict(max_parent_set=2, max_complexity=40 * 48, num_cats=c)
+    s_na = s.copy()
+    s_na[8000, 7] = NA
+    monkeypatch.setenv("CNB_STREAM_MIN", "off")
+    want = abi.search_order(s_na, **kw)
+    ok = abi.search_order(s, **kw)
+    monkeypatch.setenv("CNB_STREAM_MIN", "0")
+    for nd in _forms(2) + _forms(3):
+        got = abi.search_order(s_na, num_devices=nd, **kw)
+        assert abi.last_call_timing()["fast_path"] != 2
+        same_nets(got, want)
+        bad = s.copy()
+        bad[8100, 3] = 9
+        with pytest.raises(abi.CnbError) as e:
+            abi.search_order(bad, num_devices=nd, **kw)
+        assert "Incorrect categories" in str(e.value)
+        big = s.copy()
+        big[5, 2] = 300
+        with pytest.raises(abi.CnbError) as e:
+            abi.search_order(big, num_devices=nd, **kw)
+        assert "Incorrect categories" in str(e.value)
+        again = abi.search_order(s, num_devices=nd, **kw)     # the parked contexts stream again afterwards
+        assert abi.last_call_timing()["fast_path"] == 2
+        same_nets(again, ok)
+    abi.lib().cnb_release_cache()
+
+
+def test_streamed_search_one_rank_python_driver(abi, monkeypatch):
+    """catnet_b200/dist.py::search_order_streamed with a world of one: the slice loop of the multi-process driver
+    (upload_rows8_on on a side stream, event per slice, stream_slice, stream_end) against the resident path"""
+    import torch
+    from catnet_b200 import dist as cdist
+    dev = torch.device("cuda:0")
+    s, c = random_problem(79, 60, 20000, 4)
+    kw = dict(max_parent_set=2, max_complexity=60 * 48, order=(np.random.default_rng(2).permutation(60) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        want = ctx.search_order(**kw)
+    monkeypatch.setenv("CNB_STREAM_SLICES", "1,2,2,1")
+    with abi.Context(0) as ctx:
+        got, info = cdist.search_order_streamed(ctx, s, 0, 1, dev, c, **kw)
+        assert info["streamed"] and info["slices"] == 4 and info["h2d_bytes"] == s.size
+        same_nets(got, want)
+        s_na = s.copy()
+        s_na[19990, 3] = NA
+        got, info = cdist.search_order_streamed(ctx, s_na, 0, 1, dev, c, **kw)
+        assert not info["streamed"]
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s_na, num_cats=c)
+        same_nets(got, ctx.search_order(**kw))
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["CNB_STREAM_SLICES"] = "1,3,4,4,3,1"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from helpers import random_problem as rp
+        from catnet_b200 import _abi, dist as cdist
+        dev = torch.device("cuda", rank)
+        res = []
+        for seed, n, m, na in ((5, 70, 33000, False), (6, 45, 9001, False), (7, 50, 12000, True)):
+            s, c = rp(seed, n, m, 4)
+            if na:
+                s[m - 5, 3] = -2147483648
+            kw = dict(max_parent_set=2, max_complexity=n * 48, order=(np.random.default_rng(seed).permutation(n) + 1))
+            with _abi.Context(rank) as ctx:
+                ctx.set_samples(s, num_cats=c)
+                want = ctx.search_order(**kw)
+            with _abi.Context(rank) as ctx:
+                got, info = cdist.search_order_streamed(ctx, s, rank, world, dev, c, **kw)
+            same = len(got) == len(want) and all(
+                x["loglik"] == y["loglik"] and x["complexity"] == y["complexity"]
+                and all(np.array_equal(p, q_) for p, q_ in zip(x["parents"], y["parents"]))
+                and all(np.array_equal(p, q_) for p, q_ in zip(x["probs"], y["probs"])) for x, y in zip(got, want))
+            res.append((bool(same), bool(info["streamed"]), int(info["h2d_bytes"]), s.size))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_streamed_search_two_ranks_nccl():
+    """the multi-process driver on two real GPUs: slices all-gathered in place over NCCL while the table kernel runs"""
+    if _ngpu() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    sk = socket.socket()
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
+    sk.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        (s1, st1, h1, sz1), (s2, st2, h2, sz2), (s3, st3, _, _) = out[rank]
+        assert s1 and s2 and s3 and st1 and st2 and not st3
+        assert abs(h1 - sz1 / 2) <= 70 * 8 and abs(h2 - sz2 / 2) <= 45 * 8
