@@ -568,7 +568,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     cpu_group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from catnet_b200 import dist as cdist
+        dist.init_process_group("nccl", device_id=dev, pg_options=cdist.nccl_options())
         cpu_group = dist.new_group(backend="gloo")       # host-side barrier while rank 0 measures the single-process form
 
     # ---- synthetic data: rank 0 draws on the host (numpy, the same generator as the reference arm), everybody receives it

@@ -66,6 +66,7 @@ extern "C" int cnb_ctx_create(int32_t device, cnb_ctx **out) {
 	CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
 	for (int i = 0; i < CNB_NEV; i++) CK(cudaEventCreate(&c->ev[i]));
+	if (const char *e = getenv("CNB_HIST_MODE")) c->hist_mode = c->hist_mode_default = std::max(0, std::min(2, atoi(e)));
 	*out = c;
 	return CNB_OK;
 }
@@ -429,10 +430,14 @@ int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v
 	if (pin_offset + total > pin_capacity) { cnb_set_error("upload: staging range %zu + %zu exceeds %zu", pin_offset, total, pin_capacity); return CNB_ERR_PARAM; }
 	RC(c->pin_stage.ensure(pin_capacity));
 	uint8_t *pin = (uint8_t *)c->pin_stage.ptr + pin_offset;
-	const size_t chunk = (size_t)4 << 20;                       /* values per chunk: 16 MB of int32 -> 4 MB */
-	const int nchunks = (int)((total + chunk - 1) / chunk);
+	/* values per chunk: 16 MB of int32 -> 4 MB for whole matrices; a rank's share of a small slice still gives every thread
+	 * a few chunks (one 4 M chunk = one thread = 2.4 ms for the 3.9 M values of C5's first slice on 8 ranks) */
 	unsigned hw = std::thread::hardware_concurrency();
-	const int nthreads = (int)std::max(1u, std::min(std::min(hw ? hw : 4u, (unsigned)std::max(max_threads, 1)), (unsigned)nchunks));
+	const unsigned want_threads = std::min(hw ? hw : 4u, (unsigned)std::max(max_threads, 1));
+	size_t chunk = (size_t)4 << 20;
+	while (chunk > ((size_t)128 << 10) && total < chunk * want_threads * 3) chunk >>= 1;
+	const int nchunks = (int)((total + chunk - 1) / chunk);
+	const int nthreads = (int)std::max(1u, std::min(want_threads, (unsigned)nchunks));
 	std::vector<std::atomic<int>> done(nchunks);
 	for (auto &d : done) d.store(0, std::memory_order_relaxed);
 	std::atomic<int> next(0), big(0);
@@ -562,6 +567,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->dp_no_trap = (on & 2048) != 0;                      /* bit 11: wavefront DP one node per exchange (k_dp_wave) */
 	c->generic_epilogue = (on & 4096) != 0;                /* bit 12: generic epilogue of the tensor-core scorer also for 4-category data */
 	c->force_full = (on & 8192) != 0;
+	c->hist_mode = (on & 32768) ? 0 : ((on & 65536) ? 2 : c->hist_mode_default);   /* bit 15: generic scorer one CTA per family; bit 16: a warp per family with __match_any_sync */
 	c->dp_chains = (on & 16384) != 0;                      /* bit 14: trapezoid DP, every slot re-sums its own candidates (no work list) */                      /* bit 13: full-table tiles also on complete data (no inclusion-exclusion) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
@@ -877,7 +883,7 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 	}
 	int cells = table_stride(c->max_cats, d_max);
 	if (cells > CNB_HIST_MAX_CELLS) cells = CNB_HIST_MAX_CELLS;
-	RC(cnbk_score_hist(st, D, F, b, e, cells, O, (int *)c->b_flag.ptr + 1));
+	RC(cnbk_score_hist(st, D, F, b, e, cells, O, (int *)c->b_flag.ptr + 1, c->hist_mode));
 	c->timing.kernel_launches++;
 	return CNB_OK;
 }
@@ -1265,6 +1271,11 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	const int N = pl.N, K = pl.K;
 	size_t slots = (size_t)K + 1;
 	CK(cudaEventRecord(c->ev[EV_COL0], st));
+	static const bool trace = getenv("CNB_TRACE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+	auto t_begin = now();
+	double t_sel = 0, t_walk = 0, t_tables = 0;
 	DpState fin;
 	fin.K = K;
 	fin.exists = (unsigned char *)c->b_dp_exists.ptr + c->dp_final * slots;
@@ -1286,6 +1297,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	if (nlive) D2H(c, c->pin_sel.ptr, c->b_sel.ptr, nlive * N * sizeof(long long));
 	if (nopt) D2H(c, (void *)opt_fid, c->b_opt_fid.ptr, nopt * sizeof(long long));
 	CK(cudaStreamSynchronize(st));
+	t_sel = ms_since(t_begin);
 
 	std::unique_ptr<cnb_result> res(new cnb_result());
 	res->N = N;
@@ -1333,6 +1345,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		res->nets.push_back(std::move(net));
 	}
 	size_t nf = ex_child.size();
+	t_walk = ms_since(t_begin);
 	int dmax = 0;
 	for (int v : ex_nd) dmax = std::max(dmax, v);
 	int stride = table_stride(c->max_cats, dmax);
@@ -1358,6 +1371,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		D2H(c, prior.data(), c->b_ex_prior.ptr, nf * sizeof(double));
 		CK(cudaEventRecord(c->ev[EV_COL1], st));
 		CK(cudaStreamSynchronize(st));
+		t_tables = ms_since(t_begin);
 		res->fams.resize(nf);
 		for (size_t f = 0; f < nf; f++) {
 			CnbFamily &fm = res->fams[f];
@@ -1378,6 +1392,9 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		}
 		c->timing.collect_ms = ev_ms(c, EV_COL0, EV_COL1);
 	}
+	if (trace)
+		fprintf(stderr, "[cnb] collect: %zu networks, %zu distinct families; selection on the host after %.2f ms, families listed %.2f, tables back %.2f, "
+				"result built %.2f ms\n", nlive, nf, t_sel, t_walk, t_tables, ms_since(t_begin));
 	*out = res.release();
 	return CNB_OK;
 }
@@ -1465,7 +1482,14 @@ extern "C" int cnb_ctx_stream_begin(cnb_ctx *c, const cnb_params *p, int32_t ran
 	}
 	CK(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
-	if (!c->prep_stream) CK(cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
+	if (!c->prep_stream) {
+		/* highest priority: the packing kernels of slice k + 1 must be dispatched WHILE the table kernel's pass over slice k
+		 * still has thousands of CTAs waiting (measured without it: the block scheduler starts them only when the pass has
+		 * issued its last CTA, i.e. every pass was followed by a gap of one packing time) */
+		int lo = 0, hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CK(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi));
+	}
 	/* ---- what cnb_ctx_set_samples would set up, minus the data ---- */
 	c->have_samples = c->planned = c->dp_done = c->tables_resident = false;
 	c->N = N; c->M = M; c->W = (M + 31) / 32; c->Mpad = c->W * 32;
@@ -1532,9 +1556,9 @@ extern "C" int cnb_ctx_stream_begin(cnb_ctx *c, const cnb_params *p, int32_t ran
 	}
 	const int ns = (int)c->stream_gend.size();
 	if (slice_rows && slice_cap < ns + 1) { stream_abort(c); cnb_set_error("cnb_ctx_stream_begin: %d slices", ns); return CNB_ERR_PARAM; }
-	while ((int)c->ev_slices.size() < 2 * ns) {                    /* per slice: "copied" (the one-shot form), "packed" */
+	while ((int)c->ev_slices.size() < 4 * ns) {                    /* per slice: "copied" (the one-shot form), "here", "packed", "contracted" */
 		cudaEvent_t ev;
-		CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		CK(cudaEventCreate(&ev));                                  /* with timing: CNB_TRACE prints the slices' time line */
 		c->ev_slices.push_back(ev);
 	}
 	if (slice_rows) {
@@ -1568,21 +1592,23 @@ extern "C" int cnb_ctx_stream_slice(cnb_ctx *c, int32_t k, const uint8_t *bytes_
 	const size_t r0 = std::min<size_t>(M, (size_t)g0 * gs), r1 = last ? (size_t)M : std::min<size_t>(M, (size_t)g1 * gs);
 	if (ready_event) CK(cudaStreamWaitEvent(ps, (cudaEvent_t)ready_event, 0));
 	else {
-		CK(cudaEventRecord(c->ev_slices[2 * k], st));
-		CK(cudaStreamWaitEvent(ps, c->ev_slices[2 * k], 0));
+		CK(cudaEventRecord(c->ev_slices[4 * k], st));
+		CK(cudaStreamWaitEvent(ps, c->ev_slices[4 * k], 0));
 	}
+	CK(cudaEventRecord(c->ev_slices[4 * k + 1], ps));
 	const int w0 = (int)(r0 / 32), w1 = last ? c->W : (int)(r1 / 32);
 	RC(cnbk_pack(ps, bytes_dev, 1, nullptr, N, M, c->W, (int *)c->b_vmin.ptr, (int *)c->b_cats_lbl.ptr, (uint8_t *)c->b_codes.ptr,
 			(uint4 *)c->b_planes_lbl.ptr, nullptr, (int *)c->b_flag.ptr, w0, w1));
 	RC(cnbk_permute(ps, (const uint4 *)c->b_planes_lbl.ptr, nullptr, (const int *)c->b_order.ptr, N, c->W, (uint4 *)c->b_planes.ptr, nullptr, w0, w1));
 	RC(cnbk_umma_rows(ps, (const uint4 *)c->b_planes.ptr, N, c->W, 1, (uint4 *)c->b_rows_a.ptr, (uint4 *)c->b_rows_b.ptr, w0 / 4,
 			last ? c->stream_nq : w1 / 4));
-	CK(cudaEventRecord(c->ev_slices[2 * k + 1], ps));
-	CK(cudaStreamWaitEvent(st, c->ev_slices[2 * k + 1], 0));
+	CK(cudaEventRecord(c->ev_slices[4 * k + 2], ps));
+	CK(cudaStreamWaitEvent(st, c->ev_slices[4 * k + 2], 0));
 	DevData D = make_devdata(c);
 	RC((int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, (int *)c->b_counts_p.ptr, g0, g1, k > 0));
 	RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, D.tiles, 0, c->stream_tiles,
 			(int *)c->b_counts.ptr, g0, g1, k > 0));
+	CK(cudaEventRecord(c->ev_slices[4 * k + 3], st));
 	c->timing.kernel_launches += 5;
 	c->stream_next = k + 1;
 	return CNB_OK;
@@ -1609,6 +1635,15 @@ extern "C" int cnb_ctx_stream_end(cnb_ctx *c, double *scores_dev, int32_t *ok) {
 		return CNB_OK;
 	}
 	c->stream_active = false;
+	if (getenv("CNB_TRACE")) {                                     /* the slices' time line on the device, ms after the plan */
+		for (int k = 0; k < (int)c->stream_gend.size(); k++) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, c->ev[EV_SCORE0], c->ev_slices[4 * k + 1]);
+			cudaEventElapsedTime(&b, c->ev[EV_SCORE0], c->ev_slices[4 * k + 2]);
+			cudaEventElapsedTime(&d, c->ev[EV_SCORE0], c->ev_slices[4 * k + 3]);
+			fprintf(stderr, "[cnb] dev %d slice %d (groups < %d): here %.2f  packed %.2f  contracted %.2f ms\n", c->device, k, c->stream_gend[k], a, b, d);
+		}
+	}
 	int rc = cnbk_pairs_from_tiles_order(st, (const int *)c->b_counts_p.ptr, (const int *)c->b_order.ptr, c->N, c->M, (int *)c->b_pairs.ptr);
 	CK(cudaEventRecord(c->ev[EV_PACK1], st));
 	c->data_epoch++;
@@ -1643,9 +1678,9 @@ static int search_order_streamed(cnb_ctx *c, const cnb_params *p, cnb_result **o
 		rc = cnb_ctx_upload_bytes(c, p->samples, (size_t)rows[k] * N, (size_t)rows[k + 1] * N, (uint8_t *)c->b_stage_s.ptr, 16, &overflow,
 				c->copy_stream, (size_t)rows[k] * N, total);
 		if (rc != CNB_OK || overflow) break;
-		cudaError_t e = cudaEventRecord(c->ev_slices[2 * k], c->copy_stream);
+		cudaError_t e = cudaEventRecord(c->ev_slices[4 * k], c->copy_stream);
 		if (e != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(e)); rc = CNB_ERR_CUDA; break; }
-		rc = cnb_ctx_stream_slice(c, k, (const uint8_t *)c->b_stage_s.ptr, c->ev_slices[2 * k]);
+		rc = cnb_ctx_stream_slice(c, k, (const uint8_t *)c->b_stage_s.ptr, c->ev_slices[4 * k]);
 	}
 	cudaStreamSynchronize(c->copy_stream);
 	int32_t ok = 0;

@@ -627,6 +627,114 @@ __global__ void __launch_bounds__(256) k_score_hist(DevData Dt, DevFamilies F, l
 	}
 }
 
+/* ------------------------------------------------------------------ K2c: warp-privatised histogram scorer ---- */
+/* The scorer for nodes with more than four categories (no bit planes, no tensor tiles): one WARP per family, its
+ * conditional table in the warp's own part of shared memory, so that no two warps ever add to the same cell.  Every lane
+ * takes 16 consecutive samples per step -- one 128-bit load of the child's and of every parent's uint8 column (the
+ * column-major code matrix stays in L2: N x M bytes) -- and turns each into the mixed-radix cell index
+ * (catnet_class.h:842-857: parent configuration x child category; a missing value or a sample perturbed for the child is
+ * skipped, :849).  MATCH: lanes that hit the same cell in a step are found with __match_any_sync and the first of
+ * them adds their number with a plain read-modify-write -- no atomics at all, which is what pays on skewed data where
+ * most samples fall into a few cells; otherwise one shared-memory atomicAdd per sample (the atomics of a warp on one
+ * address are serialised by the hardware).  The fp64 epilogue (problist.h:224-250) stays in the warp: the 32 lanes
+ * compute the terms n log(n / N_k) of 32 consecutive cells side by side, then the terms are added in the reference's
+ * order -- cell after cell, empty cells skipped -- by a chain of shuffles. */
+template <int D, bool MATCH>
+__global__ void __launch_bounds__(256) k_score_hist_warp(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
+		int cells_per_warp, ScoreOut O, int *__restrict__ overflow) {
+	extern __shared__ __align__(16) int s_tab[];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+	int *tab = s_tab + (size_t)wib * cells_per_warp;
+	const unsigned FULLM = 0xFFFFFFFFu;
+	const int chunks16 = Dt.Mpad >> 4;                  /* Mpad is a multiple of 32 */
+	for (long long fid = fid_begin + (long long)blockIdx.x * wpb + wib; fid < fid_end; fid += (long long)gridDim.x * wpb) {
+		int child, pars[CNB_MAXP];
+		dev_family(Dt, F, fid, child, pars);            /* every lane: uniform, no divergence */
+		const int cc = Dt.cats[child];
+		int pc[D > 0 ? D : 1];
+		int tsize = cc;
+#pragma unroll
+		for (int i = 0; i < D; i++) { pc[i] = Dt.cats[pars[i]]; tsize = tsize > cells_per_warp ? tsize : tsize * pc[i]; }
+		if (tsize > cells_per_warp) {                   /* uniform over the warp */
+			if (lane == 0) *overflow = 1;
+			continue;
+		}
+		for (int i = lane; i < tsize; i += 32) tab[i] = 0;
+		__syncwarp();
+		const int clbl = Dt.order[child];
+		const uint4 *ccol = reinterpret_cast<const uint4 *>(Dt.codes + (size_t)clbl * Dt.Mpad);
+		const uint4 *pcol[D > 0 ? D : 1];
+#pragma unroll
+		for (int i = 0; i < D; i++) pcol[i] = reinterpret_cast<const uint4 *>(Dt.codes + (size_t)Dt.order[pars[i]] * Dt.Mpad);
+		const uint32_t *kcol = Dt.keep_lbl ? Dt.keep_lbl + clbl : nullptr;
+		for (int t0 = 0; t0 < chunks16; t0 += 32) {
+			const int t = t0 + lane;
+			const bool in = t < chunks16;
+			uint4 cv = make_uint4(~0u, ~0u, ~0u, ~0u), pv[D > 0 ? D : 1];
+			uint32_t km = 0xFFFFu;
+			if (in) {
+				cv = __ldg(ccol + t);
+#pragma unroll
+				for (int i = 0; i < D; i++) pv[i] = __ldg(pcol[i] + t);
+				if (kcol) km = (__ldg(kcol + (size_t)(t >> 1) * Dt.N) >> ((t & 1) * 16)) & 0xFFFFu;
+			}
+#pragma unroll
+			for (int q = 0; q < 16; q++) {
+				const uint32_t cw = q < 4 ? cv.x : (q < 8 ? cv.y : (q < 12 ? cv.z : cv.w));
+				const int x = (cw >> (8 * (q & 3))) & 255;
+				bool ok = in && x < cc && ((km >> q) & 1);
+				int idx = 0;
+#pragma unroll
+				for (int i = 0; i < D; i++) {
+					const uint32_t pw = q < 4 ? pv[i].x : (q < 8 ? pv[i].y : (q < 12 ? pv[i].z : pv[i].w));
+					const int v = (pw >> (8 * (q & 3))) & 255;
+					ok = ok && v < pc[i];
+					idx = idx * pc[i] + v;
+				}
+				idx = idx * cc + x;
+				if (MATCH) {
+					/* lanes without a sample get keys of their own, so that they meet nobody */
+					const unsigned peers = __match_any_sync(FULLM, ok ? idx : (int)(0x80000000u | lane));
+					if (ok && lane == __ffs(peers) - 1) tab[idx] += __popc(peers);
+					__syncwarp();
+				} else if (ok) atomicAdd(&tab[idx], 1);
+			}
+		}
+		__syncwarp();
+		double ll = 0.0;
+		long long ncount = 0;
+		for (int c0 = 0; c0 < tsize; c0 += 32) {
+			const int cell = c0 + lane;
+			int n = 0;
+			double term = 0.0;
+			if (cell < tsize) {
+				n = tab[cell];
+				if (O.counts) O.counts[(size_t)fid * O.counts_stride + cell] = n;
+				if (n > 0) {
+					const int cfg = cell / cc;
+					long long nk = 0;
+					for (int k = 0; k < cc; k++) nk += tab[cfg * cc + k];
+					const double pp = __ddiv_rn(1.0, (double)nk), dn = (double)n;
+					term = __dmul_rn(dn, cnb_log(__dmul_rn(dn, pp)));
+				}
+			}
+			int tot = n;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULLM, tot, o);
+			ncount += tot;
+			unsigned m = __ballot_sync(FULLM, n > 0);
+			while (m) {                                    /* the reference's order: cells ascending, empty ones skipped */
+				const int l = __ffs(m) - 1;
+				m &= m - 1;
+				ll = __dadd_rn(ll, __shfl_sync(FULLM, term, l));
+			}
+		}
+		if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
+		if (lane == 0) dev_store_outputs(Dt, O, fid, child, pars, D, ll, (int)ncount);
+		__syncwarp();
+	}
+}
+
 /* ------------------------------------------------------------------ K4: selection / option table ---- */
 /* One CTA per candidate block.  Equal-categories path: first maximum in enumeration order (strict '<' running
  * max from -FLT_MAX, catnet_search2.h:559,613) -> one DP option.  Otherwise every candidate becomes an option. */
@@ -1509,9 +1617,51 @@ int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &
 	return CNB_OK;
 }
 
-int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
+template <int D>
+static int launch_hist_warp(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int cpw, int wpb, bool match,
 		const ScoreOut &O, int *overflow) {
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		CK(cudaGetDevice(&dev));
+		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	const size_t smem = (size_t)cpw * wpb * sizeof(int);
+	const long long nblk = (e - b + wpb - 1) / wpb;
+	int per_sm = 1;
+	if (match) {
+		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_score_hist_warp<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_hist_warp<D, true>, wpb * 32, smem));
+		const unsigned grid = (unsigned)std::min<long long>(nblk, (long long)sms * std::max(per_sm, 1));
+		k_score_hist_warp<D, true><<<grid, wpb * 32, smem, st>>>(Dt, F, b, e, cpw, O, overflow);
+	} else {
+		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_score_hist_warp<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_hist_warp<D, false>, wpb * 32, smem));
+		const unsigned grid = (unsigned)std::min<long long>(nblk, (long long)sms * std::max(per_sm, 1));
+		k_score_hist_warp<D, false><<<grid, wpb * 32, smem, st>>>(Dt, F, b, e, cpw, O, overflow);
+	}
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
+		const ScoreOut &O, int *overflow, int mode) {
 	if (e <= b) return CNB_OK;
+	/* mode 0: one CTA per family (k_score_hist: any parent count, tables up to max_cells); 1 / 2: a warp per family with
+	 * its own table, atomics / __match_any_sync -- for up to three parents of one count and tables that leave room for at
+	 * least one warp's table in 96 KB */
+	const int cpw = (max_cells + 31) & ~31;
+	if (mode != 0 && F.d >= 0 && F.d <= 3 && !F.ex_nd && (size_t)cpw * sizeof(int) <= 96 * 1024) {
+		int wpb = 8;
+		while (wpb > 1 && (size_t)cpw * wpb * sizeof(int) > 96 * 1024) wpb >>= 1;
+		const bool match = mode == 2;
+		switch (F.d) {
+		case 0: return launch_hist_warp<0>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
+		case 1: return launch_hist_warp<1>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
+		case 2: return launch_hist_warp<2>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
+		default: return launch_hist_warp<3>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
+		}
+	}
 	size_t smem = (size_t)((max_cells + 1) & ~1) * sizeof(int) + (size_t)max_cells * sizeof(double);
 	if (smem > 48 * 1024)
 		CK(cudaFuncSetAttribute(k_score_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -116,7 +116,7 @@ int cnbk_sample_na(cudaStream_t st, int N, int M, int k, unsigned long long seed
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
-		const ScoreOut &O, int *overflow);
+		const ScoreOut &O, int *overflow, int mode);
 /* arg-max per (child, parent count) block: `chunks` = (block, chunk) per CTA, cnbk_select_chunk() candidates each;
  * blk_chunk0[nblocks + 1] = first chunk of every block; part_* = nchunks partial results */
 int cnbk_select_chunk(void);

@@ -84,6 +84,17 @@ def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, 
 _side_streams = {}
 
 
+def nccl_options():
+    """pg_options for init_process_group("nccl", ...): NCCL's kernels on a high-priority stream.  The all-gather of slice k + 1
+    has to run while the table kernel's pass over slice k still has thousands of CTAs waiting; at default priority the block
+    scheduler starts a later kernel only once the earlier one has issued its last CTA, which would put every all-gather
+    (and the packing behind it) between two passes instead of under one."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return opts
+
+
 def search_order_streamed(ctx, host_samples, rank, world, device, num_cats, want_probs=True, group=None, finish_rank=None,
                           raw=False, **kw):
     """cnSearchOrder on `world` GPUs from a HOST matrix (int32 [M][N], pageable is fine, identical on every rank), the upload
@@ -123,7 +134,7 @@ def search_order_streamed(ctx, host_samples, rank, world, device, num_cats, want
     scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
     side = _side_streams.get(str(device))
     if side is None:
-        side = _side_streams[str(device)] = torch.cuda.Stream(device)
+        side = _side_streams[str(device)] = torch.cuda.Stream(device, priority=-1)
     side.wait_stream(stream)                                   # `full` is allocated in the current stream's order
     cap, off = sum(shares) * n, 0
     threads = max(1, (os.cpu_count() or 8) // world)
@@ -149,7 +160,8 @@ def search_order_streamed(ctx, host_samples, rank, world, device, num_cats, want
     if not ctx.stream_end(scores.data_ptr()):
         info["streamed"] = False                               # missing values: the byte matrix is complete on every rank
         ctx.set_samples_dev8(full.data_ptr(), n, m, num_cats=num_cats)
-        seg, _ = ctx.plan(rank, world, **kw)
+        seg, _ = ctx.plan(rank, world, **kw)                   # other kernels, another layout of the score buffer
+        scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
         ctx.score_shard(scores.data_ptr())
     full.record_stream(side)
     gather_scores(scores, rank, world, seg, group)

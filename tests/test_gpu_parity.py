@@ -76,6 +76,42 @@ def test_family_counts_and_loglik(abi, port, cats, na, pert, m):
                     assert ll[i] == rll, (d, generic, ch, pa, ll[i], rll)   # bit-exact
 
 
+@pytest.mark.parametrize("bits", [0, 32768, 65536], ids=["warp_atomics", "cta_per_family", "warp_match_any"])
+@pytest.mark.parametrize("cats,na,pert,m", [(6, 0.0, False, 1000), (8, 0.05, True, 777), ([5, 12, 3, 7, 2, 9, 6, 4, 10, 5], 0.03, False, 2000),
+                                            (16, 0.0, False, 300), (4, 0.1, True, 33), (5, 0.0, False, 1)])
+def test_many_categories_histogram_scorers(abi, port, bits, cats, na, pert, m):
+    """more than four categories per node: the histogram scorers -- a warp per family with its own shared-memory table
+    (atomics, or __match_any_sync aggregation) and the one-CTA-per-family kernel -- against the oracle: counts exact,
+    log-likelihoods bit-identical, 0..3 parents, missing values, perturbation masks, whole searches"""
+    n = 10
+    s, c = random_problem(11 + m, n, max(m, 20), cats, na)
+    s = s[:m]
+    rng = np.random.default_rng(m)
+    p = (rng.random(s.shape) < 0.2).astype(np.int32) if pert else None
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=p, num_cats=c)
+        ctx.force_generic(bits)
+        for d in (0, 1, 2, 3):
+            if int(np.max(c)) ** (d + 1) > 16384:
+                continue
+            fams = [(ch, pa) for ch in range(n) for pa in itertools.permutations([v for v in range(n) if v != ch], d)]
+            fams = [fams[i] for i in rng.choice(len(fams), size=min(40, len(fams)), replace=False)]
+            children = [f[0] for f in fams]
+            parents = np.array([f[1] for f in fams], dtype=np.int32).reshape(len(fams), d)
+            counts, ll, nc = ctx.family_scores(children, parents, force_generic=True)
+            for i, (ch, pa) in enumerate(fams):
+                keep = None if p is None else (p[:, ch] == 0)
+                rc, rll, rnc = port.family_score(s0, c, ch, list(pa), keep=keep)
+                assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)), (d, ch, pa)
+                assert nc[i] == rnc and ll[i] == rll, (d, ch, pa, ll[i], rll)
+        if m >= 300 and int(np.max(c)) <= 12:
+            K = int(np.sum(c - 1)) + 3 * int(np.max(c)) ** 2
+            ours = ctx.search_order(max_parent_set=2, max_complexity=K)
+            theirs = port.search_order(s, 2, K, num_cats=c, perturbations=p)
+            assert compare_search(ours, theirs) == len(theirs)
+
+
 def test_family_scores_match_golden(abi):
     by_problem = {}
     for g in load_golden("ref_family_scores"):

@@ -336,7 +336,8 @@ def _nccl_worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     os.environ["CNB_STREAM_SLICES"] = "1,3,4,4,3,1"
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from catnet_b200 import dist as cdist0
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), pg_options=cdist0.nccl_options())
     try:
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -360,6 +361,9 @@ def _nccl_worker(rank, world, port, q):
                 and all(np.array_equal(p, q_) for p, q_ in zip(x["probs"], y["probs"])) for x, y in zip(got, want))
             res.append((bool(same), bool(info["streamed"]), int(info["h2d_bytes"]), s.size))
         q.put((rank, res))
+    except Exception as e:                                     # the parent fails at once instead of waiting for the queue
+        q.put((rank, "error: %r" % (e,)))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -379,11 +383,12 @@ def test_streamed_search_two_ranks_nccl():
     procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = dict(q.get(timeout=600) for _ in range(2))
+    out = dict(q.get(timeout=120) for _ in range(2))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     for rank in (0, 1):
+        assert not isinstance(out[rank], str), out[rank]
         (s1, st1, h1, sz1), (s2, st2, h2, sz2), (s3, st3, _, _) = out[rank]
         assert s1 and s2 and s3 and st1 and st2 and not st3
         assert abs(h1 - sz1 / 2) <= 70 * 8 and abs(h2 - sz2 / 2) <= 45 * 8
