@@ -9,6 +9,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -1334,16 +1335,44 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 		}
 		return id;
 	};
-	res->nets.reserve(nlive);
-	for (size_t e = 0; e < nlive; e++) {
-		const size_t j = (size_t)live[e];
-		CnbNet net;
-		net.complexity = (int32_t)j;
-		net.loglik = c->h_L[j];
-		net.fam.resize(N);
-		for (int n = 0; n < N; n++) net.fam[n] = add_family(sel[e * N + n], n);
-		res->nets.push_back(std::move(net));
-	}
+	/* the selection table is networks x nodes (C5: 2,489 x 500 option indices): a few host threads mark the options in
+	 * use, the distinct families are numbered (base families, then options ascending), the threads fill in the networks */
+	unsigned hw = std::thread::hardware_concurrency();
+	const int nthr = nlive * (size_t)N >= ((size_t)1 << 18) ? (int)std::max(1u, std::min(8u, hw ? hw : 1u)) : 1;
+	auto over_networks = [&](const std::function<void(size_t, size_t)> &fn) {
+		if (nthr == 1) { fn(0, nlive); return; }
+		std::vector<std::thread> pool;
+		for (int t = 0; t < nthr; t++) pool.emplace_back(fn, nlive * t / nthr, nlive * (t + 1) / nthr);
+		for (auto &th : pool) th.join();
+	};
+	std::vector<uint8_t> used_opt(nopt, 0), used_base(N, 0);
+	over_networks([&](size_t e0, size_t e1) {
+		for (size_t e = e0; e < e1; e++)
+			for (int n = 0; n < N; n++) {
+				const long long o = sel[e * N + n];
+				if (o >= 0) used_opt[(size_t)o] = 1;               /* idempotent byte stores: threads may repeat each other */
+				else used_base[n] = 1;
+			}
+	});
+	for (int n = 0; n < N; n++)
+		if (used_base[n]) add_family(-1, n);
+	for (int n = 0; n < N; n++)
+		for (long long o = pl.nodes[n].opt_begin; o < pl.nodes[n].opt_end; o++)
+			if (used_opt[(size_t)o]) add_family(o, n);
+	res->nets.resize(nlive);
+	over_networks([&](size_t e0, size_t e1) {
+		for (size_t e = e0; e < e1; e++) {
+			const size_t j = (size_t)live[e];
+			CnbNet &net = res->nets[e];
+			net.complexity = (int32_t)j;
+			net.loglik = c->h_L[j];
+			net.fam.resize(N);
+			for (int n = 0; n < N; n++) {
+				const long long o = sel[e * N + n];
+				net.fam[n] = o >= 0 ? fam_of_opt[(size_t)o] : fam_of_base[n];
+			}
+		}
+	});
 	size_t nf = ex_child.size();
 	t_walk = ms_since(t_begin);
 	int dmax = 0;
@@ -1605,9 +1634,11 @@ extern "C" int cnb_ctx_stream_slice(cnb_ctx *c, int32_t k, const uint8_t *bytes_
 	CK(cudaEventRecord(c->ev_slices[4 * k + 2], ps));
 	CK(cudaStreamWaitEvent(st, c->ev_slices[4 * k + 2], 0));
 	DevData D = make_devdata(c);
-	RC((int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, (int *)c->b_counts_p.ptr, g0, g1, k > 0));
+	static int acc_mode = -1;                                      /* how later slices add to the tables: 1 = 16-byte read-modify-write, 2 = RED */
+	if (acc_mode < 0) { const char *e = getenv("CNB_STREAM_ACC"); acc_mode = e ? std::max(1, std::min(2, atoi(e))) : 2; }
+	RC((int)cnbk_pair_tile_run(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, (int *)c->b_counts_p.ptr, g0, g1, k > 0 ? acc_mode : 0));
 	RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, D.tiles, 0, c->stream_tiles,
-			(int *)c->b_counts.ptr, g0, g1, k > 0));
+			(int *)c->b_counts.ptr, g0, g1, k > 0 ? acc_mode : 0));
 	CK(cudaEventRecord(c->ev_slices[4 * k + 3], st));
 	c->timing.kernel_launches += 5;
 	c->stream_next = k + 1;

@@ -1663,7 +1663,7 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 		}
 	}
 	size_t smem = (size_t)((max_cells + 1) & ~1) * sizeof(int) + (size_t)max_cells * sizeof(double);
-	if (smem > 48 * 1024)
+	if (smem > 40 * 1024)                                 /* the kernel's static shared variables count towards the 48 KB default too */
 		CK(cudaFuncSetAttribute(k_score_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	long long n = e - b;
 	unsigned grid = (unsigned)(n < (1ll << 30) ? n : (1ll << 30));

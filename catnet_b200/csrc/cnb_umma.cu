@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 					for (int k = 0; k < CPC; k++)
 						x[k] = FP4 ? __float2int_rn(__uint_as_float(v[j * CPC + k])) : (int)(v[j * CPC + k] >> 7);
 					int *dst = out + (size_t)(q * 8 + j) * SLOT_INTS;
-					if (sliced) {
+					if (sliced || accumulate == 2) {
+						/* accumulate == 2: a later slice of the samples added with fire-and-forget reductions (RED): the 16-byte
+						 * read-modify-write below leaves the SM -- tensor memory held, no other CTA can start -- waiting for
+						 * the reads */
 #pragma unroll
 						for (int k = 0; k < CPC; k++) atomicAdd(dst + k, x[k]);
 					} else if (accumulate) {
