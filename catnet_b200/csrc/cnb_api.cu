@@ -439,29 +439,26 @@ int cnb_ctx_upload_bytes(cnb_ctx *c, const int32_t *samples, size_t v0, size_t v
 	while (chunk > ((size_t)128 << 10) && total < chunk * want_threads * 3) chunk >>= 1;
 	const int nchunks = (int)((total + chunk - 1) / chunk);
 	const int nthreads = (int)std::max(1u, std::min(want_threads, (unsigned)nchunks));
-	std::vector<std::atomic<int>> done(nchunks);
-	for (auto &d : done) d.store(0, std::memory_order_relaxed);
-	std::atomic<int> next(0), big(0);
-	auto work = [&]() {
+	/* every thread (the caller is one of them: nobody spins waiting) narrows a chunk and queues its copy itself; copies of
+	 * one stream may be issued from several threads, and the chunks go to disjoint destinations, so their order is free */
+	std::atomic<int> next(0), big(0), failed(0);
+	const int device = c->device;
+	auto work = [&](bool set_device) {
+		if (set_device) cudaSetDevice(device);
 		for (;;) {
 			const int k = next.fetch_add(1);
 			if (k >= nchunks) return;
 			const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
 			if (compact_rows(samples + v0 + b, pin + b, e - b)) big.store(1, std::memory_order_relaxed);
-			done[k].store(1, std::memory_order_release);
+			if (cudaMemcpyAsync(dst_dev + v0 + b, pin + b, e - b, cudaMemcpyHostToDevice, copy_stream) != cudaSuccess)
+				failed.store(1, std::memory_order_relaxed);
 		}
 	};
 	std::vector<std::thread> pool;
-	for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
-	cudaError_t err = cudaSuccess;
-	for (int k = 0; k < nchunks; k++) {
-		while (!done[k].load(std::memory_order_acquire)) std::this_thread::yield();
-		const size_t b = (size_t)k * chunk, e = std::min(total, b + chunk);
-		if (err == cudaSuccess)
-			err = cudaMemcpyAsync(dst_dev + v0 + b, pin + b, e - b, cudaMemcpyHostToDevice, copy_stream);
-	}
+	for (int t = 1; t < nthreads; t++) pool.emplace_back(work, true);
+	work(false);
 	for (auto &th : pool) th.join();
-	if (err != cudaSuccess) { cnb_set_error("CUDA: %s", cudaGetErrorString(err)); return CNB_ERR_CUDA; }
+	if (failed.load()) { cnb_set_error("CUDA: %s", cudaGetErrorString(cudaGetLastError())); return CNB_ERR_CUDA; }
 	c->timing.h2d_bytes += (int64_t)total;
 	*overflow = big.load() != 0;
 	return CNB_OK;
@@ -569,6 +566,7 @@ extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	c->generic_epilogue = (on & 4096) != 0;                /* bit 12: generic epilogue of the tensor-core scorer also for 4-category data */
 	c->force_full = (on & 8192) != 0;
 	c->hist_mode = (on & 32768) ? 0 : ((on & 65536) ? 2 : c->hist_mode_default);   /* bit 15: generic scorer one CTA per family; bit 16: a warp per family with __match_any_sync */
+	c->no_reduced_tiles = (on & 131072) != 0;               /* bit 17: 28 x 64 tiles (3 free categories) whatever the data's categories */
 	c->dp_chains = (on & 16384) != 0;                      /* bit 14: trapezoid DP, every slot re-sums its own candidates (no work list) */                      /* bit 13: full-table tiles also on complete data (no inclusion-exclusion) */
 	if (c->no_ie) c->pairs_valid = false;
 	return CNB_OK;
@@ -645,7 +643,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	/* 1: inclusion-exclusion tiles (27 cells contracted, the rest from the pair tables: complete data only);
 	 * 2: full-table tiles (all 64 cells: missing values and perturbation masks count correctly) */
 	int tile_mode = 0;
-	if (tensor_ok && c->clean && c->pairs_valid && !c->force_full) tile_mode = 1;
+	if (tensor_ok && c->clean && c->pairs_valid && !c->force_full) tile_mode = (c->no_reduced_tiles || c->tensor_i8) ? 1 : 3;
 	else if (tensor_ok && c->max_cats <= CNB_PLANE_CATS && !c->tensor_i8) tile_mode = 2;
 	c->tables_resident = false;
 	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
@@ -757,16 +755,18 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	if (!ok) return CNB_OK;
 	const int cm = c->max_cats <= 2 ? 2 : (c->max_cats == 3 ? 3 : 4), f1 = cm - 1;
 	const long long nvirt = (long long)N * (N - 1) / 2 * f1;
-	const int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+	/* tiles of f1 free categories: f1^2 rows per (virtual pair node, c) slot, f1 columns per child (cnb_tiles.h) */
+	const int tp3 = cnb_geo_pairs(f1), tc3 = cnb_geo_child(f1);
+	const int nct = (N + tc3 - 1) / tc3;
 	std::vector<long long> base3(nct + 1, 0);
 	long long largest = 0;
 	for (int ct = 0; ct < nct; ct++) {
-		const int ce = cnb_t_ce(N, nct, ct);
-		const long long n = cnb_t_tiles(ce, f1);
+		const int ce = cnb_t_ce(N, nct, ct, tc3);
+		const long long n = cnb_t_tiles(ce, f1, tp3);
 		base3[ct + 1] = base3[ct] + n;
 		largest = std::max(largest, n);
 	}
-	const long long slot_bytes = (long long)CNBK_UMMA_SLOT_INTS * sizeof(int) * CNB_TILE_PAIRS * CNB_TILE_CHILD;
+	const long long slot_bytes = (long long)cnb_geo_slot_ints(f1) * sizeof(int) * tp3 * tc3;
 	const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * 3 * (size_t)(N + nvirt);
 	if (largest * slot_bytes > (8ll << 30) || row_bytes > (16ull << 30) || nvirt > (1ll << 28)) return CNB_OK;
 	cudaStream_t st = c->stream;
@@ -778,17 +778,19 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	RC(c->b_counts.ensure((size_t)std::max<long long>(largest, 1) * slot_bytes));
 	CnbTiles T3;
 	memset(&T3, 0, sizeof(T3));
-	CNB_TILES_DEFAULT_GEOMETRY(T3);
+	T3.tp = tp3;
+	T3.tc = tc3;
+	T3.fr = f1;
 	T3.tile_base = (const long long *)c->b_tile_base3.ptr;
 	T3.nct = nct;
-	T3.child = CNB_TILE_CHILD;
+	T3.child = tc3;
 	T3.world = 1;
 	T3.self_pairs = 2;
 	T3.f1 = f1;
 	T3.nvirt = (int)nvirt;
 	/* families of the group by child: block k of the group belongs to child 3 + k and starts at blocks[..].start */
 	for (int ct = 0; ct < nct; ct++) {
-		const int c0 = cnb_t_c0(N, nct, ct), ce = cnb_t_ce(N, nct, ct);
+		const int c0 = cnb_t_c0(N, nct, ct, tc3), ce = cnb_t_ce(N, nct, ct, tc3);
 		long long fb = -1, fe = -1;
 		for (int k = 0; k < g.nblk; k++) {
 			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
@@ -926,7 +928,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			long long t0 = 0, t1 = (g.ntiles - pl.rank + pl.world - 1) / pl.world;
 			bool uni4 = true;                                   /* every node with exactly 4 categories: specialised epilogue */
 			for (int v : pl.cats) uni4 = uni4 && v == 4;
-			const long long batch = 16384, slot_bytes = (pl.tile_full ? CNBK_UMMA_FULL_SLOT_INTS : CNBK_UMMA_SLOT_INTS) * sizeof(int)
+			const long long batch = 16384, slot_bytes = (pl.tile_full ? CNBK_UMMA_FULL_SLOT_INTS : cnb_geo_slot_ints(pl.tile_fr)) * sizeof(int)
 					* (long long)pl.tile_pairs * pl.tile_cols;
 			RC(c->b_counts.ensure((size_t)std::min<long long>(batch, std::max<long long>(t1 - t0, 1)) * slot_bytes));
 			int nb = 0;
@@ -1557,7 +1559,7 @@ extern "C" int cnb_ctx_stream_begin(cnb_ctx *c, const cnb_params *p, int32_t ran
 		return rc;                                                 /* not a tiled search after all: the resident path */
 	}
 	c->stream_tiles = (g2->ntiles - pl.rank + pl.world - 1) / pl.world;   /* this rank's tiles (dealt round-robin) */
-	const size_t slot_bytes = (size_t)CNBK_UMMA_SLOT_INTS * sizeof(int) * pl.tile_pairs * pl.tile_cols;
+	const size_t slot_bytes = (size_t)cnb_geo_slot_ints(pl.tile_fr) * sizeof(int) * pl.tile_pairs * pl.tile_cols;
 	RC(c->b_counts.ensure((size_t)std::max<long long>(c->stream_tiles, 1) * slot_bytes));
 	RC(c->b_counts_p.ensure((size_t)cnbk_pair_tiles(N) * CNB_TILE_PAIRS * CNB_TILE_CHILD * CNBK_UMMA_SLOT_INTS * sizeof(int)));
 	/* ---- slices: whole sample groups, a small first one ---- */

@@ -36,6 +36,7 @@ struct cnb_ctx {
 	std::vector<cudaEvent_t> ev_slices;   /* "slice k is on the device" */
 	bool tables_resident = false;         /* b_counts still holds the tile tables of the whole two-parent group of the current plan
 	                                         (one batch, one rank): the export reads the returned networks' tables from there */
+	bool no_reduced_tiles = false;        /* tensor-core tiles always contract 3 free categories per node (test / A-B switch) */
 	int hist_mode = 1, hist_mode_default = 1;   /* generic scorer: 0 one CTA per family, 1 a warp per family + shared atomics, 2 + __match_any_sync (CNB_HIST_MODE) */
 	bool stream_active = false;           /* between cnb_ctx_stream_begin and cnb_ctx_stream_end */
 	std::vector<int> stream_gend;         /* last sample group (exclusive) of every slice */

@@ -69,6 +69,10 @@ struct CnbTiles {
 	                                 keep mask ANDed into its rows, a missing value sets no bit: no inclusion-exclusion, so
 	                                 missing values and perturbation masks count correctly */
 	int32_t row_stride;           /* full: operand rows per node, 4 (no masks) or 8 (4 plain, then 4 under the node's own keep mask) */
+	int32_t fr;                   /* inclusion-exclusion tiles: free categories contracted per node -- 3 (data with up to four
+	                                 categories per node: 9 rows per pair, 3 columns per column node, 28 x 64 slots), 2 (up to
+	                                 three categories: 4 rows, 2 columns, 64 x 96 slots) or 1 (binary data: 1 row, 1 column,
+	                                 256 x 192 slots); cnb_geo_* in cnb_tiles.h */
 };
 #define CNB_FULL_PAIRS 16     /* full-table tile: 2 blocks of 8 parent pairs x 16 rows ... */
 #define CNB_FULL_CHILD 48     /* ... x up to 48 column nodes x 4 columns (192): 768 family slots per tile */
@@ -101,6 +105,7 @@ struct CnbPlan {
 	int32_t tile_child = 0;                    /* children per child tile */
 	int32_t tile_pairs = CNB_TILE_PAIRS, tile_cols = CNB_TILE_CHILD;   /* geometry of the tiled group (CnbTiles.tp / .tc) */
 	int32_t tile_full = 0;                     /* the tiled group runs as full-table tiles */
+	int32_t tile_fr = 3;                       /* free categories per node the inclusion-exclusion tiles contract (CnbTiles.fr) */
 	int64_t seg_len = 0;                       /* doubles per rank segment */
 	int64_t num_families = 0;
 	int64_t num_options = 0;

@@ -218,10 +218,14 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 			if (subset) full = true;
 			const int tiled_kind = subset ? 2 : 1;
 			if (full) {
-				const int tp = tile_mode == 2 ? CNB_FULL_PAIRS : CNB_TILE_PAIRS, tc = tile_mode == 2 ? CNB_FULL_CHILD : CNB_TILE_CHILD;
+				/* tile_mode 3: the inclusion-exclusion tiles contract only as many free categories as the data has
+				 * (cnb_tiles.h: cnb_geo_*) -- more families per MMA for data with two or three categories per node */
+				const int fr = tile_mode == 3 ? cnb_geo_fr(pl.max_cats) : 3;
+				const int tp = tile_mode == 2 ? CNB_FULL_PAIRS : cnb_geo_pairs(fr), tc = tile_mode == 2 ? CNB_FULL_CHILD : cnb_geo_child(fr);
 				pl.tile_pairs = tp;
 				pl.tile_cols = tc;
 				pl.tile_full = tile_mode == 2;
+				pl.tile_fr = fr;
 				int nct = (N + tc - 1) / tc;
 				int cpt = (N + nct - 1) / nct;                      /* equal child tiles (500 nodes: 8 x 63, not 7 x 64 + 52) */
 				pl.tile_child = cpt;
@@ -272,6 +276,7 @@ void cnb_plan_tiles(const CnbPlan &pl, CnbTiles *T) {
 	T->world = 1;
 	T->tp = pl.tile_pairs;
 	T->tc = pl.tile_cols;
+	T->fr = pl.tile_fr;
 	T->full = pl.tile_full;
 	T->row_stride = 4;
 }
@@ -281,13 +286,13 @@ int cnb_tile_columns(const CnbPlan &pl, int64_t tile) {
 	cnb_plan_tiles(pl, &T);
 	CnbTileInfo ti;
 	cnb_tile_decode(T, pl.N, tile, ti);
-	return ((pl.tile_full ? 4 : 3) * (ti.ze - ti.zb) + 15) / 16 * 16;
+	return ((pl.tile_full ? 4 : pl.tile_fr) * (ti.ze - ti.zb) + 15) / 16 * 16;
 }
 
 /* test hook: the tiling of the unrestricted two-parent group of N nodes is a bijection between families and tile
  * slots (family -> slot -> family), every tile has at least one column, and no two families share a slot.
  * Returns the number of tiles, or a negative value at the first inconsistency. */
-static int64_t tile_selftest(int32_t N, int tile_mode) {
+static int64_t tile_selftest(int32_t N, int tile_mode, int ncats = 2) {
 	if (N < 3) return 0;
 	cnb_params q;
 	memset(&q, 0, sizeof(q));
@@ -295,12 +300,13 @@ static int64_t tile_selftest(int32_t N, int tile_mode) {
 	q.num_samples = 1;
 	q.max_parent_set = 2;
 	q.max_complexity = 1 << 30;
-	std::vector<int32_t> cats(N, 2);
+	std::vector<int32_t> cats(N, ncats);
 	CnbPlan pl;
 	if (cnb_build_plan(&q, cats.data(), 0, 1, &pl, nullptr, tile_mode) != CNB_OK || pl.tile_base.empty()) return -1;
 	CnbTiles T;
 	cnb_plan_tiles(pl, &T);
 	const int tp = T.tp, tc = T.tc;
+	if (tile_mode == 3 && (tp != cnb_geo_pairs(ncats - 1) || tc != cnb_geo_child(ncats - 1) || T.fr != ncats - 1)) return -8;
 	const int64_t ntiles = pl.tile_base[T.nct];
 	std::vector<unsigned char> used((size_t)ntiles * tp * tc, 0);
 	int64_t nfam = 0;
@@ -336,6 +342,11 @@ static int64_t tile_selftest(int32_t N, int tile_mode) {
 extern "C" int64_t cnb_tile_selftest(int32_t N) { return tile_selftest(N, 1); }
 /* the same for the full-table geometry (16 pairs x 48 column nodes) */
 extern "C" int64_t cnb_tile_selftest_full(int32_t N) { return tile_selftest(N, 2); }
+/* ... and for the reduced inclusion-exclusion geometries of data with `free_cats` + 1 categories per node (free_cats = 1, 2, 3) */
+extern "C" int64_t cnb_tile_selftest_geo(int32_t N, int32_t free_cats) {
+	if (free_cats < 1 || free_cats > 3) return -9;
+	return tile_selftest(N, 3, free_cats + 1);
+}
 
 extern "C" int64_t cnb_num_families(const cnb_params *p) {
 	if (!p || p->num_nodes < 1) return -1;
@@ -354,40 +365,46 @@ extern "C" int64_t cnb_num_families(const cnb_params *p) {
  * of x, the slot whose "pair" is (virtual node of (a, b, i), c) and whose column is x, no two share a slot.  Returns the
  * number of tiles, negative at the first inconsistency. */
 extern "C" int64_t cnb_tile3_selftest(int32_t N, int32_t f1) {
+	/* f1 > 0: the geometry of f1 free categories (what the library runs); f1 < 0: -f1 free values in the default 28 x 64 tiles */
+	const int geo = f1 < 0 ? 3 : f1;
+	if (f1 < 0) f1 = -f1;
 	if (N < 4 || f1 < 1 || f1 > 3) return 0;
-	const int nct = (N + CNB_TILE_CHILD - 1) / CNB_TILE_CHILD;
+	const int TP = cnb_geo_pairs(geo), TCH = cnb_geo_child(geo);
+	const int nct = (N + TCH - 1) / TCH;
 	std::vector<long long> base3(nct + 1, 0);
-	for (int ct = 0; ct < nct; ct++) base3[ct + 1] = base3[ct] + cnb_t_tiles(cnb_t_ce(N, nct, ct), f1);
+	for (int ct = 0; ct < nct; ct++) base3[ct + 1] = base3[ct] + cnb_t_tiles(cnb_t_ce(N, nct, ct, TCH), f1, TP);
 	CnbTiles T;
 	memset(&T, 0, sizeof(T));
-	CNB_TILES_DEFAULT_GEOMETRY(T);
+	T.tp = TP;
+	T.tc = TCH;
+	T.fr = geo;
 	T.tile_base = base3.data();
 	T.nct = nct;
-	T.child = CNB_TILE_CHILD;
+	T.child = TCH;
 	T.world = 1;
 	T.self_pairs = 2;
 	T.f1 = f1;
 	T.nvirt = N * (N - 1) / 2 * f1;
-	std::vector<unsigned char> used((size_t)base3[nct] * CNB_TILE_PAIRS * CNB_TILE_CHILD, 0);
+	std::vector<unsigned char> used((size_t)base3[nct] * TP * TCH, 0);
 	for (int x = 3; x < N; x++) {
 		int ct = 0;
-		while (cnb_t_ce(N, nct, ct) <= x) ct++;
-		const int c0 = cnb_t_c0(N, nct, ct), ce = cnb_t_ce(N, nct, ct);
+		while (cnb_t_ce(N, nct, ct, TCH) <= x) ct++;
+		const int c0 = cnb_t_c0(N, nct, ct, TCH), ce = cnb_t_ce(N, nct, ct, TCH);
 		if (x < c0 || x >= ce) return -1;
 		for (int c = 2; c < x; c++)
 			for (int b = 1; b < c; b++)
 				for (int a = 0; a < b; a++)
 					for (int i = 0; i < f1; i++) {
 						const long long t = cnb_binom3(c) + (long long)b * (b - 1) / 2 + a, q = t * f1 + i;
-						const long long tile = base3[ct] + q / CNB_TILE_PAIRS;
+						const long long tile = base3[ct] + q / TP;
 						if (tile >= base3[ct + 1]) return -2;
-						unsigned char &u = used[((size_t)tile * CNB_TILE_PAIRS + q % CNB_TILE_PAIRS) * CNB_TILE_CHILD + (x - c0)];
+						unsigned char &u = used[((size_t)tile * TP + q % TP) * TCH + (x - c0)];
 						if (u) return -3;
 						u = 1;
 						CnbTileInfo ti;
 						cnb_tile_decode(T, N, tile, ti);
 						int px, py;
-						if (ti.kind != 3 || ti.zb != c0 || ti.ze != ce || !cnb_tile_pair(ti, (int)(q % CNB_TILE_PAIRS), px, py)) return -4;
+						if (ti.kind != 3 || ti.zb != c0 || ti.ze != ce || !cnb_tile_pair(ti, (int)(q % TP), px, py)) return -4;
 						if (py != c || px != N + (int)(((long long)b * (b - 1) / 2 + a) * f1 + i)) return -5;
 					}
 	}

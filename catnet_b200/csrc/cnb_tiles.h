@@ -42,7 +42,16 @@
 #define CNB_DT_STRIDE 74      /* >= ceil(64 * 63 / 2 / 28) + 1 (default geometry) and >= ceil(48 * 47 / 2 / 16) + 1 = 72 (full-table
                                  geometry) pair tiles of D pairs per child tile, plus the total */
 /* default geometry of a CnbTiles (the inclusion-exclusion tiles, the P and the T tiles) */
-#define CNB_TILES_DEFAULT_GEOMETRY(T) do { (T).tp = CNB_TILE_PAIRS; (T).tc = CNB_TILE_CHILD; } while (0)
+#define CNB_TILES_DEFAULT_GEOMETRY(T) do { (T).tp = CNB_TILE_PAIRS; (T).tc = CNB_TILE_CHILD; (T).fr = 3; } while (0)
+/* Geometry of the inclusion-exclusion tiles by the number fr of free categories per node (largest category count - 1):
+ * a pair takes fr^2 of the 128 rows of a block, a column node fr of the 192 columns, a slot holds fr^2 configurations x fr
+ * counts (padded to int4 at fr = 3).  With fewer categories the same MMA covers more families: 28 x 64 = 1,792 slots at
+ * fr = 3, 64 x 96 = 6,144 at fr = 2 (3.4 x fewer MACs per family), 256 x 192 = 49,152 at fr = 1. */
+CNB_HD int cnb_geo_fr(int max_cats) { return max_cats >= 4 ? 3 : (max_cats == 3 ? 2 : 1); }
+CNB_HD int cnb_geo_pairs(int fr) { return fr >= 3 ? CNB_TILE_PAIRS : (fr == 2 ? 64 : 256); }
+CNB_HD int cnb_geo_child(int fr) { return fr >= 3 ? CNB_TILE_CHILD : (fr == 2 ? 96 : 192); }
+CNB_HD int cnb_geo_cst(int fr) { return fr >= 3 ? 4 : fr; }                 /* ints stored per (configuration, column node) */
+CNB_HD int cnb_geo_slot_ints(int fr) { return fr * fr * cnb_geo_cst(fr); }  /* 36, 8, 1 */
 
 struct CnbTileInfo {
 	int kind;                 /* 0 = F, 1 = D, 2 = P, 3 = T */
@@ -84,9 +93,9 @@ CNB_HD int cnb_d_chunks(int c0, int ce, int ptile, int tp, int tc) {
 }
 
 CNB_HD long long cnb_binom3(long long n) { return n < 3 ? 0 : n * (n - 1) * (n - 2) / 6; }
-/* kind 3: children [c0, ce) of column tile ct of nct = ceil(N / 64), aligned to the end of the order */
-CNB_HD int cnb_t_ce(int N, int nct, int ct) { return N - CNB_TILE_CHILD * (nct - 1 - ct); }
-CNB_HD int cnb_t_c0(int N, int nct, int ct) { return ct == 0 ? 0 : N - CNB_TILE_CHILD * (nct - ct); }
+/* kind 3: children [c0, ce) of column tile ct of nct = ceil(N / tc), aligned to the end of the order */
+CNB_HD int cnb_t_ce(int N, int nct, int ct, int tc) { return N - tc * (nct - 1 - ct); }
+CNB_HD int cnb_t_c0(int N, int nct, int ct, int tc) { return ct == 0 ? 0 : N - tc * (nct - ct); }
 /* t = C(c,3) + C(b,2) + a, a < b < c */
 CNB_HD void cnb_triple_of(long long t, int &a, int &b, int &c) {
 	c = (int)cbrt(6.0 * (double)t) + 2;
@@ -105,8 +114,8 @@ CNB_HD void cnb_tile_decode(const CnbTiles &T, int N, long long tile, CnbTileInf
 		while (ct + 1 < T.nct && T.tile_base[ct + 1] <= tile) ct++;
 		ti.kind = 3;
 		ti.ct = ct;
-		ti.c0 = cnb_t_c0(N, T.nct, ct);
-		ti.ce = cnb_t_ce(N, T.nct, ct);
+		ti.c0 = cnb_t_c0(N, T.nct, ct, T.tc);
+		ti.ce = cnb_t_ce(N, T.nct, ct, T.tc);
 		ti.pair0 = (tile - T.tile_base[ct]) * T.tp;
 		ti.npairs = cnb_binom3(ti.ce - 1) * T.f1;
 		ti.zb = ti.c0;
@@ -189,6 +198,6 @@ CNB_HD void cnb_family_slot(const CnbTiles &T, int N, int a, int b, int c, long 
 }
 
 /* kind 3: tiles of column tile [c0, ce) and the slot of (triple rank t, value i of a, child x) */
-CNB_HD long long cnb_t_tiles(int ce, int f1) { return (cnb_binom3(ce - 1) * f1 + CNB_TILE_PAIRS - 1) / CNB_TILE_PAIRS; }   /* T tiles: default geometry */
+CNB_HD long long cnb_t_tiles(int ce, int f1, int tp) { return (cnb_binom3(ce - 1) * f1 + tp - 1) / tp; }
 
 #endif

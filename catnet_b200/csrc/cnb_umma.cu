@@ -272,15 +272,31 @@ __device__ __forceinline__ void mma_issue_loop(uint32_t smem, uint32_t idesc, in
 	umma_commit(smem_u32(bar_done), 1);
 }
 
-template <bool FP4, bool FULL>
+/* tile geometry as compile-time constants.  GEO 0: inclusion-exclusion tiles, 3 free categories per node; 1: full-table
+ * tiles; 2 / 3: inclusion-exclusion tiles with 2 / 1 free categories (data with at most three / two categories per node) */
+template <int GEO> struct UmGeo {
+	static constexpr bool FULL = GEO == 1;
+	static constexpr int FR = GEO == 0 ? 3 : (GEO == 2 ? 2 : (GEO == 3 ? 1 : 4));
+	static constexpr int CPC = FR;                    /* columns per column node */
+	static constexpr int RPP = FR * FR;               /* rows per pair */
+	static constexpr int BLKP = 128 / RPP;            /* pairs per block of 128 rows: 14, 8, 32, 128 */
+	static constexpr int TC = FULL ? UMF_CHILD : (GEO == 0 ? UM_CHILD : UM_N / FR);   /* column nodes per tile: 64, 48, 96, 192 */
+	static constexpr int CST = CPC >= 3 ? 4 : CPC;    /* ints stored per (configuration, column node) */
+	static constexpr int SLOT_INTS = RPP * CST;       /* 36, 64, 8, 1 */
+	static constexpr int SLOTS = UM_NA * BLKP * TC;
+};
+static_assert(UmGeo<0>::BLKP == UM_BLK_PAIRS && UmGeo<0>::SLOT_INTS == UM_SLOT_INTS && UmGeo<0>::SLOTS == UM_SLOTS, "default geometry");
+static_assert(UmGeo<1>::BLKP == UMF_BLK_PAIRS && UmGeo<1>::SLOT_INTS == UMF_SLOT_INTS && UmGeo<1>::SLOTS == UMF_SLOTS, "full-table geometry");
+
+template <bool FP4, int GEO>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__restrict__ rows_a, const uint4 *__restrict__ rows_b,
 		int N, int g_begin, int g_end, CnbTiles T, long long local_begin, int *__restrict__ counts, int whole, int split, int accumulate) {
 	constexpr int SRCQ = FP4 ? 2 : 1;       /* quads (uint4) of source bits per row and stage */
 	const int ngroups_all = g_end - g_begin;   /* the sample groups of this launch (all of them, or a slice of the samples) */
-	constexpr int CPC = FULL ? 4 : 3;       /* columns per column node */
-	constexpr int RPP = FULL ? 16 : 9;      /* rows per pair */
-	constexpr int BLKP = FULL ? UMF_BLK_PAIRS : UM_BLK_PAIRS;
-	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS, TC = FULL ? UMF_CHILD : UM_CHILD;
+	using G = UmGeo<GEO>;
+	constexpr bool FULL = G::FULL;
+	constexpr int CPC = G::CPC, RPP = G::RPP, BLKP = G::BLKP, CST = G::CST;
+	constexpr int SLOTS = G::SLOTS, SLOT_INTS = G::SLOT_INTS, TC = G::TC;
 	const int RS = FULL ? T.row_stride : 3; /* operand rows per node */
 	const int NRB = RS * N, NRA = RS * (N + T.nvirt);   /* operand rows per quad: column side, pair side (real + virtual nodes) */
 	/* CTAs [0, whole) contract all the samples of one tile each; the tiles behind them -- the launch's last, partial
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 		const int lq = warp & 3;
 		const int row = lq * 32 + lane, cfg = row % RPP;
 		const bool row_ok = row < BLKP * RPP;
-		int *out = counts + ((size_t)tile_local * SLOTS + (size_t)(h * BLKP + row / RPP) * TC) * SLOT_INTS + cfg * 4;
+		int *out = counts + ((size_t)tile_local * SLOTS + (size_t)(h * BLKP + row / RPP) * TC) * SLOT_INTS + cfg * CST;
 #pragma unroll 1
 		for (int q = 0; q * 8 < nchild; q++) {
 			uint32_t v[8 * CPC];
@@ -401,9 +417,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 			: "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]) \
 			: "r"(a))
 			LD8(0, taddr);
-			LD8(8, taddr + 8);
-			LD8(16, taddr + 16);
-			if constexpr (FULL) LD8(24, taddr + 24);
+			if constexpr (CPC >= 2) LD8(8, taddr + 8);
+			if constexpr (CPC >= 3) LD8(16, taddr + 16);
+			if constexpr (CPC >= 4) LD8(24, taddr + 24);
 #undef LD8
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 			if (row_ok) {
@@ -415,7 +431,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 					for (int k = 0; k < CPC; k++)
 						x[k] = FP4 ? __float2int_rn(__uint_as_float(v[j * CPC + k])) : (int)(v[j * CPC + k] >> 7);
 					int *dst = out + (size_t)(q * 8 + j) * SLOT_INTS;
-					if (sliced || accumulate == 2) {
+					if (sliced || accumulate == 2 || (accumulate && CST < 4)) {
 						/* accumulate == 2: a later slice of the samples added with fire-and-forget reductions (RED): the 16-byte
 						 * read-modify-write below leaves the SM -- tensor memory held, no other CTA can start -- waiting for
 						 * the reads */
@@ -425,7 +441,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_umma_tables(const uint4 *__re
 						/* a later slice of the samples: this CTA alone owns the tile in this launch */
 						const int4 o = *reinterpret_cast<const int4 *>(dst);
 						*reinterpret_cast<int4 *>(dst) = make_int4(o.x + x[0], o.y + x[1], o.z + x[2], o.w + x[3]);
-					} else *reinterpret_cast<int4 *>(dst) = make_int4(x[0], x[1], x[2], x[3]);
+					} else if constexpr (CST == 4) *reinterpret_cast<int4 *>(dst) = make_int4(x[0], x[1], x[2], x[3]);
+					else if constexpr (CST == 2) *reinterpret_cast<int2 *>(dst) = make_int2(x[0], x[1]);
+					else *dst = x[0];
 				}
 			}
 		}
@@ -541,8 +559,11 @@ __device__ __noinline__ double um_config_terms(double ll, int n0, int n1, int n2
 template <bool UNI4, bool FULL>
 __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long local_begin, long long local_end,
 		const int *__restrict__ counts, const int *__restrict__ pair_tab, ScoreOut O) {
-	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS, TC = FULL ? UMF_CHILD : UM_CHILD;
 	const CnbTiles &T = Dt.tiles;
+	/* geometry: constants for full-table tiles and for the 4-category specialisation (3 free categories), else the plan's */
+	const int fr = FULL ? 4 : (UNI4 ? 3 : T.fr);
+	const int SLOTS = FULL ? UMF_SLOTS : (UNI4 ? UM_SLOTS : T.tp * T.tc), TC = FULL ? UMF_CHILD : (UNI4 ? UM_CHILD : T.tc);
+	const int SLOT_INTS = FULL ? UMF_SLOT_INTS : (UNI4 ? UM_SLOT_INTS : cnb_geo_slot_ints(T.fr));
 	const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long local = local_begin + slot / SLOTS;
 	if (local >= local_end) return;
@@ -571,7 +592,7 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 				else CELL(r / 4, r % 4, q) = x4[q];
 			}
 		}
-	} else {
+	} else if (UNI4 || fr == 3) {
 	/* slot layout: 9 pair configurations x (3 column categories + pad): nine 16-byte loads */
 #pragma unroll
 	for (int r = 0; r < 9; r++) {
@@ -584,6 +605,14 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 			else CELL(r / 3, r % 3, q) = x3[q];
 		}
 	}
+	} else {
+	/* fewer free categories: fr^2 configurations x fr counts, unpadded */
+	for (int r = 0; r < fr * fr; r++)
+		for (int q = 0; q < fr; q++) {
+			const int v = __ldg(tab + r * fr + q);
+			if (dk) CELL(q, r / fr, r % fr) = v;
+			else CELL(r / fr, r % fr, q) = v;
+		}
 	}
 	const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
 	double ll;
@@ -625,15 +654,25 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 		if (ncount > 1) ll = __ddiv_rn(ll, (double)ncount);
 	} else {
 	if (!FULL) {
-	for (int i = 0; i < 3; i++)
-		for (int jj = 0; jj < 3; jj++)
-			CELL(i, jj, 3) = um_pair_count(pair_tab, l0, l1, i, jj) - (CELL(i, jj, 0) + CELL(i, jj, 1) + CELL(i, jj, 2));
-	for (int i = 0; i < 3; i++)
-		for (int k = 0; k < 4; k++)
-			CELL(i, 3, k) = um_pair_count(pair_tab, l0, lc, i, k) - (CELL(i, 0, k) + CELL(i, 1, k) + CELL(i, 2, k));
-	for (int jj = 0; jj < 4; jj++)
-		for (int k = 0; k < 4; k++)
-			CELL(3, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - (CELL(0, jj, k) + CELL(1, jj, k) + CELL(2, jj, k));
+	/* the cells with a last category (index fr), axis after axis, from the pair tables */
+	for (int i = 0; i < fr; i++)
+		for (int jj = 0; jj < fr; jj++) {
+			int sum = 0;
+			for (int k = 0; k < fr; k++) sum += CELL(i, jj, k);
+			CELL(i, jj, fr) = um_pair_count(pair_tab, l0, l1, i, jj) - sum;
+		}
+	for (int i = 0; i < fr; i++)
+		for (int k = 0; k <= fr; k++) {
+			int sum = 0;
+			for (int jj = 0; jj < fr; jj++) sum += CELL(i, jj, k);
+			CELL(i, fr, k) = um_pair_count(pair_tab, l0, lc, i, k) - sum;
+		}
+	for (int jj = 0; jj <= fr; jj++)
+		for (int k = 0; k <= fr; k++) {
+			int sum = 0;
+			for (int i = 0; i < fr; i++) sum += CELL(i, jj, k);
+			CELL(fr, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - sum;
+		}
 	}
 	const int pc0 = Dt.cats[a], pc1 = Dt.cats[b], cc = Dt.cats[c];
 	int ncount;
@@ -658,10 +697,11 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 template <bool FULL>
 __global__ void __launch_bounds__(128) k_umma_export(DevData Dt, long long f_begin, long long f_end, const int *__restrict__ ex_child,
 		const int *__restrict__ ex_pars, const int *__restrict__ counts, const int *__restrict__ pair_tab, ScoreOut O) {
-	constexpr int SLOTS = FULL ? UMF_SLOTS : UM_SLOTS, SLOT_INTS = FULL ? UMF_SLOT_INTS : UM_SLOT_INTS;
 	const long long f = f_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= f_end) return;
 	const CnbTiles &T = Dt.tiles;
+	const int fr = FULL ? 4 : T.fr, cst = cnb_geo_cst(fr);
+	const int SLOTS = FULL ? UMF_SLOTS : T.tp * T.tc, SLOT_INTS = FULL ? UMF_SLOT_INTS : cnb_geo_slot_ints(T.fr);
 	const int c = ex_child[f], p0 = ex_pars[f * CNB_MAXP], p1 = ex_pars[f * CNB_MAXP + 1];
 	const int a = min(p0, p1), b = max(p0, p1);
 	long long tile;
@@ -679,22 +719,31 @@ __global__ void __launch_bounds__(128) k_umma_export(DevData Dt, long long f_beg
 				else CELL(r / 4, r % 4, q) = v;
 			}
 	} else {
-		for (int r = 0; r < 9; r++)
-			for (int q = 0; q < 3; q++) {
-				const int v = tab[r * 4 + q];
-				if (dk) CELL(q, r / 3, r % 3) = v;
-				else CELL(r / 3, r % 3, q) = v;
+		for (int r = 0; r < fr * fr; r++)
+			for (int q = 0; q < fr; q++) {
+				const int v = tab[r * cst + q];
+				if (dk) CELL(q, r / fr, r % fr) = v;
+				else CELL(r / fr, r % fr, q) = v;
 			}
 		const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
-		for (int i = 0; i < 3; i++)
-			for (int jj = 0; jj < 3; jj++)
-				CELL(i, jj, 3) = um_pair_count(pair_tab, l0, l1, i, jj) - (CELL(i, jj, 0) + CELL(i, jj, 1) + CELL(i, jj, 2));
-		for (int i = 0; i < 3; i++)
-			for (int k = 0; k < 4; k++)
-				CELL(i, 3, k) = um_pair_count(pair_tab, l0, lc, i, k) - (CELL(i, 0, k) + CELL(i, 1, k) + CELL(i, 2, k));
-		for (int jj = 0; jj < 4; jj++)
-			for (int k = 0; k < 4; k++)
-				CELL(3, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - (CELL(0, jj, k) + CELL(1, jj, k) + CELL(2, jj, k));
+		for (int i = 0; i < fr; i++)
+			for (int jj = 0; jj < fr; jj++) {
+				int sum = 0;
+				for (int k = 0; k < fr; k++) sum += CELL(i, jj, k);
+				CELL(i, jj, fr) = um_pair_count(pair_tab, l0, l1, i, jj) - sum;
+			}
+		for (int i = 0; i < fr; i++)
+			for (int k = 0; k <= fr; k++) {
+				int sum = 0;
+				for (int jj = 0; jj < fr; jj++) sum += CELL(i, jj, k);
+				CELL(i, fr, k) = um_pair_count(pair_tab, l0, lc, i, k) - sum;
+			}
+		for (int jj = 0; jj <= fr; jj++)
+			for (int k = 0; k <= fr; k++) {
+				int sum = 0;
+				for (int i = 0; i < fr; i++) sum += CELL(i, jj, k);
+				CELL(fr, jj, k) = um_pair_count(pair_tab, l1, lc, jj, k) - sum;
+			}
 	}
 	/* table order = the family's LISTED parents (p0 most significant) */
 	const bool sw = p0 > p1;
@@ -801,17 +850,25 @@ __global__ void __launch_bounds__(BS) k_umma_epilogue3(DevData Dt, DevFamilies F
 	const int a = pars[0], b = pars[1], c = pars[2];
 	const long long t = cnb_binom3(c) + (long long)b * (b - 1) / 2 + a;
 	int *mine = s_cnt + threadIdx.x;
+	/* the T tiles of CM categories have the geometry of F1 = CM - 1 free categories (cnb_tiles.h: cnb_geo_*) */
+	constexpr int TP = F1 >= 3 ? CNB_TILE_PAIRS : (F1 == 2 ? 64 : 256), TCH = F1 >= 3 ? CNB_TILE_CHILD : (F1 == 2 ? 96 : 192);
+	constexpr int CST = F1 >= 3 ? 4 : F1, SINTS = F1 * F1 * CST;
 #pragma unroll
 	for (int i = 0; i < F1; i++) {
 		const long long q = t * F1 + i;
-		const int *tab = counts + ((size_t)(q / UM_PAIRS) * UM_SLOTS + (size_t)(q % UM_PAIRS) * UM_CHILD
-				+ (child - c0)) * UM_SLOT_INTS;
+		const int *tab = counts + ((size_t)(q / TP) * (TP * TCH) + (size_t)(q % TP) * TCH + (child - c0)) * SINTS;
 #pragma unroll
 		for (int j = 0; j < F1; j++)
 #pragma unroll
 			for (int k = 0; k < F1; k++) {
-				const int4 v = *reinterpret_cast<const int4 *>(tab + (j * 3 + k) * 4);
-				const int x[3] = {v.x, v.y, v.z};
+				int x[3] = {0, 0, 0};
+				if constexpr (CST == 4) {
+					const int4 v = *reinterpret_cast<const int4 *>(tab + (j * 3 + k) * 4);
+					x[0] = v.x; x[1] = v.y; x[2] = v.z;
+				} else if constexpr (CST == 2) {
+					const int2 v = *reinterpret_cast<const int2 *>(tab + (j * 2 + k) * 2);
+					x[0] = v.x; x[1] = v.y;
+				} else x[0] = tab[0];
 #pragma unroll
 				for (int l = 0; l < F1; l++) mine[((((i * CM + j) * CM + k) * CM + l)) * BS] = x[l];
 			}
@@ -927,20 +984,24 @@ int cnbk_umma_tables(cudaStream_t st, const uint4 *rows_a, const uint4 *rows_b, 
 	const int split = T.self_pairs ? 1 : tail_split(tiles, sms, ng);
 	const long long whole = split > 1 ? tiles - tiles % sms : tiles;
 	const long long grid = whole + (tiles - whole) * split;
-	const size_t tile_ints = T.full ? (size_t)UMF_SLOTS * UMF_SLOT_INTS : (size_t)UM_SLOTS * UM_SLOT_INTS;
+	const size_t tile_ints = T.full ? (size_t)UMF_SLOTS * UMF_SLOT_INTS : (size_t)T.tp * T.tc * cnb_geo_slot_ints(T.fr);
 	if (split > 1 && !accumulate)
 		CK(cudaMemsetAsync(counts + (size_t)whole * tile_ints, 0, (size_t)(tiles - whole) * tile_ints * sizeof(int), st));
-	if (T.full) {
-		if (!fp4) { cnb_set_error("full-table tiles need E2M1 operands"); return CNB_ERR_PROC; }
-		CK(cudaFuncSetAttribute(k_umma_tables<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true, true><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
-	} else if (fp4) {
-		CK(cudaFuncSetAttribute(k_umma_tables<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<true, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
-	} else {
-		CK(cudaFuncSetAttribute(k_umma_tables<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM));
-		k_umma_tables<false, false><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, (int)whole, split, accumulate);
+#define UM_LAUNCH(FP4_, GEO_) do { \
+		CK(cudaFuncSetAttribute(k_umma_tables<FP4_, GEO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM)); \
+		k_umma_tables<FP4_, GEO_><<<(unsigned)grid, UM_THREADS, UM_SMEM, st>>>(rows_a, rows_b, N, g_begin, g_end, Tp, tile_begin, counts, \
+				(int)whole, split, accumulate); } while (0)
+	if (!T.full && (T.tp != cnb_geo_pairs(T.fr) || T.tc != cnb_geo_child(T.fr) || T.fr < 1 || T.fr > 3)) {
+		cnb_set_error("table kernel: tile geometry %d x %d does not belong to %d free categories", T.tp, T.tc, T.fr);
+		return CNB_ERR_PROC;
 	}
+	if (!fp4 && (T.full || T.fr != 3)) { cnb_set_error("full-table and reduced tiles need E2M1 operands"); return CNB_ERR_PROC; }
+	if (T.full) UM_LAUNCH(true, 1);
+	else if (!fp4) UM_LAUNCH(false, 0);
+	else if (T.fr == 3) UM_LAUNCH(true, 0);
+	else if (T.fr == 2) UM_LAUNCH(true, 2);
+	else UM_LAUNCH(true, 3);
+#undef UM_LAUNCH
 	CK(cudaGetLastError());
 	return CNB_OK;
 }
@@ -954,7 +1015,7 @@ long long cnbk_umma_column_macs(int W, int fp4) {
 int cnbk_umma_epilogue(cudaStream_t st, const DevData &Dt, long long tile_begin, long long tile_end, const int *counts,
 		const int *pair_tab, const ScoreOut &O, bool all_four_cats) {
 	const bool full = Dt.tiles.full != 0;
-	long long slots = (tile_end - tile_begin) * (full ? UMF_SLOTS : UM_SLOTS);
+	long long slots = (tile_end - tile_begin) * (full ? UMF_SLOTS : (long long)Dt.tiles.tp * Dt.tiles.tc);
 	if (slots <= 0) return CNB_OK;
 	const unsigned grid = (unsigned)((slots + 127) / 128);
 	if (full && all_four_cats) k_umma_epilogue<true, true><<<grid, 128, 0, st>>>(Dt, tile_begin, tile_end, counts, pair_tab, O);

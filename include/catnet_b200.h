@@ -359,7 +359,10 @@ int64_t cnb_num_families(const cnb_params *p);
  * tiles, or < 0 if family <-> tile slot is not a bijection */
 int64_t cnb_tile_selftest(int32_t num_nodes);
 int64_t cnb_tile_selftest_full(int32_t num_nodes);   /* the full-table geometry (16 pairs x 48 column nodes per tile) */
-/* the same for the tiling of the unrestricted three-parent group (free_cats = max categories - 1) */
+/* the geometries of data with free_cats + 1 categories per node: 28 x 64 slots (free_cats = 3), 64 x 96 (2), 256 x 192 (1) */
+int64_t cnb_tile_selftest_geo(int32_t num_nodes, int32_t free_cats);
+/* the same for the tiling of the unrestricted three-parent group (free_cats = max categories - 1, in the geometry of that
+ * many free categories; negative: -free_cats free values in the default 28 x 64 tiles) */
 int64_t cnb_tile3_selftest(int32_t num_nodes, int32_t free_cats);
 
 /* ---- result accessors (the catNetwork slots) ---- */

@@ -514,6 +514,35 @@ def test_three_parent_inclusion_exclusion(abi, port, n, m, cats):
         assert compare_search(a, o) == len(o)
 
 
+@pytest.mark.parametrize("n,m,cats", [(40, 300, 3), (70, 9000, 2), (100, 8200, 3), (130, 500, 2), (200, 400, 3),
+                                      (97, 260, [2, 3] * 48 + [2]), (260, 300, 2), (5, 40, 2), (3, 64, 3)])
+def test_reduced_tile_geometry(abi, port, n, m, cats):
+    """data with fewer than four categories per node: the tensor-core tiles contract only the free cells there are -- 4 rows
+    per pair and 2 columns per child for three categories (64 x 96 family slots per tile), 1 and 1 for binary data
+    (256 x 192) -- and must give the tables, log-likelihoods and networks of the 28 x 64 tiles and of the bit-plane scorer"""
+    s, c = random_problem(3 * n + m, n, m, cats)
+    kw = dict(max_parent_set=2, max_complexity=n * 12, order=(np.random.default_rng(n).permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.force_generic(4)                       # tensor cores, tiles of the data's own geometry
+        a = ctx.search_order(**kw)
+        ta = ctx.timing()["tensor_tiles"]
+        ctx.force_generic(4 | 131072)              # ... always 28 x 64 tiles
+        b = ctx.search_order(**kw)
+        tb = ctx.timing()["tensor_tiles"]
+        ctx.force_generic(8)                       # bit planes
+        d = ctx.search_order(**kw)
+        assert ctx.timing()["tensor_tiles"] == 0
+    assert 0 < ta <= tb and (n < 64 or ta < tb)
+    for other in (b, d):
+        assert compare_search(a, other) == len(other)
+        for x, y in zip(a, other):
+            assert x["loglik"] == y["loglik"] and x["node_loglik"] == y["node_loglik"]
+    if m <= 300 and n <= 130:
+        o = port.search_order(s, 2, kw["max_complexity"], order=kw["order"], num_cats=c)
+        assert compare_search(a, o) == len(o)
+
+
 @pytest.mark.parametrize("n,m,cats", [(12, 300, 3), (10, 257, 4), (14, 64, 2), (11, 1000, None), (70, 200, 3), (66, 9000, 2),
                                       (30, 8300, 4), (4, 50, 3), (5, 33, 2), (65, 40, 4), (129, 70, 2)])
 def test_three_parent_tensor_core_path(abi, n, m, cats):

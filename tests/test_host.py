@@ -125,15 +125,30 @@ def test_full_table_tiling_is_a_bijection(n):
         assert ntiles < 29500          # 27,127 slots-worth + diagonal overhead; 2.33 x the 12,279 inclusion-exclusion tiles
 
 
-@pytest.mark.parametrize("n,f1", [(4, 1), (5, 2), (30, 3), (64, 2), (65, 2), (70, 3), (100, 2), (129, 1)])
+@pytest.mark.parametrize("fr,tp,tc", [(3, 28, 64), (2, 64, 96), (1, 256, 192)])
+@pytest.mark.parametrize("n", [3, 4, 9, 65, 96, 97, 100, 192, 193, 200, 400])
+def test_reduced_tiling_is_a_bijection(n, fr, tp, tc):
+    """data with fewer than four categories per node: a pair takes fr^2 rows and a column node fr columns, so a tile
+    holds 64 x 96 (three categories) or 256 x 192 (binary) family slots; same bijection"""
+    from catnet_b200 import _abi
+    ntiles = _abi.lib().cnb_tile_selftest_geo(n, fr)
+    assert ntiles > 0, ntiles
+    assert ntiles * tp * tc >= n * (n - 1) * (n - 2) // 6
+    if fr == 3:
+        assert ntiles == _abi.lib().cnb_tile_selftest(n)
+
+
+@pytest.mark.parametrize("n,f1", [(4, 1), (5, 2), (30, 3), (64, 2), (65, 2), (70, 3), (100, 2), (129, 1), (97, 2), (100, -2), (50, -1), (193, 1)])
 def test_three_parent_tiling_is_consistent(n, f1):
     """cnb_tiles.h, T tiles: every three-parent family (a < b < c | x) and free value i of a owns one slot in the column
     tile of x, and the table kernel's decode of that tile puts (virtual node of (a, b, i), c) there"""
     from catnet_b200 import _abi
     ntiles = _abi.lib().cnb_tile3_selftest(n, f1)
     assert ntiles > 0, ntiles
+    if (n, f1) == (100, -2):
+        assert ntiles == 11672             # C3 in 28 x 64 tiles: column tiles [0, 36) and [36, 100)
     if (n, f1) == (100, 2):
-        assert ntiles == 11672             # C3: column tiles [0, 36) and [36, 100)
+        assert ntiles == 4903              # 64 x 96 tiles: column tiles [0, 4) and [4, 100), 2.4 x fewer MMAs than 11,672
 
 
 @pytest.mark.parametrize("seed", range(6))
