@@ -886,7 +886,7 @@ static int score_range(cnb_ctx *c, const DevData &D, const DevFamilies &F, int d
 	}
 	int cells = table_stride(c->max_cats, d_max);
 	if (cells > CNB_HIST_MAX_CELLS) cells = CNB_HIST_MAX_CELLS;
-	RC(cnbk_score_hist(st, D, F, b, e, cells, O, (int *)c->b_flag.ptr + 1, c->hist_mode));
+	RC(cnbk_score_hist(st, D, F, b, e, cells, O, (int *)c->b_flag.ptr + 1, c->hist_mode | (c->has_na ? 0 : 4)));
 	c->timing.kernel_launches++;
 	return CNB_OK;
 }

@@ -639,14 +639,66 @@ __global__ void __launch_bounds__(256) k_score_hist(DevData Dt, DevFamilies F, l
  * address are serialised by the hardware).  The fp64 epilogue (problist.h:224-250) stays in the warp: the 32 lanes
  * compute the terms n log(n / N_k) of 32 consecutive cells side by side, then the terms are added in the reference's
  * order -- cell after cell, empty cells skipped -- by a chain of shuffles. */
-template <int D, bool MATCH>
+/* 0xFF bytes of w -> 0x80 in that byte, else 0 (a code of 255 = missing value or padding behind the last sample) */
+__device__ __forceinline__ uint32_t hist_ff_bytes(uint32_t w) { return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u; }
+
+/* 16 samples of one lane: the cell indices of TWO samples at a time in the halves of a 32-bit word (tables have fewer
+ * than 65,536 cells, so (p0 * C1 + p1) * Cc + x never carries from the low half into the high one), one ATOMS.POPC.INC per
+ * sample.  CHECK: samples with a missing value in the family (code 255) or perturbed for the child (keep bit clear) are
+ * skipped -- their bytes are cleared first, so that they cannot carry into the neighbouring sample's half. */
+template <int D, bool CHECK>
+__device__ __forceinline__ void hist_chunk16(int *tab, const uint4 cv, const uint4 *pv, const int *pc, int cc, uint32_t km) {
+	const uint32_t cwv[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+	for (int w = 0; w < 4; w++) {
+		uint32_t cw = cwv[w], pw[D > 0 ? D : 1], inv = 0;
+#pragma unroll
+		for (int i = 0; i < D; i++) pw[i] = w == 0 ? pv[i].x : (w == 1 ? pv[i].y : (w == 2 ? pv[i].z : pv[i].w));
+		if (CHECK) {
+			inv = hist_ff_bytes(cw);
+#pragma unroll
+			for (int i = 0; i < D; i++) inv |= hist_ff_bytes(pw[i]);
+			const uint32_t drop = ~(km >> (4 * w)) & 0xFu;             /* keep bit j of the word -> bit 7 of byte j */
+			inv |= ((drop * 0x00204081u) & 0x01010101u) << 7;
+			const uint32_t m = (inv >> 7) * 0xFFu;
+			cw &= ~m;
+#pragma unroll
+			for (int i = 0; i < D; i++) pw[i] &= ~m;
+		}
+		uint32_t lo, hi;                                              /* samples (0, 1) and (2, 3) of the word */
+		if (D == 0) {
+			lo = __byte_perm(cw, 0, 0x4140);
+			hi = __byte_perm(cw, 0, 0x4342);
+		} else {
+			lo = __byte_perm(pw[0], 0, 0x4140);
+			hi = __byte_perm(pw[0], 0, 0x4342);
+#pragma unroll
+			for (int i = 1; i < D; i++) {
+				lo = lo * (uint32_t)pc[i] + __byte_perm(pw[i], 0, 0x4140);
+				hi = hi * (uint32_t)pc[i] + __byte_perm(pw[i], 0, 0x4342);
+			}
+			lo = lo * (uint32_t)cc + __byte_perm(cw, 0, 0x4140);
+			hi = hi * (uint32_t)cc + __byte_perm(cw, 0, 0x4342);
+		}
+		if (!CHECK || !(inv & 0x00000080u)) atomicAdd(&tab[lo & 0xFFFFu], 1);
+		if (!CHECK || !(inv & 0x00008000u)) atomicAdd(&tab[lo >> 16], 1);
+		if (!CHECK || !(inv & 0x00800000u)) atomicAdd(&tab[hi & 0xFFFFu], 1);
+		if (!CHECK || !(inv & 0x80000000u)) atomicAdd(&tab[hi >> 16], 1);
+	}
+}
+
+/* MODE 0: shared atomics, every sample checked; 1: shared atomics on data without missing values or masks (only the chunk
+ * that holds the padding behind the last sample is checked); 2: __match_any_sync aggregation */
+template <int D, int MODE>
 __global__ void __launch_bounds__(256) k_score_hist_warp(DevData Dt, DevFamilies F, long long fid_begin, long long fid_end,
 		int cells_per_warp, ScoreOut O, int *__restrict__ overflow) {
+	constexpr bool MATCH = MODE == 2;
 	extern __shared__ __align__(16) int s_tab[];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
 	int *tab = s_tab + (size_t)wib * cells_per_warp;
 	const unsigned FULLM = 0xFFFFFFFFu;
 	const int chunks16 = Dt.Mpad >> 4;                  /* Mpad is a multiple of 32 */
+	const int whole16 = Dt.M >> 4;                      /* chunks without padding */
 	for (long long fid = fid_begin + (long long)blockIdx.x * wpb + wib; fid < fid_end; fid += (long long)gridDim.x * wpb) {
 		int child, pars[CNB_MAXP];
 		dev_family(Dt, F, fid, child, pars);            /* every lane: uniform, no divergence */
@@ -678,6 +730,12 @@ __global__ void __launch_bounds__(256) k_score_hist_warp(DevData Dt, DevFamilies
 				for (int i = 0; i < D; i++) pv[i] = __ldg(pcol[i] + t);
 				if (kcol) km = (__ldg(kcol + (size_t)(t >> 1) * Dt.N) >> ((t & 1) * 16)) & 0xFFFFu;
 			}
+			if constexpr (!MATCH) {
+				if (in) {
+					if (MODE == 1 && t < whole16) hist_chunk16<D, false>(tab, cv, pv, pc, cc, km);
+					else hist_chunk16<D, true>(tab, cv, pv, pc, cc, km);
+				}
+			} else {
 #pragma unroll
 			for (int q = 0; q < 16; q++) {
 				const uint32_t cw = q < 4 ? cv.x : (q < 8 ? cv.y : (q < 12 ? cv.z : cv.w));
@@ -692,12 +750,11 @@ __global__ void __launch_bounds__(256) k_score_hist_warp(DevData Dt, DevFamilies
 					idx = idx * pc[i] + v;
 				}
 				idx = idx * cc + x;
-				if (MATCH) {
-					/* lanes without a sample get keys of their own, so that they meet nobody */
-					const unsigned peers = __match_any_sync(FULLM, ok ? idx : (int)(0x80000000u | lane));
-					if (ok && lane == __ffs(peers) - 1) tab[idx] += __popc(peers);
-					__syncwarp();
-				} else if (ok) atomicAdd(&tab[idx], 1);
+				/* lanes without a sample get keys of their own, so that they meet nobody */
+				const unsigned peers = __match_any_sync(FULLM, ok ? idx : (int)(0x80000000u | lane));
+				if (ok && lane == __ffs(peers) - 1) tab[idx] += __popc(peers);
+				__syncwarp();
+			}
 			}
 		}
 		__syncwarp();
@@ -1617,8 +1674,8 @@ int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &
 	return CNB_OK;
 }
 
-template <int D>
-static int launch_hist_warp(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int cpw, int wpb, bool match,
+template <int D, int MODE>
+static int launch_hist_warp_mode(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int cpw, int wpb,
 		const ScoreOut &O, int *overflow) {
 	static int sms = 0;
 	if (!sms) {
@@ -1629,19 +1686,20 @@ static int launch_hist_warp(cudaStream_t st, const DevData &Dt, const DevFamilie
 	const size_t smem = (size_t)cpw * wpb * sizeof(int);
 	const long long nblk = (e - b + wpb - 1) / wpb;
 	int per_sm = 1;
-	if (match) {
-		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_score_hist_warp<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_hist_warp<D, true>, wpb * 32, smem));
-		const unsigned grid = (unsigned)std::min<long long>(nblk, (long long)sms * std::max(per_sm, 1));
-		k_score_hist_warp<D, true><<<grid, wpb * 32, smem, st>>>(Dt, F, b, e, cpw, O, overflow);
-	} else {
-		if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_score_hist_warp<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_hist_warp<D, false>, wpb * 32, smem));
-		const unsigned grid = (unsigned)std::min<long long>(nblk, (long long)sms * std::max(per_sm, 1));
-		k_score_hist_warp<D, false><<<grid, wpb * 32, smem, st>>>(Dt, F, b, e, cpw, O, overflow);
-	}
+	if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_score_hist_warp<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_hist_warp<D, MODE>, wpb * 32, smem));
+	const unsigned grid = (unsigned)std::min<long long>(nblk, (long long)sms * std::max(per_sm, 1));
+	k_score_hist_warp<D, MODE><<<grid, wpb * 32, smem, st>>>(Dt, F, b, e, cpw, O, overflow);
 	CK(cudaGetLastError());
 	return CNB_OK;
+}
+
+template <int D>
+static int launch_hist_warp(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int cpw, int wpb, int kmode,
+		const ScoreOut &O, int *overflow) {
+	if (kmode == 2) return launch_hist_warp_mode<D, 2>(st, Dt, F, b, e, cpw, wpb, O, overflow);
+	if (kmode == 1) return launch_hist_warp_mode<D, 1>(st, Dt, F, b, e, cpw, wpb, O, overflow);
+	return launch_hist_warp_mode<D, 0>(st, Dt, F, b, e, cpw, wpb, O, overflow);
 }
 
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
@@ -1651,15 +1709,17 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 	 * its own table, atomics / __match_any_sync -- for up to three parents of one count and tables that leave room for at
 	 * least one warp's table in 96 KB */
 	const int cpw = (max_cells + 31) & ~31;
-	if (mode != 0 && F.d >= 0 && F.d <= 3 && !F.ex_nd && (size_t)cpw * sizeof(int) <= 96 * 1024) {
+	if ((mode & 3) != 0 && F.d >= 0 && F.d <= 3 && !F.ex_nd && (size_t)cpw * sizeof(int) <= 96 * 1024 && cpw < 65536) {
 		int wpb = 8;
 		while (wpb > 1 && (size_t)cpw * wpb * sizeof(int) > 96 * 1024) wpb >>= 1;
-		const bool match = mode == 2;
+		/* kernel mode: __match_any_sync, or atomics with / without per-sample checks (bit 2 of mode: the data has neither
+		 * missing values nor a keep mask) */
+		const int kmode = (mode & 3) == 2 ? 2 : (((mode & 4) && !Dt.keep_lbl) ? 1 : 0);
 		switch (F.d) {
-		case 0: return launch_hist_warp<0>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
-		case 1: return launch_hist_warp<1>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
-		case 2: return launch_hist_warp<2>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
-		default: return launch_hist_warp<3>(st, Dt, F, b, e, cpw, wpb, match, O, overflow);
+		case 0: return launch_hist_warp<0>(st, Dt, F, b, e, cpw, wpb, kmode, O, overflow);
+		case 1: return launch_hist_warp<1>(st, Dt, F, b, e, cpw, wpb, kmode, O, overflow);
+		case 2: return launch_hist_warp<2>(st, Dt, F, b, e, cpw, wpb, kmode, O, overflow);
+		default: return launch_hist_warp<3>(st, Dt, F, b, e, cpw, wpb, kmode, O, overflow);
 		}
 	}
 	size_t smem = (size_t)((max_cells + 1) & ~1) * sizeof(int) + (size_t)max_cells * sizeof(double);

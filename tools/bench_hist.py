@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--modes", default="1,2,0")
     ap.add_argument("--skew", type=float, default=0.0, help="probability mass of category 1 in every column (0 = uniform-ish CPTs)")
+    ap.add_argument("--na", type=float, default=0.0, help="fraction of missing values (the warp kernel then checks every sample)")
     args = ap.parse_args()
     import torch
     from catnet_b200 import _abi
@@ -43,6 +44,10 @@ def main():
             par = rng.integers(0, i)
             base = np.where(rng.random(m) < 0.5, s[:, par] - 1, base)
         s[:, i] = base + 1
+    if args.na > 0:
+        mask = rng.random(s.shape) < args.na
+        mask[:C, :] = False
+        s[mask] = -2147483648
     cats = np.full(n, C, dtype=np.int32)
     K = n * (C - 1) * C ** args.parents
     kw = dict(max_parent_set=args.parents, max_complexity=K)
@@ -72,7 +77,7 @@ def main():
             sc = scores.cpu().numpy()
             if ref is None:
                 ref = sc
-            print(json.dumps({"mode": mode, "kernel": names[mode], "nodes": n, "cats": C, "samples": m, "parents": args.parents, "skew": args.skew,
+            print(json.dumps({"mode": mode, "kernel": names[mode], "nodes": n, "cats": C, "samples": m, "parents": args.parents, "skew": args.skew, "na": args.na,
                               "families": nf, "step_ms": 1000 * wall, "score_ms": tm["score_ms"], "score_ms_by_parents": tm["score_ms_by_parents"][:args.parents + 1],
                               "families_per_s": nf / wall, "family_samples_per_s": nf * m / (tm["score_ms"] / 1e3),
                               "fast_path": tm["fast_path"], "scores_equal_first_mode": bool(np.array_equal(sc, ref, equal_nan=True))}), flush=True)
