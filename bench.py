@@ -88,26 +88,64 @@ def config_of(wl, n_fam_total):
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML polled every 10 ms from a thread of this
+    process (a timed region of a few steps at 8 GPUs lasts ~0.1 s: nvidia-smi's 200 ms loop, the fallback when NVML cannot
+    be loaded, would miss it)."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nv, self.smax, self.quit = [], None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(index)))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nv[1], pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.quit:
+            try:
+                self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nv:
+            self.quit = True
+            self.t.join(timeout=1.0)
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            how = "nvml, 10 ms"
+            if not inside and self.rows:                      # a region shorter than one poll: the nearest sample
+                inside = [min(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))]
+                how = "nvml, nearest sample to a region shorter than the polling period"
+            mask = 0
+            for r in inside:
+                mask |= r[2]
+            return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(nm for bit, nm in self.BITS.items() if mask & bit), "samples": len(inside), "how": how}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -126,7 +164,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "how": "nvidia-smi -lms 50"}
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline
