@@ -83,7 +83,7 @@ SYMBOLS = [
     "cnb_mctx_search_order", "cnb_mctx_search_light", "cnb_mctx_collect", "cnb_mctx_search_sa", "cnb_mctx_search_hist",
     "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
     "cnb_ctx_upload_rows8", "cnb_tile_selftest_full", "cnb_last_call_timing",
-    "cnb_tile_selftest_geo", "cnb_ctx_upload_rows8_on", "cnb_ctx_stream_begin", "cnb_ctx_stream_slice", "cnb_ctx_stream_end",
+    "cnb_tile_selftest_geo", "cnb_ctx_allow_scatter", "cnb_ctx_scattered", "cnb_ctx_upload_rows8_on", "cnb_ctx_stream_begin", "cnb_ctx_stream_slice", "cnb_ctx_stream_end",
 ]
 
 _lib = None
@@ -129,6 +129,8 @@ def lib():
         "cnb_tile_selftest_full": (C.c_int64, [i32]),
         "cnb_tile3_selftest": (C.c_int64, [i32, i32]),
         "cnb_tile_selftest_geo": (C.c_int64, [i32, i32]),
+        "cnb_ctx_allow_scatter": (i32, [vp, i32]),
+        "cnb_ctx_scattered": (i32, [vp]),
         "cnb_host_entropy_order": (None, [vp, i32, vp]),
         "cnb_family_scores": (i32, [vp, i32, i32, vp, vp, i32, vp, vp, vp, i32]),
         "cnb_device_log": (i32, [i32, vp, i64, vp]),
@@ -392,6 +394,13 @@ class Context:
 
     def score_shard(self, scores_dev_ptr):
         check(lib().cnb_ctx_score_shard(self.h, scores_dev_ptr))
+
+    def allow_scatter(self, mode):
+        """0 never, 1 all ranks share one score buffer, 2 own buffers combined by an element-wise MAX (dist.gather_scores)"""
+        check(lib().cnb_ctx_allow_scatter(self.h, int(mode)))
+
+    def scattered(self):
+        return bool(lib().cnb_ctx_scattered(self.h))
 
     def select_dp(self, scores_dev_ptr):
         check(lib().cnb_ctx_select_dp(self.h, scores_dev_ptr))

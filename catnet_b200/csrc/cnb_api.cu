@@ -551,6 +551,14 @@ extern "C" int cnb_ctx_set_stream(cnb_ctx *c, void *cuda_stream) {
 	return CNB_OK;
 }
 
+extern "C" int cnb_ctx_allow_scatter(cnb_ctx *c, int32_t mode) {
+	if (!c || mode < 0 || mode > 2) return CNB_ERR_PARAM;
+	c->allow_scatter = mode;
+	return CNB_OK;
+}
+
+extern "C" int32_t cnb_ctx_scattered(const cnb_ctx *c) { return c && c->scattered ? 1 : 0; }
+
 extern "C" int cnb_ctx_force_generic(cnb_ctx *c, int32_t on) {
 	if (!c) return CNB_ERR_PARAM;
 	c->force_generic = (on & 1) != 0;     /* bit 0: generic histogram kernel everywhere */
@@ -602,6 +610,7 @@ static DevData make_devdata(cnb_ctx *c) {
 	D.blocks = (const CnbBlock *)c->b_blocks.ptr;
 	D.group_blocks = (const int32_t *)c->b_group_blocks.ptr;
 	D.edge = c->plan.has_prior ? (const double *)c->b_edge.ptr : nullptr;
+	D.fix1 = c->plan_has_fix1 ? (const int32_t *)c->b_fix1.ptr : nullptr;
 	cnb_plan_tiles(c->plan, &D.tiles);
 	D.tiles.tile_base = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_tile_base.ptr;
 	D.tiles.dtile_off = c->plan.tile_base.empty() ? nullptr : (const long long *)c->b_dtile_off.ptr;
@@ -659,6 +668,9 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	}
 	RC(upload(c, c->b_order, pl.order));
 	RC(upload(c, c->b_cats, pl.cats));
+	c->plan_has_fix1 = false;
+	for (int v : pl.fix1) c->plan_has_fix1 = c->plan_has_fix1 || v >= 0;
+	if (c->plan_has_fix1) RC(upload(c, c->b_fix1, pl.fix1));
 	RC(upload(c, c->b_lists, pl.lists));
 	RC(upload(c, c->b_blocks, pl.blocks));
 	RC(upload(c, c->b_group_blocks, pl.group_blocks));
@@ -740,42 +752,63 @@ static int ensure_triples(cnb_ctx *c, bool *ok) {
 	return CNB_OK;
 }
 
-/* the whole unrestricted three-parent group on the tensor cores (T tiles, cnb_tiles.h): per column tile of 64 children the
+/* can the unrestricted three-parent group g run as T tiles?  (sizes and switches only: every rank decides alike) */
+static bool tensor3_eligible(const cnb_ctx *c, const CnbGroup &g) {
+	const CnbPlan &pl = c->plan;
+	const int N = c->N;
+	if (g.d != 3 || !g.full || (pl.world != 1 && !c->allow_scatter) || pl.tile_base.empty() || pl.tile_full || !c->clean || !c->pairs_valid
+			|| c->force_generic || c->no_ie || c->no_ie3 || c->no_tensor3 || c->tensor_i8 || c->tensor_mode < 0
+			|| (c->tensor_mode == 0 && c->M < 8192) || c->M >= (1 << 24) || N < 4 || N > 64 * 32
+			|| cnbk_umma_row_quads(c->W, 1, nullptr) > 65535) return false;
+	const int f1 = (c->max_cats <= 2 ? 2 : (c->max_cats == 3 ? 3 : 4)) - 1;
+	const long long nvirt = (long long)N * (N - 1) / 2 * f1, nt = (long long)N * (N - 1) * (N - 2) / 6;
+	const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * 3 * (size_t)(N + nvirt);
+	return row_bytes <= (16ull << 30) && nvirt <= (1ll << 28) && nt * 256 <= (24ll << 30);
+}
+
+/* the whole unrestricted three-parent group on the tensor cores (T tiles, cnb_tiles.h): per column tile of children the
  * table kernel contracts (virtual pair node (a, b, i), c) x children, the epilogue completes the four-way tables from the
- * three-way tables of the data set.  *done = false (nothing launched) when the group does not qualify. */
+ * three-way tables of the data set.  A column tile is contracted in BATCHES of tiles that fit the table buffer (so the number
+ * of nodes is no longer bounded by one column tile's tables), and with several ranks every rank takes a contiguous share
+ * of each column tile's tiles -- i.e. a range of triples (a, b, c) for ALL children of the column tile, so its scores land
+ * in every rank's segment of the score buffer ("scattered": the exchange is then a max-reduction over a buffer that
+ * starts at -inf, or peer stores into one buffer; cnb_ctx_allow_scatter).  *done = false (nothing launched) when the group
+ * does not qualify. */
 static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, const CnbGroup &g, const ScoreOut &O, bool *done) {
 	*done = false;
 	const CnbPlan &pl = c->plan;
 	const int N = c->N;
-	if (g.d != 3 || !g.full || pl.world != 1 || pl.tile_base.empty() || pl.tile_full || !c->clean || !c->pairs_valid || c->force_generic
-			|| c->no_ie || c->no_ie3 || c->no_tensor3 || c->tensor_i8 || c->tensor_mode < 0 || (c->tensor_mode == 0 && c->M < 8192)
-			|| c->M >= (1 << 24) || N < 4 || N > 64 * 32 || cnbk_umma_row_quads(c->W, 1, nullptr) > 65535) return CNB_OK;
+	if (!tensor3_eligible(c, g)) return CNB_OK;
 	bool ok = false;
 	RC(ensure_triples(c, &ok));
-	if (!ok) return CNB_OK;
+	if (!ok) {
+		if (pl.world != 1) { cnb_set_error("three-parent tensor path: the three-way tables do not fit on this rank"); return CNB_ERR_MEM; }
+		return CNB_OK;
+	}
 	const int cm = c->max_cats <= 2 ? 2 : (c->max_cats == 3 ? 3 : 4), f1 = cm - 1;
 	const long long nvirt = (long long)N * (N - 1) / 2 * f1;
 	/* tiles of f1 free categories: f1^2 rows per (virtual pair node, c) slot, f1 columns per child (cnb_tiles.h) */
 	const int tp3 = cnb_geo_pairs(f1), tc3 = cnb_geo_child(f1);
 	const int nct = (N + tc3 - 1) / tc3;
 	std::vector<long long> base3(nct + 1, 0);
-	long long largest = 0;
-	for (int ct = 0; ct < nct; ct++) {
-		const int ce = cnb_t_ce(N, nct, ct, tc3);
-		const long long n = cnb_t_tiles(ce, f1, tp3);
-		base3[ct + 1] = base3[ct] + n;
-		largest = std::max(largest, n);
-	}
+	for (int ct = 0; ct < nct; ct++) base3[ct + 1] = base3[ct] + cnb_t_tiles(cnb_t_ce(N, nct, ct, tc3), f1, tp3);
 	const long long slot_bytes = (long long)cnb_geo_slot_ints(f1) * sizeof(int) * tp3 * tc3;
 	const size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, 1, nullptr) * sizeof(uint4) * 3 * (size_t)(N + nvirt);
-	if (largest * slot_bytes > (8ll << 30) || row_bytes > (16ull << 30) || nvirt > (1ll << 28)) return CNB_OK;
+	/* a batch / a rank's share starts on a slot that begins a triple: tile boundaries where tile * tp3 is a multiple of f1 */
+	int align = 1;
+	while ((long long)align * tp3 % f1) align++;
+	long long budget = 4ll << 30;                            /* table buffer of a batch (CNB_T3_BATCH_BYTES: tests) */
+	if (const char *e = getenv("CNB_T3_BATCH_BYTES")) budget = std::max<long long>(strtoll(e, nullptr, 10), slot_bytes);
+	long long batch = std::max<long long>(budget / slot_bytes / align * align, align);
 	cudaStream_t st = c->stream;
 	RC(upload(c, c->b_tile_base3, base3));
 	RC(c->b_rows_a3.ensure(row_bytes));
 	RC(cnbk_umma_rows3(st, (const uint4 *)c->b_planes.ptr, N, c->W, (int)nvirt, f1, (uint4 *)c->b_rows_a3.ptr));
 	c->timing.kernel_launches += 2;
 	c->tables_resident = false;                        /* the T tiles take the table buffer */
-	RC(c->b_counts.ensure((size_t)std::max<long long>(largest, 1) * slot_bytes));
+	long long widest = 1;
+	for (int ct = 0; ct < nct; ct++) widest = std::max(widest, std::min(batch, base3[ct + 1] - base3[ct]));
+	RC(c->b_counts.ensure((size_t)widest * slot_bytes));
 	CnbTiles T3;
 	memset(&T3, 0, sizeof(T3));
 	T3.tp = tp3;
@@ -784,28 +817,30 @@ static int score_tensor3(cnb_ctx *c, const DevData &D, const DevFamilies &F, con
 	T3.tile_base = (const long long *)c->b_tile_base3.ptr;
 	T3.nct = nct;
 	T3.child = tc3;
-	T3.world = 1;
+	T3.world = 1;                                      /* contiguous tile ranges: the dealing is done here, not in the kernel */
 	T3.self_pairs = 2;
 	T3.f1 = f1;
 	T3.nvirt = (int)nvirt;
-	/* families of the group by child: block k of the group belongs to child 3 + k and starts at blocks[..].start */
+	long long mine = 0;
 	for (int ct = 0; ct < nct; ct++) {
 		const int c0 = cnb_t_c0(N, nct, ct, tc3), ce = cnb_t_ce(N, nct, ct, tc3);
-		long long fb = -1, fe = -1;
-		for (int k = 0; k < g.nblk; k++) {
-			const CnbBlock &b = pl.blocks[pl.group_blocks[g.blk_off + k]];
-			if (b.child < c0 || b.child >= ce) continue;
-			if (fb < 0) fb = b.start;
-			fe = b.start + b.ncomb;
+		const long long ntile = base3[ct + 1] - base3[ct], ntrip = cnb_binom3(ce - 1);
+		if (ntile < 1 || ce <= 3) continue;
+		const long long per = ((ntile + pl.world - 1) / pl.world + align - 1) / align * align;
+		const long long lo = std::min(ntile, (long long)pl.rank * per), hi = std::min(ntile, lo + per);
+		for (long long tb = lo; tb < hi; tb += batch) {
+			const long long te = std::min(hi, tb + batch);
+			const long long t_begin = tb * tp3 / f1, t_end = te == ntile ? ntrip : std::min(ntrip, te * tp3 / f1);
+			RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a3.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, T3, base3[ct] + tb,
+					base3[ct] + te, (int *)c->b_counts.ptr));
+			RC(cnbk_umma_epilogue3_range(st, D, F, c->max_cats, t_begin, t_end, tb * tp3, c0, ce, (const int *)c->b_counts.ptr,
+					(const int *)c->b_triples.ptr, O));
+			c->timing.kernel_launches += 2;
+			mine += te - tb;
 		}
-		if (fb < 0 || fe <= fb || base3[ct + 1] <= base3[ct]) continue;
-		RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a3.ptr, (const uint4 *)c->b_rows_b.ptr, N, c->W, 1, T3, base3[ct],
-				base3[ct + 1], (int *)c->b_counts.ptr));
-		RC(cnbk_umma_epilogue3(st, D, F, c->max_cats, fb, fe, c0, (const int *)c->b_counts.ptr, (const int *)c->b_triples.ptr, O));
-		c->timing.kernel_launches += 2;
 	}
-	c->tensor3_tiles = (int)base3[nct];
-	c->timing.tensor3_tiles = base3[nct];
+	c->tensor3_tiles = (int)mine;
+	c->timing.tensor3_tiles = mine;
 	*done = true;
 	return CNB_OK;
 }
@@ -911,6 +946,13 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	c->tensor_batches = 0;
 	c->tensor3_tiles = 0;
 	c->timing.tensor3_tiles = 0;
+	/* a sharded three-parent group on T tiles writes scores into every rank's segment: with the max-reduction exchange the
+	 * buffer starts at -inf (cnb_ctx_allow_scatter) */
+	c->scattered = false;
+	if (pl.world > 1 && c->allow_scatter)
+		for (const CnbGroup &g : pl.groups) c->scattered = c->scattered || (!g.tiled && tensor3_eligible(c, g));
+	if (c->scattered && c->allow_scatter == 2)
+		RC(cnbk_fill_f64(st, scores_dev, (long long)pl.seg_len * pl.world, -INFINITY));
 	int gi = 0;
 	for (const CnbGroup &g : pl.groups) {
 		DevFamilies F;
@@ -1734,6 +1776,10 @@ extern "C" int cnb_search_order(const cnb_params *p, cnb_result **out) {
 	if (cnb_multi_devices(p) > 1 || cnb_multi_devices(p) < -1) return cnb_multi_search_order(p, out);   /* one process, several GPUs: cnb_multi.cu */
 	cnb_ctx *c = nullptr;
 	RC(cnb_ctx_acquire(p->device, &c));
+	/* CNB_FORCE_BITS: the kernel-selection switches of cnb_ctx_force_generic for the one-shot calls (fuzzing the tensor-core
+	 * and histogram paths on small problems: tools/fuzz_gpu.py) */
+	const char *fb = getenv("CNB_FORCE_BITS");
+	cnb_ctx_force_generic(c, fb ? atoi(fb) : 0);
 	bool done = false;
 	int rc = search_order_streamed(c, p, out, &done);  /* large complete matrices: upload overlapped with the table kernel */
 	if (rc == CNB_OK && !done) {

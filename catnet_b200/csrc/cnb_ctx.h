@@ -36,6 +36,9 @@ struct cnb_ctx {
 	std::vector<cudaEvent_t> ev_slices;   /* "slice k is on the device" */
 	bool tables_resident = false;         /* b_counts still holds the tile tables of the whole two-parent group of the current plan
 	                                         (one batch, one rank): the export reads the returned networks' tables from there */
+	int allow_scatter = 0;                /* a sharded search may write scores outside this rank's segment (three-parent T tiles):
+	                                         1 = every rank stores into ONE buffer (peer memory), 2 = the caller max-reduces the buffers */
+	bool scattered = false;               /* the last cnb_ctx_score_shard did */
 	bool no_reduced_tiles = false;        /* tensor-core tiles always contract 3 free categories per node (test / A-B switch) */
 	int hist_mode = 1, hist_mode_default = 1;   /* generic scorer: 0 one CTA per family, 1 a warp per family + shared atomics, 2 + __match_any_sync (CNB_HIST_MODE) */
 	bool stream_active = false;           /* between cnb_ctx_stream_begin and cnb_ctx_stream_end */
@@ -88,7 +91,8 @@ struct cnb_ctx {
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
 	/* plan */
-	DevBuf b_order, b_cats, b_lists, b_blocks, b_group_blocks, b_groups, b_edge, b_blk_equal, b_tile_base, b_dtile_off;
+	DevBuf b_order, b_cats, b_lists, b_blocks, b_group_blocks, b_groups, b_edge, b_blk_equal, b_tile_base, b_dtile_off, b_fix1;
+	bool plan_has_fix1 = false;
 	/* scoring */
 	DevBuf b_scores, b_counts, b_ex_child, b_ex_pars, b_ex_nd, b_ex_ll, b_ex_prior, b_ex_score, b_ex_ncount, b_ex_counts;
 	/* selection + DP */
@@ -98,7 +102,7 @@ struct cnb_ctx {
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3, &b_fix1};
 	}
 };
 

@@ -21,6 +21,7 @@ struct DevData {
 	const CnbBlock *blocks;
 	const int32_t *group_blocks;
 	const double *edge;         /* [N*N] order space [parent*N+child] or NULL */
+	const int32_t *fix1;        /* [N] order space: the node's only fixed parent or -1; NULL when no node has fixed parents */
 	CnbTiles tiles;             /* tensor-core tiling of the two-parent group (tile_base NULL if not tiled) */
 };
 

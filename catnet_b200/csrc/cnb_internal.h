@@ -93,6 +93,8 @@ struct CnbPlan {
 	int32_t rank = 0, world = 1;
 	bool has_prior = false;
 	std::vector<int32_t> order;                /* position -> 0-based label */
+	std::vector<int32_t> fix1;                 /* [N] the node's only fixed parent (position), or -1: a two-parent candidate (fixed f, free x)
+	                                              is LISTED [f, x] even when x precedes f, and its table and log-likelihood follow the listing */
 	std::vector<int32_t> cats;                 /* order space */
 	std::vector<int32_t> lists;
 	std::vector<CnbBlock> blocks;

@@ -1732,6 +1732,17 @@ int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, lo
 	return CNB_OK;
 }
 
+__global__ void k_fill_f64(double *__restrict__ p, long long n, double v) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int cnbk_fill_f64(cudaStream_t st, double *p, long long n, double v) {
+	if (n <= 0) return CNB_OK;
+	k_fill_f64<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(p, n, v);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
 int cnbk_select_chunk(void) { return SEL_CHUNK; }
 
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,

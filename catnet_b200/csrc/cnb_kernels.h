@@ -88,6 +88,9 @@ int cnbk_umma_export(cudaStream_t st, const DevData &Dt, long long f_begin, long
 int cnbk_umma_rows3(cudaStream_t st, const uint4 *planes, int N, int W, int nvirt, int f1, uint4 *rows_a3);
 int cnbk_umma_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long b, long long e,
 		int c0, const int *counts, const int *triple_tab, const ScoreOut &O);
+/* the same for triples [t_begin, t_end) of one column tile [c0, ce) (batches of its tiles; tiles dealt to several devices) */
+int cnbk_umma_epilogue3_range(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long t_begin, long long t_end,
+		long long q_base, int c0, int ce, const int *counts, const int *triple_tab, const ScoreOut &O);
 /* pairwise metrics (cnb_pairwise.cu): kind 0 entropy, 1 KL, 2 Pearson from the tables of the families (child n1,
  * parent n2), family index n1 * (N - 1) + rank of n2 among the others; out[n2 * N + n1] */
 int cnbk_pairwise_metric(cudaStream_t st, int kind, int N, const int *cats, const int *kept, const int *full,
@@ -115,6 +118,7 @@ int cnbk_sample(cudaStream_t st, const CnbDevNet &net, const int *order, const i
 int cnbk_sample_na(cudaStream_t st, int N, int M, int k, unsigned long long seed, unsigned long long base, int *out);
 int cnbk_epilogue_counts(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e,
 		const ScoreOut &O);
+int cnbk_fill_f64(cudaStream_t st, double *p, long long n, double v);
 int cnbk_score_hist(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long b, long long e, int max_cells,
 		const ScoreOut &O, int *overflow, int mode);
 /* arg-max per (child, parent count) block: `chunks` = (block, chunk) per CTA, cnbk_select_chunk() candidates each;

@@ -97,6 +97,9 @@ extern "C" int cnb_mctx_create(int32_t first, int32_t num_devices, cnb_mctx **ou
 			else if (pe != cudaSuccess) { cudaGetLastError(); peer = false; }
 		}
 	m->peer = peer;
+	/* with peer access every device stores its scores into the first device's buffer: the three-parent T tiles may then be
+	 * dealt to the devices by triple range (cnb_ctx_allow_scatter mode 1) */
+	for (int g = 0; g < G && rc == CNB_OK; g++) m->cs[g]->allow_scatter = (peer || m->alias) ? 1 : 0;
 	for (int g = 0; g < G && rc == CNB_OK; g++) {
 		if (cudaSetDevice(first + g * step) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_done[g], cudaEventDisableTiming) != cudaSuccess
 				|| cudaEventCreateWithFlags(&m->ev_share[g], cudaEventDisableTiming) != cudaSuccess) {
@@ -594,6 +597,8 @@ int cnb_multi_search_order(const cnb_params *p, cnb_result **out) {
 	RC(mctx_acquire(p->device, G, &m));
 	/* only the devices this search will use receive the samples */
 	const int A = devices_for(m, p, p->num_samples, m->G);
+	const char *fb = getenv("CNB_FORCE_BITS");                   /* kernel-selection switches for fuzzing (cnb_api.cu) */
+	for (int g = 0; g < m->G; g++) cnb_ctx_force_generic(m->cs[g], fb ? atoi(fb) : 0);
 	bool done = false;
 	int rc = mctx_search_streamed(m, A, p, out, &done);
 	if (rc == CNB_OK && !done) {

@@ -126,6 +126,7 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 
 	pl.nodes.resize(N);
 	std::vector<int32_t> fix, fre;
+	pl.fix1.assign(N, -1);
 	for (int c = 0; c < N; c++) {
 		CnbNodePlan &nd = pl.nodes[c];
 		fix.clear();
@@ -138,6 +139,7 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 			(fixd ? fix : fre).push_back(j);
 		}
 		nd.nfix = (int32_t)fix.size();
+		pl.fix1[c] = fix.size() == 1 ? fix[0] : -1;
 		nd.fix_off = (int32_t)pl.lists.size();
 		pl.lists.insert(pl.lists.end(), fix.begin(), fix.end());
 		int32_t free_off = (int32_t)pl.lists.size();

@@ -615,6 +615,9 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 		}
 	}
 	const int l0 = Dt.order[a], l1 = Dt.order[b], lc = Dt.order[c];
+	/* the reference sums a table in the order of the family's LISTED parents (fixed parents first, then the free ones
+	 * ascending; catnet_search2.h:532-553): the only two-parent listing that is not ascending is (fixed b, free a < b) */
+	const bool listed_ba = Dt.fix1 && Dt.fix1[c] == b;
 	double ll;
 	if (UNI4) {
 		if (!FULL) {
@@ -643,7 +646,9 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 		ll = 0.0;
 		long long ncount = 0;
 #pragma unroll
-		for (int cfg = 0; cfg < 16; cfg++) {
+		for (int cfg0 = 0; cfg0 < 16; cfg0++) {
+			/* a candidate (fixed parent b, free parent a < b) is listed [b, a]: its configurations run b-major */
+			const int cfg = listed_ba ? (cfg0 & 3) * 4 + (cfg0 >> 2) : cfg0;
 			const int n0 = full[cfg * 4], n1 = full[cfg * 4 + 1], n2 = full[cfg * 4 + 2], n3 = full[cfg * 4 + 3];
 			const long long nk = (long long)n0 + n1 + n2 + n3;
 			if (nk > 0) {
@@ -676,10 +681,16 @@ __global__ void __launch_bounds__(128) k_umma_epilogue(DevData Dt, long long loc
 	}
 	const int pc0 = Dt.cats[a], pc1 = Dt.cats[b], cc = Dt.cats[c];
 	int ncount;
-	ll = dev_loglik(pc0 * pc1, cc, [&](int cfg, int k) {
-		int i = cfg / pc1, jj = cfg - i * pc1;
-		return CELL(i, jj, k);
-	}, &ncount);
+	if (listed_ba)
+		ll = dev_loglik(pc0 * pc1, cc, [&](int cfg, int k) {
+			int jj = cfg / pc0, i = cfg - jj * pc0;
+			return CELL(i, jj, k);
+		}, &ncount);
+	else
+		ll = dev_loglik(pc0 * pc1, cc, [&](int cfg, int k) {
+			int i = cfg / pc1, jj = cfg - i * pc1;
+			return CELL(i, jj, k);
+		}, &ncount);
 	}
 #undef CELL
 	double score = ll;
@@ -871,6 +882,55 @@ __global__ void __launch_bounds__(BS) k_umma_epilogue3(DevData Dt, DevFamilies F
 				} else x[0] = tab[0];
 #pragma unroll
 				for (int l = 0; l < F1; l++) mine[((((i * CM + j) * CM + k) * CM + l)) * BS] = x[l];
+			}
+	}
+	int ncount;
+	const double ll = dev_ie3_finish<CM, BS>(mine, Dt, tt, pars, child, &ncount);
+	dev_store_outputs(Dt, O, fid, child, pars, 3, ll, ncount);
+}
+
+/* The same for a RANGE of triples of one column tile: one thread per (triple t in [t_begin, t_end), child x of the column
+ * tile [c0, ce)) with t < C(x, 3).  counts holds the tiles that contain the slots q = t * F1 + i from q_base on (q_base is a
+ * multiple of the tile's pair slots), so a column tile can be contracted in batches that fit the table buffer, and its
+ * tiles can be dealt to several devices.  The family id is the child's block start plus the LEXICOGRAPHIC rank of (a, b, c)
+ * among the 3-subsets of the child's predecessors (the candidate order of combinationSets, catnet_search2.h:102-147);
+ * the group is the unrestricted one, block k = child 3 + k. */
+template <int CM, int BS>
+__global__ void __launch_bounds__(BS) k_umma_epilogue3_range(DevData Dt, DevFamilies F, long long t_begin, long long t_end, long long q_base,
+		int c0, int ce, const int *__restrict__ counts, const int *__restrict__ tt, ScoreOut O) {
+	constexpr int F1 = CM - 1;
+	extern __shared__ __align__(16) int s_cnt[];          /* [CM^4][BS] */
+	const long long t = t_begin + (long long)blockIdx.x * BS + threadIdx.x;
+	const int child = (c0 > 3 ? c0 : 3) + (int)blockIdx.y;
+	if (t >= t_end || child >= ce || t >= cnb_binom3(child)) return;
+	int a, b, c;
+	cnb_triple_of(t, a, b, c);
+	int pars[CNB_MAXP];
+	pars[0] = a; pars[1] = b; pars[2] = c;
+	const long long x = child;
+	const long long lex = cnb_binom3(x) - cnb_binom3(x - a) + (x - a - 1) * (x - a - 2) / 2 - (x - b) * (x - b - 1) / 2 + (c - b - 1);
+	const long long fid = Dt.blocks[Dt.group_blocks[F.blk_off + (child - 3)]].start + lex;
+	int *mine = s_cnt + threadIdx.x;
+	constexpr int TP = F1 >= 3 ? CNB_TILE_PAIRS : (F1 == 2 ? 64 : 256), TCH = F1 >= 3 ? CNB_TILE_CHILD : (F1 == 2 ? 96 : 192);
+	constexpr int CST = F1 >= 3 ? 4 : F1, SINTS = F1 * F1 * CST;
+#pragma unroll
+	for (int i = 0; i < F1; i++) {
+		const long long q = t * F1 + i - q_base;
+		const int *tab = counts + ((size_t)(q / TP) * (TP * TCH) + (size_t)(q % TP) * TCH + (child - c0)) * SINTS;
+#pragma unroll
+		for (int j = 0; j < F1; j++)
+#pragma unroll
+			for (int k = 0; k < F1; k++) {
+				int v[3] = {0, 0, 0};
+				if constexpr (CST == 4) {
+					const int4 w = *reinterpret_cast<const int4 *>(tab + (j * 3 + k) * 4);
+					v[0] = w.x; v[1] = w.y; v[2] = w.z;
+				} else if constexpr (CST == 2) {
+					const int2 w = *reinterpret_cast<const int2 *>(tab + (j * 2 + k) * 2);
+					v[0] = w.x; v[1] = w.y;
+				} else v[0] = tab[0];
+#pragma unroll
+				for (int l = 0; l < F1; l++) mine[((((i * CM + j) * CM + k) * CM + l)) * BS] = v[l];
 			}
 	}
 	int ncount;
@@ -1127,6 +1187,29 @@ static int launch_epilogue3(cudaStream_t st, const DevData &Dt, const DevFamilie
 	k_umma_epilogue3<CM, BS><<<(unsigned)((e - b + BS - 1) / BS), BS, smem, st>>>(Dt, F, b, e, c0, counts, tt, O);
 	CK(cudaGetLastError());
 	return CNB_OK;
+}
+
+template <int CM, int BS>
+static int launch_epilogue3_range(cudaStream_t st, const DevData &Dt, const DevFamilies &F, long long t_begin, long long t_end,
+		long long q_base, int c0, int ce, const int *counts, const int *tt, const ScoreOut &O) {
+	const size_t smem = (size_t)CM * CM * CM * CM * BS * sizeof(int);
+	if (smem > 48 * 1024)
+		CK(cudaFuncSetAttribute(k_umma_epilogue3_range<CM, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const int first = c0 > 3 ? c0 : 3;
+	if (ce <= first) return CNB_OK;
+	dim3 grid((unsigned)((t_end - t_begin + BS - 1) / BS), (unsigned)(ce - first));
+	k_umma_epilogue3_range<CM, BS><<<grid, BS, smem, st>>>(Dt, F, t_begin, t_end, q_base, c0, ce, counts, tt, O);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+/* triples [t_begin, t_end) x the children of column tile [c0, ce); counts starts at the tile that holds slot q_base */
+int cnbk_umma_epilogue3_range(cudaStream_t st, const DevData &Dt, const DevFamilies &F, int max_cats, long long t_begin, long long t_end,
+		long long q_base, int c0, int ce, const int *counts, const int *triple_tab, const ScoreOut &O) {
+	if (t_end <= t_begin) return CNB_OK;
+	if (max_cats <= 2) return launch_epilogue3_range<2, 128>(st, Dt, F, t_begin, t_end, q_base, c0, ce, counts, triple_tab, O);
+	if (max_cats == 3) return launch_epilogue3_range<3, 128>(st, Dt, F, t_begin, t_end, q_base, c0, ce, counts, triple_tab, O);
+	return launch_epilogue3_range<4, 64>(st, Dt, F, t_begin, t_end, q_base, c0, ce, counts, triple_tab, O);
 }
 
 /* families [b, e) = those whose child lies in the column tile that starts at child c0; counts holds the tables of that

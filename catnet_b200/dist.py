@@ -33,11 +33,17 @@ def owned_range(group_size, chunk, rank):
     return b, max(b, min(group_size, b + chunk))
 
 
-def gather_scores(scores, rank, world, seg_len, group=None):
+def gather_scores(scores, rank, world, seg_len, group=None, scattered=False):
     """complete the rank-major buffer in place: every rank contributes scores[rank*seg_len:(rank+1)*seg_len].  Over NCCL the
-    segment is gathered where it lies (ncclAllGather's in-place form: input = output + rank * count); gloo gets a copy."""
+    segment is gathered where it lies (ncclAllGather's in-place form: input = output + rank * count); gloo gets a copy.
+    scattered (ctx.scattered() after score_shard, with ctx.allow_scatter(2)): the rank wrote scores into every segment of a
+    buffer that started at -inf -- the three-parent T tiles deal triples, not children, to the ranks -- and the buffers are
+    combined by an element-wise MAX instead."""
     import torch.distributed as dist
     if world == 1:
+        return scores
+    if scattered:
+        dist.all_reduce(scores, op=dist.ReduceOp.MAX, group=group)
         return scores
     mine = scores[rank * seg_len:(rank + 1) * seg_len]
     if dist.get_backend(group) != "nccl":
@@ -73,10 +79,11 @@ def search_order_sharded(ctx, rank, world, device, want_probs=True, group=None, 
     """cnSearchOrder on `world` GPUs; returns the same networks on every rank"""
     import torch
     ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)   # kernels and the all-gather on one stream
+    ctx.allow_scatter(2)                                            # three-parent T tiles may be dealt to the ranks
     seg, _ = ctx.plan(rank, world, **kw)
     scores = torch.empty(max(seg * world, 1), dtype=torch.float64, device=device)
     ctx.score_shard(scores.data_ptr())
-    gather_scores(scores, rank, world, seg, group)
+    gather_scores(scores, rank, world, seg, group, scattered=ctx.scattered())
     torch.cuda.synchronize(device)
     return ctx.finish(scores.data_ptr(), want_probs)
 

@@ -295,6 +295,15 @@ int cnb_ctx_stream_begin(cnb_ctx *ctx, const cnb_params *p, int32_t rank, int32_
 		int64_t *num_families, int32_t *num_slices, int64_t *slice_rows, int32_t slice_rows_cap);
 int cnb_ctx_stream_slice(cnb_ctx *ctx, int32_t k, const uint8_t *bytes_dev, void *ready_event);
 int cnb_ctx_stream_end(cnb_ctx *ctx, double *scores_dev, int32_t *ok);
+/* Sharded searches whose three-parent group runs on the tensor cores deal the T tiles of every column tile to the ranks:
+ * a rank then scores a range of parent triples for ALL children of the column tile, i.e. writes into every rank's segment
+ * of the score buffer.  The caller opts in by saying how the buffers are combined: mode 1 = every rank's scores_dev is
+ * the SAME buffer (peer memory; what cnb_search_order with num_devices does), mode 2 = every rank has its own buffer,
+ * cnb_ctx_score_shard starts it at -inf and the caller combines the buffers with an element-wise MAX (all-reduce) instead
+ * of the all-gather whenever cnb_ctx_scattered() says the last cnb_ctx_score_shard scattered; mode 0 (default) = never:
+ * such groups then take the bit-plane kernels on several ranks. */
+int cnb_ctx_allow_scatter(cnb_ctx *ctx, int32_t mode);
+int32_t cnb_ctx_scattered(const cnb_ctx *ctx);
 /* launch on the caller's CUDA stream (e.g. the stream its NCCL collectives use) instead of the context's own
  * non-blocking stream; NULL selects the context's own stream again -- to name the legacy default stream pass
  * cudaStreamLegacy ((cudaStream_t)0x1).  Work the caller orders against this library (copies into the sample

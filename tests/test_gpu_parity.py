@@ -561,6 +561,63 @@ def test_three_parent_tensor_core_path(abi, n, m, cats):
     assert compare_search(b, a, check_probs=False) == len(a)
 
 
+@pytest.mark.parametrize("n,m,cats", [(30, 200, 3), (70, 300, 2), (40, 8300, 4), (101, 120, 3), (20, 500, 4)])
+def test_three_parent_tiles_batched_and_dealt(abi, monkeypatch, n, m, cats):
+    """the T tiles of a column tile contracted in batches that fit a (here tiny) table buffer, and dealt to several ranks by
+    triple range -- every rank then scores ALL children of the column tile for its triples, so the rank buffers (started at
+    -inf) are combined by an element-wise maximum instead of the all-gather: same networks as one pass on one rank"""
+    import torch
+    s, c = random_problem(19 * n + m, n, m, cats)
+    kw = dict(max_parent_set=3, max_complexity=n * 30, order=(np.random.default_rng(n + m).permutation(n) + 1))
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        ctx.force_generic(4 if m < 8192 else 0)
+        a = ctx.search_order(want_probs=False, **kw)
+        whole = ctx.timing()["tensor3_tiles"]
+        assert whole > 0
+        monkeypatch.setenv("CNB_T3_BATCH_BYTES", "1")          # one aligned group of tiles per batch
+        b = ctx.search_order(want_probs=False, **kw)
+        assert ctx.timing()["tensor3_tiles"] == whole
+        assert compare_search(b, a, check_probs=False) == len(a)
+        monkeypatch.delenv("CNB_T3_BATCH_BYTES")
+        ctx.allow_scatter(2)
+        for world in (2, 3, 5):
+            seg, _ = ctx.plan(0, world, **kw)
+            bufs, tiles = [], 0
+            for r in range(world):
+                ctx.plan(r, world, **kw)
+                buf = torch.full((seg * world,), float("nan"), dtype=torch.float64, device="cuda")
+                ctx.score_shard(buf.data_ptr())
+                assert ctx.scattered()
+                tiles += ctx.timing()["tensor3_tiles"]
+                bufs.append(buf)
+            assert tiles == whole
+            full = torch.stack(bufs).amax(dim=0)                # what all_reduce(MAX) leaves on every rank
+            nets = ctx.finish(full.data_ptr(), want_probs=False)
+            assert compare_search(nets, a, check_probs=False) == len(a)
+        ctx.allow_scatter(0)                                   # without the promise: bit planes on several ranks
+        ctx.plan(0, 2, **kw)
+        buf = torch.empty((seg * 2 + 8,), dtype=torch.float64, device="cuda")
+        ctx.score_shard(buf.data_ptr())
+        assert not ctx.scattered() and ctx.timing()["tensor3_tiles"] == 0
+
+
+@pytest.mark.parametrize("seed", [4, 19, 55, 223, 226, 349, 439, 487, 958])
+def test_fixed_parent_listing_order_on_tensor_tiles(abi, port, seed):
+    """found by tools/fuzz_gpu.py with the tensor path forced: a two-parent candidate (fixed parent f, free parent x) is
+    listed [f, x] even when x precedes f in the order, and the reference sums its table in that listing's order; the tile
+    epilogue summed every slot parent-ascending -> last-bit different scores -> last-bit different DP totals"""
+    s, P, K, kw = constrained_problem(seed)
+    theirs = port.search_order(s, P, K, **kw)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, perturbations=kw.get("perturbations"), num_cats=kw.get("num_cats"))
+        ctx.force_generic(4)
+        kw2 = {k: v for k, v in kw.items() if k not in ("perturbations", "num_cats")}
+        ours = ctx.search_order(max_parent_set=P, max_complexity=K, **kw2)
+        assert ctx.timing()["tensor_tiles"] > 0
+    assert compare_search(ours, theirs) == len(theirs)
+
+
 def test_host_compacted_upload(abi, monkeypatch):
     """large host matrices cross PCIe as bytes (int32 -> uint8 by host threads, 0 = missing): same packed data, hence the
     same search, as the plain int32 upload; NA and category inference included; a value above 255 is still an error"""

@@ -247,6 +247,27 @@ def test_device_time_marks(abi):
         abi.lib().cnb_result_free(h)
 
 
+@pytest.mark.parametrize("n,m,cats,g", [(30, 200, 3, 2), (70, 300, 2, 3), (40, 8300, 4, 2), (101, 120, 3, 4)])
+def test_three_parent_tiles_dealt_over_devices(abi, monkeypatch, n, m, cats, g):
+    """three parents on the tensor cores over several devices: every device contracts a range of parent triples for all
+    children of a column tile and stores its scores straight into the first device's buffer (peer memory)"""
+    s, c = random_problem(23 * n + m, n, m, cats)
+    kw = dict(max_parent_set=3, max_complexity=n * 30, num_cats=c, order=(np.random.default_rng(n + m).permutation(n) + 1))
+    monkeypatch.setenv("CNB_FORCE_BITS", "1024")               # bit planes
+    a = abi.search_order(s, want_probs=False, **kw)
+    assert abi.last_call_timing()["tensor3_tiles"] == 0
+    monkeypatch.setenv("CNB_FORCE_BITS", "4")                  # tensor cores whatever the sample count
+    one = abi.search_order(s, want_probs=False, **kw)
+    whole = abi.last_call_timing()["tensor3_tiles"]
+    assert whole > 0 and compare_search(one, a, check_probs=False) == len(a)
+    for nd in _forms(g):
+        b = abi.search_order(s, want_probs=False, num_devices=nd, **kw)
+        t = abi.last_call_timing()["tensor3_tiles"]
+        assert 0 < t < whole                                   # the first device's share
+        assert compare_search(b, a, check_probs=False) == len(a)
+    abi.lib().cnb_release_cache()
+
+
 # ------------------------------------------------------------------ streamed search over several devices
 @pytest.mark.parametrize("n,m,cats,slices,g", [(70, 9000, 4, "1,3,4,4,3,1", 2), (40, 8192, 3, "1", 3), (130, 20001, 4, "1,1", 2),
                                                (65, 12345, 2, "1,2,3", 4), (30, 100000, 4, "1,5,10", 8)])
@@ -360,6 +381,19 @@ def _nccl_worker(rank, world, port, q):
                 and all(np.array_equal(p, q_) for p, q_ in zip(x["parents"], y["parents"]))
                 and all(np.array_equal(p, q_) for p, q_ in zip(x["probs"], y["probs"])) for x, y in zip(got, want))
             res.append((bool(same), bool(info["streamed"]), int(info["h2d_bytes"]), s.size))
+        # three parents on the tensor cores, the T tiles dealt to the ranks: scores scattered over the segments, max-reduced
+        s, c = rp(9, 40, 400, 3)
+        kw = dict(max_parent_set=3, max_complexity=40 * 30, order=(np.random.default_rng(9).permutation(40) + 1))
+        with _abi.Context(rank) as ctx:
+            ctx.set_samples(s, num_cats=c)
+            ctx.force_generic(1024)
+            want = ctx.search_order(want_probs=False, **kw)
+            ctx.force_generic(4)
+            got = cdist.search_order_sharded(ctx, rank, world, dev, want_probs=False, **kw)
+            scat, t3 = ctx.scattered(), ctx.timing()["tensor3_tiles"]
+        same = len(got) == len(want) and all(x["loglik"] == y["loglik"] and all(np.array_equal(p, q_) for p, q_ in zip(x["parents"], y["parents"]))
+                                             for x, y in zip(got, want))
+        res.append((bool(same), bool(scat), int(t3), 0))
         q.put((rank, res))
     except Exception as e:                                     # the parent fails at once instead of waiting for the queue
         q.put((rank, "error: %r" % (e,)))
@@ -389,6 +423,7 @@ def test_streamed_search_two_ranks_nccl():
         assert p.exitcode == 0
     for rank in (0, 1):
         assert not isinstance(out[rank], str), out[rank]
-        (s1, st1, h1, sz1), (s2, st2, h2, sz2), (s3, st3, _, _) = out[rank]
+        (s1, st1, h1, sz1), (s2, st2, h2, sz2), (s3, st3, _, _), (s4, scat, t3, _) = out[rank]
         assert s1 and s2 and s3 and st1 and st2 and not st3
+        assert s4 and scat and t3 > 0
         assert abs(h1 - sz1 / 2) <= 70 * 8 and abs(h2 - sz2 / 2) <= 45 * 8

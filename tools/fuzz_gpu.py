@@ -5,8 +5,10 @@ tools/fuzz_oracle.py pins against the compiled reference.  Needs a B200; reads n
     python tools/fuzz_gpu.py search 1000 3000     # tests/helpers.py::constrained_problem
     python tools/fuzz_gpu.py wide 0 3000          # tools/fuzz_oracle.py::wide_problem
     python tools/fuzz_gpu.py pert 1100 1400       # tests/helpers.py::fully_perturbed_problem
+    python tools/fuzz_gpu.py many 0 1500          # 2..9 categories per node: the histogram scorers
+    CNB_FORCE_BITS=4 python tools/fuzz_gpu.py search 0 1500    # the same problems through the tensor-core tiles
 
-Written at the end of round 1 (no GPU budget left): not run yet."""
+Totals of the runs are in DESIGN.md section 5.4."""
 import os
 import sys
 
@@ -15,11 +17,36 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
 from helpers import compare_search, constrained_problem, fully_perturbed_problem  # noqa: E402
 
 
+def many_categories_problem(seed):
+    """2..9 categories per node (more than four: no bit planes, the histogram scorers), missing values, perturbations,
+    pools, priors, 1..3 parents while the largest table stays below 16,384 cells"""
+    import numpy as np
+    from helpers import random_problem
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 9)), int(rng.integers(10, 300))
+    cats = rng.integers(2, 10, size=n) if seed % 3 else int(rng.integers(5, 10))
+    s, c = random_problem(seed, n, m, cats, na_frac=[0.0, 0.1, 0.0, 0.03][seed % 4])
+    P = 1 + seed % 3
+    while int(c.max()) ** (P + 1) > 16384:
+        P -= 1
+    kw = dict(num_cats=c, order=(rng.permutation(n) + 1).astype(np.int32))
+    if seed % 4 == 2:
+        kw["perturbations"] = (rng.random(s.shape) < 0.25).astype(np.int32)
+    if seed % 5 == 0:
+        kw["parents_pool"] = [[int(v) for v in rng.choice(np.arange(1, n + 1), size=rng.integers(0, n), replace=False)
+                               if v != i + 1] for i in range(n)]
+    if seed % 7 == 3:
+        kw["edge_prob"] = 0.05 + 0.9 * rng.random((n, n))
+    lo = int(np.sum(c - 1))
+    return s, P, int(rng.integers(lo, lo + n * int(c.max()) ** P + 1)), kw
+
+
 def main():
     from catnet_b200 import _abi
     from fuzz_oracle import wide_problem
     from oracle import port
-    gen = {"search": constrained_problem, "wide": wide_problem, "pert": fully_perturbed_problem}[sys.argv[1]]
+    gen = {"search": constrained_problem, "wide": wide_problem, "pert": fully_perturbed_problem,
+           "many": many_categories_problem}[sys.argv[1]]
     ran, bad = 0, []
     for seed in range(int(sys.argv[2]), int(sys.argv[3])):
         try:
@@ -40,7 +67,8 @@ def main():
             assert compare_search(ours, theirs) == len(theirs)
         except AssertionError as e:
             bad.append((seed, str(e)[:200]))
-    print("problems %d  mismatches %s" % (ran, bad[:20]))
+    print("%s [%s, %s) CNB_FORCE_BITS=%s: problems %d  mismatches %d %s" % (sys.argv[1], sys.argv[2], sys.argv[3],
+                                                                      os.environ.get("CNB_FORCE_BITS", "-"), ran, len(bad), bad[:20]))
     sys.exit(1 if bad else 0)
 
 
