@@ -655,8 +655,28 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	if (tensor_ok && c->clean && c->pairs_valid && !c->force_full) tile_mode = (c->no_reduced_tiles || c->tensor_i8) ? 1 : 3;
 	else if (tensor_ok && c->max_cats <= CNB_PLANE_CATS && !c->tensor_i8) tile_mode = 2;
 	c->tables_resident = false;
-	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
+	/* The plan is a pure function of its inputs, and without pools, fixed parents, parent-set sizes, priors and with one
+	 * category count for all nodes the ORDER enters it only as the order itself (every position offers all subsets of its
+	 * predecessors, whoever they are): such a plan is kept and a later call with the same shape -- the next order of an SA
+	 * chain or a histogram batch on such data, the next step of a benchmark loop -- replaces just the order. */
+	bool uniform = true;
+	for (int i = 1; i < c->N; i++) uniform = uniform && c->cats_lbl[i] == c->cats_lbl[0];
+	const bool order_free = uniform && !p->parents_pool && !p->fixed_parents && !q.parent_sizes && !p->edge_prob;
+	const CnbPlanKey key = {c->N, c->M, q.max_parent_set, q.max_complexity, rank, world, tile_mode, c->cats_lbl[0], order_free ? 1 : 0};
+	const bool reuse = order_free && c->plan_key_valid && !memcmp(&key, &c->plan_key, sizeof(key)) && !getenv("CNB_NO_PLAN_REUSE");
+	c->plan_key_valid = false;
 	CnbPlan &pl = c->plan;
+	if (reuse) {
+		std::vector<char> seen(c->N, 0);
+		for (int i = 0; i < c->N; i++) {                       /* rcatnet_search.cpp:111-128, as in cnb_build_plan */
+			const int lbl = p->order ? p->order[i] : i + 1;
+			if (lbl <= 0 || lbl > c->N || seen[lbl - 1]) { cnb_set_error("Invalid nodeOrder parameter"); return CNB_ERR_PARAM; }
+			seen[lbl - 1] = 1;
+			pl.order[i] = lbl - 1;
+		}
+		RC(upload(c, c->b_order, pl.order));
+	} else {
+	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
 	const bool masks = c->has_pert && !c->ignore_pert;
 	if (!pl.tile_base.empty()) {
 		RC(upload(c, c->b_tile_base, pl.tile_base));
@@ -697,6 +717,10 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	}
 	RC(upload(c, c->b_sel_chunks, c->sel_chunks));
 	RC(upload(c, c->b_sel_chunk0, c->sel_chunk0));
+	}
+	c->plan_key = key;
+	c->plan_key_valid = true;
+	const bool masks = c->has_pert && !c->ignore_pert;
 	c->timing.kernel_launches = 0;
 	if (c->streaming) {                                /* the streamed one-shot search moves the samples in slice by slice itself */
 		CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));

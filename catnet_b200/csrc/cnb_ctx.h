@@ -28,7 +28,14 @@ struct PinBuf {
 	void release();
 };
 
+/* what a plan depends on besides the order, when it depends on the order only through the order itself (cnb_ctx_plan) */
+struct CnbPlanKey {
+	int32_t N, M, P, K, rank, world, tile_mode, cats, order_free;
+};
+
 struct cnb_ctx {
+	CnbPlanKey plan_key = {};
+	bool plan_key_valid = false;
 	int device = 0;
 	cudaStream_t stream = nullptr, own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr;   /* host -> device copies of the streamed one-shot search (created on first use) */

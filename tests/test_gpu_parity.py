@@ -618,6 +618,36 @@ def test_fixed_parent_listing_order_on_tensor_tiles(abi, port, seed):
     assert compare_search(ours, theirs) == len(theirs)
 
 
+@pytest.mark.parametrize("n,m,cats,P", [(30, 400, 3, 2), (12, 200, 4, 3), (70, 9000, 4, 2), (9, 150, 6, 2)])
+def test_plan_is_reused_across_orders(abi, port, monkeypatch, n, m, cats, P):
+    """without pools, fixed parents, sizes, priors and with one category count the plan depends on the order only through the
+    order itself: a context keeps it and a later search replaces just the order (SA chains, histogram batches, benchmark
+    loops).  Same networks as a context that plans from scratch, for a sequence of orders; a bad order is still refused;
+    a constrained search in between plans afresh"""
+    s, c = random_problem(31 * n + m, n, m, cats)
+    rng = np.random.default_rng(n)
+    orders = [(rng.permutation(n) + 1).astype(np.int32) for _ in range(4)] + [None]
+    kw = dict(max_parent_set=P, max_complexity=n * 20)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        got = [ctx.search_order(want_probs=False, order=o, **kw) for o in orders]
+        with pytest.raises(abi.CnbError) as e:
+            ctx.search_order(order=np.r_[orders[0][:-1], orders[0][0]].astype(np.int32), **kw)
+        assert "Invalid nodeOrder" in str(e.value)
+        pools = [[j + 1 for j in range(n) if j != i and (i + j) % 3] for i in range(n)]
+        mid = ctx.search_order(want_probs=False, order=orders[1], parents_pool=pools, **kw)
+        again = ctx.search_order(want_probs=False, order=orders[2], **kw)
+        monkeypatch.setenv("CNB_NO_PLAN_REUSE", "1")
+        want = [ctx.search_order(want_probs=False, order=o, **kw) for o in orders]
+        want_mid = ctx.search_order(want_probs=False, order=orders[1], parents_pool=pools, **kw)
+    for a, b in zip(got + [mid, again], want + [want_mid, want[2]]):
+        assert compare_search(a, b, check_probs=False) == len(b)
+        assert [x["loglik"] for x in a] == [y["loglik"] for y in b]
+    if m <= 400:
+        o = port.search_order(s, P, kw["max_complexity"], order=orders[3], num_cats=c, want_probs=False)
+        assert compare_search(got[3], o, check_probs=False) == len(o)
+
+
 def test_host_compacted_upload(abi, monkeypatch):
     """large host matrices cross PCIe as bytes (int32 -> uint8 by host threads, 0 = missing): same packed data, hence the
     same search, as the plain int32 upload; NA and category inference included; a value above 255 is still an error"""
