@@ -16,10 +16,14 @@
  *   warps 8-13  column rows: thread = one B row (192); B goes to shared memory, SWIZZLE_128B K-major (3-stage ring,
  *               UM_BSTAGES)
  *   warps 14-15 one elected lane each issues the tcgen05.mma of one pair block: A from TMEM, B from shared memory
- * handed over with mbarriers (generators -> full -> MMA -> tcgen05.commit -> empty).  Two tile geometries:
- *   inclusion-exclusion tiles (complete data): 2 blocks of 14 parent pairs x 9 rows (2 x 126 of 128 rows, two
- *               accumulators) x up to 64 column nodes x 3 columns (192): only the 27 free cells of a table are
- *               contracted, the rest follows from the pair tables
+ * handed over with mbarriers (generators -> full -> MMA -> tcgen05.commit -> empty).  The tile geometry is a template
+ * parameter (UmGeo<GEO>), the pipeline is the same code for all of them:
+ *   inclusion-exclusion tiles (complete data): only the free cells of a table are contracted, the rest follows from the
+ *               pair tables.  fr = 3 free categories per node (data with four categories): 2 blocks of 14 parent pairs
+ *               x 9 rows (2 x 126 of 128 rows, two accumulators) x up to 64 column nodes x 3 columns (192);
+ *               fr = 2 (three categories): 2 x 32 pairs x 4 rows, 96 column nodes x 2 columns; fr = 1 (binary data):
+ *               2 x 128 pairs x 1 row, 192 column nodes x 1 column -- an MMA costs the same for any N <= 192, so fewer
+ *               rows and columns per family mean more families per MMA
  *   full-table tiles (missing values, perturbation masks): 2 blocks of 8 pairs x 16 rows x up to 48 column nodes x 4
  *               columns (192): all 64 cells, the child's keep mask in its rows, a missing value sets no bit
  * The column rows of a stage are generated once and consumed by both pair blocks, and the pair rows never touch shared
