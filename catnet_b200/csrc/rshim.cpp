@@ -187,10 +187,24 @@ SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP r
 	return cnet;
 }
 
+/* The library's result outlives several R allocations (every network is an S4 object with nested lists), and any of them
+ * may leave the shim by a non-local exit (allocation failure, a warning turned into an error by options(warn = 2)): the
+ * result therefore hangs on an external pointer whose finalizer frees it -- R's collector releases what the shim could not. */
+void result_finalizer(SEXP ptr) {
+	cnb_result *r = (cnb_result *)R_ExternalPtrAddr(ptr);
+	if (r) {
+		cnb_result_free(r);
+		R_ClearExternalPtr(ptr);
+	}
+}
+
 SEXP export_result(cnb_result *r, const cnb_params &p, SEXP rNodeNames) {
+	SEXP guard = PROTECT(R_MakeExternalPtr(r, R_NilValue, R_NilValue));
+	R_RegisterCFinalizerEx(guard, result_finalizer, TRUE);
 	const int N = p.num_nodes, K = cnb_result_num_networks(r);
 	if (K < 1) {
-		cnb_result_free(r);
+		result_finalizer(guard);
+		UNPROTECT(1);
 		warning("No networks are found");                                          /* rcatnet_search.cpp:279-282 */
 		return R_NilValue;
 	}
@@ -200,8 +214,8 @@ SEXP export_result(cnb_result *r, const cnb_params &p, SEXP rNodeNames) {
 		cnb_result_cats(r, i, cats_pos.data());
 		SET_VECTOR_ELT(out, i, make_catnetwork(r, i, cats_pos.data(), rNodeNames));
 	}
-	cnb_result_free(r);
-	UNPROTECT(1);
+	result_finalizer(guard);                                                       /* released here in the normal course */
+	UNPROTECT(2);
 	return out;
 }
 

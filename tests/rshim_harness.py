@@ -37,7 +37,8 @@ def lib(backend):
                                 ("mr_last_error", C.c_char_p, []), ("mr_warnings", C.c_char_p, []), ("mr_clear", None, []),
                                 ("mr_set_rng", None, [C.c_ulonglong]), ("mr_new_s4", vp, [C.c_char_p]),
                                 ("mr_set_slot", None, [vp, C.c_char_p, vp]), ("mr_category_names", vp, [C.c_int]),
-                                ("mr_set_string", None, [vp, C.c_int, C.c_char_p]), ("mr_call", vp, [C.c_char_p, C.POINTER(vp), C.c_int])]:
+                                ("mr_set_string", None, [vp, C.c_int, C.c_char_p]), ("mr_call", vp, [C.c_char_p, C.POINTER(vp), C.c_int]),
+                                ("mr_fail_alloc_after", None, [C.c_long]), ("mr_run_finalizers", C.c_int, [])]:
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
         _libs[backend] = L

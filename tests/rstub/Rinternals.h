@@ -10,6 +10,10 @@ extern "C" {
 #endif
 typedef struct SEXPREC *SEXP;
 typedef int Rboolean;
+#ifndef TRUE
+#define TRUE 1
+#define FALSE 0
+#endif
 #define INTSXP 13
 #define REALSXP 14
 #define STRSXP 16
@@ -46,6 +50,11 @@ int Rf_isNewList(SEXP);
 int IS_S4_OBJECT(SEXP);
 SEXP R_do_MAKE_CLASS(const char *);
 SEXP R_do_new_object(SEXP);
+typedef void (*R_CFinalizer_t)(SEXP);
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP);
+void R_ClearExternalPtr(SEXP);
+void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean onexit);
 void Rf_error(const char *, ...);
 void Rf_warning(const char *, ...);
 void GetRNGstate(void);

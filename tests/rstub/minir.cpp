@@ -29,10 +29,14 @@ struct SEXPREC {
 	std::vector<SEXP> elts;                /* VECSXP, STRSXP (of CHARSXP) */
 	std::string str;                       /* CHARSXP, SYMSXP, class name of an S4 object */
 	std::map<std::string, SEXP> attrs;     /* "dim", and the slots of an S4 object */
+	void *ext = nullptr;                   /* EXTPTRSXP: the address, and its C finalizer */
+	void (*fin)(SEXP) = nullptr;
 };
 
 static SEXPREC g_nil;
 static std::string g_error, g_warnings;
+static std::vector<SEXP> g_extptrs;         /* every external pointer made: mr_run_finalizers plays the garbage collector */
+static long g_alloc_countdown = -1;        /* mr_fail_alloc_after: the n-th allocVector from now raises an R error */
 static unsigned long long g_rng = 0x9e3779b97f4a7c15ull;
 
 extern "C" {
@@ -61,6 +65,7 @@ SEXP Rf_install(const char *name) {
 }
 SEXP Rf_mkChar(const char *s) { SEXP c = mk(MR_CHARSXP); c->str = s; return c; }
 SEXP Rf_allocVector(unsigned int type, long n) {
+	if (g_alloc_countdown >= 0 && g_alloc_countdown-- == 0) Rf_error("cannot allocate vector of size %ld", n);
 	SEXP s = mk((int)type);
 	if (type == INTSXP || type == MR_LGLSXP) s->ints.assign(n, 0);
 	else if (type == REALSXP) s->reals.assign(n, 0.0);
@@ -184,6 +189,11 @@ void Rf_warning(const char *fmt, ...) {
 	g_warnings += buf;
 	g_warnings += "\n";
 }
+#define MR_EXTPTRSXP 22
+SEXP R_MakeExternalPtr(void *p, SEXP, SEXP) { SEXP s = mk(MR_EXTPTRSXP); s->ext = p; g_extptrs.push_back(s); return s; }
+void *R_ExternalPtrAddr(SEXP s) { return s->ext; }
+void R_ClearExternalPtr(SEXP s) { s->ext = nullptr; }
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t f, Rboolean) { s->fin = f; }
 void GetRNGstate(void) {}
 void PutRNGstate(void) {}
 double unif_rand(void) {                                 /* splitmix64, 53 bits */
@@ -235,6 +245,19 @@ const char *mr_last_error(void) { return g_error.c_str(); }
 const char *mr_warnings(void) { return g_warnings.c_str(); }
 void mr_clear(void) { g_error.clear(); g_warnings.clear(); }
 void mr_set_rng(unsigned long long s) { g_rng = s; }
+/* the n-th allocVector from now fails like R's allocator does: with an R error, i.e. a non-local exit out of the shim */
+void mr_fail_alloc_after(long n) { g_alloc_countdown = n; }
+/* what R's garbage collector does with unreachable external pointers: run their finalizers.  Returns how many of them still
+ * held an address (= resources the shim had not released itself when it was left) */
+int mr_run_finalizers(void) {
+	int held = 0;
+	for (SEXP s : g_extptrs) {
+		if (s->ext) held++;
+		if (s->fin) s->fin(s);
+	}
+	g_extptrs.clear();
+	return held;
+}
 
 /* .Call(name, args...) through the table the shim registers; NULL + mr_last_error() if it raised an R error */
 const R_CallMethodDef *cnb_r_call_methods(void);

@@ -23,6 +23,7 @@ struct cnb_result {
 	std::vector<int32_t> order, cats_pos;  /* position -> 1-based label; categories per position */
 };
 
+static int g_live_results = 0;
 static std::string g_err;
 static int g_released = 0, g_seed = 0;
 
@@ -67,6 +68,7 @@ int cnb_search_order(const cnb_params *p, cnb_result **out) {
 			p->max_complexity, order.data(), p->num_cats, p->parents_pool, p->fixed_parents, p->edge_prob);
 	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
 	cnb_result *r = new cnb_result;
+	g_live_results++;
 	r->h = h;
 	r->N = N;
 	r->order = order;
@@ -116,10 +118,13 @@ int cnb_result_node(const cnb_result *r, int32_t i, int32_t node, double *loglik
 		for (int k = 0; k < ps && k < cap; k++) probs[k] = buf[k];
 	return ps;
 }
+/* test hook: results handed out and not yet freed */
+int mock_live_results(void) { return g_live_results; }
 void cnb_result_free(cnb_result *r) {
 	if (!r) return;
 	orc_result_free(r->h);
 	delete r;
+	g_live_results--;
 }
 
 int cnb_pairwise(int32_t kind, int32_t N, int32_t M, const int32_t *samples, const int32_t *pert, int32_t, double *out) {
@@ -145,6 +150,7 @@ int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out
 			sa->num_threads);
 	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
 	cnb_result *r = new cnb_result;
+	g_live_results++;
 	r->h = h;
 	r->N = N;
 	r->order.resize(N);

@@ -100,6 +100,29 @@ def test_shim_argument_handling():
     assert r.is_null(r.call("ccnReleaseCache"))
 
 
+def test_shim_releases_the_result_when_r_leaves_by_an_error():
+    """an R error while the networks are being built (here: the allocator fails at the 40th vector of the export) leaves
+    the shim by a non-local exit; the library's result then hangs on an external pointer and R's collector frees it
+    (export_result leaked it).  In the normal course the shim releases it itself and the finalizer finds nothing"""
+    from rshim_harness import R, RError, optimal_nets_for_order
+    s, c = random_problem(5, 6, 90, 3)
+    r = R("mock")
+    r.L.mock_live_results.restype = int
+    live0 = r.L.mock_live_results()
+    nets = optimal_nets_for_order(r, s, 2, 80, num_cats=c)
+    assert len(nets) > 1 and r.L.mock_live_results() == live0
+    assert r.L.mr_run_finalizers() == 0                     # nothing was left to the collector
+    args = [r.data_matrix(s), r.NULL, r.numeric([2]), r.NULL, r.numeric([80]), r.NULL,
+            r.list([r.integer(np.arange(1, v + 1)) for v in c]), r.NULL, r.NULL, r.NULL, r.logical(False), r.logical(False)]
+    r.L.mr_fail_alloc_after(40)
+    with pytest.raises(RError, match="cannot allocate"):
+        r.call("ccnOptimalNetsForOrder", *args)
+    r.L.mr_fail_alloc_after(-1)
+    assert r.L.mock_live_results() == live0 + 1             # the shim was left before it could free the result ...
+    assert r.L.mr_run_finalizers() == 1                     # ... the finalizer of its guard does
+    assert r.L.mock_live_results() == live0
+
+
 @pytest.mark.parametrize("kind,routine", [("entropy", "ccnEntropyPairwise"), ("kl", "ccnKLPairwise"),
                                           ("pearson", "ccnPearsonPairwise")])
 def test_shim_pairwise(kind, routine):
