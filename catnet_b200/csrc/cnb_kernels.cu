@@ -1124,11 +1124,15 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
  * it.  One cooperative launch, grid barrier per node.  Identical decisions to the sequential scan. */
 #define DPM_OPTS 2048          /* options of a node staged in shared memory (score + complexity) */
 #define DPM_SLOTS 4096         /* DP slots staged in shared memory (log-lik + exists) */
-__global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N, int base_complexity,
+/* ONE: the whole DP in one CTA of BS threads (a plain launch, block barriers): small tables -- ALARM has 601 slots -- where the
+ * grid barrier per node is most of the time, and the form in which the concurrently evaluated orders of an SA step really
+ * run side by side (cooperative launches of different streams were measured to run one after the other) */
+template <int BS, bool ONE>
+__global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
 		int *__restrict__ bp_src, int stage_state) {
-	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	auto barrier = [] { if constexpr (ONE) __syncthreads(); else cooperative_groups::this_grid().sync(); };
 	/* sbase[N] | s_sc[DPM_OPTS] | s_L[slots] | s_cx[DPM_OPTS] | s_ex[slots]: the scan of a slot reads a node's options and
 	 * the previous state 32 at a time; out of global memory every such read is an L2 round trip (21 per node on ALARM) */
 	extern __shared__ double sbase[];
@@ -1148,7 +1152,7 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 		s0.L[j] = l;
 		s0.pfx[j] = ex ? __dadd_rn(0.0, sbase[0]) : 0.0;
 	}
-	grid.sync();
+	barrier();
 	for (int c = 1; c < N; c++) {
 		const DpState &cur = (c & 1) ? s0 : s1, &nxt = (c & 1) ? s1 : s0;
 		const CnbDpNode nd = nodes[c];
@@ -1227,7 +1231,7 @@ __global__ void __launch_bounds__(256) k_dp_mixed(DpState s0, DpState s1, int N,
 				}
 			}
 		}
-		grid.sync();
+		barrier();
 	}
 }
 
@@ -1806,14 +1810,25 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 	int stage_state = s0.K + 1 <= DPM_SLOTS;
 	const size_t smem = (size_t)N * sizeof(double) + (size_t)DPM_OPTS * (sizeof(double) + sizeof(int))
 			+ (stage_state ? (size_t)(s0.K + 1) * sizeof(double) + (size_t)((s0.K + 1 + 15) & ~15) : 0);
+	/* small tables: one CTA of 1024 threads, no grid barrier (CNB_DP_ONE_CTA: largest K + 1 that takes this form, 0 = never) */
+	static int one_max = -1;
+	if (one_max < 0) { const char *e = getenv("CNB_DP_ONE_CTA"); one_max = e ? atoi(e) : 1024; }
+	if (s0.K + 1 <= one_max) {
+		if (smem > 48 * 1024)
+			CK(cudaFuncSetAttribute(k_dp_mixed<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		k_dp_mixed<1024, true><<<1, 1024, smem, st>>>(s0, s1, N, base_complexity, nodes, base_v, opt_score, opt_cx, opt_fid, bp_opt, bp_src,
+				stage_state);
+		CK(cudaGetLastError());
+		return CNB_OK;
+	}
 	if (smem > 48 * 1024)
-		CK(cudaFuncSetAttribute(k_dp_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_mixed, 256, smem));
+		CK(cudaFuncSetAttribute(k_dp_mixed<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_mixed<256, false>, 256, smem));
 	if (!coop || per_sm < 1) return CNB_ERR_PROC;
 	const int blocks = std::min(sms * per_sm, std::max(1, (s0.K + 1 + 7) / 8));      /* one warp per slot if it fits */
 	void *args[] = {(void *)&s0, (void *)&s1, (void *)&N, (void *)&base_complexity, (void *)&nodes, (void *)&base_v,
 		(void *)&opt_score, (void *)&opt_cx, (void *)&opt_fid, (void *)&bp_opt, (void *)&bp_src, (void *)&stage_state};
-	CK(cudaLaunchCooperativeKernel((const void *)k_dp_mixed, dim3(blocks), dim3(256), args, smem, st));
+	CK(cudaLaunchCooperativeKernel((const void *)k_dp_mixed<256, false>, dim3(blocks), dim3(256), args, smem, st));
 	return CNB_OK;
 }
 
