@@ -1124,9 +1124,8 @@ __global__ void __launch_bounds__(256) k_dp_all(DpState s0, DpState s1, int N, i
  * it.  One cooperative launch, grid barrier per node.  Identical decisions to the sequential scan. */
 #define DPM_OPTS 2048          /* options of a node staged in shared memory (score + complexity) */
 #define DPM_SLOTS 4096         /* DP slots staged in shared memory (log-lik + exists) */
-/* ONE: the whole DP in one CTA of BS threads (a plain launch, block barriers): small tables -- ALARM has 601 slots -- where the
- * grid barrier per node is most of the time, and the form in which the concurrently evaluated orders of an SA step really
- * run side by side (cooperative launches of different streams were measured to run one after the other) */
+/* ONE: the whole DP in one CTA of BS threads (a plain launch, block barriers); an experiment that did not pay, see
+ * cnbk_dp_mixed */
 template <int BS, bool ONE>
 __global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, int base_complexity,
 		const CnbDpNode *__restrict__ nodes, const double *__restrict__ base_v, const double *__restrict__ opt_score,
@@ -1810,9 +1809,11 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 	int stage_state = s0.K + 1 <= DPM_SLOTS;
 	const size_t smem = (size_t)N * sizeof(double) + (size_t)DPM_OPTS * (sizeof(double) + sizeof(int))
 			+ (stage_state ? (size_t)(s0.K + 1) * sizeof(double) + (size_t)((s0.K + 1 + 15) & ~15) : 0);
-	/* small tables: one CTA of 1024 threads, no grid barrier (CNB_DP_ONE_CTA: largest K + 1 that takes this form, 0 = never) */
+	/* one CTA of 1024 threads, no grid barrier (CNB_DP_ONE_CTA: largest K + 1 that takes this form).  Off by default: on
+	 * ALARM (601 slots, hundreds of options per node) it is 3.9 x SLOWER than the cooperative grid -- cnSearchSA 1.32 s
+	 * against 0.34 s -- the scan of a slot's options is real work for 600 warps, not barrier latency */
 	static int one_max = -1;
-	if (one_max < 0) { const char *e = getenv("CNB_DP_ONE_CTA"); one_max = e ? atoi(e) : 1024; }
+	if (one_max < 0) { const char *e = getenv("CNB_DP_ONE_CTA"); one_max = e ? atoi(e) : 0; }
 	if (s0.K + 1 <= one_max) {
 		if (smem > 48 * 1024)
 			CK(cudaFuncSetAttribute(k_dp_mixed<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

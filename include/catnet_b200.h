@@ -351,8 +351,10 @@ int cnb_ctx_search_scores(cnb_ctx *ctx, const double *scores_dev, int32_t nfam, 
  * the POPC kernel (set before the samples); 512 no inclusion-exclusion for three parents; 1024 three parents never on
  * the tensor cores; 2048 wavefront DP with one node per exchange; 4096 generic tensor-core epilogue also for
  * 4-category data; 8192 full-table tensor tiles (the form that takes missing values and perturbation masks) also on
- * complete data; 16384 trapezoid DP in which every slot re-sums its own candidates (no CTA-wide work list).  Every combination
- * gives the same networks. */
+ * complete data; 16384 trapezoid DP in which every slot re-sums its own candidates (no CTA-wide work list); 32768 the
+ * histogram scorer with one CTA per family, 65536 with a warp per family and __match_any_sync aggregation (default: a warp
+ * per family, shared-memory atomics); 131072 tensor-core tiles always in the 28 x 64 geometry of four categories.  Every
+ * combination gives the same networks.  The one-shot calls take the same bits from CNB_FORCE_BITS (fuzzing). */
 int cnb_ctx_force_generic(cnb_ctx *ctx, int32_t on);
 /* evaluate the device's log on n inputs (must be bit-identical to the host libm the reference links) */
 int cnb_device_log(int32_t device, const double *x, int64_t n, double *out);
