@@ -151,6 +151,111 @@ static int next_comb(int *idx, int k, int n) {
 	return 1;
 }
 
+/* ------------------------------------------------------------------ score cache ---- */
+/* c_cache (cache.cpp:142-317): one process-global table of CATNET_CACHE_EL pointers, no chaining -- a store replaces
+ * whatever sits in its slot.  R switches it on for cnSearchSA and cnSearchHist (R/catnet.search.R:293-294) after
+ * releasing it (:279), so every call starts empty.  An entry is keyed by (node, sorted pool, parent count) in LABEL
+ * space and keeps the parent set in the sequence it was LISTED in when it was scored, its table (laid out in that
+ * sequence), its log-likelihood (summed in that table order) and its prior (multiplied up in the node order of the
+ * order it was scored under): a hit under a later order returns all of that unchanged, so cache-ON results differ from
+ * cache-OFF ones in the listing order of parents and in the last bits of log-likelihoods. */
+typedef struct {
+	int node, npars, npool, *pool;     /* labels 1-based; pool sorted ascending */
+	int pars[ORC_MAXP];                /* labels 1-based, in listing order */
+	fam_t fam;                         /* counts owned (NULL for an entry that was never scored) */
+} centry_t;
+static centry_t **g_cache = NULL;
+static unsigned g_ncache = 0, g_cbits = 0;
+static int g_cache_on = 0;
+static unsigned g_primes[180];             /* PRIMES_1000 (cache.cpp:35-54): the first 180 primes */
+
+static void centry_free(centry_t *e) { if (e) { free(e->pool); free(e->fam.counts); free(e); } }
+void orc_cache_release(void) {               /* ReleaseCache (cache.cpp:62-76) */
+	if (g_cache) for (unsigned i = 0; i < g_ncache; i++) centry_free(g_cache[i]);
+	free(g_cache);
+	g_cache = NULL;
+	g_ncache = g_cbits = 0;
+}
+void orc_set_cache(int on) { g_cache_on = on; }
+
+static void cache_primes(void) {
+	if (g_primes[0]) return;
+	int n = 0;
+	for (unsigned v = 2; n < 180; v++) {
+		int isp = 1;
+		for (unsigned q = 2; q * q <= v; q++) if (v % q == 0) { isp = 0; break; }
+		if (isp) g_primes[n++] = v;
+	}
+}
+/* table size chosen at the first store (cache.cpp:225-264), unsigned 32-bit arithmetic as there */
+static void cache_init(int N, int maxParentSet) {
+	cache_primes();
+	unsigned nl = (unsigned)N;
+	int i;
+	for (i = 0; i < maxParentSet; i++) nl *= (unsigned)N;
+	if (nl < g_primes[179]) {
+		for (i = 0; i < 180; i++) if (nl >= g_primes[i]) { nl = g_primes[i]; break; }
+	} else {
+		unsigned prime = g_primes[179];
+		for (i = 0; i < 180; i++) if (g_primes[i] >= (unsigned)N) { prime = g_primes[i]; break; }
+		nl = prime;
+		for (i = 0; i < maxParentSet; i++) nl *= prime;
+	}
+	if (nl < g_primes[10]) nl = g_primes[10];
+	g_cbits = 1;
+	i = 1;
+	while (i < N * maxParentSet) { g_cbits++; i <<= 1; }
+	if (nl < 1) nl = 1;                       /* InitializeCache (cache.cpp:78-88) */
+	g_ncache = nl;
+	g_cache = (centry_t **)calloc(g_ncache, sizeof(centry_t *));
+}
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+/* slot of (sorted pool, node, parent count): cache.cpp:174-184 = :296-306 */
+static unsigned cache_slot(const int *pool, int npool, int node, int npars, int N) {
+	unsigned nl = 1;
+	for (int i = 0; i < npool; i++) {
+		int j = (pool[i] - 1) % 180;
+		nl *= g_primes[180 - j - 1];
+		nl %= g_ncache;
+	}
+	nl = (nl << g_cbits) + node + N * npars;
+	return nl % g_ncache;
+}
+/* getCachedProb (cache.cpp:142-216).  pool: labels, sorted here */
+static centry_t *cache_get(int *pool, int npool, int node, int npars, int N) {
+	if (!g_cache) return NULL;
+	qsort(pool, npool, sizeof(int), cmp_int);
+	centry_t *e = g_cache[cache_slot(pool, npool, node, npars, N)];
+	if (!e || e->node != node || e->npars != npars || e->npool != npool) return NULL;
+	for (int i = 0; i < npool; i++) if (e->pool[i] != pool[i]) return NULL;
+	return e;
+}
+/* setCachedProb (cache.cpp:218-317): f = the scored family with parents as order positions, ord = position -> label0 */
+static void cache_set(int *pool, int npool, int node, const fam_t *f, const int *ord, int N, int maxParentSet) {
+	if (!g_cache) cache_init(N, maxParentSet);
+	qsort(pool, npool, sizeof(int), cmp_int);
+	centry_t *e = (centry_t *)calloc(1, sizeof(centry_t));
+	e->node = node; e->npars = f->d; e->npool = npool;
+	e->pool = (int *)malloc((npool ? npool : 1) * sizeof(int));
+	memcpy(e->pool, pool, npool * sizeof(int));
+	for (int i = 0; i < f->d; i++) e->pars[i] = ord[f->pars[i]] + 1;
+	e->fam = *f;
+	e->fam.counts = NULL;
+	if (f->counts && f->tsize > 0) {
+		e->fam.counts = (double *)malloc((size_t)f->tsize * sizeof(double));
+		memcpy(e->fam.counts, f->counts, (size_t)f->tsize * sizeof(double));
+	}
+	unsigned s = cache_slot(pool, npool, node, f->d, N);
+	centry_free(g_cache[s]);
+	g_cache[s] = e;
+}
+/* a hit as a family of the current order: parents back to positions, in the entry's listing sequence (cache.cpp:203-205) */
+static void cache_fam(const centry_t *e, int child, const int *pos_of, fam_t *out) {
+	*out = e->fam;
+	out->child = child;
+	for (int i = 0; i < e->npars; i++) out->pars[i] = pos_of[e->pars[i] - 1];
+}
+
 /* ------------------------------------------------------------------ search for one order ---- */
 /* RCatnetSearch::estimateCatnets marshalling (rcatnet_search.cpp:111-268) + CATNET_SEARCH2::estimate
  * (catnet_search2.h:152-897).  All label-space inputs as R passes them; see catnet_oracle.h. */
@@ -217,7 +322,7 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 	double *cbuf = (double *)malloc(maxtab * sizeof(double)), *bestc = (double *)malloc(maxtab * sizeof(double));
 	unsigned char *keep = pert_lbl ? (unsigned char *)malloc(M) : NULL;
 	int *fix = (int *)malloc(N * sizeof(int)), *fre = (int *)malloc(N * sizeof(int)), *idx = (int *)malloc(N * sizeof(int));
-	int *basefam = (int *)malloc(N * sizeof(int));
+	int *basefam = (int *)malloc(N * sizeof(int)), *plbl = (int *)malloc((N + ORC_MAXP) * sizeof(int));
 
 #define SET_KEEP(node) do { if (keep) for (int q_ = 0; q_ < M; q_++) keep[q_] = pert_lbl[(size_t)q_ * N + ord[node]] == 0; } while (0)
 	/* base network: every node with its fixed parents (catnet_search2.h:359-441) */
@@ -263,11 +368,15 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 		 * -FLT_MAX for nsamples < 1 (catnet_class.h:824-826), so no candidate beats the initial fMaxLogLik = -FLT_MAX and
 		 * the node keeps its base family (equal categories: ncombMaxLogLik < 0 -> continue, catnet_search2.h:637-640;
 		 * mixed: tempLogLik == -FLT_MAX never creates or replaces a slot, :813-826) */
+		int dead = 0;
 		if (keep) {
 			int nkept = 0;
 			for (j = 0; j < M; j++) nkept += keep[j];
-			if (nkept < 1) maxpars = 0;
+			if (nkept < 1) dead = 1;
 		}
+		/* ... but with the cache on, the unequal-categories path still stores an entry per candidate (:789-797), and a store
+		 * can evict what a later order would have hit: those stores are kept, the rest of the node's work is dropped */
+		if (dead && !(g_cache_on && !equal)) maxpars = 0;
 		const fam_t *bf = &R->fams[basefam[n]];
 		int base_node_cx = fam_complexity(bf, cats);
 		double base_term = bf->loglik + bf->prior;
@@ -278,13 +387,39 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 			fam_t best, cand;
 			int have_best = 0;
 			memset(&best, 0, sizeof(best));
+			int hit = 0;
+			if (g_cache_on && equal) {
+				/* equal categories: ONE entry per (node, pool, d) holding the winner (:514-524, :642-650) */
+				for (j = 0; j < nr; j++) plbl[j] = ord[fre[j]] + 1;
+				for (j = 0; j < nf; j++) plbl[nr + j] = ord[fix[j]] + 1;
+				const centry_t *e = cache_get(plbl, nr + nf, ord[n] + 1, d, N);
+				if (e) {
+					cache_fam(e, n, pos_of, &best);
+					fMax = best.loglik;
+					if (edge) fMax += best.prior;
+					have_best = hit = 1;
+				}
+			}
 			for (j = 0; j < kk; j++) idx[j] = j;
-			do {
+			if (!hit) do {
 				memset(&cand, 0, sizeof(cand));
 				cand.child = n; cand.d = d;
 				for (j = 0; j < nf; j++) cand.pars[j] = fix[j];       /* fixed first (:532-553) */
 				for (j = 0; j < kk; j++) cand.pars[nf + j] = fre[idx[j]];
-				score_family(&cand, S, N, M, cats, keep, edge, cbuf);
+				const centry_t *ce = NULL;
+				if (g_cache_on && !equal) {
+					/* unequal categories: one entry per candidate, its own parents as the pool (:724-733, :789-797) */
+					for (j = 0; j < d; j++) plbl[j] = ord[cand.pars[j]] + 1;
+					ce = cache_get(plbl, d, ord[n] + 1, d, N);
+				}
+				if (ce) cache_fam(ce, n, pos_of, &cand);
+				else if (dead) { cand.loglik = NEG_INF; cand.cc = cats[n]; }
+				else score_family(&cand, S, N, M, cats, keep, edge, cbuf);
+				if (g_cache_on && !equal && !ce) {
+					for (j = 0; j < d; j++) plbl[j] = ord[cand.pars[j]] + 1;
+					cache_set(plbl, d, ord[n] + 1, &cand, ord, N, maxParentSet);
+				}
+				if (dead) continue;
 				double f = cand.loglik;
 				if (edge) f += cand.prior;                              /* :610 */
 				if (equal) {
@@ -318,6 +453,11 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 				}
 			} while (next_comb(idx, kk, nr));
 			if (!equal || !have_best) continue;                         /* :637-640 */
+			if (g_cache_on && !hit) {
+				for (j = 0; j < nr; j++) plbl[j] = ord[fre[j]] + 1;
+				for (j = 0; j < nf; j++) plbl[nr + j] = ord[fix[j]] + 1;
+				cache_set(plbl, nr + nf, ord[n] + 1, &best, ord, N, maxParentSet);
+			}
 			int ncx = fam_complexity(&best, cats), famid = -1;
 			for (k = 0; k < R->nslots; k++) {                           /* :657-676 */
 				if (!R->nets[k].exists) continue;
@@ -354,7 +494,7 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 	free(cur);
 done:
 	free(ord); free(pos_of); free(S); free(cats); free(edge); free(allow); free(fixd); free(cbuf); free(bestc);
-	free(keep); free(fix); free(fre); free(idx); free(basefam);
+	free(keep); free(fix); free(fre); free(idx); free(basefam); free(plbl);
 	return R;
 }
 
@@ -459,8 +599,8 @@ static void gen_order(const int *curo, int *out, int n, int shuffles, int bjump)
 	free(t);
 }
 
-/* the SA loop of RCatnetSearchSA::search (rcatnet_sa.cpp:471-820), one evaluation after the other, no score cache
- * (the cache only memoises scores, cache.cpp:142-317); dirProbs proposals are not restated here */
+/* the SA loop of RCatnetSearchSA::search (rcatnet_sa.cpp:471-820), one evaluation after the other, with the score
+ * cache when orc_set_cache(1) (R's setting, R/catnet.search.R:293-294); dirProbs proposals are not restated here */
 orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_lbl, int maxParentSet,
 		const int *parentSizes_lbl, int maxComplexity, const int *numCats_lbl, const int *parentsPool_lbl,
 		const int *fixedPool_lbl, const double *edge_lbl, int selectMode, const int *startOrder, double tempStart,
@@ -477,6 +617,13 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 	double fOpt = NEG_INF, tempCur = tempStart, *trace = NULL;
 	int *tacc = NULL, ntrace = 0, tcap = 0;
 	int nstop = 0, nstopCounter = 0, naccept = 0, nLast = 0, niter = 0;
+	/* score cache (orc_set_cache): off beyond 8 threads (rcatnet_sa.cpp:315-319).  The reference starts all the step's
+	 * searches on threads before it looks at any of them, so every proposal leaves its entries in the cache whether or not
+	 * an earlier one is accepted; with one thread that is this loop, with more the threads' stores interleave as they
+	 * come (the reference's own result then depends on timing) and the restatement takes them proposal after proposal. */
+	const int cache_was = g_cache_on;
+	if (nDrives > 8) g_cache_on = 0;
+	orc_result **pre = (orc_result **)calloc(nDrives, sizeof(orc_result *));
 	while (niter < maxIter) {
 		for (n = 0; n < nDrives; n++) {
 			int extra = 0;
@@ -485,13 +632,19 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 			skip[n] = 0;
 			for (nn = 0; nn < n && !skip[n]; nn++) skip[n] = !memcmp(test[nn], test[n], N * sizeof(int));
 		}
+		if (g_cache_on)
+			for (n = 0; n < nDrives; n++)
+				if (!skip[n]) pre[n] = orc_search_order(N, M, samples_lbl, pert_lbl, maxParentSet, parentSizes_lbl,
+						maxComplexity, test[n], numCats_lbl, parentsPool_lbl, fixedPool_lbl, edge_lbl);
 		nstop = 1;
 		int stepiters = nDrives, stepaccept = 0;
 		for (n = 0; n < nDrives; n++) {
-			if (skip[n] || stepaccept > 0) continue;
+			if (skip[n]) continue;
+			if (stepaccept > 0) { orc_result_free(pre[n]); pre[n] = NULL; continue; }
 			nstop = 0;
-			orc_result *r = orc_search_order(N, M, samples_lbl, pert_lbl, maxParentSet, parentSizes_lbl, maxComplexity,
-					test[n], numCats_lbl, parentsPool_lbl, fixedPool_lbl, edge_lbl);
+			orc_result *r = g_cache_on ? pre[n] : orc_search_order(N, M, samples_lbl, pert_lbl, maxParentSet, parentSizes_lbl,
+					maxComplexity, test[n], numCats_lbl, parentsPool_lbl, fixedPool_lbl, edge_lbl);
+			pre[n] = NULL;
 			if (!r) continue;
 			int pick = -1, k;
 			double fl = NEG_INF;
@@ -546,7 +699,8 @@ orc_result *orc_search_sa(int N, int M, const int *samples_lbl, const int *pert_
 		best->ntrace = ntrace;
 	} else { free(opt); free(trace); free(tacc); }
 	for (n = 0; n < nDrives; n++) free(test[n]);
-	free(test); free(skip);
+	free(test); free(skip); free(pre);
+	g_cache_on = cache_was;
 	return best;
 }
 
@@ -562,6 +716,8 @@ int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, i
 	for (n = 0; n < nDrives; n++) test[n] = (int *)malloc(N * sizeof(int));
 	memset(hist, 0, sizeof(double) * N * N);
 	int niter = 0, nstop = 0;
+	const int cache_was = g_cache_on;
+	if (nDrives > 8) g_cache_on = 0;                                 /* rcatnet_hist.cpp:205-209 */
 	while (niter < maxIter) {
 		for (n = 0; n < nDrives; n++) {
 			gen_permutation(test[n], N);
@@ -603,6 +759,7 @@ int orc_search_hist(int N, int M, const int *samples_lbl, const int *pert_lbl, i
 	}
 	for (n = 0; n < nDrives; n++) free(test[n]);
 	free(test); free(skip);
+	g_cache_on = cache_was;
 	return niter;
 }
 

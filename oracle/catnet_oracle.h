@@ -33,6 +33,10 @@ int orc_net_set_prob(int N, int M, const int *samples0, const int *pert, const i
 long orc_net_samples(int N, const int *cats, int maxParents, const int *numParents, const int *parents0,
 		const double *probs, const long long *offsets, int M, const int *pert, double naRate, unsigned long long seed,
 		int *out);
+/* the reference's score cache (cache.cpp): orc_set_cache(1) makes orc_search_sa / orc_search_hist (and orc_search_order)
+ * look candidates up and store them as CATNET_SEARCH2::estimate does; orc_cache_release = ReleaseCache */
+void orc_set_cache(int on);
+void orc_cache_release(void);
 void orc_set_seed(unsigned long long seed);
 void orc_set_unif(double (*fn)(void *), void *ctx);   /* caller-owned generator; cleared by orc_set_seed */
 int orc_result_nslots(const orc_result *r);

@@ -115,6 +115,17 @@ def search_order(samples, max_parent_set, max_complexity, order=None, perturbati
         L.orc_result_free(h)
 
 
+def _cache(L, on):
+    """the reference's score cache (cache.cpp) restated: released (as R does before every call,
+    R/catnet.search.R:279) and switched on or off for the next search"""
+    L.orc_set_cache.argtypes = [C.c_int]
+    L.orc_set_cache.restype = None
+    L.orc_cache_release.argtypes = []
+    L.orc_cache_release.restype = None
+    L.orc_cache_release()
+    L.orc_set_cache(int(bool(on)))
+
+
 def _set_unif(L, unif):
     if unif is not None:
         L.orc_set_unif.argtypes = [C.c_void_p, C.c_void_p]
@@ -133,12 +144,14 @@ def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=
     M, N = s.shape
     L.orc_set_seed(int(seed))
     _set_unif(L, unif)
+    _cache(L, use_cache)
     e = None if edge_prob is None else np.ascontiguousarray(np.asarray(edge_prob, dtype=np.float64).T)
     h = L.orc_search_sa(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
                         int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),
                         _p(_pool(fixed_parents, N)), _p(e), int(select_mode), _p(_i32(start_order)),
                         float(temp_start), float(temp_cool_fact), int(temp_check_orders), int(max_iter),
                         float(order_shuffles), float(stop_diff), int(num_threads))
+    _cache(L, False)
     if not h:
         return None
     try:
@@ -156,7 +169,8 @@ def search_sa(samples, max_parent_set, max_complexity, start_order, select_mode=
 
 
 def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_iter=32, num_threads=2, seed=1,
-                perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None, unif=None):
+                perturbations=None, parent_sizes=None, num_cats=None, parents_pool=None, fixed_parents=None, unif=None,
+                use_cache=False):
     """cnSearchHist: returns (hist [N][N] with hist[parent][child], iterations).  score: 0 highest complexity, 1 AIC,
     2 BIC; weight: 0 one, 1 exp(loglik/(M N)), 2 exp(score/(M N))."""
     L = lib()
@@ -164,10 +178,12 @@ def search_hist(samples, max_parent_set, max_complexity, score=2, weight=1, max_
     M, N = s.shape
     L.orc_set_seed(int(seed))
     _set_unif(L, unif)
+    _cache(L, use_cache)
     hist = np.zeros((N, N), dtype=np.float64)
     it = L.orc_search_hist(N, M, _p(s), _p(_i32(perturbations)), int(max_parent_set), _p(_i32(parent_sizes)),
                            int(max_complexity), _p(_i32(num_cats)), _p(_pool(parents_pool, N)),
                            _p(_pool(fixed_parents, N)), int(score), int(weight), int(max_iter), int(num_threads), _p(hist))
+    _cache(L, False)
     return hist, it
 
 

@@ -8,6 +8,8 @@ on some inputs (e.g. fixed parents whose base network exceeds maxComplexity, SUR
     python tools/fuzz_oracle.py unseen 0 2000         # declared but unseen categories, limits from the base network up
     python tools/fuzz_oracle.py sa 0 1500             # cnSearchSA trajectories (cache off) + cnSearchHist
     python tools/fuzz_oracle.py rest 0 3000           # pairwise metrics, cnSetProb / cnLoglik / cnNodeLoglik, cnSamples
+    python tools/fuzz_oracle.py sacache 0 1500        # the reference with its score cache ON against itself with it OFF
+    python tools/fuzz_oracle.py sacacheport 0 2000    # the restated cache against the reference's (cache ON, one thread)
 
 Round 1: 10,911 + 5,955 + 2,000 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
 since) and five reference crashes (search 3886, 9556, 10501, 11146, 11995: fixed parents put the base
@@ -142,6 +144,65 @@ def check_sacache(seed):
     assert i1 == i2 and np.array_equal(h1, h2), "histogram"
 
 
+def strict_nets(a, b):
+    """same complexity slots, same LISTED parent sequences, every fp64 bit-identical (network and node log-likelihoods,
+    priors, probabilities)"""
+    x, y = {n["complexity"]: n for n in a}, {n["complexity"]: n for n in b}
+    assert sorted(x) == sorted(y), "slots"
+    for cx in x:
+        u, v = x[cx], y[cx]
+        assert u["parents"] == v["parents"], "listed parents"
+        assert u["loglik"] == v["loglik"], "network log-likelihood"
+        assert u["node_loglik"] == v["node_loglik"] and u["node_prior"] == v["node_prior"], "node terms"
+        assert u["sample_sizes"] == v["sample_sizes"], "sample sizes"
+        assert all(np.array_equal(p, q) for p, q in zip(u["probs"], v["probs"])), "probability tables"
+
+
+def check_sacacheport(seed):
+    """the restatement WITH its restated score cache (oracle/catnet_oracle.c: cache_get / cache_set) against the compiled
+    reference with its cache ON, one thread (with more the reference's stores interleave by timing): trajectory, listed
+    parent sequences, tables and every fp64 must be identical.  Also counts how often cache-ON differs from cache-OFF in
+    the restatement (exit code 5 = identical to the reference, and cache ON != cache OFF)."""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 11)), int(rng.integers(8, 400))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4][seed % 4], na_frac=[0, 0.1][seed % 2])
+    kw = dict(num_cats=c)
+    if seed % 3 == 0:
+        kw["perturbations"] = (rng.random(s.shape) < 0.2).astype(np.int32)
+        if seed % 9 == 0:
+            kw["perturbations"][:, int(rng.integers(0, n))] = 1      # a node perturbed in every sample
+    if seed % 11 == 0:
+        kw["parents_pool"] = [sorted(rng.choice(n, size=int(rng.integers(0, n)), replace=False) + 1) for _ in range(n)]
+    if seed % 13 == 0:
+        kw["fixed_parents"] = [sorted(rng.choice(n, size=int(rng.integers(0, 2)), replace=False) + 1) for _ in range(n)]
+    kh = dict(kw)
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0, 0.0][seed % 4], temp_cool_fact=[0.9, 0.5][seed % 2],
+              temp_check_orders=int(rng.integers(1, 8)), max_iter=int(rng.integers(20, 120)),
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=[1e-10, 0.01][seed % 2],
+              num_threads=1, seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    P = 2 + (seed % 7 == 0)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** P
+    a = ref.search_sa(s, P, K, start, use_cache=True, want_probs=True, **sa, **kw)
+    b = port.search_sa(s, P, K, start, use_cache=True, want_probs=True, **sa, **kw)
+    assert np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"] and a["naccept"] == b["naccept"], "trajectory"
+    assert np.array_equal(a["trace_accept"], b["trace_accept"]), "acceptances"
+    assert np.array_equal(a["trace"], b["trace"]), "trace values"
+    strict_nets(b["nets"], a["nets"])
+    hk = dict(score=seed % 3, weight=seed % 3, max_iter=12, num_threads=1, seed=sa["seed"])
+    h1, i1 = ref.search_hist(s, 2, K, use_cache=True, **hk, **kh)
+    h2, i2 = port.search_hist(s, 2, K, use_cache=True, **hk, **kh)
+    assert i1 == i2 and np.array_equal(h1, h2), "histogram"
+    off = port.search_sa(s, P, K, start, use_cache=False, want_probs=True, **sa, **kw)
+    try:
+        assert np.array_equal(off["trace"], b["trace"]) and np.array_equal(off["order"], b["order"])
+        strict_nets(off["nets"], b["nets"])
+    except AssertionError:
+        os._exit(5)
+
+
 def check_rest(seed):
     rng = np.random.default_rng(seed)
     n, m = int(rng.integers(1, 10)), int(rng.integers(7, 150))
@@ -183,13 +244,14 @@ def check_rest(seed):
 
 
 def main():
-    check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest, "sacache": check_sacache}[sys.argv[1]]
+    check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest, "sacache": check_sacache,
+             "sacacheport": check_sacacheport}[sys.argv[1]]
     lo, hi = int(sys.argv[2]), int(sys.argv[3])
     if not ref.available():
         sys.exit("oracle/_ref is not built (needs /root/reference)")
     port.lib()
     ref.lib()
-    ran, mismatch, crash = 0, [], []
+    ran, mismatch, crash, differs = 0, [], [], 0
     for seed in range(lo, hi):
         pid = os.fork()
         if pid == 0:
@@ -209,9 +271,13 @@ def main():
             crash.append(seed)
         elif os.WEXITSTATUS(st) == 3:
             mismatch.append(seed)
+        elif os.WEXITSTATUS(st) == 5:
+            differs += 1
         if not os.WIFSIGNALED(st) and os.WEXITSTATUS(st) != 4:
             ran += 1
     print("problems %d  mismatches %s  reference crashes %s" % (ran, mismatch, crash))
+    if sys.argv[1] == "sacacheport":
+        print("of these, cache ON differs from cache OFF (listing order of parents or last bits) in %d" % differs)
     sys.exit(1 if mismatch else 0)
 
 
