@@ -84,6 +84,7 @@ SYMBOLS = [
     "cnb_mctx_mark", "cnb_mctx_elapsed_ms", "cnb_mctx_active", "cnb_ctx_search_scores",
     "cnb_ctx_upload_rows8", "cnb_tile_selftest_full", "cnb_last_call_timing",
     "cnb_tile_selftest_geo", "cnb_ctx_allow_scatter", "cnb_ctx_scattered", "cnb_ctx_upload_rows8_on", "cnb_ctx_stream_begin", "cnb_ctx_stream_slice", "cnb_ctx_stream_end",
+    "cnb_cache_trace",
 ]
 
 _lib = None
@@ -126,6 +127,7 @@ def lib():
         "cnb_last_call_timing": (i32, [P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_tile_selftest": (C.c_int64, [i32]),
+        "cnb_cache_trace": (C.c_int64, [P(Params), vp, vp, i32, vp, vp, i32, vp, vp]),
         "cnb_tile_selftest_full": (C.c_int64, [i32]),
         "cnb_tile3_selftest": (C.c_int64, [i32, i32]),
         "cnb_tile_selftest_geo": (C.c_int64, [i32, i32]),

@@ -83,6 +83,7 @@ struct CnbTiles {
 struct CnbNodePlan {
 	int32_t equal_branch;   /* catnet_search2.h:491-496 */
 	int32_t nfix, fix_off;
+	int32_t nfree, free_off;/* the free pool in lists[] (also when the node has no candidate block) */
 	int32_t base_cx;        /* (C-1) * prod C_fixed */
 	int32_t first_blk, nblk;/* blocks of this node, d ascending */
 	int64_t opt_begin, opt_end;  /* DP options of the node */

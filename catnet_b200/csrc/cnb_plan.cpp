@@ -144,6 +144,8 @@ int cnb_build_plan(const cnb_params *p, const int32_t *cats_lbl, int32_t rank, i
 		pl.lists.insert(pl.lists.end(), fix.begin(), fix.end());
 		int32_t free_off = (int32_t)pl.lists.size();
 		pl.lists.insert(pl.lists.end(), fre.begin(), fre.end());
+		nd.nfree = (int32_t)fre.size();
+		nd.free_off = free_off;
 		int64_t cx = pl.cats[c] - 1;
 		for (int v : fix) cx *= pl.cats[v];
 		if (cx > INT32_MAX) FAIL(CNB_ERR_PARAM, "fixed parent set of node %d too complex", c + 1);

@@ -86,7 +86,11 @@ typedef struct cnb_sa_params {
 	double order_shuffles;         /* <0: "jump" moves; fractional part = Bernoulli extra shuffle (:371-377) */
 	double stop_diff;
 	int32_t num_threads;           /* rThreads: proposals evaluated per SA step (first accepted wins, :646-657) */
-	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
+	int32_t use_cache;             /* rUseCache (R passes TRUE, R/catnet.search.R:293-294): reproduce what the reference's score
+	                                  cache does to the result -- parents listed, tables laid out and log-likelihoods summed in
+	                                  the sequence of the order a family was FIRST scored under (src/cache.cpp:142-216; ignored
+	                                  beyond 8 threads, rcatnet_sa.cpp:315-319).  The device still re-scores every order; a host
+	                                  model of the cache's slots decides the listing (csrc/cnb_cache.h).  0 = the cache-off result */
 	const double *dir_prob;        /* [N*N] R layout or NULL (rDirProbs) */
 	uint64_t seed;                 /* uniform stream (splitmix64) when unif is NULL; 0 = the cnb_set_seed value */
 	/* the caller's own uniform generator (the R shim passes R's unif_rand, so that set.seed() reproduces stock catnet's
@@ -102,7 +106,7 @@ typedef struct cnb_hist_params {
 	int32_t weight;                /* rWeight: 0 = 1, 1 = exp(loglik/(M N)) ("likelihood"), 2 = exp(score/(M N)) */
 	int32_t max_iter;              /* rMaxIter: orders to evaluate (rounded up to whole batches of num_threads) */
 	int32_t num_threads;           /* rThreads: orders per batch (duplicates inside a batch are skipped) */
-	int32_t use_cache;             /* rUseCache: accepted for compatibility; the device re-scores every order */
+	int32_t use_cache;             /* rUseCache: as for cnb_sa_params (the histogram's weights follow the cached log-likelihoods) */
 	uint64_t seed;                 /* uniform stream (splitmix64), as for cnb_sa_params */
 	double (*unif)(void *unif_ctx);   /* the caller's generator, as for cnb_sa_params (rcatnet_hist.cpp:124,129) */
 	void *unif_ctx;
@@ -375,6 +379,16 @@ int64_t cnb_tile_selftest_geo(int32_t num_nodes, int32_t free_cats);
 /* the same for the tiling of the unrestricted three-parent group (free_cats = max categories - 1, in the geometry of that
  * many free categories; negative: -free_cats free values in the default 28 x 64 tiles) */
 int64_t cnb_tile3_selftest(int32_t num_nodes, int32_t free_cats);
+/* the host-side model of the reference's score cache (src/cache.cpp:142-317; csrc/cnb_cache.h) on a sequence of node orders,
+ * no GPU needed.  p: the search (num_nodes, max_parent_set, parent_sizes, pools, edge_prob; order ignored); cats [N] per
+ * label; never_kept [N] bytes or NULL (nodes perturbed in every sample); orders [norders][N] 1-based labels; winners
+ * [norders][N][P][P] or NULL: the listed labels (0-padded) of the winner of (order, child label - 1, parent count - 1) where
+ * all pool members have equal category counts, as the device would report it.  Every cache HIT comes back as a row of
+ * 4 + 8 ints -- 1 equal-categories path / 2 otherwise, order index, child label, parent count, the parent labels in the
+ * cached listing sequence -- with the entry's prior beside it.  Returns the number of hits (rows beyond cap are dropped),
+ * < 0 on an error. */
+int64_t cnb_cache_trace(const cnb_params *p, const int32_t *cats, const uint8_t *never_kept, int32_t norders,
+		const int32_t *orders, const int32_t *winners, int32_t cap, int32_t *rows, double *priors);
 
 /* ---- result accessors (the catNetwork slots) ---- */
 int32_t cnb_result_num_networks(const cnb_result *r);

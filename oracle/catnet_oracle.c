@@ -169,6 +169,30 @@ static unsigned g_ncache = 0, g_cbits = 0;
 static int g_cache_on = 0;
 static unsigned g_primes[180];             /* PRIMES_1000 (cache.cpp:35-54): the first 180 primes */
 
+/* test hook: what the cache did, for checking the library's host-side model of it (catnet_b200/csrc/cnb_cache.cpp) on the
+ * CPU.  rows of ORC_TRACE_ROW ints: kind (1 hit on the equal-categories path, 2 hit otherwise, 3 store of an
+ * equal-categories winner), serial number of the search, child label, parent count, listed parent labels; the prior of a
+ * hit beside it; the node order of every search. */
+#define ORC_TRACE_ROW (4 + ORC_MAXP)
+static int *g_tr_rows = NULL, *g_tr_orders = NULL, g_tr_cap = 0, g_tr_n = 0, g_tr_ocap = 0, g_tr_serial = 0;
+static double *g_tr_prior = NULL;
+void orc_cache_trace(int *rows, double *priors, int cap_rows, int *orders, int cap_orders) {
+	g_tr_rows = rows; g_tr_prior = priors; g_tr_cap = cap_rows; g_tr_orders = orders; g_tr_ocap = cap_orders;
+	g_tr_n = 0; g_tr_serial = 0;
+}
+void orc_cache_trace_counts(int *nrows, int *nsearches) { *nrows = g_tr_n; *nsearches = g_tr_serial; }
+static void trace_row(int kind, int child, int d, const int *pars_lbl, double prior) {
+	if (!g_tr_rows) return;
+	if (g_tr_n < g_tr_cap) {
+		int *r = g_tr_rows + (size_t)g_tr_n * ORC_TRACE_ROW;
+		memset(r, 0, ORC_TRACE_ROW * sizeof(int));
+		r[0] = kind; r[1] = g_tr_serial; r[2] = child; r[3] = d;
+		for (int i = 0; i < d && i < ORC_MAXP; i++) r[4 + i] = pars_lbl[i];
+		if (g_tr_prior) g_tr_prior[g_tr_n] = prior;
+	}
+	g_tr_n++;
+}
+
 static void centry_free(centry_t *e) { if (e) { free(e->pool); free(e->fam.counts); free(e); } }
 void orc_cache_release(void) {               /* ReleaseCache (cache.cpp:62-76) */
 	if (g_cache) for (unsigned i = 0; i < g_ncache; i++) centry_free(g_cache[i]);
@@ -267,6 +291,8 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 	if (maxComplexity < N) maxComplexity = N;                           /* :182-183 */
 	int *ord = (int *)malloc(N * sizeof(int)), *pos_of = (int *)malloc(N * sizeof(int));
 	for (i = 0; i < N; i++) { ord[i] = order ? order[i] - 1 : i; pos_of[ord[i]] = i; }
+	if (g_tr_orders && g_cache_on && g_tr_serial < g_tr_ocap)
+		for (i = 0; i < N; i++) g_tr_orders[(size_t)g_tr_serial * N + i] = ord[i] + 1;
 
 	/* samples into order space, NA -> INT_MAX (rcatnet_search.cpp:151-160); categories given as 1..C or inferred
 	 * as min..max (catnet_search2.h:201-235); recode to 0-based, NA -> C (:237-257) */
@@ -398,6 +424,7 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 					fMax = best.loglik;
 					if (edge) fMax += best.prior;
 					have_best = hit = 1;
+					trace_row(1, ord[n] + 1, d, e->pars, best.prior);
 				}
 			}
 			for (j = 0; j < kk; j++) idx[j] = j;
@@ -412,7 +439,7 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 					for (j = 0; j < d; j++) plbl[j] = ord[cand.pars[j]] + 1;
 					ce = cache_get(plbl, d, ord[n] + 1, d, N);
 				}
-				if (ce) cache_fam(ce, n, pos_of, &cand);
+				if (ce) { cache_fam(ce, n, pos_of, &cand); if (!dead) trace_row(2, ord[n] + 1, d, ce->pars, cand.prior); }
 				else if (dead) { cand.loglik = NEG_INF; cand.cc = cats[n]; }
 				else score_family(&cand, S, N, M, cats, keep, edge, cbuf);
 				if (g_cache_on && !equal && !ce) {
@@ -457,6 +484,8 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 				for (j = 0; j < nr; j++) plbl[j] = ord[fre[j]] + 1;
 				for (j = 0; j < nf; j++) plbl[nr + j] = ord[fix[j]] + 1;
 				cache_set(plbl, nr + nf, ord[n] + 1, &best, ord, N, maxParentSet);
+				for (j = 0; j < d; j++) plbl[j] = ord[best.pars[j]] + 1;
+				trace_row(3, ord[n] + 1, d, plbl, best.prior);
 			}
 			int ncx = fam_complexity(&best, cats), famid = -1;
 			for (k = 0; k < R->nslots; k++) {                           /* :657-676 */
@@ -493,6 +522,7 @@ orc_result *orc_search_order(int N, int M, const int *samples_lbl, const int *pe
 	for (k = 0; k < R->nslots; k++) free(cur[k].fam);
 	free(cur);
 done:
+	if (g_cache_on) g_tr_serial++;
 	free(ord); free(pos_of); free(S); free(cats); free(edge); free(allow); free(fixd); free(cbuf); free(bestc);
 	free(keep); free(fix); free(fre); free(idx); free(basefam); free(plbl);
 	return R;

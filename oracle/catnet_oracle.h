@@ -37,6 +37,11 @@ long orc_net_samples(int N, const int *cats, int maxParents, const int *numParen
  * look candidates up and store them as CATNET_SEARCH2::estimate does; orc_cache_release = ReleaseCache */
 void orc_set_cache(int on);
 void orc_cache_release(void);
+/* test hook: record what the cache does (rows of 4 + ORC_MAXP ints: kind 1 equal-categories hit / 2 other hit / 3 store of an
+ * equal-categories winner, search serial, child label, parent count, listed parent labels; the hit's prior; every
+ * search's node order [serial][N]) -- checks the library's host-side model of the cache on the CPU */
+void orc_cache_trace(int *rows, double *priors, int cap_rows, int *orders, int cap_orders);
+void orc_cache_trace_counts(int *nrows, int *nsearches);
 void orc_set_seed(unsigned long long seed);
 void orc_set_unif(double (*fn)(void *), void *ctx);   /* caller-owned generator; cleared by orc_set_seed */
 int orc_result_nslots(const orc_result *r);

@@ -1,0 +1,133 @@
+"""The library's host-side model of the reference's score cache (catnet_b200/csrc/cnb_cache.cpp, CPU only) against the
+restated cache of the oracle (oracle/catnet_oracle.c: cache_get / cache_set, itself fuzzed against the compiled reference
+with its cache ON -- tools/fuzz_oracle.py sacacheport): on the sequence of orders an SA chain evaluates, the model must
+report the same hits, with the parents in the same listed sequence and the same stored prior, as the oracle's cache
+produced while it ran that chain."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from catnet_b200 import _abi
+from helpers import random_problem
+from oracle import port
+
+ROW = 4 + 8          # the library's rows (CNB_MAXP parents)
+OROW = 4 + 16        # the oracle's (ORC_MAXP)
+
+
+def oracle_trace(s, cats, P, K, start, sa, **kw):
+    L = port.lib()
+    cap, ocap = 400000, 2000
+    n = s.shape[1]
+    rows = np.zeros((cap, OROW), dtype=np.int32)
+    priors = np.zeros(cap, dtype=np.float64)
+    orders = np.zeros((ocap, n), dtype=np.int32)
+    L.orc_cache_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_cache_trace.restype = None
+    L.orc_cache_trace_counts.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_cache_trace_counts.restype = None
+    L.orc_cache_trace(rows.ctypes.data, priors.ctypes.data, cap, orders.ctypes.data, ocap)
+    try:
+        r = port.search_sa(s, P, K, start, use_cache=True, num_cats=cats, **sa, **kw)
+        nr, ns = C.c_int(), C.c_int()
+        L.orc_cache_trace_counts(C.byref(nr), C.byref(ns))
+    finally:
+        L.orc_cache_trace(None, None, 0, None, 0)
+    assert nr.value <= cap and ns.value <= ocap
+    assert not rows[:, ROW:].any()
+    return r, rows[:nr.value, :ROW], priors[:nr.value], orders[:ns.value]
+
+
+def model_trace(n, cats, P, K, orders, winners, never_kept=None, **kw):
+    keep = []
+
+    def hold(a):
+        if a is not None:
+            keep.append(a)
+        return _abi.ptr(a)
+    p = _abi.make_params(hold, n, 1, max_parent_set=P, max_complexity=K, **kw)
+    cap = 400000
+    rows = np.zeros((cap, ROW), dtype=np.int32)
+    priors = np.zeros(cap, dtype=np.float64)
+    c32 = np.ascontiguousarray(cats, dtype=np.int32)
+    o32 = np.ascontiguousarray(orders, dtype=np.int32)
+    w32 = np.ascontiguousarray(winners, dtype=np.int32)
+    nk = None if never_kept is None else np.ascontiguousarray(never_kept, dtype=np.uint8)
+    got = _abi.lib().cnb_cache_trace(C.byref(p), c32.ctypes.data, None if nk is None else nk.ctypes.data, len(o32),
+                                     o32.ctypes.data, w32.ctypes.data, cap, rows.ctypes.data, priors.ctypes.data)
+    assert 0 <= got <= cap, got
+    return rows[:got], priors[:got]
+
+
+def problem(seed):
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(3, 11)), int(rng.integers(8, 300))
+    s, c = random_problem(seed, n, m, [None, 2, 3, None][seed % 4], na_frac=[0, 0.1][seed % 2])
+    kw, never = {}, None
+    if seed % 3 == 0:
+        pert = (rng.random(s.shape) < 0.2).astype(np.int32)
+        if seed % 6 == 0:
+            pert[:, int(rng.integers(0, n))] = 1              # a node perturbed in every sample
+        kw["perturbations"] = pert
+        never = (pert.min(axis=0) > 0).astype(np.uint8)
+    if seed % 7 == 0:
+        kw["parents_pool"] = [sorted((rng.choice(n, size=int(rng.integers(0, n)), replace=False) + 1).tolist()) for _ in range(n)]
+    if seed % 11 == 0:
+        kw["fixed_parents"] = [sorted((rng.choice(n, size=int(rng.integers(0, 2)), replace=False) + 1).tolist()) for _ in range(n)]
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    if seed % 13 == 0:
+        kw["parent_sizes"] = rng.integers(0, 4, size=n).astype(np.int32)
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0][seed % 3], temp_cool_fact=0.9,
+              temp_check_orders=int(rng.integers(2, 8)), max_iter=int(rng.integers(30, 90)),
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=1e-10,
+              num_threads=1 + seed % 3, seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    P = 2 + (seed % 4 == 0)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** P
+    return s, c, P, K, start, sa, kw, never
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_cache_model_reports_the_oracles_hits(seed):
+    s, c, P, K, start, sa, kw, never = problem(seed)
+    n = s.shape[1]
+    r, rows, priors, orders = oracle_trace(s, c, P, K, start, sa, **kw)
+    if r is None:
+        pytest.skip("no network")
+    # equal-categories winners the oracle stored, as the device would report them
+    winners = np.zeros((len(orders), n, P, P), dtype=np.int32)
+    for row in rows[rows[:, 0] == 3]:
+        winners[row[1], row[2] - 1, row[3] - 1, :row[3]] = row[4:4 + row[3]]
+    hits, hp = rows[rows[:, 0] != 3], priors[rows[:, 0] != 3]
+    mkw = {k: v for k, v in kw.items() if k != "perturbations"}
+    got, gp = model_trace(n, c, P, K, orders, winners, never_kept=never, **mkw)
+    assert len(got) == len(hits), (len(got), len(hits))
+    assert np.array_equal(got, hits)
+    if "edge_prob" in kw:
+        assert np.array_equal(gp, hp)                         # fp64 bit equality: host prior == the oracle's
+    assert len(orders) > 1
+
+
+def test_cache_table_size_follows_the_reference():
+    """cache.cpp:225-264: N^(P+1) below 1069 collapses to 2 and is then raised to 31 slots; otherwise the first prime >= N
+    to the power P + 1"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    # indirectly: the restated cache with these sizes reproduces the compiled reference on the fuzz seeds (sacacheport);
+    # here the model's hits equal the oracle's on a problem with 37 nodes (37^3 = 50,653 slots) and mixed categories
+    rng = np.random.default_rng(5)
+    s, c = random_problem(5, 37, 60, None)
+    sa = dict(select_mode=2, temp_start=1.0, temp_cool_fact=0.9, temp_check_orders=5, max_iter=6, order_shuffles=4.0,
+              stop_diff=1e-10, num_threads=1, seed=9)
+    start = (rng.permutation(37) + 1).astype(np.int32)
+    K = int(np.sum(c - 1)) + 37 * 16
+    r, rows, priors, orders = oracle_trace(s, c, 2, K, start, sa)
+    winners = np.zeros((len(orders), 37, 2, 2), dtype=np.int32)
+    for row in rows[rows[:, 0] == 3]:
+        winners[row[1], row[2] - 1, row[3] - 1, :row[3]] = row[4:4 + row[3]]
+    hits = rows[rows[:, 0] != 3]
+    got, _ = model_trace(37, c, 2, K, orders, winners)
+    assert len(hits) > 1000 and np.array_equal(got, hits)
