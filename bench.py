@@ -223,12 +223,13 @@ def sa_workload():
     order1 = (np.asarray(cfg["order"]) + 1).astype(np.int32)
     start = order1[np.random.default_rng(7).permutation(len(order1))]
     sa = dict(select_mode=2, start_order=start, temp_start=0.0, temp_cool_fact=1.0, temp_check_orders=1000,
-              order_shuffles=0.0, stop_diff=1e-10, num_threads=4, use_cache=True)
+              order_shuffles=0.0, stop_diff=1e-10, num_threads=4, use_cache=False)
     return s, cfg["cats"], sa
 
 
 SA_DESC = ("C4: cnSearchSA on cnSamples(alarmnet, 20000), maxParentSet=2, maxComplexity=600, BIC, maxIter=%d, "
-           "numThreads=4 (proposals per step)")
+           "numThreads=4 (proposals per step), use_cache=0 (the cache-off result; `score_cache_on` = the same chain with the "
+           "reference's score cache modelled, R's setting)")
 
 
 def bic_best(nets, m):
@@ -261,7 +262,19 @@ def sa_leg_torchrun(rank, world, max_iter, dist_mod=None, dev=None):
         dist_mod.all_gather_object(chains, [{"complexity": x["complexity"], "loglik": x["loglik"]} for x in r["nets"]])
     merged = cdist.merge_evaluations(chains)
     m = s.shape[0]
-    return {"workload": (SA_DESC % max_iter) + ", one chain per GPU, merged per complexity",
+    cache_on = None
+    if world == 1:
+        # R's own setting: every proposal walks the model of the reference's score cache, one after the other, and the
+        # families the cache answers are re-scored in their cached listing (csrc/cnb_cache.h)
+        t0 = time.perf_counter()
+        rc = _abi.search_sa(s, dict(sa, max_iter=max_iter, seed=4004, use_cache=True), **kw)
+        wc = time.perf_counter() - t0
+        cache_on = {"wall_s": wc, "orders_evaluated": int(len(rc["trace"])), "ms_per_order": 1000.0 * wc / max(len(rc["trace"]), 1),
+                    "bic_best": bic_best(rc["nets"], m),
+                    "same_trajectory_as_cache_off": bool(np.array_equal(rc["trace_accept"], r["trace_accept"])
+                                                         and np.array_equal(rc["order"], r["order"]))}
+    return {"score_cache_on": cache_on,
+            "workload": (SA_DESC % max_iter) + ", one chain per GPU, merged per complexity",
             "wall_s": wall, "chains": world, "iterations": int(r["niter"]), "orders_evaluated": int(len(r["trace"])),
             "ms_per_order": 1000.0 * wall / max(len(r["trace"]), 1),
             "chain_bic_best": [bic_best(c, m) for c in chains], "merged_bic_best": bic_best(merged, m),

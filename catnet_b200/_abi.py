@@ -709,7 +709,7 @@ def _unif_ptr(unif):
     return C.cast(unif, C.c_void_p) if not isinstance(unif, int) else C.c_void_p(unif)
 
 
-def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=True, seed=1, unif=None):
+def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=False, seed=1, unif=None):
     h = HistParams()
     h.score, h.weight, h.max_iter, h.num_threads = int(score), int(weight), int(max_iter), int(num_threads)
     h.use_cache, h.seed = int(bool(use_cache)), int(seed)
@@ -718,7 +718,7 @@ def make_hist_params(score=2, weight=1, max_iter=32, num_threads=2, use_cache=Tr
 
 
 def make_sa_params(keep, select_mode=0, start_order=None, temp_start=1.0, temp_cool_fact=0.9, temp_check_orders=10,
-                   max_iter=100, order_shuffles=1.0, stop_diff=1e-10, num_threads=1, use_cache=True, dir_prob=None,
+                   max_iter=100, order_shuffles=1.0, stop_diff=1e-10, num_threads=1, use_cache=False, dir_prob=None,
                    seed=1, unif=None):
     s = SaParams()
     s.select_mode = int(select_mode)

@@ -635,6 +635,9 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	q.num_nodes = c->N;
 	q.num_samples = c->M;
 	CK(cudaEventRecord(c->ev[EV_PLAN0], c->stream));
+	c->cache_P = p->max_parent_set;
+	if (p->parent_sizes) c->cache_psizes.assign(p->parent_sizes, p->parent_sizes + c->N);
+	else c->cache_psizes.clear();
 	/* the previous plan's host vectors may still be the source of an async copy */
 	CK(cudaStreamSynchronize(c->stream));
 	std::string err;
@@ -1136,6 +1139,70 @@ static int score_explicit_groups(cnb_ctx *c, const std::vector<int32_t> &child, 
 	return CNB_OK;
 }
 
+/* The reference's score cache (cnb_cache.h): the option table of the planned order is in place; walk the order through the
+ * model of the cache (the winners of the equal-categories blocks come back from the device first), re-score every
+ * candidate the cache answers differently -- parents in the cached listing sequence -- and patch its term, and on the
+ * equal-categories path the winner itself, into the option table.  The DP then runs on what the reference's DP saw. */
+static int apply_cache(cnb_ctx *c) {
+	CnbPlan &pl = c->plan;
+	cudaStream_t st = c->stream;
+	if (pl.world != 1) { cnb_set_error("the score cache model needs the whole search on one rank"); return CNB_ERR_PARAM; }
+	const size_t nopt = (size_t)pl.num_options;
+	c->cache_ov.clear();
+	std::vector<int64_t> win(std::max<size_t>(nopt, 1), -1);
+	bool any_equal = false;
+	for (size_t b = 0; b < pl.blocks.size(); b++) any_equal = any_equal || c->blk_equal[b];
+	if (any_equal && nopt) {
+		if (nopt <= ((size_t)1 << 17)) D2H(c, win.data(), c->b_opt_fid.ptr, nopt * sizeof(long long));
+		else
+			for (size_t b = 0; b < pl.blocks.size(); b++)
+				if (c->blk_equal[b]) D2H(c, &win[pl.blocks[b].opt_off], (const long long *)c->b_opt_fid.ptr + pl.blocks[b].opt_off, sizeof(long long));
+		CK(cudaStreamSynchronize(st));
+	}
+	cnb_params cp;
+	memset(&cp, 0, sizeof(cp));
+	cp.max_parent_set = c->cache_P;
+	cp.parent_sizes = c->cache_psizes.empty() ? nullptr : c->cache_psizes.data();
+	RC(c->cache->walk(pl, &cp, c->any_never_kept ? c->never_kept.data() : nullptr, win.data(), &c->cache_ov));
+	const size_t n = c->cache_ov.size();
+	if (!n) return CNB_OK;
+	/* grouped by parent count, so that each group runs on its fast kernel (as the export does) */
+	std::vector<int32_t> perm(n);
+	for (size_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+	std::stable_sort(perm.begin(), perm.end(), [&](int32_t u, int32_t v) { return c->cache_ov[u].d < c->cache_ov[v].d; });
+	std::vector<int32_t> s_child(n), s_pars(n * CNB_MAXP, 0), s_nd(n);
+	c->cache_h_opt.resize(n);
+	c->cache_h_fid.resize(n);
+	c->cache_h_cx.resize(n);
+	c->cache_h_prior.resize(n);
+	int dmax = 0;
+	for (size_t k = 0; k < n; k++) {
+		const CnbOverride &ov = c->cache_ov[perm[k]];
+		s_child[k] = ov.child;
+		s_nd[k] = ov.d;
+		dmax = std::max(dmax, ov.d);
+		for (int q = 0; q < ov.d; q++) s_pars[k * CNB_MAXP + q] = ov.pars[q];
+		c->cache_h_opt[k] = ov.opt;
+		c->cache_h_fid[k] = ov.fid;
+		c->cache_h_cx[k] = ov.cx;
+		c->cache_h_prior[k] = ov.prior;
+	}
+	RC(score_explicit_groups(c, s_child, s_pars, s_nd, table_stride(c->max_cats, dmax), true));
+	RC(upload(c, c->b_ov_opt, c->cache_h_opt));
+	RC(upload(c, c->b_ov_fid, c->cache_h_fid));
+	RC(upload(c, c->b_ov_cx, c->cache_h_cx));
+	if (pl.has_prior) RC(upload(c, c->b_ov_prior, c->cache_h_prior));
+	RC(cnbk_patch_options(st, (int)n, (const long long *)c->b_ov_opt.ptr, (const long long *)c->b_ov_fid.ptr, (const int *)c->b_ov_cx.ptr,
+			pl.has_prior ? (const double *)c->b_ov_prior.ptr : nullptr, (const double *)c->b_ex_ll.ptr, (const double *)c->b_ex_score.ptr,
+			(double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr));
+	c->timing.kernel_launches++;
+	int ovf = 0;
+	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
+	CK(cudaStreamSynchronize(st));
+	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	return CNB_OK;
+}
+
 extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
@@ -1171,6 +1238,8 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 			(double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr,
 			(double *)c->b_sel_part_s.ptr, (long long *)c->b_sel_part_f.ptr));
 	c->timing.kernel_launches += 2;
+	if (c->cache) RC(apply_cache(c));
+	else c->cache_ov.clear();
 	CK(cudaEventRecord(c->ev[EV_SEL1], st));
 	/* DP state, double buffered */
 	size_t slots = (size_t)K + 1;
@@ -1376,7 +1445,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 	res->order_cats.push_back(pl.cats);
 	/* distinct families: one per option index, one per base family of a node */
 	std::vector<int32_t> fam_of_opt(nopt, -1), fam_of_base(N, -1);
-	std::vector<int32_t> ex_child, ex_pars, ex_nd;
+	std::vector<int32_t> ex_child, ex_pars, ex_nd, ov_of_fam;
 	auto add_family = [&](long long o, int node) -> int {
 		int32_t &slot = o >= 0 ? fam_of_opt[(size_t)o] : fam_of_base[node];
 		if (slot >= 0) return slot;
@@ -1400,6 +1469,13 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 			for (int k = 0; k < b.nfix; k++) ex_pars[base + k] = pl.lists[b.fix_off + k];
 			for (int k = 0; k < b.d - b.nfix; k++) ex_pars[base + b.nfix + k] = pl.lists[b.free_off + idx[k]];
 			ex_nd.push_back(b.d);
+			/* the score-cache model answered this candidate: its parents in the cached listing sequence (cnb_cache.h) */
+			auto ov = std::lower_bound(c->cache_ov.begin(), c->cache_ov.end(), o, [](const CnbOverride &a, long long v) { return a.opt < v; });
+			if (ov != c->cache_ov.end() && ov->opt == o) {
+				for (int k = 0; k < b.d; k++) ex_pars[base + k] = ov->pars[k];
+				ov_of_fam.resize(id + 1, -1);
+				ov_of_fam[id] = (int32_t)(ov - c->cache_ov.begin());
+			}
 		}
 		return id;
 	};
@@ -1485,6 +1561,7 @@ extern "C" int cnb_ctx_collect(cnb_ctx *c, cnb_result **out) {
 			fm.counts.assign(counts.begin() + k * stride, counts.begin() + k * stride + ts);
 			fm.loglik = ll[k];
 			fm.prior = prior[k];
+			if (pl.has_prior && f < ov_of_fam.size() && ov_of_fam[f] >= 0) fm.prior = c->cache_ov[ov_of_fam[f]].prior;   /* the prior the cache stored */
 			fm.ncount = ncount[k];
 		}
 		c->timing.collect_ms = ev_ms(c, EV_COL0, EV_COL1);

@@ -1,5 +1,6 @@
 /* cnb_cache.cpp -- the reference's score cache as a host-side model: see cnb_cache.h.  No CUDA calls. */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "cnb_cache.h"
@@ -7,18 +8,19 @@
 
 /* PRIMES_1000 (cache.cpp:35-54) is the list of the first 180 primes */
 static const uint32_t *first_primes() {
-	static uint32_t primes[180];
-	static bool done = false;
-	if (!done) {
-		int n = 0;
-		for (uint32_t v = 2; n < 180; v++) {
-			bool isp = true;
-			for (uint32_t q = 2; q * q <= v && isp; q++) isp = v % q != 0;
-			if (isp) primes[n++] = v;
+	struct Table {
+		uint32_t v[180];
+		Table() {
+			int n = 0;
+			for (uint32_t x = 2; n < 180; x++) {
+				bool isp = true;
+				for (uint32_t q = 2; q * q <= x && isp; q++) isp = x % q != 0;
+				if (isp) v[n++] = x;
+			}
 		}
-		done = true;
-	}
-	return primes;
+	};
+	static const Table t;                                  /* initialised once, also when several chains start at the same time */
+	return t.v;
 }
 
 /* table size and shift, chosen at the first store from the node count and maxParentSet in unsigned 32-bit arithmetic
@@ -122,6 +124,14 @@ double cnb_host_prior(const CnbPlan &pl, int child, const int32_t *pars, int d) 
 	t2 = t2 > 0 ? cnb_log(t2) : CNB_NEG_INF;
 	if (prior == CNB_NEG_INF || t2 == CNB_NEG_INF) return CNB_NEG_INF;
 	return prior + t2;
+}
+
+/* rUseCache as the reference reads it: off beyond 8 threads (rcatnet_sa.cpp:315-319, rcatnet_hist.cpp:205-209).
+ * CNB_SCORE_CACHE=off ignores the flag (the cache-off result, proposals of a step evaluated side by side). */
+bool cnb_cache_wanted(int use_cache, int num_threads) {
+	static const char *env = getenv("CNB_SCORE_CACHE");
+	if (env && (!strcmp(env, "off") || !strcmp(env, "0"))) return false;
+	return use_cache && num_threads <= 8;
 }
 
 static bool next_comb(int *idx, int k, int n) {

@@ -75,6 +75,7 @@ private:
 
 /* the Bernoulli edge prior of (child | pars) under the plan's order, on the host, operation for operation as dev_prior
  * (cnb_device.cuh) and catnet_search2.h:584-611 */
+bool cnb_cache_wanted(int use_cache, int num_threads);
 double cnb_host_prior(const CnbPlan &pl, int child, const int32_t *pars, int d);
 
 #endif

@@ -5,6 +5,7 @@
 #include <vector>
 #include "cnb_internal.h"
 #include "cnb_result.h"
+#include "cnb_cache.h"
 
 #define CNB_HIST_MAX_CELLS 16384   /* largest conditional table of the generic scorer (shared memory) */
 #define CNB_NEV_GROUPS 8
@@ -83,6 +84,16 @@ struct cnb_ctx {
 	std::vector<cnb_ctx *> siblings;
 	struct Crew *crew = nullptr;
 	unsigned long long data_epoch = 0, cloned_epoch = 0;   /* set_samples count of this context / of the data a sibling holds */
+	/* the reference's score cache (cnSearchSA / cnSearchHist with use_cache, cnb_cache.h): the driver's model of it; while it
+	 * is set, cnb_ctx_select_dp walks every planned order through it and patches the option table before the DP, and
+	 * cnb_ctx_collect lists the parents of the returned families in the cached sequence */
+	CnbScoreCache *cache = nullptr;
+	std::vector<CnbOverride> cache_ov;     /* overrides of the order evaluated last, ascending option slot */
+	std::vector<int32_t> cache_psizes;     /* the search's parentSizes (label space; empty = none) and maxParentSet, kept by cnb_ctx_plan */
+	int32_t cache_P = 0;
+	std::vector<int64_t> cache_h_opt, cache_h_fid;
+	std::vector<int32_t> cache_h_cx;
+	std::vector<double> cache_h_prior;
 	int dp_final = 0, tensor_batches = 0;
 	double host_ms[4] = {0, 0, 0, 0};   /* CNB_TRACE: host wall time of plan / score / select+dp, searches */
 	std::vector<int32_t> cats_lbl;
@@ -103,13 +114,15 @@ struct cnb_ctx {
 	/* scoring */
 	DevBuf b_scores, b_counts, b_ex_child, b_ex_pars, b_ex_nd, b_ex_ll, b_ex_prior, b_ex_score, b_ex_ncount, b_ex_counts;
 	/* selection + DP */
+	DevBuf b_ov_opt, b_ov_fid, b_ov_cx, b_ov_prior;
 	DevBuf b_base_v, b_opt_score, b_opt_cx, b_opt_fid, b_dp_exists, b_dp_L, b_dp_pfx, b_bp_opt, b_bp_src, b_sel, b_dp_nodes, b_dp_flags;
 	std::vector<DevBuf *> all_bufs() {
 		return {&b_counts_p, &b_pairs_ord, &b_vmin, &b_vmax, &b_cats_lbl, &b_flag, &b_codes, &b_planes_lbl, &b_keep_lbl, &b_planes, &b_keep,
 			&b_order, &b_cats, &b_lists, &b_blocks, &b_group_blocks, &b_groups, &b_edge, &b_blk_equal,
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
-			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3, &b_fix1};
+			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3, &b_fix1,
+			&b_ov_opt, &b_ov_fid, &b_ov_cx, &b_ov_prior};
 	}
 };
 

@@ -9,11 +9,15 @@
  *   weight      1, exp(loglik / (M N)) or exp(score / (M N)) (:510-515)
  *   histogram   hist[parent label][child label] += weight for every edge of the selected network (:517-528)
  * The reference evaluates the orders of a batch on pthreads and memoises family scores in a process-wide cache;
- * the device evaluates them one after the other and re-scores.  The uniform stream is drawn in the reference's order.
+ * the device evaluates them side by side and re-scores.  With use_cache (what R passes) a host model of the reference's
+ * cache walks the orders one after the other, so that the selected networks and their log-likelihoods -- the histogram's
+ * weights -- are those of the reference with its cache on (cnb_cache.h, cnb_sa.cpp).  The uniform stream is drawn in the
+ * reference's order.
  */
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <memory>
 #include <vector>
 #include "cnb_ctx.h"
 #include "cnb_rng.h"
@@ -86,7 +90,11 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 	/* the orders of a batch are independent: evaluated concurrently on sibling contexts when the data set is small */
 	std::vector<cnb_ctx *> lanes, where(nDrives, c);
 	RC(cnb_ctx_batch(c, nDrives, &lanes));
-	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1;
+	std::unique_ptr<CnbScoreCache> cache;
+	if (cnb_cache_wanted(hp->use_cache, nDrives)) cache.reset(new CnbScoreCache(N, p->max_parent_set));
+	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1 && !cache;
+	struct CacheGuard { cnb_ctx *c; ~CacheGuard() { c->cache = nullptr; } } guard{c};
+	c->cache = cache.get();                      /* every order passes through the model, one after the other */
 	std::vector<const int32_t *> todo_orders;
 	while (niter < hp->max_iter) {
 		for (int n = 0; n < nDrives; n++) {

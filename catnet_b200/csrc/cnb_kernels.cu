@@ -905,6 +905,22 @@ __global__ void k_select_combine(DevData Dt, const CnbGroup *__restrict__ groups
 	opt_cx[b.opt_off] = cx;
 }
 
+/* The reference's score cache as seen by the option table (cnb_cache.h): candidate i sits in option slot opt[i]; its
+ * log-likelihood ex_ll[i] was re-scored with the parents in the cached listing sequence; its term is that plus the prior
+ * the cache stored with the entry (prior == null: no edge priors, the explicit scorer's score as it is).  fid[i] >= 0
+ * (equal-categories path): the slot's winner becomes the cached parent set. */
+__global__ void k_patch_options(int n, const long long *__restrict__ opt, const long long *__restrict__ fid,
+		const int *__restrict__ cx, const double *__restrict__ prior, const double *__restrict__ ex_ll,
+		const double *__restrict__ ex_score, double *__restrict__ opt_score, int *__restrict__ opt_cx,
+		long long *__restrict__ opt_fid) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const long long o = opt[i];
+	opt_score[o] = prior ? __dadd_rn(ex_ll[i], prior[i]) : ex_score[i];      /* fLogLik += priorLogLik (catnet_search2.h:610) */
+	opt_cx[o] = cx[i];
+	if (fid[i] >= 0) opt_fid[o] = fid[i];
+}
+
 /* ------------------------------------------------------------------ K5: DP over complexity ---- */
 /* loglik() of a network = sum over nodes in index order of (node loglik + prior), re-summed from zero
  * (catnet_class.h:469-485).  pfx = that sum over nodes < c, f = the candidate's term for node c. */
@@ -1756,6 +1772,14 @@ int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup 
 	CK(cudaGetLastError());
 	k_select_combine<<<(nblocks + 127) / 128, 128, 0, st>>>(Dt, groups, blk_equal, blk_chunk0, nblocks, part_score, part_fid,
 			opt_score, opt_cx, opt_fid);
+	CK(cudaGetLastError());
+	return CNB_OK;
+}
+
+int cnbk_patch_options(cudaStream_t st, int n, const long long *opt, const long long *fid, const int *cx, const double *prior,
+		const double *ex_ll, const double *ex_score, double *opt_score, int *opt_cx, long long *opt_fid) {
+	if (n <= 0) return CNB_OK;
+	k_patch_options<<<(n + 127) / 128, 128, 0, st>>>(n, opt, fid, cx, prior, ex_ll, ex_score, opt_score, opt_cx, opt_fid);
 	CK(cudaGetLastError());
 	return CNB_OK;
 }

@@ -127,6 +127,9 @@ int cnbk_select_chunk(void);
 int cnbk_select(cudaStream_t st, const DevData &Dt, int nblocks, const CnbGroup *groups, const int *blk_equal,
 		const int2 *chunks, int nchunks, const int *blk_chunk0, const double *scores, long long seg_len, double *opt_score,
 		int *opt_cx, long long *opt_fid, double *part_score, long long *part_fid);
+/* overrides of the score-cache model into the option table (cnb_cache.h) */
+int cnbk_patch_options(cudaStream_t st, int n, const long long *opt, const long long *fid, const int *cx, const double *prior,
+		const double *ex_ll, const double *ex_score, double *opt_score, int *opt_cx, long long *opt_fid);
 int cnbk_dp_init(cudaStream_t st, const DpState &S, int base_complexity, const double *base_v, int N);
 int cnbk_dp_node(cudaStream_t st, const DpState &cur, const DpState &nxt, int c, int N, int base_cx_c,
 		const double *base_v, long long opt_begin, long long opt_end, const double *opt_score, const int *opt_cx,

@@ -353,6 +353,11 @@ extern "C" int cnb_mctx_search_hist(cnb_mctx *m, const cnb_params *p, const cnb_
 	const int N = m->N, A = m->loaded;
 	m->active = A;
 	const int nDrives = hp->num_threads < 1 ? 1 : hp->num_threads;
+	if (cnb_cache_wanted(hp->use_cache, nDrives)) {
+		/* the reference's score cache is one table that the orders pass through one after the other (cnb_cache.h): one device */
+		m->active = 1;
+		return cnb_ctx_search_hist(m->cs[0], p, hp, hist, iterations);
+	}
 	memset(hist, 0, sizeof(double) * (size_t)N * N);
 	CnbRng rng(hp->seed ? hp->seed : cnb_default_seed(), hp->unif, hp->unif_ctx);
 	cnb_params q0 = *p;

@@ -7,8 +7,14 @@
  *   acceptance  first evaluation unconditionally (:714-737), then Metropolis (:738-798); the first accepted
  *               proposal of a batch wins and the later ones are discarded (:655-659, :784-786)
  *   cooling     every tempCheckOrders iterations (:807-814)
- * The reference evaluates the numThreads proposals of a batch on pthreads; the device evaluates them one after the
- * other and skips the ones that can no longer matter.  The uniform stream is drawn in the reference's order.
+ * The reference evaluates the numThreads proposals of a batch on pthreads; the device evaluates them side by side on
+ * sibling contexts.  The uniform stream is drawn in the reference's order.
+ *   score cache with use_cache (what R passes): the reference memoises family scores in a process-wide table and a hit
+ *               returns the family as it was listed and summed under the order that stored it (cache.cpp:142-216).  A host
+ *               model of that table (cnb_cache.h) walks every evaluated order; the device re-scores the candidates the cache
+ *               answers differently.  Every proposal of a step passes through the cache, accepted or not, one after the
+ *               other (the reference's threads interleave their stores as they come: with more than one thread its own
+ *               result depends on timing, and this is the interleaving "proposal after proposal").
  */
 #include <stdio.h>
 #include <math.h>
@@ -137,9 +143,22 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 	 * data set is small enough to copy; the decisions below then look at them in proposal order, exactly as before */
 	std::vector<cnb_ctx *> lanes;
 	RC(cnb_ctx_batch(c, nDrives, &lanes));
-	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1;
+	std::unique_ptr<CnbScoreCache> cache;
+	if (cnb_cache_wanted(sa->use_cache, nDrives)) cache.reset(new CnbScoreCache(N, p->max_parent_set));
+	const bool have_lanes = (int)lanes.size() >= nDrives && nDrives > 1;
+	const bool batched = have_lanes && !cache;
+	/* cache mode without sibling contexts and several proposals per step: each evaluation is exported before the next one
+	 * overwrites the context */
+	const bool eager = cache && !have_lanes && nDrives > 1;
 	std::vector<cnb_ctx *> where(nDrives, c);
 	std::vector<const int32_t *> todo_orders;
+	std::vector<std::unique_ptr<cnb_result>> pre(nDrives);
+	std::vector<std::vector<int32_t>> pre_cx(nDrives);
+	std::vector<std::vector<double>> pre_ll(nDrives);
+	struct CacheGuard {                              /* no context keeps a pointer to the model past this call */
+		cnb_ctx *c; std::vector<cnb_ctx *> &l;
+		~CacheGuard() { c->cache = nullptr; for (cnb_ctx *s : l) s->cache = nullptr; }
+	} guard{c, lanes};
 
 	while (niter < sa->max_iter) {
 		for (int n = 0; n < nDrives; n++) {
@@ -162,16 +181,36 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 				if (!skip[n]) { where[n] = lanes[t++]; todo_orders.push_back(test[n].data()); }
 			RC(cnb_ctx_batch_run(c, lanes, &q, t, todo_orders.data()));
 		}
+		if (cache) {
+			/* every proposal of the step goes through the cache, in proposal order, whether or not an earlier one is accepted */
+			int t = 0;
+			for (int n = 0; n < nDrives; n++) {
+				if (skip[n]) continue;
+				cnb_ctx *ce = have_lanes ? lanes[t++] : c;
+				where[n] = ce;
+				ce->cache = cache.get();
+				q.order = test[n].data();
+				RC(cnb_ctx_search_light(ce, &q));
+				ce->cache = nullptr;
+				if (eager) {
+					RC(cnb_ctx_dp_summary(ce, &pre_cx[n], &pre_ll[n]));
+					cnb_result *r = nullptr;
+					if (!pre_cx[n].empty()) RC(cnb_ctx_collect(ce, &r));
+					pre[n].reset(r);
+				}
+			}
+		}
 		for (int n = 0; n < nDrives; n++) {
 			if (skip[n]) continue;
 			if (stepaccept > 0) continue;                /* a previous drive was accepted: discard the rest */
 			nstop = 0;
-			cnb_ctx *ce = batched ? where[n] : c;        /* the context that holds this proposal's evaluation */
-			if (!batched) {
+			cnb_ctx *ce = (batched || cache) ? where[n] : c;   /* the context that holds this proposal's evaluation */
+			if (!batched && !cache) {
 				q.order = test[n].data();
 				RC(cnb_ctx_search_light(c, &q));
 			}
-			RC(cnb_ctx_dp_summary(ce, &cx, &ll));
+			if (eager) { cx = pre_cx[n]; ll = pre_ll[n]; }
+			else RC(cnb_ctx_dp_summary(ce, &cx, &ll));
 			if (cx.empty()) continue;
 			int pick = -1;
 			double fLogLik = -(double)FLT_MAX;
@@ -219,7 +258,8 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 				haveOpt = true;
 				fOptLogLik = fLogLik;
 				cnb_result *r = nullptr;
-				RC(cnb_ctx_collect(ce, &r));
+				if (eager) r = pre[n].release();
+				else RC(cnb_ctx_collect(ce, &r));
 				best.reset(r);
 				optOrder = test[n];
 			}
@@ -266,9 +306,10 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 	return rc;
 }
 
-/* The reference keeps a process-global score cache between .Call's (cache.cpp:58-76); the device re-scores every
- * order from the resident bit planes, so there are no scores to release.  What the library does keep between one-shot
- * calls is an idle context per device with its device buffers (cnb_api.cu: cnb_ctx_park); this frees them. */
+/* The reference keeps a process-global score cache between .Call's (cache.cpp:58-76) and R releases it before every
+ * search (R/catnet.search.R:204,279, R/catnet.histo.R:119): the model of it (cnb_cache.h) lives for one cnb_search_sa /
+ * cnb_search_hist call only, which is the same thing.  What the library does keep between one-shot calls is an idle
+ * context per device with its device buffers (cnb_api.cu: cnb_ctx_park); this frees them. */
 extern "C" void cnb_release_cache(void) { cnb_multi_release(); cnb_pool_release(); }
 /* ccnSetSeed (R/catnet.def.R:743-747): the seed of searches that pass none (cnb_sa_params.seed / cnb_hist_params.seed = 0) */
 static int32_t g_seed = 0;

@@ -231,7 +231,8 @@ void fail(int rc) {
 
 extern "C" {
 
-/* catnetOptimalNetsForOrder (catnet_rexport.h:36-40); rUseCache is accepted and ignored: the device re-scores */
+/* catnetOptimalNetsForOrder (catnet_rexport.h:36-40); rUseCache changes nothing for ONE order: R releases the cache before
+ * the call (R/catnet.search.R:204) and no key comes up twice inside an order (it also passes FALSE, :214) */
 SEXP ccnOptimalNetsForOrder(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes,
 		SEXP rMaxComplexity, SEXP rOrder, SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool,
 		SEXP rMatEdgeLiks, SEXP rUseCache, SEXP rEcho) {

@@ -203,3 +203,43 @@ def ref_args(kw):
     return dict(order=kw["order"], perturbations=kw.get("perturbations"), parent_sizes=kw.get("parent_sizes"),
                 num_cats=kw.get("num_cats"), parents_pool=kw.get("parents_pool"),
                 fixed_parents=kw.get("fixed_parents"), edge_prob=kw.get("edge_prob"))
+
+# cnSearchSA / cnSearchHist with the reference's score cache ON (what R passes, R/catnet.search.R:293-294): fixtures from the
+# compiled reference with ONE thread (with more its stores interleave by timing).  big = enough complete samples for the
+# tensor-core tiles (the families the cache answers are re-scored in their cached listing from the resident tile tables).
+SA_CACHE_SEEDS = list(range(24)) + [100, 101, 102, 103]
+
+
+def sa_cache_problem(seed):
+    """-> (samples, cats, P, K, start_order, sa kwargs (num_threads = 1 + seed % 3), search kwargs, never_kept or None)"""
+    from helpers import random_problem
+    rng = np.random.default_rng(seed)
+    big = seed >= 100
+    n, m = int(rng.integers(3, 11)), int(rng.integers(8, 300))
+    if big:
+        n, m = 9 + seed % 3, 8200 + 13 * (seed % 4)
+    s, c = random_problem(seed, n, m, [None, 2, 3, None][seed % 4] if not big else [None, 4, 3, None][seed % 4],
+                          na_frac=0.0 if big else [0, 0.1][seed % 2])
+    kw, never = {}, None
+    if seed % 3 == 0 and not big:
+        pert = (rng.random(s.shape) < 0.2).astype(np.int32)
+        if seed % 6 == 0:
+            pert[:, int(rng.integers(0, n))] = 1              # a node perturbed in every sample
+        kw["perturbations"] = pert
+        never = (pert.min(axis=0) > 0).astype(np.uint8)
+    if seed % 7 == 0:
+        kw["parents_pool"] = [sorted((rng.choice(n, size=int(rng.integers(0, n)), replace=False) + 1).tolist()) for _ in range(n)]
+    if seed % 11 == 0:
+        kw["fixed_parents"] = [sorted((rng.choice(n, size=int(rng.integers(0, 2)), replace=False) + 1).tolist()) for _ in range(n)]
+    if seed % 5 == 0:
+        kw["edge_prob"] = 0.1 + 0.8 * rng.random((n, n))
+    if seed % 13 == 0:
+        kw["parent_sizes"] = rng.integers(0, 4, size=n).astype(np.int32)
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0][seed % 3], temp_cool_fact=0.9,
+              temp_check_orders=int(rng.integers(2, 8)), max_iter=int(rng.integers(30, 90)) if not big else 24,
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=1e-10,
+              num_threads=1 + seed % 3, seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    P = 2 + (seed % 4 == 0)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** P
+    return s, c, P, K, start, sa, kw, never

@@ -144,10 +144,14 @@ int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out
 	if (sa->dir_prob) return not_in_mock("cnb_search_sa with dirProb");
 	orc_set_seed(sa->seed);
 	if (sa->unif) orc_set_unif(sa->unif, sa->unif_ctx);      /* the shim's R generator, draw for draw */
+	orc_cache_release();                                     /* R releases the cache before the call; rUseCache switches it on */
+	orc_set_cache(sa->use_cache);
 	orc_result *h = orc_search_sa(N, p->num_samples, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
 			p->max_complexity, p->num_cats, p->parents_pool, p->fixed_parents, p->edge_prob, sa->select_mode, sa->start_order,
 			sa->temp_start, sa->temp_cool_fact, sa->temp_check_orders, sa->max_iter, sa->order_shuffles, sa->stop_diff,
 			sa->num_threads);
+	orc_set_cache(0);
+	orc_cache_release();
 	if (!h) { g_err = "oracle: search failed"; return CNB_ERR_PARAM; }
 	cnb_result *r = new cnb_result;
 	g_live_results++;
@@ -168,9 +172,13 @@ int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_result **out
 int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, double *hist, int32_t *iterations) {
 	orc_set_seed(hp->seed);
 	if (hp->unif) orc_set_unif(hp->unif, hp->unif_ctx);
+	orc_cache_release();
+	orc_set_cache(hp->use_cache);
 	int it = orc_search_hist(p->num_nodes, p->num_samples, p->samples, p->perturbations, p->max_parent_set, p->parent_sizes,
 			p->max_complexity, p->num_cats, p->parents_pool, p->fixed_parents, hp->score, hp->weight, hp->max_iter,
 			hp->num_threads, hist);
+	orc_set_cache(0);
+	orc_cache_release();
 	if (it < 0) { g_err = "oracle: histogram failed"; return CNB_ERR_PARAM; }
 	if (iterations) *iterations = it;
 	return CNB_OK;

@@ -1159,3 +1159,94 @@ def test_errors_are_codes_not_crashes(abi):
     assert "Invalid nodeOrder" in str(e.value)
     with pytest.raises(abi.CnbError):
         abi.search_order(s, max_parent_set=2, max_complexity=100, num_cats=c, device=99)
+
+# ---------------------------------------------------------------- the reference's score cache (use_cache, what R passes)
+def _strict_nets(a, b):
+    x, y = {n["complexity"]: n for n in a}, {n["complexity"]: n for n in b}
+    assert sorted(x) == sorted(y)
+    for cx in x:
+        u, v = x[cx], y[cx]
+        assert u["parents"] == v["parents"], (cx, u["parents"], v["parents"])
+        assert u["loglik"] == v["loglik"], (cx, u["loglik"], v["loglik"])
+        assert list(u["node_loglik"]) == list(v["node_loglik"]) and list(u["node_prior"]) == list(v["node_prior"]), cx
+        assert u["sample_sizes"] == v["sample_sizes"]
+        if len(u["probs"]) and len(v["probs"]):
+            assert all(np.array_equal(p, q) for p, q in zip(u["probs"], v["probs"])), cx
+
+
+@pytest.mark.parametrize("seed", __import__("cases").SA_CACHE_SEEDS)
+def test_sa_with_score_cache_matches_reference(abi, seed):
+    """cnSearchSA / cnSearchHist with use_cache against the COMPILED REFERENCE run with its cache ON (one thread): the
+    trajectory, the parents in the sequence the reference lists them in (that of the order which first scored the family),
+    the log-likelihoods summed in that sequence, the histogram weighted by them (csrc/cnb_cache.h)"""
+    from cases import sa_cache_problem
+    s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+    g = load_golden("ref_search_sa_cache")["seed%d" % seed]
+    r = abi.search_sa(s, dict(sa, num_threads=1, start_order=start, use_cache=True), max_parent_set=P, max_complexity=K,
+                      num_cats=c, **kw)
+    assert [int(v) for v in r["order"]] == g["order"]
+    assert (r["niter"], r["naccept"]) == (g["niter"], g["naccept"])
+    assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
+    assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
+    compare_golden(r["nets"], g["nets"])
+    hk = dict(score=seed % 3, weight=1 + seed % 2, max_iter=10, num_threads=1, seed=sa["seed"], use_cache=True)
+    kh = {k: v for k, v in kw.items() if k != "edge_prob"}
+    h, it = abi.search_hist(s, hk, max_parent_set=2, max_complexity=K, num_cats=c, **kh)
+    assert it == g["hist_iterations"]
+    assert h.tolist() == [[float.fromhex(v) for v in row] for row in g["hist"]]
+
+
+@pytest.mark.parametrize("seed", [s for s in __import__("cases").SA_CACHE_SEEDS if s % 3] + list(range(30, 48)))
+def test_sa_with_score_cache_and_threads_vs_oracle(abi, port, seed):
+    """several proposals per step pass through the cache one after the other (the reference's threads store as they come:
+    its own result depends on timing there) -- against the restatement, which takes them in the same sequence; tables and
+    priors included"""
+    from cases import sa_cache_problem
+    s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+    r = abi.search_sa(s, dict(sa, start_order=start, use_cache=True), want_probs=True, max_parent_set=P, max_complexity=K,
+                      num_cats=c, **kw)
+    o = port.search_sa(s, P, K, start, num_cats=c, use_cache=True, want_probs=True, **sa, **kw)
+    assert np.array_equal(r["order"], o["order"]) and r["niter"] == o["niter"] and r["naccept"] == o["naccept"]
+    assert np.array_equal(r["trace"], o["trace"]) and np.array_equal(r["trace_accept"], o["trace_accept"])
+    _strict_nets(r["nets"], o["nets"])
+    hk = dict(score=seed % 3, weight=seed % 3, max_iter=9, num_threads=1 + seed % 4, seed=sa["seed"])
+    kh = {k: v for k, v in kw.items() if k != "edge_prob"}
+    h, it = abi.search_hist(s, dict(hk, use_cache=True), max_parent_set=2, max_complexity=K, num_cats=c, **kh)
+    h2, it2 = port.search_hist(s, 2, K, use_cache=True, num_cats=c, **hk, **kh)
+    assert it == it2 and np.array_equal(h, h2)
+
+
+def test_sa_score_cache_switch(abi, monkeypatch):
+    """use_cache = 0 is the cache-off result; on the fixtures that differ, use_cache = 1 is not"""
+    from cases import sa_cache_problem
+    g = load_golden("ref_search_sa_cache")
+    seed = next(s for s in __import__("cases").SA_CACHE_SEEDS if g["seed%d" % s]["differs_from_cache_off"])
+    s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+    args = dict(max_parent_set=P, max_complexity=K, num_cats=c, **kw)
+    on = abi.search_sa(s, dict(sa, num_threads=1, start_order=start, use_cache=True), want_probs=True, **args)
+    off = abi.search_sa(s, dict(sa, num_threads=1, start_order=start, use_cache=False), want_probs=True, **args)
+    differs = (not np.array_equal(on["trace"], off["trace"]) or [n["parents"] for n in on["nets"]] != [n["parents"] for n in off["nets"]]
+               or [n["loglik"] for n in on["nets"]] != [n["loglik"] for n in off["nets"]])
+    assert differs
+
+
+@pytest.mark.parametrize("m,cats,na", [(300, None, 0.05), (8300, None, 0.0), (8300, 4, 0.0), (8300, 3, 0.0), (9000, None, 0.02)])
+def test_family_scores_follow_the_listing(abi, port, m, cats, na):
+    """an explicit family is counted and summed in the sequence its parents are LISTED in (first listed parent most
+    significant), whichever kernel scores it: what the score-cache overrides and cnSetProb rely on -- every permutation
+    of 2 and 3 parents, small data (bit planes) and enough complete samples for the pair / three-way tables"""
+    import itertools
+    s, c = random_problem(77, 8, m, cats, na)
+    s0 = np.where(s < 1, 99, s - 1).astype(np.int32)
+    with abi.Context(0) as ctx:
+        ctx.set_samples(s, num_cats=c)
+        for d in (1, 2, 3):
+            fams = []
+            for child in (7, 3, 5):
+                base = [q for q in range(8) if q != child][:d + 1][-d:]
+                for perm in itertools.permutations(base):
+                    fams.append((child, list(perm)))
+            counts, ll, nc = ctx.family_scores([f[0] for f in fams], np.array([f[1] for f in fams], dtype=np.int32))
+            for i, (child, pars) in enumerate(fams):
+                rc, rll, rnc = port.family_score(s0, c, child, pars)
+                assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)) and ll[i] == rll and nc[i] == rnc, (d, child, pars)

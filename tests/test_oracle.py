@@ -204,3 +204,27 @@ def test_port_samples_match_reference(ref):
         a, ca = r.net_samples(cats, parents, probs, m, pert, na, seed)
         b, cb = port.net_samples(cats, parents, probs, m, pert, na, seed)
         assert ca == cb and np.array_equal(a, b)
+
+@pytest.mark.parametrize("seed", __import__("cases").SA_CACHE_SEEDS)
+def test_sa_and_hist_with_the_score_cache_match_golden(seed):
+    """the restated score cache (cache_get / cache_set in oracle/catnet_oracle.c) against the compiled reference run with
+    its cache ON and one thread: trajectory, parents in their LISTED sequence, every node's log-likelihood, histogram"""
+    from cases import sa_cache_problem
+    s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+    g = load_golden("ref_search_sa_cache")["seed%d" % seed]
+    r = port.search_sa(s, P, K, start, num_cats=c, use_cache=True, **dict(sa, num_threads=1), **kw)
+    assert [int(v) for v in r["order"]] == g["order"]
+    assert (r["niter"], r["naccept"]) == (g["niter"], g["naccept"])
+    assert [float(v) for v in r["trace"]] == [float.fromhex(v) for v in g["trace"]]
+    assert [int(v) for v in r["trace_accept"]] == g["trace_accept"]
+    compare_golden(r["nets"], g["nets"])
+    hk = dict(score=seed % 3, weight=1 + seed % 2, max_iter=10, num_threads=1, seed=sa["seed"])
+    kh = {k: v for k, v in kw.items() if k != "edge_prob"}
+    h, it = port.search_hist(s, 2, K, use_cache=True, num_cats=c, **hk, **kh)
+    assert it == g["hist_iterations"]
+    assert h.tolist() == [[float.fromhex(v) for v in row] for row in g["hist"]]
+    if g["differs_from_cache_off"]:                              # the fixture is not the cache-off result in disguise
+        off = port.search_sa(s, P, K, start, num_cats=c, use_cache=False, **dict(sa, num_threads=1), **kw)
+        assert ([float(v) for v in off["trace"]] != [float.fromhex(v) for v in g["trace"]]
+                or [n["parents"] for n in off["nets"]] != [n["parents"] for n in g["nets"]]
+                or [n["loglik"] for n in off["nets"]] != [float.fromhex(n["loglik"]) for n in g["nets"]])

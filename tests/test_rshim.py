@@ -229,7 +229,7 @@ def check_sa_and_histogram(r, port, seed):
                  r.logical(True), r.logical(False))
     r.L.mr_set_rng(50 + seed)
     theirs = port.search_sa(s, 2, n * 20, start, select_mode={"AIC": 1, "BIC": 2}.get(model, 0), unif=r_unif, num_cats=c,
-                            want_probs=True, **SA_KW)
+                            want_probs=True, use_cache=True, **SA_KW)   # R passes TRUE (R/catnet.search.R:293-294), so does the call above
     nets = [r.catnetwork(e) for e in r.elts(out)]
     check_networks(nets, theirs["nets"], [int(v) for v in theirs["order"]], c, names)
     # the parent histogram: numeric vector N*N that R reshapes with matrix(vhisto, nrow = numnodes)
@@ -239,7 +239,7 @@ def check_sa_and_histogram(r, port, seed):
                         r.logical(True), r.logical(False)))
     r.L.mr_set_rng(90 + seed)
     hist, _ = port.search_hist(s, 2, n * 20, score={"AIC": 1, "BIC": 2}.get(model, 0), weight=seed % 3, max_iter=8,
-                               num_threads=2, unif=r_unif, num_cats=c)
+                               num_threads=2, unif=r_unif, num_cats=c, use_cache=True)
     assert np.array_equal(vh.reshape(n, n), hist)
 
 

@@ -41,6 +41,32 @@ def pack_nets(nets, with_nodes=True):
     return out
 
 
+def make_sa_cache():
+    """cnSearchSA and cnSearchHist of the compiled reference with its score cache ON and one thread (the deterministic case):
+    trajectory, networks with their parents in the LISTED sequence, every node's log-likelihood, the histogram"""
+    from cases import SA_CACHE_SEEDS, sa_cache_problem
+    out = {}
+    for seed in SA_CACHE_SEEDS:
+        s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+        sa1 = dict(sa, num_threads=1)
+        r = ref.search_sa(s, P, K, start, num_cats=c, use_cache=True, want_probs=False, **sa1, **kw)
+        off = ref.search_sa(s, P, K, start, num_cats=c, use_cache=False, want_probs=False, **sa1, **kw)
+        differs = (not np.array_equal(r["trace"], off["trace"])
+                   or [n["parents"] for n in r["nets"]] != [n["parents"] for n in off["nets"]]
+                   or [n["loglik"] for n in r["nets"]] != [n["loglik"] for n in off["nets"]])
+        hk = dict(score=seed % 3, weight=1 + seed % 2, max_iter=10, num_threads=1, seed=sa["seed"])
+        kh = {k: v for k, v in kw.items() if k != "edge_prob"}
+        h, it = ref.search_hist(s, 2, K, use_cache=True, num_cats=c, **hk, **kh)
+        out["seed%d" % seed] = {"order": [int(v) for v in r["order"]], "niter": r["niter"], "naccept": r["naccept"],
+                                "trace": [float(v).hex() for v in r["trace"]],
+                                "trace_accept": [int(v) for v in r["trace_accept"]],
+                                "nets": pack_nets(r["nets"]), "differs_from_cache_off": bool(differs),
+                                "hist_iterations": it, "hist": [[float(v).hex() for v in row] for row in h]}
+    dump(out, "ref_search_sa_cache.json")
+    print("ref_search_sa_cache.json", len(out), "cases,", sum(v["differs_from_cache_off"] for v in out.values()),
+          "of them differ from the cache-off run")
+
+
 def make_pairwise():
     """catnetEntropyPairwise / KLpairwise / PearsonPairwise / EntropyOrder of the reference's own catnet_entropy.cpp
     (oracle/_ref/libcatnet_ref_pairwise.so)"""
@@ -100,6 +126,8 @@ def main():
         return make_pairwise()
     if "--only-network" in sys.argv:
         return make_network()
+    if "--only-cache" in sys.argv:
+        return make_sa_cache()
     fam = []
     for seed, cats, na in [(1, None, 0.0), (2, 3, 0.1), (3, 2, 0.0), (4, 4, 0.05)]:
         s, c = random_problem(seed, 8, 150, cats, na)
@@ -146,6 +174,7 @@ def main():
         hist["seed%d" % case["seed"]] = {"iterations": it, "hist": [[float(v).hex() for v in row] for row in h]}
     dump(hist, "ref_search_hist.json")
     print("ref_search_hist.json", {k: v["iterations"] for k, v in hist.items()})
+    make_sa_cache()
     make_pairwise()
     make_network()
     make_samples()
