@@ -16,6 +16,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <memory>
 #include <vector>
@@ -134,6 +135,8 @@ extern "C" int cnb_search_hist(const cnb_params *p, const cnb_hist_params *hp, d
 	if (cnb_multi_devices(p) > 1 || cnb_multi_devices(p) < -1) return cnb_multi_search_hist(p, hp, hist, iterations);
 	cnb_ctx *c = nullptr;
 	RC(cnb_ctx_acquire(p->device, &c));
+	const char *fb = getenv("CNB_FORCE_BITS");                /* kernel-selection switches for fuzzing (cnb_search_order, cnb_api.cu) */
+	cnb_ctx_force_generic(c, fb ? atoi(fb) : 0);
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	if (rc == CNB_OK) rc = cnb_ctx_search_hist(c, p, hp, hist, iterations);
 	cnb_ctx_park(c);

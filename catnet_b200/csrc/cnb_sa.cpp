@@ -17,6 +17,7 @@
  *               result depends on timing, and this is the interleaving "proposal after proposal").
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <memory>
@@ -294,6 +295,8 @@ extern "C" int cnb_search_sa(const cnb_params *p, const cnb_sa_params *sa, cnb_r
 		return std::chrono::duration<double, std::milli>(b - a).count(); };
 	auto t0 = now();
 	RC(cnb_ctx_acquire(p->device, &c));
+	const char *fb = getenv("CNB_FORCE_BITS");                /* kernel-selection switches for fuzzing (cnb_search_order, cnb_api.cu) */
+	cnb_ctx_force_generic(c, fb ? atoi(fb) : 0);
 	auto t1 = now();
 	int rc = cnb_ctx_set_samples(c, p->num_nodes, p->num_samples, p->samples, p->perturbations, p->num_cats);
 	auto t2 = now();
