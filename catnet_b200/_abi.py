@@ -127,7 +127,7 @@ def lib():
         "cnb_last_call_timing": (i32, [P(Timing)]),
         "cnb_ctx_force_generic": (i32, [vp, i32]),
         "cnb_tile_selftest": (C.c_int64, [i32]),
-        "cnb_cache_trace": (C.c_int64, [P(Params), vp, vp, i32, vp, vp, i32, vp, vp]),
+        "cnb_cache_trace": (C.c_int64, [P(Params), vp, vp, i32, vp, vp, i32, i32, vp, vp]),
         "cnb_tile_selftest_full": (C.c_int64, [i32]),
         "cnb_tile3_selftest": (C.c_int64, [i32, i32]),
         "cnb_tile_selftest_geo": (C.c_int64, [i32, i32]),

@@ -46,6 +46,19 @@ void CnbScoreCache::init() {
 	if (nl < 1) nl = 1;                                   /* InitializeCache (cache.cpp:78-88) */
 	ncache = nl;
 	if (ncache <= (1u << 24)) flat.assign(ncache, 0);
+	static const char *nd = getenv("CNB_CACHE_NO_DENSE");
+	dense_on = N <= 160 && !nd;
+	if (dense_on) {
+		dense1.assign((size_t)N * N, 0);
+		dense2.assign((size_t)N * N * N, 0);
+	}
+}
+
+int32_t *CnbScoreCache::dense_cell(const int32_t *pool, int npool, int node, int npars) {
+	if (!dense_on || npool != npars) return nullptr;
+	if (npars == 1) return &dense1[(size_t)(node - 1) * N + pool[0] - 1];
+	if (npars == 2) return &dense2[((size_t)(node - 1) * N + pool[0] - 1) * N + pool[1] - 1];
+	return nullptr;
 }
 
 /* cache.cpp:174-184 (= :296-306) */
@@ -64,6 +77,11 @@ uint32_t CnbScoreCache::slot_of(const int32_t *pool, int npool, int node, int np
 CnbScoreCache::Entry *CnbScoreCache::lookup(const int32_t *pool, int npool, int node, int npars) {
 	st.lookups++;
 	if (!ncache) return nullptr;                          /* nothing stored yet (cache.cpp:152-153) */
+	if (const int32_t *cell = dense_cell(pool, npool, node, npars)) {
+		if (!*cell) return nullptr;
+		st.hits++;
+		return &entries[*cell - 1];
+	}
 	const uint32_t s = slot_of(pool, npool, node, npars);
 	int32_t id = 0;
 	if (!flat.empty()) id = flat[s];
@@ -74,7 +92,7 @@ CnbScoreCache::Entry *CnbScoreCache::lookup(const int32_t *pool, int npool, int 
 	if (!id) return nullptr;
 	Entry &e = entries[id - 1];
 	if (e.node != node || e.npars != npars || e.npool != npool) return nullptr;
-	if (memcmp(&arena[e.pool_off], pool, (size_t)npool * sizeof(int32_t))) return nullptr;
+	if (memcmp(pool_of(e), pool, (size_t)npool * sizeof(int32_t))) return nullptr;
 	st.hits++;
 	return &e;
 }
@@ -91,19 +109,24 @@ CnbScoreCache::Entry *CnbScoreCache::store(const int32_t *pool, int npool, int n
 	if (*ref) {
 		e = &entries[*ref - 1];
 		st.evictions++;
-		if (e->npool < npool) { e->pool_off = (int32_t)arena.size(); arena.resize(arena.size() + npool); }
+		if (int32_t *gone = dense_cell(pool_of(*e), e->npool, e->node, e->npars)) *gone = 0;
+		if (e->pool_off >= 0 && npool <= CNB_MAXP) { free_blocks.push_back(e->pool_off); e->pool_off = -1; }
 	} else {
 		entries.emplace_back();
 		*ref = (int32_t)entries.size();
 		e = &entries.back();
-		e->pool_off = (int32_t)arena.size();
-		arena.resize(arena.size() + npool);
+		e->pool_off = -1;
+	}
+	if (npool > CNB_MAXP && e->pool_off < 0) {
+		if (!free_blocks.empty()) { e->pool_off = free_blocks.back(); free_blocks.pop_back(); }
+		else { e->pool_off = (int32_t)arena.size(); arena.resize(arena.size() + N); }
 	}
 	e->node = node;
 	e->npars = npars;
 	e->npool = npool;
-	memcpy(&arena[e->pool_off], pool, (size_t)npool * sizeof(int32_t));
+	memcpy(e->pool_off < 0 ? e->pool_small : &arena[e->pool_off], pool, (size_t)npool * sizeof(int32_t));
 	e->prior = 0;
+	if (int32_t *cell = dense_cell(pool, npool, node, npars)) *cell = *ref;
 	return e;
 }
 
@@ -236,7 +259,23 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 				for (int j = 0; j < nf; j++) listing[j] = fix[j];
 				for (int j = 0; j < kk; j++) listing[nf + j] = fre[idx[j]];
 				for (int j = 0; j < d; j++) pool[j] = pl.order[listing[j]] + 1;
-				std::sort(pool.begin(), pool.begin() + d);
+				if (d == 2) { if (pool[0] > pool[1]) std::swap(pool[0], pool[1]); }
+				else if (d > 2) std::sort(pool.begin(), pool.begin() + d);
+				if (dense_on && d <= 2 && !dead && !emit_all_hits && !pl.has_prior) {
+					/* the common case once the chain has seen its families: the key is in the table with the listing this order
+					 * would give it -- nothing to do, no hash */
+					const int32_t cell = d == 1 ? dense1[(size_t)(node - 1) * N + pool[0] - 1]
+							: dense2[((size_t)(node - 1) * N + pool[0] - 1) * N + pool[1] - 1];
+					if (cell) {
+						const Entry &h = entries[cell - 1];
+						if (h.pars[0] == pl.order[listing[0]] + 1 && (d == 1 || h.pars[1] == pl.order[listing[1]] + 1)) {
+							st.lookups++;
+							st.hits++;
+							r++;
+							continue;
+						}
+					}
+				}
 				Entry *e = lookup(pool.data(), d, node, d);
 				if (!e) {
 					e = store(pool.data(), d, node, d);
@@ -269,12 +308,13 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 /* test hook (CPU): the model on a sequence of node orders.  p: the search (num_nodes, max_parent_set, max_complexity,
  * parent_sizes, pools, edge_prob; order ignored); cats [N] label space; never_kept [N] or null; orders [norders][N]
  * 1-based labels; winners [norders][N][P][P]: the listed labels (0-padded, all 0 = none) of the winner of (order, child
- * label - 1, parent count - 1) on the equal-categories path, as the device would report it.  Every HIT comes back as a
+ * label - 1, parent count - 1) on the equal-categories path, as the device would report it.  Every HIT (all_hits) or
+ * every hit that changes what the device computed (an override: what the search itself acts on) comes back as a
  * row of 4 + CNB_MAXP ints -- 1 equal-categories path / 2 otherwise, order index, child label, parent count, listed
  * parent labels -- with the entry's prior beside it.  Returns the number of hits (rows beyond cap are dropped), < 0 on
  * an error. */
 extern "C" int64_t cnb_cache_trace(const cnb_params *p, const int32_t *cats, const uint8_t *never_kept, int32_t norders,
-		const int32_t *orders, const int32_t *winners, int32_t cap, int32_t *rows, double *priors) {
+		const int32_t *orders, const int32_t *winners, int32_t all_hits, int32_t cap, int32_t *rows, double *priors) {
 	if (!p || !cats || !orders || norders < 0) return -1;
 	const int N = p->num_nodes, P = p->max_parent_set;
 	CnbScoreCache cache(N, P);
@@ -319,7 +359,7 @@ extern "C" int64_t cnb_cache_trace(const cnb_params *p, const int32_t *cats, con
 			win[b.opt_off] = b.start + rank;
 		}
 		std::vector<CnbOverride> ov;
-		cache.emit_all_hits = true;
+		cache.emit_all_hits = all_hits != 0;
 		if (cache.walk(pl, p, never_kept, win.data(), &ov) != CNB_OK) return -4;
 		for (const CnbOverride &v : ov) {
 			if (nrows < cap && rows) {

@@ -56,16 +56,25 @@ public:
 private:
 	struct Entry {
 		int32_t node, npars, npool;      /* labels 1-based */
-		int32_t pool_off;                /* into arena: sorted pool labels */
+		int32_t pool_off;                /* sorted pool labels: a block of N ints in arena, or -1 = pool_small (up to CNB_MAXP labels) */
+		int32_t pool_small[CNB_MAXP];
 		int32_t pars[CNB_MAXP];          /* labels 1-based, listing sequence */
 		double prior;
 	};
+	const int32_t *pool_of(const Entry &e) const { return e.pool_off < 0 ? e.pool_small : &arena[e.pool_off]; }
 	int32_t N, P;
 	uint32_t ncache = 0, nbits = 0;
 	std::vector<int32_t> flat;           /* slot -> entry index + 1 (tables up to 2^24 slots) */
 	std::unordered_map<uint32_t, int32_t> sparse;   /* larger tables: the reference allocates them in full, we do not */
 	std::vector<Entry> entries;
-	std::vector<int32_t> arena, free_entries;
+	std::vector<int32_t> arena, free_blocks;   /* pools beyond CNB_MAXP labels: blocks of N ints, recycled when their entry is evicted */
+	/* entries whose pool IS their parent set (every entry of the unequal-categories path) with one or two parents, by key:
+	 * dense1[(node-1)*N + a-1], dense2[((node-1)*N + a-1)*N + b-1] (a < b) = entry index + 1, 0 = not in the table.  Kept in
+	 * step with the slots (a store enters its key and removes the key it evicts), so a lookup of such a key needs no hash:
+	 * it hits exactly when the slot of that key still holds it.  Up to 160 nodes (16 MB). */
+	bool dense_on = false;
+	std::vector<int32_t> dense1, dense2;
+	int32_t *dense_cell(const int32_t *pool_sorted, int npool, int node, int npars);
 	CnbCacheStats st;
 	void init();
 	uint32_t slot_of(const int32_t *pool_sorted, int npool, int node, int npars) const;

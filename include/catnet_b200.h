@@ -383,12 +383,13 @@ int64_t cnb_tile3_selftest(int32_t num_nodes, int32_t free_cats);
  * no GPU needed.  p: the search (num_nodes, max_parent_set, parent_sizes, pools, edge_prob; order ignored); cats [N] per
  * label; never_kept [N] bytes or NULL (nodes perturbed in every sample); orders [norders][N] 1-based labels; winners
  * [norders][N][P][P] or NULL: the listed labels (0-padded) of the winner of (order, child label - 1, parent count - 1) where
- * all pool members have equal category counts, as the device would report it.  Every cache HIT comes back as a row of
+ * all pool members have equal category counts, as the device would report it.  Every cache HIT (all_hits != 0), or only
+ * the hits that change what the device computed for the order (the overrides the search acts on), comes back as a row of
  * 4 + 8 ints -- 1 equal-categories path / 2 otherwise, order index, child label, parent count, the parent labels in the
  * cached listing sequence -- with the entry's prior beside it.  Returns the number of hits (rows beyond cap are dropped),
  * < 0 on an error. */
 int64_t cnb_cache_trace(const cnb_params *p, const int32_t *cats, const uint8_t *never_kept, int32_t norders,
-		const int32_t *orders, const int32_t *winners, int32_t cap, int32_t *rows, double *priors);
+		const int32_t *orders, const int32_t *winners, int32_t all_hits, int32_t cap, int32_t *rows, double *priors);
 
 /* ---- result accessors (the catNetwork slots) ---- */
 int32_t cnb_result_num_networks(const cnb_result *r);

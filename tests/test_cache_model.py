@@ -40,7 +40,7 @@ def oracle_trace(s, cats, P, K, start, sa, **kw):
     return r, rows[:nr.value, :ROW], priors[:nr.value], orders[:ns.value]
 
 
-def model_trace(n, cats, P, K, orders, winners, never_kept=None, **kw):
+def model_trace(n, cats, P, K, orders, winners, never_kept=None, all_hits=True, **kw):
     keep = []
 
     def hold(a):
@@ -56,7 +56,7 @@ def model_trace(n, cats, P, K, orders, winners, never_kept=None, **kw):
     w32 = np.ascontiguousarray(winners, dtype=np.int32)
     nk = None if never_kept is None else np.ascontiguousarray(never_kept, dtype=np.uint8)
     got = _abi.lib().cnb_cache_trace(C.byref(p), c32.ctypes.data, None if nk is None else nk.ctypes.data, len(o32),
-                                     o32.ctypes.data, w32.ctypes.data, cap, rows.ctypes.data, priors.ctypes.data)
+                                     o32.ctypes.data, w32.ctypes.data, int(all_hits), cap, rows.ctypes.data, priors.ctypes.data)
     assert 0 <= got <= cap, got
     return rows[:got], priors[:got]
 
@@ -84,6 +84,23 @@ def test_cache_model_reports_the_oracles_hits(seed):
     if "edge_prob" in kw:
         assert np.array_equal(gp, hp)                         # fp64 bit equality: host prior == the oracle's
     assert len(orders) > 1
+    # what the search acts on: the hits that change what the device computed for the order -- every hit where the pool has
+    # equal category counts (the winner is replaced), otherwise the hits whose cached listing is not the one this order
+    # gives the family (fixed parents first, then the others by position), and all hits when priors are in use
+    fixed = kw.get("fixed_parents")
+    keep = []
+    for row in hits:
+        if row[0] == 1 or "edge_prob" in kw:
+            keep.append(True)
+            continue
+        pos = {int(lbl): i for i, lbl in enumerate(orders[row[1]])}
+        pars = [int(v) for v in row[4:4 + row[3]]]
+        fx = set(fixed[row[2] - 1]) if fixed is not None else set()
+        default = sorted([q for q in pars if q in fx], key=pos.get) + sorted([q for q in pars if q not in fx], key=pos.get)
+        keep.append(pars != default)
+    keep = np.array(keep, dtype=bool) if len(hits) else np.zeros(0, dtype=bool)
+    got2, _ = model_trace(n, c, P, K, orders, winners, never_kept=never, all_hits=False, **mkw)
+    assert np.array_equal(got2, hits[keep])
 
 
 def test_cache_table_size_follows_the_reference():
@@ -107,3 +124,5 @@ def test_cache_table_size_follows_the_reference():
     hits = rows[rows[:, 0] != 3]
     got, _ = model_trace(37, c, 2, K, orders, winners)
     assert len(hits) > 1000 and np.array_equal(got, hits)
+    got2, _ = model_trace(37, c, 2, K, orders, winners, all_hits=False)
+    assert 0 < len(got2) < len(got)
