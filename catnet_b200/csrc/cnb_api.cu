@@ -30,6 +30,7 @@ extern "C" const char *cnb_version(void) { return "catnet_b200 0.1 (sm_100a)"; }
 /* ------------------------------------------------------------------ context ---- */
 int DevBuf::ensure(size_t bytes) {
 	if (bytes <= cap) return CNB_OK;
+	if (view) { ptr = nullptr; view = false; }            /* outgrown its place in the packed plan: its own allocation again */
 	if (ptr) cudaFree(ptr);
 	ptr = nullptr;
 	cap = 0;
@@ -43,9 +44,16 @@ int DevBuf::ensure(size_t bytes) {
 	return CNB_OK;
 }
 void DevBuf::release() {
-	if (ptr) cudaFree(ptr);
+	if (ptr && !view) cudaFree(ptr);
 	ptr = nullptr;
 	cap = 0;
+	view = false;
+}
+void DevBuf::alias(void *p, size_t bytes) {
+	if (ptr && !view) cudaFree(ptr);
+	ptr = p;
+	cap = bytes;
+	view = true;
 }
 
 extern "C" int cnb_ctx_create(int32_t device, cnb_ctx **out) {
@@ -107,6 +115,8 @@ extern "C" void cnb_ctx_destroy(cnb_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	c->pin_sel.release();
 	c->pin_stage.release();
+	c->pin_sum.release();
+	c->pin_plan.release();
 	for (DevBuf *b : c->all_bufs()) b->release();
 	for (int i = 0; i < CNB_NEV; i++) cudaEventDestroy(c->ev[i]);
 	for (cudaEvent_t ev : c->ev_slices) cudaEventDestroy(ev);
@@ -171,9 +181,13 @@ void cnb_pool_release(void) {
 
 static float ev_ms(cnb_ctx *c, int a, int b) {
 	float ms = 0;
+	if (c->quiet) return 0;                               /* no per-phase events were recorded (EVREC) */
 	cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]);
 	return ms;
 }
+/* per-phase timing event on the context's stream; the SA / histogram drivers evaluate thousands of small orders whose cost
+ * is the number of driver calls per order, so they switch these off (cnb_ctx.quiet: cnb_timing's phase times read 0) */
+#define EVREC(c, id) do { if (!(c)->quiet) CK(cudaEventRecord((c)->ev[(id)], (c)->stream)); } while (0)
 
 /* samples_dev: [M][N] int32 (elem_bytes 4) or uint8 with 0 = missing (elem_bytes 1) in device memory */
 int cnb_ctx_set_samples_impl(cnb_ctx *c, int32_t N, int32_t M, const void *samples_dev, int elem_bytes,
@@ -363,13 +377,14 @@ int cnb_ctx_batch(cnb_ctx *c, int want, std::vector<cnb_ctx *> *ctxs) {
 	return CNB_OK;
 }
 
-int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders) {
+int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders,
+		bool to_options) {
 	if (n < 1) return CNB_OK;
 	if (n > (int)ctxs.size() || (n > 1 && (!c->crew || c->crew->G < n))) { cnb_set_error("cnb_ctx_batch_run: %d orders, %d contexts", n, (int)ctxs.size()); return CNB_ERR_PROC; }
 	auto job = [&](int t) -> int {
 		cnb_params q = *p;
 		q.order = orders[t];
-		return cnb_ctx_search_light(ctxs[t], &q);
+		return to_options ? cnb_ctx_search_to_options(ctxs[t], &q) : cnb_ctx_search_light(ctxs[t], &q);
 	};
 	if (n == 1) return job(0);
 	return c->crew->run(n, job);
@@ -634,7 +649,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	cnb_params q = *p;
 	q.num_nodes = c->N;
 	q.num_samples = c->M;
-	CK(cudaEventRecord(c->ev[EV_PLAN0], c->stream));
+	EVREC(c, EV_PLAN0);
 	c->cache_P = p->max_parent_set;
 	if (p->parent_sizes) c->cache_psizes.assign(p->parent_sizes, p->parent_sizes + c->N);
 	else c->cache_psizes.clear();
@@ -681,24 +696,29 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 	} else {
 	RC(cnb_build_plan(&q, c->cats_lbl.data(), rank, world, &c->plan, &err, tile_mode));
 	const bool masks = c->has_pert && !c->ignore_pert;
+	/* the plan's tables travel as ONE block: staged in page-locked memory, one copy, the per-table buffers are views into it
+	 * (an SA chain plans thousands of small orders, and an order costs about as much as the driver calls it makes) */
+	struct PlanItem { DevBuf *b; const void *src; size_t bytes; size_t off; };
+	std::vector<PlanItem> items;
+	auto add = [&](DevBuf &b, const void *src, size_t bytes) { items.push_back({&b, src, bytes, 0}); };
 	if (!pl.tile_base.empty()) {
-		RC(upload(c, c->b_tile_base, pl.tile_base));
-		RC(upload(c, c->b_dtile_off, pl.dtile_off));
+		add(c->b_tile_base, pl.tile_base.data(), pl.tile_base.size() * sizeof(int64_t));
+		add(c->b_dtile_off, pl.dtile_off.data(), pl.dtile_off.size() * sizeof(int64_t));
 		const size_t rows_per_node = pl.tile_full ? (masks ? 8 : 4) : 3;
 		size_t row_bytes = (size_t)cnbk_umma_row_quads(c->W, !c->tensor_i8, nullptr) * sizeof(uint4) * rows_per_node * c->N;
 		RC(c->b_rows_a.ensure(row_bytes));
 		RC(c->b_rows_b.ensure(row_bytes));
 	}
-	RC(upload(c, c->b_order, pl.order));
-	RC(upload(c, c->b_cats, pl.cats));
+	add(c->b_order, pl.order.data(), pl.order.size() * sizeof(int32_t));
+	add(c->b_cats, pl.cats.data(), pl.cats.size() * sizeof(int32_t));
 	c->plan_has_fix1 = false;
 	for (int v : pl.fix1) c->plan_has_fix1 = c->plan_has_fix1 || v >= 0;
-	if (c->plan_has_fix1) RC(upload(c, c->b_fix1, pl.fix1));
-	RC(upload(c, c->b_lists, pl.lists));
-	RC(upload(c, c->b_blocks, pl.blocks));
-	RC(upload(c, c->b_group_blocks, pl.group_blocks));
-	RC(upload(c, c->b_groups, pl.groups));
-	if (pl.has_prior) RC(upload(c, c->b_edge, pl.edge));
+	if (c->plan_has_fix1) add(c->b_fix1, pl.fix1.data(), pl.fix1.size() * sizeof(int32_t));
+	add(c->b_lists, pl.lists.data(), pl.lists.size() * sizeof(int32_t));
+	add(c->b_blocks, pl.blocks.data(), pl.blocks.size() * sizeof(CnbBlock));
+	add(c->b_group_blocks, pl.group_blocks.data(), pl.group_blocks.size() * sizeof(int32_t));
+	add(c->b_groups, pl.groups.data(), pl.groups.size() * sizeof(CnbGroup));
+	if (pl.has_prior) add(c->b_edge, pl.edge.data(), pl.edge.size() * sizeof(double));
 	c->dp_nodes.resize(pl.nodes.size());
 	for (size_t i = 0; i < pl.nodes.size(); i++) {
 		c->dp_nodes[i].opt_begin = pl.nodes[i].opt_begin;
@@ -706,10 +726,10 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 		c->dp_nodes[i].base_cx = pl.nodes[i].base_cx;
 		c->dp_nodes[i].pad = 0;
 	}
-	RC(upload(c, c->b_dp_nodes, c->dp_nodes));
+	add(c->b_dp_nodes, c->dp_nodes.data(), c->dp_nodes.size() * sizeof(CnbDpNode));
 	c->blk_equal.assign(pl.blocks.size(), 0);
 	for (size_t b = 0; b < pl.blocks.size(); b++) c->blk_equal[b] = pl.nodes[pl.blocks[b].child].equal_branch;
-	RC(upload(c, c->b_blk_equal, c->blk_equal));
+	add(c->b_blk_equal, c->blk_equal.data(), c->blk_equal.size() * sizeof(int32_t));
 	/* selection: large candidate blocks are cut into chunks, one CTA each */
 	c->sel_chunks.clear();
 	c->sel_chunk0.assign(pl.blocks.size() + 1, 0);
@@ -718,15 +738,32 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 		for (int64_t k = 0; k < nch; k++) { c->sel_chunks.push_back((int32_t)b); c->sel_chunks.push_back((int32_t)k); }
 		c->sel_chunk0[b + 1] = c->sel_chunk0[b] + (int32_t)nch;
 	}
-	RC(upload(c, c->b_sel_chunks, c->sel_chunks));
-	RC(upload(c, c->b_sel_chunk0, c->sel_chunk0));
+	add(c->b_sel_chunks, c->sel_chunks.data(), c->sel_chunks.size() * sizeof(int32_t));
+	add(c->b_sel_chunk0, c->sel_chunk0.data(), c->sel_chunk0.size() * sizeof(int32_t));
+	size_t total = 0;
+	for (PlanItem &it : items) {
+		it.off = total;
+		total += (std::max<size_t>(it.bytes, 16) + 255) / 256 * 256;
+	}
+	const void *old_plan = c->b_plan.ptr;
+	RC(c->b_plan.ensure(total));
+	RC(c->pin_plan.ensure(total));
+	if (c->b_plan.ptr != old_plan)                        /* the block moved: no table of an earlier plan may keep pointing into it */
+		for (DevBuf *b : {&c->b_tile_base, &c->b_dtile_off, &c->b_order, &c->b_cats, &c->b_fix1, &c->b_lists, &c->b_blocks, &c->b_group_blocks,
+				&c->b_groups, &c->b_edge, &c->b_dp_nodes, &c->b_blk_equal, &c->b_sel_chunks, &c->b_sel_chunk0})
+			if (b->view) b->release();
+	for (const PlanItem &it : items) {
+		if (it.bytes) memcpy((char *)c->pin_plan.ptr + it.off, it.src, it.bytes);
+		it.b->alias((char *)c->b_plan.ptr + it.off, std::max<size_t>(it.bytes, 16));
+	}
+	H2D(c, c->b_plan.ptr, c->pin_plan.ptr, total);
 	}
 	c->plan_key = key;
 	c->plan_key_valid = true;
 	const bool masks = c->has_pert && !c->ignore_pert;
 	c->timing.kernel_launches = 0;
 	if (c->streaming) {                                /* the streamed one-shot search moves the samples in slice by slice itself */
-		CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
+		EVREC(c, EV_PLAN1);
 		c->planned = true;
 		c->dp_done = false;
 		if (seg_len) *seg_len = pl.seg_len;
@@ -748,7 +785,7 @@ extern "C" int cnb_ctx_plan(cnb_ctx *c, const cnb_params *p, int32_t rank, int32
 					(uint4 *)c->b_rows_b.ptr));
 		c->timing.kernel_launches++;
 	}
-	CK(cudaEventRecord(c->ev[EV_PLAN1], c->stream));
+	EVREC(c, EV_PLAN1);
 	c->planned = true;
 	c->dp_done = false;
 	if (seg_len) *seg_len = pl.seg_len;
@@ -964,7 +1001,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 	memset(c->timing.score_ms_by_parents, 0, sizeof(c->timing.score_ms_by_parents));
 	memset(c->timing.families_by_parents, 0, sizeof(c->timing.families_by_parents));
 	CK(cudaMemsetAsync((int *)c->b_flag.ptr + 1, 0, sizeof(int), st));
-	CK(cudaEventRecord(c->ev[EV_SCORE0], st));
+	EVREC(c, EV_SCORE0);
 	c->timing.fast_path = 1;
 	c->timing.tensor_tiles = 0;
 	c->timing.tensor_ms = 0;
@@ -989,7 +1026,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		ScoreOut O;
 		memset(&O, 0, sizeof(O));
 		O.scores = scores_dev; O.chunk = g.chunk; O.seg_off = g.seg_off; O.seg_len = pl.seg_len;
-		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi], st));
+		if (gi < CNB_NEV_GROUPS) EVREC(c, EV_GROUP0 + 2 * gi);
 		if (g.tiled) {
 			/* tcgen05 path: integer tables by one-hot GEMM, tile batches bounded by the table buffer */
 			/* tiles are dealt round-robin (tile t -> rank t % world): every rank gets the same mix of full and
@@ -1003,11 +1040,11 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 			int nb = 0;
 			for (long long tb = t0; tb < t1; tb += batch, nb++) {
 				long long te = std::min(t1, tb + batch);
-				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb], st));
+				if (nb < CNB_NEV_TEN) EVREC(c, EV_TEN0 + 2 * nb);
 				if (!c->streaming)                            /* streamed search: the tables were contracted slice by slice */
 					RC(cnbk_umma_tables(st, (const uint4 *)c->b_rows_a.ptr, (const uint4 *)c->b_rows_b.ptr, c->N, c->W,
 							!c->tensor_i8, D.tiles, tb, te, (int *)c->b_counts.ptr));
-				if (nb < CNB_NEV_TEN) CK(cudaEventRecord(c->ev[EV_TEN0 + 2 * nb + 1], st));
+				if (nb < CNB_NEV_TEN) EVREC(c, EV_TEN0 + 2 * nb + 1);
 				RC(cnbk_umma_epilogue(st, D, tb, te, (const int *)c->b_counts.ptr,
 						(const int *)c->b_pairs.ptr, O, uni4 && !c->generic_epilogue));
 				c->timing.kernel_launches += 2;
@@ -1029,7 +1066,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 				if (e > b && !c->last_fast) c->timing.fast_path = 0;
 			}
 		}
-		if (gi < CNB_NEV_GROUPS) CK(cudaEventRecord(c->ev[EV_GROUP0 + 2 * gi + 1], st));
+		if (gi < CNB_NEV_GROUPS) EVREC(c, EV_GROUP0 + 2 * gi + 1);
 		if (e > b) {
 			c->timing.num_families += e - b;
 			c->timing.algorithmic_bytes += (e - b) * ((long long)(g.d + 1) * c->M + 8);
@@ -1037,7 +1074,7 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		}
 		gi++;
 	}
-	CK(cudaEventRecord(c->ev[EV_SCORE1], st));
+	EVREC(c, EV_SCORE1);
 	int ovf = 0;
 	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
 	CK(cudaStreamSynchronize(st));
@@ -1196,20 +1233,24 @@ static int apply_cache(cnb_ctx *c) {
 			pl.has_prior ? (const double *)c->b_ov_prior.ptr : nullptr, (const double *)c->b_ex_ll.ptr, (const double *)c->b_ex_score.ptr,
 			(double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr));
 	c->timing.kernel_launches++;
-	int ovf = 0;
-	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
-	CK(cudaStreamSynchronize(st));
-	if (ovf) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
+	c->cache_ovf = 1;                                                   /* the flag travels with the DP summary (cnb_ctx_dp_launch) */
 	return CNB_OK;
 }
 
-extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
+/* selection + DP in three steps, so that the SA driver can run the first for several proposals side by side, then hand them
+ * to the score-cache model one after the other while their DPs run behind one another's host work (cnb_sa.cpp):
+ *   cnb_ctx_select      base network, option table (k_select)            -- enqueued, no host wait
+ *   cnb_ctx_dp_launch   [score-cache overrides,] DP kernels, summary copy -- enqueued (the cache model waits for the winners)
+ *   cnb_ctx_dp_wait     stream drained, timings, overflow check
+ * cnb_ctx_select_dp is the three in a row. */
+int cnb_ctx_select(cnb_ctx *c, const double *scores_dev) {
 	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
 	CK(cudaSetDevice(c->device));
 	CnbPlan &pl = c->plan;
 	cudaStream_t st = c->stream;
-	const int N = pl.N, K = pl.K;
-	CK(cudaEventRecord(c->ev[EV_SEL0], st));
+	const int N = pl.N;
+	c->dp_done = false;
+	EVREC(c, EV_SEL0);
 	/* base network: every node with its fixed parents only (catnet_search2.h:359-441) */
 	{
 		std::vector<int32_t> child(N), pars((size_t)N * CNB_MAXP, 0), nd(N);
@@ -1238,9 +1279,19 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 			(double *)c->b_opt_score.ptr, (int *)c->b_opt_cx.ptr, (long long *)c->b_opt_fid.ptr,
 			(double *)c->b_sel_part_s.ptr, (long long *)c->b_sel_part_f.ptr));
 	c->timing.kernel_launches += 2;
+	return CNB_OK;
+}
+
+int cnb_ctx_dp_launch(cnb_ctx *c) {
+	if (!c || !c->planned) { cnb_set_error("cnb_ctx_plan must run first"); return CNB_ERR_PARAM; }
+	CK(cudaSetDevice(c->device));
+	CnbPlan &pl = c->plan;
+	cudaStream_t st = c->stream;
+	const int N = pl.N, K = pl.K;
+	c->cache_ovf = 0;
 	if (c->cache) RC(apply_cache(c));
 	else c->cache_ov.clear();
-	CK(cudaEventRecord(c->ev[EV_SEL1], st));
+	EVREC(c, EV_SEL1);
 	/* DP state, double buffered */
 	size_t slots = (size_t)K + 1;
 	RC(c->b_dp_exists.ensure(3 * slots));
@@ -1324,17 +1375,40 @@ extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
 	} else
 		return fused;
 	c->dp_final = cur;
-	CK(cudaEventRecord(c->ev[EV_DP1], st));
+	EVREC(c, EV_DP1);
 	/* summary to the host: which slots exist and their log-lik */
 	c->h_exists.resize(slots);
 	c->h_L.resize(slots);
-	D2H(c, c->h_exists.data(), S[cur].exists, slots);
-	D2H(c, c->h_L.data(), S[cur].L, slots * sizeof(double));
-	CK(cudaStreamSynchronize(st));
+	const size_t off_e = 16, off_l = 16 + (slots + 7) / 8 * 8;
+	RC(c->pin_sum.ensure(off_l + slots * sizeof(double)));
+	char *pin = (char *)c->pin_sum.ptr;
+	*(int *)pin = 0;
+	if (c->cache_ovf) D2H(c, pin, (int *)c->b_flag.ptr + 1, sizeof(int));   /* overflow flag of the overrides' scorer */
+	D2H(c, pin + off_e, S[cur].exists, slots);
+	D2H(c, pin + off_l, S[cur].L, slots * sizeof(double));
+	return CNB_OK;
+}
+
+int cnb_ctx_dp_wait(cnb_ctx *c) {
+	if (!c || !c->planned) return CNB_ERR_PARAM;
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	const size_t slots = c->h_exists.size(), off_e = 16, off_l = 16 + (slots + 7) / 8 * 8;
+	const char *pin = (const char *)c->pin_sum.ptr;
+	if (!pin || c->pin_sum.cap < off_l + slots * sizeof(double)) { cnb_set_error("cnb_ctx_dp_wait without cnb_ctx_dp_launch"); return CNB_ERR_PROC; }
+	memcpy(c->h_exists.data(), pin + off_e, slots);
+	memcpy(c->h_L.data(), pin + off_l, slots * sizeof(double));
+	if (*(const int *)pin) { cnb_set_error("conditional table exceeds %d cells", CNB_HIST_MAX_CELLS); return CNB_ERR_MEM; }
 	c->timing.select_ms = ev_ms(c, EV_SEL0, EV_SEL1);
 	c->timing.dp_ms = ev_ms(c, EV_SEL1, EV_DP1);
 	c->dp_done = true;
 	return CNB_OK;
+}
+
+extern "C" int cnb_ctx_select_dp(cnb_ctx *c, const double *scores_dev) {
+	RC(cnb_ctx_select(c, scores_dev));
+	RC(cnb_ctx_dp_launch(c));
+	return cnb_ctx_dp_wait(c);
 }
 
 /* host view of the DP outcome: (complexity, log-lik) of every surviving network */
@@ -1578,6 +1652,16 @@ extern "C" int cnb_ctx_finish(cnb_ctx *c, const double *scores_dev, cnb_result *
 	RC(cnb_ctx_collect(c, out));
 	c->timing.total_ms = c->timing.plan_ms + c->timing.score_ms + c->timing.select_ms + c->timing.dp_ms + c->timing.collect_ms;
 	return CNB_OK;
+}
+
+/* plan + scores + option table of one order: everything the score-cache model does not touch (cnb_sa.cpp runs it for the
+ * proposals of a step side by side; cnb_ctx_dp_launch / cnb_ctx_dp_wait finish the evaluation) */
+int cnb_ctx_search_to_options(cnb_ctx *c, const cnb_params *p) {
+	int64_t seg = 0, nf = 0;
+	RC(cnb_ctx_plan(c, p, 0, 1, &seg, &nf));
+	RC(c->b_scores.ensure(std::max<int64_t>(seg, 1) * sizeof(double)));
+	RC(cnb_ctx_score_shard(c, (double *)c->b_scores.ptr));
+	return cnb_ctx_select(c, (const double *)c->b_scores.ptr);
 }
 
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p) {

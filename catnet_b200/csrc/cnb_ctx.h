@@ -17,8 +17,10 @@ enum { EV_PACK0, EV_PACK1, EV_PLAN0, EV_PLAN1, EV_SCORE0, EV_SCORE1, EV_SEL0, EV
 struct DevBuf {
 	void *ptr = nullptr;
 	size_t cap = 0;
+	bool view = false;          /* ptr points into another buffer (the packed plan, cnb_ctx.b_plan): never freed from here */
 	int ensure(size_t bytes);   /* grow-only; contents are not preserved */
 	void release();
+	void alias(void *p, size_t bytes);   /* become a view of bytes at p (an own allocation is freed first) */
 };
 
 /* grow-only page-locked host staging buffer (device -> host results) */
@@ -77,6 +79,7 @@ struct cnb_ctx {
 	bool force_full = false;           /* full-table tensor tiles also on complete data (test hook) */
 	bool dp_no_trap = false;           /* k_dp_wave instead of the trapezoid kernel (test hook) */
 	bool has_na = false;               /* the data set has missing values */
+	bool quiet = false;                /* no per-phase timing events (the SA / histogram drivers: fewer driver calls per evaluated order) */
 	bool pairs_full = false;           /* b_pairs holds the two-way tables over ALL samples (perturbation masks ignored) */
 	bool ignore_pert = false;          /* score as if there were no perturbation masks (full tables of the pairwise metrics) */
 	/* concurrent evaluation of several orders on this device (the numThreads proposals of a cnSearchSA step, the orders of a
@@ -94,6 +97,7 @@ struct cnb_ctx {
 	std::vector<int64_t> cache_h_opt, cache_h_fid;
 	std::vector<int32_t> cache_h_cx;
 	std::vector<double> cache_h_prior;
+	int cache_ovf = 0;                     /* overflow flag of the overrides' scorer, copied back behind the DP */
 	int dp_final = 0, tensor_batches = 0;
 	double host_ms[4] = {0, 0, 0, 0};   /* CNB_TRACE: host wall time of plan / score / select+dp, searches */
 	std::vector<int32_t> cats_lbl;
@@ -104,11 +108,15 @@ struct cnb_ctx {
 	std::vector<double> h_L;
 	CnbPlan plan;
 	cnb_timing timing = {};
+	PinBuf pin_sum;                    /* DP summary on its way back (overflow flag of the cache overrides, exists[K+1], L[K+1]): page-locked so
+	                                      that the copy is queued behind the DP instead of waiting for it (cnb_ctx_dp_launch / _wait) */
 	PinBuf pin_sel, pin_stage;         /* pin_stage: host-compacted copy of a large sample matrix on its way to the device */
 	DevBuf b_counts_p, b_pairs_ord, b_sel_slots, b_stage_s, b_stage_p, b_pw_kept, b_pw_out, b_net_int, b_net_off, b_net_probs, b_net_logp, b_net_sel, b_net_fz, b_sel_chunks, b_sel_chunk0, b_sel_part_s, b_sel_part_f, b_triples, b_rows_a3, b_tile_base3;
 	/* packed samples */
 	DevBuf b_vmin, b_vmax, b_cats_lbl, b_flag, b_codes, b_planes_lbl, b_keep_lbl, b_planes, b_keep, b_pairs, b_rows_a, b_rows_b;
-	/* plan */
+	/* plan: one allocation and one host -> device copy per planned order (b_plan, staged in pin_plan); the buffers below are views into it */
+	DevBuf b_plan;
+	PinBuf pin_plan;
 	DevBuf b_order, b_cats, b_lists, b_blocks, b_group_blocks, b_groups, b_edge, b_blk_equal, b_tile_base, b_dtile_off, b_fix1;
 	bool plan_has_fix1 = false;
 	/* scoring */
@@ -122,7 +130,7 @@ struct cnb_ctx {
 			&b_scores, &b_counts, &b_ex_child, &b_ex_pars, &b_ex_nd, &b_ex_ll, &b_ex_prior, &b_ex_score, &b_ex_ncount,
 			&b_ex_counts, &b_base_v, &b_opt_score, &b_opt_cx, &b_opt_fid, &b_dp_exists, &b_dp_L, &b_dp_pfx, &b_bp_opt,
 			&b_bp_src, &b_sel, &b_pairs, &b_tile_base, &b_dtile_off, &b_rows_a, &b_rows_b, &b_dp_nodes, &b_sel_slots, &b_dp_flags, &b_stage_s, &b_stage_p, &b_pw_kept, &b_pw_out, &b_net_int, &b_net_off, &b_net_probs, &b_net_logp, &b_net_sel, &b_net_fz, &b_sel_chunks, &b_sel_chunk0, &b_sel_part_s, &b_sel_part_f, &b_triples, &b_rows_a3, &b_tile_base3, &b_fix1,
-			&b_ov_opt, &b_ov_fid, &b_ov_cx, &b_ov_prior};
+			&b_ov_opt, &b_ov_fid, &b_ov_cx, &b_ov_prior, &b_plan};
 	}
 };
 
@@ -135,9 +143,13 @@ void cnb_pool_release(void);
  * packed data (small data sets only; 1 = evaluate one after the other).  cnb_ctx_batch_run evaluates orders[t] on ctxs[t]
  * (plan + score + selection + DP, no export) concurrently, one host thread each. */
 int cnb_ctx_batch(cnb_ctx *c, int want, std::vector<cnb_ctx *> *ctxs);
-int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders);
+int cnb_ctx_batch_run(cnb_ctx *c, const std::vector<cnb_ctx *> &ctxs, const cnb_params *p, int n, const int32_t *const *orders,
+		bool to_options = false);   /* to_options: stop after the option table (cnb_ctx_search_to_options) */
 /* internal phases shared with the SA driver (cnb_sa.cpp) */
 int cnb_ctx_search_light(cnb_ctx *c, const cnb_params *p);           /* plan + score + DP, no network export */
+int cnb_ctx_search_to_options(cnb_ctx *c, const cnb_params *p);      /* plan + score + option table; then: */
+int cnb_ctx_dp_launch(cnb_ctx *c);                                   /* [score-cache overrides,] DP, summary copy enqueued */
+int cnb_ctx_dp_wait(cnb_ctx *c);                                     /* ... drained: the evaluation is complete */
 int cnb_ctx_dp_summary(const cnb_ctx *c, std::vector<int32_t> *complexity, std::vector<double> *loglik);
 /* parents (order positions, [N][CNB_MAXP]) of the surviving network with the given complexity, after select_dp */
 int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t> *num_parents, std::vector<int32_t> *parents);

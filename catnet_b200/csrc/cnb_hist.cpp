@@ -94,8 +94,14 @@ extern "C" int cnb_ctx_search_hist(cnb_ctx *c, const cnb_params *p, const cnb_hi
 	std::unique_ptr<CnbScoreCache> cache;
 	if (cnb_cache_wanted(hp->use_cache, nDrives)) cache.reset(new CnbScoreCache(N, p->max_parent_set));
 	const bool batched = (int)lanes.size() >= nDrives && nDrives > 1 && !cache;
-	struct CacheGuard { cnb_ctx *c; ~CacheGuard() { c->cache = nullptr; } } guard{c};
+	struct CacheGuard {
+		cnb_ctx *c; std::vector<cnb_ctx *> &l;
+		~CacheGuard() { c->cache = nullptr; c->quiet = false; for (cnb_ctx *s : l) s->quiet = false; }
+	} guard{c, lanes};
 	c->cache = cache.get();                      /* every order passes through the model, one after the other */
+	const bool quiet = !getenv("CNB_SA_TIMING"); /* no per-phase timing events: fewer driver calls per evaluated order */
+	c->quiet = quiet;
+	for (cnb_ctx *s : lanes) s->quiet = quiet;
 	std::vector<const int32_t *> todo_orders;
 	while (niter < hp->max_iter) {
 		for (int n = 0; n < nDrives; n++) {

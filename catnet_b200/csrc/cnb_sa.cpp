@@ -151,15 +151,21 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 	/* cache mode without sibling contexts and several proposals per step: each evaluation is exported before the next one
 	 * overwrites the context */
 	const bool eager = cache && !have_lanes && nDrives > 1;
+	const char *no_pipe = getenv("CNB_CACHE_NO_PIPELINE");            /* A/B switch: the proposals of a step strictly one after the other */
+	const bool pipelined = !no_pipe;
 	std::vector<cnb_ctx *> where(nDrives, c);
 	std::vector<const int32_t *> todo_orders;
 	std::vector<std::unique_ptr<cnb_result>> pre(nDrives);
 	std::vector<std::vector<int32_t>> pre_cx(nDrives);
 	std::vector<std::vector<double>> pre_ll(nDrives);
-	struct CacheGuard {                              /* no context keeps a pointer to the model past this call */
+	struct CacheGuard {                              /* no context keeps a pointer to the model, or stays quiet, past this call */
 		cnb_ctx *c; std::vector<cnb_ctx *> &l;
-		~CacheGuard() { c->cache = nullptr; for (cnb_ctx *s : l) s->cache = nullptr; }
+		~CacheGuard() { c->cache = nullptr; c->quiet = false; for (cnb_ctx *s : l) { s->cache = nullptr; s->quiet = false; } }
 	} guard{c, lanes};
+	/* an evaluated order costs about as much as the driver calls it makes: no per-phase timing events (CNB_SA_TIMING=1 keeps them) */
+	const bool quiet = !getenv("CNB_SA_TIMING");
+	c->quiet = quiet;
+	for (cnb_ctx *s : lanes) s->quiet = quiet;
 
 	while (niter < sa->max_iter) {
 		for (int n = 0; n < nDrives; n++) {
@@ -182,8 +188,31 @@ extern "C" int cnb_ctx_search_sa(cnb_ctx *c, const cnb_params *p, const cnb_sa_p
 				if (!skip[n]) { where[n] = lanes[t++]; todo_orders.push_back(test[n].data()); }
 			RC(cnb_ctx_batch_run(c, lanes, &q, t, todo_orders.data()));
 		}
-		if (cache) {
-			/* every proposal of the step goes through the cache, in proposal order, whether or not an earlier one is accepted */
+		if (cache && have_lanes && pipelined) {
+			/* every proposal of the step goes through the cache, in proposal order, whether or not an earlier one is accepted.
+			 * What the cache does not touch -- plan, scores, option table -- runs for all of them side by side; then each in
+			 * turn is walked through the model on this thread, its overrides and its DP are queued on its own stream, and the
+			 * next one's walk runs while that DP does */
+			todo_orders.clear();
+			int t = 0;
+			for (int n = 0; n < nDrives; n++)
+				if (!skip[n]) { where[n] = lanes[t++]; todo_orders.push_back(test[n].data()); }
+			RC(cnb_ctx_batch_run(c, lanes, &q, t, todo_orders.data(), true));
+			for (int n = 0; n < nDrives; n++) {
+				if (skip[n]) continue;
+				where[n]->cache = cache.get();
+				int rc = cnb_ctx_dp_launch(where[n]);
+				where[n]->cache = nullptr;
+				if (rc != CNB_OK) {                               /* nothing may stay in flight on the sibling contexts */
+					for (int k = 0; k < n; k++) if (!skip[k]) cnb_ctx_dp_wait(where[k]);
+					return rc;
+				}
+			}
+			int rc = CNB_OK;
+			for (int n = 0; n < nDrives; n++)
+				if (!skip[n]) { int r1 = cnb_ctx_dp_wait(where[n]); if (rc == CNB_OK) rc = r1; }
+			RC(rc);
+		} else if (cache) {
 			int t = 0;
 			for (int n = 0; n < nDrives; n++) {
 				if (skip[n]) continue;

@@ -1250,3 +1250,17 @@ def test_family_scores_follow_the_listing(abi, port, m, cats, na):
             for i, (child, pars) in enumerate(fams):
                 rc, rll, rnc = port.family_score(s0, c, child, pars)
                 assert np.array_equal(counts[i, :len(rc)], rc.astype(np.int64)) and ll[i] == rll and nc[i] == rnc, (d, child, pars)
+
+@pytest.mark.parametrize("seed", [2, 5, 7, 101])
+def test_sa_score_cache_pipelined_equals_sequential(abi, monkeypatch, seed):
+    """use_cache with several proposals per step: option tables side by side, then the walk through the cache model and the
+    DPs one behind the other (the default) -- the same chain as evaluating the proposals strictly one after the other"""
+    from cases import sa_cache_problem
+    s, c, P, K, start, sa, kw, _ = sa_cache_problem(seed)
+    args = dict(max_parent_set=P, max_complexity=K, num_cats=c, **kw)
+    sa = dict(sa, num_threads=3, start_order=start, use_cache=True)
+    a = abi.search_sa(s, sa, want_probs=True, **args)
+    monkeypatch.setenv("CNB_CACHE_NO_PIPELINE", "1")
+    b = abi.search_sa(s, sa, want_probs=True, **args)
+    assert np.array_equal(a["trace"], b["trace"]) and np.array_equal(a["order"], b["order"]) and a["niter"] == b["niter"]
+    _strict_nets(a["nets"], b["nets"])
