@@ -1075,6 +1075,13 @@ extern "C" int cnb_ctx_score_shard(cnb_ctx *c, double *scores_dev) {
 		gi++;
 	}
 	EVREC(c, EV_SCORE1);
+	if (c->quiet) {
+		/* an evaluation of the SA / histogram drivers: nobody reads the phase times, and the overflow flag of the generic
+		 * scorer travels with the DP summary (cnb_ctx_dp_launch / _wait) -- the selection and the DP are queued behind the
+		 * scorers without the host waiting in between */
+		c->defer_ovf = true;
+		return CNB_OK;
+	}
 	int ovf = 0;
 	D2H(c, &ovf, (int *)c->b_flag.ptr + 1, sizeof(int));
 	CK(cudaStreamSynchronize(st));
@@ -1383,7 +1390,8 @@ int cnb_ctx_dp_launch(cnb_ctx *c) {
 	RC(c->pin_sum.ensure(off_l + slots * sizeof(double)));
 	char *pin = (char *)c->pin_sum.ptr;
 	*(int *)pin = 0;
-	if (c->cache_ovf) D2H(c, pin, (int *)c->b_flag.ptr + 1, sizeof(int));   /* overflow flag of the overrides' scorer */
+	if (c->cache_ovf || c->defer_ovf) D2H(c, pin, (int *)c->b_flag.ptr + 1, sizeof(int));   /* overflow flag of the scorers (deferred) and of the overrides' */
+	c->defer_ovf = false;
 	D2H(c, pin + off_e, S[cur].exists, slots);
 	D2H(c, pin + off_l, S[cur].L, slots * sizeof(double));
 	return CNB_OK;

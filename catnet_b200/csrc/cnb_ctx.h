@@ -97,6 +97,7 @@ struct cnb_ctx {
 	std::vector<int64_t> cache_h_opt, cache_h_fid;
 	std::vector<int32_t> cache_h_cx;
 	std::vector<double> cache_h_prior;
+	bool defer_ovf = false;                /* a quiet cnb_ctx_score_shard left its overflow flag on the device for cnb_ctx_dp_launch */
 	int cache_ovf = 0;                     /* overflow flag of the overrides' scorer, copied back behind the DP */
 	int dp_final = 0, tensor_batches = 0;
 	double host_ms[4] = {0, 0, 0, 0};   /* CNB_TRACE: host wall time of plan / score / select+dp, searches */
