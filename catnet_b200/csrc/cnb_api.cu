@@ -1453,13 +1453,22 @@ int cnb_ctx_network_parents(cnb_ctx *c, int32_t complexity, std::vector<int32_t>
 	RC(cnbk_dp_collect_list(st, fin, N, (const long long *)c->b_bp_opt.ptr, (const int *)c->b_bp_src.ptr,
 			(const int *)c->b_sel_slots.ptr, 1, (long long *)c->b_sel.ptr));
 	c->timing.kernel_launches++;
-	RC(c->pin_sel.ensure(std::max<size_t>(2 * (size_t)N * sizeof(long long), 16)));
-	long long *sel = (long long *)c->pin_sel.ptr, *fid = sel + N;
+	/* a small option table comes back whole with the selection (one wait); a large one entry by entry after it */
+	const size_t nopt = (size_t)pl.num_options;
+	const bool whole = nopt > 0 && nopt <= ((size_t)1 << 17);
+	RC(c->pin_sel.ensure(std::max<size_t>((2 * (size_t)N + (whole ? nopt : 0)) * sizeof(long long), 16)));
+	long long *sel = (long long *)c->pin_sel.ptr, *fid = sel + N, *all = fid + N;
 	D2H(c, sel, c->b_sel.ptr, (size_t)N * sizeof(long long));
+	if (whole) D2H(c, all, c->b_opt_fid.ptr, nopt * sizeof(long long));
 	CK(cudaStreamSynchronize(st));
-	for (int n = 0; n < N; n++)
-		if (sel[n] >= 0) D2H(c, &fid[n], (const long long *)c->b_opt_fid.ptr + sel[n], sizeof(long long));
-	CK(cudaStreamSynchronize(st));
+	if (whole) {
+		for (int n = 0; n < N; n++)
+			if (sel[n] >= 0) fid[n] = all[sel[n]];
+	} else {
+		for (int n = 0; n < N; n++)
+			if (sel[n] >= 0) D2H(c, &fid[n], (const long long *)c->b_opt_fid.ptr + sel[n], sizeof(long long));
+		CK(cudaStreamSynchronize(st));
+	}
 	num_parents->assign(N, 0);
 	parents->assign((size_t)N * CNB_MAXP, 0);
 	for (int n = 0; n < N; n++) {
