@@ -157,6 +157,9 @@ bool cnb_cache_wanted(int use_cache, int num_threads) {
 	return use_cache && num_threads <= 8;
 }
 
+static inline const CnbBlock &b_ptr(int bi, const CnbPlan &pl) { return pl.blocks[bi]; }
+static inline int64_t b_opt(const CnbBlock &b, int64_t r) { return b.opt_off + r; }
+
 static bool next_comb(int *idx, int k, int n) {
 	int i = k - 1;
 	while (i >= 0 && idx[i] == n - k + i) i--;
@@ -252,6 +255,52 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 			if (!dead) {
 				if (bi >= nd.first_blk + nd.nblk || pl.blocks[bi].d != d) { cnb_set_error("score cache: plan and walk disagree on node %d", c + 1); return CNB_ERR_PROC; }
 				b = &pl.blocks[bi++];
+			}
+			if (nf == 0 && d <= 2 && dense_on && !emit_all_hits && !dead) {
+				/* the bulk of an SA chain's lookups: one or two free parents, keys that the dense index answers -- plain
+				 * loops in the enumeration order (i, then j > i = lexicographic), no hash unless the key has to be stored */
+				const size_t nbase = (size_t)(node - 1) * N;
+				const int ccx = pl.cats[c] - 1;
+				int64_t r = 0;
+				for (int i = 0; i < (d == 1 ? nr : nr - 1); i++) {
+					const int a = fre[i], la = pl.order[a] + 1;
+					for (int j = (d == 1 ? i : i + 1); j < (d == 1 ? i + 1 : nr); j++, r++) {
+						const int b = fre[j], lb = pl.order[b] + 1;
+						const int32_t cell = d == 1 ? dense1[nbase + la - 1]
+								: (la < lb ? dense2[(nbase + la - 1) * N + lb - 1] : dense2[(nbase + lb - 1) * N + la - 1]);
+						st.lookups++;
+						if (cell) {
+							st.hits++;
+							const Entry &h = entries[cell - 1];
+							const bool fwd = h.pars[0] == la;               /* d == 2: listed (a, b) as this order would, or (b, a) */
+							if (!pl.has_prior && fwd) continue;
+							out->emplace_back();
+							CnbOverride &ov = out->back();
+							ov.opt = b_opt(b_ptr(bi - 1, pl), r);
+							ov.fid = -1;
+							ov.child = c;
+							ov.d = d;
+							ov.prior = h.prior;
+							ov.pars[0] = fwd ? a : b;
+							ov.pars[1] = d == 2 ? (fwd ? b : a) : 0;
+							for (int q = 2; q < CNB_MAXP; q++) ov.pars[q] = 0;
+							ov.cx = d == 1 ? ccx * pl.cats[a] : ccx * pl.cats[a] * pl.cats[b];
+							continue;
+						}
+						st.lookups--;                                      /* lookup() below counts it */
+						pool[0] = d == 1 ? la : std::min(la, lb);
+						pool[1] = std::max(la, lb);
+						Entry *e = lookup(pool.data(), d, node, d);        /* a miss (or nothing stored at all yet) */
+						if (e) { cnb_set_error("score cache: dense index out of step"); return CNB_ERR_PROC; }
+						e = store(pool.data(), d, node, d);
+						e->pars[0] = la;
+						e->pars[1] = d == 2 ? lb : 0;
+						listing[0] = a;
+						listing[1] = b;
+						e->prior = cnb_host_prior(pl, c, listing.data(), d);
+					}
+				}
+				continue;
 			}
 			for (int j = 0; j < kk; j++) idx[j] = j;
 			int64_t r = 0;

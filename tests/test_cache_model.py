@@ -65,6 +65,24 @@ def problem(seed):
     return sa_cache_problem(seed)
 
 
+def acted_on(hits, orders, kw):
+    """what the search acts on: the hits that change what the device computed for the order -- every hit where the pool has
+    equal category counts (the winner is replaced), otherwise the hits whose cached listing is not the one this order gives
+    the family (fixed parents first, then the others by position), and all hits when priors are in use"""
+    fixed = kw.get("fixed_parents")
+    keep = []
+    for row in hits:
+        if row[0] == 1 or "edge_prob" in kw:
+            keep.append(True)
+            continue
+        pos = {int(lbl): i for i, lbl in enumerate(orders[row[1]])}
+        pars = [int(v) for v in row[4:4 + row[3]]]
+        fx = set(fixed[row[2] - 1]) if fixed is not None else set()
+        default = sorted([q for q in pars if q in fx], key=pos.get) + sorted([q for q in pars if q not in fx], key=pos.get)
+        keep.append(pars != default)
+    return np.array(keep, dtype=bool) if len(hits) else np.zeros(0, dtype=bool)
+
+
 @pytest.mark.parametrize("seed", range(60))
 def test_cache_model_reports_the_oracles_hits(seed):
     s, c, P, K, start, sa, kw, never = problem(seed)
@@ -84,21 +102,7 @@ def test_cache_model_reports_the_oracles_hits(seed):
     if "edge_prob" in kw:
         assert np.array_equal(gp, hp)                         # fp64 bit equality: host prior == the oracle's
     assert len(orders) > 1
-    # what the search acts on: the hits that change what the device computed for the order -- every hit where the pool has
-    # equal category counts (the winner is replaced), otherwise the hits whose cached listing is not the one this order
-    # gives the family (fixed parents first, then the others by position), and all hits when priors are in use
-    fixed = kw.get("fixed_parents")
-    keep = []
-    for row in hits:
-        if row[0] == 1 or "edge_prob" in kw:
-            keep.append(True)
-            continue
-        pos = {int(lbl): i for i, lbl in enumerate(orders[row[1]])}
-        pars = [int(v) for v in row[4:4 + row[3]]]
-        fx = set(fixed[row[2] - 1]) if fixed is not None else set()
-        default = sorted([q for q in pars if q in fx], key=pos.get) + sorted([q for q in pars if q not in fx], key=pos.get)
-        keep.append(pars != default)
-    keep = np.array(keep, dtype=bool) if len(hits) else np.zeros(0, dtype=bool)
+    keep = acted_on(hits, orders, kw)
     got2, _ = model_trace(n, c, P, K, orders, winners, never_kept=never, all_hits=False, **mkw)
     assert np.array_equal(got2, hits[keep])
 
@@ -125,4 +129,4 @@ def test_cache_table_size_follows_the_reference():
     got, _ = model_trace(37, c, 2, K, orders, winners)
     assert len(hits) > 1000 and np.array_equal(got, hits)
     got2, _ = model_trace(37, c, 2, K, orders, winners, all_hits=False)
-    assert 0 < len(got2) < len(got)
+    assert 0 < len(got2) < len(got) and np.array_equal(got2, hits[acted_on(hits, orders, {})])
