@@ -23,6 +23,7 @@
  *                                      grid barrier per node, a warp per slot for mixed-category nodes -- or a launch per node
  *  The two-parent tables on the tensor cores (tcgen05) are in cnb_umma.cu.
  */
+#include <atomic>
 #include <stdio.h>
 #include <cooperative_groups.h>
 #include "cnb_device.cuh"
@@ -1148,15 +1149,30 @@ __global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, 
 		const int *__restrict__ opt_cx, const long long *__restrict__ opt_fid, long long *__restrict__ bp_opt,
 		int *__restrict__ bp_src, int stage_state) {
 	auto barrier = [] { if constexpr (ONE) __syncthreads(); else cooperative_groups::this_grid().sync(); };
-	/* sbase[N] | s_sc[DPM_OPTS] | s_L[slots] | s_cx[DPM_OPTS] | s_ex[slots]: the scan of a slot reads a node's options and
-	 * the previous state 32 at a time; out of global memory every such read is an L2 round trip (21 per node on ALARM) */
+	/* sbase[N] | s_sc[2][DPM_OPTS] | s_L[slots] | s_pfx[slots] | s_cx[2][DPM_OPTS] | s_ex[slots]: the scan of a slot reads a
+	 * node's options and the previous state 32 at a time, and every record-breaking candidate starts its re-summation from
+	 * the source slot's prefix sum; out of global memory every such read is an L2 round trip on the critical path of the
+	 * node step.  The options of node c + 1 do not depend on the DP state: they are staged into the other buffer BEFORE the
+	 * barrier that ends node c, so that after it only the state is fetched. */
 	extern __shared__ double sbase[];
 	const int K = s0.K, nthr = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
 	const int lane = threadIdx.x & 31, gw = t0 >> 5, nwarps = nthr >> 5;
 	const int nslots = stage_state ? K + 1 : 0;
-	double *s_sc = sbase + N, *s_L = s_sc + DPM_OPTS;
-	int *s_cx = reinterpret_cast<int *>(s_L + nslots);
-	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_cx + DPM_OPTS);
+	double *s_sc2 = sbase + N, *s_L = s_sc2 + 2 * DPM_OPTS, *s_pfx = s_L + nslots;
+	int *s_cx2 = reinterpret_cast<int *>(s_pfx + nslots);
+	unsigned char *s_ex = reinterpret_cast<unsigned char *>(s_cx2 + 2 * DPM_OPTS);
+	/* a node's options into buffer (node & 1): complexity INT_MIN = no winner for that d */
+	auto stage_options = [&](int node) {
+		const CnbDpNode q = nodes[node];
+		const long long n = q.opt_end - q.opt_begin;
+		if (n > DPM_OPTS) return;
+		double *sc = s_sc2 + (node & 1) * DPM_OPTS;
+		int *cx = s_cx2 + (node & 1) * DPM_OPTS;
+		for (int o = threadIdx.x; o < (int)n; o += blockDim.x) {
+			sc[o] = opt_score[q.opt_begin + o];
+			cx[o] = opt_fid[q.opt_begin + o] >= 0 ? opt_cx[q.opt_begin + o] : INT_MIN;
+		}
+	};
 	for (int i = threadIdx.x; i < N; i += blockDim.x) sbase[i] = base_v[i];
 	__syncthreads();
 	for (int j = t0; j <= K; j += nthr) {
@@ -1167,25 +1183,25 @@ __global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, 
 		s0.L[j] = l;
 		s0.pfx[j] = ex ? __dadd_rn(0.0, sbase[0]) : 0.0;
 	}
+	if (N > 1) stage_options(1);
 	barrier();
 	for (int c = 1; c < N; c++) {
 		const DpState &cur = (c & 1) ? s0 : s1, &nxt = (c & 1) ? s1 : s0;
 		const CnbDpNode nd = nodes[c];
 		const double bv = sbase[c];
 		const long long nopt = nd.opt_end - nd.opt_begin;
-		/* stage the node's options (complexity INT_MIN = no winner for that d) and the previous state */
 		const bool opts_staged = nopt <= DPM_OPTS;
-		if (opts_staged)
-			for (int o = threadIdx.x; o < (int)nopt; o += blockDim.x) {
-				s_sc[o] = opt_score[nd.opt_begin + o];
-				s_cx[o] = opt_fid[nd.opt_begin + o] >= 0 ? opt_cx[nd.opt_begin + o] : INT_MIN;
-			}
+		const double *s_sc = s_sc2 + (c & 1) * DPM_OPTS;
+		const int *s_cx = s_cx2 + (c & 1) * DPM_OPTS;
+		/* the previous state */
 		for (int k = threadIdx.x; k < nslots; k += blockDim.x) {
 			s_L[k] = cur.L[k];
+			s_pfx[k] = cur.pfx[k];
 			s_ex[k] = cur.exists[k];
 		}
 		__syncthreads();
 		const double *Lp = stage_state ? s_L : cur.L;
+		const double *Pp = stage_state ? s_pfx : cur.pfx;
 		const unsigned char *Ep = stage_state ? s_ex : cur.exists;
 		for (int j = gw; j <= K; j += nwarps) {
 			bool has = false;
@@ -1216,7 +1232,7 @@ __global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, 
 					if (!m) break;
 					const int l = __ffs(m) - 1;
 					double r = 0.0;
-					if (lane == l) r = dev_resum(cur.pfx[k], f, c, N, sbase);
+					if (lane == l) r = dev_resum(Pp[k], f, c, N, sbase);
 					R = __shfl_sync(0xffffffffu, r, l);
 					bf = __shfl_sync(0xffffffffu, f, l);
 					bs = __shfl_sync(0xffffffffu, k, l);
@@ -1234,18 +1250,19 @@ __global__ void __launch_bounds__(BS) k_dp_mixed(DpState s0, DpState s1, int N, 
 				if (take) {
 					nxt.exists[j] = 1;
 					nxt.L[j] = R;
-					nxt.pfx[j] = __dadd_rn(cur.pfx[bs], bf);
+					nxt.pfx[j] = __dadd_rn(Pp[bs], bf);
 					bp_opt[bpi] = bo;
 					bp_src[bpi] = bs;
 				} else {
 					nxt.exists[j] = cur_ex;
 					nxt.L[j] = Lp[j];
-					nxt.pfx[j] = __dadd_rn(cur.pfx[j], bv);
+					nxt.pfx[j] = __dadd_rn(Pp[j], bv);
 					bp_opt[bpi] = -1;
 					bp_src[bpi] = j;
 				}
 			}
 		}
+		if (c + 1 < N) stage_options(c + 1);                       /* behind this node's scan, ahead of the barrier */
 		barrier();
 	}
 }
@@ -1831,8 +1848,8 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 	/* the previous state is staged in shared memory when it fits (K + 1 <= DPM_SLOTS), a node's options when there are
 	 * at most DPM_OPTS of them */
 	int stage_state = s0.K + 1 <= DPM_SLOTS;
-	const size_t smem = (size_t)N * sizeof(double) + (size_t)DPM_OPTS * (sizeof(double) + sizeof(int))
-			+ (stage_state ? (size_t)(s0.K + 1) * sizeof(double) + (size_t)((s0.K + 1 + 15) & ~15) : 0);
+	const size_t smem = (size_t)N * sizeof(double) + (size_t)2 * DPM_OPTS * (sizeof(double) + sizeof(int))
+			+ (stage_state ? (size_t)2 * (s0.K + 1) * sizeof(double) + (size_t)((s0.K + 1 + 15) & ~15) : 0);
 	/* one CTA of 1024 threads, no grid barrier (CNB_DP_ONE_CTA: largest K + 1 that takes this form).  Off by default: on
 	 * ALARM (601 slots, hundreds of options per node) it is 3.9 x SLOWER than the cooperative grid -- cnSearchSA 1.32 s
 	 * against 0.34 s -- the scan of a slot's options is real work for 600 warps, not barrier latency */
@@ -1846,8 +1863,12 @@ int cnbk_dp_mixed(cudaStream_t st, const DpState &s0, const DpState &s1, int N, 
 		CK(cudaGetLastError());
 		return CNB_OK;
 	}
-	if (smem > 48 * 1024)
+	/* the opt-in above 48 KB is a property of (function, device): asked for once per size, not once per evaluated order */
+	static std::atomic<size_t> opted[64];                /* zero-initialised; several host threads evaluate orders side by side */
+	if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || smem > opted[dev].load())) {
 		CK(cudaFuncSetAttribute(k_dp_mixed<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (dev >= 0 && dev < 64) opted[dev].store(smem);
+	}
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dp_mixed<256, false>, 256, smem));
 	if (!coop || per_sm < 1) return CNB_ERR_PROC;
 	const int blocks = std::min(sms * per_sm, std::max(1, (s0.K + 1 + 7) / 8));      /* one warp per slot if it fits */
