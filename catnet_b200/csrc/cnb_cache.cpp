@@ -157,9 +157,6 @@ bool cnb_cache_wanted(int use_cache, int num_threads) {
 	return use_cache && num_threads <= 8;
 }
 
-static inline const CnbBlock &b_ptr(int bi, const CnbPlan &pl) { return pl.blocks[bi]; }
-static inline int64_t b_opt(const CnbBlock &b, int64_t r) { return b.opt_off + r; }
-
 static bool next_comb(int *idx, int k, int n) {
 	int i = k - 1;
 	while (i >= 0 && idx[i] == n - k + i) i--;
@@ -276,7 +273,7 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 							if (!pl.has_prior && fwd) continue;
 							out->emplace_back();
 							CnbOverride &ov = out->back();
-							ov.opt = b_opt(b_ptr(bi - 1, pl), r);
+							ov.opt = b->opt_off + r;
 							ov.fid = -1;
 							ov.child = c;
 							ov.d = d;
