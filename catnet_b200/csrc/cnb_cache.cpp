@@ -258,6 +258,7 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 				 * loops in the enumeration order (i, then j > i = lexicographic), no hash unless the key has to be stored */
 				const size_t nbase = (size_t)(node - 1) * N;
 				const int ccx = pl.cats[c] - 1;
+				const int64_t opt0 = b->opt_off;
 				int64_t r = 0;
 				for (int i = 0; i < (d == 1 ? nr : nr - 1); i++) {
 					const int a = fre[i], la = pl.order[a] + 1;
@@ -273,7 +274,7 @@ int CnbScoreCache::walk(const CnbPlan &pl, const cnb_params *params, const uint8
 							if (!pl.has_prior && fwd) continue;
 							out->emplace_back();
 							CnbOverride &ov = out->back();
-							ov.opt = b->opt_off + r;
+							ov.opt = opt0 + r;
 							ov.fid = -1;
 							ov.child = c;
 							ov.d = d;
