@@ -10,6 +10,7 @@ on some inputs (e.g. fixed parents whose base network exceeds maxComplexity, SUR
     python tools/fuzz_oracle.py rest 0 3000           # pairwise metrics, cnSetProb / cnLoglik / cnNodeLoglik, cnSamples
     python tools/fuzz_oracle.py sacache 0 1500        # the reference with its score cache ON against itself with it OFF
     python tools/fuzz_oracle.py sacacheport 0 2000    # the restated cache against the reference's (cache ON, one thread)
+    python tools/fuzz_oracle.py sacachethreads 0 600  # the reference's cache-ON run with 2-4 threads against the sequential interleaving
 
 Round 1: 10,911 + 5,955 + 2,000 + 1,500 + 3,000 problems; one mismatch (search 3042: a node perturbed in every sample, fixed
 since) and five reference crashes (search 3886, 9556, 10501, 11146, 11995: fixed parents put the base
@@ -203,6 +204,30 @@ def check_sacacheport(seed):
         os._exit(5)
 
 
+def check_sacachethreads(seed):
+    """How the reference's OWN cache-ON result with several threads relates to the proposal-after-proposal interleaving the
+    restatement (and the library) take: its worker threads fill the one global table under a mutex in whatever order they
+    get there, so the outcome depends on timing.  Exit code 5 = the reference's run differs from the sequential
+    interleaving (not a mismatch: counted)."""
+    rng = np.random.default_rng(seed)
+    n, m = int(rng.integers(4, 11)), int(rng.integers(20, 400))
+    s, c = random_problem(seed, n, m, [None, 2, 3, 4][seed % 4], na_frac=[0, 0.1][seed % 2])
+    sa = dict(select_mode=seed % 3, temp_start=[1.0, 0.05, 10.0, 0.0][seed % 4], temp_cool_fact=[0.9, 0.5][seed % 2],
+              temp_check_orders=int(rng.integers(1, 8)), max_iter=int(rng.integers(20, 120)),
+              order_shuffles=[1.0, 1.5, -1.0, -2.5, 0.0, 3.0][seed % 6], stop_diff=[1e-10, 0.01][seed % 2],
+              num_threads=2 + seed % 3, seed=int(rng.integers(1, 1 << 40)))
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    K = int(np.sum(c - 1)) + n * int(c.max()) ** 2
+    a = ref.search_sa(s, 2, K, start, use_cache=True, want_probs=True, num_cats=c, **sa)
+    b = port.search_sa(s, 2, K, start, use_cache=True, want_probs=True, num_cats=c, **sa)
+    # the trajectory's decisions never depend on the cache beyond last bits; what may differ is listing and last bits
+    try:
+        assert np.array_equal(a["order"], b["order"]) and np.array_equal(a["trace"], b["trace"])
+        strict_nets(b["nets"], a["nets"])
+    except AssertionError:
+        os._exit(5)
+
+
 def check_rest(seed):
     rng = np.random.default_rng(seed)
     n, m = int(rng.integers(1, 10)), int(rng.integers(7, 150))
@@ -245,7 +270,7 @@ def check_rest(seed):
 
 def main():
     check = {"search": check_search, "wide": check_wide, "unseen": check_unseen, "sa": check_sa, "rest": check_rest, "sacache": check_sacache,
-             "sacacheport": check_sacacheport}[sys.argv[1]]
+             "sacacheport": check_sacacheport, "sacachethreads": check_sacachethreads}[sys.argv[1]]
     lo, hi = int(sys.argv[2]), int(sys.argv[3])
     if not ref.available():
         sys.exit("oracle/_ref is not built (needs /root/reference)")
@@ -278,6 +303,8 @@ def main():
     print("problems %d  mismatches %s  reference crashes %s" % (ran, mismatch, crash))
     if sys.argv[1] == "sacacheport":
         print("of these, cache ON differs from cache OFF (listing order of parents or last bits) in %d" % differs)
+    if sys.argv[1] == "sacachethreads":
+        print("of these, the reference with 2-4 threads and its cache ON differs from the proposal-after-proposal interleaving in %d" % differs)
     sys.exit(1 if mismatch else 0)
 
 
