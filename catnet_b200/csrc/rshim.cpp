@@ -9,7 +9,11 @@
  * implementation (this shim is linked INTO the package next to the reference sources).
  *
  * SEXP <-> C ABI only: all computation happens behind include/catnet_b200.h.  R API calls (coercion, allocation,
- * Rf_error) stay on the calling thread; nothing longjmps while library resources are held.
+ * Rf_error) stay on the calling thread.  Rf_error and (under options(warn = 2)) Rf_warning leave by longjmp, which skips
+ * C++ destructors: so no routine raises either while its std::vectors are alive -- problems found on the way are thrown
+ * as a C++ exception or noted, the routine's body unwinds normally, and `guarded` raises the R error / warnings
+ * afterwards with nothing of the call left on the C++ side.  What R itself may still do in the middle (an allocation that
+ * fails) is covered for the library's result by an external pointer with a finalizer (export_result).
  *
  * This file needs R's headers.  It is NOT part of libcatnet_b200.so; the image used to develop it has no R, so there
  * it is compiled against tests/rstub and run against the miniature R API of tests/rstub/minir.cpp
@@ -20,12 +24,65 @@
 #include <Rdefines.h>
 #include <R_ext/Rdynload.h>
 #include <float.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 #include <vector>
 #include "../../include/catnet_b200.h"
 
 namespace {
+
+/* ---- errors and warnings without longjmp over live C++ objects (see the header) ---- */
+struct ShimError {};
+thread_local char g_fail[640];
+thread_local char g_warn[4][160];
+thread_local int g_nwarn;
+
+[[noreturn]] void shim_fail(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_fail, sizeof(g_fail), fmt, ap);
+	va_end(ap);
+	throw ShimError();
+}
+void shim_warn(const char *msg) {
+	if (g_nwarn < 4) {
+		strncpy(g_warn[g_nwarn], msg, sizeof(g_warn[0]) - 1);
+		g_warn[g_nwarn][sizeof(g_warn[0]) - 1] = 0;
+		g_nwarn++;
+	}
+}
+/* run the body of a .Call routine; raise what it noted once its frame is gone */
+template <class Body>
+SEXP guarded(Body body) {
+	g_fail[0] = 0;
+	g_nwarn = 0;
+	SEXP out = R_NilValue;
+	try {
+		out = body();
+	} catch (const ShimError &) {
+		out = R_NilValue;
+	}
+	if (g_fail[0]) error("%s", g_fail);            /* R restores its protection stack when it unwinds to the caller */
+	if (g_nwarn) {
+		PROTECT(out);
+		for (int i = 0; i < g_nwarn; i++) warning("%s", g_warn[i]);
+		UNPROTECT(1);
+	}
+	return out;
+}
+/* elements of an N x M matrix as R counts them; refuses what an int-indexed buffer cannot address */
+R_xlen_t cells(int rows, int cols) {
+	const R_xlen_t n = (R_xlen_t)rows * (R_xlen_t)cols;
+	if (rows < 0 || cols < 0 || n > (R_xlen_t)2147483647) shim_fail("matrix of %d x %d is too large", rows, cols);
+	return n;
+}
+/* a fresh value into a slot: protected across install(), which may allocate */
+void set_slot(SEXP obj, const char *name, SEXP value) {
+	PROTECT(value);
+	SET_SLOT(obj, install(name), value);
+	UNPROTECT(1);
+}
 
 /* list (length N) of integer vectors, or R_NilValue -> [N][N] rows of 1-based labels, 0 padded */
 bool pool_matrix(SEXP rPool, int N, std::vector<int32_t> &out) {
@@ -56,7 +113,7 @@ void marshal(Marshalled &m, SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents
 		SEXP rMatEdgeLiks, SEXP rEcho) {
 	memset(&m.p, 0, sizeof(m.p));
 	m.nprotect = 0;
-	if (!isMatrix(rSamples)) error("Data is not a matrix");                 /* rcatnet_search.cpp:69-70 */
+	if (!isMatrix(rSamples)) shim_fail("Data is not a matrix");                 /* rcatnet_search.cpp:69-70 */
 	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
 	m.nprotect++;
 	SEXP dim = getAttrib(rSamples, R_DimSymbol);
@@ -84,7 +141,7 @@ void marshal(Marshalled &m, SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents
 		UNPROTECT(1);
 		m.p.order = m.order.data();
 	} else if (!isNull(rOrder)) {
-		warning("Invalid nodeOrder parameter - reset to default node order.");   /* rcatnet_search.cpp:112-116 */
+		shim_warn("Invalid nodeOrder parameter - reset to default node order.");   /* rcatnet_search.cpp:112-116 */
 	}
 	if (!isNull(rNodeCats) && length(rNodeCats) == N) {                     /* catIndices = 1..C per node */
 		m.num_cats.resize(N);
@@ -93,7 +150,7 @@ void marshal(Marshalled &m, SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents
 	}
 	if (pool_matrix(rParentsPool, N, m.pool)) m.p.parents_pool = m.pool.data();
 	if (pool_matrix(rFixedParentsPool, N, m.fixed)) m.p.fixed_parents = m.fixed.data();
-	if (!isNull(rMatEdgeLiks) && length(rMatEdgeLiks) == N * N) {
+	if (!isNull(rMatEdgeLiks) && (R_xlen_t)length(rMatEdgeLiks) == cells(N, N)) {
 		rMatEdgeLiks = PROTECT(coerceVector(rMatEdgeLiks, REALSXP));
 		m.nprotect++;
 		m.p.edge_prob = REAL(rMatEdgeLiks);           /* R's own column-major buffer, exactly what the ABI expects */
@@ -129,8 +186,8 @@ SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP r
 		if (cats_pos[n] > maxcat) maxcat = cats_pos[n];
 	}
 	SEXP cnet = PROTECT(NEW_OBJECT(MAKE_CLASS("catNetwork")));
-	SET_SLOT(cnet, install("objectName"), mkString("catNetwork"));
-	SET_SLOT(cnet, install("numnodes"), ScalarInteger(N));
+	set_slot(cnet, "objectName", mkString("catNetwork"));
+	set_slot(cnet, "numnodes", ScalarInteger(N));
 	SEXP names = PROTECT(allocVector(STRSXP, N));
 	char buf[64];
 	for (int n = 0; n < N; n++) {
@@ -142,7 +199,7 @@ SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP r
 		}
 	}
 	SET_SLOT(cnet, install("nodes"), names);
-	SET_SLOT(cnet, install("maxParents"), ScalarInteger(maxpar));
+	set_slot(cnet, "maxParents", ScalarInteger(maxpar));
 	SEXP plist = PROTECT(allocVector(VECSXP, N));
 	for (int n = 0; n < N; n++) {
 		if (npar[n] <= 0) continue;                                                /* NULL entry */
@@ -152,7 +209,7 @@ SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP r
 		UNPROTECT(1);
 	}
 	SET_SLOT(cnet, install("parents"), plist);
-	SET_SLOT(cnet, install("maxCategories"), ScalarInteger(maxcat));
+	set_slot(cnet, "maxCategories", ScalarInteger(maxcat));
 	SEXP clist = PROTECT(allocVector(VECSXP, N));
 	for (int n = 0; n < N; n++) {
 		SEXP cv = PROTECT(allocVector(STRSXP, cats_pos[n]));
@@ -179,9 +236,9 @@ SEXP make_catnetwork(const cnb_result *r, int i, const int32_t *cats_pos, SEXP r
 		INTEGER(sizes)[n] = ss;
 	}
 	SET_SLOT(cnet, install("probabilities"), problists);
-	SET_SLOT(cnet, install("meta"), mkString("catNetwork object"));
-	SET_SLOT(cnet, install("complexity"), ScalarInteger(complexity));
-	SET_SLOT(cnet, install("likelihood"), ScalarReal(loglik > -(double)FLT_MAX ? loglik : R_NegInf));   /* :295-300 */
+	set_slot(cnet, "meta", mkString("catNetwork object"));
+	set_slot(cnet, "complexity", ScalarInteger(complexity));
+	set_slot(cnet, "likelihood", ScalarReal(loglik > -(double)FLT_MAX ? loglik : R_NegInf));   /* :295-300 */
 	SET_SLOT(cnet, install("nodeSampleSizes"), sizes);
 	UNPROTECT(6);
 	return cnet;
@@ -205,7 +262,7 @@ SEXP export_result(cnb_result *r, const cnb_params &p, SEXP rNodeNames) {
 	if (K < 1) {
 		result_finalizer(guard);
 		UNPROTECT(1);
-		warning("No networks are found");                                          /* rcatnet_search.cpp:279-282 */
+		shim_warn("No networks are found");                                          /* rcatnet_search.cpp:279-282 */
 		return R_NilValue;
 	}
 	std::vector<int32_t> cats_pos(N);
@@ -219,12 +276,8 @@ SEXP export_result(cnb_result *r, const cnb_params &p, SEXP rNodeNames) {
 	return out;
 }
 
-void fail(int rc) {
-	/* copy the message first: Rf_error longjmps */
-	char msg[512];
-	strncpy(msg, cnb_last_error(), sizeof(msg) - 1);
-	msg[sizeof(msg) - 1] = 0;
-	error("catnet (B200): %s [code %d]", msg, rc);
+[[noreturn]] void fail(int rc) {
+	shim_fail("catnet (B200): %s [code %d]", cnb_last_error(), rc);
 }
 
 } /* namespace */
@@ -236,15 +289,17 @@ extern "C" {
 SEXP ccnOptimalNetsForOrder(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes,
 		SEXP rMaxComplexity, SEXP rOrder, SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool,
 		SEXP rMatEdgeLiks, SEXP rUseCache, SEXP rEcho) {
-	(void)rUseCache;
-	Marshalled m;
-	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, rOrder, rNodeCats, rParentsPool,
-			rFixedParentsPool, rMatEdgeLiks, rEcho);
-	cnb_result *res = NULL;
-	int rc = cnb_search_order(&m.p, &res);
-	UNPROTECT(m.nprotect);
-	if (rc != CNB_OK) fail(rc);
-	return export_result(res, m.p, R_NilValue);
+	return guarded([&]() -> SEXP {
+		(void)rUseCache;
+		Marshalled m;
+		marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, rOrder, rNodeCats, rParentsPool,
+				rFixedParentsPool, rMatEdgeLiks, rEcho);
+		cnb_result *res = NULL;
+		int rc = cnb_search_order(&m.p, &res);
+		UNPROTECT(m.nprotect);
+		if (rc != CNB_OK) fail(rc);
+		return export_result(res, m.p, R_NilValue);
+	});
 }
 
 /* catnetOptimalNetsSA (catnet_rexport.h:42-48) */
@@ -253,84 +308,88 @@ SEXP ccnOptimalNetsSA(SEXP rNodeNames, SEXP rSamples, SEXP rPerturbations, SEXP 
 		SEXP rMatEdgeLiks, SEXP rDirProbs, SEXP rModel, SEXP rStartOrder, SEXP rTempStart, SEXP rTempCoolFact,
 		SEXP rTempCheckOrders, SEXP rMaxIter, SEXP rOrderShuffles, SEXP rStopDiff, SEXP rThreads, SEXP rUseCache,
 		SEXP rEcho) {
-	(void)rMaxParentsPool;            /* R hard-codes maxParentsPool <- 0 (R/catnet.search.R:523) */
-	Marshalled m;
-	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
-			rFixedParentsPool, rMatEdgeLiks, rEcho);
-	const int N = m.p.num_nodes;
-	cnb_sa_params sa;
-	memset(&sa, 0, sizeof(sa));
-	const char *model = CHAR(STRING_ELT(PROTECT(coerceVector(rModel, STRSXP)), 0));
-	sa.select_mode = !strncmp(model, "AIC", 3) ? 1 : (!strncmp(model, "BIC", 3) ? 2 : 0);   /* rcatnet_sa.cpp:323-327 */
-	UNPROTECT(1);
-	std::vector<int32_t> start(N);
-	if (length(rStartOrder) < N) {
-		warning("Invalid nodeStartOrder parameter - reset to default node order.");
-		for (int i = 0; i < N; i++) start[i] = i + 1;
-	} else {
-		SEXP v = PROTECT(coerceVector(rStartOrder, INTSXP));
-		start.assign(INTEGER(v), INTEGER(v) + N);
+	return guarded([&]() -> SEXP {
+		(void)rMaxParentsPool;            /* R hard-codes maxParentsPool <- 0 (R/catnet.search.R:523) */
+		Marshalled m;
+		marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
+				rFixedParentsPool, rMatEdgeLiks, rEcho);
+		const int N = m.p.num_nodes;
+		cnb_sa_params sa;
+		memset(&sa, 0, sizeof(sa));
+		const char *model = CHAR(STRING_ELT(PROTECT(coerceVector(rModel, STRSXP)), 0));
+		sa.select_mode = !strncmp(model, "AIC", 3) ? 1 : (!strncmp(model, "BIC", 3) ? 2 : 0);   /* rcatnet_sa.cpp:323-327 */
 		UNPROTECT(1);
-	}
-	sa.start_order = start.data();
-	sa.temp_start = asReal(rTempStart);
-	sa.temp_cool_fact = asReal(rTempCoolFact);
-	sa.temp_check_orders = asInteger(rTempCheckOrders);
-	sa.max_iter = asInteger(rMaxIter);
-	sa.order_shuffles = asReal(rOrderShuffles);
-	sa.stop_diff = asReal(rStopDiff);
-	sa.num_threads = asInteger(rThreads);
-	sa.use_cache = asLogical(rUseCache);
-	int nprot = 0;
-	if (!isNull(rDirProbs) && length(rDirProbs) == N * N) {
-		rDirProbs = PROTECT(coerceVector(rDirProbs, REALSXP));
-		nprot++;
-		sa.dir_prob = REAL(rDirProbs);
-	}
-	/* the chain draws from R's own generator on this thread, exactly where stock catnet does (rcatnet_sa.cpp:146,151,225,
-	 * 745; utils.h:156,190): set.seed(s); cnSearchSA(...) proposes the same orders as the reference */
-	sa.unif = r_unif;
-	GetRNGstate();
-	cnb_result *res = NULL;
-	int rc = cnb_search_sa(&m.p, &sa, &res);
-	PutRNGstate();
-	UNPROTECT(m.nprotect + nprot);
-	if (rc != CNB_OK) fail(rc);
-	return export_result(res, m.p, rNodeNames);
+		std::vector<int32_t> start(N);
+		if (length(rStartOrder) < N) {
+			shim_warn("Invalid nodeStartOrder parameter - reset to default node order.");
+			for (int i = 0; i < N; i++) start[i] = i + 1;
+		} else {
+			SEXP v = PROTECT(coerceVector(rStartOrder, INTSXP));
+			start.assign(INTEGER(v), INTEGER(v) + N);
+			UNPROTECT(1);
+		}
+		sa.start_order = start.data();
+		sa.temp_start = asReal(rTempStart);
+		sa.temp_cool_fact = asReal(rTempCoolFact);
+		sa.temp_check_orders = asInteger(rTempCheckOrders);
+		sa.max_iter = asInteger(rMaxIter);
+		sa.order_shuffles = asReal(rOrderShuffles);
+		sa.stop_diff = asReal(rStopDiff);
+		sa.num_threads = asInteger(rThreads);
+		sa.use_cache = asLogical(rUseCache);
+		int nprot = 0;
+		if (!isNull(rDirProbs) && (R_xlen_t)length(rDirProbs) == cells(N, N)) {
+			rDirProbs = PROTECT(coerceVector(rDirProbs, REALSXP));
+			nprot++;
+			sa.dir_prob = REAL(rDirProbs);
+		}
+		/* the chain draws from R's own generator on this thread, exactly where stock catnet does (rcatnet_sa.cpp:146,151,225,
+		 * 745; utils.h:156,190): set.seed(s); cnSearchSA(...) proposes the same orders as the reference */
+		sa.unif = r_unif;
+		GetRNGstate();
+		cnb_result *res = NULL;
+		int rc = cnb_search_sa(&m.p, &sa, &res);
+		PutRNGstate();
+		UNPROTECT(m.nprotect + nprot);
+		if (rc != CNB_OK) fail(rc);
+		return export_result(res, m.p, rNodeNames);
+	});
 }
 
 /* catnetParHistogram (catnet_rexport.h:49-54): cnSearchHist, R/catnet.histo.R:116-129 */
 SEXP ccnParHistogram(SEXP rSamples, SEXP rPerturbations, SEXP rMaxParents, SEXP rParentSizes, SEXP rMaxComplexity,
 		SEXP rNodeCats, SEXP rParentsPool, SEXP rFixedParentsPool, SEXP rScore, SEXP rWeight, SEXP rMaxIter,
 		SEXP rThreads, SEXP rUseCache, SEXP rEcho) {
-	Marshalled m;
-	marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
-			rFixedParentsPool, R_NilValue, rEcho);
-	const int N = m.p.num_nodes;
-	cnb_hist_params hp;
-	memset(&hp, 0, sizeof(hp));
-	const char *score = CHAR(STRING_ELT(PROTECT(coerceVector(rScore, STRSXP)), 0));
-	hp.score = !strncmp(score, "AIC", 3) ? 1 : (!strncmp(score, "BIC", 3) ? 2 : 0);        /* rcatnet_hist.cpp:212-216 */
-	UNPROTECT(1);
-	hp.weight = asInteger(rWeight);
-	hp.max_iter = asInteger(rMaxIter);
-	hp.num_threads = asInteger(rThreads);
-	hp.use_cache = asLogical(rUseCache);
-	hp.unif = r_unif;                                                              /* rcatnet_hist.cpp:121-159 */
-	SEXP rmat = PROTECT(allocVector(REALSXP, N * N));                              /* :229-233 */
-	GetRNGstate();
-	int rc = cnb_search_hist(&m.p, &hp, REAL(rmat), NULL);
-	PutRNGstate();
-	UNPROTECT(m.nprotect + 1);
-	if (rc != CNB_OK) fail(rc);
-	return rmat;
+	return guarded([&]() -> SEXP {
+		Marshalled m;
+		marshal(m, rSamples, rPerturbations, rMaxParents, rParentSizes, rMaxComplexity, R_NilValue, rNodeCats, rParentsPool,
+				rFixedParentsPool, R_NilValue, rEcho);
+		const int N = m.p.num_nodes;
+		cnb_hist_params hp;
+		memset(&hp, 0, sizeof(hp));
+		const char *score = CHAR(STRING_ELT(PROTECT(coerceVector(rScore, STRSXP)), 0));
+		hp.score = !strncmp(score, "AIC", 3) ? 1 : (!strncmp(score, "BIC", 3) ? 2 : 0);        /* rcatnet_hist.cpp:212-216 */
+		UNPROTECT(1);
+		hp.weight = asInteger(rWeight);
+		hp.max_iter = asInteger(rMaxIter);
+		hp.num_threads = asInteger(rThreads);
+		hp.use_cache = asLogical(rUseCache);
+		hp.unif = r_unif;                                                              /* rcatnet_hist.cpp:121-159 */
+		SEXP rmat = PROTECT(allocVector(REALSXP, cells(N, N)));                              /* :229-233 */
+		GetRNGstate();
+		int rc = cnb_search_hist(&m.p, &hp, REAL(rmat), NULL);
+		PutRNGstate();
+		UNPROTECT(m.nprotect + 1);
+		if (rc != CNB_OK) fail(rc);
+		return rmat;
+	});
 }
 
 /* catnetEntropyPairwise / catnetKLpairwise / catnetPearsonPairwise / catnetEntropyOrder (catnet_rexport.h;
  * catnet_entropy.cpp:38-911), called from R/catnet.entropy.R:60-62, :94-96, :125-127 and R/catnet.chisq.R:27-29 */
 static void pairwise_args(SEXP &rSamples, SEXP &rPerturbations, int &N, int &M, int &nprot) {
-	if (!isMatrix(rSamples)) error("Data should be a matrix");                          /* catnet_entropy.cpp:47-48 */
-	if (!isNull(rPerturbations) && !isMatrix(rPerturbations)) error("Perturbations should be a matrix");
+	if (!isMatrix(rSamples)) shim_fail("Data should be a matrix");                          /* catnet_entropy.cpp:47-48 */
+	if (!isNull(rPerturbations) && !isMatrix(rPerturbations)) shim_fail("Perturbations should be a matrix");
 	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
 	nprot = 1;
 	SEXP dim = getAttrib(rSamples, R_DimSymbol);
@@ -345,7 +404,7 @@ static void pairwise_args(SEXP &rSamples, SEXP &rPerturbations, int &N, int &M, 
 static SEXP pairwise_call(int kind, SEXP rSamples, SEXP rPerturbations) {
 	int N, M, nprot;
 	pairwise_args(rSamples, rPerturbations, N, M, nprot);
-	SEXP rvec = PROTECT(allocVector(REALSXP, N * N));
+	SEXP rvec = PROTECT(allocVector(REALSXP, cells(N, N)));
 	int rc = cnb_pairwise(kind, N, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
 			REAL(rvec));
 	UNPROTECT(nprot + 1);
@@ -354,26 +413,34 @@ static SEXP pairwise_call(int kind, SEXP rSamples, SEXP rPerturbations) {
 }
 
 SEXP ccnEntropyPairwise(SEXP rSamples, SEXP rPerturbations) {
-	return pairwise_call(CNB_PAIRWISE_ENTROPY, rSamples, rPerturbations);
+	return guarded([&]() -> SEXP {
+		return pairwise_call(CNB_PAIRWISE_ENTROPY, rSamples, rPerturbations);
+	});
 }
 
 SEXP ccnKLPairwise(SEXP rSamples, SEXP rPerturbations) {
-	return pairwise_call(CNB_PAIRWISE_KL, rSamples, rPerturbations);
+	return guarded([&]() -> SEXP {
+		return pairwise_call(CNB_PAIRWISE_KL, rSamples, rPerturbations);
+	});
 }
 
 SEXP ccnPearsonPairwise(SEXP rSamples, SEXP rPerturbations) {
-	return pairwise_call(CNB_PAIRWISE_PEARSON, rSamples, rPerturbations);
+	return guarded([&]() -> SEXP {
+		return pairwise_call(CNB_PAIRWISE_PEARSON, rSamples, rPerturbations);
+	});
 }
 
 SEXP ccnEntropyOrder(SEXP rSamples, SEXP rPerturbations) {
-	int N, M, nprot;
-	pairwise_args(rSamples, rPerturbations, N, M, nprot);
-	SEXP rvec = PROTECT(allocVector(INTSXP, N));
-	int rc = cnb_entropy_order(N, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
-			INTEGER(rvec));
-	UNPROTECT(nprot + 1);
-	if (rc != CNB_OK) fail(rc);
-	return rvec;
+	return guarded([&]() -> SEXP {
+		int N, M, nprot;
+		pairwise_args(rSamples, rPerturbations, N, M, nprot);
+		SEXP rvec = PROTECT(allocVector(INTSXP, N));
+		int rc = cnb_entropy_order(N, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
+				INTEGER(rvec));
+		UNPROTECT(nprot + 1);
+		if (rc != CNB_OK) fail(rc);
+		return rvec;
+	});
 }
 
 /* ---- a given catNetwork against data: ccnLoglik, ccnNodeLoglik, ccnSetProb (src/ccnInit.c:32-34) ----
@@ -395,17 +462,17 @@ static void flatten_probs(SEXP node, const int *pc, int d, int level, int cc, st
 		return;
 	}
 	for (int j = 0; j < pc[level]; j++) {
-		if (!isNewList(node) || j >= length(node)) error("probabilities do not match the parents' categories");
+		if (!isNewList(node) || j >= length(node)) shim_fail("probabilities do not match the parents' categories");
 		flatten_probs(VECTOR_ELT(node, j), pc, d, level + 1, cc, out);
 	}
 }
 
 static void read_network(SEXP cnet, RNetwork &r, bool want_probs) {
-	if (!isS4(cnet)) error("cnet should be a catNetwork");
+	if (!isS4(cnet)) shim_fail("cnet should be a catNetwork");
 	const int N = INTEGER(GET_SLOT(cnet, install("numnodes")))[0];
 	SEXP rparents = GET_SLOT(cnet, install("parents")), rcats = GET_SLOT(cnet, install("categories"));
 	SEXP rprobs = GET_SLOT(cnet, install("probabilities"));
-	if (length(rparents) != N || length(rcats) != N || (want_probs && length(rprobs) != N)) error("invalid catNetwork");
+	if (length(rparents) != N || length(rcats) != N || (want_probs && length(rprobs) != N)) shim_fail("invalid catNetwork");
 	int maxp = 1;
 	for (int i = 0; i < N; i++) maxp = std::max(maxp, (int)length(VECTOR_ELT(rparents, i)));
 	r.cats.resize(N);
@@ -420,10 +487,10 @@ static void read_network(SEXP cnet, RNetwork &r, bool want_probs) {
 		r.npar[i] = d;
 		int pc[64];
 		int64_t size = r.cats[i];
-		if (d > 8) error("more than 8 parents");
+		if (d > 8) shim_fail("more than 8 parents");
 		for (int k = 0; k < d; k++) {
 			const int q = INTEGER(pv)[k];
-			if (q < 1 || q > N) error("invalid parent");
+			if (q < 1 || q > N) shim_fail("invalid parent");
 			r.pars[(size_t)i * maxp + k] = q;
 			pc[k] = r.cats[q - 1];
 			size *= pc[k];
@@ -443,11 +510,11 @@ static void read_network(SEXP cnet, RNetwork &r, bool want_probs) {
 }
 
 static void network_data(SEXP &rSamples, SEXP &rPerturbations, int N, int &M, int &nprot) {
-	if (!isMatrix(rSamples)) error("'data' should be a matrix or data frame of categories");   /* R/catnet.loglik.R:57-58 */
+	if (!isMatrix(rSamples)) shim_fail("'data' should be a matrix or data frame of categories");   /* R/catnet.loglik.R:57-58 */
 	rSamples = PROTECT(coerceVector(rSamples, INTSXP));
 	nprot = 1;
 	SEXP dim = getAttrib(rSamples, R_DimSymbol);
-	if (INTEGER(dim)[0] != N) error("The number of nodes in  the object and data should be equal");   /* :69-70 */
+	if (INTEGER(dim)[0] != N) shim_fail("The number of nodes in  the object and data should be equal");   /* :69-70 */
 	M = INTEGER(dim)[1];
 	if (!isNull(rPerturbations)) {
 		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
@@ -462,93 +529,101 @@ static void export_neg_inf(double *v, int n) {
 }
 
 SEXP ccnLoglik(SEXP cnet, SEXP rSamples, SEXP rPerturbations, SEXP rBySample) {
-	RNetwork r;
-	read_network(cnet, r, true);
-	int M, nprot;
-	network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
-	const int bysample = asLogical(rBySample) == 1;
-	const int nout = bysample ? M : r.net.num_nodes;
-	SEXP rvec = PROTECT(allocVector(REALSXP, nout));
-	int rc = cnb_loglik(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations),
-			bysample ? CNB_LOGLIK_BYSAMPLE : CNB_LOGLIK_NODES, 0, REAL(rvec));
-	if (rc == CNB_OK) export_neg_inf(REAL(rvec), nout);
-	UNPROTECT(nprot + 1);
-	if (rc != CNB_OK) fail(rc);
-	return rvec;                                   /* R sums the per-node values (R/catnet.loglik.R:103-105) */
+	return guarded([&]() -> SEXP {
+		RNetwork r;
+		read_network(cnet, r, true);
+		int M, nprot;
+		network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
+		const int bysample = asLogical(rBySample) == 1;
+		const int nout = bysample ? M : r.net.num_nodes;
+		SEXP rvec = PROTECT(allocVector(REALSXP, nout));
+		int rc = cnb_loglik(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations),
+				bysample ? CNB_LOGLIK_BYSAMPLE : CNB_LOGLIK_NODES, 0, REAL(rvec));
+		if (rc == CNB_OK) export_neg_inf(REAL(rvec), nout);
+		UNPROTECT(nprot + 1);
+		if (rc != CNB_OK) fail(rc);
+		return rvec;                                   /* R sums the per-node values (R/catnet.loglik.R:103-105) */
+	});
 }
 
 SEXP ccnNodeLoglik(SEXP cnet, SEXP rNodes, SEXP rSamples, SEXP rPerturbations) {
-	RNetwork r;
-	read_network(cnet, r, true);
-	int M, nprot;
-	network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
-	SEXP nodes = PROTECT(coerceVector(rNodes, INTSXP));
-	const int nsel = length(nodes);
-	SEXP rvec = PROTECT(allocVector(REALSXP, nsel));
-	int rc = cnb_node_loglik(&r.net, nsel, INTEGER(nodes), M, INTEGER(rSamples),
-			isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0, REAL(rvec));
-	if (rc == CNB_OK) export_neg_inf(REAL(rvec), nsel);
-	UNPROTECT(nprot + 2);
-	if (rc != CNB_OK) fail(rc);
-	return rvec;
+	return guarded([&]() -> SEXP {
+		RNetwork r;
+		read_network(cnet, r, true);
+		int M, nprot;
+		network_data(rSamples, rPerturbations, r.net.num_nodes, M, nprot);
+		SEXP nodes = PROTECT(coerceVector(rNodes, INTSXP));
+		const int nsel = length(nodes);
+		SEXP rvec = PROTECT(allocVector(REALSXP, nsel));
+		int rc = cnb_node_loglik(&r.net, nsel, INTEGER(nodes), M, INTEGER(rSamples),
+				isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0, REAL(rvec));
+		if (rc == CNB_OK) export_neg_inf(REAL(rvec), nsel);
+		UNPROTECT(nprot + 2);
+		if (rc != CNB_OK) fail(rc);
+		return rvec;
+	});
 }
 
 SEXP ccnSetProb(SEXP cnet, SEXP rSamples, SEXP rPerturbations) {
-	RNetwork r;
-	read_network(cnet, r, false);
-	const int N = r.net.num_nodes;
-	int M, nprot;
-	network_data(rSamples, rPerturbations, N, M, nprot);
-	std::vector<double> probs((size_t)r.off[N]), ll(N);
-	std::vector<int32_t> sizes(N);
-	int rc = cnb_set_prob(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
-			probs.data(), ll.data(), sizes.data());
-	UNPROTECT(nprot);
-	if (rc != CNB_OK) fail(rc);
-	/* the object with its tables, likelihood and sample sizes replaced (R keeps nodes / categories, catnet.samples.R:427-436) */
-	SEXP out = PROTECT(duplicate(cnet));
-	SEXP problists = PROTECT(allocVector(VECSXP, N));
-	SEXP rsizes = PROTECT(allocVector(INTSXP, N));
-	double total = 0;
-	bool neg_inf = false;
-	for (int i = 0; i < N; i++) {
-		int pc[8];
-		for (int k = 0; k < r.npar[i]; k++) pc[k] = r.cats[r.pars[(size_t)i * r.net.max_parents + k] - 1];
-		SET_VECTOR_ELT(problists, i, prob_list(probs.data() + r.off[i], pc, r.npar[i], r.cats[i], 0, 0));
-		INTEGER(rsizes)[i] = sizes[i];
-		if (!(ll[i] > -(double)FLT_MAX)) neg_inf = true;
-		total += ll[i];                                /* CATNET::loglik: nodes in index order (catnet_class.h:469-485) */
-	}
-	SET_SLOT(out, install("probabilities"), problists);
-	SET_SLOT(out, install("likelihood"), ScalarReal(neg_inf ? R_NegInf : total));
-	SET_SLOT(out, install("nodeSampleSizes"), rsizes);
-	UNPROTECT(3);
-	return out;
+	return guarded([&]() -> SEXP {
+		RNetwork r;
+		read_network(cnet, r, false);
+		const int N = r.net.num_nodes;
+		int M, nprot;
+		network_data(rSamples, rPerturbations, N, M, nprot);
+		std::vector<double> probs((size_t)r.off[N]), ll(N);
+		std::vector<int32_t> sizes(N);
+		int rc = cnb_set_prob(&r.net, M, INTEGER(rSamples), isNull(rPerturbations) ? NULL : INTEGER(rPerturbations), 0,
+				probs.data(), ll.data(), sizes.data());
+		UNPROTECT(nprot);
+		if (rc != CNB_OK) fail(rc);
+		/* the object with its tables, likelihood and sample sizes replaced (R keeps nodes / categories, catnet.samples.R:427-436) */
+		SEXP out = PROTECT(duplicate(cnet));
+		SEXP problists = PROTECT(allocVector(VECSXP, N));
+		SEXP rsizes = PROTECT(allocVector(INTSXP, N));
+		double total = 0;
+		bool neg_inf = false;
+		for (int i = 0; i < N; i++) {
+			int pc[8];
+			for (int k = 0; k < r.npar[i]; k++) pc[k] = r.cats[r.pars[(size_t)i * r.net.max_parents + k] - 1];
+			SET_VECTOR_ELT(problists, i, prob_list(probs.data() + r.off[i], pc, r.npar[i], r.cats[i], 0, 0));
+			INTEGER(rsizes)[i] = sizes[i];
+			if (!(ll[i] > -(double)FLT_MAX)) neg_inf = true;
+			total += ll[i];                                /* CATNET::loglik: nodes in index order (catnet_class.h:469-485) */
+		}
+		SET_SLOT(out, install("probabilities"), problists);
+		set_slot(out, "likelihood", ScalarReal(neg_inf ? R_NegInf : total));
+		SET_SLOT(out, install("nodeSampleSizes"), rsizes);
+		UNPROTECT(3);
+		return out;
+	});
 }
 
 /* cnSamples: .Call("ccnSamples", object, numsamples, perturbations, naRate) (R/catnet.samples.R:60-62) ->
  * RCatnet::genSamples (rcatnet.cpp:524-650).  R's RNG cannot cross the C ABI: one uniform from it seeds the library's
  * stream (set.seed() still makes runs reproducible; the stream differs from stock catnet). */
 SEXP ccnSamples(SEXP cnet, SEXP rNumSamples, SEXP rPerturbations, SEXP rNaRate) {
-	RNetwork r;
-	read_network(cnet, r, true);
-	const int N = r.net.num_nodes, M = asInteger(rNumSamples);
-	if (M < 1) error("The number of samples should be integer");
-	int nprot = 0;
-	const int32_t *pert = NULL;
-	if (!isNull(rPerturbations)) {
-		rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
-		nprot++;
-		if (length(rPerturbations) == N * M) pert = INTEGER(rPerturbations);
-	}
-	GetRNGstate();
-	const uint64_t seed = (uint64_t)(unif_rand() * 9007199254740992.0);
-	PutRNGstate();
-	SEXP rsamples = PROTECT(allocVector(INTSXP, N * M));           /* R reshapes it with matrix(data, ncol = numsamples) */
-	int rc = cnb_samples(&r.net, M, pert, asReal(rNaRate), seed, 0, INTEGER(rsamples));
-	UNPROTECT(nprot + 1);
-	if (rc != CNB_OK) fail(rc);
-	return rsamples;
+	return guarded([&]() -> SEXP {
+		RNetwork r;
+		read_network(cnet, r, true);
+		const int N = r.net.num_nodes, M = asInteger(rNumSamples);
+		if (M < 1) shim_fail("The number of samples should be integer");
+		int nprot = 0;
+		const int32_t *pert = NULL;
+		if (!isNull(rPerturbations)) {
+			rPerturbations = PROTECT(coerceVector(rPerturbations, INTSXP));
+			nprot++;
+			if ((R_xlen_t)length(rPerturbations) == cells(N, M)) pert = INTEGER(rPerturbations);
+		}
+		GetRNGstate();
+		const uint64_t seed = (uint64_t)(unif_rand() * 9007199254740992.0);
+		PutRNGstate();
+		SEXP rsamples = PROTECT(allocVector(INTSXP, cells(N, M)));           /* R reshapes it with matrix(data, ncol = numsamples) */
+		int rc = cnb_samples(&r.net, M, pert, asReal(rNaRate), seed, 0, INTEGER(rsamples));
+		UNPROTECT(nprot + 1);
+		if (rc != CNB_OK) fail(rc);
+		return rsamples;
+	});
 }
 
 /* R calls this right BEFORE every search (R/catnet.search.R:204, 279) to drop the reference's memoised scores.  The

@@ -23,6 +23,7 @@ extern double R_NegInf;
 SEXP Rf_protect(SEXP);
 void Rf_unprotect(int);
 SEXP Rf_coerceVector(SEXP, unsigned int);
+typedef long R_xlen_t;                       /* R: ptrdiff_t */
 SEXP Rf_allocVector(unsigned int, long);
 SEXP Rf_getAttrib(SEXP, SEXP);
 SEXP Rf_install(const char *);

@@ -202,6 +202,13 @@ def test_shim_network_argument_errors():
         r.call("ccnSetProb", obj, r.data_matrix(s[:, :-1]), r.NULL)
     with pytest.raises(RError, match="number of samples"):
         r.call("ccnSamples", obj, r.numeric([0]), r.NULL, r.numeric([0.0]))
+    # nodes x samples beyond what an int-indexed buffer addresses: refused before anything is allocated (the product used to
+    # be formed in int), and the error is raised with none of the call's C++ objects alive (rshim.cpp: guarded)
+    with pytest.raises(RError, match="too large"):
+        r.call("ccnSamples", obj, r.numeric([2 ** 30]), r.NULL, r.numeric([0.0]))
+    # the shim is still usable afterwards
+    assert len(r.ints(r.call("ccnSamples", r.call("ccnSetProb", obj, r.data_matrix(s), r.NULL), r.numeric([5]), r.NULL,
+                             r.numeric([0.0])))) == 5 * len(c)
 
 
 SA_KW = dict(temp_start=0.05, temp_cool_fact=0.8, temp_check_orders=3, max_iter=24, order_shuffles=1.5, stop_diff=1e-10,
