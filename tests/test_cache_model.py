@@ -130,3 +130,27 @@ def test_cache_table_size_follows_the_reference():
     assert len(hits) > 1000 and np.array_equal(got, hits)
     got2, _ = model_trace(37, c, 2, K, orders, winners, all_hits=False)
     assert 0 < len(got2) < len(got) and np.array_equal(got2, hits[acted_on(hits, orders, {})])
+
+
+@pytest.mark.parametrize("n", [170, 260])
+def test_cache_model_beyond_the_dense_index_and_the_flat_table(n):
+    """more than 160 nodes: every lookup goes through the hash slots (no dense key index); 260 nodes with two parents:
+    263^3 slots, more than the model keeps as a flat array (it keeps only the slots in use; the reference allocates them
+    all) -- parent pools keep the candidate lists short"""
+    rng = np.random.default_rng(n)
+    s, c = random_problem(n, n, 40, None)
+    pool = [sorted((rng.choice(n, size=5, replace=False) + 1).tolist()) for _ in range(n)]
+    sa = dict(select_mode=2, temp_start=1.0, temp_cool_fact=0.9, temp_check_orders=5, max_iter=8, order_shuffles=6.0,
+              stop_diff=1e-10, num_threads=1, seed=3)
+    start = (rng.permutation(n) + 1).astype(np.int32)
+    K = int(np.sum(c - 1)) + n * 16
+    kw = dict(parents_pool=pool)
+    r, rows, priors, orders = oracle_trace(s, c, 2, K, start, sa, **kw)
+    winners = np.zeros((len(orders), n, 2, 2), dtype=np.int32)
+    for row in rows[rows[:, 0] == 3]:
+        winners[row[1], row[2] - 1, row[3] - 1, :row[3]] = row[4:4 + row[3]]
+    hits = rows[rows[:, 0] != 3]
+    got, _ = model_trace(n, c, 2, K, orders, winners, **kw)
+    assert len(hits) > 100 and np.array_equal(got, hits)
+    got2, _ = model_trace(n, c, 2, K, orders, winners, all_hits=False, **kw)
+    assert np.array_equal(got2, hits[acted_on(hits, orders, kw)])

@@ -1,4 +1,5 @@
-import sys, time, numpy as np
+import os, sys, time, numpy as np
+os.environ.setdefault("CNB_SA_TIMING", "1")   # keep the per-phase timing events in the SA evaluations (cnb_ctx.quiet)
 sys.path.insert(0, '/root/repo')
 from catnet_b200 import _abi, synth
 sys.path.insert(0, '/root/repo')
