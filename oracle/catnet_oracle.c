@@ -8,7 +8,9 @@
  * Parity status: PINNED against the reference itself -- tests/test_oracle.py compares every function here with
  * oracle/_ref/libcatnet_ref.so (the reference's own C++ compiled unmodified) and with the committed fixtures in
  * tests/golden/ that were generated from it (tools/make_golden.py).  The reference ships no golden vectors of its
- * own.
+ * own.  The reference's score cache (cache.cpp) is restated too (cache_get / cache_set below):
+ * pinned on 9,300 fuzzed cnSearchSA / cnSearchHist problems against the compiled reference with its cache ON
+ * (tools/fuzz_oracle.py sacacheport) and by tests/golden/ref_search_sa_cache.json.gz.
  *
  * Each function cites the reference lines it follows.  The arithmetic that decides ties is kept operation for
  * operation: counts held exactly, pp = 1/N_k, loglik += n*log(n*pp) in ascending table order, division by the
